@@ -1,0 +1,140 @@
+/* include/scisim_b200.h
+ *
+ * C ABI of libscisim_b200.so -- the B200 (sm_100a) collision-detection + unconstrained-flow back end
+ * that drops in under SCISim's Ball2DSim / RigidBody2DSim / RigidBody3DSim.
+ *
+ * The reference has no FFI layer: its seam is three C++ virtual interfaces plus one free function
+ * (SURVEY.md 8b). Each entry point below names the reference interface it replaces (paths relative
+ * to the SCISim checkout); INTEGRATION.md shows the C++14 shim a maintainer adds on the SCISim side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all floating point is IEEE binary64, indices are uint32_t
+ *   - vectors use SCISim's own layouts (ball2d: q = [x0,y0,x1,y1,...]; rb3d: q = [3N pos | 9N row-major R])
+ *   - every call returns SG_OK (0) or an error code; text via sg_last_error(). The reference convention
+ *     (print to std::cerr and std::exit(EXIT_FAILURE), e.g. rigidbody3d/RigidBody3DSim.cpp:908-909) is
+ *     applied by the host shim, not by this library
+ *   - single-threaded, non-reentrant per context, like the reference's sims
+ *   - input pointers are HOST pointers unless a function says "device"; outputs returned through
+ *     sg_contacts / sg_pairs point into library-owned pinned host memory valid until the next call on
+ *     the same context
+ *   - there is no CPU fallback: if no CUDA device is usable sg_create fails
+ */
+#ifndef SCISIM_B200_H
+#define SCISIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_OK 0
+#define SG_ERR_INVALID 1     /* bad argument / call order */
+#define SG_ERR_CUDA 2        /* CUDA runtime error */
+#define SG_ERR_UNSUPPORTED 3 /* pair of geometry types the reference itself aborts on */
+#define SG_ERR_INTERNAL 4
+
+/* UnconstrainedMap implementations (created by name in ball2d/Ball2DUtilities.cpp:37,
+ * rigidbody2d/RigidBody2DUtilities.cpp:39-43, rigidbody3d/RigidBody3DUtilities.cpp:40-44) */
+#define SG_MAP_SYMPLECTIC_EULER 0 /* ball2d/SymplecticEulerMap.cpp:21-32, rigidbody2d/SymplecticEulerMap.cpp:15-38 */
+#define SG_MAP_VERLET 1           /* ball2d/VerletMap.cpp:15-41, rigidbody2d/VerletMap.cpp:27-55 */
+#define SG_MAP_SPLIT_HAM 2        /* rigidbody3d/UnconstrainedMaps/SplitHamMap.cpp:17-182 */
+#define SG_MAP_DMV 3              /* rigidbody3d/UnconstrainedMaps/DMVMap.cpp:103-207 */
+
+/* contact types, in the order the reference appends them to active_set */
+#define SG_BALL_BALL 0   /* ball2d/Constraints/BallBallConstraint */
+#define SG_BALL_DRUM 1   /* ball2d/Constraints/BallStaticDrumConstraint */
+#define SG_BALL_PLANE 2  /* ball2d/Constraints/BallStaticPlaneConstraint */
+
+/* which optional arrays sg_*_active_set copies back to the host */
+#define SG_OUT_NORMALS 1u
+#define SG_OUT_POINTS 2u
+#define SG_OUT_DEPTHS 4u
+#define SG_OUT_CANDIDATES 8u
+#define SG_OUT_ALL 15u
+
+typedef struct sg_ctx sg_ctx;
+
+/* Sorted candidate pairs: drop-in for std::set<std::pair<unsigned,unsigned>> filled by
+ * SpatialGridDetector::getPotentialOverlaps (ball2d/SpatialGridDetector.h:39). ij = [i0,j0,i1,j1,...],
+ * i<j, ascending lexicographic -- the std::set iteration order. */
+typedef struct sg_pairs
+{
+  uint64_t n;
+  const uint32_t* ij;
+} sg_pairs;
+
+/* Active set in REFERENCE ORDER (one entry per Constraint the reference would emplace_back):
+ * ball-ball ascending (i,j) | drums drum-major | planes plane-major. dim = 2 or 3. */
+typedef struct sg_contacts
+{
+  uint32_t dim;
+  uint64_t n_candidates; /* size of the broad-phase pair set (P_c) */
+  uint64_t n_active;     /* = n_body_body + n_drum + n_plane */
+  uint64_t n_body_body;
+  uint64_t n_drum;
+  uint64_t n_plane;
+  const uint32_t* type;  /* n_active: SG_BALL_BALL, ... */
+  const uint32_t* i;     /* n_active: (first) body index */
+  const uint32_t* j;     /* n_active: second body / drum / plane index */
+  const double* n;       /* dim*n_active constraint normal (body-body, drum: from q0; plane: plane normal) */
+  const double* p;       /* dim*n_active getWorldSpaceContactPoint( q0 ) */
+  const double* depth;   /* n_active penetrationDepth( q1 ) (NaN where the reference has no override) */
+  const uint32_t* cand_ij; /* 2*n_candidates, only with SG_OUT_CANDIDATES */
+} sg_contacts;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+int sg_create( sg_ctx** ctx, int device );
+void sg_destroy( sg_ctx* ctx );
+const char* sg_last_error( const sg_ctx* ctx ); /* ctx may be NULL: error of a failed sg_create */
+int sg_synchronize( sg_ctx* ctx );
+/* pinned host memory for the caller's q/v vectors (optional; pageable pointers work, slower) */
+int sg_host_alloc( sg_ctx* ctx, uint64_t bytes, void** ptr );
+int sg_host_free( sg_ctx* ctx, void* ptr );
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on */
+void* sg_stream( sg_ctx* ctx );
+
+/* per-kernel device timing (CUDA events on the context's stream; off by default) */
+int sg_profile_enable( sg_ctx* ctx, int on );
+int sg_profile_reset( sg_ctx* ctx );
+int sg_profile_count( sg_ctx* ctx );
+/* entry k: kernel name, number of launches, summed device milliseconds, summed algorithmic bytes */
+int sg_profile_get( sg_ctx* ctx, int k, const char** name, uint64_t* launches, double* ms, double* bytes );
+/* number of kernels this context has launched since creation */
+uint64_t sg_launch_count( const sg_ctx* ctx );
+
+/* ---- broad phase alone ---------------------------------------------------------------------------
+ * Replaces SpatialGridDetector::getPotentialOverlaps( aabbs, overlaps ) -- ball2d/SpatialGridDetector.cpp:106-133,
+ * rigidbody2d/SpatialGrid.cpp:114-141 (dim 2), rigidbody3d/SpatialGridDetector.cpp:110-137 (dim 3).
+ * aabbs: n boxes, each [lo(dim), hi(dim)]. */
+int sg_candidate_pairs( sg_ctx* ctx, int dim, uint32_t n, const double* aabbs, sg_pairs* out );
+
+/* ---- ball2d ----------------------------------------------------------------------------------------
+ * Static data of Ball2DState (ball2d/Ball2DState.h): radii, per-ball mass (Minv = 1.0/m as
+ * Ball2DState.cpp:54-66), gravity (Ball2DGravityForce), static planes (normal is normalised here exactly as
+ * ball2d/StaticGeometry/StaticPlane.cpp:10-14 does) and static drums. */
+int sg_ball2d_set_bodies( sg_ctx* ctx, uint32_t n, const double* r, const double* m );
+int sg_ball2d_set_gravity( sg_ctx* ctx, const double* g /* 2 */ );
+int sg_ball2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 2n */, const double* nrm /* 2n */ );
+int sg_ball2d_set_drums( sg_ctx* ctx, uint32_t n, const double* x /* 2n */, const double* r /* n */ );
+
+/* UnconstrainedMap::flow( q0, v0, fsys, iteration, dt, q1, v1 ) -- scisim/UnconstrainedMaps/UnconstrainedMap.h:33
+ * for ball2d's SymplecticEulerMap / VerletMap with the gravity force set above. q1/v1 are caller-sized (2n). */
+int sg_ball2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
+
+/* ConstrainedSystem::computeActiveSet( q0, qp, v, active_set ) -- scisim/Constraints/ConstrainedSystem.h:20 as
+ * implemented by Ball2DSim::computeActiveSet (ball2d/Ball2DSim.cpp:151-173, no portals). */
+int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
+
+/* Resident variants: state stays in HBM between calls (what `value` in bench.py times).
+ * upload: q,v -> device q0,v0.  step: flow(q0,v0)->(q1,v1) then active set on (q0,q1); nothing is copied
+ * to the host except the counts in *out (array pointers are NULL).  fetch: copy the last step's lists. */
+int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v );
+int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
+int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

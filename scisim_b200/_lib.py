@@ -1,0 +1,84 @@
+"""ctypes binding of the C ABI declared in include/scisim_b200.h.
+
+There is deliberately no fallback: if the CUDA library is missing or fails to load, importing the
+host classes raises, so a CPU path can never silently stand in for the product.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libscisim_b200.so")
+
+SG_OK = 0
+SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV = 0, 1, 2, 3
+SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
+SG_OUT_NORMALS, SG_OUT_POINTS, SG_OUT_DEPTHS, SG_OUT_CANDIDATES, SG_OUT_ALL = 1, 2, 4, 8, 15
+
+c_dp = C.POINTER(C.c_double)
+c_up = C.POINTER(C.c_uint32)
+
+
+class SgPairs(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("ij", c_up)]
+
+
+class SgContacts(C.Structure):
+    _fields_ = [("dim", C.c_uint32), ("n_candidates", C.c_uint64), ("n_active", C.c_uint64), ("n_body_body", C.c_uint64),
+                ("n_drum", C.c_uint64), ("n_plane", C.c_uint64), ("type", c_up), ("i", c_up), ("j", c_up),
+                ("n", c_dp), ("p", c_dp), ("depth", c_dp), ("cand_ij", c_up)]
+
+
+class SciSimB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads libscisim_b200.so; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SciSimB200Error("%s not built: run `python -m scisim_b200.build` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    sigs = {
+        "sg_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "sg_destroy": (None, [vp]),
+        "sg_last_error": (C.c_char_p, [vp]),
+        "sg_synchronize": (C.c_int, [vp]),
+        "sg_host_alloc": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
+        "sg_host_free": (C.c_int, [vp, vp]),
+        "sg_stream": (vp, [vp]),
+        "sg_profile_enable": (C.c_int, [vp, C.c_int]),
+        "sg_profile_reset": (C.c_int, [vp]),
+        "sg_profile_count": (C.c_int, [vp]),
+        "sg_profile_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), c_dp, c_dp]),
+        "sg_launch_count": (C.c_uint64, [vp]),
+        "sg_candidate_pairs": (C.c_int, [vp, C.c_int, C.c_uint32, vp, C.POINTER(SgPairs)]),
+        "sg_ball2d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_ball2d_set_gravity": (C.c_int, [vp, vp]),
+        "sg_ball2d_set_planes": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_ball2d_set_drums": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_ball2d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
+        "sg_ball2d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
+        "sg_ball2d_upload": (C.c_int, [vp, vp, vp]),
+        "sg_ball2d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
+        "sg_ball2d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def declared_symbols():
+    """Every function name declared in include/scisim_b200.h (used by the ABI test)."""
+    import re
+    hdr = open(os.path.join(HERE, "..", "include", "scisim_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(sg_[a-z0-9_]+)\s*\(", hdr)))

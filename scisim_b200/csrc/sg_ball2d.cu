@@ -1,0 +1,605 @@
+// sg_ball2d.cu -- ball2d hot path: unconstrained flow, broad phase + ball-ball CCD, drum and plane tests.
+//
+// Reference behaviour reproduced (file:line in the SCISim checkout):
+//   ball2d/SymplecticEulerMap.cpp:21-32, ball2d/VerletMap.cpp:15-41           k_ball2d_flow
+//   ball2d/Forces/Ball2DGravityForce.cpp:36-46, ball2d/Ball2DState.cpp:54-66  (gravity, Minv = 1.0/m)
+//   ball2d/Ball2DSim.cpp:553-608   swept AABBs + getPotentialOverlaps + CCD    Ball2DPolicy + sg_broadphase.cuh
+//   scisim/CollisionDetection/CollisionDetectionUtilities.cpp:3-121           ccd_hit()
+//   ball2d/Constraints/BallBallConstraint.cpp:22-37,219-222,270-280           normal / point / depth
+//   ball2d/Ball2DSim.cpp:730-762   drum-major and plane-major all-pairs loops   k_ball2d_static_*
+//   ball2d/Constraints/BallStaticPlaneConstraint.cpp:10-15, BallStaticDrumConstraint.cpp:8-26
+//
+// HBM layout: q0,v0,q1,v1 are SCISim's own interleaved [x,y] vectors, i.e. arrays of double2 (one
+// 128-bit access per ball); r and m are plain double arrays.  Sorted 64-byte records are described in
+// sg_broadphase.cuh.  Contacts are SoA (type,i,j,n,p,depth) in the reference's active_set order.
+#include "sg_broadphase.cuh"
+
+struct Ball2DIn
+{
+  const double2* q0;
+  const double2* q1;
+  const double* r;
+  uint32_t n;
+};
+
+struct alignas( 64 ) Ball2DRec
+{
+  double q0x, q0y, q1x, q1y;
+  double r;
+  uint32_t idx;
+  uint32_t key;
+  double pad0, pad1;
+};
+
+struct ContactOut2D
+{
+  uint32_t* type;
+  uint32_t* i;
+  uint32_t* j;
+  double2* n;
+  double2* p;
+  double* depth;
+  unsigned long long cap;
+};
+
+// scisim/CollisionDetection/CollisionDetectionUtilities.cpp:3-121 (a = lower body index)
+__device__ __forceinline__ bool ccd_hit( const Ball2DRec& a, const Ball2DRec& b )
+{
+  const double d0x = a.q0x - b.q0x;
+  const double d0y = a.q0y - b.q0y;
+  const double d1x = ( a.q1x - b.q1x ) - d0x;
+  const double d1y = ( a.q1y - b.q1y ) - d0y;
+  const double rs = a.r + b.r;
+  const double c0 = ( d0x * d0x + d0y * d0y ) - rs * rs;
+  const double c1 = 2.0 * ( d0x * d1x + d0y * d1y );
+  const double c2 = d1x * d1x + d1y * d1y;
+  if( c2 != 0.0 )
+  {
+    const double c1c1 = c1 * c1;
+    const double fc2c0 = 4.0 * c2 * c0;
+    if( c1c1 < fc2c0 ) { return false; }
+    const double s = sqrt( c1c1 - fc2c0 );
+    const double root1 = ( c1 > 0.0 ) ? ( 2.0 * c0 ) / ( -c1 - s ) : ( -c1 + s ) / ( 2.0 * c2 );
+    if( root1 < 0.0 ) { return false; }
+    const double root0 = ( c1 >= 0.0 ) ? ( -c1 - s ) / ( 2.0 * c2 ) : ( 2.0 * c0 ) / ( -c1 + s );
+    if( root0 > 1.0 ) { return false; }
+    return true;
+  }
+  return c0 <= 0.0;
+}
+
+struct Ball2DPolicy
+{
+  static constexpr int D = 2;
+  static constexpr bool HAS_NARROW = true;
+  static constexpr double IN_BYTES = 40.0;
+  using In = Ball2DIn;
+  using Rec = Ball2DRec;
+  using Out = ContactOut2D;
+
+  // ball2d/Ball2DSim.cpp:566-571: lo = min(q1,q0) - r, hi = max(q1,q0) + r
+  __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
+  {
+    const double2 a = __ldg( &in.q0[i] );
+    const double2 b = __ldg( &in.q1[i] );
+    const double r = __ldg( &in.r[i] );
+    lo[0] = fmin( b.x, a.x ) - r; lo[1] = fmin( b.y, a.y ) - r;
+    hi[0] = fmax( b.x, a.x ) + r; hi[1] = fmax( b.y, a.y ) + r;
+  }
+  __device__ static Rec make_rec( const In& in, const uint32_t i, const uint32_t key )
+  {
+    const double2 a = __ldg( &in.q0[i] );
+    const double2 b = __ldg( &in.q1[i] );
+    Rec rec;
+    rec.q0x = a.x; rec.q0y = a.y; rec.q1x = b.x; rec.q1y = b.y;
+    rec.r = __ldg( &in.r[i] );
+    rec.idx = i; rec.key = key; rec.pad0 = 0.0; rec.pad1 = 0.0;
+    return rec;
+  }
+  __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
+  {
+    lo[0] = fmin( s.q1x, s.q0x ) - s.r; lo[1] = fmin( s.q1y, s.q0y ) - s.r;
+    hi[0] = fmax( s.q1x, s.q0x ) + s.r; hi[1] = fmax( s.q1y, s.q0y ) + s.r;
+  }
+  __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
+  __device__ static uint32_t narrow_count( const Rec& a, const Rec& b ) { return ccd_hit( a, b ) ? 1u : 0u; }
+  // BallBallConstraint{ i, j, q0a, q0b, ra, rb }: n = (q0a - q0b).normalized(); point q0a - ra*n; depth at q1
+  __device__ static void narrow_emit( const Out& out, unsigned long long& k, const Rec& a, const Rec& b )
+  {
+    if( !ccd_hit( a, b ) ) { return; }
+    if( k < out.cap )
+    {
+      double nx = a.q0x - b.q0x;
+      double ny = a.q0y - b.q0y;
+      const double z = nx * nx + ny * ny;
+      if( z > 0.0 ) { const double s = sqrt( z ); nx = nx / s; ny = ny / s; }
+      const double ex = a.q1x - b.q1x;
+      const double ey = a.q1y - b.q1y;
+      out.type[k] = SG_BALL_BALL;
+      out.i[k] = a.idx;
+      out.j[k] = b.idx;
+      out.n[k] = make_double2( nx, ny );
+      out.p[k] = make_double2( a.q0x - a.r * nx, a.q0y - a.r * ny );
+      out.depth[k] = fmin( 0.0, sqrt( ex * ex + ey * ey ) - ( a.r + b.r ) );
+    }
+    ++k;
+  }
+};
+
+// ---- unconstrained flow ----------------------------------------------------------------------------
+// Arithmetic order follows Eigen's evaluation of the reference expressions:
+//   F = 0 + m*g;  SE: v1 = v0 + (0 + (dt*minv)*F), q1 = q0 + dt*v1
+//   Verlet: vh = v0 + (0 + ((0.5*dt)*minv)*F), q1 = q0 + dt*vh, v1 = vh + ((0.5*dt)*minv)*F(q1)
+__global__ void __launch_bounds__( 256 ) k_ball2d_flow( const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0, const double* __restrict__ m,
+                                                       const double gx, const double gy, const double dt, double2* __restrict__ q1, double2* __restrict__ v1 )
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i >= n ) { return; }
+  const double2 q = __ldg( &q0[i] );
+  const double2 v = __ldg( &v0[i] );
+  const double mass = __ldg( &m[i] );
+  const double minv = 1.0 / mass;
+  const double Fx = 0.0 + mass * gx;
+  const double Fy = 0.0 + mass * gy;
+  double2 qo, vo;
+  if( kind == SG_MAP_SYMPLECTIC_EULER )
+  {
+    const double s = dt * minv;
+    vo.x = v.x + ( 0.0 + s * Fx );
+    vo.y = v.y + ( 0.0 + s * Fy );
+    qo.x = q.x + dt * vo.x;
+    qo.y = q.y + dt * vo.y;
+  }
+  else
+  {
+    const double s = ( 0.5 * dt ) * minv;
+    const double vhx = v.x + ( 0.0 + s * Fx );
+    const double vhy = v.y + ( 0.0 + s * Fy );
+    qo.x = q.x + dt * vhx;
+    qo.y = q.y + dt * vhy;
+    vo.x = vhx + s * Fx;
+    vo.y = vhy + s * Fy;
+  }
+  q1[i] = qo;
+  v1[i] = vo;
+}
+
+// ---- static geometry (drums, then planes) ----------------------------------------------------------
+struct Static2D
+{
+  uint32_t ndrums;
+  uint32_t nplanes;
+  double drum_x[SG_MAX_DRUMS], drum_y[SG_MAX_DRUMS], drum_r[SG_MAX_DRUMS];
+  double plane_x[SG_MAX_PLANES], plane_y[SG_MAX_PLANES], plane_nx[SG_MAX_PLANES], plane_ny[SG_MAX_PLANES];
+};
+
+// bit g of the result: geometry g (drums first, then planes) is active for this ball at q1
+__device__ __forceinline__ unsigned long long static_mask( const Static2D& sg, const double2 x1, const double r )
+{
+  unsigned long long mask = 0ull;
+  for( uint32_t d = 0; d < sg.ndrums; ++d )
+  {
+    // ( X - q ).squaredNorm() >= ( R - r ) * ( R - r )
+    const double dx = sg.drum_x[d] - x1.x;
+    const double dy = sg.drum_y[d] - x1.y;
+    const double Rr = sg.drum_r[d] - r;
+    if( dx * dx + dy * dy >= Rr * Rr ) { mask |= 1ull << d; }
+  }
+  for( uint32_t p = 0; p < sg.nplanes; ++p )
+  {
+    // n.dot( q - x ) <= r
+    const double dist = sg.plane_nx[p] * ( x1.x - sg.plane_x[p] ) + sg.plane_ny[p] * ( x1.y - sg.plane_y[p] );
+    if( dist <= r ) { mask |= 1ull << ( sg.ndrums + p ); }
+  }
+  return mask;
+}
+
+// counts[g * nblocks + block] = number of balls of this block active against geometry g
+__global__ void __launch_bounds__( 256 ) k_ball2d_static_count( const __grid_constant__ Static2D sg, const uint32_t n, const double2* __restrict__ q1, const double* __restrict__ r, uint32_t* __restrict__ counts )
+{
+  __shared__ uint32_t s_cnt[SG_MAX_DRUMS + SG_MAX_PLANES];
+  const uint32_t ng = sg.ndrums + sg.nplanes;
+  if( threadIdx.x < ng ) { s_cnt[threadIdx.x] = 0u; }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long mask = 0ull;
+  if( i < n ) { mask = static_mask( sg, __ldg( &q1[i] ), __ldg( &r[i] ) ); }
+  const int lane = threadIdx.x & 31;
+  for( uint32_t g = 0; g < ng; ++g )
+  {
+    const unsigned b = __ballot_sync( 0xffffffffu, ( mask >> g ) & 1ull );
+    if( lane == 0 && b != 0u ) { atomicAdd( &s_cnt[g], __popc( b ) ); }
+  }
+  __syncthreads();
+  if( threadIdx.x < ng ) { counts[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x]; }
+}
+
+// Stable compaction: geometry-major, ball ascending, appended after the body-body contacts
+__global__ void __launch_bounds__( 256 ) k_ball2d_static_emit( const __grid_constant__ Static2D sg, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r,
+                                                              const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, const ScanPairCounts::Acc* __restrict__ pair_totals, const ContactOut2D out )
+{
+  __shared__ uint32_t s_warp[8];
+  const uint32_t ng = sg.ndrums + sg.nplanes;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2 x0 = make_double2( 0.0, 0.0 ), x1 = x0;
+  double rad = 0.0;
+  unsigned long long mask = 0ull;
+  if( i < n ) { x0 = __ldg( &q0[i] ); x1 = __ldg( &q1[i] ); rad = __ldg( &r[i] ); mask = static_mask( sg, x1, rad ); }
+  const unsigned long long base = pair_totals->a;
+  for( uint32_t g = 0; g < ng; ++g )
+  {
+    if( counts[g * gridDim.x + blockIdx.x] == 0u ) { continue; } // uniform across the block
+    const bool act = ( mask >> g ) & 1ull;
+    const unsigned b = __ballot_sync( 0xffffffffu, act );
+    __syncthreads();
+    if( lane == 0 ) { s_warp[warp] = __popc( b ); }
+    __syncthreads();
+    uint32_t before = 0u;
+    for( int w = 0; w < warp; ++w ) { before += s_warp[w]; }
+    if( act )
+    {
+      const unsigned long long k = base + offsets[g * gridDim.x + blockIdx.x] + before + __popc( b & ( ( 1u << lane ) - 1u ) );
+      if( k < out.cap )
+      {
+        double nx, ny, depth;
+        uint32_t type, j;
+        if( g < sg.ndrums )
+        {
+          // StaticDrumConstraint: n = ( X - q0_i ).normalized(); no depth override (NaN)
+          type = SG_BALL_DRUM; j = g;
+          nx = sg.drum_x[g] - x0.x; ny = sg.drum_y[g] - x0.y;
+          const double z = nx * nx + ny * ny;
+          if( z > 0.0 ) { const double s = sqrt( z ); nx = nx / s; ny = ny / s; }
+          depth = __longlong_as_double( 0x7ff8000000000000LL );
+        }
+        else
+        {
+          const uint32_t p = g - sg.ndrums;
+          type = SG_BALL_PLANE; j = p;
+          nx = sg.plane_nx[p]; ny = sg.plane_ny[p];
+          const double dist = nx * ( x1.x - sg.plane_x[p] ) + ny * ( x1.y - sg.plane_y[p] );
+          depth = fmin( 0.0, dist - rad );
+        }
+        out.type[k] = type;
+        out.i[k] = i;
+        out.j[k] = j;
+        out.n[k] = make_double2( nx, ny );
+        out.p[k] = make_double2( x0.x - rad * nx, x0.y - rad * ny );
+        out.depth[k] = depth;
+      }
+    }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+struct Ball2DData
+{
+  uint32_t n = 0;
+  double g[2] = { 0.0, 0.0 };
+  Static2D sg;
+  DevBuf r, m, q0, v0, q1, v1;
+  BroadScratch bp;
+  // static geometry scratch
+  DevBuf st_counts, st_offsets, st_partials, st_total;
+  // contact SoA
+  DevBuf c_type, c_i, c_j, c_n, c_p, c_depth;
+  uint64_t act_cap = 0;
+  // host staging
+  PinBuf h_totals;  // {P_c, P_a, n_static}
+  PinBuf h_out;     // contacts copied back
+  // results of the last active-set computation
+  uint64_t n_cand = 0, n_bb = 0, n_static = 0, n_drum = 0, n_plane = 0;
+  bool have_result = false;
+  bool cand_valid = false;
+  Ball2DData() { memset( &sg, 0, sizeof( sg ) ); }
+};
+
+void sg_ball2d_release( sg_ctx* ctx )
+{
+  Ball2DData* d = ctx->ball2d;
+  if( d == nullptr ) { return; }
+  d->r.release(); d->m.release(); d->q0.release(); d->v0.release(); d->q1.release(); d->v1.release();
+  d->bp.release();
+  d->st_counts.release(); d->st_offsets.release(); d->st_partials.release(); d->st_total.release();
+  d->c_type.release(); d->c_i.release(); d->c_j.release(); d->c_n.release(); d->c_p.release(); d->c_depth.release();
+  d->h_totals.release(); d->h_out.release();
+  delete d;
+  ctx->ball2d = nullptr;
+}
+
+static Ball2DData* ball2d_data( sg_ctx* ctx )
+{
+  if( ctx->ball2d == nullptr ) { ctx->ball2d = new Ball2DData; }
+  return ctx->ball2d;
+}
+
+static int ball2d_ensure_outputs( sg_ctx* ctx, Ball2DData* d, const uint64_t cand_cap, const uint64_t act_cap )
+{
+  if( cand_cap > d->bp.cand_cap )
+  {
+    SG_CUDA( ctx, d->bp.cand.ensure( size_t( cand_cap ) * sizeof( uint2 ) ) );
+    d->bp.cand_cap = d->bp.cand.cap / sizeof( uint2 );
+  }
+  if( act_cap > d->act_cap )
+  {
+    SG_CUDA( ctx, d->c_type.ensure( size_t( act_cap ) * 4 ) );
+    SG_CUDA( ctx, d->c_i.ensure( size_t( act_cap ) * 4 ) );
+    SG_CUDA( ctx, d->c_j.ensure( size_t( act_cap ) * 4 ) );
+    SG_CUDA( ctx, d->c_n.ensure( size_t( act_cap ) * 16 ) );
+    SG_CUDA( ctx, d->c_p.ensure( size_t( act_cap ) * 16 ) );
+    SG_CUDA( ctx, d->c_depth.ensure( size_t( act_cap ) * 8 ) );
+    d->act_cap = act_cap;
+  }
+  return SG_OK;
+}
+
+static int ball2d_flow_device( sg_ctx* ctx, Ball2DData* d, const int map_kind, const double dt )
+{
+  const uint32_t n = d->n;
+  if( n == 0 ) { return SG_OK; }
+  SG_LAUNCH( ctx, "ball2d_flow", double( n ) * 72.0, k_ball2d_flow<<<sg_div_up( n, 256 ), 256, 0, ctx->stream>>>( map_kind, n, d->q0.as<double2>(), d->v0.as<double2>(), d->m.as<double>(),
+             d->g[0], d->g[1], dt, d->q1.as<double2>(), d->v1.as<double2>() ) );
+  return SG_OK;
+}
+
+// Runs the whole detection pipeline on the device-resident q0,q1 and leaves the counts in d->n_*.
+static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want_cand )
+{
+  const uint32_t n = d->n;
+  d->n_cand = d->n_bb = d->n_static = d->n_drum = d->n_plane = 0;
+  d->have_result = true;
+  d->cand_valid = want_cand;
+  if( n == 0 ) { return SG_OK; }
+  int rc = sg_bp_prepare_scratch<Ball2DPolicy>( ctx, d->bp, n );
+  if( rc != SG_OK ) { return rc; }
+  SG_CUDA( ctx, d->h_totals.ensure( 64 ) );
+  // first guess at the list sizes; grown (and the emit re-run) if a step overflows them
+  rc = ball2d_ensure_outputs( ctx, d, want_cand ? ( d->bp.cand_cap > 0 ? d->bp.cand_cap : uint64_t( n ) * 6u + 1024u ) : 0u, d->act_cap > 0 ? d->act_cap : uint64_t( n ) * 4u + 1024u );
+  if( rc != SG_OK ) { return rc; }
+
+  Ball2DIn in;
+  in.q0 = d->q0.as<double2>(); in.q1 = d->q1.as<double2>(); in.r = d->r.as<double>(); in.n = n;
+  rc = sg_bp_bin_and_count<Ball2DPolicy>( ctx, d->bp, in );
+  if( rc != SG_OK ) { return rc; }
+
+  const uint32_t ng = d->sg.ndrums + d->sg.nplanes;
+  const unsigned nblk = sg_div_up( n, 256 );
+  const uint32_t nst = ng * nblk;
+  if( ng > 0 )
+  {
+    SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 ) );
+    SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 ) );
+    SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
+    SG_CUDA( ctx, d->st_total.ensure( 4 ) );
+    SG_LAUNCH( ctx, "ball2d_static_count", double( n ) * 24.0, k_ball2d_static_count<<<nblk, 256, 0, ctx->stream>>>( d->sg, n, d->q1.as<double2>(), d->r.as<double>(), d->st_counts.as<uint32_t>() ) );
+    rc = sg_exclusive_scan<ScanU32>( ctx, "ball2d_static_scan", d->st_counts.as<uint32_t>(), nullptr, nst, nst, d->st_partials.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->st_total.as<uint32_t>(), false );
+    if( rc != SG_OK ) { return rc; }
+  }
+
+  for( int attempt = 0; attempt < 2; ++attempt )
+  {
+    ContactOut2D out;
+    out.type = d->c_type.as<uint32_t>(); out.i = d->c_i.as<uint32_t>(); out.j = d->c_j.as<uint32_t>();
+    out.n = d->c_n.as<double2>(); out.p = d->c_p.as<double2>(); out.depth = d->c_depth.as<double>();
+    out.cap = d->act_cap;
+    rc = sg_bp_emit_lists<Ball2DPolicy>( ctx, d->bp, n, want_cand, out, 0.0 );
+    if( rc != SG_OK ) { return rc; }
+    if( ng > 0 )
+    {
+      SG_LAUNCH( ctx, "ball2d_static_emit", double( n ) * 40.0, k_ball2d_static_emit<<<nblk, 256, 0, ctx->stream>>>( d->sg, n, d->q0.as<double2>(), d->q1.as<double2>(), d->r.as<double>(),
+                 d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->bp.totals.as<ScanPairCounts::Acc>(), out ) );
+    }
+    // counts to the host
+    unsigned long long* ht = d->h_totals.as<unsigned long long>();
+    ht[2] = 0ull;
+    SG_CUDA( ctx, cudaMemcpyAsync( ht, d->bp.totals.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( ng > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( ht + 2, d->st_total.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    sg_prof_collect( ctx );
+    d->n_cand = ht[0];
+    d->n_bb = ht[1];
+    d->n_static = ht[2] & 0xffffffffull;
+    const uint64_t need_act = d->n_bb + d->n_static;
+    const bool cand_ok = !want_cand || d->n_cand <= d->bp.cand_cap;
+    if( cand_ok && need_act <= d->act_cap ) { break; }
+    if( attempt == 1 ) { return sg_fail( ctx, SG_ERR_INTERNAL, "ball2d: output lists still overflow after regrowth" ); }
+    rc = ball2d_ensure_outputs( ctx, d, want_cand ? d->n_cand + d->n_cand / 8 + 1024 : 0u, need_act + need_act / 8 + 1024 );
+    if( rc != SG_OK ) { return rc; }
+  }
+  return SG_OK;
+}
+
+// Copies the last result's lists into pinned memory and fills *out.  Counts per static type are derived
+// on the host from the type array tail (drums precede planes).
+static int ball2d_copy_out( sg_ctx* ctx, Ball2DData* d, const uint32_t flags, sg_contacts* out )
+{
+  memset( out, 0, sizeof( *out ) );
+  out->dim = 2;
+  out->n_candidates = d->n_cand;
+  out->n_body_body = d->n_bb;
+  const uint64_t na = d->n_bb + d->n_static;
+  out->n_active = na;
+  const bool want_cand = ( flags & SG_OUT_CANDIDATES ) != 0u && d->cand_valid;
+  size_t bytes = 64;
+  const size_t o_type = bytes; bytes += ( na * 4 + 63 ) & ~size_t( 63 );
+  const size_t o_i = bytes; bytes += ( na * 4 + 63 ) & ~size_t( 63 );
+  const size_t o_j = bytes; bytes += ( na * 4 + 63 ) & ~size_t( 63 );
+  const size_t o_n = bytes; if( flags & SG_OUT_NORMALS ) { bytes += ( na * 16 + 63 ) & ~size_t( 63 ); }
+  const size_t o_p = bytes; if( flags & SG_OUT_POINTS ) { bytes += ( na * 16 + 63 ) & ~size_t( 63 ); }
+  const size_t o_d = bytes; if( flags & SG_OUT_DEPTHS ) { bytes += ( na * 8 + 63 ) & ~size_t( 63 ); }
+  const size_t o_c = bytes; if( want_cand ) { bytes += ( d->n_cand * 8 + 63 ) & ~size_t( 63 ); }
+  SG_CUDA( ctx, d->h_out.ensure( bytes ) );
+  char* h = d->h_out.as<char>();
+  if( na > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_type, d->c_type.ptr, na * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_i, d->c_i.ptr, na * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_j, d->c_j.ptr, na * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( flags & SG_OUT_NORMALS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_n, d->c_n.ptr, na * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+    if( flags & SG_OUT_POINTS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_p, d->c_p.ptr, na * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+    if( flags & SG_OUT_DEPTHS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_d, d->c_depth.ptr, na * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  }
+  if( want_cand && d->n_cand > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_c, d->bp.cand.ptr, d->n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  out->type = reinterpret_cast<const uint32_t*>( h + o_type );
+  out->i = reinterpret_cast<const uint32_t*>( h + o_i );
+  out->j = reinterpret_cast<const uint32_t*>( h + o_j );
+  out->n = ( flags & SG_OUT_NORMALS ) ? reinterpret_cast<const double*>( h + o_n ) : nullptr;
+  out->p = ( flags & SG_OUT_POINTS ) ? reinterpret_cast<const double*>( h + o_p ) : nullptr;
+  out->depth = ( flags & SG_OUT_DEPTHS ) ? reinterpret_cast<const double*>( h + o_d ) : nullptr;
+  out->cand_ij = want_cand ? reinterpret_cast<const uint32_t*>( h + o_c ) : nullptr;
+  uint64_t nd = 0;
+  for( uint64_t k = d->n_bb; k < na; ++k ) { if( out->type[k] == SG_BALL_DRUM ) { ++nd; } else { break; } }
+  d->n_drum = nd; d->n_plane = d->n_static - nd;
+  out->n_drum = d->n_drum; out->n_plane = d->n_plane;
+  return SG_OK;
+}
+
+extern "C"
+{
+
+int sg_ball2d_set_bodies( sg_ctx* ctx, uint32_t n, const double* r, const double* m )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > 0 && ( r == nullptr || m == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_bodies: null array" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  Ball2DData* d = ball2d_data( ctx );
+  d->n = n;
+  d->have_result = false;
+  if( n == 0 ) { return SG_OK; }
+  SG_CUDA( ctx, d->r.ensure( size_t( n ) * 8 ) );
+  SG_CUDA( ctx, d->m.ensure( size_t( n ) * 8 ) );
+  SG_CUDA( ctx, d->q0.ensure( size_t( n ) * 16 ) );
+  SG_CUDA( ctx, d->v0.ensure( size_t( n ) * 16 ) );
+  SG_CUDA( ctx, d->q1.ensure( size_t( n ) * 16 ) );
+  SG_CUDA( ctx, d->v1.ensure( size_t( n ) * 16 ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->r.ptr, r, size_t( n ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->m.ptr, m, size_t( n ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_ball2d_set_gravity( sg_ctx* ctx, const double* g )
+{
+  if( ctx == nullptr || g == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  d->g[0] = g[0]; d->g[1] = g[1];
+  return SG_OK;
+}
+
+int sg_ball2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x, const double* nrm )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > SG_MAX_PLANES ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_planes: at most %d planes", SG_MAX_PLANES ); }
+  Ball2DData* d = ball2d_data( ctx );
+  d->sg.nplanes = n;
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    // StaticPlane::StaticPlane: m_n( n.normalized() )  (Eigen 3.3: n / sqrt(n.n) when n.n > 0); host FP64, no contraction
+    double nx = nrm[2 * p], ny = nrm[2 * p + 1];
+    volatile double xx = nx * nx; volatile double yy = ny * ny;
+    const double z = xx + yy;
+    if( z > 0.0 ) { const double s = sqrt( z ); nx = nx / s; ny = ny / s; }
+    d->sg.plane_x[p] = x[2 * p]; d->sg.plane_y[p] = x[2 * p + 1];
+    d->sg.plane_nx[p] = nx; d->sg.plane_ny[p] = ny;
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_set_drums( sg_ctx* ctx, uint32_t n, const double* x, const double* r )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > SG_MAX_DRUMS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_drums: at most %d drums", SG_MAX_DRUMS ); }
+  Ball2DData* d = ball2d_data( ctx );
+  d->sg.ndrums = n;
+  for( uint32_t k = 0; k < n; ++k ) { d->sg.drum_x[k] = x[2 * k]; d->sg.drum_y[k] = x[2 * k + 1]; d->sg.drum_r[k] = r[k]; }
+  return SG_OK;
+}
+
+int sg_ball2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: map kind %d is not a ball2d map", map_kind ); }
+  Ball2DData* d = ball2d_data( ctx );
+  const size_t bytes = size_t( d->n ) * 16;
+  if( d->n == 0 ) { return SG_OK; }
+  if( q0 == nullptr || v0 == nullptr || q1 == nullptr || v1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v0, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  const int rc = ball2d_flow_device( ctx, d, map_kind, dt );
+  if( rc != SG_OK ) { return rc; }
+  SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out )
+{
+  if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  const size_t bytes = size_t( d->n ) * 16;
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->n > 0 )
+  {
+    if( q0 == nullptr || q1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_active_set: null vector" ); }
+    SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  }
+  const int rc = ball2d_active_set_device( ctx, d, ( out_flags & SG_OUT_CANDIDATES ) != 0u );
+  if( rc != SG_OK ) { return rc; }
+  return ball2d_copy_out( ctx, d, out_flags, out );
+}
+
+int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( d->n == 0 ) { return SG_OK; }
+  if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_upload: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q, size_t( d->n ) * 16, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v, size_t( d->n ) * 16, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_step: map kind %d is not a ball2d map", map_kind ); }
+  Ball2DData* d = ball2d_data( ctx );
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  int rc = ball2d_flow_device( ctx, d, map_kind, dt );
+  if( rc != SG_OK ) { return rc; }
+  rc = ball2d_active_set_device( ctx, d, true );
+  if( rc != SG_OK ) { return rc; }
+  if( out != nullptr )
+  {
+    memset( out, 0, sizeof( *out ) );
+    out->dim = 2;
+    out->n_candidates = d->n_cand;
+    out->n_body_body = d->n_bb;
+    out->n_active = d->n_bb + d->n_static;
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_fetch: no step has been run" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( q1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, size_t( d->n ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( v1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( out != nullptr ) { return ball2d_copy_out( ctx, d, out_flags, out ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+}

@@ -1,0 +1,470 @@
+// sg_broadphase.cuh -- uniform-grid broad phase (+ fused narrow phase) shared by every body type.
+//
+// Replaces SpatialGridDetector::getPotentialOverlaps (ball2d/SpatialGridDetector.cpp:106-133,
+// rigidbody2d/SpatialGrid.cpp:114-141, rigidbody3d/SpatialGridDetector.cpp:110-137) and the per-pair
+// loop that follows it in each sim (e.g. ball2d/Ball2DSim.cpp:580-607).
+//
+// Contract kept from the reference: the candidate set is EXACTLY
+//   { (i<j) : for every axis  !(hi_i < lo_j) && !(hi_j < lo_i) }   in ascending (i,j) order,
+// nothing else about the grid is observable.  Pipeline (one launch each unless noted):
+//   bounds   reduce min/max of box lower corners and the largest box extent
+//   setup    lay out the grid (h >= largest extent, cell count capped), zero the cell histogram
+//   hist     cell key per body + rank inside the cell (one atomicAdd per body)
+//   scan     cell counts -> cell start offsets               (3 launches, sg_scan.cuh)
+//   scatter  write a 64-byte record per body at cell_start[key] + rank  => bodies sorted by cell
+//   count    per body: walk the 3^D neighbourhood (D-1 contiguous row segments), count candidates with a
+//            larger index and how many of them pass the narrow phase; counts stored BY BODY INDEX
+//   scan     counts -> output offsets in body-index order   (3 launches)
+//   emit     same walk; the body's candidates are ordered by partner index in registers/local memory and
+//            written at the body's offset => both lists come out in ascending (i,j) order with no sort
+// The block's own records are staged in shared memory; neighbours outside the block come through L1/L2.
+#ifndef SG_BROADPHASE_CUH
+#define SG_BROADPHASE_CUH
+
+#include "sg_common.cuh"
+#include "sg_scan.cuh"
+
+#define SG_BP_THREADS 256
+#define SG_BP_LOCAL_CAP 24
+
+// Per-pipeline device scratch (owned by the caller's data block)
+struct BroadScratch
+{
+  DevBuf bounds;        // BoundsAccum
+  DevBuf params;        // GridParams
+  DevBuf cell_count;    // u32[max_cells + 1]
+  DevBuf cell_start;    // u32[max_cells + 1]
+  DevBuf cell_partials; // u32[tiles]
+  DevBuf key;           // u32[n]
+  DevBuf rank;          // u32[n]
+  DevBuf recs;          // Rec[n]
+  DevBuf counts;        // uint2[n]
+  DevBuf offsets;       // ulonglong2[n]
+  DevBuf pair_partials; // ScanPairCounts::Acc[tiles]
+  DevBuf totals;        // ScanPairCounts::Acc
+  DevBuf cand;          // uint2[cand_cap]
+  uint64_t cand_cap = 0;
+  uint32_t max_cells = 0;
+  void release()
+  {
+    bounds.release(); params.release(); cell_count.release(); cell_start.release(); cell_partials.release(); key.release(); rank.release();
+    recs.release(); counts.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
+  }
+};
+
+// ---- record I/O: 64-byte records moved as four 128-bit accesses ------------------------------------
+template<typename Rec>
+__device__ inline Rec sg_load_rec_global( const Rec* __restrict__ p )
+{
+  static_assert( sizeof( Rec ) == 64, "records are 64 bytes" );
+  union { Rec r; int4 v[4]; } u;
+  const int4* src = reinterpret_cast<const int4*>( p );
+  u.v[0] = __ldg( src + 0 ); u.v[1] = __ldg( src + 1 ); u.v[2] = __ldg( src + 2 ); u.v[3] = __ldg( src + 3 );
+  return u.r;
+}
+template<typename Rec>
+__device__ inline Rec sg_load_rec_shared( const Rec* p )
+{
+  union { Rec r; int4 v[4]; } u;
+  const int4* src = reinterpret_cast<const int4*>( p );
+  u.v[0] = src[0]; u.v[1] = src[1]; u.v[2] = src[2]; u.v[3] = src[3];
+  return u.r;
+}
+template<typename Rec>
+__device__ inline void sg_store_rec( Rec* p, const Rec& r )
+{
+  union { Rec r; int4 v[4]; } u;
+  u.r = r;
+  int4* dst = reinterpret_cast<int4*>( p );
+  dst[0] = u.v[0]; dst[1] = u.v[1]; dst[2] = u.v[2]; dst[3] = u.v[3];
+}
+
+// ---- bounds ----------------------------------------------------------------------------------------
+static __global__ void sg_bp_bounds_init( BoundsAccum* acc )
+{
+  if( threadIdx.x == 0 && blockIdx.x == 0 )
+  {
+    for( int k = 0; k < 3; ++k )
+    {
+      acc->min_lo[k] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );  // +inf
+      acc->max_lo[k] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );  // -inf
+    }
+    acc->max_ext = sg_ordered_from_double( 0.0 );
+  }
+}
+
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_bounds( const typename P::In in, BoundsAccum* __restrict__ acc )
+{
+  constexpr int D = P::D;
+  double mn[D], mx[D], ext = 0.0;
+  #pragma unroll
+  for( int k = 0; k < D; ++k ) { mn[k] = __longlong_as_double( 0x7ff0000000000000LL ); mx[k] = __longlong_as_double( 0xfff0000000000000LL ); }
+  for( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += gridDim.x * blockDim.x )
+  {
+    double lo[D], hi[D];
+    P::load_aabb( in, i, lo, hi );
+    #pragma unroll
+    for( int k = 0; k < D; ++k )
+    {
+      mn[k] = fmin( mn[k], lo[k] );
+      mx[k] = fmax( mx[k], lo[k] );
+      ext = fmax( ext, hi[k] - lo[k] );
+    }
+  }
+  // warp reduce
+  #pragma unroll
+  for( int d = 16; d > 0; d >>= 1 )
+  {
+    #pragma unroll
+    for( int k = 0; k < D; ++k )
+    {
+      mn[k] = fmin( mn[k], __shfl_xor_sync( 0xffffffffu, mn[k], d ) );
+      mx[k] = fmax( mx[k], __shfl_xor_sync( 0xffffffffu, mx[k], d ) );
+    }
+    ext = fmax( ext, __shfl_xor_sync( 0xffffffffu, ext, d ) );
+  }
+  __shared__ double s_red[SG_BP_THREADS / 32][2 * D + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if( lane == 0 )
+  {
+    #pragma unroll
+    for( int k = 0; k < D; ++k ) { s_red[warp][k] = mn[k]; s_red[warp][D + k] = mx[k]; }
+    s_red[warp][2 * D] = ext;
+  }
+  __syncthreads();
+  if( threadIdx.x == 0 )
+  {
+    for( int w = 1; w < SG_BP_THREADS / 32; ++w )
+    {
+      for( int k = 0; k < D; ++k ) { mn[k] = fmin( mn[k], s_red[w][k] ); mx[k] = fmax( mx[k], s_red[w][D + k] ); }
+      ext = fmax( ext, s_red[w][2 * D] );
+    }
+    for( int k = 0; k < D; ++k )
+    {
+      atomicMin( &acc->min_lo[k], sg_ordered_from_double( mn[k] ) );
+      atomicMax( &acc->max_lo[k], sg_ordered_from_double( mx[k] ) );
+    }
+    atomicMax( &acc->max_ext, sg_ordered_from_double( ext ) );
+  }
+}
+
+// ---- grid layout -----------------------------------------------------------------------------------
+template<int D>
+__device__ inline void sg_cell_of( const GridParams& g, const double* lo, uint32_t* c )
+{
+  #pragma unroll
+  for( int k = 0; k < D; ++k )
+  {
+    // lo >= origin exactly (origin is the minimum over the same values); unsigned cast == floor
+    uint32_t v = uint32_t( ( lo[k] - g.origin[k] ) / g.h );
+    c[k] = ( v < g.dims[k] ) ? v : ( g.dims[k] - 1u );
+  }
+}
+
+template<int D>
+__device__ inline GridParams sg_layout_grid( const BoundsAccum& acc, const uint32_t max_cells )
+{
+  GridParams g;
+  double span[3] = { 0.0, 0.0, 0.0 };
+  for( int k = 0; k < 3; ++k ) { g.origin[k] = 0.0; g.dims[k] = 1u; }
+  for( int k = 0; k < D; ++k )
+  {
+    g.origin[k] = sg_double_from_ordered( acc.min_lo[k] );
+    span[k] = sg_double_from_ordered( acc.max_lo[k] ) - g.origin[k];
+  }
+  const double max_ext = sg_double_from_ordered( acc.max_ext );
+  // strictly larger than every extent, by a margin that dwarfs the rounding of (lo - origin) / h
+  double h = max_ext * ( 1.0 + 9.5367431640625e-07 );
+  if( !( h > 0.0 ) ) { h = 1.0; }
+  for( int iter = 0; iter < 64; ++iter )
+  {
+    double cells = 1.0;
+    bool ok = true;
+    for( int k = 0; k < D; ++k )
+    {
+      const double dk = floor( span[k] / h ) + 1.0;
+      if( !( dk < 4.0e9 ) ) { ok = false; }
+      cells *= dk;
+    }
+    if( ok && cells <= double( max_cells ) ) { break; }
+    // too many cells for the scratch arrays: coarsen (always legal, only costs extra box tests)
+    const double ratio = ok ? cells / double( max_cells ) : 1.0e6;
+    h *= 1.0009765625 * ( ( D == 2 ) ? sqrt( ratio ) : cbrt( ratio ) );
+  }
+  g.h = h;
+  uint32_t ncells = 1u;
+  for( int k = 0; k < D; ++k )
+  {
+    g.dims[k] = uint32_t( span[k] / h ) + 1u;
+    ncells *= g.dims[k];
+  }
+  g.ncells = ncells;
+  return g;
+}
+
+template<int D>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_setup( const BoundsAccum* __restrict__ acc, const uint32_t max_cells, GridParams* __restrict__ params, uint32_t* __restrict__ cell_count )
+{
+  // every block derives the same layout from the same reduced bounds, then clears its share of the histogram
+  __shared__ GridParams g_s;
+  if( threadIdx.x == 0 ) { g_s = sg_layout_grid<D>( *acc, max_cells ); }
+  __syncthreads();
+  const uint32_t ncells = g_s.ncells;
+  for( uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c <= ncells; c += gridDim.x * blockDim.x ) { cell_count[c] = 0u; }
+  if( blockIdx.x == 0 && threadIdx.x == 0 ) { *params = g_s; }
+}
+
+template<int D>
+__device__ inline uint32_t sg_key_of( const GridParams& g, const uint32_t* c )
+{
+  uint32_t key = c[0] + g.dims[0] * c[1];
+  if( D == 3 ) { key += g.dims[0] * g.dims[1] * c[2]; }
+  return key;
+}
+
+// ---- histogram / scatter ("single-digit radix sort" keyed by cell) ---------------------------------
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P::In in, const GridParams* __restrict__ params, uint32_t* __restrict__ cell_count,
+                                                              uint32_t* __restrict__ key_out, uint32_t* __restrict__ rank_out )
+{
+  constexpr int D = P::D;
+  const GridParams g = *params;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i >= in.n ) { return; }
+  double lo[D], hi[D];
+  P::load_aabb( in, i, lo, hi );
+  uint32_t c[D];
+  sg_cell_of<D>( g, lo, c );
+  const uint32_t key = sg_key_of<D>( g, c );
+  key_out[i] = key;
+  rank_out[i] = atomicAdd( &cell_count[key], 1u );
+}
+
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename P::In in, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ key_in,
+                                                                 const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs )
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i >= in.n ) { return; }
+  const uint32_t key = key_in[i];
+  const uint32_t pos = __ldg( &cell_start[key] ) + rank_in[i];
+  const typename P::Rec r = P::make_rec( in, i, key );
+  sg_store_rec( &recs[pos], r );
+}
+
+// ---- neighbourhood walk ----------------------------------------------------------------------------
+// Calls f( q, rec_q ) for every record q != p whose cell is within one cell of p's cell on every axis.
+template<typename P, typename F>
+__device__ inline void sg_bp_walk( const GridParams& g, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const typename P::Rec* s_recs,
+                                   const uint32_t block_first, const uint32_t block_count, const uint32_t p, const uint32_t key, F&& f )
+{
+  constexpr int D = P::D;
+  using Rec = typename P::Rec;
+  uint32_t c[3];
+  {
+    uint32_t k = key;
+    c[0] = k % g.dims[0]; k /= g.dims[0];
+    c[1] = ( D == 3 ) ? ( k % g.dims[1] ) : k;
+    c[2] = ( D == 3 ) ? ( k / g.dims[1] ) : 0u;
+  }
+  const uint32_t x0 = ( c[0] > 0u ) ? c[0] - 1u : 0u;
+  const uint32_t x1 = ( c[0] + 1u < g.dims[0] ) ? c[0] + 1u : c[0];
+  const uint32_t y0 = ( c[1] > 0u ) ? c[1] - 1u : 0u;
+  const uint32_t y1 = ( c[1] + 1u < g.dims[1] ) ? c[1] + 1u : c[1];
+  const uint32_t z0 = ( D == 3 && c[2] > 0u ) ? c[2] - 1u : c[2];
+  const uint32_t z1 = ( D == 3 && c[2] + 1u < g.dims[2] ) ? c[2] + 1u : c[2];
+  for( uint32_t z = z0; z <= z1; ++z )
+  {
+    for( uint32_t y = y0; y <= y1; ++y )
+    {
+      const uint32_t row = g.dims[0] * ( y + g.dims[1] * z );
+      // cells x0..x1 of one row are adjacent in the sorted order: one contiguous segment
+      const uint32_t qb = __ldg( &cell_start[row + x0] );
+      const uint32_t qe = __ldg( &cell_start[row + x1 + 1u] );
+      for( uint32_t q = qb; q < qe; ++q )
+      {
+        if( q == p ) { continue; }
+        const uint32_t rel = q - block_first;
+        const Rec o = ( rel < block_count ) ? sg_load_rec_shared<Rec>( &s_recs[rel] ) : sg_load_rec_global<Rec>( &recs[q] );
+        f( q, o );
+      }
+    }
+  }
+}
+
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_count( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts )
+{
+  constexpr int D = P::D;
+  using Rec = typename P::Rec;
+  __shared__ __align__( 64 ) unsigned char s_raw[SG_BP_THREADS * 64];
+  Rec* s_recs = reinterpret_cast<Rec*>( s_raw );
+  const GridParams g = *params;
+  const uint32_t block_first = blockIdx.x * SG_BP_THREADS;
+  const uint32_t block_count = ( n - block_first < SG_BP_THREADS ) ? ( n - block_first ) : SG_BP_THREADS;
+  const uint32_t p = block_first + threadIdx.x;
+  Rec me;
+  if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); sg_store_rec( &s_recs[threadIdx.x], me ); }
+  __syncthreads();
+  if( p >= n ) { return; }
+  double lo[D], hi[D];
+  P::rec_aabb( me, lo, hi );
+  const uint32_t my_idx = P::rec_idx( me );
+  uint32_t nc = 0u, na = 0u;
+  sg_bp_walk<P>( g, cell_start, recs, s_recs, block_first, block_count, p, P::rec_key( me ), [&]( const uint32_t, const Rec& o )
+  {
+    if( P::rec_idx( o ) <= my_idx ) { return; }
+    double olo[D], ohi[D];
+    P::rec_aabb( o, olo, ohi );
+    bool ov = true;
+    #pragma unroll
+    for( int k = 0; k < D; ++k ) { ov = ov && !( hi[k] < olo[k] ) && !( ohi[k] < lo[k] ); }
+    if( !ov ) { return; }
+    ++nc;
+    if( P::HAS_NARROW ) { na += P::narrow_count( me, o ); }
+  } );
+  counts[my_idx] = make_uint2( nc, na );
+}
+
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_emit( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                                              const typename P::Rec* __restrict__ recs, const uint2* __restrict__ counts, const ulonglong2* __restrict__ offsets,
+                                                              uint2* __restrict__ cand, const uint64_t cand_cap, const typename P::Out out )
+{
+  constexpr int D = P::D;
+  using Rec = typename P::Rec;
+  __shared__ __align__( 64 ) unsigned char s_raw[SG_BP_THREADS * 64];
+  Rec* s_recs = reinterpret_cast<Rec*>( s_raw );
+  const GridParams g = *params;
+  const uint32_t block_first = blockIdx.x * SG_BP_THREADS;
+  const uint32_t block_count = ( n - block_first < SG_BP_THREADS ) ? ( n - block_first ) : SG_BP_THREADS;
+  const uint32_t p = block_first + threadIdx.x;
+  Rec me;
+  if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); sg_store_rec( &s_recs[threadIdx.x], me ); }
+  __syncthreads();
+  if( p >= n ) { return; }
+  const uint32_t my_idx = P::rec_idx( me );
+  const uint2 cnt = counts[my_idx];
+  if( cnt.x == 0u ) { return; }
+  const ulonglong2 off = offsets[my_idx];
+  double lo[D], hi[D];
+  P::rec_aabb( me, lo, hi );
+  unsigned long long ka = off.y;
+
+  auto overlaps = [&]( const Rec& o ) -> bool
+  {
+    double olo[D], ohi[D];
+    P::rec_aabb( o, olo, ohi );
+    bool ov = true;
+    #pragma unroll
+    for( int k = 0; k < D; ++k ) { ov = ov && !( hi[k] < olo[k] ) && !( ohi[k] < lo[k] ); }
+    return ov;
+  };
+  auto fetch = [&]( const uint32_t q ) -> Rec
+  {
+    const uint32_t rel = q - block_first;
+    return ( rel < block_count ) ? sg_load_rec_shared<Rec>( &s_recs[rel] ) : sg_load_rec_global<Rec>( &recs[q] );
+  };
+  auto emit_one = [&]( const unsigned long long kc, const Rec& o )
+  {
+    if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( my_idx, P::rec_idx( o ) ); }
+    if( P::HAS_NARROW ) { P::narrow_emit( out, ka, me, o ); }
+  };
+
+  if( cnt.x <= SG_BP_LOCAL_CAP )
+  {
+    // (partner index << 32 | partner position), kept ascending by insertion
+    unsigned long long list[SG_BP_LOCAL_CAP];
+    uint32_t m = 0u;
+    sg_bp_walk<P>( g, cell_start, recs, s_recs, block_first, block_count, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
+    {
+      if( P::rec_idx( o ) <= my_idx || !overlaps( o ) ) { return; }
+      const unsigned long long v = ( static_cast<unsigned long long>( P::rec_idx( o ) ) << 32 ) | q;
+      uint32_t k = m++;
+      while( k > 0u && list[k - 1u] > v ) { list[k] = list[k - 1u]; --k; }
+      list[k] = v;
+    } );
+    for( uint32_t k = 0u; k < m; ++k )
+    {
+      const Rec o = fetch( uint32_t( list[k] & 0xffffffffull ) );
+      emit_one( off.x + k, o );
+    }
+  }
+  else
+  {
+    // Crowded body: select partners in ascending index order by repeated walks (O(count * neighbours))
+    uint32_t last = my_idx;
+    for( uint32_t k = 0u; k < cnt.x; ++k )
+    {
+      uint32_t best_idx = 0xffffffffu, best_q = 0u;
+      sg_bp_walk<P>( g, cell_start, recs, s_recs, block_first, block_count, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
+      {
+        const uint32_t oi = P::rec_idx( o );
+        if( oi <= last || oi >= best_idx || !overlaps( o ) ) { return; }
+        best_idx = oi; best_q = q;
+      } );
+      const Rec o = fetch( best_q );
+      emit_one( off.x + k, o );
+      last = best_idx;
+    }
+  }
+}
+
+// ---- host driver -----------------------------------------------------------------------------------
+template<typename P>
+static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n )
+{
+  // cell count capped at ~2 cells per body (power of two not needed: keys are row-major)
+  uint64_t mc = uint64_t( n ) * 2u + 1024u;
+  if( mc > 0x7fffffffull ) { mc = 0x7fffffffull; }
+  s.max_cells = uint32_t( mc );
+  SG_CUDA( ctx, s.bounds.ensure( sizeof( BoundsAccum ) ) );
+  SG_CUDA( ctx, s.params.ensure( sizeof( GridParams ) ) );
+  SG_CUDA( ctx, s.cell_count.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
+  SG_CUDA( ctx, s.cell_start.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
+  SG_CUDA( ctx, s.cell_partials.ensure( ( size_t( s.max_cells ) / SG_SCAN_TILE + 2 ) * 4 ) );
+  SG_CUDA( ctx, s.key.ensure( size_t( n ) * 4 ) );
+  SG_CUDA( ctx, s.rank.ensure( size_t( n ) * 4 ) );
+  SG_CUDA( ctx, s.recs.ensure( size_t( n ) * 64 ) );
+  SG_CUDA( ctx, s.counts.ensure( size_t( n ) * sizeof( uint2 ) ) );
+  SG_CUDA( ctx, s.offsets.ensure( size_t( n ) * sizeof( ulonglong2 ) ) );
+  SG_CUDA( ctx, s.pair_partials.ensure( ( size_t( n ) / SG_SCAN_TILE + 2 ) * sizeof( ScanPairCounts::Acc ) ) );
+  SG_CUDA( ctx, s.totals.ensure( sizeof( ScanPairCounts::Acc ) ) );
+  return SG_OK;
+}
+
+// Sort bodies by cell and count.  After this returns (asynchronously) s.totals holds {P_c, P_a}.
+template<typename P>
+static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::In& in )
+{
+  constexpr int D = P::D;
+  const uint32_t n = in.n;
+  const unsigned nblk = sg_div_up( n, SG_BP_THREADS );
+  const unsigned nred = nblk < unsigned( ctx->num_sms * 8 ) ? nblk : unsigned( ctx->num_sms * 8 );
+  const double nb = double( n );
+  SG_LAUNCH( ctx, "bp_bounds", nb * P::IN_BYTES, sg_bp_bounds_init<<<1, 32, 0, ctx->stream>>>( s.bounds.as<BoundsAccum>() );
+             sg_bp_bounds<P><<<nred, SG_BP_THREADS, 0, ctx->stream>>>( in, s.bounds.as<BoundsAccum>() ) );
+  ++ctx->launch_count;
+  SG_LAUNCH( ctx, "bp_setup", nb * 4.0, sg_bp_setup<D><<<unsigned( ctx->num_sms * 4 ), SG_BP_THREADS, 0, ctx->stream>>>( s.bounds.as<BoundsAccum>(), s.max_cells, s.params.as<GridParams>(), s.cell_count.as<uint32_t>() ) );
+  SG_LAUNCH( ctx, "bp_hist", nb * ( P::IN_BYTES + 8.0 ), sg_bp_hist<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_count.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>() ) );
+  const uint32_t* ncells_dev = &s.params.as<GridParams>()->ncells;
+  int rc = sg_exclusive_scan<ScanU32>( ctx, "bp_cell_scan", s.cell_count.as<uint32_t>(), ncells_dev, 0u, s.max_cells, s.cell_partials.as<uint32_t>(), s.cell_start.as<uint32_t>(), nullptr, true );
+  if( rc != SG_OK ) { return rc; }
+  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>() ) );
+  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 ), sg_bp_count<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>() ) );
+  rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false );
+  return rc;
+}
+
+template<typename P>
+static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const double out_bytes )
+{
+  const unsigned nblk = sg_div_up( n, SG_BP_THREADS );
+  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 8.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
+             s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, out ) );
+  return SG_OK;
+}
+
+#endif

@@ -1,0 +1,248 @@
+"""Host-side mirror (Python) of the reference interfaces on the hot path, over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference:
+  UnconstrainedMap::flow( q0, v0, fsys, iteration, dt, q1, v1 )       scisim/UnconstrainedMaps/UnconstrainedMap.h:33
+  ConstrainedSystem::computeActiveSet( q0, qp, v, active_set )        scisim/Constraints/ConstrainedSystem.h:20
+  SpatialGridDetector::getPotentialOverlaps( aabbs, overlaps )        ball2d/SpatialGridDetector.h:39
+Every compute call goes to the CUDA library; nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_OUT_ALL, SgContacts, SgPairs, SciSimB200Error
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One sg_ctx: one GPU, one stream, library-owned device buffers."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.sg_create(C.byref(h), int(device))
+        if rc != 0:
+            raise SciSimB200Error("sg_create failed (%d): %s" % (rc, self.lib.sg_last_error(None).decode()))
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise SciSimB200Error("libscisim_b200 error %d: %s" % (rc, self.lib.sg_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self.check(self.lib.sg_synchronize(self.h))
+
+    def stream(self):
+        return self.lib.sg_stream(self.h)
+
+    def launch_count(self):
+        return int(self.lib.sg_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        self.check(self.lib.sg_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self.check(self.lib.sg_profile_reset(self.h))
+
+    def profile(self):
+        """{kernel name: (launches, device ms, algorithmic bytes)} accumulated since the last reset."""
+        self.synchronize()
+        out = {}
+        for k in range(self.lib.sg_profile_count(self.h)):
+            name = C.c_char_p()
+            n = C.c_uint64()
+            ms = C.c_double()
+            by = C.c_double()
+            self.check(self.lib.sg_profile_get(self.h, k, C.byref(name), C.byref(n), C.byref(ms), C.byref(by)))
+            out[name.value.decode()] = (int(n.value), float(ms.value), float(by.value))
+        return out
+
+    def pinned(self, shape, dtype=np.float64):
+        """A numpy array over pinned host memory owned by this context (freed with the context's process)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self.check(self.lib.sg_host_alloc(self.h, max(n, 1), C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class SpatialGridDetector:
+    """Drop-in for the reference's namespace SpatialGridDetector (rigidbody2d: SpatialGrid)."""
+
+    @staticmethod
+    def getPotentialOverlaps(aabbs, ctx=None):
+        """aabbs: (n, 2*dim) rows [lo, hi]. Returns a (P, 2) uint32 array of (i<j), ascending -- the
+        iteration order of the std::set the reference fills."""
+        ctx = ctx or default_context()
+        a = _f64(aabbs)
+        if a.ndim != 2 or a.shape[1] not in (4, 6):
+            raise ValueError("aabbs must be (n,4) or (n,6)")
+        out = SgPairs()
+        ctx.check(ctx.lib.sg_candidate_pairs(ctx.h, a.shape[1] // 2, a.shape[0], _ptr(a), C.byref(out)))
+        if out.n == 0:
+            return np.zeros((0, 2), dtype=np.uint32)
+        return np.ctypeslib.as_array(out.ij, shape=(int(out.n), 2)).copy()
+
+
+class ActiveSet:
+    """The active set as plain arrays in the reference's active_set order (one row per Constraint)."""
+
+    def __init__(self, c, copy=True):
+        na = int(c.n_active)
+        self.dim = int(c.dim)
+        self.n_candidates = int(c.n_candidates)
+        self.n_active = na
+        self.n_body_body = int(c.n_body_body)
+        self.n_drum = int(c.n_drum)
+        self.n_plane = int(c.n_plane)
+
+        def arr(p, shape, dt):
+            if not p or na == 0:
+                return None if not p else np.zeros(shape, dtype=dt)
+            a = np.ctypeslib.as_array(p, shape=shape)
+            return a.copy() if copy else a
+
+        self.type = arr(c.type, (na,), np.uint32)
+        self.i = arr(c.i, (na,), np.uint32)
+        self.j = arr(c.j, (na,), np.uint32)
+        self.n = arr(c.n, (na, self.dim), np.float64)
+        self.p = arr(c.p, (na, self.dim), np.float64)
+        self.depth = arr(c.depth, (na,), np.float64)
+        if c.cand_ij and self.n_candidates > 0:
+            a = np.ctypeslib.as_array(c.cand_ij, shape=(self.n_candidates, 2))
+            self.candidates = a.copy() if copy else a
+        elif c.cand_ij:
+            self.candidates = np.zeros((0, 2), dtype=np.uint32)
+        else:
+            self.candidates = None
+
+
+class Ball2DState:
+    """Static part of ball2d/Ball2DState.h: radii, per-ball masses, gravity, planes, drums."""
+
+    def __init__(self, r, m, g=(0.0, 0.0), plane_x=None, plane_n=None, drum_x=None, drum_r=None):
+        self.r = _f64(r)
+        self.m = _f64(m)
+        assert self.r.shape == self.m.shape and self.r.ndim == 1
+        self.g = _f64(g)
+        self.plane_x = _f64(plane_x if plane_x is not None else np.zeros((0, 2)))
+        self.plane_n = _f64(plane_n if plane_n is not None else np.zeros((0, 2)))
+        self.drum_x = _f64(drum_x if drum_x is not None else np.zeros((0, 2)))
+        self.drum_r = _f64(drum_r if drum_r is not None else np.zeros((0,)))
+
+    def nballs(self):
+        return self.r.shape[0]
+
+
+class _Ball2DMap:
+    kind = None
+    _name = None
+
+    def name(self):
+        return self._name
+
+    def flow(self, q0, v0, fsys, iteration, dt):
+        """Same contract as UnconstrainedMap::flow; returns (q1, v1) instead of filling caller vectors."""
+        assert iteration > 0
+        return fsys._flow(self.kind, q0, v0, dt)
+
+
+class SymplecticEulerMap(_Ball2DMap):
+    """ball2d/SymplecticEulerMap.cpp"""
+    kind = SG_MAP_SYMPLECTIC_EULER
+    _name = "symplectic_euler"
+
+
+class VerletMap(_Ball2DMap):
+    """ball2d/VerletMap.cpp"""
+    kind = SG_MAP_VERLET
+    _name = "verlet"
+
+
+class Ball2DSim:
+    """GPU-backed FlowableSystem + ConstrainedSystem for ball2d (ball2d/Ball2DSim.h:26)."""
+
+    def __init__(self, state, device=0, ctx=None):
+        self.ctx = ctx or Context(device)
+        self.state = state
+        lib, h = self.ctx.lib, self.ctx.h
+        n = state.nballs()
+        self.ctx.check(lib.sg_ball2d_set_bodies(h, n, _ptr(state.r), _ptr(state.m)))
+        self.ctx.check(lib.sg_ball2d_set_gravity(h, _ptr(state.g)))
+        self.ctx.check(lib.sg_ball2d_set_planes(h, state.plane_x.shape[0], _ptr(state.plane_x), _ptr(state.plane_n)))
+        self.ctx.check(lib.sg_ball2d_set_drums(h, state.drum_x.shape[0], _ptr(state.drum_x), _ptr(state.drum_r)))
+
+    def name(self):
+        return "ball_2d"
+
+    def nqdofs(self):
+        return 2 * self.state.nballs()
+
+    nvdofs = nqdofs
+
+    def _flow(self, kind, q0, v0, dt, q1=None, v1=None):
+        q0 = _f64(q0)
+        v0 = _f64(v0)
+        assert q0.size == self.nqdofs() and v0.size == self.nqdofs()
+        q1 = np.empty_like(q0) if q1 is None else q1
+        v1 = np.empty_like(v0) if v1 is None else v1
+        self.ctx.check(self.ctx.lib.sg_ball2d_flow(self.ctx.h, kind, _ptr(q0), _ptr(v0), float(dt), _ptr(q1), _ptr(v1)))
+        return q1, v1
+
+    def computeActiveSet(self, q0, qp, v=None, flags=SG_OUT_ALL, copy=True):
+        """ConstrainedSystem::computeActiveSet( q0, qp, v, active_set ); v is unused by ball2d."""
+        q0 = _f64(q0)
+        qp = _f64(qp)
+        assert q0.size == self.nqdofs() and qp.size == self.nqdofs()
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_ball2d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags), C.byref(c)))
+        return ActiveSet(c, copy=copy)
+
+    # ---- resident path (state stays in HBM) ----
+    def upload(self, q, v):
+        q = _f64(q)
+        v = _f64(v)
+        self.ctx.check(self.ctx.lib.sg_ball2d_upload(self.ctx.h, _ptr(q), _ptr(v)))
+
+    def step(self, umap, dt):
+        """flow(q0,v0)->(q1,v1) then the active set on (q0,q1), all on the device. Returns (P_c, P_a)."""
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_ball2d_step(self.ctx.h, umap.kind, float(dt), C.byref(c)))
+        return int(c.n_candidates), int(c.n_active)
+
+    def fetch(self, flags=SG_OUT_ALL, want_state=True):
+        n = self.nqdofs()
+        q1 = np.empty(n) if want_state else None
+        v1 = np.empty(n) if want_state else None
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_ball2d_fetch(self.ctx.h, int(flags), _ptr(q1) if want_state else None, _ptr(v1) if want_state else None, C.byref(c)))
+        return q1, v1, ActiveSet(c)

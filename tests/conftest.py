@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from tests import oracle_binding
+    return oracle_binding.load()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    import scisim_b200
+    ctx = scisim_b200.Context(0)
+    yield ctx
+    ctx.close()

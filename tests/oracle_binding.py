@@ -1,0 +1,125 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU restatement of the reference (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".h")) or f == "Makefile"]
+    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", ORACLE_DIR, "-B", "liboracle.so"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, up = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)
+    sig = {
+        "orc_ccd_coeffs": (None, [vp, vp, C.c_double, vp, vp, C.c_double, vp]),
+        "orc_ccd_happens": (C.c_int, [vp, dp]),
+        "orc_aabb_overlaps": (vp, [C.c_int, C.c_uint32, vp, C.c_int]),
+        "orc_pairs_count": (C.c_uint64, [vp]),
+        "orc_pairs_seconds": (C.c_double, [vp]),
+        "orc_pairs_copy": (None, [vp, vp]),
+        "orc_pairs_free": (None, [vp]),
+        "orc_ball2d_create": (vp, [C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp]),
+        "orc_ball2d_destroy": (None, [vp]),
+        "orc_ball2d_flow": (None, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
+        "orc_ball2d_active_set": (None, [vp, vp, vp, C.c_int]),
+        "orc_ball2d_num_candidates": (C.c_uint64, [vp]),
+        "orc_ball2d_num_active": (C.c_uint64, [vp]),
+        "orc_ball2d_seconds_flow": (C.c_double, [vp]),
+        "orc_ball2d_seconds_active": (C.c_double, [vp]),
+        "orc_ball2d_copy_candidates": (None, [vp, vp]),
+        "orc_ball2d_copy_active": (None, [vp, vp, vp, vp, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ccd(q0a, q1a, ra, q0b, q1b, rb):
+    lib = load()
+    c = np.zeros(3)
+    lib.orc_ccd_coeffs(_p(_f64(q0a)), _p(_f64(q1a)), float(ra), _p(_f64(q0b)), _p(_f64(q1b)), float(rb), _p(c))
+    t = C.c_double()
+    hit = lib.orc_ccd_happens(_p(c), C.byref(t))
+    return c, bool(hit), t.value
+
+
+def aabb_overlaps(aabbs, method="grid"):
+    """(P,2) uint32 ascending pairs; method 'grid' = literal std::map/std::set algorithm, 'allpairs' = brute force."""
+    lib = load()
+    a = _f64(aabbs)
+    h = lib.orc_aabb_overlaps(a.shape[1] // 2, a.shape[0], _p(a), 0 if method == "grid" else 1)
+    n = lib.orc_pairs_count(h)
+    out = np.zeros((n, 2), dtype=np.uint32)
+    if n:
+        lib.orc_pairs_copy(h, _p(out))
+    secs = lib.orc_pairs_seconds(h)
+    lib.orc_pairs_free(h)
+    return out, secs
+
+
+class Ball2DOracle:
+    def __init__(self, scene):
+        self.lib = load()
+        self.n = scene["r"].shape[0]
+        a = lambda k: _f64(scene[k])
+        self._keep = [a("r"), a("m"), a("g"), a("plane_x"), a("plane_n"), a("drum_x"), a("drum_r")]
+        r, m, g, px, pn, dx, dr = self._keep
+        self.h = self.lib.orc_ball2d_create(self.n, _p(r), _p(m), _p(g), px.shape[0], _p(px), _p(pn), dx.shape[0], _p(dx), _p(dr))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orc_ball2d_destroy(self.h)
+            self.h = None
+
+    def flow(self, kind, q0, v0, dt):
+        q0, v0 = _f64(q0), _f64(v0)
+        q1, v1 = np.empty_like(q0), np.empty_like(v0)
+        self.lib.orc_ball2d_flow(self.h, int(kind), _p(q0), _p(v0), float(dt), _p(q1), _p(v1))
+        return q1, v1
+
+    def active_set(self, q0, q1, method="grid"):
+        q0, q1 = _f64(q0), _f64(q1)
+        self.lib.orc_ball2d_active_set(self.h, _p(q0), _p(q1), 0 if method == "grid" else 1)
+        nc = self.lib.orc_ball2d_num_candidates(self.h)
+        na = self.lib.orc_ball2d_num_active(self.h)
+        cand = np.zeros((nc, 2), dtype=np.uint32)
+        if nc:
+            self.lib.orc_ball2d_copy_candidates(self.h, _p(cand))
+        out = {"type": np.zeros(na, np.uint32), "i": np.zeros(na, np.uint32), "j": np.zeros(na, np.uint32),
+               "n": np.zeros((na, 2)), "p": np.zeros((na, 2)), "depth": np.zeros(na), "candidates": cand}
+        if na:
+            self.lib.orc_ball2d_copy_active(self.h, _p(out["type"]), _p(out["i"]), _p(out["j"]), _p(out["n"]), _p(out["p"]), _p(out["depth"]))
+        out["seconds"] = self.lib.orc_ball2d_seconds_active(self.h)
+        out["seconds_flow"] = self.lib.orc_ball2d_seconds_flow(self.h)
+        return out
