@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SCISim hot path on B200 (contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" = one pass of the hot path over a fixed state: UnconstrainedMap::flow(q0,v0)->(q1,v1)
+followed by ConstrainedSystem::computeActiveSet(q0,q1).  Metric = (candidate pairs + active contacts) per
+second, whole job.  Workload at N=1: BASELINE.json configs[1] -- 1000x1000 equal balls on a 0.99-spaced lattice,
+gravity, 3 static planes, symplectic Euler.  At N>1 the scene is N such slabs side by side along x (weak
+scaling), one slab per rank.
+
+  value     state resident in HBM, CUDA events on the library's stream, L2 flushed between steps
+  e2e       the same step through the host-buffer C ABI (sg_ball2d_flow + sg_ball2d_active_set): H2D of q0,v0
+            (+ q0,q1 for the active set) from pinned memory and D2H of q1,v1 and the whole active set inside
+            the timed region
+  roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU restatement of the reference (oracle/, single thread like the reference's path) on
+            one full step of the same scene, timed on this box
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidate+active contact pairs/sec (flow + broad phase + narrow phase, ball2d)"
+UNIT = "pairs/s"
+NX, NY = 1000, 1000
+
+
+def scene_for_rank(rank, world):
+    from scisim_b200 import scenes
+    s = scenes.ball2d_lattice(NX, NY, seed=42 + rank, with_planes=True)
+    if world > 1:
+        # slab `rank` of a (world*NX) x NY lattice: shift along x; only the outer slabs keep their side wall
+        shift = rank * NX * 0.99
+        s["q"][0::2] += shift
+        keep = [0] + ([1] if rank == 0 else []) + ([2] if rank == world - 1 else [])
+        s["plane_x"] = s["plane_x"][keep].copy()
+        s["plane_n"] = s["plane_n"][keep].copy()
+        s["plane_x"][:, 0] += shift * (s["plane_n"][:, 0] != 0.0)
+    return s
+
+
+def workload_name(world):
+    if world == 1:
+        return "configs[1]: synthetic 2D ball pile, 1M equal-radius balls (1000x1000 lattice, spacing 0.99, r=0.5) under gravity, 3 static planes, symplectic Euler"
+    return "configs[1] tiled: %d slabs of 1M balls side by side along x (one slab per GPU)" % world
+
+
+class ClockSampler:
+    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_step(scene, steps, warmup):
+    """The reference's CPU path (restated in oracle/, its own std::map/std::set data structures, 1 thread)."""
+    from tests import oracle_binding as ob
+    o = ob.Ball2DOracle(scene)
+    times, pairs = [], 0
+    for it in range(warmup + steps):
+        q1, v1 = o.flow(0, scene["q"], scene["v"], scene["dt"])
+        a = o.active_set(scene["q"], q1, "grid")
+        t = a["seconds"] + a["seconds_flow"]
+        pairs = a["candidates"].shape[0] + a["type"].shape[0]
+        if it >= warmup:
+            times.append(t)
+    return pairs, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = scene_for_rank(0, 1)
+    pairs, times = cpu_reference_step(scene, args.steps, min(args.warmup, 1))
+    total = sum(times)
+    value = pairs * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(1), "bodies": NX * NY, "note": "reference CPU path restated in oracle/ (the reference itself needs Eigen, absent here); "
+                   "its hot path is single-threaded even with USE_OPENMP (SURVEY.md F2)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": "full 1M-ball step (flow + spatial-grid broad phase + CCD + planes), %d steps" % len(times)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_per_s": len(times) / total,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import scisim_b200 as sb
+    scene = scene_for_rank(rank, world)
+    ctx = sb.Context(local_rank)
+    st = sb.Ball2DState(scene["r"], scene["m"], scene["g"], scene["plane_x"], scene["plane_n"], scene["drum_x"], scene["drum_r"])
+    sim = sb.Ball2DSim(st, ctx=ctx)
+    umap = sb.SymplecticEulerMap()
+    dt = scene["dt"]
+    n = st.nballs()
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- resident path: `value` ----------------
+    sim.upload(scene["q"], scene["v"])
+    for _ in range(args.warmup):
+        ctx.flush_l2()
+        pc, pa = sim.step(umap, dt)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count()
+    step_ms = []
+    for _ in range(args.steps):
+        ctx.flush_l2()          # cold L2 for every timed step (outside the event bracket)
+        ctx.timer_begin()
+        pc, pa = sim.step(umap, dt)
+        step_ms.append(ctx.timer_end())
+    barrier()
+    gpu_launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t_local = sum(step_ms) / 1e3
+    pairs_local = float(pc + pa)
+
+    # ---------------- per-kernel roofline (same steps, events around every kernel) ----------------
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        sim.step(umap, dt)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+
+    # ---------------- e2e through the host-buffer ABI ----------------
+    q0h, v0h = ctx.pinned((2 * n,)), ctx.pinned((2 * n,))
+    q1h, v1h = ctx.pinned((2 * n,)), ctx.pinned((2 * n,))
+    q0h[:] = scene["q"]; v0h[:] = scene["v"]
+    flags = sb.SG_OUT_NORMALS | sb.SG_OUT_POINTS | sb.SG_OUT_DEPTHS
+    e2e_steps = max(3, min(args.steps, 10))
+    for it in range(2 + e2e_steps):
+        if it == 2:
+            barrier()
+            t0 = time.perf_counter()
+        sim._flow(umap.kind, q0h, v0h, dt, q1h, v1h)
+        a = sim.computeActiveSet(q0h, q1h, flags=flags, copy=False)
+    ctx.synchronize()
+    t_e2e_local = time.perf_counter() - t0
+    h2d = 4 * 2 * n * 8
+    d2h = 2 * 2 * n * 8 + a.n_active * (4 + 4 + 4 + 16 + 16 + 8)
+    assert a.n_active == pa and a.n_candidates == pc
+
+    # ---------------- reduce over ranks: max time, summed work ----------------
+    if world > 1:
+        tt = torch.tensor([t_local, t_e2e_local], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ww = torch.tensor([pairs_local, float(pc), float(pa)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        t_max, t_e2e = float(tt[0]), float(tt[1])
+        pairs_all = float(ww[0])
+    else:
+        t_max, t_e2e, pairs_all = t_local, t_e2e_local, pairs_local
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        total_ms = sum(v[1] for v in prof.values())
+        top = max(prof.items(), key=lambda kv: kv[1][1])
+        name, (nl, ms, by) = top
+        achieved = (by / nl) / (ms / nl * 1e-3) / 1e9
+        kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps, "share": v[1] / total_ms,
+                       "alg_GBps": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        line = {
+            "metric": METRIC, "value": pairs_all * args.steps / t_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(world), "bodies_per_gpu": n, "candidates_per_gpu": pc, "active_per_gpu": pa,
+                       "l2": "384 MB buffer overwritten before every timed step (L2 flush)", "timing": "CUDA events on the library stream, per step, summed; max over ranks",
+                       "parallelism": "1 process per GPU; slabs independent in round 1 (no halo exchange yet)" if world > 1 else "single GPU"},
+            "steps_per_s": args.steps / t_max,
+            "clocks": clocks,
+            "gpu_launches": gpu_launches,
+            "e2e": {"value": pairs_all * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / e2e_steps,
+                    "api": "sg_ball2d_flow + sg_ball2d_active_set, pinned host buffers, wall clock"},
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "share_of_step": ms / total_ms, "timed": "separate pass of the same %d steps with CUDA events around every kernel" % args.steps,
+                         "kernels": kernels},
+        }
+        if not args.no_cpu_baseline:
+            pairs_cpu, times = cpu_reference_step(scene_for_rank(0, 1), 3, 1)
+            v = pairs_cpu * len(times) / sum(times)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "3 full steps of the same 1M-ball scene (oracle/: literal std::map/std::set grid + CCD + planes; reference hot path is single-threaded)"}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

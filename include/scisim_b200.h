@@ -102,6 +102,11 @@ int sg_profile_count( sg_ctx* ctx );
 int sg_profile_get( sg_ctx* ctx, int k, const char** name, uint64_t* launches, double* ms, double* bytes );
 /* number of kernels this context has launched since creation */
 uint64_t sg_launch_count( const sg_ctx* ctx );
+/* CUDA-event stopwatch on the context's stream (begin records, end records + waits + returns milliseconds) */
+int sg_timer_begin( sg_ctx* ctx );
+int sg_timer_end( sg_ctx* ctx, double* ms );
+/* overwrite a 384 MB scratch buffer on the context's stream so the next kernels start with a cold L2 */
+int sg_flush_l2( sg_ctx* ctx );
 
 /* ---- broad phase alone ---------------------------------------------------------------------------
  * Replaces SpatialGridDetector::getPotentialOverlaps( aabbs, overlaps ) -- ball2d/SpatialGridDetector.cpp:106-133,

@@ -57,6 +57,9 @@ def load():
         "sg_profile_count": (C.c_int, [vp]),
         "sg_profile_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), c_dp, c_dp]),
         "sg_launch_count": (C.c_uint64, [vp]),
+        "sg_timer_begin": (C.c_int, [vp]),
+        "sg_timer_end": (C.c_int, [vp, c_dp]),
+        "sg_flush_l2": (C.c_int, [vp]),
         "sg_candidate_pairs": (C.c_int, [vp, C.c_int, C.c_uint32, vp, C.POINTER(SgPairs)]),
         "sg_ball2d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp]),
         "sg_ball2d_set_gravity": (C.c_int, [vp, vp]),

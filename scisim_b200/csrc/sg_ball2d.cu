@@ -401,6 +401,12 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
     d->n_cand = ht[0];
     d->n_bb = ht[1];
     d->n_static = ht[2] & 0xffffffffull;
+    if( ctx->profile )
+    {
+      // list sizes are only known now: add the emitted bytes to the kernels that wrote them
+      ctx->prof[sg_prof_entry( ctx, "bp_emit" )].bytes += ( want_cand ? double( d->n_cand ) * 8.0 : 0.0 ) + double( d->n_bb ) * 52.0;
+      if( ng > 0 ) { ctx->prof[sg_prof_entry( ctx, "ball2d_static_emit" )].bytes += double( d->n_static ) * 52.0; }
+    }
     const uint64_t need_act = d->n_bb + d->n_static;
     const bool cand_ok = !want_cand || d->n_cand <= d->bp.cand_cap;
     if( cand_ok && need_act <= d->act_cap ) { break; }

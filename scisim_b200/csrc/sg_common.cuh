@@ -91,6 +91,9 @@ struct sg_ctx
   std::vector<ProfEntry> prof;
   std::vector<ProfPending> pending;
   std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t timer0 = nullptr;
+  cudaEvent_t timer1 = nullptr;
+  DevBuf l2_flush;
 
   Ball2DData* ball2d = nullptr;
   AabbData* aabb = nullptr;

@@ -108,6 +108,8 @@ void sg_destroy( sg_ctx* ctx )
   sg_ball2d_release( ctx );
   sg_aabb_release( ctx );
   for( cudaEvent_t e : ctx->event_pool ) { cudaEventDestroy( e ); }
+  if( ctx->timer0 != nullptr ) { cudaEventDestroy( ctx->timer0 ); cudaEventDestroy( ctx->timer1 ); }
+  ctx->l2_flush.release();
   cudaStreamDestroy( ctx->stream );
   delete ctx;
 }
@@ -172,5 +174,35 @@ int sg_profile_get( sg_ctx* ctx, int k, const char** name, uint64_t* launches, d
 }
 
 uint64_t sg_launch_count( const sg_ctx* ctx ) { return ( ctx != nullptr ) ? ctx->launch_count : 0; }
+
+int sg_timer_begin( sg_ctx* ctx )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( ctx->timer0 == nullptr ) { SG_CUDA( ctx, cudaEventCreate( &ctx->timer0 ) ); SG_CUDA( ctx, cudaEventCreate( &ctx->timer1 ) ); }
+  SG_CUDA( ctx, cudaEventRecord( ctx->timer0, ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_timer_end( sg_ctx* ctx, double* ms )
+{
+  if( ctx == nullptr || ms == nullptr || ctx->timer0 == nullptr ) { return SG_ERR_INVALID; }
+  SG_CUDA( ctx, cudaEventRecord( ctx->timer1, ctx->stream ) );
+  SG_CUDA( ctx, cudaEventSynchronize( ctx->timer1 ) );
+  float f = 0.0f;
+  SG_CUDA( ctx, cudaEventElapsedTime( &f, ctx->timer0, ctx->timer1 ) );
+  *ms = double( f );
+  return SG_OK;
+}
+
+int sg_flush_l2( sg_ctx* ctx )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  const size_t bytes = size_t( 384 ) << 20; // 3x the 126 MB L2
+  SG_CUDA( ctx, ctx->l2_flush.ensure( bytes ) );
+  SG_CUDA( ctx, cudaMemsetAsync( ctx->l2_flush.ptr, int( ctx->launch_count & 0xff ), bytes, ctx->stream ) );
+  return SG_OK;
+}
 
 }

@@ -58,6 +58,17 @@ class Context:
     def launch_count(self):
         return int(self.lib.sg_launch_count(self.h))
 
+    def timer_begin(self):
+        self.check(self.lib.sg_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_double()
+        self.check(self.lib.sg_timer_end(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        self.check(self.lib.sg_flush_l2(self.h))
+
     def profile_enable(self, on=True):
         self.check(self.lib.sg_profile_enable(self.h, 1 if on else 0))
 
