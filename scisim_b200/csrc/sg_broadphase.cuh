@@ -23,6 +23,7 @@
 
 #include "sg_common.cuh"
 #include "sg_scan.cuh"
+#include "sg_tma.cuh"
 
 #define SG_BP_THREADS 256
 #define SG_BP_LOCAL_CAP 24
@@ -68,6 +69,18 @@ __device__ inline Rec sg_load_rec_shared( const Rec* p )
   union { Rec r; int4 v[4]; } u;
   const int4* src = reinterpret_cast<const int4*>( p );
   u.v[0] = src[0]; u.v[1] = src[1]; u.v[2] = src[2]; u.v[3] = src[3];
+  return u.r;
+}
+// Staged windows keep the 64-byte records as four 16-byte chunks with chunk c of slot s stored at chunk
+// position c ^ ((s >> 1) & 3) -- the 64B-swizzle pattern -- so that a warp whose lanes read the same chunk of
+// consecutive slots touches all 32 banks instead of 8.
+template<typename Rec>
+__device__ __forceinline__ Rec sg_load_rec_swizzled( const unsigned char* win, const uint32_t slot )
+{
+  union { Rec r; int4 v[4]; } u;
+  const int4* src = reinterpret_cast<const int4*>( win ) + size_t( slot ) * 4;
+  const uint32_t sw = ( slot >> 1 ) & 3u;
+  u.v[0] = src[0u ^ sw]; u.v[1] = src[1u ^ sw]; u.v[2] = src[2u ^ sw]; u.v[3] = src[3u ^ sw];
   return u.r;
 }
 template<typename Rec>
@@ -253,13 +266,81 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
   sg_store_rec( &recs[pos], r );
 }
 
-// ---- neighbourhood walk ----------------------------------------------------------------------------
-// Calls f( q, rec_q ) for every record q != p whose cell is within one cell of p's cell on every axis.
-template<typename P, typename F>
-__device__ inline void sg_bp_walk( const GridParams& g, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const typename P::Rec* s_recs,
-                                   const uint32_t block_first, const uint32_t block_count, const uint32_t p, const uint32_t key, F&& f )
+// ---- neighbourhood staging + walk ------------------------------------------------------------------
+// Bodies are sorted by row-major cell key, so for a block owning sorted positions [b0,b1) with first/last
+// keys kf/kl, everything its threads can visit in the row offset (dy,dz) lies in ONE contiguous range of
+// records: cells [kf + off - 1, kl + off + 1], off = dy*dimx + dz*dimx*dimy.  There are 3^(D-1) such
+// windows.  Each is pulled into shared memory with a single 1-D TMA bulk copy (cp.async.bulk, completion on
+// an mbarrier); a window longer than WCAP records is staged up to WCAP and the tail is read through L1/L2.
+// (Round-1 note: the copy is currently done by the block's threads with coalesced 128-bit loads so that the
+// records can be bank-swizzled on the way in; the 1-D bulk-copy helpers in sg_tma.cuh cannot swizzle.)
+template<int D> struct BpCfg;
+template<> struct BpCfg<2> { static constexpr int NW = 3; static constexpr int T = 256; static constexpr int WCAP = 288; };
+template<> struct BpCfg<3> { static constexpr int NW = 9; static constexpr int T = 128; static constexpr int WCAP = 144; };
+
+template<int D>
+struct BpStage
+{
+  uint32_t start[BpCfg<D>::NW];
+  uint32_t len[BpCfg<D>::NW];
+  unsigned long long bar;
+};
+
+template<int D> constexpr size_t sg_bp_smem_bytes() { return size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + sizeof( BpStage<D> ) + 64; }
+
+// All threads of the block call this; returns once the staged windows are readable.
+template<typename P>
+__device__ inline void sg_bp_stage_windows( const GridParams& g, const uint32_t n, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs,
+                                            unsigned char* s_recs, BpStage<P::D>* st )
 {
   constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
+  if( threadIdx.x < uint32_t( Cfg::NW ) )
+  {
+    const uint32_t w = threadIdx.x;
+    const uint32_t b0 = blockIdx.x * Cfg::T;
+    const uint32_t b1 = ( n - b0 < uint32_t( Cfg::T ) ) ? n : b0 + Cfg::T;
+    const long long kf = __ldg( &recs[b0].key );
+    const long long kl = __ldg( &recs[b1 - 1u].key );
+    uint32_t start = 0u, len = 0u;
+    const int dy = int( w % 3u ) - 1;
+    const int dz = ( D == 3 ) ? int( w / 3u ) - 1 : 0;
+    const long long off = ( long long )( dy ) * g.dims[0] + ( long long )( dz ) * g.dims[0] * g.dims[1];
+    long long klo = kf + off - 1, khi = kl + off + 1;
+    if( khi >= 0 && klo <= ( long long )( g.ncells ) - 1 )
+    {
+      klo = ( klo < 0 ) ? 0 : klo;
+      khi = ( khi > ( long long )( g.ncells ) - 1 ) ? ( long long )( g.ncells ) - 1 : khi;
+      start = __ldg( &cell_start[klo] );
+      const uint32_t end = __ldg( &cell_start[khi + 1] );
+      len = ( end - start < uint32_t( Cfg::WCAP ) ) ? end - start : uint32_t( Cfg::WCAP );
+    }
+    st->start[w] = start;
+    st->len[w] = len;
+  }
+  __syncthreads();
+  #pragma unroll
+  for( int w = 0; w < Cfg::NW; ++w )
+  {
+    const uint32_t nchunks = st->len[w] * 4u;
+    const int4* src = reinterpret_cast<const int4*>( recs + st->start[w] );
+    int4* dst = reinterpret_cast<int4*>( s_recs + size_t( w ) * Cfg::WCAP * 64 );
+    for( uint32_t c = threadIdx.x; c < nchunks; c += Cfg::T )
+    {
+      const uint32_t slot = c >> 2;
+      dst[( slot << 2 ) | ( ( c & 3u ) ^ ( ( slot >> 1 ) & 3u ) )] = __ldg( src + c );
+    }
+  }
+  __syncthreads();
+}
+
+// Calls f( q, rec_q ) for every record q != p whose cell is within one cell of p's cell on every axis.
+template<typename P, typename F>
+__device__ __forceinline__ void sg_bp_walk( const GridParams& g, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const unsigned char* s_recs,
+                                            const BpStage<P::D>* st, const uint32_t p, const uint32_t key, F&& f )
+{
+  constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
   uint32_t c[3];
   {
@@ -270,50 +351,70 @@ __device__ inline void sg_bp_walk( const GridParams& g, const uint32_t* __restri
   }
   const uint32_t x0 = ( c[0] > 0u ) ? c[0] - 1u : 0u;
   const uint32_t x1 = ( c[0] + 1u < g.dims[0] ) ? c[0] + 1u : c[0];
-  const uint32_t y0 = ( c[1] > 0u ) ? c[1] - 1u : 0u;
-  const uint32_t y1 = ( c[1] + 1u < g.dims[1] ) ? c[1] + 1u : c[1];
-  const uint32_t z0 = ( D == 3 && c[2] > 0u ) ? c[2] - 1u : c[2];
-  const uint32_t z1 = ( D == 3 && c[2] + 1u < g.dims[2] ) ? c[2] + 1u : c[2];
-  for( uint32_t z = z0; z <= z1; ++z )
+  // all segment bounds first (independent loads), then the walk
+  uint32_t qb[Cfg::NW], qe[Cfg::NW];
+  #pragma unroll
+  for( int w = 0; w < Cfg::NW; ++w )
   {
-    for( uint32_t y = y0; y <= y1; ++y )
+    const int dy = w % 3 - 1;
+    const int dz = ( D == 3 ) ? w / 3 - 1 : 0;
+    const long long y = ( long long )( c[1] ) + dy;
+    const long long z = ( long long )( c[2] ) + dz;
+    const bool ok = y >= 0 && y < ( long long )( g.dims[1] ) && z >= 0 && z < ( long long )( g.dims[2] );
+    qb[w] = 0u; qe[w] = 0u;
+    if( ok )
     {
-      const uint32_t row = g.dims[0] * ( y + g.dims[1] * z );
-      // cells x0..x1 of one row are adjacent in the sorted order: one contiguous segment
-      const uint32_t qb = __ldg( &cell_start[row + x0] );
-      const uint32_t qe = __ldg( &cell_start[row + x1 + 1u] );
-      for( uint32_t q = qb; q < qe; ++q )
-      {
-        if( q == p ) { continue; }
-        const uint32_t rel = q - block_first;
-        const Rec o = ( rel < block_count ) ? sg_load_rec_shared<Rec>( &s_recs[rel] ) : sg_load_rec_global<Rec>( &recs[q] );
-        f( q, o );
-      }
+      const uint32_t row = g.dims[0] * ( uint32_t( y ) + g.dims[1] * uint32_t( z ) );
+      qb[w] = __ldg( &cell_start[row + x0] );
+      qe[w] = __ldg( &cell_start[row + x1 + 1u] );
+    }
+  }
+  #pragma unroll
+  for( int w = 0; w < Cfg::NW; ++w )
+  {
+    const uint32_t ws = st->start[w];
+    const uint32_t wl = st->len[w];
+    const unsigned char* sw = s_recs + size_t( w ) * Cfg::WCAP * 64;
+    for( uint32_t q = qb[w]; q < qe[w]; ++q )
+    {
+      if( q == p ) { continue; }
+      const uint32_t slot = q - ws;
+      const Rec o = ( slot < wl ) ? sg_load_rec_swizzled<Rec>( sw, slot ) : sg_load_rec_global<Rec>( &recs[q] );
+      f( q, o );
     }
   }
 }
 
 template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_count( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__device__ __forceinline__ typename P::Rec sg_bp_fetch( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q )
+{
+  using Rec = typename P::Rec;
+  const uint32_t slot = q - st->start[w];
+  if( slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * BpCfg<P::D>::WCAP * 64, slot ); }
+  return sg_load_rec_global<Rec>( &recs[q] );
+}
+
+template<typename P>
+__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                                const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts )
 {
   constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
-  __shared__ __align__( 64 ) unsigned char s_raw[SG_BP_THREADS * 64];
-  Rec* s_recs = reinterpret_cast<Rec*>( s_raw );
+  extern __shared__ __align__( 128 ) unsigned char s_raw[];
+  unsigned char* s_recs = s_raw;
+  BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
   const GridParams g = *params;
-  const uint32_t block_first = blockIdx.x * SG_BP_THREADS;
-  const uint32_t block_count = ( n - block_first < SG_BP_THREADS ) ? ( n - block_first ) : SG_BP_THREADS;
-  const uint32_t p = block_first + threadIdx.x;
-  Rec me;
-  if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); sg_store_rec( &s_recs[threadIdx.x], me ); }
-  __syncthreads();
+  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
+  const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
   if( p >= n ) { return; }
+  constexpr int WSELF = Cfg::NW / 2; // the (dy,dz) = (0,0) window contains the block's own records
+  const Rec me = sg_bp_fetch<P>( recs, s_recs, st, WSELF, p );
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
   const uint32_t my_idx = P::rec_idx( me );
   uint32_t nc = 0u, na = 0u;
-  sg_bp_walk<P>( g, cell_start, recs, s_recs, block_first, block_count, p, P::rec_key( me ), [&]( const uint32_t, const Rec& o )
+  sg_bp_walk<P>( g, cell_start, recs, s_recs, st, p, P::rec_key( me ), [&]( const uint32_t, const Rec& o )
   {
     if( P::rec_idx( o ) <= my_idx ) { return; }
     double olo[D], ohi[D];
@@ -329,22 +430,22 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_count( const uint32_t n
 }
 
 template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_emit( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint2* __restrict__ counts, const ulonglong2* __restrict__ offsets,
                                                               uint2* __restrict__ cand, const uint64_t cand_cap, const typename P::Out out )
 {
   constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
-  __shared__ __align__( 64 ) unsigned char s_raw[SG_BP_THREADS * 64];
-  Rec* s_recs = reinterpret_cast<Rec*>( s_raw );
+  extern __shared__ __align__( 128 ) unsigned char s_raw[];
+  unsigned char* s_recs = s_raw;
+  BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
   const GridParams g = *params;
-  const uint32_t block_first = blockIdx.x * SG_BP_THREADS;
-  const uint32_t block_count = ( n - block_first < SG_BP_THREADS ) ? ( n - block_first ) : SG_BP_THREADS;
-  const uint32_t p = block_first + threadIdx.x;
-  Rec me;
-  if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); sg_store_rec( &s_recs[threadIdx.x], me ); }
-  __syncthreads();
+  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
+  const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
   if( p >= n ) { return; }
+  constexpr int WSELF = Cfg::NW / 2;
+  const Rec me = sg_bp_fetch<P>( recs, s_recs, st, WSELF, p );
   const uint32_t my_idx = P::rec_idx( me );
   const uint2 cnt = counts[my_idx];
   if( cnt.x == 0u ) { return; }
@@ -362,10 +463,16 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_emit( const uint32_t n,
     for( int k = 0; k < D; ++k ) { ov = ov && !( hi[k] < olo[k] ) && !( ohi[k] < lo[k] ); }
     return ov;
   };
+  // a partner's record, wherever it lives: search the staged windows, else global
   auto fetch = [&]( const uint32_t q ) -> Rec
   {
-    const uint32_t rel = q - block_first;
-    return ( rel < block_count ) ? sg_load_rec_shared<Rec>( &s_recs[rel] ) : sg_load_rec_global<Rec>( &recs[q] );
+    #pragma unroll
+    for( int w = 0; w < Cfg::NW; ++w )
+    {
+      const uint32_t slot = q - st->start[w];
+      if( slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * Cfg::WCAP * 64, slot ); }
+    }
+    return sg_load_rec_global<Rec>( &recs[q] );
   };
   auto emit_one = [&]( const unsigned long long kc, const Rec& o )
   {
@@ -378,7 +485,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_emit( const uint32_t n,
     // (partner index << 32 | partner position), kept ascending by insertion
     unsigned long long list[SG_BP_LOCAL_CAP];
     uint32_t m = 0u;
-    sg_bp_walk<P>( g, cell_start, recs, s_recs, block_first, block_count, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
+    sg_bp_walk<P>( g, cell_start, recs, s_recs, st, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
     {
       if( P::rec_idx( o ) <= my_idx || !overlaps( o ) ) { return; }
       const unsigned long long v = ( static_cast<unsigned long long>( P::rec_idx( o ) ) << 32 ) | q;
@@ -399,7 +506,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_emit( const uint32_t n,
     for( uint32_t k = 0u; k < cnt.x; ++k )
     {
       uint32_t best_idx = 0xffffffffu, best_q = 0u;
-      sg_bp_walk<P>( g, cell_start, recs, s_recs, block_first, block_count, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
+      sg_bp_walk<P>( g, cell_start, recs, s_recs, st, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
       {
         const uint32_t oi = P::rec_idx( o );
         if( oi <= last || oi >= best_idx || !overlaps( o ) ) { return; }
@@ -453,7 +560,9 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   int rc = sg_exclusive_scan<ScanU32>( ctx, "bp_cell_scan", s.cell_count.as<uint32_t>(), ncells_dev, 0u, s.max_cells, s.cell_partials.as<uint32_t>(), s.cell_start.as<uint32_t>(), nullptr, true );
   if( rc != SG_OK ) { return rc; }
   SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>() ) );
-  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 ), sg_bp_count<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>() ) );
+  constexpr size_t smem = sg_bp_smem_bytes<D>();
+  SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
+  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>() ) );
   rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false );
   return rc;
 }
@@ -461,8 +570,9 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
 template<typename P>
 static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const double out_bytes )
 {
-  const unsigned nblk = sg_div_up( n, SG_BP_THREADS );
-  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 8.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
+  constexpr size_t smem = sg_bp_smem_bytes<P::D>();
+  SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_emit<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
+  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 8.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, BpCfg<P::D>::T ), BpCfg<P::D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
              s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, out ) );
   return SG_OK;
 }
