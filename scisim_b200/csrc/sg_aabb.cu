@@ -12,8 +12,8 @@ struct AabbIn
 };
 
 template<int DIM> struct AabbRec;
-template<> struct alignas( 64 ) AabbRec<2> { double lo[2]; double hi[2]; uint32_t idx; uint32_t key; double pad[3]; };
-template<> struct alignas( 64 ) AabbRec<3> { double lo[3]; double hi[3]; uint32_t idx; uint32_t key; double pad[1]; };
+template<> struct alignas( 64 ) AabbRec<2> { double lo[2]; double hi[2]; uint32_t idx; uint32_t key; uint32_t c1, c2; double pad[2]; };
+template<> struct alignas( 64 ) AabbRec<3> { double lo[3]; double hi[3]; uint32_t idx; uint32_t key; uint32_t c1, c2; };
 
 struct NoOut {};
 
@@ -26,18 +26,18 @@ struct AabbPolicy
   using In = AabbIn<DIM>;
   using Rec = AabbRec<DIM>;
   using Out = NoOut;
+  static constexpr uint32_t IDX_OFFSET = 16u * DIM;
   __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
   {
     const double* b = in.boxes + size_t( i ) * 2 * DIM;
     #pragma unroll
     for( int k = 0; k < DIM; ++k ) { lo[k] = __ldg( b + k ); hi[k] = __ldg( b + DIM + k ); }
   }
-  __device__ static Rec make_rec( const In& in, const uint32_t i, const uint32_t key )
+  __device__ static Rec make_rec( const In& in, const uint32_t i, const uint32_t key, const uint32_t c1, const uint32_t c2 )
   {
     Rec r;
     load_aabb( in, i, r.lo, r.hi );
-    r.idx = i; r.key = key;
-    for( int k = 0; k < int( sizeof( r.pad ) / 8 ); ++k ) { r.pad[k] = 0.0; }
+    r.idx = i; r.key = key; r.c1 = c1; r.c2 = c2;
     return r;
   }
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
@@ -47,8 +47,10 @@ struct AabbPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
-  __device__ static uint32_t narrow_count( const Rec&, const Rec& ) { return 0u; }
-  __device__ static void narrow_emit( const Out&, unsigned long long&, const Rec&, const Rec& ) {}
+  __device__ static uint32_t rec_c1( const Rec& s ) { return s.c1; }
+  __device__ static uint32_t rec_c2( const Rec& s ) { return s.c2; }
+  __device__ static bool narrow_test( const Rec&, const Rec& ) { return false; }
+  __device__ static void contact_emit( const Out&, unsigned long long&, const Rec&, const Rec& ) {}
 };
 
 struct AabbData
@@ -113,6 +115,7 @@ extern "C" int sg_candidate_pairs( sg_ctx* ctx, int dim, uint32_t n, const doubl
   out->n = 0; out->ij = nullptr;
   if( n == 0 ) { return SG_OK; }
   if( aabbs == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_candidate_pairs: null box array" ); }
+  if( n >= 0x80000000u ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_candidate_pairs: at most 2^31 - 1 boxes" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   if( ctx->aabb == nullptr ) { ctx->aabb = new AabbData; }
   if( dim == 2 ) { return candidate_pairs_impl<2>( ctx, ctx->aabb, n, aabbs, out ); }

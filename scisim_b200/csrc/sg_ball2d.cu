@@ -28,7 +28,8 @@ struct alignas( 64 ) Ball2DRec
   double r;
   uint32_t idx;
   uint32_t key;
-  double pad0, pad1;
+  uint32_t c1, c2; // cell row (and layer)
+  double pad1;
 };
 
 struct ContactOut2D
@@ -76,6 +77,7 @@ struct Ball2DPolicy
   using In = Ball2DIn;
   using Rec = Ball2DRec;
   using Out = ContactOut2D;
+  static constexpr uint32_t IDX_OFFSET = 40u;
 
   // ball2d/Ball2DSim.cpp:566-571: lo = min(q1,q0) - r, hi = max(q1,q0) + r
   __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
@@ -86,14 +88,14 @@ struct Ball2DPolicy
     lo[0] = fmin( b.x, a.x ) - r; lo[1] = fmin( b.y, a.y ) - r;
     hi[0] = fmax( b.x, a.x ) + r; hi[1] = fmax( b.y, a.y ) + r;
   }
-  __device__ static Rec make_rec( const In& in, const uint32_t i, const uint32_t key )
+  __device__ static Rec make_rec( const In& in, const uint32_t i, const uint32_t key, const uint32_t c1, const uint32_t c2 )
   {
     const double2 a = __ldg( &in.q0[i] );
     const double2 b = __ldg( &in.q1[i] );
     Rec rec;
     rec.q0x = a.x; rec.q0y = a.y; rec.q1x = b.x; rec.q1y = b.y;
     rec.r = __ldg( &in.r[i] );
-    rec.idx = i; rec.key = key; rec.pad0 = 0.0; rec.pad1 = 0.0;
+    rec.idx = i; rec.key = key; rec.c1 = c1; rec.c2 = c2; rec.pad1 = 0.0;
     return rec;
   }
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
@@ -103,11 +105,12 @@ struct Ball2DPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
-  __device__ static uint32_t narrow_count( const Rec& a, const Rec& b ) { return ccd_hit( a, b ) ? 1u : 0u; }
+  __device__ static uint32_t rec_c1( const Rec& s ) { return s.c1; }
+  __device__ static uint32_t rec_c2( const Rec& s ) { return s.c2; }
+  __device__ static bool narrow_test( const Rec& a, const Rec& b ) { return ccd_hit( a, b ); }
   // BallBallConstraint{ i, j, q0a, q0b, ra, rb }: n = (q0a - q0b).normalized(); point q0a - ra*n; depth at q1
-  __device__ static void narrow_emit( const Out& out, unsigned long long& k, const Rec& a, const Rec& b )
+  __device__ static void contact_emit( const Out& out, unsigned long long& k, const Rec& a, const Rec& b )
   {
-    if( !ccd_hit( a, b ) ) { return; }
     if( k < out.cap )
     {
       double nx = a.q0x - b.q0x;
@@ -195,24 +198,79 @@ __device__ __forceinline__ unsigned long long static_mask( const Static2D& sg, c
   return mask;
 }
 
-// counts[g * nblocks + block] = number of balls of this block active against geometry g
-__global__ void __launch_bounds__( 256 ) k_ball2d_static_count( const __grid_constant__ Static2D sg, const uint32_t n, const double2* __restrict__ q1, const double* __restrict__ r, uint32_t* __restrict__ counts )
+// One pass over the balls that (optionally) integrates them and, from registers, also produces everything the
+// detection pipeline needs before binning: the bounds of the swept AABBs (block reduce + one atomic per quantity
+// per block) and counts[g * nblocks + block] = number of this block's balls active against static geometry g.
+template<bool DO_FLOW>
+__global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ Static2D sg, const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0,
+                                                       const double* __restrict__ m, const double* __restrict__ r, const double gx, const double gy, const double dt,
+                                                       double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts )
 {
   __shared__ uint32_t s_cnt[SG_MAX_DRUMS + SG_MAX_PLANES];
   const uint32_t ng = sg.ndrums + sg.nplanes;
   if( threadIdx.x < ng ) { s_cnt[threadIdx.x] = 0u; }
   __syncthreads();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double mn[2] = { __longlong_as_double( 0x7ff0000000000000LL ), __longlong_as_double( 0x7ff0000000000000LL ) };
+  double mx[2] = { __longlong_as_double( 0xfff0000000000000LL ), __longlong_as_double( 0xfff0000000000000LL ) };
+  double ext = 0.0;
   unsigned long long mask = 0ull;
-  if( i < n ) { mask = static_mask( sg, __ldg( &q1[i] ), __ldg( &r[i] ) ); }
-  const int lane = threadIdx.x & 31;
-  for( uint32_t g = 0; g < ng; ++g )
+  if( i < n )
   {
-    const unsigned b = __ballot_sync( 0xffffffffu, ( mask >> g ) & 1ull );
-    if( lane == 0 && b != 0u ) { atomicAdd( &s_cnt[g], __popc( b ) ); }
+    const double2 q = __ldg( &q0[i] );
+    double2 qo;
+    if( DO_FLOW )
+    {
+      const double2 v = __ldg( &v0[i] );
+      const double mass = __ldg( &m[i] );
+      const double minv = 1.0 / mass;
+      const double Fx = 0.0 + mass * gx;
+      const double Fy = 0.0 + mass * gy;
+      double2 vo;
+      if( kind == SG_MAP_SYMPLECTIC_EULER )
+      {
+        const double s = dt * minv;
+        vo.x = v.x + ( 0.0 + s * Fx );
+        vo.y = v.y + ( 0.0 + s * Fy );
+        qo.x = q.x + dt * vo.x;
+        qo.y = q.y + dt * vo.y;
+      }
+      else
+      {
+        const double s = ( 0.5 * dt ) * minv;
+        const double vhx = v.x + ( 0.0 + s * Fx );
+        const double vhy = v.y + ( 0.0 + s * Fy );
+        qo.x = q.x + dt * vhx;
+        qo.y = q.y + dt * vhy;
+        vo.x = vhx + s * Fx;
+        vo.y = vhy + s * Fy;
+      }
+      q1[i] = qo;
+      v1[i] = vo;
+    }
+    else
+    {
+      qo = __ldg( &q1[i] );
+    }
+    const double rad = __ldg( &r[i] );
+    double lo[2], hi[2];
+    lo[0] = fmin( qo.x, q.x ) - rad; lo[1] = fmin( qo.y, q.y ) - rad;
+    hi[0] = fmax( qo.x, q.x ) + rad; hi[1] = fmax( qo.y, q.y ) + rad;
+    sg_bp_bounds_update<2>( lo, hi, mn, mx, ext );
+    mask = static_mask( sg, qo, rad );
   }
-  __syncthreads();
-  if( threadIdx.x < ng ) { counts[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x]; }
+  sg_bp_bounds_commit<2>( mn, mx, ext, acc );
+  if( ng > 0u )
+  {
+    const int lane = threadIdx.x & 31;
+    for( uint32_t g = 0; g < ng; ++g )
+    {
+      const unsigned b = __ballot_sync( 0xffffffffu, ( mask >> g ) & 1ull );
+      if( lane == 0 && b != 0u ) { atomicAdd( &s_cnt[g], __popc( b ) ); }
+    }
+    __syncthreads();
+    if( threadIdx.x < ng ) { counts[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x]; }
+  }
 }
 
 // Stable compaction: geometry-major, ball ascending, appended after the body-body contacts
@@ -221,6 +279,9 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_static_emit( const __grid_cons
 {
   __shared__ uint32_t s_warp[8];
   const uint32_t ng = sg.ndrums + sg.nplanes;
+  // most blocks touch no static geometry: find that out from the counts before reading any ball
+  const int mine = ( threadIdx.x < ng ) ? int( counts[threadIdx.x * gridDim.x + blockIdx.x] != 0u ) : 0;
+  if( __syncthreads_or( mine ) == 0 ) { return; }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 x0 = make_double2( 0.0, 0.0 ), x1 = x0;
@@ -345,7 +406,8 @@ static int ball2d_flow_device( sg_ctx* ctx, Ball2DData* d, const int map_kind, c
 }
 
 // Runs the whole detection pipeline on the device-resident q0,q1 and leaves the counts in d->n_*.
-static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want_cand )
+// flow_kind >= 0: the unconstrained map is fused into the first pass (q1,v1 are produced from q0,v0 on the way).
+static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want_cand, const int flow_kind = -1, const double dt = 0.0 )
 {
   const uint32_t n = d->n;
   d->n_cand = d->n_bb = d->n_static = d->n_drum = d->n_plane = 0;
@@ -359,21 +421,30 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   rc = ball2d_ensure_outputs( ctx, d, want_cand ? ( d->bp.cand_cap > 0 ? d->bp.cand_cap : uint64_t( n ) * 6u + 1024u ) : 0u, d->act_cap > 0 ? d->act_cap : uint64_t( n ) * 4u + 1024u );
   if( rc != SG_OK ) { return rc; }
 
-  Ball2DIn in;
-  in.q0 = d->q0.as<double2>(); in.q1 = d->q1.as<double2>(); in.r = d->r.as<double>(); in.n = n;
-  rc = sg_bp_bin_and_count<Ball2DPolicy>( ctx, d->bp, in );
-  if( rc != SG_OK ) { return rc; }
-
   const uint32_t ng = d->sg.ndrums + d->sg.nplanes;
   const unsigned nblk = sg_div_up( n, 256 );
   const uint32_t nst = ng * nblk;
+  SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
+  SG_CUDA( ctx, d->st_total.ensure( 4 ) );
+  if( flow_kind >= 0 )
+  {
+    SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->q0.as<double2>(), d->v0.as<double2>(), d->m.as<double>(),
+               d->r.as<double>(), d->g[0], d->g[1], dt, d->q1.as<double2>(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>() ) );
+  }
+  else
+  {
+    SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->q0.as<double2>(), nullptr, nullptr,
+               d->r.as<double>(), 0.0, 0.0, 0.0, d->q1.as<double2>(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>() ) );
+  }
+  Ball2DIn in;
+  in.q0 = d->q0.as<double2>(); in.q1 = d->q1.as<double2>(); in.r = d->r.as<double>(); in.n = n;
+  rc = sg_bp_bin_and_count<Ball2DPolicy>( ctx, d->bp, in, true );
+  if( rc != SG_OK ) { return rc; }
+
   if( ng > 0 )
   {
-    SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 ) );
-    SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 ) );
-    SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
-    SG_CUDA( ctx, d->st_total.ensure( 4 ) );
-    SG_LAUNCH( ctx, "ball2d_static_count", double( n ) * 24.0, k_ball2d_static_count<<<nblk, 256, 0, ctx->stream>>>( d->sg, n, d->q1.as<double2>(), d->r.as<double>(), d->st_counts.as<uint32_t>() ) );
     rc = sg_exclusive_scan<ScanU32>( ctx, "ball2d_static_scan", d->st_counts.as<uint32_t>(), nullptr, nst, nst, d->st_partials.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->st_total.as<uint32_t>(), false );
     if( rc != SG_OK ) { return rc; }
   }
@@ -470,6 +541,7 @@ int sg_ball2d_set_bodies( sg_ctx* ctx, uint32_t n, const double* r, const double
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( n > 0 && ( r == nullptr || m == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_bodies: null array" ); }
+  if( n >= 0x80000000u ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_bodies: at most 2^31 - 1 bodies" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   Ball2DData* d = ball2d_data( ctx );
   d->n = n;
@@ -580,9 +652,7 @@ int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_step: map kind %d is not a ball2d map", map_kind ); }
   Ball2DData* d = ball2d_data( ctx );
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  int rc = ball2d_flow_device( ctx, d, map_kind, dt );
-  if( rc != SG_OK ) { return rc; }
-  rc = ball2d_active_set_device( ctx, d, true );
+  const int rc = ball2d_active_set_device( ctx, d, true, map_kind, dt );
   if( rc != SG_OK ) { return rc; }
   if( out != nullptr )
   {

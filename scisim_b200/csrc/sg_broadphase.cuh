@@ -26,7 +26,8 @@
 #include "sg_tma.cuh"
 
 #define SG_BP_THREADS 256
-#define SG_BP_LOCAL_CAP 24
+#define SG_BP_LOCAL_CAP 12
+#define SG_BP_FAST_CAP 8
 
 // Per-pipeline device scratch (owned by the caller's data block)
 struct BroadScratch
@@ -39,17 +40,20 @@ struct BroadScratch
   DevBuf key;           // u32[n]
   DevBuf rank;          // u32[n]
   DevBuf recs;          // Rec[n]
-  DevBuf counts;        // uint2[n]
+  DevBuf counts;        // uint2[n]  by body index
+  DevBuf masks;         // uint2[n]  by sorted position
   DevBuf offsets;       // ulonglong2[n]
   DevBuf pair_partials; // ScanPairCounts::Acc[tiles]
   DevBuf totals;        // ScanPairCounts::Acc
   DevBuf cand;          // uint2[cand_cap]
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
+  int bounds_phase = 0; // which of the two BoundsAccum the current step reduces into
+  BoundsAccum* bounds_cur() const { return bounds.as<BoundsAccum>() + bounds_phase; }
   void release()
   {
     bounds.release(); params.release(); cell_count.release(); cell_start.release(); cell_partials.release(); key.release(); rank.release();
-    recs.release(); counts.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
+    recs.release(); counts.release(); masks.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
   }
 };
 
@@ -93,39 +97,25 @@ __device__ inline void sg_store_rec( Rec* p, const Rec& r )
 }
 
 // ---- bounds ----------------------------------------------------------------------------------------
-static __global__ void sg_bp_bounds_init( BoundsAccum* acc )
+__device__ inline void sg_bp_bounds_reset( BoundsAccum* acc )
 {
-  if( threadIdx.x == 0 && blockIdx.x == 0 )
+  for( int k = 0; k < 3; ++k )
   {
-    for( int k = 0; k < 3; ++k )
-    {
-      acc->min_lo[k] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );  // +inf
-      acc->max_lo[k] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );  // -inf
-    }
-    acc->max_ext = sg_ordered_from_double( 0.0 );
+    acc->min_lo[k] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );  // +inf
+    acc->max_lo[k] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );  // -inf
   }
+  acc->max_ext = sg_ordered_from_double( 0.0 );
 }
 
-template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_bounds( const typename P::In in, BoundsAccum* __restrict__ acc )
+static __global__ void sg_bp_bounds_init( BoundsAccum* acc )
 {
-  constexpr int D = P::D;
-  double mn[D], mx[D], ext = 0.0;
-  #pragma unroll
-  for( int k = 0; k < D; ++k ) { mn[k] = __longlong_as_double( 0x7ff0000000000000LL ); mx[k] = __longlong_as_double( 0xfff0000000000000LL ); }
-  for( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += gridDim.x * blockDim.x )
-  {
-    double lo[D], hi[D];
-    P::load_aabb( in, i, lo, hi );
-    #pragma unroll
-    for( int k = 0; k < D; ++k )
-    {
-      mn[k] = fmin( mn[k], lo[k] );
-      mx[k] = fmax( mx[k], lo[k] );
-      ext = fmax( ext, hi[k] - lo[k] );
-    }
-  }
-  // warp reduce
+  if( threadIdx.x == 0 && blockIdx.x == 0 ) { sg_bp_bounds_reset( acc ); sg_bp_bounds_reset( acc + 1 ); }
+}
+
+// Block-level reduction of per-thread partial bounds, then one atomic per quantity per block.
+template<int D>
+__device__ inline void sg_bp_bounds_commit( double* mn, double* mx, double ext, BoundsAccum* __restrict__ acc )
+{
   #pragma unroll
   for( int d = 16; d > 0; d >>= 1 )
   {
@@ -160,6 +150,34 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_bounds( const typename 
     }
     atomicMax( &acc->max_ext, sg_ordered_from_double( ext ) );
   }
+}
+
+template<int D>
+__device__ __forceinline__ void sg_bp_bounds_update( const double* lo, const double* hi, double* mn, double* mx, double& ext )
+{
+  #pragma unroll
+  for( int k = 0; k < D; ++k )
+  {
+    mn[k] = fmin( mn[k], lo[k] );
+    mx[k] = fmax( mx[k], lo[k] );
+    ext = fmax( ext, hi[k] - lo[k] );
+  }
+}
+
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_bounds( const typename P::In in, BoundsAccum* __restrict__ acc )
+{
+  constexpr int D = P::D;
+  double mn[D], mx[D], ext = 0.0;
+  #pragma unroll
+  for( int k = 0; k < D; ++k ) { mn[k] = __longlong_as_double( 0x7ff0000000000000LL ); mx[k] = __longlong_as_double( 0xfff0000000000000LL ); }
+  for( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += gridDim.x * blockDim.x )
+  {
+    double lo[D], hi[D];
+    P::load_aabb( in, i, lo, hi );
+    sg_bp_bounds_update<D>( lo, hi, mn, mx, ext );
+  }
+  sg_bp_bounds_commit<D>( mn, mx, ext, acc );
 }
 
 // ---- grid layout -----------------------------------------------------------------------------------
@@ -217,8 +235,10 @@ __device__ inline GridParams sg_layout_grid( const BoundsAccum& acc, const uint3
 }
 
 template<int D>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_setup( const BoundsAccum* __restrict__ acc, const uint32_t max_cells, GridParams* __restrict__ params, uint32_t* __restrict__ cell_count )
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_setup( const BoundsAccum* __restrict__ acc, BoundsAccum* __restrict__ acc_next, const uint32_t max_cells, GridParams* __restrict__ params, uint32_t* __restrict__ cell_count )
 {
+  // the two accumulators alternate between steps: this step's is read here, the next step's is re-armed
+  if( blockIdx.x == 0 && threadIdx.x == 32 ) { sg_bp_bounds_reset( acc_next ); }
   // every block derives the same layout from the same reduced bounds, then clears its share of the histogram
   __shared__ GridParams g_s;
   if( threadIdx.x == 0 ) { g_s = sg_layout_grid<D>( *acc, max_cells ); }
@@ -255,14 +275,17 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P:
 }
 
 template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename P::In in, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ key_in,
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename P::In in, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ key_in,
                                                                  const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs )
 {
+  const uint32_t g_dims0 = params->dims[0], g_dims1 = params->dims[1];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if( i >= in.n ) { return; }
   const uint32_t key = key_in[i];
   const uint32_t pos = __ldg( &cell_start[key] ) + rank_in[i];
-  const typename P::Rec r = P::make_rec( in, i, key );
+  // cell coordinates travel with the record (no integer division in the pair kernels)
+  const uint32_t yz = key / g_dims0;
+  const typename P::Rec r = P::make_rec( in, i, key, ( P::D == 3 ) ? yz % g_dims1 : yz, ( P::D == 3 ) ? yz / g_dims1 : 0u );
   sg_store_rec( &recs[pos], r );
 }
 
@@ -286,7 +309,7 @@ struct BpStage
   unsigned long long bar;
 };
 
-template<int D> constexpr size_t sg_bp_smem_bytes() { return size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + sizeof( BpStage<D> ) + 64; }
+template<int D> __host__ __device__ constexpr size_t sg_bp_smem_bytes() { return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + sizeof( BpStage<D> ) + 127 ) & ~size_t( 127 ); }
 
 // All threads of the block call this; returns once the staged windows are readable.
 template<typename P>
@@ -334,23 +357,16 @@ __device__ inline void sg_bp_stage_windows( const GridParams& g, const uint32_t 
   __syncthreads();
 }
 
-// Calls f( q, rec_q ) for every record q != p whose cell is within one cell of p's cell on every axis.
+// Calls f( w, q ) for every sorted position q != p whose cell is within one cell of (cx,c1,c2) on every axis,
+// in a fixed order (window-major, position ascending): both passes see the same sequence.
 template<typename P, typename F>
-__device__ __forceinline__ void sg_bp_walk( const GridParams& g, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const unsigned char* s_recs,
-                                            const BpStage<P::D>* st, const uint32_t p, const uint32_t key, F&& f )
+__device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t p, const uint32_t key, const uint32_t c1, const uint32_t c2, F&& f )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
-  using Rec = typename P::Rec;
-  uint32_t c[3];
-  {
-    uint32_t k = key;
-    c[0] = k % g.dims[0]; k /= g.dims[0];
-    c[1] = ( D == 3 ) ? ( k % g.dims[1] ) : k;
-    c[2] = ( D == 3 ) ? ( k / g.dims[1] ) : 0u;
-  }
-  const uint32_t x0 = ( c[0] > 0u ) ? c[0] - 1u : 0u;
-  const uint32_t x1 = ( c[0] + 1u < g.dims[0] ) ? c[0] + 1u : c[0];
+  const uint32_t cx = key - g.dims[0] * ( c1 + g.dims[1] * c2 );
+  const uint32_t x0 = ( cx > 0u ) ? cx - 1u : 0u;
+  const uint32_t x1 = ( cx + 1u < g.dims[0] ) ? cx + 1u : cx;
   // all segment bounds first (independent loads), then the walk
   uint32_t qb[Cfg::NW], qe[Cfg::NW];
   #pragma unroll
@@ -358,8 +374,8 @@ __device__ __forceinline__ void sg_bp_walk( const GridParams& g, const uint32_t*
   {
     const int dy = w % 3 - 1;
     const int dz = ( D == 3 ) ? w / 3 - 1 : 0;
-    const long long y = ( long long )( c[1] ) + dy;
-    const long long z = ( long long )( c[2] ) + dz;
+    const long long y = ( long long )( c1 ) + dy;
+    const long long z = ( long long )( c2 ) + dz;
     const bool ok = y >= 0 && y < ( long long )( g.dims[1] ) && z >= 0 && z < ( long long )( g.dims[2] );
     qb[w] = 0u; qe[w] = 0u;
     if( ok )
@@ -372,19 +388,14 @@ __device__ __forceinline__ void sg_bp_walk( const GridParams& g, const uint32_t*
   #pragma unroll
   for( int w = 0; w < Cfg::NW; ++w )
   {
-    const uint32_t ws = st->start[w];
-    const uint32_t wl = st->len[w];
-    const unsigned char* sw = s_recs + size_t( w ) * Cfg::WCAP * 64;
     for( uint32_t q = qb[w]; q < qe[w]; ++q )
     {
-      if( q == p ) { continue; }
-      const uint32_t slot = q - ws;
-      const Rec o = ( slot < wl ) ? sg_load_rec_swizzled<Rec>( sw, slot ) : sg_load_rec_global<Rec>( &recs[q] );
-      f( q, o );
+      if( q != p ) { f( w, q ); }
     }
   }
 }
 
+// record (or just its body index) at sorted position q, known to lie in window w's key range
 template<typename P>
 __device__ __forceinline__ typename P::Rec sg_bp_fetch( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q )
 {
@@ -393,10 +404,26 @@ __device__ __forceinline__ typename P::Rec sg_bp_fetch( const typename P::Rec* _
   if( slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * BpCfg<P::D>::WCAP * 64, slot ); }
   return sg_load_rec_global<Rec>( &recs[q] );
 }
+template<typename P>
+__device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q )
+{
+  constexpr uint32_t CH = P::IDX_OFFSET / 16u, IN = P::IDX_OFFSET % 16u;
+  const uint32_t slot = q - st->start[w];
+  if( slot < st->len[w] )
+  {
+    const unsigned char* rec = s_recs + ( size_t( w ) * BpCfg<P::D>::WCAP + slot ) * 64;
+    return *reinterpret_cast<const uint32_t*>( rec + ( ( CH ^ ( ( slot >> 1 ) & 3u ) ) << 4 ) + IN );
+  }
+  return __ldg( reinterpret_cast<const uint32_t*>( reinterpret_cast<const unsigned char*>( &recs[q] ) + P::IDX_OFFSET ) );
+}
 
+#define SG_BP_MASKS_INVALID 0x80000000u
+
+// Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active (bit 31: masks invalid) }
+//          masks[sorted position] = { bit k: k-th visited neighbour is such a candidate, bit k: ... and active }
 template<typename P>
 __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts )
+                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint2* __restrict__ masks )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -405,34 +432,39 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
   unsigned char* s_recs = s_raw;
   BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
   const GridParams g = *params;
-  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
+  Rec me;
+  if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the windows are staged
+  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
   if( p >= n ) { return; }
-  constexpr int WSELF = Cfg::NW / 2; // the (dy,dz) = (0,0) window contains the block's own records
-  const Rec me = sg_bp_fetch<P>( recs, s_recs, st, WSELF, p );
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
   const uint32_t my_idx = P::rec_idx( me );
-  uint32_t nc = 0u, na = 0u;
-  sg_bp_walk<P>( g, cell_start, recs, s_recs, st, p, P::rec_key( me ), [&]( const uint32_t, const Rec& o )
+  uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
+  sg_bp_walk_pos<P>( g, cell_start, p, P::rec_key( me ), P::rec_c1( me ), P::rec_c2( me ), [&]( const int w, const uint32_t q )
   {
+    const uint32_t bit = ( k < 32u ) ? ( 1u << k ) : 0u;
+    ++k;
+    const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
     if( P::rec_idx( o ) <= my_idx ) { return; }
     double olo[D], ohi[D];
     P::rec_aabb( o, olo, ohi );
     bool ov = true;
     #pragma unroll
-    for( int k = 0; k < D; ++k ) { ov = ov && !( hi[k] < olo[k] ) && !( ohi[k] < lo[k] ); }
+    for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
     if( !ov ) { return; }
-    ++nc;
-    if( P::HAS_NARROW ) { na += P::narrow_count( me, o ); }
+    ++nc; cmask |= bit;
+    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
   } );
-  counts[my_idx] = make_uint2( nc, na );
+  counts[my_idx] = make_uint2( nc, ( k > 32u ) ? ( na | SG_BP_MASKS_INVALID ) : na );
+  masks[p] = make_uint2( cmask, amask );
 }
 
+// Pass 2.  Each body writes its candidates (ascending partner index) at its offset; active ones also write a contact.
 template<typename P>
 __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                              const typename P::Rec* __restrict__ recs, const uint2* __restrict__ counts, const ulonglong2* __restrict__ offsets,
-                                                              uint2* __restrict__ cand, const uint64_t cand_cap, const typename P::Out out )
+                                                              const typename P::Rec* __restrict__ recs, const uint2* __restrict__ counts, const uint2* __restrict__ masks,
+                                                              const ulonglong2* __restrict__ offsets, uint2* __restrict__ cand, const uint64_t cand_cap, const typename P::Out out )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -441,30 +473,27 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
   unsigned char* s_recs = s_raw;
   BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
   const GridParams g = *params;
-  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
+  unsigned long long* s_list = reinterpret_cast<unsigned long long*>( s_raw + sg_bp_smem_bytes<D>() ); // [SG_BP_FAST_CAP][T]
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
-  if( p >= n ) { return; }
-  constexpr int WSELF = Cfg::NW / 2;
-  const Rec me = sg_bp_fetch<P>( recs, s_recs, st, WSELF, p );
-  const uint32_t my_idx = P::rec_idx( me );
-  const uint2 cnt = counts[my_idx];
-  if( cnt.x == 0u ) { return; }
-  const ulonglong2 off = offsets[my_idx];
-  double lo[D], hi[D];
-  P::rec_aabb( me, lo, hi );
-  unsigned long long ka = off.y;
-
-  auto overlaps = [&]( const Rec& o ) -> bool
+  // everything this thread needs that does not depend on the staged windows is requested first
+  Rec me;
+  uint2 cnt = make_uint2( 0u, 0u ), m = make_uint2( 0u, 0u );
+  ulonglong2 off = make_ulonglong2( 0ull, 0ull );
+  uint32_t my_idx = 0u;
+  if( p < n )
   {
-    double olo[D], ohi[D];
-    P::rec_aabb( o, olo, ohi );
-    bool ov = true;
-    #pragma unroll
-    for( int k = 0; k < D; ++k ) { ov = ov && !( hi[k] < olo[k] ) && !( ohi[k] < lo[k] ); }
-    return ov;
-  };
+    me = sg_load_rec_global<Rec>( &recs[p] );
+    my_idx = P::rec_idx( me );
+    cnt = counts[my_idx];
+    off = offsets[my_idx];
+    m = masks[p];
+  }
+  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
+  if( p >= n || cnt.x == 0u ) { return; }
+  unsigned long long ka = off.y;
+  const uint32_t key = P::rec_key( me ), c1 = P::rec_c1( me ), c2 = P::rec_c2( me );
   // a partner's record, wherever it lives: search the staged windows, else global
-  auto fetch = [&]( const uint32_t q ) -> Rec
+  auto fetch_any = [&]( const uint32_t q ) -> Rec
   {
     #pragma unroll
     for( int w = 0; w < Cfg::NW; ++w )
@@ -474,46 +503,98 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
     }
     return sg_load_rec_global<Rec>( &recs[q] );
   };
+
+  if( cnt.x <= SG_BP_FAST_CAP && ( cnt.y & SG_BP_MASKS_INVALID ) == 0u )
+  {
+    // Fast path: pass 1 already decided every neighbour; only candidates' indices and active partners' records are
+    // read.  The (partner index << 32 | active << 31 | position) entries are insertion-sorted in a per-thread column
+    // of shared memory (n < 2^31 is checked by the host).
+    unsigned long long* col = s_list + threadIdx.x;
+    uint32_t cnt_m = 0u, k = 0u;
+    sg_bp_walk_pos<P>( g, cell_start, p, key, c1, c2, [&]( const int w, const uint32_t q )
+    {
+      const uint32_t kk = k++;
+      if( ( ( m.x >> kk ) & 1u ) == 0u ) { return; }
+      const uint32_t oi = sg_bp_fetch_idx<P>( recs, s_recs, st, w, q );
+      const unsigned long long v = ( static_cast<unsigned long long>( oi ) << 32 ) | ( static_cast<unsigned long long>( ( m.y >> kk ) & 1u ) << 31 ) | q;
+      uint32_t j = cnt_m++;
+      while( j > 0u )
+      {
+        const unsigned long long prev = col[( j - 1u ) * Cfg::T];
+        if( prev <= v ) { break; }
+        col[j * Cfg::T] = prev;
+        --j;
+      }
+      col[j * Cfg::T] = v;
+    } );
+    for( uint32_t j = 0u; j < cnt_m; ++j )
+    {
+      const unsigned long long v = col[j * Cfg::T];
+      const unsigned long long kc = off.x + j;
+      if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( my_idx, uint32_t( v >> 32 ) ); }
+      if( P::HAS_NARROW && ( ( v >> 31 ) & 1ull ) )
+      {
+        const Rec o = fetch_any( uint32_t( v & 0x7fffffffull ) );
+        P::contact_emit( out, ka, me, o );
+      }
+    }
+    return;
+  }
+
+  // Slow paths: redo the tests (a body with more than 32 neighbours or more candidates than the local list holds)
+  double lo[D], hi[D];
+  P::rec_aabb( me, lo, hi );
+  auto overlaps = [&]( const Rec& o ) -> bool
+  {
+    double olo[D], ohi[D];
+    P::rec_aabb( o, olo, ohi );
+    bool ov = true;
+    #pragma unroll
+    for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
+    return ov;
+  };
   auto emit_one = [&]( const unsigned long long kc, const Rec& o )
   {
     if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( my_idx, P::rec_idx( o ) ); }
-    if( P::HAS_NARROW ) { P::narrow_emit( out, ka, me, o ); }
+    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { P::contact_emit( out, ka, me, o ); } }
   };
-
   if( cnt.x <= SG_BP_LOCAL_CAP )
   {
-    // (partner index << 32 | partner position), kept ascending by insertion
     unsigned long long list[SG_BP_LOCAL_CAP];
-    uint32_t m = 0u;
-    sg_bp_walk<P>( g, cell_start, recs, s_recs, st, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
+    uint32_t nl = 0u;
+    sg_bp_walk_pos<P>( g, cell_start, p, key, c1, c2, [&]( const int w, const uint32_t q )
     {
+      const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
       if( P::rec_idx( o ) <= my_idx || !overlaps( o ) ) { return; }
       const unsigned long long v = ( static_cast<unsigned long long>( P::rec_idx( o ) ) << 32 ) | q;
-      uint32_t k = m++;
-      while( k > 0u && list[k - 1u] > v ) { list[k] = list[k - 1u]; --k; }
-      list[k] = v;
+      uint32_t j = nl++;
+      while( j > 0u && list[j - 1u] > v ) { list[j] = list[j - 1u]; --j; }
+      list[j] = v;
     } );
-    for( uint32_t k = 0u; k < m; ++k )
+    for( uint32_t j = 0u; j < nl; ++j )
     {
-      const Rec o = fetch( uint32_t( list[k] & 0xffffffffull ) );
-      emit_one( off.x + k, o );
+      const Rec o = fetch_any( uint32_t( list[j] & 0xffffffffull ) );
+      emit_one( off.x + j, o );
     }
   }
   else
   {
     // Crowded body: select partners in ascending index order by repeated walks (O(count * neighbours))
     uint32_t last = my_idx;
-    for( uint32_t k = 0u; k < cnt.x; ++k )
+    for( uint32_t j = 0u; j < cnt.x; ++j )
     {
       uint32_t best_idx = 0xffffffffu, best_q = 0u;
-      sg_bp_walk<P>( g, cell_start, recs, s_recs, st, p, P::rec_key( me ), [&]( const uint32_t q, const Rec& o )
+      int best_w = 0;
+      sg_bp_walk_pos<P>( g, cell_start, p, key, c1, c2, [&]( const int w, const uint32_t q )
       {
-        const uint32_t oi = P::rec_idx( o );
-        if( oi <= last || oi >= best_idx || !overlaps( o ) ) { return; }
-        best_idx = oi; best_q = q;
+        const uint32_t oi = sg_bp_fetch_idx<P>( recs, s_recs, st, w, q );
+        if( oi <= last || oi >= best_idx ) { return; }
+        const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
+        if( !overlaps( o ) ) { return; }
+        best_idx = oi; best_q = q; best_w = w;
       } );
-      const Rec o = fetch( best_q );
-      emit_one( off.x + k, o );
+      const Rec o = sg_bp_fetch<P>( recs, s_recs, st, best_w, best_q );
+      emit_one( off.x + j, o );
       last = best_idx;
     }
   }
@@ -527,7 +608,12 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   uint64_t mc = uint64_t( n ) * 2u + 1024u;
   if( mc > 0x7fffffffull ) { mc = 0x7fffffffull; }
   s.max_cells = uint32_t( mc );
-  SG_CUDA( ctx, s.bounds.ensure( sizeof( BoundsAccum ) ) );
+  if( s.bounds.ptr == nullptr )
+  {
+    SG_CUDA( ctx, s.bounds.ensure( 2 * sizeof( BoundsAccum ) ) );
+    SG_LAUNCH( ctx, "bp_bounds_init", 0.0, sg_bp_bounds_init<<<1, 32, 0, ctx->stream>>>( s.bounds.as<BoundsAccum>() ) );
+    s.bounds_phase = 0;
+  }
   SG_CUDA( ctx, s.params.ensure( sizeof( GridParams ) ) );
   SG_CUDA( ctx, s.cell_count.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
   SG_CUDA( ctx, s.cell_start.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
@@ -536,6 +622,7 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   SG_CUDA( ctx, s.rank.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.recs.ensure( size_t( n ) * 64 ) );
   SG_CUDA( ctx, s.counts.ensure( size_t( n ) * sizeof( uint2 ) ) );
+  SG_CUDA( ctx, s.masks.ensure( size_t( n ) * sizeof( uint2 ) ) );
   SG_CUDA( ctx, s.offsets.ensure( size_t( n ) * sizeof( ulonglong2 ) ) );
   SG_CUDA( ctx, s.pair_partials.ensure( ( size_t( n ) / SG_SCAN_TILE + 2 ) * sizeof( ScanPairCounts::Acc ) ) );
   SG_CUDA( ctx, s.totals.ensure( sizeof( ScanPairCounts::Acc ) ) );
@@ -544,25 +631,25 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
 
 // Sort bodies by cell and count.  After this returns (asynchronously) s.totals holds {P_c, P_a}.
 template<typename P>
-static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::In& in )
+static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::In& in, const bool bounds_done = false )
 {
   constexpr int D = P::D;
   const uint32_t n = in.n;
   const unsigned nblk = sg_div_up( n, SG_BP_THREADS );
   const unsigned nred = nblk < unsigned( ctx->num_sms * 8 ) ? nblk : unsigned( ctx->num_sms * 8 );
   const double nb = double( n );
-  SG_LAUNCH( ctx, "bp_bounds", nb * P::IN_BYTES, sg_bp_bounds_init<<<1, 32, 0, ctx->stream>>>( s.bounds.as<BoundsAccum>() );
-             sg_bp_bounds<P><<<nred, SG_BP_THREADS, 0, ctx->stream>>>( in, s.bounds.as<BoundsAccum>() ) );
-  ++ctx->launch_count;
-  SG_LAUNCH( ctx, "bp_setup", nb * 4.0, sg_bp_setup<D><<<unsigned( ctx->num_sms * 4 ), SG_BP_THREADS, 0, ctx->stream>>>( s.bounds.as<BoundsAccum>(), s.max_cells, s.params.as<GridParams>(), s.cell_count.as<uint32_t>() ) );
+  if( !bounds_done ) { SG_LAUNCH( ctx, "bp_bounds", nb * P::IN_BYTES, sg_bp_bounds<P><<<nred, SG_BP_THREADS, 0, ctx->stream>>>( in, s.bounds_cur() ) ); }
+  BoundsAccum* acc_cur = s.bounds_cur();
+  s.bounds_phase ^= 1;
+  SG_LAUNCH( ctx, "bp_setup", nb * 4.0, sg_bp_setup<D><<<unsigned( ctx->num_sms * 4 ), SG_BP_THREADS, 0, ctx->stream>>>( acc_cur, s.bounds_cur(), s.max_cells, s.params.as<GridParams>(), s.cell_count.as<uint32_t>() ) );
   SG_LAUNCH( ctx, "bp_hist", nb * ( P::IN_BYTES + 8.0 ), sg_bp_hist<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_count.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>() ) );
   const uint32_t* ncells_dev = &s.params.as<GridParams>()->ncells;
   int rc = sg_exclusive_scan<ScanU32>( ctx, "bp_cell_scan", s.cell_count.as<uint32_t>(), ncells_dev, 0u, s.max_cells, s.cell_partials.as<uint32_t>(), s.cell_start.as<uint32_t>(), nullptr, true );
   if( rc != SG_OK ) { return rc; }
-  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>() ) );
+  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>() ) );
   constexpr size_t smem = sg_bp_smem_bytes<D>();
   SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
-  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>() ) );
+  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 + 8.0 ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint2>() ) );
   rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false );
   return rc;
 }
@@ -570,10 +657,10 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
 template<typename P>
 static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const double out_bytes )
 {
-  constexpr size_t smem = sg_bp_smem_bytes<P::D>();
+  constexpr size_t smem = sg_bp_smem_bytes<P::D>() + size_t( SG_BP_FAST_CAP ) * BpCfg<P::D>::T * 8;
   SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_emit<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
-  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 8.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, BpCfg<P::D>::T ), BpCfg<P::D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
-             s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, out ) );
+  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 8.0 + 8.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, BpCfg<P::D>::T ), BpCfg<P::D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
+             s.counts.as<uint2>(), s.masks.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, out ) );
   return SG_OK;
 }
 

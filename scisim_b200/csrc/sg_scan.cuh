@@ -34,7 +34,7 @@ struct ScanPairCounts
   struct Acc { unsigned long long c; unsigned long long a; };
   using Out = ulonglong2;
   __device__ static Acc zero() { return Acc{ 0ull, 0ull }; }
-  __device__ static Acc conv( const In x ) { return Acc{ x.x, x.y }; }
+  __device__ static Acc conv( const In x ) { return Acc{ x.x, x.y & 0x7fffffffu }; } // bit 31 of y is a flag (sg_broadphase.cuh)
   __device__ static Acc add( const Acc a, const Acc b ) { return Acc{ a.c + b.c, a.a + b.a }; }
   __device__ static Acc shfl_up( const Acc a, const int d )
   {
@@ -163,6 +163,36 @@ __global__ void __launch_bounds__( SG_SCAN_THREADS ) sg_scan_down( const typenam
   }
 }
 
+// Whole scan in one 1024-thread block: for arrays small enough that launch latency, not bandwidth, is the cost.
+template<typename P>
+__global__ void __launch_bounds__( 1024 ) sg_scan_small( const typename P::In* __restrict__ in, const uint32_t n, typename P::Out* __restrict__ out, typename P::Acc* __restrict__ total_out, const bool write_end )
+{
+  using Acc = typename P::Acc;
+  __shared__ Acc warp_sums[32];
+  __shared__ Acc carry_s;
+  if( threadIdx.x == 0 ) { carry_s = P::zero(); }
+  __syncthreads();
+  for( uint32_t base = 0; base < n; base += 1024 )
+  {
+    const uint32_t e = base + threadIdx.x;
+    const Acc v = ( e < n ) ? P::conv( in[e] ) : P::zero();
+    Acc total;
+    const Acc excl = sg_block_exclusive<P, 1024>( v, warp_sums, &total );
+    const Acc carry = carry_s;
+    if( e < n ) { out[e] = P::out( P::add( carry, excl ) ); }
+    __syncthreads();
+    if( threadIdx.x == 0 ) { carry_s = P::add( carry, total ); }
+    __syncthreads();
+  }
+  if( threadIdx.x == 0 )
+  {
+    if( total_out != nullptr ) { *total_out = carry_s; }
+    if( write_end ) { out[n] = P::out( carry_s ); }
+  }
+}
+
+#define SG_SCAN_SMALL_MAX 32768u
+
 // Host driver.  cap = upper bound on the element count (sizes the grid); partials must hold
 // ceil(cap / SG_SCAN_TILE) Acc entries.
 template<typename P>
@@ -170,6 +200,11 @@ static int sg_exclusive_scan( sg_ctx* ctx, const char* name, const typename P::I
                               typename P::Acc* partials, typename P::Out* out, typename P::Acc* total_out, const bool write_end )
 {
   if( cap == 0 ) { return SG_OK; }
+  if( n_dev == nullptr && n_host <= SG_SCAN_SMALL_MAX )
+  {
+    SG_LAUNCH( ctx, name, double( n_host ) * double( sizeof( typename P::In ) + sizeof( typename P::Out ) ), sg_scan_small<P><<<1, 1024, 0, ctx->stream>>>( in, n_host, out, total_out, write_end ) );
+    return SG_OK;
+  }
   const unsigned ntiles = sg_div_up( cap, SG_SCAN_TILE );
   const double nelem = double( n_dev != nullptr ? cap : n_host );
   const double bytes_reduce = nelem * double( sizeof( typename P::In ) );
