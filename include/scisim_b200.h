@@ -45,6 +45,20 @@ extern "C" {
 #define SG_BALL_BALL 0   /* ball2d/Constraints/BallBallConstraint */
 #define SG_BALL_DRUM 1   /* ball2d/Constraints/BallStaticDrumConstraint */
 #define SG_BALL_PLANE 2  /* ball2d/Constraints/BallStaticPlaneConstraint */
+/* rigidbody3d (rigidbody3d/Constraints/): body-body in ascending (i,j) candidate order, then planes plane-major */
+#define SG_SPHERE_SPHERE 10           /* SphereSphereConstraint{ i, j, n, p, ri, rj } */
+#define SG_KINEMATIC_SPHERE_SPHERE 11 /* KinematicSphereSphereConstraint: i = free sphere, j = kinematic one, p = its centre at q0 */
+#define SG_BODY_BODY 12               /* BodyBodyConstraint{ i, j, p, n, q0 } (box-box, mesh-mesh) */
+#define SG_KINEMATIC_BODY_BODY 13     /* KinematicObjectBodyConstraint{ i, j, p, n, q0 } */
+#define SG_PLANE_SPHERE 14            /* StaticPlaneSphereConstraint: j = plane */
+#define SG_PLANE_BOX 15               /* StaticPlaneBoxConstraint: j = plane, aux = corner number, p = x0 + R0*corner */
+#define SG_PLANE_BODY 16              /* StaticPlaneBodyConstraint: j = plane, aux = convex hull vertex, p = collision point at q0 */
+
+/* RigidBodyGeometryType (rigidbody3d/Geometry/RigidBodyGeometry.h:13-19) */
+#define SG_GEO_BOX 0
+#define SG_GEO_SPHERE 1
+#define SG_GEO_STAPLE 2 /* not supported (not on the north-star path) */
+#define SG_GEO_MESH 3
 
 /* which optional arrays sg_*_active_set copies back to the host */
 #define SG_OUT_NORMALS 1u
@@ -81,6 +95,7 @@ typedef struct sg_contacts
   const double* p;       /* dim*n_active getWorldSpaceContactPoint( q0 ) */
   const double* depth;   /* n_active penetrationDepth( q1 ) (NaN where the reference has no override) */
   const uint32_t* cand_ij; /* 2*n_candidates, only with SG_OUT_CANDIDATES */
+  const uint32_t* aux;   /* n_active (rigidbody3d only): corner / hull vertex number for plane-box / plane-body */
 } sg_contacts;
 
 /* ---- context ------------------------------------------------------------------------------------- */
@@ -137,6 +152,31 @@ int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint3
 int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
+
+/* ---- rigidbody3d --------------------------------------------------------------------------------------
+ * Layouts are RigidBody3DState's (rigidbody3d/RigidBody3DState.cpp:70-240): q = [3N centres | 9N row-major R],
+ * v = [3N linear | 3N angular]. Static data: the geometry list (as m_geometry) and, per body, its geometry index,
+ * the kinematically-scripted flag, total mass and body-frame inertia (the diagonals of M0).  The world-space mass
+ * matrix M = R diag(I0) R^T the reference keeps in sync with q (updateMandMinv) is recomputed on the device from
+ * R(q0) with the same evaluation order. */
+int sg_rb3d_set_geometry( sg_ctx* ctx, uint32_t ngeo, const uint32_t* type, const double* r /* ngeo */, const double* half /* 3 ngeo */, const uint32_t* mesh /* ngeo */ );
+/* a triangle mesh as RigidBodyTriangleMesh holds it (rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp:54-102): all vertices (AABB),
+ * surface samples, convex-hull vertices, and the signed distance grid (x fastest). Returns its index in *mesh_index. */
+int sg_rb3d_add_mesh( sg_ctx* ctx, uint32_t nverts, const double* verts, uint32_t nsamples, const double* samples, uint32_t nhull, const double* hull,
+                      const double* cell_delta, const uint32_t* dims, const double* origin, const double* sdf, uint32_t* mesh_index );
+int sg_rb3d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, const uint8_t* fixed, const double* m /* n */, const double* I0 /* 3n */ );
+int sg_rb3d_set_gravity( sg_ctx* ctx, const double* g /* 3 */ );
+/* normals are normalised as rigidbody3d/StaticGeometry/StaticPlane.cpp:10-15 does */
+int sg_rb3d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 3n */, const double* nrm /* 3n */ );
+/* UnconstrainedMap::flow for SplitHamMap (SG_MAP_SPLIT_HAM) / DMVMap (SG_MAP_DMV) with NearEarthGravityForce */
+int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
+/* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; no portals, no cylinders). Returns
+ * SG_ERR_UNSUPPORTED where the reference exits on a pair of geometry types it cannot collide (RigidBody3DSim.cpp:960-961). */
+int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
+/* resident variants, as for ball2d */
+int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v );
+int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
+int sg_rb3d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
 
 #ifdef __cplusplus
 }

@@ -146,3 +146,106 @@ void orc_ball2d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32
 }
 
 }
+
+// ---- rigidbody3d -----------------------------------------------------------------------------------
+#include "rb3d.h"
+
+struct RB3DHandle
+{
+  RB3DScene scene;
+  std::vector<RB3DContact> active;
+  std::vector<std::pair<unsigned,unsigned>> candidates;
+  bool supported = true;
+  double seconds_flow = 0.0;
+  double seconds_active = 0.0;
+};
+
+extern "C"
+{
+
+// geo_type/geo_r/geo_half/geo_mesh describe the geometry list (as m_geometry in RigidBody3DState); geo_of_body indexes it.
+// plane normals are normalised here exactly as rigidbody3d/StaticGeometry/StaticPlane.cpp:10-15.
+void* orc_rb3d_create( uint32_t n, const uint32_t* geo_of_body, const uint8_t* fixed, const double* m, const double* I0, const double* g,
+                       uint32_t ngeo, const uint32_t* geo_type, const double* geo_r, const double* geo_half, const uint32_t* geo_mesh,
+                       uint32_t nplanes, const double* plane_x, const double* plane_n )
+{
+  RB3DHandle* h = new RB3DHandle;
+  RB3DScene& s = h->scene;
+  s.geo_of_body.assign( geo_of_body, geo_of_body + n );
+  s.fixed.assign( fixed, fixed + n );
+  s.m.assign( m, m + n );
+  for( uint32_t b = 0; b < n; ++b ) { s.I0.push_back( V3{ I0[3 * b], I0[3 * b + 1], I0[3 * b + 2] } ); }
+  s.g = V3{ g[0], g[1], g[2] };
+  for( uint32_t k = 0; k < ngeo; ++k )
+  {
+    RB3DGeometry geo;
+    geo.type = geo_type[k]; geo.r = geo_r[k]; geo.half = V3{ geo_half[3 * k], geo_half[3 * k + 1], geo_half[3 * k + 2] }; geo.mesh = geo_mesh[k];
+    s.geometry.push_back( geo );
+  }
+  for( uint32_t p = 0; p < nplanes; ++p )
+  {
+    s.plane_x.push_back( V3{ plane_x[3 * p], plane_x[3 * p + 1], plane_x[3 * p + 2] } );
+    s.plane_n.push_back( normalized( V3{ plane_n[3 * p], plane_n[3 * p + 1], plane_n[3 * p + 2] } ) );
+  }
+  return h;
+}
+void orc_rb3d_destroy( void* h ) { delete static_cast<RB3DHandle*>( h ); }
+
+uint32_t orc_rb3d_add_mesh( void* hv, uint32_t nverts, const double* verts, uint32_t nsamples, const double* samples, uint32_t nhull, const double* hull,
+                            const double* cell_delta, const uint32_t* dims, const double* origin, const double* sdf )
+{
+  RB3DHandle* h = static_cast<RB3DHandle*>( hv );
+  RB3DMesh mesh;
+  for( uint32_t k = 0; k < nverts; ++k ) { mesh.verts.push_back( V3{ verts[3 * k], verts[3 * k + 1], verts[3 * k + 2] } ); }
+  for( uint32_t k = 0; k < nsamples; ++k ) { mesh.samples.push_back( V3{ samples[3 * k], samples[3 * k + 1], samples[3 * k + 2] } ); }
+  for( uint32_t k = 0; k < nhull; ++k ) { mesh.hull.push_back( V3{ hull[3 * k], hull[3 * k + 1], hull[3 * k + 2] } ); }
+  mesh.cell_delta = V3{ cell_delta[0], cell_delta[1], cell_delta[2] };
+  mesh.dims[0] = dims[0]; mesh.dims[1] = dims[1]; mesh.dims[2] = dims[2];
+  mesh.origin = V3{ origin[0], origin[1], origin[2] };
+  // RigidBodyTriangleMesh.cpp:102
+  mesh.grid_end = V3{ origin[0] + double( dims[0] - 1 ) * cell_delta[0], origin[1] + double( dims[1] - 1 ) * cell_delta[1], origin[2] + double( dims[2] - 1 ) * cell_delta[2] };
+  mesh.sdf.assign( sdf, sdf + std::size_t( dims[0] ) * dims[1] * dims[2] );
+  h->scene.meshes.push_back( mesh );
+  return uint32_t( h->scene.meshes.size() - 1 );
+}
+
+void orc_rb3d_flow( void* hv, int kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
+{
+  RB3DHandle* h = static_cast<RB3DHandle*>( hv );
+  const auto t0 = std::chrono::steady_clock::now();
+  flow( kind, h->scene, q0, v0, dt, q1, v1 );
+  h->seconds_flow = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+}
+
+// returns 1, or 0 when the reference would exit on an unsupported geometry pair
+int orc_rb3d_active_set( void* hv, const double* q0, const double* q1, int method )
+{
+  RB3DHandle* h = static_cast<RB3DHandle*>( hv );
+  const auto t0 = std::chrono::steady_clock::now();
+  h->supported = computeActiveSet( h->scene, q0, q1, h->active, &h->candidates, method == 0 );
+  h->seconds_active = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+  return h->supported ? 1 : 0;
+}
+uint64_t orc_rb3d_num_candidates( const void* h ) { return static_cast<const RB3DHandle*>( h )->candidates.size(); }
+uint64_t orc_rb3d_num_active( const void* h ) { return static_cast<const RB3DHandle*>( h )->active.size(); }
+double orc_rb3d_seconds_flow( const void* h ) { return static_cast<const RB3DHandle*>( h )->seconds_flow; }
+double orc_rb3d_seconds_active( const void* h ) { return static_cast<const RB3DHandle*>( h )->seconds_active; }
+void orc_rb3d_copy_candidates( const void* hv, uint32_t* ij_out )
+{
+  const RB3DHandle* h = static_cast<const RB3DHandle*>( hv );
+  for( std::size_t k = 0; k < h->candidates.size(); ++k ) { ij_out[2 * k] = h->candidates[k].first; ij_out[2 * k + 1] = h->candidates[k].second; }
+}
+void orc_rb3d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t* j, uint32_t* aux, double* n, double* p, double* depth )
+{
+  const RB3DHandle* h = static_cast<const RB3DHandle*>( hv );
+  for( std::size_t k = 0; k < h->active.size(); ++k )
+  {
+    const RB3DContact& c = h->active[k];
+    type[k] = c.type; i[k] = c.i; j[k] = c.j; aux[k] = c.aux;
+    n[3 * k] = c.n.x; n[3 * k + 1] = c.n.y; n[3 * k + 2] = c.n.z;
+    p[3 * k] = c.p.x; p[3 * k + 1] = c.p.y; p[3 * k + 2] = c.p.z;
+    depth[k] = c.depth;
+  }
+}
+
+}

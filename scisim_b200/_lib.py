@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libscisim_b200.so")
 SG_OK = 0
 SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV = 0, 1, 2, 3
 SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
+SG_SPHERE_SPHERE, SG_KINEMATIC_SPHERE_SPHERE, SG_BODY_BODY, SG_KINEMATIC_BODY_BODY, SG_PLANE_SPHERE, SG_PLANE_BOX, SG_PLANE_BODY = 10, 11, 12, 13, 14, 15, 16
 SG_OUT_NORMALS, SG_OUT_POINTS, SG_OUT_DEPTHS, SG_OUT_CANDIDATES, SG_OUT_ALL = 1, 2, 4, 8, 15
 
 c_dp = C.POINTER(C.c_double)
@@ -25,7 +26,7 @@ class SgPairs(C.Structure):
 class SgContacts(C.Structure):
     _fields_ = [("dim", C.c_uint32), ("n_candidates", C.c_uint64), ("n_active", C.c_uint64), ("n_body_body", C.c_uint64),
                 ("n_drum", C.c_uint64), ("n_plane", C.c_uint64), ("type", c_up), ("i", c_up), ("j", c_up),
-                ("n", c_dp), ("p", c_dp), ("depth", c_dp), ("cand_ij", c_up)]
+                ("n", c_dp), ("p", c_dp), ("depth", c_dp), ("cand_ij", c_up), ("aux", c_up)]
 
 
 class SciSimB200Error(RuntimeError):
@@ -70,6 +71,16 @@ def load():
         "sg_ball2d_upload": (C.c_int, [vp, vp, vp]),
         "sg_ball2d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
         "sg_ball2d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
+        "sg_rb3d_set_geometry": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),
+        "sg_rb3d_add_mesh": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, vp, C.POINTER(C.c_uint32)]),
+        "sg_rb3d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),
+        "sg_rb3d_set_gravity": (C.c_int, [vp, vp]),
+        "sg_rb3d_set_planes": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_rb3d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
+        "sg_rb3d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
+        "sg_rb3d_upload": (C.c_int, [vp, vp, vp]),
+        "sg_rb3d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
+        "sg_rb3d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -26,6 +26,7 @@ struct AabbPolicy
   using In = AabbIn<DIM>;
   using Rec = AabbRec<DIM>;
   using Out = NoOut;
+  static constexpr uint32_t IDX_MASK = 0xffffffffu;
   static constexpr uint32_t IDX_OFFSET = 16u * DIM;
   __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
   {
@@ -47,8 +48,8 @@ struct AabbPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
-  __device__ static uint32_t rec_c1( const Rec& s ) { return s.c1; }
-  __device__ static uint32_t rec_c2( const Rec& s ) { return s.c2; }
+  __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
+  __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
   __device__ static bool narrow_test( const Rec&, const Rec& ) { return false; }
   __device__ static void contact_emit( const Out&, unsigned long long&, const Rec&, const Rec& ) {}
 };

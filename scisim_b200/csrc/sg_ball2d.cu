@@ -77,6 +77,7 @@ struct Ball2DPolicy
   using In = Ball2DIn;
   using Rec = Ball2DRec;
   using Out = ContactOut2D;
+  static constexpr uint32_t IDX_MASK = 0xffffffffu;
   static constexpr uint32_t IDX_OFFSET = 40u;
 
   // ball2d/Ball2DSim.cpp:566-571: lo = min(q1,q0) - r, hi = max(q1,q0) + r
@@ -105,8 +106,8 @@ struct Ball2DPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
-  __device__ static uint32_t rec_c1( const Rec& s ) { return s.c1; }
-  __device__ static uint32_t rec_c2( const Rec& s ) { return s.c2; }
+  __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
+  __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
   __device__ static bool narrow_test( const Rec& a, const Rec& b ) { return ccd_hit( a, b ); }
   // BallBallConstraint{ i, j, q0a, q0b, ra, rb }: n = (q0a - q0b).normalized(); point q0a - ra*n; depth at q1
   __device__ static void contact_emit( const Out& out, unsigned long long& k, const Rec& a, const Rec& b )

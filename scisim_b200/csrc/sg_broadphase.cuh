@@ -412,9 +412,9 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
   if( slot < st->len[w] )
   {
     const unsigned char* rec = s_recs + ( size_t( w ) * BpCfg<P::D>::WCAP + slot ) * 64;
-    return *reinterpret_cast<const uint32_t*>( rec + ( ( CH ^ ( ( slot >> 1 ) & 3u ) ) << 4 ) + IN );
+    return *reinterpret_cast<const uint32_t*>( rec + ( ( CH ^ ( ( slot >> 1 ) & 3u ) ) << 4 ) + IN ) & P::IDX_MASK;
   }
-  return __ldg( reinterpret_cast<const uint32_t*>( reinterpret_cast<const unsigned char*>( &recs[q] ) + P::IDX_OFFSET ) );
+  return __ldg( reinterpret_cast<const uint32_t*>( reinterpret_cast<const unsigned char*>( &recs[q] ) + P::IDX_OFFSET ) ) & P::IDX_MASK;
 }
 
 #define SG_BP_MASKS_INVALID 0x80000000u
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
   P::rec_aabb( me, lo, hi );
   const uint32_t my_idx = P::rec_idx( me );
   uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
-  sg_bp_walk_pos<P>( g, cell_start, p, P::rec_key( me ), P::rec_c1( me ), P::rec_c2( me ), [&]( const int w, const uint32_t q )
+  sg_bp_walk_pos<P>( g, cell_start, p, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), [&]( const int w, const uint32_t q )
   {
     const uint32_t bit = ( k < 32u ) ? ( 1u << k ) : 0u;
     ++k;
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
   sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
   if( p >= n || cnt.x == 0u ) { return; }
   unsigned long long ka = off.y;
-  const uint32_t key = P::rec_key( me ), c1 = P::rec_c1( me ), c2 = P::rec_c2( me );
+  const uint32_t key = P::rec_key( me ), c1 = P::rec_c1( me, g ), c2 = P::rec_c2( me, g );
   // a partner's record, wherever it lives: search the staged windows, else global
   auto fetch_any = [&]( const uint32_t q ) -> Rec
   {

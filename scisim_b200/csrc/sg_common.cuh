@@ -78,6 +78,7 @@ struct ProfPending
 
 struct Ball2DData;
 struct AabbData;
+struct Rb3dData;
 
 struct sg_ctx
 {
@@ -97,6 +98,7 @@ struct sg_ctx
 
   Ball2DData* ball2d = nullptr;
   AabbData* aabb = nullptr;
+  Rb3dData* rb3d = nullptr;
 };
 
 int sg_fail( sg_ctx* ctx, int code, const char* fmt, ... );

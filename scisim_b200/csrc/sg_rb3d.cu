@@ -1,0 +1,1254 @@
+// sg_rb3d.cu -- rigidbody3d hot path: SplitHam / DMV unconstrained flow, 3-D broad phase, sphere-sphere / box-box /
+// mesh-vs-SDF narrow phase, body-plane tests.
+//
+// Reference behaviour reproduced (file:line in the SCISim checkout):
+//   rigidbody3d/UnconstrainedMaps/SplitHamMap.cpp:17-182, DMVMap.cpp:15-207            k_rb3d_flow
+//   rigidbody3d/Forces/NearEarthGravityForce.cpp:39-53, RigidBody3DState.cpp:70-240     gravity, M0, R I0 R^T
+//   rigidbody3d/RigidBody3DSim.cpp:1057-1069 + Geometry/*::computeAABB                  k_rb3d_aabb (AABBs at q1 only)
+//   rigidbody3d/RigidBody3DSim.cpp:1072-1141                                            sg_broadphase.cuh pipeline
+//   rigidbody3d/RigidBody3DSim.cpp:879-962 (dispatch, kinematic rules), :793-819 (sphere-sphere), :665-694 (box-box),
+//   :844-876 + Constraints/MeshMeshUtilities.cpp:10-65 + Geometry/RigidBodyTriangleMesh.cpp:276-335 (mesh-mesh)
+//   rigidbody3d/RigidBody3DSim.cpp:1414-1502 (body-plane), Constraints/StaticPlane{Sphere,Box,Body}Constraint.cpp
+//
+// Two pipelines share the broad phase:
+//   * all bodies are spheres: records carry (x1, x0, r) and the sphere test is fused into the pair kernels
+//     (Sphere3DPolicy), exactly like the ball2d path;
+//   * otherwise: boxes are built by k_rb3d_aabb, the broad phase emits the sorted candidate list, and the narrow
+//     phase runs over that list (one thread per sphere/box pair, one CTA per mesh pair), count -> scan -> emit so the
+//     contacts of a pair stay in the order the reference's routines produce them.
+#include "sg_boxbox.cuh"
+#include "sg_broadphase.cuh"
+
+#define SG_FIXED_BIT 0x80000000u
+
+// ---- contact output (SoA, reference order) ---------------------------------------------------------
+struct ContactOut3D
+{
+  uint32_t* type;
+  uint32_t* i;
+  uint32_t* j;
+  uint32_t* aux;
+  double* n;     // 3 per contact
+  double* p;     // 3 per contact
+  double* depth;
+  unsigned long long cap;
+};
+
+__device__ __forceinline__ void put_contact( const ContactOut3D& out, const unsigned long long k, const uint32_t type, const uint32_t i, const uint32_t j, const uint32_t aux,
+                                             const V3d n, const V3d p, const double depth )
+{
+  if( k >= out.cap ) { return; }
+  out.type[k] = type; out.i[k] = i; out.j[k] = j; out.aux[k] = aux;
+  out.n[3 * k] = n.x; out.n[3 * k + 1] = n.y; out.n[3 * k + 2] = n.z;
+  out.p[3 * k] = p.x; out.p[3 * k + 1] = p.y; out.p[3 * k + 2] = p.z;
+  out.depth[k] = depth;
+}
+
+__device__ __forceinline__ double sg_nan() { return __longlong_as_double( 0x7ff8000000000000LL ); }
+
+__device__ __forceinline__ V3d load_v3( const double* __restrict__ a, const size_t b ) { return v3( __ldg( a + 3 * b ), __ldg( a + 3 * b + 1 ), __ldg( a + 3 * b + 2 ) ); }
+__device__ __forceinline__ M3d load_m3( const double* __restrict__ a, const size_t b )
+{
+  M3d R;
+  #pragma unroll
+  for( int k = 0; k < 9; ++k ) { R.m[k] = __ldg( a + 9 * b + k ); }
+  return R;
+}
+
+// ---- sphere-sphere, shared by both pipelines (RigidBody3DSim.cpp:793-819, dispatch :879-893) --------
+// a has the lower body index.  Returns false when the pair is skipped (both kinematic) or not touching at q1.
+__device__ __forceinline__ bool sphere_pair_active( const V3d x1a, const double ra, const bool fa, const V3d x1b, const double rb, const bool fb )
+{
+  if( fa && fb ) { return false; }
+  const V3d d = x1a - x1b;
+  return dot3( d, d ) <= ( ra + rb ) * ( ra + rb );
+}
+__device__ __forceinline__ void sphere_pair_emit( const ContactOut3D& out, const unsigned long long k, uint32_t ia, V3d x0a, V3d x1a, double ra, bool fa,
+                                                  uint32_t ib, V3d x0b, V3d x1b, double rb, bool fb )
+{
+  // the kinematic body is always listed second
+  if( fa )
+  {
+    const uint32_t ti = ia; ia = ib; ib = ti;
+    V3d tv = x0a; x0a = x0b; x0b = tv;
+    tv = x1a; x1a = x1b; x1b = tv;
+    const double tr = ra; ra = rb; rb = tr;
+    fb = true;
+  }
+  const V3d n = normalized3( x0a - x0b );
+  const V3d d1 = x1a - x1b;
+  const double depth = fmin( 0.0, sqrt( dot3( d1, d1 ) ) - ra - rb );
+  if( !fb )
+  {
+    const V3d p = x0a + ( ra / ( ra + rb ) ) * ( x0b - x0a );
+    put_contact( out, k, SG_SPHERE_SPHERE, ia, ib, 0u, n, p, depth );
+  }
+  else
+  {
+    put_contact( out, k, SG_KINEMATIC_SPHERE_SPHERE, ia, ib, 0u, n, x0b, depth );
+  }
+}
+
+// ---- fused all-spheres pipeline --------------------------------------------------------------------
+struct Sphere3DIn
+{
+  const double* q0;       // 12N
+  const double* q1;
+  const double* r;        // per body radius
+  const uint32_t* flags;  // per body: SG_FIXED_BIT or 0
+  uint32_t n;
+};
+
+struct alignas( 64 ) Sphere3DRec
+{
+  double x1[3];
+  double x0[3];
+  double r;
+  uint32_t idx;  // bit 31: kinematically scripted
+  uint32_t key;
+};
+
+struct Sphere3DPolicy
+{
+  static constexpr int D = 3;
+  static constexpr bool HAS_NARROW = true;
+  static constexpr double IN_BYTES = 32.0;
+  static constexpr uint32_t IDX_OFFSET = 56u;
+  static constexpr uint32_t IDX_MASK = 0x7fffffffu;
+  using In = Sphere3DIn;
+  using Rec = Sphere3DRec;
+  using Out = ContactOut3D;
+  // RigidBodySphere::computeAABB at q1: cm -/+ r
+  __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
+  {
+    const double r = __ldg( &in.r[i] );
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { const double c = __ldg( &in.q1[3 * size_t( i ) + k] ); lo[k] = c - r; hi[k] = c + r; }
+  }
+  __device__ static Rec make_rec( const In& in, const uint32_t i, const uint32_t key, const uint32_t, const uint32_t )
+  {
+    Rec rec;
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { rec.x1[k] = __ldg( &in.q1[3 * size_t( i ) + k] ); rec.x0[k] = __ldg( &in.q0[3 * size_t( i ) + k] ); }
+    rec.r = __ldg( &in.r[i] );
+    rec.idx = i | __ldg( &in.flags[i] );
+    rec.key = key;
+    return rec;
+  }
+  __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
+  {
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { lo[k] = s.x1[k] - s.r; hi[k] = s.x1[k] + s.r; }
+  }
+  __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
+  __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
+  __device__ static uint32_t rec_c1( const Rec& s, const GridParams& g ) { return ( s.key / g.dims[0] ) % g.dims[1]; }
+  __device__ static uint32_t rec_c2( const Rec& s, const GridParams& g ) { return s.key / ( g.dims[0] * g.dims[1] ); }
+  __device__ static bool narrow_test( const Rec& a, const Rec& b )
+  {
+    return sphere_pair_active( v3( a.x1[0], a.x1[1], a.x1[2] ), a.r, ( a.idx & SG_FIXED_BIT ) != 0u, v3( b.x1[0], b.x1[1], b.x1[2] ), b.r, ( b.idx & SG_FIXED_BIT ) != 0u );
+  }
+  __device__ static void contact_emit( const Out& out, unsigned long long& k, const Rec& a, const Rec& b )
+  {
+    sphere_pair_emit( out, k, a.idx & IDX_MASK, v3( a.x0[0], a.x0[1], a.x0[2] ), v3( a.x1[0], a.x1[1], a.x1[2] ), a.r, ( a.idx & SG_FIXED_BIT ) != 0u,
+                      b.idx & IDX_MASK, v3( b.x0[0], b.x0[1], b.x0[2] ), v3( b.x1[0], b.x1[1], b.x1[2] ), b.r, ( b.idx & SG_FIXED_BIT ) != 0u );
+    ++k;
+  }
+};
+
+// ---- generic pipeline: boxes from k_rb3d_aabb --------------------------------------------------------
+struct Box3DIn
+{
+  const double* boxes; // n * 6: lo(3), hi(3)
+  uint32_t n;
+};
+struct alignas( 64 ) Box3DRec { double lo[3]; double hi[3]; uint32_t idx; uint32_t key; uint32_t c1, c2; };
+struct NoOut3D {};
+struct Box3DPolicy
+{
+  static constexpr int D = 3;
+  static constexpr bool HAS_NARROW = false;
+  static constexpr double IN_BYTES = 48.0;
+  static constexpr uint32_t IDX_OFFSET = 48u;
+  static constexpr uint32_t IDX_MASK = 0xffffffffu;
+  using In = Box3DIn;
+  using Rec = Box3DRec;
+  using Out = NoOut3D;
+  __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
+  {
+    const double* b = in.boxes + size_t( i ) * 6;
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { lo[k] = __ldg( b + k ); hi[k] = __ldg( b + 3 + k ); }
+  }
+  __device__ static Rec make_rec( const In& in, const uint32_t i, const uint32_t key, const uint32_t c1, const uint32_t c2 )
+  {
+    Rec r;
+    load_aabb( in, i, r.lo, r.hi );
+    r.idx = i; r.key = key; r.c1 = c1; r.c2 = c2;
+    return r;
+  }
+  __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
+  {
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { lo[k] = s.lo[k]; hi[k] = s.hi[k]; }
+  }
+  __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
+  __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
+  __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
+  __device__ static bool narrow_test( const Rec&, const Rec& ) { return false; }
+  __device__ static void contact_emit( const Out&, unsigned long long&, const Rec&, const Rec& ) {}
+};
+
+// ---- device-side scene description -----------------------------------------------------------------
+struct MeshDev
+{
+  const double* verts;   uint32_t nverts;
+  const double* samples; uint32_t nsamples;
+  const double* hull;    uint32_t nhull;
+  const double* sdf;
+  double delta[3];
+  double origin[3];
+  double grid_end[3];
+  uint32_t dims[3];
+};
+
+struct Rb3dDev
+{
+  uint32_t n;
+  const uint32_t* btype;   // per body: geometry type | SG_FIXED_BIT
+  const double* bparam;    // per body 4 doubles: sphere (r,-,-,-), box (hx,hy,hz,-)
+  const uint32_t* bmesh;   // per body: mesh index (meshes only)
+  const MeshDev* meshes;
+};
+
+struct Planes3D
+{
+  uint32_t n;
+  double x[SG_MAX_PLANES][3];
+  double nrm[SG_MAX_PLANES][3];
+};
+
+// ---- unconstrained flow ----------------------------------------------------------------------------
+// AngleAxis( angle, axis ).toRotationMatrix() (Eigen/src/Geometry/AngleAxis.h)
+__device__ inline M3d angle_axis_matrix( const double angle, const V3d axis )
+{
+  M3d res;
+  double sn, cs;
+  sincos( angle, &sn, &cs );
+  const V3d sin_axis = sn * axis;
+  const V3d cos1_axis = ( 1.0 - cs ) * axis;
+  double tmp;
+  tmp = cos1_axis.x * axis.y;
+  res.m[1] = tmp - sin_axis.z; res.m[3] = tmp + sin_axis.z;
+  tmp = cos1_axis.x * axis.z;
+  res.m[2] = tmp + sin_axis.y; res.m[6] = tmp - sin_axis.y;
+  tmp = cos1_axis.y * axis.z;
+  res.m[5] = tmp - sin_axis.x; res.m[7] = tmp + sin_axis.x;
+  res.m[0] = cos1_axis.x * axis.x + cs;
+  res.m[4] = cos1_axis.y * axis.y + cs;
+  res.m[8] = cos1_axis.z * axis.z + cs;
+  return res;
+}
+
+// DMVMap.cpp:15-60 + 65-100 on one body: R1 from R0 and the body-frame angular momentum
+__device__ inline M3d dmv_rotation( const M3d& R0, const V3d am, const double h, const V3d I0 )
+{
+  // Eigen::Quaternion( Matrix3 ) -- Shoemake
+  double qw, qc[3];
+  #define SGM( r, c ) R0.m[3 * ( r ) + ( c )]
+  double t = SGM( 0, 0 ) + ( SGM( 1, 1 ) + SGM( 2, 2 ) );
+  if( t > 0.0 )
+  {
+    t = sqrt( t + 1.0 );
+    qw = 0.5 * t;
+    t = 0.5 / t;
+    qc[0] = ( SGM( 2, 1 ) - SGM( 1, 2 ) ) * t;
+    qc[1] = ( SGM( 0, 2 ) - SGM( 2, 0 ) ) * t;
+    qc[2] = ( SGM( 1, 0 ) - SGM( 0, 1 ) ) * t;
+  }
+  else
+  {
+    int i = 0;
+    if( SGM( 1, 1 ) > SGM( 0, 0 ) ) { i = 1; }
+    if( SGM( 2, 2 ) > SGM( i, i ) ) { i = 2; }
+    const int j = ( i + 1 ) % 3;
+    const int k = ( j + 1 ) % 3;
+    t = sqrt( SGM( i, i ) - SGM( j, j ) - SGM( k, k ) + 1.0 );
+    qc[i] = 0.5 * t;
+    t = 0.5 / t;
+    qw = ( SGM( k, j ) - SGM( j, k ) ) * t;
+    qc[j] = ( SGM( j, i ) + SGM( i, j ) ) * t;
+    qc[k] = ( SGM( k, i ) + SGM( i, k ) ) * t;
+  }
+  #undef SGM
+  const double eps = fabs( h * 1e-15 );
+  const double ha = h / 2.0;
+  const double fac1 = ( I0.y - I0.z ) / I0.x;
+  const double fac2 = ( I0.z - I0.x ) / I0.y;
+  const double fac3 = ( I0.x - I0.y ) / I0.z;
+  const double am1i = am.x * ha / I0.x;
+  const double am2i = am.y * ha / I0.y;
+  const double am3i = am.z * ha / I0.z;
+  double cm1 = am1i + fac1 * am2i * am3i;
+  double cm2 = am2i + fac2 * cm1 * am3i;
+  double cm3 = am3i + fac3 * cm1 * cm2;
+  for( unsigned itr = 0; itr < 50; ++itr )
+  {
+    const double cm1b = cm1, cm2b = cm2, cm3b = cm3;
+    const double calpha = cm1 * cm1 + 1.0 + cm2 * cm2 + cm3 * cm3;
+    cm1 = calpha * am1i + fac1 * cm2 * cm3;
+    cm2 = calpha * am2i + fac2 * cm1 * cm3;
+    cm3 = calpha * am3i + fac3 * cm1 * cm2;
+    const double err = fabs( cm1b - cm1 ) + fabs( cm2b - cm2 ) + fabs( cm3b - cm3 );
+    if( err <= eps ) { break; }
+  }
+  const double q0 = qw, q1 = qc[0], q2 = qc[1], q3 = qc[2];
+  double w = q0 - cm1 * q1 - cm2 * q2 - cm3 * q3;
+  double x = q1 + cm1 * q0 + cm3 * q2 - cm2 * q3;
+  double y = q2 + cm2 * q0 + cm1 * q3 - cm3 * q1;
+  double z = q3 + cm3 * q0 + cm2 * q1 - cm1 * q2;
+  const double nrm = sqrt( ( x * x + y * y ) + ( z * z + w * w ) );
+  x /= nrm; y /= nrm; z /= nrm; w /= nrm;
+  // Quaternion::toRotationMatrix
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  M3d r;
+  r.m[0] = 1.0 - ( tyy + tzz ); r.m[1] = txy - twz; r.m[2] = txz + twy;
+  r.m[3] = txy + twz; r.m[4] = 1.0 - ( txx + tzz ); r.m[5] = tyz - twx;
+  r.m[6] = txz - twy; r.m[7] = tyz + twx; r.m[8] = 1.0 - ( txx + tyy );
+  return r;
+}
+
+__global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind, const uint32_t n, const double* __restrict__ q0, const double* __restrict__ v0, const double* __restrict__ mass,
+                                                     const double* __restrict__ I0, const uint32_t* __restrict__ btype, const double gx, const double gy, const double gz, const double dt,
+                                                     double* __restrict__ q1, double* __restrict__ v1 )
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if( b >= n ) { return; }
+  const size_t nb = n;
+  const double m = __ldg( &mass[b] );
+  const V3d x0 = load_v3( q0, b );
+  const M3d R0 = load_m3( q0 + 3 * nb, b );
+  const V3d vl = load_v3( v0, b );
+  const V3d w0 = load_v3( v0 + 3 * nb, b );
+  const V3d I = load_v3( I0, b );
+  // v1 = M * v0: sparse column-major accumulate into zero; the world inertia block is stored transposed
+  V3d p = v3( 0.0 + m * vl.x, 0.0 + m * vl.y, 0.0 + m * vl.z );
+  const M3d Iw = world_inertia3( R0, I );
+  V3d L = v3( ( ( 0.0 + Iw.m[0] * w0.x ) + Iw.m[3] * w0.y ) + Iw.m[6] * w0.z,
+              ( ( 0.0 + Iw.m[1] * w0.x ) + Iw.m[4] * w0.y ) + Iw.m[7] * w0.z,
+              ( ( 0.0 + Iw.m[2] * w0.x ) + Iw.m[5] * w0.y ) + Iw.m[8] * w0.z );
+  double* x1o = q1 + 3 * size_t( b );
+  double* R1o = q1 + 3 * nb + 9 * size_t( b );
+  double* vlo = v1 + 3 * size_t( b );
+  double* vao = v1 + 3 * nb + 3 * size_t( b );
+  if( __ldg( &btype[b] ) & SG_FIXED_BIT )
+  {
+    // kinematically scripted: q1 = q0, v1 keeps M * v0 (SplitHamMap.cpp:43-53)
+    x1o[0] = x0.x; x1o[1] = x0.y; x1o[2] = x0.z;
+    #pragma unroll
+    for( int k = 0; k < 9; ++k ) { R1o[k] = R0.m[k]; }
+    vlo[0] = p.x; vlo[1] = p.y; vlo[2] = p.z;
+    vao[0] = L.x; vao[1] = L.y; vao[2] = L.z;
+    return;
+  }
+  const V3d F = v3( 0.0 + m * gx, 0.0 + m * gy, 0.0 + m * gz );
+  const double hdt = 0.5 * dt;
+  p = v3( p.x + hdt * F.x, p.y + hdt * F.y, p.z + hdt * F.z );
+  L = v3( L.x + hdt * 0.0, L.y + hdt * 0.0, L.z + hdt * 0.0 );
+  const double sc = ( ( 0.5 * dt ) * dt ) * ( 1.0 / m );
+  x1o[0] = x0.x + ( dt * vl.x + ( 0.0 + sc * F.x ) );
+  x1o[1] = x0.y + ( dt * vl.y + ( 0.0 + sc * F.y ) );
+  x1o[2] = x0.z + ( dt * vl.z + ( 0.0 + sc * F.z ) );
+  M3d R1;
+  if( kind == SG_MAP_SPLIT_HAM )
+  {
+    V3d pB = mulT3( R0, L );
+    R1 = R0;
+    #pragma unroll 1
+    for( int st = 0; st < 5; ++st )
+    {
+      double angle;
+      V3d axis;
+      if( st == 0 || st == 4 ) { angle = 0.5 * dt * pB.z / I.z; axis = v3( -0.0, -0.0, -1.0 ); }
+      else if( st == 1 || st == 3 ) { angle = 0.5 * dt * pB.y / I.y; axis = v3( -0.0, -1.0, -0.0 ); }
+      else { angle = dt * pB.x / I.x; axis = v3( -1.0, -0.0, -0.0 ); }
+      R1 = mul33( R1, angle_axis_matrix( -angle, axis ) );
+      pB = mul3( angle_axis_matrix( angle, axis ), pB );
+    }
+  }
+  else
+  {
+    R1 = dmv_rotation( R0, mulT3( R0, L ), dt, I );
+  }
+  #pragma unroll
+  for( int k = 0; k < 9; ++k ) { R1o[k] = R1.m[k]; }
+  p = v3( p.x + hdt * F.x, p.y + hdt * F.y, p.z + hdt * F.z );
+  L = v3( L.x + hdt * 0.0, L.y + hdt * 0.0, L.z + hdt * 0.0 );
+  vlo[0] = p.x / m; vlo[1] = p.y / m; vlo[2] = p.z / m;
+  const V3d w1 = mul3( world_inertia3( R1, v3( 1.0 / I.x, 1.0 / I.y, 1.0 / I.z ) ), L );
+  vao[0] = w1.x; vao[1] = w1.y; vao[2] = w1.z;
+}
+
+// ---- AABBs at q1 (generic pipeline) ----------------------------------------------------------------
+__global__ void __launch_bounds__( 128 ) k_rb3d_aabb( const Rb3dDev dev, const double* __restrict__ q1, double* __restrict__ boxes )
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if( b >= dev.n ) { return; }
+  const size_t nb = dev.n;
+  const uint32_t type = __ldg( &dev.btype[b] ) & ~SG_FIXED_BIT;
+  const V3d cm = load_v3( q1, b );
+  double lo[3], hi[3];
+  if( type == SG_GEO_SPHERE )
+  {
+    const double r = __ldg( &dev.bparam[4 * size_t( b )] );
+    lo[0] = cm.x - r; lo[1] = cm.y - r; lo[2] = cm.z - r;
+    hi[0] = cm.x + r; hi[1] = cm.y + r; hi[2] = cm.z + r;
+  }
+  else if( type == SG_GEO_BOX )
+  {
+    // extents = |R| * half
+    const M3d R = load_m3( q1 + 3 * nb, b );
+    M3d A;
+    #pragma unroll
+    for( int k = 0; k < 9; ++k ) { A.m[k] = fabs( R.m[k] ); }
+    const V3d e = mul3( A, v3( __ldg( &dev.bparam[4 * size_t( b )] ), __ldg( &dev.bparam[4 * size_t( b ) + 1] ), __ldg( &dev.bparam[4 * size_t( b ) + 2] ) ) );
+    lo[0] = cm.x - e.x; lo[1] = cm.y - e.y; lo[2] = cm.z - e.z;
+    hi[0] = cm.x + e.x; hi[1] = cm.y + e.y; hi[2] = cm.z + e.z;
+  }
+  else
+  {
+    // min / max over R * vert + cm for ALL mesh vertices (RigidBodyTriangleMesh.cpp:187-200)
+    const M3d R = load_m3( q1 + 3 * nb, b );
+    const MeshDev& mesh = dev.meshes[__ldg( &dev.bmesh[b] )];
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { lo[k] = __longlong_as_double( 0x7ff0000000000000LL ); hi[k] = __longlong_as_double( 0xfff0000000000000LL ); }
+    for( uint32_t vi = 0; vi < mesh.nverts; ++vi )
+    {
+      const V3d t = mul3( R, load_v3( mesh.verts, vi ) ) + cm;
+      lo[0] = fmin( lo[0], t.x ); lo[1] = fmin( lo[1], t.y ); lo[2] = fmin( lo[2], t.z );
+      hi[0] = fmax( hi[0], t.x ); hi[1] = fmax( hi[1], t.y ); hi[2] = fmax( hi[2], t.z );
+    }
+  }
+  double* o = boxes + 6 * size_t( b );
+  o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = hi[0]; o[4] = hi[1]; o[5] = hi[2];
+}
+
+// ---- narrow phase over the candidate list (generic pipeline) ----------------------------------------
+// RigidBodyTriangleMesh::detectCollision (RigidBodyTriangleMesh.cpp:276-335); n in the mesh frame
+__device__ inline bool sdf_detect( const MeshDev& mesh, const V3d x, V3d& n )
+{
+  if( x.x < mesh.origin[0] || x.y < mesh.origin[1] || x.z < mesh.origin[2] ) { return false; }
+  if( x.x > mesh.grid_end[0] || x.y > mesh.grid_end[1] || x.z > mesh.grid_end[2] ) { return false; }
+  const unsigned ix = unsigned( floor( ( x.x - mesh.origin[0] ) / mesh.delta[0] ) );
+  const unsigned iy = unsigned( floor( ( x.y - mesh.origin[1] ) / mesh.delta[1] ) );
+  const unsigned iz = unsigned( floor( ( x.z - mesh.origin[2] ) / mesh.delta[2] ) );
+  // the reference only asserts this; a sample exactly on grid_end is treated as a miss (same guard as the oracle)
+  if( ix + 1u >= mesh.dims[0] || iy + 1u >= mesh.dims[1] || iz + 1u >= mesh.dims[2] ) { return false; }
+  const double bcx = ( x.x - ( mesh.origin[0] + double( ix ) * mesh.delta[0] ) ) / mesh.delta[0];
+  const double bcy = ( x.y - ( mesh.origin[1] + double( iy ) * mesh.delta[1] ) ) / mesh.delta[1];
+  const double bcz = ( x.z - ( mesh.origin[2] + double( iz ) * mesh.delta[2] ) ) / mesh.delta[2];
+  const double bix = 1.0 - bcx, biy = 1.0 - bcy, biz = 1.0 - bcz;
+  const size_t nx = mesh.dims[0], ny = mesh.dims[1];
+  const double* s = mesh.sdf + ( size_t( iz ) * ny + iy ) * nx + ix;
+  const double v000 = __ldg( s ),               v100 = __ldg( s + 1 );
+  const double v010 = __ldg( s + nx ),          v110 = __ldg( s + nx + 1 );
+  const double v001 = __ldg( s + nx * ny ),      v101 = __ldg( s + nx * ny + 1 );
+  const double v011 = __ldg( s + nx * ny + nx ), v111 = __ldg( s + nx * ny + nx + 1 );
+  const double dist = biz * ( biy * ( bix * v000 + bcx * v100 ) + bcy * ( bix * v010 + bcx * v110 ) ) +
+                      bcz * ( biy * ( bix * v001 + bcx * v101 ) + bcy * ( bix * v011 + bcx * v111 ) );
+  if( dist > 0.0 ) { return false; }
+  V3d g;
+  g.x = biz * ( biy * ( v100 - v000 ) + bcy * ( v110 - v010 ) ) + bcz * ( biy * ( v101 - v001 ) + bcy * ( v111 - v011 ) );
+  g.y = biz * ( bix * ( v010 - v000 ) + bcx * ( v110 - v100 ) ) + bcz * ( bix * ( v011 - v001 ) + bcx * ( v111 - v101 ) );
+  g.z = biy * ( bix * ( v001 - v000 ) + bcx * ( v101 - v100 ) ) + bcy * ( bix * ( v011 - v010 ) + bcx * ( v111 - v110 ) );
+  g.x /= mesh.delta[0]; g.y /= mesh.delta[1]; g.z /= mesh.delta[2];
+  n = normalized3( g );
+  return true;
+}
+
+#define SG_PAIR_SKIP 0u
+#define SG_PAIR_SPHERE 1u
+#define SG_PAIR_BOX 2u
+#define SG_PAIR_MESH 3u
+#define SG_PAIR_BAD 4u
+
+// kinematic rules of dispatchNarrowPhaseCollision: both fixed -> skip; the fixed body goes second
+__device__ __forceinline__ uint32_t pair_kind( const Rb3dDev& dev, const uint2 pr, uint32_t& b0, uint32_t& b1, bool& kin )
+{
+  const uint32_t t0 = __ldg( &dev.btype[pr.x] ), t1 = __ldg( &dev.btype[pr.y] );
+  b0 = pr.x; b1 = pr.y;
+  const bool f0 = ( t0 & SG_FIXED_BIT ) != 0u, f1 = ( t1 & SG_FIXED_BIT ) != 0u;
+  if( f0 && f1 ) { return SG_PAIR_SKIP; }
+  if( f0 ) { b0 = pr.y; b1 = pr.x; }
+  kin = f0 || f1;
+  const uint32_t g0 = t0 & ~SG_FIXED_BIT, g1 = t1 & ~SG_FIXED_BIT;
+  if( g0 != g1 ) { return SG_PAIR_BAD; }
+  if( g0 == SG_GEO_SPHERE ) { return SG_PAIR_SPHERE; }
+  if( g0 == SG_GEO_BOX ) { return SG_PAIR_BOX; }
+  if( g0 == SG_GEO_MESH ) { return SG_PAIR_MESH; }
+  return SG_PAIR_BAD;
+}
+
+__device__ __forceinline__ V3d body_half( const Rb3dDev& dev, const uint32_t b )
+{
+  return v3( __ldg( &dev.bparam[4 * size_t( b )] ), __ldg( &dev.bparam[4 * size_t( b ) + 1] ), __ldg( &dev.bparam[4 * size_t( b ) + 2] ) );
+}
+
+// One thread per candidate pair (sphere-sphere, box-box).  EMIT = false: counts[pair] = number of contacts;
+// EMIT = true: contacts written at offsets[pair].  Mesh pairs are left to k_rb3d_mesh_pairs (count 0 here).
+template<bool EMIT>
+__global__ void __launch_bounds__( 128 ) k_rb3d_pairs( const Rb3dDev dev, const uint2* __restrict__ pairs, const unsigned long long* __restrict__ npairs_dev,
+                                                      const double* __restrict__ q0, const double* __restrict__ q1, uint32_t* __restrict__ counts,
+                                                      const unsigned long long* __restrict__ offsets, const ContactOut3D out, uint32_t* __restrict__ bad_flag )
+{
+  const unsigned long long k = blockIdx.x * ( unsigned long long )( blockDim.x ) + threadIdx.x;
+  if( k >= *npairs_dev ) { return; }
+  const uint2 pr = pairs[k];
+  uint32_t b0, b1;
+  bool kin = false;
+  const uint32_t kind = pair_kind( dev, pr, b0, b1, kin );
+  const size_t nb = dev.n;
+  uint32_t cnt = 0u;
+  if( kind == SG_PAIR_BAD ) { if( !EMIT ) { atomicOr( bad_flag, 1u ); } }
+  else if( kind == SG_PAIR_SPHERE )
+  {
+    const double ra = __ldg( &dev.bparam[4 * size_t( pr.x )] ), rb = __ldg( &dev.bparam[4 * size_t( pr.y )] );
+    const bool fa = ( __ldg( &dev.btype[pr.x] ) & SG_FIXED_BIT ) != 0u, fb = ( __ldg( &dev.btype[pr.y] ) & SG_FIXED_BIT ) != 0u;
+    const V3d x1a = load_v3( q1, pr.x ), x1b = load_v3( q1, pr.y );
+    if( sphere_pair_active( x1a, ra, fa, x1b, rb, fb ) )
+    {
+      cnt = 1u;
+      if( EMIT ) { sphere_pair_emit( out, offsets[k], pr.x, load_v3( q0, pr.x ), x1a, ra, fa, pr.y, load_v3( q0, pr.y ), x1b, rb, fb ); }
+    }
+  }
+  else if( kind == SG_PAIR_BOX )
+  {
+    V3d n;
+    double pts[24];
+    const int nc = sg_box_box( load_v3( q1, b0 ), load_m3( q1 + 3 * nb, b0 ), body_half( dev, b0 ), load_v3( q1, b1 ), load_m3( q1 + 3 * nb, b1 ), body_half( dev, b1 ), n, pts );
+    cnt = uint32_t( nc );
+    if( EMIT )
+    {
+      const unsigned long long o = offsets[k];
+      for( int c = 0; c < nc; ++c ) { put_contact( out, o + c, kin ? SG_KINEMATIC_BODY_BODY : SG_BODY_BODY, b0, b1, 0u, n, v3( pts[3 * c], pts[3 * c + 1], pts[3 * c + 2] ), sg_nan() ); }
+    }
+  }
+  if( !EMIT ) { counts[k] = cnt; }
+}
+
+// One CTA per candidate pair; only mesh-mesh pairs do work (MeshMeshUtilities.cpp:10-65): mesh0's samples against
+// mesh1's distance field, then mesh1's samples against mesh0's, contacts in sample order.
+template<bool EMIT>
+__global__ void __launch_bounds__( 256 ) k_rb3d_mesh_pairs( const Rb3dDev dev, const uint2* __restrict__ pairs, const unsigned long long* __restrict__ npairs_dev, const double* __restrict__ q1,
+                                                           uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets, const ContactOut3D out )
+{
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_run;
+  for( unsigned long long k = blockIdx.x; k < *npairs_dev; k += gridDim.x )
+  {
+    const uint2 pr = pairs[k];
+    uint32_t b0, b1;
+    bool kin = false;
+    if( pair_kind( dev, pr, b0, b1, kin ) != SG_PAIR_MESH ) { continue; } // uniform across the CTA
+    const size_t nb = dev.n;
+    const MeshDev& mesh0 = dev.meshes[__ldg( &dev.bmesh[b0] )];
+    const MeshDev& mesh1 = dev.meshes[__ldg( &dev.bmesh[b1] )];
+    const V3d cm0 = load_v3( q1, b0 ), cm1 = load_v3( q1, b1 );
+    const M3d R0 = load_m3( q1 + 3 * nb, b0 ), R1 = load_m3( q1 + 3 * nb, b1 );
+    const unsigned long long base = EMIT ? offsets[k] : 0ull;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if( threadIdx.x == 0 ) { s_run = 0u; }
+    __syncthreads();
+    for( int dir = 0; dir < 2; ++dir )
+    {
+      const MeshDev& src = dir == 0 ? mesh0 : mesh1;
+      const MeshDev& dst = dir == 0 ? mesh1 : mesh0;
+      const M3d& Rs = dir == 0 ? R0 : R1;
+      const M3d& Rd = dir == 0 ? R1 : R0;
+      const V3d cs = dir == 0 ? cm0 : cm1;
+      const V3d cd = dir == 0 ? cm1 : cm0;
+      const M3d Rsd = mulTN33( Rd, Rs );
+      const V3d xsd = mulT3( Rd, cs - cd );
+      for( uint32_t s0 = 0; s0 < src.nsamples; s0 += blockDim.x )
+      {
+        const uint32_t si = s0 + threadIdx.x;
+        bool hit = false;
+        V3d x = v3( 0.0, 0.0, 0.0 ), normal = x;
+        if( si < src.nsamples )
+        {
+          x = mul3( Rsd, load_v3( src.samples, si ) ) + xsd;
+          hit = sdf_detect( dst, x, normal );
+        }
+        const unsigned bal = __ballot_sync( 0xffffffffu, hit );
+        if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
+        __syncthreads();
+        uint32_t before = 0u, total = 0u;
+        for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } total += c; }
+        const uint32_t run = s_run;
+        if( EMIT && hit )
+        {
+          const V3d pw = mul3( Rd, x ) + cd;
+          V3d nw = mul3( Rd, normal );
+          if( dir == 1 ) { nw = -nw; }
+          put_contact( out, base + run + before + __popc( bal & ( ( 1u << lane ) - 1u ) ), kin ? SG_KINEMATIC_BODY_BODY : SG_BODY_BODY, b0, b1, 0u, nw, pw, sg_nan() );
+        }
+        __syncthreads();
+        if( threadIdx.x == 0 ) { s_run = run + total; }
+        __syncthreads();
+      }
+    }
+    if( !EMIT && threadIdx.x == 0 ) { counts[k] = s_run; }
+  }
+}
+
+// ---- body-plane (RigidBody3DSim.cpp:1414-1502): plane-major, body ascending, corner / hull vertex ascending ----
+// Number of contacts of body b against plane pl; when emit_base != ~0 they are written starting there.
+__device__ inline uint32_t plane_contacts( const Rb3dDev& dev, const Planes3D& planes, const uint32_t pl, const uint32_t b, const double* __restrict__ q0, const double* __restrict__ q1,
+                                           const bool emit, const unsigned long long emit_base, const ContactOut3D& out )
+{
+  const uint32_t t = __ldg( &dev.btype[b] );
+  if( t & SG_FIXED_BIT ) { return 0u; }
+  const size_t nb = dev.n;
+  const V3d xp = v3( planes.x[pl][0], planes.x[pl][1], planes.x[pl][2] );
+  const V3d np = v3( planes.nrm[pl][0], planes.nrm[pl][1], planes.nrm[pl][2] );
+  const V3d x1 = load_v3( q1, b );
+  uint32_t cnt = 0u;
+  if( t == SG_GEO_SPHERE )
+  {
+    const double r = __ldg( &dev.bparam[4 * size_t( b )] );
+    const double d = dot3( np, x1 - xp );
+    if( d <= r )
+    {
+      if( emit ) { put_contact( out, emit_base, SG_PLANE_SPHERE, b, pl, 0u, np, load_v3( q0, b ) - r * np, fmin( 0.0, d - r ) ); }
+      cnt = 1u;
+    }
+  }
+  else if( t == SG_GEO_BOX )
+  {
+    const M3d R1 = load_m3( q1 + 3 * nb, b );
+    const V3d half = body_half( dev, b );
+    for( int corner = 0; corner < 8; ++corner )
+    {
+      const V3d cb = v3( half.x * double( 2 * ( corner % 2 ) - 1 ), half.y * double( 2 * ( ( corner >> 1 ) % 2 ) - 1 ), half.z * double( 2 * ( ( corner >> 2 ) % 2 ) - 1 ) );
+      const V3d wp = mul3( R1, cb ) + x1;
+      if( dot3( np, wp - xp ) <= 0.0 )
+      {
+        if( emit ) { put_contact( out, emit_base + cnt, SG_PLANE_BOX, b, pl, uint32_t( corner ), np, mul3( load_m3( q0 + 3 * nb, b ), cb ) + load_v3( q0, b ), sg_nan() ); }
+        ++cnt;
+      }
+    }
+  }
+  else
+  {
+    const M3d R1 = load_m3( q1 + 3 * nb, b );
+    const MeshDev& mesh = dev.meshes[__ldg( &dev.bmesh[b] )];
+    for( uint32_t vi = 0; vi < mesh.nhull; ++vi )
+    {
+      const V3d hv = load_v3( mesh.hull, vi );
+      const V3d v = mul3( R1, hv ) + x1;
+      if( dot3( np, v - xp ) <= 0.0 )
+      {
+        if( emit ) { put_contact( out, emit_base + cnt, SG_PLANE_BODY, b, pl, vi, np, load_v3( q0, b ) + mul3( load_m3( q0 + 3 * nb, b ), hv ), sg_nan() ); }
+        ++cnt;
+      }
+    }
+  }
+  return cnt;
+}
+
+// counts[pl * nblocks + block] = contacts of this block's bodies against plane pl
+__global__ void __launch_bounds__( 256 ) k_rb3d_plane_count( const Rb3dDev dev, const __grid_constant__ Planes3D planes, const double* __restrict__ q0, const double* __restrict__ q1, uint32_t* __restrict__ counts )
+{
+  __shared__ uint32_t s_cnt[SG_MAX_PLANES];
+  if( threadIdx.x < planes.n ) { s_cnt[threadIdx.x] = 0u; }
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const ContactOut3D none = {};
+  for( uint32_t pl = 0; pl < planes.n; ++pl )
+  {
+    uint32_t c = ( b < dev.n ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
+    #pragma unroll
+    for( int d = 16; d > 0; d >>= 1 ) { c += __shfl_xor_sync( 0xffffffffu, c, d ); }
+    if( ( threadIdx.x & 31 ) == 0 && c != 0u ) { atomicAdd( &s_cnt[pl], c ); }
+  }
+  __syncthreads();
+  if( threadIdx.x < planes.n ) { counts[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x]; }
+}
+
+__global__ void __launch_bounds__( 256 ) k_rb3d_plane_emit( const Rb3dDev dev, const __grid_constant__ Planes3D planes, const double* __restrict__ q0, const double* __restrict__ q1,
+                                                           const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, const unsigned long long* __restrict__ base_dev, const ContactOut3D out )
+{
+  __shared__ uint32_t s_warp[8];
+  const int mine = ( threadIdx.x < planes.n ) ? int( counts[threadIdx.x * gridDim.x + blockIdx.x] != 0u ) : 0;
+  if( __syncthreads_or( mine ) == 0 ) { return; }
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long base = *base_dev;
+  const ContactOut3D none = {};
+  for( uint32_t pl = 0; pl < planes.n; ++pl )
+  {
+    if( counts[pl * gridDim.x + blockIdx.x] == 0u ) { continue; }
+    const uint32_t c = ( b < dev.n ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
+    // exclusive prefix of c over the block
+    uint32_t incl = c;
+    #pragma unroll
+    for( int d = 1; d < 32; d <<= 1 ) { const uint32_t o = __shfl_up_sync( 0xffffffffu, incl, d ); if( lane >= d ) { incl += o; } }
+    __syncthreads();
+    if( lane == 31 ) { s_warp[warp] = incl; }
+    __syncthreads();
+    uint32_t before = incl - c;
+    for( int w = 0; w < warp; ++w ) { before += s_warp[w]; }
+    if( c != 0u ) { plane_contacts( dev, planes, pl, b, q0, q1, true, base + offsets[pl * gridDim.x + blockIdx.x] + before, out ); }
+  }
+}
+
+// small helper kernels
+__global__ void k_rb3d_sum_totals( const ScanPairCounts::Acc* __restrict__ bp_totals, const unsigned long long* __restrict__ narrow_total, const int fused, unsigned long long* __restrict__ out3 )
+{
+  // out3 = { P_c, n_body_body, unused }
+  out3[0] = bp_totals->c;
+  out3[1] = fused ? bp_totals->a : *narrow_total;
+}
+
+struct ScanU32To64
+{
+  using In = uint32_t;
+  using Acc = unsigned long long;
+  using Out = unsigned long long;
+  __device__ static Acc zero() { return 0ull; }
+  __device__ static Acc conv( const In x ) { return x; }
+  __device__ static Acc add( const Acc a, const Acc b ) { return a + b; }
+  __device__ static Acc shfl_up( const Acc a, const int d ) { return __shfl_up_sync( 0xffffffffu, a, d ); }
+  __device__ static Acc shfl( const Acc a, const int l ) { return __shfl_sync( 0xffffffffu, a, l ); }
+  __device__ static Out out( const Acc a ) { return a; }
+};
+
+// ---- host side -------------------------------------------------------------------------------------
+struct MeshHost
+{
+  DevBuf verts, samples, hull, sdf;
+  MeshDev dev;
+};
+
+struct Rb3dData
+{
+  uint32_t n = 0;
+  bool all_spheres = false;
+  double g[3] = { 0.0, 0.0, 0.0 };
+  Planes3D planes;
+  // geometry list (host copy) and per-body expansion
+  std::vector<uint32_t> geo_type, geo_mesh;
+  std::vector<double> geo_r, geo_half;
+  std::vector<MeshHost*> meshes;
+  DevBuf d_meshes; // MeshDev[]
+  DevBuf btype, bparam, bmesh, radius, flags, mass, I0;
+  DevBuf q0, v0, q1, v1, boxes;
+  BroadScratch bp;
+  // narrow phase over the candidate list
+  DevBuf pair_counts, pair_offsets, pair_partials, narrow_total, bad_flag, npairs_dev;
+  // planes
+  DevBuf st_counts, st_offsets, st_partials, st_total, totals3;
+  // contacts
+  DevBuf c_type, c_i, c_j, c_aux, c_n, c_p, c_depth;
+  uint64_t act_cap = 0;
+  PinBuf h_totals, h_out;
+  uint64_t n_cand = 0, n_bb = 0, n_static = 0;
+  bool have_result = false, cand_valid = false;
+  Rb3dData() { memset( &planes, 0, sizeof( planes ) ); }
+};
+
+void sg_rb3d_release( sg_ctx* ctx )
+{
+  Rb3dData* d = ctx->rb3d;
+  if( d == nullptr ) { return; }
+  for( MeshHost* m : d->meshes ) { m->verts.release(); m->samples.release(); m->hull.release(); m->sdf.release(); delete m; }
+  DevBuf* bufs[] = { &d->d_meshes, &d->btype, &d->bparam, &d->bmesh, &d->radius, &d->flags, &d->mass, &d->I0, &d->q0, &d->v0, &d->q1, &d->v1, &d->boxes,
+                     &d->pair_counts, &d->pair_offsets, &d->pair_partials, &d->narrow_total, &d->bad_flag, &d->npairs_dev,
+                     &d->st_counts, &d->st_offsets, &d->st_partials, &d->st_total, &d->totals3,
+                     &d->c_type, &d->c_i, &d->c_j, &d->c_aux, &d->c_n, &d->c_p, &d->c_depth };
+  for( DevBuf* b : bufs ) { b->release(); }
+  d->bp.release();
+  d->h_totals.release(); d->h_out.release();
+  delete d;
+  ctx->rb3d = nullptr;
+}
+
+static Rb3dData* rb3d_data( sg_ctx* ctx )
+{
+  if( ctx->rb3d == nullptr ) { ctx->rb3d = new Rb3dData; }
+  return ctx->rb3d;
+}
+
+static Rb3dDev rb3d_dev( const Rb3dData* d )
+{
+  Rb3dDev dev;
+  dev.n = d->n;
+  dev.btype = d->btype.as<uint32_t>();
+  dev.bparam = d->bparam.as<double>();
+  dev.bmesh = d->bmesh.as<uint32_t>();
+  dev.meshes = d->d_meshes.as<MeshDev>();
+  return dev;
+}
+
+static ContactOut3D rb3d_out( const Rb3dData* d )
+{
+  ContactOut3D out;
+  out.type = d->c_type.as<uint32_t>(); out.i = d->c_i.as<uint32_t>(); out.j = d->c_j.as<uint32_t>(); out.aux = d->c_aux.as<uint32_t>();
+  out.n = d->c_n.as<double>(); out.p = d->c_p.as<double>(); out.depth = d->c_depth.as<double>();
+  out.cap = d->act_cap;
+  return out;
+}
+
+static int rb3d_ensure_outputs( sg_ctx* ctx, Rb3dData* d, const uint64_t cand_cap, const uint64_t act_cap )
+{
+  if( cand_cap > d->bp.cand_cap )
+  {
+    SG_CUDA( ctx, d->bp.cand.ensure( size_t( cand_cap ) * sizeof( uint2 ) ) );
+    d->bp.cand_cap = d->bp.cand.cap / sizeof( uint2 );
+  }
+  if( act_cap > d->act_cap )
+  {
+    SG_CUDA( ctx, d->c_type.ensure( size_t( act_cap ) * 4 ) );
+    SG_CUDA( ctx, d->c_i.ensure( size_t( act_cap ) * 4 ) );
+    SG_CUDA( ctx, d->c_j.ensure( size_t( act_cap ) * 4 ) );
+    SG_CUDA( ctx, d->c_aux.ensure( size_t( act_cap ) * 4 ) );
+    SG_CUDA( ctx, d->c_n.ensure( size_t( act_cap ) * 24 ) );
+    SG_CUDA( ctx, d->c_p.ensure( size_t( act_cap ) * 24 ) );
+    SG_CUDA( ctx, d->c_depth.ensure( size_t( act_cap ) * 8 ) );
+    d->act_cap = act_cap;
+  }
+  return SG_OK;
+}
+
+static int rb3d_flow_device( sg_ctx* ctx, Rb3dData* d, const int map_kind, const double dt )
+{
+  const uint32_t n = d->n;
+  if( n == 0 ) { return SG_OK; }
+  SG_LAUNCH( ctx, "rb3d_flow", double( n ) * 336.0, k_rb3d_flow<<<sg_div_up( n, 128 ), 128, 0, ctx->stream>>>( map_kind, n, d->q0.as<double>(), d->v0.as<double>(), d->mass.as<double>(), d->I0.as<double>(),
+             d->btype.as<uint32_t>(), d->g[0], d->g[1], d->g[2], dt, d->q1.as<double>(), d->v1.as<double>() ) );
+  return SG_OK;
+}
+
+// body-plane contacts appended after the body-body ones; leaves the static total in st_total
+static int rb3d_planes_device( sg_ctx* ctx, Rb3dData* d, const bool emit )
+{
+  const uint32_t n = d->n, np = d->planes.n;
+  if( np == 0 || n == 0 ) { return SG_OK; }
+  const unsigned nblk = sg_div_up( n, 256 );
+  const uint32_t nst = np * nblk;
+  const Rb3dDev dev = rb3d_dev( d );
+  if( !emit )
+  {
+    SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 + 4 ) );
+    SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 + 4 ) );
+    SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
+    SG_LAUNCH( ctx, "rb3d_plane_count", double( n ) * 32.0, k_rb3d_plane_count<<<nblk, 256, 0, ctx->stream>>>( dev, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->st_counts.as<uint32_t>() ) );
+    return sg_exclusive_scan<ScanU32>( ctx, "rb3d_plane_scan", d->st_counts.as<uint32_t>(), nullptr, nst, nst, d->st_partials.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->st_total.as<uint32_t>(), false );
+  }
+  SG_LAUNCH( ctx, "rb3d_plane_emit", double( n ) * 4.0, k_rb3d_plane_emit<<<nblk, 256, 0, ctx->stream>>>( dev, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(),
+             d->totals3.as<unsigned long long>() + 1, rb3d_out( d ) ) );
+  return SG_OK;
+}
+
+static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_cand_in )
+{
+  const uint32_t n = d->n;
+  d->n_cand = d->n_bb = d->n_static = 0;
+  d->have_result = true;
+  if( n == 0 ) { d->cand_valid = want_cand_in; return SG_OK; }
+  const bool fused = d->all_spheres;
+  const bool want_cand = want_cand_in || !fused; // the generic narrow phase consumes the candidate list
+  d->cand_valid = want_cand;
+  SG_CUDA( ctx, d->h_totals.ensure( 64 ) );
+  SG_CUDA( ctx, d->totals3.ensure( 32 ) );
+  SG_CUDA( ctx, d->st_total.ensure( 4 ) );
+  SG_CUDA( ctx, d->narrow_total.ensure( 8 ) );
+  SG_CUDA( ctx, d->bad_flag.ensure( 4 ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->st_total.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->narrow_total.ptr, 0, 8, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->bad_flag.ptr, 0, 4, ctx->stream ) );
+  const Rb3dDev dev = rb3d_dev( d );
+  int rc;
+  unsigned long long* ht = d->h_totals.as<unsigned long long>();
+
+  if( fused )
+  {
+    rc = sg_bp_prepare_scratch<Sphere3DPolicy>( ctx, d->bp, n );
+    if( rc != SG_OK ) { return rc; }
+    rc = rb3d_ensure_outputs( ctx, d, want_cand ? ( d->bp.cand_cap > 0 ? d->bp.cand_cap : uint64_t( n ) * 16u + 1024u ) : 0u, d->act_cap > 0 ? d->act_cap : uint64_t( n ) * 5u + 1024u );
+    if( rc != SG_OK ) { return rc; }
+    Sphere3DIn in;
+    in.q0 = d->q0.as<double>(); in.q1 = d->q1.as<double>(); in.r = d->radius.as<double>(); in.flags = d->flags.as<uint32_t>(); in.n = n;
+    rc = sg_bp_bin_and_count<Sphere3DPolicy>( ctx, d->bp, in );
+    if( rc != SG_OK ) { return rc; }
+    rc = rb3d_planes_device( ctx, d, false );
+    if( rc != SG_OK ) { return rc; }
+    SG_LAUNCH( ctx, "rb3d_totals", 0.0, k_rb3d_sum_totals<<<1, 1, 0, ctx->stream>>>( d->bp.totals.as<ScanPairCounts::Acc>(), d->narrow_total.as<unsigned long long>(), 1, d->totals3.as<unsigned long long>() ) );
+    for( int attempt = 0; attempt < 2; ++attempt )
+    {
+      rc = sg_bp_emit_lists<Sphere3DPolicy>( ctx, d->bp, n, want_cand, rb3d_out( d ), 0.0 );
+      if( rc != SG_OK ) { return rc; }
+      rc = rb3d_planes_device( ctx, d, true );
+      if( rc != SG_OK ) { return rc; }
+      ht[2] = 0ull;
+      SG_CUDA( ctx, cudaMemcpyAsync( ht, d->totals3.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( ht + 2, d->st_total.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+      sg_prof_collect( ctx );
+      d->n_cand = ht[0]; d->n_bb = ht[1]; d->n_static = ht[2] & 0xffffffffull;
+      if( ctx->profile ) { ctx->prof[sg_prof_entry( ctx, "bp_emit" )].bytes += ( want_cand ? double( d->n_cand ) * 8.0 : 0.0 ) + double( d->n_bb ) * 72.0; }
+      const uint64_t need = d->n_bb + d->n_static;
+      if( ( !want_cand || d->n_cand <= d->bp.cand_cap ) && need <= d->act_cap ) { break; }
+      if( attempt == 1 ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rb3d: output lists still overflow after regrowth" ); }
+      rc = rb3d_ensure_outputs( ctx, d, want_cand ? d->n_cand + d->n_cand / 8 + 1024 : 0u, need + need / 8 + 1024 );
+      if( rc != SG_OK ) { return rc; }
+    }
+    return SG_OK;
+  }
+
+  // ---- generic pipeline ----
+  SG_CUDA( ctx, d->boxes.ensure( size_t( n ) * 48 ) );
+  SG_LAUNCH( ctx, "rb3d_aabb", double( n ) * ( 96.0 + 48.0 ), k_rb3d_aabb<<<sg_div_up( n, 128 ), 128, 0, ctx->stream>>>( dev, d->q1.as<double>(), d->boxes.as<double>() ) );
+  rc = sg_bp_prepare_scratch<Box3DPolicy>( ctx, d->bp, n );
+  if( rc != SG_OK ) { return rc; }
+  Box3DIn in;
+  in.boxes = d->boxes.as<double>(); in.n = n;
+  rc = sg_bp_bin_and_count<Box3DPolicy>( ctx, d->bp, in );
+  if( rc != SG_OK ) { return rc; }
+  // the candidate list must exist before the narrow phase can be sized: one small read-back
+  SG_CUDA( ctx, cudaMemcpyAsync( ht, d->bp.totals.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  const uint64_t np = ht[0];
+  d->n_cand = np;
+  rc = rb3d_ensure_outputs( ctx, d, np + 64, d->act_cap );
+  if( rc != SG_OK ) { return rc; }
+  if( np > 0 )
+  {
+    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, n, true, NoOut3D{}, double( np ) * 8.0 );
+    if( rc != SG_OK ) { return rc; }
+  }
+  if( np >= 0xffffffffull ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rb3d: more than 2^32 candidate pairs in the generic pipeline" ); }
+  SG_CUDA( ctx, d->pair_counts.ensure( size_t( np ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->pair_offsets.ensure( size_t( np ) * 8 + 8 ) );
+  SG_CUDA( ctx, d->pair_partials.ensure( ( size_t( np ) / SG_SCAN_TILE + 2 ) * 8 ) );
+  const unsigned long long* npairs_dev = &d->bp.totals.as<ScanPairCounts::Acc>()->c;
+  if( np > 0 )
+  {
+    SG_CUDA( ctx, cudaMemsetAsync( d->pair_counts.ptr, 0, size_t( np ) * 4, ctx->stream ) );
+    SG_LAUNCH( ctx, "rb3d_pairs_count", double( np ) * 250.0, k_rb3d_pairs<false><<<sg_div_up( np, 128 ), 128, 0, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q0.as<double>(), d->q1.as<double>(),
+               d->pair_counts.as<uint32_t>(), nullptr, rb3d_out( d ), d->bad_flag.as<uint32_t>() ) );
+    if( !d->meshes.empty() )
+    {
+      const unsigned grid = unsigned( np < uint64_t( ctx->num_sms ) * 8u ? np : uint64_t( ctx->num_sms ) * 8u );
+      SG_LAUNCH( ctx, "rb3d_mesh_count", 0.0, k_rb3d_mesh_pairs<false><<<grid, 256, 0, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q1.as<double>(), d->pair_counts.as<uint32_t>(), nullptr, rb3d_out( d ) ) );
+    }
+    rc = sg_exclusive_scan<ScanU32To64>( ctx, "rb3d_pair_scan", d->pair_counts.as<uint32_t>(), nullptr, uint32_t( np ), uint32_t( np ), d->pair_partials.as<unsigned long long>(), d->pair_offsets.as<unsigned long long>(),
+                                         d->narrow_total.as<unsigned long long>(), false );
+    if( rc != SG_OK ) { return rc; }
+  }
+  rc = rb3d_planes_device( ctx, d, false );
+  if( rc != SG_OK ) { return rc; }
+  SG_LAUNCH( ctx, "rb3d_totals", 0.0, k_rb3d_sum_totals<<<1, 1, 0, ctx->stream>>>( d->bp.totals.as<ScanPairCounts::Acc>(), d->narrow_total.as<unsigned long long>(), 0, d->totals3.as<unsigned long long>() ) );
+  // sizes to the host, then the emits
+  uint32_t* hbad = reinterpret_cast<uint32_t*>( ht + 4 );
+  ht[2] = 0ull;
+  SG_CUDA( ctx, cudaMemcpyAsync( ht, d->totals3.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( ht + 2, d->st_total.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( hbad, d->bad_flag.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  if( *hbad != 0u )
+  {
+    return sg_fail( ctx, SG_ERR_UNSUPPORTED, "collision between two different geometry types is not supported (the reference exits here: rigidbody3d/RigidBody3DSim.cpp:905-961)" );
+  }
+  d->n_bb = ht[1]; d->n_static = ht[2] & 0xffffffffull;
+  const uint64_t need = d->n_bb + d->n_static;
+  rc = rb3d_ensure_outputs( ctx, d, 0u, need + 64 );
+  if( rc != SG_OK ) { return rc; }
+  if( np > 0 && d->n_bb > 0 )
+  {
+    SG_LAUNCH( ctx, "rb3d_pairs_emit", double( np ) * 250.0 + double( d->n_bb ) * 72.0, k_rb3d_pairs<true><<<sg_div_up( np, 128 ), 128, 0, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q0.as<double>(), d->q1.as<double>(),
+               nullptr, d->pair_offsets.as<unsigned long long>(), rb3d_out( d ), d->bad_flag.as<uint32_t>() ) );
+    if( !d->meshes.empty() )
+    {
+      const unsigned grid = unsigned( np < uint64_t( ctx->num_sms ) * 8u ? np : uint64_t( ctx->num_sms ) * 8u );
+      SG_LAUNCH( ctx, "rb3d_mesh_emit", 0.0, k_rb3d_mesh_pairs<true><<<grid, 256, 0, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q1.as<double>(), nullptr, d->pair_offsets.as<unsigned long long>(), rb3d_out( d ) ) );
+    }
+  }
+  rc = rb3d_planes_device( ctx, d, true );
+  if( rc != SG_OK ) { return rc; }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+static int rb3d_copy_out( sg_ctx* ctx, Rb3dData* d, const uint32_t flags, sg_contacts* out )
+{
+  memset( out, 0, sizeof( *out ) );
+  out->dim = 3;
+  out->n_candidates = d->n_cand;
+  out->n_body_body = d->n_bb;
+  out->n_plane = d->n_static;
+  const uint64_t na = d->n_bb + d->n_static;
+  out->n_active = na;
+  const bool want_cand = ( flags & SG_OUT_CANDIDATES ) != 0u && d->cand_valid;
+  auto al = []( size_t b ) { return ( b + 63 ) & ~size_t( 63 ); };
+  size_t bytes = 64;
+  const size_t o_type = bytes; bytes += al( na * 4 );
+  const size_t o_i = bytes; bytes += al( na * 4 );
+  const size_t o_j = bytes; bytes += al( na * 4 );
+  const size_t o_aux = bytes; bytes += al( na * 4 );
+  const size_t o_n = bytes; if( flags & SG_OUT_NORMALS ) { bytes += al( na * 24 ); }
+  const size_t o_p = bytes; if( flags & SG_OUT_POINTS ) { bytes += al( na * 24 ); }
+  const size_t o_d = bytes; if( flags & SG_OUT_DEPTHS ) { bytes += al( na * 8 ); }
+  const size_t o_c = bytes; if( want_cand ) { bytes += al( d->n_cand * 8 ); }
+  SG_CUDA( ctx, d->h_out.ensure( bytes ) );
+  char* h = d->h_out.as<char>();
+  if( na > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_type, d->c_type.ptr, na * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_i, d->c_i.ptr, na * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_j, d->c_j.ptr, na * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_aux, d->c_aux.ptr, na * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( flags & SG_OUT_NORMALS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_n, d->c_n.ptr, na * 24, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+    if( flags & SG_OUT_POINTS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_p, d->c_p.ptr, na * 24, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+    if( flags & SG_OUT_DEPTHS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_d, d->c_depth.ptr, na * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  }
+  if( want_cand && d->n_cand > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_c, d->bp.cand.ptr, d->n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  out->type = reinterpret_cast<const uint32_t*>( h + o_type );
+  out->i = reinterpret_cast<const uint32_t*>( h + o_i );
+  out->j = reinterpret_cast<const uint32_t*>( h + o_j );
+  out->aux = reinterpret_cast<const uint32_t*>( h + o_aux );
+  out->n = ( flags & SG_OUT_NORMALS ) ? reinterpret_cast<const double*>( h + o_n ) : nullptr;
+  out->p = ( flags & SG_OUT_POINTS ) ? reinterpret_cast<const double*>( h + o_p ) : nullptr;
+  out->depth = ( flags & SG_OUT_DEPTHS ) ? reinterpret_cast<const double*>( h + o_d ) : nullptr;
+  out->cand_ij = want_cand ? reinterpret_cast<const uint32_t*>( h + o_c ) : nullptr;
+  return SG_OK;
+}
+
+// expands the geometry list into per-body arrays (called when bodies or geometry change)
+static int rb3d_expand_bodies( sg_ctx* ctx, Rb3dData* d, const uint32_t n, const uint32_t* geo_of_body, const uint8_t* fixed )
+{
+  std::vector<uint32_t> btype( n ), bmesh( n ), flags( n );
+  std::vector<double> bparam( size_t( n ) * 4, 0.0 ), radius( n, 0.0 );
+  bool all_spheres = n > 0;
+  for( uint32_t b = 0; b < n; ++b )
+  {
+    const uint32_t gi = geo_of_body[b];
+    if( gi >= d->geo_type.size() ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_bodies: body %u refers to geometry %u of %zu", b, gi, d->geo_type.size() ); }
+    const uint32_t t = d->geo_type[gi];
+    if( t != SG_GEO_BOX && t != SG_GEO_SPHERE && t != SG_GEO_MESH ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_set_bodies: geometry type %u is not supported", t ); }
+    if( t == SG_GEO_MESH && d->geo_mesh[gi] >= d->meshes.size() ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_bodies: geometry %u refers to mesh %u of %zu", gi, d->geo_mesh[gi], d->meshes.size() ); }
+    flags[b] = fixed[b] ? SG_FIXED_BIT : 0u;
+    btype[b] = t | flags[b];
+    bmesh[b] = d->geo_mesh[gi];
+    if( t == SG_GEO_SPHERE ) { bparam[4 * size_t( b )] = d->geo_r[gi]; radius[b] = d->geo_r[gi]; }
+    else if( t == SG_GEO_BOX ) { for( int k = 0; k < 3; ++k ) { bparam[4 * size_t( b ) + k] = d->geo_half[3 * size_t( gi ) + k]; } }
+    all_spheres = all_spheres && t == SG_GEO_SPHERE;
+  }
+  d->all_spheres = all_spheres;
+  SG_CUDA( ctx, d->btype.ensure( size_t( n ) * 4 + 4 ) ); SG_CUDA( ctx, d->bmesh.ensure( size_t( n ) * 4 + 4 ) ); SG_CUDA( ctx, d->flags.ensure( size_t( n ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->bparam.ensure( size_t( n ) * 32 + 32 ) ); SG_CUDA( ctx, d->radius.ensure( size_t( n ) * 8 + 8 ) );
+  if( n > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( d->btype.ptr, btype.data(), size_t( n ) * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->bmesh.ptr, bmesh.data(), size_t( n ) * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->flags.ptr, flags.data(), size_t( n ) * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->bparam.ptr, bparam.data(), size_t( n ) * 32, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->radius.ptr, radius.data(), size_t( n ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+  }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+extern "C"
+{
+
+int sg_rb3d_set_geometry( sg_ctx* ctx, uint32_t ngeo, const uint32_t* type, const double* r, const double* half, const uint32_t* mesh )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( ngeo > 0 && ( type == nullptr || r == nullptr || half == nullptr || mesh == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_geometry: null array" ); }
+  Rb3dData* d = rb3d_data( ctx );
+  d->geo_type.assign( type, type + ngeo );
+  d->geo_r.assign( r, r + ngeo );
+  d->geo_half.assign( half, half + 3 * size_t( ngeo ) );
+  d->geo_mesh.assign( mesh, mesh + ngeo );
+  return SG_OK;
+}
+
+int sg_rb3d_add_mesh( sg_ctx* ctx, uint32_t nverts, const double* verts, uint32_t nsamples, const double* samples, uint32_t nhull, const double* hull,
+                      const double* cell_delta, const uint32_t* dims, const double* origin, const double* sdf, uint32_t* mesh_index )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( cell_delta == nullptr || dims == nullptr || origin == nullptr || sdf == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_add_mesh: null array" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  Rb3dData* d = rb3d_data( ctx );
+  MeshHost* m = new MeshHost;
+  d->meshes.push_back( m );
+  const size_t ncell = size_t( dims[0] ) * dims[1] * dims[2];
+  SG_CUDA( ctx, m->verts.ensure( size_t( nverts ) * 24 + 8 ) );
+  SG_CUDA( ctx, m->samples.ensure( size_t( nsamples ) * 24 + 8 ) );
+  SG_CUDA( ctx, m->hull.ensure( size_t( nhull ) * 24 + 8 ) );
+  SG_CUDA( ctx, m->sdf.ensure( ncell * 8 + 8 ) );
+  if( nverts ) { SG_CUDA( ctx, cudaMemcpyAsync( m->verts.ptr, verts, size_t( nverts ) * 24, cudaMemcpyHostToDevice, ctx->stream ) ); }
+  if( nsamples ) { SG_CUDA( ctx, cudaMemcpyAsync( m->samples.ptr, samples, size_t( nsamples ) * 24, cudaMemcpyHostToDevice, ctx->stream ) ); }
+  if( nhull ) { SG_CUDA( ctx, cudaMemcpyAsync( m->hull.ptr, hull, size_t( nhull ) * 24, cudaMemcpyHostToDevice, ctx->stream ) ); }
+  SG_CUDA( ctx, cudaMemcpyAsync( m->sdf.ptr, sdf, ncell * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+  m->dev.verts = m->verts.as<double>(); m->dev.nverts = nverts;
+  m->dev.samples = m->samples.as<double>(); m->dev.nsamples = nsamples;
+  m->dev.hull = m->hull.as<double>(); m->dev.nhull = nhull;
+  m->dev.sdf = m->sdf.as<double>();
+  for( int k = 0; k < 3; ++k )
+  {
+    m->dev.delta[k] = cell_delta[k]; m->dev.origin[k] = origin[k]; m->dev.dims[k] = dims[k];
+    // RigidBodyTriangleMesh.cpp:102: grid_end = origin + (dims - 1) * delta  (host FP64; product then sum, no contraction)
+    volatile double prod = double( dims[k] - 1u ) * cell_delta[k];
+    m->dev.grid_end[k] = origin[k] + prod;
+  }
+  std::vector<MeshDev> all;
+  for( MeshHost* mh : d->meshes ) { all.push_back( mh->dev ); }
+  SG_CUDA( ctx, d->d_meshes.ensure( all.size() * sizeof( MeshDev ) ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->d_meshes.ptr, all.data(), all.size() * sizeof( MeshDev ), cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  if( mesh_index != nullptr ) { *mesh_index = uint32_t( d->meshes.size() - 1 ); }
+  return SG_OK;
+}
+
+int sg_rb3d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, const uint8_t* fixed, const double* m, const double* I0 )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > 0 && ( geo_of_body == nullptr || fixed == nullptr || m == nullptr || I0 == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_bodies: null array" ); }
+  if( n >= 0x80000000u ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_bodies: at most 2^31 - 1 bodies" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  Rb3dData* d = rb3d_data( ctx );
+  d->n = n;
+  d->have_result = false;
+  const int rc = rb3d_expand_bodies( ctx, d, n, geo_of_body, fixed );
+  if( rc != SG_OK ) { d->n = 0; return rc; }
+  if( n == 0 ) { return SG_OK; }
+  SG_CUDA( ctx, d->mass.ensure( size_t( n ) * 8 ) );
+  SG_CUDA( ctx, d->I0.ensure( size_t( n ) * 24 ) );
+  SG_CUDA( ctx, d->q0.ensure( size_t( n ) * 96 ) ); SG_CUDA( ctx, d->q1.ensure( size_t( n ) * 96 ) );
+  SG_CUDA( ctx, d->v0.ensure( size_t( n ) * 48 ) ); SG_CUDA( ctx, d->v1.ensure( size_t( n ) * 48 ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->mass.ptr, m, size_t( n ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->I0.ptr, I0, size_t( n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_rb3d_set_gravity( sg_ctx* ctx, const double* g )
+{
+  if( ctx == nullptr || g == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  d->g[0] = g[0]; d->g[1] = g[1]; d->g[2] = g[2];
+  return SG_OK;
+}
+
+int sg_rb3d_set_planes( sg_ctx* ctx, uint32_t n, const double* x, const double* nrm )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > SG_MAX_PLANES ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_planes: at most %d planes", SG_MAX_PLANES ); }
+  Rb3dData* d = rb3d_data( ctx );
+  d->planes.n = n;
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    // StaticPlane::StaticPlane: m_n( n.normalized() ), 3-term squared norm (a0*a0 + a1*a1) + a2*a2
+    double v[3] = { nrm[3 * p], nrm[3 * p + 1], nrm[3 * p + 2] };
+    volatile double xx = v[0] * v[0]; volatile double yy = v[1] * v[1]; volatile double zz = v[2] * v[2];
+    volatile double s01 = xx + yy;
+    const double z = s01 + zz;
+    if( z > 0.0 ) { const double s = sqrt( z ); v[0] = v[0] / s; v[1] = v[1] / s; v[2] = v[2] / s; }
+    for( int k = 0; k < 3; ++k ) { d->planes.x[p][k] = x[3 * p + k]; d->planes.nrm[p][k] = v[k]; }
+  }
+  return SG_OK;
+}
+
+int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( map_kind != SG_MAP_SPLIT_HAM && map_kind != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: map kind %d is not a rigidbody3d map", map_kind ); }
+  Rb3dData* d = rb3d_data( ctx );
+  if( d->n == 0 ) { return SG_OK; }
+  if( q0 == nullptr || v0 == nullptr || q1 == nullptr || v1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v0, size_t( d->n ) * 48, cudaMemcpyHostToDevice, ctx->stream ) );
+  const int rc = rb3d_flow_device( ctx, d, map_kind, dt );
+  if( rc != SG_OK ) { return rc; }
+  SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, size_t( d->n ) * 96, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 48, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out )
+{
+  if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->n > 0 )
+  {
+    if( q0 == nullptr || q1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_active_set: null vector" ); }
+    SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
+  }
+  const int rc = rb3d_active_set_device( ctx, d, ( out_flags & SG_OUT_CANDIDATES ) != 0u );
+  if( rc != SG_OK ) { return rc; }
+  return rb3d_copy_out( ctx, d, out_flags, out );
+}
+
+int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( d->n == 0 ) { return SG_OK; }
+  if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_upload: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v, size_t( d->n ) * 48, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( map_kind != SG_MAP_SPLIT_HAM && map_kind != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: map kind %d is not a rigidbody3d map", map_kind ); }
+  Rb3dData* d = rb3d_data( ctx );
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  int rc = rb3d_flow_device( ctx, d, map_kind, dt );
+  if( rc != SG_OK ) { return rc; }
+  rc = rb3d_active_set_device( ctx, d, true );
+  if( rc != SG_OK ) { return rc; }
+  if( out != nullptr )
+  {
+    memset( out, 0, sizeof( *out ) );
+    out->dim = 3;
+    out->n_candidates = d->n_cand;
+    out->n_body_body = d->n_bb;
+    out->n_plane = d->n_static;
+    out->n_active = d->n_bb + d->n_static;
+  }
+  return SG_OK;
+}
+
+int sg_rb3d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_fetch: no step has been run" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( q1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, size_t( d->n ) * 96, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( v1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 48, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( out != nullptr ) { return rb3d_copy_out( ctx, d, out_flags, out ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+}

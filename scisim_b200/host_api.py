@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_OUT_ALL, SgContacts, SgPairs, SciSimB200Error
+from ._lib import SG_MAP_DMV, SG_MAP_SPLIT_HAM, SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_OUT_ALL, SgContacts, SgPairs, SciSimB200Error
 
 
 def _f64(a):
@@ -148,6 +148,7 @@ class ActiveSet:
         self.n = arr(c.n, (na, self.dim), np.float64)
         self.p = arr(c.p, (na, self.dim), np.float64)
         self.depth = arr(c.depth, (na,), np.float64)
+        self.aux = arr(c.aux, (na,), np.uint32)
         if c.cand_ij and self.n_candidates > 0:
             a = np.ctypeslib.as_array(c.cand_ij, shape=(self.n_candidates, 2))
             self.candidates = a.copy() if copy else a
@@ -256,4 +257,122 @@ class Ball2DSim:
         v1 = np.empty(n) if want_state else None
         c = SgContacts()
         self.ctx.check(self.ctx.lib.sg_ball2d_fetch(self.ctx.h, int(flags), _ptr(q1) if want_state else None, _ptr(v1) if want_state else None, C.byref(c)))
+        return q1, v1, ActiveSet(c)
+
+
+# ---- rigidbody3d -------------------------------------------------------------------------------------
+GEO_BOX, GEO_SPHERE, GEO_MESH = 0, 1, 3
+
+
+class TriangleMesh:
+    """What RigidBodyTriangleMesh holds for the hot path (rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp:54-102)."""
+
+    def __init__(self, verts, samples, hull, cell_delta, dims, origin, sdf):
+        self.verts, self.samples, self.hull = _f64(verts).reshape(-1, 3), _f64(samples).reshape(-1, 3), _f64(hull).reshape(-1, 3)
+        self.cell_delta, self.origin = _f64(cell_delta), _f64(origin)
+        self.dims = np.ascontiguousarray(dims, dtype=np.uint32)
+        self.sdf = _f64(sdf).ravel()
+        assert self.sdf.size == int(np.prod(self.dims.astype(np.int64)))
+
+
+class RigidBody3DState:
+    """Static part of rigidbody3d/RigidBody3DState.h: geometry list, per-body geometry index / fixed flag / mass /
+    body-frame inertia, gravity, static planes."""
+
+    def __init__(self, geo_type, geo_r, geo_half, geo_mesh, meshes, geo_of_body, fixed, m, I0, g=(0.0, 0.0, 0.0), plane_x=None, plane_n=None):
+        self.geo_type = np.ascontiguousarray(geo_type, dtype=np.uint32)
+        self.geo_r = _f64(geo_r)
+        self.geo_half = _f64(geo_half).reshape(-1, 3)
+        self.geo_mesh = np.ascontiguousarray(geo_mesh, dtype=np.uint32)
+        self.meshes = list(meshes)
+        self.geo_of_body = np.ascontiguousarray(geo_of_body, dtype=np.uint32)
+        self.fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
+        self.m = _f64(m)
+        self.I0 = _f64(I0).reshape(-1, 3)
+        self.g = _f64(g)
+        self.plane_x = _f64(plane_x if plane_x is not None else np.zeros((0, 3))).reshape(-1, 3)
+        self.plane_n = _f64(plane_n if plane_n is not None else np.zeros((0, 3))).reshape(-1, 3)
+
+    def nbodies(self):
+        return self.geo_of_body.shape[0]
+
+
+class _RB3DMap:
+    kind = None
+    _name = None
+
+    def name(self):
+        return self._name
+
+    def flow(self, q0, v0, fsys, iteration, dt):
+        assert iteration > 0
+        return fsys._flow(self.kind, q0, v0, dt)
+
+
+class SplitHamMap(_RB3DMap):
+    """rigidbody3d/UnconstrainedMaps/SplitHamMap.cpp"""
+    kind = SG_MAP_SPLIT_HAM
+    _name = "split_ham"
+
+
+class DMVMap(_RB3DMap):
+    """rigidbody3d/UnconstrainedMaps/DMVMap.cpp"""
+    kind = SG_MAP_DMV
+    _name = "dmv"
+
+
+class RigidBody3DSim:
+    """GPU-backed FlowableSystem + ConstrainedSystem for rigidbody3d (rigidbody3d/RigidBody3DSim.h:34)."""
+
+    def __init__(self, state, device=0, ctx=None):
+        self.ctx = ctx or Context(device)
+        self.state = st = state
+        lib, h = self.ctx.lib, self.ctx.h
+        for mesh in st.meshes:
+            idx = C.c_uint32()
+            self.ctx.check(lib.sg_rb3d_add_mesh(h, mesh.verts.shape[0], _ptr(mesh.verts), mesh.samples.shape[0], _ptr(mesh.samples), mesh.hull.shape[0], _ptr(mesh.hull),
+                                                _ptr(mesh.cell_delta), _ptr(mesh.dims), _ptr(mesh.origin), _ptr(mesh.sdf), C.byref(idx)))
+        self.ctx.check(lib.sg_rb3d_set_geometry(h, st.geo_type.shape[0], _ptr(st.geo_type), _ptr(st.geo_r), _ptr(st.geo_half), _ptr(st.geo_mesh)))
+        self.ctx.check(lib.sg_rb3d_set_bodies(h, st.nbodies(), _ptr(st.geo_of_body), _ptr(st.fixed), _ptr(st.m), _ptr(st.I0)))
+        self.ctx.check(lib.sg_rb3d_set_gravity(h, _ptr(st.g)))
+        self.ctx.check(lib.sg_rb3d_set_planes(h, st.plane_x.shape[0], _ptr(st.plane_x), _ptr(st.plane_n)))
+
+    def name(self):
+        return "rigid_body_3d"
+
+    def nqdofs(self):
+        return 12 * self.state.nbodies()
+
+    def nvdofs(self):
+        return 6 * self.state.nbodies()
+
+    def _flow(self, kind, q0, v0, dt, q1=None, v1=None):
+        q0, v0 = _f64(q0), _f64(v0)
+        assert q0.size == self.nqdofs() and v0.size == self.nvdofs()
+        q1 = np.empty_like(q0) if q1 is None else q1
+        v1 = np.empty_like(v0) if v1 is None else v1
+        self.ctx.check(self.ctx.lib.sg_rb3d_flow(self.ctx.h, kind, _ptr(q0), _ptr(v0), float(dt), _ptr(q1), _ptr(v1)))
+        return q1, v1
+
+    def computeActiveSet(self, q0, qp, v=None, flags=SG_OUT_ALL, copy=True):
+        q0, qp = _f64(q0), _f64(qp)
+        assert q0.size == self.nqdofs() and qp.size == self.nqdofs()
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_rb3d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags), C.byref(c)))
+        return ActiveSet(c, copy=copy)
+
+    def upload(self, q, v):
+        q, v = _f64(q), _f64(v)
+        self.ctx.check(self.ctx.lib.sg_rb3d_upload(self.ctx.h, _ptr(q), _ptr(v)))
+
+    def step(self, umap, dt):
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_rb3d_step(self.ctx.h, umap.kind, float(dt), C.byref(c)))
+        return int(c.n_candidates), int(c.n_active)
+
+    def fetch(self, flags=SG_OUT_ALL, want_state=True):
+        q1 = np.empty(self.nqdofs()) if want_state else None
+        v1 = np.empty(self.nvdofs()) if want_state else None
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_rb3d_fetch(self.ctx.h, int(flags), _ptr(q1) if want_state else None, _ptr(v1) if want_state else None, C.byref(c)))
         return q1, v1, ActiveSet(c)

@@ -61,3 +61,154 @@ def ball2d_random(n, seed, box=None, rmin=0.05, rmax=0.4, nplanes=2, ndrums=1, v
         "drum_x": rng.uniform(-0.1, 0.1, size=(ndrums, 2)), "drum_r": np.full(ndrums, box * 1.2),
     }
     return scene
+
+
+# ---- rigidbody3d -------------------------------------------------------------------------------------
+def _random_rotations(rng, n):
+    """n proper rotation matrices (row-major 9-vectors) from random unit quaternions."""
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((n, 9))
+    R[:, 0] = 1 - 2 * (y * y + z * z); R[:, 1] = 2 * (x * y - w * z); R[:, 2] = 2 * (x * z + w * y)
+    R[:, 3] = 2 * (x * y + w * z); R[:, 4] = 1 - 2 * (x * x + z * z); R[:, 5] = 2 * (y * z - w * x)
+    R[:, 6] = 2 * (x * z - w * y); R[:, 7] = 2 * (y * z + w * x); R[:, 8] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def _rb3d_pack(x, R, v, w):
+    n = x.shape[0]
+    return np.concatenate([x.ravel(), R.reshape(n, 9).ravel()]), np.concatenate([v.ravel(), w.ravel()])
+
+
+def _rb3d_scene(geo_type, geo_r, geo_half, geo_mesh, meshes, geo_of_body, fixed, m, I0, q, v, g, plane_x, plane_n, dt, umap):
+    return {"geo_type": np.asarray(geo_type, np.uint32), "geo_r": np.asarray(geo_r, np.float64), "geo_half": np.asarray(geo_half, np.float64).reshape(-1, 3),
+            "geo_mesh": np.asarray(geo_mesh, np.uint32), "meshes": meshes, "geo_of_body": np.asarray(geo_of_body, np.uint32),
+            "fixed": np.asarray(fixed, np.uint8), "m": np.asarray(m, np.float64), "I0": np.asarray(I0, np.float64).reshape(-1, 3),
+            "q": q, "v": v, "g": np.asarray(g, np.float64), "plane_x": np.asarray(plane_x, np.float64).reshape(-1, 3),
+            "plane_n": np.asarray(plane_n, np.float64).reshape(-1, 3), "dt": dt, "map": umap}
+
+
+def rb3d_sphere_lattice(nx=160, ny=160, nz=160, r=0.5, spacing=0.99, jitter=0.002, seed=11, rho=1.0):
+    """Config 4: nx*ny*nz equal spheres on a cubic lattice (neighbours along the axes overlap by 1 %), R = I, v = w = 0,
+    gravity along -y, floor + 4 walls, split_ham (rigidbody3d has no Verlet map)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = nx * ny * nz
+    iz, iy, ix = np.meshgrid(np.arange(nz, dtype=np.float64), np.arange(ny, dtype=np.float64), np.arange(nx, dtype=np.float64), indexing="ij")
+    x = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1) * spacing + rng.uniform(-jitter, jitter, size=(n, 3))
+    R = np.tile(np.eye(3).ravel(), (n, 1))
+    q, v = _rb3d_pack(x, R, np.zeros((n, 3)), np.zeros((n, 3)))
+    mass = rho * 4.0 / 3.0 * np.pi * r ** 3
+    I = 0.4 * mass * r * r
+    ex, ez = (nx - 1) * spacing + r, (nz - 1) * spacing + r
+    plane_x = [[0, -r, 0], [-r, 0, 0], [ex, 0, 0], [0, 0, -r], [0, 0, ez]]
+    plane_n = [[0, 1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1]]
+    return _rb3d_scene([1], [r], [[0, 0, 0]], [0], [], np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.full(n, mass), np.full((n, 3), I),
+                       q, v, [0.0, -9.81, 0.0], plane_x, plane_n, 1.0e-3, "split_ham")
+
+
+def rb3d_random_spheres(n, seed, spin=False, nfixed_frac=0.1, nplanes=2, box=None):
+    """Messy all-sphere scenes: several radii, overlapping, some kinematically scripted, optional spin."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    box = box if box is not None else max(1.0, n ** (1.0 / 3.0) * 0.45)
+    radii = np.array([0.25, 0.4, 0.6])
+    gi = rng.integers(0, 3, size=n)
+    fixed = (rng.uniform(size=n) < nfixed_frac).astype(np.uint8)
+    x = rng.uniform(-box, box, size=(n, 3))
+    R = _random_rotations(rng, n)
+    v = rng.uniform(-5, 5, size=(n, 3))
+    w = rng.uniform(-3, 3, size=(n, 3)) if spin else np.zeros((n, 3))
+    v[fixed == 1] = 0.0
+    w[fixed == 1] = 0.0
+    m = rng.uniform(0.5, 2.0, size=n)
+    I0 = 0.4 * m[:, None] * (radii[gi] ** 2)[:, None] * np.ones((1, 3))
+    q, vv = _rb3d_pack(x, R, v, w)
+    return _rb3d_scene([1, 1, 1], radii, np.zeros((3, 3)), [0, 0, 0], [], gi, fixed, m, I0, q, vv, [0.2, -9.81, 0.1],
+                       rng.uniform(-box, box, size=(nplanes, 3)), rng.normal(size=(nplanes, 3)) * 2.0, 0.01, "split_ham")
+
+
+def rb3d_random_boxes(n, seed, spin=True, nfixed_frac=0.1, nplanes=2, box=None):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    box = box if box is not None else max(1.0, n ** (1.0 / 3.0) * 0.6)
+    ngeo = 4
+    half = rng.uniform(0.3, 0.6, size=(ngeo, 3))
+    gi = rng.integers(0, ngeo, size=n)
+    fixed = (rng.uniform(size=n) < nfixed_frac).astype(np.uint8)
+    x = rng.uniform(-box, box, size=(n, 3))
+    R = _random_rotations(rng, n)
+    v = rng.uniform(-2, 2, size=(n, 3))
+    w = rng.uniform(-2, 2, size=(n, 3)) if spin else np.zeros((n, 3))
+    v[fixed == 1] = 0.0
+    w[fixed == 1] = 0.0
+    m = rng.uniform(0.5, 2.0, size=n)
+    h = half[gi]
+    I0 = m[:, None] / 3.0 * np.stack([h[:, 1] ** 2 + h[:, 2] ** 2, h[:, 0] ** 2 + h[:, 2] ** 2, h[:, 0] ** 2 + h[:, 1] ** 2], axis=1)
+    q, vv = _rb3d_pack(x, R, v, w)
+    return _rb3d_scene([0] * ngeo, np.zeros(ngeo), half, [0] * ngeo, [], gi, fixed, m, I0, q, vv, [0.0, -9.81, 0.0],
+                       rng.uniform(-box, box, size=(nplanes, 3)), rng.normal(size=(nplanes, 3)), 0.005, "dmv")
+
+
+def torus_mesh(R=1.0, r=0.4, grid=40, nsamples=600, seed=3, pad=0.25):
+    """Synthetic stand-in for the reference's dragon.h5 (absent from the mount): an analytic torus
+    (axis z) sampled into a signed distance grid, random surface samples, a coarse vertex set and 'hull' vertices
+    (the outer ring).  Plain numpy dict in RigidBodyTriangleMesh's field layout."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ext = np.array([R + r + pad, R + r + pad, r + pad])
+    origin = -ext
+    dims = np.array([grid, grid, max(8, int(grid * ext[2] / ext[0]))], dtype=np.uint32)
+    delta = 2.0 * ext / (dims.astype(np.float64) - 1.0)
+    gx = origin[0] + delta[0] * np.arange(dims[0])
+    gy = origin[1] + delta[1] * np.arange(dims[1])
+    gz = origin[2] + delta[2] * np.arange(dims[2])
+    Z, Y, X = np.meshgrid(gz, gy, gx, indexing="ij")
+    sdf = np.sqrt((np.sqrt(X * X + Y * Y) - R) ** 2 + Z * Z) - r
+    u = rng.uniform(0, 2 * np.pi, size=nsamples)
+    t = rng.uniform(0, 2 * np.pi, size=nsamples)
+    samples = np.stack([(R + r * np.cos(t)) * np.cos(u), (R + r * np.cos(t)) * np.sin(u), r * np.sin(t)], axis=1)
+    uu, tt = np.meshgrid(np.linspace(0, 2 * np.pi, 24, endpoint=False), np.linspace(0, 2 * np.pi, 12, endpoint=False))
+    verts = np.stack([(R + r * np.cos(tt)) * np.cos(uu), (R + r * np.cos(tt)) * np.sin(uu), r * np.sin(tt)], axis=2).reshape(-1, 3)
+    keep = np.cos(tt).ravel() > 0.3
+    hull = verts[keep]
+    return {"verts": verts, "samples": samples, "hull": hull, "cell_delta": delta, "dims": dims, "origin": origin, "sdf": sdf.ravel()}
+
+
+def rb3d_random_meshes(n, seed, spin=True, nfixed_frac=0.1, nplanes=1, box=None):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    box = box if box is not None else max(1.5, n ** (1.0 / 3.0) * 1.1)
+    meshes = [torus_mesh(1.0, 0.4, 36, 500, seed=3), torus_mesh(0.8, 0.3, 30, 400, seed=4)]
+    gi = rng.integers(0, 2, size=n)
+    fixed = (rng.uniform(size=n) < nfixed_frac).astype(np.uint8)
+    x = rng.uniform(-box, box, size=(n, 3))
+    R = _random_rotations(rng, n)
+    v = rng.uniform(-1, 1, size=(n, 3))
+    w = rng.uniform(-1, 1, size=(n, 3)) if spin else np.zeros((n, 3))
+    v[fixed == 1] = 0.0
+    w[fixed == 1] = 0.0
+    m = rng.uniform(0.5, 2.0, size=n)
+    I0 = m[:, None] * rng.uniform(0.2, 0.6, size=(n, 3))
+    q, vv = _rb3d_pack(x, R, v, w)
+    return _rb3d_scene([3, 3], [0, 0], np.zeros((2, 3)), [0, 1], meshes, gi, fixed, m, I0, q, vv, [0.0, -9.81, 0.0],
+                       rng.uniform(-box, box, size=(nplanes, 3)), rng.normal(size=(nplanes, 3)), 1.0 / 10800.0, "dmv")
+
+
+def rb3d_mixed_segregated(nper=200, seed=21):
+    """Config 5 in miniature: spheres, boxes and meshes in three spatially separated blocks (mixed-type pairs make
+    the reference exit)."""
+    a = rb3d_random_spheres(nper, seed, spin=False, nplanes=0)
+    b = rb3d_random_boxes(nper, seed + 1, nplanes=0)
+    c = rb3d_random_meshes(max(8, nper // 8), seed + 2, nplanes=0)
+    scenes_ = [a, b, c]
+    shift = [np.array([0.0, 0.0, 0.0]), np.array([60.0, 0.0, 0.0]), np.array([0.0, 0.0, 80.0])]
+    xs, Rs, vs, ws, gi, fixed, m, I0 = [], [], [], [], [], [], [], []
+    geo_type, geo_r, geo_half, geo_mesh, meshes = [], [], [], [], []
+    for s, sh in zip(scenes_, shift):
+        n = s["geo_of_body"].shape[0]
+        xs.append(s["q"][:3 * n].reshape(n, 3) + sh); Rs.append(s["q"][3 * n:].reshape(n, 9))
+        vs.append(s["v"][:3 * n].reshape(n, 3)); ws.append(s["v"][3 * n:].reshape(n, 3))
+        gi.append(s["geo_of_body"] + len(geo_type)); fixed.append(s["fixed"]); m.append(s["m"]); I0.append(s["I0"])
+        geo_type += list(s["geo_type"]); geo_r += list(s["geo_r"]); geo_half += list(s["geo_half"])
+        geo_mesh += [int(k) + len(meshes) for k in s["geo_mesh"]]
+        meshes += s["meshes"]
+    q, v = _rb3d_pack(np.vstack(xs), np.vstack(Rs), np.vstack(vs), np.vstack(ws))
+    return _rb3d_scene(geo_type, geo_r, geo_half, geo_mesh, meshes, np.concatenate(gi), np.concatenate(fixed), np.concatenate(m), np.vstack(I0),
+                       q, v, [0.0, -9.81, 0.0], [[0.0, -6.0, 0.0]], [[0.0, 1.0, 0.0]], 1.0 / 10800.0, "dmv")
