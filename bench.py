@@ -34,16 +34,13 @@ NX, NY = 1000, 1000
 
 
 def scene_for_rank(rank, world):
+    """Slab `rank` of a (world*NX) x NY lattice, bodies numbered slab-major; every rank holds the same three planes
+    (plane indices are global): floor, left wall of the first slab, right wall of the last slab."""
     from scisim_b200 import scenes
     s = scenes.ball2d_lattice(NX, NY, seed=42 + rank, with_planes=True)
     if world > 1:
-        # slab `rank` of a (world*NX) x NY lattice: shift along x; only the outer slabs keep their side wall
-        shift = rank * NX * 0.99
-        s["q"][0::2] += shift
-        keep = [0] + ([1] if rank == 0 else []) + ([2] if rank == world - 1 else [])
-        s["plane_x"] = s["plane_x"][keep].copy()
-        s["plane_n"] = s["plane_n"][keep].copy()
-        s["plane_x"][:, 0] += shift * (s["plane_n"][:, 0] != 0.0)
+        s["q"][0::2] += rank * NX * 0.99
+        s["plane_x"][2, 0] += (world - 1) * NX * 0.99
     return s
 
 
@@ -166,11 +163,9 @@ def main():
     import scisim_b200 as sb
     scene = scene_for_rank(rank, world)
     ctx = sb.Context(local_rank)
-    st = sb.Ball2DState(scene["r"], scene["m"], scene["g"], scene["plane_x"], scene["plane_n"], scene["drum_x"], scene["drum_r"])
-    sim = sb.Ball2DSim(st, ctx=ctx)
     umap = sb.SymplecticEulerMap()
     dt = scene["dt"]
-    n = st.nballs()
+    n = scene["r"].shape[0]
 
     def barrier():
         ctx.synchronize()
@@ -179,11 +174,22 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    if world == 1:
+        st = sb.Ball2DState(scene["r"], scene["m"], scene["g"], scene["plane_x"], scene["plane_n"], scene["drum_x"], scene["drum_r"])
+        sim = sb.Ball2DSim(st, ctx=ctx)
+        sim.upload(scene["q"], scene["v"])
+        step = lambda: sim.step(umap, dt)
+    else:
+        # one slab per GPU, ghosts exchanged with the neighbouring slabs over NCCL every step (scisim_b200/slab.py)
+        from scisim_b200.slab import Ball2DSlabs, GpuSlabBackend
+        backend = GpuSlabBackend(ctx, scene, rank * n, ghost_cap=max(4096, n // 64))
+        slabs = Ball2DSlabs(backend, rank, world, dist)
+        step = lambda: slabs.step(umap.kind, dt)
+
     # ---------------- resident path: `value` ----------------
-    sim.upload(scene["q"], scene["v"])
     for _ in range(args.warmup):
         ctx.flush_l2()
-        pc, pa = sim.step(umap, dt)
+        pc, pa = step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count()
@@ -191,7 +197,7 @@ def main():
     for _ in range(args.steps):
         ctx.flush_l2()          # cold L2 for every timed step (outside the event bracket)
         ctx.timer_begin()
-        pc, pa = sim.step(umap, dt)
+        pc, pa = step()
         step_ms.append(ctx.timer_end())
     barrier()
     gpu_launches = ctx.launch_count() - launches0
@@ -204,27 +210,45 @@ def main():
     ctx.profile_reset()
     for _ in range(args.steps):
         ctx.flush_l2()
-        sim.step(umap, dt)
+        step()
     prof = ctx.profile()
     ctx.profile_enable(False)
 
-    # ---------------- e2e through the host-buffer ABI ----------------
+    # ---------------- e2e: host buffers in, host lists out, every step ----------------
+    flags = sb.SG_OUT_NORMALS | sb.SG_OUT_POINTS | sb.SG_OUT_DEPTHS
+    e2e_steps = max(3, min(args.steps, 10))
     q0h, v0h = ctx.pinned((2 * n,)), ctx.pinned((2 * n,))
     q1h, v1h = ctx.pinned((2 * n,)), ctx.pinned((2 * n,))
     q0h[:] = scene["q"]; v0h[:] = scene["v"]
-    flags = sb.SG_OUT_NORMALS | sb.SG_OUT_POINTS | sb.SG_OUT_DEPTHS
-    e2e_steps = max(3, min(args.steps, 10))
-    for it in range(2 + e2e_steps):
-        if it == 2:
-            barrier()
-            t0 = time.perf_counter()
-        sim._flow(umap.kind, q0h, v0h, dt, q1h, v1h)
-        a = sim.computeActiveSet(q0h, q1h, flags=flags, copy=False)
-    ctx.synchronize()
-    t_e2e_local = time.perf_counter() - t0
-    h2d = 4 * 2 * n * 8
-    d2h = 2 * 2 * n * 8 + a.n_active * (4 + 4 + 4 + 16 + 16 + 8)
-    assert a.n_active == pa and a.n_candidates == pc
+    if world == 1:
+        for it in range(2 + e2e_steps):
+            if it == 2:
+                barrier()
+                t0 = time.perf_counter()
+            sim._flow(umap.kind, q0h, v0h, dt, q1h, v1h)
+            a = sim.computeActiveSet(q0h, q1h, flags=flags, copy=False)
+        ctx.synchronize()
+        t_e2e_local = time.perf_counter() - t0
+        h2d = 4 * 2 * n * 8
+        n_act, e2e_api = a.n_active, "sg_ball2d_flow + sg_ball2d_active_set, pinned host buffers, wall clock"
+        assert a.n_active == pa and a.n_candidates == pc
+    else:
+        import ctypes as C
+        from scisim_b200._lib import SgContacts
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        for it in range(2 + e2e_steps):
+            if it == 2:
+                barrier()
+                t0 = time.perf_counter()
+            ctx.check(ctx.lib.sg_ball2d_upload(ctx.h, vp(q0h), vp(v0h)))
+            slabs.step(umap.kind, dt)
+            c = SgContacts()
+            ctx.check(ctx.lib.sg_ball2d_fetch(ctx.h, flags, vp(q1h), vp(v1h), C.byref(c)))
+        ctx.synchronize()
+        t_e2e_local = time.perf_counter() - t0
+        h2d = 2 * 2 * n * 8
+        n_act, e2e_api = int(c.n_active), "sg_ball2d_upload + slab step (NCCL halo) + sg_ball2d_fetch, pinned host buffers, wall clock"
+    d2h = 2 * 2 * n * 8 + n_act * (4 + 4 + 4 + 16 + 16 + 8)
 
     # ---------------- reduce over ranks: max time, summed work ----------------
     if world > 1:
@@ -250,12 +274,12 @@ def main():
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(world), "bodies_per_gpu": n, "candidates_per_gpu": pc, "active_per_gpu": pa,
                        "l2": "384 MB buffer overwritten before every timed step (L2 flush)", "timing": "CUDA events on the library stream, per step, summed; max over ranks",
-                       "parallelism": "1 process per GPU; slabs independent in round 1 (no halo exchange yet)" if world > 1 else "single GPU"},
+                       "parallelism": ("%d x-slabs, 1 process per GPU, ghost bodies exchanged with +-1 neighbours over NCCL each step, pair owned by the rank of its lower index" % world) if world > 1 else "single GPU"},
             "steps_per_s": args.steps / t_max,
             "clocks": clocks,
             "gpu_launches": gpu_launches,
             "e2e": {"value": pairs_all * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / e2e_steps,
-                    "api": "sg_ball2d_flow + sg_ball2d_active_set, pinned host buffers, wall clock"},
+                    "api": e2e_api},
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "share_of_step": ms / total_ms, "timed": "separate pass of the same %d steps with CUDA events around every kernel" % args.steps,
                          "kernels": kernels},

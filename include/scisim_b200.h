@@ -153,6 +153,24 @@ int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
 
+/* Slab mode (multi-GPU): this context holds bodies [gid_first, gid_first + n_owned) of a larger scene
+ * whose global numbering is slab-major, plus per-step ghost copies of neighbouring slabs' bodies.  The reference has no
+ * distributed mode; these calls are driven by scisim_b200/slab.py (one process per GPU, NCCL for the exchange).
+ *   init    reserve ghost_cap slots on either side of the owned block; upload r, m of the owned bodies
+ *   (sg_ball2d_upload / sg_ball2d_fetch then address the owned block only)
+ *   flow    integrate the owned bodies; *interval_dev (DEVICE pointer, 2 doubles) receives [min lo.x, max hi.x] of their
+ *           swept AABBs -- what the other ranks need to select the ghosts they owe this one
+ *   pack    ordered list (48-byte records) of the owned bodies whose swept AABB overlaps the x-interval at interval_dev
+ *           (DEVICE) into send_dev (DEVICE, cap records); the count goes to *count_dev (DEVICE).  cap = 0: count only
+ *   unpack  append `count` received records as ghosts on side 0 (lower global indices) or 1 (higher)
+ *   detect  broad + narrow phase over owned + ghosts; a pair is kept iff this rank owns the body with the smaller
+ *           global index; planes / drums are tested for owned bodies only; indices in the lists are global */
+int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint32_t ghost_cap, const double* r, const double* m );
+int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_dev );
+int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev, uint32_t cap, uint32_t* count_dev );
+int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev, uint32_t count );
+int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out );
+
 /* ---- rigidbody3d --------------------------------------------------------------------------------------
  * Layouts are RigidBody3DState's (rigidbody3d/RigidBody3DState.cpp:70-240): q = [3N centres | 9N row-major R],
  * v = [3N linear | 3N angular]. Static data: the geometry list (as m_geometry) and, per body, its geometry index,

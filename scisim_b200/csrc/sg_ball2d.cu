@@ -20,7 +20,11 @@ struct Ball2DIn
   const double2* q1;
   const double* r;
   uint32_t n;
+  uint32_t own_first; // bodies [own_first, own_first + own_count) belong to this rank, the rest are halo ghosts
+  uint32_t own_count;
 };
+
+#define SG_GHOST_BIT 0x80000000u
 
 struct alignas( 64 ) Ball2DRec
 {
@@ -41,6 +45,7 @@ struct ContactOut2D
   double2* p;
   double* depth;
   unsigned long long cap;
+  const uint32_t* gid; // multi-GPU: local -> global body index (nullptr on one GPU)
 };
 
 // scisim/CollisionDetection/CollisionDetectionUtilities.cpp:3-121 (a = lower body index)
@@ -77,7 +82,7 @@ struct Ball2DPolicy
   using In = Ball2DIn;
   using Rec = Ball2DRec;
   using Out = ContactOut2D;
-  static constexpr uint32_t IDX_MASK = 0xffffffffu;
+  static constexpr uint32_t IDX_MASK = 0x7fffffffu;
   static constexpr uint32_t IDX_OFFSET = 40u;
 
   // ball2d/Ball2DSim.cpp:566-571: lo = min(q1,q0) - r, hi = max(q1,q0) + r
@@ -96,7 +101,7 @@ struct Ball2DPolicy
     Rec rec;
     rec.q0x = a.x; rec.q0y = a.y; rec.q1x = b.x; rec.q1y = b.y;
     rec.r = __ldg( &in.r[i] );
-    rec.idx = i; rec.key = key; rec.c1 = c1; rec.c2 = c2; rec.pad1 = 0.0;
+    rec.idx = ( i - in.own_first < in.own_count ) ? i : ( i | SG_GHOST_BIT ); rec.key = key; rec.c1 = c1; rec.c2 = c2; rec.pad1 = 0.0;
     return rec;
   }
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
@@ -104,7 +109,8 @@ struct Ball2DPolicy
     lo[0] = fmin( s.q1x, s.q0x ) - s.r; lo[1] = fmin( s.q1y, s.q0y ) - s.r;
     hi[0] = fmax( s.q1x, s.q0x ) + s.r; hi[1] = fmax( s.q1y, s.q0y ) + s.r;
   }
-  __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
+  __device__ static bool owns( const Rec& s ) { return ( s.idx & SG_GHOST_BIT ) == 0u; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
@@ -121,8 +127,9 @@ struct Ball2DPolicy
       const double ex = a.q1x - b.q1x;
       const double ey = a.q1y - b.q1y;
       out.type[k] = SG_BALL_BALL;
-      out.i[k] = a.idx;
-      out.j[k] = b.idx;
+      const uint32_t ia = a.idx & IDX_MASK, ib = b.idx & IDX_MASK;
+      out.i[k] = ( out.gid != nullptr ) ? out.gid[ia] : ia;
+      out.j[k] = ( out.gid != nullptr ) ? out.gid[ib] : ib;
       out.n[k] = make_double2( nx, ny );
       out.p[k] = make_double2( a.q0x - a.r * nx, a.q0y - a.r * ny );
       out.depth[k] = fmin( 0.0, sqrt( ex * ex + ey * ey ) - ( a.r + b.r ) );
@@ -205,7 +212,8 @@ __device__ __forceinline__ unsigned long long static_mask( const Static2D& sg, c
 template<bool DO_FLOW>
 __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ Static2D sg, const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0,
                                                        const double* __restrict__ m, const double* __restrict__ r, const double gx, const double gy, const double dt,
-                                                       double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts )
+                                                       double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts,
+                                                       const uint32_t own_first, const uint32_t own_count )
 {
   __shared__ uint32_t s_cnt[SG_MAX_DRUMS + SG_MAX_PLANES];
   const uint32_t ng = sg.ndrums + sg.nplanes;
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
     lo[0] = fmin( qo.x, q.x ) - rad; lo[1] = fmin( qo.y, q.y ) - rad;
     hi[0] = fmax( qo.x, q.x ) + rad; hi[1] = fmax( qo.y, q.y ) + rad;
     sg_bp_bounds_update<2>( lo, hi, mn, mx, ext );
-    mask = static_mask( sg, qo, rad );
+    if( i - own_first < own_count ) { mask = static_mask( sg, qo, rad ); } // ghosts touch no static geometry here
   }
   sg_bp_bounds_commit<2>( mn, mx, ext, acc );
   if( ng > 0u )
@@ -276,7 +284,8 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
 
 // Stable compaction: geometry-major, ball ascending, appended after the body-body contacts
 __global__ void __launch_bounds__( 256 ) k_ball2d_static_emit( const __grid_constant__ Static2D sg, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r,
-                                                              const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, const ScanPairCounts::Acc* __restrict__ pair_totals, const ContactOut2D out )
+                                                              const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, const ScanPairCounts::Acc* __restrict__ pair_totals, const ContactOut2D out,
+                                                              const uint32_t own_first, const uint32_t own_count )
 {
   __shared__ uint32_t s_warp[8];
   const uint32_t ng = sg.ndrums + sg.nplanes;
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_static_emit( const __grid_cons
   double2 x0 = make_double2( 0.0, 0.0 ), x1 = x0;
   double rad = 0.0;
   unsigned long long mask = 0ull;
-  if( i < n ) { x0 = __ldg( &q0[i] ); x1 = __ldg( &q1[i] ); rad = __ldg( &r[i] ); mask = static_mask( sg, x1, rad ); }
+  if( i < n && i - own_first < own_count ) { x0 = __ldg( &q0[i] ); x1 = __ldg( &q1[i] ); rad = __ldg( &r[i] ); mask = static_mask( sg, x1, rad ); }
   const unsigned long long base = pair_totals->a;
   for( uint32_t g = 0; g < ng; ++g )
   {
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_static_emit( const __grid_cons
           depth = fmin( 0.0, dist - rad );
         }
         out.type[k] = type;
-        out.i[k] = i;
+        out.i[k] = ( out.gid != nullptr ) ? out.gid[i] : i;
         out.j[k] = j;
         out.n[k] = make_double2( nx, ny );
         out.p[k] = make_double2( x0.x - rad * nx, x0.y - rad * ny );
@@ -355,6 +364,22 @@ struct Ball2DData
   uint64_t n_cand = 0, n_bb = 0, n_static = 0, n_drum = 0, n_plane = 0;
   bool have_result = false;
   bool cand_valid = false;
+  // slab mode (one slab of a larger scene per GPU): the body arrays hold [left ghosts | owned | right ghosts] with
+  // ghost_cap slots reserved on either side of the owned block; left ghosts are packed against the owned block so
+  // the active range is contiguous and ordered by global body index.
+  bool slab = false;
+  uint32_t n_owned = 0, ghost_cap = 0, nL = 0, nR = 0, gid_first = 0;
+  DevBuf gid;          // u32 per slot: global body index
+  DevBuf interval_enc; // 2 x long long (ordered encoding of min lo.x / max hi.x over the owned swept boxes)
+  DevBuf pack_counts, pack_offsets, pack_partials;
+  size_t first_slot() const { return slab ? size_t( ghost_cap - nL ) : 0; }   // first active slot
+  size_t owned_slot() const { return slab ? size_t( ghost_cap ) : 0; }        // first owned slot
+  uint32_t own_first() const { return slab ? nL : 0u; }                        // owned range in local indices
+  uint32_t own_count() const { return slab ? n_owned : n; }
+  double2* Q0() const { return q0.as<double2>() + first_slot(); }
+  double2* Q1() const { return q1.as<double2>() + first_slot(); }
+  double* R() const { return r.as<double>() + first_slot(); }
+  const uint32_t* GID() const { return slab ? gid.as<uint32_t>() + first_slot() : nullptr; }
   Ball2DData() { memset( &sg, 0, sizeof( sg ) ); }
 };
 
@@ -367,6 +392,7 @@ void sg_ball2d_release( sg_ctx* ctx )
   d->st_counts.release(); d->st_offsets.release(); d->st_partials.release(); d->st_total.release();
   d->c_type.release(); d->c_i.release(); d->c_j.release(); d->c_n.release(); d->c_p.release(); d->c_depth.release();
   d->h_totals.release(); d->h_out.release();
+  d->gid.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release();
   delete d;
   ctx->ball2d = nullptr;
 }
@@ -399,10 +425,11 @@ static int ball2d_ensure_outputs( sg_ctx* ctx, Ball2DData* d, const uint64_t can
 
 static int ball2d_flow_device( sg_ctx* ctx, Ball2DData* d, const int map_kind, const double dt )
 {
-  const uint32_t n = d->n;
+  const uint32_t n = d->slab ? d->n_owned : d->n;
   if( n == 0 ) { return SG_OK; }
-  SG_LAUNCH( ctx, "ball2d_flow", double( n ) * 72.0, k_ball2d_flow<<<sg_div_up( n, 256 ), 256, 0, ctx->stream>>>( map_kind, n, d->q0.as<double2>(), d->v0.as<double2>(), d->m.as<double>(),
-             d->g[0], d->g[1], dt, d->q1.as<double2>(), d->v1.as<double2>() ) );
+  const size_t o = d->owned_slot();
+  SG_LAUNCH( ctx, "ball2d_flow", double( n ) * 72.0, k_ball2d_flow<<<sg_div_up( n, 256 ), 256, 0, ctx->stream>>>( map_kind, n, d->q0.as<double2>() + o, d->v0.as<double2>(), d->m.as<double>(),
+             d->g[0], d->g[1], dt, d->q1.as<double2>() + o, d->v1.as<double2>() ) );
   return SG_OK;
 }
 
@@ -429,18 +456,19 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 + 4 ) );
   SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
   SG_CUDA( ctx, d->st_total.ensure( 4 ) );
-  if( flow_kind >= 0 )
+  if( flow_kind >= 0 && !d->slab )
   {
-    SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->q0.as<double2>(), d->v0.as<double2>(), d->m.as<double>(),
-               d->r.as<double>(), d->g[0], d->g[1], dt, d->q1.as<double2>(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>() ) );
+    SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(),
+               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n ) );
   }
   else
   {
-    SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->q0.as<double2>(), nullptr, nullptr,
-               d->r.as<double>(), 0.0, 0.0, 0.0, d->q1.as<double2>(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>() ) );
+    SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr,
+               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count() ) );
   }
   Ball2DIn in;
-  in.q0 = d->q0.as<double2>(); in.q1 = d->q1.as<double2>(); in.r = d->r.as<double>(); in.n = n;
+  in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count();
+  d->bp.gid_map = d->GID();
   rc = sg_bp_bin_and_count<Ball2DPolicy>( ctx, d->bp, in, true );
   if( rc != SG_OK ) { return rc; }
 
@@ -456,12 +484,13 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
     out.type = d->c_type.as<uint32_t>(); out.i = d->c_i.as<uint32_t>(); out.j = d->c_j.as<uint32_t>();
     out.n = d->c_n.as<double2>(); out.p = d->c_p.as<double2>(); out.depth = d->c_depth.as<double>();
     out.cap = d->act_cap;
+    out.gid = d->GID();
     rc = sg_bp_emit_lists<Ball2DPolicy>( ctx, d->bp, n, want_cand, out, 0.0 );
     if( rc != SG_OK ) { return rc; }
     if( ng > 0 )
     {
-      SG_LAUNCH( ctx, "ball2d_static_emit", double( n ) * 40.0, k_ball2d_static_emit<<<nblk, 256, 0, ctx->stream>>>( d->sg, n, d->q0.as<double2>(), d->q1.as<double2>(), d->r.as<double>(),
-                 d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->bp.totals.as<ScanPairCounts::Acc>(), out ) );
+      SG_LAUNCH( ctx, "ball2d_static_emit", double( n ) * 40.0, k_ball2d_static_emit<<<nblk, 256, 0, ctx->stream>>>( d->sg, n, d->Q0(), d->Q1(), d->R(),
+                 d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->bp.totals.as<ScanPairCounts::Acc>(), out, d->own_first(), d->own_count() ) );
     }
     // counts to the host
     unsigned long long* ht = d->h_totals.as<unsigned long long>();
@@ -535,6 +564,91 @@ static int ball2d_copy_out( sg_ctx* ctx, Ball2DData* d, const uint32_t flags, sg
   return SG_OK;
 }
 
+
+// ---- slab mode: halo selection, packing and unpacking ----------------------------------------------
+struct alignas( 16 ) GhostRec { double q0x, q0y, q1x, q1y, r; uint32_t gid; uint32_t pad; };
+
+__device__ __forceinline__ void swept_x( const double2 a, const double2 b, const double r, double& lo, double& hi )
+{
+  lo = fmin( b.x, a.x ) - r;
+  hi = fmax( b.x, a.x ) + r;
+}
+
+// [min lo.x, max hi.x] over the owned swept boxes, ordered-int encoded
+__global__ void __launch_bounds__( 256 ) k_ball2d_interval( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, long long* __restrict__ enc )
+{
+  double mn = __longlong_as_double( 0x7ff0000000000000LL ), mx = __longlong_as_double( 0xfff0000000000000LL );
+  for( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+  {
+    double lo, hi;
+    swept_x( __ldg( &q0[i] ), __ldg( &q1[i] ), __ldg( &r[i] ), lo, hi );
+    mn = fmin( mn, lo ); mx = fmax( mx, hi );
+  }
+  #pragma unroll
+  for( int d = 16; d > 0; d >>= 1 ) { mn = fmin( mn, __shfl_xor_sync( 0xffffffffu, mn, d ) ); mx = fmax( mx, __shfl_xor_sync( 0xffffffffu, mx, d ) ); }
+  if( ( threadIdx.x & 31 ) == 0 ) { atomicMin( &enc[0], sg_ordered_from_double( mn ) ); atomicMax( &enc[1], sg_ordered_from_double( mx ) ); }
+}
+__global__ void k_ball2d_interval_init( long long* enc )
+{
+  enc[0] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );
+  enc[1] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );
+}
+__global__ void k_ball2d_interval_decode( const long long* enc, double* out ) { out[0] = sg_double_from_ordered( enc[0] ); out[1] = sg_double_from_ordered( enc[1] ); }
+
+// Owned bodies whose swept box overlaps [iv[0], iv[1]] on x (closed, like AABB::overlaps), in body order.
+template<bool EMIT>
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, const uint32_t* __restrict__ gid,
+                                                            const double* __restrict__ iv, uint32_t* __restrict__ block_counts, const uint32_t* __restrict__ block_offsets, GhostRec* __restrict__ out, const uint32_t cap )
+{
+  __shared__ uint32_t s_warp[8];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double ilo = iv[0], ihi = iv[1];
+  bool sel = false;
+  double2 a = make_double2( 0.0, 0.0 ), b = a;
+  double rad = 0.0;
+  if( i < n )
+  {
+    a = __ldg( &q0[i] ); b = __ldg( &q1[i] ); rad = __ldg( &r[i] );
+    double lo, hi;
+    swept_x( a, b, rad, lo, hi );
+    sel = !( hi < ilo ) && !( ihi < lo );
+  }
+  const unsigned bal = __ballot_sync( 0xffffffffu, sel );
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
+  __syncthreads();
+  uint32_t before = 0u, total = 0u;
+  for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } total += c; }
+  if( !EMIT ) { if( threadIdx.x == 0 ) { block_counts[blockIdx.x] = total; } return; }
+  if( sel )
+  {
+    const uint32_t k = block_offsets[blockIdx.x] + before + __popc( bal & ( ( 1u << lane ) - 1u ) );
+    if( k < cap )
+    {
+      GhostRec g;
+      g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
+      out[k] = g;
+    }
+  }
+}
+
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t count, const GhostRec* __restrict__ in, double2* __restrict__ q0, double2* __restrict__ q1, double* __restrict__ r, uint32_t* __restrict__ gid )
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if( k >= count ) { return; }
+  const GhostRec g = in[k];
+  q0[k] = make_double2( g.q0x, g.q0y );
+  q1[k] = make_double2( g.q1x, g.q1y );
+  r[k] = g.r;
+  gid[k] = g.gid;
+}
+
+__global__ void __launch_bounds__( 256 ) k_iota_u32( const uint32_t n, const uint32_t first, uint32_t* __restrict__ out )
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if( k < n ) { out[k] = first + k; }
+}
+
 extern "C"
 {
 
@@ -546,6 +660,7 @@ int sg_ball2d_set_bodies( sg_ctx* ctx, uint32_t n, const double* r, const double
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   Ball2DData* d = ball2d_data( ctx );
   d->n = n;
+  d->slab = false;
   d->have_result = false;
   if( n == 0 ) { return SG_OK; }
   SG_CUDA( ctx, d->r.ensure( size_t( n ) * 8 ) );
@@ -602,6 +717,7 @@ int sg_ball2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: map kind %d is not a ball2d map", map_kind ); }
   Ball2DData* d = ball2d_data( ctx );
+  if( d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: context is in slab mode, use the sg_ball2d_slab_* calls" ); }
   const size_t bytes = size_t( d->n ) * 16;
   if( d->n == 0 ) { return SG_OK; }
   if( q0 == nullptr || v0 == nullptr || q1 == nullptr || v1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: null vector" ); }
@@ -621,6 +737,7 @@ int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint3
 {
   if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
+  if( d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_active_set: context is in slab mode, use the sg_ball2d_slab_* calls" ); }
   const size_t bytes = size_t( d->n ) * 16;
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   if( d->n > 0 )
@@ -638,11 +755,12 @@ int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
-  if( d->n == 0 ) { return SG_OK; }
+  const uint32_t nown = d->slab ? d->n_owned : d->n;
+  if( nown == 0 ) { return SG_OK; }
   if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_upload: null vector" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q, size_t( d->n ) * 16, cudaMemcpyHostToDevice, ctx->stream ) );
-  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v, size_t( d->n ) * 16, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.as<double2>() + d->owned_slot(), q, size_t( nown ) * 16, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v, size_t( nown ) * 16, cudaMemcpyHostToDevice, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   return SG_OK;
 }
@@ -652,8 +770,123 @@ int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_step: map kind %d is not a ball2d map", map_kind ); }
   Ball2DData* d = ball2d_data( ctx );
+  if( d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_step: context is in slab mode, use the sg_ball2d_slab_* calls" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   const int rc = ball2d_active_set_device( ctx, d, true, map_kind, dt );
+  if( rc != SG_OK ) { return rc; }
+  if( out != nullptr )
+  {
+    memset( out, 0, sizeof( *out ) );
+    out->dim = 2;
+    out->n_candidates = d->n_cand;
+    out->n_body_body = d->n_bb;
+    out->n_active = d->n_bb + d->n_static;
+  }
+  return SG_OK;
+}
+
+
+int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint32_t ghost_cap, const double* r, const double* m )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n_owned > 0 && ( r == nullptr || m == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_init: null array" ); }
+  if( uint64_t( n_owned ) + 2ull * ghost_cap >= 0x80000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_init: slab too large" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  Ball2DData* d = ball2d_data( ctx );
+  d->slab = true; d->n_owned = n_owned; d->ghost_cap = ghost_cap; d->gid_first = gid_first; d->nL = 0; d->nR = 0; d->n = n_owned;
+  d->have_result = false;
+  const size_t slots = size_t( n_owned ) + 2 * size_t( ghost_cap );
+  SG_CUDA( ctx, d->r.ensure( slots * 8 + 8 ) );
+  SG_CUDA( ctx, d->q0.ensure( slots * 16 + 16 ) );
+  SG_CUDA( ctx, d->q1.ensure( slots * 16 + 16 ) );
+  SG_CUDA( ctx, d->gid.ensure( slots * 4 + 4 ) );
+  SG_CUDA( ctx, d->m.ensure( size_t( n_owned ) * 8 + 8 ) );
+  SG_CUDA( ctx, d->v0.ensure( size_t( n_owned ) * 16 + 16 ) );
+  SG_CUDA( ctx, d->v1.ensure( size_t( n_owned ) * 16 + 16 ) );
+  SG_CUDA( ctx, d->interval_enc.ensure( 16 ) );
+  if( n_owned > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( d->r.as<double>() + ghost_cap, r, size_t( n_owned ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->m.ptr, m, size_t( n_owned ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_LAUNCH( ctx, "slab_iota", 0.0, k_iota_u32<<<sg_div_up( n_owned, 256 ), 256, 0, ctx->stream>>>( n_owned, gid_first, d->gid.as<uint32_t>() + ghost_cap ) );
+  }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_dev )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: call sg_ball2d_slab_init first" ); }
+  if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: map kind %d is not a ball2d map", map_kind ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  d->nL = 0; d->nR = 0; d->n = d->n_owned;
+  const int rc = ball2d_flow_device( ctx, d, map_kind, dt );
+  if( rc != SG_OK ) { return rc; }
+  if( interval_dev != nullptr )
+  {
+    const size_t o = d->owned_slot();
+    const unsigned nred = sg_div_up( d->n_owned > 0 ? d->n_owned : 1, 256 ) < unsigned( ctx->num_sms * 8 ) ? sg_div_up( d->n_owned > 0 ? d->n_owned : 1, 256 ) : unsigned( ctx->num_sms * 8 );
+    SG_LAUNCH( ctx, "slab_interval", double( d->n_owned ) * 40.0, k_ball2d_interval_init<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>() );
+               k_ball2d_interval<<<nred, 256, 0, ctx->stream>>>( d->n_owned, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->interval_enc.as<long long>() );
+               k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev ) );
+    ctx->launch_count += 2;
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev, uint32_t cap, uint32_t* count_dev )
+{
+  if( ctx == nullptr || interval_dev == nullptr || count_dev == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_pack: call sg_ball2d_slab_init first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  const uint32_t n = d->n_owned;
+  const unsigned nblk = sg_div_up( n > 0 ? n : 1, 256 );
+  SG_CUDA( ctx, d->pack_counts.ensure( size_t( nblk ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->pack_offsets.ensure( size_t( nblk ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->pack_partials.ensure( ( size_t( nblk ) / SG_SCAN_TILE + 2 ) * 4 ) );
+  const size_t o = d->owned_slot();
+  SG_LAUNCH( ctx, "slab_pack_count", double( n ) * 40.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
+             interval_dev, d->pack_counts.as<uint32_t>(), nullptr, nullptr, 0u ) );
+  const int rc = sg_exclusive_scan<ScanU32>( ctx, "slab_pack_scan", d->pack_counts.as<uint32_t>(), nullptr, nblk, nblk, d->pack_partials.as<uint32_t>(), d->pack_offsets.as<uint32_t>(), count_dev, false );
+  if( rc != SG_OK ) { return rc; }
+  if( send_dev != nullptr && cap > 0 )
+  {
+    SG_LAUNCH( ctx, "slab_pack_emit", double( n ) * 40.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
+               interval_dev, nullptr, d->pack_offsets.as<uint32_t>(), static_cast<GhostRec*>( send_dev ), cap ) );
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev, uint32_t count )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: call sg_ball2d_slab_init first" ); }
+  if( count > d->ghost_cap ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: %u ghosts exceed the reserved capacity %u", count, d->ghost_cap ); }
+  if( count > 0 && recv_dev == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: null buffer" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  // side 0: ghosts with smaller global indices, packed right up against the owned block; side 1: after it
+  const size_t slot = ( side == 0 ) ? size_t( d->ghost_cap - count ) : size_t( d->ghost_cap ) + d->n_owned;
+  if( side == 0 ) { d->nL = count; } else { d->nR = count; }
+  d->n = d->nL + d->n_owned + d->nR;
+  if( count > 0 )
+  {
+    SG_LAUNCH( ctx, "slab_unpack", double( count ) * 92.0, k_ball2d_slab_unpack<<<sg_div_up( count, 256 ), 256, 0, ctx->stream>>>( count, static_cast<const GhostRec*>( recv_dev ), d->q0.as<double2>() + slot,
+               d->q1.as<double2>() + slot, d->r.as<double>() + slot, d->gid.as<uint32_t>() + slot ) );
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_detect: call sg_ball2d_slab_init first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  const int rc = ball2d_active_set_device( ctx, d, true );
   if( rc != SG_OK ) { return rc; }
   if( out != nullptr )
   {
@@ -672,8 +905,9 @@ int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg
   Ball2DData* d = ball2d_data( ctx );
   if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_fetch: no step has been run" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  if( q1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, size_t( d->n ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
-  if( v1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  const uint32_t nown = d->slab ? d->n_owned : d->n;
+  if( q1 != nullptr && nown > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.as<double2>() + d->owned_slot(), size_t( nown ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( v1 != nullptr && nown > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( nown ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
   if( out != nullptr ) { return ball2d_copy_out( ctx, d, out_flags, out ); }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   return SG_OK;

@@ -48,6 +48,7 @@ struct BroadScratch
   DevBuf cand;          // uint2[cand_cap]
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
+  const uint32_t* gid_map = nullptr; // multi-GPU: local body index -> global body index for the emitted lists
   int bounds_phase = 0; // which of the two BoundsAccum the current step reduces into
   BoundsAccum* bounds_cur() const { return bounds.as<BoundsAccum>() + bounds_phase; }
   void release()
@@ -437,9 +438,16 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
   if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the windows are staged
   sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
   if( p >= n ) { return; }
+  const uint32_t my_idx = P::rec_idx( me );
+  if( !P::owns( me ) )
+  {
+    // a ghost body (multi-GPU halo): present only as a partner, its pairs are kept by the rank that owns it
+    counts[my_idx] = make_uint2( 0u, 0u );
+    masks[p] = make_uint2( 0u, 0u );
+    return;
+  }
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
-  const uint32_t my_idx = P::rec_idx( me );
   uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
   sg_bp_walk_pos<P>( g, cell_start, p, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), [&]( const int w, const uint32_t q )
   {
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
 template<typename P>
 __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint2* __restrict__ counts, const uint2* __restrict__ masks,
-                                                              const ulonglong2* __restrict__ offsets, uint2* __restrict__ cand, const uint64_t cand_cap, const typename P::Out out )
+                                                              const ulonglong2* __restrict__ offsets, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, const typename P::Out out )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -531,7 +539,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
     {
       const unsigned long long v = col[j * Cfg::T];
       const unsigned long long kc = off.x + j;
-      if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( my_idx, uint32_t( v >> 32 ) ); }
+      if( cand != nullptr && kc < cand_cap ) { cand[kc] = ( gid != nullptr ) ? make_uint2( gid[my_idx], gid[uint32_t( v >> 32 )] ) : make_uint2( my_idx, uint32_t( v >> 32 ) ); }
       if( P::HAS_NARROW && ( ( v >> 31 ) & 1ull ) )
       {
         const Rec o = fetch_any( uint32_t( v & 0x7fffffffull ) );
@@ -555,7 +563,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
   };
   auto emit_one = [&]( const unsigned long long kc, const Rec& o )
   {
-    if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( my_idx, P::rec_idx( o ) ); }
+    if( cand != nullptr && kc < cand_cap ) { cand[kc] = ( gid != nullptr ) ? make_uint2( gid[my_idx], gid[P::rec_idx( o )] ) : make_uint2( my_idx, P::rec_idx( o ) ); }
     if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { P::contact_emit( out, ka, me, o ); } }
   };
   if( cnt.x <= SG_BP_LOCAL_CAP )
@@ -660,7 +668,7 @@ static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, con
   constexpr size_t smem = sg_bp_smem_bytes<P::D>() + size_t( SG_BP_FAST_CAP ) * BpCfg<P::D>::T * 8;
   SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_emit<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
   SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 8.0 + 8.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, BpCfg<P::D>::T ), BpCfg<P::D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
-             s.counts.as<uint2>(), s.masks.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, out ) );
+             s.counts.as<uint2>(), s.masks.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map, out ) );
   return SG_OK;
 }
 

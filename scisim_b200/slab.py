@@ -1,0 +1,176 @@
+"""Multi-GPU slab decomposition for the ball2d path: one process per GPU, one slab of a
+slab-major-numbered scene per process, ghost bodies exchanged with the neighbouring slabs every step.
+
+The reference is single-process; this module is the host logic that has no counterpart there:
+  * interval exchange: every rank publishes [min lo.x, max hi.x] of its owned swept AABBs (all_gather, 16 B/rank)
+  * halo: a rank sends rank+-1 exactly its owned bodies whose swept AABB overlaps that rank's interval (NCCL
+    send/recv over NVLink when the tensors are CUDA tensors); a body overlapping a non-neighbour's interval means
+    the slabs need re-balancing and raises
+  * ownership: pair (i<j) is kept by the rank that owns body i, so the per-rank lists are disjoint, each ascending,
+    and their concatenation in rank order is the reference's std::set order; planes / drums are tested for owned
+    bodies only and merged geometry-major
+All device work goes through a backend (GpuSlabBackend below; the CPU tests plug the oracle in as the backend to
+exercise this host logic under gloo).
+"""
+import ctypes as C
+
+import numpy as np
+
+REC_BYTES = 48
+
+
+def partition_slab_major(n_total, world):
+    """Owned global index range [first, first + count) of every rank: equal-count contiguous blocks."""
+    base, rem = divmod(n_total, world)
+    counts = [base + (1 if r < rem else 0) for r in range(world)]
+    firsts = [sum(counts[:r]) for r in range(world)]
+    return firsts, counts
+
+
+def merge_active_sets(parts, n_static_geoms):
+    """parts: per-rank dicts (rank order) with type,i,j,n,p,depth,candidates in global indices. Returns the global
+    active set in the reference's order: ball-ball (rank order == ascending (i,j)), then drums drum-major, then planes
+    plane-major, each ball-ascending (ranks own ascending index ranges)."""
+    out = {}
+    out["candidates"] = np.concatenate([p["candidates"] for p in parts]) if parts else np.zeros((0, 2), np.uint32)
+    keys = ("type", "i", "j", "n", "p", "depth")
+    chunks = {k: [] for k in keys}
+    for p in parts:
+        sel = p["type"] == 0
+        for k in keys:
+            chunks[k].append(p[k][sel])
+    for t in (1, 2):  # drums then planes
+        for g in range(n_static_geoms[t - 1]):
+            for p in parts:
+                sel = (p["type"] == t) & (p["j"] == g)
+                for k in keys:
+                    chunks[k].append(p[k][sel])
+    for k in keys:
+        out[k] = np.concatenate(chunks[k]) if chunks[k] else None
+    return out
+
+
+class GpuSlabBackend:
+    """One slab on one GPU through the sg_ball2d_slab_* calls; exchange buffers are torch CUDA tensors and every
+    torch op is issued on the library's stream, so no host synchronisation is needed except to read counts."""
+
+    def __init__(self, ctx, scene_slab, gid_first, ghost_cap):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.device = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.device)
+        self.cap = int(ghost_cap)
+        s = scene_slab
+        r = np.ascontiguousarray(s["r"], dtype=np.float64)
+        m = np.ascontiguousarray(s["m"], dtype=np.float64)
+        self.n_owned = r.shape[0]
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        ctx.check(self.lib.sg_ball2d_slab_init(ctx.h, self.n_owned, int(gid_first), self.cap, vp(r), vp(m)))
+        g = np.ascontiguousarray(s["g"], dtype=np.float64)
+        ctx.check(self.lib.sg_ball2d_set_gravity(ctx.h, vp(g)))
+        px, pn = np.ascontiguousarray(s["plane_x"], dtype=np.float64), np.ascontiguousarray(s["plane_n"], dtype=np.float64)
+        ctx.check(self.lib.sg_ball2d_set_planes(ctx.h, px.shape[0], vp(px), vp(pn)))
+        dx, dr = np.ascontiguousarray(s["drum_x"], dtype=np.float64), np.ascontiguousarray(s["drum_r"], dtype=np.float64)
+        ctx.check(self.lib.sg_ball2d_set_drums(ctx.h, dx.shape[0], vp(dx), vp(dr)))
+        q, v = np.ascontiguousarray(s["q"], dtype=np.float64), np.ascontiguousarray(s["v"], dtype=np.float64)
+        ctx.check(self.lib.sg_ball2d_upload(ctx.h, vp(q), vp(v)))
+        with torch.cuda.stream(self.stream):
+            self.iv = torch.zeros(2, dtype=torch.float64, device=self.device)
+            self.count = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.send = [torch.empty(self.cap * REC_BYTES, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self.recv = [torch.empty(self.cap * REC_BYTES, dtype=torch.uint8, device=self.device) for _ in range(2)]
+
+    def flow(self, kind, dt):
+        self.ctx.check(self.lib.sg_ball2d_slab_flow(self.ctx.h, int(kind), float(dt), C.c_void_p(self.iv.data_ptr())))
+        return self.iv
+
+    def pack(self, interval, side, count_only=False):
+        """Selects the owned bodies overlapping `interval` (a 2-element tensor on this device). Returns (buffer, count)."""
+        buf = self.send[side]
+        self.ctx.check(self.lib.sg_ball2d_slab_pack(self.ctx.h, C.c_void_p(interval.data_ptr()), None if count_only else C.c_void_p(buf.data_ptr()),
+                                                    0 if count_only else self.cap, C.c_void_p(self.count.data_ptr())))
+        with self.torch.cuda.stream(self.stream):
+            cnt = int(self.count.item())
+        if not count_only and cnt > self.cap:
+            raise RuntimeError("slab halo of %d bodies exceeds the reserved ghost capacity %d" % (cnt, self.cap))
+        return buf, cnt
+
+    def recv_buffer(self, side):
+        return self.recv[side]
+
+    def unpack(self, side, buf, count):
+        self.ctx.check(self.lib.sg_ball2d_slab_unpack(self.ctx.h, int(side), C.c_void_p(buf.data_ptr()), int(count)))
+
+    def detect(self):
+        from ._lib import SgContacts
+        c = SgContacts()
+        self.ctx.check(self.lib.sg_ball2d_slab_detect(self.ctx.h, C.byref(c)))
+        return int(c.n_candidates), int(c.n_active)
+
+    def fetch(self):
+        from ._lib import SG_OUT_ALL, SgContacts
+        from .host_api import ActiveSet
+        q1, v1 = np.empty(2 * self.n_owned), np.empty(2 * self.n_owned)
+        c = SgContacts()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.ctx.check(self.lib.sg_ball2d_fetch(self.ctx.h, SG_OUT_ALL, vp(q1), vp(v1), C.byref(c)))
+        a = ActiveSet(c)
+        return q1, v1, {"type": a.type, "i": a.i, "j": a.j, "n": a.n, "p": a.p, "depth": a.depth, "candidates": a.candidates}
+
+    def run_on_stream(self):
+        return self.torch.cuda.stream(self.stream)
+
+
+class Ball2DSlabs:
+    """Per-rank driver of one step: flow -> interval all_gather -> halo exchange -> detection."""
+
+    def __init__(self, backend, rank, world, dist, check_non_neighbours=True):
+        self.b, self.rank, self.world, self.dist = backend, rank, world, dist
+        self.check = check_non_neighbours
+        self.last_halo = (0, 0)
+
+    def step(self, kind, dt):
+        import contextlib
+        import torch
+        b, dist, rank, W = self.b, self.dist, self.rank, self.world
+        cm = b.run_on_stream() if hasattr(b, "run_on_stream") else contextlib.nullcontext()
+        with cm:
+            iv = b.flow(kind, dt)
+            if W == 1:
+                return b.detect()
+            all_iv = torch.empty(W * 2, dtype=torch.float64, device=iv.device)
+            dist.all_gather_into_tensor(all_iv, iv)
+            all_iv = all_iv.view(W, 2)
+            peers = {0: rank - 1, 1: rank + 1}
+            out = {}
+            for side, peer in peers.items():
+                out[side] = b.pack(all_iv[peer], side) if 0 <= peer < W else (None, 0)
+            if self.check:
+                for peer in range(W):
+                    if abs(peer - rank) > 1:
+                        _, c = b.pack(all_iv[peer], 0, count_only=True)
+                        if c != 0:
+                            raise RuntimeError("rank %d: %d bodies reach the slab of non-neighbour rank %d; re-balance the slabs" % (rank, c, peer))
+            counts = torch.tensor([out[0][1], out[1][1]], dtype=torch.int64, device=iv.device)
+            all_counts = torch.empty(W * 2, dtype=torch.int64, device=iv.device)
+            dist.all_gather_into_tensor(all_counts, counts)
+            all_counts = all_counts.view(W, 2).cpu()
+            # what the left neighbour sends me is its side-1 list; the right neighbour's is its side-0 list
+            incoming = {0: int(all_counts[rank - 1, 1]) if rank > 0 else 0, 1: int(all_counts[rank + 1, 0]) if rank + 1 < W else 0}
+            ops = []
+            for side, peer in peers.items():
+                if not (0 <= peer < W):
+                    continue
+                if out[side][1] > 0:
+                    ops.append(dist.P2POp(dist.isend, out[side][0][: out[side][1] * REC_BYTES], peer))
+                if incoming[side] > 0:
+                    ops.append(dist.P2POp(dist.irecv, b.recv_buffer(side)[: incoming[side] * REC_BYTES], peer))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            for side in (0, 1):
+                b.unpack(side, b.recv_buffer(side), incoming[side])
+            self.last_halo = (incoming[0], incoming[1])
+            return b.detect()

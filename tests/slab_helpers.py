@@ -1,0 +1,98 @@
+"""Shared helpers for the slab (multi-GPU) tests: scenes numbered slab-major and an oracle-backed backend that lets the
+host logic of scisim_b200/slab.py run on CPU under gloo."""
+import numpy as np
+
+from scisim_b200 import scenes
+from scisim_b200.slab import REC_BYTES
+
+
+def slab_major_scene(n, seed, vmax=6.0, nplanes=2, ndrums=1):
+    """A messy ball2d scene whose bodies are numbered in ascending x, so contiguous index blocks are spatial slabs."""
+    s = scenes.ball2d_random(n, seed, nplanes=nplanes, ndrums=ndrums, vmax=vmax, box=max(2.0, np.sqrt(n) * 0.6))
+    order = np.argsort(s["q"].reshape(-1, 2)[:, 0], kind="stable")
+    s["q"] = s["q"].reshape(-1, 2)[order].ravel().copy()
+    s["v"] = s["v"].reshape(-1, 2)[order].ravel().copy()
+    s["r"] = s["r"][order].copy()
+    s["m"] = s["m"][order].copy()
+    return s
+
+
+def slab_of(scene, first, count):
+    s = dict(scene)
+    s["q"] = scene["q"][2 * first:2 * (first + count)].copy()
+    s["v"] = scene["v"][2 * first:2 * (first + count)].copy()
+    s["r"] = scene["r"][first:first + count].copy()
+    s["m"] = scene["m"][first:first + count].copy()
+    return s
+
+
+REC_DT = np.dtype([("q0", "<f8", 2), ("q1", "<f8", 2), ("r", "<f8"), ("gid", "<u4"), ("pad", "<u4")])
+assert REC_DT.itemsize == REC_BYTES
+
+
+class OracleSlabBackend:
+    """CPU stand-in for GpuSlabBackend (same interface), built on the oracle. TEST INFRASTRUCTURE ONLY."""
+
+    def __init__(self, scene_slab, gid_first, ghost_cap, kind_map=None):
+        import torch
+        from tests import oracle_binding as ob
+        self.torch, self.ob = torch, ob
+        self.s = scene_slab
+        self.gid_first = gid_first
+        self.n_owned = scene_slab["r"].shape[0]
+        self.cap = ghost_cap
+        self.o = ob.Ball2DOracle(scene_slab)
+        self.q0 = scene_slab["q"].copy()
+        self.v0 = scene_slab["v"].copy()
+        self.ghosts = {0: np.zeros(0, REC_DT), 1: np.zeros(0, REC_DT)}
+        self.recv = [torch.empty(ghost_cap * REC_BYTES, dtype=torch.uint8) for _ in range(2)]
+
+    def flow(self, kind, dt):
+        self.q1, self.v1 = self.o.flow(kind, self.q0, self.v0, dt)
+        a, b = self.q0.reshape(-1, 2), self.q1.reshape(-1, 2)
+        self.lo = np.minimum(b[:, 0], a[:, 0]) - self.s["r"]
+        self.hi = np.maximum(b[:, 0], a[:, 0]) + self.s["r"]
+        self.ghosts = {0: np.zeros(0, REC_DT), 1: np.zeros(0, REC_DT)}
+        return self.torch.tensor([self.lo.min(), self.hi.max()], dtype=self.torch.float64)
+
+    def pack(self, interval, side, count_only=False):
+        ilo, ihi = float(interval[0]), float(interval[1])
+        sel = ~(self.hi < ilo) & ~(ihi < self.lo)
+        idx = np.nonzero(sel)[0]
+        rec = np.zeros(idx.shape[0], REC_DT)
+        rec["q0"] = self.q0.reshape(-1, 2)[idx]
+        rec["q1"] = self.q1.reshape(-1, 2)[idx]
+        rec["r"] = self.s["r"][idx]
+        rec["gid"] = self.gid_first + idx
+        return self.torch.from_numpy(rec.view(np.uint8).copy()), idx.shape[0]
+
+    def recv_buffer(self, side):
+        return self.recv[side]
+
+    def unpack(self, side, buf, count):
+        self.ghosts[side] = buf[: count * REC_BYTES].numpy().view(REC_DT).copy() if count else np.zeros(0, REC_DT)
+
+    def detect(self):
+        L, R = self.ghosts[0], self.ghosts[1]
+        nL, M = L.shape[0], self.n_owned
+        loc = dict(self.s)
+        loc["q"] = np.concatenate([L["q0"].ravel(), self.q0, R["q0"].ravel()])
+        q1 = np.concatenate([L["q1"].ravel(), self.q1, R["q1"].ravel()])
+        loc["r"] = np.concatenate([L["r"], self.s["r"], R["r"]])
+        loc["m"] = np.ones(loc["r"].shape[0])
+        gid = np.concatenate([L["gid"], self.gid_first + np.arange(M, dtype=np.uint32), R["gid"]]).astype(np.uint32)
+        assert np.all(np.diff(gid.astype(np.int64)) > 0), "local bodies must be ordered by global index"
+        a = self.ob.Ball2DOracle(loc).active_set(loc["q"], q1, "allpairs")
+        owned = lambda i: (i >= nL) & (i < nL + M)
+        ck = owned(a["candidates"][:, 0])
+        keep = np.where(a["type"] == 0, owned(a["i"]), owned(a["i"]))
+        res = {"candidates": gid[a["candidates"][ck]].astype(np.uint32).reshape(-1, 2)}
+        for k in ("type", "n", "p", "depth"):
+            res[k] = a[k][keep]
+        res["i"] = gid[a["i"][keep]]
+        res["j"] = np.where(a["type"][keep] == 0, gid[np.minimum(a["j"][keep], gid.shape[0] - 1)], a["j"][keep]).astype(np.uint32)
+        self.result = res
+        return res["candidates"].shape[0], res["type"].shape[0]
+
+    def fetch(self):
+        return self.q1, self.v1, self.result
