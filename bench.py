@@ -20,6 +20,8 @@ scaling), one slab per rank.
 import argparse
 import json
 import os
+
+os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version at INFO/VERSION)
 import statistics
 import sys
 import time
@@ -85,7 +87,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def stop(self):
         if not self.ok:
@@ -157,6 +159,10 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: anything a library prints meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -182,16 +188,17 @@ def main():
     else:
         # one slab per GPU, ghosts exchanged with the neighbouring slabs over NCCL every step (scisim_b200/slab.py)
         from scisim_b200.slab import Ball2DSlabs, GpuSlabBackend
-        backend = GpuSlabBackend(ctx, scene, rank * n, ghost_cap=max(4096, n // 64))
+        backend = GpuSlabBackend(ctx, scene, rank * n, ghost_cap=max(4096, n // 128))
         slabs = Ball2DSlabs(backend, rank, world, dist)
         step = lambda: slabs.step(umap.kind, dt)
 
     # ---------------- resident path: `value` ----------------
+    barrier()                   # also warms the barrier's own collective up before anything is timed
     for _ in range(args.warmup):
         ctx.flush_l2()
         pc, pa = step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # NVML init happens here, before the ranks line up
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count()
     step_ms = []
     for _ in range(args.steps):
@@ -276,6 +283,7 @@ def main():
                        "l2": "384 MB buffer overwritten before every timed step (L2 flush)", "timing": "CUDA events on the library stream, per step, summed; max over ranks",
                        "parallelism": ("%d x-slabs, 1 process per GPU, ghost bodies exchanged with +-1 neighbours over NCCL each step, pair owned by the rank of its lower index" % world) if world > 1 else "single GPU"},
             "steps_per_s": args.steps / t_max,
+            "step_ms_rank0": [round(x, 4) for x in step_ms],
             "clocks": clocks,
             "gpu_launches": gpu_launches,
             "e2e": {"value": pairs_all * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / e2e_steps,
@@ -289,7 +297,10 @@ def main():
             v = pairs_cpu * len(times) / sum(times)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "3 full steps of the same 1M-ball scene (oracle/: literal std::map/std::set grid + CCD + planes; reference hot path is single-threaded)"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

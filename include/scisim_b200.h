@@ -160,16 +160,18 @@ int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg
  *   (sg_ball2d_upload / sg_ball2d_fetch then address the owned block only)
  *   flow    integrate the owned bodies; *interval_dev (DEVICE pointer, 2 doubles) receives [min lo.x, max hi.x] of their
  *           swept AABBs -- what the other ranks need to select the ghosts they owe this one
- *   pack    ordered list (48-byte records) of the owned bodies whose swept AABB overlaps the x-interval at interval_dev
- *           (DEVICE) into send_dev (DEVICE, cap records); the count goes to *count_dev (DEVICE).  cap = 0: count only
- *   unpack  append `count` received records as ghosts on side 0 (lower global indices) or 1 (higher)
+ *   pack    ordered list of the owned bodies whose swept AABB overlaps the x-interval at interval_dev (DEVICE) into
+ *           send_dev (DEVICE, cap + 1 records of 48 bytes; record 0 is a header carrying the count, so the receiver learns
+ *           it on the device); the count also goes to *count_dev (DEVICE).  send_dev = NULL: count only
+ *   unpack  take a received buffer (same layout) as this step's ghosts on side 0 (lower global indices) or 1 (higher)
  *   detect  broad + narrow phase over owned + ghosts; a pair is kept iff this rank owns the body with the smaller
- *           global index; planes / drums are tested for owned bodies only; indices in the lists are global */
+ *           global index; planes / drums are tested for owned bodies only; indices in the lists are global.
+ *           ghosts_out (optional, 2 values): how many ghosts arrived on each side.  Nothing before detect blocks the host. */
 int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint32_t ghost_cap, const double* r, const double* m );
 int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_dev );
 int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev, uint32_t cap, uint32_t* count_dev );
-int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev, uint32_t count );
-int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out );
+int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev );
+int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out );
 
 /* ---- rigidbody3d --------------------------------------------------------------------------------------
  * Layouts are RigidBody3DState's (rigidbody3d/RigidBody3DState.cpp:70-240): q = [3N centres | 9N row-major R],

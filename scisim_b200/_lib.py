@@ -74,8 +74,8 @@ def load():
         "sg_ball2d_slab_init": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
         "sg_ball2d_slab_flow": (C.c_int, [vp, C.c_int, C.c_double, vp]),
         "sg_ball2d_slab_pack": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
-        "sg_ball2d_slab_unpack": (C.c_int, [vp, C.c_int, vp, C.c_uint32]),
-        "sg_ball2d_slab_detect": (C.c_int, [vp, C.POINTER(SgContacts)]),
+        "sg_ball2d_slab_unpack": (C.c_int, [vp, C.c_int, vp]),
+        "sg_ball2d_slab_detect": (C.c_int, [vp, C.POINTER(SgContacts), vp]),
         "sg_rb3d_set_geometry": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),
         "sg_rb3d_add_mesh": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, vp, C.POINTER(C.c_uint32)]),
         "sg_rb3d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),

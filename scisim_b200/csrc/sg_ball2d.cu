@@ -22,7 +22,16 @@ struct Ball2DIn
   uint32_t n;
   uint32_t own_first; // bodies [own_first, own_first + own_count) belong to this rank, the rest are halo ghosts
   uint32_t own_count;
+  // slab mode: slots [0, ghost_counts[0]) and [own_first + own_count, ... + ghost_counts[1]) hold ghosts, the other
+  // non-owned slots are unused this step.  nullptr on one GPU (every slot is a body).
+  const uint32_t* ghost_counts;
 };
+
+__device__ __forceinline__ bool ball2d_slot_valid( const Ball2DIn& in, const uint32_t i )
+{
+  if( in.ghost_counts == nullptr || i - in.own_first < in.own_count ) { return true; }
+  return ( i < in.own_first ) ? ( i < __ldg( &in.ghost_counts[0] ) ) : ( i - ( in.own_first + in.own_count ) < __ldg( &in.ghost_counts[1] ) );
+}
 
 #define SG_GHOST_BIT 0x80000000u
 
@@ -111,6 +120,7 @@ struct Ball2DPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
   __device__ static bool owns( const Rec& s ) { return ( s.idx & SG_GHOST_BIT ) == 0u; }
+  __device__ static bool valid( const In& in, const uint32_t i ) { return ball2d_slot_valid( in, i ); }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
@@ -213,7 +223,7 @@ template<bool DO_FLOW>
 __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ Static2D sg, const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0,
                                                        const double* __restrict__ m, const double* __restrict__ r, const double gx, const double gy, const double dt,
                                                        double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts,
-                                                       const uint32_t own_first, const uint32_t own_count )
+                                                       const uint32_t own_first, const uint32_t own_count, const uint32_t* __restrict__ ghost_counts )
 {
   __shared__ uint32_t s_cnt[SG_MAX_DRUMS + SG_MAX_PLANES];
   const uint32_t ng = sg.ndrums + sg.nplanes;
@@ -224,7 +234,12 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
   double mx[2] = { __longlong_as_double( 0xfff0000000000000LL ), __longlong_as_double( 0xfff0000000000000LL ) };
   double ext = 0.0;
   unsigned long long mask = 0ull;
-  if( i < n )
+  bool live = i < n;
+  if( live && ghost_counts != nullptr && i - own_first >= own_count )
+  {
+    live = ( i < own_first ) ? ( i < __ldg( &ghost_counts[0] ) ) : ( i - ( own_first + own_count ) < __ldg( &ghost_counts[1] ) );
+  }
+  if( live )
   {
     const double2 q = __ldg( &q0[i] );
     double2 qo;
@@ -365,16 +380,18 @@ struct Ball2DData
   bool have_result = false;
   bool cand_valid = false;
   // slab mode (one slab of a larger scene per GPU): the body arrays hold [left ghosts | owned | right ghosts] with
-  // ghost_cap slots reserved on either side of the owned block; left ghosts are packed against the owned block so
-  // the active range is contiguous and ordered by global body index.
+  // ghost_cap slots reserved on either side of the owned block (slot order == global index order); how many of
+  // them are in use this step is only known on the device (ghost_counts), unused slots are skipped by every kernel.
   bool slab = false;
-  uint32_t n_owned = 0, ghost_cap = 0, nL = 0, nR = 0, gid_first = 0;
+  uint32_t n_owned = 0, ghost_cap = 0, gid_first = 0;
   DevBuf gid;          // u32 per slot: global body index
   DevBuf interval_enc; // 2 x long long (ordered encoding of min lo.x / max hi.x over the owned swept boxes)
   DevBuf pack_counts, pack_offsets, pack_partials;
-  size_t first_slot() const { return slab ? size_t( ghost_cap - nL ) : 0; }   // first active slot
+  size_t first_slot() const { return 0; }
   size_t owned_slot() const { return slab ? size_t( ghost_cap ) : 0; }        // first owned slot
-  uint32_t own_first() const { return slab ? nL : 0u; }                        // owned range in local indices
+  uint32_t own_first() const { return slab ? ghost_cap : 0u; }                 // owned range in local indices
+  DevBuf ghost_counts; // u32[4]: ghosts on side 0, side 1, overflow flag, spare
+  const uint32_t* GHOSTS() const { return slab ? ghost_counts.as<uint32_t>() : nullptr; }
   uint32_t own_count() const { return slab ? n_owned : n; }
   double2* Q0() const { return q0.as<double2>() + first_slot(); }
   double2* Q1() const { return q1.as<double2>() + first_slot(); }
@@ -392,7 +409,7 @@ void sg_ball2d_release( sg_ctx* ctx )
   d->st_counts.release(); d->st_offsets.release(); d->st_partials.release(); d->st_total.release();
   d->c_type.release(); d->c_i.release(); d->c_j.release(); d->c_n.release(); d->c_p.release(); d->c_depth.release();
   d->h_totals.release(); d->h_out.release();
-  d->gid.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release();
+  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release();
   delete d;
   ctx->ball2d = nullptr;
 }
@@ -459,15 +476,15 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   if( flow_kind >= 0 && !d->slab )
   {
     SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(),
-               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n ) );
+               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr ) );
   }
   else
   {
     SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr,
-               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count() ) );
+               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS() ) );
   }
   Ball2DIn in;
-  in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count();
+  in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS();
   d->bp.gid_map = d->GID();
   rc = sg_bp_bin_and_count<Ball2DPolicy>( ctx, d->bp, in, true );
   if( rc != SG_OK ) { return rc; }
@@ -566,6 +583,8 @@ static int ball2d_copy_out( sg_ctx* ctx, Ball2DData* d, const uint32_t flags, sg
 
 
 // ---- slab mode: halo selection, packing and unpacking ----------------------------------------------
+// Exchange buffers hold ghost_cap + 1 records of 48 bytes; record 0 is a header whose gid field is the count, so the
+// receiver learns it on the device and the host never waits for it.
 struct alignas( 16 ) GhostRec { double q0x, q0y, q1x, q1y, r; uint32_t gid; uint32_t pad; };
 
 __device__ __forceinline__ void swept_x( const double2 a, const double2 b, const double r, double& lo, double& hi )
@@ -574,31 +593,68 @@ __device__ __forceinline__ void swept_x( const double2 a, const double2 b, const
   hi = fmax( b.x, a.x ) + r;
 }
 
-// [min lo.x, max hi.x] over the owned swept boxes, ordered-int encoded
-__global__ void __launch_bounds__( 256 ) k_ball2d_interval( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, long long* __restrict__ enc )
+// Flow of the owned bodies + [min lo.x, max hi.x] of their swept boxes (ordered-int encoded atomics)
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_flow( const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0, const double* __restrict__ m, const double* __restrict__ r,
+                                                            const double gx, const double gy, const double dt, double2* __restrict__ q1, double2* __restrict__ v1, long long* __restrict__ enc )
 {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   double mn = __longlong_as_double( 0x7ff0000000000000LL ), mx = __longlong_as_double( 0xfff0000000000000LL );
-  for( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+  if( i < n )
   {
-    double lo, hi;
-    swept_x( __ldg( &q0[i] ), __ldg( &q1[i] ), __ldg( &r[i] ), lo, hi );
-    mn = fmin( mn, lo ); mx = fmax( mx, hi );
+    const double2 q = __ldg( &q0[i] );
+    const double2 v = __ldg( &v0[i] );
+    const double mass = __ldg( &m[i] );
+    const double minv = 1.0 / mass;
+    const double Fx = 0.0 + mass * gx;
+    const double Fy = 0.0 + mass * gy;
+    double2 qo, vo;
+    if( kind == SG_MAP_SYMPLECTIC_EULER )
+    {
+      const double s = dt * minv;
+      vo.x = v.x + ( 0.0 + s * Fx );
+      vo.y = v.y + ( 0.0 + s * Fy );
+      qo.x = q.x + dt * vo.x;
+      qo.y = q.y + dt * vo.y;
+    }
+    else
+    {
+      const double s = ( 0.5 * dt ) * minv;
+      const double vhx = v.x + ( 0.0 + s * Fx );
+      const double vhy = v.y + ( 0.0 + s * Fy );
+      qo.x = q.x + dt * vhx;
+      qo.y = q.y + dt * vhy;
+      vo.x = vhx + s * Fx;
+      vo.y = vhy + s * Fy;
+    }
+    q1[i] = qo;
+    v1[i] = vo;
+    swept_x( q, qo, __ldg( &r[i] ), mn, mx );
   }
   #pragma unroll
   for( int d = 16; d > 0; d >>= 1 ) { mn = fmin( mn, __shfl_xor_sync( 0xffffffffu, mn, d ) ); mx = fmax( mx, __shfl_xor_sync( 0xffffffffu, mx, d ) ); }
-  if( ( threadIdx.x & 31 ) == 0 ) { atomicMin( &enc[0], sg_ordered_from_double( mn ) ); atomicMax( &enc[1], sg_ordered_from_double( mx ) ); }
+  __shared__ double s_mn[8], s_mx[8];
+  if( ( threadIdx.x & 31 ) == 0 ) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if( threadIdx.x == 0 )
+  {
+    for( int w = 1; w < 8; ++w ) { mn = fmin( mn, s_mn[w] ); mx = fmax( mx, s_mx[w] ); }
+    atomicMin( &enc[0], sg_ordered_from_double( mn ) );
+    atomicMax( &enc[1], sg_ordered_from_double( mx ) );
+  }
 }
-__global__ void k_ball2d_interval_init( long long* enc )
+__global__ void k_ball2d_slab_begin( long long* enc, uint32_t* ghost_counts )
 {
   enc[0] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );
   enc[1] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );
+  ghost_counts[0] = 0u; ghost_counts[1] = 0u;
 }
 __global__ void k_ball2d_interval_decode( const long long* enc, double* out ) { out[0] = sg_double_from_ordered( enc[0] ); out[1] = sg_double_from_ordered( enc[1] ); }
 
 // Owned bodies whose swept box overlaps [iv[0], iv[1]] on x (closed, like AABB::overlaps), in body order.
 template<bool EMIT>
 __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, const uint32_t* __restrict__ gid,
-                                                            const double* __restrict__ iv, uint32_t* __restrict__ block_counts, const uint32_t* __restrict__ block_offsets, GhostRec* __restrict__ out, const uint32_t cap )
+                                                            const double* __restrict__ iv, uint32_t* __restrict__ block_counts, const uint32_t* __restrict__ block_offsets, const uint32_t* __restrict__ total,
+                                                            GhostRec* __restrict__ out, const uint32_t cap )
 {
   __shared__ uint32_t s_warp[8];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -617,9 +673,15 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
   __syncthreads();
-  uint32_t before = 0u, total = 0u;
-  for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } total += c; }
-  if( !EMIT ) { if( threadIdx.x == 0 ) { block_counts[blockIdx.x] = total; } return; }
+  uint32_t before = 0u, tot = 0u;
+  for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } tot += c; }
+  if( !EMIT ) { if( threadIdx.x == 0 ) { block_counts[blockIdx.x] = tot; } return; }
+  if( blockIdx.x == 0 && threadIdx.x == 0 )
+  {
+    GhostRec h;
+    h.q0x = 0.0; h.q0y = 0.0; h.q1x = 0.0; h.q1y = 0.0; h.r = 0.0; h.gid = *total; h.pad = 0u;
+    out[0] = h;
+  }
   if( sel )
   {
     const uint32_t k = block_offsets[blockIdx.x] + before + __popc( bal & ( ( 1u << lane ) - 1u ) );
@@ -627,16 +689,24 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, c
     {
       GhostRec g;
       g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
-      out[k] = g;
+      out[1u + k] = g;
     }
   }
 }
 
-__global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t count, const GhostRec* __restrict__ in, double2* __restrict__ q0, double2* __restrict__ q1, double* __restrict__ r, uint32_t* __restrict__ gid )
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t cap, const int side, const GhostRec* __restrict__ in, double2* __restrict__ q0, double2* __restrict__ q1, double* __restrict__ r,
+                                                              uint32_t* __restrict__ gid, uint32_t* __restrict__ ghost_counts )
 {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sent = in[0].gid;
+  const uint32_t count = sent < cap ? sent : cap;
+  if( k == 0u )
+  {
+    ghost_counts[side] = count;
+    if( sent > cap ) { ghost_counts[2] = 1u; } // more ghosts than reserved slots: reported by detect
+  }
   if( k >= count ) { return; }
-  const GhostRec g = in[k];
+  const GhostRec g = in[1u + k];
   q0[k] = make_double2( g.q0x, g.q0y );
   q1[k] = make_double2( g.q1x, g.q1y );
   r[k] = g.r;
@@ -793,9 +863,10 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   if( uint64_t( n_owned ) + 2ull * ghost_cap >= 0x80000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_init: slab too large" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   Ball2DData* d = ball2d_data( ctx );
-  d->slab = true; d->n_owned = n_owned; d->ghost_cap = ghost_cap; d->gid_first = gid_first; d->nL = 0; d->nR = 0; d->n = n_owned;
-  d->have_result = false;
+  d->slab = true; d->n_owned = n_owned; d->ghost_cap = ghost_cap; d->gid_first = gid_first;
   const size_t slots = size_t( n_owned ) + 2 * size_t( ghost_cap );
+  d->n = uint32_t( slots );
+  d->have_result = false;
   SG_CUDA( ctx, d->r.ensure( slots * 8 + 8 ) );
   SG_CUDA( ctx, d->q0.ensure( slots * 16 + 16 ) );
   SG_CUDA( ctx, d->q1.ensure( slots * 16 + 16 ) );
@@ -804,6 +875,8 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   SG_CUDA( ctx, d->v0.ensure( size_t( n_owned ) * 16 + 16 ) );
   SG_CUDA( ctx, d->v1.ensure( size_t( n_owned ) * 16 + 16 ) );
   SG_CUDA( ctx, d->interval_enc.ensure( 16 ) );
+  SG_CUDA( ctx, d->ghost_counts.ensure( 16 ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->ghost_counts.ptr, 0, 16, ctx->stream ) );
   if( n_owned > 0 )
   {
     SG_CUDA( ctx, cudaMemcpyAsync( d->r.as<double>() + ghost_cap, r, size_t( n_owned ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
@@ -816,23 +889,18 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
 
 int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_dev )
 {
-  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( ctx == nullptr || interval_dev == nullptr ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: call sg_ball2d_slab_init first" ); }
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: map kind %d is not a ball2d map", map_kind ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  d->nL = 0; d->nR = 0; d->n = d->n_owned;
-  const int rc = ball2d_flow_device( ctx, d, map_kind, dt );
-  if( rc != SG_OK ) { return rc; }
-  if( interval_dev != nullptr )
-  {
-    const size_t o = d->owned_slot();
-    const unsigned nred = sg_div_up( d->n_owned > 0 ? d->n_owned : 1, 256 ) < unsigned( ctx->num_sms * 8 ) ? sg_div_up( d->n_owned > 0 ? d->n_owned : 1, 256 ) : unsigned( ctx->num_sms * 8 );
-    SG_LAUNCH( ctx, "slab_interval", double( d->n_owned ) * 40.0, k_ball2d_interval_init<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>() );
-               k_ball2d_interval<<<nred, 256, 0, ctx->stream>>>( d->n_owned, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->interval_enc.as<long long>() );
-               k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev ) );
-    ctx->launch_count += 2;
-  }
+  const size_t o = d->owned_slot();
+  const uint32_t n = d->n_owned;
+  SG_LAUNCH( ctx, "slab_flow_interval", double( n ) * 80.0, k_ball2d_slab_begin<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>() );
+             k_ball2d_slab_flow<<<sg_div_up( n > 0 ? n : 1, 256 ), 256, 0, ctx->stream>>>( map_kind, n, d->q0.as<double2>() + o, d->v0.as<double2>(), d->m.as<double>(), d->r.as<double>() + o,
+                                                                                      d->g[0], d->g[1], dt, d->q1.as<double2>() + o, d->v1.as<double2>(), d->interval_enc.as<long long>() );
+             k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev ) );
+  ctx->launch_count += 2;
   return SG_OK;
 }
 
@@ -849,38 +917,32 @@ int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev
   SG_CUDA( ctx, d->pack_partials.ensure( ( size_t( nblk ) / SG_SCAN_TILE + 2 ) * 4 ) );
   const size_t o = d->owned_slot();
   SG_LAUNCH( ctx, "slab_pack_count", double( n ) * 40.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
-             interval_dev, d->pack_counts.as<uint32_t>(), nullptr, nullptr, 0u ) );
+             interval_dev, d->pack_counts.as<uint32_t>(), nullptr, nullptr, nullptr, 0u ) );
   const int rc = sg_exclusive_scan<ScanU32>( ctx, "slab_pack_scan", d->pack_counts.as<uint32_t>(), nullptr, nblk, nblk, d->pack_partials.as<uint32_t>(), d->pack_offsets.as<uint32_t>(), count_dev, false );
   if( rc != SG_OK ) { return rc; }
-  if( send_dev != nullptr && cap > 0 )
+  if( send_dev != nullptr )
   {
     SG_LAUNCH( ctx, "slab_pack_emit", double( n ) * 40.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
-               interval_dev, nullptr, d->pack_offsets.as<uint32_t>(), static_cast<GhostRec*>( send_dev ), cap ) );
+               interval_dev, nullptr, d->pack_offsets.as<uint32_t>(), count_dev, static_cast<GhostRec*>( send_dev ), cap ) );
   }
   return SG_OK;
 }
 
-int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev, uint32_t count )
+int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev )
 {
-  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( ctx == nullptr || recv_dev == nullptr || ( side != 0 && side != 1 ) ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: call sg_ball2d_slab_init first" ); }
-  if( count > d->ghost_cap ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: %u ghosts exceed the reserved capacity %u", count, d->ghost_cap ); }
-  if( count > 0 && recv_dev == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: null buffer" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  // side 0: ghosts with smaller global indices, packed right up against the owned block; side 1: after it
-  const size_t slot = ( side == 0 ) ? size_t( d->ghost_cap - count ) : size_t( d->ghost_cap ) + d->n_owned;
-  if( side == 0 ) { d->nL = count; } else { d->nR = count; }
-  d->n = d->nL + d->n_owned + d->nR;
-  if( count > 0 )
-  {
-    SG_LAUNCH( ctx, "slab_unpack", double( count ) * 92.0, k_ball2d_slab_unpack<<<sg_div_up( count, 256 ), 256, 0, ctx->stream>>>( count, static_cast<const GhostRec*>( recv_dev ), d->q0.as<double2>() + slot,
-               d->q1.as<double2>() + slot, d->r.as<double>() + slot, d->gid.as<uint32_t>() + slot ) );
-  }
+  // side 0: ghosts with smaller global indices fill slots [0, count); side 1: the slots right after the owned block
+  const size_t slot = ( side == 0 ) ? 0 : size_t( d->ghost_cap ) + d->n_owned;
+  const uint32_t cap = d->ghost_cap;
+  SG_LAUNCH( ctx, "slab_unpack", double( cap ) * 4.0, k_ball2d_slab_unpack<<<sg_div_up( cap > 0 ? cap : 1, 256 ), 256, 0, ctx->stream>>>( cap, side, static_cast<const GhostRec*>( recv_dev ), d->q0.as<double2>() + slot,
+             d->q1.as<double2>() + slot, d->r.as<double>() + slot, d->gid.as<uint32_t>() + slot, d->ghost_counts.as<uint32_t>() ) );
   return SG_OK;
 }
 
-int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out )
+int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
@@ -888,6 +950,11 @@ int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out )
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   const int rc = ball2d_active_set_device( ctx, d, true );
   if( rc != SG_OK ) { return rc; }
+  uint32_t* hg = reinterpret_cast<uint32_t*>( d->h_totals.as<unsigned long long>() + 4 );
+  SG_CUDA( ctx, cudaMemcpyAsync( hg, d->ghost_counts.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  if( hg[2] != 0u ) { return sg_fail( ctx, SG_ERR_INVALID, "slab halo exceeds the reserved ghost capacity %u: results are incomplete", d->ghost_cap ); }
+  if( ghosts_out != nullptr ) { ghosts_out[0] = hg[0]; ghosts_out[1] = hg[1]; }
   if( out != nullptr )
   {
     memset( out, 0, sizeof( *out ) );

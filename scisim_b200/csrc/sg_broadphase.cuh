@@ -174,6 +174,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_bounds( const typename 
   for( int k = 0; k < D; ++k ) { mn[k] = __longlong_as_double( 0x7ff0000000000000LL ); mx[k] = __longlong_as_double( 0xfff0000000000000LL ); }
   for( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += gridDim.x * blockDim.x )
   {
+    if( !P::valid( in, i ) ) { continue; }
     double lo[D], hi[D];
     P::load_aabb( in, i, lo, hi );
     sg_bp_bounds_update<D>( lo, hi, mn, mx, ext );
@@ -260,12 +261,19 @@ __device__ inline uint32_t sg_key_of( const GridParams& g, const uint32_t* c )
 // ---- histogram / scatter ("single-digit radix sort" keyed by cell) ---------------------------------
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P::In in, const GridParams* __restrict__ params, uint32_t* __restrict__ cell_count,
-                                                              uint32_t* __restrict__ key_out, uint32_t* __restrict__ rank_out )
+                                                              uint32_t* __restrict__ key_out, uint32_t* __restrict__ rank_out, uint2* __restrict__ counts )
 {
   constexpr int D = P::D;
   const GridParams g = *params;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if( i >= in.n ) { return; }
+  if( !P::valid( in, i ) )
+  {
+    // an unused slot (multi-GPU ghost capacity): never enters the grid, owns no pairs
+    key_out[i] = 0xffffffffu;
+    counts[i] = make_uint2( 0u, 0u );
+    return;
+  }
   double lo[D], hi[D];
   P::load_aabb( in, i, lo, hi );
   uint32_t c[D];
@@ -283,6 +291,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if( i >= in.n ) { return; }
   const uint32_t key = key_in[i];
+  if( key == 0xffffffffu ) { return; }
   const uint32_t pos = __ldg( &cell_start[key] ) + rank_in[i];
   // cell coordinates travel with the record (no integer division in the pair kernels)
   const uint32_t yz = key / g_dims0;
@@ -423,7 +432,7 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
 // Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active (bit 31: masks invalid) }
 //          masks[sorted position] = { bit k: k-th visited neighbour is such a candidate, bit k: ... and active }
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                                const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint2* __restrict__ masks )
 {
   constexpr int D = P::D;
@@ -433,6 +442,8 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
   unsigned char* s_recs = s_raw;
   BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
   const GridParams g = *params;
+  const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned (unused slots are not)
+  if( blockIdx.x * Cfg::T >= n ) { return; }
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
   Rec me;
   if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the windows are staged
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
 
 // Pass 2.  Each body writes its candidates (ascending partner index) at its offset; active ones also write a contact.
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint2* __restrict__ counts, const uint2* __restrict__ masks,
                                                               const ulonglong2* __restrict__ offsets, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, const typename P::Out out )
 {
@@ -481,6 +492,8 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
   unsigned char* s_recs = s_raw;
   BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
   const GridParams g = *params;
+  const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) );
+  if( blockIdx.x * Cfg::T >= n ) { return; }
   unsigned long long* s_list = reinterpret_cast<unsigned long long*>( s_raw + sg_bp_smem_bytes<D>() ); // [SG_BP_FAST_CAP][T]
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
   // everything this thread needs that does not depend on the staged windows is requested first
@@ -650,7 +663,7 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   BoundsAccum* acc_cur = s.bounds_cur();
   s.bounds_phase ^= 1;
   SG_LAUNCH( ctx, "bp_setup", nb * 4.0, sg_bp_setup<D><<<unsigned( ctx->num_sms * 4 ), SG_BP_THREADS, 0, ctx->stream>>>( acc_cur, s.bounds_cur(), s.max_cells, s.params.as<GridParams>(), s.cell_count.as<uint32_t>() ) );
-  SG_LAUNCH( ctx, "bp_hist", nb * ( P::IN_BYTES + 8.0 ), sg_bp_hist<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_count.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>() ) );
+  SG_LAUNCH( ctx, "bp_hist", nb * ( P::IN_BYTES + 8.0 ), sg_bp_hist<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_count.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.counts.as<uint2>() ) );
   const uint32_t* ncells_dev = &s.params.as<GridParams>()->ncells;
   int rc = sg_exclusive_scan<ScanU32>( ctx, "bp_cell_scan", s.cell_count.as<uint32_t>(), ncells_dev, 0u, s.max_cells, s.cell_partials.as<uint32_t>(), s.cell_start.as<uint32_t>(), nullptr, true );
   if( rc != SG_OK ) { return rc; }

@@ -143,6 +143,7 @@ struct Sphere3DPolicy
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
+  __device__ static bool valid( const In&, const uint32_t ) { return true; }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& g ) { return ( s.key / g.dims[0] ) % g.dims[1]; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& g ) { return s.key / ( g.dims[0] * g.dims[1] ); }
   __device__ static bool narrow_test( const Rec& a, const Rec& b )
@@ -196,6 +197,7 @@ struct Box3DPolicy
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
+  __device__ static bool valid( const In&, const uint32_t ) { return true; }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
   __device__ static bool narrow_test( const Rec&, const Rec& ) { return false; }

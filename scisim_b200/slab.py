@@ -52,7 +52,8 @@ def merge_active_sets(parts, n_static_geoms):
 
 class GpuSlabBackend:
     """One slab on one GPU through the sg_ball2d_slab_* calls; exchange buffers are torch CUDA tensors and every
-    torch op is issued on the library's stream, so no host synchronisation is needed except to read counts."""
+    torch op is issued on the library's stream.  Buffers always travel at full size (ghost_cap + 1 records, the first
+    one a header with the count), so nothing on the host waits for a count before detect()."""
 
     def __init__(self, ctx, scene_slab, gid_first, ghost_cap):
         import torch
@@ -76,37 +77,43 @@ class GpuSlabBackend:
         ctx.check(self.lib.sg_ball2d_set_drums(ctx.h, dx.shape[0], vp(dx), vp(dr)))
         q, v = np.ascontiguousarray(s["q"], dtype=np.float64), np.ascontiguousarray(s["v"], dtype=np.float64)
         ctx.check(self.lib.sg_ball2d_upload(ctx.h, vp(q), vp(v)))
+        nbytes = (self.cap + 1) * REC_BYTES
         with torch.cuda.stream(self.stream):
             self.iv = torch.zeros(2, dtype=torch.float64, device=self.device)
             self.count = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self.send = [torch.empty(self.cap * REC_BYTES, dtype=torch.uint8, device=self.device) for _ in range(2)]
-            self.recv = [torch.empty(self.cap * REC_BYTES, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self.send = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self.recv = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.ghosts = (0, 0)
 
     def flow(self, kind, dt):
         self.ctx.check(self.lib.sg_ball2d_slab_flow(self.ctx.h, int(kind), float(dt), C.c_void_p(self.iv.data_ptr())))
         return self.iv
 
-    def pack(self, interval, side, count_only=False):
-        """Selects the owned bodies overlapping `interval` (a 2-element tensor on this device). Returns (buffer, count)."""
+    def pack(self, interval, side):
+        """Selects, in body order, the owned bodies overlapping `interval` (2-element tensor on this device) into the
+        side's send buffer (header + records). Asynchronous."""
         buf = self.send[side]
-        self.ctx.check(self.lib.sg_ball2d_slab_pack(self.ctx.h, C.c_void_p(interval.data_ptr()), None if count_only else C.c_void_p(buf.data_ptr()),
-                                                    0 if count_only else self.cap, C.c_void_p(self.count.data_ptr())))
+        self.ctx.check(self.lib.sg_ball2d_slab_pack(self.ctx.h, C.c_void_p(interval.data_ptr()), C.c_void_p(buf.data_ptr()), self.cap, C.c_void_p(self.count.data_ptr())))
+        return buf
+
+    def count_overlapping(self, interval):
+        """How many owned bodies reach `interval` (host-synchronous; used for the non-neighbour check only)."""
+        self.ctx.check(self.lib.sg_ball2d_slab_pack(self.ctx.h, C.c_void_p(interval.data_ptr()), None, 0, C.c_void_p(self.count.data_ptr())))
         with self.torch.cuda.stream(self.stream):
-            cnt = int(self.count.item())
-        if not count_only and cnt > self.cap:
-            raise RuntimeError("slab halo of %d bodies exceeds the reserved ghost capacity %d" % (cnt, self.cap))
-        return buf, cnt
+            return int(self.count.item())
 
     def recv_buffer(self, side):
         return self.recv[side]
 
-    def unpack(self, side, buf, count):
-        self.ctx.check(self.lib.sg_ball2d_slab_unpack(self.ctx.h, int(side), C.c_void_p(buf.data_ptr()), int(count)))
+    def unpack(self, side, buf):
+        self.ctx.check(self.lib.sg_ball2d_slab_unpack(self.ctx.h, int(side), C.c_void_p(buf.data_ptr())))
 
     def detect(self):
         from ._lib import SgContacts
         c = SgContacts()
-        self.ctx.check(self.lib.sg_ball2d_slab_detect(self.ctx.h, C.byref(c)))
+        g = (C.c_uint32 * 2)()
+        self.ctx.check(self.lib.sg_ball2d_slab_detect(self.ctx.h, C.byref(c), g))
+        self.ghosts = (int(g[0]), int(g[1]))
         return int(c.n_candidates), int(c.n_active)
 
     def fetch(self):
@@ -124,9 +131,10 @@ class GpuSlabBackend:
 
 
 class Ball2DSlabs:
-    """Per-rank driver of one step: flow -> interval all_gather -> halo exchange -> detection."""
+    """Per-rank driver of one step: flow -> interval all_gather -> halo exchange -> detection.  With the GPU backend
+    nothing blocks the host until detect() reads the list sizes."""
 
-    def __init__(self, backend, rank, world, dist, check_non_neighbours=True):
+    def __init__(self, backend, rank, world, dist, check_non_neighbours=False):
         self.b, self.rank, self.world, self.dist = backend, rank, world, dist
         self.check = check_non_neighbours
         self.last_halo = (0, 0)
@@ -138,39 +146,27 @@ class Ball2DSlabs:
         cm = b.run_on_stream() if hasattr(b, "run_on_stream") else contextlib.nullcontext()
         with cm:
             iv = b.flow(kind, dt)
-            if W == 1:
-                return b.detect()
-            all_iv = torch.empty(W * 2, dtype=torch.float64, device=iv.device)
-            dist.all_gather_into_tensor(all_iv, iv)
-            all_iv = all_iv.view(W, 2)
-            peers = {0: rank - 1, 1: rank + 1}
-            out = {}
-            for side, peer in peers.items():
-                out[side] = b.pack(all_iv[peer], side) if 0 <= peer < W else (None, 0)
-            if self.check:
-                for peer in range(W):
-                    if abs(peer - rank) > 1:
-                        _, c = b.pack(all_iv[peer], 0, count_only=True)
-                        if c != 0:
-                            raise RuntimeError("rank %d: %d bodies reach the slab of non-neighbour rank %d; re-balance the slabs" % (rank, c, peer))
-            counts = torch.tensor([out[0][1], out[1][1]], dtype=torch.int64, device=iv.device)
-            all_counts = torch.empty(W * 2, dtype=torch.int64, device=iv.device)
-            dist.all_gather_into_tensor(all_counts, counts)
-            all_counts = all_counts.view(W, 2).cpu()
-            # what the left neighbour sends me is its side-1 list; the right neighbour's is its side-0 list
-            incoming = {0: int(all_counts[rank - 1, 1]) if rank > 0 else 0, 1: int(all_counts[rank + 1, 0]) if rank + 1 < W else 0}
-            ops = []
-            for side, peer in peers.items():
-                if not (0 <= peer < W):
-                    continue
-                if out[side][1] > 0:
-                    ops.append(dist.P2POp(dist.isend, out[side][0][: out[side][1] * REC_BYTES], peer))
-                if incoming[side] > 0:
-                    ops.append(dist.P2POp(dist.irecv, b.recv_buffer(side)[: incoming[side] * REC_BYTES], peer))
-            if ops:
+            if W > 1:
+                all_iv = torch.empty(W * 2, dtype=torch.float64, device=iv.device)
+                dist.all_gather_into_tensor(all_iv, iv)
+                all_iv = all_iv.view(W, 2)
+                peers = {0: rank - 1, 1: rank + 1}
+                ops = []
+                for side, peer in peers.items():
+                    if 0 <= peer < W:
+                        ops.append(dist.P2POp(dist.isend, b.pack(all_iv[peer], side), peer))
+                        ops.append(dist.P2POp(dist.irecv, b.recv_buffer(side), peer))
+                if self.check:
+                    for peer in range(W):
+                        if abs(peer - rank) > 1:
+                            c = b.count_overlapping(all_iv[peer])
+                            if c != 0:
+                                raise RuntimeError("rank %d: %d bodies reach the slab of non-neighbour rank %d; re-balance the slabs" % (rank, c, peer))
                 for req in dist.batch_isend_irecv(ops):
                     req.wait()
-            for side in (0, 1):
-                b.unpack(side, b.recv_buffer(side), incoming[side])
-            self.last_halo = (incoming[0], incoming[1])
-            return b.detect()
+                for side, peer in peers.items():
+                    if 0 <= peer < W:
+                        b.unpack(side, b.recv_buffer(side))
+            res = b.detect()
+            self.last_halo = getattr(b, "ghosts", (0, 0))
+            return res

@@ -31,9 +31,9 @@ assert REC_DT.itemsize == REC_BYTES
 
 
 class OracleSlabBackend:
-    """CPU stand-in for GpuSlabBackend (same interface), built on the oracle. TEST INFRASTRUCTURE ONLY."""
+    """CPU stand-in for GpuSlabBackend (same interface and buffer layout), built on the oracle. TEST INFRASTRUCTURE ONLY."""
 
-    def __init__(self, scene_slab, gid_first, ghost_cap, kind_map=None):
+    def __init__(self, scene_slab, gid_first, ghost_cap):
         import torch
         from tests import oracle_binding as ob
         self.torch, self.ob = torch, ob
@@ -44,36 +44,47 @@ class OracleSlabBackend:
         self.o = ob.Ball2DOracle(scene_slab)
         self.q0 = scene_slab["q"].copy()
         self.v0 = scene_slab["v"].copy()
-        self.ghosts = {0: np.zeros(0, REC_DT), 1: np.zeros(0, REC_DT)}
-        self.recv = [torch.empty(ghost_cap * REC_BYTES, dtype=torch.uint8) for _ in range(2)]
+        self.ghost_recs = {0: np.zeros(0, REC_DT), 1: np.zeros(0, REC_DT)}
+        self.recv = [torch.zeros((ghost_cap + 1) * REC_BYTES, dtype=torch.uint8) for _ in range(2)]
+        self.ghosts = (0, 0)
 
     def flow(self, kind, dt):
         self.q1, self.v1 = self.o.flow(kind, self.q0, self.v0, dt)
         a, b = self.q0.reshape(-1, 2), self.q1.reshape(-1, 2)
         self.lo = np.minimum(b[:, 0], a[:, 0]) - self.s["r"]
         self.hi = np.maximum(b[:, 0], a[:, 0]) + self.s["r"]
-        self.ghosts = {0: np.zeros(0, REC_DT), 1: np.zeros(0, REC_DT)}
+        self.ghost_recs = {0: np.zeros(0, REC_DT), 1: np.zeros(0, REC_DT)}
         return self.torch.tensor([self.lo.min(), self.hi.max()], dtype=self.torch.float64)
 
-    def pack(self, interval, side, count_only=False):
+    def _select(self, interval):
         ilo, ihi = float(interval[0]), float(interval[1])
-        sel = ~(self.hi < ilo) & ~(ihi < self.lo)
-        idx = np.nonzero(sel)[0]
-        rec = np.zeros(idx.shape[0], REC_DT)
-        rec["q0"] = self.q0.reshape(-1, 2)[idx]
-        rec["q1"] = self.q1.reshape(-1, 2)[idx]
-        rec["r"] = self.s["r"][idx]
-        rec["gid"] = self.gid_first + idx
-        return self.torch.from_numpy(rec.view(np.uint8).copy()), idx.shape[0]
+        return np.nonzero(~(self.hi < ilo) & ~(ihi < self.lo))[0]
+
+    def pack(self, interval, side):
+        idx = self._select(interval)
+        assert idx.shape[0] <= self.cap
+        rec = np.zeros(self.cap + 1, REC_DT)
+        rec["gid"][0] = idx.shape[0]
+        k = slice(1, 1 + idx.shape[0])
+        rec["q0"][k] = self.q0.reshape(-1, 2)[idx]
+        rec["q1"][k] = self.q1.reshape(-1, 2)[idx]
+        rec["r"][k] = self.s["r"][idx]
+        rec["gid"][k] = self.gid_first + idx
+        return self.torch.from_numpy(rec.view(np.uint8).copy())
+
+    def count_overlapping(self, interval):
+        return int(self._select(interval).shape[0])
 
     def recv_buffer(self, side):
         return self.recv[side]
 
-    def unpack(self, side, buf, count):
-        self.ghosts[side] = buf[: count * REC_BYTES].numpy().view(REC_DT).copy() if count else np.zeros(0, REC_DT)
+    def unpack(self, side, buf):
+        rec = buf.numpy().view(REC_DT)
+        self.ghost_recs[side] = rec[1:1 + int(rec["gid"][0])].copy()
 
     def detect(self):
-        L, R = self.ghosts[0], self.ghosts[1]
+        L, R = self.ghost_recs[0], self.ghost_recs[1]
+        self.ghosts = (L.shape[0], R.shape[0])
         nL, M = L.shape[0], self.n_owned
         loc = dict(self.s)
         loc["q"] = np.concatenate([L["q0"].ravel(), self.q0, R["q0"].ravel()])
@@ -85,7 +96,7 @@ class OracleSlabBackend:
         a = self.ob.Ball2DOracle(loc).active_set(loc["q"], q1, "allpairs")
         owned = lambda i: (i >= nL) & (i < nL + M)
         ck = owned(a["candidates"][:, 0])
-        keep = np.where(a["type"] == 0, owned(a["i"]), owned(a["i"]))
+        keep = owned(a["i"])
         res = {"candidates": gid[a["candidates"][ck]].astype(np.uint32).reshape(-1, 2)}
         for k in ("type", "n", "p", "depth"):
             res[k] = a[k][keep]

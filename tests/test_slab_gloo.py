@@ -29,7 +29,7 @@ def _worker(rank, world, port, n, seed, outdir):
     scene = sh.slab_major_scene(n, seed)
     firsts, counts = partition_slab_major(n, world)
     backend = sh.OracleSlabBackend(sh.slab_of(scene, firsts[rank], counts[rank]), firsts[rank], ghost_cap=n)
-    drv = Ball2DSlabs(backend, rank, world, dist)
+    drv = Ball2DSlabs(backend, rank, world, dist, check_non_neighbours=True)
     pc, pa = drv.step(0, scene["dt"])
     q1, v1, res = backend.fetch()
     res["q1"], res["v1"], res["halo"] = q1, v1, drv.last_halo

@@ -22,29 +22,28 @@ def test_slab_kernels_merge_equals_oracle(oracle, world, n, seed):
     ivs = [b.flow(0, scene["dt"]) for b in bks]
     for c in ctxs:
         c.synchronize()
-    halo = 0
     for r in range(world):
         for side, peer in ((0, r - 1), (1, r + 1)):
             if not (0 <= peer < world):
                 continue
-            buf, cnt = bks[r].pack(ivs[peer], side)
+            buf = bks[r].pack(ivs[peer], side)
             ctxs[r].synchronize()
             dst = bks[peer].recv_buffer(1 - side)     # my side-1 list arrives as the peer's side-0 ghosts
-            dst[: cnt * REC_BYTES].copy_(buf[: cnt * REC_BYTES])
+            dst.copy_(buf)
             torch.cuda.synchronize()
-            bks[peer].unpack(1 - side, dst, cnt)
-            halo += cnt
+            bks[peer].unpack(1 - side, dst)
         for peer in range(world):
             if abs(peer - r) > 1:
-                assert bks[r].pack(ivs[peer], 0, count_only=True)[1] == 0
-    assert halo > 0
-    parts = []
+                assert bks[r].count_overlapping(ivs[peer]) == 0
+    parts, halo = [], 0
     for r in range(world):
         pc, pa = bks[r].detect()
         q1, v1, res = bks[r].fetch()
         assert (pc, pa) == (res["candidates"].shape[0], res["type"].shape[0])
+        halo += sum(bks[r].ghosts)
         res["q1"] = q1
         parts.append(res)
+    assert halo > 0
     o = ob.Ball2DOracle(scene)
     q1, v1 = o.flow(0, scene["q"], scene["v"], scene["dt"])
     ref = o.active_set(scene["q"], q1, "grid")
