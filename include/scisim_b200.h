@@ -54,6 +54,16 @@ extern "C" {
 #define SG_PLANE_BOX 15               /* StaticPlaneBoxConstraint: j = plane, aux = corner number, p = x0 + R0*corner */
 #define SG_PLANE_BODY 16              /* StaticPlaneBodyConstraint: j = plane, aux = convex hull vertex, p = collision point at q0 */
 
+/* rigidbody2d (rigidbody2d/*Constraint.h) */
+#define SG_CIRCLE_CIRCLE 20    /* CircleCircleConstraint{ i, j, n, p, ri, rj } */
+#define SG_KINEMATIC_CIRCLE 21 /* KinematicObjectCircleConstraint: i = free circle, j = kinematic body, p = its position at q0 */
+#define SG_BODY_BODY_2D 22     /* BodyBodyConstraint{ i, j, p, n, q0 } (box-box, circle-box) */
+#define SG_PLANE_CIRCLE 23     /* StaticPlaneCircleConstraint: j = plane */
+#define SG_PLANE_BODY_2D 24    /* StaticPlaneBodyConstraint: j = plane, aux = corner 0..3, p = body-space arm of the corner */
+/* RigidBody2DGeometryType */
+#define SG_GEO2_CIRCLE_TYPE 0
+#define SG_GEO2_BOX_TYPE 1
+
 /* RigidBodyGeometryType (rigidbody3d/Geometry/RigidBodyGeometry.h:13-19) */
 #define SG_GEO_BOX 0
 #define SG_GEO_SPHERE 1
@@ -172,6 +182,20 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
 int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev, uint32_t cap, uint32_t* count_dev );
 int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev );
 int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out );
+
+/* ---- rigidbody2d --------------------------------------------------------------------------------------
+ * q = v-layout [x, y, theta] per body (rigidbody2d/RigidBody2DState.h). M = the 3N diagonal of the mass matrix
+ * (m, m, I per body) exactly as FlowableSystem::M().valuePtr() holds it; Minv = 1.0 / M (RigidBody2DState.cpp:31-43).
+ * Plane normals are used as given (RigidBody2DStaticPlane does not normalise). */
+int sg_rb2d_set_geometry( sg_ctx* ctx, uint32_t ngeo, const uint32_t* type, const double* r /* ngeo */, const double* half /* 2 ngeo */ );
+int sg_rb2d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, const uint8_t* fixed, const double* M /* 3n */ );
+int sg_rb2d_set_gravity( sg_ctx* ctx, const double* g /* 2 */ );
+int sg_rb2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 2n */, const double* nrm /* 2n */ );
+/* rigidbody2d/SymplecticEulerMap.cpp:15-38, VerletMap.cpp:27-55 */
+int sg_rb2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
+/* RigidBody2DSim::computeActiveSet (rigidbody2d/RigidBody2DSim.cpp:696-714, no portals); SG_ERR_UNSUPPORTED where the
+ * reference exits (kinematic box-box, kinematic circle vs box: RigidBody2DSim.cpp:186-190, 210-214) */
+int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
 
 /* ---- rigidbody3d --------------------------------------------------------------------------------------
  * Layouts are RigidBody3DState's (rigidbody3d/RigidBody3DState.cpp:70-240): q = [3N centres | 9N row-major R],

@@ -249,3 +249,71 @@ void orc_rb3d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t
 }
 
 }
+
+// ---- rigidbody2d -----------------------------------------------------------------------------------
+#include "rb2d.h"
+
+struct RB2DHandle
+{
+  RB2DScene scene;
+  std::vector<RB2DContact> active;
+  std::vector<std::pair<unsigned,unsigned>> candidates;
+  double seconds_flow = 0.0, seconds_active = 0.0;
+};
+
+extern "C"
+{
+
+void* orc_rb2d_create( uint32_t n, const uint32_t* geo_of_body, const uint8_t* fixed, const double* M, const double* g,
+                       uint32_t ngeo, const uint32_t* geo_type, const double* geo_r, const double* geo_half,
+                       uint32_t nplanes, const double* plane_x, const double* plane_n )
+{
+  RB2DHandle* h = new RB2DHandle;
+  RB2DScene& s = h->scene;
+  s.geo_of_body.assign( geo_of_body, geo_of_body + n );
+  s.fixed.assign( fixed, fixed + n );
+  s.M.assign( M, M + 3 * std::size_t( n ) );
+  s.g = V2{ g[0], g[1] };
+  for( uint32_t k = 0; k < ngeo; ++k ) { s.geometry.push_back( RB2DGeometry{ geo_type[k], geo_r[k], V2{ geo_half[2 * k], geo_half[2 * k + 1] } } ); }
+  for( uint32_t p = 0; p < nplanes; ++p )
+  {
+    s.plane_x.push_back( V2{ plane_x[2 * p], plane_x[2 * p + 1] } );
+    s.plane_n.push_back( V2{ plane_n[2 * p], plane_n[2 * p + 1] } );
+  }
+  return h;
+}
+void orc_rb2d_destroy( void* h ) { delete static_cast<RB2DHandle*>( h ); }
+void orc_rb2d_flow( void* hv, int kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
+{
+  RB2DHandle* h = static_cast<RB2DHandle*>( hv );
+  const auto t0 = std::chrono::steady_clock::now();
+  flow( kind, h->scene, q0, v0, dt, q1, v1 );
+  h->seconds_flow = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+}
+int orc_rb2d_active_set( void* hv, const double* q0, const double* q1, int method )
+{
+  RB2DHandle* h = static_cast<RB2DHandle*>( hv );
+  const auto t0 = std::chrono::steady_clock::now();
+  const bool ok = computeActiveSet( h->scene, q0, q1, h->active, &h->candidates, method == 0 );
+  h->seconds_active = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+  return ok ? 1 : 0;
+}
+uint64_t orc_rb2d_num_candidates( const void* h ) { return static_cast<const RB2DHandle*>( h )->candidates.size(); }
+uint64_t orc_rb2d_num_active( const void* h ) { return static_cast<const RB2DHandle*>( h )->active.size(); }
+void orc_rb2d_copy_candidates( const void* hv, uint32_t* ij_out )
+{
+  const RB2DHandle* h = static_cast<const RB2DHandle*>( hv );
+  for( std::size_t k = 0; k < h->candidates.size(); ++k ) { ij_out[2 * k] = h->candidates[k].first; ij_out[2 * k + 1] = h->candidates[k].second; }
+}
+void orc_rb2d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t* j, uint32_t* aux, double* n, double* p, double* depth )
+{
+  const RB2DHandle* h = static_cast<const RB2DHandle*>( hv );
+  for( std::size_t k = 0; k < h->active.size(); ++k )
+  {
+    const RB2DContact& c = h->active[k];
+    type[k] = c.type; i[k] = c.i; j[k] = c.j; aux[k] = c.aux;
+    n[2 * k] = c.n.x; n[2 * k + 1] = c.n.y; p[2 * k] = c.p.x; p[2 * k + 1] = c.p.y; depth[k] = c.depth;
+  }
+}
+
+}

@@ -76,6 +76,12 @@ def load():
         "sg_ball2d_slab_pack": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
         "sg_ball2d_slab_unpack": (C.c_int, [vp, C.c_int, vp]),
         "sg_ball2d_slab_detect": (C.c_int, [vp, C.POINTER(SgContacts), vp]),
+        "sg_rb2d_set_geometry": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),
+        "sg_rb2d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),
+        "sg_rb2d_set_gravity": (C.c_int, [vp, vp]),
+        "sg_rb2d_set_planes": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_rb2d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
+        "sg_rb2d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
         "sg_rb3d_set_geometry": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),
         "sg_rb3d_add_mesh": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, vp, C.POINTER(C.c_uint32)]),
         "sg_rb3d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),

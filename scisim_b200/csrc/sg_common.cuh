@@ -79,6 +79,7 @@ struct ProfPending
 struct Ball2DData;
 struct AabbData;
 struct Rb3dData;
+struct Rb2dData;
 
 struct sg_ctx
 {
@@ -99,6 +100,7 @@ struct sg_ctx
   Ball2DData* ball2d = nullptr;
   AabbData* aabb = nullptr;
   Rb3dData* rb3d = nullptr;
+  Rb2dData* rb2d = nullptr;
 };
 
 int sg_fail( sg_ctx* ctx, int code, const char* fmt, ... );

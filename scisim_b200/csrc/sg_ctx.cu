@@ -8,6 +8,7 @@ static std::string g_create_error;
 void sg_ball2d_release( sg_ctx* ctx );
 void sg_aabb_release( sg_ctx* ctx );
 void sg_rb3d_release( sg_ctx* ctx );
+void sg_rb2d_release( sg_ctx* ctx );
 
 int sg_fail( sg_ctx* ctx, int code, const char* fmt, ... )
 {
@@ -109,6 +110,7 @@ void sg_destroy( sg_ctx* ctx )
   sg_ball2d_release( ctx );
   sg_aabb_release( ctx );
   sg_rb3d_release( ctx );
+  sg_rb2d_release( ctx );
   for( cudaEvent_t e : ctx->event_pool ) { cudaEventDestroy( e ); }
   if( ctx->timer0 != nullptr ) { cudaEventDestroy( ctx->timer0 ); cudaEventDestroy( ctx->timer1 ); }
   ctx->l2_flush.release();

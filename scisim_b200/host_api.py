@@ -376,3 +376,59 @@ class RigidBody3DSim:
         c = SgContacts()
         self.ctx.check(self.ctx.lib.sg_rb3d_fetch(self.ctx.h, int(flags), _ptr(q1) if want_state else None, _ptr(v1) if want_state else None, C.byref(c)))
         return q1, v1, ActiveSet(c)
+
+
+# ---- rigidbody2d -------------------------------------------------------------------------------------
+class RigidBody2DState:
+    """Static part of rigidbody2d/RigidBody2DState.h: geometry list, per-body geometry index / fixed flag, the 3N mass
+    diagonal (m, m, I), gravity, static planes (normals as given)."""
+
+    def __init__(self, geo_type, geo_r, geo_half, geo_of_body, fixed, M, g=(0.0, 0.0), plane_x=None, plane_n=None):
+        self.geo_type = np.ascontiguousarray(geo_type, dtype=np.uint32)
+        self.geo_r = _f64(geo_r)
+        self.geo_half = _f64(geo_half).reshape(-1, 2)
+        self.geo_of_body = np.ascontiguousarray(geo_of_body, dtype=np.uint32)
+        self.fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
+        self.M = _f64(M)
+        self.g = _f64(g)
+        self.plane_x = _f64(plane_x if plane_x is not None else np.zeros((0, 2))).reshape(-1, 2)
+        self.plane_n = _f64(plane_n if plane_n is not None else np.zeros((0, 2))).reshape(-1, 2)
+
+    def nbodies(self):
+        return self.geo_of_body.shape[0]
+
+
+class RigidBody2DSim:
+    """GPU-backed FlowableSystem + ConstrainedSystem for rigidbody2d; use SymplecticEulerMap / VerletMap with it."""
+
+    def __init__(self, state, device=0, ctx=None):
+        self.ctx = ctx or Context(device)
+        self.state = st = state
+        lib, h = self.ctx.lib, self.ctx.h
+        self.ctx.check(lib.sg_rb2d_set_geometry(h, st.geo_type.shape[0], _ptr(st.geo_type), _ptr(st.geo_r), _ptr(st.geo_half)))
+        self.ctx.check(lib.sg_rb2d_set_bodies(h, st.nbodies(), _ptr(st.geo_of_body), _ptr(st.fixed), _ptr(st.M)))
+        self.ctx.check(lib.sg_rb2d_set_gravity(h, _ptr(st.g)))
+        self.ctx.check(lib.sg_rb2d_set_planes(h, st.plane_x.shape[0], _ptr(st.plane_x), _ptr(st.plane_n)))
+
+    def name(self):
+        return "rigid_body_2d"
+
+    def nqdofs(self):
+        return 3 * self.state.nbodies()
+
+    nvdofs = nqdofs
+
+    def _flow(self, kind, q0, v0, dt, q1=None, v1=None):
+        q0, v0 = _f64(q0), _f64(v0)
+        assert q0.size == self.nqdofs() and v0.size == self.nvdofs()
+        q1 = np.empty_like(q0) if q1 is None else q1
+        v1 = np.empty_like(v0) if v1 is None else v1
+        self.ctx.check(self.ctx.lib.sg_rb2d_flow(self.ctx.h, kind, _ptr(q0), _ptr(v0), float(dt), _ptr(q1), _ptr(v1)))
+        return q1, v1
+
+    def computeActiveSet(self, q0, qp, v=None, flags=SG_OUT_ALL, copy=True):
+        q0, qp = _f64(q0), _f64(qp)
+        assert q0.size == self.nqdofs() and qp.size == self.nqdofs()
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_rb2d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags), C.byref(c)))
+        return ActiveSet(c, copy=copy)

@@ -212,3 +212,38 @@ def rb3d_mixed_segregated(nper=200, seed=21):
     q, v = _rb3d_pack(np.vstack(xs), np.vstack(Rs), np.vstack(vs), np.vstack(ws))
     return _rb3d_scene(geo_type, geo_r, geo_half, geo_mesh, meshes, np.concatenate(gi), np.concatenate(fixed), np.concatenate(m), np.vstack(I0),
                        q, v, [0.0, -9.81, 0.0], [[0.0, -6.0, 0.0]], [[0.0, 1.0, 0.0]], 1.0 / 10800.0, "dmv")
+
+
+# ---- rigidbody2d -------------------------------------------------------------------------------------
+def rb2d_random(n, seed, kinds=("circle", "box"), nfixed_frac=0.08, nplanes=2, box=None, vmax=8.0, spin=True):
+    """Messy rigidbody2d scenes: circles (several radii) and / or rotated boxes, [x,y,theta] DoFs, oblique planes.
+    Kinematic bodies are circles only, and kinematic circles are kept away from boxes' reach by giving boxes no fixed
+    flag (the reference exits on kinematic box-box and on a kinematic circle meeting a box)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    box_ = box if box is not None else max(1.5, np.sqrt(n) * 0.55)
+    geo_type, geo_r, geo_half = [], [], []
+    if "circle" in kinds:
+        for r in (0.2, 0.35, 0.5):
+            geo_type.append(0); geo_r.append(r); geo_half.append([0.0, 0.0])
+    if "box" in kinds:
+        for h in ((0.3, 0.2), (0.45, 0.45), (0.6, 0.25)):
+            geo_type.append(1); geo_r.append(0.0); geo_half.append(list(h))
+    geo_type = np.array(geo_type, np.uint32)
+    gi = rng.integers(0, geo_type.shape[0], size=n)
+    is_circle = geo_type[gi] == 0
+    fixed = ((rng.uniform(size=n) < nfixed_frac) & is_circle & (len(kinds) == 1)).astype(np.uint8)
+    q = np.empty((n, 3))
+    q[:, :2] = rng.uniform(-box_, box_, size=(n, 2))
+    q[:, 2] = rng.uniform(-np.pi, np.pi, size=n)
+    v = np.empty((n, 3))
+    v[:, :2] = rng.uniform(-vmax, vmax, size=(n, 2))
+    v[:, 2] = rng.uniform(-3, 3, size=n) if spin else 0.0
+    v[fixed == 1] = 0.0
+    m = rng.uniform(0.5, 2.0, size=n)
+    inertia = m * rng.uniform(0.05, 0.3, size=n)
+    M = np.stack([m, m, inertia], axis=1).ravel()
+    pn = rng.normal(size=(nplanes, 2))
+    pn /= np.linalg.norm(pn, axis=1, keepdims=True)
+    return {"geo_type": geo_type, "geo_r": np.array(geo_r), "geo_half": np.array(geo_half).reshape(-1, 2), "geo_of_body": gi.astype(np.uint32),
+            "fixed": fixed, "M": M, "q": q.ravel().copy(), "v": v.ravel().copy(), "g": np.array([0.0, -9.81]),
+            "plane_x": rng.uniform(-box_, box_, size=(nplanes, 2)), "plane_n": pn, "dt": 0.01, "map": "symplectic_euler"}

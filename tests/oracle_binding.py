@@ -186,3 +186,52 @@ class RB3DOracle:
         out["seconds"] = self.lib.orc_rb3d_seconds_active(self.h)
         out["seconds_flow"] = self.lib.orc_rb3d_seconds_flow(self.h)
         return out
+
+
+class RB2DOracle:
+    def __init__(self, scene):
+        self.lib = lib = load()
+        vp = C.c_void_p
+        if not hasattr(lib, "_rb2d_bound"):
+            lib.orc_rb2d_create.restype = vp
+            lib.orc_rb2d_create.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp]
+            lib.orc_rb2d_destroy.argtypes = [vp]
+            lib.orc_rb2d_flow.argtypes = [vp, C.c_int, vp, vp, C.c_double, vp, vp]
+            lib.orc_rb2d_active_set.restype = C.c_int
+            lib.orc_rb2d_active_set.argtypes = [vp, vp, vp, C.c_int]
+            for f in ("orc_rb2d_num_candidates", "orc_rb2d_num_active"):
+                getattr(lib, f).restype = C.c_uint64
+                getattr(lib, f).argtypes = [vp]
+            lib.orc_rb2d_copy_candidates.argtypes = [vp, vp]
+            lib.orc_rb2d_copy_active.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+            lib._rb2d_bound = True
+        s = scene
+        self.n = s["geo_of_body"].shape[0]
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+        k = self._keep = [u32(s["geo_of_body"]), np.ascontiguousarray(s["fixed"], dtype=np.uint8), _f64(s["M"]), _f64(s["g"]), u32(s["geo_type"]),
+                          _f64(s["geo_r"]), _f64(s["geo_half"]), _f64(s["plane_x"]), _f64(s["plane_n"])]
+        self.h = lib.orc_rb2d_create(self.n, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), k[4].shape[0], _p(k[4]), _p(k[5]), _p(k[6]), k[7].shape[0], _p(k[7]), _p(k[8]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orc_rb2d_destroy(self.h)
+            self.h = None
+
+    def flow(self, kind, q0, v0, dt):
+        q0, v0 = _f64(q0), _f64(v0)
+        q1, v1 = np.empty_like(q0), np.empty_like(v0)
+        self.lib.orc_rb2d_flow(self.h, int(kind), _p(q0), _p(v0), float(dt), _p(q1), _p(v1))
+        return q1, v1
+
+    def active_set(self, q0, q1, method="grid"):
+        q0, q1 = _f64(q0), _f64(q1)
+        ok = self.lib.orc_rb2d_active_set(self.h, _p(q0), _p(q1), 0 if method == "grid" else 1)
+        nc, na = self.lib.orc_rb2d_num_candidates(self.h), self.lib.orc_rb2d_num_active(self.h)
+        cand = np.zeros((nc, 2), dtype=np.uint32)
+        if nc:
+            self.lib.orc_rb2d_copy_candidates(self.h, _p(cand))
+        out = {"type": np.zeros(na, np.uint32), "i": np.zeros(na, np.uint32), "j": np.zeros(na, np.uint32), "aux": np.zeros(na, np.uint32),
+               "n": np.zeros((na, 2)), "p": np.zeros((na, 2)), "depth": np.zeros(na), "candidates": cand, "supported": bool(ok)}
+        if na:
+            self.lib.orc_rb2d_copy_active(self.h, _p(out["type"]), _p(out["i"]), _p(out["j"]), _p(out["aux"]), _p(out["n"]), _p(out["p"]), _p(out["depth"]))
+        return out
