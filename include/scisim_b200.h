@@ -54,7 +54,7 @@ extern "C" {
 #define SG_PLANE_BOX 15               /* StaticPlaneBoxConstraint: j = plane, aux = corner number, p = x0 + R0*corner */
 #define SG_PLANE_BODY 16              /* StaticPlaneBodyConstraint: j = plane, aux = convex hull vertex, p = collision point at q0 */
 
-/* rigidbody2d (rigidbody2d/*Constraint.h) */
+/* rigidbody2d (the constraint classes under rigidbody2d/) */
 #define SG_CIRCLE_CIRCLE 20    /* CircleCircleConstraint{ i, j, n, p, ri, rj } */
 #define SG_KINEMATIC_CIRCLE 21 /* KinematicObjectCircleConstraint: i = free circle, j = kinematic body, p = its position at q0 */
 #define SG_BODY_BODY_2D 22     /* BodyBodyConstraint{ i, j, p, n, q0 } (box-box, circle-box) */

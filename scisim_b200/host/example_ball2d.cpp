@@ -1,0 +1,71 @@
+// example_ball2d.cpp -- drives the host shim the way SCISim's maps drive a sim for one step
+// (scisim/ConstrainedMaps/ImpactMaps/ImpactMap.cpp:54-58): umap.flow( q0, v0 ) then computeActiveSet( q0, q1 ).
+// Prints one summary line; tests/test_host_shim.py compares it with the Python path on the same scene.
+#include "gpu_backend.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+struct TinySystem final : public FlowableSystem
+{
+  int n;
+  explicit TinySystem( const int nballs ) : n( nballs ) {}
+  int nqdofs() const override { return 2 * n; }
+  int nvdofs() const override { return 2 * n; }
+  unsigned numVelDoFsPerBody() const override { return 2; }
+  unsigned ambientSpaceDimensions() const override { return 2; }
+  bool isKinematicallyScripted( const int ) const override { return false; }
+  std::string name() const override { return "ball_2d"; }
+};
+
+int main( int argc, char** argv )
+{
+  const int nx = argc > 1 ? std::atoi( argv[1] ) : 40;
+  const int ny = argc > 2 ? std::atoi( argv[2] ) : 30;
+  const int n = nx * ny;
+  VectorXs q0( 2 * n ), v0( 2 * n ), q1( 2 * n ), v1( 2 * n ), r( n ), m( n );
+  for( int j = 0; j < ny; ++j )
+  {
+    for( int i = 0; i < nx; ++i )
+    {
+      const int b = j * nx + i;
+      q0( 2 * b ) = 0.99 * i + 0.001 * std::sin( 12.9898 * b );
+      q0( 2 * b + 1 ) = 0.99 * j + 0.001 * std::cos( 78.233 * b );
+      v0( 2 * b ) = 0.0; v0( 2 * b + 1 ) = 0.0;
+      r( b ) = 0.5; m( b ) = 1.0;
+    }
+  }
+  GpuBall2DBackend backend( 0 );
+  backend.setBodies( r, m );
+  backend.setGravity( 0.0, -9.81 );
+  backend.setPlanes( { 0.0, -0.5, -0.5, 0.0 }, { 0.0, 1.0, 1.0, 0.0 } );
+  TinySystem fsys( n );
+  GpuSymplecticEulerMap umap( backend );
+  umap.flow( q0, v0, fsys, 1, 1.0e-3, q1, v1 );
+  std::vector<GpuContact2D> contacts;
+  uint64_t ncand = 0;
+  backend.computeActiveSet( q0, q1, contacts, &ncand );
+  unsigned long nbb = 0, npl = 0;
+  double nsum = 0.0;
+  PairImpulseCache cache;
+  VectorXs imp( 1 );
+  for( const GpuContact2D& c : contacts )
+  {
+    if( c.type == SG_BALL_BALL ) { ++nbb; imp( 0 ) = double( c.i ) + 0.5; cache.cacheConstraint( 0, c.i, c.j, imp ); }
+    if( c.type == SG_BALL_PLANE ) { ++npl; imp( 0 ) = -1.0; cache.cacheConstraint( 1, c.j, c.i, imp ); }
+    nsum += c.n[0] * c.n[0] + c.n[1] * c.n[1];
+  }
+  // warm-start lookups: every cached pair is found, an absent one reads zero
+  unsigned long hits = 0;
+  for( const GpuContact2D& c : contacts )
+  {
+    if( c.type != SG_BALL_BALL ) { continue; }
+    cache.getCachedConstraint( 0, c.i, c.j, imp );
+    if( imp( 0 ) == double( c.i ) + 0.5 ) { ++hits; }
+  }
+  cache.getCachedConstraint( 0, 4000000000u, 7u, imp );
+  std::printf( "n=%d candidates=%llu ball_ball=%lu plane=%lu cache_hits=%lu miss_value=%g mean_n2=%.17g v1y=%.17g q1y0=%.17g\n", n, ( unsigned long long ) ncand, nbb, npl, hits, imp( 0 ),
+               contacts.empty() ? 0.0 : nsum / double( contacts.size() ), v1( 1 ), q1( 1 ) );
+  return 0;
+}

@@ -1,0 +1,159 @@
+// gpu_backend.cpp -- see gpu_backend.h
+#include "gpu_backend.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <numeric>
+
+GpuBall2DBackend::GpuBall2DBackend( const int device )
+: m_ctx( nullptr )
+, m_nbodies( 0 )
+{
+  const int rc = sg_create( &m_ctx, device );
+  if( rc != SG_OK )
+  {
+    std::cerr << "GpuBall2DBackend: " << sg_last_error( nullptr ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+GpuBall2DBackend::~GpuBall2DBackend() { sg_destroy( m_ctx ); }
+
+void GpuBall2DBackend::check( const int rc, const char* what ) const
+{
+  if( rc != SG_OK )
+  {
+    std::cerr << what << ": " << sg_last_error( m_ctx ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+void GpuBall2DBackend::setBodies( const VectorXs& r, const VectorXs& m )
+{
+  m_nbodies = static_cast<unsigned>( r.size() );
+  check( sg_ball2d_set_bodies( m_ctx, m_nbodies, r.data(), m.data() ), "sg_ball2d_set_bodies" );
+}
+
+void GpuBall2DBackend::setGravity( const double gx, const double gy )
+{
+  const double g[2] = { gx, gy };
+  check( sg_ball2d_set_gravity( m_ctx, g ), "sg_ball2d_set_gravity" );
+}
+
+void GpuBall2DBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n )
+{
+  check( sg_ball2d_set_planes( m_ctx, static_cast<uint32_t>( x.size() / 2 ), x.data(), n.data() ), "sg_ball2d_set_planes" );
+}
+
+void GpuBall2DBackend::setDrums( const std::vector<double>& x, const std::vector<double>& r )
+{
+  check( sg_ball2d_set_drums( m_ctx, static_cast<uint32_t>( r.size() ), x.data(), r.data() ), "sg_ball2d_set_drums" );
+}
+
+void GpuBall2DBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  // Outputs are pre-sized by the caller in the reference (ball2d/Ball2DSim.cpp:311-312); be lenient here
+  if( q1.size() != q0.size() ) { q1.resize( q0.size() ); }
+  if( v1.size() != v0.size() ) { v1.resize( v0.size() ); }
+  check( sg_ball2d_flow( m_ctx, map_kind, q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_ball2d_flow" );
+}
+
+void GpuBall2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates )
+{
+  sg_contacts c;
+  check( sg_ball2d_active_set( m_ctx, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS, &c ), "sg_ball2d_active_set" );
+  contacts.resize( c.n_active );
+  for( uint64_t k = 0; k < c.n_active; ++k )
+  {
+    GpuContact2D& o = contacts[k];
+    o.type = c.type[k]; o.i = c.i[k]; o.j = c.j[k];
+    o.n[0] = c.n[2 * k]; o.n[1] = c.n[2 * k + 1];
+    o.p[0] = c.p[2 * k]; o.p[1] = c.p[2 * k + 1];
+    o.depth = c.depth[k];
+  }
+  if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
+}
+
+void GpuBall2DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps )
+{
+  sg_pairs p;
+  check( sg_candidate_pairs( m_ctx, 2, static_cast<uint32_t>( aabbs.size() / 4 ), aabbs.data(), &p ), "sg_candidate_pairs" );
+  // the reference appends to a std::set; the list arrives in that set's iteration order
+  overlaps.reserve( overlaps.size() + p.n );
+  for( uint64_t k = 0; k < p.n; ++k ) { overlaps.emplace_back( p.ij[2 * k], p.ij[2 * k + 1] ); }
+}
+
+void GpuSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.flow( SG_MAP_SYMPLECTIC_EULER, q0, v0, dt, q1, v1 );
+}
+
+void GpuVerletMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.flow( SG_MAP_VERLET, q0, v0, dt, q1, v1 );
+}
+
+void PairImpulseCache::Table::sortIfNeeded()
+{
+  if( sorted ) { return; }
+  std::vector<std::size_t> order( keys.size() );
+  std::iota( order.begin(), order.end(), std::size_t( 0 ) );
+  std::sort( order.begin(), order.end(), [this]( const std::size_t a, const std::size_t b ) { return keys[a] < keys[b]; } );
+  std::vector<uint64_t> k2( keys.size() );
+  std::vector<double> v2( values.size() );
+  for( std::size_t n = 0; n < order.size(); ++n )
+  {
+    k2[n] = keys[order[n]];
+    std::memcpy( &v2[n * width], &values[order[n] * width], width * sizeof( double ) );
+  }
+  keys.swap( k2 ); values.swap( v2 );
+  sorted = true;
+}
+
+void PairImpulseCache::clear()
+{
+  for( Table& t : m_tables ) { t.keys.clear(); t.values.clear(); t.sorted = true; }
+}
+
+bool PairImpulseCache::empty() const
+{
+  return m_tables[0].keys.empty() && m_tables[1].keys.empty() && m_tables[2].keys.empty();
+}
+
+void PairImpulseCache::cacheConstraint( const int kind, const unsigned a, const unsigned b, const VectorXs& r )
+{
+  if( kind < 0 || kind > 2 )
+  {
+    std::cerr << "constraint kind " << kind << " not supported in PairImpulseCache::cacheConstraint. Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+  Table& t = m_tables[kind];
+  const uint64_t key = ( uint64_t( a ) << 32 ) | b;
+  if( t.keys.empty() ) { t.width = static_cast<unsigned>( r.size() ); }
+  if( !t.keys.empty() && key <= t.keys.back() ) { t.sorted = false; }
+  t.keys.push_back( key );
+  t.values.insert( t.values.end(), r.data(), r.data() + r.size() );
+}
+
+void PairImpulseCache::getCachedConstraint( const int kind, const unsigned a, const unsigned b, VectorXs& r ) const
+{
+  if( kind < 0 || kind > 2 )
+  {
+    std::cerr << "constraint kind " << kind << " not supported in PairImpulseCache::getCachedConstraint. Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+  Table& t = m_tables[kind];
+  t.sortIfNeeded();
+  const uint64_t key = ( uint64_t( a ) << 32 ) | b;
+  const auto it = std::lower_bound( t.keys.begin(), t.keys.end(), key );
+  if( it != t.keys.end() && *it == key )
+  {
+    const std::size_t n = static_cast<std::size_t>( it - t.keys.begin() );
+    for( long d = 0; d < r.size(); ++d ) { r( d ) = t.values[n * t.width + static_cast<std::size_t>( d )]; }
+    return;
+  }
+  // If the constraint was not found set to a default force of 0 (ball2d/ConstraintCache.cpp:122)
+  r.setZero();
+}
