@@ -6,7 +6,7 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 hdr = rows[1]
-body = rows[2:]
+body = [r for r in rows[2:] if len(r) >= len(hdr) and r[0] != "Address"]
 col = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = {s: 0 for s in stalls}

@@ -47,6 +47,7 @@ struct AabbPolicy
     for( int k = 0; k < DIM; ++k ) { lo[k] = s.lo[k]; hi[k] = s.hi[k]; }
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }

@@ -119,6 +119,7 @@ struct Ball2DPolicy
     hi[0] = fmax( s.q1x, s.q0x ) + s.r; hi[1] = fmax( s.q1y, s.q0y ) + s.r;
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
+  __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
   __device__ static bool owns( const Rec& s ) { return ( s.idx & SG_GHOST_BIT ) == 0u; }
   __device__ static bool valid( const In& in, const uint32_t i ) { return ball2d_slot_valid( in, i ); }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }

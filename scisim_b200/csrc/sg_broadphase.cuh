@@ -40,9 +40,11 @@ struct BroadScratch
   DevBuf key;           // u32[n]
   DevBuf rank;          // u32[n]
   DevBuf recs;          // Rec[n]
+  DevBuf sidx;          // u32[n]  index word of each sorted record (pass 2 stages only this)
+  DevBuf pos_of;        // u32[n]  sorted position of body i (offsets are scattered to position order)
   DevBuf counts;        // uint2[n]  by body index
-  DevBuf masks;         // uint2[n]  by sorted position
-  DevBuf offsets;       // ulonglong2[n]
+  DevBuf masks;         // uint4[n]  by sorted position
+  DevBuf offsets;       // ulonglong2[n]  by sorted position
   DevBuf pair_partials; // ScanPairCounts::Acc[tiles]
   DevBuf totals;        // ScanPairCounts::Acc
   DevBuf cand;          // uint2[cand_cap]
@@ -54,7 +56,7 @@ struct BroadScratch
   void release()
   {
     bounds.release(); params.release(); cell_count.release(); cell_start.release(); cell_partials.release(); key.release(); rank.release();
-    recs.release(); counts.release(); masks.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
+    recs.release(); sidx.release(); pos_of.release(); counts.release(); masks.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
   }
 };
 
@@ -285,46 +287,55 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P:
 
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename P::In in, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ key_in,
-                                                                 const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs )
+                                                                 const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs, uint32_t* __restrict__ sidx, uint32_t* __restrict__ pos_of )
 {
   const uint32_t g_dims0 = params->dims[0], g_dims1 = params->dims[1];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if( i >= in.n ) { return; }
   const uint32_t key = key_in[i];
-  if( key == 0xffffffffu ) { return; }
+  if( key == 0xffffffffu ) { pos_of[i] = 0xffffffffu; return; }
   const uint32_t pos = __ldg( &cell_start[key] ) + rank_in[i];
   // cell coordinates travel with the record (no integer division in the pair kernels)
   const uint32_t yz = key / g_dims0;
   const typename P::Rec r = P::make_rec( in, i, key, ( P::D == 3 ) ? yz % g_dims1 : yz, ( P::D == 3 ) ? yz / g_dims1 : 0u );
   sg_store_rec( &recs[pos], r );
+  sidx[pos] = P::rec_idx_raw( r );
+  pos_of[i] = pos;
 }
 
 // ---- neighbourhood staging + walk ------------------------------------------------------------------
 // Bodies are sorted by row-major cell key, so for a block owning sorted positions [b0,b1) with first/last
 // keys kf/kl, everything its threads can visit in the row offset (dy,dz) lies in ONE contiguous range of
-// records: cells [kf + off - 1, kl + off + 1], off = dy*dimx + dz*dimx*dimy.  There are 3^(D-1) such
-// windows.  Each is pulled into shared memory with a single 1-D TMA bulk copy (cp.async.bulk, completion on
-// an mbarrier); a window longer than WCAP records is staged up to WCAP and the tail is read through L1/L2.
-// (Round-1 note: the copy is currently done by the block's threads with coalesced 128-bit loads so that the
-// records can be bank-swizzled on the way in; the 1-D bulk-copy helpers in sg_tma.cuh cannot swizzle.)
+// cells [kf + off - 1, kl + off + 1], off = dy*dimx + dz*dimx*dimy, hence in one contiguous range of records.
+// There are 3^(D-1) such windows.  Per block and window two things are staged in shared memory with coalesced
+// loads: the records (pass 1: all 64 bytes, bank-swizzled; pass 2: only the 4-byte index words) and the slice of
+// cell_start covering the window's cells -- so the per-thread walk touches no global memory at all.  A window with
+// more than WCAP records / CSCAP cells is staged up to the cap and the tail is read through L1/L2.
+// (The copy is done by the block's threads rather than by 1-D cp.async.bulk -- helpers in sg_tma.cuh -- because the
+// bulk copy cannot apply the swizzle that removes the 4-way bank conflicts of 64-byte records.)
 template<int D> struct BpCfg;
-template<> struct BpCfg<2> { static constexpr int NW = 3; static constexpr int T = 256; static constexpr int WCAP = 288; };
-template<> struct BpCfg<3> { static constexpr int NW = 9; static constexpr int T = 128; static constexpr int WCAP = 144; };
+template<> struct BpCfg<2> { static constexpr int NW = 3; static constexpr int T = 256; static constexpr int WCAP = 272; static constexpr int CSCAP = 320; };
+template<> struct BpCfg<3> { static constexpr int NW = 9; static constexpr int T = 128; static constexpr int WCAP = 144; static constexpr int CSCAP = 288; };
 
 template<int D>
 struct BpStage
 {
-  uint32_t start[BpCfg<D>::NW];
-  uint32_t len[BpCfg<D>::NW];
-  unsigned long long bar;
+  uint32_t start[BpCfg<D>::NW];   // first sorted position of the window
+  uint32_t len[BpCfg<D>::NW];     // records staged
+  uint32_t cs_klo[BpCfg<D>::NW];  // first cell key whose cell_start entry is staged
+  uint32_t cs_len[BpCfg<D>::NW];  // cell_start entries staged
 };
 
-template<int D> __host__ __device__ constexpr size_t sg_bp_smem_bytes() { return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + sizeof( BpStage<D> ) + 127 ) & ~size_t( 127 ); }
+template<int D> __host__ __device__ constexpr size_t sg_bp_cs_bytes() { return size_t( BpCfg<D>::NW ) * BpCfg<D>::CSCAP * 4; }
+template<int D> __host__ __device__ constexpr size_t sg_bp_count_smem() { return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + sg_bp_cs_bytes<D>() + sizeof( BpStage<D> ) + 127 ) & ~size_t( 127 ); }
+template<int D> __host__ __device__ constexpr size_t sg_bp_emit_list_offset() { return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 4 + sg_bp_cs_bytes<D>() + sizeof( BpStage<D> ) + 127 ) & ~size_t( 127 ); }
+template<int D> __host__ __device__ constexpr size_t sg_bp_emit_smem() { return sg_bp_emit_list_offset<D>() + size_t( SG_BP_FAST_CAP ) * BpCfg<D>::T * 8; }
 
 // All threads of the block call this; returns once the staged windows are readable.
-template<typename P>
-__device__ inline void sg_bp_stage_windows( const GridParams& g, const uint32_t n, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs,
-                                            unsigned char* s_recs, BpStage<P::D>* st )
+// FULL: s_data receives swizzled 64-byte records; otherwise the u32 index words from sidx.
+template<typename P, bool FULL>
+__device__ inline void sg_bp_stage( const GridParams& g, const uint32_t n, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs,
+                                    const uint32_t* __restrict__ sidx, unsigned char* s_data, uint32_t* s_cs, BpStage<P::D>* st )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -335,7 +346,7 @@ __device__ inline void sg_bp_stage_windows( const GridParams& g, const uint32_t 
     const uint32_t b1 = ( n - b0 < uint32_t( Cfg::T ) ) ? n : b0 + Cfg::T;
     const long long kf = __ldg( &recs[b0].key );
     const long long kl = __ldg( &recs[b1 - 1u].key );
-    uint32_t start = 0u, len = 0u;
+    uint32_t start = 0u, len = 0u, cs_klo = 0u, cs_len = 0u;
     const int dy = int( w % 3u ) - 1;
     const int dz = ( D == 3 ) ? int( w / 3u ) - 1 : 0;
     const long long off = ( long long )( dy ) * g.dims[0] + ( long long )( dz ) * g.dims[0] * g.dims[1];
@@ -347,37 +358,59 @@ __device__ inline void sg_bp_stage_windows( const GridParams& g, const uint32_t 
       start = __ldg( &cell_start[klo] );
       const uint32_t end = __ldg( &cell_start[khi + 1] );
       len = ( end - start < uint32_t( Cfg::WCAP ) ) ? end - start : uint32_t( Cfg::WCAP );
+      cs_klo = uint32_t( klo );
+      const long long ncs = khi - klo + 2; // entries klo .. khi+1
+      cs_len = ( ncs < ( long long )( Cfg::CSCAP ) ) ? uint32_t( ncs ) : uint32_t( Cfg::CSCAP );
     }
-    st->start[w] = start;
-    st->len[w] = len;
+    st->start[w] = start; st->len[w] = len; st->cs_klo[w] = cs_klo; st->cs_len[w] = cs_len;
   }
   __syncthreads();
   #pragma unroll
   for( int w = 0; w < Cfg::NW; ++w )
   {
-    const uint32_t nchunks = st->len[w] * 4u;
-    const int4* src = reinterpret_cast<const int4*>( recs + st->start[w] );
-    int4* dst = reinterpret_cast<int4*>( s_recs + size_t( w ) * Cfg::WCAP * 64 );
-    for( uint32_t c = threadIdx.x; c < nchunks; c += Cfg::T )
+    const uint32_t len = st->len[w];
+    if( FULL )
     {
-      const uint32_t slot = c >> 2;
-      dst[( slot << 2 ) | ( ( c & 3u ) ^ ( ( slot >> 1 ) & 3u ) )] = __ldg( src + c );
+      const uint32_t nchunks = len * 4u;
+      const int4* src = reinterpret_cast<const int4*>( recs + st->start[w] );
+      int4* dst = reinterpret_cast<int4*>( s_data + size_t( w ) * Cfg::WCAP * 64 );
+      for( uint32_t c = threadIdx.x; c < nchunks; c += Cfg::T )
+      {
+        const uint32_t slot = c >> 2;
+        dst[( slot << 2 ) | ( ( c & 3u ) ^ ( ( slot >> 1 ) & 3u ) )] = __ldg( src + c );
+      }
     }
+    else
+    {
+      const uint32_t* src = sidx + st->start[w];
+      uint32_t* dst = reinterpret_cast<uint32_t*>( s_data ) + w * Cfg::WCAP;
+      for( uint32_t c = threadIdx.x; c < len; c += Cfg::T ) { dst[c] = __ldg( src + c ); }
+    }
+    const uint32_t cs_len = st->cs_len[w];
+    const uint32_t* cs_src = cell_start + st->cs_klo[w];
+    for( uint32_t c = threadIdx.x; c < cs_len; c += Cfg::T ) { s_cs[w * Cfg::CSCAP + c] = __ldg( cs_src + c ); }
   }
   __syncthreads();
+}
+
+template<int D>
+__device__ __forceinline__ uint32_t sg_bp_cs( const BpStage<D>* st, const uint32_t* s_cs, const uint32_t* __restrict__ cell_start, const int w, const uint32_t key )
+{
+  const uint32_t rel = key - st->cs_klo[w];
+  return ( rel < st->cs_len[w] ) ? s_cs[w * BpCfg<D>::CSCAP + rel] : __ldg( &cell_start[key] );
 }
 
 // Calls f( w, q ) for every sorted position q != p whose cell is within one cell of (cx,c1,c2) on every axis,
 // in a fixed order (window-major, position ascending): both passes see the same sequence.
 template<typename P, typename F>
-__device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t p, const uint32_t key, const uint32_t c1, const uint32_t c2, F&& f )
+__device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t* s_cs, const BpStage<P::D>* st,
+                                                const uint32_t p, const uint32_t key, const uint32_t c1, const uint32_t c2, F&& f )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   const uint32_t cx = key - g.dims[0] * ( c1 + g.dims[1] * c2 );
   const uint32_t x0 = ( cx > 0u ) ? cx - 1u : 0u;
   const uint32_t x1 = ( cx + 1u < g.dims[0] ) ? cx + 1u : cx;
-  // all segment bounds first (independent loads), then the walk
   uint32_t qb[Cfg::NW], qe[Cfg::NW];
   #pragma unroll
   for( int w = 0; w < Cfg::NW; ++w )
@@ -391,8 +424,8 @@ __device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint3
     if( ok )
     {
       const uint32_t row = g.dims[0] * ( uint32_t( y ) + g.dims[1] * uint32_t( z ) );
-      qb[w] = __ldg( &cell_start[row + x0] );
-      qe[w] = __ldg( &cell_start[row + x1 + 1u] );
+      qb[w] = sg_bp_cs<D>( st, s_cs, cell_start, w, row + x0 );
+      qe[w] = sg_bp_cs<D>( st, s_cs, cell_start, w, row + x1 + 1u );
     }
   }
   #pragma unroll
@@ -430,42 +463,43 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
 #define SG_BP_MASKS_INVALID 0x80000000u
 
 // Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active (bit 31: masks invalid) }
-//          masks[sorted position] = { bit k: k-th visited neighbour is such a candidate, bit k: ... and active }
+//          masks[sorted position] = { candidate mask, active mask over the visit sequence, the two counts again }
 template<typename P>
 __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint2* __restrict__ masks )
+                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint4* __restrict__ masks )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
   extern __shared__ __align__( 128 ) unsigned char s_raw[];
   unsigned char* s_recs = s_raw;
-  BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
+  uint32_t* s_cs = reinterpret_cast<uint32_t*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
+  BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 + sg_bp_cs_bytes<D>() );
   const GridParams g = *params;
   const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned (unused slots are not)
   if( blockIdx.x * Cfg::T >= n ) { return; }
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
   Rec me;
   if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the windows are staged
-  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
+  sg_bp_stage<P, true>( g, n, cell_start, recs, nullptr, s_recs, s_cs, st );
   if( p >= n ) { return; }
   const uint32_t my_idx = P::rec_idx( me );
   if( !P::owns( me ) )
   {
     // a ghost body (multi-GPU halo): present only as a partner, its pairs are kept by the rank that owns it
     counts[my_idx] = make_uint2( 0u, 0u );
-    masks[p] = make_uint2( 0u, 0u );
+    masks[p] = make_uint4( 0u, 0u, 0u, 0u );
     return;
   }
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
   uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
-  sg_bp_walk_pos<P>( g, cell_start, p, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), [&]( const int w, const uint32_t q )
+  sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), [&]( const int w, const uint32_t q )
   {
     const uint32_t bit = ( k < 32u ) ? ( 1u << k ) : 0u;
     ++k;
+    if( sg_bp_fetch_idx<P>( recs, s_recs, st, w, q ) <= my_idx ) { return; } // owned by the partner: skip before touching the record
     const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
-    if( P::rec_idx( o ) <= my_idx ) { return; }
     double olo[D], ohi[D];
     P::rec_aabb( o, olo, ohi );
     bool ov = true;
@@ -475,68 +509,62 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
     ++nc; cmask |= bit;
     if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
   } );
-  counts[my_idx] = make_uint2( nc, ( k > 32u ) ? ( na | SG_BP_MASKS_INVALID ) : na );
-  masks[p] = make_uint2( cmask, amask );
+  const uint32_t na_f = ( k > 32u ) ? ( na | SG_BP_MASKS_INVALID ) : na;
+  counts[my_idx] = make_uint2( nc, na_f );
+  masks[p] = make_uint4( cmask, amask, nc, na_f );
 }
 
 // Pass 2.  Each body writes its candidates (ascending partner index) at its offset; active ones also write a contact.
+// Everything a thread needs up front is indexed by sorted position (coalesced, independent loads).
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                              const typename P::Rec* __restrict__ recs, const uint2* __restrict__ counts, const uint2* __restrict__ masks,
-                                                              const ulonglong2* __restrict__ offsets, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, const typename P::Out out )
+__global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks,
+                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, const typename P::Out out )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
   extern __shared__ __align__( 128 ) unsigned char s_raw[];
-  unsigned char* s_recs = s_raw;
-  BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
+  uint32_t* s_idx = reinterpret_cast<uint32_t*>( s_raw );                                                 // [NW][WCAP]
+  uint32_t* s_cs = reinterpret_cast<uint32_t*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 4 );
+  BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 4 + sg_bp_cs_bytes<D>() );
+  unsigned long long* s_list = reinterpret_cast<unsigned long long*>( s_raw + sg_bp_emit_list_offset<D>() ); // [SG_BP_FAST_CAP][T]
   const GridParams g = *params;
   const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) );
   if( blockIdx.x * Cfg::T >= n ) { return; }
-  unsigned long long* s_list = reinterpret_cast<unsigned long long*>( s_raw + sg_bp_smem_bytes<D>() ); // [SG_BP_FAST_CAP][T]
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
-  // everything this thread needs that does not depend on the staged windows is requested first
   Rec me;
-  uint2 cnt = make_uint2( 0u, 0u ), m = make_uint2( 0u, 0u );
+  uint4 m = make_uint4( 0u, 0u, 0u, 0u );
   ulonglong2 off = make_ulonglong2( 0ull, 0ull );
-  uint32_t my_idx = 0u;
   if( p < n )
   {
     me = sg_load_rec_global<Rec>( &recs[p] );
-    my_idx = P::rec_idx( me );
-    cnt = counts[my_idx];
-    off = offsets[my_idx];
     m = masks[p];
+    off = offsets_pos[p];
   }
-  sg_bp_stage_windows<P>( g, n, cell_start, recs, s_recs, st );
-  if( p >= n || cnt.x == 0u ) { return; }
+  sg_bp_stage<P, false>( g, n, cell_start, recs, sidx, reinterpret_cast<unsigned char*>( s_idx ), s_cs, st );
+  if( p >= n || m.z == 0u ) { return; }
+  const uint32_t my_idx = P::rec_idx( me );
   unsigned long long ka = off.y;
   const uint32_t key = P::rec_key( me ), c1 = P::rec_c1( me, g ), c2 = P::rec_c2( me, g );
-  // a partner's record, wherever it lives: search the staged windows, else global
-  auto fetch_any = [&]( const uint32_t q ) -> Rec
+  auto idx_at = [&]( const int w, const uint32_t q ) -> uint32_t
   {
-    #pragma unroll
-    for( int w = 0; w < Cfg::NW; ++w )
-    {
-      const uint32_t slot = q - st->start[w];
-      if( slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * Cfg::WCAP * 64, slot ); }
-    }
-    return sg_load_rec_global<Rec>( &recs[q] );
+    const uint32_t slot = q - st->start[w];
+    return ( ( slot < st->len[w] ) ? s_idx[w * Cfg::WCAP + slot] : __ldg( &sidx[q] ) ) & P::IDX_MASK;
   };
 
-  if( cnt.x <= SG_BP_FAST_CAP && ( cnt.y & SG_BP_MASKS_INVALID ) == 0u )
+  if( m.z <= SG_BP_FAST_CAP && ( m.w & SG_BP_MASKS_INVALID ) == 0u )
   {
-    // Fast path: pass 1 already decided every neighbour; only candidates' indices and active partners' records are
-    // read.  The (partner index << 32 | active << 31 | position) entries are insertion-sorted in a per-thread column
-    // of shared memory (n < 2^31 is checked by the host).
+    // Fast path: pass 1 already decided every neighbour; only the candidates' indices (staged) and the active
+    // partners' records (L1/L2) are read.  The (partner index << 32 | active << 31 | position) entries are
+    // insertion-sorted in a per-thread column of shared memory (n < 2^31 is checked by the host).
     unsigned long long* col = s_list + threadIdx.x;
     uint32_t cnt_m = 0u, k = 0u;
-    sg_bp_walk_pos<P>( g, cell_start, p, key, c1, c2, [&]( const int w, const uint32_t q )
+    sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
     {
       const uint32_t kk = k++;
       if( ( ( m.x >> kk ) & 1u ) == 0u ) { return; }
-      const uint32_t oi = sg_bp_fetch_idx<P>( recs, s_recs, st, w, q );
+      const uint32_t oi = idx_at( w, q );
       const unsigned long long v = ( static_cast<unsigned long long>( oi ) << 32 ) | ( static_cast<unsigned long long>( ( m.y >> kk ) & 1u ) << 31 ) | q;
       uint32_t j = cnt_m++;
       while( j > 0u )
@@ -555,14 +583,14 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
       if( cand != nullptr && kc < cand_cap ) { cand[kc] = ( gid != nullptr ) ? make_uint2( gid[my_idx], gid[uint32_t( v >> 32 )] ) : make_uint2( my_idx, uint32_t( v >> 32 ) ); }
       if( P::HAS_NARROW && ( ( v >> 31 ) & 1ull ) )
       {
-        const Rec o = fetch_any( uint32_t( v & 0x7fffffffull ) );
+        const Rec o = sg_load_rec_global<Rec>( &recs[uint32_t( v & 0x7fffffffull )] );
         P::contact_emit( out, ka, me, o );
       }
     }
     return;
   }
 
-  // Slow paths: redo the tests (a body with more than 32 neighbours or more candidates than the local list holds)
+  // Slow paths: redo the tests (a body with more than 32 neighbours or more candidates than the fast list holds)
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
   auto overlaps = [&]( const Rec& o ) -> bool
@@ -579,22 +607,24 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
     if( cand != nullptr && kc < cand_cap ) { cand[kc] = ( gid != nullptr ) ? make_uint2( gid[my_idx], gid[P::rec_idx( o )] ) : make_uint2( my_idx, P::rec_idx( o ) ); }
     if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { P::contact_emit( out, ka, me, o ); } }
   };
-  if( cnt.x <= SG_BP_LOCAL_CAP )
+  if( m.z <= SG_BP_LOCAL_CAP )
   {
     unsigned long long list[SG_BP_LOCAL_CAP];
     uint32_t nl = 0u;
-    sg_bp_walk_pos<P>( g, cell_start, p, key, c1, c2, [&]( const int w, const uint32_t q )
+    sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
     {
-      const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
-      if( P::rec_idx( o ) <= my_idx || !overlaps( o ) ) { return; }
-      const unsigned long long v = ( static_cast<unsigned long long>( P::rec_idx( o ) ) << 32 ) | q;
+      const uint32_t oi = idx_at( w, q );
+      if( oi <= my_idx ) { return; }
+      const Rec o = sg_load_rec_global<Rec>( &recs[q] );
+      if( !overlaps( o ) ) { return; }
+      const unsigned long long v = ( static_cast<unsigned long long>( oi ) << 32 ) | q;
       uint32_t j = nl++;
       while( j > 0u && list[j - 1u] > v ) { list[j] = list[j - 1u]; --j; }
       list[j] = v;
     } );
     for( uint32_t j = 0u; j < nl; ++j )
     {
-      const Rec o = fetch_any( uint32_t( list[j] & 0xffffffffull ) );
+      const Rec o = sg_load_rec_global<Rec>( &recs[uint32_t( list[j] & 0xffffffffull )] );
       emit_one( off.x + j, o );
     }
   }
@@ -602,19 +632,18 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_emit( const uint32_t n
   {
     // Crowded body: select partners in ascending index order by repeated walks (O(count * neighbours))
     uint32_t last = my_idx;
-    for( uint32_t j = 0u; j < cnt.x; ++j )
+    for( uint32_t j = 0u; j < m.z; ++j )
     {
       uint32_t best_idx = 0xffffffffu, best_q = 0u;
-      int best_w = 0;
-      sg_bp_walk_pos<P>( g, cell_start, p, key, c1, c2, [&]( const int w, const uint32_t q )
+      sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
       {
-        const uint32_t oi = sg_bp_fetch_idx<P>( recs, s_recs, st, w, q );
+        const uint32_t oi = idx_at( w, q );
         if( oi <= last || oi >= best_idx ) { return; }
-        const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
+        const Rec o = sg_load_rec_global<Rec>( &recs[q] );
         if( !overlaps( o ) ) { return; }
-        best_idx = oi; best_q = q; best_w = w;
+        best_idx = oi; best_q = q;
       } );
-      const Rec o = sg_bp_fetch<P>( recs, s_recs, st, best_w, best_q );
+      const Rec o = sg_load_rec_global<Rec>( &recs[best_q] );
       emit_one( off.x + j, o );
       last = best_idx;
     }
@@ -642,8 +671,10 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   SG_CUDA( ctx, s.key.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.rank.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.recs.ensure( size_t( n ) * 64 ) );
+  SG_CUDA( ctx, s.sidx.ensure( size_t( n ) * 4 ) );
+  SG_CUDA( ctx, s.pos_of.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.counts.ensure( size_t( n ) * sizeof( uint2 ) ) );
-  SG_CUDA( ctx, s.masks.ensure( size_t( n ) * sizeof( uint2 ) ) );
+  SG_CUDA( ctx, s.masks.ensure( size_t( n ) * sizeof( uint4 ) ) );
   SG_CUDA( ctx, s.offsets.ensure( size_t( n ) * sizeof( ulonglong2 ) ) );
   SG_CUDA( ctx, s.pair_partials.ensure( ( size_t( n ) / SG_SCAN_TILE + 2 ) * sizeof( ScanPairCounts::Acc ) ) );
   SG_CUDA( ctx, s.totals.ensure( sizeof( ScanPairCounts::Acc ) ) );
@@ -667,21 +698,21 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   const uint32_t* ncells_dev = &s.params.as<GridParams>()->ncells;
   int rc = sg_exclusive_scan<ScanU32>( ctx, "bp_cell_scan", s.cell_count.as<uint32_t>(), ncells_dev, 0u, s.max_cells, s.cell_partials.as<uint32_t>(), s.cell_start.as<uint32_t>(), nullptr, true );
   if( rc != SG_OK ) { return rc; }
-  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>() ) );
-  constexpr size_t smem = sg_bp_smem_bytes<D>();
+  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 + 4.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>() ) );
+  constexpr size_t smem = sg_bp_count_smem<D>();
   SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
-  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 + 8.0 ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint2>() ) );
-  rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false );
+  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 + 16.0 ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>() ) );
+  rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false, s.pos_of.as<uint32_t>() );
   return rc;
 }
 
 template<typename P>
 static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const double out_bytes )
 {
-  constexpr size_t smem = sg_bp_smem_bytes<P::D>() + size_t( SG_BP_FAST_CAP ) * BpCfg<P::D>::T * 8;
+  constexpr size_t smem = sg_bp_emit_smem<P::D>();
   SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_emit<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
-  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 8.0 + 8.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, BpCfg<P::D>::T ), BpCfg<P::D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
-             s.counts.as<uint2>(), s.masks.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map, out ) );
+  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 4.0 + 16.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, BpCfg<P::D>::T ), BpCfg<P::D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
+             s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map, out ) );
   return SG_OK;
 }
 

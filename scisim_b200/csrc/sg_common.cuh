@@ -96,6 +96,7 @@ struct sg_ctx
   cudaEvent_t timer0 = nullptr;
   cudaEvent_t timer1 = nullptr;
   DevBuf l2_flush;
+  DevBuf scan_vals; // per-block chunk totals of the cooperative scan (sg_scan.cuh)
 
   Ball2DData* ball2d = nullptr;
   AabbData* aabb = nullptr;

@@ -114,6 +114,7 @@ void sg_destroy( sg_ctx* ctx )
   for( cudaEvent_t e : ctx->event_pool ) { cudaEventDestroy( e ); }
   if( ctx->timer0 != nullptr ) { cudaEventDestroy( ctx->timer0 ); cudaEventDestroy( ctx->timer1 ); }
   ctx->l2_flush.release();
+  ctx->scan_vals.release();
   cudaStreamDestroy( ctx->stream );
   delete ctx;
 }

@@ -77,6 +77,7 @@ struct Box2DPolicy
   }
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi ) { lo[0] = s.lo[0]; lo[1] = s.lo[1]; hi[0] = s.hi[0]; hi[1] = s.hi[1]; }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }

@@ -141,6 +141,7 @@ struct Sphere3DPolicy
     for( int k = 0; k < 3; ++k ) { lo[k] = s.x1[k] - s.r; hi[k] = s.x1[k] + s.r; }
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
+  __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }
@@ -195,6 +196,7 @@ struct Box3DPolicy
     for( int k = 0; k < 3; ++k ) { lo[k] = s.lo[k]; hi[k] = s.hi[k]; }
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }

@@ -9,6 +9,8 @@
 
 #include "sg_common.cuh"
 
+#include <cooperative_groups.h>
+
 #define SG_SCAN_THREADS 256
 #define SG_SCAN_ITEMS 4
 #define SG_SCAN_TILE ( SG_SCAN_THREADS * SG_SCAN_ITEMS )
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__( 1024 ) sg_scan_partials( typename P::Acc* __r
 
 template<typename P>
 __global__ void __launch_bounds__( SG_SCAN_THREADS ) sg_scan_down( const typename P::In* __restrict__ in, const uint32_t* __restrict__ n_dev, const uint32_t n_host,
-                                                                   const typename P::Acc* __restrict__ partials, typename P::Out* __restrict__ out )
+                                                                   const typename P::Acc* __restrict__ partials, typename P::Out* __restrict__ out, const uint32_t* __restrict__ scatter )
 {
   using Acc = typename P::Acc;
   __shared__ Acc warp_sums[SG_SCAN_THREADS / 32];
@@ -158,28 +160,48 @@ __global__ void __launch_bounds__( SG_SCAN_THREADS ) sg_scan_down( const typenam
   #pragma unroll
   for( int k = 0; k < SG_SCAN_ITEMS; ++k )
   {
-    if( e0 + k < n ) { out[e0 + k] = P::out( run ); }
+    if( e0 + k < n )
+    {
+      // scatter != nullptr: element e's prefix goes to out[scatter[e]] (0xffffffff = nowhere)
+      if( scatter == nullptr ) { out[e0 + k] = P::out( run ); }
+      else { const uint32_t d = __ldg( &scatter[e0 + k] ); if( d != 0xffffffffu ) { out[d] = P::out( run ); } }
+    }
     run = P::add( run, v[k] );
   }
 }
 
 // Whole scan in one 1024-thread block: for arrays small enough that launch latency, not bandwidth, is the cost.
+// Each thread owns 8 consecutive elements per round.
 template<typename P>
-__global__ void __launch_bounds__( 1024 ) sg_scan_small( const typename P::In* __restrict__ in, const uint32_t n, typename P::Out* __restrict__ out, typename P::Acc* __restrict__ total_out, const bool write_end )
+__global__ void __launch_bounds__( 1024 ) sg_scan_small( const typename P::In* __restrict__ in, const uint32_t n, typename P::Out* __restrict__ out, typename P::Acc* __restrict__ total_out, const bool write_end, const uint32_t* __restrict__ scatter )
 {
   using Acc = typename P::Acc;
+  constexpr int ITEMS = 8;
   __shared__ Acc warp_sums[32];
   __shared__ Acc carry_s;
   if( threadIdx.x == 0 ) { carry_s = P::zero(); }
   __syncthreads();
-  for( uint32_t base = 0; base < n; base += 1024 )
+  for( uint32_t base = 0; base < n; base += 1024 * ITEMS )
   {
-    const uint32_t e = base + threadIdx.x;
-    const Acc v = ( e < n ) ? P::conv( in[e] ) : P::zero();
+    const uint32_t e0 = base + threadIdx.x * ITEMS;
+    Acc v[ITEMS];
+    Acc s = P::zero();
+    #pragma unroll
+    for( int k = 0; k < ITEMS; ++k ) { v[k] = ( e0 + k < n ) ? P::conv( in[e0 + k] ) : P::zero(); s = P::add( s, v[k] ); }
     Acc total;
-    const Acc excl = sg_block_exclusive<P, 1024>( v, warp_sums, &total );
+    const Acc excl = sg_block_exclusive<P, 1024>( s, warp_sums, &total );
     const Acc carry = carry_s;
-    if( e < n ) { out[e] = P::out( P::add( carry, excl ) ); }
+    Acc run = P::add( carry, excl );
+    #pragma unroll
+    for( int k = 0; k < ITEMS; ++k )
+    {
+      if( e0 + k < n )
+      {
+        if( scatter == nullptr ) { out[e0 + k] = P::out( run ); }
+        else { const uint32_t d = __ldg( &scatter[e0 + k] ); if( d != 0xffffffffu ) { out[d] = P::out( run ); } }
+      }
+      run = P::add( run, v[k] );
+    }
     __syncthreads();
     if( threadIdx.x == 0 ) { carry_s = P::add( carry, total ); }
     __syncthreads();
@@ -193,25 +215,122 @@ __global__ void __launch_bounds__( 1024 ) sg_scan_small( const typename P::In* _
 
 #define SG_SCAN_SMALL_MAX 32768u
 
-// Host driver.  cap = upper bound on the element count (sizes the grid); partials must hold
-// ceil(cap / SG_SCAN_TILE) Acc entries.
+#define SG_LB_THREADS 256
+#define SG_LB_ITEMS 8
+#define SG_LB_TILE ( SG_LB_THREADS * SG_LB_ITEMS )
+
+template<typename Acc>
+__device__ __forceinline__ Acc sg_ld_volatile( const Acc* p )
+{
+  static_assert( sizeof( Acc ) % 4 == 0, "Acc is a multiple of 4 bytes" );
+  union { Acc a; uint32_t w[sizeof( Acc ) / 4]; } u;
+  const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>( p );
+  #pragma unroll
+  for( int k = 0; k < int( sizeof( Acc ) / 4 ); ++k ) { u.w[k] = src[k]; }
+  return u.a;
+}
+template<typename Acc>
+__device__ __forceinline__ void sg_st_volatile( Acc* p, const Acc& v )
+{
+  union { Acc a; uint32_t w[sizeof( Acc ) / 4]; } u;
+  u.a = v;
+  volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>( p );
+  #pragma unroll
+  for( int k = 0; k < int( sizeof( Acc ) / 4 ); ++k ) { dst[k] = u.w[k]; }
+}
+
+// ---- two-phase scan in one cooperative launch -------------------------------------------------------
+// All blocks are co-resident (cooperative launch, grid = a fixed multiple of the SM count): each block reduces its
+// contiguous chunk, the grid synchronises once, every block sums the (few hundred) chunk totals that precede it and
+// sweeps its chunk again (second read served by L1/L2).  Removes the serial tile-to-tile latency chain a look-back
+// scan has when every tile is resident at once.
+template<typename P>
+__global__ void __launch_bounds__( SG_LB_THREADS ) sg_scan_coop( const typename P::In* __restrict__ in, const uint32_t* __restrict__ n_dev, const uint32_t n_host, typename P::Out* __restrict__ out,
+                                                                const uint32_t* __restrict__ scatter, typename P::Acc* partials, typename P::Acc* __restrict__ total_out, const bool write_end )
+{
+  using Acc = typename P::Acc;
+  namespace cg = cooperative_groups;
+  __shared__ Acc warp_sums[SG_LB_THREADS / 32];
+  __shared__ Acc s_prefix;
+  const uint32_t n = ( n_dev != nullptr ) ? *n_dev : n_host;
+  const uint32_t nb = gridDim.x;
+  // chunk per block: whole tiles
+  const uint64_t tiles_total = ( uint64_t( n ) + SG_LB_TILE - 1 ) / SG_LB_TILE;
+  const uint64_t tiles_per_block = ( tiles_total + nb - 1 ) / nb;
+  const uint64_t c0 = uint64_t( blockIdx.x ) * tiles_per_block * SG_LB_TILE;
+  const uint64_t c1 = ( c0 + tiles_per_block * SG_LB_TILE < n ) ? c0 + tiles_per_block * SG_LB_TILE : n;
+  // phase 1: chunk total
+  Acc s = P::zero();
+  for( uint64_t e = c0 + threadIdx.x; e < c1; e += SG_LB_THREADS ) { s = P::add( s, P::conv( in[e] ) ); }
+  Acc total;
+  sg_block_exclusive<P, SG_LB_THREADS>( s, warp_sums, &total );
+  if( threadIdx.x == 0 ) { sg_st_volatile( &partials[blockIdx.x], total ); }
+  __threadfence();
+  cg::this_grid().sync();
+  // phase 2: prefix of the preceding chunk totals (+ grand total for the last block)
+  {
+    Acc pre = P::zero();
+    for( uint32_t b = threadIdx.x; b < blockIdx.x; b += SG_LB_THREADS ) { pre = P::add( pre, sg_ld_volatile( &partials[b] ) ); }
+    __syncthreads();
+    Acc tot2;
+    sg_block_exclusive<P, SG_LB_THREADS>( pre, warp_sums, &tot2 );
+    if( threadIdx.x == 0 ) { s_prefix = tot2; }
+    __syncthreads();
+  }
+  Acc carry = s_prefix;
+  for( uint64_t t0 = c0; t0 < c1; t0 += SG_LB_TILE )
+  {
+    const uint64_t e0 = t0 + uint64_t( threadIdx.x ) * SG_LB_ITEMS;
+    Acc v[SG_LB_ITEMS];
+    Acc ls = P::zero();
+    #pragma unroll
+    for( int k = 0; k < SG_LB_ITEMS; ++k ) { v[k] = ( e0 + k < c1 ) ? P::conv( in[e0 + k] ) : P::zero(); ls = P::add( ls, v[k] ); }
+    __syncthreads();
+    Acc ttot;
+    const Acc excl = sg_block_exclusive<P, SG_LB_THREADS>( ls, warp_sums, &ttot );
+    Acc run = P::add( carry, excl );
+    #pragma unroll
+    for( int k = 0; k < SG_LB_ITEMS; ++k )
+    {
+      if( e0 + k < c1 )
+      {
+        if( scatter == nullptr ) { out[e0 + k] = P::out( run ); }
+        else { const uint32_t d = __ldg( &scatter[e0 + k] ); if( d != 0xffffffffu ) { out[d] = P::out( run ); } }
+      }
+      run = P::add( run, v[k] );
+    }
+    carry = P::add( carry, ttot );
+  }
+  if( blockIdx.x == nb - 1u && threadIdx.x == 0 )
+  {
+    // the last block's carry is the grand total (empty chunks carry their prefix through unchanged)
+    if( total_out != nullptr ) { *total_out = carry; }
+    if( write_end ) { out[n] = P::out( carry ); }
+  }
+}
+
+// Host driver.  cap = upper bound on the element count.
 template<typename P>
 static int sg_exclusive_scan( sg_ctx* ctx, const char* name, const typename P::In* in, const uint32_t* n_dev, const uint32_t n_host, const uint32_t cap,
-                              typename P::Acc* partials, typename P::Out* out, typename P::Acc* total_out, const bool write_end )
+                              typename P::Acc* partials, typename P::Out* out, typename P::Acc* total_out, const bool write_end, const uint32_t* scatter = nullptr )
 {
+  ( void ) partials;
   if( cap == 0 ) { return SG_OK; }
   if( n_dev == nullptr && n_host <= SG_SCAN_SMALL_MAX )
   {
-    SG_LAUNCH( ctx, name, double( n_host ) * double( sizeof( typename P::In ) + sizeof( typename P::Out ) ), sg_scan_small<P><<<1, 1024, 0, ctx->stream>>>( in, n_host, out, total_out, write_end ) );
+    SG_LAUNCH( ctx, name, double( n_host ) * double( sizeof( typename P::In ) + sizeof( typename P::Out ) ), sg_scan_small<P><<<1, 1024, 0, ctx->stream>>>( in, n_host, out, total_out, write_end, scatter ) );
     return SG_OK;
   }
-  const unsigned ntiles = sg_div_up( cap, SG_SCAN_TILE );
+  static_assert( sizeof( typename P::Acc ) <= 16, "scan accumulators are at most 16 bytes" );
+  const unsigned nblocks = unsigned( ctx->num_sms ) * 4u; // co-resident by a wide margin (256 threads, < 48 registers)
+  if( size_t( nblocks ) * 16 + 64 > ctx->scan_vals.cap ) { SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) ); SG_CUDA( ctx, ctx->scan_vals.ensure( size_t( nblocks ) * 32 + 256 ) ); }
+  typename P::Acc* chunk_totals = reinterpret_cast<typename P::Acc*>( ctx->scan_vals.ptr );
   const double nelem = double( n_dev != nullptr ? cap : n_host );
-  const double bytes_reduce = nelem * double( sizeof( typename P::In ) );
-  const double bytes_down = nelem * double( sizeof( typename P::In ) + sizeof( typename P::Out ) );
-  SG_LAUNCH( ctx, name, bytes_reduce, sg_scan_reduce<P><<<ntiles, SG_SCAN_THREADS, 0, ctx->stream>>>( in, n_dev, n_host, partials ) );
-  SG_LAUNCH( ctx, name, 0.0, sg_scan_partials<P><<<1, 1024, 0, ctx->stream>>>( partials, n_dev, n_host, total_out, write_end ? out : nullptr ) );
-  SG_LAUNCH( ctx, name, bytes_down, sg_scan_down<P><<<ntiles, SG_SCAN_THREADS, 0, ctx->stream>>>( in, n_dev, n_host, partials, out ) );
+  bool we = write_end;
+  uint32_t nh = n_host;
+  void* args[] = { ( void* ) &in, ( void* ) &n_dev, ( void* ) &nh, ( void* ) &out, ( void* ) &scatter, ( void* ) &chunk_totals, ( void* ) &total_out, ( void* ) &we };
+  SG_LAUNCH( ctx, name, nelem * double( sizeof( typename P::In ) + sizeof( typename P::Out ) ),
+             SG_CUDA( ctx, cudaLaunchCooperativeKernel( ( const void* ) sg_scan_coop<P>, dim3( nblocks ), dim3( SG_LB_THREADS ), args, 0, ctx->stream ) ) );
   return SG_OK;
 }
 
