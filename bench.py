@@ -105,6 +105,20 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_name):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_rNN.json, written by profiles/summarize.py); None when no capture covers it."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*.json")))
+    if not files:
+        return None, None
+    data = json.load(open(files[-1]))
+    for k, v in data.items():
+        if ("sg_" + kernel_name) in k or kernel_name in k:
+            return v.get("dram_traffic"), os.path.basename(files[-1])
+    return None, os.path.basename(files[-1])
+
+
 def cpu_reference_step(scene, steps, warmup):
     """The reference's CPU path (restated in oracle/, its own std::map/std::set data structures, 1 thread)."""
     from tests import oracle_binding as ob
@@ -274,6 +288,7 @@ def main():
         top = max(prof.items(), key=lambda kv: kv[1][1])
         name, (nl, ms, by) = top
         achieved = (by / nl) / (ms / nl * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(name)
         kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps, "share": v[1] / total_ms,
                        "alg_GBps": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         line = {
@@ -288,7 +303,7 @@ def main():
             "gpu_launches": gpu_launches,
             "e2e": {"value": pairs_all * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / e2e_steps,
                     "api": e2e_api},
-            "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": by / nl,
                          "peak_source": peak_src, "share_of_step": ms / total_ms, "timed": "separate pass of the same %d steps with CUDA events around every kernel" % args.steps,
                          "kernels": kernels},
         }

@@ -75,7 +75,7 @@ if os.path.exists(rp):
 
 with open(os.path.join(PRO, "ncu_%s.md" % R), "w") as f:
     f.write("# ncu `--set full --clock-control none` capture, round %s (config 2: 1M balls)\n\n" % R)
-    f.write("| kernel | time us | DRAM read MB | DRAM write MB | occupancy %% | regs | warp insts | issue active %% | LSU wavefront %% | smem bank conflicts | L2 hit %% |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+    f.write("| kernel | time us | DRAM read MB | DRAM write MB | occupancy % | regs | warp insts | issue active % | LSU wavefront % | smem bank conflicts | L2 hit % |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
     for k, d in kern.items():
         f.write("| `%s` | %.1f | %.1f | %.1f | %.0f | %.0f | %.3g | %.0f | %.0f | %.3g | %.0f |\n" % (
             k, d.get("time_us", 0), d.get("dram_read", 0) / 1e6, d.get("dram_write", 0) / 1e6, d.get("occupancy_pct", 0), d.get("regs", 0), d.get("warp_insts", 0),

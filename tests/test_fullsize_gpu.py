@@ -66,7 +66,7 @@ def test_config4_spheres_4m(gpu_ctx):
     ak = a.i[bb].astype(np.uint64) << np.uint64(32) | a.j[bb].astype(np.uint64)
     assert np.all(ak[1:] > ak[:-1]) and np.all(np.isin(ak, ck))
     assert np.all(np.abs(np.linalg.norm(a.n, axis=1) - 1.0) < 1e-12) and np.all(a.depth <= 0.0)
-    assert a.n_plane == int((a.type == 14).sum()) and a.n_plane > 5 * 160 * 160 * 0.9
+    assert a.n_plane == int((a.type == 14).sum()) and 5 * 160 * 160 * 0.4 < a.n_plane < 5 * 160 * 160 * 0.6   # jitter: about half of each boundary layer touches its plane
     # R unchanged (no spin), x1 = x0 + (dt*v0 + 0.5 dt^2 g) with v0 = 0
     assert np.array_equal(q1[3 * n:], s["q"][3 * n:])
     x0 = s["q"][:3 * n].reshape(-1, 3)
