@@ -221,6 +221,10 @@ int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
 int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_rb3d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
+/* Diagnostics for the mesh narrow phase: how many sample sweeps (one per direction of a mesh-mesh pair,
+   MeshMeshUtilities.cpp:10-65) read the distance field from a TMA-staged shared-memory brick and how many read
+   it directly from global memory, summed since the first mesh was added. */
+int sg_rb3d_mesh_stats( sg_ctx* ctx, uint64_t* staged_sweeps, uint64_t* direct_sweeps );
 
 #ifdef __cplusplus
 }

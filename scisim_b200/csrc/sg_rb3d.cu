@@ -19,6 +19,9 @@
 #include "sg_boxbox.cuh"
 #include "sg_broadphase.cuh"
 
+#include <cstdlib>
+#include <cuda.h> // CUtensorMap (types only; the encoder is fetched at run time through cudaGetDriverEntryPoint)
+
 #define SG_FIXED_BIT 0x80000000u
 
 // ---- contact output (SoA, reference order) ---------------------------------------------------------
@@ -207,17 +210,28 @@ struct Box3DPolicy
 };
 
 // ---- device-side scene description -----------------------------------------------------------------
-struct MeshDev
+struct alignas( 128 ) MeshDev // the descriptor is fetched from global memory by the TMA unit: keep every array element's copy 128-byte aligned
 {
+  CUtensorMap tmap;      // 3-D tiled map over the (row-padded) distance grid, box = SDF_BX x SDF_BY x SDF_BZ doubles
   const double* verts;   uint32_t nverts;
   const double* samples; uint32_t nsamples;
   const double* hull;    uint32_t nhull;
-  const double* sdf;
+  const double* sdf;     // x fastest, rows padded to `pitch` doubles (even, so the TMA row stride is a multiple of 16 B)
   double delta[3];
   double origin[3];
   double grid_end[3];
   uint32_t dims[3];
+  uint32_t pitch;
+  uint32_t has_tmap;
 };
+
+// brick tile moved by one TMA tensor copy, and how many of them a CTA can hold (128 KB of shared memory)
+#define SDF_BX 16
+#define SDF_BY 8
+#define SDF_BZ 4
+#define SDF_TILE_ELEMS ( SDF_BX * SDF_BY * SDF_BZ )
+#define SDF_TILES_MAX 48
+#define SDF_TILES_DEFAULT 12
 
 struct Rb3dDev
 {
@@ -226,6 +240,7 @@ struct Rb3dDev
   const double* bparam;    // per body 4 doubles: sphere (r,-,-,-), box (hx,hy,hz,-)
   const uint32_t* bmesh;   // per body: mesh index (meshes only)
   const MeshDev* meshes;
+  unsigned long long* mesh_stats; // [0] sample sweeps served from a TMA-staged brick, [1] sweeps that read the grid directly
 };
 
 struct Planes3D
@@ -444,26 +459,50 @@ __global__ void __launch_bounds__( 128 ) k_rb3d_aabb( const Rb3dDev dev, const d
 }
 
 // ---- narrow phase over the candidate list (generic pipeline) ----------------------------------------
-// RigidBodyTriangleMesh::detectCollision (RigidBodyTriangleMesh.cpp:276-335); n in the mesh frame
-__device__ inline bool sdf_detect( const MeshDev& mesh, const V3d x, V3d& n )
+// Where the 8 corner values of a cell come from: straight from HBM/L2, or from a brick of the grid that the CTA
+// staged in shared memory with TMA tensor copies (cp.async.bulk.tensor.3d -> UTMALDG).
+struct SdfGlobal
+{
+  const double* sdf; size_t pitch, ny;
+  __device__ __forceinline__ double at( const unsigned i, const unsigned j, const unsigned k ) const { return __ldg( sdf + ( size_t( k ) * ny + j ) * pitch + i ); }
+};
+struct SdfBrick
+{
+  const double* s; uint32_t x0, y0, z0, ntx, nty;
+  __device__ __forceinline__ double at( const unsigned i, const unsigned j, const unsigned k ) const
+  {
+    const uint32_t lx = i - x0, ly = j - y0, lz = k - z0;
+    const uint32_t tile = ( ( lz / SDF_BZ ) * nty + ( ly / SDF_BY ) ) * ntx + ( lx / SDF_BX );
+    return s[tile * SDF_TILE_ELEMS + ( ( lz % SDF_BZ ) * SDF_BY + ( ly % SDF_BY ) ) * SDF_BX + ( lx % SDF_BX )];
+  }
+};
+
+// cell of a point in the mesh frame; false when RigidBodyTriangleMesh::detectCollision rejects it on bounds
+__device__ __forceinline__ bool sdf_cell( const MeshDev& mesh, const V3d x, unsigned& ix, unsigned& iy, unsigned& iz )
 {
   if( x.x < mesh.origin[0] || x.y < mesh.origin[1] || x.z < mesh.origin[2] ) { return false; }
   if( x.x > mesh.grid_end[0] || x.y > mesh.grid_end[1] || x.z > mesh.grid_end[2] ) { return false; }
-  const unsigned ix = unsigned( floor( ( x.x - mesh.origin[0] ) / mesh.delta[0] ) );
-  const unsigned iy = unsigned( floor( ( x.y - mesh.origin[1] ) / mesh.delta[1] ) );
-  const unsigned iz = unsigned( floor( ( x.z - mesh.origin[2] ) / mesh.delta[2] ) );
+  ix = unsigned( floor( ( x.x - mesh.origin[0] ) / mesh.delta[0] ) );
+  iy = unsigned( floor( ( x.y - mesh.origin[1] ) / mesh.delta[1] ) );
+  iz = unsigned( floor( ( x.z - mesh.origin[2] ) / mesh.delta[2] ) );
   // the reference only asserts this; a sample exactly on grid_end is treated as a miss (same guard as the oracle)
-  if( ix + 1u >= mesh.dims[0] || iy + 1u >= mesh.dims[1] || iz + 1u >= mesh.dims[2] ) { return false; }
+  return !( ix + 1u >= mesh.dims[0] || iy + 1u >= mesh.dims[1] || iz + 1u >= mesh.dims[2] );
+}
+
+// RigidBodyTriangleMesh::detectCollision (RigidBodyTriangleMesh.cpp:276-335); n in the mesh frame
+template<typename Acc>
+__device__ inline bool sdf_detect( const MeshDev& mesh, const Acc& acc, const V3d x, V3d& n )
+{
+  unsigned ix, iy, iz;
+  if( !sdf_cell( mesh, x, ix, iy, iz ) ) { return false; }
   const double bcx = ( x.x - ( mesh.origin[0] + double( ix ) * mesh.delta[0] ) ) / mesh.delta[0];
   const double bcy = ( x.y - ( mesh.origin[1] + double( iy ) * mesh.delta[1] ) ) / mesh.delta[1];
   const double bcz = ( x.z - ( mesh.origin[2] + double( iz ) * mesh.delta[2] ) ) / mesh.delta[2];
   const double bix = 1.0 - bcx, biy = 1.0 - bcy, biz = 1.0 - bcz;
-  const size_t nx = mesh.dims[0], ny = mesh.dims[1];
-  const double* s = mesh.sdf + ( size_t( iz ) * ny + iy ) * nx + ix;
-  const double v000 = __ldg( s ),               v100 = __ldg( s + 1 );
-  const double v010 = __ldg( s + nx ),          v110 = __ldg( s + nx + 1 );
-  const double v001 = __ldg( s + nx * ny ),      v101 = __ldg( s + nx * ny + 1 );
-  const double v011 = __ldg( s + nx * ny + nx ), v111 = __ldg( s + nx * ny + nx + 1 );
+  const double v000 = acc.at( ix, iy, iz ),         v100 = acc.at( ix + 1, iy, iz );
+  const double v010 = acc.at( ix, iy + 1, iz ),     v110 = acc.at( ix + 1, iy + 1, iz );
+  const double v001 = acc.at( ix, iy, iz + 1 ),     v101 = acc.at( ix + 1, iy, iz + 1 );
+  const double v011 = acc.at( ix, iy + 1, iz + 1 ), v111 = acc.at( ix + 1, iy + 1, iz + 1 );
   const double dist = biz * ( biy * ( bix * v000 + bcx * v100 ) + bcy * ( bix * v010 + bcx * v110 ) ) +
                       bcz * ( biy * ( bix * v001 + bcx * v101 ) + bcy * ( bix * v011 + bcx * v111 ) );
   if( dist > 0.0 ) { return false; }
@@ -474,6 +513,12 @@ __device__ inline bool sdf_detect( const MeshDev& mesh, const V3d x, V3d& n )
   g.x /= mesh.delta[0]; g.y /= mesh.delta[1]; g.z /= mesh.delta[2];
   n = normalized3( g );
   return true;
+}
+
+__device__ __forceinline__ void sg_tma_load_3d( void* smem_dst, const CUtensorMap* map, const int c0, const int c1, const int c2, uint64_t* bar )
+{
+  asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"( sg_smem_u32( smem_dst ) ), "l"( map ), "r"( c0 ), "r"( c1 ), "r"( c2 ), "r"( sg_smem_u32( bar ) ) : "memory" );
 }
 
 #define SG_PAIR_SKIP 0u
@@ -546,14 +591,65 @@ __global__ void __launch_bounds__( 128 ) k_rb3d_pairs( const Rb3dDev dev, const 
   if( !EMIT ) { counts[k] = cnt; }
 }
 
+// One direction of MeshMeshUtilities::computeActiveSet for one pair: src's samples against dst's distance field.
+// Counting needs no order (per-thread tallies, summed by the caller); emitting writes contacts in sample order:
+// ballot inside the warp, per-warp totals through a double-buffered shared array (one barrier per 256 samples),
+// the running offset carried in a register by every thread.  Returns the number of hits this thread saw (count
+// pass) / the new running offset (emit pass).
+template<bool EMIT, typename Acc>
+__device__ inline uint32_t mesh_dir_samples( const MeshDev& src, const MeshDev& dst, const Acc& acc, const M3d& Rsd, const V3d xsd, const M3d& Rd, const V3d cd, const int dir, const bool kin,
+                                             const uint32_t b0, const uint32_t b1, const unsigned long long base, const ContactOut3D& out, uint32_t ( *s_warp )[8], uint32_t run )
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t buf = 0u;
+  for( uint32_t s0 = 0; s0 < src.nsamples; s0 += blockDim.x )
+  {
+    const uint32_t si = s0 + threadIdx.x;
+    bool hit = false;
+    V3d x = v3( 0.0, 0.0, 0.0 ), normal = x;
+    if( si < src.nsamples )
+    {
+      x = mul3( Rsd, load_v3( src.samples, si ) ) + xsd;
+      hit = sdf_detect( dst, acc, x, normal );
+    }
+    if( !EMIT ) { run += hit ? 1u : 0u; continue; }
+    const unsigned bal = __ballot_sync( 0xffffffffu, hit );
+    if( lane == 0 ) { s_warp[buf][warp] = __popc( bal ); }
+    __syncthreads();
+    uint32_t before = 0u, total = 0u;
+    #pragma unroll
+    for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[buf][w]; if( w < warp ) { before += c; } total += c; }
+    if( hit )
+    {
+      const V3d pw = mul3( Rd, x ) + cd;
+      V3d nw = mul3( Rd, normal );
+      if( dir == 1 ) { nw = -nw; }
+      put_contact( out, base + run + before + __popc( bal & ( ( 1u << lane ) - 1u ) ), kin ? SG_KINEMATIC_BODY_BODY : SG_BODY_BODY, b0, b1, 0u, nw, pw, sg_nan() );
+    }
+    run += total;
+    buf ^= 1u;
+  }
+  return run;
+}
+
 // One CTA per candidate pair; only mesh-mesh pairs do work (MeshMeshUtilities.cpp:10-65): mesh0's samples against
-// mesh1's distance field, then mesh1's samples against mesh0's, contacts in sample order.
+// mesh1's distance field, then mesh1's samples against mesh0's.  Per direction the CTA first finds the brick of
+// grid cells its in-range samples fall into and, when it fits, pulls it into shared memory with TMA tensor copies
+// (one SDF_BX x SDF_BY x SDF_BZ tile each, completion on an mbarrier); the trilinear lookups then read shared memory.
 template<bool EMIT>
 __global__ void __launch_bounds__( 256 ) k_rb3d_mesh_pairs( const Rb3dDev dev, const uint2* __restrict__ pairs, const unsigned long long* __restrict__ npairs_dev, const double* __restrict__ q1,
-                                                           uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets, const ContactOut3D out )
+                                                           uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets, const ContactOut3D out, const uint32_t tile_cap )
 {
-  __shared__ uint32_t s_warp[8];
-  __shared__ uint32_t s_run;
+  extern __shared__ __align__( 128 ) unsigned char s_dyn[];
+  double* s_brick = reinterpret_cast<double*>( s_dyn );
+  __shared__ uint32_t s_warp[2][8];
+  __shared__ uint32_t s_count;
+  __shared__ int s_ext[6];
+  __shared__ __align__( 8 ) unsigned long long s_bar;
+  uint64_t* bar = reinterpret_cast<uint64_t*>( &s_bar );
+  if( threadIdx.x == 0 ) { sg_mbar_init( bar, 1u ); }
+  __syncthreads();
+  uint32_t phase = 0u;
   for( unsigned long long k = blockIdx.x; k < *npairs_dev; k += gridDim.x )
   {
     const uint2 pr = pairs[k];
@@ -566,10 +662,7 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_mesh_pairs( const Rb3dDev dev, c
     const V3d cm0 = load_v3( q1, b0 ), cm1 = load_v3( q1, b1 );
     const M3d R0 = load_m3( q1 + 3 * nb, b0 ), R1 = load_m3( q1 + 3 * nb, b1 );
     const unsigned long long base = EMIT ? offsets[k] : 0ull;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if( threadIdx.x == 0 ) { s_run = 0u; }
-    __syncthreads();
+    uint32_t run = 0u; // count pass: this thread's hits; emit pass: contacts written so far for the pair (uniform)
     for( int dir = 0; dir < 2; ++dir )
     {
       const MeshDev& src = dir == 0 ? mesh0 : mesh1;
@@ -580,35 +673,81 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_mesh_pairs( const Rb3dDev dev, c
       const V3d cd = dir == 0 ? cm1 : cm0;
       const M3d Rsd = mulTN33( Rd, Rs );
       const V3d xsd = mulT3( Rd, cs - cd );
-      for( uint32_t s0 = 0; s0 < src.nsamples; s0 += blockDim.x )
+      // brick of cells touched by the in-range samples
+      if( threadIdx.x < 6 ) { s_ext[threadIdx.x] = ( threadIdx.x < 3 ) ? 0x7fffffff : -1; }
+      __syncthreads();
       {
-        const uint32_t si = s0 + threadIdx.x;
-        bool hit = false;
-        V3d x = v3( 0.0, 0.0, 0.0 ), normal = x;
-        if( si < src.nsamples )
+        // Only a covering brick is needed here, so the cell is estimated with a reciprocal multiply (no fp64 divide)
+        // and widened by one cell each way; the exact reference arithmetic runs in the sweep below.
+        int mn[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff }, mx[3] = { -1, -1, -1 };
+        const double inv0 = 1.0 / dst.delta[0], inv1 = 1.0 / dst.delta[1], inv2 = 1.0 / dst.delta[2];
+        for( uint32_t si = threadIdx.x; si < src.nsamples; si += blockDim.x )
         {
-          x = mul3( Rsd, load_v3( src.samples, si ) ) + xsd;
-          hit = sdf_detect( dst, x, normal );
+          const V3d x = mul3( Rsd, load_v3( src.samples, si ) ) + xsd;
+          if( x.x < dst.origin[0] || x.y < dst.origin[1] || x.z < dst.origin[2] || x.x > dst.grid_end[0] || x.y > dst.grid_end[1] || x.z > dst.grid_end[2] ) { continue; }
+          const int ex = int( ( x.x - dst.origin[0] ) * inv0 ), ey = int( ( x.y - dst.origin[1] ) * inv1 ), ez = int( ( x.z - dst.origin[2] ) * inv2 );
+          mn[0] = min( mn[0], ex - 1 ); mn[1] = min( mn[1], ey - 1 ); mn[2] = min( mn[2], ez - 1 );
+          mx[0] = max( mx[0], ex + 1 ); mx[1] = max( mx[1], ey + 1 ); mx[2] = max( mx[2], ez + 1 );
         }
-        const unsigned bal = __ballot_sync( 0xffffffffu, hit );
-        if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
-        __syncthreads();
-        uint32_t before = 0u, total = 0u;
-        for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } total += c; }
-        const uint32_t run = s_run;
-        if( EMIT && hit )
+        #pragma unroll
+        for( int a = 0; a < 3; ++a )
         {
-          const V3d pw = mul3( Rd, x ) + cd;
-          V3d nw = mul3( Rd, normal );
-          if( dir == 1 ) { nw = -nw; }
-          put_contact( out, base + run + before + __popc( bal & ( ( 1u << lane ) - 1u ) ), kin ? SG_KINEMATIC_BODY_BODY : SG_BODY_BODY, b0, b1, 0u, nw, pw, sg_nan() );
+          #pragma unroll
+          for( int d = 16; d > 0; d >>= 1 ) { mn[a] = min( mn[a], __shfl_xor_sync( 0xffffffffu, mn[a], d ) ); mx[a] = max( mx[a], __shfl_xor_sync( 0xffffffffu, mx[a], d ) ); }
+          if( ( threadIdx.x & 31 ) == 0 ) { atomicMin( &s_ext[a], mn[a] ); atomicMax( &s_ext[3 + a], mx[a] ); }
         }
-        __syncthreads();
-        if( threadIdx.x == 0 ) { s_run = run + total; }
-        __syncthreads();
       }
+      __syncthreads();
+      // measured on B200: a tensor copy of 8-byte elements faults (illegal instruction) unless the innermost start
+      // coordinate is 16-byte aligned, so bricks start on an even x
+      const int x0 = max( s_ext[0], 0 ) & ~1, y0 = max( s_ext[1], 0 ), z0 = max( s_ext[2], 0 );
+      const bool any = s_ext[3] >= 0;
+      // corners go one cell beyond the largest cell index; cells past dims-2 are rejected by the sweep
+      const int x1 = min( s_ext[3], int( dst.dims[0] ) - 2 ) + 2, y1 = min( s_ext[4], int( dst.dims[1] ) - 2 ) + 2, z1 = min( s_ext[5], int( dst.dims[2] ) - 2 ) + 2;
+      const uint32_t ntx = any ? uint32_t( x1 - x0 + SDF_BX - 1 ) / SDF_BX : 0u;
+      const uint32_t nty = any ? uint32_t( y1 - y0 + SDF_BY - 1 ) / SDF_BY : 0u;
+      const uint32_t ntz = any ? uint32_t( z1 - z0 + SDF_BZ - 1 ) / SDF_BZ : 0u;
+      const uint32_t ntiles = ntx * nty * ntz;
+      const bool staged = any && dst.has_tmap != 0u && ntiles <= tile_cap;
+      __syncthreads(); // s_ext is consumed; the next direction may reset it
+      if( !any ) { continue; } // no sample of src lies inside dst's grid: nothing can collide (uniform)
+      if( !EMIT && threadIdx.x == 0 ) { atomicAdd( &dev.mesh_stats[staged ? 0 : 1], 1ull ); }
+      if( staged )
+      {
+        if( threadIdx.x == 0 )
+        {
+          asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); // earlier generic reads of the brick vs the async writes to come
+          // the descriptor was written to global memory by a host copy: acquire it for the tensormap proxy
+          asm volatile( "fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"( &dst.tmap ) : "memory" );
+          sg_mbar_arrive_expect_tx( bar, ntiles * SDF_TILE_ELEMS * 8u );
+          for( uint32_t t = 0; t < ntiles; ++t )
+          {
+            const uint32_t tx = t % ntx, ty = ( t / ntx ) % nty, tz = t / ( ntx * nty );
+            sg_tma_load_3d( s_brick + size_t( t ) * SDF_TILE_ELEMS, &dst.tmap, x0 + int( tx ) * SDF_BX, y0 + int( ty ) * SDF_BY, z0 + int( tz ) * SDF_BZ, bar );
+          }
+        }
+        sg_mbar_wait( bar, phase );
+        phase ^= 1u;
+        SdfBrick acc; acc.s = s_brick; acc.x0 = uint32_t( x0 ); acc.y0 = uint32_t( y0 ); acc.z0 = uint32_t( z0 ); acc.ntx = ntx; acc.nty = nty;
+        run = mesh_dir_samples<EMIT>( src, dst, acc, Rsd, xsd, Rd, cd, dir, kin, b0, b1, base, out, s_warp, run );
+      }
+      else
+      {
+        SdfGlobal acc; acc.sdf = dst.sdf; acc.pitch = dst.pitch; acc.ny = dst.dims[1];
+        run = mesh_dir_samples<EMIT>( src, dst, acc, Rsd, xsd, Rd, cd, dir, kin, b0, b1, base, out, s_warp, run );
+      }
+      __syncthreads();
     }
-    if( !EMIT && threadIdx.x == 0 ) { counts[k] = s_run; }
+    if( !EMIT )
+    {
+      if( threadIdx.x == 0 ) { s_count = 0u; }
+      __syncthreads();
+      #pragma unroll
+      for( int d = 16; d > 0; d >>= 1 ) { run += __shfl_xor_sync( 0xffffffffu, run, d ); }
+      if( ( threadIdx.x & 31 ) == 0 && run != 0u ) { atomicAdd( &s_count, run ); }
+      __syncthreads();
+      if( threadIdx.x == 0 ) { counts[k] = s_count; }
+    }
   }
 }
 
@@ -752,6 +891,7 @@ struct Rb3dData
   std::vector<double> geo_r, geo_half;
   std::vector<MeshHost*> meshes;
   DevBuf d_meshes; // MeshDev[]
+  DevBuf mesh_stats;
   DevBuf btype, bparam, bmesh, radius, flags, mass, I0;
   DevBuf q0, v0, q1, v1, boxes;
   BroadScratch bp;
@@ -773,7 +913,7 @@ void sg_rb3d_release( sg_ctx* ctx )
   Rb3dData* d = ctx->rb3d;
   if( d == nullptr ) { return; }
   for( MeshHost* m : d->meshes ) { m->verts.release(); m->samples.release(); m->hull.release(); m->sdf.release(); delete m; }
-  DevBuf* bufs[] = { &d->d_meshes, &d->btype, &d->bparam, &d->bmesh, &d->radius, &d->flags, &d->mass, &d->I0, &d->q0, &d->v0, &d->q1, &d->v1, &d->boxes,
+  DevBuf* bufs[] = { &d->d_meshes, &d->mesh_stats, &d->btype, &d->bparam, &d->bmesh, &d->radius, &d->flags, &d->mass, &d->I0, &d->q0, &d->v0, &d->q1, &d->v1, &d->boxes,
                      &d->pair_counts, &d->pair_offsets, &d->pair_partials, &d->narrow_total, &d->bad_flag, &d->npairs_dev,
                      &d->st_counts, &d->st_offsets, &d->st_partials, &d->st_total, &d->totals3,
                      &d->c_type, &d->c_i, &d->c_j, &d->c_aux, &d->c_n, &d->c_p, &d->c_depth };
@@ -798,6 +938,7 @@ static Rb3dDev rb3d_dev( const Rb3dData* d )
   dev.bparam = d->bparam.as<double>();
   dev.bmesh = d->bmesh.as<uint32_t>();
   dev.meshes = d->d_meshes.as<MeshDev>();
+  dev.mesh_stats = d->mesh_stats.as<unsigned long long>();
   return dev;
 }
 
@@ -930,6 +1071,7 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
   SG_CUDA( ctx, cudaMemcpyAsync( ht, d->bp.totals.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   const uint64_t np = ht[0];
+  uint32_t mesh_tiles = SDF_TILES_DEFAULT;
   d->n_cand = np;
   rc = rb3d_ensure_outputs( ctx, d, np + 64, d->act_cap );
   if( rc != SG_OK ) { return rc; }
@@ -951,7 +1093,12 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
     if( !d->meshes.empty() )
     {
       const unsigned grid = unsigned( np < uint64_t( ctx->num_sms ) * 8u ? np : uint64_t( ctx->num_sms ) * 8u );
-      SG_LAUNCH( ctx, "rb3d_mesh_count", 0.0, k_rb3d_mesh_pairs<false><<<grid, 256, 0, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q1.as<double>(), d->pair_counts.as<uint32_t>(), nullptr, rb3d_out( d ) ) );
+      SG_CUDA( ctx, cudaFuncSetAttribute( k_rb3d_mesh_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_TILES_MAX * SDF_TILE_ELEMS * 8 ) );
+      SG_CUDA( ctx, cudaFuncSetAttribute( k_rb3d_mesh_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_TILES_MAX * SDF_TILE_ELEMS * 8 ) );
+      const char* tiles_env = getenv( "SG_RB3D_TILES" ); // tuning knob: brick capacity per CTA in 4 KB tiles
+      mesh_tiles = tiles_env != nullptr ? uint32_t( atoi( tiles_env ) ) : SDF_TILES_DEFAULT;
+      mesh_tiles = mesh_tiles < 1u ? 1u : ( mesh_tiles > SDF_TILES_MAX ? SDF_TILES_MAX : mesh_tiles );
+      SG_LAUNCH( ctx, "rb3d_mesh_count", 0.0, k_rb3d_mesh_pairs<false><<<grid, 256, mesh_tiles * SDF_TILE_ELEMS * 8, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q1.as<double>(), d->pair_counts.as<uint32_t>(), nullptr, rb3d_out( d ), mesh_tiles ) );
     }
     rc = sg_exclusive_scan<ScanU32To64>( ctx, "rb3d_pair_scan", d->pair_counts.as<uint32_t>(), nullptr, uint32_t( np ), uint32_t( np ), d->pair_partials.as<unsigned long long>(), d->pair_offsets.as<unsigned long long>(),
                                          d->narrow_total.as<unsigned long long>(), false );
@@ -982,7 +1129,7 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
     if( !d->meshes.empty() )
     {
       const unsigned grid = unsigned( np < uint64_t( ctx->num_sms ) * 8u ? np : uint64_t( ctx->num_sms ) * 8u );
-      SG_LAUNCH( ctx, "rb3d_mesh_emit", 0.0, k_rb3d_mesh_pairs<true><<<grid, 256, 0, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q1.as<double>(), nullptr, d->pair_offsets.as<unsigned long long>(), rb3d_out( d ) ) );
+      SG_LAUNCH( ctx, "rb3d_mesh_emit", 0.0, k_rb3d_mesh_pairs<true><<<grid, 256, mesh_tiles * SDF_TILE_ELEMS * 8, ctx->stream>>>( dev, d->bp.cand.as<uint2>(), npairs_dev, d->q1.as<double>(), nullptr, d->pair_offsets.as<unsigned long long>(), rb3d_out( d ), mesh_tiles ) );
     }
   }
   rc = rb3d_planes_device( ctx, d, true );
@@ -1096,7 +1243,8 @@ int sg_rb3d_add_mesh( sg_ctx* ctx, uint32_t nverts, const double* verts, uint32_
   Rb3dData* d = rb3d_data( ctx );
   MeshHost* m = new MeshHost;
   d->meshes.push_back( m );
-  const size_t ncell = size_t( dims[0] ) * dims[1] * dims[2];
+  const uint32_t pitch = ( dims[0] + 1u ) & ~1u; // even row length: TMA global strides must be multiples of 16 bytes
+  const size_t ncell = size_t( pitch ) * dims[1] * dims[2];
   SG_CUDA( ctx, m->verts.ensure( size_t( nverts ) * 24 + 8 ) );
   SG_CUDA( ctx, m->samples.ensure( size_t( nsamples ) * 24 + 8 ) );
   SG_CUDA( ctx, m->hull.ensure( size_t( nhull ) * 24 + 8 ) );
@@ -1104,7 +1252,7 @@ int sg_rb3d_add_mesh( sg_ctx* ctx, uint32_t nverts, const double* verts, uint32_
   if( nverts ) { SG_CUDA( ctx, cudaMemcpyAsync( m->verts.ptr, verts, size_t( nverts ) * 24, cudaMemcpyHostToDevice, ctx->stream ) ); }
   if( nsamples ) { SG_CUDA( ctx, cudaMemcpyAsync( m->samples.ptr, samples, size_t( nsamples ) * 24, cudaMemcpyHostToDevice, ctx->stream ) ); }
   if( nhull ) { SG_CUDA( ctx, cudaMemcpyAsync( m->hull.ptr, hull, size_t( nhull ) * 24, cudaMemcpyHostToDevice, ctx->stream ) ); }
-  SG_CUDA( ctx, cudaMemcpyAsync( m->sdf.ptr, sdf, ncell * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpy2DAsync( m->sdf.ptr, size_t( pitch ) * 8, sdf, size_t( dims[0] ) * 8, size_t( dims[0] ) * 8, size_t( dims[1] ) * dims[2], cudaMemcpyHostToDevice, ctx->stream ) );
   m->dev.verts = m->verts.as<double>(); m->dev.nverts = nverts;
   m->dev.samples = m->samples.as<double>(); m->dev.nsamples = nsamples;
   m->dev.hull = m->hull.as<double>(); m->dev.nhull = nhull;
@@ -1115,6 +1263,34 @@ int sg_rb3d_add_mesh( sg_ctx* ctx, uint32_t nverts, const double* verts, uint32_
     // RigidBodyTriangleMesh.cpp:102: grid_end = origin + (dims - 1) * delta  (host FP64; product then sum, no contraction)
     volatile double prod = double( dims[k] - 1u ) * cell_delta[k];
     m->dev.grid_end[k] = origin[k] + prod;
+  }
+  m->dev.pitch = pitch;
+  m->dev.has_tmap = 0u;
+  memset( &m->dev.tmap, 0, sizeof( m->dev.tmap ) );
+  {
+    // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+    typedef CUresult ( *EncodeFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // SG_RB3D_NO_TMA=1 keeps every lookup on the direct path (A/B timing only; results are identical either way)
+    const char* no_tma = getenv( "SG_RB3D_NO_TMA" );
+    if( ( no_tma == nullptr || no_tma[0] == '0' ) && cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn != nullptr )
+    {
+      const cuuint64_t gdim[3] = { pitch, dims[1], dims[2] };
+      const cuuint64_t gstride[2] = { cuuint64_t( pitch ) * 8, cuuint64_t( pitch ) * dims[1] * 8 };
+      const cuuint32_t box[3] = { SDF_BX, SDF_BY, SDF_BZ };
+      const cuuint32_t estr[3] = { 1, 1, 1 };
+      const CUresult r = reinterpret_cast<EncodeFn>( fn )( &m->dev.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, m->sdf.ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+      m->dev.has_tmap = ( r == CUDA_SUCCESS ) ? 1u : 0u;
+    }
+    cudaGetLastError();
+  }
+  if( d->mesh_stats.ptr == nullptr )
+  {
+    SG_CUDA( ctx, d->mesh_stats.ensure( 16 ) );
+    SG_CUDA( ctx, cudaMemsetAsync( d->mesh_stats.ptr, 0, 16, ctx->stream ) );
   }
   std::vector<MeshDev> all;
   for( MeshHost* mh : d->meshes ) { all.push_back( mh->dev ); }
@@ -1241,6 +1417,22 @@ int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
     out->n_plane = d->n_static;
     out->n_active = d->n_bb + d->n_static;
   }
+  return SG_OK;
+}
+
+int sg_rb3d_mesh_stats( sg_ctx* ctx, uint64_t* staged_sweeps, uint64_t* direct_sweeps )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  unsigned long long h[2] = { 0ull, 0ull };
+  if( d->mesh_stats.ptr != nullptr )
+  {
+    SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h, d->mesh_stats.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  }
+  if( staged_sweeps != nullptr ) { *staged_sweeps = h[0]; }
+  if( direct_sweeps != nullptr ) { *direct_sweeps = h[1]; }
   return SG_OK;
 }
 

@@ -365,6 +365,12 @@ class RigidBody3DSim:
         q, v = _f64(q), _f64(v)
         self.ctx.check(self.ctx.lib.sg_rb3d_upload(self.ctx.h, _ptr(q), _ptr(v)))
 
+    def meshStats(self):
+        """(sample sweeps served from a TMA-staged SDF brick, sweeps that read the grid directly)"""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.sg_rb3d_mesh_stats(self.ctx.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def step(self, umap, dt):
         c = SgContacts()
         self.ctx.check(self.ctx.lib.sg_rb3d_step(self.ctx.h, umap.kind, float(dt), C.byref(c)))

@@ -172,10 +172,10 @@ def torus_mesh(R=1.0, r=0.4, grid=40, nsamples=600, seed=3, pad=0.25):
     return {"verts": verts, "samples": samples, "hull": hull, "cell_delta": delta, "dims": dims, "origin": origin, "sdf": sdf.ravel()}
 
 
-def rb3d_random_meshes(n, seed, spin=True, nfixed_frac=0.1, nplanes=1, box=None):
+def rb3d_random_meshes(n, seed, spin=True, nfixed_frac=0.1, nplanes=1, box=None, grid=(36, 30), nsamples=(500, 400)):
     rng = np.random.Generator(np.random.PCG64(seed))
     box = box if box is not None else max(1.5, n ** (1.0 / 3.0) * 1.1)
-    meshes = [torus_mesh(1.0, 0.4, 36, 500, seed=3), torus_mesh(0.8, 0.3, 30, 400, seed=4)]
+    meshes = [torus_mesh(1.0, 0.4, grid[0], nsamples[0], seed=3), torus_mesh(0.8, 0.3, grid[1], nsamples[1], seed=4)]
     gi = rng.integers(0, 2, size=n)
     fixed = (rng.uniform(size=n) < nfixed_frac).astype(np.uint8)
     x = rng.uniform(-box, box, size=(n, 3))

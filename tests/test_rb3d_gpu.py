@@ -200,3 +200,20 @@ def test_empty_rb3d(gpu_ctx):
     sim = sb.RigidBody3DSim(st, ctx=gpu_ctx)
     a = sim.computeActiveSet(np.zeros(0), np.zeros(0))
     assert a.n_active == 0 and a.n_candidates == 0
+
+
+def test_meshes_use_tma_bricks(gpu_ctx, oracle):
+    """The mesh narrow phase must serve (most of) its distance-field lookups from TMA-staged bricks, and the
+    result must be the oracle's either way."""
+    from tests import oracle_binding as ob
+    s = scenes.rb3d_random_meshes(150, 3)
+    sim = make_sim(s, gpu_ctx)
+    o = ob.RB3DOracle(s)
+    q1, _ = o.flow(3, s["q"], s["v"], s["dt"])
+    ref = o.active_set(s["q"], q1, "allpairs")
+    s0, d0 = sim.meshStats()
+    got = sim.computeActiveSet(s["q"], q1)
+    s1, d1 = sim.meshStats()
+    assert s1 - s0 > 0, "no sweep was staged through TMA"
+    assert (s1 - s0) > (d1 - d0), "most sweeps should fit the shared-memory brick: staged %d direct %d" % (s1 - s0, d1 - d0)
+    assert_active_equal(got, ref)
