@@ -487,10 +487,13 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   Ball2DIn in;
   in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS();
   d->bp.gid_map = d->GID();
+  // the (tiny, latency-bound) scan of the static-geometry counts rides along with the pair-count scan
+  const bool side_scan = ng > 0 && nst <= SG_SIDE_SCAN_MAX;
+  if( side_scan ) { d->bp.side.in = d->st_counts.as<uint32_t>(); d->bp.side.n = nst; d->bp.side.out = d->st_offsets.as<uint32_t>(); d->bp.side.total = d->st_total.as<uint32_t>(); }
   rc = sg_bp_bin_and_count<Ball2DPolicy>( ctx, d->bp, in, true );
   if( rc != SG_OK ) { return rc; }
 
-  if( ng > 0 )
+  if( ng > 0 && !side_scan )
   {
     rc = sg_exclusive_scan<ScanU32>( ctx, "ball2d_static_scan", d->st_counts.as<uint32_t>(), nullptr, nst, nst, d->st_partials.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->st_total.as<uint32_t>(), false );
     if( rc != SG_OK ) { return rc; }
@@ -503,12 +506,25 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
     out.n = d->c_n.as<double2>(); out.p = d->c_p.as<double2>(); out.depth = d->c_depth.as<double>();
     out.cap = d->act_cap;
     out.gid = d->GID();
+    // The static-geometry contacts go behind the body-body ones (their base is the pair scan's total) and touch
+    // nothing the pair emit does, so the two kernels run side by side (serially when kernels are being timed).
+    cudaStream_t side = ( ng > 0 && !ctx->profile ) ? ctx->stream2 : ctx->stream;
+    if( side != ctx->stream )
+    {
+      SG_CUDA( ctx, cudaEventRecord( ctx->ev_fork, ctx->stream ) );
+      SG_CUDA( ctx, cudaStreamWaitEvent( side, ctx->ev_fork, 0 ) );
+    }
     rc = sg_bp_emit_lists<Ball2DPolicy>( ctx, d->bp, n, want_cand, out, 0.0 );
     if( rc != SG_OK ) { return rc; }
     if( ng > 0 )
     {
-      SG_LAUNCH( ctx, "ball2d_static_emit", double( n ) * 40.0, k_ball2d_static_emit<<<nblk, 256, 0, ctx->stream>>>( d->sg, n, d->Q0(), d->Q1(), d->R(),
+      SG_LAUNCH( ctx, "ball2d_static_emit", double( n ) * 40.0, k_ball2d_static_emit<<<nblk, 256, 0, side>>>( d->sg, n, d->Q0(), d->Q1(), d->R(),
                  d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->bp.totals.as<ScanPairCounts::Acc>(), out, d->own_first(), d->own_count() ) );
+    }
+    if( side != ctx->stream )
+    {
+      SG_CUDA( ctx, cudaEventRecord( ctx->ev_join, side ) );
+      SG_CUDA( ctx, cudaStreamWaitEvent( ctx->stream, ctx->ev_join, 0 ) );
     }
     // counts to the host
     unsigned long long* ht = d->h_totals.as<unsigned long long>();

@@ -44,19 +44,21 @@ struct BroadScratch
   DevBuf pos_of;        // u32[n]  sorted position of body i (offsets are scattered to position order)
   DevBuf counts;        // uint2[n]  by body index
   DevBuf masks;         // uint4[n]  by sorted position
+  DevBuf plan;          // uint4[NPLAN][n]  by sorted position: where each window of the body's walk starts and how long it is
   DevBuf offsets;       // ulonglong2[n]  by sorted position
   DevBuf pair_partials; // ScanPairCounts::Acc[tiles]
   DevBuf totals;        // ScanPairCounts::Acc
   DevBuf cand;          // uint2[cand_cap]
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
+  SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
   const uint32_t* gid_map = nullptr; // multi-GPU: local body index -> global body index for the emitted lists
   int bounds_phase = 0; // which of the two BoundsAccum the current step reduces into
   BoundsAccum* bounds_cur() const { return bounds.as<BoundsAccum>() + bounds_phase; }
   void release()
   {
     bounds.release(); params.release(); cell_count.release(); cell_start.release(); cell_partials.release(); key.release(); rank.release();
-    recs.release(); sidx.release(); pos_of.release(); counts.release(); masks.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
+    recs.release(); sidx.release(); pos_of.release(); counts.release(); masks.release(); plan.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
   }
 };
 
@@ -328,8 +330,6 @@ struct BpStage
 
 template<int D> __host__ __device__ constexpr size_t sg_bp_cs_bytes() { return size_t( BpCfg<D>::NW ) * BpCfg<D>::CSCAP * 4; }
 template<int D> __host__ __device__ constexpr size_t sg_bp_count_smem() { return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + sg_bp_cs_bytes<D>() + sizeof( BpStage<D> ) + 127 ) & ~size_t( 127 ); }
-template<int D> __host__ __device__ constexpr size_t sg_bp_emit_list_offset() { return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 4 + sg_bp_cs_bytes<D>() + sizeof( BpStage<D> ) + 127 ) & ~size_t( 127 ); }
-template<int D> __host__ __device__ constexpr size_t sg_bp_emit_smem() { return sg_bp_emit_list_offset<D>() + size_t( SG_BP_FAST_CAP ) * BpCfg<D>::T * 8; }
 
 // All threads of the block call this; returns once the staged windows are readable.
 // FULL: s_data receives swizzled 64-byte records; otherwise the u32 index words from sidx.
@@ -400,18 +400,16 @@ __device__ __forceinline__ uint32_t sg_bp_cs( const BpStage<D>* st, const uint32
   return ( rel < st->cs_len[w] ) ? s_cs[w * BpCfg<D>::CSCAP + rel] : __ldg( &cell_start[key] );
 }
 
-// Calls f( w, q ) for every sorted position q != p whose cell is within one cell of (cx,c1,c2) on every axis,
-// in a fixed order (window-major, position ascending): both passes see the same sequence.
-template<typename P, typename F>
-__device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t* s_cs, const BpStage<P::D>* st,
-                                                const uint32_t p, const uint32_t key, const uint32_t c1, const uint32_t c2, F&& f )
+// [qb[w], qe[w]) = sorted positions of the bodies whose cell is within one cell of (cx,c1,c2) in row window w
+template<typename P>
+__device__ __forceinline__ void sg_bp_ranges( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t* s_cs, const BpStage<P::D>* st,
+                                              const uint32_t key, const uint32_t c1, const uint32_t c2, uint32_t* qb, uint32_t* qe )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   const uint32_t cx = key - g.dims[0] * ( c1 + g.dims[1] * c2 );
   const uint32_t x0 = ( cx > 0u ) ? cx - 1u : 0u;
   const uint32_t x1 = ( cx + 1u < g.dims[0] ) ? cx + 1u : cx;
-  uint32_t qb[Cfg::NW], qe[Cfg::NW];
   #pragma unroll
   for( int w = 0; w < Cfg::NW; ++w )
   {
@@ -428,14 +426,69 @@ __device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint3
       qe[w] = sg_bp_cs<D>( st, s_cs, cell_start, w, row + x1 + 1u );
     }
   }
+}
+
+// Calls f( w, q ) for every sorted position q != p of the ranges, in a fixed order (window-major, position
+// ascending): this is THE visit sequence -- bit k of the pass-1 masks is the k-th call.
+template<typename P, typename F>
+__device__ __forceinline__ void sg_bp_walk_ranges( const uint32_t* qb, const uint32_t* qe, const uint32_t p, F&& f )
+{
   #pragma unroll
-  for( int w = 0; w < Cfg::NW; ++w )
+  for( int w = 0; w < BpCfg<P::D>::NW; ++w )
   {
     for( uint32_t q = qb[w]; q < qe[w]; ++q )
     {
       if( q != p ) { f( w, q ); }
     }
   }
+}
+
+template<typename P, typename F>
+__device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t* s_cs, const BpStage<P::D>* st,
+                                                const uint32_t p, const uint32_t key, const uint32_t c1, const uint32_t c2, F&& f )
+{
+  uint32_t qb[BpCfg<P::D>::NW], qe[BpCfg<P::D>::NW];
+  sg_bp_ranges<P>( g, cell_start, s_cs, st, key, c1, c2, qb, qe );
+  sg_bp_walk_ranges<P>( qb, qe, p, f );
+}
+
+// The walk plan pass 1 leaves for pass 2: per body the window starts and lengths (clipped to 255; a body whose
+// walk is longer than 32 visits has invalid masks anyway), NPLAN uint4 per body, plane c of body p at plan[c*n+p].
+template<int D> struct BpPlan;
+template<> struct BpPlan<2> { static constexpr int NPLAN = 1; };
+template<> struct BpPlan<3> { static constexpr int NPLAN = 3; };
+
+template<int D>
+__device__ __forceinline__ void sg_bp_plan_store( uint4* __restrict__ plan, const uint32_t n, const uint32_t p, const uint32_t* qb, const uint32_t* qe )
+{
+  constexpr int NW = BpCfg<D>::NW;
+  uint32_t words[BpPlan<D>::NPLAN * 4];
+  #pragma unroll
+  for( int k = 0; k < BpPlan<D>::NPLAN * 4; ++k ) { words[k] = 0u; }
+  #pragma unroll
+  for( int w = 0; w < NW; ++w )
+  {
+    words[w] = qb[w];
+    const uint32_t len = ( qe[w] - qb[w] < 255u ) ? qe[w] - qb[w] : 255u;
+    words[NW + w / 4] |= len << ( 8 * ( w % 4 ) );
+  }
+  #pragma unroll
+  for( int c = 0; c < BpPlan<D>::NPLAN; ++c ) { plan[size_t( c ) * n + p] = make_uint4( words[4 * c], words[4 * c + 1], words[4 * c + 2], words[4 * c + 3] ); }
+}
+
+template<int D>
+__device__ __forceinline__ void sg_bp_plan_load( const uint4* __restrict__ plan, const uint32_t n, const uint32_t p, uint32_t* qb, uint32_t* len )
+{
+  constexpr int NW = BpCfg<D>::NW;
+  uint32_t words[BpPlan<D>::NPLAN * 4];
+  #pragma unroll
+  for( int c = 0; c < BpPlan<D>::NPLAN; ++c )
+  {
+    const uint4 v = __ldg( &plan[size_t( c ) * n + p] );
+    words[4 * c] = v.x; words[4 * c + 1] = v.y; words[4 * c + 2] = v.z; words[4 * c + 3] = v.w;
+  }
+  #pragma unroll
+  for( int w = 0; w < NW; ++w ) { qb[w] = words[w]; len[w] = ( words[NW + w / 4] >> ( 8 * ( w % 4 ) ) ) & 255u; }
 }
 
 // record (or just its body index) at sorted position q, known to lie in window w's key range
@@ -465,8 +518,8 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
 // Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active (bit 31: masks invalid) }
 //          masks[sorted position] = { candidate mask, active mask over the visit sequence, the two counts again }
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint4* __restrict__ masks )
+__global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -477,8 +530,9 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
   BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 + sg_bp_cs_bytes<D>() );
   const GridParams g = *params;
   const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned (unused slots are not)
-  if( blockIdx.x * Cfg::T >= n ) { return; }
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
+  if( p >= n && p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slot: pass 2 skips it
+  if( blockIdx.x * Cfg::T >= n ) { return; }
   Rec me;
   if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the windows are staged
   sg_bp_stage<P, true>( g, n, cell_start, recs, nullptr, s_recs, s_cs, st );
@@ -494,7 +548,10 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
   uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
-  sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), [&]( const int w, const uint32_t q )
+  uint32_t qb[Cfg::NW], qe[Cfg::NW];
+  sg_bp_ranges<P>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
+  sg_bp_plan_store<D>( plan, n_slots, p, qb, qe );
+  sg_bp_walk_ranges<P>( qb, qe, p, [&]( const int w, const uint32_t q )
   {
     const uint32_t bit = ( k < 32u ) ? ( 1u << k ) : 0u;
     ++k;
@@ -514,83 +571,26 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T ) sg_bp_count( const uint32_t 
   masks[p] = make_uint4( cmask, amask, nc, na_f );
 }
 
-// Pass 2.  Each body writes its candidates (ascending partner index) at its offset; active ones also write a contact.
-// Everything a thread needs up front is indexed by sorted position (coalesced, independent loads).
+// Slow paths of pass 2: redo the tests (a body with more than 32 neighbours or more candidates than the sorting
+// network holds); everything comes through L1/L2.  Kept out of line so the common path stays lean in registers.
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks,
-                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, const typename P::Out out )
+__device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, const ulonglong2 off, const uint32_t my_idx, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, uint2* __restrict__ cand, const uint64_t cand_cap,
+                                              const uint32_t* __restrict__ gid, const typename P::Out& out )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
-  extern __shared__ __align__( 128 ) unsigned char s_raw[];
-  uint32_t* s_idx = reinterpret_cast<uint32_t*>( s_raw );                                                 // [NW][WCAP]
-  uint32_t* s_cs = reinterpret_cast<uint32_t*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 4 );
-  BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 4 + sg_bp_cs_bytes<D>() );
-  unsigned long long* s_list = reinterpret_cast<unsigned long long*>( s_raw + sg_bp_emit_list_offset<D>() ); // [SG_BP_FAST_CAP][T]
-  const GridParams g = *params;
-  const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) );
-  if( blockIdx.x * Cfg::T >= n ) { return; }
-  const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
-  Rec me;
-  uint4 m = make_uint4( 0u, 0u, 0u, 0u );
-  ulonglong2 off = make_ulonglong2( 0ull, 0ull );
-  if( p < n )
-  {
-    me = sg_load_rec_global<Rec>( &recs[p] );
-    m = masks[p];
-    off = offsets_pos[p];
-  }
-  sg_bp_stage<P, false>( g, n, cell_start, recs, sidx, reinterpret_cast<unsigned char*>( s_idx ), s_cs, st );
-  if( p >= n || m.z == 0u ) { return; }
-  const uint32_t my_idx = P::rec_idx( me );
   unsigned long long ka = off.y;
+  const GridParams g = *params;
+  const Rec me = sg_load_rec_global<Rec>( &recs[p] );
   const uint32_t key = P::rec_key( me ), c1 = P::rec_c1( me, g ), c2 = P::rec_c2( me, g );
-  auto idx_at = [&]( const int w, const uint32_t q ) -> uint32_t
-  {
-    const uint32_t slot = q - st->start[w];
-    return ( ( slot < st->len[w] ) ? s_idx[w * Cfg::WCAP + slot] : __ldg( &sidx[q] ) ) & P::IDX_MASK;
-  };
-
-  if( m.z <= SG_BP_FAST_CAP && ( m.w & SG_BP_MASKS_INVALID ) == 0u )
-  {
-    // Fast path: pass 1 already decided every neighbour; only the candidates' indices (staged) and the active
-    // partners' records (L1/L2) are read.  The (partner index << 32 | active << 31 | position) entries are
-    // insertion-sorted in a per-thread column of shared memory (n < 2^31 is checked by the host).
-    unsigned long long* col = s_list + threadIdx.x;
-    uint32_t cnt_m = 0u, k = 0u;
-    sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
-    {
-      const uint32_t kk = k++;
-      if( ( ( m.x >> kk ) & 1u ) == 0u ) { return; }
-      const uint32_t oi = idx_at( w, q );
-      const unsigned long long v = ( static_cast<unsigned long long>( oi ) << 32 ) | ( static_cast<unsigned long long>( ( m.y >> kk ) & 1u ) << 31 ) | q;
-      uint32_t j = cnt_m++;
-      while( j > 0u )
-      {
-        const unsigned long long prev = col[( j - 1u ) * Cfg::T];
-        if( prev <= v ) { break; }
-        col[j * Cfg::T] = prev;
-        --j;
-      }
-      col[j * Cfg::T] = v;
-    } );
-    for( uint32_t j = 0u; j < cnt_m; ++j )
-    {
-      const unsigned long long v = col[j * Cfg::T];
-      const unsigned long long kc = off.x + j;
-      if( cand != nullptr && kc < cand_cap ) { cand[kc] = ( gid != nullptr ) ? make_uint2( gid[my_idx], gid[uint32_t( v >> 32 )] ) : make_uint2( my_idx, uint32_t( v >> 32 ) ); }
-      if( P::HAS_NARROW && ( ( v >> 31 ) & 1ull ) )
-      {
-        const Rec o = sg_load_rec_global<Rec>( &recs[uint32_t( v & 0x7fffffffull )] );
-        P::contact_emit( out, ka, me, o );
-      }
-    }
-    return;
-  }
-
-  // Slow paths: redo the tests (a body with more than 32 neighbours or more candidates than the fast list holds)
+  BpStage<D> none; // nothing staged: sg_bp_cs falls through to cell_start
+  #pragma unroll
+  for( int w = 0; w < Cfg::NW; ++w ) { none.start[w] = 0u; none.len[w] = 0u; none.cs_klo[w] = 0u; none.cs_len[w] = 0u; }
+  const BpStage<D>* st = &none;
+  const uint32_t* s_cs = nullptr;
+  auto idx_at = [&]( const int, const uint32_t q ) -> uint32_t { return __ldg( &sidx[q] ) & P::IDX_MASK; };
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
   auto overlaps = [&]( const Rec& o ) -> bool
@@ -650,6 +650,107 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_emit( const uint32_
   }
 }
 
+// compare-exchange on packed (partner index << 32 | ...) keys
+__device__ __forceinline__ void sg_cex( unsigned long long& a, unsigned long long& b )
+{
+  const unsigned long long lo = ( a < b ) ? a : b;
+  const unsigned long long hi = ( a < b ) ? b : a;
+  a = lo; b = hi;
+}
+
+// Pass 2.  Each body writes its candidates (ascending partner index) at its offset; active ones also write a contact.
+// Nothing is shared between threads: pass 1 left, per sorted position, the candidate/active masks over the visit
+// sequence and the walk plan (window starts and lengths), so a thread decodes its set bits straight to sorted
+// positions, gathers the partners' index words (L1/L2: neighbouring threads read the same few rows), orders its
+// <= 8 candidates with a register sorting network and stores them.  No staging, no barriers, no shared memory.
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan,
+                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, const typename P::Out out )
+{
+  constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
+  using Rec = typename P::Rec;
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if( p >= n_slots ) { return; }
+  const uint4 m = __ldg( &masks[p] ); // zero for ghosts and for slots past the binned bodies (cleared by the host driver)
+  if( m.z == 0u ) { return; }
+  const ulonglong2 off = offsets_pos[p];
+  const uint32_t my_idx = __ldg( &sidx[p] ) & P::IDX_MASK;
+  unsigned long long ka = off.y;
+
+  if( m.z <= SG_BP_FAST_CAP && ( m.w & SG_BP_MASKS_INVALID ) == 0u )
+  {
+    uint32_t qb[Cfg::NW], len[Cfg::NW];
+    sg_bp_plan_load<D>( plan, n_slots, p, qb, len );
+    // visits before window w (the body itself is skipped inside its own window)
+    unsigned long long v[SG_BP_FAST_CAP];
+    uint32_t cm = m.x;
+    #pragma unroll
+    for( int b = 0; b < SG_BP_FAST_CAP; ++b )
+    {
+      v[b] = ~0ull;
+      if( cm != 0u )
+      {
+        const uint32_t kk = __ffs( cm ) - 1u;
+        cm &= cm - 1u;
+        uint32_t rem = kk, q = 0u;
+        bool found = false;
+        #pragma unroll
+        for( int w = 0; w < Cfg::NW; ++w )
+        {
+          const bool mine = p - qb[w] < len[w]; // p inside this window (unsigned compare)
+          const uint32_t L = len[w] - ( mine ? 1u : 0u );
+          if( !found )
+          {
+            if( rem < L ) { q = qb[w] + rem; if( mine && q >= p ) { ++q; } found = true; }
+            else { rem -= L; }
+          }
+        }
+        const uint32_t oi = __ldg( &sidx[q] ) & P::IDX_MASK;
+        v[b] = ( static_cast<unsigned long long>( oi ) << 32 ) | ( static_cast<unsigned long long>( ( m.y >> kk ) & 1u ) << 31 ) | q;
+      }
+    }
+    // Batcher odd-even merge sort, 8 keys / 19 compare-exchanges (empty slots hold ~0 and sink to the end)
+    static_assert( SG_BP_FAST_CAP == 8, "the sorting network below is for 8 keys" );
+    if( m.z > 1u )
+    {
+      sg_cex( v[0], v[1] ); sg_cex( v[2], v[3] ); sg_cex( v[4], v[5] ); sg_cex( v[6], v[7] );
+      sg_cex( v[0], v[2] ); sg_cex( v[1], v[3] ); sg_cex( v[4], v[6] ); sg_cex( v[5], v[7] );
+      sg_cex( v[1], v[2] ); sg_cex( v[5], v[6] );
+      sg_cex( v[0], v[4] ); sg_cex( v[1], v[5] ); sg_cex( v[2], v[6] ); sg_cex( v[3], v[7] );
+      sg_cex( v[2], v[4] ); sg_cex( v[3], v[5] );
+      sg_cex( v[1], v[2] ); sg_cex( v[3], v[4] ); sg_cex( v[5], v[6] );
+    }
+    if( cand != nullptr )
+    {
+      const uint32_t gi = ( gid != nullptr ) ? gid[my_idx] : my_idx;
+      #pragma unroll
+      for( int j = 0; j < SG_BP_FAST_CAP; ++j )
+      {
+        const unsigned long long kc = off.x + j;
+        if( uint32_t( j ) < m.z && kc < cand_cap ) { const uint32_t oj = uint32_t( v[j] >> 32 ); cand[kc] = make_uint2( gi, ( gid != nullptr ) ? gid[oj] : oj ); }
+      }
+    }
+    if( P::HAS_NARROW && m.y != 0u )
+    {
+      const Rec me = sg_load_rec_global<Rec>( &recs[p] );
+      #pragma unroll
+      for( int j = 0; j < SG_BP_FAST_CAP; ++j )
+      {
+        if( uint32_t( j ) < m.z && ( ( v[j] >> 31 ) & 1ull ) )
+        {
+          const Rec o = sg_load_rec_global<Rec>( &recs[uint32_t( v[j] & 0x7fffffffull )] );
+          P::contact_emit( out, ka, me, o );
+        }
+      }
+    }
+    return;
+  }
+
+  sg_bp_emit_slow<P>( p, m, off, my_idx, params, cell_start, recs, sidx, cand, cand_cap, gid, out );
+}
+
 // ---- host driver -----------------------------------------------------------------------------------
 template<typename P>
 static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n )
@@ -675,6 +776,7 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   SG_CUDA( ctx, s.pos_of.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.counts.ensure( size_t( n ) * sizeof( uint2 ) ) );
   SG_CUDA( ctx, s.masks.ensure( size_t( n ) * sizeof( uint4 ) ) );
+  SG_CUDA( ctx, s.plan.ensure( size_t( n ) * sizeof( uint4 ) * BpPlan<P::D>::NPLAN ) );
   SG_CUDA( ctx, s.offsets.ensure( size_t( n ) * sizeof( ulonglong2 ) ) );
   SG_CUDA( ctx, s.pair_partials.ensure( ( size_t( n ) / SG_SCAN_TILE + 2 ) * sizeof( ScanPairCounts::Acc ) ) );
   SG_CUDA( ctx, s.totals.ensure( sizeof( ScanPairCounts::Acc ) ) );
@@ -701,18 +803,17 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 + 4.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>() ) );
   constexpr size_t smem = sg_bp_count_smem<D>();
   SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
-  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 + 16.0 ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>() ) );
-  rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false, s.pos_of.as<uint32_t>() );
+  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<D>::NPLAN ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
+  rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false, s.pos_of.as<uint32_t>(), s.side.n != 0u ? &s.side : nullptr );
+  s.side.n = 0u;
   return rc;
 }
 
 template<typename P>
 static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const double out_bytes )
 {
-  constexpr size_t smem = sg_bp_emit_smem<P::D>();
-  SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_emit<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
-  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 64.0 + 4.0 + 16.0 + 16.0 ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, BpCfg<P::D>::T ), BpCfg<P::D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
-             s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map, out ) );
+  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map, out ) );
   return SG_OK;
 }
 

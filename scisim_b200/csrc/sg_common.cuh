@@ -86,6 +86,8 @@ struct sg_ctx
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;              // side stream: independent kernels of one step run beside the main chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   uint64_t launch_count = 0;
 

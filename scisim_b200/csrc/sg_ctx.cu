@@ -97,6 +97,10 @@ int sg_create( sg_ctx** out, int device )
   ctx->num_sms = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking );
   if( e != cudaSuccess ) { delete ctx; return sg_fail( nullptr, SG_ERR_CUDA, "sg_create: cudaStreamCreate: %s", cudaGetErrorString( e ) ); }
+  e = cudaStreamCreateWithFlags( &ctx->stream2, cudaStreamNonBlocking );
+  if( e == cudaSuccess ) { e = cudaEventCreateWithFlags( &ctx->ev_fork, cudaEventDisableTiming ); }
+  if( e == cudaSuccess ) { e = cudaEventCreateWithFlags( &ctx->ev_join, cudaEventDisableTiming ); }
+  if( e != cudaSuccess ) { cudaStreamDestroy( ctx->stream ); delete ctx; return sg_fail( nullptr, SG_ERR_CUDA, "sg_create: side stream: %s", cudaGetErrorString( e ) ); }
   *out = ctx;
   return SG_OK;
 }
@@ -116,6 +120,9 @@ void sg_destroy( sg_ctx* ctx )
   ctx->l2_flush.release();
   ctx->scan_vals.release();
   cudaStreamDestroy( ctx->stream );
+  if( ctx->stream2 != nullptr ) { cudaStreamDestroy( ctx->stream2 ); }
+  if( ctx->ev_fork != nullptr ) { cudaEventDestroy( ctx->ev_fork ); }
+  if( ctx->ev_join != nullptr ) { cudaEventDestroy( ctx->ev_join ); }
   delete ctx;
 }
 

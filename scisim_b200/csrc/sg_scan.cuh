@@ -239,6 +239,52 @@ __device__ __forceinline__ void sg_st_volatile( Acc* p, const Acc& v )
   for( int k = 0; k < int( sizeof( Acc ) / 4 ); ++k ) { dst[k] = u.w[k]; }
 }
 
+// A small u32 exclusive scan that rides along with a cooperative scan launch (one extra block), so that a second,
+// latency-bound scan does not cost a launch of its own.
+struct SideScan
+{
+  const uint32_t* in;
+  uint32_t n;
+  uint32_t* out;
+  uint32_t* total;
+};
+#define SG_SIDE_SCAN_MAX 131072u // 64 extra blocks at most
+
+// Extra block `sb` of the launch owns tile sb of the side array (SG_LB_TILE elements, kept in registers across the
+// grid barrier); tile totals go through side_partials.
+__device__ inline void sg_side_scan( const SideScan side, const uint32_t sb, uint32_t* side_partials, cooperative_groups::grid_group grid )
+{
+  __shared__ uint32_t side_warp[SG_LB_THREADS / 32];
+  __shared__ uint32_t side_prefix;
+  const uint32_t e0 = sb * SG_LB_TILE + threadIdx.x * SG_LB_ITEMS;
+  uint32_t v[SG_LB_ITEMS];
+  uint32_t ls = 0u;
+  #pragma unroll
+  for( int k = 0; k < SG_LB_ITEMS; ++k ) { v[k] = ( e0 + k < side.n ) ? side.in[e0 + k] : 0u; ls += v[k]; }
+  uint32_t ttot;
+  const uint32_t excl = sg_block_exclusive<ScanU32, SG_LB_THREADS>( ls, side_warp, &ttot );
+  if( threadIdx.x == 0 ) { sg_st_volatile( &side_partials[sb], ttot ); }
+  __threadfence();
+  grid.sync();
+  const uint32_t ntiles = ( side.n + SG_LB_TILE - 1u ) / SG_LB_TILE;
+  if( threadIdx.x < 32 )
+  {
+    uint32_t pre = 0u, all = 0u;
+    for( uint32_t b = threadIdx.x; b < ntiles; b += 32u ) { const uint32_t t = sg_ld_volatile( &side_partials[b] ); all += t; if( b < sb ) { pre += t; } }
+    #pragma unroll
+    for( int d = 16; d > 0; d >>= 1 ) { pre += __shfl_xor_sync( 0xffffffffu, pre, d ); all += __shfl_xor_sync( 0xffffffffu, all, d ); }
+    if( threadIdx.x == 0 ) { side_prefix = pre; if( sb == 0u && side.total != nullptr ) { *side.total = all; } }
+  }
+  __syncthreads();
+  uint32_t run = side_prefix + excl;
+  #pragma unroll
+  for( int k = 0; k < SG_LB_ITEMS; ++k )
+  {
+    if( e0 + k < side.n ) { side.out[e0 + k] = run; }
+    run += v[k];
+  }
+}
+
 // ---- two-phase scan in one cooperative launch -------------------------------------------------------
 // All blocks are co-resident (cooperative launch, grid = a fixed multiple of the SM count): each block reduces its
 // contiguous chunk, the grid synchronises once, every block sums the (few hundred) chunk totals that precede it and
@@ -246,14 +292,21 @@ __device__ __forceinline__ void sg_st_volatile( Acc* p, const Acc& v )
 // scan has when every tile is resident at once.
 template<typename P>
 __global__ void __launch_bounds__( SG_LB_THREADS ) sg_scan_coop( const typename P::In* __restrict__ in, const uint32_t* __restrict__ n_dev, const uint32_t n_host, typename P::Out* __restrict__ out,
-                                                                const uint32_t* __restrict__ scatter, typename P::Acc* partials, typename P::Acc* __restrict__ total_out, const bool write_end )
+                                                                const uint32_t* __restrict__ scatter, typename P::Acc* partials, typename P::Acc* __restrict__ total_out, const bool write_end,
+                                                                const SideScan side )
 {
   using Acc = typename P::Acc;
   namespace cg = cooperative_groups;
   __shared__ Acc warp_sums[SG_LB_THREADS / 32];
   __shared__ Acc s_prefix;
   const uint32_t n = ( n_dev != nullptr ) ? *n_dev : n_host;
-  const uint32_t nb = gridDim.x;
+  const uint32_t nb = gridDim.x - ( side.n + SG_LB_TILE - 1u ) / SG_LB_TILE;
+  if( blockIdx.x >= nb )
+  {
+    // extra blocks: a small independent u32 scan that shares this launch and its grid barrier
+    sg_side_scan( side, blockIdx.x - nb, reinterpret_cast<uint32_t*>( partials + nb ), cg::this_grid() );
+    return;
+  }
   // chunk per block: whole tiles
   const uint64_t tiles_total = ( uint64_t( n ) + SG_LB_TILE - 1 ) / SG_LB_TILE;
   const uint64_t tiles_per_block = ( tiles_total + nb - 1 ) / nb;
@@ -312,25 +365,39 @@ __global__ void __launch_bounds__( SG_LB_THREADS ) sg_scan_coop( const typename 
 // Host driver.  cap = upper bound on the element count.
 template<typename P>
 static int sg_exclusive_scan( sg_ctx* ctx, const char* name, const typename P::In* in, const uint32_t* n_dev, const uint32_t n_host, const uint32_t cap,
-                              typename P::Acc* partials, typename P::Out* out, typename P::Acc* total_out, const bool write_end, const uint32_t* scatter = nullptr )
+                              typename P::Acc* partials, typename P::Out* out, typename P::Acc* total_out, const bool write_end, const uint32_t* scatter = nullptr,
+                              const SideScan* side_job = nullptr )
 {
   ( void ) partials;
   if( cap == 0 ) { return SG_OK; }
-  if( n_dev == nullptr && n_host <= SG_SCAN_SMALL_MAX )
+  SideScan side;
+  side.in = nullptr; side.n = 0u; side.out = nullptr; side.total = nullptr;
+  if( side_job != nullptr ) { side = *side_job; }
+  if( side.n == 0u && n_dev == nullptr && n_host <= SG_SCAN_SMALL_MAX )
   {
     SG_LAUNCH( ctx, name, double( n_host ) * double( sizeof( typename P::In ) + sizeof( typename P::Out ) ), sg_scan_small<P><<<1, 1024, 0, ctx->stream>>>( in, n_host, out, total_out, write_end, scatter ) );
     return SG_OK;
   }
   static_assert( sizeof( typename P::Acc ) <= 16, "scan accumulators are at most 16 bytes" );
-  const unsigned nblocks = unsigned( ctx->num_sms ) * 4u; // co-resident by a wide margin (256 threads, < 48 registers)
-  if( size_t( nblocks ) * 16 + 64 > ctx->scan_vals.cap ) { SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) ); SG_CUDA( ctx, ctx->scan_vals.ensure( size_t( nblocks ) * 32 + 256 ) ); }
+  // every block must be resident at once: ask the runtime how many fit (cached per scan type), use at most 4 per SM
+  static int per_sm = 0;
+  if( per_sm == 0 )
+  {
+    int occ = 0;
+    SG_CUDA( ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor( &occ, sg_scan_coop<P>, SG_LB_THREADS, 0 ) );
+    if( occ < 1 ) { return sg_fail( ctx, SG_ERR_INTERNAL, "sg_exclusive_scan: cooperative scan kernel does not fit on an SM" ); }
+    per_sm = occ < 4 ? occ : 4;
+  }
+  const unsigned side_blocks = ( side.n + SG_LB_TILE - 1u ) / SG_LB_TILE;
+  const unsigned nblocks = unsigned( ctx->num_sms ) * unsigned( per_sm ) - side_blocks;
+  if( size_t( nblocks + side_blocks ) * 16 + 64 > ctx->scan_vals.cap ) { SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) ); SG_CUDA( ctx, ctx->scan_vals.ensure( size_t( ctx->num_sms ) * 4 * 32 + 256 ) ); }
   typename P::Acc* chunk_totals = reinterpret_cast<typename P::Acc*>( ctx->scan_vals.ptr );
   const double nelem = double( n_dev != nullptr ? cap : n_host );
   bool we = write_end;
   uint32_t nh = n_host;
-  void* args[] = { ( void* ) &in, ( void* ) &n_dev, ( void* ) &nh, ( void* ) &out, ( void* ) &scatter, ( void* ) &chunk_totals, ( void* ) &total_out, ( void* ) &we };
-  SG_LAUNCH( ctx, name, nelem * double( sizeof( typename P::In ) + sizeof( typename P::Out ) ),
-             SG_CUDA( ctx, cudaLaunchCooperativeKernel( ( const void* ) sg_scan_coop<P>, dim3( nblocks ), dim3( SG_LB_THREADS ), args, 0, ctx->stream ) ) );
+  void* args[] = { ( void* ) &in, ( void* ) &n_dev, ( void* ) &nh, ( void* ) &out, ( void* ) &scatter, ( void* ) &chunk_totals, ( void* ) &total_out, ( void* ) &we, ( void* ) &side };
+  SG_LAUNCH( ctx, name, nelem * double( sizeof( typename P::In ) + sizeof( typename P::Out ) ) + double( side.n ) * 8.0,
+             SG_CUDA( ctx, cudaLaunchCooperativeKernel( ( const void* ) sg_scan_coop<P>, dim3( nblocks + side_blocks ), dim3( SG_LB_THREADS ), args, 0, ctx->stream ) ) );
   return SG_OK;
 }
 
