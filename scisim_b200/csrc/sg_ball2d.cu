@@ -514,7 +514,7 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
       SG_CUDA( ctx, cudaEventRecord( ctx->ev_fork, ctx->stream ) );
       SG_CUDA( ctx, cudaStreamWaitEvent( side, ctx->ev_fork, 0 ) );
     }
-    rc = sg_bp_emit_lists<Ball2DPolicy>( ctx, d->bp, n, want_cand, out, 0.0 );
+    rc = sg_bp_emit_lists<Ball2DPolicy>( ctx, d->bp, n, want_cand, out, d->act_cap );
     if( rc != SG_OK ) { return rc; }
     if( ng > 0 )
     {
@@ -539,7 +539,8 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
     if( ctx->profile )
     {
       // list sizes are only known now: add the emitted bytes to the kernels that wrote them
-      ctx->prof[sg_prof_entry( ctx, "bp_emit" )].bytes += ( want_cand ? double( d->n_cand ) * 8.0 : 0.0 ) + double( d->n_bb ) * 52.0;
+      ctx->prof[sg_prof_entry( ctx, "bp_emit" )].bytes += ( want_cand ? double( d->n_cand ) * 8.0 : 0.0 ) + double( d->n_bb ) * 8.0;
+      ctx->prof[sg_prof_entry( ctx, "bp_contacts" )].bytes += double( d->n_bb ) * ( 8.0 + 52.0 ) + double( n ) * 64.0; // every record is needed once; repeats hit L1/L2
       if( ng > 0 ) { ctx->prof[sg_prof_entry( ctx, "ball2d_static_emit" )].bytes += double( d->n_static ) * 52.0; }
     }
     const uint64_t need_act = d->n_bb + d->n_static;

@@ -8,8 +8,8 @@
 //   { (i<j) : for every axis  !(hi_i < lo_j) && !(hi_j < lo_i) }   in ascending (i,j) order,
 // nothing else about the grid is observable.  Pipeline (one launch each unless noted):
 //   bounds   reduce min/max of box lower corners and the largest box extent
-//   setup    lay out the grid (h >= largest extent, cell count capped), zero the cell histogram
-//   hist     cell key per body + rank inside the cell (one atomicAdd per body)
+//   hist     lay out the grid (h >= largest extent, cell count capped); cell key per body + rank inside the cell
+//            (one atomicAdd per body; the histogram is re-zeroed by the scatter of the step before)
 //   scan     cell counts -> cell start offsets               (3 launches, sg_scan.cuh)
 //   scatter  write a 64-byte record per body at cell_start[key] + rank  => bodies sorted by cell
 //   count    per body: walk the 3^D neighbourhood (D-1 contiguous row segments), count candidates with a
@@ -49,16 +49,21 @@ struct BroadScratch
   DevBuf pair_partials; // ScanPairCounts::Acc[tiles]
   DevBuf totals;        // ScanPairCounts::Acc
   DevBuf cand;          // uint2[cand_cap]
+  DevBuf work;          // uint2[work_cap]  (own position, partner position) of every active pair, in output order
+  uint64_t work_cap = 0;
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
   SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
   const uint32_t* gid_map = nullptr; // multi-GPU: local body index -> global body index for the emitted lists
+  bool hist_clean = false; // cell_count is all zero (true after every scatter; false after (re)allocation or an aborted step)
+  const void* hist_ptr = nullptr;
+  uint32_t hist_slots = 0;
   int bounds_phase = 0; // which of the two BoundsAccum the current step reduces into
   BoundsAccum* bounds_cur() const { return bounds.as<BoundsAccum>() + bounds_phase; }
   void release()
   {
     bounds.release(); params.release(); cell_count.release(); cell_start.release(); cell_partials.release(); key.release(); rank.release();
-    recs.release(); sidx.release(); pos_of.release(); counts.release(); masks.release(); plan.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release();
+    recs.release(); sidx.release(); pos_of.release(); counts.release(); masks.release(); plan.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release(); work.release();
   }
 };
 
@@ -241,20 +246,6 @@ __device__ inline GridParams sg_layout_grid( const BoundsAccum& acc, const uint3
 }
 
 template<int D>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_setup( const BoundsAccum* __restrict__ acc, BoundsAccum* __restrict__ acc_next, const uint32_t max_cells, GridParams* __restrict__ params, uint32_t* __restrict__ cell_count )
-{
-  // the two accumulators alternate between steps: this step's is read here, the next step's is re-armed
-  if( blockIdx.x == 0 && threadIdx.x == 32 ) { sg_bp_bounds_reset( acc_next ); }
-  // every block derives the same layout from the same reduced bounds, then clears its share of the histogram
-  __shared__ GridParams g_s;
-  if( threadIdx.x == 0 ) { g_s = sg_layout_grid<D>( *acc, max_cells ); }
-  __syncthreads();
-  const uint32_t ncells = g_s.ncells;
-  for( uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c <= ncells; c += gridDim.x * blockDim.x ) { cell_count[c] = 0u; }
-  if( blockIdx.x == 0 && threadIdx.x == 0 ) { *params = g_s; }
-}
-
-template<int D>
 __device__ inline uint32_t sg_key_of( const GridParams& g, const uint32_t* c )
 {
   uint32_t key = c[0] + g.dims[0] * c[1];
@@ -264,11 +255,19 @@ __device__ inline uint32_t sg_key_of( const GridParams& g, const uint32_t* c )
 
 // ---- histogram / scatter ("single-digit radix sort" keyed by cell) ---------------------------------
 template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P::In in, const GridParams* __restrict__ params, uint32_t* __restrict__ cell_count,
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P::In in, const BoundsAccum* __restrict__ acc, BoundsAccum* __restrict__ acc_next, const uint32_t max_cells,
+                                                              GridParams* __restrict__ params, uint32_t* __restrict__ cell_count,
                                                               uint32_t* __restrict__ key_out, uint32_t* __restrict__ rank_out, uint2* __restrict__ counts )
 {
   constexpr int D = P::D;
-  const GridParams g = *params;
+  // Every block derives the same grid layout from the reduced bounds (h >= largest extent, cell count capped);
+  // block 0 publishes it for the later kernels and re-arms the accumulator the next step will reduce into.
+  // The histogram itself was left zeroed by the previous step's scatter.
+  __shared__ GridParams g_s;
+  if( threadIdx.x == 0 ) { g_s = sg_layout_grid<D>( *acc, max_cells ); if( blockIdx.x == 0 ) { *params = g_s; } }
+  if( blockIdx.x == 0 && threadIdx.x == 32 ) { sg_bp_bounds_reset( acc_next ); }
+  __syncthreads();
+  const GridParams g = g_s;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if( i >= in.n ) { return; }
   if( !P::valid( in, i ) )
@@ -289,9 +288,12 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P:
 
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename P::In in, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ key_in,
-                                                                 const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs, uint32_t* __restrict__ sidx, uint32_t* __restrict__ pos_of )
+                                                                 const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs, uint32_t* __restrict__ sidx, uint32_t* __restrict__ pos_of,
+                                                                 uint32_t* __restrict__ cell_count, const uint32_t cell_slots )
 {
   const uint32_t g_dims0 = params->dims[0], g_dims1 = params->dims[1];
+  // the histogram has been consumed by the scan: leave it zeroed for the next step (grid-stride, coalesced)
+  for( uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < cell_slots; c += gridDim.x * blockDim.x ) { cell_count[c] = 0u; }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if( i >= in.n ) { return; }
   const uint32_t key = key_in[i];
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp
 template<typename P>
 __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, const ulonglong2 off, const uint32_t my_idx, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, uint2* __restrict__ cand, const uint64_t cand_cap,
-                                              const uint32_t* __restrict__ gid, const typename P::Out& out )
+                                              const uint32_t* __restrict__ gid, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -602,10 +604,10 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, c
     for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
     return ov;
   };
-  auto emit_one = [&]( const unsigned long long kc, const Rec& o )
+  auto emit_one = [&]( const unsigned long long kc, const Rec& o, const uint32_t q )
   {
     if( cand != nullptr && kc < cand_cap ) { cand[kc] = ( gid != nullptr ) ? make_uint2( gid[my_idx], gid[P::rec_idx( o )] ) : make_uint2( my_idx, P::rec_idx( o ) ); }
-    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { P::contact_emit( out, ka, me, o ); } }
+    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { if( ka < work_cap ) { work[ka] = make_uint2( p, q ); } ++ka; } }
   };
   if( m.z <= SG_BP_LOCAL_CAP )
   {
@@ -624,8 +626,9 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, c
     } );
     for( uint32_t j = 0u; j < nl; ++j )
     {
-      const Rec o = sg_load_rec_global<Rec>( &recs[uint32_t( list[j] & 0xffffffffull )] );
-      emit_one( off.x + j, o );
+      const uint32_t q = uint32_t( list[j] & 0xffffffffull );
+      const Rec o = sg_load_rec_global<Rec>( &recs[q] );
+      emit_one( off.x + j, o, q );
     }
   }
   else
@@ -644,7 +647,7 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, c
         best_idx = oi; best_q = q;
       } );
       const Rec o = sg_load_rec_global<Rec>( &recs[best_q] );
-      emit_one( off.x + j, o );
+      emit_one( off.x + j, o, best_q );
       last = best_idx;
     }
   }
@@ -666,7 +669,7 @@ __device__ __forceinline__ void sg_cex( unsigned long long& a, unsigned long lon
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan,
-                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, const typename P::Out out )
+                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -734,21 +737,42 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t
     }
     if( P::HAS_NARROW && m.y != 0u )
     {
-      const Rec me = sg_load_rec_global<Rec>( &recs[p] );
+      // active pairs: only (own position, partner position) is recorded here, in output order; the contact
+      // geometry is computed by sg_bp_contacts, one thread per contact, with fully coalesced stores
       #pragma unroll
       for( int j = 0; j < SG_BP_FAST_CAP; ++j )
       {
         if( uint32_t( j ) < m.z && ( ( v[j] >> 31 ) & 1ull ) )
         {
-          const Rec o = sg_load_rec_global<Rec>( &recs[uint32_t( v[j] & 0x7fffffffull )] );
-          P::contact_emit( out, ka, me, o );
+          if( ka < work_cap ) { work[ka] = make_uint2( p, uint32_t( v[j] & 0x7fffffffull ) ); }
+          ++ka;
         }
       }
     }
     return;
   }
 
-  sg_bp_emit_slow<P>( p, m, off, my_idx, params, cell_start, recs, sidx, cand, cand_cap, gid, out );
+  sg_bp_emit_slow<P>( p, m, off, my_idx, params, cell_start, recs, sidx, cand, cand_cap, gid, work, work_cap );
+}
+
+// Pass 3 (policies with a fused narrow phase).  One thread per active pair, grid-stride over the work list pass 2
+// left in output order: both records come through L1/L2 (consecutive contacts share the first body), the contact
+// is written at its own index => every store of the SoA contact arrays is fully coalesced.
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_contacts( const ScanPairCounts::Acc* __restrict__ totals, const uint2* __restrict__ work, const uint64_t work_cap,
+                                                                  const typename P::Rec* __restrict__ recs, const typename P::Out out )
+{
+  using Rec = typename P::Rec;
+  unsigned long long na = totals->a;
+  if( na > work_cap ) { na = work_cap; }
+  for( unsigned long long c = blockIdx.x * uint64_t( blockDim.x ) + threadIdx.x; c < na; c += uint64_t( gridDim.x ) * blockDim.x )
+  {
+    const uint2 w = __ldg( &work[c] );
+    const Rec a = sg_load_rec_global<Rec>( &recs[w.x] );
+    const Rec b = sg_load_rec_global<Rec>( &recs[w.y] );
+    unsigned long long k = c;
+    P::contact_emit( out, k, a, b );
+  }
 }
 
 // ---- host driver -----------------------------------------------------------------------------------
@@ -767,6 +791,7 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   }
   SG_CUDA( ctx, s.params.ensure( sizeof( GridParams ) ) );
   SG_CUDA( ctx, s.cell_count.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
+  if( s.cell_count.ptr != s.hist_ptr || s.max_cells + 2u > s.hist_slots ) { s.hist_clean = false; s.hist_ptr = s.cell_count.ptr; s.hist_slots = s.max_cells + 2u; }
   SG_CUDA( ctx, s.cell_start.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
   SG_CUDA( ctx, s.cell_partials.ensure( ( size_t( s.max_cells ) / SG_SCAN_TILE + 2 ) * 4 ) );
   SG_CUDA( ctx, s.key.ensure( size_t( n ) * 4 ) );
@@ -795,12 +820,18 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   if( !bounds_done ) { SG_LAUNCH( ctx, "bp_bounds", nb * P::IN_BYTES, sg_bp_bounds<P><<<nred, SG_BP_THREADS, 0, ctx->stream>>>( in, s.bounds_cur() ) ); }
   BoundsAccum* acc_cur = s.bounds_cur();
   s.bounds_phase ^= 1;
-  SG_LAUNCH( ctx, "bp_setup", nb * 4.0, sg_bp_setup<D><<<unsigned( ctx->num_sms * 4 ), SG_BP_THREADS, 0, ctx->stream>>>( acc_cur, s.bounds_cur(), s.max_cells, s.params.as<GridParams>(), s.cell_count.as<uint32_t>() ) );
-  SG_LAUNCH( ctx, "bp_hist", nb * ( P::IN_BYTES + 8.0 ), sg_bp_hist<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_count.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.counts.as<uint2>() ) );
+  if( !s.hist_clean )
+  {
+    SG_CUDA( ctx, cudaMemsetAsync( s.cell_count.ptr, 0, ( size_t( s.max_cells ) + 2 ) * 4, ctx->stream ) );
+  }
+  s.hist_clean = false;
+  SG_LAUNCH( ctx, "bp_hist", nb * ( P::IN_BYTES + 8.0 ), sg_bp_hist<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, acc_cur, s.bounds_cur(), s.max_cells, s.params.as<GridParams>(), s.cell_count.as<uint32_t>(), s.key.as<uint32_t>(),
+             s.rank.as<uint32_t>(), s.counts.as<uint2>() ) );
   const uint32_t* ncells_dev = &s.params.as<GridParams>()->ncells;
   int rc = sg_exclusive_scan<ScanU32>( ctx, "bp_cell_scan", s.cell_count.as<uint32_t>(), ncells_dev, 0u, s.max_cells, s.cell_partials.as<uint32_t>(), s.cell_start.as<uint32_t>(), nullptr, true );
   if( rc != SG_OK ) { return rc; }
-  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 + 4.0 ), sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>() ) );
+  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 + 4.0 ) + double( s.max_cells ) * 4.0, sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>(), s.cell_count.as<uint32_t>(), s.max_cells + 2u ) );
+  s.hist_clean = true;
   constexpr size_t smem = sg_bp_count_smem<D>();
   SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
   SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<D>::NPLAN ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
@@ -809,12 +840,34 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   return rc;
 }
 
-template<typename P>
-static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const double out_bytes )
+template<bool> struct SgBpContactsLaunch;
+template<> struct SgBpContactsLaunch<false>
 {
-  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ) + out_bytes, sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map, out ) );
-  return SG_OK;
+  template<typename P> static int run( sg_ctx*, BroadScratch&, const typename P::Out&, const uint64_t ) { return SG_OK; }
+};
+template<> struct SgBpContactsLaunch<true>
+{
+  template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const typename P::Out& out, const uint64_t act_cap )
+  {
+    SG_LAUNCH( ctx, "bp_contacts", 0.0, sg_bp_contacts<P><<<unsigned( ctx->num_sms ) * 8u, SG_BP_THREADS, 0, ctx->stream>>>( s.totals.as<ScanPairCounts::Acc>(), s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap,
+               s.recs.as<typename P::Rec>(), out ) );
+    return SG_OK;
+  }
+};
+
+// act_cap = capacity of the caller's contact arrays (0 for policies without a narrow phase)
+template<typename P>
+static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const uint64_t act_cap )
+{
+  if( P::HAS_NARROW && act_cap > s.work_cap )
+  {
+    SG_CUDA( ctx, s.work.ensure( act_cap * sizeof( uint2 ) ) );
+    s.work_cap = act_cap;
+  }
+  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ), sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map,
+             s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap ) );
+  return SgBpContactsLaunch<P::HAS_NARROW>::template run<P>( ctx, s, out, act_cap );
 }
 
 #endif

@@ -533,7 +533,7 @@ static int rb2d_active_set_device( sg_ctx* ctx, Rb2dData* d )
   if( np + 64 > d->bp.cand_cap ) { SG_CUDA( ctx, d->bp.cand.ensure( size_t( np + 64 ) * sizeof( uint2 ) ) ); d->bp.cand_cap = d->bp.cand.cap / sizeof( uint2 ); }
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<Box2DPolicy>( ctx, d->bp, n, true, NoOut2D{}, double( np ) * 8.0 );
+    rc = sg_bp_emit_lists<Box2DPolicy>( ctx, d->bp, n, true, NoOut2D{}, 0u );
     if( rc != SG_OK ) { return rc; }
   }
   SG_CUDA( ctx, d->pair_counts.ensure( size_t( np ) * 4 + 4 ) );

@@ -1038,7 +1038,7 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
     SG_LAUNCH( ctx, "rb3d_totals", 0.0, k_rb3d_sum_totals<<<1, 1, 0, ctx->stream>>>( d->bp.totals.as<ScanPairCounts::Acc>(), d->narrow_total.as<unsigned long long>(), 1, d->totals3.as<unsigned long long>() ) );
     for( int attempt = 0; attempt < 2; ++attempt )
     {
-      rc = sg_bp_emit_lists<Sphere3DPolicy>( ctx, d->bp, n, want_cand, rb3d_out( d ), 0.0 );
+      rc = sg_bp_emit_lists<Sphere3DPolicy>( ctx, d->bp, n, want_cand, rb3d_out( d ), d->act_cap );
       if( rc != SG_OK ) { return rc; }
       rc = rb3d_planes_device( ctx, d, true );
       if( rc != SG_OK ) { return rc; }
@@ -1077,7 +1077,7 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
   if( rc != SG_OK ) { return rc; }
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, n, true, NoOut3D{}, double( np ) * 8.0 );
+    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, n, true, NoOut3D{}, 0u );
     if( rc != SG_OK ) { return rc; }
   }
   if( np >= 0xffffffffull ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rb3d: more than 2^32 candidate pairs in the generic pipeline" ); }
