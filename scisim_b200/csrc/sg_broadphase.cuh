@@ -25,6 +25,8 @@
 #include "sg_scan.cuh"
 #include "sg_tma.cuh"
 
+#include <cuda.h> // CUtensorMap (type only; the encoder is fetched at run time, see sg_bp_encode_recs_map)
+
 #define SG_BP_THREADS 256
 #define SG_BP_LOCAL_CAP 12
 #define SG_BP_FAST_CAP 8
@@ -55,6 +57,9 @@ struct BroadScratch
   uint32_t max_cells = 0;
   SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
   const uint32_t* gid_map = nullptr; // multi-GPU: local body index -> global body index for the emitted lists
+  CUtensorMap tm_recs;  // tensor map over recs for the TMA-fed pass 1 (re-encoded when the buffer or n changes)
+  const void* tm_ptr = nullptr;
+  uint32_t tm_rows = 0;
   bool hist_clean = false; // cell_count is all zero (true after every scatter; false after (re)allocation or an aborted step)
   const void* hist_ptr = nullptr;
   uint32_t hist_slots = 0;
@@ -395,15 +400,15 @@ __device__ inline void sg_bp_stage( const GridParams& g, const uint32_t n, const
   __syncthreads();
 }
 
-template<int D>
+template<int D, int CSCAP = BpCfg<D>::CSCAP>
 __device__ __forceinline__ uint32_t sg_bp_cs( const BpStage<D>* st, const uint32_t* s_cs, const uint32_t* __restrict__ cell_start, const int w, const uint32_t key )
 {
   const uint32_t rel = key - st->cs_klo[w];
-  return ( rel < st->cs_len[w] ) ? s_cs[w * BpCfg<D>::CSCAP + rel] : __ldg( &cell_start[key] );
+  return ( rel < st->cs_len[w] ) ? s_cs[w * CSCAP + rel] : __ldg( &cell_start[key] );
 }
 
 // [qb[w], qe[w]) = sorted positions of the bodies whose cell is within one cell of (cx,c1,c2) in row window w
-template<typename P>
+template<typename P, int CSCAP = BpCfg<P::D>::CSCAP>
 __device__ __forceinline__ void sg_bp_ranges( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t* s_cs, const BpStage<P::D>* st,
                                               const uint32_t key, const uint32_t c1, const uint32_t c2, uint32_t* qb, uint32_t* qe )
 {
@@ -424,8 +429,8 @@ __device__ __forceinline__ void sg_bp_ranges( const GridParams& g, const uint32_
     if( ok )
     {
       const uint32_t row = g.dims[0] * ( uint32_t( y ) + g.dims[1] * uint32_t( z ) );
-      qb[w] = sg_bp_cs<D>( st, s_cs, cell_start, w, row + x0 );
-      qe[w] = sg_bp_cs<D>( st, s_cs, cell_start, w, row + x1 + 1u );
+      qb[w] = sg_bp_cs<D, CSCAP>( st, s_cs, cell_start, w, row + x0 );
+      qe[w] = sg_bp_cs<D, CSCAP>( st, s_cs, cell_start, w, row + x1 + 1u );
     }
   }
 }
@@ -572,6 +577,230 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp
   counts[my_idx] = make_uint2( nc, na_f );
   masks[p] = make_uint4( cmask, amask, nc, na_f );
 }
+
+// ---- pass 1, TMA-fed (D = 2) -------------------------------------------------------------------------
+// Same work as sg_bp_count, restructured so no thread ever waits for the staging: persistent CTAs (2 per SM),
+// each with 8 consumer warps and 1 producer warp.  The producer runs one tile ahead: it reads the tile's first/last
+// cell keys and the cell_start entries that bound its three row windows, then asks the TMA unit for the windows --
+// the 64-byte records as 2-D tensor copies with the hardware 64B swizzle (the same chunk ^ ((row >> 1) & 3)
+// pattern the software staging used), the cell_start slices as 1-D bulk copies -- into the other half of a
+// double-buffered shared-memory stage, completion counted in bytes on an mbarrier.  Consumers wait on that
+// barrier, walk entirely out of shared memory, and hand the stage back through a second mbarrier.
+#define SG_BP_TMA_ROWS 136   // rows per tensor copy (<= 256); two copies cover WCAP = 272
+#define SG_BP_TMA_CSCAP 288
+template<int D> __host__ __device__ constexpr size_t sg_bp_tma_stage_bytes()
+{
+  return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + size_t( BpCfg<D>::NW ) * SG_BP_TMA_CSCAP * 4 + sizeof( BpStage<D> ) + 1023 ) & ~size_t( 1023 );
+}
+template<int D> __host__ __device__ constexpr size_t sg_bp_tma_smem() { return 2 * sg_bp_tma_stage_bytes<D>() + 64; }
+
+template<typename P>
+__global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( const __grid_constant__ CUtensorMap tm_recs, const uint32_t n_slots, const GridParams* __restrict__ params,
+                                                                            const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts,
+                                                                            uint4* __restrict__ masks, uint4* __restrict__ plan )
+{
+  constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
+  using Rec = typename P::Rec;
+  static_assert( D == 2, "the TMA-fed pass 1 is laid out for the 2-D pipelines" );
+  static_assert( Cfg::WCAP == 2 * SG_BP_TMA_ROWS, "two tensor copies per window" );
+  extern __shared__ __align__( 1024 ) unsigned char s_raw[];
+  constexpr size_t STAGE = sg_bp_tma_stage_bytes<D>();
+  constexpr size_t CS_OFF = size_t( Cfg::NW ) * Cfg::WCAP * 64;
+  constexpr size_t ST_OFF = CS_OFF + size_t( Cfg::NW ) * SG_BP_TMA_CSCAP * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>( s_raw + 2 * STAGE ); // full[0], full[1], empty[0], empty[1]
+  const GridParams g = *params;
+  const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned
+  const uint32_t ntiles = ( n_slots + Cfg::T - 1u ) / Cfg::T;
+  const bool producer = threadIdx.x >= uint32_t( Cfg::T );
+  if( threadIdx.x == 0 )
+  {
+    sg_mbar_init( &bars[0], 1u ); sg_mbar_init( &bars[1], 1u );
+    sg_mbar_init( &bars[2], Cfg::T / 32u ); sg_mbar_init( &bars[3], Cfg::T / 32u );
+  }
+  __syncthreads();
+
+  if( producer )
+  {
+    if( threadIdx.x != uint32_t( Cfg::T ) ) { return; } // one elected lane drives the copies
+    uint32_t it = 0u;
+    for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
+    {
+      const uint32_t b0 = t * Cfg::T;
+      if( b0 >= n ) { break; } // tiles past the binned bodies have nothing to stage (consumers only clear masks)
+      const uint32_t sgi = it & 1u, use = it >> 1;
+      if( use > 0u ) { sg_mbar_wait( &bars[2 + sgi], ( use - 1u ) & 1u ); }
+      unsigned char* stage = s_raw + sgi * STAGE;
+      BpStage<D>* st = reinterpret_cast<BpStage<D>*>( stage + ST_OFF );
+      const uint32_t b1 = ( n - b0 < uint32_t( Cfg::T ) ) ? n : b0 + Cfg::T;
+      const long long kf = __ldg( &recs[b0].key );
+      const long long kl = __ldg( &recs[b1 - 1u].key );
+      long long klo[Cfg::NW], khi[Cfg::NW];
+      uint32_t start[Cfg::NW], end[Cfg::NW];
+      #pragma unroll
+      for( int w = 0; w < Cfg::NW; ++w )
+      {
+        const long long off = ( long long )( w % 3 - 1 ) * g.dims[0];
+        klo[w] = kf + off - 1; khi[w] = kl + off + 1;
+        const bool ok = khi[w] >= 0 && klo[w] <= ( long long )( g.ncells ) - 1;
+        klo[w] = ( klo[w] < 0 ) ? 0 : klo[w];
+        khi[w] = ( khi[w] > ( long long )( g.ncells ) - 1 ) ? ( long long )( g.ncells ) - 1 : khi[w];
+        if( !ok ) { klo[w] = 0; khi[w] = -1; }
+        start[w] = ok ? __ldg( &cell_start[klo[w]] ) : 0u;
+        end[w] = ok ? __ldg( &cell_start[khi[w] + 1] ) : 0u;
+      }
+      uint32_t bytes = 0u;
+      uint32_t ncopies[Cfg::NW], cs_first[Cfg::NW], cs_n[Cfg::NW];
+      #pragma unroll
+      for( int w = 0; w < Cfg::NW; ++w )
+      {
+        const uint32_t len = ( end[w] - start[w] < uint32_t( Cfg::WCAP ) ) ? end[w] - start[w] : uint32_t( Cfg::WCAP );
+        ncopies[w] = ( len + SG_BP_TMA_ROWS - 1u ) / SG_BP_TMA_ROWS;
+        // cell_start slice: entries klo .. khi+1, widened to whole 16-byte groups for the bulk copy
+        const long long ncs = khi[w] - klo[w] + 2;
+        cs_first[w] = uint32_t( klo[w] ) & ~3u;
+        uint32_t want = ( khi[w] < klo[w] ) ? 0u : uint32_t( klo[w] - cs_first[w] + ncs );
+        want = ( want + 3u ) & ~3u;
+        cs_n[w] = ( want < uint32_t( SG_BP_TMA_CSCAP ) ) ? want : uint32_t( SG_BP_TMA_CSCAP );
+        st->start[w] = start[w]; st->len[w] = len; st->cs_klo[w] = cs_first[w]; st->cs_len[w] = cs_n[w];
+        bytes += ncopies[w] * uint32_t( SG_BP_TMA_ROWS * 64 ) + cs_n[w] * 4u;
+      }
+      asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); // the stage's earlier generic reads vs the async writes to come
+      sg_mbar_arrive_expect_tx( &bars[sgi], bytes );
+      #pragma unroll
+      for( int w = 0; w < Cfg::NW; ++w )
+      {
+        for( uint32_t c = 0u; c < ncopies[w]; ++c )
+        {
+          sg_tma_load_2d( stage + ( size_t( w ) * Cfg::WCAP + size_t( c ) * SG_BP_TMA_ROWS ) * 64, &tm_recs, 0, int( start[w] + c * SG_BP_TMA_ROWS ), &bars[sgi] );
+        }
+        if( cs_n[w] != 0u ) { sg_bulk_g2s( stage + CS_OFF + size_t( w ) * SG_BP_TMA_CSCAP * 4, cell_start + cs_first[w], cs_n[w] * 4u, &bars[sgi] ); }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  uint32_t it = 0u;
+  for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
+  {
+    const uint32_t p = t * Cfg::T + threadIdx.x;
+    if( t * Cfg::T >= n )
+    {
+      if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slots: pass 2 skips them
+      continue;
+    }
+    const uint32_t sgi = it & 1u, use = it >> 1;
+    const unsigned char* stage = s_raw + sgi * STAGE;
+    const unsigned char* s_recs = stage;
+    const uint32_t* s_cs = reinterpret_cast<const uint32_t*>( stage + CS_OFF );
+    const BpStage<D>* st = reinterpret_cast<const BpStage<D>*>( stage + ST_OFF );
+    sg_mbar_wait( &bars[sgi], use & 1u );
+    if( p < n )
+    {
+      const Rec me = sg_bp_fetch<P>( recs, s_recs, st, 1, p ); // own row is window 1 (dy = 0)
+      const uint32_t my_idx = P::rec_idx( me );
+      if( !P::owns( me ) )
+      {
+        counts[my_idx] = make_uint2( 0u, 0u );
+        masks[p] = make_uint4( 0u, 0u, 0u, 0u );
+      }
+      else
+      {
+        double lo[D], hi[D];
+        P::rec_aabb( me, lo, hi );
+        uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
+        uint32_t qb[Cfg::NW], qe[Cfg::NW];
+        sg_bp_ranges<P, SG_BP_TMA_CSCAP>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
+        sg_bp_plan_store<D>( plan, n_slots, p, qb, qe );
+        sg_bp_walk_ranges<P>( qb, qe, p, [&]( const int w, const uint32_t q )
+        {
+          const uint32_t bit = ( k < 32u ) ? ( 1u << k ) : 0u;
+          ++k;
+          if( sg_bp_fetch_idx<P>( recs, s_recs, st, w, q ) <= my_idx ) { return; }
+          const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
+          double olo[D], ohi[D];
+          P::rec_aabb( o, olo, ohi );
+          bool ov = true;
+          #pragma unroll
+          for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
+          if( !ov ) { return; }
+          ++nc; cmask |= bit;
+          if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
+        } );
+        const uint32_t na_f = ( k > 32u ) ? ( na | SG_BP_MASKS_INVALID ) : na;
+        counts[my_idx] = make_uint2( nc, na_f );
+        masks[p] = make_uint4( cmask, amask, nc, na_f );
+      }
+    }
+    else if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); }
+    // this warp is done with the stage
+    __syncwarp();
+    if( ( threadIdx.x & 31u ) == 0u ) { sg_mbar_arrive( &bars[2 + sgi] ); }
+  }
+}
+
+// Tensor map over the sorted records: n rows of 16 x u32, box = 16 x SG_BP_TMA_ROWS, 64-byte swizzle.
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
+static inline int sg_bp_encode_recs_map( sg_ctx* ctx, const void* recs, const uint32_t n, CUtensorMap* out )
+{
+  typedef CUresult ( *EncodeFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+  static EncodeFn encode = nullptr;
+  if( encode == nullptr )
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr )
+    {
+      cudaGetLastError();
+      return sg_fail( ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver" );
+    }
+    encode = reinterpret_cast<EncodeFn>( fn );
+  }
+  const cuuint64_t gdim[2] = { 16, n };
+  const cuuint64_t gstride[1] = { 64 };
+  const cuuint32_t box[2] = { 16, SG_BP_TMA_ROWS };
+  const cuuint32_t estr[2] = { 1, 1 };
+  const CUresult r = encode( out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>( recs ), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+  if( r != CUDA_SUCCESS ) { return sg_fail( ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled( sorted records ) -> %d", int( r ) ); }
+  return SG_OK;
+}
+
+// Dispatch: the 2-D pipelines take the TMA-fed kernel, the 3-D ones the block-staged kernel (their 9 windows do not
+// fit a double-buffered stage at a useful occupancy).
+template<int D> struct SgBpCountLaunch;
+template<> struct SgBpCountLaunch<3>
+{
+  template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const uint32_t n )
+  {
+    constexpr size_t smem = sg_bp_count_smem<3>();
+    SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
+    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<3>::NPLAN ), sg_bp_count<P><<<sg_div_up( n, BpCfg<3>::T ), BpCfg<3>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+               s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
+    return SG_OK;
+  }
+};
+template<> struct SgBpCountLaunch<2>
+{
+  template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const uint32_t n )
+  {
+    if( s.recs.ptr != s.tm_ptr || n != s.tm_rows )
+    {
+      const int rc = sg_bp_encode_recs_map( ctx, s.recs.ptr, n, &s.tm_recs );
+      if( rc != SG_OK ) { return rc; }
+      s.tm_ptr = s.recs.ptr; s.tm_rows = n;
+    }
+    constexpr size_t smem = sg_bp_tma_smem<2>();
+    SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_tma<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
+    const unsigned ntiles = sg_div_up( n, BpCfg<2>::T );
+    const unsigned grid = ntiles < unsigned( ctx->num_sms ) * 2u ? ntiles : unsigned( ctx->num_sms ) * 2u;
+    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_tma<P><<<grid, BpCfg<2>::T + 32, smem, ctx->stream>>>( s.tm_recs, n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+               s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
+    return SG_OK;
+  }
+};
 
 // Slow paths of pass 2: redo the tests (a body with more than 32 neighbours or more candidates than the sorting
 // network holds); everything comes through L1/L2.  Kept out of line so the common path stays lean in registers.
@@ -792,7 +1021,7 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   SG_CUDA( ctx, s.params.ensure( sizeof( GridParams ) ) );
   SG_CUDA( ctx, s.cell_count.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
   if( s.cell_count.ptr != s.hist_ptr || s.max_cells + 2u > s.hist_slots ) { s.hist_clean = false; s.hist_ptr = s.cell_count.ptr; s.hist_slots = s.max_cells + 2u; }
-  SG_CUDA( ctx, s.cell_start.ensure( ( size_t( s.max_cells ) + 2 ) * 4 ) );
+  SG_CUDA( ctx, s.cell_start.ensure( ( size_t( s.max_cells ) + 8 ) * 4 ) ); // + slack: bulk copies read whole 16-byte groups
   SG_CUDA( ctx, s.cell_partials.ensure( ( size_t( s.max_cells ) / SG_SCAN_TILE + 2 ) * 4 ) );
   SG_CUDA( ctx, s.key.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.rank.ensure( size_t( n ) * 4 ) );
@@ -832,9 +1061,8 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   if( rc != SG_OK ) { return rc; }
   SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 + 4.0 ) + double( s.max_cells ) * 4.0, sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>(), s.cell_count.as<uint32_t>(), s.max_cells + 2u ) );
   s.hist_clean = true;
-  constexpr size_t smem = sg_bp_count_smem<D>();
-  SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
-  SG_LAUNCH( ctx, "bp_count", nb * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<D>::NPLAN ), sg_bp_count<P><<<sg_div_up( n, BpCfg<D>::T ), BpCfg<D>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
+  rc = SgBpCountLaunch<D>::template run<P>( ctx, s, n );
+  if( rc != SG_OK ) { return rc; }
   rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false, s.pos_of.as<uint32_t>(), s.side.n != 0u ? &s.side : nullptr );
   s.side.n = 0u;
   return rc;

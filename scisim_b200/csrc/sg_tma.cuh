@@ -36,4 +36,17 @@ __device__ __forceinline__ void sg_mbar_wait( uint64_t* bar, const uint32_t pari
   } while( done == 0 );
 }
 
+// non-blocking arrive (count 1) -- consumers releasing a stage back to the producer
+__device__ __forceinline__ void sg_mbar_arrive( uint64_t* bar )
+{
+  asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( sg_smem_u32( bar ) ) : "memory" );
+}
+
+// 2-D tiled tensor copy global -> shared (SASS: UTMALDG.2D); c0 = innermost coordinate
+__device__ __forceinline__ void sg_tma_load_2d( void* smem_dst, const void* tensor_map, const int c0, const int c1, uint64_t* bar )
+{
+  asm volatile( "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"( sg_smem_u32( smem_dst ) ), "l"( tensor_map ), "r"( c0 ), "r"( c1 ), "r"( sg_smem_u32( bar ) ) : "memory" );
+}
+
 #endif
