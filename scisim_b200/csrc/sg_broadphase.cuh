@@ -905,16 +905,18 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t
   using Rec = typename P::Rec;
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if( p >= n_slots ) { return; }
-  const uint4 m = __ldg( &masks[p] ); // zero for ghosts and for slots past the binned bodies (cleared by the host driver)
-  if( m.z == 0u ) { return; }
+  // everything the common path needs is position-indexed: issue all the loads before looking at any of them
+  // (one round trip instead of two; unused slots just read stale plan words they never use)
+  const uint4 m = __ldg( &masks[p] ); // zero for ghosts and for slots past the binned bodies (cleared by pass 1)
   const ulonglong2 off = offsets_pos[p];
   const uint32_t my_idx = __ldg( &sidx[p] ) & P::IDX_MASK;
+  uint32_t qb[Cfg::NW], len[Cfg::NW];
+  sg_bp_plan_load<D>( plan, n_slots, p, qb, len );
+  if( m.z == 0u ) { return; }
   unsigned long long ka = off.y;
 
   if( m.z <= SG_BP_FAST_CAP && ( m.w & SG_BP_MASKS_INVALID ) == 0u )
   {
-    uint32_t qb[Cfg::NW], len[Cfg::NW];
-    sg_bp_plan_load<D>( plan, n_slots, p, qb, len );
     // visits before window w (the body itself is skipped inside its own window)
     unsigned long long v[SG_BP_FAST_CAP];
     uint32_t cm = m.x;
