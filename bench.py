@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: peer-memory mailboxes over NVLink (CUDA IPC) or NCCL all_gather + send/recv")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -200,10 +201,11 @@ def main():
         sim.upload(scene["q"], scene["v"])
         step = lambda: sim.step(umap, dt)
     else:
-        # one slab per GPU, ghosts exchanged with the neighbouring slabs over NCCL every step (scisim_b200/slab.py)
+        # one slab per GPU, ghosts exchanged with the neighbouring slabs every step (scisim_b200/slab.py): by the kernels
+        # themselves through peer-mapped mailboxes (default), or by NCCL all_gather + send/recv
         from scisim_b200.slab import Ball2DSlabs, GpuSlabBackend
         backend = GpuSlabBackend(ctx, scene, rank * n, ghost_cap=max(4096, n // 128))
-        slabs = Ball2DSlabs(backend, rank, world, dist)
+        slabs = Ball2DSlabs(backend, rank, world, dist, transport=args.transport)
         step = lambda: slabs.step(umap.kind, dt)
 
     # ---------------- resident path: `value` ----------------
@@ -268,7 +270,7 @@ def main():
         ctx.synchronize()
         t_e2e_local = time.perf_counter() - t0
         h2d = 2 * 2 * n * 8
-        n_act, e2e_api = int(c.n_active), "sg_ball2d_upload + slab step (NCCL halo) + sg_ball2d_fetch, pinned host buffers, wall clock"
+        n_act, e2e_api = int(c.n_active), "sg_ball2d_upload + slab step (%s halo) + sg_ball2d_fetch, pinned host buffers, wall clock" % args.transport
     d2h = 2 * 2 * n * 8 + n_act * (4 + 4 + 4 + 16 + 16 + 8)
 
     # ---------------- reduce over ranks: max time, summed work ----------------
@@ -296,7 +298,7 @@ def main():
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(world), "bodies_per_gpu": n, "candidates_per_gpu": pc, "active_per_gpu": pa,
                        "l2": "384 MB buffer overwritten before every timed step (L2 flush)", "timing": "CUDA events on the library stream, per step, summed; max over ranks",
-                       "parallelism": ("%d x-slabs, 1 process per GPU, ghost bodies exchanged with +-1 neighbours over NCCL each step, pair owned by the rank of its lower index" % world) if world > 1 else "single GPU"},
+                       "parallelism": ("%d x-slabs, 1 process per GPU, ghost bodies exchanged with +-1 neighbours each step (%s), pair owned by the rank of its lower index" % (world, "peer-memory mailboxes over NVLink, no collective in the step" if args.transport == "p2p" else "NCCL all_gather + send/recv")) if world > 1 else "single GPU"},
             "steps_per_s": args.steps / t_max,
             "step_ms_rank0": [round(x, 4) for x in step_ms],
             "clocks": clocks,

@@ -163,6 +163,23 @@ int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
 
+/* Peer-memory halo exchange (one process per GPU, neighbours' mailboxes mapped over NVLink with CUDA IPC; no
+   collective, no host round trip).  No reference counterpart (SCISim is single-process); see DESIGN.md section 5.
+   sg_ball2d_slab_mailbox    allocates this rank's mailbox (once) and returns its device address and/or its CUDA IPC
+                             handle (64 opaque bytes) for the neighbours.
+   sg_ball2d_slab_connect    maps the mailbox of the neighbour on `side` (0 = lower ranks, 1 = higher): either from
+                             its IPC handle (other process) or from its address (same process; peer_device = its
+                             device ordinal, -1 if the same device).  Exactly one of the two must be given.
+   After both calls sg_ball2d_slab_flow also posts this rank's swept interval to the neighbours (interval_dev may
+   then be NULL) and sg_ball2d_slab_exchange( phase ) replaces pack / send / recv / unpack:
+     phase 1  wait for each neighbour's interval, pack the bodies that reach it straight into its mailbox, raise its flag
+     phase 2  wait for the neighbours' halos, move them into the ghost slots
+     phase 0  both.  Everything is asynchronous on the context's stream; waits give up after 10 s and
+              sg_ball2d_slab_detect then returns SG_ERR_INTERNAL. */
+int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64 );
+int sg_ball2d_slab_connect( sg_ctx* ctx, int side, const void* ipc_handle_64, void* same_process_mailbox, int peer_device );
+int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase );
+
 /* Slab mode (multi-GPU): this context holds bodies [gid_first, gid_first + n_owned) of a larger scene
  * whose global numbering is slab-major, plus per-step ghost copies of neighbouring slabs' bodies.  The reference has no
  * distributed mode; these calls are driven by scisim_b200/slab.py (one process per GPU, NCCL for the exchange).

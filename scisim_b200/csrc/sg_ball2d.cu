@@ -387,7 +387,12 @@ struct Ball2DData
   uint32_t n_owned = 0, ghost_cap = 0, gid_first = 0;
   DevBuf gid;          // u32 per slot: global body index
   DevBuf interval_enc; // 2 x long long (ordered encoding of min lo.x / max hi.x over the owned swept boxes)
-  DevBuf pack_counts, pack_offsets, pack_partials;
+  DevBuf pack_counts, pack_offsets, pack_partials, pack_total;
+  // peer-memory halo exchange (NVLink): this rank's mailbox and the neighbours' mailboxes mapped into this process
+  DevBuf mailbox;
+  void* peer_mb[2] = { nullptr, nullptr };
+  bool peer_ipc[2] = { false, false };
+  uint32_t slab_step = 0; // tag of the current step's flags (all ranks step in lockstep)
   size_t first_slot() const { return 0; }
   size_t owned_slot() const { return slab ? size_t( ghost_cap ) : 0; }        // first owned slot
   uint32_t own_first() const { return slab ? ghost_cap : 0u; }                 // owned range in local indices
@@ -410,7 +415,9 @@ void sg_ball2d_release( sg_ctx* ctx )
   d->st_counts.release(); d->st_offsets.release(); d->st_partials.release(); d->st_total.release();
   d->c_type.release(); d->c_i.release(); d->c_j.release(); d->c_n.release(); d->c_p.release(); d->c_depth.release();
   d->h_totals.release(); d->h_out.release();
-  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release();
+  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release();
+  for( int sde = 0; sde < 2; ++sde ) { if( d->peer_mb[sde] != nullptr && d->peer_ipc[sde] ) { cudaIpcCloseMemHandle( d->peer_mb[sde] ); } d->peer_mb[sde] = nullptr; }
+  d->mailbox.release();
   delete d;
   ctx->ball2d = nullptr;
 }
@@ -731,6 +738,59 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t ca
   gid[k] = g.gid;
 }
 
+
+// ---- peer-memory halo exchange -----------------------------------------------------------------------
+// Each rank owns a mailbox in its own HBM that its two neighbours write over NVLink (mapped with CUDA IPC, or
+// directly when the neighbour lives in the same process): the neighbour's swept interval, then -- packed by the
+// neighbour's own pack kernel straight through the peer mapping -- its halo records, each followed by a
+// system-scope fence and a step-tagged flag.  The consumer side is a one-thread kernel spinning on the flag in
+// LOCAL memory, so the whole exchange is stream-ordered device work: no collective, no host round trip.
+struct alignas( 128 ) SlabMailboxHdr
+{
+  double iv[2][2];        // [side]: interval of the neighbour on that side (0 = lower ranks, 1 = higher)
+  uint32_t iv_flag[2];    // step tag of iv[side]
+  uint32_t halo_flag[2];  // step tag of the halo records from that side
+  uint32_t err;           // a wait timed out
+};
+__host__ __device__ inline GhostRec* slab_mailbox_halo( void* mb, const int side, const uint32_t cap )
+{
+  return reinterpret_cast<GhostRec*>( static_cast<unsigned char*>( mb ) + sizeof( SlabMailboxHdr ) ) + size_t( side ) * ( size_t( cap ) + 1 );
+}
+__device__ __forceinline__ void st_release_sys( uint32_t* p, const uint32_t v ) { asm volatile( "st.release.sys.global.u32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" ); }
+__device__ __forceinline__ uint32_t ld_acquire_sys( const uint32_t* p ) { uint32_t v; asm volatile( "ld.acquire.sys.global.u32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" ); return v; }
+
+// decodes this rank's interval, keeps a local copy and posts it to the neighbours (lower = side 0, higher = side 1)
+__global__ void k_ball2d_slab_post_interval( const long long* enc, double* local_out, SlabMailboxHdr* lower, SlabMailboxHdr* higher, const uint32_t step )
+{
+  const double lo = sg_double_from_ordered( enc[0] ), hi = sg_double_from_ordered( enc[1] );
+  if( local_out != nullptr ) { local_out[0] = lo; local_out[1] = hi; }
+  if( lower != nullptr ) { lower->iv[1][0] = lo; lower->iv[1][1] = hi; }     // seen from the lower rank I am its side-1 neighbour
+  if( higher != nullptr ) { higher->iv[0][0] = lo; higher->iv[0][1] = hi; }
+  __threadfence_system();
+  if( lower != nullptr ) { st_release_sys( &lower->iv_flag[1], step ); }
+  if( higher != nullptr ) { st_release_sys( &higher->iv_flag[0], step ); }
+}
+
+// one thread: returns when *flag has reached `step` (bounded: a dead neighbour must not hang the GPU)
+__global__ void k_ball2d_slab_wait( const uint32_t* flag, const uint32_t step, uint32_t* err )
+{
+  unsigned long long t0, t1;
+  asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t0 ) );
+  while( int( ld_acquire_sys( flag ) - step ) < 0 )
+  {
+    __nanosleep( 200 );
+    asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t1 ) );
+    if( t1 - t0 > 10000000000ull ) { *err = 1u; break; } // 10 s
+  }
+}
+
+// after the pack kernel: make its peer writes visible system-wide, then raise the flag
+__global__ void k_ball2d_slab_post_flag( uint32_t* peer_flag, const uint32_t step )
+{
+  __threadfence_system();
+  st_release_sys( peer_flag, step );
+}
+
 __global__ void __launch_bounds__( 256 ) k_iota_u32( const uint32_t n, const uint32_t first, uint32_t* __restrict__ out )
 {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -907,8 +967,9 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
 
 int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_dev )
 {
-  if( ctx == nullptr || interval_dev == nullptr ) { return SG_ERR_INVALID; }
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
+  if( interval_dev == nullptr && d->mailbox.ptr == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: interval_dev may only be null once a mailbox exists" ); }
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: call sg_ball2d_slab_init first" ); }
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: map kind %d is not a ball2d map", map_kind ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
@@ -917,7 +978,12 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
   SG_LAUNCH( ctx, "slab_flow_interval", double( n ) * 80.0, k_ball2d_slab_begin<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>() );
              k_ball2d_slab_flow<<<sg_div_up( n > 0 ? n : 1, 256 ), 256, 0, ctx->stream>>>( map_kind, n, d->q0.as<double2>() + o, d->v0.as<double2>(), d->m.as<double>(), d->r.as<double>() + o,
                                                                                       d->g[0], d->g[1], dt, d->q1.as<double2>() + o, d->v1.as<double2>(), d->interval_enc.as<long long>() );
-             k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev ) );
+             if( d->mailbox.ptr == nullptr ) { k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev ); }
+             else
+             {
+               ++d->slab_step;
+               k_ball2d_slab_post_interval<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev, static_cast<SlabMailboxHdr*>( d->peer_mb[0] ), static_cast<SlabMailboxHdr*>( d->peer_mb[1] ), d->slab_step );
+             } );
   ctx->launch_count += 2;
   return SG_OK;
 }
@@ -960,6 +1026,102 @@ int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev )
   return SG_OK;
 }
 
+int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64 )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_mailbox: call sg_ball2d_slab_init first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  static_assert( sizeof( cudaIpcMemHandle_t ) == 64, "the ABI passes IPC handles as 64 opaque bytes" );
+  if( d->mailbox.ptr == nullptr )
+  {
+    const size_t bytes = sizeof( SlabMailboxHdr ) + 2 * ( size_t( d->ghost_cap ) + 1 ) * sizeof( GhostRec );
+    SG_CUDA( ctx, d->mailbox.ensure( bytes ) );
+    SG_CUDA( ctx, cudaMemsetAsync( d->mailbox.ptr, 0, bytes, ctx->stream ) );
+    SG_CUDA( ctx, d->pack_total.ensure( 16 ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    d->slab_step = 0;
+  }
+  if( mailbox_dev != nullptr ) { *mailbox_dev = d->mailbox.ptr; }
+  if( ipc_handle_64 != nullptr )
+  {
+    cudaIpcMemHandle_t h;
+    SG_CUDA( ctx, cudaIpcGetMemHandle( &h, d->mailbox.ptr ) );
+    memcpy( ipc_handle_64, &h, 64 );
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_slab_connect( sg_ctx* ctx, int side, const void* ipc_handle_64, void* same_process_mailbox, int peer_device )
+{
+  if( ctx == nullptr || ( side != 0 && side != 1 ) || ( ipc_handle_64 == nullptr ) == ( same_process_mailbox == nullptr ) ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab || d->mailbox.ptr == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_connect: create this rank's mailbox first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->peer_mb[side] != nullptr && d->peer_ipc[side] ) { cudaIpcCloseMemHandle( d->peer_mb[side] ); }
+  d->peer_mb[side] = nullptr;
+  if( ipc_handle_64 != nullptr )
+  {
+    cudaIpcMemHandle_t h;
+    memcpy( &h, ipc_handle_64, 64 );
+    void* p = nullptr;
+    SG_CUDA( ctx, cudaIpcOpenMemHandle( &p, h, cudaIpcMemLazyEnablePeerAccess ) );
+    d->peer_mb[side] = p; d->peer_ipc[side] = true;
+  }
+  else
+  {
+    if( peer_device >= 0 && peer_device != ctx->device )
+    {
+      int can = 0;
+      SG_CUDA( ctx, cudaDeviceCanAccessPeer( &can, ctx->device, peer_device ) );
+      if( !can ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "device %d cannot map the memory of device %d", ctx->device, peer_device ); }
+      const cudaError_t e = cudaDeviceEnablePeerAccess( peer_device, 0 );
+      if( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled ) { return sg_fail( ctx, SG_ERR_CUDA, "cudaDeviceEnablePeerAccess( %d ): %s", peer_device, cudaGetErrorString( e ) ); }
+      cudaGetLastError();
+    }
+    d->peer_mb[side] = same_process_mailbox; d->peer_ipc[side] = false;
+  }
+  return SG_OK;
+}
+
+// phase 1: for each connected neighbour wait for its interval, pack the owned bodies that reach it straight into
+//          its mailbox, raise its halo flag;  phase 2: wait for the neighbours' halos and move them into the ghost
+//          slots;  phase 0: both.  (A driver with several ranks in ONE process must run phase 1 on every rank
+//          before phase 2 on any, because a wait kernel only returns once the neighbour's work has been launched.)
+int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
+{
+  if( ctx == nullptr || phase < 0 || phase > 2 ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab || d->mailbox.ptr == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_exchange: no mailbox" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SlabMailboxHdr* mine = d->mailbox.as<SlabMailboxHdr>();
+  const uint32_t step = d->slab_step;
+  if( phase == 0 || phase == 1 )
+  {
+    for( int side = 0; side < 2; ++side )
+    {
+      if( d->peer_mb[side] == nullptr ) { continue; }
+      SlabMailboxHdr* peer = static_cast<SlabMailboxHdr*>( d->peer_mb[side] );
+      SG_LAUNCH( ctx, "slab_wait", 0.0, k_ball2d_slab_wait<<<1, 1, 0, ctx->stream>>>( &mine->iv_flag[side], step, &mine->err ) );
+      // seen from the neighbour on `side`, this rank sits on its side 1 - side
+      const int rc = sg_ball2d_slab_pack( ctx, &mine->iv[side][0], slab_mailbox_halo( peer, 1 - side, d->ghost_cap ), d->ghost_cap, d->pack_total.as<uint32_t>() + side );
+      if( rc != SG_OK ) { return rc; }
+      SG_LAUNCH( ctx, "slab_post", 0.0, k_ball2d_slab_post_flag<<<1, 1, 0, ctx->stream>>>( &peer->halo_flag[1 - side], step ) );
+    }
+  }
+  if( phase == 0 || phase == 2 )
+  {
+    for( int side = 0; side < 2; ++side )
+    {
+      if( d->peer_mb[side] == nullptr ) { continue; }
+      SG_LAUNCH( ctx, "slab_wait", 0.0, k_ball2d_slab_wait<<<1, 1, 0, ctx->stream>>>( &mine->halo_flag[side], step, &mine->err ) );
+      const int rc = sg_ball2d_slab_unpack( ctx, side, slab_mailbox_halo( mine, side, d->ghost_cap ) );
+      if( rc != SG_OK ) { return rc; }
+    }
+  }
+  return SG_OK;
+}
+
 int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
@@ -972,6 +1134,12 @@ int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
   SG_CUDA( ctx, cudaMemcpyAsync( hg, d->ghost_counts.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   if( hg[2] != 0u ) { return sg_fail( ctx, SG_ERR_INVALID, "slab halo exceeds the reserved ghost capacity %u: results are incomplete", d->ghost_cap ); }
+  if( d->mailbox.ptr != nullptr )
+  {
+    uint32_t err = 0u;
+    SG_CUDA( ctx, cudaMemcpy( &err, &d->mailbox.as<SlabMailboxHdr>()->err, 4, cudaMemcpyDeviceToHost ) );
+    if( err != 0u ) { return sg_fail( ctx, SG_ERR_INTERNAL, "slab exchange: a neighbour did not post its interval or halo within 10 s" ); }
+  }
   if( ghosts_out != nullptr ) { ghosts_out[0] = hg[0]; ghosts_out[1] = hg[1]; }
   if( out != nullptr )
   {

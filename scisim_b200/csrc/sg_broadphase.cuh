@@ -531,7 +531,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
-  extern __shared__ __align__( 128 ) unsigned char s_raw[];
+  extern __shared__ __align__( 1024 ) unsigned char s_raw[];
   unsigned char* s_recs = s_raw;
   uint32_t* s_cs = reinterpret_cast<uint32_t*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 );
   BpStage<D>* st = reinterpret_cast<BpStage<D>*>( s_raw + size_t( Cfg::NW ) * Cfg::WCAP * 64 + sg_bp_cs_bytes<D>() );

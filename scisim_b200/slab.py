@@ -89,6 +89,21 @@ class GpuSlabBackend:
         self.ctx.check(self.lib.sg_ball2d_slab_flow(self.ctx.h, int(kind), float(dt), C.c_void_p(self.iv.data_ptr())))
         return self.iv
 
+    # ---- peer-memory transport (NVLink, no collective in the step) ----
+    def mailbox(self):
+        """(device address, 64-byte CUDA IPC handle) of this rank's mailbox; creates it on first use."""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self.ctx.check(self.lib.sg_ball2d_slab_mailbox(self.ctx.h, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def connect(self, side, ipc_handle=None, same_process_ptr=None, peer_device=-1):
+        h = (C.c_ubyte * 64).from_buffer_copy(ipc_handle) if ipc_handle is not None else None
+        self.ctx.check(self.lib.sg_ball2d_slab_connect(self.ctx.h, int(side), h, C.c_void_p(same_process_ptr) if same_process_ptr is not None else None, int(peer_device)))
+
+    def exchange(self, phase=0):
+        self.ctx.check(self.lib.sg_ball2d_slab_exchange(self.ctx.h, int(phase)))
+
     def pack(self, interval, side):
         """Selects, in body order, the owned bodies overlapping `interval` (2-element tensor on this device) into the
         side's send buffer (header + records). Asynchronous."""
@@ -134,10 +149,25 @@ class Ball2DSlabs:
     """Per-rank driver of one step: flow -> interval all_gather -> halo exchange -> detection.  With the GPU backend
     nothing blocks the host until detect() reads the list sizes."""
 
-    def __init__(self, backend, rank, world, dist, check_non_neighbours=False):
+    def __init__(self, backend, rank, world, dist, check_non_neighbours=False, transport="nccl"):
+        """transport "nccl": intervals by all_gather, halos by send/recv (any backend, also gloo + the oracle backend);
+        "p2p": the neighbours' mailboxes are mapped once with CUDA IPC (handles travel through `dist`), after that a
+        step issues no collective at all -- intervals and halos are written over NVLink by the kernels themselves."""
         self.b, self.rank, self.world, self.dist = backend, rank, world, dist
         self.check = check_non_neighbours
         self.last_halo = (0, 0)
+        self.transport = transport if world > 1 else "nccl"
+        if self.transport == "p2p":
+            import torch
+            _, handle = backend.mailbox()
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=backend.device)
+            allh = torch.empty(world * 64, dtype=torch.uint8, device=backend.device)
+            dist.all_gather_into_tensor(allh, mine)
+            allh = allh.cpu().numpy().reshape(world, 64)
+            for side, peer in ((0, rank - 1), (1, rank + 1)):
+                if 0 <= peer < world:
+                    backend.connect(side, ipc_handle=bytes(allh[peer]))
+            dist.barrier()
 
     def step(self, kind, dt):
         import contextlib
@@ -146,7 +176,9 @@ class Ball2DSlabs:
         cm = b.run_on_stream() if hasattr(b, "run_on_stream") else contextlib.nullcontext()
         with cm:
             iv = b.flow(kind, dt)
-            if W > 1:
+            if W > 1 and self.transport == "p2p":
+                b.exchange(0)
+            elif W > 1:
                 all_iv = torch.empty(W * 2, dtype=torch.float64, device=iv.device)
                 dist.all_gather_into_tensor(all_iv, iv)
                 all_iv = all_iv.view(W, 2)
