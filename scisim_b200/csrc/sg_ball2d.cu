@@ -54,7 +54,7 @@ struct ContactOut2D
   double2* p;
   double* depth;
   unsigned long long cap;
-  const uint32_t* gid; // multi-GPU: local -> global body index (nullptr on one GPU)
+  GidMap gid; // multi-GPU: local -> global body index (identity on one GPU)
 };
 
 // scisim/CollisionDetection/CollisionDetectionUtilities.cpp:3-121 (a = lower body index)
@@ -139,8 +139,8 @@ struct Ball2DPolicy
       const double ey = a.q1y - b.q1y;
       out.type[k] = SG_BALL_BALL;
       const uint32_t ia = a.idx & IDX_MASK, ib = b.idx & IDX_MASK;
-      out.i[k] = ( out.gid != nullptr ) ? out.gid[ia] : ia;
-      out.j[k] = ( out.gid != nullptr ) ? out.gid[ib] : ib;
+      out.i[k] = out.gid( ia );
+      out.j[k] = out.gid( ib );
       out.n[k] = make_double2( nx, ny );
       out.p[k] = make_double2( a.q0x - a.r * nx, a.q0y - a.r * ny );
       out.depth[k] = fmin( 0.0, sqrt( ex * ex + ey * ey ) - ( a.r + b.r ) );
@@ -224,8 +224,12 @@ template<bool DO_FLOW>
 __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ Static2D sg, const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0,
                                                        const double* __restrict__ m, const double* __restrict__ r, const double gx, const double gy, const double dt,
                                                        double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts,
-                                                       const uint32_t own_first, const uint32_t own_count, const uint32_t* __restrict__ ghost_counts )
+                                                       const uint32_t own_first, const uint32_t own_count, const uint32_t* __restrict__ ghost_counts, long long* __restrict__ interval_enc )
 {
+  // q0, q1, r are indexed by slot ([ghosts | owned | ghosts] in slab mode); v0, m, v1 exist for owned bodies only.
+  // interval_enc != nullptr (slab mode, DO_FLOW): the ghosts have not arrived yet -- only owned bodies are live, and
+  // [min lo.x, max hi.x] of their swept boxes is reduced for the neighbours; the ghosts' share of the bounds is added
+  // by the unpack kernel.
   __shared__ uint32_t s_cnt[SG_MAX_DRUMS + SG_MAX_PLANES];
   const uint32_t ng = sg.ndrums + sg.nplanes;
   if( threadIdx.x < ng ) { s_cnt[threadIdx.x] = 0u; }
@@ -236,18 +240,21 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
   double ext = 0.0;
   unsigned long long mask = 0ull;
   bool live = i < n;
-  if( live && ghost_counts != nullptr && i - own_first >= own_count )
+  if( live && DO_FLOW && interval_enc != nullptr ) { live = i - own_first < own_count; }
+  else if( live && ghost_counts != nullptr && i - own_first >= own_count )
   {
     live = ( i < own_first ) ? ( i < __ldg( &ghost_counts[0] ) ) : ( i - ( own_first + own_count ) < __ldg( &ghost_counts[1] ) );
   }
+  double ivlo = __longlong_as_double( 0x7ff0000000000000LL ), ivhi = __longlong_as_double( 0xfff0000000000000LL );
   if( live )
   {
     const double2 q = __ldg( &q0[i] );
     double2 qo;
     if( DO_FLOW )
     {
-      const double2 v = __ldg( &v0[i] );
-      const double mass = __ldg( &m[i] );
+      const uint32_t io = i - own_first;
+      const double2 v = __ldg( &v0[io] );
+      const double mass = __ldg( &m[io] );
       const double minv = 1.0 / mass;
       const double Fx = 0.0 + mass * gx;
       const double Fy = 0.0 + mass * gy;
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
         vo.y = vhy + s * Fy;
       }
       q1[i] = qo;
-      v1[i] = vo;
+      v1[io] = vo;
     }
     else
     {
@@ -281,10 +288,29 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
     double lo[2], hi[2];
     lo[0] = fmin( qo.x, q.x ) - rad; lo[1] = fmin( qo.y, q.y ) - rad;
     hi[0] = fmax( qo.x, q.x ) + rad; hi[1] = fmax( qo.y, q.y ) + rad;
+    ivlo = lo[0]; ivhi = hi[0];
     sg_bp_bounds_update<2>( lo, hi, mn, mx, ext );
     if( i - own_first < own_count ) { mask = static_mask( sg, qo, rad ); } // ghosts touch no static geometry here
   }
   sg_bp_bounds_commit<2>( mn, mx, ext, acc );
+  if( DO_FLOW && interval_enc != nullptr )
+  {
+    // block reduce, then two atomics per block (same-address atomics from every warp would serialise in L2)
+    __shared__ double s_iv[8][2];
+    #pragma unroll
+    for( int dd = 16; dd > 0; dd >>= 1 ) { ivlo = fmin( ivlo, __shfl_xor_sync( 0xffffffffu, ivlo, dd ) ); ivhi = fmax( ivhi, __shfl_xor_sync( 0xffffffffu, ivhi, dd ) ); }
+    if( ( threadIdx.x & 31 ) == 0 ) { s_iv[threadIdx.x >> 5][0] = ivlo; s_iv[threadIdx.x >> 5][1] = ivhi; }
+    __syncthreads();
+    if( threadIdx.x == 0 )
+    {
+      for( int w = 1; w < 8; ++w ) { ivlo = fmin( ivlo, s_iv[w][0] ); ivhi = fmax( ivhi, s_iv[w][1] ); }
+      if( ivlo <= ivhi )
+      {
+        atomicMin( &interval_enc[0], sg_ordered_from_double( ivlo ) );
+        atomicMax( &interval_enc[1], sg_ordered_from_double( ivhi ) );
+      }
+    }
+  }
   if( ng > 0u )
   {
     const int lane = threadIdx.x & 31;
@@ -350,7 +376,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_static_emit( const __grid_cons
           depth = fmin( 0.0, dist - rad );
         }
         out.type[k] = type;
-        out.i[k] = ( out.gid != nullptr ) ? out.gid[i] : i;
+        out.i[k] = out.gid( i );
         out.j[k] = j;
         out.n[k] = make_double2( nx, ny );
         out.p[k] = make_double2( x0.x - rad * nx, x0.y - rad * ny );
@@ -393,6 +419,8 @@ struct Ball2DData
   void* peer_mb[2] = { nullptr, nullptr };
   bool peer_ipc[2] = { false, false };
   uint32_t slab_step = 0; // tag of the current step's flags (all ranks step in lockstep)
+  bool slab_prep_done = false; // this step's bounds / static counts were already produced by sg_ball2d_slab_flow
+  DevBuf pack_done;            // block counter of the pack kernel's "last block raises the flag"
   size_t first_slot() const { return 0; }
   size_t owned_slot() const { return slab ? size_t( ghost_cap ) : 0; }        // first owned slot
   uint32_t own_first() const { return slab ? ghost_cap : 0u; }                 // owned range in local indices
@@ -403,6 +431,12 @@ struct Ball2DData
   double2* Q1() const { return q1.as<double2>() + first_slot(); }
   double* R() const { return r.as<double>() + first_slot(); }
   const uint32_t* GID() const { return slab ? gid.as<uint32_t>() + first_slot() : nullptr; }
+  GidMap gid_map() const
+  {
+    GidMap g;
+    if( slab ) { g.gid = gid.as<uint32_t>(); g.own_first = ghost_cap; g.own_count = n_owned; g.gid_first = gid_first; }
+    return g;
+  }
   Ball2DData() { memset( &sg, 0, sizeof( sg ) ); }
 };
 
@@ -415,7 +449,7 @@ void sg_ball2d_release( sg_ctx* ctx )
   d->st_counts.release(); d->st_offsets.release(); d->st_partials.release(); d->st_total.release();
   d->c_type.release(); d->c_i.release(); d->c_j.release(); d->c_n.release(); d->c_p.release(); d->c_depth.release();
   d->h_totals.release(); d->h_out.release();
-  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release();
+  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release(); d->pack_done.release();
   for( int sde = 0; sde < 2; ++sde ) { if( d->peer_mb[sde] != nullptr && d->peer_ipc[sde] ) { cudaIpcCloseMemHandle( d->peer_mb[sde] ); } d->peer_mb[sde] = nullptr; }
   d->mailbox.release();
   delete d;
@@ -460,6 +494,17 @@ static int ball2d_flow_device( sg_ctx* ctx, Ball2DData* d, const int map_kind, c
 
 // Runs the whole detection pipeline on the device-resident q0,q1 and leaves the counts in d->n_*.
 // flow_kind >= 0: the unconstrained map is fused into the first pass (q1,v1 are produced from q0,v0 on the way).
+static int ball2d_static_scratch( sg_ctx* ctx, Ball2DData* d )
+{
+  const uint32_t ng = d->sg.ndrums + d->sg.nplanes;
+  const uint32_t nst = ng * sg_div_up( d->n, 256 );
+  SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
+  SG_CUDA( ctx, d->st_total.ensure( 4 ) );
+  return SG_OK;
+}
+
 static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want_cand, const int flow_kind = -1, const double dt = 0.0 )
 {
   const uint32_t n = d->n;
@@ -477,23 +522,27 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   const uint32_t ng = d->sg.ndrums + d->sg.nplanes;
   const unsigned nblk = sg_div_up( n, 256 );
   const uint32_t nst = ng * nblk;
-  SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 + 4 ) );
-  SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 + 4 ) );
-  SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
-  SG_CUDA( ctx, d->st_total.ensure( 4 ) );
-  if( flow_kind >= 0 && !d->slab )
+  rc = ball2d_static_scratch( ctx, d );
+  if( rc != SG_OK ) { return rc; }
+  if( d->slab && d->slab_prep_done )
+  {
+    // slab mode: the flow kernel already reduced the owned bodies' bounds and static counts, the unpack kernels
+    // added the ghosts' bounds
+    d->slab_prep_done = false;
+  }
+  else if( flow_kind >= 0 && !d->slab )
   {
     SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(),
-               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr ) );
+               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr, nullptr ) );
   }
   else
   {
     SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr,
-               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS() ) );
+               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS(), nullptr ) );
   }
   Ball2DIn in;
   in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS();
-  d->bp.gid_map = d->GID();
+  d->bp.gid_map = d->gid_map();
   // the (tiny, latency-bound) scan of the static-geometry counts rides along with the pair-count scan
   const bool side_scan = ng > 0 && nst <= SG_SIDE_SCAN_MAX;
   if( side_scan ) { d->bp.side.in = d->st_counts.as<uint32_t>(); d->bp.side.n = nst; d->bp.side.out = d->st_offsets.as<uint32_t>(); d->bp.side.total = d->st_total.as<uint32_t>(); }
@@ -512,7 +561,7 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
     out.type = d->c_type.as<uint32_t>(); out.i = d->c_i.as<uint32_t>(); out.j = d->c_j.as<uint32_t>();
     out.n = d->c_n.as<double2>(); out.p = d->c_p.as<double2>(); out.depth = d->c_depth.as<double>();
     out.cap = d->act_cap;
-    out.gid = d->GID();
+    out.gid = d->gid_map();
     // The static-geometry contacts go behind the body-body ones (their base is the pair scan's total) and touch
     // nothing the pair emit does, so the two kernels run side by side (serially when kernels are being timed).
     cudaStream_t side = ( ng > 0 && !ctx->profile ) ? ctx->stream2 : ctx->stream;
@@ -618,126 +667,26 @@ __device__ __forceinline__ void swept_x( const double2 a, const double2 b, const
   hi = fmax( b.x, a.x ) + r;
 }
 
-// Flow of the owned bodies + [min lo.x, max hi.x] of their swept boxes (ordered-int encoded atomics)
-__global__ void __launch_bounds__( 256 ) k_ball2d_slab_flow( const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0, const double* __restrict__ m, const double* __restrict__ r,
-                                                            const double gx, const double gy, const double dt, double2* __restrict__ q1, double2* __restrict__ v1, long long* __restrict__ enc )
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  double mn = __longlong_as_double( 0x7ff0000000000000LL ), mx = __longlong_as_double( 0xfff0000000000000LL );
-  if( i < n )
-  {
-    const double2 q = __ldg( &q0[i] );
-    const double2 v = __ldg( &v0[i] );
-    const double mass = __ldg( &m[i] );
-    const double minv = 1.0 / mass;
-    const double Fx = 0.0 + mass * gx;
-    const double Fy = 0.0 + mass * gy;
-    double2 qo, vo;
-    if( kind == SG_MAP_SYMPLECTIC_EULER )
-    {
-      const double s = dt * minv;
-      vo.x = v.x + ( 0.0 + s * Fx );
-      vo.y = v.y + ( 0.0 + s * Fy );
-      qo.x = q.x + dt * vo.x;
-      qo.y = q.y + dt * vo.y;
-    }
-    else
-    {
-      const double s = ( 0.5 * dt ) * minv;
-      const double vhx = v.x + ( 0.0 + s * Fx );
-      const double vhy = v.y + ( 0.0 + s * Fy );
-      qo.x = q.x + dt * vhx;
-      qo.y = q.y + dt * vhy;
-      vo.x = vhx + s * Fx;
-      vo.y = vhy + s * Fy;
-    }
-    q1[i] = qo;
-    v1[i] = vo;
-    swept_x( q, qo, __ldg( &r[i] ), mn, mx );
-  }
-  #pragma unroll
-  for( int d = 16; d > 0; d >>= 1 ) { mn = fmin( mn, __shfl_xor_sync( 0xffffffffu, mn, d ) ); mx = fmax( mx, __shfl_xor_sync( 0xffffffffu, mx, d ) ); }
-  __shared__ double s_mn[8], s_mx[8];
-  if( ( threadIdx.x & 31 ) == 0 ) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
-  __syncthreads();
-  if( threadIdx.x == 0 )
-  {
-    for( int w = 1; w < 8; ++w ) { mn = fmin( mn, s_mn[w] ); mx = fmax( mx, s_mx[w] ); }
-    atomicMin( &enc[0], sg_ordered_from_double( mn ) );
-    atomicMax( &enc[1], sg_ordered_from_double( mx ) );
-  }
-}
 __global__ void k_ball2d_slab_begin( long long* enc, uint32_t* ghost_counts )
 {
   enc[0] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );
   enc[1] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );
   ghost_counts[0] = 0u; ghost_counts[1] = 0u;
 }
-__global__ void k_ball2d_interval_decode( const long long* enc, double* out ) { out[0] = sg_double_from_ordered( enc[0] ); out[1] = sg_double_from_ordered( enc[1] ); }
-
-// Owned bodies whose swept box overlaps [iv[0], iv[1]] on x (closed, like AABB::overlaps), in body order.
-template<bool EMIT>
-__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, const uint32_t* __restrict__ gid,
-                                                            const double* __restrict__ iv, uint32_t* __restrict__ block_counts, const uint32_t* __restrict__ block_offsets, const uint32_t* __restrict__ total,
-                                                            GhostRec* __restrict__ out, const uint32_t cap )
+// reads the reduced interval, re-arms the accumulator for the next step and clears this step's ghost counts
+__device__ inline void slab_take_interval( long long* enc, uint32_t* ghost_counts, double& lo, double& hi )
 {
-  __shared__ uint32_t s_warp[8];
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const double ilo = iv[0], ihi = iv[1];
-  bool sel = false;
-  double2 a = make_double2( 0.0, 0.0 ), b = a;
-  double rad = 0.0;
-  if( i < n )
-  {
-    a = __ldg( &q0[i] ); b = __ldg( &q1[i] ); rad = __ldg( &r[i] );
-    double lo, hi;
-    swept_x( a, b, rad, lo, hi );
-    sel = !( hi < ilo ) && !( ihi < lo );
-  }
-  const unsigned bal = __ballot_sync( 0xffffffffu, sel );
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
-  __syncthreads();
-  uint32_t before = 0u, tot = 0u;
-  for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } tot += c; }
-  if( !EMIT ) { if( threadIdx.x == 0 ) { block_counts[blockIdx.x] = tot; } return; }
-  if( blockIdx.x == 0 && threadIdx.x == 0 )
-  {
-    GhostRec h;
-    h.q0x = 0.0; h.q0y = 0.0; h.q1x = 0.0; h.q1y = 0.0; h.r = 0.0; h.gid = *total; h.pad = 0u;
-    out[0] = h;
-  }
-  if( sel )
-  {
-    const uint32_t k = block_offsets[blockIdx.x] + before + __popc( bal & ( ( 1u << lane ) - 1u ) );
-    if( k < cap )
-    {
-      GhostRec g;
-      g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
-      out[1u + k] = g;
-    }
-  }
+  lo = sg_double_from_ordered( enc[0] ); hi = sg_double_from_ordered( enc[1] );
+  enc[0] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );
+  enc[1] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );
+  ghost_counts[0] = 0u; ghost_counts[1] = 0u;
 }
-
-__global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t cap, const int side, const GhostRec* __restrict__ in, double2* __restrict__ q0, double2* __restrict__ q1, double* __restrict__ r,
-                                                              uint32_t* __restrict__ gid, uint32_t* __restrict__ ghost_counts )
+__global__ void k_ball2d_interval_decode( long long* enc, uint32_t* ghost_counts, double* out )
 {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t sent = in[0].gid;
-  const uint32_t count = sent < cap ? sent : cap;
-  if( k == 0u )
-  {
-    ghost_counts[side] = count;
-    if( sent > cap ) { ghost_counts[2] = 1u; } // more ghosts than reserved slots: reported by detect
-  }
-  if( k >= count ) { return; }
-  const GhostRec g = in[1u + k];
-  q0[k] = make_double2( g.q0x, g.q0y );
-  q1[k] = make_double2( g.q1x, g.q1y );
-  r[k] = g.r;
-  gid[k] = g.gid;
+  double lo, hi;
+  slab_take_interval( enc, ghost_counts, lo, hi );
+  out[0] = lo; out[1] = hi;
 }
-
 
 // ---- peer-memory halo exchange -----------------------------------------------------------------------
 // Each rank owns a mailbox in its own HBM that its two neighbours write over NVLink (mapped with CUDA IPC, or
@@ -759,20 +708,9 @@ __host__ __device__ inline GhostRec* slab_mailbox_halo( void* mb, const int side
 __device__ __forceinline__ void st_release_sys( uint32_t* p, const uint32_t v ) { asm volatile( "st.release.sys.global.u32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" ); }
 __device__ __forceinline__ uint32_t ld_acquire_sys( const uint32_t* p ) { uint32_t v; asm volatile( "ld.acquire.sys.global.u32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" ); return v; }
 
-// decodes this rank's interval, keeps a local copy and posts it to the neighbours (lower = side 0, higher = side 1)
-__global__ void k_ball2d_slab_post_interval( const long long* enc, double* local_out, SlabMailboxHdr* lower, SlabMailboxHdr* higher, const uint32_t step )
-{
-  const double lo = sg_double_from_ordered( enc[0] ), hi = sg_double_from_ordered( enc[1] );
-  if( local_out != nullptr ) { local_out[0] = lo; local_out[1] = hi; }
-  if( lower != nullptr ) { lower->iv[1][0] = lo; lower->iv[1][1] = hi; }     // seen from the lower rank I am its side-1 neighbour
-  if( higher != nullptr ) { higher->iv[0][0] = lo; higher->iv[0][1] = hi; }
-  __threadfence_system();
-  if( lower != nullptr ) { st_release_sys( &lower->iv_flag[1], step ); }
-  if( higher != nullptr ) { st_release_sys( &higher->iv_flag[0], step ); }
-}
 
 // one thread: returns when *flag has reached `step` (bounded: a dead neighbour must not hang the GPU)
-__global__ void k_ball2d_slab_wait( const uint32_t* flag, const uint32_t step, uint32_t* err )
+__device__ inline void slab_wait_flag( const uint32_t* flag, const uint32_t step, uint32_t* err )
 {
   unsigned long long t0, t1;
   asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t0 ) );
@@ -784,11 +722,168 @@ __global__ void k_ball2d_slab_wait( const uint32_t* flag, const uint32_t step, u
   }
 }
 
-// after the pack kernel: make its peer writes visible system-wide, then raise the flag
-__global__ void k_ball2d_slab_post_flag( uint32_t* peer_flag, const uint32_t step )
+// What a pack / unpack launch has to synchronise with when the exchange goes through peer-mapped mailboxes
+struct SlabSync
 {
+  const uint32_t* wait_flag; // local flag that must reach `step` before the kernel reads its input (nullptr: none)
+  uint32_t* post_flag;       // peer flag raised (after a system fence) by the last block to finish (nullptr: none)
+  uint32_t* done_ctr;        // block counter for "last block"
+  uint32_t* err;
+  uint32_t step;
+};
+
+// Owned bodies whose swept box overlaps [iv[0], iv[1]] on x (closed, like AABB::overlaps), in body order.
+// Two launches: count per block, then emit -- a block that selected anything sums the (L2-resident, few KB) counts
+// of the blocks before it instead of a separate scan launch; block 0 also writes the header with the total.
+template<bool EMIT>
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, const uint32_t* __restrict__ gid,
+                                                            const double* iv, uint32_t* __restrict__ block_counts, uint32_t* __restrict__ total, GhostRec* __restrict__ out, const uint32_t cap,
+                                                            const SlabSync sync )
+{
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_red[8], s_nz[8];
+  uint32_t participants = 1u; // block 0 only: itself + the other blocks that selected something
+  if( !EMIT && sync.wait_flag != nullptr )
+  {
+    if( threadIdx.x == 0 ) { slab_wait_flag( sync.wait_flag, sync.step, sync.err ); }
+    __syncthreads();
+  }
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double ilo = iv[0], ihi = iv[1]; // first read in this launch, after the wait + barrier above: L1 cannot hold a stale line
+  bool sel = false;
+  double2 a = make_double2( 0.0, 0.0 ), b = a;
+  double rad = 0.0;
+  if( i < n )
+  {
+    a = __ldg( &q0[i] ); b = __ldg( &q1[i] ); rad = __ldg( &r[i] );
+    double lo, hi;
+    swept_x( a, b, rad, lo, hi );
+    sel = !( hi < ilo ) && !( ihi < lo );
+  }
+  const unsigned bal = __ballot_sync( 0xffffffffu, sel );
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
+  __syncthreads();
+  uint32_t before = 0u, tot = 0u;
+  for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } tot += c; }
+  if( !EMIT ) { if( threadIdx.x == 0 ) { block_counts[blockIdx.x] = tot; } return; }
+  if( tot != 0u || blockIdx.x == 0u )
+  {
+    // prefix of the preceding blocks' counts (block 0: the grand total, for the header)
+    const uint32_t upto = ( blockIdx.x == 0u ) ? gridDim.x : blockIdx.x;
+    uint32_t acc = 0u, nz = 0u;
+    for( uint32_t bb = threadIdx.x; bb < upto; bb += blockDim.x ) { const uint32_t c = block_counts[bb]; acc += c; nz += ( c != 0u && bb != 0u ) ? 1u : 0u; }
+    #pragma unroll
+    for( int dd = 16; dd > 0; dd >>= 1 ) { acc += __shfl_xor_sync( 0xffffffffu, acc, dd ); nz += __shfl_xor_sync( 0xffffffffu, nz, dd ); }
+    if( lane == 0 ) { s_red[warp] = acc; s_nz[warp] = nz; }
+    __syncthreads();
+    uint32_t sum = 0u;
+    for( int w = 0; w < 8; ++w ) { sum += s_red[w]; participants += s_nz[w]; }
+    if( blockIdx.x == 0u )
+    {
+      if( threadIdx.x == 0 )
+      {
+        GhostRec h;
+        h.q0x = 0.0; h.q0y = 0.0; h.q1x = 0.0; h.q1y = 0.0; h.r = 0.0; h.gid = sum; h.pad = 0u;
+        out[0] = h;
+        if( total != nullptr ) { *total = sum; }
+      }
+      sum = 0u; // block 0 starts the list
+    }
+    if( sel )
+    {
+      const uint32_t k = sum + before + __popc( bal & ( ( 1u << lane ) - 1u ) );
+      if( k < cap )
+      {
+        GhostRec g;
+        g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
+        out[1u + k] = g;
+      }
+    }
+  }
+  if( sync.post_flag != nullptr && ( tot != 0u || blockIdx.x == 0u ) )
+  {
+    // The last of the blocks that wrote anything raises the neighbour's flag.  Each of them adds 1 to the counter,
+    // block 0 (which knows how many there are) adds 1 - participants: exactly one add lands on zero, the last.
+    // (one system-scope fence per block, by thread 0 after the barrier: the barrier orders the block's peer
+    // writes before it and the fence is cumulative; the flag itself is a release store)
+    __syncthreads();
+    if( threadIdx.x == 0 )
+    {
+      __threadfence_system();
+      const int delta = ( blockIdx.x == 0u ) ? 1 - int( participants ) : 1;
+      const int prev = atomicAdd( reinterpret_cast<int*>( sync.done_ctr ), delta );
+      if( prev + delta == 0 ) { st_release_sys( sync.post_flag, sync.step ); }
+    }
+  }
+}
+
+// Count only (sg_ball2d_slab_pack with no send buffer): total of the per-block counts
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack_total( const uint32_t nblk, const uint32_t* __restrict__ block_counts, uint32_t* __restrict__ total )
+{
+  __shared__ uint32_t s_red[8];
+  uint32_t acc = 0u;
+  for( uint32_t bb = threadIdx.x; bb < nblk; bb += blockDim.x ) { acc += block_counts[bb]; }
+  #pragma unroll
+  for( int dd = 16; dd > 0; dd >>= 1 ) { acc += __shfl_xor_sync( 0xffffffffu, acc, dd ); }
+  if( ( threadIdx.x & 31 ) == 0 ) { s_red[threadIdx.x >> 5] = acc; }
+  __syncthreads();
+  if( threadIdx.x == 0 ) { uint32_t sum = 0u; for( int w = 0; w < 8; ++w ) { sum += s_red[w]; } *total = sum; }
+}
+
+// Ghost records into the slots on `side` of the owned block; their swept boxes join this step's bounds reduction
+// (the owned bodies' share was reduced by the flow kernel).
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t cap, const int side, const GhostRec* in, double2* __restrict__ q0, double2* __restrict__ q1, double* __restrict__ r,
+                                                              uint32_t* __restrict__ gid, uint32_t* __restrict__ ghost_counts, BoundsAccum* __restrict__ acc, const SlabSync sync )
+{
+  if( sync.wait_flag != nullptr )
+  {
+    if( threadIdx.x == 0 ) { slab_wait_flag( sync.wait_flag, sync.step, sync.err ); }
+    __syncthreads();
+  }
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sent = *reinterpret_cast<const volatile uint32_t*>( &in[0].gid );
+  const uint32_t count = sent < cap ? sent : cap;
+  if( k == 0u )
+  {
+    ghost_counts[side] = count;
+    if( sent > cap ) { ghost_counts[2] = 1u; } // more ghosts than reserved slots: reported by detect
+  }
+  if( blockIdx.x * blockDim.x >= count ) { return; } // whole block past the list
+  double mn[2] = { __longlong_as_double( 0x7ff0000000000000LL ), __longlong_as_double( 0x7ff0000000000000LL ) };
+  double mx[2] = { __longlong_as_double( 0xfff0000000000000LL ), __longlong_as_double( 0xfff0000000000000LL ) };
+  double ext = 0.0;
+  if( k < count )
+  {
+    const int4* src = reinterpret_cast<const int4*>( &in[1u + k] );
+    union { GhostRec g; int4 v[3]; } u;
+    u.v[0] = src[0]; u.v[1] = src[1]; u.v[2] = src[2];
+    const GhostRec& g = u.g;
+    q0[k] = make_double2( g.q0x, g.q0y );
+    q1[k] = make_double2( g.q1x, g.q1y );
+    r[k] = g.r;
+    gid[k] = g.gid;
+    double lo[2], hi[2];
+    lo[0] = fmin( g.q1x, g.q0x ) - g.r; lo[1] = fmin( g.q1y, g.q0y ) - g.r;
+    hi[0] = fmax( g.q1x, g.q0x ) + g.r; hi[1] = fmax( g.q1y, g.q0y ) + g.r;
+    sg_bp_bounds_update<2>( lo, hi, mn, mx, ext );
+  }
+  if( acc != nullptr ) { sg_bp_bounds_commit<2>( mn, mx, ext, acc ); }
+}
+
+
+
+// decodes this rank's interval, keeps a local copy and posts it to the neighbours (lower = side 0, higher = side 1)
+__global__ void k_ball2d_slab_post_interval( long long* enc, uint32_t* ghost_counts, double* local_out, SlabMailboxHdr* lower, SlabMailboxHdr* higher, const uint32_t step )
+{
+  double lo, hi;
+  slab_take_interval( enc, ghost_counts, lo, hi );
+  if( local_out != nullptr ) { local_out[0] = lo; local_out[1] = hi; }
+  if( lower != nullptr ) { lower->iv[1][0] = lo; lower->iv[1][1] = hi; }     // seen from the lower rank I am its side-1 neighbour
+  if( higher != nullptr ) { higher->iv[0][0] = lo; higher->iv[0][1] = hi; }
   __threadfence_system();
-  st_release_sys( peer_flag, step );
+  if( lower != nullptr ) { st_release_sys( &lower->iv_flag[1], step ); }
+  if( higher != nullptr ) { st_release_sys( &higher->iv_flag[0], step ); }
 }
 
 __global__ void __launch_bounds__( 256 ) k_iota_u32( const uint32_t n, const uint32_t first, uint32_t* __restrict__ out )
@@ -955,6 +1050,7 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   SG_CUDA( ctx, d->interval_enc.ensure( 16 ) );
   SG_CUDA( ctx, d->ghost_counts.ensure( 16 ) );
   SG_CUDA( ctx, cudaMemsetAsync( d->ghost_counts.ptr, 0, 16, ctx->stream ) );
+  k_ball2d_slab_begin<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>() );
   if( n_owned > 0 )
   {
     SG_CUDA( ctx, cudaMemcpyAsync( d->r.as<double>() + ghost_cap, r, size_t( n_owned ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
@@ -973,18 +1069,47 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: call sg_ball2d_slab_init first" ); }
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: map kind %d is not a ball2d map", map_kind ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  const size_t o = d->owned_slot();
-  const uint32_t n = d->n_owned;
-  SG_LAUNCH( ctx, "slab_flow_interval", double( n ) * 80.0, k_ball2d_slab_begin<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>() );
-             k_ball2d_slab_flow<<<sg_div_up( n > 0 ? n : 1, 256 ), 256, 0, ctx->stream>>>( map_kind, n, d->q0.as<double2>() + o, d->v0.as<double2>(), d->m.as<double>(), d->r.as<double>() + o,
-                                                                                      d->g[0], d->g[1], dt, d->q1.as<double2>() + o, d->v1.as<double2>(), d->interval_enc.as<long long>() );
-             if( d->mailbox.ptr == nullptr ) { k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev ); }
+  // One kernel over all slots: flow of the owned bodies, their share of the broad-phase bounds, the static-geometry
+  // counts and [min lo.x, max hi.x] for the neighbours; then the interval is decoded / posted.
+  int rc = sg_bp_prepare_scratch<Ball2DPolicy>( ctx, d->bp, d->n );
+  if( rc != SG_OK ) { return rc; }
+  rc = ball2d_static_scratch( ctx, d );
+  if( rc != SG_OK ) { return rc; }
+  const uint32_t n = d->n;
+  SG_LAUNCH( ctx, "slab_flow_prep", double( d->n_owned ) * 80.0,
+             k_ball2d_prep<true><<<sg_div_up( n > 0 ? n : 1, 256 ), 256, 0, ctx->stream>>>( d->sg, map_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(), d->R(), d->g[0], d->g[1], dt, d->Q1(),
+                                                                                       d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), nullptr,
+                                                                                       d->interval_enc.as<long long>() );
+             if( d->mailbox.ptr == nullptr ) { k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev ); }
              else
              {
                ++d->slab_step;
-               k_ball2d_slab_post_interval<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), interval_dev, static_cast<SlabMailboxHdr*>( d->peer_mb[0] ), static_cast<SlabMailboxHdr*>( d->peer_mb[1] ), d->slab_step );
+               k_ball2d_slab_post_interval<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev, static_cast<SlabMailboxHdr*>( d->peer_mb[0] ), static_cast<SlabMailboxHdr*>( d->peer_mb[1] ), d->slab_step );
              } );
-  ctx->launch_count += 2;
+  ctx->launch_count += 1;
+  d->slab_prep_done = true;
+  return SG_OK;
+}
+
+static int ball2d_slab_pack_impl( sg_ctx* ctx, Ball2DData* d, const double* interval_dev, void* send_dev, const uint32_t cap, uint32_t* count_dev, const SlabSync& sync )
+{
+  const uint32_t n = d->n_owned;
+  const unsigned nblk = sg_div_up( n > 0 ? n : 1, 256 );
+  SG_CUDA( ctx, d->pack_counts.ensure( size_t( nblk ) * 4 + 4 ) );
+  const size_t o = d->owned_slot();
+  SlabSync wait_only = sync; wait_only.post_flag = nullptr;
+  SG_LAUNCH( ctx, "slab_pack_count", double( n ) * 40.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
+             interval_dev, d->pack_counts.as<uint32_t>(), nullptr, nullptr, 0u, wait_only ) );
+  if( send_dev != nullptr )
+  {
+    SlabSync post_only = sync; post_only.wait_flag = nullptr;
+    SG_LAUNCH( ctx, "slab_pack_emit", double( n ) * 40.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
+               interval_dev, d->pack_counts.as<uint32_t>(), count_dev, static_cast<GhostRec*>( send_dev ), cap, post_only ) );
+  }
+  else if( count_dev != nullptr )
+  {
+    SG_LAUNCH( ctx, "slab_pack_total", double( nblk ) * 4.0, k_ball2d_slab_pack_total<<<1, 256, 0, ctx->stream>>>( nblk, d->pack_counts.as<uint32_t>(), count_dev ) );
+  }
   return SG_OK;
 }
 
@@ -994,21 +1119,19 @@ int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev
   Ball2DData* d = ball2d_data( ctx );
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_pack: call sg_ball2d_slab_init first" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  const uint32_t n = d->n_owned;
-  const unsigned nblk = sg_div_up( n > 0 ? n : 1, 256 );
-  SG_CUDA( ctx, d->pack_counts.ensure( size_t( nblk ) * 4 + 4 ) );
-  SG_CUDA( ctx, d->pack_offsets.ensure( size_t( nblk ) * 4 + 4 ) );
-  SG_CUDA( ctx, d->pack_partials.ensure( ( size_t( nblk ) / SG_SCAN_TILE + 2 ) * 4 ) );
-  const size_t o = d->owned_slot();
-  SG_LAUNCH( ctx, "slab_pack_count", double( n ) * 40.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
-             interval_dev, d->pack_counts.as<uint32_t>(), nullptr, nullptr, nullptr, 0u ) );
-  const int rc = sg_exclusive_scan<ScanU32>( ctx, "slab_pack_scan", d->pack_counts.as<uint32_t>(), nullptr, nblk, nblk, d->pack_partials.as<uint32_t>(), d->pack_offsets.as<uint32_t>(), count_dev, false );
-  if( rc != SG_OK ) { return rc; }
-  if( send_dev != nullptr )
-  {
-    SG_LAUNCH( ctx, "slab_pack_emit", double( n ) * 40.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
-               interval_dev, nullptr, d->pack_offsets.as<uint32_t>(), count_dev, static_cast<GhostRec*>( send_dev ), cap ) );
-  }
+  SlabSync none; none.wait_flag = nullptr; none.post_flag = nullptr; none.done_ctr = nullptr; none.err = nullptr; none.step = 0u;
+  return ball2d_slab_pack_impl( ctx, d, interval_dev, send_dev, cap, count_dev, none );
+}
+
+static int ball2d_slab_unpack_impl( sg_ctx* ctx, Ball2DData* d, const int side, const void* recv_dev, const SlabSync& sync )
+{
+  // side 0: ghosts with smaller global indices fill slots [0, count); side 1: the slots right after the owned block
+  const size_t slot = ( side == 0 ) ? 0 : size_t( d->ghost_cap ) + d->n_owned;
+  const uint32_t cap = d->ghost_cap;
+  // the ghosts' boxes join the bounds the flow kernel started (when this step went through sg_ball2d_slab_flow)
+  BoundsAccum* acc = ( d->slab_prep_done && d->bp.bounds.ptr != nullptr ) ? d->bp.bounds_cur() : nullptr;
+  SG_LAUNCH( ctx, "slab_unpack", double( cap ) * 4.0, k_ball2d_slab_unpack<<<sg_div_up( cap > 0 ? cap : 1, 256 ), 256, 0, ctx->stream>>>( cap, side, static_cast<const GhostRec*>( recv_dev ), d->q0.as<double2>() + slot,
+             d->q1.as<double2>() + slot, d->r.as<double>() + slot, d->gid.as<uint32_t>() + slot, d->ghost_counts.as<uint32_t>(), acc, sync ) );
   return SG_OK;
 }
 
@@ -1018,12 +1141,8 @@ int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev )
   Ball2DData* d = ball2d_data( ctx );
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: call sg_ball2d_slab_init first" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  // side 0: ghosts with smaller global indices fill slots [0, count); side 1: the slots right after the owned block
-  const size_t slot = ( side == 0 ) ? 0 : size_t( d->ghost_cap ) + d->n_owned;
-  const uint32_t cap = d->ghost_cap;
-  SG_LAUNCH( ctx, "slab_unpack", double( cap ) * 4.0, k_ball2d_slab_unpack<<<sg_div_up( cap > 0 ? cap : 1, 256 ), 256, 0, ctx->stream>>>( cap, side, static_cast<const GhostRec*>( recv_dev ), d->q0.as<double2>() + slot,
-             d->q1.as<double2>() + slot, d->r.as<double>() + slot, d->gid.as<uint32_t>() + slot, d->ghost_counts.as<uint32_t>() ) );
-  return SG_OK;
+  SlabSync none; none.wait_flag = nullptr; none.post_flag = nullptr; none.done_ctr = nullptr; none.err = nullptr; none.step = 0u;
+  return ball2d_slab_unpack_impl( ctx, d, side, recv_dev, none );
 }
 
 int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64 )
@@ -1039,6 +1158,8 @@ int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64
     SG_CUDA( ctx, d->mailbox.ensure( bytes ) );
     SG_CUDA( ctx, cudaMemsetAsync( d->mailbox.ptr, 0, bytes, ctx->stream ) );
     SG_CUDA( ctx, d->pack_total.ensure( 16 ) );
+    SG_CUDA( ctx, d->pack_done.ensure( 16 ) );
+    SG_CUDA( ctx, cudaMemsetAsync( d->pack_done.ptr, 0, 16, ctx->stream ) );
     SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
     d->slab_step = 0;
   }
@@ -1102,11 +1223,11 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
     {
       if( d->peer_mb[side] == nullptr ) { continue; }
       SlabMailboxHdr* peer = static_cast<SlabMailboxHdr*>( d->peer_mb[side] );
-      SG_LAUNCH( ctx, "slab_wait", 0.0, k_ball2d_slab_wait<<<1, 1, 0, ctx->stream>>>( &mine->iv_flag[side], step, &mine->err ) );
       // seen from the neighbour on `side`, this rank sits on its side 1 - side
-      const int rc = sg_ball2d_slab_pack( ctx, &mine->iv[side][0], slab_mailbox_halo( peer, 1 - side, d->ghost_cap ), d->ghost_cap, d->pack_total.as<uint32_t>() + side );
+      SlabSync sync;
+      sync.wait_flag = &mine->iv_flag[side]; sync.post_flag = &peer->halo_flag[1 - side]; sync.done_ctr = d->pack_done.as<uint32_t>() + side; sync.err = &mine->err; sync.step = step;
+      const int rc = ball2d_slab_pack_impl( ctx, d, &mine->iv[side][0], slab_mailbox_halo( peer, 1 - side, d->ghost_cap ), d->ghost_cap, d->pack_total.as<uint32_t>() + side, sync );
       if( rc != SG_OK ) { return rc; }
-      SG_LAUNCH( ctx, "slab_post", 0.0, k_ball2d_slab_post_flag<<<1, 1, 0, ctx->stream>>>( &peer->halo_flag[1 - side], step ) );
     }
   }
   if( phase == 0 || phase == 2 )
@@ -1114,8 +1235,9 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
     for( int side = 0; side < 2; ++side )
     {
       if( d->peer_mb[side] == nullptr ) { continue; }
-      SG_LAUNCH( ctx, "slab_wait", 0.0, k_ball2d_slab_wait<<<1, 1, 0, ctx->stream>>>( &mine->halo_flag[side], step, &mine->err ) );
-      const int rc = sg_ball2d_slab_unpack( ctx, side, slab_mailbox_halo( mine, side, d->ghost_cap ) );
+      SlabSync sync;
+      sync.wait_flag = &mine->halo_flag[side]; sync.post_flag = nullptr; sync.done_ctr = nullptr; sync.err = &mine->err; sync.step = step;
+      const int rc = ball2d_slab_unpack_impl( ctx, d, side, slab_mailbox_halo( mine, side, d->ghost_cap ), sync );
       if( rc != SG_OK ) { return rc; }
     }
   }

@@ -56,7 +56,7 @@ struct BroadScratch
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
   SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
-  const uint32_t* gid_map = nullptr; // multi-GPU: local body index -> global body index for the emitted lists
+  GidMap gid_map; // multi-GPU: local body index -> global body index for the emitted lists
   CUtensorMap tm_recs;  // tensor map over recs for the TMA-fed pass 1 (re-encoded when the buffer or n changes)
   const void* tm_ptr = nullptr;
   uint32_t tm_rows = 0;
@@ -793,7 +793,8 @@ template<> struct SgBpCountLaunch<2>
       s.tm_ptr = s.recs.ptr; s.tm_rows = n;
     }
     constexpr size_t smem = sg_bp_tma_smem<2>();
-    SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_tma<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
+    static int attr_dev = -1; // opt-in to > 48 KB of dynamic shared memory: once per device
+    if( attr_dev != ctx->device ) { SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_tma<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) ); attr_dev = ctx->device; }
     const unsigned ntiles = sg_div_up( n, BpCfg<2>::T );
     const unsigned grid = ntiles < unsigned( ctx->num_sms ) * 2u ? ntiles : unsigned( ctx->num_sms ) * 2u;
     SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_tma<P><<<grid, BpCfg<2>::T + 32, smem, ctx->stream>>>( s.tm_recs, n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
@@ -807,7 +808,7 @@ template<> struct SgBpCountLaunch<2>
 template<typename P>
 __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, const ulonglong2 off, const uint32_t my_idx, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, uint2* __restrict__ cand, const uint64_t cand_cap,
-                                              const uint32_t* __restrict__ gid, uint2* __restrict__ work, const uint64_t work_cap )
+                                              const GidMap gid, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -835,7 +836,7 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, c
   };
   auto emit_one = [&]( const unsigned long long kc, const Rec& o, const uint32_t q )
   {
-    if( cand != nullptr && kc < cand_cap ) { cand[kc] = ( gid != nullptr ) ? make_uint2( gid[my_idx], gid[P::rec_idx( o )] ) : make_uint2( my_idx, P::rec_idx( o ) ); }
+    if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( gid( my_idx ), gid( P::rec_idx( o ) ) ); }
     if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { if( ka < work_cap ) { work[ka] = make_uint2( p, q ); } ++ka; } }
   };
   if( m.z <= SG_BP_LOCAL_CAP )
@@ -898,7 +899,7 @@ __device__ __forceinline__ void sg_cex( unsigned long long& a, unsigned long lon
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan,
-                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const uint32_t* __restrict__ gid, uint2* __restrict__ work, const uint64_t work_cap )
+                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const GidMap gid, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -958,12 +959,12 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t
     }
     if( cand != nullptr )
     {
-      const uint32_t gi = ( gid != nullptr ) ? gid[my_idx] : my_idx;
+      const uint32_t gi = gid( my_idx );
       #pragma unroll
       for( int j = 0; j < SG_BP_FAST_CAP; ++j )
       {
         const unsigned long long kc = off.x + j;
-        if( uint32_t( j ) < m.z && kc < cand_cap ) { const uint32_t oj = uint32_t( v[j] >> 32 ); cand[kc] = make_uint2( gi, ( gid != nullptr ) ? gid[oj] : oj ); }
+        if( uint32_t( j ) < m.z && kc < cand_cap ) { const uint32_t oj = uint32_t( v[j] >> 32 ); cand[kc] = make_uint2( gi, gid( oj ) ); }
       }
     }
     if( P::HAS_NARROW && m.y != 0u )
