@@ -732,89 +732,115 @@ struct SlabSync
   uint32_t step;
 };
 
-// Owned bodies whose swept box overlaps [iv[0], iv[1]] on x (closed, like AABB::overlaps), in body order.
+// Owned bodies whose swept box overlaps [iv[0], iv[1]] on x (closed, like AABB::overlaps), in body order -- for up
+// to two target intervals (both neighbours) in one pass over the bodies.
 // Two launches: count per block, then emit -- a block that selected anything sums the (L2-resident, few KB) counts
 // of the blocks before it instead of a separate scan launch; block 0 also writes the header with the total.
+struct PackArgs
+{
+  const double* iv[2];
+  uint32_t* block_counts[2];
+  uint32_t* total[2];
+  GhostRec* out[2];
+  SlabSync sync[2];
+  bool on[2];
+};
+
 template<bool EMIT>
 __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, const uint32_t* __restrict__ gid,
-                                                            const double* iv, uint32_t* __restrict__ block_counts, uint32_t* __restrict__ total, GhostRec* __restrict__ out, const uint32_t cap,
-                                                            const SlabSync sync )
+                                                            const uint32_t cap, const PackArgs args )
 {
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_red[8], s_nz[8];
-  uint32_t participants = 1u; // block 0 only: itself + the other blocks that selected something
-  if( !EMIT && sync.wait_flag != nullptr )
+  if( !EMIT )
   {
-    if( threadIdx.x == 0 ) { slab_wait_flag( sync.wait_flag, sync.step, sync.err ); }
+    if( threadIdx.x < 2 && args.on[threadIdx.x] && args.sync[threadIdx.x].wait_flag != nullptr )
+    {
+      slab_wait_flag( args.sync[threadIdx.x].wait_flag, args.sync[threadIdx.x].step, args.sync[threadIdx.x].err );
+    }
     __syncthreads();
   }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const double ilo = iv[0], ihi = iv[1]; // first read in this launch, after the wait + barrier above: L1 cannot hold a stale line
-  bool sel = false;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 a = make_double2( 0.0, 0.0 ), b = a;
-  double rad = 0.0;
+  double rad = 0.0, lo = 0.0, hi = 0.0;
   if( i < n )
   {
     a = __ldg( &q0[i] ); b = __ldg( &q1[i] ); rad = __ldg( &r[i] );
-    double lo, hi;
     swept_x( a, b, rad, lo, hi );
-    sel = !( hi < ilo ) && !( ihi < lo );
   }
-  const unsigned bal = __ballot_sync( 0xffffffffu, sel );
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
-  __syncthreads();
-  uint32_t before = 0u, tot = 0u;
-  for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } tot += c; }
-  if( !EMIT ) { if( threadIdx.x == 0 ) { block_counts[blockIdx.x] = tot; } return; }
-  if( tot != 0u || blockIdx.x == 0u )
+  #pragma unroll
+  for( int sd = 0; sd < 2; ++sd )
   {
-    // prefix of the preceding blocks' counts (block 0: the grand total, for the header)
-    const uint32_t upto = ( blockIdx.x == 0u ) ? gridDim.x : blockIdx.x;
-    uint32_t acc = 0u, nz = 0u;
-    for( uint32_t bb = threadIdx.x; bb < upto; bb += blockDim.x ) { const uint32_t c = block_counts[bb]; acc += c; nz += ( c != 0u && bb != 0u ) ? 1u : 0u; }
-    #pragma unroll
-    for( int dd = 16; dd > 0; dd >>= 1 ) { acc += __shfl_xor_sync( 0xffffffffu, acc, dd ); nz += __shfl_xor_sync( 0xffffffffu, nz, dd ); }
-    if( lane == 0 ) { s_red[warp] = acc; s_nz[warp] = nz; }
+    if( !args.on[sd] ) { continue; }
+    const SlabSync sync = args.sync[sd];
+    uint32_t* block_counts = args.block_counts[sd];
+    GhostRec* out = args.out[sd];
+    // first read of the interval in this launch comes after the wait + barrier above: L1 cannot hold a stale line
+    const double ilo = args.iv[sd][0], ihi = args.iv[sd][1];
+    const bool sel = i < n && !( hi < ilo ) && !( ihi < lo );
+    const unsigned bal = __ballot_sync( 0xffffffffu, sel );
+    if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
     __syncthreads();
-    uint32_t sum = 0u;
-    for( int w = 0; w < 8; ++w ) { sum += s_red[w]; participants += s_nz[w]; }
-    if( blockIdx.x == 0u )
+    uint32_t before = 0u, tot = 0u;
+    for( int w = 0; w < 8; ++w ) { const uint32_t c = s_warp[w]; if( w < warp ) { before += c; } tot += c; }
+    if( !EMIT )
     {
-      if( threadIdx.x == 0 )
-      {
-        GhostRec h;
-        h.q0x = 0.0; h.q0y = 0.0; h.q1x = 0.0; h.q1y = 0.0; h.r = 0.0; h.gid = sum; h.pad = 0u;
-        out[0] = h;
-        if( total != nullptr ) { *total = sum; }
-      }
-      sum = 0u; // block 0 starts the list
+      if( threadIdx.x == 0 ) { block_counts[blockIdx.x] = tot; }
+      __syncthreads();
+      continue;
     }
-    if( sel )
+    uint32_t participants = 1u; // block 0 only: itself + the other blocks that selected something
+    if( tot != 0u || blockIdx.x == 0u )
     {
-      const uint32_t k = sum + before + __popc( bal & ( ( 1u << lane ) - 1u ) );
-      if( k < cap )
+      // prefix of the preceding blocks' counts (block 0: the grand total, for the header)
+      const uint32_t upto = ( blockIdx.x == 0u ) ? gridDim.x : blockIdx.x;
+      uint32_t acc = 0u, nz = 0u;
+      for( uint32_t bb = threadIdx.x; bb < upto; bb += blockDim.x ) { const uint32_t c = block_counts[bb]; acc += c; nz += ( c != 0u && bb != 0u ) ? 1u : 0u; }
+      #pragma unroll
+      for( int dd = 16; dd > 0; dd >>= 1 ) { acc += __shfl_xor_sync( 0xffffffffu, acc, dd ); nz += __shfl_xor_sync( 0xffffffffu, nz, dd ); }
+      if( lane == 0 ) { s_red[warp] = acc; s_nz[warp] = nz; }
+      __syncthreads();
+      uint32_t sum = 0u;
+      for( int w = 0; w < 8; ++w ) { sum += s_red[w]; participants += s_nz[w]; }
+      if( blockIdx.x == 0u )
       {
-        GhostRec g;
-        g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
-        out[1u + k] = g;
+        if( threadIdx.x == 0 )
+        {
+          GhostRec h;
+          h.q0x = 0.0; h.q0y = 0.0; h.q1x = 0.0; h.q1y = 0.0; h.r = 0.0; h.gid = sum; h.pad = 0u;
+          out[0] = h;
+          if( args.total[sd] != nullptr ) { *args.total[sd] = sum; }
+        }
+        sum = 0u; // block 0 starts the list
+      }
+      if( sel )
+      {
+        const uint32_t k = sum + before + __popc( bal & ( ( 1u << lane ) - 1u ) );
+        if( k < cap )
+        {
+          GhostRec g;
+          g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
+          out[1u + k] = g;
+        }
+      }
+      if( sync.post_flag != nullptr )
+      {
+        // The last of the blocks that wrote anything raises the neighbour's flag.  Each of them adds 1 to the counter,
+        // block 0 (which knows how many there are) adds 1 - participants: exactly one add lands on zero, the last.
+        // (One system-scope fence per block, by thread 0 after the barrier: the barrier orders the block's peer
+        // writes before it and the fence is cumulative; the flag itself is a release store.)
+        __syncthreads();
+        if( threadIdx.x == 0 )
+        {
+          __threadfence_system();
+          const int delta = ( blockIdx.x == 0u ) ? 1 - int( participants ) : 1;
+          const int prev = atomicAdd( reinterpret_cast<int*>( sync.done_ctr ), delta );
+          if( prev + delta == 0 ) { st_release_sys( sync.post_flag, sync.step ); }
+        }
       }
     }
-  }
-  if( sync.post_flag != nullptr && ( tot != 0u || blockIdx.x == 0u ) )
-  {
-    // The last of the blocks that wrote anything raises the neighbour's flag.  Each of them adds 1 to the counter,
-    // block 0 (which knows how many there are) adds 1 - participants: exactly one add lands on zero, the last.
-    // (one system-scope fence per block, by thread 0 after the barrier: the barrier orders the block's peer
-    // writes before it and the fence is cumulative; the flag itself is a release store)
     __syncthreads();
-    if( threadIdx.x == 0 )
-    {
-      __threadfence_system();
-      const int delta = ( blockIdx.x == 0u ) ? 1 - int( participants ) : 1;
-      const int prev = atomicAdd( reinterpret_cast<int*>( sync.done_ctr ), delta );
-      if( prev + delta == 0 ) { st_release_sys( sync.post_flag, sync.step ); }
-    }
   }
 }
 
@@ -1091,24 +1117,39 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
   return SG_OK;
 }
 
-static int ball2d_slab_pack_impl( sg_ctx* ctx, Ball2DData* d, const double* interval_dev, void* send_dev, const uint32_t cap, uint32_t* count_dev, const SlabSync& sync )
+// One or two targets (sides) per call: target t packs against interval_dev[t] into send_dev[t] (nullptr: count only)
+static int ball2d_slab_pack_impl( sg_ctx* ctx, Ball2DData* d, const int ntargets, const double* const* interval_dev, void* const* send_dev, const uint32_t cap, uint32_t* const* count_dev, const SlabSync* sync )
 {
   const uint32_t n = d->n_owned;
   const unsigned nblk = sg_div_up( n > 0 ? n : 1, 256 );
-  SG_CUDA( ctx, d->pack_counts.ensure( size_t( nblk ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->pack_counts.ensure( 2 * ( size_t( nblk ) * 4 + 4 ) ) );
   const size_t o = d->owned_slot();
-  SlabSync wait_only = sync; wait_only.post_flag = nullptr;
-  SG_LAUNCH( ctx, "slab_pack_count", double( n ) * 40.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
-             interval_dev, d->pack_counts.as<uint32_t>(), nullptr, nullptr, 0u, wait_only ) );
-  if( send_dev != nullptr )
+  PackArgs count_args, emit_args;
+  bool any_emit = false;
+  for( int t = 0; t < 2; ++t )
   {
-    SlabSync post_only = sync; post_only.wait_flag = nullptr;
-    SG_LAUNCH( ctx, "slab_pack_emit", double( n ) * 40.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o,
-               interval_dev, d->pack_counts.as<uint32_t>(), count_dev, static_cast<GhostRec*>( send_dev ), cap, post_only ) );
+    const bool on = t < ntargets;
+    count_args.on[t] = on; emit_args.on[t] = on && send_dev[t] != nullptr;
+    count_args.iv[t] = emit_args.iv[t] = on ? interval_dev[t] : nullptr;
+    count_args.block_counts[t] = emit_args.block_counts[t] = d->pack_counts.as<uint32_t>() + size_t( t ) * ( nblk + 1 );
+    count_args.total[t] = nullptr; emit_args.total[t] = on ? count_dev[t] : nullptr;
+    count_args.out[t] = nullptr; emit_args.out[t] = on ? static_cast<GhostRec*>( send_dev[t] ) : nullptr;
+    SlabSync none; none.wait_flag = nullptr; none.post_flag = nullptr; none.done_ctr = nullptr; none.err = nullptr; none.step = 0u;
+    count_args.sync[t] = on ? sync[t] : none; count_args.sync[t].post_flag = nullptr;
+    emit_args.sync[t] = on ? sync[t] : none; emit_args.sync[t].wait_flag = nullptr;
+    any_emit = any_emit || emit_args.on[t];
   }
-  else if( count_dev != nullptr )
+  SG_LAUNCH( ctx, "slab_pack_count", double( n ) * 40.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o, cap, count_args ) );
+  if( any_emit )
   {
-    SG_LAUNCH( ctx, "slab_pack_total", double( nblk ) * 4.0, k_ball2d_slab_pack_total<<<1, 256, 0, ctx->stream>>>( nblk, d->pack_counts.as<uint32_t>(), count_dev ) );
+    SG_LAUNCH( ctx, "slab_pack_emit", double( n ) * 40.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o, cap, emit_args ) );
+  }
+  for( int t = 0; t < ntargets; ++t )
+  {
+    if( send_dev[t] == nullptr && count_dev[t] != nullptr )
+    {
+      SG_LAUNCH( ctx, "slab_pack_total", double( nblk ) * 4.0, k_ball2d_slab_pack_total<<<1, 256, 0, ctx->stream>>>( nblk, count_args.block_counts[t], count_dev[t] ) );
+    }
   }
   return SG_OK;
 }
@@ -1120,7 +1161,10 @@ int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_pack: call sg_ball2d_slab_init first" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   SlabSync none; none.wait_flag = nullptr; none.post_flag = nullptr; none.done_ctr = nullptr; none.err = nullptr; none.step = 0u;
-  return ball2d_slab_pack_impl( ctx, d, interval_dev, send_dev, cap, count_dev, none );
+  const double* ivs[1] = { interval_dev };
+  void* sends[1] = { send_dev };
+  uint32_t* counts[1] = { count_dev };
+  return ball2d_slab_pack_impl( ctx, d, 1, ivs, sends, cap, counts, &none );
 }
 
 static int ball2d_slab_unpack_impl( sg_ctx* ctx, Ball2DData* d, const int side, const void* recv_dev, const SlabSync& sync )
@@ -1219,14 +1263,23 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
   const uint32_t step = d->slab_step;
   if( phase == 0 || phase == 1 )
   {
+    // both neighbours in one pass over the owned bodies
+    const double* ivs[2]; void* sends[2]; uint32_t* counts[2]; SlabSync syncs[2];
+    int nt = 0;
     for( int side = 0; side < 2; ++side )
     {
       if( d->peer_mb[side] == nullptr ) { continue; }
       SlabMailboxHdr* peer = static_cast<SlabMailboxHdr*>( d->peer_mb[side] );
       // seen from the neighbour on `side`, this rank sits on its side 1 - side
-      SlabSync sync;
-      sync.wait_flag = &mine->iv_flag[side]; sync.post_flag = &peer->halo_flag[1 - side]; sync.done_ctr = d->pack_done.as<uint32_t>() + side; sync.err = &mine->err; sync.step = step;
-      const int rc = ball2d_slab_pack_impl( ctx, d, &mine->iv[side][0], slab_mailbox_halo( peer, 1 - side, d->ghost_cap ), d->ghost_cap, d->pack_total.as<uint32_t>() + side, sync );
+      ivs[nt] = &mine->iv[side][0];
+      sends[nt] = slab_mailbox_halo( peer, 1 - side, d->ghost_cap );
+      counts[nt] = d->pack_total.as<uint32_t>() + side;
+      syncs[nt].wait_flag = &mine->iv_flag[side]; syncs[nt].post_flag = &peer->halo_flag[1 - side]; syncs[nt].done_ctr = d->pack_done.as<uint32_t>() + side; syncs[nt].err = &mine->err; syncs[nt].step = step;
+      ++nt;
+    }
+    if( nt > 0 )
+    {
+      const int rc = ball2d_slab_pack_impl( ctx, d, nt, ivs, sends, d->ghost_cap, counts, syncs );
       if( rc != SG_OK ) { return rc; }
     }
   }
