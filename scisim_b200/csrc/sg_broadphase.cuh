@@ -127,21 +127,40 @@ static __global__ void sg_bp_bounds_init( BoundsAccum* acc )
   if( threadIdx.x == 0 && blockIdx.x == 0 ) { sg_bp_bounds_reset( acc ); sg_bp_bounds_reset( acc + 1 ); }
 }
 
+// Monotone float <-> u32 map (the same trick as the ordered doubles) for the single-instruction warp reductions
+__device__ __forceinline__ uint32_t sg_ordered_from_float( const float f )
+{
+  const uint32_t u = __float_as_uint( f );
+  return ( u & 0x80000000u ) ? ~u : ( u | 0x80000000u );
+}
+__device__ __forceinline__ float sg_float_from_ordered( const uint32_t o )
+{
+  return __uint_as_float( ( o & 0x80000000u ) ? ( o & 0x7fffffffu ) : ~o );
+}
+// min / max over the warp of a double, rounded OUTWARD to float first so that REDUX (one instruction) can do the
+// work of five 64-bit shuffle + compare rounds.  The grid only needs origin <= every lower corner, the far corner
+// >= every lower corner and h >= every extent (the candidate set does not depend on the grid), so outward rounding
+// by one float ulp is free.  Coordinates beyond the float range would round to +-inf and are not supported.
+__device__ __forceinline__ double sg_warp_min_outward( const double x )
+{
+  return double( sg_float_from_ordered( __reduce_min_sync( 0xffffffffu, sg_ordered_from_float( __double2float_rd( x ) ) ) ) );
+}
+__device__ __forceinline__ double sg_warp_max_outward( const double x )
+{
+  return double( sg_float_from_ordered( __reduce_max_sync( 0xffffffffu, sg_ordered_from_float( __double2float_ru( x ) ) ) ) );
+}
+
 // Block-level reduction of per-thread partial bounds, then one atomic per quantity per block.
 template<int D>
 __device__ inline void sg_bp_bounds_commit( double* mn, double* mx, double ext, BoundsAccum* __restrict__ acc )
 {
   #pragma unroll
-  for( int d = 16; d > 0; d >>= 1 )
+  for( int k = 0; k < D; ++k )
   {
-    #pragma unroll
-    for( int k = 0; k < D; ++k )
-    {
-      mn[k] = fmin( mn[k], __shfl_xor_sync( 0xffffffffu, mn[k], d ) );
-      mx[k] = fmax( mx[k], __shfl_xor_sync( 0xffffffffu, mx[k], d ) );
-    }
-    ext = fmax( ext, __shfl_xor_sync( 0xffffffffu, ext, d ) );
+    mn[k] = sg_warp_min_outward( mn[k] );
+    mx[k] = sg_warp_max_outward( mx[k] );
   }
+  ext = sg_warp_max_outward( ext );
   __shared__ double s_red[SG_BP_THREADS / 32][2 * D + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if( lane == 0 )
