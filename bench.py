@@ -154,6 +154,27 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on (and therefore allocate pinned host buffers from) the CPU cores NVML reports as
+    local to this GPU, so that N ranks' host<->device copies do not all cross the same socket link.  Returns the number
+    of cores bound to, or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +192,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import numpy as np
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -299,6 +321,7 @@ def main():
             "config": {"workload": workload_name(world), "bodies_per_gpu": n, "candidates_per_gpu": pc, "active_per_gpu": pa,
                        "l2": "384 MB buffer overwritten before every timed step (L2 flush)", "timing": "CUDA events on the library stream, per step, summed; max over ranks",
                        "parallelism": ("%d x-slabs, 1 process per GPU, ghost bodies exchanged with +-1 neighbours each step (%s), pair owned by the rank of its lower index" % (world, "peer-memory mailboxes over NVLink, no collective in the step" if args.transport == "p2p" else "NCCL all_gather + send/recv")) if world > 1 else "single GPU"},
+            "host_cores_bound": numa,
             "steps_per_s": args.steps / t_max,
             "step_ms_rank0": [round(x, 4) for x in step_ms],
             "clocks": clocks,
