@@ -29,7 +29,6 @@
 
 #define SG_BP_THREADS 256
 #define SG_BP_LOCAL_CAP 12
-#define SG_BP_FAST_CAP 8
 
 // Per-pipeline device scratch (owned by the caller's data block)
 struct BroadScratch
@@ -342,8 +341,8 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
 // (The copy is done by the block's threads rather than by 1-D cp.async.bulk -- helpers in sg_tma.cuh -- because the
 // bulk copy cannot apply the swizzle that removes the 4-way bank conflicts of 64-byte records.)
 template<int D> struct BpCfg;
-template<> struct BpCfg<2> { static constexpr int NW = 3; static constexpr int T = 256; static constexpr int WCAP = 272; static constexpr int CSCAP = 320; };
-template<> struct BpCfg<3> { static constexpr int NW = 9; static constexpr int T = 128; static constexpr int WCAP = 144; static constexpr int CSCAP = 288; };
+template<> struct BpCfg<2> { static constexpr int NW = 3; static constexpr int T = 256; static constexpr int WCAP = 272; static constexpr int CSCAP = 320; static constexpr int FAST = 8; };
+template<> struct BpCfg<3> { static constexpr int NW = 9; static constexpr int T = 128; static constexpr int WCAP = 144; static constexpr int CSCAP = 288; static constexpr int FAST = 16; };
 
 template<int D>
 struct BpStage
@@ -479,7 +478,7 @@ __device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint3
 }
 
 // The walk plan pass 1 leaves for pass 2: per body the window starts and lengths (clipped to 255; a body whose
-// walk is longer than 32 visits has invalid masks anyway), NPLAN uint4 per body, plane c of body p at plan[c*n+p].
+// walk is longer than 63 visits has incomplete masks anyway), NPLAN uint4 per body, plane c of body p at plan[c*n+p].
 template<int D> struct BpPlan;
 template<> struct BpPlan<2> { static constexpr int NPLAN = 1; };
 template<> struct BpPlan<3> { static constexpr int NPLAN = 3; };
@@ -539,10 +538,12 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
   return __ldg( reinterpret_cast<const uint32_t*>( reinterpret_cast<const unsigned char*>( &recs[q] ) + P::IDX_OFFSET ) ) & P::IDX_MASK;
 }
 
-#define SG_BP_MASKS_INVALID 0x80000000u
+// masks cover the first 63 visits of a body's walk; bit 63 of the active mask flags a longer walk (masks incomplete)
+#define SG_BP_MASK_BITS 63u
+#define SG_BP_MASKS_INVALID 0x8000000000000000ull
 
-// Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active (bit 31: masks invalid) }
-//          masks[sorted position] = { candidate mask, active mask over the visit sequence, the two counts again }
+// Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active }
+//          masks[sorted position] = { candidate mask (64 bit), active mask (64 bit) } over the visit sequence
 template<typename P>
 __global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                                const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
@@ -573,13 +574,14 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp
   }
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
-  uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
+  uint32_t nc = 0u, na = 0u, k = 0u;
+  unsigned long long cmask = 0ull, amask = 0ull;
   uint32_t qb[Cfg::NW], qe[Cfg::NW];
   sg_bp_ranges<P>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
   sg_bp_plan_store<D>( plan, n_slots, p, qb, qe );
   sg_bp_walk_ranges<P>( qb, qe, p, [&]( const int w, const uint32_t q )
   {
-    const uint32_t bit = ( k < 32u ) ? ( 1u << k ) : 0u;
+    const unsigned long long bit = ( k < SG_BP_MASK_BITS ) ? ( 1ull << k ) : 0ull;
     ++k;
     if( sg_bp_fetch_idx<P>( recs, s_recs, st, w, q ) <= my_idx ) { return; } // owned by the partner: skip before touching the record
     const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
@@ -592,9 +594,9 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp
     ++nc; cmask |= bit;
     if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
   } );
-  const uint32_t na_f = ( k > 32u ) ? ( na | SG_BP_MASKS_INVALID ) : na;
-  counts[my_idx] = make_uint2( nc, na_f );
-  masks[p] = make_uint4( cmask, amask, nc, na_f );
+  if( k > SG_BP_MASK_BITS ) { amask |= SG_BP_MASKS_INVALID; }
+  counts[my_idx] = make_uint2( nc, na );
+  masks[p] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
 }
 
 // ---- pass 1, TMA-fed (D = 2) -------------------------------------------------------------------------
@@ -728,13 +730,14 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
       {
         double lo[D], hi[D];
         P::rec_aabb( me, lo, hi );
-        uint32_t nc = 0u, na = 0u, k = 0u, cmask = 0u, amask = 0u;
+        uint32_t nc = 0u, na = 0u, k = 0u;
+        unsigned long long cmask = 0ull, amask = 0ull;
         uint32_t qb[Cfg::NW], qe[Cfg::NW];
         sg_bp_ranges<P, SG_BP_TMA_CSCAP>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
         sg_bp_plan_store<D>( plan, n_slots, p, qb, qe );
         sg_bp_walk_ranges<P>( qb, qe, p, [&]( const int w, const uint32_t q )
         {
-          const uint32_t bit = ( k < 32u ) ? ( 1u << k ) : 0u;
+          const unsigned long long bit = ( k < SG_BP_MASK_BITS ) ? ( 1ull << k ) : 0ull;
           ++k;
           if( sg_bp_fetch_idx<P>( recs, s_recs, st, w, q ) <= my_idx ) { return; }
           const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
@@ -747,9 +750,9 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
           ++nc; cmask |= bit;
           if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
         } );
-        const uint32_t na_f = ( k > 32u ) ? ( na | SG_BP_MASKS_INVALID ) : na;
-        counts[my_idx] = make_uint2( nc, na_f );
-        masks[p] = make_uint4( cmask, amask, nc, na_f );
+        if( k > SG_BP_MASK_BITS ) { amask |= SG_BP_MASKS_INVALID; }
+        counts[my_idx] = make_uint2( nc, na );
+        masks[p] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
       }
     }
     else if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); }
@@ -825,13 +828,15 @@ template<> struct SgBpCountLaunch<2>
 // Slow paths of pass 2: redo the tests (a body with more than 32 neighbours or more candidates than the sorting
 // network holds); everything comes through L1/L2.  Kept out of line so the common path stays lean in registers.
 template<typename P>
-__device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, const ulonglong2 off, const uint32_t my_idx, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, const uint2* __restrict__ counts, const ulonglong2 off, const uint32_t my_idx, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, uint2* __restrict__ cand, const uint64_t cand_cap,
                                               const GidMap gid, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
+  if( nc == 0xffffffffu ) { nc = counts[my_idx].x; } // masks incomplete: the count comes from pass 1's by-index array
+  if( nc == 0u ) { return; }
   unsigned long long ka = off.y;
   const GridParams g = *params;
   const Rec me = sg_load_rec_global<Rec>( &recs[p] );
@@ -858,7 +863,7 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, c
     if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( gid( my_idx ), gid( P::rec_idx( o ) ) ); }
     if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { if( ka < work_cap ) { work[ka] = make_uint2( p, q ); } ++ka; } }
   };
-  if( m.z <= SG_BP_LOCAL_CAP )
+  if( nc <= SG_BP_LOCAL_CAP )
   {
     unsigned long long list[SG_BP_LOCAL_CAP];
     uint32_t nl = 0u;
@@ -884,7 +889,7 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, const uint4 m, c
   {
     // Crowded body: select partners in ascending index order by repeated walks (O(count * neighbours))
     uint32_t last = my_idx;
-    for( uint32_t j = 0u; j < m.z; ++j )
+    for( uint32_t j = 0u; j < nc; ++j )
     {
       uint32_t best_idx = 0xffffffffu, best_q = 0u;
       sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
@@ -910,14 +915,37 @@ __device__ __forceinline__ void sg_cex( unsigned long long& a, unsigned long lon
   a = lo; b = hi;
 }
 
+template<int N> __device__ __forceinline__ void sg_sort_keys( unsigned long long* v, const uint32_t count );
+template<> __device__ __forceinline__ void sg_sort_keys<8>( unsigned long long* v, const uint32_t )
+{
+  sg_cex( v[0], v[1] ); sg_cex( v[2], v[3] ); sg_cex( v[4], v[5] ); sg_cex( v[6], v[7] );
+  sg_cex( v[0], v[2] ); sg_cex( v[1], v[3] ); sg_cex( v[4], v[6] ); sg_cex( v[5], v[7] );
+  sg_cex( v[1], v[2] ); sg_cex( v[5], v[6] );
+  sg_cex( v[0], v[4] ); sg_cex( v[1], v[5] ); sg_cex( v[2], v[6] ); sg_cex( v[3], v[7] );
+  sg_cex( v[2], v[4] ); sg_cex( v[3], v[5] );
+  sg_cex( v[1], v[2] ); sg_cex( v[3], v[4] ); sg_cex( v[5], v[6] );
+}
+template<> __device__ __forceinline__ void sg_sort_keys<16>( unsigned long long* v, const uint32_t count )
+{
+  if( count <= 8u ) { sg_sort_keys<8>( v, count ); return; } // keys fill v[0..count) in visit order, the rest is ~0
+  sg_cex( v[0], v[1] ); sg_cex( v[2], v[3] ); sg_cex( v[0], v[2] ); sg_cex( v[1], v[3] ); sg_cex( v[1], v[2] ); sg_cex( v[4], v[5] ); sg_cex( v[6], v[7] ); sg_cex( v[4], v[6] );
+  sg_cex( v[5], v[7] ); sg_cex( v[5], v[6] ); sg_cex( v[0], v[4] ); sg_cex( v[2], v[6] ); sg_cex( v[2], v[4] ); sg_cex( v[1], v[5] ); sg_cex( v[3], v[7] ); sg_cex( v[3], v[5] );
+  sg_cex( v[1], v[2] ); sg_cex( v[3], v[4] ); sg_cex( v[5], v[6] ); sg_cex( v[8], v[9] ); sg_cex( v[10], v[11] ); sg_cex( v[8], v[10] ); sg_cex( v[9], v[11] ); sg_cex( v[9], v[10] );
+  sg_cex( v[12], v[13] ); sg_cex( v[14], v[15] ); sg_cex( v[12], v[14] ); sg_cex( v[13], v[15] ); sg_cex( v[13], v[14] ); sg_cex( v[8], v[12] ); sg_cex( v[10], v[14] ); sg_cex( v[10], v[12] );
+  sg_cex( v[9], v[13] ); sg_cex( v[11], v[15] ); sg_cex( v[11], v[13] ); sg_cex( v[9], v[10] ); sg_cex( v[11], v[12] ); sg_cex( v[13], v[14] ); sg_cex( v[0], v[8] ); sg_cex( v[4], v[12] );
+  sg_cex( v[4], v[8] ); sg_cex( v[2], v[10] ); sg_cex( v[6], v[14] ); sg_cex( v[6], v[10] ); sg_cex( v[2], v[4] ); sg_cex( v[6], v[8] ); sg_cex( v[10], v[12] ); sg_cex( v[1], v[9] );
+  sg_cex( v[5], v[13] ); sg_cex( v[5], v[9] ); sg_cex( v[3], v[11] ); sg_cex( v[7], v[15] ); sg_cex( v[7], v[11] ); sg_cex( v[3], v[5] ); sg_cex( v[7], v[9] ); sg_cex( v[11], v[13] );
+  sg_cex( v[1], v[2] ); sg_cex( v[3], v[4] ); sg_cex( v[5], v[6] ); sg_cex( v[7], v[8] ); sg_cex( v[9], v[10] ); sg_cex( v[11], v[12] ); sg_cex( v[13], v[14] );
+}
+
 // Pass 2.  Each body writes its candidates (ascending partner index) at its offset; active ones also write a contact.
 // Nothing is shared between threads: pass 1 left, per sorted position, the candidate/active masks over the visit
 // sequence and the walk plan (window starts and lengths), so a thread decodes its set bits straight to sorted
 // positions, gathers the partners' index words (L1/L2: neighbouring threads read the same few rows), orders its
-// <= 8 candidates with a register sorting network and stores them.  No staging, no barriers, no shared memory.
+// candidates (up to 8 in 2-D, 16 in 3-D) with a register sorting network and stores them.  No staging, no barriers, no shared memory.
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan,
+                                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan, const uint2* __restrict__ counts,
                                                               const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const GidMap gid, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
@@ -932,22 +960,26 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t
   const uint32_t my_idx = __ldg( &sidx[p] ) & P::IDX_MASK;
   uint32_t qb[Cfg::NW], len[Cfg::NW];
   sg_bp_plan_load<D>( plan, n_slots, p, qb, len );
-  if( m.z == 0u ) { return; }
+  const unsigned long long cmask = m.x | ( static_cast<unsigned long long>( m.y ) << 32 );
+  const unsigned long long amask = m.z | ( static_cast<unsigned long long>( m.w ) << 32 );
+  const bool complete = ( amask & SG_BP_MASKS_INVALID ) == 0ull;
+  if( complete && cmask == 0ull ) { return; }
+  const uint32_t nc = uint32_t( __popcll( cmask ) );
   unsigned long long ka = off.y;
 
-  if( m.z <= SG_BP_FAST_CAP && ( m.w & SG_BP_MASKS_INVALID ) == 0u )
+  if( complete && nc <= uint32_t( Cfg::FAST ) )
   {
     // visits before window w (the body itself is skipped inside its own window)
-    unsigned long long v[SG_BP_FAST_CAP];
-    uint32_t cm = m.x;
+    unsigned long long v[Cfg::FAST];
+    unsigned long long cm = cmask;
     #pragma unroll
-    for( int b = 0; b < SG_BP_FAST_CAP; ++b )
+    for( int b = 0; b < Cfg::FAST; ++b )
     {
       v[b] = ~0ull;
-      if( cm != 0u )
+      if( cm != 0ull )
       {
-        const uint32_t kk = __ffs( cm ) - 1u;
-        cm &= cm - 1u;
+        const uint32_t kk = uint32_t( __ffsll( static_cast<long long>( cm ) ) ) - 1u;
+        cm &= cm - 1ull;
         uint32_t rem = kk, q = 0u;
         bool found = false;
         #pragma unroll
@@ -962,38 +994,30 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t
           }
         }
         const uint32_t oi = __ldg( &sidx[q] ) & P::IDX_MASK;
-        v[b] = ( static_cast<unsigned long long>( oi ) << 32 ) | ( static_cast<unsigned long long>( ( m.y >> kk ) & 1u ) << 31 ) | q;
+        v[b] = ( static_cast<unsigned long long>( oi ) << 32 ) | ( ( ( amask >> kk ) & 1ull ) << 31 ) | q;
       }
     }
-    // Batcher odd-even merge sort, 8 keys / 19 compare-exchanges (empty slots hold ~0 and sink to the end)
-    static_assert( SG_BP_FAST_CAP == 8, "the sorting network below is for 8 keys" );
-    if( m.z > 1u )
-    {
-      sg_cex( v[0], v[1] ); sg_cex( v[2], v[3] ); sg_cex( v[4], v[5] ); sg_cex( v[6], v[7] );
-      sg_cex( v[0], v[2] ); sg_cex( v[1], v[3] ); sg_cex( v[4], v[6] ); sg_cex( v[5], v[7] );
-      sg_cex( v[1], v[2] ); sg_cex( v[5], v[6] );
-      sg_cex( v[0], v[4] ); sg_cex( v[1], v[5] ); sg_cex( v[2], v[6] ); sg_cex( v[3], v[7] );
-      sg_cex( v[2], v[4] ); sg_cex( v[3], v[5] );
-      sg_cex( v[1], v[2] ); sg_cex( v[3], v[4] ); sg_cex( v[5], v[6] );
-    }
+    // Batcher odd-even merge sort networks (empty slots hold ~0 and sink to the end): 8 keys / 19 exchanges,
+    // 16 keys / 63 exchanges (3-D pipelines, where a lattice body owns 13 of its 26 neighbours)
+    if( nc > 1u ) { sg_sort_keys<Cfg::FAST>( v, nc ); }
     if( cand != nullptr )
     {
       const uint32_t gi = gid( my_idx );
       #pragma unroll
-      for( int j = 0; j < SG_BP_FAST_CAP; ++j )
+      for( int j = 0; j < Cfg::FAST; ++j )
       {
         const unsigned long long kc = off.x + j;
-        if( uint32_t( j ) < m.z && kc < cand_cap ) { const uint32_t oj = uint32_t( v[j] >> 32 ); cand[kc] = make_uint2( gi, gid( oj ) ); }
+        if( uint32_t( j ) < nc && kc < cand_cap ) { const uint32_t oj = uint32_t( v[j] >> 32 ); cand[kc] = make_uint2( gi, gid( oj ) ); }
       }
     }
-    if( P::HAS_NARROW && m.y != 0u )
+    if( P::HAS_NARROW && amask != 0ull )
     {
       // active pairs: only (own position, partner position) is recorded here, in output order; the contact
       // geometry is computed by sg_bp_contacts, one thread per contact, with fully coalesced stores
       #pragma unroll
-      for( int j = 0; j < SG_BP_FAST_CAP; ++j )
+      for( int j = 0; j < Cfg::FAST; ++j )
       {
-        if( uint32_t( j ) < m.z && ( ( v[j] >> 31 ) & 1ull ) )
+        if( uint32_t( j ) < nc && ( ( v[j] >> 31 ) & 1ull ) )
         {
           if( ka < work_cap ) { work[ka] = make_uint2( p, uint32_t( v[j] & 0x7fffffffull ) ); }
           ++ka;
@@ -1003,7 +1027,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t
     return;
   }
 
-  sg_bp_emit_slow<P>( p, m, off, my_idx, params, cell_start, recs, sidx, cand, cand_cap, gid, work, work_cap );
+  sg_bp_emit_slow<P>( p, complete ? nc : 0xffffffffu, counts, off, my_idx, params, cell_start, recs, sidx, cand, cand_cap, gid, work, work_cap );
 }
 
 // Pass 3 (policies with a fused narrow phase).  One thread per active pair, grid-stride over the work list pass 2
@@ -1115,7 +1139,7 @@ static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, con
     s.work_cap = act_cap;
   }
   SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ), sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map,
+             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map,
              s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap ) );
   return SgBpContactsLaunch<P::HAS_NARROW>::template run<P>( ctx, s, out, act_cap );
 }
