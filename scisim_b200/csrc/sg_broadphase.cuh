@@ -342,7 +342,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
 // bulk copy cannot apply the swizzle that removes the 4-way bank conflicts of 64-byte records.)
 template<int D> struct BpCfg;
 template<> struct BpCfg<2> { static constexpr int NW = 3; static constexpr int T = 256; static constexpr int WCAP = 272; static constexpr int CSCAP = 320; static constexpr int FAST = 8; };
-template<> struct BpCfg<3> { static constexpr int NW = 9; static constexpr int T = 128; static constexpr int WCAP = 144; static constexpr int CSCAP = 288; static constexpr int FAST = 16; };
+template<> struct BpCfg<3> { static constexpr int NW = 9; static constexpr int T = 256; static constexpr int WCAP = 16; static constexpr int CSCAP = 320; static constexpr int FAST = 16; };
 
 template<int D>
 struct BpStage
@@ -545,7 +545,7 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
 // Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active }
 //          masks[sorted position] = { candidate mask (64 bit), active mask (64 bit) } over the visit sequence
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T, ( P::D == 2 ) ? 4 : 5 ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                                const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
 {
   constexpr int D = P::D;
