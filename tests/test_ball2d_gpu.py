@@ -214,3 +214,21 @@ def test_million_ball_properties(gpu_ctx):
     assert np.array_equal(q1, s["q"] + s["dt"] * v1)
     pc2, pa2 = sim.step(sb.SymplecticEulerMap(), s["dt"])
     assert (pc2, pa2) == (pc, pa)
+
+
+@pytest.mark.parametrize("per_cell", [3.0, 7.0, 12.0])
+def test_dense_scene_mask_regimes(gpu_ctx, oracle, per_cell):
+    """Densities chosen so that a body's walk is ~27, ~63 and ~108 visits long: below, around and beyond what the 64-bit
+    pass-1 masks cover, with candidate counts on both sides of the 8-key register sort and of the 12-entry local list."""
+    from tests import oracle_binding as ob
+    n = 5000
+    s = scenes.ball2d_random(n, 31, nplanes=2, ndrums=1, rmin=0.2, rmax=0.4, vmax=2.0, dt=0.01)
+    rng = np.random.default_rng(int(per_cell))
+    half = 0.5 * np.sqrt(n * 0.85 * 0.85 / per_cell)   # cell width ~ largest swept extent ~ 0.85
+    s["q"] = rng.uniform(-half, half, size=2 * n)
+    sim = make_sim(s, gpu_ctx)
+    o = ob.Ball2DOracle(s)
+    q1, _ = o.flow(0, s["q"], s["v"], s["dt"])
+    ref = o.active_set(s["q"], q1, "grid")
+    assert ref["candidates"].shape[0] > 2 * n
+    assert_active_equal(sim.computeActiveSet(s["q"], q1), ref)

@@ -217,3 +217,17 @@ def test_meshes_use_tma_bricks(gpu_ctx, oracle):
     assert s1 - s0 > 0, "no sweep was staged through TMA"
     assert (s1 - s0) > (d1 - d0), "most sweeps should fit the shared-memory brick: staged %d direct %d" % (s1 - s0, d1 - d0)
     assert_active_equal(got, ref)
+
+
+@pytest.mark.parametrize("box", [3.0, 5.0])
+def test_dense_spheres_sort_regimes(gpu_ctx, oracle, box):
+    """Crowded all-sphere scenes: owned-candidate counts on both sides of the 16-key register sort, walks longer than the
+    64-bit masks (the ordered-selection path) next to short ones."""
+    from tests import oracle_binding as ob
+    s = scenes.rb3d_random_spheres(4000, 17, spin=False, box=box)
+    sim = make_sim(s, gpu_ctx)
+    o = ob.RB3DOracle(s)
+    q1, _ = o.flow(kind_of(s), s["q"], s["v"], s["dt"])
+    ref = o.active_set(s["q"], q1, "grid")
+    assert ref["candidates"].shape[0] > 8 * 4000
+    assert_active_equal(sim.computeActiveSet(s["q"], q1), ref)
