@@ -944,7 +944,7 @@ template<> __device__ __forceinline__ void sg_sort_keys<16>( unsigned long long*
 // positions, gathers the partners' index words (L1/L2: neighbouring threads read the same few rows), orders its
 // candidates (up to 8 in 2-D, 16 in 3-D) with a register sorting network and stores them.  No staging, no barriers, no shared memory.
 template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan, const uint2* __restrict__ counts,
                                                               const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const GidMap gid, uint2* __restrict__ work, const uint64_t work_cap )
 {
@@ -1034,7 +1034,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 3 ) sg_bp_emit( const uint32_t
 // left in output order: both records come through L1/L2 (consecutive contacts share the first body), the contact
 // is written at its own index => every store of the SoA contact arrays is fully coalesced.
 template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_contacts( const ScanPairCounts::Acc* __restrict__ totals, const uint2* __restrict__ work, const uint64_t work_cap,
+__global__ void __launch_bounds__( SG_BP_THREADS, 5 ) sg_bp_contacts( const ScanPairCounts::Acc* __restrict__ totals, const uint2* __restrict__ work, const uint64_t work_cap,
                                                                   const typename P::Rec* __restrict__ recs, const typename P::Out out )
 {
   using Rec = typename P::Rec;
@@ -1123,7 +1123,7 @@ template<> struct SgBpContactsLaunch<true>
 {
   template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const typename P::Out& out, const uint64_t act_cap )
   {
-    SG_LAUNCH( ctx, "bp_contacts", 0.0, sg_bp_contacts<P><<<unsigned( ctx->num_sms ) * 8u, SG_BP_THREADS, 0, ctx->stream>>>( s.totals.as<ScanPairCounts::Acc>(), s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap,
+    SG_LAUNCH( ctx, "bp_contacts", 0.0, sg_bp_contacts<P><<<unsigned( ctx->num_sms ) * 5u, SG_BP_THREADS, 0, ctx->stream>>>( s.totals.as<ScanPairCounts::Acc>(), s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap,
                s.recs.as<typename P::Rec>(), out ) );
     return SG_OK;
   }
