@@ -351,6 +351,7 @@ struct BpStage
   uint32_t len[BpCfg<D>::NW];     // records staged
   uint32_t cs_klo[BpCfg<D>::NW];  // first cell key whose cell_start entry is staged
   uint32_t cs_len[BpCfg<D>::NW];  // cell_start entries staged
+  uint32_t full;                  // every window and every cell_start slice of the tile is staged completely
 };
 
 template<int D> __host__ __device__ constexpr size_t sg_bp_cs_bytes() { return size_t( BpCfg<D>::NW ) * BpCfg<D>::CSCAP * 4; }
@@ -388,6 +389,7 @@ __device__ inline void sg_bp_stage( const GridParams& g, const uint32_t n, const
       cs_len = ( ncs < ( long long )( Cfg::CSCAP ) ) ? uint32_t( ncs ) : uint32_t( Cfg::CSCAP );
     }
     st->start[w] = start; st->len[w] = len; st->cs_klo[w] = cs_klo; st->cs_len[w] = cs_len;
+    if( w == 0u ) { st->full = 0u; }
   }
   __syncthreads();
   #pragma unroll
@@ -418,15 +420,17 @@ __device__ inline void sg_bp_stage( const GridParams& g, const uint32_t n, const
   __syncthreads();
 }
 
-template<int D, int CSCAP = BpCfg<D>::CSCAP>
+// STAGED: the caller knows (BpStage::full) that the lookup cannot miss the staged slice -- no fallback code at all
+template<int D, int CSCAP = BpCfg<D>::CSCAP, bool STAGED = false>
 __device__ __forceinline__ uint32_t sg_bp_cs( const BpStage<D>* st, const uint32_t* s_cs, const uint32_t* __restrict__ cell_start, const int w, const uint32_t key )
 {
   const uint32_t rel = key - st->cs_klo[w];
+  if( STAGED ) { return s_cs[w * CSCAP + rel]; }
   return ( rel < st->cs_len[w] ) ? s_cs[w * CSCAP + rel] : __ldg( &cell_start[key] );
 }
 
 // [qb[w], qe[w]) = sorted positions of the bodies whose cell is within one cell of (cx,c1,c2) in row window w
-template<typename P, int CSCAP = BpCfg<P::D>::CSCAP>
+template<typename P, int CSCAP = BpCfg<P::D>::CSCAP, bool STAGED = false>
 __device__ __forceinline__ void sg_bp_ranges( const GridParams& g, const uint32_t* __restrict__ cell_start, const uint32_t* s_cs, const BpStage<P::D>* st,
                                               const uint32_t key, const uint32_t c1, const uint32_t c2, uint32_t* qb, uint32_t* qe )
 {
@@ -447,8 +451,8 @@ __device__ __forceinline__ void sg_bp_ranges( const GridParams& g, const uint32_
     if( ok )
     {
       const uint32_t row = g.dims[0] * ( uint32_t( y ) + g.dims[1] * uint32_t( z ) );
-      qb[w] = sg_bp_cs<D, CSCAP>( st, s_cs, cell_start, w, row + x0 );
-      qe[w] = sg_bp_cs<D, CSCAP>( st, s_cs, cell_start, w, row + x1 + 1u );
+      qb[w] = sg_bp_cs<D, CSCAP, STAGED>( st, s_cs, cell_start, w, row + x0 );
+      qe[w] = sg_bp_cs<D, CSCAP, STAGED>( st, s_cs, cell_start, w, row + x1 + 1u );
     }
   }
 }
@@ -517,20 +521,20 @@ __device__ __forceinline__ void sg_bp_plan_load( const uint4* __restrict__ plan,
 }
 
 // record (or just its body index) at sorted position q, known to lie in window w's key range
-template<typename P>
+template<typename P, bool STAGED = false>
 __device__ __forceinline__ typename P::Rec sg_bp_fetch( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q )
 {
   using Rec = typename P::Rec;
   const uint32_t slot = q - st->start[w];
-  if( slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * BpCfg<P::D>::WCAP * 64, slot ); }
+  if( STAGED || slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * BpCfg<P::D>::WCAP * 64, slot ); }
   return sg_load_rec_global<Rec>( &recs[q] );
 }
-template<typename P>
+template<typename P, bool STAGED = false>
 __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q )
 {
   constexpr uint32_t CH = P::IDX_OFFSET / 16u, IN = P::IDX_OFFSET % 16u;
   const uint32_t slot = q - st->start[w];
-  if( slot < st->len[w] )
+  if( STAGED || slot < st->len[w] )
   {
     const unsigned char* rec = s_recs + ( size_t( w ) * BpCfg<P::D>::WCAP + slot ) * 64;
     return *reinterpret_cast<const uint32_t*>( rec + ( ( CH ^ ( ( slot >> 1 ) & 3u ) ) << 4 ) + IN ) & P::IDX_MASK;
@@ -541,6 +545,42 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
 // masks cover the first 63 visits of a body's walk; bit 63 of the active mask flags a longer walk (masks incomplete)
 #define SG_BP_MASK_BITS 63u
 #define SG_BP_MASKS_INVALID 0x8000000000000000ull
+
+// One body's pass-1 walk: candidates with a larger index, how many are active, the two visit masks, the walk plan.
+template<typename P, int CSCAP, bool STAGED>
+__device__ __forceinline__ void sg_bp_count_body( const GridParams& g, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const uint32_t* s_cs,
+                                                  const BpStage<P::D>* st, const uint32_t n_slots, const uint32_t p, const typename P::Rec& me, const uint32_t my_idx,
+                                                  uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
+{
+  constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
+  using Rec = typename P::Rec;
+  double lo[D], hi[D];
+  P::rec_aabb( me, lo, hi );
+  uint32_t nc = 0u, na = 0u, k = 0u;
+  unsigned long long cmask = 0ull, amask = 0ull;
+  uint32_t qb[Cfg::NW], qe[Cfg::NW];
+  sg_bp_ranges<P, CSCAP, STAGED>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
+  sg_bp_plan_store<D>( plan, n_slots, p, qb, qe );
+  sg_bp_walk_ranges<P>( qb, qe, p, [&]( const int w, const uint32_t q )
+  {
+    const unsigned long long bit = ( k < SG_BP_MASK_BITS ) ? ( 1ull << k ) : 0ull;
+    ++k;
+    if( sg_bp_fetch_idx<P, STAGED>( recs, s_recs, st, w, q ) <= my_idx ) { return; } // owned by the partner: skip before touching the record
+    const Rec o = sg_bp_fetch<P, STAGED>( recs, s_recs, st, w, q );
+    double olo[D], ohi[D];
+    P::rec_aabb( o, olo, ohi );
+    bool ov = true;
+    #pragma unroll
+    for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
+    if( !ov ) { return; }
+    ++nc; cmask |= bit;
+    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
+  } );
+  if( k > SG_BP_MASK_BITS ) { amask |= SG_BP_MASKS_INVALID; }
+  counts[my_idx] = make_uint2( nc, na );
+  masks[p] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
+}
 
 // Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active }
 //          masks[sorted position] = { candidate mask (64 bit), active mask (64 bit) } over the visit sequence
@@ -572,31 +612,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
     masks[p] = make_uint4( 0u, 0u, 0u, 0u );
     return;
   }
-  double lo[D], hi[D];
-  P::rec_aabb( me, lo, hi );
-  uint32_t nc = 0u, na = 0u, k = 0u;
-  unsigned long long cmask = 0ull, amask = 0ull;
-  uint32_t qb[Cfg::NW], qe[Cfg::NW];
-  sg_bp_ranges<P>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
-  sg_bp_plan_store<D>( plan, n_slots, p, qb, qe );
-  sg_bp_walk_ranges<P>( qb, qe, p, [&]( const int w, const uint32_t q )
-  {
-    const unsigned long long bit = ( k < SG_BP_MASK_BITS ) ? ( 1ull << k ) : 0ull;
-    ++k;
-    if( sg_bp_fetch_idx<P>( recs, s_recs, st, w, q ) <= my_idx ) { return; } // owned by the partner: skip before touching the record
-    const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
-    double olo[D], ohi[D];
-    P::rec_aabb( o, olo, ohi );
-    bool ov = true;
-    #pragma unroll
-    for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
-    if( !ov ) { return; }
-    ++nc; cmask |= bit;
-    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
-  } );
-  if( k > SG_BP_MASK_BITS ) { amask |= SG_BP_MASKS_INVALID; }
-  counts[my_idx] = make_uint2( nc, na );
-  masks[p] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
+  sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan );
 }
 
 // ---- pass 1, TMA-fed (D = 2) -------------------------------------------------------------------------
@@ -650,9 +666,9 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
       const uint32_t b0 = t * Cfg::T;
       if( b0 >= n ) { break; } // tiles past the binned bodies have nothing to stage (consumers only clear masks)
       const uint32_t sgi = it & 1u, use = it >> 1;
-      if( use > 0u ) { sg_mbar_wait( &bars[2 + sgi], ( use - 1u ) & 1u ); }
       unsigned char* stage = s_raw + sgi * STAGE;
       BpStage<D>* st = reinterpret_cast<BpStage<D>*>( stage + ST_OFF );
+      // the tile's plan (two dependent rounds of global loads) does not need the stage: fetch it first, wait after
       const uint32_t b1 = ( n - b0 < uint32_t( Cfg::T ) ) ? n : b0 + Cfg::T;
       const long long kf = __ldg( &recs[b0].key );
       const long long kl = __ldg( &recs[b1 - 1u].key );
@@ -672,6 +688,8 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
       }
       uint32_t bytes = 0u;
       uint32_t ncopies[Cfg::NW], cs_first[Cfg::NW], cs_n[Cfg::NW];
+      uint32_t all_staged = 1u;
+      if( use > 0u ) { sg_mbar_wait_backoff( &bars[2 + sgi], ( use - 1u ) & 1u ); } // consumers are done with this stage
       #pragma unroll
       for( int w = 0; w < Cfg::NW; ++w )
       {
@@ -684,8 +702,10 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
         want = ( want + 3u ) & ~3u;
         cs_n[w] = ( want < uint32_t( SG_BP_TMA_CSCAP ) ) ? want : uint32_t( SG_BP_TMA_CSCAP );
         st->start[w] = start[w]; st->len[w] = len; st->cs_klo[w] = cs_first[w]; st->cs_len[w] = cs_n[w];
+        if( end[w] - start[w] > uint32_t( Cfg::WCAP ) || want > uint32_t( SG_BP_TMA_CSCAP ) ) { all_staged = 0u; }
         bytes += ncopies[w] * uint32_t( SG_BP_TMA_ROWS * 64 ) + cs_n[w] * 4u;
       }
+      st->full = all_staged;
       asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); // the stage's earlier generic reads vs the async writes to come
       sg_mbar_arrive_expect_tx( &bars[sgi], bytes );
       #pragma unroll
@@ -728,31 +748,10 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
       }
       else
       {
-        double lo[D], hi[D];
-        P::rec_aabb( me, lo, hi );
-        uint32_t nc = 0u, na = 0u, k = 0u;
-        unsigned long long cmask = 0ull, amask = 0ull;
-        uint32_t qb[Cfg::NW], qe[Cfg::NW];
-        sg_bp_ranges<P, SG_BP_TMA_CSCAP>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
-        sg_bp_plan_store<D>( plan, n_slots, p, qb, qe );
-        sg_bp_walk_ranges<P>( qb, qe, p, [&]( const int w, const uint32_t q )
-        {
-          const unsigned long long bit = ( k < SG_BP_MASK_BITS ) ? ( 1ull << k ) : 0ull;
-          ++k;
-          if( sg_bp_fetch_idx<P>( recs, s_recs, st, w, q ) <= my_idx ) { return; }
-          const Rec o = sg_bp_fetch<P>( recs, s_recs, st, w, q );
-          double olo[D], ohi[D];
-          P::rec_aabb( o, olo, ohi );
-          bool ov = true;
-          #pragma unroll
-          for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
-          if( !ov ) { return; }
-          ++nc; cmask |= bit;
-          if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { ++na; amask |= bit; } }
-        } );
-        if( k > SG_BP_MASK_BITS ) { amask |= SG_BP_MASKS_INVALID; }
-        counts[my_idx] = make_uint2( nc, na );
-        masks[p] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
+        // tiles whose windows and cell_start slices were staged completely (the rule, not the exception) run a
+        // walk with no fallback code in it at all
+        if( st->full != 0u ) { sg_bp_count_body<P, SG_BP_TMA_CSCAP, true>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan ); }
+        else { sg_bp_count_body<P, SG_BP_TMA_CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan ); }
       }
     }
     else if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); }

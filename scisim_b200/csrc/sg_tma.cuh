@@ -36,6 +36,20 @@ __device__ __forceinline__ void sg_mbar_wait( uint64_t* bar, const uint32_t pari
   } while( done == 0 );
 }
 
+// same wait for a thread whose spinning would only steal issue slots from the warps doing the work (a producer
+// waiting for its consumers): back off between polls
+__device__ __forceinline__ void sg_mbar_wait_backoff( uint64_t* bar, const uint32_t parity )
+{
+  uint32_t done = 0;
+  const uint32_t addr = sg_smem_u32( bar );
+  for( ;; )
+  {
+    asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"( done ) : "r"( addr ), "r"( parity ) : "memory" );
+    if( done != 0 ) { break; }
+    __nanosleep( 256 );
+  }
+}
+
 // non-blocking arrive (count 1) -- consumers releasing a stage back to the producer
 __device__ __forceinline__ void sg_mbar_arrive( uint64_t* bar )
 {
