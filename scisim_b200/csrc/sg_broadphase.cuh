@@ -629,10 +629,12 @@ template<int D> __host__ __device__ constexpr size_t sg_bp_tma_stage_bytes()
 {
   return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + size_t( BpCfg<D>::NW ) * SG_BP_TMA_CSCAP * 4 + sizeof( BpStage<D> ) + 1023 ) & ~size_t( 1023 );
 }
-template<int D> __host__ __device__ constexpr size_t sg_bp_tma_smem() { return 2 * sg_bp_tma_stage_bytes<D>() + 64; }
+#define SG_BP_TMA_STAGES 2      // shared-memory stages per CTA (measured: 1 stage x 4 CTAs/SM is 1.5x slower)
+#define SG_BP_TMA_CTAS_PER_SM 2 // resident CTAs per SM (stages x CTAs x 55 KB must fit the SM's 227 KB)
+template<int D> __host__ __device__ constexpr size_t sg_bp_tma_smem() { return SG_BP_TMA_STAGES * sg_bp_tma_stage_bytes<D>() + 64; }
 
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( const __grid_constant__ CUtensorMap tm_recs, const uint32_t n_slots, const GridParams* __restrict__ params,
+__global__ void __launch_bounds__( BpCfg<P::D>::T + 32, SG_BP_TMA_CTAS_PER_SM ) sg_bp_count_tma( const __grid_constant__ CUtensorMap tm_recs, const uint32_t n_slots, const GridParams* __restrict__ params,
                                                                             const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts,
                                                                             uint4* __restrict__ masks, uint4* __restrict__ plan )
 {
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
   constexpr size_t STAGE = sg_bp_tma_stage_bytes<D>();
   constexpr size_t CS_OFF = size_t( Cfg::NW ) * Cfg::WCAP * 64;
   constexpr size_t ST_OFF = CS_OFF + size_t( Cfg::NW ) * SG_BP_TMA_CSCAP * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>( s_raw + 2 * STAGE ); // full[0], full[1], empty[0], empty[1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>( s_raw + SG_BP_TMA_STAGES * STAGE ); // full[0], full[1], empty[0], empty[1] (stage s uses full[s], empty[s])
   const GridParams g = *params;
   const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned
   const uint32_t ntiles = ( n_slots + Cfg::T - 1u ) / Cfg::T;
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
     {
       const uint32_t b0 = t * Cfg::T;
       if( b0 >= n ) { break; } // tiles past the binned bodies have nothing to stage (consumers only clear masks)
-      const uint32_t sgi = it & 1u, use = it >> 1;
+      const uint32_t sgi = it % SG_BP_TMA_STAGES, use = it / SG_BP_TMA_STAGES;
       unsigned char* stage = s_raw + sgi * STAGE;
       BpStage<D>* st = reinterpret_cast<BpStage<D>*>( stage + ST_OFF );
       // the tile's plan (two dependent rounds of global loads) does not need the stage: fetch it first, wait after
@@ -731,7 +733,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, 2 ) sg_bp_count_tma( con
       if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slots: pass 2 skips them
       continue;
     }
-    const uint32_t sgi = it & 1u, use = it >> 1;
+    const uint32_t sgi = it % SG_BP_TMA_STAGES, use = it / SG_BP_TMA_STAGES;
     const unsigned char* stage = s_raw + sgi * STAGE;
     const unsigned char* s_recs = stage;
     const uint32_t* s_cs = reinterpret_cast<const uint32_t*>( stage + CS_OFF );
@@ -817,7 +819,7 @@ template<> struct SgBpCountLaunch<2>
     static int attr_dev = -1; // opt-in to > 48 KB of dynamic shared memory: once per device
     if( attr_dev != ctx->device ) { SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_tma<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) ); attr_dev = ctx->device; }
     const unsigned ntiles = sg_div_up( n, BpCfg<2>::T );
-    const unsigned grid = ntiles < unsigned( ctx->num_sms ) * 2u ? ntiles : unsigned( ctx->num_sms ) * 2u;
+    const unsigned grid = ntiles < unsigned( ctx->num_sms ) * SG_BP_TMA_CTAS_PER_SM ? ntiles : unsigned( ctx->num_sms ) * SG_BP_TMA_CTAS_PER_SM;
     SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_tma<P><<<grid, BpCfg<2>::T + 32, smem, ctx->stream>>>( s.tm_recs, n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
                s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
     return SG_OK;
