@@ -246,7 +246,6 @@ def main():
         step_ms.append(ctx.timer_end())
     barrier()
     gpu_launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
     t_local = sum(step_ms) / 1e3
     pairs_local = float(pc + pa)
 
@@ -271,11 +270,11 @@ def main():
                 barrier()
                 t0 = time.perf_counter()
             sim._flow(umap.kind, q0h, v0h, dt, q1h, v1h)
-            a = sim.computeActiveSet(q0h, q1h, flags=flags, copy=False)
+            a = sim.computeActiveSet(q0h, q1h, flags=flags, copy=False, resident=True)   # (q0, q1) of the flow just done, as ImpactMap::flow passes them
         ctx.synchronize()
         t_e2e_local = time.perf_counter() - t0
-        h2d = 4 * 2 * n * 8
-        n_act, e2e_api = a.n_active, "sg_ball2d_flow + sg_ball2d_active_set, pinned host buffers, wall clock"
+        h2d = 2 * 2 * n * 8
+        n_act, e2e_api = a.n_active, "sg_ball2d_flow (q0,v0 up; q1,v1 down) + sg_ball2d_active_set(SG_IN_RESIDENT: the flow's q0,q1 stay on the device; contacts down), pinned host buffers, wall clock"
         assert a.n_active == pa and a.n_candidates == pc
     else:
         import ctypes as C
@@ -294,6 +293,8 @@ def main():
         h2d = 2 * 2 * n * 8
         n_act, e2e_api = int(c.n_active), "sg_ball2d_upload + slab step (%s halo) + sg_ball2d_fetch, pinned host buffers, wall clock" % args.transport
     d2h = 2 * 2 * n * 8 + n_act * (4 + 4 + 4 + 16 + 16 + 8)
+    # the sampler ran from just before the timed steps to here (timed region, per-kernel pass, e2e pass: all under load)
+    clocks = sampler.stop() if sampler else None
 
     # ---------------- reduce over ranks: max time, summed work ----------------
     if world > 1:

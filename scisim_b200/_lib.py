@@ -14,6 +14,7 @@ SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV = 0, 1, 2, 
 SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
 SG_SPHERE_SPHERE, SG_KINEMATIC_SPHERE_SPHERE, SG_BODY_BODY, SG_KINEMATIC_BODY_BODY, SG_PLANE_SPHERE, SG_PLANE_BOX, SG_PLANE_BODY = 10, 11, 12, 13, 14, 15, 16
 SG_OUT_NORMALS, SG_OUT_POINTS, SG_OUT_DEPTHS, SG_OUT_CANDIDATES, SG_OUT_ALL = 1, 2, 4, 8, 15
+SG_IN_RESIDENT = 256
 
 c_dp = C.POINTER(C.c_double)
 c_up = C.POINTER(C.c_uint32)

@@ -418,6 +418,7 @@ struct Ball2DData
   DevBuf mailbox;
   void* peer_mb[2] = { nullptr, nullptr };
   bool peer_ipc[2] = { false, false };
+  bool flow_resident = false; // q0 (as given) and q1 (as computed) of the last sg_ball2d_flow are still in q0/q1 on the device
   uint32_t slab_step = 0; // tag of the current step's flags (all ranks step in lockstep)
   bool slab_prep_done = false; // this step's bounds / static counts were already produced by sg_ball2d_slab_flow
   DevBuf pack_done;            // block counter of the pack kernel's "last block raises the flag"
@@ -931,6 +932,7 @@ int sg_ball2d_set_bodies( sg_ctx* ctx, uint32_t n, const double* r, const double
   d->n = n;
   d->slab = false;
   d->have_result = false;
+  d->flow_resident = false;
   if( n == 0 ) { return SG_OK; }
   SG_CUDA( ctx, d->r.ensure( size_t( n ) * 8 ) );
   SG_CUDA( ctx, d->m.ensure( size_t( n ) * 8 ) );
@@ -999,6 +1001,7 @@ int sg_ball2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v
   SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   sg_prof_collect( ctx );
+  d->flow_resident = true;
   return SG_OK;
 }
 
@@ -1009,11 +1012,18 @@ int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint3
   if( d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_active_set: context is in slab mode, use the sg_ball2d_slab_* calls" ); }
   const size_t bytes = size_t( d->n ) * 16;
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  if( d->n > 0 )
+  if( ( out_flags & SG_IN_RESIDENT ) != 0u )
+  {
+    // the caller vouches that (q0, q1) are the input and output of the last sg_ball2d_flow on this context: they are
+    // still on the device, nothing is uploaded
+    if( !d->flow_resident ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_active_set: SG_IN_RESIDENT without a preceding sg_ball2d_flow on this context" ); }
+  }
+  else if( d->n > 0 )
   {
     if( q0 == nullptr || q1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_active_set: null vector" ); }
     SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
     SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+    d->flow_resident = false;
   }
   const int rc = ball2d_active_set_device( ctx, d, ( out_flags & SG_OUT_CANDIDATES ) != 0u );
   if( rc != SG_OK ) { return rc; }
@@ -1024,6 +1034,7 @@ int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
+  d->flow_resident = false;
   const uint32_t nown = d->slab ? d->n_owned : d->n;
   if( nown == 0 ) { return SG_OK; }
   if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_upload: null vector" ); }
@@ -1066,6 +1077,7 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   const size_t slots = size_t( n_owned ) + 2 * size_t( ghost_cap );
   d->n = uint32_t( slots );
   d->have_result = false;
+  d->flow_resident = false;
   SG_CUDA( ctx, d->r.ensure( slots * 8 + 8 ) );
   SG_CUDA( ctx, d->q0.ensure( slots * 16 + 16 ) );
   SG_CUDA( ctx, d->q1.ensure( slots * 16 + 16 ) );

@@ -47,7 +47,9 @@ public:
   // UnconstrainedMap::flow for the two ball2d maps
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
   // Ball2DSim::computeActiveSet (ball2d/Ball2DSim.cpp:151-173): contacts in active_set order
-  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr );
+  // from_last_flow: (q0, q1) are the vectors the last flow() call read and wrote, unchanged since -- what
+  // ImpactMap::flow hands to computeActiveSet (ImpactMap.cpp:54-58); they are then not uploaded a second time.
+  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
   // SpatialGridDetector::getPotentialOverlaps (ball2d/SpatialGridDetector.h:39) on caller-built boxes [minx,miny,maxx,maxy]
   void getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps );
 

@@ -232,3 +232,21 @@ def test_dense_scene_mask_regimes(gpu_ctx, oracle, per_cell):
     ref = o.active_set(s["q"], q1, "grid")
     assert ref["candidates"].shape[0] > 2 * n
     assert_active_equal(sim.computeActiveSet(s["q"], q1), ref)
+
+
+def test_active_set_on_resident_flow_result(gpu_ctx, oracle):
+    """SG_IN_RESIDENT: the flow's (q0, q1) are reused on the device; same lists as with uploaded vectors, and an error
+    when no flow preceded the call."""
+    import scisim_b200 as sb
+    s = scenes.ball2d_random(3000, 41, nplanes=2, ndrums=1)
+    sim = make_sim(s, gpu_ctx)
+    with pytest.raises(sb.SciSimB200Error):
+        sim.computeActiveSet(s["q"], s["q"], resident=True)
+    q1, v1 = sim._flow(0, s["q"], s["v"], s["dt"], np.empty_like(s["q"]), np.empty_like(s["v"]))
+    a = sim.computeActiveSet(s["q"], q1, resident=True)
+    b = sim.computeActiveSet(s["q"], q1)
+    assert a.n_active == b.n_active and a.n_candidates == b.n_candidates and a.n_active > 0
+    for k in ("type", "i", "j", "n", "p", "candidates"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    with pytest.raises(sb.SciSimB200Error):
+        sim.computeActiveSet(s["q"], q1, resident=True)   # the upload above replaced the resident pair
