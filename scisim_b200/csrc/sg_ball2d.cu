@@ -483,16 +483,6 @@ static int ball2d_ensure_outputs( sg_ctx* ctx, Ball2DData* d, const uint64_t can
   return SG_OK;
 }
 
-static int ball2d_flow_device( sg_ctx* ctx, Ball2DData* d, const int map_kind, const double dt )
-{
-  const uint32_t n = d->slab ? d->n_owned : d->n;
-  if( n == 0 ) { return SG_OK; }
-  const size_t o = d->owned_slot();
-  SG_LAUNCH( ctx, "ball2d_flow", double( n ) * 72.0, k_ball2d_flow<<<sg_div_up( n, 256 ), 256, 0, ctx->stream>>>( map_kind, n, d->q0.as<double2>() + o, d->v0.as<double2>(), d->m.as<double>(),
-             d->g[0], d->g[1], dt, d->q1.as<double2>() + o, d->v1.as<double2>() ) );
-  return SG_OK;
-}
-
 // Runs the whole detection pipeline on the device-resident q0,q1 and leaves the counts in d->n_*.
 // flow_kind >= 0: the unconstrained map is fused into the first pass (q1,v1 are produced from q0,v0 on the way).
 static int ball2d_static_scratch( sg_ctx* ctx, Ball2DData* d )
@@ -989,16 +979,39 @@ int sg_ball2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: map kind %d is not a ball2d map", map_kind ); }
   Ball2DData* d = ball2d_data( ctx );
   if( d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: context is in slab mode, use the sg_ball2d_slab_* calls" ); }
-  const size_t bytes = size_t( d->n ) * 16;
   if( d->n == 0 ) { return SG_OK; }
   if( q0 == nullptr || v0 == nullptr || q1 == nullptr || v1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_flow: null vector" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
-  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v0, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
-  const int rc = ball2d_flow_device( ctx, d, map_kind, dt );
-  if( rc != SG_OK ) { return rc; }
-  SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
-  SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  // The map is per-body, so the call is pipelined over chunks of bodies on the context's two streams: while one chunk's
+  // q1,v1 travel down, the next chunk's q0,v0 travel up (the two copy directions have their own engines and PCIe is
+  // full duplex).  Small systems and timed (profile) runs take one chunk.
+  const uint32_t n = d->n;
+  const uint32_t nchunks = ( n >= ( 1u << 18 ) && !ctx->profile ) ? 8u : 1u;
+  const uint32_t per = ( ( n + nchunks - 1u ) / nchunks + 255u ) & ~255u;
+  if( nchunks > 1u )
+  {
+    SG_CUDA( ctx, cudaEventRecord( ctx->ev_fork, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamWaitEvent( ctx->stream2, ctx->ev_fork, 0 ) );
+  }
+  for( uint32_t c = 0; c < nchunks; ++c )
+  {
+    const uint32_t b0 = c * per;
+    if( b0 >= n ) { break; }
+    const uint32_t cnt = ( n - b0 < per ) ? n - b0 : per;
+    cudaStream_t st = ( c & 1u ) ? ctx->stream2 : ctx->stream;
+    const size_t off = size_t( b0 ) * 2, cb = size_t( cnt ) * 16;
+    SG_CUDA( ctx, cudaMemcpyAsync( d->q0.as<double>() + off, q0 + off, cb, cudaMemcpyHostToDevice, st ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( d->v0.as<double>() + off, v0 + off, cb, cudaMemcpyHostToDevice, st ) );
+    SG_LAUNCH( ctx, "ball2d_flow", double( cnt ) * 72.0, k_ball2d_flow<<<sg_div_up( cnt, 256 ), 256, 0, st>>>( map_kind, cnt, d->q0.as<double2>() + b0, d->v0.as<double2>() + b0, d->m.as<double>() + b0,
+               d->g[0], d->g[1], dt, d->q1.as<double2>() + b0, d->v1.as<double2>() + b0 ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( q1 + off, d->q1.as<double>() + off, cb, cudaMemcpyDeviceToHost, st ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( v1 + off, d->v1.as<double>() + off, cb, cudaMemcpyDeviceToHost, st ) );
+  }
+  if( nchunks > 1u )
+  {
+    SG_CUDA( ctx, cudaEventRecord( ctx->ev_join, ctx->stream2 ) );
+    SG_CUDA( ctx, cudaStreamWaitEvent( ctx->stream, ctx->ev_join, 0 ) );
+  }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   sg_prof_collect( ctx );
   d->flow_resident = true;
