@@ -1,4 +1,5 @@
 // oracle/boxbox.h
+// Checked bit for bit against the reference's own source compiled unchanged (oracle/Makefile.ref, tests/test_oracle_vs_reference.py).
 //
 // TEST INFRASTRUCTURE ONLY (see oracle/oracle_math.h header). CPU restatement of the reference's ODE-derived
 // 3-D box-box test:

@@ -316,4 +316,38 @@ void orc_rb2d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t
   }
 }
 
+// ---- leaf routines by themselves (checked against the reference's own sources in tests/test_oracle_vs_reference.py) ----
+int orc_box_box_3d( const double* cm0, const double* R0, const double* side0, const double* cm1, const double* R1, const double* side1, double* n, double* points )
+{
+  using namespace orc;
+  M3 A, B;
+  for( int i = 0; i < 3; ++i ) { for( int j = 0; j < 3; ++j ) { A.m[3 * i + j] = R0[3 * i + j]; B.m[3 * i + j] = R1[3 * i + j]; } }
+  V3 nn{ 0.0, 0.0, 0.0 };
+  std::vector<V3> pts;
+  boxbox::isActive( V3{ cm0[0], cm0[1], cm0[2] }, A, V3{ side0[0], side0[1], side0[2] }, V3{ cm1[0], cm1[1], cm1[2] }, B, V3{ side1[0], side1[1], side1[2] }, nn, pts );
+  n[0] = nn.x; n[1] = nn.y; n[2] = nn.z;
+  int k = 0;
+  for( const V3& p : pts ) { if( k < 8 ) { points[3 * k] = p.x; points[3 * k + 1] = p.y; points[3 * k + 2] = p.z; } ++k; }
+  return k;
+}
+int orc_box_box_2d( const double* x0, const double theta0, const double* r0, const double* x1, const double theta1, const double* r1, double* n, double* points )
+{
+  using namespace orc;
+  V2 nn{ 0.0, 0.0 };
+  std::vector<V2> pts;
+  boxbox2d::isActive( V2{ x0[0], x0[1] }, theta0, V2{ r0[0], r0[1] }, V2{ x1[0], x1[1] }, theta1, V2{ r1[0], r1[1] }, nn, pts );
+  n[0] = nn.x; n[1] = nn.y;
+  int k = 0;
+  for( const V2& p : pts ) { if( k < 2 ) { points[2 * k] = p.x; points[2 * k + 1] = p.y; } ++k; }
+  return k;
+}
+int orc_circle_box_2d( const double* x0, const double r0, const double* x1, const double theta1, const double* r1, double* n, double* p )
+{
+  using namespace orc;
+  V2 nn{ 0.0, 0.0 }, pp{ 0.0, 0.0 };
+  const bool hit = circleBoxActive( V2{ x0[0], x0[1] }, r0, V2{ x1[0], x1[1] }, theta1, V2{ r1[0], r1[1] }, nn, pp );
+  n[0] = nn.x; n[1] = nn.y; p[0] = pp.x; p[1] = pp.y;
+  return hit ? 1 : 0;
+}
+
 }

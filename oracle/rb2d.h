@@ -1,4 +1,5 @@
 // oracle/rb2d.h
+// Checked bit for bit against the reference's own source compiled unchanged (oracle/Makefile.ref, tests/test_oracle_vs_reference.py).
 //
 // TEST INFRASTRUCTURE ONLY (see oracle/oracle_math.h header). CPU restatement of the rigidbody2d hot path:
 //   rigidbody2d/SymplecticEulerMap.cpp:15-38, VerletMap.cpp:15-55        flow (forces zeroed on kinematic bodies)

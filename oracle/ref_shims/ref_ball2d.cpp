@@ -1,0 +1,69 @@
+// oracle/ref_shims/ref_ball2d.cpp -- TEST INFRASTRUCTURE.  C entry points around the reference's own, unmodified
+//   ball2d/SpatialGridDetector.cpp                               (AABB, getPotentialOverlaps, getPotentialOverlapsAllPairs)
+//   scisim/CollisionDetection/CollisionDetectionUtilities.cpp    (computeCCDQuadraticCoeffs, ballBallCCDCollisionHappens)
+// compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).  The glue between them (swept boxes,
+// pair loop) restates ball2d/Ball2DSim.cpp:553-608 and is marked as such.
+#include "ball2d/SpatialGridDetector.h"
+#include "scisim/CollisionDetection/CollisionDetectionUtilities.h"
+
+#include <cstdint>
+
+extern "C"
+{
+
+// boxes: n x [minx, miny, maxx, maxy]; writes up to cap pairs (i<j, std::set order); returns the number of pairs
+uint64_t ref_ball2d_overlaps( const uint32_t n, const double* boxes, const int all_pairs, uint32_t* ij, const uint64_t cap )
+{
+  std::vector<AABB> aabbs;
+  aabbs.reserve( n );
+  for( uint32_t i = 0; i < n; ++i ) { aabbs.emplace_back( Array2s{ boxes[4 * i], boxes[4 * i + 1] }, Array2s{ boxes[4 * i + 2], boxes[4 * i + 3] } ); }
+  std::set<std::pair<unsigned,unsigned>> overlaps;
+  if( all_pairs ) { SpatialGridDetector::getPotentialOverlapsAllPairs( aabbs, overlaps ); }
+  else { SpatialGridDetector::getPotentialOverlaps( aabbs, overlaps ); }
+  uint64_t k = 0;
+  for( const std::pair<unsigned,unsigned>& p : overlaps ) { if( k < cap ) { ij[2 * k] = p.first; ij[2 * k + 1] = p.second; } ++k; }
+  return k;
+}
+
+// returns hit (0/1); coeffs[3] = quadratic coefficients, *toi = time of impact when hit
+int ref_ball2d_ccd( const double* q0a, const double* q1a, const double ra, const double* q0b, const double* q1b, const double rb, double* coeffs, double* toi )
+{
+  const Vector3s c{ CollisionDetectionUtilities::computeCCDQuadraticCoeffs( Vector2s{ q0a[0], q0a[1] }, Vector2s{ q1a[0], q1a[1] }, ra, Vector2s{ q0b[0], q0b[1] }, Vector2s{ q1b[0], q1b[1] }, rb ) };
+  if( coeffs != nullptr ) { coeffs[0] = c( 0 ); coeffs[1] = c( 1 ); coeffs[2] = c( 2 ); }
+  const std::pair<bool,scalar> r{ CollisionDetectionUtilities::ballBallCCDCollisionHappens( c ) };
+  if( toi != nullptr ) { *toi = r.first ? r.second : -1.0; }
+  return r.first ? 1 : 0;
+}
+
+// Ball2DSim::computeBallBallActiveSetSpatialGrid (ball2d/Ball2DSim.cpp:553-608) without the constraint objects:
+// swept boxes (restated :566-572) -> getPotentialOverlaps (reference) -> CCD per candidate (reference); counts both lists
+// and writes up to cap active pairs in the order they are found (= std::set order of the candidates).
+void ref_ball2d_detect( const uint32_t n, const double* q0, const double* q1, const double* r, uint64_t* n_candidates, uint64_t* n_active, uint32_t* active_ij, const uint64_t cap )
+{
+  std::vector<AABB> aabbs;
+  aabbs.reserve( n );
+  for( uint32_t i = 0; i < n; ++i )
+  {
+    const Array2s a{ q0[2 * i], q0[2 * i + 1] };
+    const Array2s b{ q1[2 * i], q1[2 * i + 1] };
+    aabbs.emplace_back( b.min( a ) - r[i], b.max( a ) + r[i] );
+  }
+  std::set<std::pair<unsigned,unsigned>> overlaps;
+  SpatialGridDetector::getPotentialOverlaps( aabbs, overlaps );
+  uint64_t na = 0;
+  for( const std::pair<unsigned,unsigned>& p : overlaps )
+  {
+    const unsigned i = p.first, j = p.second;
+    const std::pair<bool,scalar> hit{ CollisionDetectionUtilities::ballBallCCDCollisionHappens( Vector2s{ q0[2 * i], q0[2 * i + 1] }, Vector2s{ q1[2 * i], q1[2 * i + 1] }, r[i],
+                                                                                              Vector2s{ q0[2 * j], q0[2 * j + 1] }, Vector2s{ q1[2 * j], q1[2 * j + 1] }, r[j] ) };
+    if( hit.first )
+    {
+      if( active_ij != nullptr && na < cap ) { active_ij[2 * na] = i; active_ij[2 * na + 1] = j; }
+      ++na;
+    }
+  }
+  *n_candidates = overlaps.size();
+  *n_active = na;
+}
+
+}

@@ -1,0 +1,49 @@
+// oracle/ref_shims/ref_rb2d.cpp -- TEST INFRASTRUCTURE.  C entry points around the reference's own, unmodified
+//   rigidbody2d/SpatialGrid.cpp     (2-D AABB grid of the rigid-body sim)
+//   rigidbody2d/BoxBoxTools.cpp     (BoxBoxTools::isActive)
+//   rigidbody2d/CircleBoxTools.cpp  (CircleBoxTools::isActive)
+// compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).
+#include "rigidbody2d/SpatialGrid.h"
+#include "rigidbody2d/BoxBoxTools.h"
+#include "rigidbody2d/CircleBoxTools.h"
+
+#include <cstdint>
+
+extern "C"
+{
+
+uint64_t ref_rb2d_overlaps( const uint32_t n, const double* boxes, uint32_t* ij, const uint64_t cap )
+{
+  std::vector<AABB> aabbs;
+  aabbs.reserve( n );
+  for( uint32_t i = 0; i < n; ++i ) { aabbs.emplace_back( Array2s{ boxes[4 * i], boxes[4 * i + 1] }, Array2s{ boxes[4 * i + 2], boxes[4 * i + 3] } ); }
+  std::set<std::pair<unsigned,unsigned>> overlaps;
+  SpatialGrid::getPotentialOverlaps( aabbs, overlaps );
+  uint64_t k = 0;
+  for( const std::pair<unsigned,unsigned>& p : overlaps ) { if( k < cap ) { ij[2 * k] = p.first; ij[2 * k + 1] = p.second; } ++k; }
+  return k;
+}
+
+// returns the number of contact points (<= 2 written, 2 doubles each)
+int ref_rb2d_box_box( const double* x0, const double theta0, const double* r0, const double* x1, const double theta1, const double* r1, double* n, double* points )
+{
+  Vector2s nn;
+  nn.setZero();
+  std::vector<Vector2s> pts;
+  BoxBoxTools::isActive( Vector2s{ x0[0], x0[1] }, theta0, Vector2s{ r0[0], r0[1] }, Vector2s{ x1[0], x1[1] }, theta1, Vector2s{ r1[0], r1[1] }, nn, pts );
+  n[0] = nn.x(); n[1] = nn.y();
+  int k = 0;
+  for( const Vector2s& p : pts ) { if( k < 2 ) { points[2 * k] = p.x(); points[2 * k + 1] = p.y(); } ++k; }
+  return k;
+}
+
+int ref_rb2d_circle_box( const double* x0, const double r0, const double* x1, const double theta1, const double* r1, double* n, double* p )
+{
+  Vector2s nn, pp;
+  nn.setZero(); pp.setZero();
+  const bool hit = CircleBoxTools::isActive( Vector2s{ x0[0], x0[1] }, r0, Vector2s{ x1[0], x1[1] }, theta1, Vector2s{ r1[0], r1[1] }, nn, pp );
+  n[0] = nn.x(); n[1] = nn.y(); p[0] = pp.x(); p[1] = pp.y();
+  return hit ? 1 : 0;
+}
+
+}

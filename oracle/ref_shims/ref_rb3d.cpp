@@ -1,0 +1,48 @@
+// oracle/ref_shims/ref_rb3d.cpp -- TEST INFRASTRUCTURE.  C entry points around the reference's own, unmodified
+//   rigidbody3d/SpatialGridDetector.cpp          (3-D AABB grid)
+//   rigidbody3d/Constraints/BoxBoxUtilities.cpp  (ODE-derived box-box: BoxBoxUtilities::isActive)
+// compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).
+#include "rigidbody3d/SpatialGridDetector.h"
+#include "rigidbody3d/Constraints/BoxBoxUtilities.h"
+
+#include <cstdint>
+
+extern "C"
+{
+
+// boxes: n x [minx, miny, minz, maxx, maxy, maxz]
+uint64_t ref_rb3d_overlaps( const uint32_t n, const double* boxes, const int all_pairs, uint32_t* ij, const uint64_t cap )
+{
+  std::vector<AABB> aabbs;
+  std::vector<AABB>& v = aabbs;
+  v.resize( n ); // the 3-D AABB has no (min, max) constructor: RigidBody3DSim fills min()/max() (RigidBody3DSim.cpp:1057-1069)
+  for( uint32_t i = 0; i < n; ++i )
+  {
+    v[i].min() = Array3s{ boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2] };
+    v[i].max() = Array3s{ boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5] };
+  }
+  std::set<std::pair<unsigned,unsigned>> overlaps;
+  if( all_pairs ) { SpatialGridDetector::getPotentialOverlapsAllPairs( aabbs, overlaps ); }
+  else { SpatialGridDetector::getPotentialOverlaps( aabbs, overlaps ); }
+  uint64_t k = 0;
+  for( const std::pair<unsigned,unsigned>& p : overlaps ) { if( k < cap ) { ij[2 * k] = p.first; ij[2 * k + 1] = p.second; } ++k; }
+  return k;
+}
+
+// cm: 3 doubles, R: 9 doubles row-major, side: 3 doubles (full widths).  Returns the number of contact points (<= 8
+// written to points, 3 doubles each); n = contact normal.
+int ref_rb3d_box_box( const double* cm0, const double* R0, const double* side0, const double* cm1, const double* R1, const double* side1, double* n, double* points )
+{
+  Matrix33sr A, B;
+  for( int i = 0; i < 3; ++i ) { for( int j = 0; j < 3; ++j ) { A( i, j ) = R0[3 * i + j]; B( i, j ) = R1[3 * i + j]; } }
+  Vector3s nn;
+  nn.setZero();
+  std::vector<Vector3s> pts;
+  BoxBoxUtilities::isActive( Vector3s{ cm0[0], cm0[1], cm0[2] }, A, Vector3s{ side0[0], side0[1], side0[2] }, Vector3s{ cm1[0], cm1[1], cm1[2] }, B, Vector3s{ side1[0], side1[1], side1[2] }, nn, pts );
+  n[0] = nn.x(); n[1] = nn.y(); n[2] = nn.z();
+  int k = 0;
+  for( const Vector3s& p : pts ) { if( k < 8 ) { points[3 * k] = p.x(); points[3 * k + 1] = p.y(); points[3 * k + 2] = p.z(); } ++k; }
+  return k;
+}
+
+}

@@ -1,0 +1,194 @@
+"""CPU: the oracle's restatement against the reference's OWN source files, compiled unchanged from /root/reference against
+the Eigen stand-in in oracle/eigen_standin (oracle/Makefile.ref -> oracle/_ref/*.so, built by __graft_entry__.build() in
+the container that has the reference; the libraries travel with the snapshot).  Skipped where oracle/_ref is absent.
+
+Covered: the three broad-phase grids (ball2d/SpatialGridDetector.cpp, rigidbody3d/SpatialGridDetector.cpp,
+rigidbody2d/SpatialGrid.cpp), ball-ball CCD (scisim/CollisionDetection/CollisionDetectionUtilities.cpp), the 3-D box-box
+routine (rigidbody3d/Constraints/BoxBoxUtilities.cpp) and the 2-D box-box / circle-box routines
+(rigidbody2d/BoxBoxTools.cpp, CircleBoxTools.cpp).  Everything is compared bit for bit."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+def _load(name):
+    path = os.path.join(REFDIR, name)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/%s not built (no /root/reference in this container)" % name)
+    return C.CDLL(path)
+
+
+def _ref_pairs(fn, n, boxes, *extra):
+    fn.restype = C.c_uint64
+    cnt = int(fn(C.c_uint32(n), vp(boxes), *extra, None, C.c_uint64(0)))
+    out = np.zeros((max(cnt, 1), 2), dtype=np.uint32)
+    fn(C.c_uint32(n), vp(boxes), *extra, vp(out), C.c_uint64(cnt))
+    return out[:cnt]
+
+
+def _random_boxes(rng, n, dim, side, ext):
+    lo = rng.uniform(0.0, side, size=(n, dim))
+    hi = lo + rng.uniform(0.05 * ext, ext, size=(n, dim))
+    return np.ascontiguousarray(np.concatenate([lo, hi], axis=1))
+
+
+@pytest.mark.parametrize("n,seed", [(2, 1), (300, 2), (6000, 3)])
+def test_grid_2d_ball2d_and_rb2d(oracle, n, seed):
+    from tests import oracle_binding as ob
+    ref = _load("libref_ball2d.so")
+    ref2 = _load("libref_rb2d.so")
+    rng = np.random.default_rng(seed)
+    boxes = _random_boxes(rng, n, 2, np.sqrt(n) * 0.6, 1.0)
+    grid = _ref_pairs(ref.ref_ball2d_overlaps, n, boxes, C.c_int(0))
+    brute = _ref_pairs(ref.ref_ball2d_overlaps, n, boxes, C.c_int(1))
+    rb2d = _ref_pairs(ref2.ref_rb2d_overlaps, n, boxes)
+    assert np.array_equal(grid, brute) and np.array_equal(grid, rb2d)
+    assert np.array_equal(ob.aabb_overlaps(boxes, "grid")[0], grid)
+    assert np.array_equal(ob.aabb_overlaps(boxes, "allpairs")[0], grid)
+    assert n <= 2 or grid.shape[0] > 0
+
+
+def test_grid_2d_on_the_reference_fixtures(oracle):
+    from tests import oracle_binding as ob
+    ref = _load("libref_ball2d.so")
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "aabb_fixtures.npz"))
+    for name in ("spatial_grid_00", "spatial_grid_01", "spatial_grid_02"):
+        boxes = np.ascontiguousarray(fx[name], dtype=np.float64)
+        n = boxes.shape[0]
+        grid = _ref_pairs(ref.ref_ball2d_overlaps, n, boxes, C.c_int(0))
+        assert np.array_equal(ob.aabb_overlaps(boxes, "grid")[0], grid)
+
+
+@pytest.mark.parametrize("n,seed", [(2, 4), (500, 5), (5000, 6)])
+def test_grid_3d(oracle, n, seed):
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    rng = np.random.default_rng(seed)
+    boxes = _random_boxes(rng, n, 3, n ** (1.0 / 3.0) * 0.7, 1.0)
+    grid = _ref_pairs(ref.ref_rb3d_overlaps, n, boxes, C.c_int(0))
+    brute = _ref_pairs(ref.ref_rb3d_overlaps, n, boxes, C.c_int(1))
+    assert np.array_equal(grid, brute)
+    assert np.array_equal(ob.aabb_overlaps(boxes, "grid")[0], grid)
+    assert n <= 2 or grid.shape[0] > 0
+
+
+def test_ccd_random_and_golden(oracle):
+    ref = _load("libref_ball2d.so")
+    ref.ref_ball2d_ccd.restype = C.c_int
+    ref.ref_ball2d_ccd.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    from tests import oracle_binding as ob
+    rng = np.random.default_rng(7)
+    cases = []
+    for _ in range(20000):
+        q0a, q0b = rng.uniform(-1, 1, 2), rng.uniform(-1, 1, 2)
+        mode = rng.integers(0, 4)
+        va = rng.uniform(-3, 3, 2) if mode else np.zeros(2)
+        vb = rng.uniform(-3, 3, 2) if mode > 1 else va.copy()
+        cases.append((q0a, q0a + va, rng.uniform(0.05, 0.6), q0b, q0b + vb, rng.uniform(0.05, 0.6)))
+    for c in json.load(open(os.path.join(ROOT, "tests", "golden", "ccd_cases.json"))):
+        cases.append((np.array(c["q0a"], float), np.array(c["q1a"], float), float(c["ra"]), np.array(c["q0b"], float), np.array(c["q1b"], float), float(c["rb"])))
+    hits = 0
+    for q0a, q1a, ra, q0b, q1b, rb in cases:
+        q0a, q1a, q0b, q1b = (np.ascontiguousarray(x, dtype=np.float64) for x in (q0a, q1a, q0b, q1b))
+        cr, tr = np.zeros(3), np.zeros(1)
+        hr = ref.ref_ball2d_ccd(vp(q0a), vp(q1a), ra, vp(q0b), vp(q1b), rb, vp(cr), vp(tr))
+        co, ho, to = ob.ccd(q0a, q1a, ra, q0b, q1b, rb)
+        to = [to]
+        assert np.array_equal(cr, co), (cr, co)
+        assert bool(hr) == ho
+        if hr:
+            assert tr[0] == to[0]
+            hits += 1
+    assert 1000 < hits < len(cases) - 1000
+
+
+def test_ball2d_detection_pipeline(oracle):
+    """Swept boxes -> reference grid -> reference CCD per candidate, against the oracle's computeActiveSet."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_ball2d.so")
+    s = scenes.ball2d_random(4000, 12, nplanes=0, ndrums=0)
+    o = ob.Ball2DOracle(s)
+    q1, _ = o.flow(0, s["q"], s["v"], s["dt"])
+    want = o.active_set(s["q"], q1, "grid")
+    nc, na = C.c_uint64(0), C.c_uint64(0)
+    q0 = np.ascontiguousarray(s["q"]); r = np.ascontiguousarray(s["r"])
+    act = np.zeros((want["type"].shape[0] + 8, 2), dtype=np.uint32)
+    ref.ref_ball2d_detect(C.c_uint32(4000), vp(q0), vp(q1), vp(r), C.byref(nc), C.byref(na), vp(act), C.c_uint64(act.shape[0]))
+    assert nc.value == want["candidates"].shape[0] and na.value == want["type"].shape[0] and na.value > 100
+    assert np.array_equal(act[:na.value, 0], want["i"]) and np.array_equal(act[:na.value, 1], want["j"])
+
+
+def _rot3(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def test_box_box_3d(oracle):
+    ref = _load("libref_rb3d.so")
+    ref.ref_rb3d_box_box.restype = C.c_int
+    oracle.orc_box_box_3d.restype = C.c_int
+    rng = np.random.default_rng(9)
+    hits, multi = 0, 0
+    for k in range(6000):
+        axis_aligned = k % 5 == 0     # exercises the degenerate (parallel-edge) branches
+        R0 = np.eye(3) if axis_aligned else _rot3(rng)
+        R1 = np.eye(3) if (axis_aligned and k % 10 == 0) else _rot3(rng)
+        s0, s1 = rng.uniform(0.3, 1.5, 3), rng.uniform(0.3, 1.5, 3)
+        c0 = rng.uniform(-0.2, 0.2, 3)
+        c1 = c0 + rng.uniform(-1.3, 1.3, 3)
+        args = [np.ascontiguousarray(a, dtype=np.float64) for a in (c0, R0.ravel(), s0, c1, R1.ravel(), s1)]
+        nr, pr = np.zeros(3), np.zeros(24)
+        no, po = np.zeros(3), np.zeros(24)
+        kr = ref.ref_rb3d_box_box(*[vp(a) for a in args], vp(nr), vp(pr))
+        ko = oracle.orc_box_box_3d(*[vp(a) for a in args], vp(no), vp(po))
+        assert kr == ko, (k, kr, ko)
+        assert np.array_equal(nr, no), (k, nr, no)
+        assert np.array_equal(pr[:3 * kr], po[:3 * ko]), k
+        hits += kr > 0
+        multi += kr > 1
+    assert hits > 1500 and multi > 300
+
+
+def test_box_box_and_circle_box_2d(oracle):
+    ref = _load("libref_rb2d.so")
+    ref.ref_rb2d_box_box.restype = C.c_int
+    ref.ref_rb2d_box_box.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    ref.ref_rb2d_circle_box.restype = C.c_int
+    ref.ref_rb2d_circle_box.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    oracle.orc_box_box_2d.restype = C.c_int
+    oracle.orc_box_box_2d.argtypes = ref.ref_rb2d_box_box.argtypes
+    oracle.orc_circle_box_2d.restype = C.c_int
+    oracle.orc_circle_box_2d.argtypes = ref.ref_rb2d_circle_box.argtypes
+    rng = np.random.default_rng(10)
+    bb_hits = cb_hits = 0
+    for k in range(8000):
+        x0 = np.ascontiguousarray(rng.uniform(-0.2, 0.2, 2)); x1 = np.ascontiguousarray(x0 + rng.uniform(-1.2, 1.2, 2))
+        r0 = np.ascontiguousarray(rng.uniform(0.2, 0.8, 2)); r1 = np.ascontiguousarray(rng.uniform(0.2, 0.8, 2))
+        t0 = 0.0 if k % 7 == 0 else float(rng.uniform(-4, 4))
+        t1 = 0.0 if k % 14 == 0 else float(rng.uniform(-4, 4))
+        nr, pr, no, po = np.zeros(2), np.zeros(4), np.zeros(2), np.zeros(4)
+        kr = ref.ref_rb2d_box_box(vp(x0), t0, vp(r0), vp(x1), t1, vp(r1), vp(nr), vp(pr))
+        ko = oracle.orc_box_box_2d(vp(x0), t0, vp(r0), vp(x1), t1, vp(r1), vp(no), vp(po))
+        assert kr == ko and np.array_equal(nr, no) and np.array_equal(pr[:2 * kr], po[:2 * ko]), k
+        bb_hits += kr > 0
+        rad = float(rng.uniform(0.1, 0.7))
+        nr, pr, no, po = np.zeros(2), np.zeros(2), np.zeros(2), np.zeros(2)
+        hr = ref.ref_rb2d_circle_box(vp(x0), rad, vp(x1), t1, vp(r1), vp(nr), vp(pr))
+        ho = oracle.orc_circle_box_2d(vp(x0), rad, vp(x1), t1, vp(r1), vp(no), vp(po))
+        assert hr == ho, k
+        if hr:
+            assert np.array_equal(nr, no) and np.array_equal(pr, po), k
+            cb_hits += 1
+    assert bb_hits > 2000 and cb_hits > 2000
