@@ -224,7 +224,8 @@ template<bool DO_FLOW>
 __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ Static2D sg, const int kind, const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ v0,
                                                        const double* __restrict__ m, const double* __restrict__ r, const double gx, const double gy, const double dt,
                                                        double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts,
-                                                       const uint32_t own_first, const uint32_t own_count, const uint32_t* __restrict__ ghost_counts, long long* __restrict__ interval_enc )
+                                                       const uint32_t own_first, const uint32_t own_count, const uint32_t* __restrict__ ghost_counts, long long* __restrict__ interval_enc,
+                                                       double2* __restrict__ block_iv )
 {
   // q0, q1, r are indexed by slot ([ghosts | owned | ghosts] in slab mode); v0, m, v1 exist for owned bodies only.
   // interval_enc != nullptr (slab mode, DO_FLOW): the ghosts have not arrived yet -- only owned bodies are live, and
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
     if( threadIdx.x == 0 )
     {
       for( int w = 1; w < 8; ++w ) { ivlo = fmin( ivlo, s_iv[w][0] ); ivhi = fmax( ivhi, s_iv[w][1] ); }
+      if( block_iv != nullptr ) { block_iv[blockIdx.x] = make_double2( ivlo, ivhi ); } // lets the halo pack skip whole blocks
       if( ivlo <= ivhi )
       {
         atomicMin( &interval_enc[0], sg_ordered_from_double( ivlo ) );
@@ -422,6 +424,7 @@ struct Ball2DData
   uint32_t slab_step = 0; // tag of the current step's flags (all ranks step in lockstep)
   bool slab_prep_done = false; // this step's bounds / static counts were already produced by sg_ball2d_slab_flow
   DevBuf pack_done;            // block counter of the pack kernel's "last block raises the flag"
+  DevBuf block_iv;             // double2 per 256-slot block: [min lo.x, max hi.x] of its owned swept boxes (from the flow kernel)
   size_t first_slot() const { return 0; }
   size_t owned_slot() const { return slab ? size_t( ghost_cap ) : 0; }        // first owned slot
   uint32_t own_first() const { return slab ? ghost_cap : 0u; }                 // owned range in local indices
@@ -450,7 +453,7 @@ void sg_ball2d_release( sg_ctx* ctx )
   d->st_counts.release(); d->st_offsets.release(); d->st_partials.release(); d->st_total.release();
   d->c_type.release(); d->c_i.release(); d->c_j.release(); d->c_n.release(); d->c_p.release(); d->c_depth.release();
   d->h_totals.release(); d->h_out.release();
-  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release(); d->pack_done.release();
+  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release(); d->pack_done.release(); d->block_iv.release();
   for( int sde = 0; sde < 2; ++sde ) { if( d->peer_mb[sde] != nullptr && d->peer_ipc[sde] ) { cudaIpcCloseMemHandle( d->peer_mb[sde] ); } d->peer_mb[sde] = nullptr; }
   d->mailbox.release();
   delete d;
@@ -524,12 +527,12 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   else if( flow_kind >= 0 && !d->slab )
   {
     SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(),
-               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr, nullptr ) );
+               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr, nullptr, nullptr ) );
   }
   else
   {
     SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr,
-               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS(), nullptr ) );
+               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS(), nullptr, nullptr ) );
   }
   Ball2DIn in;
   in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS();
@@ -737,9 +740,11 @@ struct PackArgs
   bool on[2];
 };
 
+// The grid covers all slots with the flow kernel's block partition, so that kernel's per-block x-interval (block_iv)
+// tells a block whether any of its owned bodies can reach a target at all: almost every block stops there.
 template<bool EMIT>
-__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, const double2* __restrict__ q0, const double2* __restrict__ q1, const double* __restrict__ r, const uint32_t* __restrict__ gid,
-                                                            const uint32_t cap, const PackArgs args )
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, const uint32_t own_first, const uint32_t own_count, const double2* __restrict__ q0, const double2* __restrict__ q1,
+                                                            const double* __restrict__ r, const uint32_t* __restrict__ gid, const double2* __restrict__ block_iv, const uint32_t cap, const PackArgs args )
 {
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_red[8], s_nz[8];
@@ -753,9 +758,26 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, c
   }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool owned = i < n && i - own_first < own_count;
+  // can this block contribute to any target?  (block 0 always runs the emit pass: it writes the headers)
+  bool reach[2] = { false, false };
+  {
+    const double2 biv = ( block_iv != nullptr ) ? block_iv[blockIdx.x] : make_double2( -1.0e300, 1.0e300 );
+    #pragma unroll
+    for( int sd = 0; sd < 2; ++sd ) { if( args.on[sd] ) { reach[sd] = !( biv.y < args.iv[sd][0] ) && !( args.iv[sd][1] < biv.x ); } }
+  }
+  if( !reach[0] && !reach[1] )
+  {
+    if( !EMIT )
+    {
+      if( threadIdx.x < 2 && args.on[threadIdx.x] ) { args.block_counts[threadIdx.x][blockIdx.x] = 0u; }
+      return;
+    }
+    if( blockIdx.x != 0u ) { return; }
+  }
   double2 a = make_double2( 0.0, 0.0 ), b = a;
   double rad = 0.0, lo = 0.0, hi = 0.0;
-  if( i < n )
+  if( owned )
   {
     a = __ldg( &q0[i] ); b = __ldg( &q1[i] ); rad = __ldg( &r[i] );
     swept_x( a, b, rad, lo, hi );
@@ -769,7 +791,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, c
     GhostRec* out = args.out[sd];
     // first read of the interval in this launch comes after the wait + barrier above: L1 cannot hold a stale line
     const double ilo = args.iv[sd][0], ihi = args.iv[sd][1];
-    const bool sel = i < n && !( hi < ilo ) && !( ihi < lo );
+    const bool sel = owned && !( hi < ilo ) && !( ihi < lo );
     const unsigned bal = __ballot_sync( 0xffffffffu, sel );
     if( lane == 0 ) { s_warp[warp] = __popc( bal ); }
     __syncthreads();
@@ -848,17 +870,30 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack_total( const uint32_
   if( threadIdx.x == 0 ) { uint32_t sum = 0u; for( int w = 0; w < 8; ++w ) { sum += s_red[w]; } *total = sum; }
 }
 
-// Ghost records into the slots on `side` of the owned block; their swept boxes join this step's bounds reduction
-// (the owned bodies' share was reduced by the flow kernel).
-__global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t cap, const int side, const GhostRec* in, double2* __restrict__ q0, double2* __restrict__ q1, double* __restrict__ r,
-                                                              uint32_t* __restrict__ gid, uint32_t* __restrict__ ghost_counts, BoundsAccum* __restrict__ acc, const SlabSync sync )
+// Ghost records into the slots either side of the owned block (both sides in one launch: the first half of the grid
+// serves side 0, the second half side 1); their swept boxes join this step's bounds reduction (the owned bodies'
+// share was reduced by the flow kernel).
+struct UnpackArgs
 {
+  const GhostRec* in[2];
+  uint32_t slot[2];   // first ghost slot of the side
+  SlabSync sync[2];
+  bool on[2];
+};
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t cap, const uint32_t blocks_per_side, const UnpackArgs args, double2* __restrict__ q0, double2* __restrict__ q1, double* __restrict__ r,
+                                                              uint32_t* __restrict__ gid, uint32_t* __restrict__ ghost_counts, BoundsAccum* __restrict__ acc )
+{
+  const int side = ( blockIdx.x >= blocks_per_side ) ? 1 : 0;
+  if( !args.on[side] ) { return; }
+  const SlabSync sync = args.sync[side];
+  const GhostRec* in = args.in[side];
   if( sync.wait_flag != nullptr )
   {
     if( threadIdx.x == 0 ) { slab_wait_flag( sync.wait_flag, sync.step, sync.err ); }
     __syncthreads();
   }
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t blk = blockIdx.x - uint32_t( side ) * blocks_per_side;
+  const uint32_t k = blk * blockDim.x + threadIdx.x;
   const uint32_t sent = *reinterpret_cast<const volatile uint32_t*>( &in[0].gid );
   const uint32_t count = sent < cap ? sent : cap;
   if( k == 0u )
@@ -866,7 +901,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t ca
     ghost_counts[side] = count;
     if( sent > cap ) { ghost_counts[2] = 1u; } // more ghosts than reserved slots: reported by detect
   }
-  if( blockIdx.x * blockDim.x >= count ) { return; } // whole block past the list
+  if( blk * blockDim.x >= count ) { return; } // whole block past the list
   double mn[2] = { __longlong_as_double( 0x7ff0000000000000LL ), __longlong_as_double( 0x7ff0000000000000LL ) };
   double mx[2] = { __longlong_as_double( 0xfff0000000000000LL ), __longlong_as_double( 0xfff0000000000000LL ) };
   double ext = 0.0;
@@ -876,10 +911,11 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t ca
     union { GhostRec g; int4 v[3]; } u;
     u.v[0] = src[0]; u.v[1] = src[1]; u.v[2] = src[2];
     const GhostRec& g = u.g;
-    q0[k] = make_double2( g.q0x, g.q0y );
-    q1[k] = make_double2( g.q1x, g.q1y );
-    r[k] = g.r;
-    gid[k] = g.gid;
+    const uint32_t dst = args.slot[side] + k;
+    q0[dst] = make_double2( g.q0x, g.q0y );
+    q1[dst] = make_double2( g.q1x, g.q1y );
+    r[dst] = g.r;
+    gid[dst] = g.gid;
     double lo[2], hi[2];
     lo[0] = fmin( g.q1x, g.q0x ) - g.r; lo[1] = fmin( g.q1y, g.q0y ) - g.r;
     hi[0] = fmax( g.q1x, g.q0x ) + g.r; hi[1] = fmax( g.q1y, g.q0y ) + g.r;
@@ -1127,10 +1163,11 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
   rc = ball2d_static_scratch( ctx, d );
   if( rc != SG_OK ) { return rc; }
   const uint32_t n = d->n;
+  SG_CUDA( ctx, d->block_iv.ensure( size_t( sg_div_up( n > 0 ? n : 1, 256 ) ) * 16 + 16 ) );
   SG_LAUNCH( ctx, "slab_flow_prep", double( d->n_owned ) * 80.0,
              k_ball2d_prep<true><<<sg_div_up( n > 0 ? n : 1, 256 ), 256, 0, ctx->stream>>>( d->sg, map_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(), d->R(), d->g[0], d->g[1], dt, d->Q1(),
                                                                                        d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), nullptr,
-                                                                                       d->interval_enc.as<long long>() );
+                                                                                       d->interval_enc.as<long long>(), d->block_iv.as<double2>() );
              if( d->mailbox.ptr == nullptr ) { k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev ); }
              else
              {
@@ -1145,10 +1182,11 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
 // One or two targets (sides) per call: target t packs against interval_dev[t] into send_dev[t] (nullptr: count only)
 static int ball2d_slab_pack_impl( sg_ctx* ctx, Ball2DData* d, const int ntargets, const double* const* interval_dev, void* const* send_dev, const uint32_t cap, uint32_t* const* count_dev, const SlabSync* sync )
 {
-  const uint32_t n = d->n_owned;
+  const uint32_t n = d->n; // all slots: same block partition as the flow kernel
   const unsigned nblk = sg_div_up( n > 0 ? n : 1, 256 );
   SG_CUDA( ctx, d->pack_counts.ensure( 2 * ( size_t( nblk ) * 4 + 4 ) ) );
-  const size_t o = d->owned_slot();
+  // block intervals are valid when this step's flow went through sg_ball2d_slab_flow
+  const double2* biv = ( d->slab_prep_done && d->block_iv.ptr != nullptr ) ? d->block_iv.as<double2>() : nullptr;
   PackArgs count_args, emit_args;
   bool any_emit = false;
   for( int t = 0; t < 2; ++t )
@@ -1164,10 +1202,12 @@ static int ball2d_slab_pack_impl( sg_ctx* ctx, Ball2DData* d, const int ntargets
     emit_args.sync[t] = on ? sync[t] : none; emit_args.sync[t].wait_flag = nullptr;
     any_emit = any_emit || emit_args.on[t];
   }
-  SG_LAUNCH( ctx, "slab_pack_count", double( n ) * 40.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o, cap, count_args ) );
+  SG_LAUNCH( ctx, "slab_pack_count", double( nblk ) * 16.0, k_ball2d_slab_pack<false><<<nblk, 256, 0, ctx->stream>>>( n, d->own_first(), d->own_count(), d->q0.as<double2>(), d->q1.as<double2>(), d->r.as<double>(),
+             d->gid.as<uint32_t>(), biv, cap, count_args ) );
   if( any_emit )
   {
-    SG_LAUNCH( ctx, "slab_pack_emit", double( n ) * 40.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->q0.as<double2>() + o, d->q1.as<double2>() + o, d->r.as<double>() + o, d->gid.as<uint32_t>() + o, cap, emit_args ) );
+    SG_LAUNCH( ctx, "slab_pack_emit", double( nblk ) * 16.0, k_ball2d_slab_pack<true><<<nblk, 256, 0, ctx->stream>>>( n, d->own_first(), d->own_count(), d->q0.as<double2>(), d->q1.as<double2>(), d->r.as<double>(),
+               d->gid.as<uint32_t>(), biv, cap, emit_args ) );
   }
   for( int t = 0; t < ntargets; ++t )
   {
@@ -1192,15 +1232,24 @@ int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev
   return ball2d_slab_pack_impl( ctx, d, 1, ivs, sends, cap, counts, &none );
 }
 
-static int ball2d_slab_unpack_impl( sg_ctx* ctx, Ball2DData* d, const int side, const void* recv_dev, const SlabSync& sync )
+// recv_dev[s] != nullptr: unpack side s (both sides go in one launch)
+static int ball2d_slab_unpack_impl( sg_ctx* ctx, Ball2DData* d, const void* const* recv_dev, const SlabSync* sync )
 {
-  // side 0: ghosts with smaller global indices fill slots [0, count); side 1: the slots right after the owned block
-  const size_t slot = ( side == 0 ) ? 0 : size_t( d->ghost_cap ) + d->n_owned;
   const uint32_t cap = d->ghost_cap;
+  const unsigned bps = sg_div_up( cap > 0 ? cap : 1, 256 );
+  UnpackArgs args;
+  for( int sde = 0; sde < 2; ++sde )
+  {
+    args.on[sde] = recv_dev[sde] != nullptr;
+    args.in[sde] = static_cast<const GhostRec*>( recv_dev[sde] );
+    // side 0: ghosts with smaller global indices fill slots [0, count); side 1: the slots right after the owned block
+    args.slot[sde] = ( sde == 0 ) ? 0u : d->ghost_cap + d->n_owned;
+    args.sync[sde] = sync[sde];
+  }
   // the ghosts' boxes join the bounds the flow kernel started (when this step went through sg_ball2d_slab_flow)
   BoundsAccum* acc = ( d->slab_prep_done && d->bp.bounds.ptr != nullptr ) ? d->bp.bounds_cur() : nullptr;
-  SG_LAUNCH( ctx, "slab_unpack", double( cap ) * 4.0, k_ball2d_slab_unpack<<<sg_div_up( cap > 0 ? cap : 1, 256 ), 256, 0, ctx->stream>>>( cap, side, static_cast<const GhostRec*>( recv_dev ), d->q0.as<double2>() + slot,
-             d->q1.as<double2>() + slot, d->r.as<double>() + slot, d->gid.as<uint32_t>() + slot, d->ghost_counts.as<uint32_t>(), acc, sync ) );
+  SG_LAUNCH( ctx, "slab_unpack", double( cap ) * 4.0, k_ball2d_slab_unpack<<<2 * bps, 256, 0, ctx->stream>>>( cap, bps, args, d->q0.as<double2>(), d->q1.as<double2>(), d->r.as<double>(), d->gid.as<uint32_t>(),
+             d->ghost_counts.as<uint32_t>(), acc ) );
   return SG_OK;
 }
 
@@ -1211,7 +1260,9 @@ int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev )
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_unpack: call sg_ball2d_slab_init first" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   SlabSync none; none.wait_flag = nullptr; none.post_flag = nullptr; none.done_ctr = nullptr; none.err = nullptr; none.step = 0u;
-  return ball2d_slab_unpack_impl( ctx, d, side, recv_dev, none );
+  const void* recv[2] = { side == 0 ? recv_dev : nullptr, side == 1 ? recv_dev : nullptr };
+  const SlabSync syncs[2] = { none, none };
+  return ball2d_slab_unpack_impl( ctx, d, recv, syncs );
 }
 
 int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64 )
@@ -1310,12 +1361,20 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
   }
   if( phase == 0 || phase == 2 )
   {
+    const void* recv[2] = { nullptr, nullptr };
+    SlabSync syncs[2];
+    bool any = false;
     for( int side = 0; side < 2; ++side )
     {
+      syncs[side].wait_flag = nullptr; syncs[side].post_flag = nullptr; syncs[side].done_ctr = nullptr; syncs[side].err = &mine->err; syncs[side].step = step;
       if( d->peer_mb[side] == nullptr ) { continue; }
-      SlabSync sync;
-      sync.wait_flag = &mine->halo_flag[side]; sync.post_flag = nullptr; sync.done_ctr = nullptr; sync.err = &mine->err; sync.step = step;
-      const int rc = ball2d_slab_unpack_impl( ctx, d, side, slab_mailbox_halo( mine, side, d->ghost_cap ), sync );
+      recv[side] = slab_mailbox_halo( mine, side, d->ghost_cap );
+      syncs[side].wait_flag = &mine->halo_flag[side];
+      any = true;
+    }
+    if( any )
+    {
+      const int rc = ball2d_slab_unpack_impl( ctx, d, recv, syncs );
       if( rc != SG_OK ) { return rc; }
     }
   }
