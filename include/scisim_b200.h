@@ -69,6 +69,9 @@ extern "C" {
 #define SG_GEO_SPHERE 1
 #define SG_GEO_STAPLE 2 /* not supported (not on the north-star path) */
 #define SG_GEO_MESH 3
+/* rigidbody2d geometry types: values of RigidBody2DGeometryType (rigidbody2d/RigidBody2DGeometry.h) */
+#define SG_GEO2D_CIRCLE 0
+#define SG_GEO2D_BOX 1
 
 /* which optional arrays sg_*_active_set copies back to the host */
 #define SG_OUT_NORMALS 1u
@@ -209,6 +212,7 @@ int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
  * q = v-layout [x, y, theta] per body (rigidbody2d/RigidBody2DState.h). M = the 3N diagonal of the mass matrix
  * (m, m, I per body) exactly as FlowableSystem::M().valuePtr() holds it; Minv = 1.0 / M (RigidBody2DState.cpp:31-43).
  * Plane normals are used as given (RigidBody2DStaticPlane does not normalise). */
+/* type: SG_GEO2D_CIRCLE (r) or SG_GEO2D_BOX (half-widths) per geometry entry */
 int sg_rb2d_set_geometry( sg_ctx* ctx, uint32_t ngeo, const uint32_t* type, const double* r /* ngeo */, const double* half /* 2 ngeo */ );
 int sg_rb2d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, const uint8_t* fixed, const double* M /* 3n */ );
 int sg_rb2d_set_gravity( sg_ctx* ctx, const double* g /* 2 */ );

@@ -119,12 +119,12 @@ void PairImpulseCache::clear()
 
 bool PairImpulseCache::empty() const
 {
-  return m_tables[0].keys.empty() && m_tables[1].keys.empty() && m_tables[2].keys.empty();
+  return m_tables[0].keys.empty() && m_tables[1].keys.empty() && m_tables[2].keys.empty() && m_tables[3].keys.empty();
 }
 
 void PairImpulseCache::cacheConstraint( const int kind, const unsigned a, const unsigned b, const VectorXs& r )
 {
-  if( kind < 0 || kind > 2 )
+  if( kind < 0 || kind > 3 )
   {
     std::cerr << "constraint kind " << kind << " not supported in PairImpulseCache::cacheConstraint. Exiting." << std::endl;
     std::exit( EXIT_FAILURE );
@@ -139,7 +139,7 @@ void PairImpulseCache::cacheConstraint( const int kind, const unsigned a, const 
 
 void PairImpulseCache::getCachedConstraint( const int kind, const unsigned a, const unsigned b, VectorXs& r ) const
 {
-  if( kind < 0 || kind > 2 )
+  if( kind < 0 || kind > 3 )
   {
     std::cerr << "constraint kind " << kind << " not supported in PairImpulseCache::getCachedConstraint. Exiting." << std::endl;
     std::exit( EXIT_FAILURE );
@@ -156,4 +156,180 @@ void PairImpulseCache::getCachedConstraint( const int kind, const unsigned a, co
   }
   // If the constraint was not found set to a default force of 0 (ball2d/ConstraintCache.cpp:122)
   r.setZero();
+}
+
+// ---- rigidbody3d ---------------------------------------------------------------------------------------------------
+GpuRigidBody3DBackend::GpuRigidBody3DBackend( const int device )
+: m_ctx( nullptr )
+, m_nbodies( 0 )
+{
+  const int rc = sg_create( &m_ctx, device );
+  if( rc != SG_OK )
+  {
+    std::cerr << "GpuRigidBody3DBackend: " << sg_last_error( nullptr ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+GpuRigidBody3DBackend::~GpuRigidBody3DBackend() { sg_destroy( m_ctx ); }
+
+void GpuRigidBody3DBackend::check( const int rc, const char* what ) const
+{
+  if( rc != SG_OK )
+  {
+    // includes SG_ERR_UNSUPPORTED: the pairings for which RigidBody3DSim::dispatchNarrowPhaseCollision prints and
+    // exits (RigidBody3DSim.cpp:905-961)
+    std::cerr << what << ": " << sg_last_error( m_ctx ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+void GpuRigidBody3DBackend::setGeometry( const std::vector<uint32_t>& type, const std::vector<double>& r, const std::vector<double>& half_widths, const std::vector<uint32_t>& mesh )
+{
+  check( sg_rb3d_set_geometry( m_ctx, static_cast<uint32_t>( type.size() ), type.data(), r.data(), half_widths.data(), mesh.data() ), "sg_rb3d_set_geometry" );
+}
+
+uint32_t GpuRigidBody3DBackend::addMesh( const std::vector<double>& verts, const std::vector<double>& samples, const std::vector<double>& hull, const double cell_delta[3], const uint32_t dims[3],
+                                         const double origin[3], const std::vector<double>& sdf )
+{
+  uint32_t index = 0;
+  check( sg_rb3d_add_mesh( m_ctx, static_cast<uint32_t>( verts.size() / 3 ), verts.data(), static_cast<uint32_t>( samples.size() / 3 ), samples.data(), static_cast<uint32_t>( hull.size() / 3 ), hull.data(),
+                           cell_delta, dims, origin, sdf.data(), &index ), "sg_rb3d_add_mesh" );
+  return index;
+}
+
+void GpuRigidBody3DBackend::setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& m, const VectorXs& I0 )
+{
+  m_nbodies = static_cast<unsigned>( geo_of_body.size() );
+  check( sg_rb3d_set_bodies( m_ctx, m_nbodies, geo_of_body.data(), fixed.data(), m.data(), I0.data() ), "sg_rb3d_set_bodies" );
+}
+
+void GpuRigidBody3DBackend::setGravity( const double gx, const double gy, const double gz )
+{
+  const double g[3] = { gx, gy, gz };
+  check( sg_rb3d_set_gravity( m_ctx, g ), "sg_rb3d_set_gravity" );
+}
+
+void GpuRigidBody3DBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n )
+{
+  check( sg_rb3d_set_planes( m_ctx, static_cast<uint32_t>( x.size() / 3 ), x.data(), n.data() ), "sg_rb3d_set_planes" );
+}
+
+void GpuRigidBody3DBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  if( q1.size() != q0.size() ) { q1.resize( q0.size() ); }
+  if( v1.size() != v0.size() ) { v1.resize( v0.size() ); }
+  check( sg_rb3d_flow( m_ctx, map_kind, q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_rb3d_flow" );
+}
+
+void GpuRigidBody3DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates )
+{
+  sg_contacts c;
+  check( sg_rb3d_active_set( m_ctx, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS, &c ), "sg_rb3d_active_set" );
+  contacts.resize( c.n_active );
+  for( uint64_t k = 0; k < c.n_active; ++k )
+  {
+    GpuContact3D& o = contacts[k];
+    o.type = c.type[k]; o.i = c.i[k]; o.j = c.j[k]; o.aux = ( c.aux != nullptr ) ? c.aux[k] : 0u;
+    for( int a = 0; a < 3; ++a ) { o.n[a] = c.n[3 * k + a]; o.p[a] = c.p[3 * k + a]; }
+    o.depth = c.depth[k];
+  }
+  if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
+}
+
+void GpuRigidBody3DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps )
+{
+  sg_pairs p;
+  check( sg_candidate_pairs( m_ctx, 3, static_cast<uint32_t>( aabbs.size() / 6 ), aabbs.data(), &p ), "sg_candidate_pairs" );
+  overlaps.reserve( overlaps.size() + p.n );
+  for( uint64_t k = 0; k < p.n; ++k ) { overlaps.emplace_back( p.ij[2 * k], p.ij[2 * k + 1] ); }
+}
+
+void GpuSplitHamMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.flow( SG_MAP_SPLIT_HAM, q0, v0, dt, q1, v1 );
+}
+
+void GpuDMVMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.flow( SG_MAP_DMV, q0, v0, dt, q1, v1 );
+}
+
+// ---- rigidbody2d ---------------------------------------------------------------------------------------------------
+GpuRigidBody2DBackend::GpuRigidBody2DBackend( const int device )
+: m_ctx( nullptr )
+, m_nbodies( 0 )
+{
+  const int rc = sg_create( &m_ctx, device );
+  if( rc != SG_OK )
+  {
+    std::cerr << "GpuRigidBody2DBackend: " << sg_last_error( nullptr ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+GpuRigidBody2DBackend::~GpuRigidBody2DBackend() { sg_destroy( m_ctx ); }
+
+void GpuRigidBody2DBackend::check( const int rc, const char* what ) const
+{
+  if( rc != SG_OK )
+  {
+    std::cerr << what << ": " << sg_last_error( m_ctx ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+void GpuRigidBody2DBackend::setGeometry( const std::vector<uint32_t>& type, const std::vector<double>& r, const std::vector<double>& half_widths )
+{
+  check( sg_rb2d_set_geometry( m_ctx, static_cast<uint32_t>( type.size() ), type.data(), r.data(), half_widths.data() ), "sg_rb2d_set_geometry" );
+}
+
+void GpuRigidBody2DBackend::setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& M )
+{
+  m_nbodies = static_cast<unsigned>( geo_of_body.size() );
+  check( sg_rb2d_set_bodies( m_ctx, m_nbodies, geo_of_body.data(), fixed.data(), M.data() ), "sg_rb2d_set_bodies" );
+}
+
+void GpuRigidBody2DBackend::setGravity( const double gx, const double gy )
+{
+  const double g[2] = { gx, gy };
+  check( sg_rb2d_set_gravity( m_ctx, g ), "sg_rb2d_set_gravity" );
+}
+
+void GpuRigidBody2DBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n )
+{
+  check( sg_rb2d_set_planes( m_ctx, static_cast<uint32_t>( x.size() / 2 ), x.data(), n.data() ), "sg_rb2d_set_planes" );
+}
+
+void GpuRigidBody2DBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  if( q1.size() != q0.size() ) { q1.resize( q0.size() ); }
+  if( v1.size() != v0.size() ) { v1.resize( v0.size() ); }
+  check( sg_rb2d_flow( m_ctx, map_kind, q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_rb2d_flow" );
+}
+
+void GpuRigidBody2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates )
+{
+  sg_contacts c;
+  check( sg_rb2d_active_set( m_ctx, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS, &c ), "sg_rb2d_active_set" );
+  contacts.resize( c.n_active );
+  for( uint64_t k = 0; k < c.n_active; ++k )
+  {
+    GpuContact2D& o = contacts[k];
+    o.type = c.type[k]; o.i = c.i[k]; o.j = c.j[k];
+    o.n[0] = c.n[2 * k]; o.n[1] = c.n[2 * k + 1];
+    o.p[0] = c.p[2 * k]; o.p[1] = c.p[2 * k + 1];
+    o.depth = c.depth[k];
+  }
+  if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
+}
+
+void GpuRB2DSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.flow( SG_MAP_SYMPLECTIC_EULER, q0, v0, dt, q1, v1 );
+}
+
+void GpuRB2DVerletMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.flow( SG_MAP_VERLET, q0, v0, dt, q1, v1 );
 }

@@ -1,11 +1,15 @@
 // gpu_backend.h -- C++14 host shim over the C ABI (include/scisim_b200.h): the classes a SCISim maintainer links in so
-// that Ball2DSim / RigidBody3DSim run their unconstrained flow and active-set computation on the GPU.
+// that Ball2DSim / RigidBody2DSim / RigidBody3DSim run their unconstrained flow and active-set computation on the GPU
+// (INTEGRATION.md).
 //
 //   GpuBall2DBackend        owns the sg_ctx; static scene data in, contact records out (reference order)
 //   GpuSymplecticEulerMap,
 //   GpuVerletMap            UnconstrainedMap implementations registered beside ball2d's own maps
 //                           (ball2d/Ball2DUtilities.cpp:37, ball2dutils/Ball2DSceneParser.cpp:624-631)
-//   PairImpulseCache        flat sorted replacement for ball2d/ConstraintCache.{h,cpp} (std::map keyed by pair)
+//   PairImpulseCache        flat sorted replacement for the three ConstraintCache classes (std::map keyed by pair)
+//   GpuRigidBody3DBackend,  the same for rigidbody3d (SplitHam / DMV maps; spheres, boxes, meshes, planes) and
+//   GpuRigidBody2DBackend   rigidbody2d (symplectic Euler / Verlet; circles, boxes, planes)
+//   GpuSplitHamMap, GpuDMVMap, GpuRB2DSymplecticEulerMap, GpuRB2DVerletMap   their UnconstrainedMap faces
 //
 // Error convention of the reference: print to std::cerr and std::exit( EXIT_FAILURE ).
 #ifndef SCISIM_B200_GPU_BACKEND_H
@@ -91,7 +95,11 @@ class PairImpulseCache final
 public:
   void clear();
   bool empty() const;
-  // kind: 0 ball-ball (i,j), 1 plane-ball (plane, ball), 2 drum-ball (drum, ball) -- the three maps of the reference
+  // kind selects one of the reference's keyed maps:
+  //   ball2d       0 ball-ball (i,j)      1 plane-ball (plane, ball)    2 drum-ball (drum, ball)      (ball2d/ConstraintCache.cpp:20-122)
+  //   rigidbody3d  0 sphere-sphere (i,j)  1 plane-sphere (plane, body)  2 cylinder-sphere (cyl, body)  3 kinematic sphere-sphere
+  //                (rigidbody3d/ConstraintCache.cpp:14-72 -- like the reference, only sphere constraints can be cached)
+  //   rigidbody2d  0 circle-circle (i,j)  1 plane-circle (plane, body)  3 kinematic circle-circle
   void cacheConstraint( const int kind, const unsigned a, const unsigned b, const VectorXs& r );
   void getCachedConstraint( const int kind, const unsigned a, const unsigned b, VectorXs& r ) const;
 private:
@@ -103,7 +111,126 @@ private:
     bool sorted = true;
     void sortIfNeeded();
   };
-  mutable Table m_tables[3];
+  mutable Table m_tables[4];
+};
+
+// ---- rigidbody3d ---------------------------------------------------------------------------------------------------
+// One entry per Constraint RigidBody3DSim::computeActiveSet would emplace_back (RigidBody3DSim.cpp:250-262), same order
+struct GpuContact3D
+{
+  uint32_t type; // SG_SPHERE_SPHERE ... SG_PLANE_BODY (constructor table in INTEGRATION.md section 3)
+  uint32_t i;    // (first) body
+  uint32_t j;    // second body / plane
+  uint32_t aux;  // box corner / convex-hull vertex number for plane-box / plane-body
+  double n[3];
+  double p[3];
+  double depth;  // NaN where the reference's constraint has no penetrationDepth override
+};
+
+class GpuRigidBody3DBackend final
+{
+public:
+  explicit GpuRigidBody3DBackend( const int device = 0 );
+  ~GpuRigidBody3DBackend();
+  GpuRigidBody3DBackend( const GpuRigidBody3DBackend& ) = delete;
+  GpuRigidBody3DBackend& operator=( const GpuRigidBody3DBackend& ) = delete;
+
+  // RigidBody3DState::geometry(): per entry its type (SG_GEO_BOX / SG_GEO_SPHERE / SG_GEO_MESH), sphere radius, box
+  // half-widths (3 per entry) and, for meshes, the index returned by addMesh
+  void setGeometry( const std::vector<uint32_t>& type, const std::vector<double>& r, const std::vector<double>& half_widths, const std::vector<uint32_t>& mesh );
+  // RigidBodyTriangleMesh members: vertices, surface samples, convex-hull vertices (3 x n, column major as stored by the
+  // reference), signed-distance grid (cell_delta, dimensions, origin, values with x fastest)
+  uint32_t addMesh( const std::vector<double>& verts, const std::vector<double>& samples, const std::vector<double>& hull, const double cell_delta[3], const uint32_t dims[3],
+                    const double origin[3], const std::vector<double>& sdf );
+  // per body: geometry index, isKinematicallyScripted, total mass and body-frame inertia (the diagonals of M0)
+  void setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& m, const VectorXs& I0 );
+  void setGravity( const double gx, const double gy, const double gz );
+  void setPlanes( const std::vector<double>& x, const std::vector<double>& n );
+
+  void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
+  // false + message on std::cerr where the reference would print and exit (unsupported geometry pairing): the caller exits
+  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates = nullptr );
+  // rigidbody3d/SpatialGridDetector.h:37 on caller-built boxes [minx,miny,minz,maxx,maxy,maxz]
+  void getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps );
+
+  sg_ctx* context() { return m_ctx; }
+
+private:
+  void check( const int rc, const char* what ) const;
+  sg_ctx* m_ctx;
+  unsigned m_nbodies;
+};
+
+class GpuSplitHamMap final : public UnconstrainedMap
+{
+public:
+  explicit GpuSplitHamMap( GpuRigidBody3DBackend& backend ) : m_backend( backend ) {}
+  virtual void flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 ) override;
+  virtual std::string name() const override { return "split_ham"; }
+  virtual void serialize( std::ostream& ) const override {}
+private:
+  GpuRigidBody3DBackend& m_backend;
+};
+
+class GpuDMVMap final : public UnconstrainedMap
+{
+public:
+  explicit GpuDMVMap( GpuRigidBody3DBackend& backend ) : m_backend( backend ) {}
+  virtual void flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 ) override;
+  virtual std::string name() const override { return "dmv"; }
+  virtual void serialize( std::ostream& ) const override {}
+private:
+  GpuRigidBody3DBackend& m_backend;
+};
+
+// ---- rigidbody2d ---------------------------------------------------------------------------------------------------
+class GpuRigidBody2DBackend final
+{
+public:
+  explicit GpuRigidBody2DBackend( const int device = 0 );
+  ~GpuRigidBody2DBackend();
+  GpuRigidBody2DBackend( const GpuRigidBody2DBackend& ) = delete;
+  GpuRigidBody2DBackend& operator=( const GpuRigidBody2DBackend& ) = delete;
+
+  // RigidBody2DState::geometry(): type (SG_GEO2D_CIRCLE / SG_GEO2D_BOX), circle radius, box half-widths (2 per entry)
+  void setGeometry( const std::vector<uint32_t>& type, const std::vector<double>& r, const std::vector<double>& half_widths );
+  // geometry index, fixed flag and the 3N diagonal of M() = [m, m, I] per body
+  void setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& M );
+  void setGravity( const double gx, const double gy );
+  void setPlanes( const std::vector<double>& x, const std::vector<double>& n );
+
+  void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
+  // contacts use GpuContact2D with the rigidbody2d type codes (SG_CIRCLE_CIRCLE ... SG_PLANE_BODY_2D)
+  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr );
+
+  sg_ctx* context() { return m_ctx; }
+
+private:
+  void check( const int rc, const char* what ) const;
+  sg_ctx* m_ctx;
+  unsigned m_nbodies;
+};
+
+class GpuRB2DSymplecticEulerMap final : public UnconstrainedMap
+{
+public:
+  explicit GpuRB2DSymplecticEulerMap( GpuRigidBody2DBackend& backend ) : m_backend( backend ) {}
+  virtual void flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 ) override;
+  virtual std::string name() const override { return "symplectic_euler"; }
+  virtual void serialize( std::ostream& ) const override {}
+private:
+  GpuRigidBody2DBackend& m_backend;
+};
+
+class GpuRB2DVerletMap final : public UnconstrainedMap
+{
+public:
+  explicit GpuRB2DVerletMap( GpuRigidBody2DBackend& backend ) : m_backend( backend ) {}
+  virtual void flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 ) override;
+  virtual std::string name() const override { return "verlet"; }
+  virtual void serialize( std::ostream& ) const override {}
+private:
+  GpuRigidBody2DBackend& m_backend;
 };
 
 #endif

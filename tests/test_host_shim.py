@@ -22,7 +22,10 @@ def test_host_shim_builds_and_links():
     _build()
     assert os.path.exists(os.path.join(HOST, "libscisim_b200_host.so")) and os.path.exists(os.path.join(HOST, "example_ball2d"))
     syms = subprocess.run(["nm", "-DC", os.path.join(HOST, "libscisim_b200_host.so")], stdout=subprocess.PIPE, text=True).stdout
-    for name in ("GpuBall2DBackend::computeActiveSet", "GpuSymplecticEulerMap::flow", "GpuVerletMap::flow", "PairImpulseCache::getCachedConstraint"):
+    assert os.path.exists(os.path.join(HOST, "example_rigidbody"))
+    for name in ("GpuBall2DBackend::computeActiveSet", "GpuSymplecticEulerMap::flow", "GpuVerletMap::flow", "PairImpulseCache::getCachedConstraint",
+                 "GpuRigidBody3DBackend::computeActiveSet", "GpuRigidBody3DBackend::addMesh", "GpuSplitHamMap::flow", "GpuDMVMap::flow",
+                 "GpuRigidBody2DBackend::computeActiveSet", "GpuRB2DSymplecticEulerMap::flow", "GpuRB2DVerletMap::flow"):
         assert name in syms, name
 
 
@@ -47,3 +50,60 @@ def test_host_shim_example_matches_python_path(gpu_ctx):
     assert int(vals["ball_ball"]) == a.n_body_body and int(vals["plane"]) == a.n_plane
     assert int(vals["cache_hits"]) == a.n_body_body and float(vals["miss_value"]) == 0.0
     assert float(vals["v1y"]) == v1[1] and float(vals["q1y0"]) == q1[1]
+
+
+@pytest.mark.gpu
+def test_host_shim_rigidbody_example_matches_python_path(gpu_ctx):
+    """rigidbody3d (spheres + boxes, DMV) and rigidbody2d (circles + rotated boxes, symplectic Euler) through the C++ shim
+    against the Python mirror on identically generated scenes."""
+    import scisim_b200 as sb
+    _build()
+    nx, ny, nz = 7, 5, 4
+    out = subprocess.run([os.path.join(HOST, "example_rigidbody"), str(nx), str(ny), str(nz)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True).stdout
+    lines = {l.split()[0]: dict(re.findall(r"(\w+)=([-0-9.e+]+)", l)) for l in out.strip().splitlines()}
+    # ---- rigidbody3d
+    ns = nx * ny * nz
+    n = 2 * ns
+    b = np.arange(n)
+    k = b % ns
+    box = b >= ns
+    s = np.where(box, 0.95, 0.99)
+    x = np.empty((n, 3))
+    x[:, 0] = np.where(box, 100.0, 0.0) + s * (k % nx) + 0.001 * np.array([math.sin(12.9898 * i) for i in b])
+    x[:, 1] = s * ((k // nx) % ny) + 0.001 * np.array([math.cos(78.233 * i) for i in b])
+    x[:, 2] = s * (k // (nx * ny)) + 0.001 * np.array([math.sin(37.719 * i) for i in b])
+    q0 = np.concatenate([x.ravel(), np.tile(np.eye(3).ravel(), n)])
+    v0 = np.zeros(6 * n)
+    st = sb.RigidBody3DState([1, 0], [0.5, 0.0], [[0, 0, 0], [0.5, 0.5, 0.5]], [0, 0], [], box.astype(np.uint32), np.zeros(n, np.uint8), np.ones(n), np.full((n, 3), 0.1),
+                             (0.0, -9.81, 0.0), [[0.0, -0.5, 0.0]], [[0.0, 1.0, 0.0]])
+    sim = sb.RigidBody3DSim(st, ctx=gpu_ctx)
+    q1, v1 = sb.DMVMap().flow(q0, v0, sim, 1, 1.0e-3)
+    a = sim.computeActiveSet(q0, q1)
+    v = lines["rb3d"]
+    assert int(v["n"]) == n and int(v["candidates"]) == a.n_candidates
+    assert int(v["sphere_sphere"]) == int((a.type == 10).sum()) > 0 and int(v["body_body"]) == int((a.type == 12).sum()) > 0
+    assert int(v["plane_sphere"]) == int((a.type == 14).sum()) > 0 and int(v["plane_box"]) == int((a.type == 15).sum()) > 0
+    assert float(v["v1y"]) == v1[1] and float(v["q1y0"]) == q1[1]
+    assert abs(float(v["psum"]) - float(a.p.sum())) <= 1e-9 * max(1.0, abs(float(a.p.sum())))
+    # ---- rigidbody2d
+    nx2, ny2 = 3 * nx, 3 * ny
+    ns = nx2 * ny2
+    n = 2 * ns
+    b = np.arange(n)
+    k = b % ns
+    box = b >= ns
+    q0 = np.empty(3 * n)
+    q0[0::3] = np.where(box, 100.0, 0.0) + 0.99 * (k % nx2) + 0.001 * np.array([math.sin(12.9898 * i) for i in b])
+    q0[1::3] = 0.99 * (k // nx2) + 0.001 * np.array([math.cos(78.233 * i) for i in b])
+    q0[2::3] = np.where(box, 0.1 * k, 0.0)
+    M = np.tile([1.0, 1.0, 0.2], n)
+    st2 = sb.RigidBody2DState([0, 1], [0.5, 0.0], [[0, 0], [0.5, 0.4]], box.astype(np.uint32), np.zeros(n, np.uint8), M, (0.0, -9.81), [[0.0, -0.5]], [[0.0, 1.0]])
+    sim2 = sb.RigidBody2DSim(st2, ctx=gpu_ctx)
+    q1, v1 = sim2._flow(0, q0, np.zeros(3 * n), 1.0e-3)
+    a = sim2.computeActiveSet(q0, q1)
+    v = lines["rb2d"]
+    assert int(v["n"]) == n and int(v["candidates"]) == a.n_candidates
+    assert int(v["circle_circle"]) == int((a.type == 20).sum()) > 0 and int(v["body_body"]) == int((a.type == 22).sum()) > 0
+    assert int(v["plane_circle"]) == int((a.type == 23).sum()) > 0 and int(v["plane_body"]) == int((a.type == 24).sum())
+    assert float(v["v1y"]) == v1[1] and float(v["q1y0"]) == q1[1]
+    assert abs(float(v["psum"]) - float(a.p.sum())) <= 1e-9 * max(1.0, abs(float(a.p.sum())))
