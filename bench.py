@@ -259,6 +259,7 @@ def main():
         backend = GpuSlabBackend(ctx, scene, rank * n, ghost_cap=max(4096, n // 128))
         slabs = Ball2DSlabs(backend, rank, world, dist, transport=args.transport)
         step = lambda: slabs.step(umap.kind, dt)
+        args.transport = slabs.transport   # what the ranks agreed on (p2p falls back to nccl when a mailbox cannot be mapped)
 
     # ---------------- resident path: `value` ----------------
     barrier()                   # also warms the barrier's own collective up before anything is timed

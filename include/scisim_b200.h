@@ -187,6 +187,8 @@ int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg
 int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64 );
 int sg_ball2d_slab_connect( sg_ctx* ctx, int side, const void* ipc_handle_64, void* same_process_mailbox, int peer_device );
 int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase );
+/* drops the mailbox and the neighbour mappings: the context is back on the pack / unpack calls (collective transport) */
+int sg_ball2d_slab_disconnect( sg_ctx* ctx );
 
 /* Slab mode (multi-GPU): this context holds bodies [gid_first, gid_first + n_owned) of a larger scene
  * whose global numbering is slab-major, plus per-step ghost copies of neighbouring slabs' bodies.  The reference has no

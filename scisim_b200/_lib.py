@@ -79,6 +79,7 @@ def load():
         "sg_ball2d_slab_mailbox": (C.c_int, [vp, C.POINTER(C.c_void_p), vp]),
         "sg_ball2d_slab_connect": (C.c_int, [vp, C.c_int, vp, vp, C.c_int]),
         "sg_ball2d_slab_exchange": (C.c_int, [vp, C.c_int]),
+        "sg_ball2d_slab_disconnect": (C.c_int, [vp]),
         "sg_ball2d_slab_detect": (C.c_int, [vp, C.POINTER(SgContacts), vp]),
         "sg_rb2d_set_geometry": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),
         "sg_rb2d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),

@@ -1325,6 +1325,22 @@ int sg_ball2d_slab_connect( sg_ctx* ctx, int side, const void* ipc_handle_64, vo
   return SG_OK;
 }
 
+int sg_ball2d_slab_disconnect( sg_ctx* ctx )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  for( int sde = 0; sde < 2; ++sde )
+  {
+    if( d->peer_mb[sde] != nullptr && d->peer_ipc[sde] ) { cudaIpcCloseMemHandle( d->peer_mb[sde] ); }
+    d->peer_mb[sde] = nullptr; d->peer_ipc[sde] = false;
+  }
+  d->mailbox.release();
+  cudaGetLastError();
+  return SG_OK;
+}
+
 // phase 1: for each connected neighbour wait for its interval, pack the owned bodies that reach it straight into
 //          its mailbox, raise its halo flag;  phase 2: wait for the neighbours' halos and move them into the ghost
 //          slots;  phase 0: both.  (A driver with several ranks in ONE process must run phase 1 on every rank

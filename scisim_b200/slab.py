@@ -104,6 +104,10 @@ class GpuSlabBackend:
     def exchange(self, phase=0):
         self.ctx.check(self.lib.sg_ball2d_slab_exchange(self.ctx.h, int(phase)))
 
+    def disconnect(self):
+        """Back to the collective transport: drops the mailbox and the neighbour mappings."""
+        self.ctx.check(self.lib.sg_ball2d_slab_disconnect(self.ctx.h))
+
     def pack(self, interval, side):
         """Selects, in body order, the owned bodies overlapping `interval` (2-element tensor on this device) into the
         side's send buffer (header + records). Asynchronous."""
@@ -159,14 +163,30 @@ class Ball2DSlabs:
         self.transport = transport if world > 1 else "nccl"
         if self.transport == "p2p":
             import torch
-            _, handle = backend.mailbox()
-            mine = torch.tensor(list(handle), dtype=torch.uint8, device=backend.device)
+            ok = 1
+            try:
+                _, handle = backend.mailbox()
+                mine = torch.tensor(list(handle), dtype=torch.uint8, device=backend.device)
+            except Exception:
+                ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device=backend.device)
             allh = torch.empty(world * 64, dtype=torch.uint8, device=backend.device)
             dist.all_gather_into_tensor(allh, mine)
             allh = allh.cpu().numpy().reshape(world, 64)
-            for side, peer in ((0, rank - 1), (1, rank + 1)):
-                if 0 <= peer < world:
-                    backend.connect(side, ipc_handle=bytes(allh[peer]))
+            if ok:
+                try:
+                    for side, peer in ((0, rank - 1), (1, rank + 1)):
+                        if 0 <= peer < world:
+                            backend.connect(side, ipc_handle=bytes(allh[peer]))
+                except Exception:
+                    ok = 0
+            # every rank must take the same transport: fall back to NCCL everywhere if any mapping failed (no peer
+            # access between two of the GPUs, CUDA IPC not permitted in this container, ...)
+            flag = torch.tensor([ok], dtype=torch.int32, device=backend.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.transport = "nccl"
+                if hasattr(backend, "disconnect"):
+                    backend.disconnect()
             dist.barrier()
 
     def step(self, kind, dt):
