@@ -53,6 +53,8 @@ extern "C" {
 #define SG_PLANE_SPHERE 14            /* StaticPlaneSphereConstraint: j = plane */
 #define SG_PLANE_BOX 15               /* StaticPlaneBoxConstraint: j = plane, aux = corner number, p = x0 + R0*corner */
 #define SG_PLANE_BODY 16              /* StaticPlaneBodyConstraint: j = plane, aux = convex hull vertex, p = collision point at q0 */
+#define SG_CYLINDER_SPHERE 17         /* StaticCylinderSphereConstraint{ i, r_i, staticCylinder(j), j }: n = computeN( q0 ), p = x0 - r n */
+#define SG_CYLINDER_BODY 18           /* StaticCylinderBodyConstraint{ i, p, staticCylinder(j), j, q0 }: aux = hull vertex, n from the centre of mass */
 
 /* rigidbody2d (the constraint classes under rigidbody2d/) */
 #define SG_CIRCLE_CIRCLE 20    /* CircleCircleConstraint{ i, j, n, p, ri, rj } */
@@ -240,6 +242,11 @@ int sg_rb3d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, co
 int sg_rb3d_set_gravity( sg_ctx* ctx, const double* g /* 3 */ );
 /* normals are normalised as rigidbody3d/StaticGeometry/StaticPlane.cpp:10-15 does */
 int sg_rb3d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 3n */, const double* nrm /* 3n */ );
+/* static cylinders (rigidbody3d/StaticGeometry/StaticCylinder.cpp:8-19: axis normalised; at most 8): bodies live INSIDE them.
+ * Contacts follow the plane contacts, cylinder-major (RigidBody3DSim::computeBodyCylinderActiveSetAllPairs,
+ * RigidBody3DSim.cpp:1504-1557): spheres and mesh convex-hull vertices; a non-kinematic box makes sg_rb3d_active_set /
+ * sg_rb3d_step return SG_ERR_UNSUPPORTED where the reference prints and exits. */
+int sg_rb3d_set_cylinders( sg_ctx* ctx, uint32_t n, const double* x /* 3n */, const double* axis /* 3n */, const double* r /* n */ );
 /* UnconstrainedMap::flow for SplitHamMap (SG_MAP_SPLIT_HAM) / DMVMap (SG_MAP_DMV) with NearEarthGravityForce */
 int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
 /* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; no portals, no cylinders). Returns

@@ -189,6 +189,18 @@ void* orc_rb3d_create( uint32_t n, const uint32_t* geo_of_body, const uint8_t* f
   }
   return h;
 }
+// axes are normalised here exactly as rigidbody3d/StaticGeometry/StaticCylinder.cpp:8-19
+void orc_rb3d_set_cylinders( void* hv, uint32_t n, const double* x, const double* axis, const double* r )
+{
+  RB3DScene& s = static_cast<RB3DHandle*>( hv )->scene;
+  s.cyl_x.clear(); s.cyl_axis.clear(); s.cyl_r.clear();
+  for( uint32_t c = 0; c < n; ++c )
+  {
+    s.cyl_x.push_back( V3{ x[3 * c], x[3 * c + 1], x[3 * c + 2] } );
+    s.cyl_axis.push_back( normalized( V3{ axis[3 * c], axis[3 * c + 1], axis[3 * c + 2] } ) );
+    s.cyl_r.push_back( r[c] );
+  }
+}
 void orc_rb3d_destroy( void* h ) { delete static_cast<RB3DHandle*>( h ); }
 
 uint32_t orc_rb3d_add_mesh( void* hv, uint32_t nverts, const double* verts, uint32_t nsamples, const double* samples, uint32_t nhull, const double* hull,

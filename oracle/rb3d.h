@@ -42,7 +42,8 @@ enum RB3DGeoType : uint32_t { GEO_BOX = 0, GEO_SPHERE = 1, GEO_MESH = 3 };
 enum RB3DContactType : uint32_t
 {
   SPHERE_SPHERE = 10, KINEMATIC_SPHERE_SPHERE = 11, BODY_BODY = 12, KINEMATIC_BODY_BODY = 13,
-  PLANE_SPHERE = 14, PLANE_BOX = 15, PLANE_BODY = 16
+  PLANE_SPHERE = 14, PLANE_BOX = 15, PLANE_BODY = 16,
+  CYLINDER_SPHERE = 17, CYLINDER_BODY = 18
 };
 
 struct RB3DMesh
@@ -117,6 +118,10 @@ struct RB3DScene
   V3 g{ 0.0, 0.0, 0.0 };
   std::vector<V3> plane_x;
   std::vector<V3> plane_n;            // already normalised
+  // static cylinders (rigidbody3d/StaticGeometry/StaticCylinder.cpp:8-19): point on the axis, unit axis, radius
+  std::vector<V3> cyl_x;
+  std::vector<V3> cyl_axis;           // already normalised
+  std::vector<double> cyl_r;
   std::size_t nbodies() const { return geo_of_body.size(); }
   const RB3DGeometry& geo( const std::size_t b ) const { return geometry[geo_of_body[b]]; }
 };
@@ -499,6 +504,62 @@ inline bool computeActiveSet( const RB3DScene& s, const double* q0, const double
             active_set.emplace_back( c );
           }
         }
+      }
+    }
+  }
+  // cylinders: cylinder-major, body ascending, hull vertex ascending; kinematic bodies skipped; boxes are not supported
+  // (RigidBody3DSim::computeBodyCylinderActiveSetAllPairs, RigidBody3DSim.cpp:1504-1557)
+  for( uint32_t cy = 0; cy < uint32_t( s.cyl_x.size() ); ++cy )
+  {
+    const V3 xc = s.cyl_x[cy], ax = s.cyl_axis[cy];
+    const double rc = s.cyl_r[cy];
+    for( uint32_t b = 0; b < uint32_t( nb ); ++b )
+    {
+      if( s.fixed[b] ) { continue; }
+      const RB3DGeometry& g = s.geo( b );
+      const V3 x1 = loadX( q1, b ), x0 = loadX( q0, b );
+      // StaticCylinder{Sphere,Body}Constraint::computeN at q0 (StaticCylinderSphereConstraint.cpp:237-244,
+      // StaticCylinderBodyConstraint.cpp:84-91): minus the part of (x - xc) perpendicular to the axis, normalised
+      const V3 e0 = ( x0 - xc ) - dot( ax, x0 - xc ) * ax;
+      const V3 m0 = V3{ -e0.x, -e0.y, -e0.z };
+      if( g.type == GEO_SPHERE )
+      {
+        // StaticCylinderSphereConstraint::isActive (StaticCylinderSphereConstraint.cpp:10-19) at q1
+        const V3 d = ( x1 - xc ) - dot( ax, x1 - xc ) * ax;
+        if( dot( d, d ) >= ( rc - g.r ) * ( rc - g.r ) )
+        {
+          RB3DContact c;
+          c.type = CYLINDER_SPHERE; c.i = b; c.j = cy; c.aux = 0;
+          c.n = normalized( m0 );
+          c.p = x0 - g.r * c.n;         // getWorldSpaceContactPoint (:324-327)
+          c.depth = NaN;
+          active_set.emplace_back( c );
+        }
+      }
+      else if( g.type == GEO_MESH )
+      {
+        // MeshMeshUtilities::computeMeshCylinderActiveSet (MeshMeshUtilities.cpp:88-109) at q1
+        const RB3DMesh& mesh = s.meshes[g.mesh];
+        const M3 R1 = loadR( q1, nb, b ), R0 = loadR( q0, nb, b );
+        for( uint32_t vi = 0; vi < uint32_t( mesh.hull.size() ); ++vi )
+        {
+          const V3 v = mul( R1, mesh.hull[vi] ) + x1;
+          const V3 d = ( v - xc ) - dot( ax, v - xc ) * ax;
+          if( dot( d, d ) >= rc * rc )
+          {
+            RB3DContact c;
+            c.type = CYLINDER_BODY; c.i = b; c.j = cy; c.aux = vi;
+            const double nrm = std::sqrt( dot( m0, m0 ) );   // n / n.norm()
+            c.n = V3{ m0.x / nrm, m0.y / nrm, m0.z / nrm };
+            c.p = x0 + mul( R0, mesh.hull[vi] );
+            c.depth = NaN;
+            active_set.emplace_back( c );
+          }
+        }
+      }
+      else
+      {
+        return false; // "Collision between static cylinders and box not supported. Exiting."
       }
     }
   }

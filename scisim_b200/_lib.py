@@ -97,6 +97,7 @@ def load():
         "sg_rb3d_upload": (C.c_int, [vp, vp, vp]),
         "sg_rb3d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
         "sg_rb3d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
+        "sg_rb3d_set_cylinders": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),
         "sg_rb3d_mesh_stats": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sigs.items():

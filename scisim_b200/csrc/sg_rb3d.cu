@@ -243,11 +243,17 @@ struct Rb3dDev
   unsigned long long* mesh_stats; // [0] sample sweeps served from a TMA-staged brick, [1] sweeps that read the grid directly
 };
 
+#define SG_MAX_CYLINDERS 8
+// static geometry: planes, then cylinders (the order RigidBody3DSim::computeActiveSet visits them, RigidBody3DSim.cpp:259-261)
 struct Planes3D
 {
   uint32_t n;
+  uint32_t ncyl;
   double x[SG_MAX_PLANES][3];
   double nrm[SG_MAX_PLANES][3];
+  double cx[SG_MAX_CYLINDERS][3];  // point on the axis
+  double cax[SG_MAX_CYLINDERS][3]; // unit axis
+  double cr[SG_MAX_CYLINDERS];
 };
 
 // ---- unconstrained flow ----------------------------------------------------------------------------
@@ -759,6 +765,57 @@ __device__ inline uint32_t plane_contacts( const Rb3dDev& dev, const Planes3D& p
   const uint32_t t = __ldg( &dev.btype[b] );
   if( t & SG_FIXED_BIT ) { return 0u; }
   const size_t nb = dev.n;
+  if( pl >= planes.n )
+  {
+    // static cylinder pl - planes.n (RigidBody3DSim.cpp:1504-1557): spheres and mesh hull vertices OUTSIDE the cylinder
+    // are in contact; boxes are rejected on the host like the reference does
+    const uint32_t cy = pl - planes.n;
+    const V3d xc = v3( planes.cx[cy][0], planes.cx[cy][1], planes.cx[cy][2] );
+    const V3d ax = v3( planes.cax[cy][0], planes.cax[cy][1], planes.cax[cy][2] );
+    const double rc = planes.cr[cy];
+    const V3d x1 = load_v3( q1, b );
+    uint32_t cnt = 0u;
+    if( t == SG_GEO_SPHERE )
+    {
+      const double r = __ldg( &dev.bparam[4 * size_t( b )] );
+      const V3d d = ( x1 - xc ) - dot3( ax, x1 - xc ) * ax;           // StaticCylinderSphereConstraint.cpp:10-19
+      if( dot3( d, d ) >= ( rc - r ) * ( rc - r ) )
+      {
+        if( emit )
+        {
+          const V3d x0 = load_v3( q0, b );
+          const V3d e0 = ( x0 - xc ) - dot3( ax, x0 - xc ) * ax;
+          const V3d n = normalized3( -e0 );                          // computeN( q0 ) (:237-244)
+          put_contact( out, emit_base, SG_CYLINDER_SPHERE, b, cy, 0u, n, x0 - r * n, sg_nan() );
+        }
+        cnt = 1u;
+      }
+    }
+    else if( t == SG_GEO_MESH )
+    {
+      const M3d R1 = load_m3( q1 + 3 * nb, b );
+      const MeshDev& mesh = dev.meshes[__ldg( &dev.bmesh[b] )];
+      for( uint32_t vi = 0; vi < mesh.nhull; ++vi )
+      {
+        const V3d hv = load_v3( mesh.hull, vi );
+        const V3d v = mul3( R1, hv ) + x1;
+        const V3d d = ( v - xc ) - dot3( ax, v - xc ) * ax;          // MeshMeshUtilities.cpp:88-109
+        if( dot3( d, d ) >= rc * rc )
+        {
+          if( emit )
+          {
+            const V3d x0 = load_v3( q0, b );
+            const V3d e0 = ( x0 - xc ) - dot3( ax, x0 - xc ) * ax;
+            const V3d m0 = -e0;
+            const double nrm = sqrt( dot3( m0, m0 ) );               // n / n.norm() (StaticCylinderBodyConstraint.cpp:84-91)
+            put_contact( out, emit_base + cnt, SG_CYLINDER_BODY, b, cy, vi, v3( m0.x / nrm, m0.y / nrm, m0.z / nrm ), x0 + mul3( load_m3( q0 + 3 * nb, b ), hv ), sg_nan() );
+          }
+          ++cnt;
+        }
+      }
+    }
+    return cnt;
+  }
   const V3d xp = v3( planes.x[pl][0], planes.x[pl][1], planes.x[pl][2] );
   const V3d np = v3( planes.nrm[pl][0], planes.nrm[pl][1], planes.nrm[pl][2] );
   const V3d x1 = load_v3( q1, b );
@@ -809,12 +866,13 @@ __device__ inline uint32_t plane_contacts( const Rb3dDev& dev, const Planes3D& p
 // counts[pl * nblocks + block] = contacts of this block's bodies against plane pl
 __global__ void __launch_bounds__( 256 ) k_rb3d_plane_count( const Rb3dDev dev, const __grid_constant__ Planes3D planes, const double* __restrict__ q0, const double* __restrict__ q1, uint32_t* __restrict__ counts )
 {
-  __shared__ uint32_t s_cnt[SG_MAX_PLANES];
-  if( threadIdx.x < planes.n ) { s_cnt[threadIdx.x] = 0u; }
+  __shared__ uint32_t s_cnt[SG_MAX_PLANES + SG_MAX_CYLINDERS];
+  const uint32_t ng = planes.n + planes.ncyl;
+  if( threadIdx.x < ng ) { s_cnt[threadIdx.x] = 0u; }
   __syncthreads();
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   const ContactOut3D none = {};
-  for( uint32_t pl = 0; pl < planes.n; ++pl )
+  for( uint32_t pl = 0; pl < ng; ++pl )
   {
     uint32_t c = ( b < dev.n ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
     #pragma unroll
@@ -822,20 +880,21 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_plane_count( const Rb3dDev dev, 
     if( ( threadIdx.x & 31 ) == 0 && c != 0u ) { atomicAdd( &s_cnt[pl], c ); }
   }
   __syncthreads();
-  if( threadIdx.x < planes.n ) { counts[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x]; }
+  if( threadIdx.x < ng ) { counts[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x]; }
 }
 
 __global__ void __launch_bounds__( 256 ) k_rb3d_plane_emit( const Rb3dDev dev, const __grid_constant__ Planes3D planes, const double* __restrict__ q0, const double* __restrict__ q1,
                                                            const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, const unsigned long long* __restrict__ base_dev, const ContactOut3D out )
 {
   __shared__ uint32_t s_warp[8];
-  const int mine = ( threadIdx.x < planes.n ) ? int( counts[threadIdx.x * gridDim.x + blockIdx.x] != 0u ) : 0;
+  const uint32_t ng = planes.n + planes.ncyl;
+  const int mine = ( threadIdx.x < ng ) ? int( counts[threadIdx.x * gridDim.x + blockIdx.x] != 0u ) : 0;
   if( __syncthreads_or( mine ) == 0 ) { return; }
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long base = *base_dev;
   const ContactOut3D none = {};
-  for( uint32_t pl = 0; pl < planes.n; ++pl )
+  for( uint32_t pl = 0; pl < ng; ++pl )
   {
     if( counts[pl * gridDim.x + blockIdx.x] == 0u ) { continue; }
     const uint32_t c = ( b < dev.n ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
@@ -884,6 +943,7 @@ struct Rb3dData
 {
   uint32_t n = 0;
   bool all_spheres = false;
+  bool has_free_box = false; // a box that is not kinematically scripted (static cylinders reject those)
   double g[3] = { 0.0, 0.0, 0.0 };
   Planes3D planes;
   // geometry list (host copy) and per-body expansion
@@ -984,8 +1044,12 @@ static int rb3d_flow_device( sg_ctx* ctx, Rb3dData* d, const int map_kind, const
 // body-plane contacts appended after the body-body ones; leaves the static total in st_total
 static int rb3d_planes_device( sg_ctx* ctx, Rb3dData* d, const bool emit )
 {
-  const uint32_t n = d->n, np = d->planes.n;
+  const uint32_t n = d->n, np = d->planes.n + d->planes.ncyl;
   if( np == 0 || n == 0 ) { return SG_OK; }
+  if( d->planes.ncyl > 0u && d->has_free_box )
+  {
+    return sg_fail( ctx, SG_ERR_UNSUPPORTED, "Collision between static cylinders and box not supported." ); // RigidBody3DSim.cpp:1550-1553
+  }
   const unsigned nblk = sg_div_up( n, 256 );
   const uint32_t nst = np * nblk;
   const Rb3dDev dev = rb3d_dev( d );
@@ -1190,6 +1254,7 @@ static int rb3d_expand_bodies( sg_ctx* ctx, Rb3dData* d, const uint32_t n, const
   std::vector<uint32_t> btype( n ), bmesh( n ), flags( n );
   std::vector<double> bparam( size_t( n ) * 4, 0.0 ), radius( n, 0.0 );
   bool all_spheres = n > 0;
+  bool has_free_box = false;
   for( uint32_t b = 0; b < n; ++b )
   {
     const uint32_t gi = geo_of_body[b];
@@ -1203,8 +1268,10 @@ static int rb3d_expand_bodies( sg_ctx* ctx, Rb3dData* d, const uint32_t n, const
     if( t == SG_GEO_SPHERE ) { bparam[4 * size_t( b )] = d->geo_r[gi]; radius[b] = d->geo_r[gi]; }
     else if( t == SG_GEO_BOX ) { for( int k = 0; k < 3; ++k ) { bparam[4 * size_t( b ) + k] = d->geo_half[3 * size_t( gi ) + k]; } }
     all_spheres = all_spheres && t == SG_GEO_SPHERE;
+    has_free_box = has_free_box || ( t == SG_GEO_BOX && !fixed[b] );
   }
   d->all_spheres = all_spheres;
+  d->has_free_box = has_free_box;
   SG_CUDA( ctx, d->btype.ensure( size_t( n ) * 4 + 4 ) ); SG_CUDA( ctx, d->bmesh.ensure( size_t( n ) * 4 + 4 ) ); SG_CUDA( ctx, d->flags.ensure( size_t( n ) * 4 + 4 ) );
   SG_CUDA( ctx, d->bparam.ensure( size_t( n ) * 32 + 32 ) ); SG_CUDA( ctx, d->radius.ensure( size_t( n ) * 8 + 8 ) );
   if( n > 0 )
@@ -1346,6 +1413,27 @@ int sg_rb3d_set_planes( sg_ctx* ctx, uint32_t n, const double* x, const double* 
     const double z = s01 + zz;
     if( z > 0.0 ) { const double s = sqrt( z ); v[0] = v[0] / s; v[1] = v[1] / s; v[2] = v[2] / s; }
     for( int k = 0; k < 3; ++k ) { d->planes.x[p][k] = x[3 * p + k]; d->planes.nrm[p][k] = v[k]; }
+  }
+  return SG_OK;
+}
+
+int sg_rb3d_set_cylinders( sg_ctx* ctx, uint32_t n, const double* x, const double* axis, const double* r )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > SG_MAX_CYLINDERS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_cylinders: at most %d cylinders", SG_MAX_CYLINDERS ); }
+  if( n > 0 && ( x == nullptr || axis == nullptr || r == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_cylinders: null array" ); }
+  Rb3dData* d = rb3d_data( ctx );
+  d->planes.ncyl = n;
+  for( uint32_t c = 0; c < n; ++c )
+  {
+    // StaticCylinder::StaticCylinder: m_n( axis.normalized() ), 3-term squared norm (a0*a0 + a1*a1) + a2*a2
+    double v[3] = { axis[3 * c], axis[3 * c + 1], axis[3 * c + 2] };
+    volatile double xx = v[0] * v[0]; volatile double yy = v[1] * v[1]; volatile double zz = v[2] * v[2];
+    volatile double s01 = xx + yy;
+    const double z = s01 + zz;
+    if( z > 0.0 ) { const double s = sqrt( z ); v[0] = v[0] / s; v[1] = v[1] / s; v[2] = v[2] / s; }
+    for( int k = 0; k < 3; ++k ) { d->planes.cx[c][k] = x[3 * c + k]; d->planes.cax[c][k] = v[k]; }
+    d->planes.cr[c] = r[c];
   }
   return SG_OK;
 }

@@ -215,6 +215,11 @@ void GpuRigidBody3DBackend::setPlanes( const std::vector<double>& x, const std::
   check( sg_rb3d_set_planes( m_ctx, static_cast<uint32_t>( x.size() / 3 ), x.data(), n.data() ), "sg_rb3d_set_planes" );
 }
 
+void GpuRigidBody3DBackend::setCylinders( const std::vector<double>& x, const std::vector<double>& axis, const std::vector<double>& r )
+{
+  check( sg_rb3d_set_cylinders( m_ctx, static_cast<uint32_t>( r.size() ), x.data(), axis.data(), r.data() ), "sg_rb3d_set_cylinders" );
+}
+
 void GpuRigidBody3DBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
   if( q1.size() != q0.size() ) { q1.resize( q0.size() ); }

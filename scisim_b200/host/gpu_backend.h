@@ -146,6 +146,8 @@ public:
   void setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& m, const VectorXs& I0 );
   void setGravity( const double gx, const double gy, const double gz );
   void setPlanes( const std::vector<double>& x, const std::vector<double>& n );
+  // RigidBody3DState::staticCylinders(): point on the axis, axis, radius per cylinder
+  void setCylinders( const std::vector<double>& x, const std::vector<double>& axis, const std::vector<double>& r );
 
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
   // false + message on std::cerr where the reference would print and exit (unsupported geometry pairing): the caller exits

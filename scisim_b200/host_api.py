@@ -280,9 +280,13 @@ class TriangleMesh:
 
 class RigidBody3DState:
     """Static part of rigidbody3d/RigidBody3DState.h: geometry list, per-body geometry index / fixed flag / mass /
-    body-frame inertia, gravity, static planes."""
+    body-frame inertia, gravity, static planes, static cylinders."""
 
-    def __init__(self, geo_type, geo_r, geo_half, geo_mesh, meshes, geo_of_body, fixed, m, I0, g=(0.0, 0.0, 0.0), plane_x=None, plane_n=None):
+    def __init__(self, geo_type, geo_r, geo_half, geo_mesh, meshes, geo_of_body, fixed, m, I0, g=(0.0, 0.0, 0.0), plane_x=None, plane_n=None,
+                 cyl_x=None, cyl_axis=None, cyl_r=None):
+        self.cyl_x = _f64(cyl_x if cyl_x is not None else np.zeros((0, 3))).reshape(-1, 3)
+        self.cyl_axis = _f64(cyl_axis if cyl_axis is not None else np.zeros((0, 3))).reshape(-1, 3)
+        self.cyl_r = _f64(cyl_r if cyl_r is not None else np.zeros(0))
         self.geo_type = np.ascontiguousarray(geo_type, dtype=np.uint32)
         self.geo_r = _f64(geo_r)
         self.geo_half = _f64(geo_half).reshape(-1, 3)
@@ -339,6 +343,7 @@ class RigidBody3DSim:
         self.ctx.check(lib.sg_rb3d_set_bodies(h, st.nbodies(), _ptr(st.geo_of_body), _ptr(st.fixed), _ptr(st.m), _ptr(st.I0)))
         self.ctx.check(lib.sg_rb3d_set_gravity(h, _ptr(st.g)))
         self.ctx.check(lib.sg_rb3d_set_planes(h, st.plane_x.shape[0], _ptr(st.plane_x), _ptr(st.plane_n)))
+        self.ctx.check(lib.sg_rb3d_set_cylinders(h, st.cyl_r.shape[0], _ptr(st.cyl_x), _ptr(st.cyl_axis), _ptr(st.cyl_r)))
 
     def name(self):
         return "rigid_body_3d"

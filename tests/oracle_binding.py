@@ -155,6 +155,10 @@ class RB3DOracle:
         k = self._keep
         self.h = lib.orc_rb3d_create(self.n, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]), k[5].shape[0], _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]),
                                      k[9].shape[0], _p(k[9]), _p(k[10]))
+        if "cyl_r" in s and len(s["cyl_r"]):
+            cx, ca, cr = _f64(s["cyl_x"]), _f64(s["cyl_axis"]), _f64(s["cyl_r"])
+            lib.orc_rb3d_set_cylinders.argtypes = [vp, C.c_uint32, vp, vp, vp]
+            lib.orc_rb3d_set_cylinders(self.h, cr.shape[0], _p(cx), _p(ca), _p(cr))
         for mesh in s["meshes"]:
             v, sm, hl = _f64(mesh["verts"]), _f64(mesh["samples"]), _f64(mesh["hull"])
             lib.orc_rb3d_add_mesh(self.h, v.shape[0], _p(v), sm.shape[0], _p(sm), hl.shape[0], _p(hl), _p(_f64(mesh["cell_delta"])), _p(u32(mesh["dims"])),

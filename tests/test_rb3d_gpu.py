@@ -15,7 +15,8 @@ REL = 1.0e-12
 def make_sim(s, ctx):
     import scisim_b200 as sb
     meshes = [sb.TriangleMesh(m["verts"], m["samples"], m["hull"], m["cell_delta"], m["dims"], m["origin"], m["sdf"]) for m in s["meshes"]]
-    st = sb.RigidBody3DState(s["geo_type"], s["geo_r"], s["geo_half"], s["geo_mesh"], meshes, s["geo_of_body"], s["fixed"], s["m"], s["I0"], s["g"], s["plane_x"], s["plane_n"])
+    st = sb.RigidBody3DState(s["geo_type"], s["geo_r"], s["geo_half"], s["geo_mesh"], meshes, s["geo_of_body"], s["fixed"], s["m"], s["I0"], s["g"], s["plane_x"], s["plane_n"],
+                             s.get("cyl_x"), s.get("cyl_axis"), s.get("cyl_r"))
     return sb.RigidBody3DSim(st, ctx=ctx)
 
 
@@ -231,3 +232,39 @@ def test_dense_spheres_sort_regimes(gpu_ctx, oracle, box):
     ref = o.active_set(s["q"], q1, "grid")
     assert ref["candidates"].shape[0] > 8 * 4000
     assert_active_equal(sim.computeActiveSet(s["q"], q1), ref)
+
+
+@pytest.mark.parametrize("kind", ["spheres", "meshes"])
+def test_static_cylinders(gpu_ctx, oracle, kind):
+    """Static cylinders (RigidBody3DSim.cpp:1504-1557): bodies live inside; spheres / mesh hull vertices that reach the
+    wall are in contact; the contacts follow the plane contacts, cylinder-major.  Two cylinders with oblique,
+    un-normalised axes."""
+    from tests import oracle_binding as ob
+    s = scenes.rb3d_random_spheres(3000, 23, spin=False, nplanes=1) if kind == "spheres" else scenes.rb3d_random_meshes(60, 24, nplanes=1)
+    x = s["q"][:3 * s["geo_of_body"].shape[0]].reshape(-1, 3)
+    ext = float(np.abs(x).max())
+    s["cyl_x"] = np.array([[0.1, -0.2, 0.3], [0.0, 0.0, 0.0]])
+    s["cyl_axis"] = np.array([[0.2, 3.0, -0.1], [1.0, 0.1, 0.05]])
+    s["cyl_r"] = np.array([0.8 * ext, 0.95 * ext])
+    sim = make_sim(s, gpu_ctx)
+    o = ob.RB3DOracle(s)
+    q1, _ = o.flow(kind_of(s), s["q"], s["v"], s["dt"])
+    ref = o.active_set(s["q"], q1, "grid")
+    got = sim.computeActiveSet(s["q"], q1)
+    code = 17 if kind == "spheres" else 18
+    assert (ref["type"] == code).sum() > 20
+    assert ref["type"][-1] == code and (ref["j"][ref["type"] == code] == 1).any() and (ref["j"][ref["type"] == code] == 0).any()
+    assert_active_equal(got, ref)
+
+
+def test_static_cylinder_with_free_box_is_an_error(gpu_ctx, oracle):
+    import scisim_b200 as sb
+    from tests import oracle_binding as ob
+    s = scenes.rb3d_random_boxes(50, 25, nplanes=0)
+    s["cyl_x"] = np.zeros((1, 3)); s["cyl_axis"] = np.array([[0.0, 1.0, 0.0]]); s["cyl_r"] = np.array([100.0])
+    o = ob.RB3DOracle(s)
+    q1, _ = o.flow(kind_of(s), s["q"], s["v"], s["dt"])
+    assert not o.active_set(s["q"], q1, "grid")["supported"]
+    sim = make_sim(s, gpu_ctx)
+    with pytest.raises(sb.SciSimB200Error):
+        sim.computeActiveSet(s["q"], q1)
