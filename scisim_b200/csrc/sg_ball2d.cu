@@ -1099,6 +1099,7 @@ int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_step: map kind %d is not a ball2d map", map_kind ); }
   Ball2DData* d = ball2d_data( ctx );
+  d->flow_resident = false; // q1 is about to be overwritten by the resident step
   if( d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_step: context is in slab mode, use the sg_ball2d_slab_* calls" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   const int rc = ball2d_active_set_device( ctx, d, true, map_kind, dt );

@@ -944,6 +944,7 @@ struct Rb3dData
   uint32_t n = 0;
   bool all_spheres = false;
   bool has_free_box = false; // a box that is not kinematically scripted (static cylinders reject those)
+  bool flow_resident = false; // q0 (as given) and q1 (as computed) of the last sg_rb3d_flow are still on the device
   double g[3] = { 0.0, 0.0, 0.0 };
   Planes3D planes;
   // geometry list (host copy) and per-body expansion
@@ -1377,6 +1378,7 @@ int sg_rb3d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, co
   Rb3dData* d = rb3d_data( ctx );
   d->n = n;
   d->have_result = false;
+  d->flow_resident = false;
   const int rc = rb3d_expand_bodies( ctx, d, n, geo_of_body, fixed );
   if( rc != SG_OK ) { d->n = 0; return rc; }
   if( n == 0 ) { return SG_OK; }
@@ -1454,6 +1456,7 @@ int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0,
   SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 48, cudaMemcpyDeviceToHost, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   sg_prof_collect( ctx );
+  d->flow_resident = true;
   return SG_OK;
 }
 
@@ -1462,11 +1465,17 @@ int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
   if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
   Rb3dData* d = rb3d_data( ctx );
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  if( d->n > 0 )
+  if( ( out_flags & SG_IN_RESIDENT ) != 0u )
+  {
+    // (q0, q1) are the input and output of the last sg_rb3d_flow on this context: still on the device, nothing is uploaded
+    if( !d->flow_resident ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_active_set: SG_IN_RESIDENT without a preceding sg_rb3d_flow on this context" ); }
+  }
+  else if( d->n > 0 )
   {
     if( q0 == nullptr || q1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_active_set: null vector" ); }
     SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
     SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
+    d->flow_resident = false;
   }
   const int rc = rb3d_active_set_device( ctx, d, ( out_flags & SG_OUT_CANDIDATES ) != 0u );
   if( rc != SG_OK ) { return rc; }
@@ -1477,6 +1486,7 @@ int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   Rb3dData* d = rb3d_data( ctx );
+  d->flow_resident = false;
   if( d->n == 0 ) { return SG_OK; }
   if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_upload: null vector" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
@@ -1491,6 +1501,7 @@ int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( map_kind != SG_MAP_SPLIT_HAM && map_kind != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: map kind %d is not a rigidbody3d map", map_kind ); }
   Rb3dData* d = rb3d_data( ctx );
+  d->flow_resident = false; // q1 is about to be overwritten by the resident step
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   int rc = rb3d_flow_device( ctx, d, map_kind, dt );
   if( rc != SG_OK ) { return rc; }

@@ -268,3 +268,17 @@ def test_static_cylinder_with_free_box_is_an_error(gpu_ctx, oracle):
     sim = make_sim(s, gpu_ctx)
     with pytest.raises(sb.SciSimB200Error):
         sim.computeActiveSet(s["q"], q1)
+
+
+def test_rb3d_active_set_on_resident_flow_result(gpu_ctx, oracle):
+    import scisim_b200 as sb
+    s = scenes.rb3d_random_spheres(2000, 31, spin=True)
+    sim = make_sim(s, gpu_ctx)
+    with pytest.raises(sb.SciSimB200Error):
+        sim.computeActiveSet(s["q"], s["q"], resident=True)
+    q1, v1 = sim._flow(kind_of(s), s["q"], s["v"], s["dt"])
+    a = sim.computeActiveSet(s["q"], q1, resident=True)
+    b = sim.computeActiveSet(s["q"], q1)
+    assert a.n_active == b.n_active > 0 and a.n_candidates == b.n_candidates
+    for k in ("type", "i", "j", "n", "p", "candidates"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
