@@ -970,8 +970,47 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t
 
   if( complete && nc <= uint32_t( Cfg::FAST ) )
   {
-    // visits before window w (the body itself is skipped inside its own window)
     unsigned long long v[Cfg::FAST];
+    if( Cfg::NW > 3 )
+    {
+      // Many windows (3-D: 9): walk the windows once and peel each window's bits off the mask -- O(windows + bits)
+      // instead of O(windows x bits).  The decoded (position, active) words go through a small local array (dynamic
+      // index); the index gathers are then issued from an unrolled loop so that they overlap.
+      uint32_t dec[Cfg::FAST];
+      uint32_t cnt = 0u, base = 0u;
+      #pragma unroll
+      for( int w = 0; w < Cfg::NW; ++w )
+      {
+        const bool mine = p - qb[w] < len[w]; // p inside this window (unsigned compare)
+        const uint32_t L = len[w] - ( mine ? 1u : 0u );
+        unsigned long long sub = ( base < 64u ) ? ( cmask >> base ) : 0ull;
+        if( L < 64u ) { sub &= ( 1ull << L ) - 1ull; }
+        while( sub != 0ull )
+        {
+          const uint32_t kk = uint32_t( __ffsll( static_cast<long long>( sub ) ) ) - 1u;
+          sub &= sub - 1ull;
+          uint32_t q = qb[w] + kk;
+          if( mine && q >= p ) { ++q; }
+          if( cnt < uint32_t( Cfg::FAST ) ) { dec[cnt] = q | ( uint32_t( ( amask >> ( base + kk ) ) & 1ull ) << 31 ); }
+          ++cnt;
+        }
+        base += L;
+      }
+      #pragma unroll
+      for( int b = 0; b < Cfg::FAST; ++b )
+      {
+        v[b] = ~0ull;
+        if( uint32_t( b ) < nc )
+        {
+          const uint32_t w32 = dec[b];
+          const uint32_t oi = __ldg( &sidx[w32 & 0x7fffffffu] ) & P::IDX_MASK;
+          v[b] = ( static_cast<unsigned long long>( oi ) << 32 ) | w32;
+        }
+      }
+    }
+    else
+    {
+    // visits before window w (the body itself is skipped inside its own window)
     unsigned long long cm = cmask;
     #pragma unroll
     for( int b = 0; b < Cfg::FAST; ++b )
@@ -997,6 +1036,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t
         const uint32_t oi = __ldg( &sidx[q] ) & P::IDX_MASK;
         v[b] = ( static_cast<unsigned long long>( oi ) << 32 ) | ( ( ( amask >> kk ) & 1ull ) << 31 ) | q;
       }
+    }
     }
     // Batcher odd-even merge sort networks (empty slots hold ~0 and sink to the end): 8 keys / 19 exchanges,
     // 16 keys / 63 exchanges (3-D pipelines, where a lattice body owns 13 of its 26 neighbours)
