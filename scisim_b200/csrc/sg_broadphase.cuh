@@ -530,7 +530,8 @@ __device__ __forceinline__ typename P::Rec sg_bp_fetch( const typename P::Rec* _
   return sg_load_rec_global<Rec>( &recs[q] );
 }
 template<typename P, bool STAGED = false>
-__device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q )
+__device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q,
+                                                     const uint32_t* __restrict__ sidx = nullptr )
 {
   constexpr uint32_t CH = P::IDX_OFFSET / 16u, IN = P::IDX_OFFSET % 16u;
   const uint32_t slot = q - st->start[w];
@@ -539,6 +540,8 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
     const unsigned char* rec = s_recs + ( size_t( w ) * BpCfg<P::D>::WCAP + slot ) * 64;
     return *reinterpret_cast<const uint32_t*>( rec + ( ( CH ^ ( ( slot >> 1 ) & 3u ) ) << 4 ) + IN ) & P::IDX_MASK;
   }
+  // un-staged: the dense index array (4 B/body, eight bodies per sector) rather than one sector of every record visited
+  if( sidx != nullptr ) { return __ldg( &sidx[q] ) & P::IDX_MASK; }
   return __ldg( reinterpret_cast<const uint32_t*>( reinterpret_cast<const unsigned char*>( &recs[q] ) + P::IDX_OFFSET ) ) & P::IDX_MASK;
 }
 
@@ -550,7 +553,7 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
 template<typename P, int CSCAP, bool STAGED>
 __device__ __forceinline__ void sg_bp_count_body( const GridParams& g, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const uint32_t* s_cs,
                                                   const BpStage<P::D>* st, const uint32_t n_slots, const uint32_t p, const typename P::Rec& me, const uint32_t my_idx,
-                                                  uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
+                                                  uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan, const uint32_t* __restrict__ sidx = nullptr )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -566,7 +569,7 @@ __device__ __forceinline__ void sg_bp_count_body( const GridParams& g, const uin
   {
     const unsigned long long bit = ( k < SG_BP_MASK_BITS ) ? ( 1ull << k ) : 0ull;
     ++k;
-    if( sg_bp_fetch_idx<P, STAGED>( recs, s_recs, st, w, q ) <= my_idx ) { return; } // owned by the partner: skip before touching the record
+    if( sg_bp_fetch_idx<P, STAGED>( recs, s_recs, st, w, q, sidx ) <= my_idx ) { return; } // owned by the partner: skip before touching the record
     const Rec o = sg_bp_fetch<P, STAGED>( recs, s_recs, st, w, q );
     double olo[D], ohi[D];
     P::rec_aabb( o, olo, ohi );
@@ -586,7 +589,8 @@ __device__ __forceinline__ void sg_bp_count_body( const GridParams& g, const uin
 //          masks[sorted position] = { candidate mask (64 bit), active mask (64 bit) } over the visit sequence
 template<typename P>
 __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                               const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
+                                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, uint2* __restrict__ counts, uint4* __restrict__ masks,
+                                                               uint4* __restrict__ plan )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
     masks[p] = make_uint4( 0u, 0u, 0u, 0u );
     return;
   }
-  sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan );
+  sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan, sidx );
 }
 
 // ---- pass 1, TMA-fed (D = 2) -------------------------------------------------------------------------
@@ -801,7 +805,7 @@ template<> struct SgBpCountLaunch<3>
     constexpr size_t smem = sg_bp_count_smem<3>();
     SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
     SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<3>::NPLAN ), sg_bp_count<P><<<sg_div_up( n, BpCfg<3>::T ), BpCfg<3>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-               s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
+               s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
     return SG_OK;
   }
 };
