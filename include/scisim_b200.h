@@ -81,8 +81,8 @@ extern "C" {
 #define SG_OUT_DEPTHS 4u
 #define SG_OUT_CANDIDATES 8u
 #define SG_OUT_ALL 15u
-/* Input flag for sg_ball2d_active_set / sg_rb3d_active_set (or-ed into out_flags): q0 and q1 are exactly the input and
-   the output of the last sg_ball2d_flow / sg_rb3d_flow on this context -- as in ImpactMap::flow, which passes the unconstrained map's (q0, q1) straight
+/* Input flag for sg_ball2d_active_set / sg_rb2d_active_set / sg_rb3d_active_set (or-ed into out_flags): q0 and q1 are
+   exactly the input and the output of the last sg_*_flow on this context -- as in ImpactMap::flow, which passes the unconstrained map's (q0, q1) straight
    to computeActiveSet (scisim/ConstrainedMaps/ImpactMaps/ImpactMap.cpp:54-58) -- so they are not uploaded again.
    The pointers may then be NULL.  SG_ERR_INVALID if no such flow preceded the call. */
 #define SG_IN_RESIDENT 256u

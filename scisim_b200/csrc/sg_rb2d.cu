@@ -457,6 +457,7 @@ struct ScanU32To64b
 struct Rb2dData
 {
   uint32_t n = 0;
+  bool flow_resident = false; // q0 (as given) and q1 (as computed) of the last sg_rb2d_flow are still on the device
   double g[2] = { 0.0, 0.0 };
   Planes2D planes;
   std::vector<uint32_t> geo_type;
@@ -659,6 +660,7 @@ int sg_rb2d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, co
   }
   d->n = n;
   d->have_result = false;
+  d->flow_resident = false;
   if( n == 0 ) { return SG_OK; }
   SG_CUDA( ctx, d->btype.ensure( size_t( n ) * 4 ) ); SG_CUDA( ctx, d->bparam.ensure( size_t( n ) * 16 ) ); SG_CUDA( ctx, d->M.ensure( size_t( n ) * 24 ) );
   SG_CUDA( ctx, d->q0.ensure( size_t( n ) * 24 ) ); SG_CUDA( ctx, d->q1.ensure( size_t( n ) * 24 ) ); SG_CUDA( ctx, d->v0.ensure( size_t( n ) * 24 ) ); SG_CUDA( ctx, d->v1.ensure( size_t( n ) * 24 ) );
@@ -704,6 +706,7 @@ int sg_rb2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0,
   SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   sg_prof_collect( ctx );
+  d->flow_resident = true;
   return SG_OK;
 }
 
@@ -712,11 +715,17 @@ int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
   if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
   Rb2dData* d = rb2d_data( ctx );
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  if( d->n > 0 )
+  if( ( out_flags & SG_IN_RESIDENT ) != 0u )
+  {
+    // (q0, q1) are the input and output of the last sg_rb2d_flow on this context: still on the device, nothing is uploaded
+    if( !d->flow_resident ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_active_set: SG_IN_RESIDENT without a preceding sg_rb2d_flow on this context" ); }
+  }
+  else if( d->n > 0 )
   {
     if( q0 == nullptr || q1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_active_set: null vector" ); }
     SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, size_t( d->n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
     SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, size_t( d->n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
+    d->flow_resident = false;
   }
   const int rc = rb2d_active_set_device( ctx, d );
   if( rc != SG_OK ) { return rc; }

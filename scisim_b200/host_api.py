@@ -442,9 +442,11 @@ class RigidBody2DSim:
         self.ctx.check(self.ctx.lib.sg_rb2d_flow(self.ctx.h, kind, _ptr(q0), _ptr(v0), float(dt), _ptr(q1), _ptr(v1)))
         return q1, v1
 
-    def computeActiveSet(self, q0, qp, v=None, flags=SG_OUT_ALL, copy=True):
+    def computeActiveSet(self, q0, qp, v=None, flags=SG_OUT_ALL, copy=True, resident=False):
+        """resident=True: (q0, qp) are the input and output of the last flow() on this sim (SG_IN_RESIDENT)."""
+        from ._lib import SG_IN_RESIDENT
         q0, qp = _f64(q0), _f64(qp)
         assert q0.size == self.nqdofs() and qp.size == self.nqdofs()
         c = SgContacts()
-        self.ctx.check(self.ctx.lib.sg_rb2d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags), C.byref(c)))
+        self.ctx.check(self.ctx.lib.sg_rb2d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags) | (SG_IN_RESIDENT if resident else 0), C.byref(c)))
         return ActiveSet(c, copy=copy)
