@@ -227,10 +227,10 @@ void GpuRigidBody3DBackend::flow( const int map_kind, const VectorXs& q0, const 
   check( sg_rb3d_flow( m_ctx, map_kind, q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_rb3d_flow" );
 }
 
-void GpuRigidBody3DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates )
+void GpuRigidBody3DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates, const bool from_last_flow )
 {
   sg_contacts c;
-  check( sg_rb3d_active_set( m_ctx, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS, &c ), "sg_rb3d_active_set" );
+  check( sg_rb3d_active_set( m_ctx, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS | ( from_last_flow ? SG_IN_RESIDENT : 0u ), &c ), "sg_rb3d_active_set" );
   contacts.resize( c.n_active );
   for( uint64_t k = 0; k < c.n_active; ++k )
   {
@@ -313,10 +313,10 @@ void GpuRigidBody2DBackend::flow( const int map_kind, const VectorXs& q0, const 
   check( sg_rb2d_flow( m_ctx, map_kind, q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_rb2d_flow" );
 }
 
-void GpuRigidBody2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates )
+void GpuRigidBody2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates, const bool from_last_flow )
 {
   sg_contacts c;
-  check( sg_rb2d_active_set( m_ctx, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS, &c ), "sg_rb2d_active_set" );
+  check( sg_rb2d_active_set( m_ctx, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS | ( from_last_flow ? SG_IN_RESIDENT : 0u ), &c ), "sg_rb2d_active_set" );
   contacts.resize( c.n_active );
   for( uint64_t k = 0; k < c.n_active; ++k )
   {

@@ -151,7 +151,7 @@ public:
 
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
   // false + message on std::cerr where the reference would print and exit (unsupported geometry pairing): the caller exits
-  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates = nullptr );
+  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
   // rigidbody3d/SpatialGridDetector.h:37 on caller-built boxes [minx,miny,minz,maxx,maxy,maxz]
   void getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps );
 
@@ -203,7 +203,7 @@ public:
 
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
   // contacts use GpuContact2D with the rigidbody2d type codes (SG_CIRCLE_CIRCLE ... SG_PLANE_BODY_2D)
-  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr );
+  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
 
   sg_ctx* context() { return m_ctx; }
 
