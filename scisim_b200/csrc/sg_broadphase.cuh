@@ -6,18 +6,22 @@
 //
 // Contract kept from the reference: the candidate set is EXACTLY
 //   { (i<j) : for every axis  !(hi_i < lo_j) && !(hi_j < lo_i) }   in ascending (i,j) order,
-// nothing else about the grid is observable.  Pipeline (one launch each unless noted):
-//   bounds   reduce min/max of box lower corners and the largest box extent
+// nothing else about the grid is observable.  Pipeline (one launch each):
+//   bounds   reduce min/max of box lower corners and the largest box extent (fused into the caller's first kernel
+//            where there is one: k_ball2d_prep)
 //   hist     lay out the grid (h >= largest extent, cell count capped); cell key per body + rank inside the cell
 //            (one atomicAdd per body; the histogram is re-zeroed by the scatter of the step before)
-//   scan     cell counts -> cell start offsets               (3 launches, sg_scan.cuh)
+//   scan     cell counts -> cell start offsets               (one cooperative launch, sg_scan.cuh)
 //   scatter  write a 64-byte record per body at cell_start[key] + rank  => bodies sorted by cell
-//   count    per body: walk the 3^D neighbourhood (D-1 contiguous row segments), count candidates with a
-//            larger index and how many of them pass the narrow phase; counts stored BY BODY INDEX
-//   scan     counts -> output offsets in body-index order   (3 launches)
-//   emit     same walk; the body's candidates are ordered by partner index in registers/local memory and
-//            written at the body's offset => both lists come out in ascending (i,j) order with no sort
-// The block's own records are staged in shared memory; neighbours outside the block come through L1/L2.
+//   pass 1   (count) per body: walk the 3^D neighbourhood as 3^(D-1) contiguous row segments, AABB test (+ narrow
+//            test) against partners with a larger index; leaves counts BY BODY INDEX and, by sorted position, 64-bit
+//            candidate / active masks over the visit sequence plus the walk plan.  2-D: TMA-fed, warp-specialised,
+//            double-buffered (sg_bp_count_tma); 3-D: records through L1/L2, cell ranges staged (sg_bp_count)
+//   scan     counts -> output offsets in body-index order, scattered to sorted-position order (cooperative launch)
+//   pass 2   (emit) no shared memory, no barriers: set mask bits -> partner positions via the plan -> partner indices
+//            -> register sorting network -> candidate pairs at the body's offset + a (p,q) work item per active pair
+//            => both lists come out in ascending (i,j) order with no sort of pairs
+//   pass 3   (contacts, policies with a fused narrow phase) one thread per active pair, coalesced SoA contact stores
 #ifndef SG_BROADPHASE_CUH
 #define SG_BROADPHASE_CUH
 

@@ -1,6 +1,6 @@
 // sg_scan.cuh -- exclusive prefix sums over device arrays whose length is only known on the device.
 //
-// Three launches (tile reduce -> one-block scan of tile sums -> tile down-sweep).  Deterministic,
+// One cooperative launch (chunk reduce -> grid barrier -> chunk scan), or one block for small arrays.  Deterministic,
 // order-preserving, no atomics.  Used for (a) cell start offsets from per-cell counts ("prefix-sum cell
 // ranges") and (b) per-body output offsets from per-body (candidate, active) counts, which is what puts
 // the pair lists in the reference's ascending (i,j) order without a sort of the pairs themselves.
