@@ -85,91 +85,6 @@ __device__ inline typename P::Acc sg_block_exclusive( const typename P::Acc v, t
   return excl;
 }
 
-// n_dev (nullable): element count on the device; n_host is used when n_dev == nullptr
-template<typename P>
-__global__ void __launch_bounds__( SG_SCAN_THREADS ) sg_scan_reduce( const typename P::In* __restrict__ in, const uint32_t* __restrict__ n_dev, const uint32_t n_host, typename P::Acc* __restrict__ partials )
-{
-  using Acc = typename P::Acc;
-  __shared__ Acc warp_sums[SG_SCAN_THREADS / 32];
-  const uint32_t n = ( n_dev != nullptr ) ? *n_dev : n_host;
-  const uint64_t base = uint64_t( blockIdx.x ) * SG_SCAN_TILE;
-  if( base >= n ) { return; }
-  Acc s = P::zero();
-  #pragma unroll
-  for( int k = 0; k < SG_SCAN_ITEMS; ++k )
-  {
-    const uint64_t e = base + uint64_t( k ) * SG_SCAN_THREADS + threadIdx.x;
-    if( e < n ) { s = P::add( s, P::conv( in[e] ) ); }
-  }
-  Acc total;
-  sg_block_exclusive<P, SG_SCAN_THREADS>( s, warp_sums, &total );
-  if( threadIdx.x == 0 ) { partials[blockIdx.x] = total; }
-}
-
-// One block: exclusive scan of the tile sums in place; total -> *total_out (and out_end[n] if given)
-template<typename P>
-__global__ void __launch_bounds__( 1024 ) sg_scan_partials( typename P::Acc* __restrict__ partials, const uint32_t* __restrict__ n_dev, const uint32_t n_host,
-                                                            typename P::Acc* __restrict__ total_out, typename P::Out* __restrict__ out_end )
-{
-  using Acc = typename P::Acc;
-  __shared__ Acc warp_sums[32];
-  __shared__ Acc carry_s;
-  const uint32_t n = ( n_dev != nullptr ) ? *n_dev : n_host;
-  const uint32_t ntiles = uint32_t( ( uint64_t( n ) + SG_SCAN_TILE - 1 ) / SG_SCAN_TILE );
-  if( threadIdx.x == 0 ) { carry_s = P::zero(); }
-  __syncthreads();
-  for( uint32_t base = 0; base < ntiles; base += 1024 )
-  {
-    const uint32_t e = base + threadIdx.x;
-    const Acc v = ( e < ntiles ) ? partials[e] : P::zero();
-    Acc total;
-    const Acc excl = sg_block_exclusive<P, 1024>( v, warp_sums, &total );
-    const Acc carry = carry_s;
-    if( e < ntiles ) { partials[e] = P::add( carry, excl ); }
-    __syncthreads();
-    if( threadIdx.x == 0 ) { carry_s = P::add( carry, total ); }
-    __syncthreads();
-  }
-  if( threadIdx.x == 0 )
-  {
-    if( total_out != nullptr ) { *total_out = carry_s; }
-    if( out_end != nullptr ) { out_end[n] = P::out( carry_s ); }
-  }
-}
-
-template<typename P>
-__global__ void __launch_bounds__( SG_SCAN_THREADS ) sg_scan_down( const typename P::In* __restrict__ in, const uint32_t* __restrict__ n_dev, const uint32_t n_host,
-                                                                   const typename P::Acc* __restrict__ partials, typename P::Out* __restrict__ out, const uint32_t* __restrict__ scatter )
-{
-  using Acc = typename P::Acc;
-  __shared__ Acc warp_sums[SG_SCAN_THREADS / 32];
-  const uint32_t n = ( n_dev != nullptr ) ? *n_dev : n_host;
-  const uint64_t base = uint64_t( blockIdx.x ) * SG_SCAN_TILE;
-  if( base >= n ) { return; }
-  // blocked arrangement: thread t owns SG_SCAN_ITEMS consecutive elements
-  Acc v[SG_SCAN_ITEMS];
-  Acc s = P::zero();
-  const uint64_t e0 = base + uint64_t( threadIdx.x ) * SG_SCAN_ITEMS;
-  #pragma unroll
-  for( int k = 0; k < SG_SCAN_ITEMS; ++k )
-  {
-    v[k] = ( e0 + k < n ) ? P::conv( in[e0 + k] ) : P::zero();
-    s = P::add( s, v[k] );
-  }
-  Acc run = P::add( partials[blockIdx.x], sg_block_exclusive<P, SG_SCAN_THREADS>( s, warp_sums, nullptr ) );
-  #pragma unroll
-  for( int k = 0; k < SG_SCAN_ITEMS; ++k )
-  {
-    if( e0 + k < n )
-    {
-      // scatter != nullptr: element e's prefix goes to out[scatter[e]] (0xffffffff = nowhere)
-      if( scatter == nullptr ) { out[e0 + k] = P::out( run ); }
-      else { const uint32_t d = __ldg( &scatter[e0 + k] ); if( d != 0xffffffffu ) { out[d] = P::out( run ); } }
-    }
-    run = P::add( run, v[k] );
-  }
-}
-
 // Whole scan in one 1024-thread block: for arrays small enough that launch latency, not bandwidth, is the cost.
 // Each thread owns 8 consecutive elements per round.
 template<typename P>
