@@ -163,13 +163,14 @@ class Ball2DSlabs:
         self.transport = transport if world > 1 else "nccl"
         if self.transport == "p2p":
             import torch
+            dev = getattr(backend, "device", "cpu")   # a backend without device memory (the oracle stand-in) cannot map anything
             ok = 1
             try:
                 _, handle = backend.mailbox()
-                mine = torch.tensor(list(handle), dtype=torch.uint8, device=backend.device)
+                mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
             except Exception:
-                ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device=backend.device)
-            allh = torch.empty(world * 64, dtype=torch.uint8, device=backend.device)
+                ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device=dev)
+            allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, mine)
             allh = allh.cpu().numpy().reshape(world, 64)
             if ok:
@@ -181,7 +182,7 @@ class Ball2DSlabs:
                     ok = 0
             # every rank must take the same transport: fall back to NCCL everywhere if any mapping failed (no peer
             # access between two of the GPUs, CUDA IPC not permitted in this container, ...)
-            flag = torch.tensor([ok], dtype=torch.int32, device=backend.device)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 self.transport = "nccl"

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, seed, outdir):
+def _worker(rank, world, port, n, seed, outdir, transport="nccl"):
     import torch.distributed as dist
     from scisim_b200.slab import Ball2DSlabs, partition_slab_major
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -29,7 +29,8 @@ def _worker(rank, world, port, n, seed, outdir):
     scene = sh.slab_major_scene(n, seed)
     firsts, counts = partition_slab_major(n, world)
     backend = sh.OracleSlabBackend(sh.slab_of(scene, firsts[rank], counts[rank]), firsts[rank], ghost_cap=n)
-    drv = Ball2DSlabs(backend, rank, world, dist, check_non_neighbours=True)
+    drv = Ball2DSlabs(backend, rank, world, dist, check_non_neighbours=True, transport=transport)
+    assert drv.transport == "nccl"   # "p2p" must fall back on every rank when a backend cannot export a mailbox
     pc, pa = drv.step(0, scene["dt"])
     q1, v1, res = backend.fetch()
     res["q1"], res["v1"], res["halo"] = q1, v1, drv.last_halo
@@ -63,3 +64,23 @@ def test_partition_slab_major():
     from scisim_b200.slab import partition_slab_major
     firsts, counts = partition_slab_major(10, 4)
     assert counts == [3, 3, 2, 2] and firsts == [0, 3, 6, 8]
+
+
+def test_p2p_request_falls_back_to_collectives_when_no_mailbox_can_be_mapped():
+    """The driver is asked for the peer-memory transport with a backend that has no device memory: every rank must agree
+    to fall back to the collective transport, and the result must still be the reference's."""
+    import torch.multiprocessing as mp
+    from scisim_b200.slab import merge_active_sets
+    from tests import oracle_binding as ob
+    world, n, seed = 2, 500, 3
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), n, seed, d, "p2p"), nprocs=world, join=True)
+        parts = [pickle.load(open(os.path.join(d, "rank%d.pkl" % r), "rb")) for r in range(world)]
+    scene = sh.slab_major_scene(n, seed)
+    o = ob.Ball2DOracle(scene)
+    q1, v1 = o.flow(0, scene["q"], scene["v"], scene["dt"])
+    ref = o.active_set(scene["q"], q1, "allpairs")
+    merged = merge_active_sets(parts, (scene["drum_x"].shape[0], scene["plane_x"].shape[0]))
+    assert np.array_equal(merged["candidates"], ref["candidates"])
+    for k in ("type", "i", "j"):
+        assert np.array_equal(merged[k], ref[k]), k
