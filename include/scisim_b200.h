@@ -45,6 +45,9 @@ extern "C" {
 #define SG_BALL_BALL 0   /* ball2d/Constraints/BallBallConstraint */
 #define SG_BALL_DRUM 1   /* ball2d/Constraints/BallStaticDrumConstraint */
 #define SG_BALL_PLANE 2  /* ball2d/Constraints/BallStaticPlaneConstraint */
+/* with portals (ball2d/Ball2DSim.cpp:653-728): after the regular ball-ball contacts, ascending (i,j) */
+#define SG_BALL_BALL_TELEPORTED 3      /* BallBallConstraint{ i, j, x0, x1, ri, rj, teleported = true } */
+#define SG_BALL_BALL_KICK_TELEPORTED 4 /* KinematicKickBallBallConstraint{ i, j, x0, x1, ri, rj, kick, true } (Lees-Edwards portal) */
 /* rigidbody3d (rigidbody3d/Constraints/): body-body in ascending (i,j) candidate order, then planes plane-major */
 #define SG_SPHERE_SPHERE 10           /* SphereSphereConstraint{ i, j, n, p, ri, rj } */
 #define SG_KINEMATIC_SPHERE_SPHERE 11 /* KinematicSphereSphereConstraint: i = free sphere, j = kinematic one, p = its centre at q0 */
@@ -118,6 +121,26 @@ typedef struct sg_contacts
   const uint32_t* aux;   /* n_active (rigidbody3d only): corner / hull vertex number for plane-box / plane-body */
 } sg_contacts;
 
+/* What the portal path of ball2d adds to an active set (sg_ball2d_teleported).  Portal words hold the portal index, with
+ * bit 31 set when the ball went through plane B (TeleportedBall::planeIndex() == 1); 0xffffffff = that ball was not
+ * teleported.  The teleported contacts are entries [n_regular, n_regular + n_teleported) of the sg_contacts arrays; for
+ * each, x0 / x1 are the teleported centres at q0 and kick the kinematic kick -- the arguments generateTeleportedBallBallCollision
+ * (ball2d/Ball2DSim.cpp:653-728) passes to the constraint constructors.  Candidate pairs of that active set index the
+ * extended box list: i >= n is teleported box i - n of this table. */
+typedef struct sg_teleported
+{
+  uint64_t n_boxes;           /* teleported AABBs appended after the n real ones, portal-major (Ball2DSim.cpp:390-413) */
+  const uint32_t* box_body;   /* n_boxes: TeleportedBall::bodyIndex() */
+  const uint32_t* box_portal; /* n_boxes: portal word */
+  uint64_t n_regular;         /* ball-ball contacts between un-teleported balls */
+  uint64_t n_teleported;      /* teleported contacts (n_body_body = n_regular + n_teleported) */
+  const uint32_t* portal0;    /* n_teleported: portal word of body i */
+  const uint32_t* portal1;    /* n_teleported: portal word of body j */
+  const double* x0;           /* 2 n_teleported */
+  const double* x1;           /* 2 n_teleported */
+  const double* kick;         /* 2 n_teleported (0 for SG_BALL_BALL_TELEPORTED) */
+} sg_teleported;
+
 /* ---- context ------------------------------------------------------------------------------------- */
 int sg_create( sg_ctx** ctx, int device );
 void sg_destroy( sg_ctx* ctx );
@@ -158,12 +181,30 @@ int sg_ball2d_set_gravity( sg_ctx* ctx, const double* g /* 2 */ );
 int sg_ball2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 2n */, const double* nrm /* 2n */ );
 int sg_ball2d_set_drums( sg_ctx* ctx, uint32_t n, const double* x /* 2n */, const double* r /* n */ );
 
+/* Planar and Lees-Edwards portals (ball2d/Portals/PlanarPortal.h; at most 8).  Per portal: the two StaticPlanes (point and
+ * normal, normalised here as StaticPlane's constructor does), the tangential velocity v (0 = plain periodic portal) and the
+ * bounds of the periodic tangential coordinate (0 for plain portals), as PlanarPortal( plane_a, plane_b, velocity, bounds ).
+ * Once portals are set, sg_ball2d_active_set / sg_ball2d_step follow Ball2DSim::computeBallBallActiveSetSpatialGridWithPortals
+ * (ball2d/Ball2DSim.cpp:368-546): boxes at q1 only, BallBallConstraint::isActive at q1 instead of CCD, teleported copies of the
+ * balls that touch a portal plane, SG_BALL_BALL_TELEPORTED / SG_BALL_BALL_KICK_TELEPORTED contacts after the regular ones.
+ * SG_ERR_UNSUPPORTED where the reference exits (a ball touching both planes of one portal, PlanarPortal.cpp:117-121).
+ * n = 0 removes the portals.  Not available in slab mode.
+ *   update_portals   Ball2DSim::updatePeriodicBoundaryConditionsStartOfStep (Ball2DSim.cpp:327-334) with t = next_iteration * dt;
+ *                    dx_out (optional, n values) receives each portal's tangential offset
+ *   enforce_portals  Ball2DSim::enforcePeriodicBoundaryConditions (Ball2DSim.cpp:336-366) on host vectors q, v (2n each), in place
+ *   teleported       details of the last active set computed with portals (pinned memory, valid until the next call) */
+int sg_ball2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x /* 2n */, const double* plane_a_n /* 2n */, const double* plane_b_x /* 2n */, const double* plane_b_n /* 2n */,
+                           const double* v /* n */, const double* bounds /* n */ );
+int sg_ball2d_update_portals( sg_ctx* ctx, double t, double* dx_out );
+int sg_ball2d_enforce_portals( sg_ctx* ctx, double* q, double* v );
+int sg_ball2d_teleported( sg_ctx* ctx, sg_teleported* out );
+
 /* UnconstrainedMap::flow( q0, v0, fsys, iteration, dt, q1, v1 ) -- scisim/UnconstrainedMaps/UnconstrainedMap.h:33
  * for ball2d's SymplecticEulerMap / VerletMap with the gravity force set above. q1/v1 are caller-sized (2n). */
 int sg_ball2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
 
 /* ConstrainedSystem::computeActiveSet( q0, qp, v, active_set ) -- scisim/Constraints/ConstrainedSystem.h:20 as
- * implemented by Ball2DSim::computeActiveSet (ball2d/Ball2DSim.cpp:151-173, no portals). */
+ * implemented by Ball2DSim::computeActiveSet (ball2d/Ball2DSim.cpp:151-173; with portals set: the portal branch, see above). */
 int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
 
 /* Resident variants: state stays in HBM between calls (what `value` in bench.py times).

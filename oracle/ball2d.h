@@ -118,36 +118,10 @@ inline Ball2DContact makeBallBall( const uint32_t i, const uint32_t j, const dou
   return c;
 }
 
-// candidates_out (optional): the broad-phase pair set, ascending (i,j)
-// use_grid: true = literal std::map/std::set spatial grid, false = all pairs (same set, F3)
-inline void computeActiveSet( const Ball2DScene& s, const double* q0, const double* q1, std::vector<Ball2DContact>& active_set,
-                              std::vector<std::pair<unsigned,unsigned>>* candidates_out = nullptr, const bool use_grid = true )
+// Drums then planes, appended to active_set (ball2d/Ball2DSim.cpp:730-762)
+inline void computeStaticActiveSet( const Ball2DScene& s, const double* q0, const double* q1, std::vector<Ball2DContact>& active_set )
 {
   const uint32_t nb = uint32_t( s.r.size() );
-  active_set.clear();
-  // Ball-ball
-  if( nb > 0 )
-  {
-    PairSet possible_overlaps;
-    {
-      std::vector<Box<2>> aabbs;
-      buildAABBs( s, q0, q1, aabbs );
-      if( use_grid ) { getPotentialOverlaps<2>( aabbs, possible_overlaps ); }
-      else { getPotentialOverlapsAllPairs<2>( aabbs, possible_overlaps ); }
-    }
-    if( candidates_out != nullptr ) { candidates_out->assign( possible_overlaps.begin(), possible_overlaps.end() ); }
-    for( const auto& pr : possible_overlaps )
-    {
-      const uint32_t a = pr.first;
-      const uint32_t b = pr.second;
-      const V2 q0a{ q0[2 * a], q0[2 * a + 1] };
-      const V2 q1a{ q1[2 * a], q1[2 * a + 1] };
-      const V2 q0b{ q0[2 * b], q0[2 * b + 1] };
-      const V2 q1b{ q1[2 * b], q1[2 * b + 1] };
-      const std::pair<bool,double> ccd = ballBallCCDCollisionHappens( q0a, q1a, s.r[a], q0b, q1b, s.r[b] );
-      if( ccd.first ) { active_set.emplace_back( makeBallBall( a, b, q0, q1, s.r[a], s.r[b] ) ); }
-    }
-  }
   // Drums: drum-major, ball ascending
   for( uint32_t d = 0; d < uint32_t( s.drum_x.size() ); ++d )
   {
@@ -186,6 +160,39 @@ inline void computeActiveSet( const Ball2DScene& s, const double* q0, const doub
       }
     }
   }
+}
+
+// candidates_out (optional): the broad-phase pair set, ascending (i,j)
+// use_grid: true = literal std::map/std::set spatial grid, false = all pairs (same set, F3)
+inline void computeActiveSet( const Ball2DScene& s, const double* q0, const double* q1, std::vector<Ball2DContact>& active_set,
+                              std::vector<std::pair<unsigned,unsigned>>* candidates_out = nullptr, const bool use_grid = true )
+{
+  const uint32_t nb = uint32_t( s.r.size() );
+  active_set.clear();
+  // Ball-ball
+  if( nb > 0 )
+  {
+    PairSet possible_overlaps;
+    {
+      std::vector<Box<2>> aabbs;
+      buildAABBs( s, q0, q1, aabbs );
+      if( use_grid ) { getPotentialOverlaps<2>( aabbs, possible_overlaps ); }
+      else { getPotentialOverlapsAllPairs<2>( aabbs, possible_overlaps ); }
+    }
+    if( candidates_out != nullptr ) { candidates_out->assign( possible_overlaps.begin(), possible_overlaps.end() ); }
+    for( const auto& pr : possible_overlaps )
+    {
+      const uint32_t a = pr.first;
+      const uint32_t b = pr.second;
+      const V2 q0a{ q0[2 * a], q0[2 * a + 1] };
+      const V2 q1a{ q1[2 * a], q1[2 * a + 1] };
+      const V2 q0b{ q0[2 * b], q0[2 * b + 1] };
+      const V2 q1b{ q1[2 * b], q1[2 * b + 1] };
+      const std::pair<bool,double> ccd = ballBallCCDCollisionHappens( q0a, q1a, s.r[a], q0b, q1b, s.r[b] );
+      if( ccd.first ) { active_set.emplace_back( makeBallBall( a, b, q0, q1, s.r[a], s.r[b] ) ); }
+    }
+  }
+  computeStaticActiveSet( s, q0, q1, active_set );
 }
 
 }

@@ -4,6 +4,7 @@
 // restatement so that tests/ (ctypes) and bench.py's cpu_baseline leg can call it. Never linked into
 // or loaded by the product library.
 #include "ball2d.h"
+#include "ball2d_portals.h"
 #include "broadphase.h"
 #include "ccd.h"
 
@@ -82,6 +83,8 @@ struct Ball2DHandle
   std::vector<std::pair<unsigned,unsigned>> candidates;
   double seconds_flow = 0.0;
   double seconds_active = 0.0;
+  std::vector<Portal2D> portals;
+  PortalActiveSetResult pres;
 };
 
 // plane_n is normalised here exactly as StaticPlane's constructor does (ball2d/StaticGeometry/StaticPlane.cpp:10-14)
@@ -142,6 +145,91 @@ void orc_ball2d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32
     n[2 * k] = c.n.x; n[2 * k + 1] = c.n.y;
     p[2 * k] = c.p.x; p[2 * k + 1] = c.p.y;
     depth[k] = c.depth;
+  }
+}
+
+// ---- ball2d portals (oracle/ball2d_portals.h) ----------------------------------------------------------
+// plane normals are normalised as StaticPlane's constructor does; dx starts at 0 (PlanarPortal.cpp:61-69)
+void orc_ball2d_set_portals( void* hv, uint32_t n, const double* ax, const double* an, const double* bx, const double* bn, const double* v, const double* bounds )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  h->portals.clear();
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    Portal2D pt;
+    pt.a = makePlane2D( V2{ ax[2 * p], ax[2 * p + 1] }, V2{ an[2 * p], an[2 * p + 1] } );
+    pt.b = makePlane2D( V2{ bx[2 * p], bx[2 * p + 1] }, V2{ bn[2 * p], bn[2 * p + 1] } );
+    pt.v = v[p]; pt.bounds = bounds[p]; pt.dx = 0.0;
+    h->portals.push_back( pt );
+  }
+}
+// Ball2DSim::updatePeriodicBoundaryConditionsStartOfStep with t = next_iteration * dt (ball2d/Ball2DSim.cpp:327-334)
+void orc_ball2d_update_portals( void* hv, double t, double* dx_out )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  for( std::size_t p = 0; p < h->portals.size(); ++p ) { updateMovingPortals( h->portals[p], t ); if( dx_out != nullptr ) { dx_out[p] = h->portals[p].dx; } }
+}
+void orc_ball2d_enforce_portals( void* hv, double* q, double* v )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  enforcePeriodicBoundaryConditions( h->portals, uint32_t( h->scene.r.size() ), q, v );
+}
+// one portal's primitives at one point, for the bit-for-bit check against the reference's own PlanarPortal.cpp:
+// out[0..1] through plane A, [2..3] through plane B, [4..5] teleportBall, [6..7] teleportPointInsidePortal,
+// [8..9] getKinematicVelocityOfBall, [10..11] getKinematicVelocityOfPoint; flags: bit 0 ballTouchesPortal, bit 1 its plane index,
+// bit 2 touches both, bit 3 pointInsidePortal
+uint32_t orc_ball2d_portal_probe( const void* hv, uint32_t p, const double* x, double r, double* out )
+{
+  const Ball2DHandle* h = static_cast<const Ball2DHandle*>( hv );
+  const Portal2D& pt = h->portals[p];
+  const V2 xin{ x[0], x[1] };
+  const V2 a = teleportPointThroughPlaneA( pt, xin ), b = teleportPointThroughPlaneB( pt, xin );
+  const V2 tb = teleportBall( pt, xin, r ), ti = teleportPointInsidePortal( pt, xin );
+  const V2 kb = getKinematicVelocityOfBall( pt, xin, r ), kp = getKinematicVelocityOfPoint( pt, xin );
+  out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y; out[4] = tb.x; out[5] = tb.y; out[6] = ti.x; out[7] = ti.y;
+  out[8] = kb.x; out[9] = kb.y; out[10] = kp.x; out[11] = kp.y;
+  const int touch = ballTouchesPortal( pt, xin, r );
+  uint32_t flags = 0u;
+  if( touch != 0 ) { flags |= 1u; }
+  if( touch == 2 ) { flags |= 2u; }
+  if( touch < 0 ) { flags |= 4u; }
+  if( pointInsidePortal( pt, xin ) ) { flags |= 8u; }
+  return flags;
+}
+// returns 0, or -1 where the reference exits (a ball touching both planes of one portal)
+int orc_ball2d_active_set_portals( void* hv, const double* q0, const double* q1, int method )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  const auto t0 = std::chrono::steady_clock::now();
+  computeActiveSetWithPortals( h->scene, h->portals, q0, q1, h->pres, method == 0 );
+  h->seconds_active = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+  h->active = h->pres.active;
+  h->candidates = h->pres.candidates;
+  return h->pres.both_planes_touched ? -1 : 0;
+}
+uint64_t orc_ball2d_portals_num_regular( const void* h ) { return static_cast<const Ball2DHandle*>( h )->pres.n_regular; }
+uint64_t orc_ball2d_portals_num_boxes( const void* h ) { return static_cast<const Ball2DHandle*>( h )->pres.teleported_boxes.size(); }
+uint64_t orc_ball2d_portals_num_teleported( const void* h ) { return static_cast<const Ball2DHandle*>( h )->pres.teleported_info.size(); }
+// box_portal: portal index | plane index << 31
+void orc_ball2d_portals_copy_boxes( const void* hv, uint32_t* box_body, uint32_t* box_portal )
+{
+  const Ball2DHandle* h = static_cast<const Ball2DHandle*>( hv );
+  for( std::size_t k = 0; k < h->pres.teleported_boxes.size(); ++k )
+  {
+    const TeleportedBall2D& tb = h->pres.teleported_boxes[k];
+    box_body[k] = tb.body; box_portal[k] = tb.portal | ( tb.plane ? 0x80000000u : 0u );
+  }
+}
+// portal0/1: portal index | plane index << 31, 0xffffffff when that body was not teleported; x0, x1, kick: 2 doubles each
+void orc_ball2d_portals_copy_teleported( const void* hv, uint32_t* portal0, uint32_t* portal1, double* x0, double* x1, double* kick )
+{
+  const Ball2DHandle* h = static_cast<const Ball2DHandle*>( hv );
+  for( std::size_t k = 0; k < h->pres.teleported_info.size(); ++k )
+  {
+    const TeleportedContactInfo& t = h->pres.teleported_info[k];
+    portal0[k] = t.p0 == NO_PORTAL ? NO_PORTAL : ( t.p0 | ( t.pl0 ? 0x80000000u : 0u ) );
+    portal1[k] = t.p1 == NO_PORTAL ? NO_PORTAL : ( t.p1 | ( t.pl1 ? 0x80000000u : 0u ) );
+    x0[2 * k] = t.x0.x; x0[2 * k + 1] = t.x0.y; x1[2 * k] = t.x1.x; x1[2 * k + 1] = t.x1.y; kick[2 * k] = t.kick.x; kick[2 * k + 1] = t.kick.y;
   }
 }
 

@@ -1,10 +1,12 @@
 // oracle/ref_shims/ref_ball2d.cpp -- TEST INFRASTRUCTURE.  C entry points around the reference's own, unmodified
 //   ball2d/SpatialGridDetector.cpp                               (AABB, getPotentialOverlaps, getPotentialOverlapsAllPairs)
 //   scisim/CollisionDetection/CollisionDetectionUtilities.cpp    (computeCCDQuadraticCoeffs, ballBallCCDCollisionHappens)
+//   ball2d/StaticGeometry/StaticPlane.cpp, ball2d/Portals/PlanarPortal.cpp   (portal touch tests, teleports, kinematic velocities)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).  The glue between them (swept boxes,
 // pair loop) restates ball2d/Ball2DSim.cpp:553-608 and is marked as such.
 #include "ball2d/SpatialGridDetector.h"
 #include "scisim/CollisionDetection/CollisionDetectionUtilities.h"
+#include "ball2d/Portals/PlanarPortal.h"
 
 #include <cstdint>
 
@@ -64,6 +66,42 @@ void ref_ball2d_detect( const uint32_t n, const double* q0, const double* q1, co
   }
   *n_candidates = overlaps.size();
   *n_active = na;
+}
+
+// ---- PlanarPortal (ball2d/Portals/PlanarPortal.cpp) -----------------------------------------------------------------
+void* ref_portal_create( const double* ax, const double* an, const double* bx, const double* bn, const double v, const double bounds )
+{
+  const StaticPlane a{ Vector2s{ ax[0], ax[1] }, Vector2s{ an[0], an[1] } };
+  const StaticPlane b{ Vector2s{ bx[0], bx[1] }, Vector2s{ bn[0], bn[1] } };
+  return new PlanarPortal{ a, b, v, bounds };
+}
+void ref_portal_destroy( void* p ) { delete static_cast<PlanarPortal*>( p ); }
+void ref_portal_update( void* p, const double t ) { static_cast<PlanarPortal*>( p )->updateMovingPortals( t ); }
+// same layout as orc_ball2d_portal_probe (oracle/capi.cpp)
+uint32_t ref_portal_probe( const void* pv, const double* x, const double r, double* out )
+{
+  const PlanarPortal& p = *static_cast<const PlanarPortal*>( pv );
+  const Vector2s xin{ x[0], x[1] };
+  Vector2s a, b, tb, ti;
+  p.teleportPointThroughPlaneA( xin, a );
+  p.teleportPointThroughPlaneB( xin, b );
+  p.teleportBall( xin, r, tb );
+  p.teleportPointInsidePortal( xin, ti );
+  const Vector2s kb{ p.getKinematicVelocityOfBall( xin, r ) };
+  const Vector2s kp{ p.getKinematicVelocityOfPoint( xin ) };
+  out[0] = a.x(); out[1] = a.y(); out[2] = b.x(); out[3] = b.y(); out[4] = tb.x(); out[5] = tb.y(); out[6] = ti.x(); out[7] = ti.y();
+  out[8] = kb.x(); out[9] = kb.y(); out[10] = kp.x(); out[11] = kp.y();
+  uint32_t flags = 0u;
+  // ballTouchesPortal exits the process when both planes are touched: test that case through the planes themselves
+  const bool both = p.planeA().distanceLessThanOrEqualZero( xin, r ) && p.planeB().distanceLessThanOrEqualZero( xin, r );
+  if( both ) { flags |= 4u; }
+  else
+  {
+    bool plane_idx = false;
+    if( p.ballTouchesPortal( xin, r, plane_idx ) ) { flags |= 1u; if( plane_idx ) { flags |= 2u; } }
+  }
+  if( p.pointInsidePortal( xin ) ) { flags |= 8u; }
+  return flags;
 }
 
 }

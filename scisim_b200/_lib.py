@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, "libscisim_b200.so")
 SG_OK = 0
 SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV = 0, 1, 2, 3
 SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
+SG_BALL_BALL_TELEPORTED, SG_BALL_BALL_KICK_TELEPORTED = 3, 4
+SG_NO_PORTAL, SG_PLANE_B_BIT = 0xFFFFFFFF, 0x80000000
 SG_SPHERE_SPHERE, SG_KINEMATIC_SPHERE_SPHERE, SG_BODY_BODY, SG_KINEMATIC_BODY_BODY, SG_PLANE_SPHERE, SG_PLANE_BOX, SG_PLANE_BODY = 10, 11, 12, 13, 14, 15, 16
 SG_OUT_NORMALS, SG_OUT_POINTS, SG_OUT_DEPTHS, SG_OUT_CANDIDATES, SG_OUT_ALL = 1, 2, 4, 8, 15
 SG_IN_RESIDENT = 256
@@ -28,6 +30,11 @@ class SgContacts(C.Structure):
     _fields_ = [("dim", C.c_uint32), ("n_candidates", C.c_uint64), ("n_active", C.c_uint64), ("n_body_body", C.c_uint64),
                 ("n_drum", C.c_uint64), ("n_plane", C.c_uint64), ("type", c_up), ("i", c_up), ("j", c_up),
                 ("n", c_dp), ("p", c_dp), ("depth", c_dp), ("cand_ij", c_up), ("aux", c_up)]
+
+
+class SgTeleported(C.Structure):
+    _fields_ = [("n_boxes", C.c_uint64), ("box_body", c_up), ("box_portal", c_up), ("n_regular", C.c_uint64), ("n_teleported", C.c_uint64),
+                ("portal0", c_up), ("portal1", c_up), ("x0", c_dp), ("x1", c_dp), ("kick", c_dp)]
 
 
 class SciSimB200Error(RuntimeError):
@@ -67,6 +74,10 @@ def load():
         "sg_ball2d_set_gravity": (C.c_int, [vp, vp]),
         "sg_ball2d_set_planes": (C.c_int, [vp, C.c_uint32, vp, vp]),
         "sg_ball2d_set_drums": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_ball2d_set_portals": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp, vp, vp]),
+        "sg_ball2d_update_portals": (C.c_int, [vp, C.c_double, vp]),
+        "sg_ball2d_enforce_portals": (C.c_int, [vp, vp, vp]),
+        "sg_ball2d_teleported": (C.c_int, [vp, C.POINTER(SgTeleported)]),
         "sg_ball2d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
         "sg_ball2d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
         "sg_ball2d_upload": (C.c_int, [vp, vp, vp]),

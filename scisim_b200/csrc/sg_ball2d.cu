@@ -389,6 +389,8 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_static_emit( const __grid_cons
 }
 
 // ---- host side -------------------------------------------------------------------------------------
+struct PortalData; // sg_ball2d_portals.cuh
+
 struct Ball2DData
 {
   uint32_t n = 0;
@@ -408,6 +410,9 @@ struct Ball2DData
   uint64_t n_cand = 0, n_bb = 0, n_static = 0, n_drum = 0, n_plane = 0;
   bool have_result = false;
   bool cand_valid = false;
+  // planar / Lees-Edwards portals (sg_ball2d_portals.cuh): allocated by sg_ball2d_set_portals
+  PortalData* px = nullptr;
+  bool portal_result = false; // the last result came from the portal path (its candidate list lives in px->bp)
   // slab mode (one slab of a larger scene per GPU): the body arrays hold [left ghosts | owned | right ghosts] with
   // ghost_cap slots reserved on either side of the owned block (slot order == global index order); how many of
   // them are in use this step is only known on the device (ghost_counts), unused slots are skipped by every kernel.
@@ -444,6 +449,11 @@ struct Ball2DData
   Ball2DData() { memset( &sg, 0, sizeof( sg ) ); }
 };
 
+static void ball2d_portal_release( Ball2DData* d );
+static bool ball2d_has_portals( const Ball2DData* d );
+static int ball2d_portal_active_set_device( sg_ctx* ctx, Ball2DData* d, const int flow_kind, const double dt );
+static const DevBuf& ball2d_result_candidates( const Ball2DData* d );
+
 void sg_ball2d_release( sg_ctx* ctx )
 {
   Ball2DData* d = ctx->ball2d;
@@ -456,6 +466,7 @@ void sg_ball2d_release( sg_ctx* ctx )
   d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release(); d->pack_done.release(); d->block_iv.release();
   for( int sde = 0; sde < 2; ++sde ) { if( d->peer_mb[sde] != nullptr && d->peer_ipc[sde] ) { cudaIpcCloseMemHandle( d->peer_mb[sde] ); } d->peer_mb[sde] = nullptr; }
   d->mailbox.release();
+  ball2d_portal_release( d );
   delete d;
   ctx->ball2d = nullptr;
 }
@@ -502,6 +513,9 @@ static int ball2d_static_scratch( sg_ctx* ctx, Ball2DData* d )
 static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want_cand, const int flow_kind = -1, const double dt = 0.0 )
 {
   const uint32_t n = d->n;
+  // with portals the reference takes another road altogether (Ball2DSim.cpp:159-166): boxes at q1, no CCD, teleported copies
+  if( ball2d_has_portals( d ) ) { return ball2d_portal_active_set_device( ctx, d, flow_kind, dt ); }
+  d->portal_result = false;
   d->n_cand = d->n_bb = d->n_static = d->n_drum = d->n_plane = 0;
   d->have_result = true;
   d->cand_valid = want_cand;
@@ -633,7 +647,7 @@ static int ball2d_copy_out( sg_ctx* ctx, Ball2DData* d, const uint32_t flags, sg
     if( flags & SG_OUT_POINTS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_p, d->c_p.ptr, na * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
     if( flags & SG_OUT_DEPTHS ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_d, d->c_depth.ptr, na * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
   }
-  if( want_cand && d->n_cand > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_c, d->bp.cand.ptr, d->n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( want_cand && d->n_cand > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_c, ball2d_result_candidates( d ).ptr, d->n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   out->type = reinterpret_cast<const uint32_t*>( h + o_type );
   out->i = reinterpret_cast<const uint32_t*>( h + o_i );
@@ -649,6 +663,14 @@ static int ball2d_copy_out( sg_ctx* ctx, Ball2DData* d, const uint32_t flags, sg
   return SG_OK;
 }
 
+#include "sg_ball2d_portals.cuh"
+
+static void ball2d_portal_release( Ball2DData* d )
+{
+  if( d->px != nullptr ) { d->px->release(); delete d->px; d->px = nullptr; }
+}
+static bool ball2d_has_portals( const Ball2DData* d ) { return d->px != nullptr && d->px->portals.n > 0u; }
+static const DevBuf& ball2d_result_candidates( const Ball2DData* d ) { return ( d->portal_result && d->px != nullptr ) ? d->px->bp.cand : d->bp.cand; }
 
 // ---- slab mode: halo selection, packing and unpacking ----------------------------------------------
 // Exchange buffers hold ghost_cap + 1 records of 48 bytes; record 0 is a header whose gid field is the count, so the
@@ -1009,6 +1031,107 @@ int sg_ball2d_set_drums( sg_ctx* ctx, uint32_t n, const double* x, const double*
   return SG_OK;
 }
 
+int sg_ball2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x, const double* plane_a_n, const double* plane_b_x, const double* plane_b_n, const double* v, const double* bounds )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > SG_MAX_PORTALS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_portals: at most %d portals", SG_MAX_PORTALS ); }
+  if( n > 0 && ( plane_a_x == nullptr || plane_a_n == nullptr || plane_b_x == nullptr || plane_b_n == nullptr || v == nullptr || bounds == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_portals: null array" ); }
+  Ball2DData* d = ball2d_data( ctx );
+  if( d->slab && n > 0 ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_set_portals: portals are not supported in slab mode" ); }
+  if( n == 0 && d->px == nullptr ) { return SG_OK; }
+  PortalData* x = ball2d_portal_data( d );
+  memset( &x->portals, 0, sizeof( x->portals ) );
+  x->portals.n = n;
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    SgPortal2D& pt = x->portals.p[p];
+    for( int k = 0; k < 2; ++k ) { pt.ax[k] = plane_a_x[2 * p + k]; pt.bx[k] = plane_b_x[2 * p + k]; }
+    // StaticPlane::StaticPlane (ball2d/StaticGeometry/StaticPlane.cpp:10-14)
+    sg_portal_plane_frame( plane_a_n + 2 * p, pt.an, pt.at );
+    sg_portal_plane_frame( plane_b_n + 2 * p, pt.bn, pt.bt );
+    if( bounds[p] < 0.0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_portals: portal %u has negative bounds", p ); }
+    pt.v = v[p]; pt.bounds = bounds[p]; pt.dx = 0.0; // PlanarPortal::PlanarPortal: m_dx( 0.0 )
+  }
+  d->have_result = false;
+  return SG_OK;
+}
+
+int sg_ball2d_update_portals( sg_ctx* ctx, double t, double* dx_out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( d->px == nullptr ) { return SG_OK; }
+  for( uint32_t p = 0; p < d->px->portals.n; ++p )
+  {
+    SgPortal2D& pt = d->px->portals.p[p];
+    pt.dx = sg_portal_offset( pt.v, pt.bounds, t );
+    if( dx_out != nullptr ) { dx_out[p] = pt.dx; }
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_enforce_portals( sg_ctx* ctx, double* q, double* v )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( d->slab ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_enforce_portals: portals are not supported in slab mode" ); }
+  if( !ball2d_has_portals( d ) || d->n == 0 ) { return SG_OK; }
+  if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_enforce_portals: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  // q1 / v1 serve as the staging copies: whatever flow left there is overwritten, so residency ends here
+  d->flow_resident = false;
+  const size_t bytes = size_t( d->n ) * 16;
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v1.ptr, v, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_LAUNCH( ctx, "b2p_enforce", double( d->n ) * 64.0, k_b2p_enforce<<<sg_div_up( d->n, 256 ), 256, 0, ctx->stream>>>( d->px->portals, d->n, d->q1.as<double2>(), d->v1.as<double2>() ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( q, d->q1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( v, d->v1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+int sg_ball2d_teleported( sg_ctx* ctx, sg_teleported* out )
+{
+  if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
+  memset( out, 0, sizeof( *out ) );
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->have_result || !d->portal_result || d->px == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_teleported: the last active set was not computed with portals" ); }
+  PortalData* x = d->px;
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  auto al = []( size_t b ) { return ( b + 63 ) & ~size_t( 63 ); };
+  const size_t nb = x->n_boxes, nt = x->n_tel;
+  size_t bytes = 64;
+  const size_t o_bb = bytes; bytes += al( nb * 4 );
+  const size_t o_bp = bytes; bytes += al( nb * 4 );
+  const size_t o_p0 = bytes; bytes += al( nt * 4 );
+  const size_t o_p1 = bytes; bytes += al( nt * 4 );
+  const size_t o_x0 = bytes; bytes += al( nt * 16 );
+  const size_t o_x1 = bytes; bytes += al( nt * 16 );
+  const size_t o_k = bytes; bytes += al( nt * 16 );
+  SG_CUDA( ctx, x->h_tele.ensure( bytes ) );
+  char* h = x->h_tele.as<char>();
+  if( nb > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_bb, x->box_body.ptr, nb * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_bp, x->box_portal.ptr, nb * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  }
+  if( nt > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_p0, x->tp0.ptr, nt * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_p1, x->tp1.ptr, nt * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_x0, x->x0t.ptr, nt * 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_x1, x->x1t.ptr, nt * 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_k, x->kick.ptr, nt * 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+  }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  out->n_boxes = nb; out->n_regular = x->n_reg; out->n_teleported = nt;
+  out->box_body = reinterpret_cast<const uint32_t*>( h + o_bb ); out->box_portal = reinterpret_cast<const uint32_t*>( h + o_bp );
+  out->portal0 = reinterpret_cast<const uint32_t*>( h + o_p0 ); out->portal1 = reinterpret_cast<const uint32_t*>( h + o_p1 );
+  out->x0 = reinterpret_cast<const double*>( h + o_x0 ); out->x1 = reinterpret_cast<const double*>( h + o_x1 ); out->kick = reinterpret_cast<const double*>( h + o_k );
+  return SG_OK;
+}
+
 int sg_ball2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
@@ -1123,6 +1246,7 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   if( uint64_t( n_owned ) + 2ull * ghost_cap >= 0x80000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_init: slab too large" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   Ball2DData* d = ball2d_data( ctx );
+  if( ball2d_has_portals( d ) ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_slab_init: portals are not supported in slab mode" ); }
   d->slab = true; d->n_owned = n_owned; d->ghost_cap = ghost_cap; d->gid_first = gid_first;
   const size_t slots = size_t( n_owned ) + 2 * size_t( ghost_cap );
   d->n = uint32_t( slots );

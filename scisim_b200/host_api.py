@@ -158,10 +158,45 @@ class ActiveSet:
             self.candidates = None
 
 
-class Ball2DState:
-    """Static part of ball2d/Ball2DState.h: radii, per-ball masses, gravity, planes, drums."""
+class PlanarPortal:
+    """ball2d/Portals/PlanarPortal.h: PlanarPortal( plane_a, plane_b, velocity, bounds ); planes as (point, normal)."""
 
-    def __init__(self, r, m, g=(0.0, 0.0), plane_x=None, plane_n=None, drum_x=None, drum_r=None):
+    def __init__(self, plane_a_x, plane_a_n, plane_b_x, plane_b_n, velocity=0.0, bounds=0.0):
+        self.plane_a_x, self.plane_a_n = _f64(plane_a_x), _f64(plane_a_n)
+        self.plane_b_x, self.plane_b_n = _f64(plane_b_x), _f64(plane_b_n)
+        self.velocity, self.bounds = float(velocity), float(bounds)
+
+    def isLeesEdwards(self):
+        return self.velocity != 0.0
+
+    @staticmethod
+    def from_arrays(portals):
+        """The dict layout of scenes.ball2d_periodic -> list of PlanarPortal."""
+        return [PlanarPortal(portals["plane_a_x"][p], portals["plane_a_n"][p], portals["plane_b_x"][p], portals["plane_b_n"][p], portals["v"][p], portals["bounds"][p])
+                for p in range(len(portals["v"]))]
+
+
+class TeleportedInfo:
+    """What the portal branch adds to an ActiveSet (sg_teleported, include/scisim_b200.h)."""
+
+    def __init__(self, t):
+        nb, nt = int(t.n_boxes), int(t.n_teleported)
+        self.n_regular = int(t.n_regular)
+        self.n_teleported = nt
+        arr = lambda p, shape, dt: np.ctypeslib.as_array(p, shape=shape).copy() if shape[0] > 0 else np.zeros(shape, dtype=dt)
+        self.box_body = arr(t.box_body, (nb,), np.uint32)
+        self.box_portal = arr(t.box_portal, (nb,), np.uint32)
+        self.portal0 = arr(t.portal0, (nt,), np.uint32)
+        self.portal1 = arr(t.portal1, (nt,), np.uint32)
+        self.x0 = arr(t.x0, (nt, 2), np.float64)
+        self.x1 = arr(t.x1, (nt, 2), np.float64)
+        self.kick = arr(t.kick, (nt, 2), np.float64)
+
+
+class Ball2DState:
+    """Static part of ball2d/Ball2DState.h: radii, per-ball masses, gravity, planes, drums, planar portals."""
+
+    def __init__(self, r, m, g=(0.0, 0.0), plane_x=None, plane_n=None, drum_x=None, drum_r=None, planar_portals=None):
         self.r = _f64(r)
         self.m = _f64(m)
         assert self.r.shape == self.m.shape and self.r.ndim == 1
@@ -170,9 +205,13 @@ class Ball2DState:
         self.plane_n = _f64(plane_n if plane_n is not None else np.zeros((0, 2)))
         self.drum_x = _f64(drum_x if drum_x is not None else np.zeros((0, 2)))
         self.drum_r = _f64(drum_r if drum_r is not None else np.zeros((0,)))
+        self.planar_portals = list(planar_portals) if planar_portals is not None else []
 
     def nballs(self):
         return self.r.shape[0]
+
+    def numPlanarPortals(self):
+        return len(self.planar_portals)
 
 
 class _Ball2DMap:
@@ -212,9 +251,38 @@ class Ball2DSim:
         self.ctx.check(lib.sg_ball2d_set_gravity(h, _ptr(state.g)))
         self.ctx.check(lib.sg_ball2d_set_planes(h, state.plane_x.shape[0], _ptr(state.plane_x), _ptr(state.plane_n)))
         self.ctx.check(lib.sg_ball2d_set_drums(h, state.drum_x.shape[0], _ptr(state.drum_x), _ptr(state.drum_r)))
+        pp = state.planar_portals
+        if pp:
+            cat = lambda f: _f64(np.array([f(p) for p in pp], dtype=np.float64))
+            arrs = [cat(lambda p: p.plane_a_x), cat(lambda p: p.plane_a_n), cat(lambda p: p.plane_b_x), cat(lambda p: p.plane_b_n),
+                    cat(lambda p: p.velocity), cat(lambda p: p.bounds)]
+            self.ctx.check(lib.sg_ball2d_set_portals(h, len(pp), *[_ptr(a) for a in arrs]))
+        else:
+            self.ctx.check(lib.sg_ball2d_set_portals(h, 0, None, None, None, None, None, None))
 
     def name(self):
         return "ball_2d"
+
+    # ---- portals (ball2d/Ball2DSim.cpp:327-366) ----
+    def updatePeriodicBoundaryConditionsStartOfStep(self, next_iteration, dt):
+        """Moves the Lees-Edwards portals to t = next_iteration * dt; returns their tangential offsets."""
+        dx = np.zeros(max(1, self.state.numPlanarPortals()))
+        self.ctx.check(self.ctx.lib.sg_ball2d_update_portals(self.ctx.h, float(next_iteration * dt), _ptr(dx)))
+        return dx[: self.state.numPlanarPortals()]
+
+    def enforcePeriodicBoundaryConditions(self, q, v):
+        """Teleports the balls that left through a portal (and adds the Lees-Edwards velocity); returns new (q, v)."""
+        q = _f64(q).copy()
+        v = _f64(v).copy()
+        self.ctx.check(self.ctx.lib.sg_ball2d_enforce_portals(self.ctx.h, _ptr(q), _ptr(v)))
+        return q, v
+
+    def teleported(self):
+        """Details of the last active set computed with portals (teleported boxes, constructor arguments of the teleported contacts)."""
+        from ._lib import SgTeleported
+        t = SgTeleported()
+        self.ctx.check(self.ctx.lib.sg_ball2d_teleported(self.ctx.h, C.byref(t)))
+        return TeleportedInfo(t)
 
     def nqdofs(self):
         return 2 * self.state.nballs()

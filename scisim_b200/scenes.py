@@ -63,6 +63,56 @@ def ball2d_random(n, seed, box=None, rmin=0.05, rmax=0.4, nplanes=2, ndrums=1, v
     return scene
 
 
+def ball2d_periodic(n, seed, side=None, rmin=0.1, rmax=0.35, axes="xy", lees_edwards=0.0, t=0.0, vmax=2.0, dt=0.01, oblique=False):
+    """Balls in a periodic box [0, side)^2 with planar portals (ball2d/Portals/PlanarPortal.h).
+
+    axes: which directions are periodic ("x", "y" or "xy"); the others get walls (static planes).  lees_edwards != 0 turns
+    the y pair (or the x pair when only x is periodic) into a Lees-Edwards portal with that tangential velocity and bounds
+    side / 2 (so the tangential coordinate wraps with the box).  Plane points sit at the middle of each side, normals point
+    into the box and are deliberately not unit length.  oblique rotates the whole set-up by 0.3 rad about the box centre so
+    that no expression is axis aligned."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    side = float(side) if side is not None else max(2.0, np.sqrt(n) * 0.7)
+    r = rng.uniform(rmin, rmax, size=n)
+    q = rng.uniform(0.0, side, size=(n, 2))
+    v = rng.uniform(-vmax, vmax, size=(n, 2))
+    h = 0.5 * side
+    pairs = {"x": (([0.0, h], [2.0, 0.0]), ([side, h], [-3.0, 0.0])), "y": (([h, 0.0], [0.0, 1.5]), ([h, side], [0.0, -0.5]))}
+    pax, pan, pbx, pbn, pv, pb = [], [], [], [], [], []
+    plane_x, plane_n = [], []
+    le_axis = "y" if "y" in axes else "x"
+    for ax in "xy":
+        (xa, na), (xb, nb) = pairs[ax]
+        if ax in axes:
+            pax.append(xa); pan.append(na); pbx.append(xb); pbn.append(nb)
+            is_le = lees_edwards != 0.0 and ax == le_axis
+            pv.append(lees_edwards if is_le else 0.0)
+            pb.append(h if is_le else 0.0)
+        else:
+            plane_x += [xa, xb]; plane_n += [na, nb]
+    arr = lambda a, w: np.array(a, dtype=np.float64).reshape(-1, w)
+    portals = {"plane_a_x": arr(pax, 2), "plane_a_n": arr(pan, 2), "plane_b_x": arr(pbx, 2), "plane_b_n": arr(pbn, 2),
+               "v": np.array(pv, dtype=np.float64), "bounds": np.array(pb, dtype=np.float64)}
+    planes_x, planes_n = arr(plane_x, 2), arr(plane_n, 2)
+    if oblique:
+        c, s_ = np.cos(0.3), np.sin(0.3)
+        R = np.array([[c, -s_], [s_, c]])
+        ctr = np.array([h, h])
+        rot_p = lambda a: (a - ctr) @ R.T + ctr
+        rot_v = lambda a: a @ R.T
+        q, v = rot_p(q), rot_v(v)
+        for k in ("plane_a_x", "plane_b_x"):
+            portals[k] = rot_p(portals[k])
+        for k in ("plane_a_n", "plane_b_n"):
+            portals[k] = rot_v(portals[k])
+        planes_x, planes_n = (rot_p(planes_x), rot_v(planes_n)) if planes_x.shape[0] else (planes_x, planes_n)
+    return {
+        "q": np.ascontiguousarray(q).ravel().copy(), "v": np.ascontiguousarray(v).ravel().copy(), "r": r, "m": rng.uniform(0.5, 3.0, size=n),
+        "g": np.array([0.0, 0.0]), "dt": dt, "map": "symplectic_euler", "side": side, "t": float(t),
+        "plane_x": np.ascontiguousarray(planes_x), "plane_n": np.ascontiguousarray(planes_n), "drum_x": np.zeros((0, 2)), "drum_r": np.zeros(0),
+        "portals": {k: np.ascontiguousarray(a) for k, a in portals.items()},
+    }
+
 # ---- rigidbody3d -------------------------------------------------------------------------------------
 def _random_rotations(rng, n):
     """n proper rotation matrices (row-major 9-vectors) from random unit quaternions."""

@@ -48,6 +48,16 @@ def load():
         "orc_ball2d_seconds_active": (C.c_double, [vp]),
         "orc_ball2d_copy_candidates": (None, [vp, vp]),
         "orc_ball2d_copy_active": (None, [vp, vp, vp, vp, vp, vp, vp]),
+        "orc_ball2d_set_portals": (None, [vp, C.c_uint32, vp, vp, vp, vp, vp, vp]),
+        "orc_ball2d_update_portals": (None, [vp, C.c_double, vp]),
+        "orc_ball2d_enforce_portals": (None, [vp, vp, vp]),
+        "orc_ball2d_portal_probe": (C.c_uint32, [vp, C.c_uint32, vp, C.c_double, vp]),
+        "orc_ball2d_active_set_portals": (C.c_int, [vp, vp, vp, C.c_int]),
+        "orc_ball2d_portals_num_regular": (C.c_uint64, [vp]),
+        "orc_ball2d_portals_num_boxes": (C.c_uint64, [vp]),
+        "orc_ball2d_portals_num_teleported": (C.c_uint64, [vp]),
+        "orc_ball2d_portals_copy_boxes": (None, [vp, vp, vp]),
+        "orc_ball2d_portals_copy_teleported": (None, [vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -122,6 +132,55 @@ class Ball2DOracle:
             self.lib.orc_ball2d_copy_active(self.h, _p(out["type"]), _p(out["i"]), _p(out["j"]), _p(out["n"]), _p(out["p"]), _p(out["depth"]))
         out["seconds"] = self.lib.orc_ball2d_seconds_active(self.h)
         out["seconds_flow"] = self.lib.orc_ball2d_seconds_flow(self.h)
+        return out
+
+    # ---- portals (oracle/ball2d_portals.h) ----
+    def set_portals(self, portals):
+        """portals: dict with plane_a_x, plane_a_n, plane_b_x, plane_b_n (P,2), v (P), bounds (P)."""
+        a = [_f64(portals[k]) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n", "v", "bounds")]
+        self.nportals = a[4].shape[0]
+        self.lib.orc_ball2d_set_portals(self.h, self.nportals, *[_p(x) for x in a])
+
+    def update_portals(self, t):
+        dx = np.zeros(self.nportals)
+        self.lib.orc_ball2d_update_portals(self.h, float(t), _p(dx))
+        return dx
+
+    def enforce_portals(self, q, v):
+        q, v = _f64(q).copy(), _f64(v).copy()
+        self.lib.orc_ball2d_enforce_portals(self.h, _p(q), _p(v))
+        return q, v
+
+    def portal_probe(self, p, x, r):
+        out = np.zeros(12)
+        flags = self.lib.orc_ball2d_portal_probe(self.h, int(p), _p(_f64(x)), float(r), _p(out))
+        return int(flags), out
+
+    def active_set_portals(self, q0, q1, method="grid"):
+        """None where the reference exits (a ball touching both planes of one portal)."""
+        q0, q1 = _f64(q0), _f64(q1)
+        if self.lib.orc_ball2d_active_set_portals(self.h, _p(q0), _p(q1), 0 if method == "grid" else 1) != 0:
+            return None
+        nc = self.lib.orc_ball2d_num_candidates(self.h)
+        na = self.lib.orc_ball2d_num_active(self.h)
+        cand = np.zeros((nc, 2), dtype=np.uint32)
+        if nc:
+            self.lib.orc_ball2d_copy_candidates(self.h, _p(cand))
+        out = {"type": np.zeros(na, np.uint32), "i": np.zeros(na, np.uint32), "j": np.zeros(na, np.uint32),
+               "n": np.zeros((na, 2)), "p": np.zeros((na, 2)), "depth": np.zeros(na), "candidates": cand}
+        if na:
+            self.lib.orc_ball2d_copy_active(self.h, _p(out["type"]), _p(out["i"]), _p(out["j"]), _p(out["n"]), _p(out["p"]), _p(out["depth"]))
+        nbx = self.lib.orc_ball2d_portals_num_boxes(self.h)
+        nt = self.lib.orc_ball2d_portals_num_teleported(self.h)
+        out["n_regular"] = int(self.lib.orc_ball2d_portals_num_regular(self.h))
+        out["box_body"], out["box_portal"] = np.zeros(nbx, np.uint32), np.zeros(nbx, np.uint32)
+        if nbx:
+            self.lib.orc_ball2d_portals_copy_boxes(self.h, _p(out["box_body"]), _p(out["box_portal"]))
+        out["portal0"], out["portal1"] = np.zeros(nt, np.uint32), np.zeros(nt, np.uint32)
+        out["x0"], out["x1"], out["kick"] = np.zeros((nt, 2)), np.zeros((nt, 2)), np.zeros((nt, 2))
+        if nt:
+            self.lib.orc_ball2d_portals_copy_teleported(self.h, _p(out["portal0"]), _p(out["portal1"]), _p(out["x0"]), _p(out["x1"]), _p(out["kick"]))
+        out["seconds"] = self.lib.orc_ball2d_seconds_active(self.h)
         return out
 
 

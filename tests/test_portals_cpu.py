@@ -1,0 +1,268 @@
+"""CPU: ball2d portals -- the oracle restatement (oracle/ball2d_portals.h), the reference's own
+PlanarPortal.cpp / StaticPlane.cpp compiled unchanged (oracle/_ref, skipped where absent) and the product's portal
+arithmetic (scisim_b200/csrc/sg_portal2d.h, the header the kernels include, compiled here as plain C++).
+
+  * portal primitives: oracle == reference == product header, bit for bit, plain and Lees-Edwards, oblique planes
+  * the product's teleported-collision sort (bitonic network + first-of-run) == std::set insertion semantics
+  * the oracle's active set on a periodic box == brute-force minimum-image contacts (exact arithmetic on a dyadic grid)
+  * enforcePeriodicBoundaryConditions puts every ball back inside and applies the Lees-Edwards velocity
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from scisim_b200 import scenes
+from tests import oracle_binding as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def pm(tmp_path_factory):
+    """The product header compiled for the host (no FMA contraction, as the library's -fmad=false)."""
+    out = str(tmp_path_factory.mktemp("pm") / "libportal_math.so")
+    src = os.path.join(ROOT, "tests", "portal_math_harness.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src], check=True)
+    lib = C.CDLL(out)
+    lib.pm_probe.restype = C.c_uint32
+    lib.pm_probe.argtypes = [C.c_uint32, C.c_void_p, C.c_double, C.c_void_p]
+    lib.pm_update_portals.argtypes = [C.c_double, C.c_void_p]
+    lib.pm_set_portals.argtypes = [C.c_uint32] + [C.c_void_p] * 6
+    lib.pm_enforce.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.pm_bitonic_sort.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.pm_tele_happens.restype = C.c_int
+    lib.pm_tele_happens.argtypes = [C.c_uint32] * 4 + [C.c_void_p] * 3
+    return lib
+
+
+def _pm_set(pm, portals):
+    a = [np.ascontiguousarray(portals[k], dtype=np.float64) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n", "v", "bounds")]
+    pm.pm_set_portals(a[4].shape[0], *[vp(x) for x in a])
+    return a
+
+
+def _oracle(scene):
+    o = ob.Ball2DOracle(scene)
+    o.set_portals(scene["portals"])
+    return o
+
+
+def _probe_points(scene, rng, count):
+    side = scene["side"]
+    pts = rng.uniform(-0.6 * side, 1.6 * side, size=(count, 2))
+    # many points right at the planes, where the <= / < decisions are made
+    edge = rng.integers(0, 4, size=count // 2)
+    pts[: count // 2, 0] = np.where(edge == 0, 0.0, np.where(edge == 1, side, pts[: count // 2, 0]))
+    pts[: count // 2, 1] = np.where(edge == 2, 0.0, np.where(edge == 3, side, pts[: count // 2, 1]))
+    pts[: count // 4] += rng.uniform(-0.4, 0.4, size=(count // 4, 2))
+    return pts
+
+
+CASES = [dict(axes="xy", lees_edwards=0.0, oblique=False), dict(axes="xy", lees_edwards=0.75, oblique=False, t=3.7),
+         dict(axes="x", lees_edwards=-1.25, oblique=True, t=11.3), dict(axes="y", lees_edwards=0.0, oblique=True)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-le%g-%s" % (c["axes"], c["lees_edwards"], "obl" if c["oblique"] else "axis"))
+def test_portal_primitives_oracle_reference_product(case, pm, oracle):
+    scene = scenes.ball2d_periodic(64, 5, **case)
+    o = _oracle(scene)
+    _pm_set(pm, scene["portals"])
+    t = scene["t"]
+    dx_o = o.update_portals(t)
+    dx_p = np.zeros_like(dx_o)
+    pm.pm_update_portals(t, vp(dx_p))
+    assert np.array_equal(dx_o, dx_p)
+    ref = None
+    path = os.path.join(REFDIR, "libref_ball2d.so")
+    if os.path.exists(path):
+        ref = C.CDLL(path)
+        if not hasattr(ref, "ref_portal_probe"):
+            ref = None
+    handles = []
+    if ref is not None:
+        ref.ref_portal_create.restype = C.c_void_p
+        ref.ref_portal_create.argtypes = [C.c_void_p] * 4 + [C.c_double, C.c_double]
+        ref.ref_portal_update.argtypes = [C.c_void_p, C.c_double]
+        ref.ref_portal_probe.restype = C.c_uint32
+        ref.ref_portal_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        ref.ref_portal_destroy.argtypes = [C.c_void_p]
+        P = scene["portals"]
+        for p in range(P["v"].shape[0]):
+            h = ref.ref_portal_create(vp(P["plane_a_x"][p]), vp(P["plane_a_n"][p]), vp(P["plane_b_x"][p]), vp(P["plane_b_n"][p]), float(P["v"][p]), float(P["bounds"][p]))
+            ref.ref_portal_update(h, t)
+            handles.append(h)
+    rng = np.random.default_rng(17)
+    pts = _probe_points(scene, rng, 4000)
+    radii = rng.uniform(0.05, 0.4, size=pts.shape[0])
+    seen = set()
+    for p in range(scene["portals"]["v"].shape[0]):
+        for x, r in zip(pts, radii):
+            x = np.ascontiguousarray(x)
+            fo, oo = o.portal_probe(p, x, r)
+            op = np.zeros(12)
+            fp = pm.pm_probe(p, vp(x), float(r), vp(op))
+            assert fo == fp and np.array_equal(oo.view(np.uint64), op.view(np.uint64)), (p, x, r)
+            if ref is not None:
+                orf = np.zeros(12)
+                fr = ref.ref_portal_probe(handles[p], vp(x), float(r), vp(orf))
+                assert fr == fo and np.array_equal(orf.view(np.uint64), oo.view(np.uint64)), (p, x, r)
+            seen.add(fo)
+    # the sample exercises every decision: no touch, plane A, plane B, inside, outside
+    assert {0, 1, 3}.issubset({f & 3 for f in seen}) and any(f & 8 for f in seen) and any(not (f & 8) for f in seen)
+    for h in handles:
+        ref.ref_portal_destroy(h)
+    if ref is None and os.path.isdir("/root/reference"):
+        pytest.fail("oracle/_ref/libref_ball2d.so lacks the portal shim: run make -C oracle -f Makefile.ref")
+
+
+def test_reference_library_has_portals_when_the_reference_is_here():
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("no /root/reference in this container")
+    lib = C.CDLL(os.path.join(REFDIR, "libref_ball2d.so"))
+    assert hasattr(lib, "ref_portal_probe")
+
+
+def test_bitonic_sort_is_set_insertion(pm):
+    rng = np.random.default_rng(3)
+    for nraw in (1, 2, 3, 7, 8, 33, 500, 1025):
+        b0 = rng.integers(0, 12, size=nraw).astype(np.uint64)
+        b1 = b0 + rng.integers(1, 6, size=nraw).astype(np.uint64)
+        keys = (b0 << np.uint64(32)) | b1
+        m = 1
+        while m < nraw:
+            m <<= 1
+        k = np.full(m, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+        i = np.full(m, 0xFFFFFFFF, dtype=np.uint32)
+        k[:nraw] = keys
+        i[:nraw] = np.arange(nraw, dtype=np.uint32)
+        pm.pm_bitonic_sort(m, vp(k), vp(i))
+        order = np.lexsort((np.arange(nraw), keys))
+        assert np.array_equal(k[:nraw], keys[order]) and np.array_equal(i[:nraw], order.astype(np.uint32))
+        first = np.ones(nraw, dtype=bool)
+        first[1:] = k[1:nraw] != k[: nraw - 1]
+        # std::set semantics: one entry per key, the earliest inserted one
+        kept = {}
+        for pos, key in enumerate(keys):
+            kept.setdefault(int(key), pos)
+        assert [int(x) for x in i[:nraw][first]] == [kept[key] for key in sorted(kept)]
+
+
+def _min_image_pairs(q, r, side, axes):
+    n = r.shape[0]
+    d = q[:, None, :] - q[None, :, :]
+    for k, ax in enumerate("xy"):
+        if ax in axes:
+            d[..., k] -= side * np.round(d[..., k] / side)
+    hit = (d ** 2).sum(-1) <= (r[:, None] + r[None, :]) ** 2
+    i, j = np.nonzero(np.triu(hit, 1))
+    return set(zip(i.tolist(), j.tolist()))
+
+
+@pytest.mark.parametrize("axes", ["x", "y"])
+def test_oracle_active_set_equals_minimum_image(axes, oracle):
+    # dyadic coordinates and a power-of-two box: every teleport is exact, so the comparison has no rounding slack
+    n, side = 700, 16.0
+    rng = np.random.default_rng(9)
+    scene = scenes.ball2d_periodic(n, 2, side=side, axes=axes)
+    q = np.round(rng.uniform(0.0, side, size=(n, 2)) * 1024.0) / 1024.0
+    q = np.minimum(q, side - 1.0 / 1024.0)
+    r = np.round(rng.uniform(0.1, 0.45, size=n) * 1024.0) / 1024.0
+    # keep balls off the walls of the non-periodic direction (the walls are static planes, not ball-ball business)
+    scene["r"], scene["q"] = r, q.ravel().copy()
+    scene["portals"]["plane_a_n"] = np.sign(scene["portals"]["plane_a_n"])
+    scene["portals"]["plane_b_n"] = np.sign(scene["portals"]["plane_b_n"])
+    o = _oracle(scene)
+    o.update_portals(0.0)
+    res = o.active_set_portals(scene["q"], scene["q"])
+    assert res is not None
+    bb = res["type"] != 2
+    got = set(zip(res["i"][bb].tolist(), res["j"][bb].tolist()))
+    assert len(got) == int(bb.sum()), "a body pair appears twice"
+    want = _min_image_pairs(q, r, side, axes)
+    assert got == want
+    tel = np.isin(res["type"], [3, 4])
+    assert tel.sum() > 3 and res["n_regular"] > 50
+    # order: regular ascending, then teleported ascending, then planes
+    ij = np.stack([res["i"], res["j"]], axis=1).astype(np.int64)
+    nr, nt = res["n_regular"], int(tel.sum())
+    for blk in (ij[:nr], ij[nr:nr + nt]):
+        key = blk[:, 0] * n + blk[:, 1]
+        assert np.all(np.diff(key) > 0)
+    assert np.all(res["type"][:nr] == 0) and np.all(tel[nr:nr + nt]) and np.all(res["type"][nr + nt:] == 2)
+    # grid == all pairs for the extended box set too
+    res2 = o.active_set_portals(scene["q"], scene["q"], method="allpairs")
+    assert np.array_equal(res["candidates"], res2["candidates"]) and np.array_equal(res["i"], res2["i"])
+
+
+def test_both_planes_touched_is_reported(oracle):
+    scene = scenes.ball2d_periodic(4, 1, side=1.0, rmin=0.6, rmax=0.7, axes="x")
+    o = _oracle(scene)
+    o.update_portals(0.0)
+    assert o.active_set_portals(scene["q"], scene["q"]) is None
+
+
+@pytest.mark.parametrize("le", [0.0, 1.5])
+def test_enforce_periodic_boundary_conditions(le, pm, oracle):
+    scene = scenes.ball2d_periodic(3000, 4, lees_edwards=le, t=2.3, oblique=True)
+    o = _oracle(scene)
+    _pm_set(pm, scene["portals"])
+    o.update_portals(scene["t"])
+    pm.pm_update_portals(scene["t"], None)
+    rng = np.random.default_rng(8)
+    q = scene["q"] + rng.uniform(-0.45, 0.45, size=scene["q"].shape) * scene["side"]
+    v = scene["v"].copy()
+    q1, v1 = o.enforce_portals(q, v)
+    qp, vpm = q.copy(), v.copy()
+    pm.pm_enforce(3000, vp(qp), vp(vpm))
+    assert np.array_equal(q1, qp) and np.array_equal(v1, vpm)
+    moved = np.any(q1.reshape(-1, 2) != q.reshape(-1, 2), axis=1)
+    assert moved.sum() > 500
+    # afterwards no ball is inside any portal
+    for p in range(scene["portals"]["v"].shape[0]):
+        for x in q1.reshape(-1, 2)[::7]:
+            flags, _ = o.portal_probe(p, np.ascontiguousarray(x), 0.1)
+            assert not (flags & 8)
+    changed = np.any(v1.reshape(-1, 2) != v.reshape(-1, 2), axis=1)
+    assert (changed.sum() > 100) if le != 0.0 else (changed.sum() == 0)
+    assert np.all(~changed | moved)
+
+
+def test_product_teleported_collision_matches_oracle(pm, oracle):
+    """sg_tele_collision / sg_tele_center / sg_ball_ball_active on the oracle's own teleported candidates."""
+    scene = scenes.ball2d_periodic(900, 12, side=12.0, lees_edwards=0.5, t=1.7)
+    o = _oracle(scene)
+    _pm_set(pm, scene["portals"])
+    o.update_portals(scene["t"])
+    pm.pm_update_portals(scene["t"], None)
+    q0 = scene["q"]
+    q1 = q0 + scene["dt"] * scene["v"]
+    res = o.active_set_portals(q0, q1)
+    n = scene["r"].shape[0]
+    r = np.ascontiguousarray(scene["r"])
+    q1c = np.ascontiguousarray(q1)
+    kept = {}
+    for a, b in res["candidates"]:
+        ft, st = a >= n, b >= n
+        if not (ft or st):
+            continue
+        b0, p0 = (int(res["box_body"][a - n]), int(res["box_portal"][a - n])) if ft else (int(a), 0xFFFFFFFF)
+        b1, p1 = (int(res["box_body"][b - n]), int(res["box_portal"][b - n])) if st else (int(b), 0xFFFFFFFF)
+        if ft and st:
+            d = q1c.reshape(-1, 2)[b0] - q1c.reshape(-1, 2)[b1]
+            if d[0] * d[0] + d[1] * d[1] <= (r[b0] + r[b1]) * (r[b0] + r[b1]):
+                continue
+        ordered = np.zeros(4, dtype=np.uint32)
+        if pm.pm_tele_happens(b0, b1, p0, p1, vp(q1c), vp(r), vp(ordered)):
+            kept.setdefault((int(ordered[0]), int(ordered[1])), (int(ordered[2]), int(ordered[3])))
+    tel = np.isin(res["type"], [3, 4])
+    got = list(zip(res["i"][tel].tolist(), res["j"][tel].tolist()))
+    assert got == sorted(kept) and len(got) > 10
+    assert [kept[k] for k in got] == list(zip(res["portal0"].tolist(), res["portal1"].tolist()))
+    assert np.any(res["type"] == 4) and np.any(res["type"] == 3)
+    assert np.all(np.isnan(res["depth"][tel]))
+    assert np.all((res["kick"] != 0.0).any(axis=1) == (res["type"][tel] == 4))
