@@ -52,6 +52,38 @@ void GpuBall2DBackend::setDrums( const std::vector<double>& x, const std::vector
   check( sg_ball2d_set_drums( m_ctx, static_cast<uint32_t>( r.size() ), x.data(), r.data() ), "sg_ball2d_set_drums" );
 }
 
+void GpuBall2DBackend::setPortals( const std::vector<double>& plane_a_x, const std::vector<double>& plane_a_n, const std::vector<double>& plane_b_x, const std::vector<double>& plane_b_n,
+                                   const std::vector<double>& velocity, const std::vector<double>& bounds )
+{
+  check( sg_ball2d_set_portals( m_ctx, static_cast<uint32_t>( velocity.size() ), plane_a_x.data(), plane_a_n.data(), plane_b_x.data(), plane_b_n.data(), velocity.data(), bounds.data() ), "sg_ball2d_set_portals" );
+}
+
+void GpuBall2DBackend::updatePeriodicBoundaryConditionsStartOfStep( const unsigned next_iteration, const scalar& dt )
+{
+  // const scalar t{ next_iteration * dt };  (ball2d/Ball2DSim.cpp:329)
+  const scalar t{ next_iteration * dt };
+  check( sg_ball2d_update_portals( m_ctx, t, nullptr ), "sg_ball2d_update_portals" );
+}
+
+void GpuBall2DBackend::enforcePeriodicBoundaryConditions( VectorXs& q, VectorXs& v )
+{
+  check( sg_ball2d_enforce_portals( m_ctx, q.data(), v.data() ), "sg_ball2d_enforce_portals" );
+}
+
+void GpuBall2DBackend::teleportedContacts( std::vector<GpuTeleportedContact2D>& teleported, uint64_t* num_regular )
+{
+  sg_teleported t;
+  check( sg_ball2d_teleported( m_ctx, &t ), "sg_ball2d_teleported" );
+  teleported.resize( t.n_teleported );
+  for( uint64_t k = 0; k < t.n_teleported; ++k )
+  {
+    GpuTeleportedContact2D& o = teleported[k];
+    o.portal0 = t.portal0[k]; o.portal1 = t.portal1[k];
+    for( int c = 0; c < 2; ++c ) { o.x0[c] = t.x0[2 * k + c]; o.x1[c] = t.x1[2 * k + c]; o.kick[c] = t.kick[2 * k + c]; }
+  }
+  if( num_regular != nullptr ) { *num_regular = t.n_regular; }
+}
+
 void GpuBall2DBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
   // Outputs are pre-sized by the caller in the reference (ball2d/Ball2DSim.cpp:311-312); be lenient here

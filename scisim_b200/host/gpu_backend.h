@@ -26,12 +26,21 @@
 // One entry per Constraint the reference would emplace_back, in the reference's order
 struct GpuContact2D
 {
-  uint32_t type; // SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE
+  uint32_t type; // SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE; with portals also SG_BALL_BALL_TELEPORTED, SG_BALL_BALL_KICK_TELEPORTED
   uint32_t i;    // ball (first ball for ball-ball)
   uint32_t j;    // second ball / drum / plane
   double n[2];
   double p[2];
   double depth;
+};
+
+// Constructor arguments of a teleported contact (ball2d/Ball2DSim.cpp:653-728): BallBallConstraint{ i, j, x0, x1, ri, rj, true }
+// or KinematicKickBallBallConstraint{ i, j, x0, x1, ri, rj, kick, true }.  portal0 / portal1: portal index with bit 31 set
+// when the ball went through plane B, 0xffffffff when that ball was not teleported.
+struct GpuTeleportedContact2D
+{
+  uint32_t portal0, portal1;
+  double x0[2], x1[2], kick[2];
 };
 
 class GpuBall2DBackend final
@@ -47,6 +56,15 @@ public:
   void setGravity( const double gx, const double gy );
   void setPlanes( const std::vector<double>& x, const std::vector<double>& n );
   void setDrums( const std::vector<double>& x, const std::vector<double>& r );
+  // Ball2DState::planarPortals() (ball2d/Portals/PlanarPortal.h): per portal plane A and B as (x, n), velocity, bounds.
+  // With portals set computeActiveSet follows computeBallBallActiveSetSpatialGridWithPortals (ball2d/Ball2DSim.cpp:368-546).
+  void setPortals( const std::vector<double>& plane_a_x, const std::vector<double>& plane_a_n, const std::vector<double>& plane_b_x, const std::vector<double>& plane_b_n,
+                   const std::vector<double>& velocity, const std::vector<double>& bounds );
+  // Ball2DSim::updatePeriodicBoundaryConditionsStartOfStep / enforcePeriodicBoundaryConditions (ball2d/Ball2DSim.cpp:327-366)
+  void updatePeriodicBoundaryConditionsStartOfStep( const unsigned next_iteration, const scalar& dt );
+  void enforcePeriodicBoundaryConditions( VectorXs& q, VectorXs& v );
+  // After a computeActiveSet with portals: contacts [num_regular, num_regular + teleported.size()) are the teleported ones
+  void teleportedContacts( std::vector<GpuTeleportedContact2D>& teleported, uint64_t* num_regular = nullptr );
 
   // UnconstrainedMap::flow for the two ball2d maps
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );

@@ -1,0 +1,175 @@
+// tests/portal_kernel_harness.cpp -- TEST INFRASTRUCTURE.  Runs the product's portal KERNELS
+// (scisim_b200/csrc/sg_ball2d_portal_kernels.cuh, exactly the source nvcc compiles) on the CPU: the CUDA keywords are
+// defined away, blockIdx / threadIdx are plain variables and a "launch" is a loop over blocks and threads (legal because
+// none of these kernels has a barrier or shared memory).  The launch sequence mirrors ball2d_portal_active_set_device
+// (sg_ball2d_portals.cuh); the two pieces that are not portal code -- the prefix sums and the box broad phase, both
+// covered by the GPU parity tests of the other paths -- are a sequential scan and an all-pairs sweep here.
+// Built by tests/test_portals_cpu.py with g++ -O2 -std=c++17 -ffp-contract=off.  Nothing here is shipped.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../include/scisim_b200.h"
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__( ... )
+#define __grid_constant__
+struct EmuDim { unsigned x, y, z; };
+static EmuDim blockIdx, blockDim, threadIdx, gridDim;
+struct double2 { double x, y; };
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+static inline double2 make_double2( double x, double y ) { return double2{ x, y }; }
+static inline uint4 make_uint4( unsigned x, unsigned y, unsigned z, unsigned w ) { return uint4{ x, y, z, w }; }
+template<typename T> static inline T __ldg( const T* p ) { return *p; }
+static inline unsigned atomicOr( unsigned* p, unsigned v ) { const unsigned o = *p; *p |= v; return o; }
+static inline double __longlong_as_double( long long b ) { double x; std::memcpy( &x, &b, 8 ); return x; }
+
+// as in sg_ball2d.cu, minus the multi-GPU index map
+struct ContactOut2D
+{
+  uint32_t* type; uint32_t* i; uint32_t* j;
+  double2* n; double2* p; double* depth;
+  unsigned long long cap;
+};
+
+#include "../scisim_b200/csrc/sg_ball2d_portal_kernels.cuh"
+
+template<typename F>
+static void launch( unsigned gx, unsigned gy, unsigned block, F f )
+{
+  gridDim = EmuDim{ gx, gy, 1 }; blockDim = EmuDim{ block, 1, 1 };
+  for( unsigned by = 0; by < gy; ++by ) for( unsigned bx = 0; bx < gx; ++bx ) for( unsigned t = 0; t < block; ++t )
+  {
+    blockIdx = EmuDim{ bx, by, 0 }; threadIdx = EmuDim{ t, 0, 0 };
+    f();
+  }
+}
+static unsigned div_up( unsigned long long a, unsigned long long b ) { return unsigned( ( a + b - 1 ) / b ); }
+static uint32_t exclusive_scan( const std::vector<uint32_t>& in, std::vector<uint32_t>& out )
+{
+  uint32_t run = 0; out.resize( in.size() + 1 );
+  for( size_t k = 0; k < in.size(); ++k ) { out[k] = run; run += in[k]; }
+  return run;
+}
+
+struct Result
+{
+  std::vector<uint2> cand;
+  std::vector<uint32_t> box_body, box_portal, type, ci, cj, tp0, tp1;
+  std::vector<double2> cn, cp, x0t, x1t, kick;
+  std::vector<double> depth;
+  uint32_t n_reg = 0, n_tel = 0;
+  int err = 0;
+};
+static Result g_res;
+static SgPortals2D g_ps;
+
+extern "C"
+{
+
+void pk_set_portals( uint32_t n, const double* ax, const double* an, const double* bx, const double* bn, const double* v, const double* bounds, const double* dx )
+{
+  std::memset( &g_ps, 0, sizeof( g_ps ) );
+  g_ps.n = n;
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    SgPortal2D& pt = g_ps.p[p];
+    for( int k = 0; k < 2; ++k ) { pt.ax[k] = ax[2 * p + k]; pt.bx[k] = bx[2 * p + k]; }
+    sg_portal_plane_frame( an + 2 * p, pt.an, pt.at );
+    sg_portal_plane_frame( bn + 2 * p, pt.bn, pt.bt );
+    pt.v = v[p]; pt.bounds = bounds[p]; pt.dx = dx[p];
+  }
+}
+
+// body-body part of the portal active set; returns 0, or 1 where a ball touches both planes of a portal
+int pk_active_set( uint32_t n, const double* q0v, const double* q1v, const double* r )
+{
+  Result& R = g_res;
+  R = Result{};
+  const double2* q0 = reinterpret_cast<const double2*>( q0v );
+  const double2* q1 = reinterpret_cast<const double2*>( q1v );
+  const uint32_t P = g_ps.n;
+  const unsigned nblk = div_up( n, 256 );
+  std::vector<uint32_t> tflag( size_t( n ) * P + 1, 0xdeadbeefu ), toff;
+  unsigned err = 0;
+  launch( nblk, P, 256, [&]() { k_b2p_touch( g_ps, n, q1, r, tflag.data(), &err ); } );
+  if( err != 0 ) { R.err = 1; return 1; }
+  tflag.resize( size_t( n ) * P );
+  const uint32_t nt = exclusive_scan( tflag, toff );
+  const uint32_t next = n + nt;
+  std::vector<double> boxes( size_t( next ) * 4, std::nan( "" ) );
+  R.box_body.assign( nt, 0xdeadbeefu ); R.box_portal.assign( nt, 0xdeadbeefu );
+  launch( nblk, 1, 256, [&]() { k_b2p_boxes( n, q1, r, boxes.data() ); } );
+  if( nt > 0 ) { launch( nblk, P, 256, [&]() { k_b2p_tele_boxes( g_ps, n, q1, r, tflag.data(), toff.data(), boxes.data(), R.box_body.data(), R.box_portal.data() ); } ); }
+  // stand-in for the box pipeline: every (i<j) whose closed boxes overlap, ascending
+  for( uint32_t i = 0; i < next; ++i ) for( uint32_t j = i + 1; j < next; ++j )
+  {
+    const double* a = &boxes[4 * size_t( i )]; const double* b = &boxes[4 * size_t( j )];
+    if( !( a[2] < b[0] ) && !( b[2] < a[0] ) && !( a[3] < b[1] ) && !( b[3] < a[1] ) ) { R.cand.push_back( uint2{ i, j } ); }
+  }
+  const unsigned long long np = R.cand.size();
+  std::vector<uint32_t> reg_cnt( np, 0xdeadbeefu ), tel_cnt( np, 0xdeadbeefu ), reg_off, tel_off;
+  const ContactOut2D none{};
+  if( np > 0 )
+  {
+    launch( div_up( np, 128 ), 1, 128, [&]() { k_b2p_pairs<false>( g_ps, n, R.cand.data(), np, q0, q1, r, R.box_body.data(), R.box_portal.data(), reg_cnt.data(), tel_cnt.data(), nullptr, nullptr, none, nullptr, nullptr, nullptr ); } );
+  }
+  R.n_reg = exclusive_scan( reg_cnt, reg_off );
+  const uint32_t nraw = exclusive_scan( tel_cnt, tel_off );
+  const size_t cap = size_t( R.n_reg ) + nraw + 64;
+  R.type.assign( cap, 0xdeadbeefu ); R.ci.assign( cap, 0xdeadbeefu ); R.cj.assign( cap, 0xdeadbeefu );
+  R.cn.assign( cap, double2{ 0, 0 } ); R.cp.assign( cap, double2{ 0, 0 } ); R.depth.assign( cap, 0.0 );
+  ContactOut2D out;
+  out.type = R.type.data(); out.i = R.ci.data(); out.j = R.cj.data(); out.n = R.cn.data(); out.p = R.cp.data(); out.depth = R.depth.data(); out.cap = cap;
+  uint32_t m = 1u;
+  while( m < nraw ) { m <<= 1; }
+  std::vector<unsigned long long> tc_key( m, 0x1234ull );
+  std::vector<uint32_t> tc_idx( m, 0xdeadbeefu ), uflag( nraw, 0xdeadbeefu ), uoff;
+  std::vector<uint4> tc_info( nraw + 1 );
+  if( np > 0 && ( R.n_reg > 0 || nraw > 0 ) )
+  {
+    launch( div_up( np, 128 ), 1, 128, [&]() { k_b2p_pairs<true>( g_ps, n, R.cand.data(), np, q0, q1, r, R.box_body.data(), R.box_portal.data(), reg_cnt.data(), tel_cnt.data(), reg_off.data(), tel_off.data(), out,
+                                                                  tc_key.data(), tc_idx.data(), tc_info.data() ); } );
+  }
+  if( nraw > 0 )
+  {
+    if( m > nraw ) { launch( div_up( m - nraw, 256 ), 1, 256, [&]() { k_b2p_sort_pad( nraw, m, tc_key.data(), tc_idx.data() ); } ); }
+    for( uint32_t k = 2u; k <= m; k <<= 1 ) { for( uint32_t j = k >> 1; j > 0u; j >>= 1 ) { launch( div_up( m, 256 ), 1, 256, [&]() { k_b2p_bitonic( m, j, k, tc_key.data(), tc_idx.data() ); } ); } }
+    launch( div_up( nraw, 256 ), 1, 256, [&]() { k_b2p_unique( nraw, tc_key.data(), uflag.data() ); } );
+    R.n_tel = exclusive_scan( uflag, uoff );
+    R.x0t.assign( nraw, double2{ 0, 0 } ); R.x1t.assign( nraw, double2{ 0, 0 } ); R.kick.assign( nraw, double2{ 0, 0 } ); R.tp0.assign( nraw, 0 ); R.tp1.assign( nraw, 0 );
+    launch( div_up( nraw, 128 ), 1, 128, [&]() { k_b2p_tele_contacts( g_ps, nraw, tc_idx.data(), uflag.data(), uoff.data(), tc_info.data(), q0, q1, r, R.n_reg, out, R.x0t.data(), R.x1t.data(), R.kick.data(),
+                                                                       R.tp0.data(), R.tp1.data() ); } );
+  }
+  return 0;
+}
+
+uint64_t pk_num_candidates() { return g_res.cand.size(); }
+uint32_t pk_num_boxes() { return uint32_t( g_res.box_body.size() ); }
+uint32_t pk_num_regular() { return g_res.n_reg; }
+uint32_t pk_num_teleported() { return g_res.n_tel; }
+void pk_copy( uint32_t* cand, uint32_t* box_body, uint32_t* box_portal, uint32_t* type, uint32_t* i, uint32_t* j, double* n, double* p, double* depth, uint32_t* tp0, uint32_t* tp1, double* x0, double* x1,
+              double* kick )
+{
+  const Result& R = g_res;
+  std::memcpy( cand, R.cand.data(), R.cand.size() * 8 );
+  std::memcpy( box_body, R.box_body.data(), R.box_body.size() * 4 ); std::memcpy( box_portal, R.box_portal.data(), R.box_portal.size() * 4 );
+  const size_t na = size_t( R.n_reg ) + R.n_tel;
+  std::memcpy( type, R.type.data(), na * 4 ); std::memcpy( i, R.ci.data(), na * 4 ); std::memcpy( j, R.cj.data(), na * 4 );
+  std::memcpy( n, R.cn.data(), na * 16 ); std::memcpy( p, R.cp.data(), na * 16 ); std::memcpy( depth, R.depth.data(), na * 8 );
+  std::memcpy( tp0, R.tp0.data(), size_t( R.n_tel ) * 4 ); std::memcpy( tp1, R.tp1.data(), size_t( R.n_tel ) * 4 );
+  std::memcpy( x0, R.x0t.data(), size_t( R.n_tel ) * 16 ); std::memcpy( x1, R.x1t.data(), size_t( R.n_tel ) * 16 ); std::memcpy( kick, R.kick.data(), size_t( R.n_tel ) * 16 );
+}
+
+void pk_enforce( uint32_t n, double* q, double* v )
+{
+  launch( div_up( n, 256 ), 1, 256, [&]() { k_b2p_enforce( g_ps, n, reinterpret_cast<double2*>( q ), reinterpret_cast<double2*>( v ) ); } );
+}
+
+}

@@ -266,3 +266,89 @@ def test_product_teleported_collision_matches_oracle(pm, oracle):
     assert np.any(res["type"] == 4) and np.any(res["type"] == 3)
     assert np.all(np.isnan(res["depth"][tel]))
     assert np.all((res["kick"] != 0.0).any(axis=1) == (res["type"][tel] == 4))
+
+
+# ---- the product's portal kernels, run on the CPU (tests/portal_kernel_harness.cpp) -----------------------------------
+@pytest.fixture(scope="module")
+def pk(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("pk") / "libportal_kernels.so")
+    src = os.path.join(ROOT, "tests", "portal_kernel_harness.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src], check=True)
+    lib = C.CDLL(out)
+    lib.pk_set_portals.argtypes = [C.c_uint32] + [C.c_void_p] * 7
+    lib.pk_active_set.restype = C.c_int
+    lib.pk_active_set.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pk_num_candidates.restype = C.c_uint64
+    for f in ("pk_num_boxes", "pk_num_regular", "pk_num_teleported"):
+        getattr(lib, f).restype = C.c_uint32
+    lib.pk_copy.argtypes = [C.c_void_p] * 14
+    lib.pk_enforce.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def _pk_run(pk, scene, dx, q0, q1):
+    P = scene["portals"]
+    a = [np.ascontiguousarray(P[k], dtype=np.float64) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n", "v", "bounds")]
+    dx = np.ascontiguousarray(dx, dtype=np.float64)
+    pk.pk_set_portals(a[4].shape[0], *[vp(x) for x in a], vp(dx))
+    n = scene["r"].shape[0]
+    q0, q1, r = [np.ascontiguousarray(x, dtype=np.float64) for x in (q0, q1, scene["r"])]
+    if pk.pk_active_set(n, vp(q0), vp(q1), vp(r)) != 0:
+        return None
+    nc, nb, nr, nt = int(pk.pk_num_candidates()), int(pk.pk_num_boxes()), int(pk.pk_num_regular()), int(pk.pk_num_teleported())
+    na = nr + nt
+    out = {"candidates": np.zeros((nc, 2), np.uint32), "box_body": np.zeros(nb, np.uint32), "box_portal": np.zeros(nb, np.uint32),
+           "type": np.zeros(na, np.uint32), "i": np.zeros(na, np.uint32), "j": np.zeros(na, np.uint32), "n": np.zeros((na, 2)), "p": np.zeros((na, 2)),
+           "depth": np.zeros(na), "portal0": np.zeros(nt, np.uint32), "portal1": np.zeros(nt, np.uint32), "x0": np.zeros((nt, 2)), "x1": np.zeros((nt, 2)),
+           "kick": np.zeros((nt, 2)), "n_regular": nr}
+    pk.pk_copy(*[vp(out[k]) for k in ("candidates", "box_body", "box_portal", "type", "i", "j", "n", "p", "depth", "portal0", "portal1", "x0", "x1", "kick")])
+    return out
+
+
+KERNEL_CASES = [dict(n=1, seed=1, axes="xy"), dict(n=2, seed=2, axes="x", side=1.5), dict(n=300, seed=3, axes="xy", side=8.0),
+                dict(n=300, seed=4, axes="x", side=8.0, oblique=True), dict(n=1500, seed=5, axes="xy", side=20.0, lees_edwards=0.75, t=3.7),
+                dict(n=1500, seed=6, axes="y", side=20.0, lees_edwards=-1.25, t=11.3, oblique=True),
+                dict(n=400, seed=11, side=6.0, rmin=0.2, rmax=0.45, axes="xy", static=True)]
+
+
+@pytest.mark.parametrize("case", KERNEL_CASES, ids=lambda c: "n%d-%s-le%g" % (c["n"], c["axes"], c.get("lees_edwards", 0.0)))
+def test_portal_kernels_on_cpu_match_oracle(case, pk, oracle):
+    kw = dict(case)
+    static = kw.pop("static", False)
+    scene = scenes.ball2d_periodic(kw.pop("n"), kw.pop("seed"), **kw)
+    o = _oracle(scene)
+    dx = o.update_portals(scene["t"])
+    q0 = scene["q"]
+    q1 = q0.copy() if static else o.flow(0, q0, scene["v"], scene["dt"])[0]
+    ref = o.active_set_portals(q0, q1, "allpairs")
+    got = _pk_run(pk, scene, dx, q0, q1)
+    assert ref is not None and got is not None
+    bb = ref["type"] != 2
+    for k in ("candidates", "box_body", "box_portal", "portal0", "portal1"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in ("type", "i", "j"):
+        assert np.array_equal(got[k], ref[k][bb]), k
+    for k in ("n", "p", "x0", "x1", "kick"):
+        want = ref[k][bb] if k in ("n", "p") else ref[k]
+        assert np.array_equal(got[k].view(np.uint64), want.view(np.uint64)), k
+    assert np.array_equal(np.isnan(got["depth"]), np.isnan(ref["depth"][bb]))
+    ok = ~np.isnan(got["depth"])
+    assert np.array_equal(got["depth"][ok], ref["depth"][bb][ok])
+    assert got["n_regular"] == ref["n_regular"]
+
+
+def test_portal_kernels_on_cpu_both_planes_and_enforce(pk, oracle):
+    scene = scenes.ball2d_periodic(4, 1, side=1.0, rmin=0.6, rmax=0.7, axes="x")
+    assert _pk_run(pk, scene, np.zeros(1), scene["q"], scene["q"]) is None
+    scene = scenes.ball2d_periodic(3000, 4, lees_edwards=1.5, t=2.3, oblique=True)
+    o = _oracle(scene)
+    dx = o.update_portals(scene["t"])
+    P = scene["portals"]
+    a = [np.ascontiguousarray(P[k], dtype=np.float64) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n", "v", "bounds")]
+    pk.pk_set_portals(a[4].shape[0], *[vp(x) for x in a], vp(np.ascontiguousarray(dx)))
+    rng = np.random.default_rng(8)
+    q = scene["q"] + rng.uniform(-0.45, 0.45, size=scene["q"].shape) * scene["side"]
+    rq, rv = o.enforce_portals(q, scene["v"])
+    gq, gv = q.copy(), scene["v"].copy()
+    pk.pk_enforce(3000, vp(gq), vp(gv))
+    assert np.array_equal(gq, rq) and np.array_equal(gv, rv)
