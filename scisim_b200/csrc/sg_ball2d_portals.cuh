@@ -16,12 +16,16 @@
 //   broad     the generic box pipeline of sg_broadphase.cuh over n + T boxes -> ascending candidate list
 //   pairs     one thread per candidate: real-real -> isActive( q1 ); otherwise the TeleportedCollision tests.  Count, two
 //             scans, then emit: regular contacts land in candidate order, teleported collisions in a (key, insertion) list
-//   sort      bitonic network on (body pair, insertion number); first of each body pair survives == std::set::insert
+//   sort      bitonic network on (body pair, insertion number), tiles of 2048 in shared memory (one launch for the usual
+//             few thousand boundary collisions); first of each body pair survives == std::set::insert
 //   contacts  teleported contacts behind the regular ones (plain or kinematic-kick), then drums and planes as always
 #include "sg_boxes.cuh"
 #include "sg_portal2d.h"
 
 using PortalBoxPolicy = AabbPolicy<2, 1>;
+
+#define SG_B2P_SORT_TILE 2048   // elements of the teleported-collision list sorted per CTA in shared memory (24 KB)
+#define SG_B2P_SORT_THREADS 1024
 
 struct PortalData
 {
@@ -207,12 +211,16 @@ static int ball2d_portal_active_set_device( sg_ctx* ctx, Ball2DData* d, const in
   if( nraw > 0 )
   {
     if( m > nraw ) { SG_LAUNCH( ctx, "b2p_sort_pad", 0.0, k_b2p_sort_pad<<<sg_div_up( m - nraw, 256 ), 256, 0, ctx->stream>>>( nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) ); }
-    for( uint32_t k = 2u; k <= m; k <<= 1 )
+    // tiles of SG_B2P_SORT_TILE elements are sorted in shared memory; only strides that cross tiles take a launch each
+    const unsigned ntiles = sg_div_up( m, SG_B2P_SORT_TILE );
+    SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, true><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, 0u, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
+    for( uint32_t k = 2u * SG_B2P_SORT_TILE; k <= m; k <<= 1 )
     {
-      for( uint32_t j = k >> 1; j > 0u; j >>= 1 )
+      for( uint32_t j = k >> 1; j >= uint32_t( SG_B2P_SORT_TILE ); j >>= 1 )
       {
         SG_LAUNCH( ctx, "b2p_bitonic", double( m ) * 24.0, k_b2p_bitonic<<<sg_div_up( m, 256 ), 256, 0, ctx->stream>>>( m, j, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
       }
+      SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, false><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
     }
     SG_CUDA( ctx, cudaMemsetAsync( x->utotal.ptr, 0, 4, ctx->stream ) );
     SG_LAUNCH( ctx, "b2p_unique", double( nraw ) * 12.0, k_b2p_unique<<<sg_div_up( nraw, 256 ), 256, 0, ctx->stream>>>( nraw, x->tc_key.as<unsigned long long>(), x->uflag.as<uint32_t>() ) );

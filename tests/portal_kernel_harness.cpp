@@ -1,14 +1,18 @@
 // tests/portal_kernel_harness.cpp -- TEST INFRASTRUCTURE.  Runs the product's portal KERNELS
 // (scisim_b200/csrc/sg_ball2d_portal_kernels.cuh, exactly the source nvcc compiles) on the CPU: the CUDA keywords are
-// defined away, blockIdx / threadIdx are plain variables and a "launch" is a loop over blocks and threads (legal because
-// none of these kernels has a barrier or shared memory).  The launch sequence mirrors ball2d_portal_active_set_device
+// defined away, blockIdx / threadIdx are plain (thread-local) variables and a "launch" is a loop over blocks and threads --
+// legal for the kernels without barriers; the one kernel with __syncthreads (the shared-memory tile sort) gets one host
+// thread per CUDA thread and a pthread barrier.  The launch sequence mirrors ball2d_portal_active_set_device
 // (sg_ball2d_portals.cuh); the two pieces that are not portal code -- the prefix sums and the box broad phase, both
 // covered by the GPU parity tests of the other paths -- are a sequential scan and an all-pairs sweep here.
 // Built by tests/test_portals_cpu.py with g++ -O2 -std=c++17 -ffp-contract=off.  Nothing here is shipped.
+#include <pthread.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../include/scisim_b200.h"
@@ -19,8 +23,11 @@
 #define __forceinline__ inline
 #define __launch_bounds__( ... )
 #define __grid_constant__
+#define __shared__ static
 struct EmuDim { unsigned x, y, z; };
-static EmuDim blockIdx, blockDim, threadIdx, gridDim;
+static thread_local EmuDim blockIdx, blockDim, threadIdx, gridDim;
+static pthread_barrier_t g_block_barrier;
+static inline void __syncthreads() { pthread_barrier_wait( &g_block_barrier ); }
 struct double2 { double x, y; };
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
@@ -50,12 +57,47 @@ static void launch( unsigned gx, unsigned gy, unsigned block, F f )
     f();
   }
 }
+// kernels with __syncthreads: blocks one after another, the threads of a block as host threads
+template<typename F>
+static void launch_with_barriers( unsigned gx, unsigned block, F f )
+{
+  for( unsigned bx = 0; bx < gx; ++bx )
+  {
+    pthread_barrier_init( &g_block_barrier, nullptr, block );
+    std::vector<std::thread> threads;
+    for( unsigned t = 0; t < block; ++t )
+    {
+      threads.emplace_back( [=]() { gridDim = EmuDim{ gx, 1, 1 }; blockDim = EmuDim{ block, 1, 1 }; blockIdx = EmuDim{ bx, 0, 0 }; threadIdx = EmuDim{ t, 0, 0 }; f(); } );
+    }
+    for( std::thread& th : threads ) { th.join(); }
+    pthread_barrier_destroy( &g_block_barrier );
+  }
+}
 static unsigned div_up( unsigned long long a, unsigned long long b ) { return unsigned( ( a + b - 1 ) / b ); }
 static uint32_t exclusive_scan( const std::vector<uint32_t>& in, std::vector<uint32_t>& out )
 {
   uint32_t run = 0; out.resize( in.size() + 1 );
   for( size_t k = 0; k < in.size(); ++k ) { out[k] = run; run += in[k]; }
   return run;
+}
+
+// the sort's launch sequence as in ball2d_portal_active_set_device; TILE / THREADS are the library's (2048, 1024) or a
+// small pair that makes multi-tile lists cheap to emulate
+template<int TILE, int THREADS>
+static void tile_sort( const uint32_t m, unsigned long long* keys, uint32_t* idxs )
+{
+  const unsigned ntiles = div_up( m, TILE );
+  launch_with_barriers( ntiles, THREADS, [=]() { k_b2p_bitonic_tile<TILE, THREADS, true>( m, 0u, keys, idxs ); } );
+  for( uint32_t k = 2u * TILE; k <= m; k <<= 1 )
+  {
+    for( uint32_t j = k >> 1; j >= uint32_t( TILE ); j >>= 1 ) { launch( div_up( m, 256 ), 1, 256, [&]() { k_b2p_bitonic( m, j, k, keys, idxs ); } ); }
+    launch_with_barriers( ntiles, THREADS, [=]() { k_b2p_bitonic_tile<TILE, THREADS, false>( m, k, keys, idxs ); } );
+  }
+}
+static int g_sort_mode = 0; // 0: tiles of 64 / 16 threads, 1: the library's 2048 / 1024
+static void sort_teleported( const uint32_t m, unsigned long long* keys, uint32_t* idxs )
+{
+  if( g_sort_mode == 1 ) { tile_sort<2048, 1024>( m, keys, idxs ); } else { tile_sort<64, 16>( m, keys, idxs ); }
 }
 
 struct Result
@@ -140,7 +182,7 @@ int pk_active_set( uint32_t n, const double* q0v, const double* q1v, const doubl
   if( nraw > 0 )
   {
     if( m > nraw ) { launch( div_up( m - nraw, 256 ), 1, 256, [&]() { k_b2p_sort_pad( nraw, m, tc_key.data(), tc_idx.data() ); } ); }
-    for( uint32_t k = 2u; k <= m; k <<= 1 ) { for( uint32_t j = k >> 1; j > 0u; j >>= 1 ) { launch( div_up( m, 256 ), 1, 256, [&]() { k_b2p_bitonic( m, j, k, tc_key.data(), tc_idx.data() ); } ); } }
+    sort_teleported( m, tc_key.data(), tc_idx.data() );
     launch( div_up( nraw, 256 ), 1, 256, [&]() { k_b2p_unique( nraw, tc_key.data(), uflag.data() ); } );
     R.n_tel = exclusive_scan( uflag, uoff );
     R.x0t.assign( nraw, double2{ 0, 0 } ); R.x1t.assign( nraw, double2{ 0, 0 } ); R.kick.assign( nraw, double2{ 0, 0 } ); R.tp0.assign( nraw, 0 ); R.tp1.assign( nraw, 0 );
@@ -166,6 +208,9 @@ void pk_copy( uint32_t* cand, uint32_t* box_body, uint32_t* box_portal, uint32_t
   std::memcpy( tp0, R.tp0.data(), size_t( R.n_tel ) * 4 ); std::memcpy( tp1, R.tp1.data(), size_t( R.n_tel ) * 4 );
   std::memcpy( x0, R.x0t.data(), size_t( R.n_tel ) * 16 ); std::memcpy( x1, R.x1t.data(), size_t( R.n_tel ) * 16 ); std::memcpy( kick, R.kick.data(), size_t( R.n_tel ) * 16 );
 }
+
+void pk_set_sort_mode( int mode ) { g_sort_mode = mode; }
+void pk_sort( uint32_t m, unsigned long long* keys, uint32_t* idxs ) { sort_teleported( m, keys, idxs ); }
 
 void pk_enforce( uint32_t n, double* q, double* v )
 {

@@ -273,8 +273,10 @@ def test_product_teleported_collision_matches_oracle(pm, oracle):
 def pk(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("pk") / "libportal_kernels.so")
     src = os.path.join(ROOT, "tests", "portal_kernel_harness.cpp")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-o", out, src], check=True)
     lib = C.CDLL(out)
+    lib.pk_set_sort_mode.argtypes = [C.c_int]
+    lib.pk_sort.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
     lib.pk_set_portals.argtypes = [C.c_uint32] + [C.c_void_p] * 7
     lib.pk_active_set.restype = C.c_int
     lib.pk_active_set.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -352,3 +354,29 @@ def test_portal_kernels_on_cpu_both_planes_and_enforce(pk, oracle):
     gq, gv = q.copy(), scene["v"].copy()
     pk.pk_enforce(3000, vp(gq), vp(gv))
     assert np.array_equal(gq, rq) and np.array_equal(gv, rv)
+
+
+@pytest.mark.parametrize("mode,sizes", [(0, (1, 2, 3, 31, 64, 65, 200, 1000, 5000)), (1, (700, 2048, 5000))], ids=["tile64", "tile2048"])
+def test_tile_sort_kernel_on_cpu(pk, mode, sizes):
+    """k_b2p_bitonic_tile (+ k_b2p_bitonic for the strides that cross tiles), launch sequence as in the driver: one tile,
+    several tiles, lists shorter than a tile; mode 1 uses the library's own tile size and thread count."""
+    pk.pk_set_sort_mode(mode)
+    rng = np.random.default_rng(5)
+    try:
+        for nraw in sizes:
+            b0 = rng.integers(0, max(2, nraw // 3), size=nraw).astype(np.uint64)
+            b1 = b0 + rng.integers(1, 4, size=nraw).astype(np.uint64)
+            keys = (b0 << np.uint64(32)) | b1
+            m = 1
+            while m < nraw:
+                m <<= 1
+            k = np.full(m, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+            i = np.full(m, 0xFFFFFFFF, dtype=np.uint32)
+            k[:nraw] = keys
+            i[:nraw] = np.arange(nraw, dtype=np.uint32)
+            pk.pk_sort(m, vp(k), vp(i))
+            order = np.lexsort((np.arange(nraw), keys))
+            assert np.array_equal(k[:nraw], keys[order]) and np.array_equal(i[:nraw], order.astype(np.uint32)), nraw
+            assert np.all(k[nraw:] == np.uint64(0xFFFFFFFFFFFFFFFF))
+    finally:
+        pk.pk_set_sort_mode(0)
