@@ -352,6 +352,7 @@ void orc_rb3d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t
 
 // ---- rigidbody2d -----------------------------------------------------------------------------------
 #include "rb2d.h"
+#include "rb2d_portals.h"
 
 struct RB2DHandle
 {
@@ -359,6 +360,8 @@ struct RB2DHandle
   std::vector<RB2DContact> active;
   std::vector<std::pair<unsigned,unsigned>> candidates;
   double seconds_flow = 0.0, seconds_active = 0.0;
+  std::vector<Portal2D> portals;
+  RB2DPortalResult pres;
 };
 
 extern "C"
@@ -413,6 +416,81 @@ void orc_rb2d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t
     const RB2DContact& c = h->active[k];
     type[k] = c.type; i[k] = c.i; j[k] = c.j; aux[k] = c.aux;
     n[2 * k] = c.n.x; n[2 * k + 1] = c.n.y; p[2 * k] = c.p.x; p[2 * k + 1] = c.p.y; depth[k] = c.depth;
+  }
+}
+
+// ---- rigidbody2d portals (oracle/rb2d_portals.h) ---------------------------------------------------------
+// plane normals are used as given (RigidBody2DStaticPlane does not normalise)
+void orc_rb2d_set_portals( void* hv, uint32_t n, const double* ax, const double* an, const double* bx, const double* bn, const double* v, const double* bounds )
+{
+  RB2DHandle* h = static_cast<RB2DHandle*>( hv );
+  h->portals.clear();
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    Portal2D pt;
+    pt.a = makePlaneRB2D( V2{ ax[2 * p], ax[2 * p + 1] }, V2{ an[2 * p], an[2 * p + 1] } );
+    pt.b = makePlaneRB2D( V2{ bx[2 * p], bx[2 * p + 1] }, V2{ bn[2 * p], bn[2 * p + 1] } );
+    pt.v = v[p]; pt.bounds = bounds[p]; pt.dx = 0.0;
+    h->portals.push_back( pt );
+  }
+}
+void orc_rb2d_update_portals( void* hv, double t, double* dx_out )
+{
+  RB2DHandle* h = static_cast<RB2DHandle*>( hv );
+  for( std::size_t p = 0; p < h->portals.size(); ++p ) { updateMovingPortals( h->portals[p], t ); if( dx_out != nullptr ) { dx_out[p] = h->portals[p].dx; } }
+}
+void orc_rb2d_enforce_portals( void* hv, double* q, double* v )
+{
+  RB2DHandle* h = static_cast<RB2DHandle*>( hv );
+  enforcePeriodicBoundaryConditionsRB2D( h->portals, uint32_t( h->scene.nbodies() ), q, v );
+}
+// box = [minx, miny, maxx, maxy]; out[0..1] teleportPoint through the touched plane ( A when nothing is touched ), [2..3]
+// getKinematicVelocityOfAABB; returns aabbTouchesPortal: 0 = no, 1 = plane A, 2 = plane B
+uint32_t orc_rb2d_portal_probe( const void* hv, uint32_t p, const double* box, const double* x, double* out )
+{
+  const RB2DHandle* h = static_cast<const RB2DHandle*>( hv );
+  const Portal2D& pt = h->portals[p];
+  Box<2> b;
+  b.lo[0] = box[0]; b.lo[1] = box[1]; b.hi[0] = box[2]; b.hi[1] = box[3];
+  const int touch = aabbTouchesPortal( pt, b );
+  const V2 xin{ x[0], x[1] };
+  const V2 xo = touch == 2 ? teleportPointThroughPlaneB( pt, xin ) : teleportPointThroughPlaneA( pt, xin );
+  const V2 k = getKinematicVelocityOfAABB( pt, b );
+  out[0] = xo.x; out[1] = xo.y; out[2] = k.x; out[3] = k.y;
+  return uint32_t( touch );
+}
+// returns 1, or 0 where the reference exits (boxes or kinematic bodies in a teleported collision, unsupported regular pairs)
+int orc_rb2d_active_set_portals( void* hv, const double* q0, const double* q1, int method )
+{
+  RB2DHandle* h = static_cast<RB2DHandle*>( hv );
+  computeActiveSetWithPortalsRB2D( h->scene, h->portals, q0, q1, h->pres, method == 0 );
+  h->active = h->pres.active;
+  h->candidates = h->pres.candidates;
+  return h->pres.supported ? 1 : 0;
+}
+uint64_t orc_rb2d_portals_num_regular( const void* h ) { return static_cast<const RB2DHandle*>( h )->pres.n_regular; }
+uint64_t orc_rb2d_portals_num_boxes( const void* h ) { return static_cast<const RB2DHandle*>( h )->pres.teleported_boxes.size(); }
+uint64_t orc_rb2d_portals_num_teleported( const void* h ) { return static_cast<const RB2DHandle*>( h )->pres.teleported_info.size(); }
+void orc_rb2d_portals_copy_boxes( const void* hv, uint32_t* box_body, uint32_t* box_portal )
+{
+  const RB2DHandle* h = static_cast<const RB2DHandle*>( hv );
+  for( std::size_t k = 0; k < h->pres.teleported_boxes.size(); ++k )
+  {
+    const TeleportedBall2D& tb = h->pres.teleported_boxes[k];
+    box_body[k] = tb.body; box_portal[k] = tb.portal | ( tb.plane ? 0x80000000u : 0u );
+  }
+}
+void orc_rb2d_portals_copy_teleported( const void* hv, uint32_t* portal0, uint32_t* portal1, double* x0, double* x1, double* delta0, double* delta1, double* kick )
+{
+  const RB2DHandle* h = static_cast<const RB2DHandle*>( hv );
+  for( std::size_t k = 0; k < h->pres.teleported_info.size(); ++k )
+  {
+    const RB2DTeleportedInfo& t = h->pres.teleported_info[k];
+    portal0[k] = t.p0 == NO_PORTAL ? NO_PORTAL : ( t.p0 | ( t.pl0 ? 0x80000000u : 0u ) );
+    portal1[k] = t.p1 == NO_PORTAL ? NO_PORTAL : ( t.p1 | ( t.pl1 ? 0x80000000u : 0u ) );
+    x0[2 * k] = t.x0.x; x0[2 * k + 1] = t.x0.y; x1[2 * k] = t.x1.x; x1[2 * k + 1] = t.x1.y;
+    delta0[2 * k] = t.delta0.x; delta0[2 * k + 1] = t.delta0.y; delta1[2 * k] = t.delta1.x; delta1[2 * k + 1] = t.delta1.y;
+    kick[2 * k] = t.kick.x; kick[2 * k + 1] = t.kick.y;
   }
 }
 

@@ -228,28 +228,16 @@ inline bool circleBoxActive( const V2& x0, const double r0, const V2& x1, const 
   return true;
 }
 
-// returns false where the reference exits (kinematic box-box, kinematic circle vs box)
-inline bool computeActiveSet( const RB2DScene& s, const double* q0, const double* q1, std::vector<RB2DContact>& active_set,
-                              std::vector<std::pair<unsigned,unsigned>>* candidates_out = nullptr, const bool use_grid = true )
+// RigidBody2DSim::dispatchNarrowPhaseCollision for one candidate pair (rigidbody2d/RigidBody2DSim.cpp:248-348); appends to
+// active_set; returns false where the reference exits (kinematic box-box, kinematic circle vs box)
+inline bool dispatchNarrowPhaseCollision( const RB2DScene& s, const unsigned first, const unsigned second, const double* q0, const double* q1, std::vector<RB2DContact>& active_set )
 {
-  const std::size_t nb = s.nbodies();
   const double NaN = std::numeric_limits<double>::quiet_NaN();
-  active_set.clear();
   auto X = [&]( const double* q, unsigned b ) { return V2{ q[3 * b], q[3 * b + 1] }; };
-  if( nb > 0 )
   {
-    PairSet possible_overlaps;
     {
-      std::vector<Box<2>> aabbs( nb );
-      for( std::size_t b = 0; b < nb; ++b ) { computeCollisionAABB( s.geo( b ), q0 + 3 * b, q1 + 3 * b, aabbs[b] ); }
-      if( use_grid ) { getPotentialOverlaps<2>( aabbs, possible_overlaps ); }
-      else { getPotentialOverlapsAllPairs<2>( aabbs, possible_overlaps ); }
-    }
-    if( candidates_out != nullptr ) { candidates_out->assign( possible_overlaps.begin(), possible_overlaps.end() ); }
-    for( const auto& pr : possible_overlaps )
-    {
-      unsigned i0 = pr.first, i1 = pr.second;
-      if( s.fixed[i0] && s.fixed[i1] ) { continue; }
+      unsigned i0 = first, i1 = second;
+      if( s.fixed[i0] && s.fixed[i1] ) { return true; }
       if( s.fixed[i0] ) { std::swap( i0, i1 ); }
       const RB2DGeometry& g0 = s.geo( i0 );
       const RB2DGeometry& g1 = s.geo( i1 );
@@ -315,6 +303,15 @@ inline bool computeActiveSet( const RB2DScene& s, const double* q0, const double
       }
     }
   }
+  return true;
+}
+
+// RigidBody2DSim::computeBodyPlaneActiveSetAllPairs (rigidbody2d/RigidBody2DSim.cpp:638-694); appends
+inline void computeBodyPlaneActiveSet( const RB2DScene& s, const double* q0, const double* q1, std::vector<RB2DContact>& active_set )
+{
+  const std::size_t nb = s.nbodies();
+  const double NaN = std::numeric_limits<double>::quiet_NaN();
+  auto X = [&]( const double* q, unsigned b ) { return V2{ q[3 * b], q[3 * b + 1] }; };
   for( uint32_t pl = 0; pl < uint32_t( s.plane_x.size() ); ++pl )
   {
     const V2 xp = s.plane_x[pl], np = s.plane_n[pl];
@@ -357,6 +354,30 @@ inline bool computeActiveSet( const RB2DScene& s, const double* q0, const double
       }
     }
   }
+}
+
+// returns false where the reference exits (kinematic box-box, kinematic circle vs box)
+inline bool computeActiveSet( const RB2DScene& s, const double* q0, const double* q1, std::vector<RB2DContact>& active_set,
+                              std::vector<std::pair<unsigned,unsigned>>* candidates_out = nullptr, const bool use_grid = true )
+{
+  const std::size_t nb = s.nbodies();
+  active_set.clear();
+  if( nb > 0 )
+  {
+    PairSet possible_overlaps;
+    {
+      std::vector<Box<2>> aabbs( nb );
+      for( std::size_t b = 0; b < nb; ++b ) { computeCollisionAABB( s.geo( b ), q0 + 3 * b, q1 + 3 * b, aabbs[b] ); }
+      if( use_grid ) { getPotentialOverlaps<2>( aabbs, possible_overlaps ); }
+      else { getPotentialOverlapsAllPairs<2>( aabbs, possible_overlaps ); }
+    }
+    if( candidates_out != nullptr ) { candidates_out->assign( possible_overlaps.begin(), possible_overlaps.end() ); }
+    for( const auto& pr : possible_overlaps )
+    {
+      if( !dispatchNarrowPhaseCollision( s, pr.first, pr.second, q0, q1, active_set ) ) { return false; }
+    }
+  }
+  computeBodyPlaneActiveSet( s, q0, q1, active_set );
   return true;
 }
 

@@ -7,6 +7,7 @@
 #define SCISIM_B200_MATH_UTILITIES_OVERRIDE
 
 #include "scisim/Math/MathDefines.h"
+#include "scisim/Utilities.h" // as the real header does (scisim/Math/MathUtilities.h:10); plain C++, no Eigen
 
 #include <istream>
 #include <ostream>

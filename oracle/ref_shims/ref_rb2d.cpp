@@ -7,6 +7,8 @@
 #include "rigidbody2d/BoxBoxTools.h"
 #include "rigidbody2d/CircleBoxTools.h"
 
+#include "rigidbody2d/PlanarPortal.h"
+
 #include <cstdint>
 
 extern "C"
@@ -44,6 +46,30 @@ int ref_rb2d_circle_box( const double* x0, const double r0, const double* x1, co
   const bool hit = CircleBoxTools::isActive( Vector2s{ x0[0], x0[1] }, r0, Vector2s{ x1[0], x1[1] }, theta1, Vector2s{ r1[0], r1[1] }, nn, pp );
   n[0] = nn.x(); n[1] = nn.y(); p[0] = pp.x(); p[1] = pp.y();
   return hit ? 1 : 0;
+}
+
+// ---- PlanarPortal (rigidbody2d/PlanarPortal.cpp, RigidBody2DStaticPlane.cpp) ------------------------------------------
+void* ref_rb2d_portal_create( const double* ax, const double* an, const double* bx, const double* bn, const double v, const double bounds )
+{
+  const RigidBody2DStaticPlane a{ Vector2s{ ax[0], ax[1] }, Vector2s{ an[0], an[1] } };
+  const RigidBody2DStaticPlane b{ Vector2s{ bx[0], bx[1] }, Vector2s{ bn[0], bn[1] } };
+  return new PlanarPortal{ a, b, v, bounds };
+}
+void ref_rb2d_portal_destroy( void* p ) { delete static_cast<PlanarPortal*>( p ); }
+void ref_rb2d_portal_update( void* p, const double t ) { static_cast<PlanarPortal*>( p )->updateMovingPortals( t ); }
+// same layout as orc_rb2d_portal_probe (oracle/capi.cpp)
+uint32_t ref_rb2d_portal_probe( const void* pv, const double* box, const double* x, double* out )
+{
+  const PlanarPortal& p = *static_cast<const PlanarPortal*>( pv );
+  const Array2s mn{ box[0], box[1] }, mx{ box[2], box[3] };
+  bool plane_idx = false;
+  const bool touches = p.aabbTouchesPortal( mn, mx, plane_idx );
+  const uint32_t touch = touches ? ( plane_idx ? 2u : 1u ) : 0u;
+  Vector2s xo;
+  p.teleportPoint( Vector2s{ x[0], x[1] }, touch == 2u, xo );
+  const Vector2s k{ p.getKinematicVelocityOfAABB( mn, mx ) };
+  out[0] = xo.x(); out[1] = xo.y(); out[2] = k.x(); out[3] = k.y();
+  return touch;
 }
 
 }

@@ -24,9 +24,6 @@
 
 using PortalBoxPolicy = AabbPolicy<2, 1>;
 
-#define SG_B2P_SORT_TILE 2048   // elements of the teleported-collision list sorted per CTA in shared memory (24 KB)
-#define SG_B2P_SORT_THREADS 1024
-
 struct PortalData
 {
   SgPortals2D portals;

@@ -10,6 +10,8 @@
 //   ball2d/Portals/PlanarPortal.cpp:167-193       getKinematicVelocityOfBall / OfPoint
 //   ball2d/Portals/PlanarPortal.cpp:195-229       teleportPointThroughPlaneA / B
 //   ball2d/Portals/PlanarPortal.cpp:231-236       updateMovingPortals
+//   rigidbody2d/PlanarPortal.cpp:143-246,298-350  the rigid-body sim's PlanarPortal: identical teleports / offsets, AABB touch tests
+//   rigidbody2d/RigidBody2DStaticPlane.cpp:10-14  its plane: normal used as given
 // FP64 throughout, evaluation order as written there (Eigen evaluates these 2-vector expressions coefficient by
 // coefficient, dot( a, b ) = a0*b0 + a1*b1); the library is compiled without FMA contraction.
 #ifndef SG_PORTAL2D_H
@@ -137,6 +139,41 @@ SG_HD void sg_portal_plane_frame( const double* n_in, double* n_out, double* t_o
   if( z > 0.0 ) { const double s = sqrt( z ); nx = nx / s; ny = ny / s; }
   n_out[0] = nx; n_out[1] = ny;
   t_out[0] = -ny; t_out[1] = nx;
+}
+
+// ---- rigidbody2d's PlanarPortal (rigidbody2d/PlanarPortal.cpp): same teleports and offsets, AABB-based touch tests -------
+// RigidBody2DStaticPlane's constructor (rigidbody2d/RigidBody2DStaticPlane.cpp:10-14): the normal is used as given
+SG_HD void sg_portal_plane_frame_as_given( const double* n_in, double* n_out, double* t_out )
+{
+  n_out[0] = n_in[0]; n_out[1] = n_in[1];
+  t_out[0] = -n_in[1]; t_out[1] = n_in[0];
+}
+
+// aabbInHalfPlane (PlanarPortal.cpp:143-165): some corner has distanceToPoint <= 0; corners in the reference's order
+SG_HD bool sg_aabb_in_half_plane( const double* px, const double* pn, const double* lo, const double* hi )
+{
+  if( sg_plane_dist( px, pn, SgVec2{ lo[0], lo[1] } ) <= 0.0 ) { return true; }
+  if( sg_plane_dist( px, pn, SgVec2{ lo[0], hi[1] } ) <= 0.0 ) { return true; }
+  if( sg_plane_dist( px, pn, SgVec2{ hi[0], lo[1] } ) <= 0.0 ) { return true; }
+  if( sg_plane_dist( px, pn, SgVec2{ hi[0], hi[1] } ) <= 0.0 ) { return true; }
+  return false;
+}
+
+// PlanarPortal::aabbTouchesPortal, release build (PlanarPortal.cpp:167-189): 0 = no, 1 = plane A, 2 = plane B; A wins
+SG_HD int sg_portal_aabb_touch( const SgPortal2D& p, const double* lo, const double* hi )
+{
+  if( sg_aabb_in_half_plane( p.ax, p.an, lo, hi ) ) { return 1; }
+  if( sg_aabb_in_half_plane( p.bx, p.bn, lo, hi ) ) { return 2; }
+  return 0;
+}
+
+// PlanarPortal::getKinematicVelocityOfAABB (PlanarPortal.cpp:218-230)
+SG_HD SgVec2 sg_portal_kinematic_velocity_of_aabb( const SgPortal2D& p, const double* lo, const double* hi )
+{
+  const bool a = sg_aabb_in_half_plane( p.ax, p.an, lo, hi );
+  SgVec2 out;
+  out.x = ( -p.v ) * ( a ? p.at[0] : p.bt[0] ); out.y = ( -p.v ) * ( a ? p.at[1] : p.bt[1] );
+  return out;
 }
 
 // Enforces every portal on one body, portal-major like Ball2DSim::enforcePeriodicBoundaryConditions

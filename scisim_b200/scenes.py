@@ -297,3 +297,65 @@ def rb2d_random(n, seed, kinds=("circle", "box"), nfixed_frac=0.08, nplanes=2, b
     return {"geo_type": geo_type, "geo_r": np.array(geo_r), "geo_half": np.array(geo_half).reshape(-1, 2), "geo_of_body": gi.astype(np.uint32),
             "fixed": fixed, "M": M, "q": q.ravel().copy(), "v": v.ravel().copy(), "g": np.array([0.0, -9.81]),
             "plane_x": rng.uniform(-box_, box_, size=(nplanes, 2)), "plane_n": pn, "dt": 0.01, "map": "symplectic_euler"}
+
+
+def rb2d_periodic(n, seed, side=None, axes="xy", lees_edwards=0.0, t=0.0, oblique=False, boxes=False, nfixed_frac=0.0, vmax=2.0, dt=0.01):
+    """rigidbody2d in a periodic box [0, side)^2 with planar portals (rigidbody2d/PlanarPortal.h): circles everywhere,
+    optionally rotated boxes in the middle of the domain (a box reaching a portal makes the reference exit).  Portal
+    layout as ball2d_periodic, but with unit normals: RigidBody2DStaticPlane does not normalise.  nfixed_frac marks some
+    interior circles as kinematically scripted (a kinematic body in a teleported collision makes the reference exit)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    side = float(side) if side is not None else max(3.0, np.sqrt(n) * 0.9)
+    h = 0.5 * side
+    geo_type, geo_r, geo_half = [0, 0, 0], [0.2, 0.35, 0.5], [[0.0, 0.0]] * 3
+    if boxes:
+        geo_type += [1, 1]; geo_r += [0.0, 0.0]; geo_half += [[0.3, 0.2], [0.45, 0.3]]
+    geo_type = np.array(geo_type, np.uint32)
+    gi = rng.integers(0, geo_type.shape[0], size=n)
+    is_box = geo_type[gi] == 1
+    q = np.empty((n, 3))
+    q[:, :2] = rng.uniform(0.0, side, size=(n, 2))
+    inner = rng.uniform(0.3 * side, 0.7 * side, size=(n, 2))
+    q[is_box, :2] = inner[is_box]
+    q[:, 2] = rng.uniform(-np.pi, np.pi, size=n)
+    v = np.empty((n, 3))
+    v[:, :2] = rng.uniform(-vmax, vmax, size=(n, 2))
+    v[:, 2] = rng.uniform(-3, 3, size=n)
+    interior = np.all(np.abs(q[:, :2] - h) < 0.3 * side, axis=1)
+    fixed = ((rng.uniform(size=n) < nfixed_frac) & ~is_box & interior & (not boxes)).astype(np.uint8)
+    v[fixed == 1] = 0.0
+    m = rng.uniform(0.5, 2.0, size=n)
+    M = np.stack([m, m, m * rng.uniform(0.05, 0.3, size=n)], axis=1).ravel()
+    pairs = {"x": (([0.0, h], [1.0, 0.0]), ([side, h], [-1.0, 0.0])), "y": (([h, 0.0], [0.0, 1.0]), ([h, side], [0.0, -1.0]))}
+    pax, pan, pbx, pbn, pv, pb, plane_x, plane_n = [], [], [], [], [], [], [], []
+    le_axis = "y" if "y" in axes else "x"
+    for ax in "xy":
+        (xa, na), (xb, nb) = pairs[ax]
+        if ax in axes:
+            pax.append(xa); pan.append(na); pbx.append(xb); pbn.append(nb)
+            is_le = lees_edwards != 0.0 and ax == le_axis
+            pv.append(lees_edwards if is_le else 0.0)
+            pb.append(h if is_le else 0.0)
+        else:
+            plane_x += [xa, xb]; plane_n += [na, nb]
+    arr = lambda a, w: np.array(a, dtype=np.float64).reshape(-1, w)
+    portals = {"plane_a_x": arr(pax, 2), "plane_a_n": arr(pan, 2), "plane_b_x": arr(pbx, 2), "plane_b_n": arr(pbn, 2),
+               "v": np.array(pv, dtype=np.float64), "bounds": np.array(pb, dtype=np.float64)}
+    planes_x, planes_n = arr(plane_x, 2), arr(plane_n, 2)
+    if oblique:
+        c, s_ = np.cos(0.3), np.sin(0.3)
+        R = np.array([[c, -s_], [s_, c]])
+        ctr = np.array([h, h])
+        rot_p = lambda a: (a - ctr) @ R.T + ctr
+        q[:, :2] = rot_p(q[:, :2]); q[:, 2] += 0.3
+        v[:, :2] = v[:, :2] @ R.T
+        for k in ("plane_a_x", "plane_b_x"):
+            portals[k] = rot_p(portals[k])
+        for k in ("plane_a_n", "plane_b_n"):
+            portals[k] = portals[k] @ R.T
+        if planes_x.shape[0]:
+            planes_x, planes_n = rot_p(planes_x), planes_n @ R.T
+    return {"geo_type": geo_type, "geo_r": np.array(geo_r), "geo_half": np.array(geo_half, dtype=np.float64).reshape(-1, 2), "geo_of_body": gi.astype(np.uint32),
+            "fixed": fixed, "M": M, "q": q.ravel().copy(), "v": v.ravel().copy(), "g": np.array([0.0, 0.0]),
+            "plane_x": np.ascontiguousarray(planes_x), "plane_n": np.ascontiguousarray(planes_n), "dt": dt, "map": "symplectic_euler", "side": side, "t": float(t),
+            "portals": {k: np.ascontiguousarray(a) for k, a in portals.items()}}

@@ -267,6 +267,18 @@ class RB2DOracle:
                 getattr(lib, f).argtypes = [vp]
             lib.orc_rb2d_copy_candidates.argtypes = [vp, vp]
             lib.orc_rb2d_copy_active.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+            lib.orc_rb2d_set_portals.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, vp, vp]
+            lib.orc_rb2d_update_portals.argtypes = [vp, C.c_double, vp]
+            lib.orc_rb2d_enforce_portals.argtypes = [vp, vp, vp]
+            lib.orc_rb2d_portal_probe.restype = C.c_uint32
+            lib.orc_rb2d_portal_probe.argtypes = [vp, C.c_uint32, vp, vp, vp]
+            lib.orc_rb2d_active_set_portals.restype = C.c_int
+            lib.orc_rb2d_active_set_portals.argtypes = [vp, vp, vp, C.c_int]
+            for f in ("orc_rb2d_portals_num_regular", "orc_rb2d_portals_num_boxes", "orc_rb2d_portals_num_teleported"):
+                getattr(lib, f).restype = C.c_uint64
+                getattr(lib, f).argtypes = [vp]
+            lib.orc_rb2d_portals_copy_boxes.argtypes = [vp, vp, vp]
+            lib.orc_rb2d_portals_copy_teleported.argtypes = [vp] * 8
             lib._rb2d_bound = True
         s = scene
         self.n = s["geo_of_body"].shape[0]
@@ -297,4 +309,48 @@ class RB2DOracle:
                "n": np.zeros((na, 2)), "p": np.zeros((na, 2)), "depth": np.zeros(na), "candidates": cand, "supported": bool(ok)}
         if na:
             self.lib.orc_rb2d_copy_active(self.h, _p(out["type"]), _p(out["i"]), _p(out["j"]), _p(out["aux"]), _p(out["n"]), _p(out["p"]), _p(out["depth"]))
+        return out
+
+    # ---- portals (oracle/rb2d_portals.h) ----
+    def set_portals(self, portals):
+        a = [_f64(portals[k]) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n", "v", "bounds")]
+        self.nportals = a[4].shape[0]
+        self.lib.orc_rb2d_set_portals(self.h, self.nportals, *[_p(x) for x in a])
+
+    def update_portals(self, t):
+        dx = np.zeros(self.nportals)
+        self.lib.orc_rb2d_update_portals(self.h, float(t), _p(dx))
+        return dx
+
+    def enforce_portals(self, q, v):
+        q, v = _f64(q).copy(), _f64(v).copy()
+        self.lib.orc_rb2d_enforce_portals(self.h, _p(q), _p(v))
+        return q, v
+
+    def portal_probe(self, p, box, x):
+        out = np.zeros(4)
+        touch = self.lib.orc_rb2d_portal_probe(self.h, int(p), _p(_f64(box)), _p(_f64(x)), _p(out))
+        return int(touch), out
+
+    def active_set_portals(self, q0, q1, method="grid"):
+        q0, q1 = _f64(q0), _f64(q1)
+        ok = self.lib.orc_rb2d_active_set_portals(self.h, _p(q0), _p(q1), 0 if method == "grid" else 1)
+        nc, na = self.lib.orc_rb2d_num_candidates(self.h), self.lib.orc_rb2d_num_active(self.h)
+        cand = np.zeros((nc, 2), dtype=np.uint32)
+        if nc:
+            self.lib.orc_rb2d_copy_candidates(self.h, _p(cand))
+        out = {"type": np.zeros(na, np.uint32), "i": np.zeros(na, np.uint32), "j": np.zeros(na, np.uint32), "aux": np.zeros(na, np.uint32),
+               "n": np.zeros((na, 2)), "p": np.zeros((na, 2)), "depth": np.zeros(na), "candidates": cand, "supported": bool(ok)}
+        if na:
+            self.lib.orc_rb2d_copy_active(self.h, _p(out["type"]), _p(out["i"]), _p(out["j"]), _p(out["aux"]), _p(out["n"]), _p(out["p"]), _p(out["depth"]))
+        nbx, nt = self.lib.orc_rb2d_portals_num_boxes(self.h), self.lib.orc_rb2d_portals_num_teleported(self.h)
+        out["n_regular"] = int(self.lib.orc_rb2d_portals_num_regular(self.h))
+        out["box_body"], out["box_portal"] = np.zeros(nbx, np.uint32), np.zeros(nbx, np.uint32)
+        if nbx:
+            self.lib.orc_rb2d_portals_copy_boxes(self.h, _p(out["box_body"]), _p(out["box_portal"]))
+        out["portal0"], out["portal1"] = np.zeros(nt, np.uint32), np.zeros(nt, np.uint32)
+        for k in ("x0", "x1", "delta0", "delta1", "kick"):
+            out[k] = np.zeros((nt, 2))
+        if nt:
+            self.lib.orc_rb2d_portals_copy_teleported(self.h, _p(out["portal0"]), _p(out["portal1"]), _p(out["x0"]), _p(out["x1"]), _p(out["delta0"]), _p(out["delta1"]), _p(out["kick"]))
         return out
