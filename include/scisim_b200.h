@@ -65,6 +65,9 @@ extern "C" {
 #define SG_BODY_BODY_2D 22     /* BodyBodyConstraint{ i, j, p, n, q0 } (box-box, circle-box) */
 #define SG_PLANE_CIRCLE 23     /* StaticPlaneCircleConstraint: j = plane */
 #define SG_PLANE_BODY_2D 24    /* StaticPlaneBodyConstraint: j = plane, aux = corner 0..3, p = body-space arm of the corner */
+/* with portals (rigidbody2d/RigidBody2DSim.cpp:477-636): after the contacts of the un-teleported pairs, ascending (i,j) */
+#define SG_CIRCLE_CIRCLE_TELEPORTED 25      /* TeleportedCircleCircleConstraint{ i, j, x0, x1, ri, rj, delta0, delta1, ri, rj }: p = q0_i + ri/(ri+rj) (x1 - x0) */
+#define SG_CIRCLE_CIRCLE_KICK_TELEPORTED 26 /* KinematicKickCircleCircleConstraint{ i, j, x0, x1, ri, rj, kick } (Lees-Edwards portal) */
 /* RigidBody2DGeometryType */
 #define SG_GEO2_CIRCLE_TYPE 0
 #define SG_GEO2_BOX_TYPE 1
@@ -138,7 +141,9 @@ typedef struct sg_teleported
   const uint32_t* portal1;    /* n_teleported: portal word of body j */
   const double* x0;           /* 2 n_teleported */
   const double* x1;           /* 2 n_teleported */
-  const double* kick;         /* 2 n_teleported (0 for SG_BALL_BALL_TELEPORTED) */
+  const double* kick;         /* 2 n_teleported (0 for SG_BALL_BALL_TELEPORTED / SG_CIRCLE_CIRCLE_TELEPORTED) */
+  const double* delta0;       /* 2 n_teleported, rigidbody2d only (NULL for ball2d): x0 - q0_i, TeleportedCircleCircleConstraint's delta0 */
+  const double* delta1;       /* 2 n_teleported, rigidbody2d only: x1 - q0_j (both NaN for kinematic-kick contacts, as the reference stores) */
 } sg_teleported;
 
 /* ---- context ------------------------------------------------------------------------------------- */
@@ -267,6 +272,21 @@ int sg_rb2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0,
 /* RigidBody2DSim::computeActiveSet (rigidbody2d/RigidBody2DSim.cpp:696-714, no portals); SG_ERR_UNSUPPORTED where the
  * reference exits (kinematic box-box, kinematic circle vs box: RigidBody2DSim.cpp:186-190, 210-214) */
 int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
+
+/* Planar and Lees-Edwards portals of the 2-D rigid-body sim (rigidbody2d/PlanarPortal.h; at most 8), arguments as
+ * sg_ball2d_set_portals except that plane normals are used as given (RigidBody2DStaticPlane does not normalise).  With portals
+ * set, sg_rb2d_active_set follows RigidBody2DSim::computeBodyBodyActiveSetSpatialGridWithPortals (RigidBody2DSim.cpp:876-1040):
+ * boxes at q1 (computeAABB, not the swept computeCollisionAABB), a teleported box per body whose box reaches a portal plane
+ * (plane A first; the both-planes check of aabbTouchesPortal is debug-only), un-teleported pairs through the regular narrow
+ * phase, SG_CIRCLE_CIRCLE_TELEPORTED / SG_CIRCLE_CIRCLE_KICK_TELEPORTED contacts after them, then the planes.
+ * SG_ERR_UNSUPPORTED where the reference exits: a box in a teleported candidate (RigidBody2DSim.cpp:374-385), a kinematic
+ * body in a teleported collision (:481-485).  update / enforce / teleported as for ball2d (RigidBody2DSim.cpp:832-874);
+ * q, v are [x, y, theta] per body. */
+int sg_rb2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x /* 2n */, const double* plane_a_n /* 2n */, const double* plane_b_x /* 2n */, const double* plane_b_n /* 2n */,
+                         const double* v /* n */, const double* bounds /* n */ );
+int sg_rb2d_update_portals( sg_ctx* ctx, double t, double* dx_out );
+int sg_rb2d_enforce_portals( sg_ctx* ctx, double* q, double* v );
+int sg_rb2d_teleported( sg_ctx* ctx, sg_teleported* out );
 
 /* ---- rigidbody3d --------------------------------------------------------------------------------------
  * Layouts are RigidBody3DState's (rigidbody3d/RigidBody3DState.cpp:70-240): q = [3N centres | 9N row-major R],

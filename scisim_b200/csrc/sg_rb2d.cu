@@ -453,6 +453,35 @@ struct ScanU32To64b
   __device__ static Out out( const Acc a ) { return a; }
 };
 
+// ---- portals (rigidbody2d/PlanarPortal.h): kernels, per-context data ------------------------------------
+#include "sg_rb2d_portal_kernels.cuh"
+
+struct Rb2dPortalData
+{
+  SgPortals2D portals;
+  DevBuf rboxes;                                   // double[4 n]: boxes at q1 (the touch tests read them before n + T is known)
+  DevBuf tflag, toff, t_partials, ttotal;          // u32[P n] flags / teleported box numbers; T
+  DevBuf box_body, box_portal;                     // u32[T]: TeleportedBody table
+  DevBuf reg_cnt, tel_cnt, tel_off, pr_partials, tel_total; // u32 per candidate
+  DevBuf reg_off, reg_total;                       // u64 per candidate; number of un-teleported pairs
+  DevBuf reg_pairs;                                // uint2[]: the un-teleported candidates, in order
+  DevBuf tc_key, tc_idx, tc_info, uflag, uoff, u_partials, utotal;
+  DevBuf x0t, x1t, delta0, delta1, kick, tp0, tp1; // per teleported contact: constructor arguments
+  DevBuf base;                                     // u64: contacts in front of the plane contacts
+  DevBuf bad;                                      // u32: bit 0 box in a teleported candidate, bit 1 kinematic body in a teleported collision
+  PinBuf h, h_tele;
+  uint64_t n_boxes = 0, n_reg = 0, n_tel = 0;
+  bool result = false;                             // the last active set came from the portal path
+  Rb2dPortalData() { memset( &portals, 0, sizeof( portals ) ); }
+  void release()
+  {
+    DevBuf* bufs[] = { &rboxes, &tflag, &toff, &t_partials, &ttotal, &box_body, &box_portal, &reg_cnt, &tel_cnt, &tel_off, &pr_partials, &tel_total, &reg_off, &reg_total, &reg_pairs,
+                       &tc_key, &tc_idx, &tc_info, &uflag, &uoff, &u_partials, &utotal, &x0t, &x1t, &delta0, &delta1, &kick, &tp0, &tp1, &base, &bad };
+    for( DevBuf* b : bufs ) { b->release(); }
+    h.release(); h_tele.release();
+  }
+};
+
 // ---- host ------------------------------------------------------------------------------------------
 struct Rb2dData
 {
@@ -471,6 +500,7 @@ struct Rb2dData
   PinBuf h_totals, h_out;
   uint64_t n_cand = 0, n_bb = 0, n_static = 0;
   bool have_result = false;
+  Rb2dPortalData* px = nullptr; // allocated by sg_rb2d_set_portals
   Rb2dData() { memset( &planes, 0, sizeof( planes ) ); }
 };
 
@@ -482,6 +512,7 @@ void sg_rb2d_release( sg_ctx* ctx )
                      &d->st_counts, &d->st_offsets, &d->st_partials, &d->st_total, &d->c_type, &d->c_i, &d->c_j, &d->c_aux, &d->c_n, &d->c_p, &d->c_depth };
   for( DevBuf* b : bufs ) { b->release(); }
   d->bp.release(); d->h_totals.release(); d->h_out.release();
+  if( d->px != nullptr ) { d->px->release(); delete d->px; d->px = nullptr; }
   delete d;
   ctx->rb2d = nullptr;
 }
@@ -511,6 +542,7 @@ static int rb2d_active_set_device( sg_ctx* ctx, Rb2dData* d )
   const uint32_t n = d->n;
   d->n_cand = d->n_bb = d->n_static = 0;
   d->have_result = true;
+  if( d->px != nullptr ) { d->px->result = false; }
   if( n == 0 ) { return SG_OK; }
   Rb2dDev dev; dev.n = n; dev.btype = d->btype.as<uint32_t>(); dev.bparam = d->bparam.as<double2>();
   SG_CUDA( ctx, d->h_totals.ensure( 64 ) );
@@ -585,6 +617,199 @@ static int rb2d_active_set_device( sg_ctx* ctx, Rb2dData* d )
   }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+// RigidBody2DSim::computeActiveSet with portals (rigidbody2d/RigidBody2DSim.cpp:696-714 -> :876-1040): boxes at q1, teleported copies,
+// un-teleported candidates through the regular narrow phase (k_rb2d_pairs), TeleportedCollision set for the rest, then the planes.
+// Same sequence as the ball2d portal path (sg_ball2d_portals.cuh); list sizes are read back where buffers have to be sized.
+static int rb2d_portal_active_set_device( sg_ctx* ctx, Rb2dData* d )
+{
+  Rb2dPortalData* x = d->px;
+  const uint32_t n = d->n;
+  const uint32_t np_portals = x->portals.n;
+  d->n_cand = d->n_bb = d->n_static = 0;
+  x->n_boxes = x->n_reg = x->n_tel = 0;
+  d->have_result = true;
+  x->result = true;
+  if( n == 0 ) { return SG_OK; }
+  if( uint64_t( n ) * np_portals >= 0x80000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "rigidbody2d portals: bodies x portals must stay below 2^31" ); }
+  Rb2dDev dev; dev.n = n; dev.btype = d->btype.as<uint32_t>(); dev.bparam = d->bparam.as<double2>();
+  const unsigned nblk = sg_div_up( n, 256 );
+  const uint32_t nflag = n * np_portals;
+  SG_CUDA( ctx, x->h.ensure( 128 ) );
+  SG_CUDA( ctx, d->st_total.ensure( 4 ) ); SG_CUDA( ctx, d->narrow_total.ensure( 8 ) ); SG_CUDA( ctx, d->bad_flag.ensure( 4 ) ); SG_CUDA( ctx, x->bad.ensure( 4 ) );
+  SG_CUDA( ctx, x->ttotal.ensure( 4 ) ); SG_CUDA( ctx, x->reg_total.ensure( 8 ) ); SG_CUDA( ctx, x->tel_total.ensure( 4 ) ); SG_CUDA( ctx, x->utotal.ensure( 4 ) ); SG_CUDA( ctx, x->base.ensure( 8 ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->st_total.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->narrow_total.ptr, 0, 8, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->bad_flag.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->bad.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->ttotal.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->reg_total.ptr, 0, 8, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->tel_total.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->utotal.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, x->rboxes.ensure( size_t( n ) * 32 ) );
+  SG_CUDA( ctx, x->tflag.ensure( size_t( nflag ) * 4 + 4 ) ); SG_CUDA( ctx, x->toff.ensure( size_t( nflag ) * 4 + 4 ) );
+  SG_CUDA( ctx, x->t_partials.ensure( ( size_t( nflag ) / SG_SCAN_TILE + 2 ) * 4 ) );
+  SG_LAUNCH( ctx, "r2p_boxes", double( n ) * ( 44.0 + 32.0 ), k_r2p_boxes<<<nblk, 256, 0, ctx->stream>>>( dev, d->q1.as<double>(), x->rboxes.as<double>() ) );
+  SG_LAUNCH( ctx, "r2p_touch", double( nflag ) * 36.0, k_r2p_touch<<<dim3( nblk, np_portals ), 256, 0, ctx->stream>>>( x->portals, n, x->rboxes.as<double>(), x->tflag.as<uint32_t>() ) );
+  int rc = sg_exclusive_scan<ScanU32>( ctx, "r2p_touch_scan", x->tflag.as<uint32_t>(), nullptr, nflag, nflag, x->t_partials.as<uint32_t>(), x->toff.as<uint32_t>(), x->ttotal.as<uint32_t>(), false );
+  if( rc != SG_OK ) { return rc; }
+  // the planes do not depend on the portals
+  const uint32_t npl = d->planes.n;
+  const uint32_t nst = npl * nblk;
+  if( npl > 0 )
+  {
+    SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 + 4 ) ); SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 + 4 ) );
+    SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
+    SG_LAUNCH( ctx, "rb2d_plane_count", double( n ) * 40.0, k_rb2d_plane_count<<<nblk, 256, 0, ctx->stream>>>( dev, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->st_counts.as<uint32_t>() ) );
+    rc = sg_exclusive_scan<ScanU32>( ctx, "rb2d_plane_scan", d->st_counts.as<uint32_t>(), nullptr, nst, nst, d->st_partials.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->st_total.as<uint32_t>(), false );
+    if( rc != SG_OK ) { return rc; }
+  }
+  uint32_t* h32 = x->h.as<uint32_t>();
+  unsigned long long* h64 = x->h.as<unsigned long long>() + 8; // bytes 64...
+  h32[1] = 0u;
+  SG_CUDA( ctx, cudaMemcpyAsync( h32, x->ttotal.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( npl > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( h32 + 1, d->st_total.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  const uint32_t nt = h32[0];
+  d->n_static = h32[1];
+  x->n_boxes = nt;
+  if( uint64_t( n ) + nt >= 0x80000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "rigidbody2d portals: more than 2^31 - 1 boxes" ); }
+  const uint32_t next = n + nt;
+  SG_CUDA( ctx, d->boxes.ensure( size_t( next ) * 32 ) );
+  SG_CUDA( ctx, x->box_body.ensure( size_t( nt ) * 4 + 4 ) ); SG_CUDA( ctx, x->box_portal.ensure( size_t( nt ) * 4 + 4 ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->boxes.ptr, x->rboxes.ptr, size_t( n ) * 32, cudaMemcpyDeviceToDevice, ctx->stream ) );
+  if( nt > 0 )
+  {
+    SG_LAUNCH( ctx, "r2p_tele_boxes", double( nflag ) * 8.0 + double( nt ) * 100.0, k_r2p_tele_boxes<<<dim3( nblk, np_portals ), 256, 0, ctx->stream>>>( x->portals, dev, d->q1.as<double>(), x->rboxes.as<double>(),
+               x->tflag.as<uint32_t>(), x->toff.as<uint32_t>(), d->boxes.as<double>(), x->box_body.as<uint32_t>(), x->box_portal.as<uint32_t>() ) );
+  }
+  rc = sg_bp_prepare_scratch<Box2DPolicy>( ctx, d->bp, next );
+  if( rc != SG_OK ) { return rc; }
+  Box2DIn in; in.boxes = d->boxes.as<double>(); in.n = next;
+  rc = sg_bp_bin_and_count<Box2DPolicy>( ctx, d->bp, in );
+  if( rc != SG_OK ) { return rc; }
+  SG_CUDA( ctx, cudaMemcpyAsync( h64, d->bp.totals.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  const uint64_t np = h64[0];
+  d->n_cand = np;
+  if( np >= 0xffffffffull ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rigidbody2d portals: more than 2^32 candidate pairs" ); }
+  if( np + 64 > d->bp.cand_cap ) { SG_CUDA( ctx, d->bp.cand.ensure( size_t( np + 64 ) * sizeof( uint2 ) ) ); d->bp.cand_cap = d->bp.cand.cap / sizeof( uint2 ); }
+  uint64_t nreg_pairs = 0;
+  uint32_t nraw = 0;
+  if( np > 0 )
+  {
+    rc = sg_bp_emit_lists<Box2DPolicy>( ctx, d->bp, next, true, NoOut2D{}, 0u );
+    if( rc != SG_OK ) { return rc; }
+    SG_CUDA( ctx, x->reg_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->reg_off.ensure( size_t( np ) * 8 + 8 ) );
+    SG_CUDA( ctx, x->tel_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->tel_off.ensure( size_t( np ) * 4 + 4 ) );
+    SG_CUDA( ctx, x->pr_partials.ensure( ( size_t( np ) / SG_SCAN_TILE + 2 ) * 8 ) );
+    SG_LAUNCH( ctx, "r2p_classify_count", double( np ) * 60.0, k_r2p_classify<false><<<sg_div_up( np, 128 ), 128, 0, ctx->stream>>>( x->portals, dev, d->bp.cand.as<uint2>(), np, d->q1.as<double>(),
+               x->box_body.as<uint32_t>(), x->box_portal.as<uint32_t>(), x->reg_cnt.as<uint32_t>(), x->tel_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, x->bad.as<uint32_t>() ) );
+    rc = sg_exclusive_scan<ScanU32To64b>( ctx, "r2p_regular_scan", x->reg_cnt.as<uint32_t>(), nullptr, uint32_t( np ), uint32_t( np ), x->pr_partials.as<unsigned long long>(), x->reg_off.as<unsigned long long>(),
+                                          x->reg_total.as<unsigned long long>(), false );
+    if( rc != SG_OK ) { return rc; }
+    rc = sg_exclusive_scan<ScanU32>( ctx, "r2p_teleported_scan", x->tel_cnt.as<uint32_t>(), nullptr, uint32_t( np ), uint32_t( np ), x->pr_partials.as<uint32_t>(), x->tel_off.as<uint32_t>(), x->tel_total.as<uint32_t>(), false );
+    if( rc != SG_OK ) { return rc; }
+    SG_CUDA( ctx, cudaMemcpyAsync( h64 + 2, x->reg_total.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h32 + 2, x->tel_total.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h32 + 3, x->bad.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    if( h32[3] != 0u )
+    {
+      return sg_fail( ctx, SG_ERR_UNSUPPORTED, "a box takes part in a teleported collision (the reference exits here: rigidbody2d/RigidBody2DSim.cpp:374-385)" );
+    }
+    nreg_pairs = h64[2];
+    nraw = h32[2];
+  }
+  if( nraw > 0x40000000u ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rigidbody2d portals: more than 2^30 teleported collisions" ); }
+  uint32_t m = 1u;
+  while( m < nraw ) { m <<= 1; }
+  SG_CUDA( ctx, x->reg_pairs.ensure( size_t( nreg_pairs ) * 8 + 8 ) );
+  if( nraw > 0 )
+  {
+    SG_CUDA( ctx, x->tc_key.ensure( size_t( m ) * 8 ) ); SG_CUDA( ctx, x->tc_idx.ensure( size_t( m ) * 4 ) ); SG_CUDA( ctx, x->tc_info.ensure( size_t( nraw ) * 16 ) );
+    SG_CUDA( ctx, x->uflag.ensure( size_t( nraw ) * 4 + 4 ) ); SG_CUDA( ctx, x->uoff.ensure( size_t( nraw ) * 4 + 4 ) );
+    SG_CUDA( ctx, x->u_partials.ensure( ( size_t( nraw ) / SG_SCAN_TILE + 2 ) * 4 ) );
+    for( DevBuf* b : { &x->x0t, &x->x1t, &x->delta0, &x->delta1, &x->kick } ) { SG_CUDA( ctx, b->ensure( size_t( nraw ) * 16 ) ); }
+    SG_CUDA( ctx, x->tp0.ensure( size_t( nraw ) * 4 ) ); SG_CUDA( ctx, x->tp1.ensure( size_t( nraw ) * 4 ) );
+  }
+  if( np > 0 )
+  {
+    SG_LAUNCH( ctx, "r2p_classify_emit", double( np ) * 28.0, k_r2p_classify<true><<<sg_div_up( np, 128 ), 128, 0, ctx->stream>>>( x->portals, dev, d->bp.cand.as<uint2>(), np, d->q1.as<double>(),
+               x->box_body.as<uint32_t>(), x->box_portal.as<uint32_t>(), x->reg_cnt.as<uint32_t>(), x->tel_cnt.as<uint32_t>(), x->reg_off.as<unsigned long long>(), x->tel_off.as<uint32_t>(),
+               x->reg_pairs.as<uint2>(), x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>(), x->tc_info.as<uint4>(), x->bad.as<uint32_t>() ) );
+  }
+  // regular narrow phase over the un-teleported candidates: count -> scan (the emit follows once the contact arrays are sized)
+  SG_CUDA( ctx, d->pair_counts.ensure( size_t( nreg_pairs ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->pair_offsets.ensure( size_t( nreg_pairs ) * 8 + 8 ) );
+  SG_CUDA( ctx, d->pair_partials.ensure( ( size_t( nreg_pairs ) / SG_SCAN_TILE + 2 ) * 8 ) );
+  const unsigned long long* nreg_dev = x->reg_total.as<unsigned long long>();
+  if( nreg_pairs > 0 )
+  {
+    SG_LAUNCH( ctx, "rb2d_pairs_count", double( nreg_pairs ) * 120.0, k_rb2d_pairs<false><<<sg_div_up( nreg_pairs, 128 ), 128, 0, ctx->stream>>>( dev, x->reg_pairs.as<uint2>(), nreg_dev, d->q0.as<double>(), d->q1.as<double>(),
+               d->pair_counts.as<uint32_t>(), nullptr, rb2d_out( d ), d->bad_flag.as<uint32_t>() ) );
+    rc = sg_exclusive_scan<ScanU32To64b>( ctx, "rb2d_pair_scan", d->pair_counts.as<uint32_t>(), nullptr, uint32_t( nreg_pairs ), uint32_t( nreg_pairs ), d->pair_partials.as<unsigned long long>(),
+                                          d->pair_offsets.as<unsigned long long>(), d->narrow_total.as<unsigned long long>(), false );
+    if( rc != SG_OK ) { return rc; }
+  }
+  if( nraw > 0 )
+  {
+    if( m > nraw ) { SG_LAUNCH( ctx, "b2p_sort_pad", 0.0, k_b2p_sort_pad<<<sg_div_up( m - nraw, 256 ), 256, 0, ctx->stream>>>( nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) ); }
+    const unsigned ntiles = sg_div_up( m, SG_B2P_SORT_TILE );
+    SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, true><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, 0u, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
+    for( uint32_t k = 2u * SG_B2P_SORT_TILE; k <= m; k <<= 1 )
+    {
+      for( uint32_t j = k >> 1; j >= uint32_t( SG_B2P_SORT_TILE ); j >>= 1 )
+      {
+        SG_LAUNCH( ctx, "b2p_bitonic", double( m ) * 24.0, k_b2p_bitonic<<<sg_div_up( m, 256 ), 256, 0, ctx->stream>>>( m, j, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
+      }
+      SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, false><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
+    }
+    SG_LAUNCH( ctx, "b2p_unique", double( nraw ) * 12.0, k_b2p_unique<<<sg_div_up( nraw, 256 ), 256, 0, ctx->stream>>>( nraw, x->tc_key.as<unsigned long long>(), x->uflag.as<uint32_t>() ) );
+    rc = sg_exclusive_scan<ScanU32>( ctx, "b2p_unique_scan", x->uflag.as<uint32_t>(), nullptr, nraw, nraw, x->u_partials.as<uint32_t>(), x->uoff.as<uint32_t>(), x->utotal.as<uint32_t>(), false );
+    if( rc != SG_OK ) { return rc; }
+  }
+  h64[3] = 0ull; h32[4] = 0u; h32[5] = 0u;
+  SG_CUDA( ctx, cudaMemcpyAsync( h64 + 3, d->narrow_total.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( h32 + 4, d->bad_flag.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( nraw > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( h32 + 5, x->utotal.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  if( h32[4] != 0u )
+  {
+    return sg_fail( ctx, SG_ERR_UNSUPPORTED, "kinematic box-box / kinematic-circle-vs-box collisions are not supported (the reference exits here: rigidbody2d/RigidBody2DSim.cpp:186-190, 210-214)" );
+  }
+  x->n_reg = h64[3];
+  x->n_tel = h32[5];
+  d->n_bb = x->n_reg + x->n_tel;
+  rc = rb2d_ensure_contacts( ctx, d, d->n_bb + d->n_static + 64 );
+  if( rc != SG_OK ) { return rc; }
+  if( nreg_pairs > 0 && x->n_reg > 0 )
+  {
+    SG_LAUNCH( ctx, "rb2d_pairs_emit", double( nreg_pairs ) * 120.0 + double( x->n_reg ) * 60.0, k_rb2d_pairs<true><<<sg_div_up( nreg_pairs, 128 ), 128, 0, ctx->stream>>>( dev, x->reg_pairs.as<uint2>(), nreg_dev, d->q0.as<double>(),
+               d->q1.as<double>(), nullptr, d->pair_offsets.as<unsigned long long>(), rb2d_out( d ), d->bad_flag.as<uint32_t>() ) );
+  }
+  if( x->n_tel > 0 )
+  {
+    SG_LAUNCH( ctx, "r2p_tele_contacts", double( nraw ) * 250.0, k_r2p_tele_contacts<<<sg_div_up( nraw, 128 ), 128, 0, ctx->stream>>>( x->portals, dev, nraw, x->tc_idx.as<uint32_t>(), x->uflag.as<uint32_t>(), x->uoff.as<uint32_t>(),
+               x->tc_info.as<uint4>(), d->q0.as<double>(), d->q1.as<double>(), x->n_reg, rb2d_out( d ), x->x0t.as<double2>(), x->x1t.as<double2>(), x->delta0.as<double2>(), x->delta1.as<double2>(),
+               x->kick.as<double2>(), x->tp0.as<uint32_t>(), x->tp1.as<uint32_t>(), x->bad.as<uint32_t>() ) );
+  }
+  if( npl > 0 && d->n_static > 0 )
+  {
+    h64[4] = d->n_bb;
+    SG_CUDA( ctx, cudaMemcpyAsync( x->base.ptr, h64 + 4, 8, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_LAUNCH( ctx, "rb2d_plane_emit", double( n ) * 4.0, k_rb2d_plane_emit<<<nblk, 256, 0, ctx->stream>>>( dev, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(),
+               x->base.as<unsigned long long>(), rb2d_out( d ) ) );
+  }
+  SG_CUDA( ctx, cudaMemcpyAsync( h32 + 3, x->bad.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  if( h32[3] != 0u )
+  {
+    return sg_fail( ctx, SG_ERR_UNSUPPORTED, "a kinematically scripted body takes part in a teleported collision (the reference exits here: rigidbody2d/RigidBody2DSim.cpp:481-485)" );
+  }
   return SG_OK;
 }
 
@@ -689,6 +914,104 @@ int sg_rb2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x, const double* 
   return SG_OK;
 }
 
+int sg_rb2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x, const double* plane_a_n, const double* plane_b_x, const double* plane_b_n, const double* v, const double* bounds )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > SG_MAX_PORTALS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_set_portals: at most %d portals", SG_MAX_PORTALS ); }
+  if( n > 0 && ( plane_a_x == nullptr || plane_a_n == nullptr || plane_b_x == nullptr || plane_b_n == nullptr || v == nullptr || bounds == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_set_portals: null array" ); }
+  Rb2dData* d = rb2d_data( ctx );
+  if( n == 0 && d->px == nullptr ) { return SG_OK; }
+  if( d->px == nullptr ) { d->px = new Rb2dPortalData; }
+  Rb2dPortalData* x = d->px;
+  memset( &x->portals, 0, sizeof( x->portals ) );
+  x->portals.n = n;
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    SgPortal2D& pt = x->portals.p[p];
+    for( int k = 0; k < 2; ++k ) { pt.ax[k] = plane_a_x[2 * p + k]; pt.bx[k] = plane_b_x[2 * p + k]; }
+    // RigidBody2DStaticPlane::RigidBody2DStaticPlane( x, n ): n as given (rigidbody2d/RigidBody2DStaticPlane.cpp:10-14)
+    sg_portal_plane_frame_as_given( plane_a_n + 2 * p, pt.an, pt.at );
+    sg_portal_plane_frame_as_given( plane_b_n + 2 * p, pt.bn, pt.bt );
+    if( bounds[p] < 0.0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_set_portals: portal %u has negative bounds", p ); }
+    pt.v = v[p]; pt.bounds = bounds[p]; pt.dx = 0.0;
+  }
+  d->have_result = false;
+  return SG_OK;
+}
+
+int sg_rb2d_update_portals( sg_ctx* ctx, double t, double* dx_out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb2dData* d = rb2d_data( ctx );
+  if( d->px == nullptr ) { return SG_OK; }
+  for( uint32_t p = 0; p < d->px->portals.n; ++p )
+  {
+    SgPortal2D& pt = d->px->portals.p[p];
+    pt.dx = sg_portal_offset( pt.v, pt.bounds, t );
+    if( dx_out != nullptr ) { dx_out[p] = pt.dx; }
+  }
+  return SG_OK;
+}
+
+int sg_rb2d_enforce_portals( sg_ctx* ctx, double* q, double* v )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb2dData* d = rb2d_data( ctx );
+  if( d->px == nullptr || d->px->portals.n == 0u || d->n == 0 ) { return SG_OK; }
+  if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_enforce_portals: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  d->flow_resident = false; // q1 / v1 serve as the staging copies
+  const size_t bytes = size_t( d->n ) * 24;
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v1.ptr, v, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_LAUNCH( ctx, "r2p_enforce", double( d->n ) * 64.0, k_r2p_enforce<<<sg_div_up( d->n, 256 ), 256, 0, ctx->stream>>>( d->px->portals, d->n, d->q1.as<double>(), d->v1.as<double>() ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( q, d->q1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( v, d->v1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+int sg_rb2d_teleported( sg_ctx* ctx, sg_teleported* out )
+{
+  if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
+  memset( out, 0, sizeof( *out ) );
+  Rb2dData* d = rb2d_data( ctx );
+  if( !d->have_result || d->px == nullptr || !d->px->result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_teleported: the last active set was not computed with portals" ); }
+  Rb2dPortalData* x = d->px;
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  auto al = []( size_t b ) { return ( b + 63 ) & ~size_t( 63 ); };
+  const size_t nb = x->n_boxes, nt = x->n_tel;
+  size_t bytes = 64;
+  const size_t o_bb = bytes; bytes += al( nb * 4 );
+  const size_t o_bp = bytes; bytes += al( nb * 4 );
+  const size_t o_p0 = bytes; bytes += al( nt * 4 );
+  const size_t o_p1 = bytes; bytes += al( nt * 4 );
+  size_t o_d[5];
+  for( int k = 0; k < 5; ++k ) { o_d[k] = bytes; bytes += al( nt * 16 ); }
+  SG_CUDA( ctx, x->h_tele.ensure( bytes ) );
+  char* h = x->h_tele.as<char>();
+  if( nb > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_bb, x->box_body.ptr, nb * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_bp, x->box_portal.ptr, nb * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  }
+  if( nt > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_p0, x->tp0.ptr, nt * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_p1, x->tp1.ptr, nt * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    const DevBuf* src[5] = { &x->x0t, &x->x1t, &x->kick, &x->delta0, &x->delta1 };
+    for( int k = 0; k < 5; ++k ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_d[k], src[k]->ptr, nt * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  out->n_boxes = nb; out->n_regular = x->n_reg; out->n_teleported = nt;
+  out->box_body = reinterpret_cast<const uint32_t*>( h + o_bb ); out->box_portal = reinterpret_cast<const uint32_t*>( h + o_bp );
+  out->portal0 = reinterpret_cast<const uint32_t*>( h + o_p0 ); out->portal1 = reinterpret_cast<const uint32_t*>( h + o_p1 );
+  out->x0 = reinterpret_cast<const double*>( h + o_d[0] ); out->x1 = reinterpret_cast<const double*>( h + o_d[1] ); out->kick = reinterpret_cast<const double*>( h + o_d[2] );
+  out->delta0 = reinterpret_cast<const double*>( h + o_d[3] ); out->delta1 = reinterpret_cast<const double*>( h + o_d[4] );
+  return SG_OK;
+}
+
 int sg_rb2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
@@ -727,7 +1050,7 @@ int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
     SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, size_t( d->n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
     d->flow_resident = false;
   }
-  const int rc = rb2d_active_set_device( ctx, d );
+  const int rc = ( d->px != nullptr && d->px->portals.n > 0u ) ? rb2d_portal_active_set_device( ctx, d ) : rb2d_active_set_device( ctx, d );
   if( rc != SG_OK ) { return rc; }
   return rb2d_copy_out( ctx, d, out_flags, out );
 }

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <limits>
 #include <numeric>
 
 GpuBall2DBackend::GpuBall2DBackend( const int device )
@@ -79,7 +80,12 @@ void GpuBall2DBackend::teleportedContacts( std::vector<GpuTeleportedContact2D>& 
   {
     GpuTeleportedContact2D& o = teleported[k];
     o.portal0 = t.portal0[k]; o.portal1 = t.portal1[k];
-    for( int c = 0; c < 2; ++c ) { o.x0[c] = t.x0[2 * k + c]; o.x1[c] = t.x1[2 * k + c]; o.kick[c] = t.kick[2 * k + c]; }
+    for( int c = 0; c < 2; ++c )
+    {
+      o.x0[c] = t.x0[2 * k + c]; o.x1[c] = t.x1[2 * k + c]; o.kick[c] = t.kick[2 * k + c];
+      o.delta0[c] = t.delta0 != nullptr ? t.delta0[2 * k + c] : std::numeric_limits<double>::quiet_NaN();
+      o.delta1[c] = t.delta1 != nullptr ? t.delta1[2 * k + c] : std::numeric_limits<double>::quiet_NaN();
+    }
   }
   if( num_regular != nullptr ) { *num_regular = t.n_regular; }
 }
@@ -336,6 +342,41 @@ void GpuRigidBody2DBackend::setGravity( const double gx, const double gy )
 void GpuRigidBody2DBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n )
 {
   check( sg_rb2d_set_planes( m_ctx, static_cast<uint32_t>( x.size() / 2 ), x.data(), n.data() ), "sg_rb2d_set_planes" );
+}
+
+void GpuRigidBody2DBackend::setPortals( const std::vector<double>& plane_a_x, const std::vector<double>& plane_a_n, const std::vector<double>& plane_b_x, const std::vector<double>& plane_b_n,
+                                        const std::vector<double>& velocity, const std::vector<double>& bounds )
+{
+  check( sg_rb2d_set_portals( m_ctx, static_cast<uint32_t>( velocity.size() ), plane_a_x.data(), plane_a_n.data(), plane_b_x.data(), plane_b_n.data(), velocity.data(), bounds.data() ), "sg_rb2d_set_portals" );
+}
+
+void GpuRigidBody2DBackend::updatePeriodicBoundaryConditionsStartOfStep( const unsigned next_iteration, const scalar& dt )
+{
+  const scalar t{ next_iteration * dt }; // rigidbody2d/RigidBody2DSim.cpp:834
+  check( sg_rb2d_update_portals( m_ctx, t, nullptr ), "sg_rb2d_update_portals" );
+}
+
+void GpuRigidBody2DBackend::enforcePeriodicBoundaryConditions( VectorXs& q, VectorXs& v )
+{
+  check( sg_rb2d_enforce_portals( m_ctx, q.data(), v.data() ), "sg_rb2d_enforce_portals" );
+}
+
+void GpuRigidBody2DBackend::teleportedContacts( std::vector<GpuTeleportedContact2D>& teleported, uint64_t* num_regular )
+{
+  sg_teleported t;
+  check( sg_rb2d_teleported( m_ctx, &t ), "sg_rb2d_teleported" );
+  teleported.resize( t.n_teleported );
+  for( uint64_t k = 0; k < t.n_teleported; ++k )
+  {
+    GpuTeleportedContact2D& o = teleported[k];
+    o.portal0 = t.portal0[k]; o.portal1 = t.portal1[k];
+    for( int c = 0; c < 2; ++c )
+    {
+      o.x0[c] = t.x0[2 * k + c]; o.x1[c] = t.x1[2 * k + c]; o.kick[c] = t.kick[2 * k + c];
+      o.delta0[c] = t.delta0[2 * k + c]; o.delta1[c] = t.delta1[2 * k + c];
+    }
+  }
+  if( num_regular != nullptr ) { *num_regular = t.n_regular; }
 }
 
 void GpuRigidBody2DBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )

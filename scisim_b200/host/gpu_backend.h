@@ -41,6 +41,7 @@ struct GpuTeleportedContact2D
 {
   uint32_t portal0, portal1;
   double x0[2], x1[2], kick[2];
+  double delta0[2], delta1[2]; // rigidbody2d only (TeleportedCircleCircleConstraint's displacements); NaN otherwise
 };
 
 class GpuBall2DBackend final
@@ -218,6 +219,17 @@ public:
   void setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& M );
   void setGravity( const double gx, const double gy );
   void setPlanes( const std::vector<double>& x, const std::vector<double>& n );
+
+  // RigidBody2DState::planarPortals() (rigidbody2d/PlanarPortal.h): plane A and B as (x, n; n used as given), velocity, bounds.
+  // With portals set computeActiveSet follows computeBodyBodyActiveSetSpatialGridWithPortals (rigidbody2d/RigidBody2DSim.cpp:876-1040).
+  void setPortals( const std::vector<double>& plane_a_x, const std::vector<double>& plane_a_n, const std::vector<double>& plane_b_x, const std::vector<double>& plane_b_n,
+                   const std::vector<double>& velocity, const std::vector<double>& bounds );
+  // RigidBody2DSim::updatePeriodicBoundaryConditionsStartOfStep / enforcePeriodicBoundaryConditions (RigidBody2DSim.cpp:832-874)
+  void updatePeriodicBoundaryConditionsStartOfStep( const unsigned next_iteration, const scalar& dt );
+  void enforcePeriodicBoundaryConditions( VectorXs& q, VectorXs& v );
+  // after a computeActiveSet with portals: constructor arguments of the SG_CIRCLE_CIRCLE_TELEPORTED / _KICK_TELEPORTED contacts,
+  // which are entries [num_regular, num_regular + teleported.size()) of the contact list
+  void teleportedContacts( std::vector<GpuTeleportedContact2D>& teleported, uint64_t* num_regular = nullptr );
 
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
   // contacts use GpuContact2D with the rigidbody2d type codes (SG_CIRCLE_CIRCLE ... SG_PLANE_BODY_2D)

@@ -191,6 +191,9 @@ class TeleportedInfo:
         self.x0 = arr(t.x0, (nt, 2), np.float64)
         self.x1 = arr(t.x1, (nt, 2), np.float64)
         self.kick = arr(t.kick, (nt, 2), np.float64)
+        # rigidbody2d only: TeleportedCircleCircleConstraint's displacements
+        self.delta0 = arr(t.delta0, (nt, 2), np.float64) if t.delta0 else None
+        self.delta1 = arr(t.delta1, (nt, 2), np.float64) if t.delta1 else None
 
 
 class Ball2DState:
@@ -467,7 +470,8 @@ class RigidBody2DState:
     """Static part of rigidbody2d/RigidBody2DState.h: geometry list, per-body geometry index / fixed flag, the 3N mass
     diagonal (m, m, I), gravity, static planes (normals as given)."""
 
-    def __init__(self, geo_type, geo_r, geo_half, geo_of_body, fixed, M, g=(0.0, 0.0), plane_x=None, plane_n=None):
+    def __init__(self, geo_type, geo_r, geo_half, geo_of_body, fixed, M, g=(0.0, 0.0), plane_x=None, plane_n=None, planar_portals=None):
+        self.planar_portals = list(planar_portals) if planar_portals is not None else []
         self.geo_type = np.ascontiguousarray(geo_type, dtype=np.uint32)
         self.geo_r = _f64(geo_r)
         self.geo_half = _f64(geo_half).reshape(-1, 2)
@@ -493,9 +497,35 @@ class RigidBody2DSim:
         self.ctx.check(lib.sg_rb2d_set_bodies(h, st.nbodies(), _ptr(st.geo_of_body), _ptr(st.fixed), _ptr(st.M)))
         self.ctx.check(lib.sg_rb2d_set_gravity(h, _ptr(st.g)))
         self.ctx.check(lib.sg_rb2d_set_planes(h, st.plane_x.shape[0], _ptr(st.plane_x), _ptr(st.plane_n)))
+        pp = st.planar_portals
+        if pp:
+            cat = lambda f: _f64(np.array([f(p) for p in pp], dtype=np.float64))
+            arrs = [cat(lambda p: p.plane_a_x), cat(lambda p: p.plane_a_n), cat(lambda p: p.plane_b_x), cat(lambda p: p.plane_b_n),
+                    cat(lambda p: p.velocity), cat(lambda p: p.bounds)]
+            self.ctx.check(lib.sg_rb2d_set_portals(h, len(pp), *[_ptr(a) for a in arrs]))
+        else:
+            self.ctx.check(lib.sg_rb2d_set_portals(h, 0, None, None, None, None, None, None))
 
     def name(self):
         return "rigid_body_2d"
+
+    # ---- portals (rigidbody2d/RigidBody2DSim.cpp:832-874) ----
+    def updatePeriodicBoundaryConditionsStartOfStep(self, next_iteration, dt):
+        dx = np.zeros(max(1, len(self.state.planar_portals)))
+        self.ctx.check(self.ctx.lib.sg_rb2d_update_portals(self.ctx.h, float(next_iteration * dt), _ptr(dx)))
+        return dx[: len(self.state.planar_portals)]
+
+    def enforcePeriodicBoundaryConditions(self, q, v):
+        q = _f64(q).copy()
+        v = _f64(v).copy()
+        self.ctx.check(self.ctx.lib.sg_rb2d_enforce_portals(self.ctx.h, _ptr(q), _ptr(v)))
+        return q, v
+
+    def teleported(self):
+        from ._lib import SgTeleported
+        t = SgTeleported()
+        self.ctx.check(self.ctx.lib.sg_rb2d_teleported(self.ctx.h, C.byref(t)))
+        return TeleportedInfo(t)
 
     def nqdofs(self):
         return 3 * self.state.nbodies()

@@ -380,3 +380,174 @@ def test_tile_sort_kernel_on_cpu(pk, mode, sizes):
             assert np.all(k[nraw:] == np.uint64(0xFFFFFFFFFFFFFFFF))
     finally:
         pk.pk_set_sort_mode(0)
+
+
+# ---- rigidbody2d portals ------------------------------------------------------------------------------------------------------
+def _rb2d_oracle(scene):
+    o = ob.RB2DOracle(scene)
+    o.set_portals(scene["portals"])
+    return o
+
+
+def _bind_rb2d(pk):
+    if getattr(pk, "_rb2d_bound", False):
+        return
+    pk.pk_rb2d_set_portals.argtypes = [C.c_uint32] + [C.c_void_p] * 7
+    pk.pk_rb2d_active_set.restype = C.c_uint
+    pk.pk_rb2d_active_set.argtypes = [C.c_uint32] + [C.c_void_p] * 4
+    for f in ("pk_rb2d_num_candidates", "pk_rb2d_num_regular_pairs"):
+        getattr(pk, f).restype = C.c_uint64
+    for f in ("pk_rb2d_num_boxes", "pk_rb2d_num_teleported"):
+        getattr(pk, f).restype = C.c_uint32
+    pk.pk_rb2d_copy.argtypes = [C.c_void_p] * 17
+    pk.pk_rb2d_enforce.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    pk.pk_rb2d_probe.restype = C.c_uint32
+    pk.pk_rb2d_probe.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    pk._rb2d_bound = True
+
+
+def _pk_rb2d_set(pk, scene, dx):
+    _bind_rb2d(pk)
+    P = scene["portals"]
+    a = [np.ascontiguousarray(P[k], dtype=np.float64) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n", "v", "bounds")]
+    pk.pk_rb2d_set_portals(a[4].shape[0], *[vp(x) for x in a], vp(np.ascontiguousarray(dx, dtype=np.float64)))
+
+
+def _rb2d_device_arrays(scene):
+    """btype / bparam exactly as sg_rb2d_set_bodies lays them out."""
+    gi = scene["geo_of_body"]
+    t = scene["geo_type"][gi].astype(np.uint32)
+    btype = (t | (scene["fixed"].astype(np.uint32) << np.uint32(31))).astype(np.uint32)
+    bparam = np.zeros((gi.shape[0], 2))
+    circ = t == 0
+    bparam[circ, 0] = scene["geo_r"][gi][circ]
+    bparam[~circ] = scene["geo_half"][gi][~circ]
+    return np.ascontiguousarray(btype), np.ascontiguousarray(bparam)
+
+
+@pytest.mark.parametrize("case", [dict(axes="xy"), dict(axes="xy", lees_edwards=0.75, t=3.7), dict(axes="x", lees_edwards=-1.25, t=11.3, oblique=True)],
+                         ids=["plain", "lees-edwards", "oblique"])
+def test_rb2d_portal_primitives_oracle_reference_product(case, pk, oracle):
+    scene = scenes.rb2d_periodic(32, 5, side=12.0, **case)
+    o = _rb2d_oracle(scene)
+    dx = o.update_portals(scene["t"])
+    _pk_rb2d_set(pk, scene, dx)
+    path = os.path.join(REFDIR, "libref_rb2d.so")
+    ref, handles = None, []
+    if os.path.exists(path) and hasattr(C.CDLL(path), "ref_rb2d_portal_probe"):
+        ref = C.CDLL(path)
+        ref.ref_rb2d_portal_create.restype = C.c_void_p
+        ref.ref_rb2d_portal_create.argtypes = [C.c_void_p] * 4 + [C.c_double, C.c_double]
+        ref.ref_rb2d_portal_update.argtypes = [C.c_void_p, C.c_double]
+        ref.ref_rb2d_portal_probe.restype = C.c_uint32
+        ref.ref_rb2d_portal_probe.argtypes = [C.c_void_p] * 4
+        ref.ref_rb2d_portal_destroy.argtypes = [C.c_void_p]
+        P = scene["portals"]
+        for p in range(P["v"].shape[0]):
+            h = ref.ref_rb2d_portal_create(vp(P["plane_a_x"][p]), vp(P["plane_a_n"][p]), vp(P["plane_b_x"][p]), vp(P["plane_b_n"][p]), float(P["v"][p]), float(P["bounds"][p]))
+            ref.ref_rb2d_portal_update(h, scene["t"])
+            handles.append(h)
+    elif os.path.isdir("/root/reference"):
+        pytest.fail("oracle/_ref/libref_rb2d.so lacks the portal shim: run make -C oracle -f Makefile.ref")
+    rng = np.random.default_rng(23)
+    ctr = _probe_points(scene, rng, 3000)
+    ext = rng.uniform(0.05, 0.6, size=(ctr.shape[0], 2))
+    seen = set()
+    for p in range(scene["portals"]["v"].shape[0]):
+        for c, e in zip(ctr, ext):
+            box = np.ascontiguousarray(np.concatenate([c - e, c + e]))
+            c = np.ascontiguousarray(c)
+            to, oo = o.portal_probe(p, box, c)
+            op = np.zeros(4)
+            tp = pk.pk_rb2d_probe(p, vp(box), vp(c), vp(op))
+            assert to == tp and np.array_equal(oo.view(np.uint64), op.view(np.uint64)), (p, box)
+            if ref is not None:
+                orf = np.zeros(4)
+                tr = ref.ref_rb2d_portal_probe(handles[p], vp(box), vp(c), vp(orf))
+                assert tr == to and np.array_equal(orf.view(np.uint64), oo.view(np.uint64)), (p, box)
+            seen.add(to)
+    assert seen == {0, 1, 2}
+    for h in handles:
+        ref.ref_rb2d_portal_destroy(h)
+
+
+RB2D_KERNEL_CASES = [dict(n=1, seed=1), dict(n=2, seed=2, side=3.0, axes="x"), dict(n=400, seed=1, side=10.0), dict(n=400, seed=2, side=10.0, lees_edwards=0.7, t=1.3, oblique=True),
+                     dict(n=600, seed=3, side=16.0, boxes=True, axes="x"), dict(n=400, seed=4, side=10.0, nfixed_frac=0.3), dict(n=500, seed=6, side=7.0, axes="y", lees_edwards=-0.9, t=4.0)]
+
+
+@pytest.mark.parametrize("case", RB2D_KERNEL_CASES, ids=lambda c: "n%d-s%d" % (c["n"], c["seed"]))
+def test_rb2d_portal_kernels_on_cpu_match_oracle(case, pk, oracle):
+    scene = scenes.rb2d_periodic(**case)
+    o = _rb2d_oracle(scene)
+    dx = o.update_portals(scene["t"])
+    q0 = scene["q"]
+    q1, _ = o.flow(0, q0, scene["v"], scene["dt"])
+    ref = o.active_set_portals(q0, q1, "allpairs")
+    assert ref["supported"]
+    _pk_rb2d_set(pk, scene, dx)
+    btype, bparam = _rb2d_device_arrays(scene)
+    q0c, q1c = np.ascontiguousarray(q0), np.ascontiguousarray(q1)
+    bad = pk.pk_rb2d_active_set(scene["geo_of_body"].shape[0], vp(btype), vp(bparam), vp(q0c), vp(q1c))
+    assert bad == 0
+    nc, nrp, nb, nt = int(pk.pk_rb2d_num_candidates()), int(pk.pk_rb2d_num_regular_pairs()), int(pk.pk_rb2d_num_boxes()), int(pk.pk_rb2d_num_teleported())
+    got = {"candidates": np.zeros((nc, 2), np.uint32), "reg_pairs": np.zeros((nrp, 2), np.uint32), "box_body": np.zeros(nb, np.uint32), "box_portal": np.zeros(nb, np.uint32),
+           "type": np.zeros(nt, np.uint32), "i": np.zeros(nt, np.uint32), "j": np.zeros(nt, np.uint32), "n": np.zeros((nt, 2)), "p": np.zeros((nt, 2)), "depth": np.zeros(nt),
+           "portal0": np.zeros(nt, np.uint32), "portal1": np.zeros(nt, np.uint32), "x0": np.zeros((nt, 2)), "x1": np.zeros((nt, 2)), "delta0": np.zeros((nt, 2)), "delta1": np.zeros((nt, 2)),
+           "kick": np.zeros((nt, 2))}
+    pk.pk_rb2d_copy(*[vp(got[k]) for k in ("candidates", "reg_pairs", "box_body", "box_portal", "type", "i", "j", "n", "p", "depth", "portal0", "portal1", "x0", "x1", "delta0", "delta1", "kick")])
+    n = scene["geo_of_body"].shape[0]
+    for k in ("candidates", "box_body", "box_portal", "portal0", "portal1"):
+        assert np.array_equal(got[k], ref[k]), k
+    real = (ref["candidates"][:, 0] < n) & (ref["candidates"][:, 1] < n)
+    assert np.array_equal(got["reg_pairs"], ref["candidates"][real])
+    nr = ref["n_regular"]
+    tel = slice(nr, nr + nt)
+    assert np.all(np.isin(ref["type"][tel], [25, 26])) and not np.any(np.isin(ref["type"][nr + nt:], [25, 26]))
+    for k in ("type", "i", "j"):
+        assert np.array_equal(got[k], ref[k][tel]), k
+    eq = lambda a, b: np.array_equal(a.view(np.uint64), b.view(np.uint64)) or (np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]))
+    for k in ("n", "p", "depth"):
+        assert eq(got[k], ref[k][tel]), k
+    for k in ("x0", "x1", "delta0", "delta1", "kick"):
+        assert eq(got[k], ref[k]), k
+    if case["n"] >= 400:
+        assert nt > 5
+    if case.get("lees_edwards", 0.0) != 0.0:
+        assert np.any(got["type"] == 26) and np.all(np.isnan(got["delta0"][got["type"] == 26])) and np.all(got["depth"][got["type"] == 26] == 0.0)
+
+
+def test_rb2d_portal_kernels_on_cpu_unsupported_and_enforce(pk, oracle):
+    # boxes at the portals: the reference exits, the classify kernel raises bit 0
+    scene = scenes.rb2d_periodic(300, 8, side=9.0, boxes=True)
+    rng = np.random.default_rng(2)
+    q = scene["q"].reshape(-1, 3)
+    q[:, :2] = rng.uniform(0.0, scene["side"], size=q[:, :2].shape)
+    scene["q"] = q.ravel().copy()
+    o = _rb2d_oracle(scene)
+    dx = o.update_portals(0.0)
+    assert not o.active_set_portals(scene["q"], scene["q"], "allpairs")["supported"]
+    _pk_rb2d_set(pk, scene, dx)
+    btype, bparam = _rb2d_device_arrays(scene)
+    qc = np.ascontiguousarray(scene["q"])
+    assert pk.pk_rb2d_active_set(300, vp(btype), vp(bparam), vp(qc), vp(qc)) & 1
+    # kinematic circles at the portals: bit 1
+    scene = scenes.rb2d_periodic(300, 9, side=9.0)
+    scene["fixed"][::3] = 1
+    o = _rb2d_oracle(scene)
+    dx = o.update_portals(0.0)
+    assert not o.active_set_portals(scene["q"], scene["q"], "allpairs")["supported"]
+    _pk_rb2d_set(pk, scene, dx)
+    btype, bparam = _rb2d_device_arrays(scene)
+    qc = np.ascontiguousarray(scene["q"])
+    assert pk.pk_rb2d_active_set(300, vp(btype), vp(bparam), vp(qc), vp(qc)) & 2
+    # enforce
+    scene = scenes.rb2d_periodic(2000, 4, lees_edwards=1.5, t=2.3, oblique=True)
+    o = _rb2d_oracle(scene)
+    dx = o.update_portals(scene["t"])
+    _pk_rb2d_set(pk, scene, dx)
+    q = scene["q"].copy()
+    q.reshape(-1, 3)[:, :2] += np.random.default_rng(8).uniform(-0.45, 0.45, size=(2000, 2)) * scene["side"]
+    rq, rv = o.enforce_portals(q, scene["v"])
+    gq, gv = q.copy(), scene["v"].copy()
+    pk.pk_rb2d_enforce(2000, vp(gq), vp(gv))
+    assert np.array_equal(gq, rq) and np.array_equal(gv, rv) and np.any(gq != q) and np.any(gv != scene["v"])
