@@ -165,6 +165,25 @@ def cpu_reference_step(scene, steps, warmup):
     return pairs, times, "port", "reference CPU path restated in oracle/ (its own std::map/std::set data structures)"
 
 
+def cpu_parallel_step(scene, steps, warmup):
+    """NOT reference behaviour (the optional second CPU figure): the same step written for a multi-core CPU
+    (oracle/ball2d_parallel.h -- all host threads over bodies, flat grid by counting sort), lists built, results identical to
+    the restatement's (tests/test_oracle_parallel.py).  Returns the cpu_baseline_parallel object."""
+    from tests import oracle_binding as ob
+    o = ob.Ball2DOracle(scene)
+    kind = 0 if scene["map"] == "symplectic_euler" else 1
+    times, pairs, threads = [], 0, 1
+    for it in range(warmup + steps):
+        r = o.parallel_step(kind, scene["q"], scene["v"], scene["dt"], keep_lists=True)
+        pairs, threads = r["n_candidates"] + r["n_active"] + r["n_static"], r["threads"]
+        if it >= warmup:
+            times.append(r["seconds"])
+    return {"value": pairs * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port-multithreaded",
+            "sample": "%d full steps of the same scene, candidate and contact lists built" % len(times),
+            "note": "NOT reference behaviour: SCISim's hot path is single-threaded even with USE_OPENMP (that is cpu_baseline); this is the same step "
+                    "written for a multi-core CPU (oracle/ball2d_parallel.h), reported so that the GPU figure is not compared with one core only"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,6 +199,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "full 1M-ball step (flow + spatial-grid broad phase + CCD), %d steps; %s" % (len(times), how)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": len(times) / total,
+        "cpu_baseline_parallel": cpu_parallel_step(scene, 5, 1),
     }
     print(json.dumps(line))
 
@@ -369,6 +389,7 @@ def main():
             v = pairs_cpu * len(times) / sum(times)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": "3 full steps of the same 1M-ball scene; %s; the reference's hot path is single-threaded" % how}
+            line["cpu_baseline_parallel"] = cpu_parallel_step(scene_for_rank(0, 1), 5, 1)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -5,6 +5,7 @@
 // or loaded by the product library.
 #include "ball2d.h"
 #include "ball2d_portals.h"
+#include "ball2d_parallel.h"
 #include "broadphase.h"
 #include "ccd.h"
 
@@ -85,6 +86,7 @@ struct Ball2DHandle
   double seconds_active = 0.0;
   std::vector<Portal2D> portals;
   PortalActiveSetResult pres;
+  std::vector<std::pair<unsigned,unsigned>> par_active;
 };
 
 // plane_n is normalised here exactly as StaticPlane's constructor does (ball2d/StaticGeometry/StaticPlane.cpp:10-14)
@@ -146,6 +148,28 @@ void orc_ball2d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32
     p[2 * k] = c.p.x; p[2 * k + 1] = c.p.y;
     depth[k] = c.depth;
   }
+}
+
+// ---- multi-core ball2d step (oracle/ball2d_parallel.h): NOT reference behaviour, the optional second CPU figure ----
+// returns seconds; counts in out[0..2] = candidates, ball-ball contacts, static contacts; out[3] = threads used.
+// keep_lists != 0 also leaves the two pair lists for orc_ball2d_parallel_copy.
+double orc_ball2d_parallel_step( void* hv, int kind, const double* q0, const double* v0, double dt, double* q1, double* v1, int keep_lists, uint64_t* out )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  static ParallelStepResult res;
+  const auto t0 = std::chrono::steady_clock::now();
+  parallelStep( kind, h->scene, q0, v0, dt, q1, v1, res, keep_lists != 0 );
+  const double secs = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+  out[0] = res.n_candidates; out[1] = res.n_active; out[2] = res.n_static; out[3] = uint64_t( res.threads );
+  h->candidates = res.candidates;
+  h->par_active = res.active;
+  return secs;
+}
+void orc_ball2d_parallel_copy( const void* hv, uint32_t* cand_ij, uint32_t* active_ij )
+{
+  const Ball2DHandle* h = static_cast<const Ball2DHandle*>( hv );
+  for( std::size_t k = 0; k < h->candidates.size(); ++k ) { cand_ij[2 * k] = h->candidates[k].first; cand_ij[2 * k + 1] = h->candidates[k].second; }
+  for( std::size_t k = 0; k < h->par_active.size(); ++k ) { active_ij[2 * k] = h->par_active[k].first; active_ij[2 * k + 1] = h->par_active[k].second; }
 }
 
 // ---- ball2d portals (oracle/ball2d_portals.h) ----------------------------------------------------------

@@ -48,6 +48,8 @@ def load():
         "orc_ball2d_seconds_active": (C.c_double, [vp]),
         "orc_ball2d_copy_candidates": (None, [vp, vp]),
         "orc_ball2d_copy_active": (None, [vp, vp, vp, vp, vp, vp, vp]),
+        "orc_ball2d_parallel_step": (C.c_double, [vp, C.c_int, vp, vp, C.c_double, vp, vp, C.c_int, vp]),
+        "orc_ball2d_parallel_copy": (None, [vp, vp, vp]),
         "orc_ball2d_set_portals": (None, [vp, C.c_uint32, vp, vp, vp, vp, vp, vp]),
         "orc_ball2d_update_portals": (None, [vp, C.c_double, vp]),
         "orc_ball2d_enforce_portals": (None, [vp, vp, vp]),
@@ -133,6 +135,20 @@ class Ball2DOracle:
         out["seconds"] = self.lib.orc_ball2d_seconds_active(self.h)
         out["seconds_flow"] = self.lib.orc_ball2d_seconds_flow(self.h)
         return out
+
+    # ---- multi-core step (oracle/ball2d_parallel.h): NOT reference behaviour, the optional second CPU baseline ----
+    def parallel_step(self, kind, q0, v0, dt, keep_lists=True):
+        """flow + active set on all host threads. Returns dict(q1, v1, seconds, n_candidates, n_active, n_static, threads[, candidates, active])."""
+        q0, v0 = _f64(q0), _f64(v0)
+        q1, v1 = np.empty_like(q0), np.empty_like(v0)
+        out = np.zeros(4, dtype=np.uint64)
+        secs = self.lib.orc_ball2d_parallel_step(self.h, int(kind), _p(q0), _p(v0), float(dt), _p(q1), _p(v1), 1 if keep_lists else 0, _p(out))
+        res = {"q1": q1, "v1": v1, "seconds": float(secs), "n_candidates": int(out[0]), "n_active": int(out[1]), "n_static": int(out[2]), "threads": int(out[3])}
+        if keep_lists:
+            cand, act = np.zeros((int(out[0]), 2), np.uint32), np.zeros((int(out[1]), 2), np.uint32)
+            self.lib.orc_ball2d_parallel_copy(self.h, _p(cand), _p(act))
+            res["candidates"], res["active"] = cand, act
+        return res
 
     # ---- portals (oracle/ball2d_portals.h) ----
     def set_portals(self, portals):
