@@ -518,6 +518,30 @@ void orc_rb2d_portals_copy_teleported( const void* hv, uint32_t* portal0, uint32
   }
 }
 
+// geometry AABBs by themselves (checked against the reference's own Geometry sources in tests/test_oracle_vs_reference.py)
+// type: RigidBodyGeometryType (0 box, 1 sphere); R row-major; out = min(3), max(3)
+void orc_rb3d_aabb( int type, double r, const double* half, const double* cm, const double* R, double* out )
+{
+  RB3DScene s;
+  RB3DGeometry g;
+  g.type = uint32_t( type ); g.r = r; g.half = V3{ half[0], half[1], half[2] }; g.mesh = 0;
+  s.geometry.push_back( g );
+  s.geo_of_body.push_back( 0 );
+  M3 Rm;
+  for( int k = 0; k < 9; ++k ) { Rm.m[k] = R[k]; }
+  Box<3> b;
+  computeAABB( s, 0, V3{ cm[0], cm[1], cm[2] }, Rm, b );
+  for( int k = 0; k < 3; ++k ) { out[k] = b.lo[k]; out[3 + k] = b.hi[k]; }
+}
+// type 0 circle, 1 box; swept != 0: computeCollisionAABB, else computeAABB at q1; out = min(2), max(2)
+void orc_rb2d_aabb( int type, double r, const double* half, const double* q0b, const double* q1b, int swept, double* out )
+{
+  const RB2DGeometry g{ uint32_t( type ), r, V2{ half[0], half[1] } };
+  Box<2> b;
+  if( swept ) { computeCollisionAABB( g, q0b, q1b, b ); } else { computeAABBAt( g, V2{ q1b[0], q1b[1] }, q1b[2], b ); }
+  out[0] = b.lo[0]; out[1] = b.lo[1]; out[2] = b.hi[0]; out[3] = b.hi[1];
+}
+
 // ---- leaf routines by themselves (checked against the reference's own sources in tests/test_oracle_vs_reference.py) ----
 int orc_box_box_3d( const double* cm0, const double* R0, const double* side0, const double* cm1, const double* R1, const double* side1, double* n, double* points )
 {

@@ -2,12 +2,15 @@
 //   rigidbody2d/SpatialGrid.cpp     (2-D AABB grid of the rigid-body sim)
 //   rigidbody2d/BoxBoxTools.cpp     (BoxBoxTools::isActive)
 //   rigidbody2d/CircleBoxTools.cpp  (CircleBoxTools::isActive)
+//   rigidbody2d/CircleGeometry.cpp, BoxGeometry.cpp (+ RigidBody2DGeometry.cpp)   (computeCollisionAABB, computeAABB)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).
 #include "rigidbody2d/SpatialGrid.h"
 #include "rigidbody2d/BoxBoxTools.h"
 #include "rigidbody2d/CircleBoxTools.h"
 
 #include "rigidbody2d/PlanarPortal.h"
+#include "rigidbody2d/CircleGeometry.h"
+#include "rigidbody2d/BoxGeometry.h"
 
 #include <cstdint>
 
@@ -70,6 +73,24 @@ uint32_t ref_rb2d_portal_probe( const void* pv, const double* box, const double*
   const Vector2s k{ p.getKinematicVelocityOfAABB( mn, mx ) };
   out[0] = xo.x(); out[1] = xo.y(); out[2] = k.x(); out[3] = k.y();
   return touch;
+}
+
+// type 0 circle ( r ), 1 box ( half ); swept != 0: computeCollisionAABB( x0, theta0, x1, theta1 ), else computeAABB( x1, theta1 ); out = min(2), max(2)
+void ref_rb2d_aabb( const int type, const double r, const double* half, const double* q0b, const double* q1b, const int swept, double* out )
+{
+  Array2s mn, mx;
+  const Vector2s x0{ q0b[0], q0b[1] }, x1{ q1b[0], q1b[1] };
+  if( type == 0 )
+  {
+    const CircleGeometry g{ r };
+    if( swept ) { g.computeCollisionAABB( x0, q0b[2], x1, q1b[2], mn, mx ); } else { g.computeAABB( x1, q1b[2], mn, mx ); }
+  }
+  else
+  {
+    const BoxGeometry g{ Vector2s{ half[0], half[1] } };
+    if( swept ) { g.computeCollisionAABB( x0, q0b[2], x1, q1b[2], mn, mx ); } else { g.computeAABB( x1, q1b[2], mn, mx ); }
+  }
+  out[0] = mn( 0 ); out[1] = mn( 1 ); out[2] = mx( 0 ); out[3] = mx( 1 );
 }
 
 }

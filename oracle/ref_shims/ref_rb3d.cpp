@@ -1,9 +1,12 @@
 // oracle/ref_shims/ref_rb3d.cpp -- TEST INFRASTRUCTURE.  C entry points around the reference's own, unmodified
 //   rigidbody3d/SpatialGridDetector.cpp          (3-D AABB grid)
 //   rigidbody3d/Constraints/BoxBoxUtilities.cpp  (ODE-derived box-box: BoxBoxUtilities::isActive)
+//   rigidbody3d/Geometry/RigidBodySphere.cpp, RigidBodyBox.cpp (+ RigidBodyGeometry.cpp)   (computeAABB)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).
 #include "rigidbody3d/SpatialGridDetector.h"
 #include "rigidbody3d/Constraints/BoxBoxUtilities.h"
+#include "rigidbody3d/Geometry/RigidBodySphere.h"
+#include "rigidbody3d/Geometry/RigidBodyBox.h"
 
 #include <cstdint>
 
@@ -43,6 +46,17 @@ int ref_rb3d_box_box( const double* cm0, const double* R0, const double* side0, 
   int k = 0;
   for( const Vector3s& p : pts ) { if( k < 8 ) { points[3 * k] = p.x(); points[3 * k + 1] = p.y(); points[3 * k + 2] = p.z(); } ++k; }
   return k;
+}
+
+// RigidBodySphere::computeAABB (type 1) / RigidBodyBox::computeAABB (type 0); R row-major; out = min(3), max(3)
+void ref_rb3d_aabb( const int type, const double r, const double* half, const double* cm, const double* R, double* out )
+{
+  Matrix33sr Rm;
+  for( int i = 0; i < 3; ++i ) { for( int j = 0; j < 3; ++j ) { Rm( i, j ) = R[3 * i + j]; } }
+  Array3s mn, mx;
+  if( type == 1 ) { const RigidBodySphere g{ r }; g.computeAABB( Vector3s{ cm[0], cm[1], cm[2] }, Rm, mn, mx ); }
+  else { const RigidBodyBox g{ Vector3s{ half[0], half[1], half[2] } }; g.computeAABB( Vector3s{ cm[0], cm[1], cm[2] }, Rm, mn, mx ); }
+  for( int k = 0; k < 3; ++k ) { out[k] = mn( k ); out[3 + k] = mx( k ); }
 }
 
 }

@@ -192,3 +192,43 @@ def test_box_box_and_circle_box_2d(oracle):
             assert np.array_equal(nr, no) and np.array_equal(pr, po), k
             cb_hits += 1
     assert bb_hits > 2000 and cb_hits > 2000
+
+
+def test_geometry_aabbs_3d_and_2d(oracle):
+    """computeAABB of spheres / boxes (rigidbody3d/Geometry/RigidBodySphere.cpp:45-49, RigidBodyBox.cpp:45-51) and of circles /
+    boxes in 2-D (rigidbody2d/CircleGeometry.cpp:32-43, BoxGeometry.cpp:32-42: swept and at one configuration)."""
+    ref3 = _load("libref_rb3d.so")
+    ref2 = _load("libref_rb2d.so")
+    if not hasattr(ref3, "ref_rb3d_aabb") or not hasattr(ref2, "ref_rb2d_aabb"):
+        pytest.skip("oracle/_ref predates the geometry shims")
+    lib = oracle
+    for f, lb in ((lib.orc_rb3d_aabb, None), (ref3.ref_rb3d_aabb, None)):
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for f in (lib.orc_rb2d_aabb, ref2.ref_rb2d_aabb):
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(41)
+    from scisim_b200.scenes import _random_rotations
+    Rs = _random_rotations(rng, 3000)
+    Rs[:50] = np.eye(3).ravel()  # axis aligned: zeros in |R|
+    for k in range(3000):
+        t = int(rng.integers(0, 2))
+        half = np.ascontiguousarray(rng.uniform(0.1, 2.0, size=3))
+        cm = np.ascontiguousarray(rng.uniform(-50, 50, size=3))
+        R = np.ascontiguousarray(Rs[k])
+        a, b = np.zeros(6), np.zeros(6)
+        lib.orc_rb3d_aabb(t, 0.7, vp(half), vp(cm), vp(R), vp(a))
+        ref3.ref_rb3d_aabb(t, 0.7, vp(half), vp(cm), vp(R), vp(b))
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (t, k)
+    for k in range(4000):
+        t, swept = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        half = np.ascontiguousarray(rng.uniform(0.1, 2.0, size=2))
+        q0b = np.ascontiguousarray(rng.uniform(-9, 9, size=3))
+        q1b = np.ascontiguousarray(q0b + rng.uniform(-1, 1, size=3))
+        if k < 40:
+            q1b[2] = [0.0, np.pi / 2, np.pi, -np.pi / 2][k % 4]
+        a, b = np.zeros(4), np.zeros(4)
+        lib.orc_rb2d_aabb(t, 0.45, vp(half), vp(q0b), vp(q1b), swept, vp(a))
+        ref2.ref_rb2d_aabb(t, 0.45, vp(half), vp(q0b), vp(q1b), swept, vp(b))
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (t, swept, k)
