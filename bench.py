@@ -173,6 +173,11 @@ def cpu_parallel_step(scene, steps, warmup):
     o = ob.Ball2DOracle(scene)
     kind = 0 if scene["map"] == "symplectic_euler" else 1
     times, pairs, threads = [], 0, 1
+    # one thread per core this process may run on (cgroup / affinity aware), not per core of the machine
+    try:
+        os.environ["ORC_THREADS"] = str(max(1, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        pass
     for it in range(warmup + steps):
         r = o.parallel_step(kind, scene["q"], scene["v"], scene["dt"], keep_lists=True)
         pairs, threads = r["n_candidates"] + r["n_active"] + r["n_static"], r["threads"]
