@@ -269,7 +269,7 @@ int sg_rb2d_set_gravity( sg_ctx* ctx, const double* g /* 2 */ );
 int sg_rb2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 2n */, const double* nrm /* 2n */ );
 /* rigidbody2d/SymplecticEulerMap.cpp:15-38, VerletMap.cpp:27-55 */
 int sg_rb2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
-/* RigidBody2DSim::computeActiveSet (rigidbody2d/RigidBody2DSim.cpp:696-714, no portals); SG_ERR_UNSUPPORTED where the
+/* RigidBody2DSim::computeActiveSet (rigidbody2d/RigidBody2DSim.cpp:696-714; with portals set: the portal branch, see below); SG_ERR_UNSUPPORTED where the
  * reference exits (kinematic box-box, kinematic circle vs box: RigidBody2DSim.cpp:186-190, 210-214) */
 int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
 
@@ -310,7 +310,7 @@ int sg_rb3d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 3n */, const
 int sg_rb3d_set_cylinders( sg_ctx* ctx, uint32_t n, const double* x /* 3n */, const double* axis /* 3n */, const double* r /* n */ );
 /* UnconstrainedMap::flow for SplitHamMap (SG_MAP_SPLIT_HAM) / DMVMap (SG_MAP_DMV) with NearEarthGravityForce */
 int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
-/* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; no portals, no cylinders). Returns
+/* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; no portals; cylinders via sg_rb3d_set_cylinders). Returns
  * SG_ERR_UNSUPPORTED where the reference exits on a pair of geometry types it cannot collide (RigidBody3DSim.cpp:960-961). */
 int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
 /* resident variants, as for ball2d */

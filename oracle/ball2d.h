@@ -5,7 +5,7 @@
 //   ball2d/VerletMap.cpp:15-41                     flowVerlet
 //   ball2d/Forces/Ball2DGravityForce.cpp:36-46     gravity ( F.setZero(); F_i += m_i * g, Ball2DSim.cpp:72-78 )
 //   ball2d/Ball2DState.cpp:54-66                   Minv = 1.0 / m
-//   ball2d/Ball2DSim.cpp:151-173                   computeActiveSet (no portals)
+//   ball2d/Ball2DSim.cpp:151-173                   computeActiveSet (no portals: those are in ball2d_portals.h)
 //   ball2d/Ball2DSim.cpp:553-608                   computeBallBallActiveSetSpatialGrid
 //   ball2d/Ball2DSim.cpp:730-745                   computeBallDrumActiveSetAllPairs
 //   ball2d/Ball2DSim.cpp:747-762                   computeBallPlaneActiveSetAllPairs

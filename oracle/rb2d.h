@@ -5,7 +5,7 @@
 //   rigidbody2d/SymplecticEulerMap.cpp:15-38, VerletMap.cpp:15-55        flow (forces zeroed on kinematic bodies)
 //   rigidbody2d/NearEarthGravityForce.cpp:35-48, RigidBody2DSim.cpp:104-113, RigidBody2DState.cpp:31-43 (Minv = 1/m)
 //   rigidbody2d/CircleGeometry.cpp:32-37 (swept AABB), BoxGeometry.cpp:32-42 (AABB at q1, |Rot(theta1)| r)
-//   rigidbody2d/RigidBody2DSim.cpp:696-714   computeActiveSet (no portals)
+//   rigidbody2d/RigidBody2DSim.cpp:696-714   computeActiveSet (no portals: those are in rb2d_portals.h)
 //   rigidbody2d/RigidBody2DSim.cpp:1066-1100 computeBodyBodyActiveSetSpatialGrid
 //   rigidbody2d/RigidBody2DSim.cpp:248-348   dispatchNarrowPhaseCollision (kinematic rules, type switch)
 //   rigidbody2d/RigidBody2DSim.cpp:184-246   boxBox / boxCircle narrow phase callers
