@@ -5,7 +5,7 @@
 //   rigidbody3d/UnconstrainedMaps/DMVMap.cpp:15-60,65-100,103-207   flowDMV (solveDMV, DMV)
 //   rigidbody3d/Forces/NearEarthGravityForce.cpp:39-53, RigidBody3DSim.cpp:169-181   gravity (F.setZero(); F_lin += m g)
 //   rigidbody3d/RigidBody3DState.cpp:70-240                  M0/Minv0 diagonals, world-space inertia R I0 R^T
-//   rigidbody3d/RigidBody3DSim.cpp:250-262                   computeActiveSet (no portals, no cylinders)
+//   rigidbody3d/RigidBody3DSim.cpp:250-262                   computeActiveSet (no portals: those are in rb3d_portals.h)
 //   rigidbody3d/RigidBody3DSim.cpp:1057-1141                 generateAABBs(q1) + getPotentialOverlaps + dispatch
 //   rigidbody3d/RigidBody3DSim.cpp:879-962                   dispatchNarrowPhaseCollision (kinematic rules, type switch)
 //   rigidbody3d/RigidBody3DSim.cpp:793-819                   sphereSphereNarrowPhaseCollision
@@ -352,27 +352,17 @@ inline V3 boxCorner( const V3& half, const int i )
   return V3{ half.x * double( 2 * ( i % 2 ) - 1 ), half.y * double( 2 * ( ( i >> 1 ) % 2 ) - 1 ), half.z * double( 2 * ( ( i >> 2 ) % 2 ) - 1 ) };
 }
 
-// returns false if the reference would exit( EXIT_FAILURE ) on an unsupported pair of geometry types
-inline bool computeActiveSet( const RB3DScene& s, const double* q0, const double* q1, std::vector<RB3DContact>& active_set,
-                              std::vector<std::pair<unsigned,unsigned>>* candidates_out = nullptr, const bool use_grid = true )
+// One un-teleported candidate pair: the kinematic-kinematic skip (RigidBody3DSim.cpp:1134-1137) and
+// RigidBody3DSim::dispatchNarrowPhaseCollision (:879-962); appends to active_set; returns false if the reference would
+// exit( EXIT_FAILURE ) on an unsupported pair of geometry types
+inline bool dispatchNarrowPhaseCollision( const RB3DScene& s, const unsigned first, const unsigned second, const double* q0, const double* q1, std::vector<RB3DContact>& active_set )
 {
   const std::size_t nb = s.nbodies();
   const double NaN = std::numeric_limits<double>::quiet_NaN();
-  active_set.clear();
-  if( nb > 0 )
   {
-    PairSet possible_overlaps;
     {
-      std::vector<Box<3>> aabbs( nb );
-      for( std::size_t b = 0; b < nb; ++b ) { computeAABB( s, b, loadX( q1, b ), loadR( q1, nb, b ), aabbs[b] ); }
-      if( use_grid ) { getPotentialOverlaps<3>( aabbs, possible_overlaps ); }
-      else { getPotentialOverlapsAllPairs<3>( aabbs, possible_overlaps ); }
-    }
-    if( candidates_out != nullptr ) { candidates_out->assign( possible_overlaps.begin(), possible_overlaps.end() ); }
-    for( const auto& pr : possible_overlaps )
-    {
-      if( s.fixed[pr.first] && s.fixed[pr.second] ) { continue; }
-      unsigned b0 = pr.first, b1 = pr.second;
+      if( s.fixed[first] && s.fixed[second] ) { return true; }
+      unsigned b0 = first, b1 = second;
       if( s.fixed[b0] ) { std::swap( b0, b1 ); }
       const RB3DGeometry& g0 = s.geo( b0 );
       const RB3DGeometry& g1 = s.geo( b1 );
@@ -451,6 +441,15 @@ inline bool computeActiveSet( const RB3DScene& s, const double* q0, const double
       }
     }
   }
+  return true;
+}
+
+// RigidBody3DSim::computeBodyPlaneActiveSetAllPairs / computeBodyCylinderActiveSetAllPairs (RigidBody3DSim.cpp:1414-1557); appends;
+// returns false where the reference exits (cylinder vs box)
+inline bool computeStaticActiveSet( const RB3DScene& s, const double* q0, const double* q1, std::vector<RB3DContact>& active_set )
+{
+  const std::size_t nb = s.nbodies();
+  const double NaN = std::numeric_limits<double>::quiet_NaN();
   // planes: plane-major, body ascending, corner / hull vertex ascending; kinematic bodies skipped
   for( uint32_t pl = 0; pl < uint32_t( s.plane_x.size() ); ++pl )
   {
@@ -564,6 +563,30 @@ inline bool computeActiveSet( const RB3DScene& s, const double* q0, const double
     }
   }
   return true;
+}
+
+// returns false if the reference would exit( EXIT_FAILURE ) on an unsupported pair of geometry types
+inline bool computeActiveSet( const RB3DScene& s, const double* q0, const double* q1, std::vector<RB3DContact>& active_set,
+                              std::vector<std::pair<unsigned,unsigned>>* candidates_out = nullptr, const bool use_grid = true )
+{
+  const std::size_t nb = s.nbodies();
+  active_set.clear();
+  if( nb > 0 )
+  {
+    PairSet possible_overlaps;
+    {
+      std::vector<Box<3>> aabbs( nb );
+      for( std::size_t b = 0; b < nb; ++b ) { computeAABB( s, b, loadX( q1, b ), loadR( q1, nb, b ), aabbs[b] ); }
+      if( use_grid ) { getPotentialOverlaps<3>( aabbs, possible_overlaps ); }
+      else { getPotentialOverlapsAllPairs<3>( aabbs, possible_overlaps ); }
+    }
+    if( candidates_out != nullptr ) { candidates_out->assign( possible_overlaps.begin(), possible_overlaps.end() ); }
+    for( const auto& pr : possible_overlaps )
+    {
+      if( !dispatchNarrowPhaseCollision( s, pr.first, pr.second, q0, q1, active_set ) ) { return false; }
+    }
+  }
+  return computeStaticActiveSet( s, q0, q1, active_set );
 }
 
 }
