@@ -261,12 +261,15 @@ void orc_ball2d_portals_copy_teleported( const void* hv, uint32_t* portal0, uint
 
 // ---- rigidbody3d -----------------------------------------------------------------------------------
 #include "rb3d.h"
+#include "rb3d_portals.h"
 
 struct RB3DHandle
 {
   RB3DScene scene;
   std::vector<RB3DContact> active;
   std::vector<std::pair<unsigned,unsigned>> candidates;
+  std::vector<Portal3D> portals;
+  RB3DPortalResult pres;
   bool supported = true;
   double seconds_flow = 0.0;
   double seconds_active = 0.0;
@@ -369,6 +372,76 @@ void orc_rb3d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t
     n[3 * k] = c.n.x; n[3 * k + 1] = c.n.y; n[3 * k + 2] = c.n.z;
     p[3 * k] = c.p.x; p[3 * k + 1] = c.p.y; p[3 * k + 2] = c.p.z;
     depth[k] = c.depth;
+  }
+}
+
+// ---- rigidbody3d portals (oracle/rb3d_portals.h) ---------------------------------------------------------
+// StaticPlane( x, n ) frame: out = n (3), t0 (3), t1 (3)
+void orc_rb3d_plane_frame( const double* x, const double* n, double* out )
+{
+  const Plane3D p = makePlane3D( V3{ x[0], x[1], x[2] }, V3{ n[0], n[1], n[2] } );
+  out[0] = p.n.x; out[1] = p.n.y; out[2] = p.n.z; out[3] = p.t0.x; out[4] = p.t0.y; out[5] = p.t0.z; out[6] = p.t1.x; out[7] = p.t1.y; out[8] = p.t1.z;
+}
+void orc_rb3d_set_portals( void* hv, uint32_t n, const double* ax, const double* an, const double* bx, const double* bn, const int* mult )
+{
+  RB3DHandle* h = static_cast<RB3DHandle*>( hv );
+  h->portals.clear();
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    Portal3D pt;
+    pt.a = makePlane3D( V3{ ax[3 * p], ax[3 * p + 1], ax[3 * p + 2] }, V3{ an[3 * p], an[3 * p + 1], an[3 * p + 2] } );
+    pt.b = makePlane3D( V3{ bx[3 * p], bx[3 * p + 1], bx[3 * p + 2] }, V3{ bn[3 * p], bn[3 * p + 1], bn[3 * p + 2] } );
+    for( int k = 0; k < 3; ++k ) { pt.mult[k] = mult[3 * p + k]; }
+    h->portals.push_back( pt );
+  }
+}
+// layout of ref_rb3d_portal_probe (oracle/ref_shims/ref_rb3d.cpp)
+uint32_t orc_rb3d_portal_probe( const void* hv, uint32_t p, const double* box, const double* x, double* out )
+{
+  const RB3DHandle* h = static_cast<const RB3DHandle*>( hv );
+  const Portal3D& pt = h->portals[p];
+  const V3 xin{ x[0], x[1], x[2] };
+  const V3 a = teleportPointThroughPlaneA( pt, xin ), b = teleportPointThroughPlaneB( pt, xin ), ti = teleportPointInsidePortal( pt, xin );
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = b.x; out[4] = b.y; out[5] = b.z; out[6] = ti.x; out[7] = ti.y; out[8] = ti.z;
+  Box<3> bb;
+  for( int k = 0; k < 3; ++k ) { bb.lo[k] = box[k]; bb.hi[k] = box[3 + k]; }
+  return uint32_t( aabbTouchesPortal( pt, bb ) ) | ( pointInsidePortal( pt, xin ) ? 4u : 0u );
+}
+void orc_rb3d_enforce_portals( void* hv, double* q )
+{
+  RB3DHandle* h = static_cast<RB3DHandle*>( hv );
+  enforcePeriodicBoundaryConditionsRB3D( h->portals, uint32_t( h->scene.nbodies() ), q );
+}
+int orc_rb3d_active_set_portals( void* hv, const double* q0, const double* q1, int method )
+{
+  RB3DHandle* h = static_cast<RB3DHandle*>( hv );
+  computeActiveSetWithPortalsRB3D( h->scene, h->portals, q0, q1, h->pres, method == 0 );
+  h->active = h->pres.active;
+  h->candidates = h->pres.candidates;
+  h->supported = h->pres.supported;
+  return h->pres.supported ? 1 : 0;
+}
+uint64_t orc_rb3d_portals_num_regular( const void* h ) { return static_cast<const RB3DHandle*>( h )->pres.n_regular; }
+uint64_t orc_rb3d_portals_num_boxes( const void* h ) { return static_cast<const RB3DHandle*>( h )->pres.teleported_boxes.size(); }
+uint64_t orc_rb3d_portals_num_teleported( const void* h ) { return static_cast<const RB3DHandle*>( h )->pres.teleported_info.size(); }
+void orc_rb3d_portals_copy_boxes( const void* hv, uint32_t* box_body, uint32_t* box_portal )
+{
+  const RB3DHandle* h = static_cast<const RB3DHandle*>( hv );
+  for( std::size_t k = 0; k < h->pres.teleported_boxes.size(); ++k )
+  {
+    const TeleportedBall2D& tb = h->pres.teleported_boxes[k];
+    box_body[k] = tb.body; box_portal[k] = tb.portal | ( tb.plane ? 0x80000000u : 0u );
+  }
+}
+void orc_rb3d_portals_copy_teleported( const void* hv, uint32_t* portal0, uint32_t* portal1, double* x0, double* x1 )
+{
+  const RB3DHandle* h = static_cast<const RB3DHandle*>( hv );
+  for( std::size_t k = 0; k < h->pres.teleported_info.size(); ++k )
+  {
+    const RB3DTeleportedInfo& t = h->pres.teleported_info[k];
+    portal0[k] = t.p0 == NO_PORTAL ? NO_PORTAL : ( t.p0 | ( t.pl0 ? 0x80000000u : 0u ) );
+    portal1[k] = t.p1 == NO_PORTAL ? NO_PORTAL : ( t.p1 | ( t.pl1 ? 0x80000000u : 0u ) );
+    x0[3 * k] = t.x0.x; x0[3 * k + 1] = t.x0.y; x0[3 * k + 2] = t.x0.z; x1[3 * k] = t.x1.x; x1[3 * k + 1] = t.x1.y; x1[3 * k + 2] = t.x1.z;
   }
 }
 

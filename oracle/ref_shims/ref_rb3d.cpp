@@ -2,11 +2,13 @@
 //   rigidbody3d/SpatialGridDetector.cpp          (3-D AABB grid)
 //   rigidbody3d/Constraints/BoxBoxUtilities.cpp  (ODE-derived box-box: BoxBoxUtilities::isActive)
 //   rigidbody3d/Geometry/RigidBodySphere.cpp, RigidBodyBox.cpp (+ RigidBodyGeometry.cpp)   (computeAABB)
+//   rigidbody3d/StaticGeometry/StaticPlane.cpp, rigidbody3d/Portals/PlanarPortal.cpp         (plane frames, portal touch tests and teleports)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).
 #include "rigidbody3d/SpatialGridDetector.h"
 #include "rigidbody3d/Constraints/BoxBoxUtilities.h"
 #include "rigidbody3d/Geometry/RigidBodySphere.h"
 #include "rigidbody3d/Geometry/RigidBodyBox.h"
+#include "rigidbody3d/Portals/PlanarPortal.h"
 
 #include <cstdint>
 
@@ -57,6 +59,36 @@ void ref_rb3d_aabb( const int type, const double r, const double* half, const do
   if( type == 1 ) { const RigidBodySphere g{ r }; g.computeAABB( Vector3s{ cm[0], cm[1], cm[2] }, Rm, mn, mx ); }
   else { const RigidBodyBox g{ Vector3s{ half[0], half[1], half[2] } }; g.computeAABB( Vector3s{ cm[0], cm[1], cm[2] }, Rm, mn, mx ); }
   for( int k = 0; k < 3; ++k ) { out[k] = mn( k ); out[3 + k] = mx( k ); }
+}
+
+// StaticPlane( x, n ): out = n (3), t0 (3), t1 (3)
+void ref_rb3d_plane_frame( const double* x, const double* n, double* out )
+{
+  const StaticPlane p{ Vector3s{ x[0], x[1], x[2] }, Vector3s{ n[0], n[1], n[2] } };
+  const Vector3s nn{ p.n() }, t0{ p.t0() }, t1{ p.t1() };
+  for( int k = 0; k < 3; ++k ) { out[k] = nn( k ); out[3 + k] = t0( k ); out[6 + k] = t1( k ); }
+}
+void* ref_rb3d_portal_create( const double* ax, const double* an, const double* bx, const double* bn, const int* mult )
+{
+  const StaticPlane a{ Vector3s{ ax[0], ax[1], ax[2] }, Vector3s{ an[0], an[1], an[2] } };
+  const StaticPlane b{ Vector3s{ bx[0], bx[1], bx[2] }, Vector3s{ bn[0], bn[1], bn[2] } };
+  return new PlanarPortal{ a, b, Array3i{ mult[0], mult[1], mult[2] } };
+}
+void ref_rb3d_portal_destroy( void* p ) { delete static_cast<PlanarPortal*>( p ); }
+// box = min(3), max(3).  out = through A (3), through B (3), teleportPointInsidePortal (3).  Returns aabbTouchesPortal ( 0 no, 1 plane A,
+// 2 plane B ) | 4 * pointInsidePortal
+uint32_t ref_rb3d_portal_probe( const void* pv, const double* box, const double* x, double* out )
+{
+  const PlanarPortal& p = *static_cast<const PlanarPortal*>( pv );
+  const Vector3s xin{ x[0], x[1], x[2] };
+  Vector3s a, b, ti;
+  p.teleportPointThroughPlaneA( xin, a );
+  p.teleportPointThroughPlaneB( xin, b );
+  p.teleportPointInsidePortal( xin, ti );
+  for( int k = 0; k < 3; ++k ) { out[k] = a( k ); out[3 + k] = b( k ); out[6 + k] = ti( k ); }
+  bool plane_idx = false;
+  const bool touches = p.aabbTouchesPortal( Array3s{ box[0], box[1], box[2] }, Array3s{ box[3], box[4], box[5] }, plane_idx );
+  return ( touches ? ( plane_idx ? 2u : 1u ) : 0u ) | ( p.pointInsidePortal( xin ) ? 4u : 0u );
 }
 
 }

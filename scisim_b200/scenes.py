@@ -359,3 +359,57 @@ def rb2d_periodic(n, seed, side=None, axes="xy", lees_edwards=0.0, t=0.0, obliqu
             "fixed": fixed, "M": M, "q": q.ravel().copy(), "v": v.ravel().copy(), "g": np.array([0.0, 0.0]),
             "plane_x": np.ascontiguousarray(planes_x), "plane_n": np.ascontiguousarray(planes_n), "dt": dt, "map": "symplectic_euler", "side": side, "t": float(t),
             "portals": {k: np.ascontiguousarray(a) for k, a in portals.items()}}
+
+
+def rb3d_periodic_spheres(n, seed, side=None, axes="xz", nfixed_frac=0.0, tilt=False, mult=None):
+    """Spheres in a box [0, side)^3 with planar portals (rigidbody3d/Portals/PlanarPortal.h) along the axes named in `axes`
+    (walls = static planes along the others).  Plane points sit in the middle of each face, normals point into the box and
+    are not unit length; tilt rotates everything about z so that no plane is axis aligned (and none faces -y, where Eigen's
+    FromTwoVectors takes its SVD branch).  nfixed_frac marks spheres as kinematically scripted.  mult: the integer portal
+    multipliers; None picks, per axis, the signs that make the pair of plane frames a pure translation (the tangents of two
+    opposite planes, both built by FromTwoVectors( UnitY, n ), mirror one tangential coordinate otherwise)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    side = float(side) if side is not None else max(3.0, n ** (1.0 / 3.0) * 0.9)
+    translation = {"x": (1, 1, -1), "y": (1, 1, 1), "z": (1, -1, 1)}
+    h = 0.5 * side
+    radii = np.array([0.25, 0.4, 0.6])
+    gi = rng.integers(0, 3, size=n)
+    fixed = (rng.uniform(size=n) < nfixed_frac).astype(np.uint8)
+    x = rng.uniform(0.0, side, size=(n, 3))
+    R = _random_rotations(rng, n)
+    v = rng.uniform(-2, 2, size=(n, 3))
+    w = np.zeros((n, 3))
+    v[fixed == 1] = 0.0
+    m = rng.uniform(0.5, 2.0, size=n)
+    I0 = 0.4 * m[:, None] * (radii[gi] ** 2)[:, None] * np.ones((1, 3))
+    faces = {"x": (([0.0, h, h], [2.0, 0.0, 0.0]), ([side, h, h], [-3.0, 0.0, 0.0])),
+             "y": (([h, 0.0, h], [0.0, 1.5, 0.0]), ([h, side, h], [0.0, -0.5, 0.0])),
+             "z": (([h, h, 0.0], [0.0, 0.0, 1.0]), ([h, h, side], [0.0, 0.0, -2.0]))}
+    pax, pan, pbx, pbn, pm, plane_x, plane_n = [], [], [], [], [], [], []
+    for ax in "xyz":
+        (xa, na), (xb, nb) = faces[ax]
+        if ax in axes:
+            pax.append(xa); pan.append(na); pbx.append(xb); pbn.append(nb); pm.append(mult if mult is not None else translation[ax])
+        else:
+            plane_x += [xa, xb]; plane_n += [na, nb]
+    arr = lambda a: np.array(a, dtype=np.float64).reshape(-1, 3)
+    portals = {"plane_a_x": arr(pax), "plane_a_n": arr(pan), "plane_b_x": arr(pbx), "plane_b_n": arr(pbn),
+               "mult": np.array(pm, dtype=np.int32).reshape(-1, 3)}
+    planes_x, planes_n = arr(plane_x), arr(plane_n)
+    if tilt:
+        c, s_ = np.cos(0.35), np.sin(0.35)
+        Rz = np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]])
+        ctr = np.array([h, h, h])
+        rot_p = lambda a: (a - ctr) @ Rz.T + ctr
+        x = rot_p(x); v = v @ Rz.T
+        for k in ("plane_a_x", "plane_b_x"):
+            portals[k] = rot_p(portals[k])
+        for k in ("plane_a_n", "plane_b_n"):
+            portals[k] = portals[k] @ Rz.T
+        if planes_x.shape[0]:
+            planes_x, planes_n = rot_p(planes_x), planes_n @ Rz.T
+    q, vv = _rb3d_pack(x, R, v, w)
+    s = _rb3d_scene([1, 1, 1], radii, np.zeros((3, 3)), [0, 0, 0], [], gi, fixed, m, I0, q, vv, [0.0, 0.0, 0.0], planes_x, planes_n, 0.01, "split_ham")
+    s["portals"] = {k: np.ascontiguousarray(a) for k, a in portals.items()}
+    s["side"] = side
+    return s

@@ -266,6 +266,70 @@ class RB3DOracle:
         out["seconds_flow"] = self.lib.orc_rb3d_seconds_flow(self.h)
         return out
 
+    # ---- portals (oracle/rb3d_portals.h) ----
+    def _bind_portals(self):
+        lib, vp = self.lib, C.c_void_p
+        if hasattr(lib, "_rb3d_portals_bound"):
+            return
+        lib.orc_rb3d_plane_frame.argtypes = [vp, vp, vp]
+        lib.orc_rb3d_set_portals.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, vp]
+        lib.orc_rb3d_portal_probe.restype = C.c_uint32
+        lib.orc_rb3d_portal_probe.argtypes = [vp, C.c_uint32, vp, vp, vp]
+        lib.orc_rb3d_enforce_portals.argtypes = [vp, vp]
+        lib.orc_rb3d_active_set_portals.restype = C.c_int
+        lib.orc_rb3d_active_set_portals.argtypes = [vp, vp, vp, C.c_int]
+        for f in ("orc_rb3d_portals_num_regular", "orc_rb3d_portals_num_boxes", "orc_rb3d_portals_num_teleported"):
+            getattr(lib, f).restype = C.c_uint64
+            getattr(lib, f).argtypes = [vp]
+        lib.orc_rb3d_portals_copy_boxes.argtypes = [vp, vp, vp]
+        lib.orc_rb3d_portals_copy_teleported.argtypes = [vp] * 5
+        lib._rb3d_portals_bound = True
+
+    def plane_frame(self, x, n):
+        self._bind_portals()
+        out = np.zeros(9)
+        self.lib.orc_rb3d_plane_frame(_p(_f64(x)), _p(_f64(n)), _p(out))
+        return out
+
+    def set_portals(self, portals):
+        """portals: dict with plane_a_x, plane_a_n, plane_b_x, plane_b_n (P,3) and mult (P,3) int32."""
+        self._bind_portals()
+        a = [_f64(portals[k]) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n")]
+        m = np.ascontiguousarray(portals["mult"], dtype=np.int32)
+        self.nportals = m.shape[0]
+        self.lib.orc_rb3d_set_portals(self.h, self.nportals, *[_p(x) for x in a], _p(m))
+
+    def portal_probe(self, p, box, x):
+        out = np.zeros(9)
+        code = self.lib.orc_rb3d_portal_probe(self.h, int(p), _p(_f64(box)), _p(_f64(x)), _p(out))
+        return int(code), out
+
+    def enforce_portals(self, q):
+        q = _f64(q).copy()
+        self.lib.orc_rb3d_enforce_portals(self.h, _p(q))
+        return q
+
+    def active_set_portals(self, q0, q1, method="grid"):
+        q0, q1 = _f64(q0), _f64(q1)
+        ok = self.lib.orc_rb3d_active_set_portals(self.h, _p(q0), _p(q1), 0 if method == "grid" else 1)
+        nc, na = self.lib.orc_rb3d_num_candidates(self.h), self.lib.orc_rb3d_num_active(self.h)
+        cand = np.zeros((nc, 2), dtype=np.uint32)
+        if nc:
+            self.lib.orc_rb3d_copy_candidates(self.h, _p(cand))
+        out = {"type": np.zeros(na, np.uint32), "i": np.zeros(na, np.uint32), "j": np.zeros(na, np.uint32), "aux": np.zeros(na, np.uint32),
+               "n": np.zeros((na, 3)), "p": np.zeros((na, 3)), "depth": np.zeros(na), "candidates": cand, "supported": bool(ok)}
+        if na:
+            self.lib.orc_rb3d_copy_active(self.h, _p(out["type"]), _p(out["i"]), _p(out["j"]), _p(out["aux"]), _p(out["n"]), _p(out["p"]), _p(out["depth"]))
+        nbx, nt = self.lib.orc_rb3d_portals_num_boxes(self.h), self.lib.orc_rb3d_portals_num_teleported(self.h)
+        out["n_regular"] = int(self.lib.orc_rb3d_portals_num_regular(self.h))
+        out["box_body"], out["box_portal"] = np.zeros(nbx, np.uint32), np.zeros(nbx, np.uint32)
+        if nbx:
+            self.lib.orc_rb3d_portals_copy_boxes(self.h, _p(out["box_body"]), _p(out["box_portal"]))
+        out["portal0"], out["portal1"], out["x0"], out["x1"] = np.zeros(nt, np.uint32), np.zeros(nt, np.uint32), np.zeros((nt, 3)), np.zeros((nt, 3))
+        if nt:
+            self.lib.orc_rb3d_portals_copy_teleported(self.h, _p(out["portal0"]), _p(out["portal1"]), _p(out["x0"]), _p(out["x1"]))
+        return out
+
 
 class RB2DOracle:
     def __init__(self, scene):
