@@ -58,6 +58,9 @@ extern "C" {
 #define SG_PLANE_BODY 16              /* StaticPlaneBodyConstraint: j = plane, aux = convex hull vertex, p = collision point at q0 */
 #define SG_CYLINDER_SPHERE 17         /* StaticCylinderSphereConstraint{ i, r_i, staticCylinder(j), j }: n = computeN( q0 ), p = x0 - r n */
 #define SG_CYLINDER_BODY 18           /* StaticCylinderBodyConstraint{ i, p, staticCylinder(j), j, q0 }: aux = hull vertex, n from the centre of mass */
+/* with portals (rigidbody3d/RigidBody3DSim.cpp:1338-1397): after the contacts of the un-teleported pairs, ascending body pair */
+#define SG_SPHERE_SPHERE_TELEPORTED 19           /* TeleportedSphereSphereConstraint{ i, j, x0, x1, ri, rj }: p = q0_i + ri/(ri+rj) (x1 - x0) */
+#define SG_KINEMATIC_OBJECT_SPHERE_TELEPORTED 30 /* KinematicObjectSphereConstraint{ i, ri, n, j, X, 0, 0 }: i = free sphere, j = kinematic one, p = X = its teleported centre */
 
 /* rigidbody2d (the constraint classes under rigidbody2d/) */
 #define SG_CIRCLE_CIRCLE 20    /* CircleCircleConstraint{ i, j, n, p, ri, rj } */
@@ -139,8 +142,8 @@ typedef struct sg_teleported
   uint64_t n_teleported;      /* teleported contacts (n_body_body = n_regular + n_teleported) */
   const uint32_t* portal0;    /* n_teleported: portal word of body i */
   const uint32_t* portal1;    /* n_teleported: portal word of body j */
-  const double* x0;           /* 2 n_teleported */
-  const double* x1;           /* 2 n_teleported */
+  const double* x0;           /* dim * n_teleported (dim = 2; 3 for rigidbody3d) */
+  const double* x1;           /* dim * n_teleported */
   const double* kick;         /* 2 n_teleported (0 for SG_BALL_BALL_TELEPORTED / SG_CIRCLE_CIRCLE_TELEPORTED) */
   const double* delta0;       /* 2 n_teleported, rigidbody2d only (NULL for ball2d): x0 - q0_i, TeleportedCircleCircleConstraint's delta0 */
   const double* delta1;       /* 2 n_teleported, rigidbody2d only: x1 - q0_j (both NaN for kinematic-kick contacts, as the reference stores) */
@@ -308,6 +311,20 @@ int sg_rb3d_set_planes( sg_ctx* ctx, uint32_t n, const double* x /* 3n */, const
  * RigidBody3DSim.cpp:1504-1557): spheres and mesh convex-hull vertices; a non-kinematic box makes sg_rb3d_active_set /
  * sg_rb3d_step return SG_ERR_UNSUPPORTED where the reference prints and exits. */
 int sg_rb3d_set_cylinders( sg_ctx* ctx, uint32_t n, const double* x /* 3n */, const double* axis /* 3n */, const double* r /* n */ );
+/* Planar portals of the 3-D rigid-body sim (rigidbody3d/Portals/PlanarPortal.h; at most 8): per portal plane A and B as
+ * (point, normal; the normal is normalised and the tangents t0, t1 are built as StaticPlane does, FromTwoVectors( UnitY, n ) * UnitX / UnitZ
+ * -- a normal within 1e-12 of -UnitY takes Eigen's SVD branch and is rejected with SG_ERR_UNSUPPORTED) and the three integer
+ * multipliers of PlanarPortal( plane_a, plane_b, portal_multiplier ).  With portals set, sg_rb3d_active_set / sg_rb3d_step follow
+ * RigidBody3DSim::computeActiveSetBodyBodySpatialGrid with its portal loop (RigidBody3DSim.cpp:1072-1260): a teleported box per body
+ * whose box reaches a portal plane, un-teleported pairs through the regular narrow phase, then SG_SPHERE_SPHERE_TELEPORTED /
+ * SG_KINEMATIC_OBJECT_SPHERE_TELEPORTED contacts, then planes and cylinders.  The reference supports teleported collisions for
+ * spheres only (everything else exits, RigidBody3DSim.cpp:1262-1292): this path is limited to all-sphere scenes and returns
+ * SG_ERR_UNSUPPORTED otherwise.  enforce_portals: RigidBody3DSim::enforcePeriodicBoundaryConditions (:642-663) on a host q
+ * ( centres of mass only ), in place; teleported: as sg_ball2d_teleported with 3 doubles per point ( kick, delta0, delta1 = NULL ). */
+int sg_rb3d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x /* 3n */, const double* plane_a_n /* 3n */, const double* plane_b_x /* 3n */, const double* plane_b_n /* 3n */,
+                         const int32_t* multiplier /* 3n */ );
+int sg_rb3d_enforce_portals( sg_ctx* ctx, double* q );
+int sg_rb3d_teleported( sg_ctx* ctx, sg_teleported* out );
 /* UnconstrainedMap::flow for SplitHamMap (SG_MAP_SPLIT_HAM) / DMVMap (SG_MAP_DMV) with NearEarthGravityForce */
 int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
 /* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; no portals; cylinders via sg_rb3d_set_cylinders). Returns

@@ -15,6 +15,7 @@ SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
 SG_BALL_BALL_TELEPORTED, SG_BALL_BALL_KICK_TELEPORTED = 3, 4
 SG_NO_PORTAL, SG_PLANE_B_BIT = 0xFFFFFFFF, 0x80000000
 SG_CIRCLE_CIRCLE_TELEPORTED, SG_CIRCLE_CIRCLE_KICK_TELEPORTED = 25, 26
+SG_SPHERE_SPHERE_TELEPORTED, SG_KINEMATIC_OBJECT_SPHERE_TELEPORTED = 19, 30
 SG_SPHERE_SPHERE, SG_KINEMATIC_SPHERE_SPHERE, SG_BODY_BODY, SG_KINEMATIC_BODY_BODY, SG_PLANE_SPHERE, SG_PLANE_BOX, SG_PLANE_BODY = 10, 11, 12, 13, 14, 15, 16
 SG_OUT_NORMALS, SG_OUT_POINTS, SG_OUT_DEPTHS, SG_OUT_CANDIDATES, SG_OUT_ALL = 1, 2, 4, 8, 15
 SG_IN_RESIDENT = 256
@@ -108,6 +109,9 @@ def load():
         "sg_rb3d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),
         "sg_rb3d_set_gravity": (C.c_int, [vp, vp]),
         "sg_rb3d_set_planes": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_rb3d_set_portals": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp, vp]),
+        "sg_rb3d_enforce_portals": (C.c_int, [vp, vp]),
+        "sg_rb3d_teleported": (C.c_int, [vp, C.POINTER(SgTeleported)]),
         "sg_rb3d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
         "sg_rb3d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
         "sg_rb3d_upload": (C.c_int, [vp, vp, vp]),

@@ -932,6 +932,33 @@ struct ScanU32To64
   __device__ static Out out( const Acc a ) { return a; }
 };
 
+// ---- portals (rigidbody3d/Portals/PlanarPortal.h), sphere scenes: kernels, per-context data ----------------
+#include "sg_rb3d_portal_kernels.cuh"
+
+struct Rb3dPortalData
+{
+  SgPortals3D portals;
+  DevBuf rboxes;                                   // double[6 n]: boxes at q1 (the touch tests read them before n + T is known)
+  DevBuf tflag, toff, t_partials, ttotal;          // u32[P n] flags / teleported box numbers; T
+  DevBuf box_body, box_portal;                     // u32[T]: TeleportedBody table
+  DevBuf reg_cnt, tel_cnt, tel_off, pr_partials, tel_total;
+  DevBuf reg_off, reg_total;                       // u64 per candidate; number of un-teleported pairs
+  DevBuf reg_pairs;                                // uint2[]: the un-teleported candidates, in order
+  DevBuf tc_key, tc_idx, tc_info, uflag, uoff, u_partials, utotal;
+  DevBuf x0t, x1t, tp0, tp1;                       // per teleported contact: constructor arguments
+  PinBuf h, h_tele;
+  uint64_t n_boxes = 0, n_reg = 0, n_tel = 0;
+  bool result = false;                             // the last active set came from the portal path
+  Rb3dPortalData() { memset( &portals, 0, sizeof( portals ) ); }
+  void release()
+  {
+    DevBuf* bufs[] = { &rboxes, &tflag, &toff, &t_partials, &ttotal, &box_body, &box_portal, &reg_cnt, &tel_cnt, &tel_off, &pr_partials, &tel_total, &reg_off, &reg_total, &reg_pairs,
+                       &tc_key, &tc_idx, &tc_info, &uflag, &uoff, &u_partials, &utotal, &x0t, &x1t, &tp0, &tp1 };
+    for( DevBuf* b : bufs ) { b->release(); }
+    h.release(); h_tele.release();
+  }
+};
+
 // ---- host side -------------------------------------------------------------------------------------
 struct MeshHost
 {
@@ -966,6 +993,7 @@ struct Rb3dData
   PinBuf h_totals, h_out;
   uint64_t n_cand = 0, n_bb = 0, n_static = 0;
   bool have_result = false, cand_valid = false;
+  Rb3dPortalData* px = nullptr; // allocated by sg_rb3d_set_portals
   Rb3dData() { memset( &planes, 0, sizeof( planes ) ); }
 };
 
@@ -981,6 +1009,7 @@ void sg_rb3d_release( sg_ctx* ctx )
   for( DevBuf* b : bufs ) { b->release(); }
   d->bp.release();
   d->h_totals.release(); d->h_out.release();
+  if( d->px != nullptr ) { d->px->release(); delete d->px; d->px = nullptr; }
   delete d;
   ctx->rb3d = nullptr;
 }
@@ -1067,9 +1096,14 @@ static int rb3d_planes_device( sg_ctx* ctx, Rb3dData* d, const bool emit )
   return SG_OK;
 }
 
+static int rb3d_portal_active_set_device( sg_ctx* ctx, Rb3dData* d );
+
 static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_cand_in )
 {
   const uint32_t n = d->n;
+  // with portals the body-body path grows teleported boxes and collisions (RigidBody3DSim.cpp:1088-1115, 1139-1199)
+  if( d->px != nullptr && d->px->portals.n > 0u ) { return rb3d_portal_active_set_device( ctx, d ); }
+  if( d->px != nullptr ) { d->px->result = false; }
   d->n_cand = d->n_bb = d->n_static = 0;
   d->have_result = true;
   if( n == 0 ) { d->cand_valid = want_cand_in; return SG_OK; }
@@ -1199,6 +1233,188 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
   }
   rc = rb3d_planes_device( ctx, d, true );
   if( rc != SG_OK ) { return rc; }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+// RigidBody3DSim::computeActiveSet with portals, all-sphere scenes (RigidBody3DSim.cpp:250-262 -> :1072-1260): boxes at q1, teleported
+// copies, un-teleported candidates through the regular narrow phase (k_rb3d_pairs), TeleportedCollision set for the rest, then planes
+// and cylinders.  Same sequence as the rigidbody2d portal driver (sg_rb2d.cu).
+static int rb3d_portal_active_set_device( sg_ctx* ctx, Rb3dData* d )
+{
+  Rb3dPortalData* x = d->px;
+  const uint32_t n = d->n;
+  const uint32_t np_portals = x->portals.n;
+  d->n_cand = d->n_bb = d->n_static = 0;
+  x->n_boxes = x->n_reg = x->n_tel = 0;
+  d->have_result = true;
+  d->cand_valid = true;
+  x->result = true;
+  if( n == 0 ) { return SG_OK; }
+  if( !d->all_spheres )
+  {
+    return sg_fail( ctx, SG_ERR_UNSUPPORTED, "rigidbody3d portals are implemented for all-sphere scenes (the reference supports teleported collisions for spheres only: rigidbody3d/RigidBody3DSim.cpp:1262-1292)" );
+  }
+  if( uint64_t( n ) * np_portals >= 0x80000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "rigidbody3d portals: bodies x portals must stay below 2^31" ); }
+  const Rb3dDev dev = rb3d_dev( d );
+  const unsigned nblk = sg_div_up( n, 256 );
+  const uint32_t nflag = n * np_portals;
+  SG_CUDA( ctx, x->h.ensure( 128 ) );
+  SG_CUDA( ctx, d->totals3.ensure( 32 ) ); SG_CUDA( ctx, d->st_total.ensure( 4 ) ); SG_CUDA( ctx, d->narrow_total.ensure( 8 ) ); SG_CUDA( ctx, d->bad_flag.ensure( 4 ) );
+  SG_CUDA( ctx, x->ttotal.ensure( 4 ) ); SG_CUDA( ctx, x->reg_total.ensure( 8 ) ); SG_CUDA( ctx, x->tel_total.ensure( 4 ) ); SG_CUDA( ctx, x->utotal.ensure( 4 ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->st_total.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->narrow_total.ptr, 0, 8, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->bad_flag.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->ttotal.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->reg_total.ptr, 0, 8, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->tel_total.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( x->utotal.ptr, 0, 4, ctx->stream ) );
+  SG_CUDA( ctx, x->rboxes.ensure( size_t( n ) * 48 ) );
+  SG_CUDA( ctx, x->tflag.ensure( size_t( nflag ) * 4 + 4 ) ); SG_CUDA( ctx, x->toff.ensure( size_t( nflag ) * 4 + 4 ) );
+  SG_CUDA( ctx, x->t_partials.ensure( ( size_t( nflag ) / SG_SCAN_TILE + 2 ) * 4 ) );
+  SG_LAUNCH( ctx, "rb3d_aabb", double( n ) * ( 96.0 + 48.0 ), k_rb3d_aabb<<<sg_div_up( n, 128 ), 128, 0, ctx->stream>>>( dev, d->q1.as<double>(), x->rboxes.as<double>() ) );
+  SG_LAUNCH( ctx, "r3p_touch", double( nflag ) * 52.0, k_r3p_touch<<<dim3( nblk, np_portals ), 256, 0, ctx->stream>>>( x->portals, n, x->rboxes.as<double>(), x->tflag.as<uint32_t>() ) );
+  int rc = sg_exclusive_scan<ScanU32>( ctx, "r3p_touch_scan", x->tflag.as<uint32_t>(), nullptr, nflag, nflag, x->t_partials.as<uint32_t>(), x->toff.as<uint32_t>(), x->ttotal.as<uint32_t>(), false );
+  if( rc != SG_OK ) { return rc; }
+  // planes and cylinders do not depend on the portals: count them now (their emit follows the body-body contacts)
+  rc = rb3d_planes_device( ctx, d, false );
+  if( rc != SG_OK ) { return rc; }
+  uint32_t* h32 = x->h.as<uint32_t>();
+  unsigned long long* h64 = x->h.as<unsigned long long>() + 8; // bytes 64...
+  h32[1] = 0u;
+  SG_CUDA( ctx, cudaMemcpyAsync( h32, x->ttotal.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( h32 + 1, d->st_total.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  const uint32_t nt = h32[0];
+  d->n_static = h32[1];
+  x->n_boxes = nt;
+  if( uint64_t( n ) + nt >= 0x80000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "rigidbody3d portals: more than 2^31 - 1 boxes" ); }
+  const uint32_t next = n + nt;
+  SG_CUDA( ctx, d->boxes.ensure( size_t( next ) * 48 ) );
+  SG_CUDA( ctx, x->box_body.ensure( size_t( nt ) * 4 + 4 ) ); SG_CUDA( ctx, x->box_portal.ensure( size_t( nt ) * 4 + 4 ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->boxes.ptr, x->rboxes.ptr, size_t( n ) * 48, cudaMemcpyDeviceToDevice, ctx->stream ) );
+  if( nt > 0 )
+  {
+    SG_LAUNCH( ctx, "r3p_tele_boxes", double( nflag ) * 8.0 + double( nt ) * 140.0, k_r3p_tele_boxes<<<dim3( nblk, np_portals ), 256, 0, ctx->stream>>>( x->portals, dev, d->q1.as<double>(), x->rboxes.as<double>(),
+               x->tflag.as<uint32_t>(), x->toff.as<uint32_t>(), d->boxes.as<double>(), x->box_body.as<uint32_t>(), x->box_portal.as<uint32_t>() ) );
+  }
+  rc = sg_bp_prepare_scratch<Box3DPolicy>( ctx, d->bp, next );
+  if( rc != SG_OK ) { return rc; }
+  Box3DIn in;
+  in.boxes = d->boxes.as<double>(); in.n = next;
+  rc = sg_bp_bin_and_count<Box3DPolicy>( ctx, d->bp, in );
+  if( rc != SG_OK ) { return rc; }
+  SG_CUDA( ctx, cudaMemcpyAsync( h64, d->bp.totals.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  const uint64_t np = h64[0];
+  d->n_cand = np;
+  if( np >= 0xffffffffull ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rigidbody3d portals: more than 2^32 candidate pairs" ); }
+  rc = rb3d_ensure_outputs( ctx, d, np + 64, d->act_cap );
+  if( rc != SG_OK ) { return rc; }
+  uint64_t nreg_pairs = 0;
+  uint32_t nraw = 0;
+  if( np > 0 )
+  {
+    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, next, true, NoOut3D{}, 0u );
+    if( rc != SG_OK ) { return rc; }
+    SG_CUDA( ctx, x->reg_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->reg_off.ensure( size_t( np ) * 8 + 8 ) );
+    SG_CUDA( ctx, x->tel_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->tel_off.ensure( size_t( np ) * 4 + 4 ) );
+    SG_CUDA( ctx, x->pr_partials.ensure( ( size_t( np ) / SG_SCAN_TILE + 2 ) * 8 ) );
+    SG_LAUNCH( ctx, "r3p_classify_count", double( np ) * 80.0, k_r3p_classify<false><<<sg_div_up( np, 128 ), 128, 0, ctx->stream>>>( x->portals, dev, d->bp.cand.as<uint2>(), np, d->q1.as<double>(),
+               x->box_body.as<uint32_t>(), x->box_portal.as<uint32_t>(), x->reg_cnt.as<uint32_t>(), x->tel_cnt.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr ) );
+    rc = sg_exclusive_scan<ScanU32To64>( ctx, "r3p_regular_scan", x->reg_cnt.as<uint32_t>(), nullptr, uint32_t( np ), uint32_t( np ), x->pr_partials.as<unsigned long long>(), x->reg_off.as<unsigned long long>(),
+                                         x->reg_total.as<unsigned long long>(), false );
+    if( rc != SG_OK ) { return rc; }
+    rc = sg_exclusive_scan<ScanU32>( ctx, "r3p_teleported_scan", x->tel_cnt.as<uint32_t>(), nullptr, uint32_t( np ), uint32_t( np ), x->pr_partials.as<uint32_t>(), x->tel_off.as<uint32_t>(), x->tel_total.as<uint32_t>(), false );
+    if( rc != SG_OK ) { return rc; }
+    SG_CUDA( ctx, cudaMemcpyAsync( h64 + 2, x->reg_total.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h32 + 2, x->tel_total.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    nreg_pairs = h64[2];
+    nraw = h32[2];
+  }
+  if( nraw > 0x40000000u ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rigidbody3d portals: more than 2^30 teleported collisions" ); }
+  uint32_t m = 1u;
+  while( m < nraw ) { m <<= 1; }
+  SG_CUDA( ctx, x->reg_pairs.ensure( size_t( nreg_pairs ) * 8 + 8 ) );
+  if( nraw > 0 )
+  {
+    SG_CUDA( ctx, x->tc_key.ensure( size_t( m ) * 8 ) ); SG_CUDA( ctx, x->tc_idx.ensure( size_t( m ) * 4 ) ); SG_CUDA( ctx, x->tc_info.ensure( size_t( nraw ) * 16 ) );
+    SG_CUDA( ctx, x->uflag.ensure( size_t( nraw ) * 4 + 4 ) ); SG_CUDA( ctx, x->uoff.ensure( size_t( nraw ) * 4 + 4 ) );
+    SG_CUDA( ctx, x->u_partials.ensure( ( size_t( nraw ) / SG_SCAN_TILE + 2 ) * 4 ) );
+    SG_CUDA( ctx, x->x0t.ensure( size_t( nraw ) * 24 ) ); SG_CUDA( ctx, x->x1t.ensure( size_t( nraw ) * 24 ) );
+    SG_CUDA( ctx, x->tp0.ensure( size_t( nraw ) * 4 ) ); SG_CUDA( ctx, x->tp1.ensure( size_t( nraw ) * 4 ) );
+  }
+  if( np > 0 )
+  {
+    SG_LAUNCH( ctx, "r3p_classify_emit", double( np ) * 28.0, k_r3p_classify<true><<<sg_div_up( np, 128 ), 128, 0, ctx->stream>>>( x->portals, dev, d->bp.cand.as<uint2>(), np, d->q1.as<double>(),
+               x->box_body.as<uint32_t>(), x->box_portal.as<uint32_t>(), x->reg_cnt.as<uint32_t>(), x->tel_cnt.as<uint32_t>(), x->reg_off.as<unsigned long long>(), x->tel_off.as<uint32_t>(),
+               x->reg_pairs.as<uint2>(), x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>(), x->tc_info.as<uint4>() ) );
+  }
+  // regular narrow phase over the un-teleported candidates: count -> scan (the emit follows once the contact arrays are sized)
+  SG_CUDA( ctx, d->pair_counts.ensure( size_t( nreg_pairs ) * 4 + 4 ) );
+  SG_CUDA( ctx, d->pair_offsets.ensure( size_t( nreg_pairs ) * 8 + 8 ) );
+  SG_CUDA( ctx, d->pair_partials.ensure( ( size_t( nreg_pairs ) / SG_SCAN_TILE + 2 ) * 8 ) );
+  const unsigned long long* nreg_dev = x->reg_total.as<unsigned long long>();
+  if( nreg_pairs > 0 )
+  {
+    SG_CUDA( ctx, cudaMemsetAsync( d->pair_counts.ptr, 0, size_t( nreg_pairs ) * 4, ctx->stream ) );
+    SG_LAUNCH( ctx, "rb3d_pairs_count", double( nreg_pairs ) * 250.0, k_rb3d_pairs<false><<<sg_div_up( nreg_pairs, 128 ), 128, 0, ctx->stream>>>( dev, x->reg_pairs.as<uint2>(), nreg_dev, d->q0.as<double>(), d->q1.as<double>(),
+               d->pair_counts.as<uint32_t>(), nullptr, rb3d_out( d ), d->bad_flag.as<uint32_t>() ) );
+    rc = sg_exclusive_scan<ScanU32To64>( ctx, "rb3d_pair_scan", d->pair_counts.as<uint32_t>(), nullptr, uint32_t( nreg_pairs ), uint32_t( nreg_pairs ), d->pair_partials.as<unsigned long long>(),
+                                         d->pair_offsets.as<unsigned long long>(), d->narrow_total.as<unsigned long long>(), false );
+    if( rc != SG_OK ) { return rc; }
+  }
+  if( nraw > 0 )
+  {
+    if( m > nraw ) { SG_LAUNCH( ctx, "b2p_sort_pad", 0.0, k_b2p_sort_pad<<<sg_div_up( m - nraw, 256 ), 256, 0, ctx->stream>>>( nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) ); }
+    const unsigned ntiles = sg_div_up( m, SG_B2P_SORT_TILE );
+    SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, true><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, 0u, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
+    for( uint32_t k = 2u * SG_B2P_SORT_TILE; k <= m; k <<= 1 )
+    {
+      for( uint32_t j = k >> 1; j >= uint32_t( SG_B2P_SORT_TILE ); j >>= 1 )
+      {
+        SG_LAUNCH( ctx, "b2p_bitonic", double( m ) * 24.0, k_b2p_bitonic<<<sg_div_up( m, 256 ), 256, 0, ctx->stream>>>( m, j, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
+      }
+      SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, false><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
+    }
+    SG_LAUNCH( ctx, "b2p_unique", double( nraw ) * 12.0, k_b2p_unique<<<sg_div_up( nraw, 256 ), 256, 0, ctx->stream>>>( nraw, x->tc_key.as<unsigned long long>(), x->uflag.as<uint32_t>() ) );
+    rc = sg_exclusive_scan<ScanU32>( ctx, "b2p_unique_scan", x->uflag.as<uint32_t>(), nullptr, nraw, nraw, x->u_partials.as<uint32_t>(), x->uoff.as<uint32_t>(), x->utotal.as<uint32_t>(), false );
+    if( rc != SG_OK ) { return rc; }
+  }
+  h64[3] = 0ull; h32[4] = 0u; h32[5] = 0u;
+  SG_CUDA( ctx, cudaMemcpyAsync( h64 + 3, d->narrow_total.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( h32 + 4, d->bad_flag.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  if( nraw > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( h32 + 5, x->utotal.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  if( h32[4] != 0u )
+  {
+    return sg_fail( ctx, SG_ERR_UNSUPPORTED, "collision between two different geometry types is not supported (the reference exits here: rigidbody3d/RigidBody3DSim.cpp:905-961)" );
+  }
+  x->n_reg = h64[3];
+  x->n_tel = h32[5];
+  d->n_bb = x->n_reg + x->n_tel;
+  rc = rb3d_ensure_outputs( ctx, d, 0u, d->n_bb + d->n_static + 64 );
+  if( rc != SG_OK ) { return rc; }
+  if( nreg_pairs > 0 && x->n_reg > 0 )
+  {
+    SG_LAUNCH( ctx, "rb3d_pairs_emit", double( nreg_pairs ) * 250.0 + double( x->n_reg ) * 72.0, k_rb3d_pairs<true><<<sg_div_up( nreg_pairs, 128 ), 128, 0, ctx->stream>>>( dev, x->reg_pairs.as<uint2>(), nreg_dev, d->q0.as<double>(),
+               d->q1.as<double>(), nullptr, d->pair_offsets.as<unsigned long long>(), rb3d_out( d ), d->bad_flag.as<uint32_t>() ) );
+  }
+  if( x->n_tel > 0 )
+  {
+    SG_LAUNCH( ctx, "r3p_tele_contacts", double( nraw ) * 250.0, k_r3p_tele_contacts<<<sg_div_up( nraw, 128 ), 128, 0, ctx->stream>>>( x->portals, dev, nraw, x->tc_idx.as<uint32_t>(), x->uflag.as<uint32_t>(), x->uoff.as<uint32_t>(),
+               x->tc_info.as<uint4>(), d->q0.as<double>(), x->n_reg, rb3d_out( d ), x->x0t.as<double>(), x->x1t.as<double>(), x->tp0.as<uint32_t>(), x->tp1.as<uint32_t>() ) );
+  }
+  // the plane / cylinder emit reads its base (all body-body contacts) from totals3[1]
+  h64[4] = d->n_cand; h64[5] = d->n_bb;
+  SG_CUDA( ctx, cudaMemcpyAsync( d->totals3.ptr, h64 + 4, 16, cudaMemcpyHostToDevice, ctx->stream ) );
+  if( d->n_static > 0 )
+  {
+    rc = rb3d_planes_device( ctx, d, true );
+    if( rc != SG_OK ) { return rc; }
+  }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   sg_prof_collect( ctx );
   return SG_OK;
@@ -1437,6 +1653,88 @@ int sg_rb3d_set_cylinders( sg_ctx* ctx, uint32_t n, const double* x, const doubl
     for( int k = 0; k < 3; ++k ) { d->planes.cx[c][k] = x[3 * c + k]; d->planes.cax[c][k] = v[k]; }
     d->planes.cr[c] = r[c];
   }
+  return SG_OK;
+}
+
+int sg_rb3d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x, const double* plane_a_n, const double* plane_b_x, const double* plane_b_n, const int32_t* multiplier )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n > SG_MAX_PORTALS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_portals: at most %d portals", SG_MAX_PORTALS ); }
+  if( n > 0 && ( plane_a_x == nullptr || plane_a_n == nullptr || plane_b_x == nullptr || plane_b_n == nullptr || multiplier == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_portals: null array" ); }
+  Rb3dData* d = rb3d_data( ctx );
+  if( n == 0 && d->px == nullptr ) { return SG_OK; }
+  if( d->px == nullptr ) { d->px = new Rb3dPortalData; }
+  SgPortals3D ps;
+  memset( &ps, 0, sizeof( ps ) );
+  ps.n = n;
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    SgPortal3D& pt = ps.p[p];
+    for( int k = 0; k < 3; ++k ) { pt.ax[k] = plane_a_x[3 * p + k]; pt.bx[k] = plane_b_x[3 * p + k]; pt.mult[k] = multiplier[3 * p + k]; }
+    // StaticPlane::StaticPlane + t0() / t1() (rigidbody3d/StaticGeometry/StaticPlane.cpp:10-15,58-66)
+    if( !sg_portal3_plane_frame( plane_a_n + 3 * p, pt.an, pt.at0, pt.at1 ) || !sg_portal3_plane_frame( plane_b_n + 3 * p, pt.bn, pt.bt0, pt.bt1 ) )
+    {
+      return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_set_portals: portal %u has a plane normal opposite to the y axis (Eigen's FromTwoVectors takes its SVD branch there; not reproduced)", p );
+    }
+  }
+  d->px->portals = ps;
+  d->have_result = false;
+  return SG_OK;
+}
+
+int sg_rb3d_enforce_portals( sg_ctx* ctx, double* q )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( d->px == nullptr || d->px->portals.n == 0u || d->n == 0 ) { return SG_OK; }
+  if( q == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_enforce_portals: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  d->flow_resident = false; // q1 serves as the staging copy
+  const size_t bytes = size_t( d->n ) * 24; // only the centres of mass move
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_LAUNCH( ctx, "r3p_enforce", double( d->n ) * 48.0, k_r3p_enforce<<<sg_div_up( d->n, 256 ), 256, 0, ctx->stream>>>( d->px->portals, d->n, d->q1.as<double>() ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( q, d->q1.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
+int sg_rb3d_teleported( sg_ctx* ctx, sg_teleported* out )
+{
+  if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
+  memset( out, 0, sizeof( *out ) );
+  Rb3dData* d = rb3d_data( ctx );
+  if( !d->have_result || d->px == nullptr || !d->px->result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_teleported: the last active set was not computed with portals" ); }
+  Rb3dPortalData* x = d->px;
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  auto al = []( size_t b ) { return ( b + 63 ) & ~size_t( 63 ); };
+  const size_t nb = x->n_boxes, nt = x->n_tel;
+  size_t bytes = 64;
+  const size_t o_bb = bytes; bytes += al( nb * 4 );
+  const size_t o_bp = bytes; bytes += al( nb * 4 );
+  const size_t o_p0 = bytes; bytes += al( nt * 4 );
+  const size_t o_p1 = bytes; bytes += al( nt * 4 );
+  const size_t o_x0 = bytes; bytes += al( nt * 24 );
+  const size_t o_x1 = bytes; bytes += al( nt * 24 );
+  SG_CUDA( ctx, x->h_tele.ensure( bytes ) );
+  char* h = x->h_tele.as<char>();
+  if( nb > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_bb, x->box_body.ptr, nb * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_bp, x->box_portal.ptr, nb * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+  }
+  if( nt > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_p0, x->tp0.ptr, nt * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_p1, x->tp1.ptr, nt * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_x0, x->x0t.ptr, nt * 24, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( h + o_x1, x->x1t.ptr, nt * 24, cudaMemcpyDeviceToHost, ctx->stream ) );
+  }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  out->n_boxes = nb; out->n_regular = x->n_reg; out->n_teleported = nt;
+  out->box_body = reinterpret_cast<const uint32_t*>( h + o_bb ); out->box_portal = reinterpret_cast<const uint32_t*>( h + o_bp );
+  out->portal0 = reinterpret_cast<const uint32_t*>( h + o_p0 ); out->portal1 = reinterpret_cast<const uint32_t*>( h + o_p1 );
+  out->x0 = reinterpret_cast<const double*>( h + o_x0 ); out->x1 = reinterpret_cast<const double*>( h + o_x1 );
   return SG_OK;
 }
 

@@ -258,6 +258,31 @@ void GpuRigidBody3DBackend::setCylinders( const std::vector<double>& x, const st
   check( sg_rb3d_set_cylinders( m_ctx, static_cast<uint32_t>( r.size() ), x.data(), axis.data(), r.data() ), "sg_rb3d_set_cylinders" );
 }
 
+void GpuRigidBody3DBackend::setPortals( const std::vector<double>& plane_a_x, const std::vector<double>& plane_a_n, const std::vector<double>& plane_b_x, const std::vector<double>& plane_b_n,
+                                        const std::vector<int32_t>& multiplier )
+{
+  check( sg_rb3d_set_portals( m_ctx, static_cast<uint32_t>( multiplier.size() / 3 ), plane_a_x.data(), plane_a_n.data(), plane_b_x.data(), plane_b_n.data(), multiplier.data() ), "sg_rb3d_set_portals" );
+}
+
+void GpuRigidBody3DBackend::enforcePeriodicBoundaryConditions( VectorXs& q )
+{
+  check( sg_rb3d_enforce_portals( m_ctx, q.data() ), "sg_rb3d_enforce_portals" );
+}
+
+void GpuRigidBody3DBackend::teleportedContacts( std::vector<GpuTeleportedContact3D>& teleported, uint64_t* num_regular )
+{
+  sg_teleported t;
+  check( sg_rb3d_teleported( m_ctx, &t ), "sg_rb3d_teleported" );
+  teleported.resize( t.n_teleported );
+  for( uint64_t k = 0; k < t.n_teleported; ++k )
+  {
+    GpuTeleportedContact3D& o = teleported[k];
+    o.portal0 = t.portal0[k]; o.portal1 = t.portal1[k];
+    for( int c = 0; c < 3; ++c ) { o.x0[c] = t.x0[3 * k + c]; o.x1[c] = t.x1[3 * k + c]; }
+  }
+  if( num_regular != nullptr ) { *num_regular = t.n_regular; }
+}
+
 void GpuRigidBody3DBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
   if( q1.size() != q0.size() ) { q1.resize( q0.size() ); }

@@ -146,6 +146,14 @@ struct GpuContact3D
   double depth;  // NaN where the reference's constraint has no penetrationDepth override
 };
 
+// Constructor arguments of a teleported rigidbody3d contact (RigidBody3DSim.cpp:1338-1397): TeleportedSphereSphereConstraint{ i, j, x0, x1, ri, rj }
+// or KinematicObjectSphereConstraint{ free sphere, r, n, kinematic sphere, its teleported centre, 0, 0 }
+struct GpuTeleportedContact3D
+{
+  uint32_t portal0, portal1;
+  double x0[3], x1[3];
+};
+
 class GpuRigidBody3DBackend final
 {
 public:
@@ -167,6 +175,16 @@ public:
   void setPlanes( const std::vector<double>& x, const std::vector<double>& n );
   // RigidBody3DState::staticCylinders(): point on the axis, axis, radius per cylinder
   void setCylinders( const std::vector<double>& x, const std::vector<double>& axis, const std::vector<double>& r );
+
+  // RigidBody3DState::planarPortals() (rigidbody3d/Portals/PlanarPortal.h): plane A and B as (x, n), the integer portal multipliers (3 per portal).
+  // All-sphere scenes only (the reference's teleported collisions are sphere-only); computeActiveSet then lists the contacts of un-teleported
+  // pairs | SG_SPHERE_SPHERE_TELEPORTED / SG_KINEMATIC_OBJECT_SPHERE_TELEPORTED | planes | cylinders (RigidBody3DSim.cpp:1072-1397)
+  void setPortals( const std::vector<double>& plane_a_x, const std::vector<double>& plane_a_n, const std::vector<double>& plane_b_x, const std::vector<double>& plane_b_n,
+                   const std::vector<int32_t>& multiplier );
+  // RigidBody3DSim::enforcePeriodicBoundaryConditions (RigidBody3DSim.cpp:642-663): centres of mass in q, in place
+  void enforcePeriodicBoundaryConditions( VectorXs& q );
+  // after a computeActiveSet with portals: teleported centres ( x0, x1 at q0 ) of contacts [num_regular, num_regular + teleported.size())
+  void teleportedContacts( std::vector<GpuTeleportedContact3D>& teleported, uint64_t* num_regular = nullptr );
 
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
   // false + message on std::cerr where the reference would print and exit (unsupported geometry pairing): the caller exits

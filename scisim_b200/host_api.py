@@ -179,7 +179,7 @@ class PlanarPortal:
 class TeleportedInfo:
     """What the portal branch adds to an ActiveSet (sg_teleported, include/scisim_b200.h)."""
 
-    def __init__(self, t):
+    def __init__(self, t, dim=2):
         nb, nt = int(t.n_boxes), int(t.n_teleported)
         self.n_regular = int(t.n_regular)
         self.n_teleported = nt
@@ -188,12 +188,27 @@ class TeleportedInfo:
         self.box_portal = arr(t.box_portal, (nb,), np.uint32)
         self.portal0 = arr(t.portal0, (nt,), np.uint32)
         self.portal1 = arr(t.portal1, (nt,), np.uint32)
-        self.x0 = arr(t.x0, (nt, 2), np.float64)
-        self.x1 = arr(t.x1, (nt, 2), np.float64)
-        self.kick = arr(t.kick, (nt, 2), np.float64)
+        self.x0 = arr(t.x0, (nt, dim), np.float64)
+        self.x1 = arr(t.x1, (nt, dim), np.float64)
+        self.kick = arr(t.kick, (nt, 2), np.float64) if t.kick else None  # 2-D sims only (Lees-Edwards)
         # rigidbody2d only: TeleportedCircleCircleConstraint's displacements
         self.delta0 = arr(t.delta0, (nt, 2), np.float64) if t.delta0 else None
         self.delta1 = arr(t.delta1, (nt, 2), np.float64) if t.delta1 else None
+
+
+class PlanarPortal3D:
+    """rigidbody3d/Portals/PlanarPortal.h: PlanarPortal( plane_a, plane_b, portal_multiplier ); planes as (point, normal)."""
+
+    def __init__(self, plane_a_x, plane_a_n, plane_b_x, plane_b_n, multiplier=(1, 1, 1)):
+        self.plane_a_x, self.plane_a_n = _f64(plane_a_x), _f64(plane_a_n)
+        self.plane_b_x, self.plane_b_n = _f64(plane_b_x), _f64(plane_b_n)
+        self.multiplier = np.ascontiguousarray(multiplier, dtype=np.int32)
+
+    @staticmethod
+    def from_arrays(portals):
+        """The dict layout of scenes.rb3d_periodic_spheres -> list of PlanarPortal3D."""
+        return [PlanarPortal3D(portals["plane_a_x"][p], portals["plane_a_n"][p], portals["plane_b_x"][p], portals["plane_b_n"][p], portals["mult"][p])
+                for p in range(len(portals["mult"]))]
 
 
 class Ball2DState:
@@ -354,7 +369,8 @@ class RigidBody3DState:
     body-frame inertia, gravity, static planes, static cylinders."""
 
     def __init__(self, geo_type, geo_r, geo_half, geo_mesh, meshes, geo_of_body, fixed, m, I0, g=(0.0, 0.0, 0.0), plane_x=None, plane_n=None,
-                 cyl_x=None, cyl_axis=None, cyl_r=None):
+                 cyl_x=None, cyl_axis=None, cyl_r=None, planar_portals=None):
+        self.planar_portals = list(planar_portals) if planar_portals is not None else []
         self.cyl_x = _f64(cyl_x if cyl_x is not None else np.zeros((0, 3))).reshape(-1, 3)
         self.cyl_axis = _f64(cyl_axis if cyl_axis is not None else np.zeros((0, 3))).reshape(-1, 3)
         self.cyl_r = _f64(cyl_r if cyl_r is not None else np.zeros(0))
@@ -415,9 +431,30 @@ class RigidBody3DSim:
         self.ctx.check(lib.sg_rb3d_set_gravity(h, _ptr(st.g)))
         self.ctx.check(lib.sg_rb3d_set_planes(h, st.plane_x.shape[0], _ptr(st.plane_x), _ptr(st.plane_n)))
         self.ctx.check(lib.sg_rb3d_set_cylinders(h, st.cyl_r.shape[0], _ptr(st.cyl_x), _ptr(st.cyl_axis), _ptr(st.cyl_r)))
+        pp = st.planar_portals
+        if pp:
+            cat = lambda f: _f64(np.array([f(p) for p in pp], dtype=np.float64))
+            mult = np.ascontiguousarray(np.array([p.multiplier for p in pp]), dtype=np.int32)
+            self.ctx.check(lib.sg_rb3d_set_portals(h, len(pp), _ptr(cat(lambda p: p.plane_a_x)), _ptr(cat(lambda p: p.plane_a_n)), _ptr(cat(lambda p: p.plane_b_x)),
+                                                   _ptr(cat(lambda p: p.plane_b_n)), _ptr(mult)))
+        else:
+            self.ctx.check(lib.sg_rb3d_set_portals(h, 0, None, None, None, None, None))
 
     def name(self):
         return "rigid_body_3d"
+
+    # ---- portals (rigidbody3d/RigidBody3DSim.cpp:642-663) ----
+    def enforcePeriodicBoundaryConditions(self, q):
+        """Teleports the centres of mass that left through a portal; returns the new q."""
+        q = _f64(q).copy()
+        self.ctx.check(self.ctx.lib.sg_rb3d_enforce_portals(self.ctx.h, _ptr(q)))
+        return q
+
+    def teleported(self):
+        from ._lib import SgTeleported
+        t = SgTeleported()
+        self.ctx.check(self.ctx.lib.sg_rb3d_teleported(self.ctx.h, C.byref(t)))
+        return TeleportedInfo(t, dim=3)
 
     def nqdofs(self):
         return 12 * self.state.nbodies()

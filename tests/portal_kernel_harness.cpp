@@ -367,4 +367,130 @@ uint32_t pk_rb2d_probe( uint32_t p, const double* box, const double* x, double* 
   return uint32_t( touch );
 }
 
+// ---- rigidbody3d portal kernels (scisim_b200/csrc/sg_rb3d_portal_kernels.cuh), sphere scenes --------------------------------
+}
+
+// what sg_rb3d.cu provides to that header
+#define SG_FIXED_BIT 0x80000000u
+struct Rb3dDev { uint32_t n; const uint32_t* btype; const double* bparam; };
+struct ContactOut3D
+{
+  uint32_t* type; uint32_t* i; uint32_t* j; uint32_t* aux;
+  double* n; double* p; double* depth;
+  unsigned long long cap;
+};
+
+#include "../scisim_b200/csrc/sg_rb3d_portal_kernels.cuh"
+
+struct ResultRB3D
+{
+  std::vector<uint2> cand, reg_pairs;
+  std::vector<uint32_t> box_body, box_portal, type, ci, cj, aux, tp0, tp1;
+  std::vector<double> cn, cp, depth, x0t, x1t;
+  uint32_t n_tel = 0;
+};
+static ResultRB3D g_r3;
+static SgPortals3D g_ps3;
+
+extern "C"
+{
+
+int pk_rb3d_set_portals( uint32_t n, const double* ax, const double* an, const double* bx, const double* bn, const int* mult )
+{
+  std::memset( &g_ps3, 0, sizeof( g_ps3 ) );
+  g_ps3.n = n;
+  int ok = 1;
+  for( uint32_t p = 0; p < n; ++p )
+  {
+    SgPortal3D& pt = g_ps3.p[p];
+    for( int k = 0; k < 3; ++k ) { pt.ax[k] = ax[3 * p + k]; pt.bx[k] = bx[3 * p + k]; pt.mult[k] = mult[3 * p + k]; }
+    ok = ok && sg_portal3_plane_frame( an + 3 * p, pt.an, pt.at0, pt.at1 ) && sg_portal3_plane_frame( bn + 3 * p, pt.bn, pt.bt0, pt.bt1 );
+  }
+  return ok;
+}
+
+// the portal-specific part of rb3d_portal_active_set_device for an all-sphere scene: candidates, un-teleported pair list, teleported
+// contacts (written from index 0).  btype: SG_FIXED_BIT for kinematic spheres; bparam: 4 doubles per body, radius first
+void pk_rb3d_active_set( uint32_t n, const uint32_t* btype, const double* bparam, const double* q0, const double* q1 )
+{
+  ResultRB3D& R = g_r3;
+  R = ResultRB3D{};
+  Rb3dDev dev; dev.n = n; dev.btype = btype; dev.bparam = bparam;
+  const uint32_t P = g_ps3.n;
+  const unsigned nblk = div_up( n, 256 );
+  // real boxes: RigidBodySphere::computeAABB ( k_rb3d_aabb in the library )
+  std::vector<double> rboxes( size_t( n ) * 6 );
+  for( uint32_t b = 0; b < n; ++b ) { for( int k = 0; k < 3; ++k ) { rboxes[6 * size_t( b ) + k] = q1[3 * size_t( b ) + k] - bparam[4 * size_t( b )]; rboxes[6 * size_t( b ) + 3 + k] = q1[3 * size_t( b ) + k] + bparam[4 * size_t( b )]; } }
+  std::vector<uint32_t> tflag( size_t( n ) * P, 0xdeadbeefu ), toff;
+  launch( nblk, P, 256, [&]() { k_r3p_touch( g_ps3, n, rboxes.data(), tflag.data() ); } );
+  const uint32_t nt = exclusive_scan( tflag, toff );
+  const uint32_t next = n + nt;
+  std::vector<double> boxes( size_t( next ) * 6, std::nan( "" ) );
+  std::copy( rboxes.begin(), rboxes.end(), boxes.begin() );
+  R.box_body.assign( nt, 0xdeadbeefu ); R.box_portal.assign( nt, 0xdeadbeefu );
+  if( nt > 0 ) { launch( nblk, P, 256, [&]() { k_r3p_tele_boxes( g_ps3, dev, q1, rboxes.data(), tflag.data(), toff.data(), boxes.data(), R.box_body.data(), R.box_portal.data() ); } ); }
+  for( uint32_t i = 0; i < next; ++i ) for( uint32_t j = i + 1; j < next; ++j )
+  {
+    const double* a = &boxes[6 * size_t( i )]; const double* b = &boxes[6 * size_t( j )];
+    bool ov = true;
+    for( int k = 0; k < 3; ++k ) { if( a[3 + k] < b[k] || b[3 + k] < a[k] ) { ov = false; } }
+    if( ov ) { R.cand.push_back( uint2{ i, j } ); }
+  }
+  const unsigned long long np = R.cand.size();
+  std::vector<uint32_t> reg_cnt( np, 0xdeadbeefu ), tel_cnt( np, 0xdeadbeefu ), reg_off32, tel_off;
+  if( np > 0 )
+  {
+    launch( div_up( np, 128 ), 1, 128, [&]() { k_r3p_classify<false>( g_ps3, dev, R.cand.data(), np, q1, R.box_body.data(), R.box_portal.data(), reg_cnt.data(), tel_cnt.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr ); } );
+  }
+  const uint32_t nreg = exclusive_scan( reg_cnt, reg_off32 );
+  const uint32_t nraw = exclusive_scan( tel_cnt, tel_off );
+  std::vector<unsigned long long> reg_off( reg_off32.begin(), reg_off32.end() );
+  R.reg_pairs.assign( nreg, uint2{ 0xdeadbeefu, 0xdeadbeefu } );
+  uint32_t m = 1u;
+  while( m < nraw ) { m <<= 1; }
+  std::vector<unsigned long long> tc_key( m, 0x1234ull );
+  std::vector<uint32_t> tc_idx( m, 0xdeadbeefu ), uflag( nraw, 0xdeadbeefu ), uoff;
+  std::vector<uint4> tc_info( nraw + 1 );
+  if( np > 0 )
+  {
+    launch( div_up( np, 128 ), 1, 128, [&]() { k_r3p_classify<true>( g_ps3, dev, R.cand.data(), np, q1, R.box_body.data(), R.box_portal.data(), reg_cnt.data(), tel_cnt.data(), reg_off.data(), tel_off.data(),
+                                                                     R.reg_pairs.data(), tc_key.data(), tc_idx.data(), tc_info.data() ); } );
+  }
+  if( nraw > 0 )
+  {
+    if( m > nraw ) { launch( div_up( m - nraw, 256 ), 1, 256, [&]() { k_b2p_sort_pad( nraw, m, tc_key.data(), tc_idx.data() ); } ); }
+    sort_teleported( m, tc_key.data(), tc_idx.data() );
+    launch( div_up( nraw, 256 ), 1, 256, [&]() { k_b2p_unique( nraw, tc_key.data(), uflag.data() ); } );
+    R.n_tel = exclusive_scan( uflag, uoff );
+    const size_t cap = size_t( R.n_tel ) + 8;
+    R.type.assign( cap, 0xdeadbeefu ); R.ci.assign( cap, 0xdeadbeefu ); R.cj.assign( cap, 0xdeadbeefu ); R.aux.assign( cap, 0xdeadbeefu );
+    R.cn.assign( 3 * cap, 0.0 ); R.cp.assign( 3 * cap, 0.0 ); R.depth.assign( cap, -1.0 );
+    R.x0t.assign( 3 * size_t( nraw ), 0.0 ); R.x1t.assign( 3 * size_t( nraw ), 0.0 ); R.tp0.assign( nraw, 0 ); R.tp1.assign( nraw, 0 );
+    ContactOut3D out;
+    out.type = R.type.data(); out.i = R.ci.data(); out.j = R.cj.data(); out.aux = R.aux.data(); out.n = R.cn.data(); out.p = R.cp.data(); out.depth = R.depth.data(); out.cap = cap;
+    launch( div_up( nraw, 128 ), 1, 128, [&]() { k_r3p_tele_contacts( g_ps3, dev, nraw, tc_idx.data(), uflag.data(), uoff.data(), tc_info.data(), q0, 0ull, out, R.x0t.data(), R.x1t.data(), R.tp0.data(), R.tp1.data() ); } );
+  }
+}
+uint64_t pk_rb3d_num_candidates() { return g_r3.cand.size(); }
+uint64_t pk_rb3d_num_regular_pairs() { return g_r3.reg_pairs.size(); }
+uint32_t pk_rb3d_num_boxes() { return uint32_t( g_r3.box_body.size() ); }
+uint32_t pk_rb3d_num_teleported() { return g_r3.n_tel; }
+void pk_rb3d_copy( uint32_t* cand, uint32_t* reg_pairs, uint32_t* box_body, uint32_t* box_portal, uint32_t* type, uint32_t* i, uint32_t* j, double* n, double* p, double* depth, uint32_t* tp0, uint32_t* tp1,
+                   double* x0, double* x1 )
+{
+  const ResultRB3D& R = g_r3;
+  std::memcpy( cand, R.cand.data(), R.cand.size() * 8 ); std::memcpy( reg_pairs, R.reg_pairs.data(), R.reg_pairs.size() * 8 );
+  std::memcpy( box_body, R.box_body.data(), R.box_body.size() * 4 ); std::memcpy( box_portal, R.box_portal.data(), R.box_portal.size() * 4 );
+  const size_t nt = R.n_tel;
+  if( nt == 0 ) { return; }
+  std::memcpy( type, R.type.data(), nt * 4 ); std::memcpy( i, R.ci.data(), nt * 4 ); std::memcpy( j, R.cj.data(), nt * 4 );
+  std::memcpy( n, R.cn.data(), nt * 24 ); std::memcpy( p, R.cp.data(), nt * 24 ); std::memcpy( depth, R.depth.data(), nt * 8 );
+  std::memcpy( tp0, R.tp0.data(), nt * 4 ); std::memcpy( tp1, R.tp1.data(), nt * 4 );
+  std::memcpy( x0, R.x0t.data(), nt * 24 ); std::memcpy( x1, R.x1t.data(), nt * 24 );
+}
+void pk_rb3d_enforce( uint32_t n, double* q )
+{
+  launch( div_up( n, 256 ), 1, 256, [&]() { k_r3p_enforce( g_ps3, n, q ); } );
+}
+
 }

@@ -24,7 +24,7 @@ def test_host_shim_builds_and_links():
     syms = subprocess.run(["nm", "-DC", os.path.join(HOST, "libscisim_b200_host.so")], stdout=subprocess.PIPE, text=True).stdout
     assert os.path.exists(os.path.join(HOST, "example_rigidbody"))
     for name in ("GpuBall2DBackend::computeActiveSet", "GpuBall2DBackend::setPortals", "GpuBall2DBackend::enforcePeriodicBoundaryConditions", "GpuBall2DBackend::teleportedContacts", "GpuSymplecticEulerMap::flow", "GpuVerletMap::flow", "PairImpulseCache::getCachedConstraint",
-                 "GpuRigidBody3DBackend::computeActiveSet", "GpuRigidBody3DBackend::addMesh", "GpuSplitHamMap::flow", "GpuDMVMap::flow",
+                 "GpuRigidBody3DBackend::computeActiveSet", "GpuRigidBody3DBackend::setPortals", "GpuRigidBody3DBackend::teleportedContacts", "GpuRigidBody3DBackend::addMesh", "GpuSplitHamMap::flow", "GpuDMVMap::flow",
                  "GpuRigidBody2DBackend::computeActiveSet", "GpuRigidBody2DBackend::setPortals", "GpuRigidBody2DBackend::teleportedContacts", "GpuRB2DSymplecticEulerMap::flow", "GpuRB2DVerletMap::flow"):
         assert name in syms, name
 

@@ -174,3 +174,86 @@ def test_kinematic_variants_and_enforce(oracle):
         for xb in q2[: 3 * n].reshape(-1, 3)[::5]:
             code, _ = o.portal_probe(p, np.zeros(6), np.ascontiguousarray(xb))
             assert not (code & 4)
+
+
+# ---- the product's rigidbody3d portal kernels, run on the CPU (tests/portal_kernel_harness.cpp) ------------------------------
+@pytest.fixture(scope="module")
+def pk(tmp_path_factory):
+    import subprocess
+    out = str(tmp_path_factory.mktemp("pk3") / "libportal_kernels.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-o", out, os.path.join(ROOT, "tests", "portal_kernel_harness.cpp")], check=True)
+    lib = C.CDLL(out)
+    lib.pk_rb3d_set_portals.restype = C.c_int
+    lib.pk_rb3d_set_portals.argtypes = [C.c_uint32] + [C.c_void_p] * 5
+    lib.pk_rb3d_active_set.argtypes = [C.c_uint32] + [C.c_void_p] * 4
+    for f in ("pk_rb3d_num_candidates", "pk_rb3d_num_regular_pairs"):
+        getattr(lib, f).restype = C.c_uint64
+    for f in ("pk_rb3d_num_boxes", "pk_rb3d_num_teleported"):
+        getattr(lib, f).restype = C.c_uint32
+    lib.pk_rb3d_copy.argtypes = [C.c_void_p] * 14
+    lib.pk_rb3d_enforce.argtypes = [C.c_uint32, C.c_void_p]
+    return lib
+
+
+def _pk3_set(pk, scene):
+    P = scene["portals"]
+    a = [np.ascontiguousarray(P[k], dtype=np.float64) for k in ("plane_a_x", "plane_a_n", "plane_b_x", "plane_b_n")]
+    m = np.ascontiguousarray(P["mult"], dtype=np.int32)
+    assert pk.pk_rb3d_set_portals(m.shape[0], *[vp(x) for x in a], vp(m)) == 1
+
+
+K3_CASES = [dict(n=1, seed=1), dict(n=2, seed=2, side=3.0, axes="x"), dict(n=500, seed=3, side=7.0, axes="xz"), dict(n=600, seed=4, side=7.0, axes="xyz", tilt=True),
+            dict(n=700, seed=6, side=7.0, axes="xyz", nfixed_frac=0.35, tilt=True), dict(n=400, seed=7, side=5.0, axes="z", mult=(1, 1, 1))]
+
+
+@pytest.mark.parametrize("case", K3_CASES, ids=lambda c: "n%d-s%d" % (c["n"], c["seed"]))
+def test_rb3d_portal_kernels_on_cpu_match_oracle(case, pk, oracle):
+    scene = scenes.rb3d_periodic_spheres(**case)
+    o = _oracle(scene)
+    q0 = scene["q"]
+    q1, _ = o.flow(2, q0, scene["v"], scene["dt"])
+    ref = o.active_set_portals(q0, q1, "allpairs")
+    assert ref["supported"]
+    _pk3_set(pk, scene)
+    n = scene["geo_of_body"].shape[0]
+    btype = np.ascontiguousarray(np.uint32(1) | (scene["fixed"].astype(np.uint32) << np.uint32(31)))
+    bparam = np.zeros((n, 4))
+    bparam[:, 0] = scene["geo_r"][scene["geo_of_body"]]
+    q0c, q1c = np.ascontiguousarray(q0), np.ascontiguousarray(q1)
+    pk.pk_rb3d_active_set(n, vp(btype), vp(bparam), vp(q0c), vp(q1c))
+    nc, nrp, nb, nt = int(pk.pk_rb3d_num_candidates()), int(pk.pk_rb3d_num_regular_pairs()), int(pk.pk_rb3d_num_boxes()), int(pk.pk_rb3d_num_teleported())
+    got = {"candidates": np.zeros((nc, 2), np.uint32), "reg_pairs": np.zeros((nrp, 2), np.uint32), "box_body": np.zeros(nb, np.uint32), "box_portal": np.zeros(nb, np.uint32),
+           "type": np.zeros(nt, np.uint32), "i": np.zeros(nt, np.uint32), "j": np.zeros(nt, np.uint32), "n": np.zeros((nt, 3)), "p": np.zeros((nt, 3)), "depth": np.zeros(nt),
+           "portal0": np.zeros(nt, np.uint32), "portal1": np.zeros(nt, np.uint32), "x0": np.zeros((nt, 3)), "x1": np.zeros((nt, 3))}
+    pk.pk_rb3d_copy(*[vp(got[k]) for k in ("candidates", "reg_pairs", "box_body", "box_portal", "type", "i", "j", "n", "p", "depth", "portal0", "portal1", "x0", "x1")])
+    for k in ("candidates", "box_body", "box_portal", "portal0", "portal1"):
+        assert np.array_equal(got[k], ref[k]), k
+    real = (ref["candidates"][:, 0] < n) & (ref["candidates"][:, 1] < n)
+    assert np.array_equal(got["reg_pairs"], ref["candidates"][real])
+    nr = ref["n_regular"]
+    tel = slice(nr, nr + nt)
+    assert nt == ref["portal0"].shape[0]
+    for k in ("type", "i", "j"):
+        assert np.array_equal(got[k], ref[k][tel]), k
+    for k in ("n", "p"):
+        assert np.array_equal(got[k].view(np.uint64), ref[k][tel].view(np.uint64)), k
+    assert np.all(np.isnan(got["depth"]))
+    for k in ("x0", "x1"):
+        assert np.array_equal(got[k].view(np.uint64), ref[k].view(np.uint64)), k
+    if case["n"] >= 400:
+        assert nt > 3
+    if case.get("nfixed_frac", 0.0) > 0.0:
+        assert np.any(got["type"] == 30) and np.any(got["type"] == 19)
+
+
+def test_rb3d_portal_enforce_kernel_on_cpu(pk, oracle):
+    scene = scenes.rb3d_periodic_spheres(3000, 8, axes="xyz", tilt=True)
+    o = _oracle(scene)
+    _pk3_set(pk, scene)
+    n = 3000
+    q = scene["q"].copy()
+    q[: 3 * n] += np.random.default_rng(5).uniform(-0.4, 0.4, size=3 * n) * scene["side"]
+    ref = o.enforce_portals(q)
+    got = q.copy()
+    pk.pk_rb3d_enforce(n, vp(got))
+    assert np.array_equal(got, ref) and np.any(got != q)
