@@ -150,3 +150,4 @@ def test_portals_cleared_restores_the_ccd_path(gpu_ctx, oracle):
     assert np.array_equal(got.i, ref["i"]) and np.array_equal(got.j, ref["j"]) and np.array_equal(got.n, ref["n"])
     with pytest.raises(sb.SciSimB200Error):
         sim.teleported()
+
