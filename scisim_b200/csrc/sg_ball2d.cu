@@ -1040,11 +1040,12 @@ int sg_ball2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x, con
   if( d->slab && n > 0 ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_set_portals: portals are not supported in slab mode" ); }
   if( n == 0 && d->px == nullptr ) { return SG_OK; }
   PortalData* x = ball2d_portal_data( d );
-  memset( &x->portals, 0, sizeof( x->portals ) );
-  x->portals.n = n;
+  SgPortals2D ps; // assembled on the side: a rejected call leaves the portals as they were
+  memset( &ps, 0, sizeof( ps ) );
+  ps.n = n;
   for( uint32_t p = 0; p < n; ++p )
   {
-    SgPortal2D& pt = x->portals.p[p];
+    SgPortal2D& pt = ps.p[p];
     for( int k = 0; k < 2; ++k ) { pt.ax[k] = plane_a_x[2 * p + k]; pt.bx[k] = plane_b_x[2 * p + k]; }
     // StaticPlane::StaticPlane (ball2d/StaticGeometry/StaticPlane.cpp:10-14)
     sg_portal_plane_frame( plane_a_n + 2 * p, pt.an, pt.at );
@@ -1052,6 +1053,7 @@ int sg_ball2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x, con
     if( bounds[p] < 0.0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_portals: portal %u has negative bounds", p ); }
     pt.v = v[p]; pt.bounds = bounds[p]; pt.dx = 0.0; // PlanarPortal::PlanarPortal: m_dx( 0.0 )
   }
+  x->portals = ps;
   d->have_result = false;
   return SG_OK;
 }

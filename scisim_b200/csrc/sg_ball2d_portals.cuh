@@ -21,6 +21,7 @@
 //   contacts  teleported contacts behind the regular ones (plain or kinematic-kick), then drums and planes as always
 #include "sg_boxes.cuh"
 #include "sg_portal2d.h"
+#include "sg_pair_sort_host.cuh"
 
 using PortalBoxPolicy = AabbPolicy<2, 1>;
 
@@ -207,21 +208,7 @@ static int ball2d_portal_active_set_device( sg_ctx* ctx, Ball2DData* d, const in
   }
   if( nraw > 0 )
   {
-    if( m > nraw ) { SG_LAUNCH( ctx, "b2p_sort_pad", 0.0, k_b2p_sort_pad<<<sg_div_up( m - nraw, 256 ), 256, 0, ctx->stream>>>( nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) ); }
-    // tiles of SG_B2P_SORT_TILE elements are sorted in shared memory; only strides that cross tiles take a launch each
-    const unsigned ntiles = sg_div_up( m, SG_B2P_SORT_TILE );
-    SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, true><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, 0u, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-    for( uint32_t k = 2u * SG_B2P_SORT_TILE; k <= m; k <<= 1 )
-    {
-      for( uint32_t j = k >> 1; j >= uint32_t( SG_B2P_SORT_TILE ); j >>= 1 )
-      {
-        SG_LAUNCH( ctx, "b2p_bitonic", double( m ) * 24.0, k_b2p_bitonic<<<sg_div_up( m, 256 ), 256, 0, ctx->stream>>>( m, j, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-      }
-      SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, false><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-    }
-    SG_CUDA( ctx, cudaMemsetAsync( x->utotal.ptr, 0, 4, ctx->stream ) );
-    SG_LAUNCH( ctx, "b2p_unique", double( nraw ) * 12.0, k_b2p_unique<<<sg_div_up( nraw, 256 ), 256, 0, ctx->stream>>>( nraw, x->tc_key.as<unsigned long long>(), x->uflag.as<uint32_t>() ) );
-    rc = sg_exclusive_scan<ScanU32>( ctx, "b2p_unique_scan", x->uflag.as<uint32_t>(), nullptr, nraw, nraw, x->u_partials.as<uint32_t>(), x->uoff.as<uint32_t>(), x->utotal.as<uint32_t>(), false );
+    rc = sg_tele_sort_unique( ctx, nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>(), x->uflag.as<uint32_t>(), x->uoff.as<uint32_t>(), x->u_partials.as<uint32_t>(), x->utotal.as<uint32_t>() );
     if( rc != SG_OK ) { return rc; }
     SG_LAUNCH( ctx, "b2p_tele_contacts", double( nraw ) * 200.0, k_b2p_tele_contacts<<<sg_div_up( nraw, 128 ), 128, 0, ctx->stream>>>( x->portals, nraw, x->tc_idx.as<uint32_t>(), x->uflag.as<uint32_t>(), x->uoff.as<uint32_t>(),
                x->tc_info.as<uint4>(), d->Q0(), d->Q1(), d->R(), x->n_reg, out, x->x0t.as<double2>(), x->x1t.as<double2>(), x->kick.as<double2>(), x->tp0.as<uint32_t>(), x->tp1.as<uint32_t>() ) );

@@ -455,6 +455,7 @@ struct ScanU32To64b
 
 // ---- portals (rigidbody2d/PlanarPortal.h): kernels, per-context data ------------------------------------
 #include "sg_rb2d_portal_kernels.cuh"
+#include "sg_pair_sort_host.cuh"
 
 struct Rb2dPortalData
 {
@@ -756,19 +757,7 @@ static int rb2d_portal_active_set_device( sg_ctx* ctx, Rb2dData* d )
   }
   if( nraw > 0 )
   {
-    if( m > nraw ) { SG_LAUNCH( ctx, "b2p_sort_pad", 0.0, k_b2p_sort_pad<<<sg_div_up( m - nraw, 256 ), 256, 0, ctx->stream>>>( nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) ); }
-    const unsigned ntiles = sg_div_up( m, SG_B2P_SORT_TILE );
-    SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, true><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, 0u, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-    for( uint32_t k = 2u * SG_B2P_SORT_TILE; k <= m; k <<= 1 )
-    {
-      for( uint32_t j = k >> 1; j >= uint32_t( SG_B2P_SORT_TILE ); j >>= 1 )
-      {
-        SG_LAUNCH( ctx, "b2p_bitonic", double( m ) * 24.0, k_b2p_bitonic<<<sg_div_up( m, 256 ), 256, 0, ctx->stream>>>( m, j, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-      }
-      SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, false><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-    }
-    SG_LAUNCH( ctx, "b2p_unique", double( nraw ) * 12.0, k_b2p_unique<<<sg_div_up( nraw, 256 ), 256, 0, ctx->stream>>>( nraw, x->tc_key.as<unsigned long long>(), x->uflag.as<uint32_t>() ) );
-    rc = sg_exclusive_scan<ScanU32>( ctx, "b2p_unique_scan", x->uflag.as<uint32_t>(), nullptr, nraw, nraw, x->u_partials.as<uint32_t>(), x->uoff.as<uint32_t>(), x->utotal.as<uint32_t>(), false );
+    rc = sg_tele_sort_unique( ctx, nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>(), x->uflag.as<uint32_t>(), x->uoff.as<uint32_t>(), x->u_partials.as<uint32_t>(), x->utotal.as<uint32_t>() );
     if( rc != SG_OK ) { return rc; }
   }
   h64[3] = 0ull; h32[4] = 0u; h32[5] = 0u;
@@ -923,11 +912,12 @@ int sg_rb2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x, const
   if( n == 0 && d->px == nullptr ) { return SG_OK; }
   if( d->px == nullptr ) { d->px = new Rb2dPortalData; }
   Rb2dPortalData* x = d->px;
-  memset( &x->portals, 0, sizeof( x->portals ) );
-  x->portals.n = n;
+  SgPortals2D ps; // assembled on the side: a rejected call leaves the portals as they were
+  memset( &ps, 0, sizeof( ps ) );
+  ps.n = n;
   for( uint32_t p = 0; p < n; ++p )
   {
-    SgPortal2D& pt = x->portals.p[p];
+    SgPortal2D& pt = ps.p[p];
     for( int k = 0; k < 2; ++k ) { pt.ax[k] = plane_a_x[2 * p + k]; pt.bx[k] = plane_b_x[2 * p + k]; }
     // RigidBody2DStaticPlane::RigidBody2DStaticPlane( x, n ): n as given (rigidbody2d/RigidBody2DStaticPlane.cpp:10-14)
     sg_portal_plane_frame_as_given( plane_a_n + 2 * p, pt.an, pt.at );
@@ -935,6 +925,7 @@ int sg_rb2d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x, const
     if( bounds[p] < 0.0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_set_portals: portal %u has negative bounds", p ); }
     pt.v = v[p]; pt.bounds = bounds[p]; pt.dx = 0.0;
   }
+  x->portals = ps;
   d->have_result = false;
   return SG_OK;
 }

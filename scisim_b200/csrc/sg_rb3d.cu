@@ -934,6 +934,7 @@ struct ScanU32To64
 
 // ---- portals (rigidbody3d/Portals/PlanarPortal.h), sphere scenes: kernels, per-context data ----------------
 #include "sg_rb3d_portal_kernels.cuh"
+#include "sg_pair_sort_host.cuh"
 
 struct Rb3dPortalData
 {
@@ -1368,19 +1369,7 @@ static int rb3d_portal_active_set_device( sg_ctx* ctx, Rb3dData* d )
   }
   if( nraw > 0 )
   {
-    if( m > nraw ) { SG_LAUNCH( ctx, "b2p_sort_pad", 0.0, k_b2p_sort_pad<<<sg_div_up( m - nraw, 256 ), 256, 0, ctx->stream>>>( nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) ); }
-    const unsigned ntiles = sg_div_up( m, SG_B2P_SORT_TILE );
-    SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, true><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, 0u, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-    for( uint32_t k = 2u * SG_B2P_SORT_TILE; k <= m; k <<= 1 )
-    {
-      for( uint32_t j = k >> 1; j >= uint32_t( SG_B2P_SORT_TILE ); j >>= 1 )
-      {
-        SG_LAUNCH( ctx, "b2p_bitonic", double( m ) * 24.0, k_b2p_bitonic<<<sg_div_up( m, 256 ), 256, 0, ctx->stream>>>( m, j, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-      }
-      SG_LAUNCH( ctx, "b2p_bitonic_tile", double( m ) * 24.0, k_b2p_bitonic_tile<SG_B2P_SORT_TILE, SG_B2P_SORT_THREADS, false><<<ntiles, SG_B2P_SORT_THREADS, 0, ctx->stream>>>( m, k, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>() ) );
-    }
-    SG_LAUNCH( ctx, "b2p_unique", double( nraw ) * 12.0, k_b2p_unique<<<sg_div_up( nraw, 256 ), 256, 0, ctx->stream>>>( nraw, x->tc_key.as<unsigned long long>(), x->uflag.as<uint32_t>() ) );
-    rc = sg_exclusive_scan<ScanU32>( ctx, "b2p_unique_scan", x->uflag.as<uint32_t>(), nullptr, nraw, nraw, x->u_partials.as<uint32_t>(), x->uoff.as<uint32_t>(), x->utotal.as<uint32_t>(), false );
+    rc = sg_tele_sort_unique( ctx, nraw, m, x->tc_key.as<unsigned long long>(), x->tc_idx.as<uint32_t>(), x->uflag.as<uint32_t>(), x->uoff.as<uint32_t>(), x->u_partials.as<uint32_t>(), x->utotal.as<uint32_t>() );
     if( rc != SG_OK ) { return rc; }
   }
   h64[3] = 0ull; h32[4] = 0u; h32[5] = 0u;
