@@ -139,3 +139,27 @@ def test_rb2d_portals_cleared_restores_the_swept_path(gpu_ctx, oracle):
     assert np.array_equal(got.i, ref["i"]) and np.array_equal(got.j, ref["j"]) and np.array_equal(got.n, ref["n"])
     with pytest.raises(sb.SciSimB200Error):
         sim.teleported()
+
+
+def test_rb2d_portal_trajectory(gpu_ctx, oracle):
+    """RigidBody2DSim::flow's portal bookkeeping over 12 steps without contact response (RigidBody2DSim.cpp:818-874)."""
+    import scisim_b200 as sb
+    s = scenes.rb2d_periodic(1500, 21, side=30.0, lees_edwards=2.0, vmax=20.0, dt=0.02)
+    sim = make_sim(s, gpu_ctx)
+    o = make_oracle(s)
+    q, v = s["q"].copy(), s["v"].copy()
+    rq, rv = q.copy(), v.copy()
+    crossed = 0
+    for it in range(1, 13):
+        assert np.array_equal(sim.updatePeriodicBoundaryConditionsStartOfStep(it, s["dt"]), o.update_portals(it * s["dt"]))
+        q1, v1 = sb.SymplecticEulerMap().flow(q, v, sim, it, s["dt"])
+        rq1, rv1 = o.flow(0, rq, rv, s["dt"])
+        assert np.array_equal(q1, rq1) and np.array_equal(v1, rv1)
+        ref = o.active_set_portals(rq, rq1)
+        got = sim.computeActiveSet(q, q1, resident=True)
+        assert_equal(got, sim.teleported(), ref, exact=True)
+        q, v = sim.enforcePeriodicBoundaryConditions(q1, v1)
+        rq, rv = o.enforce_portals(rq1, rv1)
+        assert np.array_equal(q, rq) and np.array_equal(v, rv)
+        crossed += int(np.any(q.reshape(-1, 3) != q1.reshape(-1, 3), axis=1).sum())
+    assert crossed > 50

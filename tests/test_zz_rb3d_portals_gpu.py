@@ -121,3 +121,28 @@ def test_rb3d_portals_cleared_restores_the_fused_sphere_path(gpu_ctx, oracle):
     assert np.array_equal(got.i, ref["i"]) and np.array_equal(got.j, ref["j"]) and np.array_equal(got.n, ref["n"])
     with pytest.raises(sb.SciSimB200Error):
         sim.teleported()
+
+
+def test_rb3d_portal_trajectory(gpu_ctx, oracle):
+    """RigidBody3DSim::flow's portal bookkeeping over 10 steps without contact response (RigidBody3DSim.cpp:513-550)."""
+    import scisim_b200 as sb
+    s = scenes.rb3d_periodic_spheres(2000, 21, side=14.0, axes="xz")
+    s["v"][: 3 * 2000] *= 8.0
+    sim = make_sim(s, gpu_ctx)
+    o = make_oracle(s)
+    q, v = s["q"].copy(), s["v"].copy()
+    rq, rv = q.copy(), v.copy()
+    crossed = 0
+    for it in range(1, 11):
+        q1, v1 = sb.SplitHamMap().flow(q, v, sim, it, s["dt"])
+        rq1, rv1 = o.flow(2, rq, rv, s["dt"])
+        assert np.array_equal(q1, rq1) and np.array_equal(v1, rv1)
+        ref = o.active_set_portals(rq, rq1)
+        got = sim.computeActiveSet(q, q1, resident=True)
+        assert_equal(got, sim.teleported(), ref)
+        q = sim.enforcePeriodicBoundaryConditions(q1)
+        rq = o.enforce_portals(rq1)
+        v, rv = v1, rv1
+        assert np.array_equal(q, rq)
+        crossed += int(np.any(q[: 6000].reshape(-1, 3) != q1[: 6000].reshape(-1, 3), axis=1).sum())
+    assert crossed > 30
