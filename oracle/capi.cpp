@@ -375,6 +375,26 @@ void orc_rb3d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32_t
   }
 }
 
+// single-mesh routines by themselves (checked against the reference's own RigidBodyTriangleMesh.cpp in tests/test_oracle_vs_reference.py)
+int orc_rb3d_mesh_detect( const void* hv, uint32_t mesh, const double* x, double* n_out )
+{
+  const RB3DHandle* h = static_cast<const RB3DHandle*>( hv );
+  V3 n{ 0.0, 0.0, 0.0 };
+  const bool hit = h->scene.meshes[mesh].detectCollision( V3{ x[0], x[1], x[2] }, n );
+  n_out[0] = n.x; n_out[1] = n.y; n_out[2] = n.z;
+  return hit ? 1 : 0;
+}
+// RigidBodyTriangleMesh::computeAABB for body b of the scene placed at ( cm, R ); out = min(3), max(3)
+void orc_rb3d_body_aabb( const void* hv, uint32_t b, const double* cm, const double* R, double* out )
+{
+  const RB3DHandle* h = static_cast<const RB3DHandle*>( hv );
+  M3 Rm;
+  for( int k = 0; k < 9; ++k ) { Rm.m[k] = R[k]; }
+  Box<3> bx;
+  computeAABB( h->scene, b, V3{ cm[0], cm[1], cm[2] }, Rm, bx );
+  for( int k = 0; k < 3; ++k ) { out[k] = bx.lo[k]; out[3 + k] = bx.hi[k]; }
+}
+
 // ---- rigidbody3d portals (oracle/rb3d_portals.h) ---------------------------------------------------------
 // StaticPlane( x, n ) frame: out = n (3), t0 (3), t1 (3)
 void orc_rb3d_plane_frame( const double* x, const double* n, double* out )

@@ -14,8 +14,23 @@
 
 namespace MathUtilities
 {
-  template<typename T> T deserialize( std::istream& stm ) { T v; stm.read( reinterpret_cast<char*>( v.data() ), v.size() * sizeof( scalar ) ); return v; }
-  template<typename T> void serialize( const T& v, std::ostream& stm ) { stm.write( reinterpret_cast<const char*>( v.data() ), v.size() * sizeof( scalar ) ); }
+  // fixed sizes: the raw coefficients; the dynamic shapes of the stand-in ( R x N, N x 1 ): rows, cols, then the coefficients.  Both ends
+  // of every stream that goes through here are written by oracle/ref_shims (the reference's own file format is not involved).
+  template<typename T> void readShape( T&, std::istream&, decltype( &T::s )* = nullptr ) {}
+  template<typename T> void readShape( T& v, std::istream& stm, decltype( &T::v )* = nullptr )
+  {
+    long long rc[2];
+    stm.read( reinterpret_cast<char*>( rc ), sizeof( rc ) );
+    v.resize( int( rc[0] ), int( rc[1] ) );
+  }
+  template<typename T> void writeShape( const T&, std::ostream&, decltype( &T::s )* = nullptr ) {}
+  template<typename T> void writeShape( const T& v, std::ostream& stm, decltype( &T::v )* = nullptr )
+  {
+    const long long rc[2] = { v.rows(), v.cols() };
+    stm.write( reinterpret_cast<const char*>( rc ), sizeof( rc ) );
+  }
+  template<typename T> T deserialize( std::istream& stm ) { T v; readShape( v, stm ); stm.read( reinterpret_cast<char*>( v.data() ), v.size() * sizeof( *v.data() ) ); return v; }
+  template<typename T> void serialize( const T& v, std::ostream& stm ) { writeShape( v, stm ); stm.write( reinterpret_cast<const char*>( v.data() ), v.size() * sizeof( *v.data() ) ); }
 }
 
 #endif

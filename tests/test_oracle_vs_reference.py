@@ -232,3 +232,98 @@ def test_geometry_aabbs_3d_and_2d(oracle):
         lib.orc_rb2d_aabb(t, 0.45, vp(half), vp(q0b), vp(q1b), swept, vp(a))
         ref2.ref_rb2d_aabb(t, 0.45, vp(half), vp(q0b), vp(q1b), swept, vp(b))
         assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (t, swept, k)
+
+
+def _ref_mesh(ref, m):
+    ref.ref_rb3d_mesh_create.restype = C.c_void_p
+    ref.ref_rb3d_mesh_create.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    a = [np.ascontiguousarray(m[k], dtype=np.float64) for k in ("verts", "samples", "hull", "cell_delta", "origin", "sdf")]
+    dims = np.ascontiguousarray(m["dims"], dtype=np.uint32)
+    return ref.ref_rb3d_mesh_create(a[0].shape[0], vp(a[0]), a[1].shape[0], vp(a[1]), a[2].shape[0], vp(a[2]), vp(a[3]), vp(dims), vp(a[4]), vp(a[5]))
+
+
+def test_mesh_sdf_narrow_phase_against_the_reference_sources(oracle):
+    """a15: RigidBodyTriangleMesh::computeAABB / detectCollision (trilinear distance + gradient on the signed distance grid) and
+    MeshMeshUtilities::computeActiveSet / computeMeshHalfPlaneActiveSet -- the reference's own sources (built through the mesh class's
+    stream constructor) against the restatement, bit for bit: single samples, whole mesh pairs in both directions, hull-vertex sets."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    if not hasattr(ref, "ref_rb3d_mesh_mesh"):
+        pytest.skip("oracle/_ref predates the mesh shims")
+    s = scenes.rb3d_random_meshes(14, 31, nplanes=2)
+    o = ob.RB3DOracle(s)
+    lib = oracle
+    lib.orc_rb3d_mesh_detect.restype = C.c_int
+    lib.orc_rb3d_mesh_detect.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.orc_rb3d_body_aabb.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    ref.ref_rb3d_mesh_detect.restype = C.c_int
+    ref.ref_rb3d_mesh_detect.argtypes = [C.c_void_p] * 3
+    ref.ref_rb3d_mesh_aabb.argtypes = [C.c_void_p] * 4
+    ref.ref_rb3d_mesh_mesh.restype = C.c_uint64
+    ref.ref_rb3d_mesh_mesh.argtypes = [C.c_void_p] * 8 + [C.c_uint64]
+    ref.ref_rb3d_mesh_halfplane.restype = C.c_uint64
+    ref.ref_rb3d_mesh_halfplane.argtypes = [C.c_void_p] * 6 + [C.c_uint64]
+    ref.ref_rb3d_mesh_destroy.argtypes = [C.c_void_p]
+    meshes = [_ref_mesh(ref, m) for m in s["meshes"]]
+    rng = np.random.default_rng(12)
+    # ---- detectCollision: points all over (and beyond) the grid
+    hits = 0
+    for mi, m in enumerate(s["meshes"]):
+        lo = np.asarray(m["origin"], dtype=np.float64)
+        hi = lo + (np.asarray(m["dims"]) - 1) * np.asarray(m["cell_delta"])
+        for k in range(6000):
+            x = np.ascontiguousarray(rng.uniform(lo - 0.1, hi + 0.1))
+            a, b = np.zeros(3), np.zeros(3)
+            ha = lib.orc_rb3d_mesh_detect(o.h, mi, vp(x), vp(a))
+            hb = ref.ref_rb3d_mesh_detect(meshes[mi], vp(x), vp(b))
+            assert ha == hb and (not ha or np.array_equal(a.view(np.uint64), b.view(np.uint64))), (mi, x)
+            hits += ha
+    assert hits > 500
+    # ---- AABBs and whole pairs at the scene's own configuration
+    n = s["geo_of_body"].shape[0]
+    q = s["q"]
+    X = q[: 3 * n].reshape(n, 3)
+    R = q[3 * n:].reshape(n, 9)
+    for b in range(n):
+        a, c = np.zeros(6), np.zeros(6)
+        lib.orc_rb3d_body_aabb(o.h, b, vp(np.ascontiguousarray(X[b])), vp(np.ascontiguousarray(R[b])), vp(a))
+        ref.ref_rb3d_mesh_aabb(meshes[int(s["geo_mesh"][s["geo_of_body"][b]])], vp(np.ascontiguousarray(X[b])), vp(np.ascontiguousarray(R[b])), vp(c))
+        assert np.array_equal(a.view(np.uint64), c.view(np.uint64)), b
+    act = o.active_set(q, q, "allpairs")
+    assert act["supported"]
+    fixed = s["fixed"].astype(bool)
+    bb = np.isin(act["type"], [12, 13])
+    total = 0
+    for (i, j) in act["candidates"]:
+        if fixed[i] and fixed[j]:
+            continue
+        b0, b1 = (int(j), int(i)) if fixed[i] else (int(i), int(j))   # the kinematic body goes second
+        cap = 20000
+        p, nn = np.zeros((cap, 3)), np.zeros((cap, 3))
+        cnt = int(ref.ref_rb3d_mesh_mesh(meshes[int(s["geo_mesh"][s["geo_of_body"][b0]])], vp(np.ascontiguousarray(X[b0])), vp(np.ascontiguousarray(R[b0])),
+                                         meshes[int(s["geo_mesh"][s["geo_of_body"][b1]])], vp(np.ascontiguousarray(X[b1])), vp(np.ascontiguousarray(R[b1])), vp(p), vp(nn), cap))
+        sel = bb & (act["i"] == b0) & (act["j"] == b1)
+        assert int(sel.sum()) == cnt, (i, j)
+        assert np.array_equal(act["p"][sel].view(np.uint64), p[:cnt].view(np.uint64)) and np.array_equal(act["n"][sel].view(np.uint64), nn[:cnt].view(np.uint64)), (i, j)
+        total += cnt
+    assert total == int(bb.sum()) and total > 200
+    # ---- plane vs mesh: hull vertices below each plane
+    pl = act["type"] == 16
+    assert pl.sum() > 10
+    for k in range(s["plane_x"].shape[0]):
+        x0 = np.ascontiguousarray(s["plane_x"][k])
+        nrm = np.ascontiguousarray(s["plane_n"][k] / np.linalg.norm(s["plane_n"][k]))
+        # the oracle normalises the plane as StaticPlane does; take its stored normal from a contact when there is one
+        sel = pl & (act["j"] == k)
+        if sel.any():
+            nrm = np.ascontiguousarray(act["n"][sel][0])
+        for b in range(n):
+            if fixed[b]:
+                continue
+            out = np.zeros(4096, dtype=np.uint32)
+            cnt = int(ref.ref_rb3d_mesh_halfplane(meshes[int(s["geo_mesh"][s["geo_of_body"][b]])], vp(np.ascontiguousarray(X[b])), vp(np.ascontiguousarray(R[b])), vp(x0), vp(nrm), vp(out), 4096))
+            mine = act["aux"][sel & (act["i"] == b)]
+            assert np.array_equal(mine, out[:cnt]), (k, b)
+    for m in meshes:
+        ref.ref_rb3d_mesh_destroy(m)
