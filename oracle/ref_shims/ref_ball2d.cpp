@@ -2,11 +2,17 @@
 //   ball2d/SpatialGridDetector.cpp                               (AABB, getPotentialOverlaps, getPotentialOverlapsAllPairs)
 //   scisim/CollisionDetection/CollisionDetectionUtilities.cpp    (computeCCDQuadraticCoeffs, ballBallCCDCollisionHappens)
 //   ball2d/StaticGeometry/StaticPlane.cpp, ball2d/Portals/PlanarPortal.cpp   (portal touch tests, teleports, kinematic velocities)
+//   ball2d/SymplecticEulerMap.cpp, ball2d/VerletMap.cpp, ball2d/Forces/Ball2DGravityForce.cpp (+ Ball2DForce.cpp,
+//   scisim/UnconstrainedMaps/UnconstrainedMap.cpp, FlowableSystem.cpp)       (the two unconstrained maps with the gravity force)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).  The glue between them (swept boxes,
 // pair loop) restates ball2d/Ball2DSim.cpp:553-608 and is marked as such.
 #include "ball2d/SpatialGridDetector.h"
 #include "scisim/CollisionDetection/CollisionDetectionUtilities.h"
 #include "ball2d/Portals/PlanarPortal.h"
+#include "ball2d/SymplecticEulerMap.h"
+#include "ball2d/VerletMap.h"
+#include "ball2d/Forces/Ball2DGravityForce.h"
+#include "scisim/UnconstrainedMaps/FlowableSystem.h"
 
 #include <cstdint>
 
@@ -102,6 +108,65 @@ uint32_t ref_portal_probe( const void* pv, const double* x, const double r, doub
   }
   if( p.pointInsidePortal( xin ) ) { flags |= 8u; }
   return flags;
+}
+
+}
+
+// ---- the unconstrained maps: a FlowableSystem with just what SymplecticEulerMap / VerletMap ask of Ball2DSim -- the diagonal M and Minv
+// ( Minv = 1.0 / m, ball2d/Ball2DState.cpp:54-66 ) and computeForce = setZero + the gravity force ( ball2d/Ball2DSim.cpp:72-78 ) ------------
+namespace
+{
+class ShimBall2DSystem final : public FlowableSystem
+{
+public:
+  ShimBall2DSystem( const uint32_t n, const double* m, const double* r, const double* g )
+  : m_force( Vector2s{ g[0], g[1] } )
+  {
+    std::vector<double> md( 2 * size_t( n ) ), mi( 2 * size_t( n ) );
+    for( uint32_t b = 0; b < n; ++b ) { md[2 * b] = md[2 * b + 1] = m[b]; mi[2 * b] = mi[2 * b + 1] = 1.0 / m[b]; }
+    m_M.setDiagonal( md.data(), int( md.size() ) ); m_Minv.setDiagonal( mi.data(), int( mi.size() ) );
+    m_r.resize( int( n ) );
+    for( uint32_t b = 0; b < n; ++b ) { m_r( int( b ) ) = r[b]; }
+  }
+  virtual int nqdofs() const override { return m_M.rows(); }
+  virtual int nvdofs() const override { return m_M.rows(); }
+  virtual unsigned numVelDoFsPerBody() const override { return 2; }
+  virtual unsigned ambientSpaceDimensions() const override { return 2; }
+  virtual bool isKinematicallyScripted( const int ) const override { return false; }
+  virtual void computeForce( const VectorXs& q, const VectorXs& v, const scalar& t, VectorXs& F ) override
+  {
+    F.setZero();
+    m_force.computeForce( q, v, m_M, m_r, F );
+  }
+  virtual void zeroOutForcesOnFixedBodies( VectorXs& ) const override {}
+  virtual void linearInertialConfigurationUpdate( const VectorXs&, const VectorXs&, const scalar&, VectorXs& ) const override { std::abort(); }
+  virtual const SparseMatrixsc& M() const override { return m_M; }
+  virtual const SparseMatrixsc& Minv() const override { return m_Minv; }
+  virtual const SparseMatrixsc& M0() const override { return m_M; }
+  virtual const SparseMatrixsc& Minv0() const override { return m_Minv; }
+  virtual void computeMomentum( const VectorXs&, VectorXs& ) const override { std::abort(); }
+  virtual void computeAngularMomentum( const VectorXs&, VectorXs& ) const override { std::abort(); }
+  virtual std::string name() const override { return "shim_ball_2d"; }
+private:
+  SparseMatrixsc m_M, m_Minv;
+  VectorXs m_r;
+  Ball2DGravityForce m_force;
+};
+}
+
+extern "C"
+{
+
+// kind 0: SymplecticEulerMap::flow, 1: VerletMap::flow; q, v: 2n doubles
+void ref_ball2d_flow( const int kind, const uint32_t n, const double* m, const double* r, const double* g, const double* q0, const double* v0, const unsigned iteration, const double dt,
+                      double* q1, double* v1 )
+{
+  ShimBall2DSystem sys{ n, m, r, g };
+  VectorXs vq0( int( 2 * n ) ), vv0( int( 2 * n ) ), vq1( int( 2 * n ) ), vv1( int( 2 * n ) );
+  for( uint32_t k = 0; k < 2 * n; ++k ) { vq0( int( k ) ) = q0[k]; vv0( int( k ) ) = v0[k]; }
+  if( kind == 0 ) { SymplecticEulerMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
+  else { VerletMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
+  for( uint32_t k = 0; k < 2 * n; ++k ) { q1[k] = vq1( int( k ) ); v1[k] = vv1( int( k ) ); }
 }
 
 }

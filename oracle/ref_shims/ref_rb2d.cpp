@@ -3,6 +3,7 @@
 //   rigidbody2d/BoxBoxTools.cpp     (BoxBoxTools::isActive)
 //   rigidbody2d/CircleBoxTools.cpp  (CircleBoxTools::isActive)
 //   rigidbody2d/CircleGeometry.cpp, BoxGeometry.cpp (+ RigidBody2DGeometry.cpp)   (computeCollisionAABB, computeAABB)
+//   rigidbody2d/SymplecticEulerMap.cpp, VerletMap.cpp, NearEarthGravityForce.cpp (+ RigidBody2DForce.cpp, scisim/UnconstrainedMaps/*.cpp)   (the maps)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).
 #include "rigidbody2d/SpatialGrid.h"
 #include "rigidbody2d/BoxBoxTools.h"
@@ -11,6 +12,10 @@
 #include "rigidbody2d/PlanarPortal.h"
 #include "rigidbody2d/CircleGeometry.h"
 #include "rigidbody2d/BoxGeometry.h"
+#include "rigidbody2d/SymplecticEulerMap.h"
+#include "rigidbody2d/VerletMap.h"
+#include "rigidbody2d/NearEarthGravityForce.h"
+#include "scisim/UnconstrainedMaps/FlowableSystem.h"
 
 #include <cstdint>
 
@@ -91,6 +96,64 @@ void ref_rb2d_aabb( const int type, const double r, const double* half, const do
     if( swept ) { g.computeCollisionAABB( x0, q0b[2], x1, q1b[2], mn, mx ); } else { g.computeAABB( x1, q1b[2], mn, mx ); }
   }
   out[0] = mn( 0 ); out[1] = mn( 1 ); out[2] = mx( 0 ); out[3] = mx( 1 );
+}
+
+}
+
+// ---- the unconstrained maps: a FlowableSystem with what they ask of RigidBody2DSim -- the diagonal M ( m, m, I per body ), Minv = 1 / M
+// ( rigidbody2d/RigidBody2DState.cpp:31-43 ), the kinematic flags and computeForce = setZero + the forces ( RigidBody2DSim.cpp:104-113 ) -------
+namespace
+{
+class ShimRB2DSystem final : public FlowableSystem
+{
+public:
+  ShimRB2DSystem( const uint32_t n, const double* M, const uint8_t* fixed, const double* g )
+  : m_fixed( fixed, fixed + n )
+  , m_force( Vector2s{ g[0], g[1] } )
+  {
+    std::vector<double> mi( 3 * size_t( n ) );
+    for( size_t k = 0; k < mi.size(); ++k ) { mi[k] = 1.0 / M[k]; }
+    m_M.setDiagonal( M, int( 3 * n ) ); m_Minv.setDiagonal( mi.data(), int( 3 * n ) );
+  }
+  virtual int nqdofs() const override { return m_M.rows(); }
+  virtual int nvdofs() const override { return m_M.rows(); }
+  virtual unsigned numVelDoFsPerBody() const override { return 3; }
+  virtual unsigned ambientSpaceDimensions() const override { return 2; }
+  virtual bool isKinematicallyScripted( const int i ) const override { return m_fixed[size_t( i )] != 0; }
+  virtual void computeForce( const VectorXs& q, const VectorXs& v, const scalar& t, VectorXs& F ) override
+  {
+    F.setZero();
+    m_force.computeForce( q, v, m_M, F );
+  }
+  virtual void zeroOutForcesOnFixedBodies( VectorXs& ) const override { std::abort(); }
+  virtual void linearInertialConfigurationUpdate( const VectorXs&, const VectorXs&, const scalar&, VectorXs& ) const override { std::abort(); }
+  virtual const SparseMatrixsc& M() const override { return m_M; }
+  virtual const SparseMatrixsc& Minv() const override { return m_Minv; }
+  virtual const SparseMatrixsc& M0() const override { return m_M; }
+  virtual const SparseMatrixsc& Minv0() const override { return m_Minv; }
+  virtual void computeMomentum( const VectorXs&, VectorXs& ) const override { std::abort(); }
+  virtual void computeAngularMomentum( const VectorXs&, VectorXs& ) const override { std::abort(); }
+  virtual std::string name() const override { return "shim_rigid_body_2d"; }
+private:
+  SparseMatrixsc m_M, m_Minv;
+  std::vector<uint8_t> m_fixed;
+  NearEarthGravityForce m_force;
+};
+}
+
+extern "C"
+{
+
+// kind 0: SymplecticEulerMap::flow, 1: VerletMap::flow; q, v: 3n doubles ( x, y, theta per body ); M: the 3n mass diagonal
+void ref_rb2d_flow( const int kind, const uint32_t n, const double* M, const uint8_t* fixed, const double* g, const double* q0, const double* v0, const unsigned iteration, const double dt,
+                    double* q1, double* v1 )
+{
+  ShimRB2DSystem sys{ n, M, fixed, g };
+  VectorXs vq0( int( 3 * n ) ), vv0( int( 3 * n ) ), vq1( int( 3 * n ) ), vv1( int( 3 * n ) );
+  for( uint32_t k = 0; k < 3 * n; ++k ) { vq0( int( k ) ) = q0[k]; vv0( int( k ) ) = v0[k]; }
+  if( kind == 0 ) { SymplecticEulerMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
+  else { VerletMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
+  for( uint32_t k = 0; k < 3 * n; ++k ) { q1[k] = vq1( int( k ) ); v1[k] = vv1( int( k ) ); }
 }
 
 }

@@ -327,3 +327,46 @@ def test_mesh_sdf_narrow_phase_against_the_reference_sources(oracle):
             assert np.array_equal(mine, out[:cnt]), (k, b)
     for m in meshes:
         ref.ref_rb3d_mesh_destroy(m)
+
+
+@pytest.mark.parametrize("kind", [0, 1], ids=["symplectic_euler", "verlet"])
+def test_ball2d_maps_against_the_reference_sources(oracle, kind):
+    """a1 / a2 / a6: ball2d/SymplecticEulerMap.cpp, VerletMap.cpp and Forces/Ball2DGravityForce.cpp, compiled unchanged and driven
+    through a FlowableSystem with Ball2DSim's diagonal M / Minv and computeForce ( setZero + gravity ), against the restated flow."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_ball2d.so")
+    if not hasattr(ref, "ref_ball2d_flow"):
+        pytest.skip("oracle/_ref predates the map shim")
+    ref.ref_ball2d_flow.argtypes = [C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint, C.c_double, C.c_void_p, C.c_void_p]
+    for n, seed in ((1, 1), (37, 2), (5000, 3)):
+        s = scenes.ball2d_random(n, seed)
+        o = ob.Ball2DOracle(s)
+        q1, v1 = o.flow(kind, s["q"], s["v"], s["dt"])
+        a = [np.ascontiguousarray(s[k], dtype=np.float64) for k in ("m", "r", "g", "q", "v")]
+        rq1, rv1 = np.zeros(2 * n), np.zeros(2 * n)
+        ref.ref_ball2d_flow(kind, n, vp(a[0]), vp(a[1]), vp(a[2]), vp(a[3]), vp(a[4]), 3, float(s["dt"]), vp(rq1), vp(rv1))
+        assert np.array_equal(q1.view(np.uint64), rq1.view(np.uint64)) and np.array_equal(v1.view(np.uint64), rv1.view(np.uint64)), (n, seed)
+        assert np.any(q1 != s["q"]) and np.any(v1 != s["v"])
+
+
+@pytest.mark.parametrize("kind", [0, 1], ids=["symplectic_euler", "verlet"])
+def test_rb2d_maps_against_the_reference_sources(oracle, kind):
+    """a3: rigidbody2d/SymplecticEulerMap.cpp, VerletMap.cpp and NearEarthGravityForce.cpp compiled unchanged ( time argument
+    ( iteration - 1 ) * dt, forces zeroed on kinematically scripted bodies ) against the restated flow."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb2d.so")
+    if not hasattr(ref, "ref_rb2d_flow"):
+        pytest.skip("oracle/_ref predates the map shim")
+    ref.ref_rb2d_flow.argtypes = [C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint, C.c_double, C.c_void_p, C.c_void_p]
+    for n, seed, kw in ((1, 1, {}), (60, 2, {}), (3000, 3, dict(kinds=("circle",), nfixed_frac=0.3))):
+        s = scenes.rb2d_random(n, seed, **kw)
+        o = ob.RB2DOracle(s)
+        q1, v1 = o.flow(kind, s["q"], s["v"], s["dt"])
+        M, g, q0, v0 = [np.ascontiguousarray(s[k], dtype=np.float64) for k in ("M", "g", "q", "v")]
+        fixed = np.ascontiguousarray(s["fixed"], dtype=np.uint8)
+        rq1, rv1 = np.zeros(3 * n), np.zeros(3 * n)
+        ref.ref_rb2d_flow(kind, n, vp(M), vp(fixed), vp(g), vp(q0), vp(v0), 2, float(s["dt"]), vp(rq1), vp(rv1))
+        assert np.array_equal(q1.view(np.uint64), rq1.view(np.uint64)) and np.array_equal(v1.view(np.uint64), rv1.view(np.uint64)), (n, seed)
+    assert fixed.sum() > 100
