@@ -175,7 +175,7 @@ def cpu_parallel_step(scene, steps, warmup):
     times, pairs, threads = [], 0, 1
     # one thread per core this process may run on (cgroup / affinity aware), not per core of the machine
     try:
-        os.environ["ORC_THREADS"] = str(max(1, len(os.sched_getaffinity(0))))
+        os.environ["ORC_THREADS"] = str(max(1, min(64, len(os.sched_getaffinity(0)))))
     except AttributeError:
         pass
     for it in range(warmup + steps):
@@ -187,6 +187,19 @@ def cpu_parallel_step(scene, steps, warmup):
             "sample": "%d full steps of the same scene, candidate and contact lists built" % len(times),
             "note": "NOT reference behaviour: SCISim's hot path is single-threaded even with USE_OPENMP (that is cpu_baseline); this is the same step "
                     "written for a multi-core CPU (oracle/ball2d_parallel.h), reported so that the GPU figure is not compared with one core only"}
+
+
+def cpu_parallel_guarded(steps, warmup):
+    """cpu_parallel_step in a child process with a time limit: an optional figure must not be able to take the bench line down."""
+    import subprocess
+    code = "import json, bench; print(json.dumps(bench.cpu_parallel_step(bench.scene_for_rank(0, 1), %d, %d)))" % (steps, warmup)
+    try:
+        out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
+        if out.returncode != 0:
+            return {"unavailable": "child exited with %d: %s" % (out.returncode, out.stderr.strip()[-200:])}
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001 -- reported, never raised
+        return {"unavailable": repr(e)[:200]}
 
 
 def run_reference(args):
@@ -204,7 +217,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "full 1M-ball step (flow + spatial-grid broad phase + CCD), %d steps; %s" % (len(times), how)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": len(times) / total,
-        "cpu_baseline_parallel": cpu_parallel_step(scene, 5, 1),
+        "cpu_baseline_parallel": cpu_parallel_guarded(5, 1),
     }
     print(json.dumps(line))
 
@@ -394,7 +407,7 @@ def main():
             v = pairs_cpu * len(times) / sum(times)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": "3 full steps of the same 1M-ball scene; %s; the reference's hot path is single-threaded" % how}
-            line["cpu_baseline_parallel"] = cpu_parallel_step(scene_for_rank(0, 1), 5, 1)
+            line["cpu_baseline_parallel"] = cpu_parallel_guarded(5, 1)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
