@@ -73,17 +73,3 @@ def test_rb2d_kinematic_box_is_an_error(gpu_ctx, oracle):
     assert not ref["supported"]
     with pytest.raises(sb.SciSimB200Error):
         sim.computeActiveSet(s["q"], s["q"])
-
-
-def test_rb2d_active_set_on_resident_flow_result(gpu_ctx, oracle):
-    import scisim_b200 as sb
-    s = scenes.rb2d_random(3000, 9, kinds=("circle", "box"))
-    sim = make_sim(s, gpu_ctx)
-    with pytest.raises(sb.SciSimB200Error):
-        sim.computeActiveSet(s["q"], s["q"], resident=True)
-    q1, v1 = sim._flow(0, s["q"], s["v"], s["dt"])
-    a = sim.computeActiveSet(s["q"], q1, resident=True)
-    b = sim.computeActiveSet(s["q"], q1)
-    assert a.n_active == b.n_active > 0 and a.n_candidates == b.n_candidates
-    for k in ("type", "i", "j", "n", "p", "candidates"):
-        assert np.array_equal(getattr(a, k), getattr(b, k)), k
