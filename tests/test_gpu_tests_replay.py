@@ -1,0 +1,107 @@
+"""CPU-only: the bodies of the GPU tests that were written after the round's last GPU run (tests/test_z*_gpu.py), replayed with
+an oracle-backed stand-in for the sim.
+
+This says NOTHING about the kernels -- the stand-in answers with the oracle's own results, so every product-vs-oracle comparison
+is trivially true.  What it does establish, before those files first execute on a B200: the test code itself runs (scene
+generator arguments, dictionary keys, attribute names, shapes), and the assertions that depend on the SCENE rather than on the
+product hold -- enough teleported contacts, Lees-Edwards kick contacts present, kinematic-object contacts present, bodies really
+cross the portals during the trajectories, the unsupported cases really are unsupported.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import scisim_b200 as sb
+
+
+class _Tele(SimpleNamespace):
+    pass
+
+
+def _active(ref, dim):
+    na = ref["type"].shape[0]
+    nbb = ref["n_regular"] + ref["portal0"].shape[0]
+    return SimpleNamespace(n_candidates=ref["candidates"].shape[0], candidates=ref["candidates"], n_active=na, n_body_body=nbb,
+                           type=ref["type"], i=ref["i"], j=ref["j"], aux=ref.get("aux", np.zeros(na, np.uint32)), n=ref["n"], p=ref["p"], depth=ref["depth"],
+                           n_plane=int((ref["type"] == 2).sum()), n_drum=int((ref["type"] == 1).sum()))  # ball2d's counters (SG_BALL_PLANE, SG_BALL_DRUM)
+
+
+def _tele(ref, keys):
+    t = _Tele(n_regular=ref["n_regular"], n_teleported=ref["portal0"].shape[0], box_body=ref["box_body"], box_portal=ref["box_portal"],
+              portal0=ref["portal0"], portal1=ref["portal1"], x0=ref["x0"], x1=ref["x1"], kick=None, delta0=None, delta1=None)
+    for k in keys:
+        setattr(t, k, ref[k])
+    return t
+
+
+class OracleBackedSim:
+    """The calls the replayed tests make on a sim, answered by the oracle (portals set by the test module's make_oracle)."""
+
+    def __init__(self, oracle_obj, dim, tele_keys, flow_codes):
+        self.o, self.dim, self.tele_keys, self.flow_codes = oracle_obj, dim, tele_keys, flow_codes
+        self.last = None
+
+    def updatePeriodicBoundaryConditionsStartOfStep(self, it, dt):
+        return self.o.update_portals(it * dt)
+
+    def _flow(self, kind, q0, v0, dt, q1=None, v1=None):
+        return self.o.flow(self.flow_codes[kind], q0, v0, dt)
+
+    def computeActiveSet(self, q0, q1, v=None, resident=False, **kw):
+        ref = self.o.active_set_portals(q0, q1)
+        if ref is None or not ref.get("supported", True):
+            raise sb.SciSimB200Error("unsupported (replay)")
+        self.last = ref
+        return _active(ref, self.dim)
+
+    def teleported(self):
+        return _tele(self.last, self.tele_keys)
+
+    def enforcePeriodicBoundaryConditions(self, *a):
+        return self.o.enforce_portals(*a)
+
+    # resident stepping (rigidbody3d test)
+    def upload(self, q, v):
+        self.q, self.v = q.copy(), v.copy()
+
+    def step(self, umap, dt):
+        self.q1, self.v1 = self._flow(umap.kind, self.q, self.v, dt)
+        self.res = self.computeActiveSet(self.q, self.q1)
+        return self.res.n_candidates, self.res.n_active
+
+    def fetch(self):
+        return self.q1, self.v1, self.res
+
+
+def _patch(monkeypatch, mod, dim, tele_keys, flow_codes):
+    monkeypatch.setattr(mod, "make_sim", lambda s, ctx: OracleBackedSim(mod.make_oracle(s), dim, tele_keys, flow_codes))
+
+
+def test_replay_rb2d_portal_gpu_tests(monkeypatch, oracle):
+    import tests.test_zz_rb2d_portals_gpu as m
+    from scisim_b200 import SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET
+    _patch(monkeypatch, m, 2, ("kick", "delta0", "delta1"), {SG_MAP_SYMPLECTIC_EULER: 0, SG_MAP_VERLET: 1})
+    for case in m.CASES:
+        m.test_rb2d_portal_active_set_matches_oracle(None, oracle, case)
+    m.test_rb2d_portal_flow_resident_and_enforce(None, oracle)
+    m.test_rb2d_portal_unsupported_cases(None, oracle)
+    m.test_rb2d_portal_trajectory(None, oracle)
+
+
+def test_replay_rb3d_portal_gpu_tests(monkeypatch, oracle):
+    import tests.test_zz_rb3d_portals_gpu as m
+    from scisim_b200._lib import SG_MAP_DMV, SG_MAP_SPLIT_HAM
+    _patch(monkeypatch, m, 3, (), {SG_MAP_SPLIT_HAM: 2, SG_MAP_DMV: 3})
+    for case in m.CASES:
+        m.test_rb3d_portal_active_set_matches_oracle(None, oracle, case)
+    m.test_rb3d_portal_resident_step_and_enforce(None, oracle)
+    m.test_rb3d_portal_trajectory(None, oracle)
+
+
+def test_replay_ball2d_portal_trajectory(monkeypatch, oracle):
+    import tests.test_zy_portal_trajectory_gpu as m
+    from scisim_b200 import SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET
+    import tests.test_portals_gpu as base
+    monkeypatch.setattr(m, "make_sim", lambda s, ctx: OracleBackedSim(base.make_oracle(s), 2, ("kick",), {SG_MAP_SYMPLECTIC_EULER: 0, SG_MAP_VERLET: 1}))
+    m.test_portal_trajectory_many_steps(None, oracle)
