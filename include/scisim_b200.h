@@ -40,6 +40,13 @@ extern "C" {
 #define SG_MAP_VERLET 1           /* ball2d/VerletMap.cpp:15-41, rigidbody2d/VerletMap.cpp:27-55 */
 #define SG_MAP_SPLIT_HAM 2        /* rigidbody3d/UnconstrainedMaps/SplitHamMap.cpp:17-182 */
 #define SG_MAP_DMV 3              /* rigidbody3d/UnconstrainedMaps/DMVMap.cpp:103-207 */
+/* OR into the map kind of sg_rb3d_flow / sg_rb3d_step for every flow after a simulation's first.  Both maps start with
+ * v1 = fsys.M() * v0 (SplitHamMap.cpp:44, DMVMap.cpp:130).  RigidBody3DState's constructor stores the world-space inertia block
+ * transposed, M(r,c) = I(c,r) (formWorldSpaceMassMatrix, RigidBody3DState.cpp:165-182); RigidBody3DSim::flow then calls
+ * updateMandMinv (RigidBody3DSim.cpp:442,517,592), which assigns I = R I0 R^T through a column-major map over the same values
+ * (RigidBody3DState.cpp:444-446): from then on M(r,c) = I(r,c).  I is symmetric only up to rounding, so the two differ in the last
+ * bit of the angular momentum when the angular velocity is not zero.  Without the flag: M as constructed. */
+#define SG_MAP_M_UPDATED 0x100
 
 /* contact types, in the order the reference appends them to active_set */
 #define SG_BALL_BALL 0   /* ball2d/Constraints/BallBallConstraint */
@@ -325,7 +332,13 @@ int sg_rb3d_set_portals( sg_ctx* ctx, uint32_t n, const double* plane_a_x /* 3n 
                          const int32_t* multiplier /* 3n */ );
 int sg_rb3d_enforce_portals( sg_ctx* ctx, double* q );
 int sg_rb3d_teleported( sg_ctx* ctx, sg_teleported* out );
-/* UnconstrainedMap::flow for SplitHamMap (SG_MAP_SPLIT_HAM) / DMVMap (SG_MAP_DMV) with NearEarthGravityForce */
+/* RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462), the last thing RigidBody3DSim::flow does to the
+ * state: per body I = R I0 R^T and Iinv = R Iinv0 R^T, 9 doubles each, column-major -- exactly the runs
+ * M.data().value( 3 N + 9 b ... ) / Minv.data().value( 3 N + 9 b ... ) of the reference's sparse matrices, so a shim passes
+ * &M.data().value( 3 N ) and &Minv.data().value( 3 N ).  q: host vector [3N x | 9N R row-major], or NULL for the device copy of
+ * q1 the last sg_rb3d_flow / sg_rb3d_step on this context left (no upload). */
+int sg_rb3d_update_m_and_minv( sg_ctx* ctx, const double* q, double* m_blocks /* 9N */, double* minv_blocks /* 9N */ );
+/* UnconstrainedMap::flow for SplitHamMap (SG_MAP_SPLIT_HAM) / DMVMap (SG_MAP_DMV) with NearEarthGravityForce; see SG_MAP_M_UPDATED */
 int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
 /* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; no portals; cylinders via sg_rb3d_set_cylinders). Returns
  * SG_ERR_UNSUPPORTED where the reference exits on a pair of geometry types it cannot collide (RigidBody3DSim.cpp:960-961). */

@@ -344,6 +344,18 @@ void orc_rb3d_flow( void* hv, int kind, const double* q0, const double* v0, doub
   h->seconds_flow = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
 }
 
+// the flow of every step after the first: M as left by updateMandMinv ( see flow() )
+void orc_rb3d_flow_m_updated( void* hv, int kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
+{
+  RB3DHandle* h = static_cast<RB3DHandle*>( hv );
+  flow( kind, h->scene, q0, v0, dt, q1, v1, true );
+}
+
+void orc_rb3d_update_m_minv( void* hv, const double* q, double* I_blocks, double* Iinv_blocks )
+{
+  updateMandMinv( static_cast<RB3DHandle*>( hv )->scene, q, I_blocks, Iinv_blocks );
+}
+
 // returns 1, or 0 when the reference would exit on an unsupported geometry pair
 int orc_rb3d_active_set( void* hv, const double* q0, const double* q1, int method )
 {

@@ -250,7 +250,12 @@ inline void solveDMV( const V3& am, const double h, const V3& I0, Quat& q )
 }
 
 // kind: 2 = split_ham, 3 = dmv.  q: [3N x | 9N R row-major], v: [3N lin | 3N ang]
-inline void flow( const int kind, const RB3DScene& s, const double* q0, const double* v0, const double dt, double* q1, double* v1 )
+// m_updated: which of the reference's two world-space mass matrices multiplies v0.  RigidBody3DState's constructor stores the
+// inertia block transposed, M(r,c) = I(c,r) ( formWorldSpaceMassMatrix, RigidBody3DState.cpp:165-182 ), and that is what the first
+// flow of a simulation reads; RigidBody3DSim::flow then calls updateMandMinv ( RigidBody3DSim.cpp:442,517,592 ), which assigns
+// I = R I0 R^T through a column-major map over the same values ( RigidBody3DState.cpp:444-446 ), so every later flow reads
+// M(r,c) = I(r,c).  I is symmetric only up to rounding: ( R(r,k) d_k ) R(c,k) vs ( R(c,k) d_k ) R(r,k).
+inline void flow( const int kind, const RB3DScene& s, const double* q0, const double* v0, const double dt, double* q1, double* v1, const bool m_updated = false )
 {
   const std::size_t nb = s.nbodies();
   for( std::size_t k = 0; k < 12 * nb; ++k ) { q1[k] = q0[k]; }
@@ -266,6 +271,12 @@ inline void flow( const int kind, const RB3DScene& s, const double* q0, const do
     V3 L{ ( ( 0.0 + Iw.m[0] * w0.x ) + Iw.m[3] * w0.y ) + Iw.m[6] * w0.z,
           ( ( 0.0 + Iw.m[1] * w0.x ) + Iw.m[4] * w0.y ) + Iw.m[7] * w0.z,
           ( ( 0.0 + Iw.m[2] * w0.x ) + Iw.m[5] * w0.y ) + Iw.m[8] * w0.z };
+    if( m_updated )
+    {
+      L = V3{ ( ( 0.0 + Iw.m[0] * w0.x ) + Iw.m[1] * w0.y ) + Iw.m[2] * w0.z,
+              ( ( 0.0 + Iw.m[3] * w0.x ) + Iw.m[4] * w0.y ) + Iw.m[5] * w0.z,
+              ( ( 0.0 + Iw.m[6] * w0.x ) + Iw.m[7] * w0.y ) + Iw.m[8] * w0.z };
+    }
     if( s.fixed[b] )
     {
       v1[3 * b] = p.x; v1[3 * b + 1] = p.y; v1[3 * b + 2] = p.z;
@@ -589,6 +600,23 @@ inline bool computeActiveSet( const RB3DScene& s, const double* q0, const double
   return computeStaticActiveSet( s, q0, q1, active_set );
 }
 
+}
+
+// RigidBody3DState::updateMandMinv ( rigidbody3d/RigidBody3DState.cpp:428-462 ): per body the 3 x 3 blocks I = R I0 R^T and
+// Iinv = R Iinv0 R^T as they land in the value arrays of M and Minv ( column-major maps: entry ( r, c ) at 3 c + r ), Iinv0 = 1 / I0
+// ( formBodySpaceInverseMassMatrix, RigidBody3DState.cpp:116-133 ).  q: [3N x | 9N R row-major]; outputs 9 doubles per body.
+inline void updateMandMinv( const RB3DScene& s, const double* q, double* I_blocks, double* Iinv_blocks )
+{
+  const std::size_t nb = s.nbodies();
+  for( std::size_t b = 0; b < nb; ++b )
+  {
+    const M3 R = loadR( q, nb, b );
+    const V3 I0 = s.I0[b];
+    const M3 I = worldInertia( R, I0 );
+    const M3 Ii = worldInertia( R, V3{ 1.0 / I0.x, 1.0 / I0.y, 1.0 / I0.z } );
+    for( int r = 0; r < 3; ++r )
+      for( int c = 0; c < 3; ++c ) { I_blocks[9 * b + 3 * c + r] = I.m[3 * r + c]; Iinv_blocks[9 * b + 3 * c + r] = Ii.m[3 * r + c]; }
+  }
 }
 
 #endif

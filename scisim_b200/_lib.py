@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libscisim_b200.so")
 
 SG_OK = 0
 SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV = 0, 1, 2, 3
+SG_MAP_M_UPDATED = 0x100  # rigidbody3d flows after the first: M as updateMandMinv leaves it (include/scisim_b200.h)
 SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
 SG_BALL_BALL_TELEPORTED, SG_BALL_BALL_KICK_TELEPORTED = 3, 4
 SG_NO_PORTAL, SG_PLANE_B_BIT = 0xFFFFFFFF, 0x80000000
@@ -112,6 +113,7 @@ def load():
         "sg_rb3d_set_portals": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp, vp]),
         "sg_rb3d_enforce_portals": (C.c_int, [vp, vp]),
         "sg_rb3d_teleported": (C.c_int, [vp, C.POINTER(SgTeleported)]),
+        "sg_rb3d_update_m_and_minv": (C.c_int, [vp, vp, vp, vp]),
         "sg_rb3d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
         "sg_rb3d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
         "sg_rb3d_upload": (C.c_int, [vp, vp, vp]),

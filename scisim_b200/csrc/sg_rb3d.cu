@@ -349,12 +349,13 @@ __device__ inline M3d dmv_rotation( const M3d& R0, const V3d am, const double h,
   return r;
 }
 
-__global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind, const uint32_t n, const double* __restrict__ q0, const double* __restrict__ v0, const double* __restrict__ mass,
+__global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind_flags, const uint32_t n, const double* __restrict__ q0, const double* __restrict__ v0, const double* __restrict__ mass,
                                                      const double* __restrict__ I0, const uint32_t* __restrict__ btype, const double gx, const double gy, const double gz, const double dt,
                                                      double* __restrict__ q1, double* __restrict__ v1 )
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if( b >= n ) { return; }
+  const int kind = kind_flags & 0xff;
   const size_t nb = n;
   const double m = __ldg( &mass[b] );
   const V3d x0 = load_v3( q0, b );
@@ -362,12 +363,23 @@ __global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind, const uint
   const V3d vl = load_v3( v0, b );
   const V3d w0 = load_v3( v0 + 3 * nb, b );
   const V3d I = load_v3( I0, b );
-  // v1 = M * v0: sparse column-major accumulate into zero; the world inertia block is stored transposed
+  // v1 = M * v0: sparse column-major accumulate into zero.  The world inertia block is stored transposed by the state's
+  // constructor and as computed once updateMandMinv has run (SG_MAP_M_UPDATED, include/scisim_b200.h)
   V3d p = v3( 0.0 + m * vl.x, 0.0 + m * vl.y, 0.0 + m * vl.z );
   const M3d Iw = world_inertia3( R0, I );
-  V3d L = v3( ( ( 0.0 + Iw.m[0] * w0.x ) + Iw.m[3] * w0.y ) + Iw.m[6] * w0.z,
-              ( ( 0.0 + Iw.m[1] * w0.x ) + Iw.m[4] * w0.y ) + Iw.m[7] * w0.z,
-              ( ( 0.0 + Iw.m[2] * w0.x ) + Iw.m[5] * w0.y ) + Iw.m[8] * w0.z );
+  V3d L;
+  if( ( kind_flags & SG_MAP_M_UPDATED ) == 0 )
+  {
+    L = v3( ( ( 0.0 + Iw.m[0] * w0.x ) + Iw.m[3] * w0.y ) + Iw.m[6] * w0.z,
+            ( ( 0.0 + Iw.m[1] * w0.x ) + Iw.m[4] * w0.y ) + Iw.m[7] * w0.z,
+            ( ( 0.0 + Iw.m[2] * w0.x ) + Iw.m[5] * w0.y ) + Iw.m[8] * w0.z );
+  }
+  else
+  {
+    L = v3( ( ( 0.0 + Iw.m[0] * w0.x ) + Iw.m[1] * w0.y ) + Iw.m[2] * w0.z,
+            ( ( 0.0 + Iw.m[3] * w0.x ) + Iw.m[4] * w0.y ) + Iw.m[5] * w0.z,
+            ( ( 0.0 + Iw.m[6] * w0.x ) + Iw.m[7] * w0.y ) + Iw.m[8] * w0.z );
+  }
   double* x1o = q1 + 3 * size_t( b );
   double* R1o = q1 + 3 * nb + 9 * size_t( b );
   double* vlo = v1 + 3 * size_t( b );
@@ -418,6 +430,27 @@ __global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind, const uint
   vlo[0] = p.x / m; vlo[1] = p.y / m; vlo[2] = p.z / m;
   const V3d w1 = mul3( world_inertia3( R1, v3( 1.0 / I.x, 1.0 / I.y, 1.0 / I.z ) ), L );
   vao[0] = w1.x; vao[1] = w1.y; vao[2] = w1.z;
+}
+
+// RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462): I = R I0 R^T, Iinv = R ( 1 / I0 ) R^T per body,
+// written column-major ( entry ( r, c ) at 3 c + r ) as the reference's maps over M's and Minv's value arrays store them
+__global__ void __launch_bounds__( 128 ) k_rb3d_update_minertia( const uint32_t n, const double* __restrict__ q, const double* __restrict__ I0, double* __restrict__ I_blocks,
+                                                                double* __restrict__ Iinv_blocks )
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if( b >= n ) { return; }
+  const M3d R = load_m3( q + 3 * size_t( n ), b );
+  const V3d I = load_v3( I0, b );
+  const M3d Iw = world_inertia3( R, I );
+  const M3d Ii = world_inertia3( R, v3( 1.0 / I.x, 1.0 / I.y, 1.0 / I.z ) );
+  double* o = I_blocks + 9 * size_t( b );
+  double* oi = Iinv_blocks + 9 * size_t( b );
+  #pragma unroll
+  for( int r = 0; r < 3; ++r )
+  {
+    #pragma unroll
+    for( int c = 0; c < 3; ++c ) { o[3 * c + r] = Iw.m[3 * r + c]; oi[3 * c + r] = Ii.m[3 * r + c]; }
+  }
 }
 
 // ---- AABBs at q1 (generic pipeline) ----------------------------------------------------------------
@@ -973,6 +1006,8 @@ struct Rb3dData
   bool all_spheres = false;
   bool has_free_box = false; // a box that is not kinematically scripted (static cylinders reject those)
   bool flow_resident = false; // q0 (as given) and q1 (as computed) of the last sg_rb3d_flow are still on the device
+  bool q1_valid = false;      // q1 on the device is the output of the last flow kernel (sg_rb3d_flow or sg_rb3d_step)
+  DevBuf minertia;            // double[18 n]: I blocks, then Iinv blocks (sg_rb3d_update_m_and_minv)
   double g[3] = { 0.0, 0.0, 0.0 };
   Planes3D planes;
   // geometry list (host copy) and per-body expansion
@@ -1006,7 +1041,7 @@ void sg_rb3d_release( sg_ctx* ctx )
   DevBuf* bufs[] = { &d->d_meshes, &d->mesh_stats, &d->btype, &d->bparam, &d->bmesh, &d->radius, &d->flags, &d->mass, &d->I0, &d->q0, &d->v0, &d->q1, &d->v1, &d->boxes,
                      &d->pair_counts, &d->pair_offsets, &d->pair_partials, &d->narrow_total, &d->bad_flag, &d->npairs_dev,
                      &d->st_counts, &d->st_offsets, &d->st_partials, &d->st_total, &d->totals3,
-                     &d->c_type, &d->c_i, &d->c_j, &d->c_aux, &d->c_n, &d->c_p, &d->c_depth };
+                     &d->c_type, &d->c_i, &d->c_j, &d->c_aux, &d->c_n, &d->c_p, &d->c_depth, &d->minertia };
   for( DevBuf* b : bufs ) { b->release(); }
   d->bp.release();
   d->h_totals.release(); d->h_out.release();
@@ -1067,6 +1102,7 @@ static int rb3d_flow_device( sg_ctx* ctx, Rb3dData* d, const int map_kind, const
 {
   const uint32_t n = d->n;
   if( n == 0 ) { return SG_OK; }
+  d->q1_valid = true;
   SG_LAUNCH( ctx, "rb3d_flow", double( n ) * 336.0, k_rb3d_flow<<<sg_div_up( n, 128 ), 128, 0, ctx->stream>>>( map_kind, n, d->q0.as<double>(), d->v0.as<double>(), d->mass.as<double>(), d->I0.as<double>(),
              d->btype.as<uint32_t>(), d->g[0], d->g[1], d->g[2], dt, d->q1.as<double>(), d->v1.as<double>() ) );
   return SG_OK;
@@ -1584,6 +1620,7 @@ int sg_rb3d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, co
   d->n = n;
   d->have_result = false;
   d->flow_resident = false;
+  d->q1_valid = false;
   const int rc = rb3d_expand_bodies( ctx, d, n, geo_of_body, fixed );
   if( rc != SG_OK ) { d->n = 0; return rc; }
   if( n == 0 ) { return SG_OK; }
@@ -1679,6 +1716,7 @@ int sg_rb3d_enforce_portals( sg_ctx* ctx, double* q )
   if( q == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_enforce_portals: null vector" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   d->flow_resident = false; // q1 serves as the staging copy
+  d->q1_valid = false;
   const size_t bytes = size_t( d->n ) * 24; // only the centres of mass move
   SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
   SG_LAUNCH( ctx, "r3p_enforce", double( d->n ) * 48.0, k_r3p_enforce<<<sg_div_up( d->n, 256 ), 256, 0, ctx->stream>>>( d->px->portals, d->n, d->q1.as<double>() ) );
@@ -1727,10 +1765,37 @@ int sg_rb3d_teleported( sg_ctx* ctx, sg_teleported* out )
   return SG_OK;
 }
 
+int sg_rb3d_update_m_and_minv( sg_ctx* ctx, const double* q, double* m_blocks, double* minv_blocks )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( d->n == 0 ) { return SG_OK; }
+  if( m_blocks == nullptr || minv_blocks == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_update_m_and_minv: null output" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( q != nullptr )
+  {
+    // q1 serves as the staging copy: whatever a flow left there is replaced
+    d->flow_resident = false;
+    d->q1_valid = false;
+    SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
+  }
+  else if( !d->q1_valid ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_update_m_and_minv: q == NULL without a preceding sg_rb3d_flow / sg_rb3d_step on this context" ); }
+  const size_t bytes = size_t( d->n ) * 72;
+  SG_CUDA( ctx, d->minertia.ensure( 2 * bytes ) );
+  double* blocks = d->minertia.as<double>();
+  SG_LAUNCH( ctx, "rb3d_update_minertia", double( d->n ) * ( 96.0 + 144.0 ), k_rb3d_update_minertia<<<sg_div_up( d->n, 128 ), 128, 0, ctx->stream>>>( d->n, d->q1.as<double>(), d->I0.as<double>(), blocks,
+             blocks + 9 * size_t( d->n ) ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( m_blocks, blocks, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( minv_blocks, blocks + 9 * size_t( d->n ), bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  return SG_OK;
+}
+
 int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
-  if( map_kind != SG_MAP_SPLIT_HAM && map_kind != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: map kind %d is not a rigidbody3d map", map_kind ); }
+  if( ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_SPLIT_HAM && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: map kind %d is not a rigidbody3d map", map_kind ); }
   Rb3dData* d = rb3d_data( ctx );
   if( d->n == 0 ) { return SG_OK; }
   if( q0 == nullptr || v0 == nullptr || q1 == nullptr || v1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: null vector" ); }
@@ -1763,6 +1828,7 @@ int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
     SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
     SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
     d->flow_resident = false;
+    d->q1_valid = false;
   }
   const int rc = rb3d_active_set_device( ctx, d, ( out_flags & SG_OUT_CANDIDATES ) != 0u );
   if( rc != SG_OK ) { return rc; }
@@ -1786,7 +1852,7 @@ int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v )
 int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
-  if( map_kind != SG_MAP_SPLIT_HAM && map_kind != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: map kind %d is not a rigidbody3d map", map_kind ); }
+  if( ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_SPLIT_HAM && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: map kind %d is not a rigidbody3d map", map_kind ); }
   Rb3dData* d = rb3d_data( ctx );
   d->flow_resident = false; // q1 is about to be overwritten by the resident step
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );

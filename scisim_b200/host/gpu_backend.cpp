@@ -287,7 +287,13 @@ void GpuRigidBody3DBackend::flow( const int map_kind, const VectorXs& q0, const 
 {
   if( q1.size() != q0.size() ) { q1.resize( q0.size() ); }
   if( v1.size() != v0.size() ) { v1.resize( v0.size() ); }
-  check( sg_rb3d_flow( m_ctx, map_kind, q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_rb3d_flow" );
+  check( sg_rb3d_flow( m_ctx, map_kind | ( m_m_updated ? SG_MAP_M_UPDATED : 0 ), q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_rb3d_flow" );
+}
+
+void GpuRigidBody3DBackend::updateMandMinv( const VectorXs& q, double* m_values, double* minv_values, const bool from_last_flow )
+{
+  check( sg_rb3d_update_m_and_minv( m_ctx, from_last_flow ? nullptr : q.data(), m_values, minv_values ), "sg_rb3d_update_m_and_minv" );
+  m_m_updated = true;
 }
 
 void GpuRigidBody3DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates, const bool from_last_flow )

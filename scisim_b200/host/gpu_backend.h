@@ -187,6 +187,10 @@ public:
   void teleportedContacts( std::vector<GpuTeleportedContact3D>& teleported, uint64_t* num_regular = nullptr );
 
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
+  // RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462) on the GPU: writes the 9 N values of the inertia
+  // blocks of M and of Minv in place -- pass &M.data().value( 3 * nbodies ) and &Minv.data().value( 3 * nbodies ).  from_last_flow:
+  // q is the q1 the last flow() wrote (still on the device).  Flows after this call read the updated M (SG_MAP_M_UPDATED).
+  void updateMandMinv( const VectorXs& q, double* m_values, double* minv_values, const bool from_last_flow = false );
   // false + message on std::cerr where the reference would print and exit (unsupported geometry pairing): the caller exits
   void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
   // rigidbody3d/SpatialGridDetector.h:37 on caller-built boxes [minx,miny,minz,maxx,maxy,maxz]
@@ -198,6 +202,7 @@ private:
   void check( const int rc, const char* what ) const;
   sg_ctx* m_ctx;
   unsigned m_nbodies;
+  bool m_m_updated = false;
 };
 
 class GpuSplitHamMap final : public UnconstrainedMap

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import SG_MAP_DMV, SG_MAP_SPLIT_HAM, SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_OUT_ALL, SgContacts, SgPairs, SciSimB200Error
+from ._lib import SG_MAP_DMV, SG_MAP_M_UPDATED, SG_MAP_SPLIT_HAM, SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_OUT_ALL, SgContacts, SgPairs, SciSimB200Error
 
 
 def _f64(a):
@@ -439,9 +439,24 @@ class RigidBody3DSim:
                                                    _ptr(cat(lambda p: p.plane_b_n)), _ptr(mult)))
         else:
             self.ctx.check(lib.sg_rb3d_set_portals(h, 0, None, None, None, None, None))
+        # RigidBody3DState's M: as its constructor formed it until updateMandMinv has run once (SG_MAP_M_UPDATED, include/scisim_b200.h)
+        self.m_updated = False
 
     def name(self):
         return "rigid_body_3d"
+
+    def updateMandMinv(self, q=None):
+        """RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462): returns ( I blocks, Iinv blocks ), 9 doubles per
+        body, column-major as they sit in the value arrays of M and Minv.  q=None: the device copy of the last flow's / step's q1.
+        Every flow after this call multiplies v0 by the updated M, as the reference does from its second step on."""
+        n = self.state.nbodies()
+        I, Ii = np.zeros(9 * n), np.zeros(9 * n)
+        if q is not None:
+            q = _f64(q)
+            assert q.size == self.nqdofs()
+        self.ctx.check(self.ctx.lib.sg_rb3d_update_m_and_minv(self.ctx.h, _ptr(q) if q is not None else None, _ptr(I), _ptr(Ii)))
+        self.m_updated = True
+        return I, Ii
 
     # ---- portals (rigidbody3d/RigidBody3DSim.cpp:642-663) ----
     def enforcePeriodicBoundaryConditions(self, q):
@@ -467,7 +482,7 @@ class RigidBody3DSim:
         assert q0.size == self.nqdofs() and v0.size == self.nvdofs()
         q1 = np.empty_like(q0) if q1 is None else q1
         v1 = np.empty_like(v0) if v1 is None else v1
-        self.ctx.check(self.ctx.lib.sg_rb3d_flow(self.ctx.h, kind, _ptr(q0), _ptr(v0), float(dt), _ptr(q1), _ptr(v1)))
+        self.ctx.check(self.ctx.lib.sg_rb3d_flow(self.ctx.h, kind | (SG_MAP_M_UPDATED if self.m_updated else 0), _ptr(q0), _ptr(v0), float(dt), _ptr(q1), _ptr(v1)))
         return q1, v1
 
     def computeActiveSet(self, q0, qp, v=None, flags=SG_OUT_ALL, copy=True, resident=False):
@@ -491,7 +506,7 @@ class RigidBody3DSim:
 
     def step(self, umap, dt):
         c = SgContacts()
-        self.ctx.check(self.ctx.lib.sg_rb3d_step(self.ctx.h, umap.kind, float(dt), C.byref(c)))
+        self.ctx.check(self.ctx.lib.sg_rb3d_step(self.ctx.h, umap.kind | (SG_MAP_M_UPDATED if self.m_updated else 0), float(dt), C.byref(c)))
         return int(c.n_candidates), int(c.n_active)
 
     def fetch(self, flags=SG_OUT_ALL, want_state=True):

@@ -244,11 +244,24 @@ class RB3DOracle:
             self.lib.orc_rb3d_destroy(self.h)
             self.h = None
 
-    def flow(self, kind, q0, v0, dt):
+    def flow(self, kind, q0, v0, dt, m_updated=False):
+        """m_updated: M as RigidBody3DState::updateMandMinv leaves it (every flow after a simulation's first), see oracle/rb3d.h."""
         q0, v0 = _f64(q0), _f64(v0)
         q1, v1 = np.empty_like(q0), np.empty_like(v0)
-        self.lib.orc_rb3d_flow(self.h, int(kind), _p(q0), _p(v0), float(dt), _p(q1), _p(v1))
+        fn = self.lib.orc_rb3d_flow_m_updated if m_updated else self.lib.orc_rb3d_flow
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        fn.restype = None
+        fn(self.h, int(kind), _p(q0), _p(v0), float(dt), _p(q1), _p(v1))
         return q1, v1
+
+    def update_m_and_minv(self, q):
+        """RigidBody3DState::updateMandMinv: ( I blocks, Iinv blocks ), 9 doubles per body, column-major as in M's value array."""
+        q = _f64(q)
+        I, Ii = np.zeros(9 * self.n), np.zeros(9 * self.n)
+        self.lib.orc_rb3d_update_m_minv.argtypes = [C.c_void_p] * 4
+        self.lib.orc_rb3d_update_m_minv.restype = None
+        self.lib.orc_rb3d_update_m_minv(self.h, _p(q), _p(I), _p(Ii))
+        return I, Ii
 
     def active_set(self, q0, q1, method="grid"):
         q0, q1 = _f64(q0), _f64(q1)

@@ -105,3 +105,40 @@ def test_replay_ball2d_portal_trajectory(monkeypatch, oracle):
     import tests.test_portals_gpu as base
     monkeypatch.setattr(m, "make_sim", lambda s, ctx: OracleBackedSim(base.make_oracle(s), 2, ("kick",), {SG_MAP_SYMPLECTIC_EULER: 0, SG_MAP_VERLET: 1}))
     m.test_portal_trajectory_many_steps(None, oracle)
+
+
+class OracleBackedRB3D:
+    """RigidBody3DSim's flow / updateMandMinv / resident stepping answered by the oracle (no portals)."""
+
+    def __init__(self, s):
+        from tests import oracle_binding as ob
+        self.o, self.m_updated, self.q1 = ob.RB3DOracle(s), False, None
+
+    def _flow(self, kind, q0, v0, dt, q1=None, v1=None):
+        self.q1, v1 = self.o.flow(kind, q0, v0, dt, m_updated=self.m_updated)
+        return self.q1, v1
+
+    def updateMandMinv(self, q=None):
+        if q is None and self.q1 is None:
+            raise sb.SciSimB200Error("no configuration (replay)")
+        self.m_updated = True
+        return self.o.update_m_and_minv(self.q1 if q is None else q)
+
+    def upload(self, q, v):
+        self.q, self.v = q.copy(), v.copy()
+
+    def step(self, umap, dt):
+        self.res = self._flow(umap.kind, self.q, self.v, dt)
+
+    def fetch(self):
+        return self.res[0], self.res[1], None
+
+
+def test_replay_rb3d_minertia_gpu_tests(monkeypatch, oracle):
+    import tests.test_zw_rb3d_minertia_gpu as m
+    monkeypatch.setattr(m, "make_sim", lambda s, ctx: OracleBackedRB3D(s))
+    for n, seed in ((1, 1), (777, 2), (20000, 3)):
+        m.test_update_m_and_minv_matches_oracle(None, oracle, n, seed)
+    m.test_flows_after_the_first_read_the_updated_matrix(None, oracle)
+    m.test_split_ham_with_the_updated_matrix(None, oracle)
+    m.test_update_without_a_configuration_is_an_error(None, oracle)

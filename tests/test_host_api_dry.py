@@ -126,6 +126,23 @@ def test_rb3d_portal_calls_convert(dry):
     assert mults.dtype == np.int32 and mults.shape == (len(s["portals"]["mult"]), 3)
 
 
+def test_rb3d_update_m_and_minv_calls_convert(dry):
+    import scisim_b200 as sb
+    from scisim_b200._lib import SG_MAP_M_UPDATED
+    from tests.test_rb3d_gpu import make_sim
+    s = scenes.rb3d_random_boxes(20, 1)
+    sim = make_sim(s, dry)
+    seen = []
+    real = dry.lib.__getattr__("sg_rb3d_flow")
+    dry.lib.__dict__["sg_rb3d_flow"] = lambda *a: (seen.append(a[1]), real(*a))[1]
+    sb.DMVMap().flow(s["q"], s["v"], sim, 1, s["dt"])
+    I, Ii = sim.updateMandMinv(s["q"])
+    assert I.shape == (180,) and Ii.shape == (180,)
+    sim.updateMandMinv()
+    sb.DMVMap().flow(s["q"], s["v"], sim, 2, s["dt"])
+    assert seen == [3, 3 | SG_MAP_M_UPDATED]  # SG_MAP_DMV, then with the flag once updateMandMinv has run
+
+
 def test_a_wrong_argument_is_caught(dry):
     with pytest.raises(AssertionError):
         dry.lib.sg_rb3d_enforce_portals(dry.h, None, None)

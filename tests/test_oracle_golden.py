@@ -95,3 +95,32 @@ def test_ball2d_active_set_grid_equals_all_pairs_and_order():
     nn = np.linalg.norm(a["n"], axis=1)
     assert np.all(np.abs(nn - 1.0) < 1e-12)
     assert np.all(np.isnan(a["depth"][t == 1])) and np.all(a["depth"][t != 1] <= 0.0)
+
+
+def test_rb3d_update_m_and_minv_and_the_two_mass_matrices(oracle):
+    """oracle/rb3d.h: updateMandMinv (RigidBody3DState.cpp:428-462) against a plain numpy R diag R^T (rounding-level agreement, the
+    column-major layout of the blocks exact), and the two matrices a flow can read -- as constructed (inertia block transposed,
+    RigidBody3DState.cpp:165-182) or as updated: identical results without spin, last-bit differences with it."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    s = scenes.rb3d_random_boxes(500, 11)
+    o = ob.RB3DOracle(s)
+    n = 500
+    I, Ii = o.update_m_and_minv(s["q"])
+    R = s["q"][3 * n:].reshape(n, 3, 3)
+    I0 = np.asarray(s["I0"]).reshape(n, 3)
+    ref = np.einsum("bik,bk,bjk->bij", R, I0, R)          # ref[b][r][c]
+    refi = np.einsum("bik,bk,bjk->bij", R, 1.0 / I0, R)
+    got = I.reshape(n, 3, 3).transpose(0, 2, 1)             # stored at 3 c + r
+    goti = Ii.reshape(n, 3, 3).transpose(0, 2, 1)
+    assert np.abs(got - ref).max() <= 1e-14 * np.abs(ref).max() and np.abs(goti - refi).max() <= 1e-14 * np.abs(refi).max()
+    assert np.any(got != got.transpose(0, 2, 1))            # symmetric only up to rounding: the layout matters
+    for kind in (2, 3):
+        a = o.flow(kind, s["q"], s["v"], s["dt"])
+        b = o.flow(kind, s["q"], s["v"], s["dt"], m_updated=True)
+        assert not np.array_equal(a[1], b[1]) and np.abs(a[1] - b[1]).max() <= 1e-13 * np.abs(a[1]).max()
+        assert np.abs(a[0] - b[0]).max() <= 1e-13
+    s0 = scenes.rb3d_random_spheres(300, 12)               # no spin: the angular momentum is zero either way
+    o0 = ob.RB3DOracle(s0)
+    a, b = o0.flow(2, s0["q"], s0["v"], s0["dt"]), o0.flow(2, s0["q"], s0["v"], s0["dt"], m_updated=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
