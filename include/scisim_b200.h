@@ -340,7 +340,8 @@ int sg_rb3d_teleported( sg_ctx* ctx, sg_teleported* out );
 int sg_rb3d_update_m_and_minv( sg_ctx* ctx, const double* q, double* m_blocks /* 9N */, double* minv_blocks /* 9N */ );
 /* UnconstrainedMap::flow for SplitHamMap (SG_MAP_SPLIT_HAM) / DMVMap (SG_MAP_DMV) with NearEarthGravityForce; see SG_MAP_M_UPDATED */
 int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
-/* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; no portals; cylinders via sg_rb3d_set_cylinders). Returns
+/* RigidBody3DSim::computeActiveSet (rigidbody3d/RigidBody3DSim.cpp:250-262; cylinders via sg_rb3d_set_cylinders; with portals set: the
+ * portal loop of computeActiveSetBodyBodySpatialGrid, all-sphere scenes, see sg_rb3d_set_portals). Returns
  * SG_ERR_UNSUPPORTED where the reference exits on a pair of geometry types it cannot collide (RigidBody3DSim.cpp:960-961). */
 int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
 /* resident variants, as for ball2d */
