@@ -1,9 +1,14 @@
-"""Resident-step timing of the ball2d portal path on ONE B200 (run under gpurun):  python profiles/portal_timing.py [n]
-Periodic box, plain portal pair in x + Lees-Edwards pair in y, Verlet.  Prints one JSON line: pairs/s, ms/step, launches per
-step and per-kernel microseconds (CUDA events inside the library)."""
+"""Timing of the portal paths on ONE B200 (run under gpurun):  python profiles/portal_timing.py [ball2d|rb2d|rb3d] [n]
+
+ball2d: periodic box, plain portal pair in x + Lees-Edwards pair in y, Verlet, resident step (sg_ball2d_step).
+rb3d:   periodic box of spheres, portals in x and z, DMV, resident step (sg_rb3d_step).
+rb2d:   periodic box of circles, x plain + y Lees-Edwards, Verlet; rigidbody2d has no resident step, so the timed call is
+        flow + computeActiveSet( SG_IN_RESIDENT ) through host buffers (copies inside the timed region).
+Prints one JSON line: pairs/s, ms/step, launches per step and per-kernel microseconds (CUDA events inside the library)."""
 import json
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -12,31 +17,64 @@ import scisim_b200 as sb
 from scisim_b200 import scenes
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-    steps, warmup = 5, 2
-    s = scenes.ball2d_periodic(n, 7, axes="xy", lees_edwards=0.4, t=0.9)
-    ctx = sb.Context(0)
-    st = sb.Ball2DState(s["r"], s["m"], s["g"], s["plane_x"], s["plane_n"], s["drum_x"], s["drum_r"], planar_portals=sb.PlanarPortal.from_arrays(s["portals"]))
-    sim = sb.Ball2DSim(st, ctx=ctx)
+def build(system, n, ctx):
+    if system == "ball2d":
+        s = scenes.ball2d_periodic(n, 7, axes="xy", lees_edwards=0.4, t=0.9)
+        st = sb.Ball2DState(s["r"], s["m"], s["g"], s["plane_x"], s["plane_n"], s["drum_x"], s["drum_r"], planar_portals=sb.PlanarPortal.from_arrays(s["portals"]))
+        sim = sb.Ball2DSim(st, ctx=ctx)
+        sim.updatePeriodicBoundaryConditionsStartOfStep(1, s["t"])
+        return s, sim, sb.VerletMap(), "ball2d periodic box, %d balls, x: planar portal, y: Lees-Edwards portal, Verlet, resident step" % n
+    if system == "rb3d":
+        s = scenes.rb3d_periodic_spheres(n, 7, axes="xz")
+        st = sb.RigidBody3DState(s["geo_type"], s["geo_r"], s["geo_half"], s["geo_mesh"], [], s["geo_of_body"], s["fixed"], s["m"], s["I0"], s["g"], s["plane_x"], s["plane_n"],
+                                 planar_portals=sb.PlanarPortal3D.from_arrays(s["portals"]))
+        return s, sb.RigidBody3DSim(st, ctx=ctx), sb.DMVMap(), "rigidbody3d periodic box, %d spheres, portals in x and z, DMV, resident step" % n
+    s = scenes.rb2d_periodic(n, 7, lees_edwards=0.4, t=0.9)
+    st = sb.RigidBody2DState(s["geo_type"], s["geo_r"], s["geo_half"], s["geo_of_body"], s["fixed"], s["M"], s["g"], s["plane_x"], s["plane_n"],
+                             planar_portals=sb.PlanarPortal.from_arrays(s["portals"]))
+    sim = sb.RigidBody2DSim(st, ctx=ctx)
     sim.updatePeriodicBoundaryConditionsStartOfStep(1, s["t"])
-    sim.upload(s["q"], s["v"])
-    umap = sb.VerletMap()
+    return s, sim, sb.VerletMap(), "rigidbody2d periodic box, %d circles, x: planar portal, y: Lees-Edwards portal, Verlet, flow + active set through host buffers" % n
+
+
+def main():
+    system = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] in ("ball2d", "rb2d", "rb3d") else "ball2d"
+    nums = [a for a in sys.argv[1:] if a.isdigit()]
+    n = int(nums[0]) if nums else 1 << 20
+    steps, warmup = 5, 2
+    ctx = sb.Context(0)
+    s, sim, umap, workload = build(system, n, ctx)
+    resident = system != "rb2d"
+    if resident:
+        sim.upload(s["q"], s["v"])
+
+        def step():
+            return sim.step(umap, s["dt"])
+    else:
+        def step():
+            q1, _ = umap.flow(s["q"], s["v"], sim, 1, s["dt"])
+            a = sim.computeActiveSet(s["q"], q1, resident=True, copy=False)
+            return a.n_candidates, a.n_active
     for _ in range(warmup):
-        ctx.flush_l2(); r = sim.step(umap, s["dt"])
+        ctx.flush_l2(); r = step()
     ms = []
     l0 = ctx.launch_count()
     for _ in range(steps):
-        ctx.flush_l2(); ctx.timer_begin(); r = sim.step(umap, s["dt"]); ms.append(ctx.timer_end())
+        ctx.flush_l2()
+        if resident:
+            ctx.timer_begin(); r = step(); ms.append(ctx.timer_end())
+        else:
+            ctx.synchronize(); t0 = time.perf_counter(); r = step(); ctx.synchronize(); ms.append(1e3 * (time.perf_counter() - t0))
     launches = (ctx.launch_count() - l0) / steps
     ctx.profile_enable(True); ctx.profile_reset()
     for _ in range(steps):
-        ctx.flush_l2(); sim.step(umap, s["dt"])
+        ctx.flush_l2(); step()
     prof = ctx.profile(); ctx.profile_enable(False)
     tele = sim.teleported()
     pc, pa = r
-    print(json.dumps({"workload": "ball2d periodic box, %d balls, x: planar portal, y: Lees-Edwards portal, Verlet" % n, "candidates": int(pc), "active": int(pa),
+    print(json.dumps({"workload": workload, "candidates": int(pc), "active": int(pa),
                       "teleported_boxes": int(tele.box_body.shape[0]), "teleported_contacts": int(tele.n_teleported), "ms_per_step": round(float(np.mean(ms)), 4),
+                      "timed": "CUDA events around the resident step" if resident else "host clock around flow + active set (host buffers)",
                       "pairs_per_s": (pc + pa) / (float(np.mean(ms)) * 1e-3), "launches_per_step": launches,
                       "kernels_us": {k: round(1e3 * v[1] / steps, 1) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}))
 
