@@ -154,7 +154,7 @@ def cpu_reference_step(scene, steps, warmup):
                 times.append(t)
         assert int(nc.value) == a["candidates"].shape[0] and int(na.value) + n_static == a["type"].shape[0]
         return pairs, times, "reference", ("broad phase + CCD = the reference's own SpatialGridDetector.cpp / CollisionDetectionUtilities.cpp (compiled unchanged against "
-                                           "oracle/eigen_standin), map + swept boxes = oracle restatement")
+                                           "oracle/eigen_standin), map + swept boxes = oracle restatement (the map checked bit for bit against the reference's compiled SymplecticEulerMap.cpp, tests/test_oracle_vs_reference.py)")
     for it in range(warmup + steps):
         q1, v1 = o.flow(0, scene["q"], scene["v"], scene["dt"])
         a = o.active_set(scene["q"], q1, "grid")
