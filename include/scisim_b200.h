@@ -282,6 +282,11 @@ int sg_rb2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0,
 /* RigidBody2DSim::computeActiveSet (rigidbody2d/RigidBody2DSim.cpp:696-714; with portals set: the portal branch, see below); SG_ERR_UNSUPPORTED where the
  * reference exits (kinematic box-box, kinematic circle vs box: RigidBody2DSim.cpp:186-190, 210-214) */
 int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
+/* resident variants, as for ball2d and rigidbody3d: upload (q, v) once, step = flow + active set on the device copies ( only the
+ * list sizes come back in *out ), fetch copies q1, v1 and the lists the flags ask for */
+int sg_rb2d_upload( sg_ctx* ctx, const double* q, const double* v );
+int sg_rb2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
+int sg_rb2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
 
 /* Planar and Lees-Edwards portals of the 2-D rigid-body sim (rigidbody2d/PlanarPortal.h; at most 8), arguments as
  * sg_ball2d_set_portals except that plane normals are used as given (RigidBody2DStaticPlane does not normalise).  With portals

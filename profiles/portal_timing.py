@@ -2,13 +2,11 @@
 
 ball2d: periodic box, plain portal pair in x + Lees-Edwards pair in y, Verlet, resident step (sg_ball2d_step).
 rb3d:   periodic box of spheres, portals in x and z, DMV, resident step (sg_rb3d_step).
-rb2d:   periodic box of circles, x plain + y Lees-Edwards, Verlet; rigidbody2d has no resident step, so the timed call is
-        flow + computeActiveSet( SG_IN_RESIDENT ) through host buffers (copies inside the timed region).
+rb2d:   periodic box of circles, x plain + y Lees-Edwards, Verlet, resident step (sg_rb2d_step).
 Prints one JSON line: pairs/s, ms/step, launches per step and per-kernel microseconds (CUDA events inside the library)."""
 import json
 import os
 import sys
-import time
 
 import numpy as np
 
@@ -34,7 +32,7 @@ def build(system, n, ctx):
                              planar_portals=sb.PlanarPortal.from_arrays(s["portals"]))
     sim = sb.RigidBody2DSim(st, ctx=ctx)
     sim.updatePeriodicBoundaryConditionsStartOfStep(1, s["t"])
-    return s, sim, sb.VerletMap(), "rigidbody2d periodic box, %d circles, x: planar portal, y: Lees-Edwards portal, Verlet, flow + active set through host buffers" % n
+    return s, sim, sb.VerletMap(), "rigidbody2d periodic box, %d circles, x: planar portal, y: Lees-Edwards portal, Verlet, resident step" % n
 
 
 def main():
@@ -44,27 +42,16 @@ def main():
     steps, warmup = 5, 2
     ctx = sb.Context(0)
     s, sim, umap, workload = build(system, n, ctx)
-    resident = system != "rb2d"
-    if resident:
-        sim.upload(s["q"], s["v"])
+    sim.upload(s["q"], s["v"])
 
-        def step():
-            return sim.step(umap, s["dt"])
-    else:
-        def step():
-            q1, _ = umap.flow(s["q"], s["v"], sim, 1, s["dt"])
-            a = sim.computeActiveSet(s["q"], q1, resident=True, copy=False)
-            return a.n_candidates, a.n_active
+    def step():
+        return sim.step(umap, s["dt"])
     for _ in range(warmup):
         ctx.flush_l2(); r = step()
     ms = []
     l0 = ctx.launch_count()
     for _ in range(steps):
-        ctx.flush_l2()
-        if resident:
-            ctx.timer_begin(); r = step(); ms.append(ctx.timer_end())
-        else:
-            ctx.synchronize(); t0 = time.perf_counter(); r = step(); ctx.synchronize(); ms.append(1e3 * (time.perf_counter() - t0))
+        ctx.flush_l2(); ctx.timer_begin(); r = step(); ms.append(ctx.timer_end())
     launches = (ctx.launch_count() - l0) / steps
     ctx.profile_enable(True); ctx.profile_reset()
     for _ in range(steps):
@@ -74,7 +61,7 @@ def main():
     pc, pa = r
     print(json.dumps({"workload": workload, "candidates": int(pc), "active": int(pa),
                       "teleported_boxes": int(tele.box_body.shape[0]), "teleported_contacts": int(tele.n_teleported), "ms_per_step": round(float(np.mean(ms)), 4),
-                      "timed": "CUDA events around the resident step" if resident else "host clock around flow + active set (host buffers)",
+                      "timed": "CUDA events around the resident step",
                       "pairs_per_s": (pc + pa) / (float(np.mean(ms)) * 1e-3), "launches_per_step": launches,
                       "kernels_us": {k: round(1e3 * v[1] / steps, 1) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}))
 

@@ -105,6 +105,9 @@ def load():
         "sg_rb2d_teleported": (C.c_int, [vp, C.POINTER(SgTeleported)]),
         "sg_rb2d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
         "sg_rb2d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
+        "sg_rb2d_upload": (C.c_int, [vp, vp, vp]),
+        "sg_rb2d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
+        "sg_rb2d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
         "sg_rb3d_set_geometry": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),
         "sg_rb3d_add_mesh": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, vp, C.POINTER(C.c_uint32)]),
         "sg_rb3d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp]),

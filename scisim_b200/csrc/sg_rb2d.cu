@@ -1046,4 +1046,57 @@ int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
   return rb2d_copy_out( ctx, d, out_flags, out );
 }
 
+int sg_rb2d_upload( sg_ctx* ctx, const double* q, const double* v )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb2dData* d = rb2d_data( ctx );
+  d->flow_resident = false;
+  if( d->n == 0 ) { return SG_OK; }
+  if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_upload: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q, size_t( d->n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v, size_t( d->n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_rb2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_step: map kind %d is not a rigidbody2d map", map_kind ); }
+  Rb2dData* d = rb2d_data( ctx );
+  d->flow_resident = false; // q1 is about to be overwritten by the resident step
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->n > 0 )
+  {
+    SG_LAUNCH( ctx, "rb2d_flow", double( d->n ) * 120.0, k_rb2d_flow<<<sg_div_up( d->n, 256 ), 256, 0, ctx->stream>>>( map_kind, d->n, d->q0.as<double>(), d->v0.as<double>(), d->M.as<double>(), d->btype.as<uint32_t>(),
+               d->g[0], d->g[1], dt, d->q1.as<double>(), d->v1.as<double>() ) );
+  }
+  const int rc = ( d->px != nullptr && d->px->portals.n > 0u ) ? rb2d_portal_active_set_device( ctx, d ) : rb2d_active_set_device( ctx, d );
+  if( rc != SG_OK ) { return rc; }
+  if( out != nullptr )
+  {
+    memset( out, 0, sizeof( *out ) );
+    out->dim = 2;
+    out->n_candidates = d->n_cand;
+    out->n_body_body = d->n_bb;
+    out->n_plane = d->n_static;
+    out->n_active = d->n_bb + d->n_static;
+  }
+  return SG_OK;
+}
+
+int sg_rb2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb2dData* d = rb2d_data( ctx );
+  if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_fetch: no step has been run" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( q1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, size_t( d->n ) * 24, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( v1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 24, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( out != nullptr ) { return rb2d_copy_out( ctx, d, out_flags, out ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
 }

@@ -600,3 +600,22 @@ class RigidBody2DSim:
         c = SgContacts()
         self.ctx.check(self.ctx.lib.sg_rb2d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags) | (SG_IN_RESIDENT if resident else 0), C.byref(c)))
         return ActiveSet(c, copy=copy)
+
+    # ---- resident stepping: the state stays on the device between the map and the detection ----
+    def upload(self, q, v):
+        q, v = _f64(q), _f64(v)
+        assert q.size == self.nqdofs() and v.size == self.nvdofs()
+        self.ctx.check(self.ctx.lib.sg_rb2d_upload(self.ctx.h, _ptr(q), _ptr(v)))
+
+    def step(self, umap, dt):
+        """flow + computeActiveSet on the device copies; returns (number of candidates, number of active contacts)."""
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_rb2d_step(self.ctx.h, umap.kind, float(dt), C.byref(c)))
+        return int(c.n_candidates), int(c.n_active)
+
+    def fetch(self, flags=SG_OUT_ALL, want_state=True):
+        q1 = np.empty(self.nqdofs()) if want_state else None
+        v1 = np.empty(self.nvdofs()) if want_state else None
+        c = SgContacts()
+        self.ctx.check(self.ctx.lib.sg_rb2d_fetch(self.ctx.h, int(flags), _ptr(q1) if want_state else None, _ptr(v1) if want_state else None, C.byref(c)))
+        return q1, v1, ActiveSet(c)

@@ -142,3 +142,39 @@ def test_replay_rb3d_minertia_gpu_tests(monkeypatch, oracle):
     m.test_flows_after_the_first_read_the_updated_matrix(None, oracle)
     m.test_split_ham_with_the_updated_matrix(None, oracle)
     m.test_update_without_a_configuration_is_an_error(None, oracle)
+
+
+class OracleBackedRB2D:
+    """RigidBody2DSim without portals: flow, active set and the resident step answered by the oracle."""
+
+    def __init__(self, s):
+        from tests import oracle_binding as ob
+        self.o, self.res = ob.RB2DOracle(s), None
+
+    def _flow(self, kind, q0, v0, dt, q1=None, v1=None):
+        return self.o.flow(kind, q0, v0, dt)
+
+    def computeActiveSet(self, q0, q1, v=None, resident=False, **kw):
+        ref = self.o.active_set(q0, q1, "grid")
+        if not ref["supported"]:
+            raise sb.SciSimB200Error("unsupported (replay)")
+        return SimpleNamespace(n_candidates=ref["candidates"].shape[0], n_active=ref["type"].shape[0], **{k: ref[k] for k in ("candidates", "type", "i", "j", "aux", "n", "p", "depth")})
+
+    def upload(self, q, v):
+        self.q, self.v = q.copy(), v.copy()
+
+    def step(self, umap, dt):
+        q1, v1 = self._flow(umap.kind, self.q, self.v, dt)
+        self.res = (q1, v1, self.computeActiveSet(self.q, q1))
+        return self.res[2].n_candidates, self.res[2].n_active
+
+    def fetch(self):
+        if self.res is None:
+            raise sb.SciSimB200Error("no step (replay)")
+        return self.res
+
+
+def test_replay_rb2d_resident_gpu_tests(monkeypatch, oracle):
+    import tests.test_zx_rb2d_resident_gpu as m
+    monkeypatch.setattr(m, "make_sim", lambda s, ctx: OracleBackedRB2D(s))
+    m.test_rb2d_resident_step_matches_oracle(None, oracle)

@@ -143,6 +143,20 @@ def test_rb3d_update_m_and_minv_calls_convert(dry):
     assert seen == [3, 3 | SG_MAP_M_UPDATED]  # SG_MAP_DMV, then with the flag once updateMandMinv has run
 
 
+def test_rb2d_resident_calls_convert(dry):
+    import scisim_b200 as sb
+    from tests.test_rb2d_gpu import make_sim
+    s = scenes.rb2d_random(30, 2)
+    sim = make_sim(s, dry)
+    sim.upload(s["q"], s["v"])
+    assert sim.step(sb.VerletMap(), s["dt"]) == (0, 0)
+    q1, v1, a = sim.fetch()
+    assert q1.shape == s["q"].shape and v1.shape == s["v"].shape and a.n_active == 0
+    q1, v1, a = sim.fetch(want_state=False)
+    assert q1 is None and v1 is None
+    assert [c for c in dry.lib.calls if c.startswith("sg_rb2d_") and c.split("_")[-1] in ("upload", "step", "fetch")] == ["sg_rb2d_upload", "sg_rb2d_step", "sg_rb2d_fetch", "sg_rb2d_fetch"]
+
+
 def test_a_wrong_argument_is_caught(dry):
     with pytest.raises(AssertionError):
         dry.lib.sg_rb3d_enforce_portals(dry.h, None, None)
