@@ -1,27 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the SCISim hot path on B200 (contract in the task statement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 3|2|1]
 
 A "step" = one pass of the hot path over a fixed state: UnconstrainedMap::flow(q0,v0)->(q1,v1)
 followed by ConstrainedSystem::computeActiveSet(q0,q1).  Metric = (candidate pairs + active contacts) per
-second, whole job.  Workload at N=1: BASELINE.json configs[1] -- 1000x1000 equal balls on a 0.99-spaced lattice,
-gravity, 3 static planes, symplectic Euler.  At N>1 the scene is N such slabs side by side along x (weak
-scaling), one slab per rank.
+second, whole job.
+
+Workload (default, every N): BASELINE.json configs[2] -- the north-star scene: 16 777 216 polydisperse balls (radii
+log-uniform in [0.25, 1], area fraction 0.55, random numbering), 4 walls, Verlet.  It fits one B200, so N = 1 runs it
+whole; N > 1 cuts it into N equal-count x-quantile slabs, one per rank ("scaling": "strong"), ghosts exchanged with
+the neighbouring slabs every step through peer-mapped mailboxes (NVLink), pairs owned by the rank of their lower
+global index.  --config 2 (N = 1 only) is configs[1], the 1M-ball pile round 1 was quoted on; --config 1 is the
+reference's own bundled scene (tests/golden/ball2d_assets.npz).
 
   value     state resident in HBM, CUDA events on the library's stream, L2 flushed between steps
-  e2e       the same step through the host-buffer C ABI (sg_ball2d_flow + sg_ball2d_active_set): H2D of q0,v0
-            (+ q0,q1 for the active set) from pinned memory and D2H of q1,v1 and the whole active set inside
-            the timed region
+  e2e       the same step through the host-buffer C ABI: H2D of q0,v0 from pinned memory and D2H of q1,v1 and the
+            whole active set inside the timed region
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU restatement of the reference (oracle/, single thread like the reference's path) on
-            one full step of the same scene, timed on this box
+  cpu_baseline  the reference's own CPU path (its SpatialGridDetector.cpp / CollisionDetectionUtilities.cpp compiled
+            unchanged, single thread like the reference) on a bounded sample of the same workload, timed on this box
+  parity_check  a reduced-size scene of the same kind through the same code path at this N (partition, halo exchange,
+            merge included), compared with the CPU oracle bit for bit
 """
 import argparse
 import json
 import os
-
-os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version at INFO/VERSION)
 import statistics
 import sys
 import time
@@ -32,24 +36,35 @@ if ROOT not in sys.path:
 
 METRIC = "candidate+active contact pairs/sec (flow + broad phase + narrow phase, ball2d)"
 UNIT = "pairs/s"
-NX, NY = 1000, 1000
+N_CONFIG3 = 1 << 24
+N_CPU_SAMPLE = 1 << 21      # bodies of the CPU arms' bounded sample of config 3 (the per-GPU share at 8 GPUs)
+N_PARITY = 200_000
 
 
-def scene_for_rank(rank, world):
-    """Slab `rank` of a (world*NX) x NY lattice, bodies numbered slab-major; every rank holds the same three planes
-    (plane indices are global): floor, left wall of the first slab, right wall of the last slab."""
+def make_scene(config, n=None):
     from scisim_b200 import scenes
-    s = scenes.ball2d_lattice(NX, NY, seed=42 + rank, with_planes=True)
-    if world > 1:
-        s["q"][0::2] += rank * NX * 0.99
-        s["plane_x"][2, 0] += (world - 1) * NX * 0.99
-    return s
+    if config == 3:
+        return scenes.ball2d_gas(n=n or N_CONFIG3)
+    if config == 2:
+        return scenes.ball2d_lattice(1000, 1000, seed=42, with_planes=True)
+    if config == 1:
+        return scenes.ball2d_asset("different_friction")
+    raise SystemExit("unknown --config %r" % config)
 
 
-def workload_name(world):
-    if world == 1:
-        return "configs[1]: synthetic 2D ball pile, 1M equal-radius balls (1000x1000 lattice, spacing 0.99, r=0.5) under gravity, 3 static planes, symplectic Euler"
-    return "configs[1] tiled: %d slabs of 1M balls side by side along x (one slab per GPU)" % world
+def workload_name(config):
+    return {3: "configs[2]: synthetic polydisperse 2D ball gas, 16 777 216 balls (radius ratio 1:4, log-uniform radii, area fraction 0.55, random numbering), 4 walls, Verlet",
+            2: "configs[1]: synthetic 2D ball pile, 1M equal-radius balls (1000x1000 lattice, spacing 0.99, r=0.5) under gravity, 3 static planes, symplectic Euler",
+            1: "configs[0]: bundled assets/ball2d scene tests_python_serialization/different_friction.xml (6 079 balls, 3 static planes; portal ignored), integrator forced to symplectic_euler, dt = 1/10080"}[config]
+
+
+def config_dict(config, scene_n):
+    """Identical in both arms (the driver compares it)."""
+    return {"workload": workload_name(config), "bodies": int(scene_n)}
+
+
+def map_kind(scene):
+    return 0 if scene["map"] == "symplectic_euler" else 1
 
 
 class ClockSampler:
@@ -105,17 +120,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel_name):
-    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/ncu_rNN.json, written by profiles/summarize.py); None when no capture covers it."""
+def ncu_traffic(kernel_name, config):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    workload (profiles/ncu_rNN_cK.json, written by profiles/summarize.py); None when no capture covers it."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_c%d.json" % config))) or (sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*.json"))) if config == 2 else [])
     if not files:
         return None, None
     data = json.load(open(files[-1]))
     for k, v in data.items():
         if ("sg_" + kernel_name) in k or kernel_name in k:
-            return v.get("dram_traffic"), os.path.basename(files[-1])
+            scale = v.get("bodies_scale", 1.0)   # capture taken on a smaller slice of the workload: traffic scales with the bodies
+            t = v.get("dram_traffic")
+            return (t * scale if t is not None else None), os.path.basename(files[-1])
     return None, os.path.basename(files[-1])
 
 
@@ -125,10 +142,12 @@ def cpu_reference_step(scene, steps, warmup):
     kind "reference": broad phase + CCD are the reference's OWN ball2d/SpatialGridDetector.cpp and
     scisim/CollisionDetection/CollisionDetectionUtilities.cpp, compiled unchanged from the reference tree against the Eigen
     stand-in (oracle/_ref/libref_ball2d.so, oracle/Makefile.ref); the map and the swept boxes around them are the oracle's
-    restatement.  kind "port": everything is the restatement (oracle/_ref not built)."""
+    restatement; the static-plane pass (a few thousand contacts) is neither timed nor counted.
+    kind "port": everything is the restatement (oracle/_ref not built)."""
     import ctypes as C
     from tests import oracle_binding as ob
     o = ob.Ball2DOracle(scene)
+    kind = map_kind(scene)
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_ball2d.so")
     times, pairs = [], 0
     if os.path.exists(ref_path):
@@ -137,26 +156,22 @@ def cpu_reference_step(scene, steps, warmup):
         q0 = np.ascontiguousarray(scene["q"], dtype=np.float64)
         r = np.ascontiguousarray(scene["r"], dtype=np.float64)
         n = r.shape[0]
-        # static-geometry contacts (a few thousand, O(N x planes) to find) are counted once with the restatement
-        q1, _ = o.flow(0, scene["q"], scene["v"], scene["dt"])
-        a = o.active_set(scene["q"], q1, "grid")
-        n_static = int((a["type"] != 0).sum())
         for it in range(warmup + steps):
-            q1, v1 = o.flow(0, scene["q"], scene["v"], scene["dt"])
+            q1, v1 = o.flow(kind, scene["q"], scene["v"], scene["dt"])
             t_flow = float(o.lib.orc_ball2d_seconds_flow(o.h))
             nc, na = C.c_uint64(0), C.c_uint64(0)
             q1c = np.ascontiguousarray(q1)
             t0 = time.perf_counter()
             ref.ref_ball2d_detect(C.c_uint32(n), q0.ctypes.data_as(C.c_void_p), q1c.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), C.byref(nc), C.byref(na), None, C.c_uint64(0))
             t = time.perf_counter() - t0 + t_flow
-            pairs = int(nc.value) + int(na.value) + n_static
+            pairs = int(nc.value) + int(na.value)
             if it >= warmup:
                 times.append(t)
-        assert int(nc.value) == a["candidates"].shape[0] and int(na.value) + n_static == a["type"].shape[0]
         return pairs, times, "reference", ("broad phase + CCD = the reference's own SpatialGridDetector.cpp / CollisionDetectionUtilities.cpp (compiled unchanged against "
-                                           "oracle/eigen_standin), map + swept boxes = oracle restatement (the map checked bit for bit against the reference's compiled SymplecticEulerMap.cpp, tests/test_oracle_vs_reference.py)")
+                                           "oracle/eigen_standin), map + swept boxes = oracle restatement (the map checked bit for bit against the reference's compiled maps, tests/test_oracle_vs_reference.py); "
+                                           "static-plane contacts neither timed nor counted")
     for it in range(warmup + steps):
-        q1, v1 = o.flow(0, scene["q"], scene["v"], scene["dt"])
+        q1, v1 = o.flow(kind, scene["q"], scene["v"], scene["dt"])
         a = o.active_set(scene["q"], q1, "grid")
         t = a["seconds"] + a["seconds_flow"]
         pairs = a["candidates"].shape[0] + a["type"].shape[0]
@@ -165,13 +180,21 @@ def cpu_reference_step(scene, steps, warmup):
     return pairs, times, "port", "reference CPU path restated in oracle/ (its own std::map/std::set data structures)"
 
 
+def cpu_sample_scene(config):
+    """The bounded sample the CPU arms run: configs 1 and 2 whole, config 3 at N_CPU_SAMPLE bodies (same generator, same
+    density and radius distribution)."""
+    if config == 3:
+        return make_scene(3, N_CPU_SAMPLE), "config 3 at %d balls (same generator: same density, radius distribution, walls and map; the 16M scene's std::set alone would need > 4 GB and minutes per step)" % N_CPU_SAMPLE
+    return make_scene(config), "the whole scene"
+
+
 def cpu_parallel_step(scene, steps, warmup):
     """NOT reference behaviour (the optional second CPU figure): the same step written for a multi-core CPU
     (oracle/ball2d_parallel.h -- all host threads over bodies, flat grid by counting sort), lists built, results identical to
     the restatement's (tests/test_oracle_parallel.py).  Returns the cpu_baseline_parallel object."""
     from tests import oracle_binding as ob
     o = ob.Ball2DOracle(scene)
-    kind = 0 if scene["map"] == "symplectic_euler" else 1
+    kind = map_kind(scene)
     times, pairs, threads = [], 0, 1
     # one thread per core this process may run on (cgroup / affinity aware), not per core of the machine
     try:
@@ -184,15 +207,15 @@ def cpu_parallel_step(scene, steps, warmup):
         if it >= warmup:
             times.append(r["seconds"])
     return {"value": pairs * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port-multithreaded",
-            "sample": "%d full steps of the same scene, candidate and contact lists built" % len(times),
+            "sample": "%d full steps of the CPU sample scene, candidate and contact lists built" % len(times),
             "note": "NOT reference behaviour: SCISim's hot path is single-threaded even with USE_OPENMP (that is cpu_baseline); this is the same step "
                     "written for a multi-core CPU (oracle/ball2d_parallel.h), reported so that the GPU figure is not compared with one core only"}
 
 
-def cpu_parallel_guarded(steps, warmup):
+def cpu_parallel_guarded(config, steps, warmup):
     """cpu_parallel_step in a child process with a time limit: an optional figure must not be able to take the bench line down."""
     import subprocess
-    code = "import json, bench; print(json.dumps(bench.cpu_parallel_step(bench.scene_for_rank(0, 1), %d, %d)))" % (steps, warmup)
+    code = "import json, bench; print(json.dumps(bench.cpu_parallel_step(bench.cpu_sample_scene(%d)[0], %d, %d)))" % (config, steps, warmup)
     try:
         out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
         if out.returncode != 0:
@@ -206,18 +229,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = scene_for_rank(0, 1)
-    pairs, times, kind, how = cpu_reference_step(scene, args.steps, min(args.warmup, 1))
+    scene, sample = cpu_sample_scene(args.config)
+    full_n = N_CONFIG3 if args.config == 3 else scene["r"].shape[0]
+    warm = min(args.warmup, 1)
+    pairs, times, kind, how = cpu_reference_step(scene, args.steps, warm)
     total = sum(times)
     value = pairs * len(times) / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(1), "bodies": NX * NY, "note": how + "; the reference's hot path is single-threaded even with USE_OPENMP (SURVEY.md F2)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "full 1M-ball step (flow + spatial-grid broad phase + CCD), %d steps; %s" % (len(times), how)},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.config, full_n),
+        "note": how + "; the reference's hot path is single-threaded even with USE_OPENMP (SURVEY.md F2); warm-up steps actually run: %d" % warm,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "%s, %d bodies, %d timed steps (flow + spatial-grid broad phase + CCD); %s" % (sample, scene["r"].shape[0], len(times), how)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": len(times) / total,
-        "cpu_baseline_parallel": cpu_parallel_guarded(5, 1),
+        "cpu_baseline_parallel": cpu_parallel_guarded(args.config, 3, 1),
     }
     print(json.dumps(line))
 
@@ -243,13 +269,56 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def parity_check(config, world, rank, dist, ctx, transport):
+    """A reduced-size scene of the same kind through the SAME code path the timed steps take at this N -- on N > 1:
+    x-quantile partition, halo exchange, per-rank detection, merge into the reference's order -- against the CPU oracle."""
+    import numpy as np
+    import scisim_b200 as sb
+    s = make_scene(3, N_PARITY) if config == 3 else make_scene(config)
+    kind = map_kind(s)
+    umap = sb.SymplecticEulerMap() if kind == 0 else sb.VerletMap()
+    if world == 1:
+        st = sb.Ball2DState(s["r"], s["m"], s["g"], s["plane_x"], s["plane_n"], s["drum_x"], s["drum_r"])
+        sim = sb.Ball2DSim(st, ctx=ctx)
+        sim.upload(s["q"], s["v"])
+        sim.step(umap, s["dt"])
+        q1, v1, a = sim.fetch()
+        got = {"q1": q1, "v1": v1, "candidates": a.candidates, "type": a.type, "i": a.i, "j": a.j, "n": a.n, "p": a.p, "depth": a.depth}
+        parts = 1
+    else:
+        from scisim_b200.slab import Ball2DSlabSim, GpuSlabBackend
+        factory = lambda sl, gids, lim, cap: GpuSlabBackend(ctx, sl, 0, cap, gids=gids, x_limits=lim)
+        sim = Ball2DSlabSim(s, rank, world, dist, factory, transport=transport)
+        sim.upload(s["q"], s["v"])
+        sim.step(kind, s["dt"])
+        got = sim.gather_merged(0)
+        parts = sim.n_partitions
+        sim.backend.disconnect()
+    if rank != 0:
+        return None
+    from tests import oracle_binding as ob
+    o = ob.Ball2DOracle(s)
+    rq1, rv1 = o.flow(kind, s["q"], s["v"], s["dt"])
+    ref = o.active_set(s["q"], rq1, "grid")
+    bad = [k for k in ("q1", "v1") if not np.array_equal(got[k], (rq1, rv1)[k == "v1"])]
+    bad += [k for k in ("candidates", "type", "i", "j", "n", "p") if not np.array_equal(got[k], ref[k])]
+    if not np.array_equal(got["depth"], ref["depth"], equal_nan=True):
+        bad.append("depth")
+    return {"ok": not bad, "mismatch": bad, "bodies": int(s["r"].shape[0]), "candidates": int(ref["candidates"].shape[0]), "active": int(ref["type"].shape[0]), "partitions": parts,
+            "what": "q1, v1, candidate list and active set (type, i, j, n, p, depth) of a reduced-size scene of this workload, through the same path as the timed steps at this N, bit-identical to the CPU oracle in the reference's order"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3], help="3: BASELINE configs[2] (16M polydisperse balls; default, any N); 2: configs[1] (1M pile, N = 1); 1: configs[0] (bundled scene, N = 1)")
+    ap.add_argument("--bodies", type=int, default=0, help="config 3 only: override the body count (for experiments; the headline is 16 777 216)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-2 side measurement at N = 1")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: peer-memory mailboxes over NVLink (CUDA IPC) or NCCL all_gather + send/recv")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -259,6 +328,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.config != 3:
+        raise SystemExit("--config %d is a single-GPU workload" % args.config)
     import numpy as np
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
@@ -272,11 +343,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import scisim_b200 as sb
-    scene = scene_for_rank(rank, world)
+    scene = make_scene(args.config, args.bodies or None)
+    n_total = scene["r"].shape[0]
     ctx = sb.Context(local_rank)
-    umap = sb.SymplecticEulerMap()
+    kind = map_kind(scene)
+    umap = sb.SymplecticEulerMap() if kind == 0 else sb.VerletMap()
     dt = scene["dt"]
-    n = scene["r"].shape[0]
 
     def barrier():
         ctx.synchronize()
@@ -285,19 +357,28 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(args.config, world, rank, dist, ctx, args.transport)
+        barrier()
+
     if world == 1:
         st = sb.Ball2DState(scene["r"], scene["m"], scene["g"], scene["plane_x"], scene["plane_n"], scene["drum_x"], scene["drum_r"])
         sim = sb.Ball2DSim(st, ctx=ctx)
         sim.upload(scene["q"], scene["v"])
         step = lambda: sim.step(umap, dt)
+        n_local = n_total
+        halo = (0, 0)
     else:
-        # one slab per GPU, ghosts exchanged with the neighbouring slabs every step (scisim_b200/slab.py): by the kernels
-        # themselves through peer-mapped mailboxes (default), or by NCCL all_gather + send/recv
-        from scisim_b200.slab import Ball2DSlabs, GpuSlabBackend
-        backend = GpuSlabBackend(ctx, scene, rank * n, ghost_cap=max(4096, n // 128))
-        slabs = Ball2DSlabs(backend, rank, world, dist, transport=args.transport)
-        step = lambda: slabs.step(umap.kind, dt)
+        # one x-quantile slab per GPU, ghosts exchanged with the neighbouring slabs every step (scisim_b200/slab.py): by the
+        # kernels themselves through peer-mapped mailboxes (default), or by NCCL all_gather + send/recv
+        from scisim_b200.slab import Ball2DSlabSim, GpuSlabBackend
+        factory = lambda sl, gids, lim, cap: GpuSlabBackend(ctx, sl, 0, cap, gids=gids, x_limits=lim)
+        slabs = Ball2DSlabSim(scene, rank, world, dist, factory, transport=args.transport)
+        slabs.upload(scene["q"], scene["v"])
+        step = lambda: slabs.step(kind, dt)
         args.transport = slabs.transport   # what the ranks agreed on (p2p falls back to nccl when a mailbox cannot be mapped)
+        n_local = int(slabs.gids.shape[0])
 
     # ---------------- resident path: `value` ----------------
     barrier()                   # also warms the barrier's own collective up before anything is timed
@@ -317,6 +398,8 @@ def main():
     gpu_launches = ctx.launch_count() - launches0
     t_local = sum(step_ms) / 1e3
     pairs_local = float(pc + pa)
+    if world > 1:
+        halo = slabs.driver.last_halo
 
     # ---------------- per-kernel roofline (same steps, events around every kernel) ----------------
     ctx.profile_enable(True)
@@ -329,39 +412,40 @@ def main():
 
     # ---------------- e2e: host buffers in, host lists out, every step ----------------
     flags = sb.SG_OUT_NORMALS | sb.SG_OUT_POINTS | sb.SG_OUT_DEPTHS
-    e2e_steps = max(3, min(args.steps, 10))
-    q0h, v0h = ctx.pinned((2 * n,)), ctx.pinned((2 * n,))
-    q1h, v1h = ctx.pinned((2 * n,)), ctx.pinned((2 * n,))
-    q0h[:] = scene["q"]; v0h[:] = scene["v"]
+    e2e_steps = max(3, min(args.steps, 5))
+    q0h, v0h = ctx.pinned((2 * n_local,)), ctx.pinned((2 * n_local,))
+    q1h, v1h = ctx.pinned((2 * n_local,)), ctx.pinned((2 * n_local,))
     if world == 1:
-        for it in range(2 + e2e_steps):
-            if it == 2:
+        q0h[:] = scene["q"]; v0h[:] = scene["v"]
+        for it in range(1 + e2e_steps):
+            if it == 1:
                 barrier()
                 t0 = time.perf_counter()
             sim._flow(umap.kind, q0h, v0h, dt, q1h, v1h)
             a = sim.computeActiveSet(q0h, q1h, flags=flags, copy=False, resident=True)   # (q0, q1) of the flow just done, as ImpactMap::flow passes them
         ctx.synchronize()
         t_e2e_local = time.perf_counter() - t0
-        h2d = 2 * 2 * n * 8
         n_act, e2e_api = a.n_active, "sg_ball2d_flow (q0,v0 up; q1,v1 down) + sg_ball2d_active_set(SG_IN_RESIDENT: the flow's q0,q1 stay on the device; contacts down), pinned host buffers, wall clock"
         assert a.n_active == pa and a.n_candidates == pc
     else:
         import ctypes as C
         from scisim_b200._lib import SgContacts
         vp = lambda x: x.ctypes.data_as(C.c_void_p)
-        for it in range(2 + e2e_steps):
-            if it == 2:
+        q0h[:] = scene["q"].reshape(-1, 2)[slabs.gids].ravel(); v0h[:] = scene["v"].reshape(-1, 2)[slabs.gids].ravel()
+        for it in range(1 + e2e_steps):
+            if it == 1:
                 barrier()
                 t0 = time.perf_counter()
             ctx.check(ctx.lib.sg_ball2d_upload(ctx.h, vp(q0h), vp(v0h)))
-            slabs.step(umap.kind, dt)
+            slabs.step(kind, dt)
             c = SgContacts()
             ctx.check(ctx.lib.sg_ball2d_fetch(ctx.h, flags, vp(q1h), vp(v1h), C.byref(c)))
         ctx.synchronize()
         t_e2e_local = time.perf_counter() - t0
-        h2d = 2 * 2 * n * 8
-        n_act, e2e_api = int(c.n_active), "sg_ball2d_upload + slab step (%s halo) + sg_ball2d_fetch, pinned host buffers, wall clock" % args.transport
-    d2h = 2 * 2 * n * 8 + n_act * (4 + 4 + 4 + 16 + 16 + 8)
+        n_act, e2e_api = int(c.n_active), ("per rank: sg_ball2d_upload (owned q0,v0) + slab step (%s halo) + sg_ball2d_fetch (owned q1,v1 + this rank's contact list in global indices), pinned host buffers, wall clock; "
+                                           "the per-rank lists are each ascending and merge into the reference's order body by body (sg_slab_merge_dest) -- not inside this timed region" % args.transport)
+    h2d = 2 * 2 * n_local * 8
+    d2h = 2 * 2 * n_local * 8 + n_act * (4 + 4 + 4 + 16 + 16 + 8)
     # the sampler ran from just before the timed steps to here (timed region, per-kernel pass, e2e pass: all under load)
     clocks = sampler.stop() if sampler else None
 
@@ -369,12 +453,32 @@ def main():
     if world > 1:
         tt = torch.tensor([t_local, t_e2e_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ww = torch.tensor([pairs_local, float(pc), float(pa)], dtype=torch.float64, device="cuda")
+        ww = torch.tensor([pairs_local, float(pc), float(pa), float(h2d), float(d2h), float(halo[0] + halo[1])], dtype=torch.float64, device="cuda")
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
         t_max, t_e2e = float(tt[0]), float(tt[1])
-        pairs_all = float(ww[0])
+        pairs_all, pc_all, pa_all, h2d_all, d2h_all, halo_all = [float(x) for x in ww]
     else:
-        t_max, t_e2e, pairs_all = t_local, t_e2e_local, pairs_local
+        t_max, t_e2e, pairs_all, pc_all, pa_all, h2d_all, d2h_all, halo_all = t_local, t_e2e_local, pairs_local, float(pc), float(pa), float(h2d), float(d2h), 0.0
+
+    # ---------------- N = 1 extra: the config round 1 was quoted on ----------------
+    extra = None
+    if world == 1 and args.config == 3 and not args.no_extras:
+        del sim
+        s2 = make_scene(2)
+        sim2 = sb.Ball2DSim(sb.Ball2DState(s2["r"], s2["m"], s2["g"], s2["plane_x"], s2["plane_n"], s2["drum_x"], s2["drum_r"]), ctx=ctx)
+        sim2.upload(s2["q"], s2["v"])
+        for _ in range(3):
+            ctx.flush_l2(); sim2.step(sb.SymplecticEulerMap(), s2["dt"])
+        ms2 = []
+        for _ in range(20):
+            ctx.flush_l2(); ctx.timer_begin(); c2 = sim2.step(sb.SymplecticEulerMap(), s2["dt"]); ms2.append(ctx.timer_end())
+        ctx.profile_enable(True); ctx.profile_reset()
+        for _ in range(20):
+            ctx.flush_l2(); sim2.step(sb.SymplecticEulerMap(), s2["dt"])
+        p2 = ctx.profile(); ctx.profile_enable(False)
+        extra = {"workload": workload_name(2), "value": (c2[0] + c2[1]) * len(ms2) / (sum(ms2) / 1e3), "unit": UNIT, "ms_per_step": sum(ms2) / len(ms2), "candidates": c2[0], "active": c2[1],
+                 "kernels_us": {k: round(1e3 * v[1] / 20, 1) for k, v in sorted(p2.items(), key=lambda kv: -kv[1][1])},
+                 "kernels_alg_GBps": {k: round(v[2] / (v[1] * 1e-3) / 1e9, 0) for k, v in p2.items() if v[1] > 0}}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -382,32 +486,39 @@ def main():
         top = max(prof.items(), key=lambda kv: kv[1][1])
         name, (nl, ms, by) = top
         achieved = (by / nl) / (ms / nl * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(name)
+        traffic, traffic_src = ncu_traffic(name, args.config)
         kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps, "share": v[1] / total_ms,
                        "alg_GBps": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        cfg = config_dict(args.config, n_total)
         line = {
             "metric": METRIC, "value": pairs_all * args.steps / t_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(world), "bodies_per_gpu": n, "candidates_per_gpu": pc, "active_per_gpu": pa,
-                       "l2": "384 MB buffer overwritten before every timed step (L2 flush)", "timing": "CUDA events on the library stream, per step, summed; max over ranks",
-                       "parallelism": ("%d x-slabs, 1 process per GPU, ghost bodies exchanged with +-1 neighbours each step (%s), pair owned by the rank of its lower index" % (world, "peer-memory mailboxes over NVLink, no collective in the step" if args.transport == "p2p" else "NCCL all_gather + send/recv")) if world > 1 else "single GPU"},
+            "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "run": {"bodies_rank0": n_local, "candidates": pc_all, "active": pa_all, "candidate_pairs_per_s": pc_all * args.steps / t_max, "halo_bodies_per_step": halo_all,
+                    "l2": "384 MB buffer overwritten before every timed step (L2 flush)", "timing": "CUDA events on the library stream, per step, summed; max over ranks",
+                    "parallelism": ("%d equal-count x-quantile slabs of the randomly numbered scene, 1 process per GPU, ghost bodies exchanged with +-1 neighbours each step (%s), pair owned by the rank of its lower global index, "
+                                    "per-step agreement on re-partitioning (one 4-byte all_reduce)" % (world, "peer-memory mailboxes over NVLink, no collective on the data path" if args.transport == "p2p" else "NCCL all_gather + send/recv")) if world > 1 else "single GPU"},
             "host_cores_bound": numa,
             "steps_per_s": args.steps / t_max,
             "step_ms_rank0": [round(x, 4) for x in step_ms],
             "clocks": clocks,
             "gpu_launches": gpu_launches,
-            "e2e": {"value": pairs_all * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / e2e_steps,
+            "parity_check": parity,
+            "e2e": {"value": pairs_all * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": 1e3 * t_e2e / e2e_steps,
                     "api": e2e_api},
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": by / nl,
-                         "peak_source": peak_src, "share_of_step": ms / total_ms, "timed": "separate pass of the same %d steps with CUDA events around every kernel" % args.steps,
+                         "peak_source": peak_src, "share_of_step": ms / total_ms, "timed": "separate pass of the same %d steps with CUDA events around every kernel (rank 0)" % args.steps,
                          "kernels": kernels},
         }
+        if extra is not None:
+            line["config2"] = extra
         if not args.no_cpu_baseline:
-            pairs_cpu, times, kind, how = cpu_reference_step(scene_for_rank(0, 1), 3, 1)
+            sc, sample = cpu_sample_scene(args.config)
+            pairs_cpu, times, ckind, how = cpu_reference_step(sc, 2, 1)
             v = pairs_cpu * len(times) / sum(times)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
-                                    "sample": "3 full steps of the same 1M-ball scene; %s; the reference's hot path is single-threaded" % how}
-            line["cpu_baseline_parallel"] = cpu_parallel_guarded(5, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": ckind,
+                                    "sample": "%d timed steps of %s; %s; the reference's hot path is single-threaded" % (len(times), sample, how)}
+            line["cpu_baseline_parallel"] = cpu_parallel_guarded(args.config, 3, 1)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

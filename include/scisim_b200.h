@@ -33,6 +33,7 @@ extern "C" {
 #define SG_ERR_CUDA 2        /* CUDA runtime error */
 #define SG_ERR_UNSUPPORTED 3 /* pair of geometry types the reference itself aborts on */
 #define SG_ERR_INTERNAL 4
+#define SG_ERR_REBALANCE 5   /* multi-GPU slabs: a body left its slab's neighbourhood -- re-partition the scene and repeat the step */
 
 /* UnconstrainedMap implementations (created by name in ball2d/Ball2DUtilities.cpp:37,
  * rigidbody2d/RigidBody2DUtilities.cpp:39-43, rigidbody3d/RigidBody3DUtilities.cpp:40-44) */
@@ -47,6 +48,7 @@ extern "C" {
  * (RigidBody3DState.cpp:444-446): from then on M(r,c) = I(r,c).  I is symmetric only up to rounding, so the two differ in the last
  * bit of the angular momentum when the angular velocity is not zero.  Without the flag: M as constructed. */
 #define SG_MAP_M_UPDATED 0x100
+#define SG_MAP_NONE (-1)           /* slab calls only: q1 was supplied by the caller (sg_ball2d_slab_upload_q1), nothing is integrated */
 
 /* contact types, in the order the reference appends them to active_set */
 #define SG_BALL_BALL 0   /* ball2d/Constraints/BallBallConstraint */
@@ -228,6 +230,8 @@ int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint3
 int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
+/* q1, v1 (either may be NULL) as the last flow / step / sg_ball2d_slab_flow on this context left them on the device (slab mode: the owned block) */
+int sg_ball2d_fetch_state( sg_ctx* ctx, double* q1, double* v1 );
 
 /* Peer-memory halo exchange (one process per GPU, neighbours' mailboxes mapped over NVLink with CUDA IPC; no
    collective, no host round trip).  No reference counterpart (SCISim is single-process); see DESIGN.md section 5.
@@ -248,25 +252,79 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase );
 /* drops the mailbox and the neighbour mappings: the context is back on the pack / unpack calls (collective transport) */
 int sg_ball2d_slab_disconnect( sg_ctx* ctx );
 
-/* Slab mode (multi-GPU): this context holds bodies [gid_first, gid_first + n_owned) of a larger scene
- * whose global numbering is slab-major, plus per-step ghost copies of neighbouring slabs' bodies.  The reference has no
- * distributed mode; these calls are driven by scisim_b200/slab.py (one process per GPU, NCCL for the exchange).
- *   init    reserve ghost_cap slots on either side of the owned block; upload r, m of the owned bodies
- *   (sg_ball2d_upload / sg_ball2d_fetch then address the owned block only)
- *   flow    integrate the owned bodies; *interval_dev (DEVICE pointer, 2 doubles) receives [min lo.x, max hi.x] of their
- *           swept AABBs -- what the other ranks need to select the ghosts they owe this one
- *   pack    ordered list of the owned bodies whose swept AABB overlaps the x-interval at interval_dev (DEVICE) into
- *           send_dev (DEVICE, cap + 1 records of 48 bytes; record 0 is a header carrying the count, so the receiver learns
- *           it on the device); the count also goes to *count_dev (DEVICE).  send_dev = NULL: count only
- *   unpack  take a received buffer (same layout) as this step's ghosts on side 0 (lower global indices) or 1 (higher)
- *   detect  broad + narrow phase over owned + ghosts; a pair is kept iff this rank owns the body with the smaller
- *           global index; planes / drums are tested for owned bodies only; indices in the lists are global.
- *           ghosts_out (optional, 2 values): how many ghosts arrived on each side.  Nothing before detect blocks the host. */
+/* Slab mode (multi-GPU): this context holds ONE spatial slab of a larger scene -- n_owned bodies of arbitrary global
+ * numbering, stored in ascending global index -- plus per-step ghost copies of the neighbouring slabs' bodies.  The reference has no
+ * distributed mode; these calls are driven by sg_multi (one process, N GPUs: below) or by scisim_b200/slab.py (one process per GPU).
+ *   init      reserve ghost_cap slots on either side of the owned block; upload r, m of the owned bodies; the owned bodies get the
+ *             global indices gid_first, gid_first + 1, ... until set_gids says otherwise
+ *   set_gids  gid_owned (n_owned values, strictly ascending): global index of every owned body; x_limits (2 values, either may be
+ *             NULL): the x-range the owned bodies' swept boxes must stay inside.  A body outside could touch a body of a
+ *             NON-neighbouring slab, which no halo carries: detect then returns SG_ERR_REBALANCE (re-partition, repeat the step)
+ *   (sg_ball2d_upload / sg_ball2d_fetch then address the owned block only; sg_ball2d_slab_upload_q1 supplies an externally
+ *   computed q1 for the owned block, to be followed by flow( SG_MAP_NONE ))
+ *   flow      integrate the owned bodies; *interval_dev (DEVICE pointer, 2 doubles) receives [min lo.x, max hi.x] of their
+ *             swept AABBs -- what the other ranks need to select the ghosts they owe this one
+ *   pack      list of the owned bodies whose swept AABB overlaps the x-interval at interval_dev (DEVICE) into
+ *             send_dev (DEVICE, cap + 1 records of 48 bytes; record 0 is a header carrying the count, so the receiver learns
+ *             it on the device); the count also goes to *count_dev (DEVICE).  send_dev = NULL: count only
+ *   unpack    take a received buffer (same layout) as this step's ghosts from the neighbour on side 0 (lower x) or 1 (higher x)
+ *   detect    broad + narrow phase over owned + ghosts; a pair is kept iff this rank owns the body with the smaller
+ *             global index; planes / drums are tested for owned bodies only; indices in the lists are global and every list is
+ *             ascending, so the per-rank lists merge into the reference's order (sg_slab_merge_dest).
+ *             ghosts_out (optional, 2 values): how many ghosts arrived on each side.  Nothing before detect blocks the host. */
 int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint32_t ghost_cap, const double* r, const double* m );
+int sg_ball2d_slab_set_gids( sg_ctx* ctx, const uint32_t* gid_owned, const double* x_limits );
+int sg_ball2d_slab_upload_q1( sg_ctx* ctx, const double* q1 );
 int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_dev );
 int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev, uint32_t cap, uint32_t* count_dev );
 int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev );
 int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out );
+
+/* ---- multi-GPU: host helpers of the slab decomposition (no device work, no context) -----------------------------
+ * sg_slab_partition   equal-count x-quantiles: bodies ranked by ( x, index ), slab k takes ranks
+ *                     [ k n / world, (k+1) n / world ).  x[ i * x_stride ] = x of body i (ball2d: q, stride 2).
+ *                     rank_of[n] <- slab of every body; cuts[world + 1] (may be NULL) <- scene extent and the world - 1 cut positions
+ * sg_slab_limits      the x-range bodies of slab `rank` must stay inside (sg_ball2d_slab_set_gids): the slab widened by half the
+ *                     width of each neighbouring slab, so that bodies of slabs k and k + 2 can never touch
+ * sg_slab_merge_dest  per-slab lists, each ascending in its first index and with every body's entries in ONE slab (the owner of
+ *                     the pair's lower index), merge body by body: dest[k][e] <- position of entry e of slab k in the merged list,
+ *                     which is the reference's ascending (i,j) order (the std::set of ball2d/Ball2DSim.cpp:580).
+ *                     first[k][e * stride] = first index of the entry (stride 2 for a candidate list, 1 for the i column)
+ * sg_slab_merge_static_dest  the same for the static contacts behind them: ordered by ( type, j = geometry, i = body ),
+ *                     i.e. drums drum-major then planes plane-major, body ascending (Ball2DSim.cpp:735-761) */
+int sg_slab_partition( uint32_t n, const double* x, uint32_t x_stride, uint32_t world, uint32_t* rank_of, double* cuts );
+int sg_slab_limits( uint32_t world, const double* cuts, uint32_t rank, double* limits /* 2 */ );
+int sg_slab_merge_dest( uint32_t n_bodies, uint32_t n_parts, const uint32_t* const* first, uint32_t stride, const uint64_t* len, uint64_t* const* dest );
+int sg_slab_merge_static_dest( uint32_t n_parts, const uint32_t* const* type, const uint32_t* const* i, const uint32_t* const* j, const uint64_t* len, uint64_t* const* dest );
+
+/* ---- multi-GPU in ONE process (what a SCISim process links against to use several GPUs; SURVEY.md 8b sketched it as
+ * sg_create( ctx, n_gpus, devices )).  sg_multi owns one context and one worker thread per GPU, partitions the scene into
+ * x-slabs, and offers the calls of a single ball2d context over GLOBAL vectors and indices:
+ *   set_bodies / set_gravity / set_planes / set_drums     as sg_ball2d_set_*
+ *   flow        UnconstrainedMap::flow over host vectors (q0, v0 are partitioned and uploaded, q1, v1 come back)
+ *   active_set  ConstrainedSystem::computeActiveSet: merged lists in the reference's order, pointers into memory owned by
+ *               sg_multi, valid until the next call.  SG_IN_RESIDENT: (q0, q1) of the flow just done (ImpactMap.cpp:54-58)
+ *   upload / step / fetch   the resident variant (step leaves everything on the GPUs, *out carries the counts only)
+ * The scene is (re-)partitioned at the first upload, whenever a slab reports SG_ERR_REBALANCE or runs out of ghost slots (the
+ * step is then repeated on the new partition, invisibly to the caller), and every `every_n_uploads` uploads if set.
+ * devices = NULL: GPUs 0 .. n_gpus - 1.  The same device may be listed more than once (testing on one GPU). */
+typedef struct sg_multi sg_multi;
+int sg_create_multi( sg_multi** m, int n_gpus, const int* devices );
+void sg_destroy_multi( sg_multi* m );
+const char* sg_multi_last_error( const sg_multi* m ); /* m may be NULL: error of a failed sg_create_multi */
+int sg_multi_n_gpus( const sg_multi* m );
+sg_ctx* sg_multi_context( sg_multi* m, int k );       /* slab k's context (timers, profile, launch count) */
+int sg_multi_set_rebalance( sg_multi* m, uint32_t every_n_uploads, uint32_t ghost_cap /* 0: chosen from the slab size */ );
+int sg_multi_partition_info( sg_multi* m, double* cuts /* n_gpus + 1 */, uint32_t* n_owned /* n_gpus */, uint32_t* ghosts /* 2 n_gpus */, uint64_t* n_partitions );
+int sg_multi_ball2d_set_bodies( sg_multi* m, uint32_t n, const double* r, const double* mass );
+int sg_multi_ball2d_set_gravity( sg_multi* m, const double* g /* 2 */ );
+int sg_multi_ball2d_set_planes( sg_multi* m, uint32_t n, const double* x /* 2n */, const double* nrm /* 2n */ );
+int sg_multi_ball2d_set_drums( sg_multi* m, uint32_t n, const double* x /* 2n */, const double* r /* n */ );
+int sg_multi_ball2d_flow( sg_multi* m, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 );
+int sg_multi_ball2d_active_set( sg_multi* m, const double* q0, const double* q1, uint32_t out_flags, sg_contacts* out );
+int sg_multi_ball2d_upload( sg_multi* m, const double* q, const double* v );
+int sg_multi_ball2d_step( sg_multi* m, int map_kind, double dt, sg_contacts* out );
+int sg_multi_ball2d_fetch( sg_multi* m, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
 
 /* ---- rigidbody2d --------------------------------------------------------------------------------------
  * q = v-layout [x, y, theta] per body (rigidbody2d/RigidBody2DState.h). M = the 3N diagonal of the mass matrix

@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libscisim_b200.so")
 
 SG_OK = 0
+SG_ERR_INVALID, SG_ERR_CUDA, SG_ERR_UNSUPPORTED, SG_ERR_INTERNAL, SG_ERR_REBALANCE = 1, 2, 3, 4, 5
+SG_MAP_NONE = -1
 SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV = 0, 1, 2, 3
 SG_MAP_M_UPDATED = 0x100  # rigidbody3d flows after the first: M as updateMandMinv leaves it (include/scisim_b200.h)
 SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
@@ -87,6 +89,29 @@ def load():
         "sg_ball2d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
         "sg_ball2d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
         "sg_ball2d_slab_init": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
+        "sg_ball2d_slab_set_gids": (C.c_int, [vp, vp, vp]),
+        "sg_ball2d_slab_upload_q1": (C.c_int, [vp, vp]),
+        "sg_ball2d_fetch_state": (C.c_int, [vp, vp, vp]),
+        "sg_slab_partition": (C.c_int, [C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp]),
+        "sg_slab_limits": (C.c_int, [C.c_uint32, vp, C.c_uint32, vp]),
+        "sg_slab_merge_dest": (C.c_int, [C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp]),
+        "sg_slab_merge_static_dest": (C.c_int, [C.c_uint32, vp, vp, vp, vp, vp]),
+        "sg_create_multi": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
+        "sg_destroy_multi": (None, [vp]),
+        "sg_multi_last_error": (C.c_char_p, [vp]),
+        "sg_multi_n_gpus": (C.c_int, [vp]),
+        "sg_multi_context": (vp, [vp, C.c_int]),
+        "sg_multi_set_rebalance": (C.c_int, [vp, C.c_uint32, C.c_uint32]),
+        "sg_multi_partition_info": (C.c_int, [vp, vp, vp, vp, vp]),
+        "sg_multi_ball2d_set_bodies": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_multi_ball2d_set_gravity": (C.c_int, [vp, vp]),
+        "sg_multi_ball2d_set_planes": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_multi_ball2d_set_drums": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "sg_multi_ball2d_flow": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, vp, vp]),
+        "sg_multi_ball2d_active_set": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(SgContacts)]),
+        "sg_multi_ball2d_upload": (C.c_int, [vp, vp, vp]),
+        "sg_multi_ball2d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
+        "sg_multi_ball2d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
         "sg_ball2d_slab_flow": (C.c_int, [vp, C.c_int, C.c_double, vp]),
         "sg_ball2d_slab_pack": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
         "sg_ball2d_slab_unpack": (C.c_int, [vp, C.c_int, vp]),

@@ -25,6 +25,7 @@ struct Ball2DIn
   // slab mode: slots [0, ghost_counts[0]) and [own_first + own_count, ... + ghost_counts[1]) hold ghosts, the other
   // non-owned slots are unused this step.  nullptr on one GPU (every slot is a body).
   const uint32_t* ghost_counts;
+  const uint32_t* gid; // slab mode: global body index of every slot; nullptr on one GPU (identity)
 };
 
 __device__ __forceinline__ bool ball2d_slot_valid( const Ball2DIn& in, const uint32_t i )
@@ -42,7 +43,8 @@ struct alignas( 64 ) Ball2DRec
   uint32_t idx;
   uint32_t key;
   uint32_t c1, c2; // cell row (and layer)
-  double pad1;
+  uint32_t gid;    // ORDER word: global body index (== idx on one GPU); ranks the bodies in the emitted lists and is what they carry
+  uint32_t pad1;
 };
 
 struct ContactOut2D
@@ -93,6 +95,7 @@ struct Ball2DPolicy
   using Out = ContactOut2D;
   static constexpr uint32_t IDX_MASK = 0x7fffffffu;
   static constexpr uint32_t IDX_OFFSET = 40u;
+  static constexpr uint32_t ORD_OFFSET = 56u;
 
   // ball2d/Ball2DSim.cpp:566-571: lo = min(q1,q0) - r, hi = max(q1,q0) + r
   __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
@@ -110,7 +113,8 @@ struct Ball2DPolicy
     Rec rec;
     rec.q0x = a.x; rec.q0y = a.y; rec.q1x = b.x; rec.q1y = b.y;
     rec.r = __ldg( &in.r[i] );
-    rec.idx = ( i - in.own_first < in.own_count ) ? i : ( i | SG_GHOST_BIT ); rec.key = key; rec.c1 = c1; rec.c2 = c2; rec.pad1 = 0.0;
+    rec.idx = ( i - in.own_first < in.own_count ) ? i : ( i | SG_GHOST_BIT ); rec.key = key; rec.c1 = c1; rec.c2 = c2;
+    rec.gid = ( in.gid != nullptr ) ? __ldg( &in.gid[i] ) : i; rec.pad1 = 0u;
     return rec;
   }
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
@@ -120,6 +124,8 @@ struct Ball2DPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
   __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_ord( const Rec& s ) { return s.gid; }
+  __device__ static uint32_t rec_ord_raw( const Rec& s ) { return s.gid; }
   __device__ static bool owns( const Rec& s ) { return ( s.idx & SG_GHOST_BIT ) == 0u; }
   __device__ static bool valid( const In& in, const uint32_t i ) { return ball2d_slot_valid( in, i ); }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
@@ -138,9 +144,8 @@ struct Ball2DPolicy
       const double ex = a.q1x - b.q1x;
       const double ey = a.q1y - b.q1y;
       out.type[k] = SG_BALL_BALL;
-      const uint32_t ia = a.idx & IDX_MASK, ib = b.idx & IDX_MASK;
-      out.i[k] = out.gid( ia );
-      out.j[k] = out.gid( ib );
+      out.i[k] = a.gid;
+      out.j[k] = b.gid;
       out.n[k] = make_double2( nx, ny );
       out.p[k] = make_double2( a.q0x - a.r * nx, a.q0y - a.r * ny );
       out.depth[k] = fmin( 0.0, sqrt( ex * ex + ey * ey ) - ( a.r + b.r ) );
@@ -225,10 +230,10 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
                                                        const double* __restrict__ m, const double* __restrict__ r, const double gx, const double gy, const double dt,
                                                        double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts,
                                                        const uint32_t own_first, const uint32_t own_count, const uint32_t* __restrict__ ghost_counts, long long* __restrict__ interval_enc,
-                                                       double2* __restrict__ block_iv )
+                                                       double2* __restrict__ block_iv, const double xlim_lo, const double xlim_hi, uint32_t* __restrict__ slab_flags )
 {
   // q0, q1, r are indexed by slot ([ghosts | owned | ghosts] in slab mode); v0, m, v1 exist for owned bodies only.
-  // interval_enc != nullptr (slab mode, DO_FLOW): the ghosts have not arrived yet -- only owned bodies are live, and
+  // interval_enc != nullptr (slab mode, before the exchange): the ghosts have not arrived yet -- only owned bodies are live, and
   // [min lo.x, max hi.x] of their swept boxes is reduced for the neighbours; the ghosts' share of the bounds is added
   // by the unpack kernel.
   __shared__ uint32_t s_cnt[SG_MAX_DRUMS + SG_MAX_PLANES];
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
   double ext = 0.0;
   unsigned long long mask = 0ull;
   bool live = i < n;
-  if( live && DO_FLOW && interval_enc != nullptr ) { live = i - own_first < own_count; }
+  if( live && interval_enc != nullptr ) { live = i - own_first < own_count; }
   else if( live && ghost_counts != nullptr && i - own_first >= own_count )
   {
     live = ( i < own_first ) ? ( i < __ldg( &ghost_counts[0] ) ) : ( i - ( own_first + own_count ) < __ldg( &ghost_counts[1] ) );
@@ -290,11 +295,14 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
     lo[0] = fmin( qo.x, q.x ) - rad; lo[1] = fmin( qo.y, q.y ) - rad;
     hi[0] = fmax( qo.x, q.x ) + rad; hi[1] = fmax( qo.y, q.y ) + rad;
     ivlo = lo[0]; ivhi = hi[0];
+    // slab mode: an owned body whose swept box leaves [xlim_lo, xlim_hi] (this slab widened by half of each neighbouring slab) could reach a
+    // body of a non-neighbouring rank, which no halo would carry: flag it, sg_ball2d_slab_detect then asks for a re-partition
+    if( slab_flags != nullptr && ( lo[0] < xlim_lo || hi[0] > xlim_hi ) ) { slab_flags[3] = 1u; }
     sg_bp_bounds_update<2>( lo, hi, mn, mx, ext );
     if( i - own_first < own_count ) { mask = static_mask( sg, qo, rad ); } // ghosts touch no static geometry here
   }
   sg_bp_bounds_commit<2>( mn, mx, ext, acc );
-  if( DO_FLOW && interval_enc != nullptr )
+  if( interval_enc != nullptr )
   {
     // block reduce, then two atomics per block (same-address atomics from every warp would serialise in L2)
     __shared__ double s_iv[8][2];
@@ -418,6 +426,7 @@ struct Ball2DData
   // them are in use this step is only known on the device (ghost_counts), unused slots are skipped by every kernel.
   bool slab = false;
   uint32_t n_owned = 0, ghost_cap = 0, gid_first = 0;
+  double xlim[2] = { -1.0e308, 1.0e308 }; // owned swept boxes must stay inside (sg_ball2d_slab_set_gids); outside => SG_ERR_REBALANCE
   DevBuf gid;          // u32 per slot: global body index
   DevBuf interval_enc; // 2 x long long (ordered encoding of min lo.x / max hi.x over the owned swept boxes)
   DevBuf pack_counts, pack_offsets, pack_partials, pack_total;
@@ -443,7 +452,7 @@ struct Ball2DData
   GidMap gid_map() const
   {
     GidMap g;
-    if( slab ) { g.gid = gid.as<uint32_t>(); g.own_first = ghost_cap; g.own_count = n_owned; g.gid_first = gid_first; }
+    if( slab ) { g.gid = gid.as<uint32_t>(); }
     return g;
   }
   Ball2DData() { memset( &sg, 0, sizeof( sg ) ); }
@@ -541,16 +550,15 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   else if( flow_kind >= 0 && !d->slab )
   {
     SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(),
-               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr, nullptr, nullptr ) );
+               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr, nullptr, nullptr, 0.0, 0.0, nullptr ) );
   }
   else
   {
     SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr,
-               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS(), nullptr, nullptr ) );
+               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS(), nullptr, nullptr, 0.0, 0.0, nullptr ) );
   }
   Ball2DIn in;
-  in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS();
-  d->bp.gid_map = d->gid_map();
+  in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS(); in.gid = d->GID();
   // the (tiny, latency-bound) scan of the static-geometry counts rides along with the pair-count scan
   const bool side_scan = ng > 0 && nst <= SG_SIDE_SCAN_MAX;
   if( side_scan ) { d->bp.side.in = d->st_counts.as<uint32_t>(); d->bp.side.n = nst; d->bp.side.out = d->st_offsets.as<uint32_t>(); d->bp.side.total = d->st_total.as<uint32_t>(); }
@@ -1219,6 +1227,19 @@ int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v )
   return SG_OK;
 }
 
+int sg_ball2d_slab_upload_q1( sg_ctx* ctx, const double* q1 )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_upload_q1: call sg_ball2d_slab_init first" ); }
+  if( d->n_owned == 0 ) { return SG_OK; }
+  if( q1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_upload_q1: null vector" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( d->q1.as<double2>() + d->owned_slot(), q1, size_t( d->n_owned ) * 16, cudaMemcpyHostToDevice, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
 int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
@@ -1250,6 +1271,7 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   Ball2DData* d = ball2d_data( ctx );
   if( ball2d_has_portals( d ) ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_slab_init: portals are not supported in slab mode" ); }
   d->slab = true; d->n_owned = n_owned; d->ghost_cap = ghost_cap; d->gid_first = gid_first;
+  d->xlim[0] = -1.0e308; d->xlim[1] = 1.0e308;
   const size_t slots = size_t( n_owned ) + 2 * size_t( ghost_cap );
   d->n = uint32_t( slots );
   d->have_result = false;
@@ -1275,13 +1297,39 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   return SG_OK;
 }
 
+int sg_ball2d_slab_set_gids( sg_ctx* ctx, const uint32_t* gid_owned, const double* x_limits )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_set_gids: call sg_ball2d_slab_init first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( gid_owned != nullptr && d->n_owned > 0 )
+  {
+    // owned bodies are stored in ascending global order: their slot order is then the order of the emitted lists
+    for( uint32_t k = 0; k < d->n_owned; ++k )
+    {
+      if( gid_owned[k] >= 0x80000000u || ( k > 0 && gid_owned[k] <= gid_owned[k - 1] ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_set_gids: global indices must be strictly ascending and below 2^31 (entry %u)", k ); }
+    }
+    SG_CUDA( ctx, cudaMemcpyAsync( d->gid.as<uint32_t>() + d->ghost_cap, gid_owned, size_t( d->n_owned ) * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  }
+  if( x_limits != nullptr )
+  {
+    if( !( x_limits[0] <= x_limits[1] ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_set_gids: empty x range" ); }
+    d->xlim[0] = x_limits[0]; d->xlim[1] = x_limits[1];
+  }
+  SG_CUDA( ctx, cudaMemsetAsync( d->ghost_counts.ptr, 0, 16, ctx->stream ) ); // clears a pending re-partition request
+  d->have_result = false;
+  return SG_OK;
+}
+
 int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_dev )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   Ball2DData* d = ball2d_data( ctx );
   if( interval_dev == nullptr && d->mailbox.ptr == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: interval_dev may only be null once a mailbox exists" ); }
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: call sg_ball2d_slab_init first" ); }
-  if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: map kind %d is not a ball2d map", map_kind ); }
+  if( map_kind != SG_MAP_SYMPLECTIC_EULER && map_kind != SG_MAP_VERLET && map_kind != SG_MAP_NONE ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_flow: map kind %d is not a ball2d map", map_kind ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   // One kernel over all slots: flow of the owned bodies, their share of the broad-phase bounds, the static-geometry
   // counts and [min lo.x, max hi.x] for the neighbours; then the interval is decoded / posted.
@@ -1291,17 +1339,31 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
   if( rc != SG_OK ) { return rc; }
   const uint32_t n = d->n;
   SG_CUDA( ctx, d->block_iv.ensure( size_t( sg_div_up( n > 0 ? n : 1, 256 ) ) * 16 + 16 ) );
-  SG_LAUNCH( ctx, "slab_flow_prep", double( d->n_owned ) * 80.0,
-             k_ball2d_prep<true><<<sg_div_up( n > 0 ? n : 1, 256 ), 256, 0, ctx->stream>>>( d->sg, map_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(), d->R(), d->g[0], d->g[1], dt, d->Q1(),
-                                                                                       d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), nullptr,
-                                                                                       d->interval_enc.as<long long>(), d->block_iv.as<double2>() );
-             if( d->mailbox.ptr == nullptr ) { k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev ); }
-             else
-             {
-               ++d->slab_step;
-               k_ball2d_slab_post_interval<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev, static_cast<SlabMailboxHdr*>( d->peer_mb[0] ), static_cast<SlabMailboxHdr*>( d->peer_mb[1] ), d->slab_step );
-             } );
-  ctx->launch_count += 1;
+  const unsigned nblk_prep = sg_div_up( n > 0 ? n : 1, 256 );
+  if( map_kind == SG_MAP_NONE )
+  {
+    // q1 of the owned bodies was uploaded (sg_ball2d_slab_upload_q1): everything but the integration
+    SG_LAUNCH( ctx, "slab_prep", double( d->n_owned ) * 40.0,
+               k_ball2d_prep<false><<<nblk_prep, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr, d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(),
+                                                                       d->own_first(), d->own_count(), nullptr, d->interval_enc.as<long long>(), d->block_iv.as<double2>(), d->xlim[0], d->xlim[1], d->ghost_counts.as<uint32_t>() ) );
+  }
+  else
+  {
+    SG_LAUNCH( ctx, "slab_flow_prep", double( d->n_owned ) * 80.0,
+               k_ball2d_prep<true><<<nblk_prep, 256, 0, ctx->stream>>>( d->sg, map_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(), d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(),
+                                                                      d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), nullptr, d->interval_enc.as<long long>(),
+                                                                      d->block_iv.as<double2>(), d->xlim[0], d->xlim[1], d->ghost_counts.as<uint32_t>() ) );
+  }
+  if( d->mailbox.ptr == nullptr )
+  {
+    SG_LAUNCH( ctx, "slab_interval", 16.0, k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev ) );
+  }
+  else
+  {
+    ++d->slab_step;
+    SG_LAUNCH( ctx, "slab_interval", 16.0, k_ball2d_slab_post_interval<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev, static_cast<SlabMailboxHdr*>( d->peer_mb[0] ),
+               static_cast<SlabMailboxHdr*>( d->peer_mb[1] ), d->slab_step ) );
+  }
   d->slab_prep_done = true;
   return SG_OK;
 }
@@ -1536,6 +1598,7 @@ int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
   SG_CUDA( ctx, cudaMemcpyAsync( hg, d->ghost_counts.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   if( hg[2] != 0u ) { return sg_fail( ctx, SG_ERR_INVALID, "slab halo exceeds the reserved ghost capacity %u: results are incomplete", d->ghost_cap ); }
+  if( hg[3] != 0u ) { return sg_fail( ctx, SG_ERR_REBALANCE, "a body of this slab left [%g, %g]: it may reach a non-neighbouring slab, re-partition the scene", d->xlim[0], d->xlim[1] ); }
   if( d->mailbox.ptr != nullptr )
   {
     uint32_t err = 0u;
@@ -1551,6 +1614,19 @@ int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
     out->n_body_body = d->n_bb;
     out->n_active = d->n_bb + d->n_static;
   }
+  return SG_OK;
+}
+
+int sg_ball2d_fetch_state( sg_ctx* ctx, double* q1, double* v1 )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  const uint32_t nown = d->slab ? d->n_owned : d->n;
+  if( q1 != nullptr && nown > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.as<double2>() + d->owned_slot(), size_t( nown ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( v1 != nullptr && nown > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( nown ) * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
   return SG_OK;
 }
 

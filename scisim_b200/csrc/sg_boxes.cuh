@@ -30,6 +30,7 @@ struct AabbPolicy
   using Out = NoOut;
   static constexpr uint32_t IDX_MASK = 0xffffffffu;
   static constexpr uint32_t IDX_OFFSET = 16u * DIM;
+  static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
   __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
   {
     const double* b = in.boxes + size_t( i ) * 2 * DIM;
@@ -50,6 +51,8 @@ struct AabbPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_ord( const Rec& s ) { return rec_idx( s ); }
+  __device__ static uint32_t rec_ord_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }

@@ -45,7 +45,8 @@ struct BroadScratch
   DevBuf key;           // u32[n]
   DevBuf rank;          // u32[n]
   DevBuf recs;          // Rec[n]
-  DevBuf sidx;          // u32[n]  index word of each sorted record (pass 2 stages only this)
+  DevBuf sidx;          // u32[n]  ORDER word of each sorted record: the number that ranks bodies in the emitted lists and is written into them
+                        //         (the body index on one GPU, the global body index in slab mode)
   DevBuf pos_of;        // u32[n]  sorted position of body i (offsets are scattered to position order)
   DevBuf counts;        // uint2[n]  by body index
   DevBuf masks;         // uint4[n]  by sorted position
@@ -59,7 +60,6 @@ struct BroadScratch
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
   SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
-  GidMap gid_map; // multi-GPU: local body index -> global body index for the emitted lists
   CUtensorMap tm_recs;  // tensor map over recs for the TMA-fed pass 1 (re-encoded when the buffer or n changes)
   const void* tm_ptr = nullptr;
   uint32_t tm_rows = 0;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
   const uint32_t yz = key / g_dims0;
   const typename P::Rec r = P::make_rec( in, i, key, ( P::D == 3 ) ? yz % g_dims1 : yz, ( P::D == 3 ) ? yz / g_dims1 : 0u );
   sg_store_rec( &recs[pos], r );
-  sidx[pos] = P::rec_idx_raw( r );
+  sidx[pos] = P::rec_ord_raw( r );
   pos_of[i] = pos;
 }
 
@@ -533,20 +533,22 @@ __device__ __forceinline__ typename P::Rec sg_bp_fetch( const typename P::Rec* _
   if( STAGED || slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * BpCfg<P::D>::WCAP * 64, slot ); }
   return sg_load_rec_global<Rec>( &recs[q] );
 }
+// ORDER word of the body at sorted position q (window w): what decides which body of a pair owns it and how a body's partners are
+// ranked.  Policies keep it inside the record (P::ORD_OFFSET) so that the staged walk never leaves shared memory.
 template<typename P, bool STAGED = false>
-__device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q,
+__device__ __forceinline__ uint32_t sg_bp_fetch_ord( const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const BpStage<P::D>* st, const int w, const uint32_t q,
                                                      const uint32_t* __restrict__ sidx = nullptr )
 {
-  constexpr uint32_t CH = P::IDX_OFFSET / 16u, IN = P::IDX_OFFSET % 16u;
+  constexpr uint32_t CH = P::ORD_OFFSET / 16u, IN = P::ORD_OFFSET % 16u;
   const uint32_t slot = q - st->start[w];
   if( STAGED || slot < st->len[w] )
   {
     const unsigned char* rec = s_recs + ( size_t( w ) * BpCfg<P::D>::WCAP + slot ) * 64;
     return *reinterpret_cast<const uint32_t*>( rec + ( ( CH ^ ( ( slot >> 1 ) & 3u ) ) << 4 ) + IN ) & P::IDX_MASK;
   }
-  // un-staged: the dense index array (4 B/body, eight bodies per sector) rather than one sector of every record visited
+  // un-staged: the dense order array (4 B/body, eight bodies per sector) rather than one sector of every record visited
   if( sidx != nullptr ) { return __ldg( &sidx[q] ) & P::IDX_MASK; }
-  return __ldg( reinterpret_cast<const uint32_t*>( reinterpret_cast<const unsigned char*>( &recs[q] ) + P::IDX_OFFSET ) ) & P::IDX_MASK;
+  return __ldg( reinterpret_cast<const uint32_t*>( reinterpret_cast<const unsigned char*>( &recs[q] ) + P::ORD_OFFSET ) ) & P::IDX_MASK;
 }
 
 // masks cover the first 63 visits of a body's walk; bit 63 of the active mask flags a longer walk (masks incomplete)
@@ -556,7 +558,7 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_idx( const typename P::Rec* __re
 // One body's pass-1 walk: candidates with a larger index, how many are active, the two visit masks, the walk plan.
 template<typename P, int CSCAP, bool STAGED>
 __device__ __forceinline__ void sg_bp_count_body( const GridParams& g, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const unsigned char* s_recs, const uint32_t* s_cs,
-                                                  const BpStage<P::D>* st, const uint32_t n_slots, const uint32_t p, const typename P::Rec& me, const uint32_t my_idx,
+                                                  const BpStage<P::D>* st, const uint32_t n_slots, const uint32_t p, const typename P::Rec& me, const uint32_t my_idx, const uint32_t my_ord,
                                                   uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan, const uint32_t* __restrict__ sidx = nullptr )
 {
   constexpr int D = P::D;
@@ -573,7 +575,7 @@ __device__ __forceinline__ void sg_bp_count_body( const GridParams& g, const uin
   {
     const unsigned long long bit = ( k < SG_BP_MASK_BITS ) ? ( 1ull << k ) : 0ull;
     ++k;
-    if( sg_bp_fetch_idx<P, STAGED>( recs, s_recs, st, w, q, sidx ) <= my_idx ) { return; } // owned by the partner: skip before touching the record
+    if( sg_bp_fetch_ord<P, STAGED>( recs, s_recs, st, w, q, sidx ) <= my_ord ) { return; } // owned by the partner: skip before touching the record
     const Rec o = sg_bp_fetch<P, STAGED>( recs, s_recs, st, w, q );
     double olo[D], ohi[D];
     P::rec_aabb( o, olo, ohi );
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
     masks[p] = make_uint4( 0u, 0u, 0u, 0u );
     return;
   }
-  sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan, sidx );
+  sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan, sidx );
 }
 
 // ---- pass 1, TMA-fed (D = 2) -------------------------------------------------------------------------
@@ -760,8 +762,8 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, SG_BP_TMA_CTAS_PER_SM ) 
       {
         // tiles whose windows and cell_start slices were staged completely (the rule, not the exception) run a
         // walk with no fallback code in it at all
-        if( st->full != 0u ) { sg_bp_count_body<P, SG_BP_TMA_CSCAP, true>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan ); }
-        else { sg_bp_count_body<P, SG_BP_TMA_CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, counts, masks, plan ); }
+        if( st->full != 0u ) { sg_bp_count_body<P, SG_BP_TMA_CSCAP, true>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan ); }
+        else { sg_bp_count_body<P, SG_BP_TMA_CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan ); }
       }
     }
     else if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); }
@@ -837,25 +839,25 @@ template<> struct SgBpCountLaunch<2>
 // Slow paths of pass 2: redo the tests (a body with more than 32 neighbours or more candidates than the sorting
 // network holds); everything comes through L1/L2.  Kept out of line so the common path stays lean in registers.
 template<typename P>
-__device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, const uint2* __restrict__ counts, const ulonglong2 off, const uint32_t my_idx, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+__device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, const uint2* __restrict__ counts, const ulonglong2 off, const uint32_t my_ord, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, uint2* __restrict__ cand, const uint64_t cand_cap,
-                                              const GidMap gid, uint2* __restrict__ work, const uint64_t work_cap )
+                                              uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
-  if( nc == 0xffffffffu ) { nc = counts[my_idx].x; } // masks incomplete: the count comes from pass 1's by-index array
+  const Rec me = sg_load_rec_global<Rec>( &recs[p] );
+  if( nc == 0xffffffffu ) { nc = counts[P::rec_idx( me )].x; } // masks incomplete: the count comes from pass 1's by-index array
   if( nc == 0u ) { return; }
   unsigned long long ka = off.y;
   const GridParams g = *params;
-  const Rec me = sg_load_rec_global<Rec>( &recs[p] );
   const uint32_t key = P::rec_key( me ), c1 = P::rec_c1( me, g ), c2 = P::rec_c2( me, g );
   BpStage<D> none; // nothing staged: sg_bp_cs falls through to cell_start
   #pragma unroll
   for( int w = 0; w < Cfg::NW; ++w ) { none.start[w] = 0u; none.len[w] = 0u; none.cs_klo[w] = 0u; none.cs_len[w] = 0u; }
   const BpStage<D>* st = &none;
   const uint32_t* s_cs = nullptr;
-  auto idx_at = [&]( const int, const uint32_t q ) -> uint32_t { return __ldg( &sidx[q] ) & P::IDX_MASK; };
+  auto ord_at = [&]( const int, const uint32_t q ) -> uint32_t { return __ldg( &sidx[q] ) & P::IDX_MASK; };
   double lo[D], hi[D];
   P::rec_aabb( me, lo, hi );
   auto overlaps = [&]( const Rec& o ) -> bool
@@ -867,9 +869,9 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, con
     for( int a = 0; a < D; ++a ) { ov = ov && !( hi[a] < olo[a] ) && !( ohi[a] < lo[a] ); }
     return ov;
   };
-  auto emit_one = [&]( const unsigned long long kc, const Rec& o, const uint32_t q )
+  auto emit_one = [&]( const unsigned long long kc, const Rec& o, const uint32_t o_ord, const uint32_t q )
   {
-    if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( gid( my_idx ), gid( P::rec_idx( o ) ) ); }
+    if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( my_ord, o_ord ); }
     if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { if( ka < work_cap ) { work[ka] = make_uint2( p, q ); } ++ka; } }
   };
   if( nc <= SG_BP_LOCAL_CAP )
@@ -878,8 +880,8 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, con
     uint32_t nl = 0u;
     sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
     {
-      const uint32_t oi = idx_at( w, q );
-      if( oi <= my_idx ) { return; }
+      const uint32_t oi = ord_at( w, q );
+      if( oi <= my_ord ) { return; }
       const Rec o = sg_load_rec_global<Rec>( &recs[q] );
       if( !overlaps( o ) ) { return; }
       const unsigned long long v = ( static_cast<unsigned long long>( oi ) << 32 ) | q;
@@ -891,27 +893,27 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, con
     {
       const uint32_t q = uint32_t( list[j] & 0xffffffffull );
       const Rec o = sg_load_rec_global<Rec>( &recs[q] );
-      emit_one( off.x + j, o, q );
+      emit_one( off.x + j, o, uint32_t( list[j] >> 32 ), q );
     }
   }
   else
   {
-    // Crowded body: select partners in ascending index order by repeated walks (O(count * neighbours))
-    uint32_t last = my_idx;
+    // Crowded body: select partners in ascending order by repeated walks (O(count * neighbours))
+    uint32_t last = my_ord;
     for( uint32_t j = 0u; j < nc; ++j )
     {
-      uint32_t best_idx = 0xffffffffu, best_q = 0u;
+      uint32_t best_ord = 0xffffffffu, best_q = 0u;
       sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
       {
-        const uint32_t oi = idx_at( w, q );
-        if( oi <= last || oi >= best_idx ) { return; }
+        const uint32_t oi = ord_at( w, q );
+        if( oi <= last || oi >= best_ord ) { return; }
         const Rec o = sg_load_rec_global<Rec>( &recs[q] );
         if( !overlaps( o ) ) { return; }
-        best_idx = oi; best_q = q;
+        best_ord = oi; best_q = q;
       } );
       const Rec o = sg_load_rec_global<Rec>( &recs[best_q] );
-      emit_one( off.x + j, o, best_q );
-      last = best_idx;
+      emit_one( off.x + j, o, best_ord, best_q );
+      last = best_ord;
     }
   }
 }
@@ -955,7 +957,7 @@ template<> __device__ __forceinline__ void sg_sort_keys<16>( unsigned long long*
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan, const uint2* __restrict__ counts,
-                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, const GidMap gid, uint2* __restrict__ work, const uint64_t work_cap )
+                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
@@ -966,7 +968,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t
   // (one round trip instead of two; unused slots just read stale plan words they never use)
   const uint4 m = __ldg( &masks[p] ); // zero for ghosts and for slots past the binned bodies (cleared by pass 1)
   const ulonglong2 off = offsets_pos[p];
-  const uint32_t my_idx = __ldg( &sidx[p] ) & P::IDX_MASK;
+  const uint32_t my_ord = __ldg( &sidx[p] ) & P::IDX_MASK; // the order word is what the lists carry (== the body index on one GPU)
   uint32_t qb[Cfg::NW], len[Cfg::NW];
   sg_bp_plan_load<D>( plan, n_slots, p, qb, len );
   const unsigned long long cmask = m.x | ( static_cast<unsigned long long>( m.y ) << 32 );
@@ -1051,12 +1053,11 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t
     if( nc > 1u ) { sg_sort_keys<Cfg::FAST>( v, nc ); }
     if( cand != nullptr )
     {
-      const uint32_t gi = gid( my_idx );
       #pragma unroll
       for( int j = 0; j < Cfg::FAST; ++j )
       {
         const unsigned long long kc = off.x + j;
-        if( uint32_t( j ) < nc && kc < cand_cap ) { const uint32_t oj = uint32_t( v[j] >> 32 ); cand[kc] = make_uint2( gi, gid( oj ) ); }
+        if( uint32_t( j ) < nc && kc < cand_cap ) { cand[kc] = make_uint2( my_ord, uint32_t( v[j] >> 32 ) ); }
       }
     }
     if( P::HAS_NARROW && amask != 0ull )
@@ -1076,7 +1077,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t
     return;
   }
 
-  sg_bp_emit_slow<P>( p, complete ? nc : 0xffffffffu, counts, off, my_idx, params, cell_start, recs, sidx, cand, cand_cap, gid, work, work_cap );
+  sg_bp_emit_slow<P>( p, complete ? nc : 0xffffffffu, counts, off, my_ord, params, cell_start, recs, sidx, cand, cand_cap, work, work_cap );
 }
 
 // Pass 3 (policies with a fused narrow phase).  One thread per active pair, grid-stride over the work list pass 2
@@ -1188,7 +1189,7 @@ static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, con
     s.work_cap = act_cap;
   }
   SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ), sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.gid_map,
+             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap,
              s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap ) );
   return SgBpContactsLaunch<P::HAS_NARROW>::template run<P>( ctx, s, out, act_cap );
 }

@@ -175,19 +175,12 @@ struct GridParams
   uint32_t ncells;
 };
 
-// Local body index -> global body index for emitted lists (multi-GPU slabs).  Owned bodies are numbered
-// consecutively, so only ghost slots need the table.
+// Local body slot -> global body index (multi-GPU slabs: a table over all slots, owned and ghost; identity on one GPU)
 struct GidMap
 {
-  const uint32_t* gid = nullptr; // nullptr: identity (one GPU)
-  uint32_t own_first = 0, own_count = 0, gid_first = 0;
+  const uint32_t* gid = nullptr;
 #ifdef __CUDACC__
-  __device__ __forceinline__ uint32_t operator()( const uint32_t i ) const
-  {
-    if( gid == nullptr ) { return i; }
-    const uint32_t k = i - own_first;
-    return ( k < own_count ) ? gid_first + k : __ldg( &gid[i] );
-  }
+  __device__ __forceinline__ uint32_t operator()( const uint32_t i ) const { return ( gid == nullptr ) ? i : __ldg( &gid[i] ); }
 #endif
 };
 

@@ -59,6 +59,7 @@ struct Box2DPolicy
   static constexpr bool HAS_NARROW = false;
   static constexpr double IN_BYTES = 32.0;
   static constexpr uint32_t IDX_OFFSET = 32u;
+  static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
   static constexpr uint32_t IDX_MASK = 0xffffffffu;
   using In = Box2DIn;
   using Rec = Box2DRec;
@@ -78,6 +79,8 @@ struct Box2DPolicy
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi ) { lo[0] = s.lo[0]; lo[1] = s.lo[1]; hi[0] = s.hi[0]; hi[1] = s.hi[1]; }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_ord( const Rec& s ) { return rec_idx( s ); }
+  __device__ static uint32_t rec_ord_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }

@@ -117,6 +117,7 @@ struct Sphere3DPolicy
   static constexpr bool HAS_NARROW = true;
   static constexpr double IN_BYTES = 32.0;
   static constexpr uint32_t IDX_OFFSET = 56u;
+  static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
   static constexpr uint32_t IDX_MASK = 0x7fffffffu;
   using In = Sphere3DIn;
   using Rec = Sphere3DRec;
@@ -145,6 +146,8 @@ struct Sphere3DPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
   __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_ord( const Rec& s ) { return rec_idx( s ); }
+  __device__ static uint32_t rec_ord_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }
@@ -176,6 +179,7 @@ struct Box3DPolicy
   static constexpr bool HAS_NARROW = false;
   static constexpr double IN_BYTES = 48.0;
   static constexpr uint32_t IDX_OFFSET = 48u;
+  static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
   static constexpr uint32_t IDX_MASK = 0xffffffffu;
   using In = Box3DIn;
   using Rec = Box3DRec;
@@ -200,6 +204,8 @@ struct Box3DPolicy
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
+  __device__ static uint32_t rec_ord( const Rec& s ) { return rec_idx( s ); }
+  __device__ static uint32_t rec_ord_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static bool owns( const Rec& ) { return true; }
   __device__ static bool valid( const In&, const uint32_t ) { return true; }

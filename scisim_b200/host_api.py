@@ -349,6 +349,95 @@ class Ball2DSim:
         return q1, v1, ActiveSet(c)
 
 
+class MultiGpuBall2DSim:
+    """Ball2DSim over several GPUs of ONE process (sg_multi, include/scisim_b200.h): the same calls, global vectors and
+    indices; the scene is cut into x-slabs behind the interface, the lists come back merged in the reference's order."""
+
+    def __init__(self, state, devices):
+        if state.planar_portals:
+            raise SciSimB200Error("portals are not supported in slab mode")
+        self.lib = _lib.load()
+        self.state = state
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.sg_create_multi(C.byref(h), len(devices), devs)
+        if rc != 0:
+            raise SciSimB200Error("sg_create_multi failed (%d): %s" % (rc, self.lib.sg_multi_last_error(None).decode()))
+        self.h = h
+        self.world = len(devices)
+        n = state.nballs()
+        self.check(self.lib.sg_multi_ball2d_set_bodies(h, n, _ptr(state.r), _ptr(state.m)))
+        self.check(self.lib.sg_multi_ball2d_set_gravity(h, _ptr(state.g)))
+        self.check(self.lib.sg_multi_ball2d_set_planes(h, state.plane_x.shape[0], _ptr(state.plane_x), _ptr(state.plane_n)))
+        self.check(self.lib.sg_multi_ball2d_set_drums(h, state.drum_x.shape[0], _ptr(state.drum_x), _ptr(state.drum_r)))
+
+    def check(self, rc):
+        if rc != 0:
+            raise SciSimB200Error("libscisim_b200 (multi) error %d: %s" % (rc, self.lib.sg_multi_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sg_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nqdofs(self):
+        return 2 * self.state.nballs()
+
+    nvdofs = nqdofs
+
+    def set_rebalance(self, every_n_uploads=0, ghost_cap=0):
+        self.check(self.lib.sg_multi_set_rebalance(self.h, int(every_n_uploads), int(ghost_cap)))
+
+    def partition_info(self):
+        cuts = np.zeros(self.world + 1)
+        owned = np.zeros(self.world, dtype=np.uint32)
+        ghosts = np.zeros(2 * self.world, dtype=np.uint32)
+        npart = C.c_uint64()
+        self.check(self.lib.sg_multi_partition_info(self.h, _ptr(cuts), _ptr(owned), _ptr(ghosts), C.byref(npart)))
+        return {"cuts": cuts, "n_owned": owned, "ghosts": ghosts.reshape(-1, 2), "n_partitions": int(npart.value)}
+
+    def slab_launch_counts(self):
+        return [int(self.lib.sg_launch_count(self.lib.sg_multi_context(self.h, k))) for k in range(self.world)]
+
+    def _flow(self, kind, q0, v0, dt, q1=None, v1=None):
+        q0, v0 = _f64(q0), _f64(v0)
+        assert q0.size == self.nqdofs() and v0.size == self.nqdofs()
+        q1 = np.empty_like(q0) if q1 is None else q1
+        v1 = np.empty_like(v0) if v1 is None else v1
+        self.check(self.lib.sg_multi_ball2d_flow(self.h, kind, _ptr(q0), _ptr(v0), float(dt), _ptr(q1), _ptr(v1)))
+        return q1, v1
+
+    def computeActiveSet(self, q0, qp, v=None, flags=SG_OUT_ALL, copy=True, resident=False):
+        from ._lib import SG_IN_RESIDENT
+        q0, qp = _f64(q0), _f64(qp)
+        c = SgContacts()
+        self.check(self.lib.sg_multi_ball2d_active_set(self.h, _ptr(q0), _ptr(qp), int(flags) | (SG_IN_RESIDENT if resident else 0), C.byref(c)))
+        return ActiveSet(c, copy=copy)
+
+    def upload(self, q, v):
+        q, v = _f64(q), _f64(v)
+        self.check(self.lib.sg_multi_ball2d_upload(self.h, _ptr(q), _ptr(v)))
+
+    def step(self, umap, dt):
+        c = SgContacts()
+        self.check(self.lib.sg_multi_ball2d_step(self.h, umap.kind, float(dt), C.byref(c)))
+        return int(c.n_candidates), int(c.n_active)
+
+    def fetch(self, flags=SG_OUT_ALL, want_state=True, copy=True):
+        n = self.nqdofs()
+        q1 = np.empty(n) if want_state else None
+        v1 = np.empty(n) if want_state else None
+        c = SgContacts()
+        self.check(self.lib.sg_multi_ball2d_fetch(self.h, int(flags), _ptr(q1) if want_state else None, _ptr(v1) if want_state else None, C.byref(c)))
+        return q1, v1, ActiveSet(c, copy=copy)
+
+
 # ---- rigidbody3d -------------------------------------------------------------------------------------
 GEO_BOX, GEO_SPHERE, GEO_MESH = 0, 1, 3
 

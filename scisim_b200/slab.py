@@ -1,14 +1,21 @@
-"""Multi-GPU slab decomposition for the ball2d path: one process per GPU, one slab of a
-slab-major-numbered scene per process, ghost bodies exchanged with the neighbouring slabs every step.
+"""Multi-GPU slab decomposition for the ball2d path, one process per GPU: the scene -- bodies numbered
+arbitrarily -- is cut into equal-count x-quantile slabs, one per rank; ghost bodies are exchanged with the neighbouring
+slabs every step.
 
 The reference is single-process; this module is the host logic that has no counterpart there:
-  * interval exchange: every rank publishes [min lo.x, max hi.x] of its owned swept AABBs (all_gather, 16 B/rank)
-  * halo: a rank sends rank+-1 exactly its owned bodies whose swept AABB overlaps that rank's interval (NCCL
-    send/recv over NVLink when the tensors are CUDA tensors); a body overlapping a non-neighbour's interval means
-    the slabs need re-balancing and raises
-  * ownership: pair (i<j) is kept by the rank that owns body i, so the per-rank lists are disjoint, each ascending,
-    and their concatenation in rank order is the reference's std::set order; planes / drums are tested for owned
-    bodies only and merged geometry-major
+  * partition: sg_slab_partition (C, the same code the single-process sg_multi driver uses) ranks bodies by (x, index);
+    a rank stores its bodies in ascending GLOBAL index, so its lists come out in the reference's order restricted to
+    the pairs it owns
+  * halo: a rank sends rank+-1 exactly its owned bodies whose swept AABB overlaps that rank's interval [min lo.x,
+    max hi.x] -- by the kernels themselves through peer-mapped mailboxes ("p2p", NVLink, no collective in the step), or
+    by all_gather + send/recv ("nccl", also gloo for the CPU tests)
+  * non-neighbours: every owned body must stay inside its slab widened by half of each neighbouring slab
+    (sg_slab_limits); a body outside could touch a body two slabs away, which no halo carries.  The device flags it
+    (every step, either transport), sg_ball2d_slab_detect returns SG_ERR_REBALANCE, the ranks agree on it and the scene
+    is re-partitioned from the current state (Ball2DSlabSim.step)
+  * ownership: pair (i<j) is kept by the rank that owns body i, so the per-rank lists are disjoint and each ascending;
+    merge_active_sets interleaves them body by body into the reference's std::set order (ball2d/Ball2DSim.cpp:580),
+    then drums drum-major, then planes plane-major
 All device work goes through a backend (GpuSlabBackend below; the CPU tests plug the oracle in as the backend to
 exercise this host logic under gloo).
 """
@@ -19,34 +26,106 @@ import numpy as np
 REC_BYTES = 48
 
 
+class RebalanceNeeded(RuntimeError):
+    """A body left its slab's neighbourhood (SG_ERR_REBALANCE): the step's lists may miss contacts with a
+    non-neighbouring slab; re-partition and repeat the step."""
+
+
+def _lib():
+    from . import _lib as L
+    return L.load()
+
+
 def partition_slab_major(n_total, world):
-    """Owned global index range [first, first + count) of every rank: equal-count contiguous blocks."""
+    """Owned global index range [first, first + count) of every rank: equal-count contiguous blocks (a scene that is
+    already numbered slab-major)."""
     base, rem = divmod(n_total, world)
     counts = [base + (1 if r < rem else 0) for r in range(world)]
     firsts = [sum(counts[:r]) for r in range(world)]
     return firsts, counts
 
 
-def merge_active_sets(parts, n_static_geoms):
-    """parts: per-rank dicts (rank order) with type,i,j,n,p,depth,candidates in global indices. Returns the global
-    active set in the reference's order: ball-ball (rank order == ascending (i,j)), then drums drum-major, then planes
-    plane-major, each ball-ascending (ranks own ascending index ranges)."""
+def partition_quantiles(q, world):
+    """Equal-count x-quantile slabs of an arbitrarily numbered 2-D scene (q = [x0,y0,x1,y1,...]).  Returns
+    (rank_of[n], cuts[world+1], [ascending global indices of rank k for k in range(world)])."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    n = q.shape[0] // 2
+    rank_of = np.zeros(n, dtype=np.uint32)
+    cuts = np.zeros(world + 1, dtype=np.float64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _lib().sg_slab_partition(n, vp(q), 2, world, vp(rank_of), vp(cuts))
+    if rc != 0:
+        raise RuntimeError("sg_slab_partition failed (%d)" % rc)
+    gids = [np.nonzero(rank_of == k)[0].astype(np.uint32) for k in range(world)]
+    return rank_of, cuts, gids
+
+
+def slab_limits(cuts, rank):
+    cuts = np.ascontiguousarray(cuts, dtype=np.float64)
+    lim = np.zeros(2, dtype=np.float64)
+    rc = _lib().sg_slab_limits(cuts.shape[0] - 1, cuts.ctypes.data_as(C.c_void_p), rank, lim.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("sg_slab_limits failed (%d)" % rc)
+    return lim
+
+
+def _merge_dest(n_bodies, firsts, stride):
+    """dest arrays of sg_slab_merge_dest for per-part first-index columns (uint32 arrays, element stride `stride`)."""
+    k = len(firsts)
+    firsts = [np.ascontiguousarray(f, dtype=np.uint32) for f in firsts]
+    lens = np.array([f.shape[0] // stride for f in firsts], dtype=np.uint64)
+    dests = [np.zeros(int(l), dtype=np.uint64) for l in lens]
+    fp = (C.c_void_p * k)(*[f.ctypes.data for f in firsts])
+    dp = (C.c_void_p * k)(*[d.ctypes.data for d in dests])
+    rc = _lib().sg_slab_merge_dest(int(n_bodies), k, fp, stride, lens.ctypes.data_as(C.c_void_p), dp)
+    if rc != 0:
+        raise RuntimeError("sg_slab_merge_dest failed (%d): a per-rank list is not ascending in its first index" % rc)
+    return dests
+
+
+def merge_active_sets(parts, n_static_geoms=None, n_bodies=None):
+    """parts: per-rank dicts (any order) with type,i,j,n,p,depth,candidates in global indices, each list in the order
+    sg_ball2d_slab_detect leaves it.  Returns the global active set in the reference's order: ball-ball ascending (i,j),
+    then drums drum-major, then planes plane-major, each ball-ascending."""
     out = {}
-    out["candidates"] = np.concatenate([p["candidates"] for p in parts]) if parts else np.zeros((0, 2), np.uint32)
+    if not parts:
+        return {"candidates": np.zeros((0, 2), np.uint32)}
+    if n_bodies is None:
+        n_bodies = 1
+        for p in parts:
+            for a in (p["candidates"], p["i"], p["j"][p["type"] == 0]):
+                if a.size:
+                    n_bodies = max(n_bodies, int(a.max()) + 1)
+    cands = [np.ascontiguousarray(p["candidates"], dtype=np.uint32).reshape(-1, 2) for p in parts]
+    dests = _merge_dest(n_bodies, [c.ravel() for c in cands], 2)
+    total = sum(c.shape[0] for c in cands)
+    out["candidates"] = np.zeros((total, 2), dtype=np.uint32)
+    for c, d in zip(cands, dests):
+        out["candidates"][d] = c
     keys = ("type", "i", "j", "n", "p", "depth")
-    chunks = {k: [] for k in keys}
-    for p in parts:
-        sel = p["type"] == 0
-        for k in keys:
-            chunks[k].append(p[k][sel])
-    for t in (1, 2):  # drums then planes
-        for g in range(n_static_geoms[t - 1]):
-            for p in parts:
-                sel = (p["type"] == t) & (p["j"] == g)
-                for k in keys:
-                    chunks[k].append(p[k][sel])
-    for k in keys:
-        out[k] = np.concatenate(chunks[k]) if chunks[k] else None
+    nbb = [int(np.count_nonzero(p["type"] == 0)) for p in parts]
+    for p, k in zip(parts, nbb):
+        assert np.all(p["type"][:k] == 0), "ball-ball contacts come first in a rank's list"
+    bb_dest = _merge_dest(n_bodies, [p["i"][:k] for p, k in zip(parts, nbb)], 1)
+    n_bb = sum(nbb)
+    # static contacts: (type, geometry, body)
+    kk = len(parts)
+    st = [[np.ascontiguousarray(p[c][k:], dtype=np.uint32) for p, k in zip(parts, nbb)] for c in ("type", "i", "j")]
+    slens = np.array([a.shape[0] for a in st[0]], dtype=np.uint64)
+    sdest = [np.zeros(int(l), dtype=np.uint64) for l in slens]
+    arr = lambda lst: (C.c_void_p * kk)(*[a.ctypes.data for a in lst])
+    rc = _lib().sg_slab_merge_static_dest(kk, arr(st[0]), arr(st[1]), arr(st[2]), slens.ctypes.data_as(C.c_void_p), arr(sdest))
+    if rc != 0:
+        raise RuntimeError("sg_slab_merge_static_dest failed (%d)" % rc)
+    n_all = n_bb + int(slens.sum())
+    for key in keys:
+        proto = parts[0][key]
+        shape = (n_all,) + tuple(proto.shape[1:])
+        o = np.zeros(shape, dtype=proto.dtype)
+        for p, k, db, ds in zip(parts, nbb, bb_dest, sdest):
+            o[db] = p[key][:k]
+            o[n_bb + ds] = p[key][k:]
+        out[key] = o
     return out
 
 
@@ -55,7 +134,7 @@ class GpuSlabBackend:
     torch op is issued on the library's stream.  Buffers always travel at full size (ghost_cap + 1 records, the first
     one a header with the count), so nothing on the host waits for a count before detect()."""
 
-    def __init__(self, ctx, scene_slab, gid_first, ghost_cap):
+    def __init__(self, ctx, scene_slab, gid_first, ghost_cap, gids=None, x_limits=None):
         import torch
         self.torch = torch
         self.ctx = ctx
@@ -63,20 +142,6 @@ class GpuSlabBackend:
         self.device = torch.device("cuda", ctx.device)
         self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.device)
         self.cap = int(ghost_cap)
-        s = scene_slab
-        r = np.ascontiguousarray(s["r"], dtype=np.float64)
-        m = np.ascontiguousarray(s["m"], dtype=np.float64)
-        self.n_owned = r.shape[0]
-        vp = lambda a: a.ctypes.data_as(C.c_void_p)
-        ctx.check(self.lib.sg_ball2d_slab_init(ctx.h, self.n_owned, int(gid_first), self.cap, vp(r), vp(m)))
-        g = np.ascontiguousarray(s["g"], dtype=np.float64)
-        ctx.check(self.lib.sg_ball2d_set_gravity(ctx.h, vp(g)))
-        px, pn = np.ascontiguousarray(s["plane_x"], dtype=np.float64), np.ascontiguousarray(s["plane_n"], dtype=np.float64)
-        ctx.check(self.lib.sg_ball2d_set_planes(ctx.h, px.shape[0], vp(px), vp(pn)))
-        dx, dr = np.ascontiguousarray(s["drum_x"], dtype=np.float64), np.ascontiguousarray(s["drum_r"], dtype=np.float64)
-        ctx.check(self.lib.sg_ball2d_set_drums(ctx.h, dx.shape[0], vp(dx), vp(dr)))
-        q, v = np.ascontiguousarray(s["q"], dtype=np.float64), np.ascontiguousarray(s["v"], dtype=np.float64)
-        ctx.check(self.lib.sg_ball2d_upload(ctx.h, vp(q), vp(v)))
         nbytes = (self.cap + 1) * REC_BYTES
         with torch.cuda.stream(self.stream):
             self.iv = torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -84,6 +149,34 @@ class GpuSlabBackend:
             self.send = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
             self.recv = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.ghosts = (0, 0)
+        self.reinit(scene_slab, gid_first, gids, x_limits)
+
+    def reinit(self, scene_slab, gid_first=0, gids=None, x_limits=None):
+        """(Re)loads the slab: bodies (r, m, q, v of the owned bodies in ascending global index), their global indices,
+        the x-range they must stay inside, the static geometry.  Mailboxes and neighbour mappings stay as they are."""
+        ctx = self.ctx
+        s = scene_slab
+        r = np.ascontiguousarray(s["r"], dtype=np.float64)
+        m = np.ascontiguousarray(s["m"], dtype=np.float64)
+        self.n_owned = r.shape[0]
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        ctx.check(self.lib.sg_ball2d_slab_init(ctx.h, self.n_owned, int(gid_first), self.cap, vp(r), vp(m)))
+        if gids is not None or x_limits is not None:
+            g = np.ascontiguousarray(gids, dtype=np.uint32) if gids is not None else None
+            lim = np.ascontiguousarray(x_limits, dtype=np.float64) if x_limits is not None else None
+            ctx.check(self.lib.sg_ball2d_slab_set_gids(ctx.h, vp(g) if g is not None else None, vp(lim) if lim is not None else None))
+        g = np.ascontiguousarray(s["g"], dtype=np.float64)
+        ctx.check(self.lib.sg_ball2d_set_gravity(ctx.h, vp(g)))
+        px, pn = np.ascontiguousarray(s["plane_x"], dtype=np.float64), np.ascontiguousarray(s["plane_n"], dtype=np.float64)
+        ctx.check(self.lib.sg_ball2d_set_planes(ctx.h, px.shape[0], vp(px), vp(pn)))
+        dx, dr = np.ascontiguousarray(s["drum_x"], dtype=np.float64), np.ascontiguousarray(s["drum_r"], dtype=np.float64)
+        ctx.check(self.lib.sg_ball2d_set_drums(ctx.h, dx.shape[0], vp(dx), vp(dr)))
+        self.upload(s["q"], s["v"])
+
+    def upload(self, q, v):
+        q, v = np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.ctx.check(self.lib.sg_ball2d_upload(self.ctx.h, vp(q), vp(v)))
 
     def flow(self, kind, dt):
         self.ctx.check(self.lib.sg_ball2d_slab_flow(self.ctx.h, int(kind), float(dt), C.c_void_p(self.iv.data_ptr())))
@@ -116,7 +209,8 @@ class GpuSlabBackend:
         return buf
 
     def count_overlapping(self, interval):
-        """How many owned bodies reach `interval` (host-synchronous; used for the non-neighbour check only)."""
+        """How many owned bodies reach `interval` (host-synchronous; diagnostics only -- the non-neighbour guarantee is
+        the x-limit test the flow kernel makes every step)."""
         self.ctx.check(self.lib.sg_ball2d_slab_pack(self.ctx.h, C.c_void_p(interval.data_ptr()), None, 0, C.c_void_p(self.count.data_ptr())))
         with self.torch.cuda.stream(self.stream):
             return int(self.count.item())
@@ -128,10 +222,13 @@ class GpuSlabBackend:
         self.ctx.check(self.lib.sg_ball2d_slab_unpack(self.ctx.h, int(side), C.c_void_p(buf.data_ptr())))
 
     def detect(self):
-        from ._lib import SgContacts
+        from ._lib import SG_ERR_REBALANCE, SgContacts
         c = SgContacts()
         g = (C.c_uint32 * 2)()
-        self.ctx.check(self.lib.sg_ball2d_slab_detect(self.ctx.h, C.byref(c), g))
+        rc = self.lib.sg_ball2d_slab_detect(self.ctx.h, C.byref(c), g)
+        if rc == SG_ERR_REBALANCE:
+            raise RebalanceNeeded(self.lib.sg_last_error(self.ctx.h).decode())
+        self.ctx.check(rc)
         self.ghosts = (int(g[0]), int(g[1]))
         return int(c.n_candidates), int(c.n_active)
 
@@ -150,13 +247,15 @@ class GpuSlabBackend:
 
 
 class Ball2DSlabs:
-    """Per-rank driver of one step: flow -> interval all_gather -> halo exchange -> detection.  With the GPU backend
+    """Per-rank driver of one step: flow -> interval exchange -> halo exchange -> detection.  With the GPU backend
     nothing blocks the host until detect() reads the list sizes."""
 
     def __init__(self, backend, rank, world, dist, check_non_neighbours=False, transport="nccl"):
         """transport "nccl": intervals by all_gather, halos by send/recv (any backend, also gloo + the oracle backend);
         "p2p": the neighbours' mailboxes are mapped once with CUDA IPC (handles travel through `dist`), after that a
-        step issues no collective at all -- intervals and halos are written over NVLink by the kernels themselves."""
+        step issues no collective at all -- intervals and halos are written over NVLink by the kernels themselves.
+        check_non_neighbours: additionally count (host-synchronously, collective transport only) the owned bodies that
+        reach a non-neighbour's interval -- a diagnostic on top of the x-limit test every step makes on the device."""
         self.b, self.rank, self.world, self.dist = backend, rank, world, dist
         self.check = check_non_neighbours
         self.last_halo = (0, 0)
@@ -214,7 +313,7 @@ class Ball2DSlabs:
                         if abs(peer - rank) > 1:
                             c = b.count_overlapping(all_iv[peer])
                             if c != 0:
-                                raise RuntimeError("rank %d: %d bodies reach the slab of non-neighbour rank %d; re-balance the slabs" % (rank, c, peer))
+                                raise RebalanceNeeded("rank %d: %d bodies reach the slab of non-neighbour rank %d" % (rank, c, peer))
                 for req in dist.batch_isend_irecv(ops):
                     req.wait()
                 for side, peer in peers.items():
@@ -223,3 +322,114 @@ class Ball2DSlabs:
             res = b.detect()
             self.last_halo = getattr(b, "ghosts", (0, 0))
             return res
+
+
+class Ball2DSlabSim:
+    """One rank's handle on a WHOLE ball2d scene (global arrays, arbitrary numbering) spread over `world` ranks.
+    upload() partitions (the same partition on every rank: it is a deterministic function of q), step() runs one
+    resident step and re-partitions when any rank asks for it, gather_merged() assembles the reference-order lists.
+
+    backend_factory( scene_slab, gids, x_limits, ghost_cap ) -> backend (GpuSlabBackend for the product; the CPU tests
+    pass the oracle stand-in)."""
+
+    def __init__(self, scene, rank, world, dist, backend_factory, transport="p2p", ghost_cap=None, agree=True):
+        self.scene = scene           # r, m, g, plane_x, plane_n, drum_x, drum_r (global); q, v come through upload()
+        self.rank, self.world, self.dist = rank, world, dist
+        self.factory = backend_factory
+        self.want_transport = transport
+        self.ghost_cap = ghost_cap
+        self.agree = agree           # all ranks agree on "re-partition" after every step (one 4-byte all_reduce)
+        self.backend = None
+        self.driver = None
+        self.n = int(np.asarray(scene["r"]).shape[0])
+        self.n_partitions = 0
+        self.q = self.v = None
+        self.gids = None
+
+    def _slab_scene(self, gids, q, v):
+        s = dict(self.scene)
+        s["r"] = np.ascontiguousarray(np.asarray(self.scene["r"])[gids])
+        s["m"] = np.ascontiguousarray(np.asarray(self.scene["m"])[gids])
+        s["q"] = np.ascontiguousarray(q.reshape(-1, 2)[gids].ravel())
+        s["v"] = np.ascontiguousarray(v.reshape(-1, 2)[gids].ravel())
+        return s
+
+    def _partition(self, q, v):
+        rank_of, cuts, gids = partition_quantiles(q, self.world)
+        self.cuts, self.all_gids, self.gids = cuts, gids, gids[self.rank]
+        lim = slab_limits(cuts, self.rank)
+        cap = self.ghost_cap or max(4096, max(g.shape[0] for g in gids) // 32)
+        s = self._slab_scene(self.gids, q, v)
+        if self.backend is None:
+            self.ghost_cap = cap
+            self.backend = self.factory(s, self.gids, lim, cap)
+            self.driver = Ball2DSlabs(self.backend, self.rank, self.world, self.dist, transport=self.want_transport)
+        else:
+            self.backend.reinit(s, 0, self.gids, lim)
+        self.n_partitions += 1
+
+    def upload(self, q, v, repartition=False):
+        """q, v: the GLOBAL state (identical arrays on every rank)."""
+        q, v = np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)
+        if self.backend is None or repartition:
+            self._partition(q, v)
+        else:
+            self.backend.upload(q.reshape(-1, 2)[self.gids].ravel(), v.reshape(-1, 2)[self.gids].ravel())
+        self.q, self.v = q, v
+
+    @property
+    def transport(self):
+        return self.driver.transport if self.driver is not None else None
+
+    def _agree(self, flag):
+        if self.world == 1 or not self.agree:
+            return flag
+        import torch
+        dev = getattr(self.backend, "device", "cpu")
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return bool(int(t.item()))
+
+    def step(self, kind, dt):
+        """One resident step of this rank's slab: (candidates, contacts) it owns.  If any rank reports a body outside its
+        slab's neighbourhood, all ranks re-partition from the uploaded state and repeat the step (once)."""
+        for attempt in range(2):
+            need = False
+            try:
+                res = self.driver.step(kind, dt)
+            except RebalanceNeeded:
+                need, res = True, (0, 0)
+            if not self._agree(need):
+                if need:
+                    raise RebalanceNeeded("rank %d needs a re-partition but the ranks do not agree on steps (agree=False)" % self.rank)
+                return res
+            if attempt == 1:
+                raise RuntimeError("the slabs of this scene are too thin for %d ranks: bodies reach beyond the neighbouring slab even after a fresh partition" % self.world)
+            self._partition(self.q, self.v)
+        return res
+
+    def fetch(self):
+        """(global indices of the owned bodies, q1, v1 of those bodies, this rank's lists)"""
+        q1, v1, res = self.backend.fetch()
+        return self.gids, q1, v1, res
+
+    def gather_merged(self, dst=0):
+        """Collects every rank's lists and state on rank `dst` and merges them into the reference's order (parity checks;
+        the lists travel as pickled numpy arrays)."""
+        gids, q1, v1, res = self.fetch()
+        res = dict(res)
+        res["gids"], res["q1"], res["v1"] = gids, q1, v1
+        if self.world == 1:
+            parts = [res]
+        else:
+            parts = [None] * self.world if self.rank == dst else None
+            self.dist.gather_object(res, parts, dst=dst)
+            if self.rank != dst:
+                return None
+        merged = merge_active_sets(parts, n_bodies=self.n)
+        q1g, v1g = np.zeros(2 * self.n), np.zeros(2 * self.n)
+        for p in parts:
+            q1g.reshape(-1, 2)[p["gids"]] = p["q1"].reshape(-1, 2)
+            v1g.reshape(-1, 2)[p["gids"]] = p["v1"].reshape(-1, 2)
+        merged["q1"], merged["v1"] = q1g, v1g
+        return merged

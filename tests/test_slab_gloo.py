@@ -84,3 +84,54 @@ def test_p2p_request_falls_back_to_collectives_when_no_mailbox_can_be_mapped():
     assert np.array_equal(merged["candidates"], ref["candidates"])
     for k in ("type", "i", "j"):
         assert np.array_equal(merged[k], ref[k]), k
+
+
+# ---- arbitrary numbering: x-quantile partition, re-partition on demand, general merge ---------------------------------
+def _sim_worker(rank, world, port, n, seed, outdir, mode):
+    import torch.distributed as dist
+    from scisim_b200.slab import Ball2DSlabSim
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scene = sh.random_numbered_scene(n, seed, box=max(4.0, np.sqrt(n) * 1.2))
+    factory = lambda s, gids, lim, cap: sh.OracleSlabBackend(s, 0, cap, gids=gids, x_limits=lim)
+    sim = Ball2DSlabSim(scene, rank, world, dist, factory, transport="nccl", ghost_cap=n)
+    q, v = scene["q"].copy(), scene["v"].copy()
+    if mode == "stale":
+        # partition a state, then upload (without re-partitioning) one in which the bodies have swapped sides: every
+        # rank's bodies are now far outside its slab -> the step must ask for, and get, a fresh partition
+        sim.upload(q, v)
+        x = q[0::2]
+        q = q.copy()
+        q[0::2] = x.min() + x.max() - x
+        sim.upload(q, v)
+    else:
+        sim.upload(q, v)
+    pc, pa = sim.step(0, scene["dt"])
+    merged = sim.gather_merged(0)
+    if rank == 0:
+        merged["n_partitions"] = sim.n_partitions
+        merged["q0"] = q
+        pickle.dump(merged, open(os.path.join(outdir, "merged.pkl"), "wb"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,seed,mode", [(2, 700, 11, "fresh"), (3, 1200, 12, "fresh"), (3, 900, 13, "stale")])
+def test_quantile_slabs_of_a_randomly_numbered_scene(world, n, seed, mode):
+    import torch.multiprocessing as mp
+    from tests import oracle_binding as ob
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_sim_worker, args=(world, _free_port(), n, seed, d, mode), nprocs=world, join=True)
+        m = pickle.load(open(os.path.join(d, "merged.pkl"), "rb"))
+    scene = sh.random_numbered_scene(n, seed, box=max(4.0, np.sqrt(n) * 1.2))
+    o = ob.Ball2DOracle(scene)
+    q1, v1 = o.flow(0, m["q0"], scene["v"], scene["dt"])
+    ref = o.active_set(m["q0"], q1, "allpairs")
+    assert m["n_partitions"] == (2 if mode == "stale" else 1)
+    assert np.array_equal(m["q1"], q1) and np.array_equal(m["v1"], v1)
+    assert ref["candidates"].shape[0] > 0
+    assert np.array_equal(m["candidates"], ref["candidates"])
+    for k in ("type", "i", "j", "n", "p"):
+        assert np.array_equal(m[k], ref[k]), k
+    assert np.array_equal(m["depth"], ref["depth"], equal_nan=True)

@@ -26,7 +26,7 @@ def test_two_process_slab_exchange(oracle, transport):
     world = 4 if ng >= 4 else 2
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", "29533",
-           os.path.join(root, "tests", "slab_p2p_worker.py"), transport, "20000", "4"]
+           os.path.join(root, "tests", "slab_p2p_worker.py"), transport, "30000", "4"]
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(": OK") == 4, out.stdout[-3000:]
