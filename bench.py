@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 METRIC = "candidate+active contact pairs/sec (flow + broad phase + narrow phase, ball2d)"
 UNIT = "pairs/s"
 N_CONFIG3 = 1 << 24
-N_CPU_SAMPLE = 1 << 21      # bodies of the CPU arms' bounded sample of config 3 (the per-GPU share at 8 GPUs)
+N_CPU_SAMPLE = 1 << 19      # bodies of the CPU arms' bounded sample of config 3 (the reference needs ~6 us per body per step on this scene)
 N_PARITY = 200_000
 
 

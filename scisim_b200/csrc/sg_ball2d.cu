@@ -559,6 +559,7 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   }
   Ball2DIn in;
   in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS(); in.gid = d->GID();
+  d->bp.ord_by_index = d->GID();
   // the (tiny, latency-bound) scan of the static-geometry counts rides along with the pair-count scan
   const bool side_scan = ng > 0 && nst <= SG_SIDE_SCAN_MAX;
   if( side_scan ) { d->bp.side.in = d->st_counts.as<uint32_t>(); d->bp.side.n = nst; d->bp.side.out = d->st_offsets.as<uint32_t>(); d->bp.side.total = d->st_total.as<uint32_t>(); }

@@ -47,11 +47,10 @@ struct BroadScratch
   DevBuf recs;          // Rec[n]
   DevBuf sidx;          // u32[n]  ORDER word of each sorted record: the number that ranks bodies in the emitted lists and is written into them
                         //         (the body index on one GPU, the global body index in slab mode)
-  DevBuf pos_of;        // u32[n]  sorted position of body i (offsets are scattered to position order)
+  DevBuf pos_of;        // u32[n]  sorted position of body i (0xffffffff: unused slot); pass 2 runs in index order and finds its body's masks through it
   DevBuf counts;        // uint2[n]  by body index
-  DevBuf masks;         // uint4[n]  by sorted position
-  DevBuf plan;          // uint4[NPLAN][n]  by sorted position: where each window of the body's walk starts and how long it is
-  DevBuf offsets;       // ulonglong2[n]  by sorted position
+  DevBuf masks;         // uint4[n][1 + NPLAN]  by sorted position: candidate / active masks, then where each window of the body's walk starts and how long it is
+  DevBuf offsets;       // ulonglong2[n]  by body index
   DevBuf pair_partials; // ScanPairCounts::Acc[tiles]
   DevBuf totals;        // ScanPairCounts::Acc
   DevBuf cand;          // uint2[cand_cap]
@@ -60,9 +59,9 @@ struct BroadScratch
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
   SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
-  CUtensorMap tm_recs;  // tensor map over recs for the TMA-fed pass 1 (re-encoded when the buffer or n changes)
-  const void* tm_ptr = nullptr;
-  uint32_t tm_rows = 0;
+  DevBuf boxf;          // float4[n]  by sorted position (2-D pipelines): the body's box rounded outward to floats -- what pass 1's walk tests
+  const uint32_t* ord_by_index = nullptr; // order word of body i (multi-GPU: the global-index table; nullptr: i itself), set per step by the caller
+  int attr_dev = -1;    // device on which pass 1's shared-memory opt-in was made for this context's kernels
   bool hist_clean = false; // cell_count is all zero (true after every scatter; false after (re)allocation or an aborted step)
   const void* hist_ptr = nullptr;
   uint32_t hist_slots = 0;
@@ -71,7 +70,7 @@ struct BroadScratch
   void release()
   {
     bounds.release(); params.release(); cell_count.release(); cell_start.release(); cell_partials.release(); key.release(); rank.release();
-    recs.release(); sidx.release(); pos_of.release(); counts.release(); masks.release(); plan.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release(); work.release();
+    recs.release(); sidx.release(); boxf.release(); pos_of.release(); counts.release(); masks.release(); offsets.release(); pair_partials.release(); totals.release(); cand.release(); work.release();
   }
 };
 
@@ -280,6 +279,12 @@ __device__ inline uint32_t sg_key_of( const GridParams& g, const uint32_t* c )
   return key;
 }
 
+// the outward-rounded float box of a double box: { lo.x, lo.y, hi.x, hi.y }
+__device__ __forceinline__ float4 sg_box_outward( const double* lo, const double* hi )
+{
+  return make_float4( __double2float_rd( lo[0] ), __double2float_rd( lo[1] ), __double2float_ru( hi[0] ), __double2float_ru( hi[1] ) );
+}
+
 // ---- histogram / scatter ("single-digit radix sort" keyed by cell) ---------------------------------
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P::In in, const BoundsAccum* __restrict__ acc, BoundsAccum* __restrict__ acc_next, const uint32_t max_cells,
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_hist( const typename P:
 
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename P::In in, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ key_in,
-                                                                 const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs, uint32_t* __restrict__ sidx, uint32_t* __restrict__ pos_of,
+                                                                 const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs, uint32_t* __restrict__ pos_of,
                                                                  uint32_t* __restrict__ cell_count, const uint32_t cell_slots )
 {
   const uint32_t g_dims0 = params->dims[0], g_dims1 = params->dims[1];
@@ -330,8 +335,26 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
   const uint32_t yz = key / g_dims0;
   const typename P::Rec r = P::make_rec( in, i, key, ( P::D == 3 ) ? yz % g_dims1 : yz, ( P::D == 3 ) ? yz / g_dims1 : 0u );
   sg_store_rec( &recs[pos], r );
-  sidx[pos] = P::rec_ord_raw( r );
   pos_of[i] = pos;
+}
+
+// The dense by-position side arrays of the sorted records, written in one coalesced pass (the scatter's writes are random:
+// it moves the 64-byte records only): the ORDER word of every record and, for the 2-D pipelines, its box rounded outward to floats.
+template<typename P>
+__global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_side_arrays( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs,
+                                                                      uint32_t* __restrict__ sidx, float4* __restrict__ boxf )
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = min( n_slots, __ldg( &cell_start[params->ncells] ) ); // bodies actually binned
+  if( p >= n ) { return; }
+  const typename P::Rec r = sg_load_rec_global<typename P::Rec>( &recs[p] );
+  sidx[p] = P::rec_ord_raw( r );
+  if( P::D == 2 && boxf != nullptr )
+  {
+    double lo[P::D], hi[P::D];
+    P::rec_aabb( r, lo, hi );
+    boxf[p] = sg_box_outward( lo, hi );
+  }
 }
 
 // ---- neighbourhood staging + walk ------------------------------------------------------------------
@@ -486,10 +509,13 @@ __device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint3
 }
 
 // The walk plan pass 1 leaves for pass 2: per body the window starts and lengths (clipped to 255; a body whose
-// walk is longer than 63 visits has incomplete masks anyway), NPLAN uint4 per body, plane c of body p at plan[c*n+p].
+// walk is longer than 63 visits has incomplete masks anyway), NPLAN uint4 per body.  Masks and plan of sorted position p sit
+// side by side -- STRIDE = 1 + NPLAN uint4 words: [masks | plan words] -- so that pass 2, which visits the bodies in INDEX
+// order, finds everything it needs about a body in one 32-byte sector (2-D) / two (3-D).  `masks` and `plan` below are the
+// same buffer, offset by one word.
 template<int D> struct BpPlan;
-template<> struct BpPlan<2> { static constexpr int NPLAN = 1; };
-template<> struct BpPlan<3> { static constexpr int NPLAN = 3; };
+template<> struct BpPlan<2> { static constexpr int NPLAN = 1; static constexpr int STRIDE = 2; };
+template<> struct BpPlan<3> { static constexpr int NPLAN = 3; static constexpr int STRIDE = 4; };
 
 template<int D>
 __device__ __forceinline__ void sg_bp_plan_store( uint4* __restrict__ plan, const uint32_t n, const uint32_t p, const uint32_t* qb, const uint32_t* qe )
@@ -506,7 +532,7 @@ __device__ __forceinline__ void sg_bp_plan_store( uint4* __restrict__ plan, cons
     words[NW + w / 4] |= len << ( 8 * ( w % 4 ) );
   }
   #pragma unroll
-  for( int c = 0; c < BpPlan<D>::NPLAN; ++c ) { plan[size_t( c ) * n + p] = make_uint4( words[4 * c], words[4 * c + 1], words[4 * c + 2], words[4 * c + 3] ); }
+  for( int c = 0; c < BpPlan<D>::NPLAN; ++c ) { plan[size_t( p ) * BpPlan<D>::STRIDE + c] = make_uint4( words[4 * c], words[4 * c + 1], words[4 * c + 2], words[4 * c + 3] ); }
 }
 
 template<int D>
@@ -517,7 +543,7 @@ __device__ __forceinline__ void sg_bp_plan_load( const uint4* __restrict__ plan,
   #pragma unroll
   for( int c = 0; c < BpPlan<D>::NPLAN; ++c )
   {
-    const uint4 v = __ldg( &plan[size_t( c ) * n + p] );
+    const uint4 v = __ldg( &plan[size_t( p ) * BpPlan<D>::STRIDE + c] );
     words[4 * c] = v.x; words[4 * c + 1] = v.y; words[4 * c + 2] = v.z; words[4 * c + 3] = v.w;
   }
   #pragma unroll
@@ -588,7 +614,7 @@ __device__ __forceinline__ void sg_bp_count_body( const GridParams& g, const uin
   } );
   if( k > SG_BP_MASK_BITS ) { amask |= SG_BP_MASKS_INVALID; }
   counts[my_idx] = make_uint2( nc, na );
-  masks[p] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
+  masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
 }
 
 // Pass 1.  counts[body index] = { #candidates with a larger index, #of those that are active }
@@ -608,7 +634,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
   const GridParams g = *params;
   const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned (unused slots are not)
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
-  if( p >= n && p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slot: pass 2 skips it
+  if( p >= n && p < n_slots ) { masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slot: pass 2 skips it
   if( blockIdx.x * Cfg::T >= n ) { return; }
   Rec me;
   if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the windows are staged
@@ -619,77 +645,252 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
   {
     // a ghost body (multi-GPU halo): present only as a partner, its pairs are kept by the rank that owns it
     counts[my_idx] = make_uint2( 0u, 0u );
-    masks[p] = make_uint4( 0u, 0u, 0u, 0u );
+    masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u );
     return;
   }
   sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan, sidx );
 }
 
-// ---- pass 1, TMA-fed (D = 2) -------------------------------------------------------------------------
-// Same work as sg_bp_count, restructured so no thread ever waits for the staging: persistent CTAs (2 per SM),
-// each with 8 consumer warps and 1 producer warp.  The producer runs one tile ahead: it reads the tile's first/last
-// cell keys and the cell_start entries that bound its three row windows, then asks the TMA unit for the windows --
-// the 64-byte records as 2-D tensor copies with the hardware 64B swizzle (the same chunk ^ ((row >> 1) & 3)
-// pattern the software staging used), the cell_start slices as 1-D bulk copies -- into the other half of a
-// double-buffered shared-memory stage, completion counted in bytes on an mbarrier.  Consumers wait on that
-// barrier, walk entirely out of shared memory, and hand the stage back through a second mbarrier.
-#define SG_BP_TMA_ROWS 136   // rows per tensor copy (<= 256); two copies cover WCAP = 272
-#define SG_BP_TMA_CSCAP 288
-template<int D> __host__ __device__ constexpr size_t sg_bp_tma_stage_bytes()
+// ---- pass 1, box-prefiltered and bulk-copy fed (D = 2) ------------------------------------------------
+// What a body's walk over its 3 row windows needs per partner is a box test that almost always fails (config 3: 19 visits,
+// 2.7 boxes touched, 1.3 pairs owned).  So the walk does not touch the 64-byte records at all: the scatter also leaves, by
+// sorted position, the body's box rounded OUTWARD to four floats (16 bytes); a tile stages just those -- plus the 4-byte ORDER
+// words and the cell_start slices -- and the walk is one 128-bit shared-memory load and four float compares per partner,
+// branch-free, recording the survivors as one bit each.  Only the survivors (a conservative superset of the overlapping boxes:
+// outward rounding can add, never drop) get the exact FP64 test of the reference -- AABB::overlaps on the swept boxes, then
+// the narrow phase -- on the full records, read through L1/L2.
+// Structure: persistent CTAs, 8 consumer warps + 1 producer warp, double-buffered 26 KB stages (a third of the record stage:
+// three CTAs per SM instead of two, windows of 384 instead of 272).  The producer runs one tile ahead: the tile's first/last cell
+// keys -> the cell_start entries bounding its three row windows -> per window three 1-D bulk copies (cp.async.bulk: boxes, order
+// words, cell_start slice) completing on the stage's `full` mbarrier by byte count; consumers wait on it and hand the stage back
+// through the `empty` mbarrier.
+#define SG_BPX_WCAP 352
+#define SG_BPX_CSCAP 288
+#define SG_BPX_STAGES 2
+#define SG_BPX_CTAS_PER_SM 3
+#define SG_BPX_T 256
+
+struct BpxHdr
 {
-  return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + size_t( BpCfg<D>::NW ) * SG_BP_TMA_CSCAP * 4 + sizeof( BpStage<D> ) + 1023 ) & ~size_t( 1023 );
+  BpStage<2> st;          // start, len (boxes staged), cs_klo, cs_len, full
+  uint32_t ord_shift[3];  // the order words were copied from a 16-byte aligned address: entry of slot 0
+};
+__host__ __device__ constexpr size_t sg_bpx_ord_off() { return size_t( 3 ) * SG_BPX_WCAP * 16; }
+__host__ __device__ constexpr size_t sg_bpx_cs_off() { return sg_bpx_ord_off() + size_t( 3 ) * ( SG_BPX_WCAP + 4 ) * 4; }
+__host__ __device__ constexpr size_t sg_bpx_hdr_off() { return sg_bpx_cs_off() + size_t( 3 ) * SG_BPX_CSCAP * 4; }
+__host__ __device__ constexpr size_t sg_bpx_stage_bytes() { return ( sg_bpx_hdr_off() + sizeof( BpxHdr ) + 127 ) & ~size_t( 127 ); }
+__host__ __device__ constexpr size_t sg_bpx_smem() { return SG_BPX_STAGES * sg_bpx_stage_bytes() + 64 + size_t( SG_BPX_T / 32 ) * 32 * 6 * sizeof( uint2 ); } // stages, barriers, per-warp survivor queues
+
+// A body whose walk does not fit the survivor bitmaps (a window of more than 64 positions, or more than 63 visits in all):
+// the plain walk with exact tests, everything through L1/L2.  Leaves exact counts and the (incomplete) masks pass 2 expects.
+template<typename P>
+__device__ __noinline__ void sg_bpx_body_slow( const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx,
+                                               const uint32_t n_slots, const uint32_t p, uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
+{
+  using Rec = typename P::Rec;
+  const GridParams g = *params;
+  BpStage<2> none;
+  #pragma unroll
+  for( int w = 0; w < 3; ++w ) { none.start[w] = 0u; none.len[w] = 0u; none.cs_klo[w] = 0u; none.cs_len[w] = 0u; }
+  none.full = 0u;
+  const Rec me = sg_load_rec_global<Rec>( &recs[p] );
+  sg_bp_count_body<P, BpCfg<2>::CSCAP, false>( g, cell_start, recs, nullptr, nullptr, &none, n_slots, p, me, P::rec_idx( me ), P::rec_ord( me ), counts, masks, plan, sidx );
 }
-#define SG_BP_TMA_STAGES 2      // shared-memory stages per CTA (measured: 1 stage x 4 CTAs/SM is 1.5x slower)
-#define SG_BP_TMA_CTAS_PER_SM 2 // resident CTAs per SM (stages x CTAs x 55 KB must fit the SM's 227 KB)
-template<int D> __host__ __device__ constexpr size_t sg_bp_tma_smem() { return SG_BP_TMA_STAGES * sg_bp_tma_stage_bytes<D>() + 64; }
+
+// The exact tests of one owned survivor pair -- AABB::overlaps on the swept boxes, then the narrow phase: bit 0 candidate, bit 1 active
+template<typename P>
+__device__ __forceinline__ uint32_t sg_bpx_exact( const typename P::Rec& a, const typename P::Rec& b )
+{
+  double lo[2], hi[2], olo[2], ohi[2];
+  P::rec_aabb( a, lo, hi );
+  P::rec_aabb( b, olo, ohi );
+  const bool ov = !( hi[0] < olo[0] ) && !( ohi[0] < lo[0] ) && !( hi[1] < olo[1] ) && !( ohi[1] < lo[1] );
+  if( !ov ) { return 0u; }
+  uint32_t res = 1u;
+  if( P::HAS_NARROW ) { if( P::narrow_test( a, b ) ) { res |= 2u; } }
+  return res;
+}
+
+#define SG_BPX_QLANE 6u                       // survivors a lane hands to the warp's queue (the rest it tests itself)
+#define SG_BPX_QCAP ( 32u * SG_BPX_QLANE )    // queue entries per warp
+
+// One warp's share of a tile (32 consecutive sorted bodies; every lane calls, `part` = this lane has an owned body).
+//  1. walk: per lane, one 128-bit + one 32-bit shared-memory load and five compares per partner, branch-free; a set bit =
+//     "float boxes touch AND the partner's order word is larger than mine" (so the pair is mine to list)
+//  2. the few survivors of all 32 lanes are compacted into the warp's queue (shuffle prefix sum), so that
+//  3. the expensive part -- exact FP64 box test, ball-ball CCD with its divisions and square root -- runs with all lanes
+//     busy, one pair per lane, instead of inside 32 divergent per-lane loops
+//  4. every lane collects the verdicts of its own pairs into its masks and counts.
+template<typename P, bool STAGED>
+__device__ __forceinline__ void sg_bpx_warp( const GridParams& g, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const float4* __restrict__ boxf,
+                                             const uint32_t* __restrict__ sidx, const unsigned char* stage, const uint32_t n_slots, const uint32_t p, const typename P::Rec& me, bool part,
+                                             uint2* wq, uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
+{
+  using Rec = typename P::Rec;
+  const float4* s_box = reinterpret_cast<const float4*>( stage );
+  const uint32_t* s_ord = reinterpret_cast<const uint32_t*>( stage + sg_bpx_ord_off() );
+  const uint32_t* s_cs = reinterpret_cast<const uint32_t*>( stage + sg_bpx_cs_off() );
+  const BpxHdr* hdr = reinterpret_cast<const BpxHdr*>( stage + sg_bpx_hdr_off() );
+  const BpStage<2>* st = &hdr->st;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t qb[3] = { 0u, 0u, 0u }, qe[3] = { 0u, 0u, 0u };
+  unsigned long long pm[3] = { 0ull, 0ull, 0ull };
+  uint32_t my_idx = 0u;
+  if( part )
+  {
+    my_idx = P::rec_idx( me );
+    const uint32_t my_ord = P::rec_ord( me );
+    sg_bp_ranges<P, SG_BPX_CSCAP, STAGED>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
+    uint32_t total = 0u;
+    bool fits = true;
+    #pragma unroll
+    for( int w = 0; w < 3; ++w )
+    {
+      const uint32_t L = qe[w] - qb[w];
+      fits = fits && L <= 64u;
+      total += L - ( ( p - qb[w] < L ) ? 1u : 0u );
+    }
+    if( !fits || total > SG_BP_MASK_BITS )
+    {
+      // does not fit the bitmaps: the plain walk, on its own
+      sg_bpx_body_slow<P>( params, cell_start, recs, sidx, n_slots, p, counts, masks, plan );
+      part = false;
+    }
+    else
+    {
+      sg_bp_plan_store<2>( plan, n_slots, p, qb, qe );
+      double lo[2], hi[2];
+      P::rec_aabb( me, lo, hi );
+      const float4 mb = sg_box_outward( lo, hi );
+      #pragma unroll
+      for( int w = 0; w < 3; ++w )
+      {
+        unsigned long long m = 0ull;
+        const uint32_t s0 = qb[w] - st->start[w];
+        const uint32_t L = qe[w] - qb[w];
+        const float4* wb = s_box + w * SG_BPX_WCAP;
+        const uint32_t* wo = s_ord + w * ( SG_BPX_WCAP + 4 ) + hdr->ord_shift[w];
+        #pragma unroll 2
+        for( uint32_t j = 0u; j < L; ++j )
+        {
+          const uint32_t slot = s0 + j;
+          const bool in = STAGED || slot < st->len[w];
+          const float4 b = in ? wb[slot] : __ldg( &boxf[qb[w] + j] );
+          const uint32_t o_ord = ( in ? wo[slot] : __ldg( &sidx[qb[w] + j] ) ) & P::IDX_MASK;
+          const bool pass = !( mb.z < b.x ) && !( b.z < mb.x ) && !( mb.w < b.y ) && !( b.w < mb.y ) && o_ord > my_ord; // never the body itself: equal order words
+          m |= static_cast<unsigned long long>( pass ? 1u : 0u ) << j;
+        }
+        pm[w] = m;
+      }
+    }
+  }
+  // ---- compact the survivors of the warp
+  const uint32_t cnt = uint32_t( __popcll( pm[0] ) + __popcll( pm[1] ) + __popcll( pm[2] ) ); // 0 for lanes that do not take part
+  const uint32_t cq = ( cnt < SG_BPX_QLANE ) ? cnt : SG_BPX_QLANE;
+  uint32_t off = cq;
+  #pragma unroll
+  for( int d = 1; d < 32; d <<= 1 ) { const uint32_t v = __shfl_up_sync( 0xffffffffu, off, d ); if( lane >= uint32_t( d ) ) { off += v; } }
+  const uint32_t total_q = __shfl_sync( 0xffffffffu, off, 31 );
+  off -= cq;
+  uint32_t nc = 0u, na = 0u;
+  unsigned long long cmask = 0ull, amask = 0ull;
+  if( cnt != 0u )
+  {
+    uint32_t taken = 0u, base = 0u;
+    #pragma unroll
+    for( int w = 0; w < 3; ++w )
+    {
+      const uint32_t L = qe[w] - qb[w];
+      const bool mine = p - qb[w] < L;
+      unsigned long long m = pm[w];
+      while( m != 0ull )
+      {
+        const uint32_t j = uint32_t( __ffsll( static_cast<long long>( m ) ) ) - 1u;
+        m &= m - 1ull;
+        const uint32_t q = qb[w] + j;
+        const uint32_t k = base + j - ( ( mine && q > p ) ? 1u : 0u );
+        if( taken < SG_BPX_QLANE ) { wq[off + taken] = make_uint2( q, k | ( lane << 8 ) ); }
+        else
+        {
+          // more survivors than this lane's share of the queue (dense scenes): tested here
+          const uint32_t res = sg_bpx_exact<P>( sg_load_rec_global<Rec>( &recs[p] ), sg_load_rec_global<Rec>( &recs[q] ) ); // (own record re-read: keeping it live through the warp phases would cost 16 registers)
+          if( res & 1u ) { ++nc; cmask |= 1ull << k; }
+          if( res & 2u ) { ++na; amask |= 1ull << k; }
+        }
+        ++taken;
+      }
+      base += L - ( mine ? 1u : 0u );
+    }
+  }
+  __syncwarp();
+  // ---- exact tests, one pair per lane
+  const uint32_t warp_first = p - lane; // sorted position of lane 0's body
+  for( uint32_t e = lane; e < total_q; e += 32u )
+  {
+    const uint2 ent = wq[e];
+    const Rec a = sg_load_rec_global<Rec>( &recs[warp_first + ( ( ent.y >> 8 ) & 31u )] );
+    const Rec b = sg_load_rec_global<Rec>( &recs[ent.x] );
+    wq[e].y = ent.y | ( sg_bpx_exact<P>( a, b ) << 30 );
+  }
+  __syncwarp();
+  // ---- verdicts back to the owners
+  for( uint32_t i = 0u; i < cq; ++i )
+  {
+    const uint32_t y = wq[off + i].y;
+    const unsigned long long bit = 1ull << ( y & 63u );
+    if( y & 0x40000000u ) { ++nc; cmask |= bit; }
+    if( y & 0x80000000u ) { ++na; amask |= bit; }
+  }
+  __syncwarp(); // the queue is reused by the next tile
+  if( part )
+  {
+    counts[my_idx] = make_uint2( nc, na );
+    masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
+  }
+}
 
 template<typename P>
-__global__ void __launch_bounds__( BpCfg<P::D>::T + 32, SG_BP_TMA_CTAS_PER_SM ) sg_bp_count_tma( const __grid_constant__ CUtensorMap tm_recs, const uint32_t n_slots, const GridParams* __restrict__ params,
-                                                                            const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts,
-                                                                            uint4* __restrict__ masks, uint4* __restrict__ plan )
+__global__ void __launch_bounds__( SG_BPX_T + 32, SG_BPX_CTAS_PER_SM ) sg_bp_count_tma( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                                                                const typename P::Rec* __restrict__ recs, const float4* __restrict__ boxf, const uint32_t* __restrict__ sidx,
+                                                                                uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
 {
-  constexpr int D = P::D;
-  using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
-  static_assert( D == 2, "the TMA-fed pass 1 is laid out for the 2-D pipelines" );
-  static_assert( Cfg::WCAP == 2 * SG_BP_TMA_ROWS, "two tensor copies per window" );
+  static_assert( P::D == 2, "the box-prefiltered pass 1 is laid out for the 2-D pipelines" );
   extern __shared__ __align__( 1024 ) unsigned char s_raw[];
-  constexpr size_t STAGE = sg_bp_tma_stage_bytes<D>();
-  constexpr size_t CS_OFF = size_t( Cfg::NW ) * Cfg::WCAP * 64;
-  constexpr size_t ST_OFF = CS_OFF + size_t( Cfg::NW ) * SG_BP_TMA_CSCAP * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>( s_raw + SG_BP_TMA_STAGES * STAGE ); // full[0], full[1], empty[0], empty[1] (stage s uses full[s], empty[s])
+  constexpr size_t STAGE = sg_bpx_stage_bytes();
+  uint64_t* bars = reinterpret_cast<uint64_t*>( s_raw + SG_BPX_STAGES * STAGE ); // full[0], full[1], empty[0], empty[1]
   const GridParams g = *params;
   const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned
-  const uint32_t ntiles = ( n_slots + Cfg::T - 1u ) / Cfg::T;
-  const bool producer = threadIdx.x >= uint32_t( Cfg::T );
+  const uint32_t ntiles = ( n_slots + SG_BPX_T - 1u ) / SG_BPX_T;
+  const bool producer = threadIdx.x >= uint32_t( SG_BPX_T );
   if( threadIdx.x == 0 )
   {
     sg_mbar_init( &bars[0], 1u ); sg_mbar_init( &bars[1], 1u );
-    sg_mbar_init( &bars[2], Cfg::T / 32u ); sg_mbar_init( &bars[3], Cfg::T / 32u );
+    sg_mbar_init( &bars[2], SG_BPX_T / 32u ); sg_mbar_init( &bars[3], SG_BPX_T / 32u );
   }
   __syncthreads();
 
   if( producer )
   {
-    if( threadIdx.x != uint32_t( Cfg::T ) ) { return; } // one elected lane drives the copies
+    if( threadIdx.x != uint32_t( SG_BPX_T ) ) { return; } // one elected lane drives the copies
     uint32_t it = 0u;
     for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
     {
-      const uint32_t b0 = t * Cfg::T;
+      const uint32_t b0 = t * SG_BPX_T;
       if( b0 >= n ) { break; } // tiles past the binned bodies have nothing to stage (consumers only clear masks)
-      const uint32_t sgi = it % SG_BP_TMA_STAGES, use = it / SG_BP_TMA_STAGES;
+      const uint32_t sgi = it % SG_BPX_STAGES, use = it / SG_BPX_STAGES;
       unsigned char* stage = s_raw + sgi * STAGE;
-      BpStage<D>* st = reinterpret_cast<BpStage<D>*>( stage + ST_OFF );
+      BpxHdr* hdr = reinterpret_cast<BpxHdr*>( stage + sg_bpx_hdr_off() );
       // the tile's plan (two dependent rounds of global loads) does not need the stage: fetch it first, wait after
-      const uint32_t b1 = ( n - b0 < uint32_t( Cfg::T ) ) ? n : b0 + Cfg::T;
+      const uint32_t b1 = ( n - b0 < uint32_t( SG_BPX_T ) ) ? n : b0 + SG_BPX_T;
       const long long kf = __ldg( &recs[b0].key );
       const long long kl = __ldg( &recs[b1 - 1u].key );
-      long long klo[Cfg::NW], khi[Cfg::NW];
-      uint32_t start[Cfg::NW], end[Cfg::NW];
+      long long klo[3], khi[3];
+      uint32_t start[3], end[3];
       #pragma unroll
-      for( int w = 0; w < Cfg::NW; ++w )
+      for( int w = 0; w < 3; ++w )
       {
-        const long long off = ( long long )( w % 3 - 1 ) * g.dims[0];
+        const long long off = ( long long )( w - 1 ) * g.dims[0];
         klo[w] = kf + off - 1; khi[w] = kl + off + 1;
         const bool ok = khi[w] >= 0 && klo[w] <= ( long long )( g.ncells ) - 1;
         klo[w] = ( klo[w] < 0 ) ? 0 : klo[w];
@@ -698,107 +899,78 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T + 32, SG_BP_TMA_CTAS_PER_SM ) 
         start[w] = ok ? __ldg( &cell_start[klo[w]] ) : 0u;
         end[w] = ok ? __ldg( &cell_start[khi[w] + 1] ) : 0u;
       }
-      uint32_t bytes = 0u;
-      uint32_t ncopies[Cfg::NW], cs_first[Cfg::NW], cs_n[Cfg::NW];
-      uint32_t all_staged = 1u;
+      uint32_t bytes = 0u, all_staged = 1u;
+      uint32_t len[3], ord_first[3], ord_n[3], cs_first[3], cs_n[3];
       if( use > 0u ) { sg_mbar_wait_backoff( &bars[2 + sgi], ( use - 1u ) & 1u ); } // consumers are done with this stage
       #pragma unroll
-      for( int w = 0; w < Cfg::NW; ++w )
+      for( int w = 0; w < 3; ++w )
       {
-        const uint32_t len = ( end[w] - start[w] < uint32_t( Cfg::WCAP ) ) ? end[w] - start[w] : uint32_t( Cfg::WCAP );
-        ncopies[w] = ( len + SG_BP_TMA_ROWS - 1u ) / SG_BP_TMA_ROWS;
-        // cell_start slice: entries klo .. khi+1, widened to whole 16-byte groups for the bulk copy
+        len[w] = ( end[w] - start[w] < uint32_t( SG_BPX_WCAP ) ) ? end[w] - start[w] : uint32_t( SG_BPX_WCAP );
+        // order words: from a 16-byte aligned entry, whole 16-byte groups (the array has slack behind its end)
+        ord_first[w] = start[w] & ~3u;
+        ord_n[w] = ( len[w] == 0u ) ? 0u : ( ( start[w] - ord_first[w] + len[w] + 3u ) & ~3u );
+        // cell_start slice: entries klo .. khi+1, widened to whole 16-byte groups
         const long long ncs = khi[w] - klo[w] + 2;
         cs_first[w] = uint32_t( klo[w] ) & ~3u;
         uint32_t want = ( khi[w] < klo[w] ) ? 0u : uint32_t( klo[w] - cs_first[w] + ncs );
         want = ( want + 3u ) & ~3u;
-        cs_n[w] = ( want < uint32_t( SG_BP_TMA_CSCAP ) ) ? want : uint32_t( SG_BP_TMA_CSCAP );
-        st->start[w] = start[w]; st->len[w] = len; st->cs_klo[w] = cs_first[w]; st->cs_len[w] = cs_n[w];
-        if( end[w] - start[w] > uint32_t( Cfg::WCAP ) || want > uint32_t( SG_BP_TMA_CSCAP ) ) { all_staged = 0u; }
-        bytes += ncopies[w] * uint32_t( SG_BP_TMA_ROWS * 64 ) + cs_n[w] * 4u;
+        cs_n[w] = ( want < uint32_t( SG_BPX_CSCAP ) ) ? want : uint32_t( SG_BPX_CSCAP );
+        hdr->st.start[w] = start[w]; hdr->st.len[w] = len[w]; hdr->st.cs_klo[w] = cs_first[w]; hdr->st.cs_len[w] = cs_n[w];
+        hdr->ord_shift[w] = start[w] - ord_first[w];
+        if( end[w] - start[w] > uint32_t( SG_BPX_WCAP ) || want > uint32_t( SG_BPX_CSCAP ) ) { all_staged = 0u; }
+        bytes += len[w] * 16u + ord_n[w] * 4u + cs_n[w] * 4u;
       }
-      st->full = all_staged;
+      hdr->st.full = all_staged;
       asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); // the stage's earlier generic reads vs the async writes to come
       sg_mbar_arrive_expect_tx( &bars[sgi], bytes );
       #pragma unroll
-      for( int w = 0; w < Cfg::NW; ++w )
+      for( int w = 0; w < 3; ++w )
       {
-        for( uint32_t c = 0u; c < ncopies[w]; ++c )
+        if( len[w] != 0u )
         {
-          sg_tma_load_2d( stage + ( size_t( w ) * Cfg::WCAP + size_t( c ) * SG_BP_TMA_ROWS ) * 64, &tm_recs, 0, int( start[w] + c * SG_BP_TMA_ROWS ), &bars[sgi] );
+          sg_bulk_g2s( stage + size_t( w ) * SG_BPX_WCAP * 16, boxf + start[w], len[w] * 16u, &bars[sgi] );
+          sg_bulk_g2s( stage + sg_bpx_ord_off() + size_t( w ) * ( SG_BPX_WCAP + 4 ) * 4, sidx + ord_first[w], ord_n[w] * 4u, &bars[sgi] );
         }
-        if( cs_n[w] != 0u ) { sg_bulk_g2s( stage + CS_OFF + size_t( w ) * SG_BP_TMA_CSCAP * 4, cell_start + cs_first[w], cs_n[w] * 4u, &bars[sgi] ); }
+        if( cs_n[w] != 0u ) { sg_bulk_g2s( stage + sg_bpx_cs_off() + size_t( w ) * SG_BPX_CSCAP * 4, cell_start + cs_first[w], cs_n[w] * 4u, &bars[sgi] ); }
       }
     }
     return;
   }
 
   // ---- consumers ----
+  uint2* wq = reinterpret_cast<uint2*>( s_raw + SG_BPX_STAGES * STAGE + 64 ) + ( threadIdx.x >> 5 ) * SG_BPX_QCAP; // this warp's survivor queue
   uint32_t it = 0u;
   for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
   {
-    const uint32_t p = t * Cfg::T + threadIdx.x;
-    if( t * Cfg::T >= n )
+    const uint32_t p = t * SG_BPX_T + threadIdx.x;
+    if( t * SG_BPX_T >= n )
     {
-      if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slots: pass 2 skips them
+      if( p < n_slots ) { masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slots: pass 2 skips them
       continue;
     }
-    const uint32_t sgi = it % SG_BP_TMA_STAGES, use = it / SG_BP_TMA_STAGES;
+    const uint32_t sgi = it % SG_BPX_STAGES, use = it / SG_BPX_STAGES;
     const unsigned char* stage = s_raw + sgi * STAGE;
-    const unsigned char* s_recs = stage;
-    const uint32_t* s_cs = reinterpret_cast<const uint32_t*>( stage + CS_OFF );
-    const BpStage<D>* st = reinterpret_cast<const BpStage<D>*>( stage + ST_OFF );
+    Rec me;
+    if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the stage lands
     sg_mbar_wait( &bars[sgi], use & 1u );
-    if( p < n )
+    bool part = p < n;
+    if( part && !P::owns( me ) )
     {
-      const Rec me = sg_bp_fetch<P>( recs, s_recs, st, 1, p ); // own row is window 1 (dy = 0)
-      const uint32_t my_idx = P::rec_idx( me );
-      if( !P::owns( me ) )
-      {
-        counts[my_idx] = make_uint2( 0u, 0u );
-        masks[p] = make_uint4( 0u, 0u, 0u, 0u );
-      }
-      else
-      {
-        // tiles whose windows and cell_start slices were staged completely (the rule, not the exception) run a
-        // walk with no fallback code in it at all
-        if( st->full != 0u ) { sg_bp_count_body<P, SG_BP_TMA_CSCAP, true>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan ); }
-        else { sg_bp_count_body<P, SG_BP_TMA_CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan ); }
-      }
+      // a ghost body (multi-GPU halo): present only as a partner, its pairs are kept by the rank that owns it
+      counts[P::rec_idx( me )] = make_uint2( 0u, 0u );
+      masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u );
+      part = false;
     }
-    else if( p < n_slots ) { masks[p] = make_uint4( 0u, 0u, 0u, 0u ); }
+    else if( !part && p < n_slots ) { masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u ); }
+    // tiles whose windows and cell_start slices were staged completely (the rule, not the exception) run a
+    // walk with no fallback code in it at all
+    const BpxHdr* hdr = reinterpret_cast<const BpxHdr*>( stage + sg_bpx_hdr_off() );
+    if( hdr->st.full != 0u ) { sg_bpx_warp<P, true>( g, params, cell_start, recs, boxf, sidx, stage, n_slots, p, me, part, wq, counts, masks, plan ); }
+    else { sg_bpx_warp<P, false>( g, params, cell_start, recs, boxf, sidx, stage, n_slots, p, me, part, wq, counts, masks, plan ); }
     // this warp is done with the stage
     __syncwarp();
     if( ( threadIdx.x & 31u ) == 0u ) { sg_mbar_arrive( &bars[2 + sgi] ); }
   }
-}
-
-// Tensor map over the sorted records: n rows of 16 x u32, box = 16 x SG_BP_TMA_ROWS, 64-byte swizzle.
-// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
-static inline int sg_bp_encode_recs_map( sg_ctx* ctx, const void* recs, const uint32_t n, CUtensorMap* out )
-{
-  typedef CUresult ( *EncodeFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
-  static EncodeFn encode = nullptr;
-  if( encode == nullptr )
-  {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr )
-    {
-      cudaGetLastError();
-      return sg_fail( ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver" );
-    }
-    encode = reinterpret_cast<EncodeFn>( fn );
-  }
-  const cuuint64_t gdim[2] = { 16, n };
-  const cuuint64_t gstride[1] = { 64 };
-  const cuuint32_t box[2] = { 16, SG_BP_TMA_ROWS };
-  const cuuint32_t estr[2] = { 1, 1 };
-  const CUresult r = encode( out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>( recs ), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
-  if( r != CUDA_SUCCESS ) { return sg_fail( ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled( sorted records ) -> %d", int( r ) ); }
-  return SG_OK;
 }
 
 // Dispatch: the 2-D pipelines take the TMA-fed kernel, the 3-D ones the block-staged kernel (their 9 windows do not
@@ -811,7 +983,7 @@ template<> struct SgBpCountLaunch<3>
     constexpr size_t smem = sg_bp_count_smem<3>();
     SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) );
     SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<3>::NPLAN ), sg_bp_count<P><<<sg_div_up( n, BpCfg<3>::T ), BpCfg<3>::T, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-               s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
+               s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
     return SG_OK;
   }
 };
@@ -819,19 +991,12 @@ template<> struct SgBpCountLaunch<2>
 {
   template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const uint32_t n )
   {
-    if( s.recs.ptr != s.tm_ptr || n != s.tm_rows )
-    {
-      const int rc = sg_bp_encode_recs_map( ctx, s.recs.ptr, n, &s.tm_recs );
-      if( rc != SG_OK ) { return rc; }
-      s.tm_ptr = s.recs.ptr; s.tm_rows = n;
-    }
-    constexpr size_t smem = sg_bp_tma_smem<2>();
-    static int attr_dev = -1; // opt-in to > 48 KB of dynamic shared memory: once per device
-    if( attr_dev != ctx->device ) { SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_tma<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) ); attr_dev = ctx->device; }
-    const unsigned ntiles = sg_div_up( n, BpCfg<2>::T );
-    const unsigned grid = ntiles < unsigned( ctx->num_sms ) * SG_BP_TMA_CTAS_PER_SM ? ntiles : unsigned( ctx->num_sms ) * SG_BP_TMA_CTAS_PER_SM;
-    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_tma<P><<<grid, BpCfg<2>::T + 32, smem, ctx->stream>>>( s.tm_recs, n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-               s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.plan.as<uint4>() ) );
+    constexpr size_t smem = sg_bpx_smem();
+    if( s.attr_dev != ctx->device ) { SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_tma<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) ); s.attr_dev = ctx->device; } // opt-in to > 48 KB, once per context
+    const unsigned ntiles = sg_div_up( n, SG_BPX_T );
+    const unsigned grid = ntiles < unsigned( ctx->num_sms ) * SG_BPX_CTAS_PER_SM ? ntiles : unsigned( ctx->num_sms ) * SG_BPX_CTAS_PER_SM;
+    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_tma<P><<<grid, SG_BPX_T + 32, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+               s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
     return SG_OK;
   }
 };
@@ -949,26 +1114,30 @@ template<> __device__ __forceinline__ void sg_sort_keys<16>( unsigned long long*
   sg_cex( v[1], v[2] ); sg_cex( v[3], v[4] ); sg_cex( v[5], v[6] ); sg_cex( v[7], v[8] ); sg_cex( v[9], v[10] ); sg_cex( v[11], v[12] ); sg_cex( v[13], v[14] );
 }
 
-// Pass 2.  Each body writes its candidates (ascending partner index) at its offset; active ones also write a contact.
+// Pass 2.  Each body writes its candidates (ascending partner order word) at its offset; active ones also leave a work item.
+// One thread per body IN INDEX ORDER -- the order of the lists: consecutive threads own consecutive output ranges, so the
+// stores are coalesced whatever the numbering of the scene has to do with space; what is random for a randomly numbered scene
+// is one 32-byte read per body (masks + walk plan of its sorted position) and the gathers of its few partners' order words.
 // Nothing is shared between threads: pass 1 left, per sorted position, the candidate/active masks over the visit
 // sequence and the walk plan (window starts and lengths), so a thread decodes its set bits straight to sorted
-// positions, gathers the partners' index words (L1/L2: neighbouring threads read the same few rows), orders its
-// candidates (up to 8 in 2-D, 16 in 3-D) with a register sorting network and stores them.  No staging, no barriers, no shared memory.
+// positions, gathers the partners' order words, orders its candidates (up to 8 in 2-D, 16 in 3-D) with a register sorting
+// network and stores them.  No staging, no barriers, no shared memory.
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint4* __restrict__ masks, const uint4* __restrict__ plan, const uint2* __restrict__ counts,
-                                                              const ulonglong2* __restrict__ offsets_pos, uint2* __restrict__ cand, const uint64_t cand_cap, uint2* __restrict__ work, const uint64_t work_cap )
+                                                              const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ pos_of, const uint32_t* __restrict__ ord_by_index,
+                                                              const uint4* __restrict__ masks, const uint4* __restrict__ plan, const uint2* __restrict__ counts,
+                                                              const ulonglong2* __restrict__ offsets, uint2* __restrict__ cand, const uint64_t cand_cap, uint2* __restrict__ work, const uint64_t work_cap )
 {
   constexpr int D = P::D;
   using Cfg = BpCfg<D>;
   using Rec = typename P::Rec;
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if( p >= n_slots ) { return; }
-  // everything the common path needs is position-indexed: issue all the loads before looking at any of them
-  // (one round trip instead of two; unused slots just read stale plan words they never use)
-  const uint4 m = __ldg( &masks[p] ); // zero for ghosts and for slots past the binned bodies (cleared by pass 1)
-  const ulonglong2 off = offsets_pos[p];
-  const uint32_t my_ord = __ldg( &sidx[p] ) & P::IDX_MASK; // the order word is what the lists carry (== the body index on one GPU)
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i >= n_slots ) { return; }
+  const uint32_t p = __ldg( &pos_of[i] );
+  const ulonglong2 off = offsets[i];
+  const uint32_t my_ord = ( ord_by_index != nullptr ) ? __ldg( &ord_by_index[i] ) : i; // the order word is what the lists carry (== the body index on one GPU)
+  if( p == 0xffffffffu ) { return; } // an unused slot (multi-GPU ghost capacity)
+  const uint4 m = __ldg( &masks[size_t( p ) * BpPlan<D>::STRIDE] ); // zero for ghosts
   uint32_t qb[Cfg::NW], len[Cfg::NW];
   sg_bp_plan_load<D>( plan, n_slots, p, qb, len );
   const unsigned long long cmask = m.x | ( static_cast<unsigned long long>( m.y ) << 32 );
@@ -1122,11 +1291,11 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   SG_CUDA( ctx, s.key.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.rank.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.recs.ensure( size_t( n ) * 64 ) );
-  SG_CUDA( ctx, s.sidx.ensure( size_t( n ) * 4 ) );
+  SG_CUDA( ctx, s.sidx.ensure( size_t( n ) * 4 + 64 ) ); // + slack: bulk copies read whole 16-byte groups
+  if( P::D == 2 ) { SG_CUDA( ctx, s.boxf.ensure( size_t( n ) * 16 ) ); }
   SG_CUDA( ctx, s.pos_of.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.counts.ensure( size_t( n ) * sizeof( uint2 ) ) );
-  SG_CUDA( ctx, s.masks.ensure( size_t( n ) * sizeof( uint4 ) ) );
-  SG_CUDA( ctx, s.plan.ensure( size_t( n ) * sizeof( uint4 ) * BpPlan<P::D>::NPLAN ) );
+  SG_CUDA( ctx, s.masks.ensure( size_t( n ) * sizeof( uint4 ) * BpPlan<P::D>::STRIDE ) ); // masks and walk plan interleaved by position
   SG_CUDA( ctx, s.offsets.ensure( size_t( n ) * sizeof( ulonglong2 ) ) );
   SG_CUDA( ctx, s.pair_partials.ensure( ( size_t( n ) / SG_SCAN_TILE + 2 ) * sizeof( ScanPairCounts::Acc ) ) );
   SG_CUDA( ctx, s.totals.ensure( sizeof( ScanPairCounts::Acc ) ) );
@@ -1155,11 +1324,13 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   const uint32_t* ncells_dev = &s.params.as<GridParams>()->ncells;
   int rc = sg_exclusive_scan<ScanU32>( ctx, "bp_cell_scan", s.cell_count.as<uint32_t>(), ncells_dev, 0u, s.max_cells, s.cell_partials.as<uint32_t>(), s.cell_start.as<uint32_t>(), nullptr, true );
   if( rc != SG_OK ) { return rc; }
-  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 + 4.0 ) + double( s.max_cells ) * 4.0, sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>(), s.cell_count.as<uint32_t>(), s.max_cells + 2u ) );
+  SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 ) + double( s.max_cells ) * 4.0, sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.pos_of.as<uint32_t>(), s.cell_count.as<uint32_t>(), s.max_cells + 2u ) );
+  SG_LAUNCH( ctx, "bp_side", nb * ( 64.0 + 4.0 + ( D == 2 ? 16.0 : 0.0 ) ), sg_bp_side_arrays<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
+             s.sidx.as<uint32_t>(), D == 2 ? s.boxf.as<float4>() : nullptr ) );
   s.hist_clean = true;
   rc = SgBpCountLaunch<D>::template run<P>( ctx, s, n );
   if( rc != SG_OK ) { return rc; }
-  rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false, s.pos_of.as<uint32_t>(), s.side.n != 0u ? &s.side : nullptr );
+  rc = sg_exclusive_scan<ScanPairCounts>( ctx, "bp_pair_scan", s.counts.as<uint2>(), nullptr, n, n, s.pair_partials.as<ScanPairCounts::Acc>(), s.offsets.as<ulonglong2>(), s.totals.as<ScanPairCounts::Acc>(), false, nullptr, s.side.n != 0u ? &s.side : nullptr );
   s.side.n = 0u;
   return rc;
 }
@@ -1189,7 +1360,7 @@ static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, con
     s.work_cap = act_cap;
   }
   SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ), sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.masks.as<uint4>(), s.plan.as<uint4>(), s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap,
+             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>(), s.ord_by_index, s.masks.as<uint4>(), s.masks.as<uint4>() + 1, s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap,
              s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap ) );
   return SgBpContactsLaunch<P::HAS_NARROW>::template run<P>( ctx, s, out, act_cap );
 }

@@ -44,9 +44,10 @@ __device__ __forceinline__ void sg_mbar_wait_backoff( uint64_t* bar, const uint3
   const uint32_t addr = sg_smem_u32( bar );
   for( ;; )
   {
-    asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"( done ) : "r"( addr ), "r"( parity ) : "memory" );
+    // suspend-time hint: the hardware may park the thread for up to ~20 us per try instead of returning at once
+    asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"( done ) : "r"( addr ), "r"( parity ), "r"( 20000u ) : "memory" );
     if( done != 0 ) { break; }
-    __nanosleep( 256 );
+    __nanosleep( 1000 );
   }
 }
 

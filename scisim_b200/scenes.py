@@ -45,6 +45,30 @@ def ball2d_gas(n=1 << 20, rmin=0.25, rmax=1.0, phi=0.55, seeds=(7, 8, 9), dt=1.0
     return scene
 
 
+def ball2d_asset(name="different_friction", portal=False, map="symplectic_euler"):
+    """BASELINE configs[0]: a scene bundled with the reference (assets/ball2d/...), from the committed fixture
+    tests/golden/ball2d_assets.npz (written by tests/golden/make_ball2d_assets.py from the reference's XML; the GPU box has no
+    reference tree).  name: "pool_break_ten_deep" (56 balls, no gravity, dt 0.1) or "different_friction" (6 079 balls, gravity
+    at 23 degrees, 3 static planes, dt 1/10080).  The integrator is forced to symplectic_euler (every bundled scene says
+    verlet; the parser accepts both, ball2dutils/Ball2DSceneParser.cpp:624-636).  portal=True keeps the scene's
+    <planar_portal planeA planeB>: those two planes leave the static-plane list and form a planar portal (parser :369-585)."""
+    import os
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ball2d_assets.npz"))
+    g = lambda k: f["%s/%s" % (name, k)]
+    px, pn = g("plane_x").reshape(-1, 2).copy(), g("plane_n").reshape(-1, 2).copy()
+    scene = {"q": g("q").copy(), "v": g("v").copy(), "r": g("r").copy(), "m": g("m").copy(), "g": g("g").copy(), "dt": float(g("dt")), "map": map,
+             "drum_x": np.zeros((0, 2)), "drum_r": np.zeros(0), "t": 0.0}
+    pp = g("portal_planes").reshape(-1, 2)
+    if portal and pp.shape[0]:
+        used = sorted(set(int(k) for k in pp.ravel()))
+        scene["portals"] = {"plane_a_x": px[pp[:, 0]].copy(), "plane_a_n": pn[pp[:, 0]].copy(), "plane_b_x": px[pp[:, 1]].copy(), "plane_b_n": pn[pp[:, 1]].copy(),
+                            "v": np.zeros(pp.shape[0]), "bounds": np.zeros(pp.shape[0])}
+        keep = [k for k in range(px.shape[0]) if k not in used]
+        px, pn = px[keep], pn[keep]
+    scene["plane_x"], scene["plane_n"] = np.ascontiguousarray(px), np.ascontiguousarray(pn)
+    return scene
+
+
 def ball2d_random(n, seed, box=None, rmin=0.05, rmax=0.4, nplanes=2, ndrums=1, vmax=40.0, dt=0.01):
     """Small messy scenes for parity tests: overlapping balls, fast movers (tunnelling CCD hits), oblique
     un-normalised planes and a drum."""
