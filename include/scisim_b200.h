@@ -279,6 +279,9 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
 int sg_ball2d_slab_pack( sg_ctx* ctx, const double* interval_dev, void* send_dev, uint32_t cap, uint32_t* count_dev );
 int sg_ball2d_slab_unpack( sg_ctx* ctx, int side, const void* recv_dev );
 int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out );
+/* diagnostics (4 values): ghosts held on side 0 / 1, steps since the mailbox was created in which the halo pack had to scan all bodies
+   (the candidate band did not hold: the first step always, later ones only after a jump), capacity of the candidate lists */
+int sg_ball2d_slab_stats( sg_ctx* ctx, uint32_t* out4 );
 
 /* ---- multi-GPU: host helpers of the slab decomposition (no device work, no context) -----------------------------
  * sg_slab_partition   equal-count x-quantiles: bodies ranked by ( x, index ), slab k takes ranks

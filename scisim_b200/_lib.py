@@ -91,6 +91,7 @@ def load():
         "sg_ball2d_slab_init": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
         "sg_ball2d_slab_set_gids": (C.c_int, [vp, vp, vp]),
         "sg_ball2d_slab_upload_q1": (C.c_int, [vp, vp]),
+        "sg_ball2d_slab_stats": (C.c_int, [vp, vp]),
         "sg_ball2d_fetch_state": (C.c_int, [vp, vp, vp]),
         "sg_slab_partition": (C.c_int, [C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp]),
         "sg_slab_limits": (C.c_int, [C.c_uint32, vp, C.c_uint32, vp]),

@@ -222,6 +222,21 @@ __device__ __forceinline__ unsigned long long static_mask( const Static2D& sg, c
   return mask;
 }
 
+// Slab mode, peer-memory exchange: while the flow kernel has every owned body's swept box in registers it also lists the bodies
+// that COULD be owed to a neighbour this step -- those reaching the band next to that neighbour, band = the neighbour's interval
+// of the previous step widened by a margin -- so that the halo pack, once the neighbour's actual interval has arrived, only looks
+// at that short list (and checks that the actual interval lies inside the band; if not, it scans all bodies: correctness never
+// depends on the guess).  state: [0] = left band's upper edge (a body is a candidate for the lower neighbour if lo.x <= it),
+// [1] = right band's lower edge (candidate for the higher neighbour if hi.x >= it).
+struct SlabCand
+{
+  const double* band;      // 2 doubles (device); nullptr: no candidate lists
+  uint32_t* count;         // 2 counters
+  uint32_t* list[2];       // slot indices
+  uint32_t cap;
+  bool on[2];
+};
+
 // One pass over the balls that (optionally) integrates them and, from registers, also produces everything the
 // detection pipeline needs before binning: the bounds of the swept AABBs (block reduce + one atomic per quantity
 // per block) and counts[g * nblocks + block] = number of this block's balls active against static geometry g.
@@ -230,7 +245,7 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
                                                        const double* __restrict__ m, const double* __restrict__ r, const double gx, const double gy, const double dt,
                                                        double2* __restrict__ q1, double2* __restrict__ v1, BoundsAccum* __restrict__ acc, uint32_t* __restrict__ counts,
                                                        const uint32_t own_first, const uint32_t own_count, const uint32_t* __restrict__ ghost_counts, long long* __restrict__ interval_enc,
-                                                       double2* __restrict__ block_iv, const double xlim_lo, const double xlim_hi, uint32_t* __restrict__ slab_flags )
+                                                       double2* __restrict__ block_iv, const double xlim_lo, const double xlim_hi, uint32_t* __restrict__ slab_flags, const SlabCand sc )
 {
   // q0, q1, r are indexed by slot ([ghosts | owned | ghosts] in slab mode); v0, m, v1 exist for owned bodies only.
   // interval_enc != nullptr (slab mode, before the exchange): the ghosts have not arrived yet -- only owned bodies are live, and
@@ -300,6 +315,26 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_prep( const __grid_constant__ 
     if( slab_flags != nullptr && ( lo[0] < xlim_lo || hi[0] > xlim_hi ) ) { slab_flags[3] = 1u; }
     sg_bp_bounds_update<2>( lo, hi, mn, mx, ext );
     if( i - own_first < own_count ) { mask = static_mask( sg, qo, rad ); } // ghosts touch no static geometry here
+  }
+  if( sc.band != nullptr )
+  {
+    // candidate lists for the halo pack (order is irrelevant: the lists are ranked by global index later)
+    #pragma unroll
+    for( int sd = 0; sd < 2; ++sd )
+    {
+      if( !sc.on[sd] ) { continue; }
+      const bool c = live && ( ( sd == 0 ) ? ( ivlo <= sc.band[0] ) : ( ivhi >= sc.band[1] ) );
+      const unsigned bal = __ballot_sync( 0xffffffffu, c );
+      if( bal != 0u )
+      {
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0u;
+        if( lane == __ffs( bal ) - 1 ) { base = atomicAdd( &sc.count[sd], uint32_t( __popc( bal ) ) ); }
+        base = __shfl_sync( 0xffffffffu, base, __ffs( bal ) - 1 );
+        const uint32_t k = base + __popc( bal & ( ( 1u << lane ) - 1u ) );
+        if( c && k < sc.cap ) { sc.list[sd][k] = i; }
+      }
+    }
   }
   sg_bp_bounds_commit<2>( mn, mx, ext, acc );
   if( interval_enc != nullptr )
@@ -438,6 +473,9 @@ struct Ball2DData
   uint32_t slab_step = 0; // tag of the current step's flags (all ranks step in lockstep)
   bool slab_prep_done = false; // this step's bounds / static counts were already produced by sg_ball2d_slab_flow
   DevBuf pack_done;            // block counter of the pack kernel's "last block raises the flag"
+  DevBuf cand_state;           // SlabCandState: bands, candidate counters, pack cursors and tickets (peer-memory exchange)
+  DevBuf cand_list;            // u32[2][cand_cap]: slots of the bodies that could be owed to the lower / higher neighbour this step
+  uint32_t cand_cap = 0;
   DevBuf block_iv;             // double2 per 256-slot block: [min lo.x, max hi.x] of its owned swept boxes (from the flow kernel)
   size_t first_slot() const { return 0; }
   size_t owned_slot() const { return slab ? size_t( ghost_cap ) : 0; }        // first owned slot
@@ -472,7 +510,7 @@ void sg_ball2d_release( sg_ctx* ctx )
   d->st_counts.release(); d->st_offsets.release(); d->st_partials.release(); d->st_total.release();
   d->c_type.release(); d->c_i.release(); d->c_j.release(); d->c_n.release(); d->c_p.release(); d->c_depth.release();
   d->h_totals.release(); d->h_out.release();
-  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release(); d->pack_done.release(); d->block_iv.release();
+  d->gid.release(); d->ghost_counts.release(); d->interval_enc.release(); d->pack_counts.release(); d->pack_offsets.release(); d->pack_partials.release(); d->pack_total.release(); d->pack_done.release(); d->block_iv.release(); d->cand_state.release(); d->cand_list.release();
   for( int sde = 0; sde < 2; ++sde ) { if( d->peer_mb[sde] != nullptr && d->peer_ipc[sde] ) { cudaIpcCloseMemHandle( d->peer_mb[sde] ); } d->peer_mb[sde] = nullptr; }
   d->mailbox.release();
   ball2d_portal_release( d );
@@ -550,12 +588,12 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
   else if( flow_kind >= 0 && !d->slab )
   {
     SG_LAUNCH( ctx, "ball2d_flow_prep", double( n ) * ( 72.0 + 8.0 ), k_ball2d_prep<true><<<nblk, 256, 0, ctx->stream>>>( d->sg, flow_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(),
-               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr, nullptr, nullptr, 0.0, 0.0, nullptr ) );
+               d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(), d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), 0u, n, nullptr, nullptr, nullptr, 0.0, 0.0, nullptr, SlabCand{ nullptr, nullptr, { nullptr, nullptr }, 0u, { false, false } } ) );
   }
   else
   {
     SG_LAUNCH( ctx, "ball2d_prep", double( n ) * 40.0, k_ball2d_prep<false><<<nblk, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr,
-               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS(), nullptr, nullptr, 0.0, 0.0, nullptr ) );
+               d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), d->GHOSTS(), nullptr, nullptr, 0.0, 0.0, nullptr, SlabCand{ nullptr, nullptr, { nullptr, nullptr }, 0u, { false, false } } ) );
   }
   Ball2DIn in;
   in.q0 = d->Q0(); in.q1 = d->Q1(); in.r = d->R(); in.n = n; in.own_first = d->own_first(); in.own_count = d->own_count(); in.ghost_counts = d->GHOSTS(); in.gid = d->GID();
@@ -886,6 +924,130 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, c
     }
     __syncthreads();
   }
+}
+
+// ---- single-pass halo pack over the candidate lists (peer-memory exchange) ----------------------------------------------
+struct SlabCandState
+{
+  double band[2];        // see SlabCand
+  uint32_t count[2];     // candidates listed by this step's flow kernel
+  uint32_t cursor[2];    // records written into the neighbour's mailbox so far
+  uint32_t ticket;       // blocks done (the last one publishes)
+  uint32_t fallbacks;    // steps in which a band did not hold and all bodies were scanned (diagnostics)
+};
+
+static SlabCand ball2d_slab_cand( const Ball2DData* d )
+{
+  SlabCand sc;
+  sc.band = nullptr; sc.count = nullptr; sc.list[0] = sc.list[1] = nullptr; sc.cap = 0u; sc.on[0] = sc.on[1] = false;
+  if( d->mailbox.ptr == nullptr || d->cand_state.ptr == nullptr ) { return sc; }
+  SlabCandState* st = d->cand_state.as<SlabCandState>();
+  sc.band = st->band; sc.count = st->count;
+  sc.list[0] = d->cand_list.as<uint32_t>(); sc.list[1] = d->cand_list.as<uint32_t>() + d->cand_cap;
+  sc.cap = d->cand_cap;
+  sc.on[0] = d->peer_mb[0] != nullptr; sc.on[1] = d->peer_mb[1] != nullptr;
+  return sc;
+}
+
+__global__ void k_ball2d_slab_cand_reset( SlabCandState* st )
+{
+  // bands that make every body a candidate: the first step after (re)initialisation overflows the lists and scans all bodies
+  st->band[0] = __longlong_as_double( 0x7ff0000000000000LL ); st->band[1] = __longlong_as_double( 0xfff0000000000000LL );
+  st->count[0] = st->count[1] = 0u; st->cursor[0] = st->cursor[1] = 0u; st->ticket = 0u; st->fallbacks = 0u;
+}
+
+struct Pack2Args
+{
+  const double* iv[2];      // the neighbour's interval of this step (local mailbox)
+  const uint32_t* wait[2];  // its step-tagged flag
+  GhostRec* out[2];         // the neighbour's mailbox (peer memory): header + records
+  uint32_t* post[2];        // the neighbour's halo flag
+  bool on[2];
+  uint32_t* err;
+  uint32_t step;
+};
+
+// Small persistent grid.  Every block: wait for the neighbours' intervals; per side, if the interval lies inside the band the
+// candidates were collected with (and the list did not overflow) test the candidates, else all owned bodies; selected bodies go
+// straight into the neighbour's mailbox at a slot taken from an atomic cursor.  The last block to finish writes the headers
+// (counts), raises the neighbours' flags and sets the bands for the next step: this step's interval edge widened by `margin`.
+__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack2( const uint32_t n, const uint32_t own_first, const uint32_t own_count, const double2* __restrict__ q0, const double2* __restrict__ q1,
+                                                             const double* __restrict__ r, const uint32_t* __restrict__ gid, const uint32_t cap, const SlabCand sc, SlabCandState* st,
+                                                             const GridParams* __restrict__ last_grid, const Pack2Args args )
+{
+  if( threadIdx.x < 2 && args.on[threadIdx.x] ) { slab_wait_flag( args.wait[threadIdx.x], args.step, args.err ); }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  #pragma unroll
+  for( int sd = 0; sd < 2; ++sd )
+  {
+    if( !args.on[sd] ) { continue; }
+    const double ilo = args.iv[sd][0], ihi = args.iv[sd][1];
+    const uint32_t listed = st->count[sd];
+    // the band holds if every body the neighbour could need was listed: its interval does not reach past the band edge
+    const bool band_ok = listed <= sc.cap && ( ( sd == 0 ) ? ( ihi <= st->band[0] ) : ( ilo >= st->band[1] ) );
+    const uint32_t total = band_ok ? listed : own_count;
+    for( uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x ) // whole warps stay together for the ballot
+    {
+      const uint32_t e = base + threadIdx.x;
+      bool sel = false;
+      uint32_t i = 0u;
+      double2 a = make_double2( 0.0, 0.0 ), b = a;
+      double rad = 0.0;
+      if( e < total )
+      {
+        i = band_ok ? sc.list[sd][e] : own_first + e;
+        a = __ldg( &q0[i] ); b = __ldg( &q1[i] ); rad = __ldg( &r[i] );
+        double lo, hi;
+        swept_x( a, b, rad, lo, hi );
+        sel = !( hi < ilo ) && !( ihi < lo );
+      }
+      const unsigned bal = __ballot_sync( 0xffffffffu, sel );
+      if( bal != 0u )
+      {
+        uint32_t k0 = 0u;
+        if( lane == __ffs( bal ) - 1 ) { k0 = atomicAdd( &st->cursor[sd], uint32_t( __popc( bal ) ) ); }
+        k0 = __shfl_sync( 0xffffffffu, k0, __ffs( bal ) - 1 );
+        const uint32_t k = k0 + __popc( bal & ( ( 1u << lane ) - 1u ) );
+        if( sel && k < cap )
+        {
+          GhostRec g;
+          g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
+          args.out[sd][1u + k] = g;
+        }
+      }
+    }
+  }
+  // ---- the last block publishes
+  __shared__ uint32_t s_last;
+  __syncthreads();
+  if( threadIdx.x == 0 )
+  {
+    __threadfence_system(); // this block's peer writes before its ticket
+    s_last = ( atomicAdd( &st->ticket, 1u ) == gridDim.x - 1u ) ? 1u : 0u;
+  }
+  __syncthreads();
+  if( s_last == 0u || threadIdx.x != 0 ) { return; }
+  __threadfence();
+  const double margin = ( last_grid != nullptr && last_grid->h > 0.0 && last_grid->h < 1.0e300 ) ? last_grid->h : 0.0; // the last step's cell width (>= every swept extent); anything >= 0 is safe
+  for( int sd = 0; sd < 2; ++sd )
+  {
+    if( !args.on[sd] ) { continue; }
+    const uint32_t listed = st->count[sd];
+    const double ilo = args.iv[sd][0], ihi = args.iv[sd][1];
+    const bool band_ok = listed <= sc.cap && ( ( sd == 0 ) ? ( ihi <= st->band[0] ) : ( ilo >= st->band[1] ) );
+    if( !band_ok ) { st->fallbacks += 1u; }
+    GhostRec h;
+    h.q0x = 0.0; h.q0y = 0.0; h.q1x = 0.0; h.q1y = 0.0; h.r = 0.0; h.gid = *reinterpret_cast<volatile uint32_t*>( &st->cursor[sd] ); h.pad = 0u;
+    args.out[sd][0] = h;
+    // next step's band: the neighbour's edge of this step, widened (an empty neighbour posts [+inf, -inf]: nobody is a candidate)
+    if( sd == 0 ) { st->band[0] = ( ilo <= ihi ) ? ihi + margin : __longlong_as_double( 0xfff0000000000000LL ); }
+    else { st->band[1] = ( ilo <= ihi ) ? ilo - margin : __longlong_as_double( 0x7ff0000000000000LL ); }
+    st->cursor[sd] = 0u; st->count[sd] = 0u;
+  }
+  st->ticket = 0u;
+  __threadfence_system();
+  for( int sd = 0; sd < 2; ++sd ) { if( args.on[sd] ) { st_release_sys( args.post[sd], args.step ); } }
 }
 
 // Count only (sg_ball2d_slab_pack with no send buffer): total of the per-block counts
@@ -1341,19 +1503,21 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
   const uint32_t n = d->n;
   SG_CUDA( ctx, d->block_iv.ensure( size_t( sg_div_up( n > 0 ? n : 1, 256 ) ) * 16 + 16 ) );
   const unsigned nblk_prep = sg_div_up( n > 0 ? n : 1, 256 );
+  const SlabCand sc = ball2d_slab_cand( d );
+  if( sc.band != nullptr ) { SG_CUDA( ctx, cudaMemsetAsync( sc.count, 0, 8, ctx->stream ) ); } // a flow that was never followed by an exchange must not leave candidates behind
   if( map_kind == SG_MAP_NONE )
   {
     // q1 of the owned bodies was uploaded (sg_ball2d_slab_upload_q1): everything but the integration
     SG_LAUNCH( ctx, "slab_prep", double( d->n_owned ) * 40.0,
                k_ball2d_prep<false><<<nblk_prep, 256, 0, ctx->stream>>>( d->sg, 0, n, d->Q0(), nullptr, nullptr, d->R(), 0.0, 0.0, 0.0, d->Q1(), nullptr, d->bp.bounds_cur(), d->st_counts.as<uint32_t>(),
-                                                                       d->own_first(), d->own_count(), nullptr, d->interval_enc.as<long long>(), d->block_iv.as<double2>(), d->xlim[0], d->xlim[1], d->ghost_counts.as<uint32_t>() ) );
+                                                                       d->own_first(), d->own_count(), nullptr, d->interval_enc.as<long long>(), d->block_iv.as<double2>(), d->xlim[0], d->xlim[1], d->ghost_counts.as<uint32_t>(), sc ) );
   }
   else
   {
     SG_LAUNCH( ctx, "slab_flow_prep", double( d->n_owned ) * 80.0,
                k_ball2d_prep<true><<<nblk_prep, 256, 0, ctx->stream>>>( d->sg, map_kind, n, d->Q0(), d->v0.as<double2>(), d->m.as<double>(), d->R(), d->g[0], d->g[1], dt, d->Q1(), d->v1.as<double2>(),
                                                                       d->bp.bounds_cur(), d->st_counts.as<uint32_t>(), d->own_first(), d->own_count(), nullptr, d->interval_enc.as<long long>(),
-                                                                      d->block_iv.as<double2>(), d->xlim[0], d->xlim[1], d->ghost_counts.as<uint32_t>() ) );
+                                                                      d->block_iv.as<double2>(), d->xlim[0], d->xlim[1], d->ghost_counts.as<uint32_t>(), sc ) );
   }
   if( d->mailbox.ptr == nullptr )
   {
@@ -1470,6 +1634,10 @@ int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64
     SG_CUDA( ctx, d->pack_total.ensure( 16 ) );
     SG_CUDA( ctx, d->pack_done.ensure( 16 ) );
     SG_CUDA( ctx, cudaMemsetAsync( d->pack_done.ptr, 0, 16, ctx->stream ) );
+    d->cand_cap = 4u * d->ghost_cap + 1024u;
+    SG_CUDA( ctx, d->cand_state.ensure( sizeof( SlabCandState ) ) );
+    SG_CUDA( ctx, d->cand_list.ensure( 2 * size_t( d->cand_cap ) * 4 ) );
+    k_ball2d_slab_cand_reset<<<1, 1, 0, ctx->stream>>>( d->cand_state.as<SlabCandState>() );
     SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
     d->slab_step = 0;
   }
@@ -1545,24 +1713,29 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
   const uint32_t step = d->slab_step;
   if( phase == 0 || phase == 1 )
   {
-    // both neighbours in one pass over the owned bodies
-    const double* ivs[2]; void* sends[2]; uint32_t* counts[2]; SlabSync syncs[2];
-    int nt = 0;
+    // both neighbours in one launch: the candidates the flow kernel listed (or, when a band did not hold, all owned bodies) against
+    // the neighbours' intervals, selected records straight into their mailboxes, flags raised by the last block
+    Pack2Args pa;
+    bool any = false;
     for( int side = 0; side < 2; ++side )
     {
-      if( d->peer_mb[side] == nullptr ) { continue; }
+      pa.on[side] = d->peer_mb[side] != nullptr;
+      pa.iv[side] = &mine->iv[side][0]; pa.wait[side] = &mine->iv_flag[side]; pa.out[side] = nullptr; pa.post[side] = nullptr;
+      if( !pa.on[side] ) { continue; }
       SlabMailboxHdr* peer = static_cast<SlabMailboxHdr*>( d->peer_mb[side] );
       // seen from the neighbour on `side`, this rank sits on its side 1 - side
-      ivs[nt] = &mine->iv[side][0];
-      sends[nt] = slab_mailbox_halo( peer, 1 - side, d->ghost_cap );
-      counts[nt] = d->pack_total.as<uint32_t>() + side;
-      syncs[nt].wait_flag = &mine->iv_flag[side]; syncs[nt].post_flag = &peer->halo_flag[1 - side]; syncs[nt].done_ctr = d->pack_done.as<uint32_t>() + side; syncs[nt].err = &mine->err; syncs[nt].step = step;
-      ++nt;
+      pa.out[side] = slab_mailbox_halo( peer, 1 - side, d->ghost_cap );
+      pa.post[side] = &peer->halo_flag[1 - side];
+      any = true;
     }
-    if( nt > 0 )
+    pa.err = &mine->err; pa.step = step;
+    if( any )
     {
-      const int rc = ball2d_slab_pack_impl( ctx, d, nt, ivs, sends, d->ghost_cap, counts, syncs );
-      if( rc != SG_OK ) { return rc; }
+      if( !d->slab_prep_done ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_exchange: call sg_ball2d_slab_flow first" ); }
+      const SlabCand sc = ball2d_slab_cand( d );
+      const unsigned grid = unsigned( ctx->num_sms ); // one block per SM: the candidate lists are a few thousand entries
+      SG_LAUNCH( ctx, "slab_pack", double( d->ghost_cap ) * 2.0 * 48.0, k_ball2d_slab_pack2<<<grid, 256, 0, ctx->stream>>>( d->n, d->own_first(), d->own_count(), d->q0.as<double2>(), d->q1.as<double2>(), d->r.as<double>(),
+                 d->gid.as<uint32_t>(), d->ghost_cap, sc, d->cand_state.as<SlabCandState>(), d->bp.params.as<GridParams>(), pa ) );
     }
   }
   if( phase == 0 || phase == 2 )
@@ -1614,6 +1787,27 @@ int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
     out->n_candidates = d->n_cand;
     out->n_body_body = d->n_bb;
     out->n_active = d->n_bb + d->n_static;
+  }
+  return SG_OK;
+}
+
+int sg_ball2d_slab_stats( sg_ctx* ctx, uint32_t* out4 )
+{
+  if( ctx == nullptr || out4 == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  out4[0] = out4[1] = out4[2] = out4[3] = 0u;
+  if( !d->slab ) { return SG_OK; }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  uint32_t g[4];
+  SG_CUDA( ctx, cudaMemcpy( g, d->ghost_counts.ptr, 16, cudaMemcpyDeviceToHost ) );
+  out4[0] = g[0]; out4[1] = g[1];
+  if( d->cand_state.ptr != nullptr && d->mailbox.ptr != nullptr )
+  {
+    SlabCandState st;
+    SG_CUDA( ctx, cudaMemcpy( &st, d->cand_state.ptr, sizeof( st ), cudaMemcpyDeviceToHost ) );
+    out4[2] = st.fallbacks;
+    out4[3] = d->cand_cap;
   }
   return SG_OK;
 }

@@ -402,6 +402,15 @@ class MultiGpuBall2DSim:
         self.check(self.lib.sg_multi_partition_info(self.h, _ptr(cuts), _ptr(owned), _ptr(ghosts), C.byref(npart)))
         return {"cuts": cuts, "n_owned": owned, "ghosts": ghosts.reshape(-1, 2), "n_partitions": int(npart.value)}
 
+    def slab_stats(self):
+        """per slab: (ghosts on side 0, ghosts on side 1, halo packs that had to scan all bodies, candidate-list capacity)"""
+        out = []
+        for k in range(self.world):
+            a = np.zeros(4, dtype=np.uint32)
+            self.lib.sg_ball2d_slab_stats(self.lib.sg_multi_context(self.h, k), _ptr(a))
+            out.append(tuple(int(x) for x in a))
+        return out
+
     def slab_launch_counts(self):
         return [int(self.lib.sg_launch_count(self.lib.sg_multi_context(self.h, k))) for k in range(self.world)]
 
