@@ -41,6 +41,7 @@ extern "C" {
 #define SG_MAP_VERLET 1           /* ball2d/VerletMap.cpp:15-41, rigidbody2d/VerletMap.cpp:27-55 */
 #define SG_MAP_SPLIT_HAM 2        /* rigidbody3d/UnconstrainedMaps/SplitHamMap.cpp:17-182 */
 #define SG_MAP_DMV 3              /* rigidbody3d/UnconstrainedMaps/DMVMap.cpp:103-207 */
+#define SG_MAP_EXPONENTIAL_EULER 4 /* rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.cpp:13-91 (orientation = orthogonal polar factor, 1e-12 of the reference's JacobiSVD route) */
 /* OR into the map kind of sg_rb3d_flow / sg_rb3d_step for every flow after a simulation's first.  Both maps start with
  * v1 = fsys.M() * v0 (SplitHamMap.cpp:44, DMVMap.cpp:130).  RigidBody3DState's constructor stores the world-space inertia block
  * transposed, M(r,c) = I(c,r) (formWorldSpaceMassMatrix, RigidBody3DState.cpp:165-182); RigidBody3DSim::flow then calls
@@ -232,6 +233,13 @@ int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
 /* q1, v1 (either may be NULL) as the last flow / step / sg_ball2d_slab_flow on this context left them on the device (slab mode: the owned block) */
 int sg_ball2d_fetch_state( sg_ctx* ctx, double* q1, double* v1 );
+
+/* State I/O at the seam: Ball2DState's binary snapshot (ball2d/Ball2DState.cpp:259-312, scisim/Utilities.h:43-94,
+   scisim/Math/MathUtilities.h:42-60, MathUtilities.cpp:142-177), byte for byte, written from / read into the device-resident state.
+   serialize   which = 0: ( q0, v0 ) as uploaded, 1: ( q1, v1 ) of the last flow / step.  buf = NULL: *bytes <- size needed
+   deserialize configures bodies, gravity, planes, drums and portals from a snapshot and uploads ( q, v ) */
+int sg_ball2d_state_serialize( sg_ctx* ctx, int which, void* buf, uint64_t cap, uint64_t* bytes );
+int sg_ball2d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes );
 
 /* Peer-memory halo exchange (one process per GPU, neighbours' mailboxes mapped over NVLink with CUDA IPC; no
    collective, no host round trip).  No reference counterpart (SCISim is single-process); see DESIGN.md section 5.

@@ -255,8 +255,10 @@ inline void solveDMV( const V3& am, const double h, const V3& I0, Quat& q )
 // flow of a simulation reads; RigidBody3DSim::flow then calls updateMandMinv ( RigidBody3DSim.cpp:442,517,592 ), which assigns
 // I = R I0 R^T through a column-major map over the same values ( RigidBody3DState.cpp:444-446 ), so every later flow reads
 // M(r,c) = I(r,c).  I is symmetric only up to rounding: ( R(r,k) d_k ) R(c,k) vs ( R(c,k) d_k ) R(r,k).
+inline void flowExponentialEuler( const RB3DScene& s, const double* q0, const double* v0, const double dt, double* q1, double* v1 );
 inline void flow( const int kind, const RB3DScene& s, const double* q0, const double* v0, const double dt, double* q1, double* v1, const bool m_updated = false )
 {
+  if( kind == 4 ) { flowExponentialEuler( s, q0, v0, dt, q1, v1 ); return; }
   const std::size_t nb = s.nbodies();
   for( std::size_t k = 0; k < 12 * nb; ++k ) { q1[k] = q0[k]; }
   for( std::size_t b = 0; b < nb; ++b )
@@ -327,6 +329,84 @@ inline void flow( const int kind, const RB3DScene& s, const double* q0, const do
     const V3 Iinv{ 1.0 / I.x, 1.0 / I.y, 1.0 / I.z };
     const V3 w1 = mul( worldInertia( R1, Iinv ), L );
     v1[3 * nb + 3 * b] = w1.x; v1[3 * nb + 3 * b + 1] = w1.y; v1[3 * nb + 3 * b + 2] = w1.z;
+  }
+}
+
+// ---- ExponentialEulerMap (rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.cpp:13-91) ---------------------------------
+// projectOrientation (:13-32): R <- U V^T of R's singular value decomposition, i.e. the orthogonal factor of its polar
+// decomposition.  The reference gets U, V from Eigen::JacobiSVD; that factor is unique for a non-singular R, so any accurate
+// SVD gives it to rounding.  PARITY UNPINNED BIT FOR BIT (Eigen's sweep order is not restated): the GPU is held to 1e-12.
+// Here: cyclic one-sided Jacobi (Hestenes) on the columns, a different algorithm from the kernel's Newton iteration on purpose.
+inline M3 polarOrthogonalFactor( const M3& A )
+{
+  // columns of W are rotated until mutually orthogonal: A V = W, W = U S  =>  U V^T = W S^-1 V^T
+  double W[3][3], V[3][3];
+  for( int r = 0; r < 3; ++r ) { for( int c = 0; c < 3; ++c ) { W[r][c] = A.m[3 * r + c]; V[r][c] = ( r == c ) ? 1.0 : 0.0; } }
+  for( int sweep = 0; sweep < 60; ++sweep )
+  {
+    double off = 0.0;
+    for( int p = 0; p < 2; ++p )
+    {
+      for( int q = p + 1; q < 3; ++q )
+      {
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for( int r = 0; r < 3; ++r ) { alpha += W[r][p] * W[r][p]; beta += W[r][q] * W[r][q]; gamma += W[r][p] * W[r][q]; }
+        if( gamma == 0.0 ) { continue; }
+        off = std::max( off, std::fabs( gamma ) / std::sqrt( alpha * beta ) );
+        const double zeta = ( beta - alpha ) / ( 2.0 * gamma );
+        const double t = ( ( zeta >= 0.0 ) ? 1.0 : -1.0 ) / ( std::fabs( zeta ) + std::sqrt( 1.0 + zeta * zeta ) );
+        const double c = 1.0 / std::sqrt( 1.0 + t * t ), sn = c * t;
+        for( int r = 0; r < 3; ++r )
+        {
+          const double wp = W[r][p], wq = W[r][q];
+          W[r][p] = c * wp - sn * wq; W[r][q] = sn * wp + c * wq;
+          const double vp = V[r][p], vq = V[r][q];
+          V[r][p] = c * vp - sn * vq; V[r][q] = sn * vp + c * vq;
+        }
+      }
+    }
+    if( off < 1.0e-17 ) { break; }
+  }
+  M3 out;
+  for( int r = 0; r < 3; ++r ) { for( int c = 0; c < 3; ++c ) { out.m[3 * r + c] = 0.0; } }
+  for( int k = 0; k < 3; ++k )
+  {
+    double sk = 0.0;
+    for( int r = 0; r < 3; ++r ) { sk += W[r][k] * W[r][k]; }
+    sk = std::sqrt( sk );
+    for( int r = 0; r < 3; ++r ) { for( int c = 0; c < 3; ++c ) { out.m[3 * r + c] += ( W[r][k] / sk ) * V[c][k]; } }
+  }
+  return out;
+}
+
+// flow (:34-91).  x1 = x0 + dt v0; every column of R advanced by dt omega x column, then projected; A = Minv * F with F the
+// gravity force (angular part zero: the 3x3 inverse-inertia block times zeros accumulates to +0.0); v1 = v0 + dt A.
+// Kinematically scripted bodies are integrated like the rest (the reference only asserts there are none).
+inline void flowExponentialEuler( const RB3DScene& s, const double* q0, const double* v0, const double dt, double* q1, double* v1 )
+{
+  const std::size_t nb = s.nbodies();
+  for( std::size_t b = 0; b < nb; ++b )
+  {
+    const double m = s.m[b];
+    const M3 R0 = loadR( q0, nb, b );
+    const V3 w{ v0[3 * nb + 3 * b], v0[3 * nb + 3 * b + 1], v0[3 * nb + 3 * b + 2] };
+    for( int k = 0; k < 3; ++k ) { q1[3 * b + k] = q0[3 * b + k] + dt * v0[3 * b + k]; }
+    M3 R1;
+    for( int j = 0; j < 3; ++j )
+    {
+      const V3 c{ R0.m[j], R0.m[3 + j], R0.m[6 + j] };
+      // omega.cross( c )  (Eigen cross3: a1 b2 - a2 b1, a2 b0 - a0 b2, a0 b1 - a1 b0)
+      const V3 x{ w.y * c.z - w.z * c.y, w.z * c.x - w.x * c.z, w.x * c.y - w.y * c.x };
+      R1.m[j] = c.x + dt * x.x; R1.m[3 + j] = c.y + dt * x.y; R1.m[6 + j] = c.z + dt * x.z;
+    }
+    const M3 P = polarOrthogonalFactor( R1 );
+    for( int k = 0; k < 9; ++k ) { q1[3 * nb + 9 * b + k] = P.m[k]; }
+    const double minv = 1.0 / m;
+    const V3 F{ 0.0 + m * s.g.x, 0.0 + m * s.g.y, 0.0 + m * s.g.z };
+    const V3 A{ 0.0 + minv * F.x, 0.0 + minv * F.y, 0.0 + minv * F.z };
+    v1[3 * b] = v0[3 * b] + dt * A.x; v1[3 * b + 1] = v0[3 * b + 1] + dt * A.y; v1[3 * b + 2] = v0[3 * b + 2] + dt * A.z;
+    const double Aang = ( ( 0.0 + 0.0 ) + 0.0 ) + 0.0;
+    for( int k = 0; k < 3; ++k ) { v1[3 * nb + 3 * b + k] = v0[3 * nb + 3 * b + k] + dt * Aang; }
   }
 }
 

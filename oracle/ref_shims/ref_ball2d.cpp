@@ -13,6 +13,11 @@
 #include "ball2d/VerletMap.h"
 #include "ball2d/Forces/Ball2DGravityForce.h"
 #include "scisim/UnconstrainedMaps/FlowableSystem.h"
+#include "ball2d/StaticGeometry/StaticDrum.h"
+#include "scisim/Utilities.h"
+
+#include <memory>
+#include <sstream>
 
 #include <cstdint>
 
@@ -72,6 +77,37 @@ void ref_ball2d_detect( const uint32_t n, const double* q0, const double* q1, co
   }
   *n_candidates = overlaps.size();
   *n_active = na;
+}
+
+// ---- the part of Ball2DState::serialize (ball2d/Ball2DState.cpp:259-272) that the compiled reference classes write themselves:
+// m_fixed, m_static_drums, m_static_planes, m_planar_portals, m_forces -- through Utilities::serialize (scisim/Utilities.h:43-94,
+// Utilities.cpp:9-18) and the classes' own serialize methods.  Returns the number of bytes (written up to cap).
+uint64_t ref_ball2d_snapshot_tail( const uint32_t nballs, const uint32_t ndrums, const double* dx, const double* dr, const uint32_t nplanes, const double* px, const double* pn,
+                                   const uint32_t nportals, const double* pax, const double* pan, const double* pbx, const double* pbn, const double* pv, const double* pb, const double t,
+                                   const double* g, unsigned char* out, const uint64_t cap )
+{
+  std::vector<bool> fixed( nballs, false );
+  std::vector<StaticDrum> drums;
+  for( uint32_t k = 0; k < ndrums; ++k ) { drums.emplace_back( Vector2s{ dx[2 * k], dx[2 * k + 1] }, dr[k] ); }
+  std::vector<StaticPlane> planes;
+  for( uint32_t k = 0; k < nplanes; ++k ) { planes.emplace_back( Vector2s{ px[2 * k], px[2 * k + 1] }, Vector2s{ pn[2 * k], pn[2 * k + 1] } ); }
+  std::vector<PlanarPortal> portals;
+  for( uint32_t k = 0; k < nportals; ++k )
+  {
+    portals.emplace_back( StaticPlane{ Vector2s{ pax[2 * k], pax[2 * k + 1] }, Vector2s{ pan[2 * k], pan[2 * k + 1] } }, StaticPlane{ Vector2s{ pbx[2 * k], pbx[2 * k + 1] }, Vector2s{ pbn[2 * k], pbn[2 * k + 1] } }, pv[k], pb[k] );
+    if( pv[k] != 0.0 ) { portals.back().updateMovingPortals( t ); }
+  }
+  std::vector<std::unique_ptr<Ball2DForce>> forces;
+  forces.emplace_back( new Ball2DGravityForce{ Vector2s{ g[0], g[1] } } );
+  std::ostringstream stm;
+  Utilities::serialize( fixed, stm );
+  Utilities::serialize( drums, stm );
+  Utilities::serialize( planes, stm );
+  Utilities::serialize( portals, stm );
+  Utilities::serialize( forces, stm );
+  const std::string bytes = stm.str();
+  for( uint64_t k = 0; k < bytes.size() && k < cap; ++k ) { out[k] = static_cast<unsigned char>( bytes[k] ); }
+  return bytes.size();
 }
 
 // ---- PlanarPortal (ball2d/Portals/PlanarPortal.cpp) -----------------------------------------------------------------

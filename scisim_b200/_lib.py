@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libscisim_b200.so")
 SG_OK = 0
 SG_ERR_INVALID, SG_ERR_CUDA, SG_ERR_UNSUPPORTED, SG_ERR_INTERNAL, SG_ERR_REBALANCE = 1, 2, 3, 4, 5
 SG_MAP_NONE = -1
-SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV = 0, 1, 2, 3
+SG_MAP_SYMPLECTIC_EULER, SG_MAP_VERLET, SG_MAP_SPLIT_HAM, SG_MAP_DMV, SG_MAP_EXPONENTIAL_EULER = 0, 1, 2, 3, 4
 SG_MAP_M_UPDATED = 0x100  # rigidbody3d flows after the first: M as updateMandMinv leaves it (include/scisim_b200.h)
 SG_BALL_BALL, SG_BALL_DRUM, SG_BALL_PLANE = 0, 1, 2
 SG_BALL_BALL_TELEPORTED, SG_BALL_BALL_KICK_TELEPORTED = 3, 4
@@ -92,6 +92,8 @@ def load():
         "sg_ball2d_slab_set_gids": (C.c_int, [vp, vp, vp]),
         "sg_ball2d_slab_upload_q1": (C.c_int, [vp, vp]),
         "sg_ball2d_slab_stats": (C.c_int, [vp, vp]),
+        "sg_ball2d_state_serialize": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+        "sg_ball2d_state_deserialize": (C.c_int, [vp, vp, C.c_uint64]),
         "sg_ball2d_fetch_state": (C.c_int, [vp, vp, vp]),
         "sg_slab_partition": (C.c_int, [C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp]),
         "sg_slab_limits": (C.c_int, [C.c_uint32, vp, C.c_uint32, vp]),

@@ -1138,6 +1138,23 @@ __global__ void __launch_bounds__( 256 ) k_iota_u32( const uint32_t n, const uin
   if( k < n ) { out[k] = first + k; }
 }
 
+namespace
+{
+struct ByteSink
+{
+  unsigned char* p; uint64_t cap; uint64_t n;
+  void put( const void* src, const uint64_t bytes ) { if( p != nullptr && n + bytes <= cap ) { memcpy( p + n, src, bytes ); } n += bytes; }
+  template<typename T> void val( const T v ) { put( &v, sizeof( T ) ); }
+  unsigned char* reserve( const uint64_t bytes ) { unsigned char* at = ( p != nullptr && n + bytes <= cap ) ? p + n : nullptr; n += bytes; return at; }
+};
+struct ByteSource
+{
+  const unsigned char* p; uint64_t cap; uint64_t n; bool ok;
+  const unsigned char* take( const uint64_t bytes ) { if( !ok || n + bytes > cap ) { ok = false; return nullptr; } const unsigned char* at = p + n; n += bytes; return at; }
+  template<typename T> T val() { T v{}; const unsigned char* at = take( sizeof( T ) ); if( at != nullptr ) { memcpy( &v, at, sizeof( T ) ); } return v; }
+};
+}
+
 extern "C"
 {
 
@@ -1837,6 +1854,156 @@ int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg
   if( out != nullptr ) { return ball2d_copy_out( ctx, d, out_flags, out ); }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   return SG_OK;
+}
+
+
+// ---- state I/O at the seam: Ball2DState's binary snapshot --------------------------------------------
+// The byte stream Ball2DState::serialize writes (ball2d/Ball2DState.cpp:259-272) with the helpers of scisim/Utilities.h:43-94 and
+// scisim/Math/MathUtilities.h:42-60, MathUtilities.cpp:142-154 -- raw little-endian values, no padding:
+//   q, v, r            Eigen::Index rows (int64) + doubles
+//   fixed              size_t count + one byte per ball
+//   M, Minv            Index rows, cols, nnz; int inner[nnz]; int outer[cols + 1]; double values[nnz]   (diagonal: m resp. 1 / m per DoF)
+//   drums              size_t count + { x (2 doubles), r }
+//   planes             size_t count + { x, v, n, t } (2 doubles each; v = 0, n unit, t = ( -n.y, n.x ))
+//   portals            size_t count + { plane A, plane B, v, bounds, dx }
+//   forces             size_t count + { size_t length + "ball2d_gravity_force", g (2 doubles) }
+// so that a device-resident state can be checkpointed in the reference's own format, and a reference snapshot resumed on the GPU.
+// which = 0: ( q0, v0 ) as uploaded; 1: ( q1, v1 ) as the last flow / step left them.  buf = NULL: size query.
+int sg_ball2d_state_serialize( sg_ctx* ctx, int which, void* buf, uint64_t cap, uint64_t* bytes )
+{
+  if( ctx == nullptr || bytes == nullptr || ( which != 0 && which != 1 ) ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( d->slab ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_state_serialize: a slab holds part of a scene; serialise through the owner of the whole state" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  const uint64_t n = d->n;
+  ByteSink out{ static_cast<unsigned char*>( buf ), cap, 0 };
+  const long long dofs = ( long long )( 2 * n );
+  std::vector<double> mass( n );
+  if( n > 0 && buf != nullptr ) { SG_CUDA( ctx, cudaMemcpyAsync( mass.data(), d->m.ptr, n * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  // q, v straight from the device into the stream
+  for( int k = 0; k < 2; ++k )
+  {
+    out.val<long long>( dofs );
+    unsigned char* at = out.reserve( n * 16 );
+    const void* src = ( k == 0 ) ? ( which == 0 ? d->q0.ptr : d->q1.ptr ) : ( which == 0 ? d->v0.ptr : d->v1.ptr );
+    if( at != nullptr && n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( at, src, n * 16, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  }
+  out.val<long long>( ( long long )( n ) );
+  {
+    unsigned char* at = out.reserve( n * 8 );
+    if( at != nullptr && n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( at, d->r.ptr, n * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  out.val<size_t>( size_t( n ) );
+  for( uint64_t i = 0; i < n; ++i ) { out.val<unsigned char>( 0 ); } // m_fixed: stored by the reference, never read on this path
+  for( int inv = 0; inv < 2; ++inv )
+  {
+    out.val<long long>( dofs ); out.val<long long>( dofs ); out.val<long long>( dofs );
+    for( long long k = 0; k < dofs; ++k ) { out.val<int>( int( k ) ); }
+    for( long long k = 0; k <= dofs; ++k ) { out.val<int>( int( k ) ); }
+    for( uint64_t i = 0; i < n; ++i ) { const double v = inv ? 1.0 / mass[i] : mass[i]; out.val<double>( v ); out.val<double>( v ); } // createMinv: 1.0 / m (Ball2DState.cpp:54-66)
+  }
+  out.val<size_t>( size_t( d->sg.ndrums ) );
+  for( uint32_t k = 0; k < d->sg.ndrums; ++k ) { out.val<double>( d->sg.drum_x[k] ); out.val<double>( d->sg.drum_y[k] ); out.val<double>( d->sg.drum_r[k] ); }
+  out.val<size_t>( size_t( d->sg.nplanes ) );
+  for( uint32_t k = 0; k < d->sg.nplanes; ++k )
+  {
+    out.val<double>( d->sg.plane_x[k] ); out.val<double>( d->sg.plane_y[k] ); out.val<double>( 0.0 ); out.val<double>( 0.0 );
+    out.val<double>( d->sg.plane_nx[k] ); out.val<double>( d->sg.plane_ny[k] ); out.val<double>( -d->sg.plane_ny[k] ); out.val<double>( d->sg.plane_nx[k] );
+  }
+  const uint32_t np = ( d->px != nullptr ) ? d->px->portals.n : 0u;
+  out.val<size_t>( size_t( np ) );
+  for( uint32_t k = 0; k < np; ++k )
+  {
+    const SgPortal2D& pt = d->px->portals.p[k];
+    out.put( pt.ax, 16 ); out.val<double>( 0.0 ); out.val<double>( 0.0 ); out.put( pt.an, 16 ); out.put( pt.at, 16 );
+    out.put( pt.bx, 16 ); out.val<double>( 0.0 ); out.val<double>( 0.0 ); out.put( pt.bn, 16 ); out.put( pt.bt, 16 );
+    out.val<double>( pt.v ); out.val<double>( pt.bounds ); out.val<double>( pt.dx );
+  }
+  out.val<size_t>( size_t( 1 ) );
+  const char name[] = "ball2d_gravity_force";
+  out.val<size_t>( sizeof( name ) - 1 ); out.put( name, sizeof( name ) - 1 );
+  out.val<double>( d->g[0] ); out.val<double>( d->g[1] );
+  *bytes = out.n;
+  if( buf != nullptr && out.n > cap ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_serialize: buffer of %llu bytes, %llu needed", ( unsigned long long )( cap ), ( unsigned long long )( out.n ) ); }
+  return SG_OK;
+}
+
+// Ball2DState::deserialize (ball2d/Ball2DState.cpp:274-312): configures the context from a snapshot and uploads ( q, v ).
+int sg_ball2d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes )
+{
+  if( ctx == nullptr || buf == nullptr ) { return SG_ERR_INVALID; }
+  ByteSource in{ static_cast<const unsigned char*>( buf ), bytes, 0, true };
+  const long long nq = in.val<long long>();
+  if( !in.ok || nq < 0 || ( nq & 1 ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: bad q header" ); }
+  const uint64_t n = uint64_t( nq ) / 2;
+  const unsigned char* q = in.take( n * 16 );
+  const long long nv = in.val<long long>();
+  const unsigned char* v = in.take( n * 16 );
+  const long long nr = in.val<long long>();
+  const unsigned char* r = in.take( n * 8 );
+  const size_t nfixed = in.val<size_t>();
+  in.take( nfixed );
+  if( !in.ok || nv != nq || uint64_t( nr ) != n || nfixed != n ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: inconsistent vector sizes" ); }
+  std::vector<double> mass( n );
+  for( int inv = 0; inv < 2; ++inv )
+  {
+    const long long rows = in.val<long long>(), cols = in.val<long long>(), nnz = in.val<long long>();
+    if( !in.ok || rows != nq || cols != nq || nnz != nq ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: the mass matrix is not the 2N diagonal" ); }
+    in.take( uint64_t( nnz ) * 4 ); in.take( uint64_t( cols + 1 ) * 4 );
+    const unsigned char* vals = in.take( uint64_t( nnz ) * 8 );
+    if( inv == 0 && vals != nullptr ) { for( uint64_t i = 0; i < n; ++i ) { memcpy( &mass[i], vals + 16 * i, 8 ); } }
+  }
+  if( !in.ok ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: truncated snapshot" ); }
+  std::vector<double> rr( n );
+  if( n > 0 ) { memcpy( rr.data(), r, n * 8 ); }
+  int rc = sg_ball2d_set_bodies( ctx, uint32_t( n ), rr.data(), mass.data() );
+  if( rc != SG_OK ) { return rc; }
+  Ball2DData* d = ball2d_data( ctx );
+  const size_t nd = in.val<size_t>();
+  if( !in.ok || nd > SG_MAX_DRUMS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: bad drum count" ); }
+  d->sg.ndrums = uint32_t( nd );
+  for( size_t k = 0; k < nd; ++k ) { d->sg.drum_x[k] = in.val<double>(); d->sg.drum_y[k] = in.val<double>(); d->sg.drum_r[k] = in.val<double>(); }
+  const size_t npl = in.val<size_t>();
+  if( !in.ok || npl > SG_MAX_PLANES ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: bad plane count" ); }
+  d->sg.nplanes = uint32_t( npl );
+  for( size_t k = 0; k < npl; ++k )
+  {
+    // StaticPlane( std::istream& ): x, v, n, t read back as stored -- the normal is NOT normalised again (StaticPlane.cpp:22-32)
+    d->sg.plane_x[k] = in.val<double>(); d->sg.plane_y[k] = in.val<double>(); in.val<double>(); in.val<double>();
+    d->sg.plane_nx[k] = in.val<double>(); d->sg.plane_ny[k] = in.val<double>(); in.val<double>(); in.val<double>();
+  }
+  const size_t npo = in.val<size_t>();
+  if( !in.ok || npo > SG_MAX_PORTALS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: bad portal count" ); }
+  if( npo > 0 || d->px != nullptr )
+  {
+    PortalData* x = ball2d_portal_data( d );
+    memset( &x->portals, 0, sizeof( x->portals ) );
+    x->portals.n = uint32_t( npo );
+    for( size_t k = 0; k < npo; ++k )
+    {
+      SgPortal2D& pt = x->portals.p[k];
+      pt.ax[0] = in.val<double>(); pt.ax[1] = in.val<double>(); in.val<double>(); in.val<double>(); pt.an[0] = in.val<double>(); pt.an[1] = in.val<double>(); pt.at[0] = in.val<double>(); pt.at[1] = in.val<double>();
+      pt.bx[0] = in.val<double>(); pt.bx[1] = in.val<double>(); in.val<double>(); in.val<double>(); pt.bn[0] = in.val<double>(); pt.bn[1] = in.val<double>(); pt.bt[0] = in.val<double>(); pt.bt[1] = in.val<double>();
+      pt.v = in.val<double>(); pt.bounds = in.val<double>(); pt.dx = in.val<double>();
+    }
+  }
+  const size_t nf = in.val<size_t>();
+  d->g[0] = 0.0; d->g[1] = 0.0;
+  for( size_t k = 0; k < nf && in.ok; ++k )
+  {
+    const size_t len = in.val<size_t>();
+    const unsigned char* nm = in.take( len );
+    if( nm == nullptr || len != 20 || memcmp( nm, "ball2d_gravity_force", 20 ) != 0 ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_state_deserialize: a force other than ball2d_gravity_force (the reference exits too: Ball2DState.cpp:302-310)" ); }
+    // forces accumulate (Ball2DState::accumulateForce): several gravity forces add up
+    d->g[0] += in.val<double>(); d->g[1] += in.val<double>();
+  }
+  if( !in.ok ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_state_deserialize: truncated snapshot" ); }
+  if( n == 0 ) { return SG_OK; }
+  // q, v may sit unaligned in the stream: through aligned copies
+  std::vector<double> qq( 2 * n ), vv( 2 * n );
+  memcpy( qq.data(), q, n * 16 ); memcpy( vv.data(), v, n * 16 );
+  return sg_ball2d_upload( ctx, qq.data(), vv.data() );
 }
 
 }

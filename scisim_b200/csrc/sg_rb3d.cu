@@ -355,6 +355,55 @@ __device__ inline M3d dmv_rotation( const M3d& R0, const V3d am, const double h,
   return r;
 }
 
+// ExponentialEulerMap::flow on one body (ExponentialEulerMap.cpp:34-91): explicit Euler on x and on the columns of R, then
+// projectOrientation (:13-32) = the orthogonal factor of R's polar decomposition (the reference: U V^T from Eigen::JacobiSVD).
+// Here by Newton's iteration X <- ( X + X^-T ) / 2, which converges quadratically to that same factor; the input is within
+// O( dt^2 ) of a rotation, so a handful of iterations reach rounding level (tests hold it to 1e-12 of the oracle's Jacobi SVD).
+__device__ inline void rb3d_flow_exponential_euler( const uint32_t b, const size_t nb, const V3d x0, const M3d& R0, const V3d vl, const V3d w, const double m, const double gx, const double gy, const double gz,
+                                                    const double dt, double* __restrict__ q1, double* __restrict__ v1 )
+{
+  double* x1o = q1 + 3 * size_t( b );
+  double* R1o = q1 + 3 * nb + 9 * size_t( b );
+  double* vlo = v1 + 3 * size_t( b );
+  double* vao = v1 + 3 * nb + 3 * size_t( b );
+  x1o[0] = x0.x + dt * vl.x; x1o[1] = x0.y + dt * vl.y; x1o[2] = x0.z + dt * vl.z;
+  double X[9];
+  #pragma unroll
+  for( int j = 0; j < 3; ++j )
+  {
+    const double cx = R0.m[j], cy = R0.m[3 + j], cz = R0.m[6 + j];
+    X[j] = cx + dt * ( w.y * cz - w.z * cy );
+    X[3 + j] = cy + dt * ( w.z * cx - w.x * cz );
+    X[6 + j] = cz + dt * ( w.x * cy - w.y * cx );
+  }
+  for( int it = 0; it < 40; ++it )
+  {
+    // inverse transpose = cofactor matrix / determinant
+    double C[9];
+    C[0] = X[4] * X[8] - X[5] * X[7]; C[1] = X[5] * X[6] - X[3] * X[8]; C[2] = X[3] * X[7] - X[4] * X[6];
+    C[3] = X[2] * X[7] - X[1] * X[8]; C[4] = X[0] * X[8] - X[2] * X[6]; C[5] = X[1] * X[6] - X[0] * X[7];
+    C[6] = X[1] * X[5] - X[2] * X[4]; C[7] = X[2] * X[3] - X[0] * X[5]; C[8] = X[0] * X[4] - X[1] * X[3];
+    const double det = X[0] * C[0] + X[1] * C[1] + X[2] * C[2];
+    double change = 0.0, size = 0.0;
+    #pragma unroll
+    for( int k = 0; k < 9; ++k )
+    {
+      const double y = 0.5 * ( X[k] + C[k] / det );
+      change += ( y - X[k] ) * ( y - X[k] );
+      size += y * y;
+      X[k] = y;
+    }
+    if( !( change > 1.0e-32 * size ) ) { break; }
+  }
+  #pragma unroll
+  for( int k = 0; k < 9; ++k ) { R1o[k] = X[k]; }
+  // A = Minv * F: linear 0 + ( 1 / m ) * ( 0 + m g ); angular: the inverse-inertia block times a zero torque
+  const double minv = 1.0 / m;
+  const double Ax = 0.0 + minv * ( 0.0 + m * gx ), Ay = 0.0 + minv * ( 0.0 + m * gy ), Az = 0.0 + minv * ( 0.0 + m * gz );
+  vlo[0] = vl.x + dt * Ax; vlo[1] = vl.y + dt * Ay; vlo[2] = vl.z + dt * Az;
+  vao[0] = w.x + dt * 0.0; vao[1] = w.y + dt * 0.0; vao[2] = w.z + dt * 0.0;
+}
+
 __global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind_flags, const uint32_t n, const double* __restrict__ q0, const double* __restrict__ v0, const double* __restrict__ mass,
                                                      const double* __restrict__ I0, const uint32_t* __restrict__ btype, const double gx, const double gy, const double gz, const double dt,
                                                      double* __restrict__ q1, double* __restrict__ v1 )
@@ -369,6 +418,11 @@ __global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind_flags, cons
   const V3d vl = load_v3( v0, b );
   const V3d w0 = load_v3( v0 + 3 * nb, b );
   const V3d I = load_v3( I0, b );
+  if( kind == SG_MAP_EXPONENTIAL_EULER )
+  {
+    rb3d_flow_exponential_euler( b, nb, x0, R0, vl, w0, m, gx, gy, gz, dt, q1, v1 );
+    return;
+  }
   // v1 = M * v0: sparse column-major accumulate into zero.  The world inertia block is stored transposed by the state's
   // constructor and as computed once updateMandMinv has run (SG_MAP_M_UPDATED, include/scisim_b200.h)
   V3d p = v3( 0.0 + m * vl.x, 0.0 + m * vl.y, 0.0 + m * vl.z );
@@ -1801,7 +1855,7 @@ int sg_rb3d_update_m_and_minv( sg_ctx* ctx, const double* q, double* m_blocks, d
 int sg_rb3d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0, double dt, double* q1, double* v1 )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
-  if( ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_SPLIT_HAM && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: map kind %d is not a rigidbody3d map", map_kind ); }
+  if( ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_SPLIT_HAM && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_DMV && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_EXPONENTIAL_EULER ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: map kind %d is not a rigidbody3d map", map_kind ); }
   Rb3dData* d = rb3d_data( ctx );
   if( d->n == 0 ) { return SG_OK; }
   if( q0 == nullptr || v0 == nullptr || q1 == nullptr || v1 == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_flow: null vector" ); }
@@ -1858,7 +1912,7 @@ int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v )
 int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
-  if( ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_SPLIT_HAM && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_DMV ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: map kind %d is not a rigidbody3d map", map_kind ); }
+  if( ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_SPLIT_HAM && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_DMV && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_EXPONENTIAL_EULER ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: map kind %d is not a rigidbody3d map", map_kind ); }
   Rb3dData* d = rb3d_data( ctx );
   d->flow_resident = false; // q1 is about to be overwritten by the resident step
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );

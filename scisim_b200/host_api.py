@@ -328,6 +328,26 @@ class Ball2DSim:
         self.ctx.check(self.ctx.lib.sg_ball2d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags) | (SG_IN_RESIDENT if resident else 0), C.byref(c)))
         return ActiveSet(c, copy=copy)
 
+    # ---- state I/O: Ball2DState's binary snapshot (ball2d/Ball2DState.cpp:259-312) ----
+    def serializeState(self, which=1):
+        """bytes of Ball2DState::serialize for the device-resident state: which = 0 the uploaded ( q0, v0 ), 1 the last flow's ( q1, v1 )."""
+        need = C.c_uint64()
+        self.ctx.check(self.ctx.lib.sg_ball2d_state_serialize(self.ctx.h, int(which), None, 0, C.byref(need)))
+        buf = np.zeros(int(need.value), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.sg_ball2d_state_serialize(self.ctx.h, int(which), _ptr(buf), buf.shape[0], C.byref(need)))
+        return buf.tobytes()
+
+    @staticmethod
+    def deserializeState(blob, ctx):
+        """Ball2DState::deserialize: a sim configured from a snapshot, its ( q, v ) uploaded."""
+        sim = Ball2DSim.__new__(Ball2DSim)
+        sim.ctx = ctx
+        buf = np.frombuffer(blob, dtype=np.uint8).copy()
+        ctx.check(ctx.lib.sg_ball2d_state_deserialize(ctx.h, _ptr(buf), buf.shape[0]))
+        n = int(np.frombuffer(blob[:8], dtype=np.int64)[0]) // 2
+        sim.state = Ball2DState(np.ones(n), np.ones(n))   # the context holds the real values; only nballs() is used on the host side
+        return sim
+
     # ---- resident path (state stays in HBM) ----
     def upload(self, q, v):
         q = _f64(q)
@@ -511,6 +531,12 @@ class DMVMap(_RB3DMap):
     """rigidbody3d/UnconstrainedMaps/DMVMap.cpp"""
     kind = SG_MAP_DMV
     _name = "dmv"
+
+
+class ExponentialEulerMap(_RB3DMap):
+    """rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.cpp"""
+    kind = 4  # SG_MAP_EXPONENTIAL_EULER
+    _name = "exponential_euler"
 
 
 class RigidBody3DSim:

@@ -282,3 +282,24 @@ def test_rb3d_active_set_on_resident_flow_result(gpu_ctx, oracle):
     assert a.n_active == b.n_active > 0 and a.n_candidates == b.n_candidates
     for k in ("type", "i", "j", "n", "p", "candidates"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_flow_exponential_euler(gpu_ctx, oracle):
+    """ExponentialEulerMap.cpp:13-91: explicit Euler parts bit-exact; the re-orthonormalised orientation (the reference: U V^T from
+    Eigen::JacobiSVD; oracle: one-sided Jacobi; device: Newton's polar iteration -- three routes to the same unique factor) to 1e-12."""
+    import scisim_b200 as sb
+    from tests import oracle_binding as ob
+    s = scenes.rb3d_random_boxes(3000, 8, spin=True)
+    sim = make_sim(s, gpu_ctx)
+    n = 3000
+    q1, v1 = sb.ExponentialEulerMap().flow(s["q"], s["v"], sim, 1, s["dt"])
+    rq1, rv1 = ob.RB3DOracle(s).flow(4, s["q"], s["v"], s["dt"])
+    assert np.array_equal(q1[:3 * n], rq1[:3 * n]) and np.array_equal(v1, rv1)
+    assert close(q1[3 * n:], rq1[3 * n:])
+    R = q1[3 * n:].reshape(n, 3, 3)
+    assert np.abs(np.einsum("bij,bkj->bik", R, R) - np.eye(3)).max() < 1e-14
+    # and through the resident step
+    sim.upload(s["q"], s["v"])
+    sim.step(sb.ExponentialEulerMap(), s["dt"])
+    q1s, v1s, _ = sim.fetch()
+    assert np.array_equal(q1s, q1) and np.array_equal(v1s, v1)

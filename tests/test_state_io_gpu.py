@@ -1,0 +1,88 @@
+"""GPU: state I/O at the seam.  sg_ball2d_state_serialize writes Ball2DState::serialize's byte stream
+(ball2d/Ball2DState.cpp:259-272) from the device-resident state:
+  * the tail (fixed flags, drums, planes, portals, forces) is compared byte for byte with what the reference's OWN compiled classes write
+    (oracle/_ref/libref_ball2d.so: Utilities.cpp, StaticDrum.cpp, StaticPlane.cpp, PlanarPortal.cpp, Ball2DGravityForce.cpp)
+  * the head (q, v, r, M, Minv) is decoded with the layout of scisim/Math/MathUtilities.h:42-60 / MathUtilities.cpp:142-154
+  * run-vs-resume bit-identity, the reference's own integration-test idea (assets/*/shell_scripts/execute_serialization_test.sh):
+    a sim resumed from the snapshot steps exactly like the one that wrote it."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from scisim_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libref_ball2d.so")
+
+
+def _head(blob, n):
+    off = 0
+    out = {}
+    for name, cnt in (("q", 2 * n), ("v", 2 * n), ("r", n)):
+        assert np.frombuffer(blob, np.int64, 1, off)[0] == cnt
+        out[name] = np.frombuffer(blob, np.float64, cnt, off + 8)
+        off += 8 + 8 * cnt
+    assert np.frombuffer(blob, np.uint64, 1, off)[0] == n
+    tail_start = off
+    off += 8 + n
+    for name in ("M", "Minv"):
+        rows, cols, nnz = np.frombuffer(blob, np.int64, 3, off)
+        assert rows == cols == nnz == 2 * n
+        off += 24
+        assert np.array_equal(np.frombuffer(blob, np.int32, 2 * n, off), np.arange(2 * n)); off += 8 * n
+        assert np.array_equal(np.frombuffer(blob, np.int32, 2 * n + 1, off), np.arange(2 * n + 1)); off += 4 * (2 * n + 1)
+        out[name] = np.frombuffer(blob, np.float64, 2 * n, off); off += 16 * n
+    return out, tail_start, off
+
+
+def test_snapshot_layout_and_resume(oracle, gpu_ctx):
+    import scisim_b200 as sb
+    s = scenes.ball2d_periodic(3000, 5, axes="x", lees_edwards=0.7, t=0.3)
+    s["drum_x"], s["drum_r"] = np.array([[3.0, 4.0]]), np.array([90.0])
+    s["g"] = np.array([0.3, -9.81])
+    n = 3000
+    st = sb.Ball2DState(s["r"], s["m"], s["g"], s["plane_x"], s["plane_n"], s["drum_x"], s["drum_r"], planar_portals=sb.PlanarPortal.from_arrays(s["portals"]))
+    sim = sb.Ball2DSim(st, ctx=gpu_ctx)
+    sim.updatePeriodicBoundaryConditionsStartOfStep(3, 0.1)     # t = 0.3: the Lees-Edwards portal has moved
+    sim.upload(s["q"], s["v"])
+    pc, pa = sim.step(sb.SymplecticEulerMap(), s["dt"])
+    q1, v1, a = sim.fetch()
+    blob = sim.serializeState(which=1)
+    head, tail_start, mats_end = _head(blob, n)
+    assert np.array_equal(head["q"], q1) and np.array_equal(head["v"], v1) and np.array_equal(head["r"], s["r"])
+    assert np.array_equal(head["M"], np.repeat(s["m"], 2)) and np.array_equal(head["Minv"], np.repeat(1.0 / s["m"], 2))
+    if os.path.exists(REF):
+        ref = C.CDLL(REF)
+        ref.ref_ball2d_snapshot_tail.restype = C.c_uint64
+        p = s["portals"]
+        vp = lambda x: np.ascontiguousarray(x, dtype=np.float64).ctypes.data_as(C.c_void_p)
+        out = np.zeros(1 << 20, dtype=np.uint8)
+        arrs = [s["drum_x"], s["drum_r"], s["plane_x"], s["plane_n"], p["plane_a_x"], p["plane_a_n"], p["plane_b_x"], p["plane_b_n"], p["v"], p["bounds"], s["g"]]
+        keep = [np.ascontiguousarray(x, dtype=np.float64) for x in arrs]
+        k = [x.ctypes.data_as(C.c_void_p) for x in keep]
+        nb = ref.ref_ball2d_snapshot_tail(C.c_uint32(n), C.c_uint32(1), k[0], k[1], C.c_uint32(s["plane_x"].shape[0]), k[2], k[3], C.c_uint32(p["v"].shape[0]), k[4], k[5], k[6], k[7], k[8], k[9],
+                                          C.c_double(3 * 0.1), k[10], out.ctypes.data_as(C.c_void_p), C.c_uint64(out.shape[0]))
+        ref_tail = out[: int(nb)].tobytes()
+        fixed_len = 8 + n
+        mine = blob[tail_start:tail_start + fixed_len] + blob[mats_end:]
+        assert mine == ref_tail, "tail of the snapshot differs from what the reference's classes write"
+    # resume: a fresh context configured from the snapshot continues exactly like the original
+    ctx2 = sb.Context(0)
+    sim2 = sb.Ball2DSim.deserializeState(blob, ctx2)
+    blob2 = sim2.serializeState(which=0)
+    assert blob2 == blob
+    sim.upload(q1, v1)
+    c1 = sim.step(sb.SymplecticEulerMap(), s["dt"])
+    c2 = sim2.step(sb.SymplecticEulerMap(), s["dt"])
+    assert c1 == c2
+    qa, va, aa = sim.fetch()
+    qb, vb, ab = sim2.fetch()
+    assert np.array_equal(qa, qb) and np.array_equal(va, vb)
+    assert np.array_equal(aa.candidates, ab.candidates)
+    for k in ("type", "i", "j", "n", "p"):
+        assert np.array_equal(getattr(aa, k), getattr(ab, k)), k
+    assert np.array_equal(aa.depth, ab.depth, equal_nan=True)
+    ctx2.close()
