@@ -18,7 +18,7 @@
 //
 // Eigen 3.3.4 semantics assumed where the reference delegates arithmetic to it (see oracle_math.h): 3-term
 // reductions (a0+a1)+a2; Quaternion(Matrix3) by Shoemake's method; Quaternion::normalize with the squared
-// norm reduced as (x^2+y^2)+(z^2+w^2); AngleAxis::toRotationMatrix and Quaternion::toRotationMatrix as in
+// norm reduced as (x^2+z^2)+(y^2+w^2) (packet reduction, see solveDMV); AngleAxis::toRotationMatrix and Quaternion::toRotationMatrix as in
 // Eigen/src/Geometry. PARITY UNPINNED: no reference test stores expected values for any of this
 // (SURVEY.md 8c); sin/cos come from libm here (as in the reference) and from CUDA on the device, so rotating
 // bodies are compared to 1e-12, everything else bit for bit.
@@ -244,8 +244,11 @@ inline void solveDMV( const V3& am, const double h, const V3& I0, Quat& q )
   q.x = q1 + cm1 * q0 + cm3 * q2 - cm2 * q3;
   q.y = q2 + cm2 * q0 + cm1 * q3 - cm3 * q1;
   q.z = q3 + cm3 * q0 + cm2 * q1 - cm1 * q2;
-  // Quaternion::normalize(): coeffs() /= norm(); coeffs are stored (x,y,z,w); 4-wide reduction (x^2+y^2)+(z^2+w^2)
-  const double nrm = std::sqrt( ( q.x * q.x + q.y * q.y ) + ( q.z * q.z + q.w * q.w ) );
+  // Quaternion::normalize(): coeffs() /= norm(), norm = sqrt( coeffs.cwiseAbs2().sum() ); coeffs are stored ( x, y, z, w ).  Eigen 3.3.4
+  // sums a fixed 4-vector of doubles by packets (Core/Redux.h: redux_impl<LinearVectorizedTraversal, CompleteUnrolling>): with SSE2 two
+  // packets ( x2, y2 ) + ( z2, w2 ) are added lane-wise and then across (redux_vec_unroller + predux), with AVX the one packet is folded
+  // high half onto low half (predux<Packet4d>) -- either way ( x2 + z2 ) + ( y2 + w2 )
+  const double nrm = std::sqrt( ( q.x * q.x + q.z * q.z ) + ( q.y * q.y + q.w * q.w ) );
   q.x /= nrm; q.y /= nrm; q.z /= nrm; q.w /= nrm;
 }
 

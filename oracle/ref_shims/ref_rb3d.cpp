@@ -5,6 +5,8 @@
 //   rigidbody3d/StaticGeometry/StaticPlane.cpp, rigidbody3d/Portals/PlanarPortal.cpp         (plane frames, portal touch tests and teleports)
 //   rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp, rigidbody3d/Constraints/MeshMeshUtilities.cpp (+ scisim/StringUtilities.cpp)
 //                                                  (mesh AABB, detectCollision on the signed distance grid, mesh-mesh and mesh-half-plane sets)
+//   rigidbody3d/UnconstrainedMaps/SplitHamMap.cpp, DMVMap.cpp, rigidbody3d/Forces/NearEarthGravityForce.cpp (+ Force.cpp, scisim/UnconstrainedMaps/*.cpp)
+//                                                  (the two kick-drift-kick maps, driven through a shim FlowableSystem: see ShimRB3DSystem)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).
 #include "rigidbody3d/SpatialGridDetector.h"
 #include "rigidbody3d/Constraints/BoxBoxUtilities.h"
@@ -16,6 +18,11 @@
 #include "scisim/Math/MathUtilities.h"
 #include "scisim/StringUtilities.h"
 #include "scisim/Utilities.h"
+#include "rigidbody3d/UnconstrainedMaps/SplitHamMap.h"
+#include "rigidbody3d/UnconstrainedMaps/DMVMap.h"
+#include "rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.h"
+#include "rigidbody3d/Forces/NearEarthGravityForce.h"
+#include "scisim/UnconstrainedMaps/FlowableSystem.h"
 
 #include <sstream>
 
@@ -179,4 +186,105 @@ uint64_t ref_rb3d_mesh_halfplane( const void* m, const double* cm, const double*
   return verts.size();
 }
 
+}
+
+// ---- the rigidbody3d maps: a FlowableSystem with what SplitHamMap / DMVMap ask of RigidBody3DSim -- M0, Minv0 (diagonal: m, m, m per body, then
+// the body-frame inertias), M, Minv (the same 3N linear entries, then one 3x3 world-space block per body), the kinematic flags and
+// computeForce = setZero + NearEarthGravityForce ( RigidBody3DSim.cpp:169-181 ).  The blocks are filled as the reference fills them:
+//   first flow of a simulation   formWorldSpaceMassMatrix / ...InverseMassMatrix ( RigidBody3DState.cpp:140-240 ):
+//                                I = R * I0.asDiagonal() * R^T, stored with insert( row = base + col_idx, col = base + row_idx ) = I( row_idx, col_idx )
+//   later flows ( m_updated )    updateMandMinv ( RigidBody3DState.cpp:428-462 ): the same product assigned through a column-major map
+// The products themselves are the reference's expressions, evaluated by the stand-in. -----------------------------------------------------------
+namespace
+{
+class ShimRB3DSystem final : public FlowableSystem
+{
+public:
+  ShimRB3DSystem( const uint32_t n, const double* q, const double* m, const double* I0, const uint8_t* fixed, const double* g, const bool m_updated )
+  : m_n( n ), m_force( Vector3s{ g[0], g[1], g[2] } ), m_fixed( fixed, fixed + n )
+  {
+    std::vector<double> d0( 6 * size_t( n ) ), di0( 6 * size_t( n ) );
+    for( uint32_t b = 0; b < n; ++b )
+    {
+      for( int k = 0; k < 3; ++k ) { d0[3 * b + k] = m[b]; di0[3 * b + k] = 1.0 / m[b]; d0[3 * n + 3 * b + k] = I0[3 * b + k]; di0[3 * n + 3 * b + k] = 1.0 / I0[3 * b + k]; }
+    }
+    m_M0.setDiagonal( d0.data(), int( d0.size() ) ); m_Minv0.setDiagonal( di0.data(), int( di0.size() ) );
+    std::vector<int> outer( 6 * size_t( n ) + 1 ), inner( 12 * size_t( n ) );
+    std::vector<double> vm( 12 * size_t( n ) ), vi( 12 * size_t( n ) );
+    for( uint32_t c = 0; c < 3 * n; ++c ) { outer[c] = int( c ); inner[c] = int( c ); vm[c] = m[c / 3]; vi[c] = 1.0 / m[c / 3]; }
+    for( uint32_t b = 0; b < n; ++b )
+    {
+      const Eigen::Map<const Matrix33sr> Rmat{ q + 3 * size_t( n ) + 9 * size_t( b ) };
+      const Vector3s I0b{ I0[3 * b], I0[3 * b + 1], I0[3 * b + 2] };
+      const Vector3s Iinv0b{ 1.0 / I0[3 * b], 1.0 / I0[3 * b + 1], 1.0 / I0[3 * b + 2] };
+      const Matrix33sr I = Rmat * I0b.asDiagonal() * Rmat.transpose();
+      const Matrix33sr Iinv = Rmat * Iinv0b.asDiagonal() * Rmat.transpose();
+      for( int c = 0; c < 3; ++c )
+      {
+        const size_t col = 3 * size_t( n ) + 3 * size_t( b ) + c;
+        outer[col] = int( 3 * n + 9 * b + 3 * c );
+        for( int r = 0; r < 3; ++r )
+        {
+          inner[3 * n + 9 * b + 3 * c + r] = int( 3 * n + 3 * b + r );
+          // constructor: entry ( row r, column c ) <- I( c, r );  updateMandMinv: column-major map, entry ( r, c ) <- I( r, c )
+          vm[3 * n + 9 * b + 3 * c + r] = m_updated ? I( r, c ) : I( c, r );
+          vi[3 * n + 9 * b + 3 * c + r] = m_updated ? Iinv( r, c ) : Iinv( c, r );
+        }
+      }
+    }
+    outer[6 * size_t( n )] = int( 12 * n );
+    m_M.setCompressed( int( 6 * n ), outer, inner, vm ); m_Minv.setCompressed( int( 6 * n ), outer, inner, vi );
+  }
+  virtual int nqdofs() const override { return int( 12 * m_n ); }
+  virtual int nvdofs() const override { return int( 6 * m_n ); }
+  virtual unsigned numVelDoFsPerBody() const override { return 6; }
+  virtual unsigned ambientSpaceDimensions() const override { return 3; }
+  virtual bool isKinematicallyScripted( const int i ) const override { return m_fixed[size_t( i )] != 0; }
+  virtual void computeForce( const VectorXs& q, const VectorXs& v, const scalar&, VectorXs& F ) override
+  {
+    F.setZero();
+    m_force.computeForce( q, v, m_M, F );
+  }
+  virtual void zeroOutForcesOnFixedBodies( VectorXs& ) const override {}
+  virtual void linearInertialConfigurationUpdate( const VectorXs&, const VectorXs&, const scalar&, VectorXs& ) const override {}
+  virtual const SparseMatrixsc& M() const override { return m_M; }
+  virtual const SparseMatrixsc& Minv() const override { return m_Minv; }
+  virtual const SparseMatrixsc& M0() const override { return m_M0; }
+  virtual const SparseMatrixsc& Minv0() const override { return m_Minv0; }
+  virtual void computeMomentum( const VectorXs&, VectorXs& ) const override {}
+  virtual void computeAngularMomentum( const VectorXs&, VectorXs& ) const override {}
+  virtual std::string name() const override { return "shim_rigid_body_3d"; }
+  const double* mValues() const { return m_M.valuePtr(); }
+  const double* minvValues() const { return m_Minv.valuePtr(); }
+private:
+  uint32_t m_n;
+  NearEarthGravityForce m_force;
+  std::vector<uint8_t> m_fixed;
+  SparseMatrixsc m_M0, m_Minv0, m_M, m_Minv;
+};
+}
+
+extern "C"
+{
+// kind 2: SplitHamMap::flow, 3: DMVMap::flow (the reference's own code); q: 12 n, v: 6 n
+void ref_rb3d_flow( const int kind, const uint32_t n, const double* q0, const double* v0, const double* m, const double* I0, const uint8_t* fixed, const double* g, const double dt,
+                    const int m_updated, double* q1, double* v1 )
+{
+  ShimRB3DSystem sys{ n, q0, m, I0, fixed, g, m_updated != 0 };
+  VectorXs q0v( int( 12 * n ) ), v0v( int( 6 * n ) ), q1v( int( 12 * n ) ), v1v( int( 6 * n ) );
+  for( uint32_t k = 0; k < 12 * n; ++k ) { q0v( int( k ) ) = q0[k]; }
+  for( uint32_t k = 0; k < 6 * n; ++k ) { v0v( int( k ) ) = v0[k]; }
+  if( kind == 2 ) { SplitHamMap map; map.flow( q0v, v0v, sys, 1, dt, q1v, v1v ); }
+  else { DMVMap map; map.flow( q0v, v0v, sys, 1, dt, q1v, v1v ); }
+  for( uint32_t k = 0; k < 12 * n; ++k ) { q1[k] = q1v( int( k ) ); }
+  for( uint32_t k = 0; k < 6 * n; ++k ) { v1[k] = v1v( int( k ) ); }
+}
+// the 3x3 blocks of M and Minv as the shim builds them (column-major values, 9 per body) -- to compare with the oracle's updateMandMinv
+void ref_rb3d_mass_blocks( const uint32_t n, const double* q, const double* m, const double* I0, const int m_updated, double* I_blocks, double* Iinv_blocks )
+{
+  std::vector<uint8_t> fixed( n, 0 );
+  const double g[3] = { 0.0, 0.0, 0.0 };
+  ShimRB3DSystem sys{ n, q, m, I0, fixed.data(), g, m_updated != 0 };
+  for( size_t k = 0; k < 9 * size_t( n ); ++k ) { I_blocks[k] = sys.mValues()[3 * size_t( n ) + k]; Iinv_blocks[k] = sys.minvValues()[3 * size_t( n ) + k]; }
+}
 }

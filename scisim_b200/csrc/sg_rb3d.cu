@@ -341,7 +341,7 @@ __device__ inline M3d dmv_rotation( const M3d& R0, const V3d am, const double h,
   double x = q1 + cm1 * q0 + cm3 * q2 - cm2 * q3;
   double y = q2 + cm2 * q0 + cm1 * q3 - cm3 * q1;
   double z = q3 + cm3 * q0 + cm2 * q1 - cm1 * q2;
-  const double nrm = sqrt( ( x * x + y * y ) + ( z * z + w * w ) );
+  const double nrm = sqrt( ( x * x + z * z ) + ( y * y + w * w ) ); // Eigen's packet reduction of the ( x, y, z, w ) coefficients: see oracle/rb3d.h solveDMV
   x /= nrm; y /= nrm; z /= nrm; w /= nrm;
   // Quaternion::toRotationMatrix
   const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;

@@ -370,3 +370,56 @@ def test_rb2d_maps_against_the_reference_sources(oracle, kind):
         ref.ref_rb2d_flow(kind, n, vp(M), vp(fixed), vp(g), vp(q0), vp(v0), 2, float(s["dt"]), vp(rq1), vp(rv1))
         assert np.array_equal(q1.view(np.uint64), rq1.view(np.uint64)) and np.array_equal(v1.view(np.uint64), rv1.view(np.uint64)), (n, seed)
     assert fixed.sum() > 100
+
+
+# ---- rigidbody3d maps: SplitHamMap.cpp / DMVMap.cpp compiled unchanged, driven through a shim FlowableSystem -----------------------------
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("m_updated", [False, True])
+@pytest.mark.parametrize("scene_kind,n,seed", [("spheres_nospin", 500, 1), ("boxes_spin", 600, 2), ("spheres_spin_fixed", 400, 3), ("one", 1, 4)])
+def test_rb3d_maps_equal_reference_sources(oracle, kind, m_updated, scene_kind, n, seed):
+    """q1, v1 of the oracle's restated SplitHamMap (kind 2) / DMVMap (kind 3) == the reference's own SplitHamMap.cpp:17-182 / DMVMap.cpp:15-207,
+    bit for bit: spinning boxes with anisotropic inertia, kinematically scripted bodies, both mass-matrix layouts (the constructor's transposed
+    blocks for a simulation's first flow, updateMandMinv's for the later ones)."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    if scene_kind == "boxes_spin":
+        s = scenes.rb3d_random_boxes(n, seed, spin=True)
+    elif scene_kind == "spheres_nospin":
+        s = scenes.rb3d_random_spheres(n, seed, spin=False)
+    else:
+        s = scenes.rb3d_random_spheres(n, seed, spin=True, nfixed_frac=0.2 if scene_kind == "spheres_spin_fixed" else 0.0)
+    if scene_kind == "spheres_spin_fixed":
+        # kinematically scripted bodies are asserted to be at rest by the maps
+        fx = s["fixed"].astype(bool)
+        v = s["v"].copy()
+        v[:3 * n].reshape(n, 3)[fx] = 0.0
+        v[3 * n:].reshape(n, 3)[fx] = 0.0
+        s["v"] = v
+    o = ob.RB3DOracle(s)
+    q1, v1 = o.flow(kind, s["q"], s["v"], s["dt"], m_updated=m_updated)
+    rq1, rv1 = np.zeros_like(q1), np.zeros_like(v1)
+    q0, v0 = np.ascontiguousarray(s["q"]), np.ascontiguousarray(s["v"])
+    m, I0 = np.ascontiguousarray(s["m"], dtype=np.float64), np.ascontiguousarray(s["I0"], dtype=np.float64)
+    fixed = np.ascontiguousarray(s["fixed"], dtype=np.uint8)
+    g = np.ascontiguousarray(s["g"], dtype=np.float64)
+    ref.ref_rb3d_flow(C.c_int(kind), C.c_uint32(n), vp(q0), vp(v0), vp(m), vp(I0), vp(fixed), vp(g), C.c_double(s["dt"]), C.c_int(1 if m_updated else 0), vp(rq1), vp(rv1))
+    assert np.array_equal(q1, rq1), np.abs(q1 - rq1).max()
+    assert np.array_equal(v1, rv1), np.abs(v1 - rv1).max()
+    if scene_kind == "boxes_spin":
+        assert np.abs(q1[3 * n:] - q0[3 * n:]).max() > 1e-6   # the orientations did move
+
+
+def test_rb3d_update_m_and_minv_equals_reference_expression(oracle):
+    """The oracle's updateMandMinv blocks == R * I0.asDiagonal() * R^T evaluated by the stand-in in the layout of RigidBody3DState.cpp:428-462."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    n = 700
+    s = scenes.rb3d_random_boxes(n, 9, spin=True)
+    I, Ii = ob.RB3DOracle(s).update_m_and_minv(s["q"])
+    rI, rIi = np.zeros(9 * n), np.zeros(9 * n)
+    q = np.ascontiguousarray(s["q"])
+    m, I0 = np.ascontiguousarray(s["m"], dtype=np.float64), np.ascontiguousarray(s["I0"], dtype=np.float64)
+    ref.ref_rb3d_mass_blocks(C.c_uint32(n), vp(q), vp(m), vp(I0), C.c_int(1), vp(rI), vp(rIi))
+    assert np.array_equal(I, rI) and np.array_equal(Ii, rIi)
