@@ -427,6 +427,26 @@ int sg_rb3d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_c
    it directly from global memory, summed since the first mesh was added. */
 int sg_rb3d_mesh_stats( sg_ctx* ctx, uint64_t* staged_sweeps, uint64_t* direct_sweeps );
 
+/* Slab mode for rigidbody3d (multi-GPU, all-sphere scenes: BASELINE configs[3]) -- the ball2d slab calls for spheres, peer-memory exchange only.
+ * Reference path being sharded: RigidBody3DSim::computeActiveSetBodyBodySpatialGrid (rigidbody3d/RigidBody3DSim.cpp:1072-1260) and
+ * computeBodyPlaneActiveSetAllPairs (:1414-1502).
+ *   init      after sg_rb3d_set_geometry: this rank's n_owned spheres (geometry index, mass, body-frame inertia, strictly ascending global
+ *             indices), ghost_cap halo slots per neighbour, the x-range the owned spheres' boxes must stay inside (sg_slab_limits; NULL:
+ *             unlimited).  Kinematically scripted bodies and portals are not supported in slab mode.  sg_rb3d_upload / sg_rb3d_fetch then
+ *             address the owned bodies only ( q = [3 n_owned | 9 n_owned], v = [3 n_owned | 3 n_owned] )
+ *   mailbox / connect / disconnect / exchange   as sg_ball2d_slab_*
+ *   flow      integrate the owned bodies, post [min lo.x, max hi.x] of their boxes at q1 to the neighbours' mailboxes, list the halo candidates
+ *   detect    broad + narrow phase over owned + ghosts; a pair is kept iff this rank owns the body with the smaller global index; planes and
+ *             cylinders are tested for owned bodies only; indices are global, lists ascending.  SG_ERR_REBALANCE as for ball2d. */
+int sg_rb3d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t ghost_cap, const uint32_t* geo_of_body, const double* m /* n_owned */, const double* I0 /* 3 n_owned */,
+                       const uint32_t* gid_owned, const double* x_limits /* 2 or NULL */ );
+int sg_rb3d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64 );
+int sg_rb3d_slab_connect( sg_ctx* ctx, int side, const void* ipc_handle_64, void* same_process_mailbox, int peer_device );
+int sg_rb3d_slab_disconnect( sg_ctx* ctx );
+int sg_rb3d_slab_flow( sg_ctx* ctx, int map_kind, double dt );
+int sg_rb3d_slab_exchange( sg_ctx* ctx, int phase );
+int sg_rb3d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out );
+
 #ifdef __cplusplus
 }
 #endif

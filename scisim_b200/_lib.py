@@ -150,6 +150,13 @@ def load():
         "sg_rb3d_upload": (C.c_int, [vp, vp, vp]),
         "sg_rb3d_step": (C.c_int, [vp, C.c_int, C.c_double, C.POINTER(SgContacts)]),
         "sg_rb3d_fetch": (C.c_int, [vp, C.c_uint32, vp, vp, C.POINTER(SgContacts)]),
+        "sg_rb3d_slab_init": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]),
+        "sg_rb3d_slab_mailbox": (C.c_int, [vp, C.POINTER(C.c_void_p), vp]),
+        "sg_rb3d_slab_connect": (C.c_int, [vp, C.c_int, vp, vp, C.c_int]),
+        "sg_rb3d_slab_disconnect": (C.c_int, [vp]),
+        "sg_rb3d_slab_flow": (C.c_int, [vp, C.c_int, C.c_double]),
+        "sg_rb3d_slab_exchange": (C.c_int, [vp, C.c_int]),
+        "sg_rb3d_slab_detect": (C.c_int, [vp, C.POINTER(SgContacts), vp]),
         "sg_rb3d_set_cylinders": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),
         "sg_rb3d_mesh_stats": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     }

@@ -13,6 +13,7 @@
 // 128-bit access per ball); r and m are plain double arrays.  Sorted 64-byte records are described in
 // sg_broadphase.cuh.  Contacts are SoA (type,i,j,n,p,depth) in the reference's active_set order.
 #include "sg_broadphase.cuh"
+#include "sg_slab.cuh"
 
 struct Ball2DIn
 {
@@ -96,6 +97,7 @@ struct Ball2DPolicy
   static constexpr uint32_t IDX_MASK = 0x7fffffffu;
   static constexpr uint32_t IDX_OFFSET = 40u;
   static constexpr uint32_t ORD_OFFSET = 56u;
+  static constexpr bool ORD_IN_REC = true;
 
   // ball2d/Ball2DSim.cpp:566-571: lo = min(q1,q0) - r, hi = max(q1,q0) + r
   __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
@@ -221,21 +223,6 @@ __device__ __forceinline__ unsigned long long static_mask( const Static2D& sg, c
   }
   return mask;
 }
-
-// Slab mode, peer-memory exchange: while the flow kernel has every owned body's swept box in registers it also lists the bodies
-// that COULD be owed to a neighbour this step -- those reaching the band next to that neighbour, band = the neighbour's interval
-// of the previous step widened by a margin -- so that the halo pack, once the neighbour's actual interval has arrived, only looks
-// at that short list (and checks that the actual interval lies inside the band; if not, it scans all bodies: correctness never
-// depends on the guess).  state: [0] = left band's upper edge (a body is a candidate for the lower neighbour if lo.x <= it),
-// [1] = right band's lower edge (candidate for the higher neighbour if hi.x >= it).
-struct SlabCand
-{
-  const double* band;      // 2 doubles (device); nullptr: no candidate lists
-  uint32_t* count;         // 2 counters
-  uint32_t* list[2];       // slot indices
-  uint32_t cap;
-  bool on[2];
-};
 
 // One pass over the balls that (optionally) integrates them and, from registers, also produces everything the
 // detection pipeline needs before binning: the bounds of the swept AABBs (block reduce + one atomic per quantity
@@ -730,61 +717,6 @@ __device__ __forceinline__ void swept_x( const double2 a, const double2 b, const
   hi = fmax( b.x, a.x ) + r;
 }
 
-__global__ void k_ball2d_slab_begin( long long* enc, uint32_t* ghost_counts )
-{
-  enc[0] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );
-  enc[1] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );
-  ghost_counts[0] = 0u; ghost_counts[1] = 0u;
-}
-// reads the reduced interval, re-arms the accumulator for the next step and clears this step's ghost counts
-__device__ inline void slab_take_interval( long long* enc, uint32_t* ghost_counts, double& lo, double& hi )
-{
-  lo = sg_double_from_ordered( enc[0] ); hi = sg_double_from_ordered( enc[1] );
-  enc[0] = sg_ordered_from_double( __longlong_as_double( 0x7ff0000000000000LL ) );
-  enc[1] = sg_ordered_from_double( __longlong_as_double( 0xfff0000000000000LL ) );
-  ghost_counts[0] = 0u; ghost_counts[1] = 0u;
-}
-__global__ void k_ball2d_interval_decode( long long* enc, uint32_t* ghost_counts, double* out )
-{
-  double lo, hi;
-  slab_take_interval( enc, ghost_counts, lo, hi );
-  out[0] = lo; out[1] = hi;
-}
-
-// ---- peer-memory halo exchange -----------------------------------------------------------------------
-// Each rank owns a mailbox in its own HBM that its two neighbours write over NVLink (mapped with CUDA IPC, or
-// directly when the neighbour lives in the same process): the neighbour's swept interval, then -- packed by the
-// neighbour's own pack kernel straight through the peer mapping -- its halo records, each followed by a
-// system-scope fence and a step-tagged flag.  The consumer side is a one-thread kernel spinning on the flag in
-// LOCAL memory, so the whole exchange is stream-ordered device work: no collective, no host round trip.
-struct alignas( 128 ) SlabMailboxHdr
-{
-  double iv[2][2];        // [side]: interval of the neighbour on that side (0 = lower ranks, 1 = higher)
-  uint32_t iv_flag[2];    // step tag of iv[side]
-  uint32_t halo_flag[2];  // step tag of the halo records from that side
-  uint32_t err;           // a wait timed out
-};
-__host__ __device__ inline GhostRec* slab_mailbox_halo( void* mb, const int side, const uint32_t cap )
-{
-  return reinterpret_cast<GhostRec*>( static_cast<unsigned char*>( mb ) + sizeof( SlabMailboxHdr ) ) + size_t( side ) * ( size_t( cap ) + 1 );
-}
-__device__ __forceinline__ void st_release_sys( uint32_t* p, const uint32_t v ) { asm volatile( "st.release.sys.global.u32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" ); }
-__device__ __forceinline__ uint32_t ld_acquire_sys( const uint32_t* p ) { uint32_t v; asm volatile( "ld.acquire.sys.global.u32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" ); return v; }
-
-
-// one thread: returns when *flag has reached `step` (bounded: a dead neighbour must not hang the GPU)
-__device__ inline void slab_wait_flag( const uint32_t* flag, const uint32_t step, uint32_t* err )
-{
-  unsigned long long t0, t1;
-  asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t0 ) );
-  while( int( ld_acquire_sys( flag ) - step ) < 0 )
-  {
-    __nanosleep( 200 );
-    asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t1 ) );
-    if( t1 - t0 > 10000000000ull ) { *err = 1u; break; } // 10 s
-  }
-}
-
 // What a pack / unpack launch has to synchronise with when the exchange goes through peer-mapped mailboxes
 struct SlabSync
 {
@@ -926,14 +858,20 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack( const uint32_t n, c
   }
 }
 
-// ---- single-pass halo pack over the candidate lists (peer-memory exchange) ----------------------------------------------
-struct SlabCandState
+// what the shared halo pack (sg_slab.cuh) needs to know about balls
+struct Ball2DSlabTraits
 {
-  double band[2];        // see SlabCand
-  uint32_t count[2];     // candidates listed by this step's flow kernel
-  uint32_t cursor[2];    // records written into the neighbour's mailbox so far
-  uint32_t ticket;       // blocks done (the last one publishes)
-  uint32_t fallbacks;    // steps in which a band did not hold and all bodies were scanned (diagnostics)
+  using Rec = GhostRec;
+  struct Src { const double2* q0; const double2* q1; const double* r; const uint32_t* gid; };
+  __device__ static bool select( const Src& s, const uint32_t i, const double ilo, const double ihi, Rec& g )
+  {
+    const double2 a = __ldg( &s.q0[i] ), b = __ldg( &s.q1[i] );
+    const double rad = __ldg( &s.r[i] );
+    double lo, hi;
+    swept_x( a, b, rad, lo, hi );
+    g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = s.gid[i]; g.pad = 0u;
+    return !( hi < ilo ) && !( ihi < lo );
+  }
 };
 
 static SlabCand ball2d_slab_cand( const Ball2DData* d )
@@ -947,107 +885,6 @@ static SlabCand ball2d_slab_cand( const Ball2DData* d )
   sc.cap = d->cand_cap;
   sc.on[0] = d->peer_mb[0] != nullptr; sc.on[1] = d->peer_mb[1] != nullptr;
   return sc;
-}
-
-__global__ void k_ball2d_slab_cand_reset( SlabCandState* st )
-{
-  // bands that make every body a candidate: the first step after (re)initialisation overflows the lists and scans all bodies
-  st->band[0] = __longlong_as_double( 0x7ff0000000000000LL ); st->band[1] = __longlong_as_double( 0xfff0000000000000LL );
-  st->count[0] = st->count[1] = 0u; st->cursor[0] = st->cursor[1] = 0u; st->ticket = 0u; st->fallbacks = 0u;
-}
-
-struct Pack2Args
-{
-  const double* iv[2];      // the neighbour's interval of this step (local mailbox)
-  const uint32_t* wait[2];  // its step-tagged flag
-  GhostRec* out[2];         // the neighbour's mailbox (peer memory): header + records
-  uint32_t* post[2];        // the neighbour's halo flag
-  bool on[2];
-  uint32_t* err;
-  uint32_t step;
-};
-
-// Small persistent grid.  Every block: wait for the neighbours' intervals; per side, if the interval lies inside the band the
-// candidates were collected with (and the list did not overflow) test the candidates, else all owned bodies; selected bodies go
-// straight into the neighbour's mailbox at a slot taken from an atomic cursor.  The last block to finish writes the headers
-// (counts), raises the neighbours' flags and sets the bands for the next step: this step's interval edge widened by `margin`.
-__global__ void __launch_bounds__( 256 ) k_ball2d_slab_pack2( const uint32_t n, const uint32_t own_first, const uint32_t own_count, const double2* __restrict__ q0, const double2* __restrict__ q1,
-                                                             const double* __restrict__ r, const uint32_t* __restrict__ gid, const uint32_t cap, const SlabCand sc, SlabCandState* st,
-                                                             const GridParams* __restrict__ last_grid, const Pack2Args args )
-{
-  if( threadIdx.x < 2 && args.on[threadIdx.x] ) { slab_wait_flag( args.wait[threadIdx.x], args.step, args.err ); }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  #pragma unroll
-  for( int sd = 0; sd < 2; ++sd )
-  {
-    if( !args.on[sd] ) { continue; }
-    const double ilo = args.iv[sd][0], ihi = args.iv[sd][1];
-    const uint32_t listed = st->count[sd];
-    // the band holds if every body the neighbour could need was listed: its interval does not reach past the band edge
-    const bool band_ok = listed <= sc.cap && ( ( sd == 0 ) ? ( ihi <= st->band[0] ) : ( ilo >= st->band[1] ) );
-    const uint32_t total = band_ok ? listed : own_count;
-    for( uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x ) // whole warps stay together for the ballot
-    {
-      const uint32_t e = base + threadIdx.x;
-      bool sel = false;
-      uint32_t i = 0u;
-      double2 a = make_double2( 0.0, 0.0 ), b = a;
-      double rad = 0.0;
-      if( e < total )
-      {
-        i = band_ok ? sc.list[sd][e] : own_first + e;
-        a = __ldg( &q0[i] ); b = __ldg( &q1[i] ); rad = __ldg( &r[i] );
-        double lo, hi;
-        swept_x( a, b, rad, lo, hi );
-        sel = !( hi < ilo ) && !( ihi < lo );
-      }
-      const unsigned bal = __ballot_sync( 0xffffffffu, sel );
-      if( bal != 0u )
-      {
-        uint32_t k0 = 0u;
-        if( lane == __ffs( bal ) - 1 ) { k0 = atomicAdd( &st->cursor[sd], uint32_t( __popc( bal ) ) ); }
-        k0 = __shfl_sync( 0xffffffffu, k0, __ffs( bal ) - 1 );
-        const uint32_t k = k0 + __popc( bal & ( ( 1u << lane ) - 1u ) );
-        if( sel && k < cap )
-        {
-          GhostRec g;
-          g.q0x = a.x; g.q0y = a.y; g.q1x = b.x; g.q1y = b.y; g.r = rad; g.gid = gid[i]; g.pad = 0u;
-          args.out[sd][1u + k] = g;
-        }
-      }
-    }
-  }
-  // ---- the last block publishes
-  __shared__ uint32_t s_last;
-  __syncthreads();
-  if( threadIdx.x == 0 )
-  {
-    __threadfence_system(); // this block's peer writes before its ticket
-    s_last = ( atomicAdd( &st->ticket, 1u ) == gridDim.x - 1u ) ? 1u : 0u;
-  }
-  __syncthreads();
-  if( s_last == 0u || threadIdx.x != 0 ) { return; }
-  __threadfence();
-  const double margin = ( last_grid != nullptr && last_grid->h > 0.0 && last_grid->h < 1.0e300 ) ? last_grid->h : 0.0; // the last step's cell width (>= every swept extent); anything >= 0 is safe
-  for( int sd = 0; sd < 2; ++sd )
-  {
-    if( !args.on[sd] ) { continue; }
-    const uint32_t listed = st->count[sd];
-    const double ilo = args.iv[sd][0], ihi = args.iv[sd][1];
-    const bool band_ok = listed <= sc.cap && ( ( sd == 0 ) ? ( ihi <= st->band[0] ) : ( ilo >= st->band[1] ) );
-    if( !band_ok ) { st->fallbacks += 1u; }
-    GhostRec h;
-    h.q0x = 0.0; h.q0y = 0.0; h.q1x = 0.0; h.q1y = 0.0; h.r = 0.0; h.gid = *reinterpret_cast<volatile uint32_t*>( &st->cursor[sd] ); h.pad = 0u;
-    args.out[sd][0] = h;
-    // next step's band: the neighbour's edge of this step, widened (an empty neighbour posts [+inf, -inf]: nobody is a candidate)
-    if( sd == 0 ) { st->band[0] = ( ilo <= ihi ) ? ihi + margin : __longlong_as_double( 0xfff0000000000000LL ); }
-    else { st->band[1] = ( ilo <= ihi ) ? ilo - margin : __longlong_as_double( 0x7ff0000000000000LL ); }
-    st->cursor[sd] = 0u; st->count[sd] = 0u;
-  }
-  st->ticket = 0u;
-  __threadfence_system();
-  for( int sd = 0; sd < 2; ++sd ) { if( args.on[sd] ) { st_release_sys( args.post[sd], args.step ); } }
 }
 
 // Count only (sg_ball2d_slab_pack with no send buffer): total of the per-block counts
@@ -1118,25 +955,6 @@ __global__ void __launch_bounds__( 256 ) k_ball2d_slab_unpack( const uint32_t ca
 }
 
 
-
-// decodes this rank's interval, keeps a local copy and posts it to the neighbours (lower = side 0, higher = side 1)
-__global__ void k_ball2d_slab_post_interval( long long* enc, uint32_t* ghost_counts, double* local_out, SlabMailboxHdr* lower, SlabMailboxHdr* higher, const uint32_t step )
-{
-  double lo, hi;
-  slab_take_interval( enc, ghost_counts, lo, hi );
-  if( local_out != nullptr ) { local_out[0] = lo; local_out[1] = hi; }
-  if( lower != nullptr ) { lower->iv[1][0] = lo; lower->iv[1][1] = hi; }     // seen from the lower rank I am its side-1 neighbour
-  if( higher != nullptr ) { higher->iv[0][0] = lo; higher->iv[0][1] = hi; }
-  __threadfence_system();
-  if( lower != nullptr ) { st_release_sys( &lower->iv_flag[1], step ); }
-  if( higher != nullptr ) { st_release_sys( &higher->iv_flag[0], step ); }
-}
-
-__global__ void __launch_bounds__( 256 ) k_iota_u32( const uint32_t n, const uint32_t first, uint32_t* __restrict__ out )
-{
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if( k < n ) { out[k] = first + k; }
-}
 
 namespace
 {
@@ -1466,7 +1284,7 @@ int sg_ball2d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t gid_first, uint
   SG_CUDA( ctx, d->interval_enc.ensure( 16 ) );
   SG_CUDA( ctx, d->ghost_counts.ensure( 16 ) );
   SG_CUDA( ctx, cudaMemsetAsync( d->ghost_counts.ptr, 0, 16, ctx->stream ) );
-  k_ball2d_slab_begin<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>() );
+  k_slab_begin<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>() );
   if( n_owned > 0 )
   {
     SG_CUDA( ctx, cudaMemcpyAsync( d->r.as<double>() + ghost_cap, r, size_t( n_owned ) * 8, cudaMemcpyHostToDevice, ctx->stream ) );
@@ -1538,12 +1356,12 @@ int sg_ball2d_slab_flow( sg_ctx* ctx, int map_kind, double dt, double* interval_
   }
   if( d->mailbox.ptr == nullptr )
   {
-    SG_LAUNCH( ctx, "slab_interval", 16.0, k_ball2d_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev ) );
+    SG_LAUNCH( ctx, "slab_interval", 16.0, k_slab_interval_decode<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev ) );
   }
   else
   {
     ++d->slab_step;
-    SG_LAUNCH( ctx, "slab_interval", 16.0, k_ball2d_slab_post_interval<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev, static_cast<SlabMailboxHdr*>( d->peer_mb[0] ),
+    SG_LAUNCH( ctx, "slab_interval", 16.0, k_slab_post_interval<<<1, 1, 0, ctx->stream>>>( d->interval_enc.as<long long>(), d->ghost_counts.as<uint32_t>(), interval_dev, static_cast<SlabMailboxHdr*>( d->peer_mb[0] ),
                static_cast<SlabMailboxHdr*>( d->peer_mb[1] ), d->slab_step ) );
   }
   d->slab_prep_done = true;
@@ -1654,7 +1472,7 @@ int sg_ball2d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64
     d->cand_cap = 4u * d->ghost_cap + 1024u;
     SG_CUDA( ctx, d->cand_state.ensure( sizeof( SlabCandState ) ) );
     SG_CUDA( ctx, d->cand_list.ensure( 2 * size_t( d->cand_cap ) * 4 ) );
-    k_ball2d_slab_cand_reset<<<1, 1, 0, ctx->stream>>>( d->cand_state.as<SlabCandState>() );
+    k_slab_cand_reset<<<1, 1, 0, ctx->stream>>>( d->cand_state.as<SlabCandState>() );
     SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
     d->slab_step = 0;
   }
@@ -1732,7 +1550,7 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
   {
     // both neighbours in one launch: the candidates the flow kernel listed (or, when a band did not hold, all owned bodies) against
     // the neighbours' intervals, selected records straight into their mailboxes, flags raised by the last block
-    Pack2Args pa;
+    Pack2Args<GhostRec> pa;
     bool any = false;
     for( int side = 0; side < 2; ++side )
     {
@@ -1741,7 +1559,7 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
       if( !pa.on[side] ) { continue; }
       SlabMailboxHdr* peer = static_cast<SlabMailboxHdr*>( d->peer_mb[side] );
       // seen from the neighbour on `side`, this rank sits on its side 1 - side
-      pa.out[side] = slab_mailbox_halo( peer, 1 - side, d->ghost_cap );
+      pa.out[side] = slab_mailbox_halo<GhostRec>( peer, 1 - side, d->ghost_cap );
       pa.post[side] = &peer->halo_flag[1 - side];
       any = true;
     }
@@ -1751,8 +1569,10 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
       if( !d->slab_prep_done ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_exchange: call sg_ball2d_slab_flow first" ); }
       const SlabCand sc = ball2d_slab_cand( d );
       const unsigned grid = unsigned( ctx->num_sms ); // one block per SM: the candidate lists are a few thousand entries
-      SG_LAUNCH( ctx, "slab_pack", double( d->ghost_cap ) * 2.0 * 48.0, k_ball2d_slab_pack2<<<grid, 256, 0, ctx->stream>>>( d->n, d->own_first(), d->own_count(), d->q0.as<double2>(), d->q1.as<double2>(), d->r.as<double>(),
-                 d->gid.as<uint32_t>(), d->ghost_cap, sc, d->cand_state.as<SlabCandState>(), d->bp.params.as<GridParams>(), pa ) );
+      Ball2DSlabTraits::Src src;
+      src.q0 = d->q0.as<double2>(); src.q1 = d->q1.as<double2>(); src.r = d->r.as<double>(); src.gid = d->gid.as<uint32_t>();
+      SG_LAUNCH( ctx, "slab_pack", double( d->ghost_cap ) * 2.0 * 48.0, k_slab_pack2<Ball2DSlabTraits><<<grid, 256, 0, ctx->stream>>>( d->own_first(), d->own_count(), src, d->ghost_cap, sc, d->cand_state.as<SlabCandState>(),
+                 d->bp.params.as<GridParams>(), pa ) );
     }
   }
   if( phase == 0 || phase == 2 )
@@ -1764,7 +1584,7 @@ int sg_ball2d_slab_exchange( sg_ctx* ctx, int phase )
     {
       syncs[side].wait_flag = nullptr; syncs[side].post_flag = nullptr; syncs[side].done_ctr = nullptr; syncs[side].err = &mine->err; syncs[side].step = step;
       if( d->peer_mb[side] == nullptr ) { continue; }
-      recv[side] = slab_mailbox_halo( mine, side, d->ghost_cap );
+      recv[side] = slab_mailbox_halo<GhostRec>( mine, side, d->ghost_cap );
       syncs[side].wait_flag = &mine->halo_flag[side];
       any = true;
     }

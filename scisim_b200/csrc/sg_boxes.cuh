@@ -31,6 +31,7 @@ struct AabbPolicy
   static constexpr uint32_t IDX_MASK = 0xffffffffu;
   static constexpr uint32_t IDX_OFFSET = 16u * DIM;
   static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
+  static constexpr bool ORD_IN_REC = true;
   __device__ static void load_aabb( const In& in, const uint32_t i, double* lo, double* hi )
   {
     const double* b = in.boxes + size_t( i ) * 2 * DIM;

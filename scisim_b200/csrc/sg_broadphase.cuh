@@ -342,13 +342,13 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
 // it moves the 64-byte records only): the ORDER word of every record and, for the 2-D pipelines, its box rounded outward to floats.
 template<typename P>
 __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_side_arrays( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs,
-                                                                      uint32_t* __restrict__ sidx, float4* __restrict__ boxf )
+                                                                      uint32_t* __restrict__ sidx, float4* __restrict__ boxf, const uint32_t* __restrict__ ord_by_index )
 {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = min( n_slots, __ldg( &cell_start[params->ncells] ) ); // bodies actually binned
   if( p >= n ) { return; }
   const typename P::Rec r = sg_load_rec_global<typename P::Rec>( &recs[p] );
-  sidx[p] = P::rec_ord_raw( r );
+  sidx[p] = ( ord_by_index != nullptr ) ? __ldg( &ord_by_index[P::rec_idx( r )] ) : P::rec_ord_raw( r );
   if( P::D == 2 && boxf != nullptr )
   {
     double lo[P::D], hi[P::D];
@@ -567,7 +567,7 @@ __device__ __forceinline__ uint32_t sg_bp_fetch_ord( const typename P::Rec* __re
 {
   constexpr uint32_t CH = P::ORD_OFFSET / 16u, IN = P::ORD_OFFSET % 16u;
   const uint32_t slot = q - st->start[w];
-  if( STAGED || slot < st->len[w] )
+  if( P::ORD_IN_REC && ( STAGED || slot < st->len[w] ) )
   {
     const unsigned char* rec = s_recs + ( size_t( w ) * BpCfg<P::D>::WCAP + slot ) * 64;
     return *reinterpret_cast<const uint32_t*>( rec + ( ( CH ^ ( ( slot >> 1 ) & 3u ) ) << 4 ) + IN ) & P::IDX_MASK;
@@ -648,7 +648,8 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
     masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u );
     return;
   }
-  sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan, sidx );
+  const uint32_t my_ord = P::ORD_IN_REC ? P::rec_ord( me ) : ( __ldg( &sidx[p] ) & P::IDX_MASK );
+  sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, my_ord, counts, masks, plan, sidx );
 }
 
 // ---- pass 1, box-prefiltered and bulk-copy fed (D = 2) ------------------------------------------------
@@ -1326,7 +1327,7 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
   if( rc != SG_OK ) { return rc; }
   SG_LAUNCH( ctx, "bp_scatter", nb * ( P::IN_BYTES + 8.0 + 4.0 + 64.0 + 4.0 ) + double( s.max_cells ) * 4.0, sg_bp_scatter<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( in, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.key.as<uint32_t>(), s.rank.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.pos_of.as<uint32_t>(), s.cell_count.as<uint32_t>(), s.max_cells + 2u ) );
   SG_LAUNCH( ctx, "bp_side", nb * ( 64.0 + 4.0 + ( D == 2 ? 16.0 : 0.0 ) ), sg_bp_side_arrays<P><<<nblk, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(),
-             s.sidx.as<uint32_t>(), D == 2 ? s.boxf.as<float4>() : nullptr ) );
+             s.sidx.as<uint32_t>(), D == 2 ? s.boxf.as<float4>() : nullptr, s.ord_by_index ) );
   s.hist_clean = true;
   rc = SgBpCountLaunch<D>::template run<P>( ctx, s, n );
   if( rc != SG_OK ) { return rc; }

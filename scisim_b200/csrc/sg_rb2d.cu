@@ -60,6 +60,7 @@ struct Box2DPolicy
   static constexpr double IN_BYTES = 32.0;
   static constexpr uint32_t IDX_OFFSET = 32u;
   static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
+  static constexpr bool ORD_IN_REC = true;
   static constexpr uint32_t IDX_MASK = 0xffffffffu;
   using In = Box2DIn;
   using Rec = Box2DRec;

@@ -18,11 +18,13 @@
 //     contacts of a pair stay in the order the reference's routines produce them.
 #include "sg_boxbox.cuh"
 #include "sg_broadphase.cuh"
+#include "sg_slab.cuh"
 
 #include <cstdlib>
 #include <cuda.h> // CUtensorMap (types only; the encoder is fetched at run time through cudaGetDriverEntryPoint)
 
 #define SG_FIXED_BIT 0x80000000u
+#define SG_GHOST_BIT3 0x40000000u // slab mode: the record is a halo copy of a body another rank owns
 
 // ---- contact output (SoA, reference order) ---------------------------------------------------------
 struct ContactOut3D
@@ -35,13 +37,16 @@ struct ContactOut3D
   double* p;     // 3 per contact
   double* depth;
   unsigned long long cap;
+  GidMap gid; // multi-GPU slabs: local body slot -> global body index (identity on one GPU)
 };
 
 __device__ __forceinline__ void put_contact( const ContactOut3D& out, const unsigned long long k, const uint32_t type, const uint32_t i, const uint32_t j, const uint32_t aux,
                                              const V3d n, const V3d p, const double depth )
 {
   if( k >= out.cap ) { return; }
-  out.type[k] = type; out.i[k] = i; out.j[k] = j; out.aux[k] = aux;
+  // j is a body for the body-body types, a plane / cylinder number otherwise
+  const bool j_is_body = type <= SG_KINEMATIC_BODY_BODY || type == SG_SPHERE_SPHERE_TELEPORTED || type == SG_KINEMATIC_OBJECT_SPHERE_TELEPORTED;
+  out.type[k] = type; out.i[k] = out.gid( i ); out.j[k] = j_is_body ? out.gid( j ) : j; out.aux[k] = aux;
   out.n[3 * k] = n.x; out.n[3 * k + 1] = n.y; out.n[3 * k + 2] = n.z;
   out.p[3 * k] = p.x; out.p[3 * k + 1] = p.y; out.p[3 * k + 2] = p.z;
   out.depth[k] = depth;
@@ -100,6 +105,11 @@ struct Sphere3DIn
   const double* r;        // per body radius
   const uint32_t* flags;  // per body: SG_FIXED_BIT or 0
   uint32_t n;
+  // slab mode (multi-GPU): slots [0, n_owned) are this rank's bodies, [n_owned, n_owned + ghost_cap) / the next ghost_cap slots hold the
+  // halo copies from the lower / higher neighbour, ghost_counts[side] of them in use this step.  ghost_counts == nullptr: every slot is a body
+  uint32_t n_owned;
+  uint32_t ghost_cap;
+  const uint32_t* ghost_counts;
 };
 
 struct alignas( 64 ) Sphere3DRec
@@ -117,8 +127,9 @@ struct Sphere3DPolicy
   static constexpr bool HAS_NARROW = true;
   static constexpr double IN_BYTES = 32.0;
   static constexpr uint32_t IDX_OFFSET = 56u;
-  static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
-  static constexpr uint32_t IDX_MASK = 0x7fffffffu;
+  static constexpr uint32_t ORD_OFFSET = IDX_OFFSET;
+  static constexpr bool ORD_IN_REC = false; // the record is full: a body's order word (its global index in slab mode) lives in the dense sidx array only
+  static constexpr uint32_t IDX_MASK = 0x3fffffffu;
   using In = Sphere3DIn;
   using Rec = Sphere3DRec;
   using Out = ContactOut3D;
@@ -135,7 +146,7 @@ struct Sphere3DPolicy
     #pragma unroll
     for( int k = 0; k < 3; ++k ) { rec.x1[k] = __ldg( &in.q1[3 * size_t( i ) + k] ); rec.x0[k] = __ldg( &in.q0[3 * size_t( i ) + k] ); }
     rec.r = __ldg( &in.r[i] );
-    rec.idx = i | __ldg( &in.flags[i] );
+    rec.idx = i | __ldg( &in.flags[i] ) | ( ( in.ghost_counts != nullptr && i >= in.n_owned ) ? SG_GHOST_BIT3 : 0u );
     rec.key = key;
     return rec;
   }
@@ -149,8 +160,13 @@ struct Sphere3DPolicy
   __device__ static uint32_t rec_ord( const Rec& s ) { return rec_idx( s ); }
   __device__ static uint32_t rec_ord_raw( const Rec& s ) { return s.idx; }
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
-  __device__ static bool owns( const Rec& ) { return true; }
-  __device__ static bool valid( const In&, const uint32_t ) { return true; }
+  __device__ static bool owns( const Rec& s ) { return ( s.idx & SG_GHOST_BIT3 ) == 0u; }
+  __device__ static bool valid( const In& in, const uint32_t i )
+  {
+    if( in.ghost_counts == nullptr || i < in.n_owned ) { return true; }
+    const uint32_t k = i - in.n_owned;
+    return ( k < in.ghost_cap ) ? ( k < __ldg( &in.ghost_counts[0] ) ) : ( k - in.ghost_cap < __ldg( &in.ghost_counts[1] ) );
+  }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& g ) { return ( s.key / g.dims[0] ) % g.dims[1]; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& g ) { return s.key / ( g.dims[0] * g.dims[1] ); }
   __device__ static bool narrow_test( const Rec& a, const Rec& b )
@@ -180,6 +196,7 @@ struct Box3DPolicy
   static constexpr double IN_BYTES = 48.0;
   static constexpr uint32_t IDX_OFFSET = 48u;
   static constexpr uint32_t ORD_OFFSET = IDX_OFFSET; // bodies are ranked by their index
+  static constexpr bool ORD_IN_REC = true;
   static constexpr uint32_t IDX_MASK = 0xffffffffu;
   using In = Box3DIn;
   using Rec = Box3DRec;
@@ -242,6 +259,7 @@ struct alignas( 128 ) MeshDev // the descriptor is fetched from global memory by
 struct Rb3dDev
 {
   uint32_t n;
+  uint32_t n_live;         // bodies the body-plane loops visit: n, or this rank's own bodies in slab mode (the ghosts that follow them are not its to test)
   const uint32_t* btype;   // per body: geometry type | SG_FIXED_BIT
   const double* bparam;    // per body 4 doubles: sphere (r,-,-,-), box (hx,hy,hz,-)
   const uint32_t* bmesh;   // per body: mesh index (meshes only)
@@ -341,7 +359,7 @@ __device__ inline M3d dmv_rotation( const M3d& R0, const V3d am, const double h,
   double x = q1 + cm1 * q0 + cm3 * q2 - cm2 * q3;
   double y = q2 + cm2 * q0 + cm1 * q3 - cm3 * q1;
   double z = q3 + cm3 * q0 + cm2 * q1 - cm1 * q2;
-  const double nrm = sqrt( ( x * x + z * z ) + ( y * y + w * w ) ); // Eigen's packet reduction of the ( x, y, z, w ) coefficients: see oracle/rb3d.h solveDMV
+  const double nrm = sqrt( ( x * x + z * z ) + ( y * y + w * w ) ); // Eigen 3.3.4 sums the squared ( x, y, z, w ) coefficients by packets (Core/Redux.h: redux_vec_unroller + predux): ( x2 + z2 ) + ( y2 + w2 )
   x /= nrm; y /= nrm; z /= nrm; w /= nrm;
   // Quaternion::toRotationMatrix
   const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
@@ -404,12 +422,13 @@ __device__ inline void rb3d_flow_exponential_euler( const uint32_t b, const size
   vao[0] = w.x + dt * 0.0; vao[1] = w.y + dt * 0.0; vao[2] = w.z + dt * 0.0;
 }
 
-__global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind_flags, const uint32_t n, const double* __restrict__ q0, const double* __restrict__ v0, const double* __restrict__ mass,
+__global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind_flags, const uint32_t n, const uint32_t nrun, const double* __restrict__ q0, const double* __restrict__ v0, const double* __restrict__ mass,
                                                      const double* __restrict__ I0, const uint32_t* __restrict__ btype, const double gx, const double gy, const double gz, const double dt,
                                                      double* __restrict__ q1, double* __restrict__ v1 )
 {
+  // n = slots (the stride of the [3n | 9n] / [3n | 3n] layouts), nrun = bodies to integrate (the leading ones)
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if( b >= n ) { return; }
+  if( b >= nrun ) { return; }
   const int kind = kind_flags & 0xff;
   const size_t nb = n;
   const double m = __ldg( &mass[b] );
@@ -967,7 +986,7 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_plane_count( const Rb3dDev dev, 
   const ContactOut3D none = {};
   for( uint32_t pl = 0; pl < ng; ++pl )
   {
-    uint32_t c = ( b < dev.n ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
+    uint32_t c = ( b < dev.n_live ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
     #pragma unroll
     for( int d = 16; d > 0; d >>= 1 ) { c += __shfl_xor_sync( 0xffffffffu, c, d ); }
     if( ( threadIdx.x & 31 ) == 0 && c != 0u ) { atomicAdd( &s_cnt[pl], c ); }
@@ -990,7 +1009,7 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_plane_emit( const Rb3dDev dev, c
   for( uint32_t pl = 0; pl < ng; ++pl )
   {
     if( counts[pl * gridDim.x + blockIdx.x] == 0u ) { continue; }
-    const uint32_t c = ( b < dev.n ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
+    const uint32_t c = ( b < dev.n_live ) ? plane_contacts( dev, planes, pl, b, q0, q1, false, 0ull, none ) : 0u;
     // exclusive prefix of c over the block
     uint32_t incl = c;
     #pragma unroll
@@ -1002,6 +1021,112 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_plane_emit( const Rb3dDev dev, c
     for( int w = 0; w < warp; ++w ) { before += s_warp[w]; }
     if( c != 0u ) { plane_contacts( dev, planes, pl, b, q0, q1, true, base + offsets[pl * gridDim.x + blockIdx.x] + before, out ); }
   }
+}
+
+// ---- slab mode (multi-GPU, all-sphere scenes): what sg_slab.cuh needs to know about spheres -------------------------------------
+// A sphere's broad-phase box is taken at q1 only (RigidBodySphere::computeAABB through RigidBody3DSim::generateAABBs, RigidBody3DSim.cpp:1057-1069),
+// so its reach on x is [ x1.x - r, x1.x + r ]; the record carries x0 as well because the contact is built from the start-of-step positions.
+struct alignas( 16 ) SphereGhostRec { double x0[3]; double x1[3]; double r; uint32_t gid; uint32_t pad; };
+static_assert( sizeof( SphereGhostRec ) == 64, "sphere halo records are 64 bytes" );
+
+struct Sphere3DSlabTraits
+{
+  using Rec = SphereGhostRec;
+  struct Src { const double* q0; const double* q1; const double* r; const uint32_t* gid; };
+  __device__ static bool select( const Src& s, const uint32_t i, const double ilo, const double ihi, Rec& g )
+  {
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { g.x0[k] = __ldg( &s.q0[3 * size_t( i ) + k] ); g.x1[k] = __ldg( &s.q1[3 * size_t( i ) + k] ); }
+    g.r = __ldg( &s.r[i] ); g.gid = s.gid[i]; g.pad = 0u;
+    const double lo = g.x1[0] - g.r, hi = g.x1[0] + g.r;
+    return !( hi < ilo ) && !( ihi < lo );
+  }
+};
+
+// After the flow: [min lo.x, max hi.x] over this rank's spheres for the neighbours, the x-limit guard (a sphere outside could touch a body two
+// slabs away: SG_ERR_REBALANCE), and the candidate lists for the halo pack (see SlabCand in sg_slab.cuh).
+__global__ void __launch_bounds__( 256 ) k_rb3d_slab_scan( const uint32_t n_owned, const double* __restrict__ q1, const double* __restrict__ r, long long* __restrict__ interval_enc,
+                                                          const double xlim_lo, const double xlim_hi, uint32_t* __restrict__ slab_flags, const SlabCand sc )
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n_owned;
+  double lo = __longlong_as_double( 0x7ff0000000000000LL ), hi = __longlong_as_double( 0xfff0000000000000LL );
+  if( live )
+  {
+    const double x = __ldg( &q1[3 * size_t( i )] ), rad = __ldg( &r[i] );
+    lo = x - rad; hi = x + rad;
+    if( lo < xlim_lo || hi > xlim_hi ) { slab_flags[3] = 1u; }
+  }
+  const int lane = threadIdx.x & 31;
+  if( sc.band != nullptr )
+  {
+    #pragma unroll
+    for( int sd = 0; sd < 2; ++sd )
+    {
+      if( !sc.on[sd] ) { continue; }
+      const bool c = live && ( ( sd == 0 ) ? ( lo <= sc.band[0] ) : ( hi >= sc.band[1] ) );
+      const unsigned bal = __ballot_sync( 0xffffffffu, c );
+      if( bal != 0u )
+      {
+        uint32_t base = 0u;
+        if( lane == __ffs( bal ) - 1 ) { base = atomicAdd( &sc.count[sd], uint32_t( __popc( bal ) ) ); }
+        base = __shfl_sync( 0xffffffffu, base, __ffs( bal ) - 1 );
+        const uint32_t k = base + __popc( bal & ( ( 1u << lane ) - 1u ) );
+        if( c && k < sc.cap ) { sc.list[sd][k] = i; }
+      }
+    }
+  }
+  __shared__ double s_iv[8][2];
+  #pragma unroll
+  for( int dd = 16; dd > 0; dd >>= 1 ) { lo = fmin( lo, __shfl_xor_sync( 0xffffffffu, lo, dd ) ); hi = fmax( hi, __shfl_xor_sync( 0xffffffffu, hi, dd ) ); }
+  if( lane == 0 ) { s_iv[threadIdx.x >> 5][0] = lo; s_iv[threadIdx.x >> 5][1] = hi; }
+  __syncthreads();
+  if( threadIdx.x == 0 )
+  {
+    for( int w = 1; w < 8; ++w ) { lo = fmin( lo, s_iv[w][0] ); hi = fmax( hi, s_iv[w][1] ); }
+    if( lo <= hi )
+    {
+      atomicMin( &interval_enc[0], sg_ordered_from_double( lo ) );
+      atomicMax( &interval_enc[1], sg_ordered_from_double( hi ) );
+    }
+  }
+}
+
+// Halo records from the neighbours' mailboxes into the ghost slots behind the owned bodies (first half of the grid: side 0, second: side 1)
+struct SphereUnpackArgs
+{
+  const SphereGhostRec* in[2];
+  const uint32_t* wait[2];
+  bool on[2];
+  uint32_t* err;
+  uint32_t step;
+};
+__global__ void __launch_bounds__( 256 ) k_rb3d_slab_unpack( const uint32_t cap, const uint32_t blocks_per_side, const SphereUnpackArgs args, const uint32_t n_owned, double* __restrict__ q0, double* __restrict__ q1,
+                                                            double* __restrict__ radius, uint32_t* __restrict__ gid, uint32_t* __restrict__ ghost_counts )
+{
+  const int side = ( blockIdx.x >= blocks_per_side ) ? 1 : 0;
+  if( !args.on[side] ) { return; }
+  if( threadIdx.x == 0 ) { slab_wait_flag( args.wait[side], args.step, args.err ); }
+  __syncthreads();
+  const SphereGhostRec* in = args.in[side];
+  const uint32_t blk = blockIdx.x - uint32_t( side ) * blocks_per_side;
+  const uint32_t k = blk * blockDim.x + threadIdx.x;
+  const uint32_t sent = *reinterpret_cast<const volatile uint32_t*>( &in[0].gid );
+  const uint32_t count = sent < cap ? sent : cap;
+  if( k == 0u )
+  {
+    ghost_counts[side] = count;
+    if( sent > cap ) { ghost_counts[2] = 1u; } // more ghosts than reserved slots: reported by detect
+  }
+  if( k >= count ) { return; }
+  const int4* src = reinterpret_cast<const int4*>( &in[1u + k] );
+  union { SphereGhostRec g; int4 v[4]; } u;
+  u.v[0] = src[0]; u.v[1] = src[1]; u.v[2] = src[2]; u.v[3] = src[3];
+  const size_t slot = size_t( n_owned ) + size_t( side ) * cap + k;
+  #pragma unroll
+  for( int c = 0; c < 3; ++c ) { q0[3 * slot + c] = u.g.x0[c]; q1[3 * slot + c] = u.g.x1[c]; }
+  radius[slot] = u.g.r;
+  gid[slot] = u.g.gid;
 }
 
 // small helper kernels
@@ -1090,6 +1215,7 @@ struct Rb3dData
   uint64_t n_cand = 0, n_bb = 0, n_static = 0;
   bool have_result = false, cand_valid = false;
   Rb3dPortalData* px = nullptr; // allocated by sg_rb3d_set_portals
+  SlabComm slab;                // multi-GPU slab mode (all-sphere scenes): slots [0, n_owned) are this rank's bodies, 2 x ghost_cap halo slots follow
   Rb3dData() { memset( &planes, 0, sizeof( planes ) ); }
 };
 
@@ -1105,6 +1231,7 @@ void sg_rb3d_release( sg_ctx* ctx )
   for( DevBuf* b : bufs ) { b->release(); }
   d->bp.release();
   d->h_totals.release(); d->h_out.release();
+  d->slab.release();
   if( d->px != nullptr ) { d->px->release(); delete d->px; d->px = nullptr; }
   delete d;
   ctx->rb3d = nullptr;
@@ -1120,6 +1247,7 @@ static Rb3dDev rb3d_dev( const Rb3dData* d )
 {
   Rb3dDev dev;
   dev.n = d->n;
+  dev.n_live = d->slab.on ? d->slab.n_owned : d->n;
   dev.btype = d->btype.as<uint32_t>();
   dev.bparam = d->bparam.as<double>();
   dev.bmesh = d->bmesh.as<uint32_t>();
@@ -1134,6 +1262,7 @@ static ContactOut3D rb3d_out( const Rb3dData* d )
   out.type = d->c_type.as<uint32_t>(); out.i = d->c_i.as<uint32_t>(); out.j = d->c_j.as<uint32_t>(); out.aux = d->c_aux.as<uint32_t>();
   out.n = d->c_n.as<double>(); out.p = d->c_p.as<double>(); out.depth = d->c_depth.as<double>();
   out.cap = d->act_cap;
+  if( d->slab.on ) { out.gid.gid = d->slab.gid.as<uint32_t>(); }
   return out;
 }
 
@@ -1163,7 +1292,8 @@ static int rb3d_flow_device( sg_ctx* ctx, Rb3dData* d, const int map_kind, const
   const uint32_t n = d->n;
   if( n == 0 ) { return SG_OK; }
   d->q1_valid = true;
-  SG_LAUNCH( ctx, "rb3d_flow", double( n ) * 336.0, k_rb3d_flow<<<sg_div_up( n, 128 ), 128, 0, ctx->stream>>>( map_kind, n, d->q0.as<double>(), d->v0.as<double>(), d->mass.as<double>(), d->I0.as<double>(),
+  const uint32_t nrun = d->slab.on ? d->slab.n_owned : n;
+  SG_LAUNCH( ctx, "rb3d_flow", double( nrun ) * 336.0, k_rb3d_flow<<<sg_div_up( nrun > 0 ? nrun : 1, 128 ), 128, 0, ctx->stream>>>( map_kind, n, nrun, d->q0.as<double>(), d->v0.as<double>(), d->mass.as<double>(), d->I0.as<double>(),
              d->btype.as<uint32_t>(), d->g[0], d->g[1], d->g[2], dt, d->q1.as<double>(), d->v1.as<double>() ) );
   return SG_OK;
 }
@@ -1227,6 +1357,8 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
     if( rc != SG_OK ) { return rc; }
     Sphere3DIn in;
     in.q0 = d->q0.as<double>(); in.q1 = d->q1.as<double>(); in.r = d->radius.as<double>(); in.flags = d->flags.as<uint32_t>(); in.n = n;
+    in.n_owned = d->slab.on ? d->slab.n_owned : n; in.ghost_cap = d->slab.ghost_cap; in.ghost_counts = d->slab.on ? d->slab.ghost_counts.as<uint32_t>() : nullptr;
+    d->bp.ord_by_index = d->slab.on ? d->slab.gid.as<uint32_t>() : nullptr;
     rc = sg_bp_bin_and_count<Sphere3DPolicy>( ctx, d->bp, in );
     if( rc != SG_OK ) { return rc; }
     rc = rb3d_planes_device( ctx, d, false );
@@ -1678,6 +1810,7 @@ int sg_rb3d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, co
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   Rb3dData* d = rb3d_data( ctx );
   d->n = n;
+  d->slab.on = false; // a plain body table: back to the single-GPU calls (sg_rb3d_slab_init re-enters slab mode)
   d->have_result = false;
   d->flow_resident = false;
   d->q1_valid = false;
@@ -1903,6 +2036,20 @@ int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v )
   if( d->n == 0 ) { return SG_OK; }
   if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_upload: null vector" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->slab.on )
+  {
+    // the caller's vectors hold the owned bodies only; on the device the [3n | 9n] / [3n | 3n] blocks are spaced by the slot count
+    const size_t no = d->slab.n_owned, ns = d->n;
+    if( no > 0 )
+    {
+      SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q, no * 24, cudaMemcpyHostToDevice, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( d->q0.as<double>() + 3 * ns, q + 3 * no, no * 72, cudaMemcpyHostToDevice, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v, no * 24, cudaMemcpyHostToDevice, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( d->v0.as<double>() + 3 * ns, v + 3 * no, no * 24, cudaMemcpyHostToDevice, ctx->stream ) );
+    }
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    return SG_OK;
+  }
   SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q, size_t( d->n ) * 96, cudaMemcpyHostToDevice, ctx->stream ) );
   SG_CUDA( ctx, cudaMemcpyAsync( d->v0.ptr, v, size_t( d->n ) * 48, cudaMemcpyHostToDevice, ctx->stream ) );
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
@@ -1914,6 +2061,7 @@ int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_SPLIT_HAM && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_DMV && ( map_kind & ~SG_MAP_M_UPDATED ) != SG_MAP_EXPONENTIAL_EULER ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: map kind %d is not a rigidbody3d map", map_kind ); }
   Rb3dData* d = rb3d_data( ctx );
+  if( d->slab.on ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_step: context is in slab mode, use the sg_rb3d_slab_* calls" ); }
   d->flow_resident = false; // q1 is about to be overwritten by the resident step
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   int rc = rb3d_flow_device( ctx, d, map_kind, dt );
@@ -1954,10 +2102,206 @@ int sg_rb3d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_c
   Rb3dData* d = rb3d_data( ctx );
   if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_fetch: no step has been run" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
-  if( q1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, size_t( d->n ) * 96, cudaMemcpyDeviceToHost, ctx->stream ) ); }
-  if( v1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 48, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  if( d->slab.on )
+  {
+    const size_t no = d->slab.n_owned, ns = d->n;
+    if( q1 != nullptr && no > 0 )
+    {
+      SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, no * 24, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( q1 + 3 * no, d->q1.as<double>() + 3 * ns, no * 72, cudaMemcpyDeviceToHost, ctx->stream ) );
+    }
+    if( v1 != nullptr && no > 0 )
+    {
+      SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, no * 24, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( v1 + 3 * no, d->v1.as<double>() + 3 * ns, no * 24, cudaMemcpyDeviceToHost, ctx->stream ) );
+    }
+  }
+  else
+  {
+    if( q1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( q1, d->q1.ptr, size_t( d->n ) * 96, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+    if( v1 != nullptr && d->n > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( v1, d->v1.ptr, size_t( d->n ) * 48, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  }
   if( out != nullptr ) { return rb3d_copy_out( ctx, d, out_flags, out ); }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+
+// ---- slab mode (multi-GPU), all-sphere scenes: the calls of the ball2d slab mode for rigidbody3d --------------------------------
+// One spatial slab of a larger scene per context: n_owned spheres in ascending global index in slots [0, n_owned), then ghost_cap halo
+// slots for the lower neighbour and ghost_cap for the higher one.  q, v of sg_rb3d_upload / sg_rb3d_fetch address the owned bodies
+// ( [3 n_owned | 9 n_owned], [3 n_owned | 3 n_owned] ).  Peer-memory exchange only (sg_slab.cuh); DESIGN.md section 5.
+int sg_rb3d_slab_init( sg_ctx* ctx, uint32_t n_owned, uint32_t ghost_cap, const uint32_t* geo_of_body, const double* m, const double* I0, const uint32_t* gid_owned, const double* x_limits )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  if( n_owned > 0 && ( geo_of_body == nullptr || m == nullptr || I0 == nullptr || gid_owned == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_init: null array" ); }
+  if( uint64_t( n_owned ) + 2ull * ghost_cap >= 0x40000000ull ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_init: slab too large" ); }
+  Rb3dData* d = rb3d_data( ctx );
+  if( d->px != nullptr && d->px->portals.n > 0u ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_slab_init: portals are not supported in slab mode" ); }
+  if( d->geo_type.empty() ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_init: call sg_rb3d_set_geometry first" ); }
+  for( uint32_t k = 0; k < n_owned; ++k )
+  {
+    if( gid_owned[k] >= 0x40000000u || ( k > 0 && gid_owned[k] <= gid_owned[k - 1] ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_init: global indices must be strictly ascending and below 2^30 (entry %u)", k ); }
+  }
+  const size_t slots = size_t( n_owned ) + 2 * size_t( ghost_cap );
+  // every slot gets a body: the ghosts are spheres of the first geometry until a halo record overwrites their radius
+  uint32_t sphere_geo = 0u;
+  while( sphere_geo < d->geo_type.size() && d->geo_type[sphere_geo] != SG_GEO_SPHERE ) { ++sphere_geo; }
+  if( sphere_geo == d->geo_type.size() ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_slab_init: slab mode is for all-sphere scenes" ); }
+  std::vector<uint32_t> geo( slots, sphere_geo );
+  std::vector<uint8_t> fixed( slots, 0 );
+  std::vector<double> mm( slots, 1.0 ), ii( 3 * slots, 1.0 );
+  for( uint32_t k = 0; k < n_owned; ++k ) { geo[k] = geo_of_body[k]; mm[k] = m[k]; ii[3 * size_t( k )] = I0[3 * size_t( k )]; ii[3 * size_t( k ) + 1] = I0[3 * size_t( k ) + 1]; ii[3 * size_t( k ) + 2] = I0[3 * size_t( k ) + 2]; }
+  d->slab.on = false;
+  int rc = sg_rb3d_set_bodies( ctx, uint32_t( slots ), geo.data(), fixed.data(), mm.data(), ii.data() );
+  if( rc != SG_OK ) { return rc; }
+  if( !d->all_spheres ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_slab_init: slab mode is for all-sphere scenes" ); }
+  SlabComm& c = d->slab;
+  c.on = true; c.n_owned = n_owned; c.ghost_cap = ghost_cap; c.rec_bytes = sizeof( SphereGhostRec ); c.scan_done = false;
+  c.xlim[0] = ( x_limits != nullptr ) ? x_limits[0] : -1.0e308; c.xlim[1] = ( x_limits != nullptr ) ? x_limits[1] : 1.0e308;
+  SG_CUDA( ctx, c.gid.ensure( slots * 4 + 4 ) );
+  SG_CUDA( ctx, c.interval_enc.ensure( 16 ) );
+  SG_CUDA( ctx, c.ghost_counts.ensure( 16 ) );
+  SG_CUDA( ctx, cudaMemsetAsync( c.gid.ptr, 0, slots * 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( c.ghost_counts.ptr, 0, 16, ctx->stream ) );
+  if( n_owned > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( c.gid.ptr, gid_owned, size_t( n_owned ) * 4, cudaMemcpyHostToDevice, ctx->stream ) ); }
+  k_slab_begin<<<1, 1, 0, ctx->stream>>>( c.interval_enc.as<long long>(), c.ghost_counts.as<uint32_t>() );
+  // the orientation slots of the ghosts are never read; zero the state once so that nothing uninitialised travels
+  SG_CUDA( ctx, cudaMemsetAsync( d->q0.ptr, 0, slots * 96, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->q1.ptr, 0, slots * 96, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->v0.ptr, 0, slots * 48, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( d->v1.ptr, 0, slots * 48, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  return SG_OK;
+}
+
+int sg_rb3d_slab_flow( sg_ctx* ctx, int map_kind, double dt )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( !d->slab.on ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_flow: call sg_rb3d_slab_init first" ); }
+  if( d->slab.mailbox.ptr == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_flow: create the mailbox first (sg_rb3d_slab_mailbox)" ); }
+  const int k = map_kind & ~SG_MAP_M_UPDATED;
+  if( k != SG_MAP_SPLIT_HAM && k != SG_MAP_DMV && k != SG_MAP_EXPONENTIAL_EULER ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_flow: map kind %d is not a rigidbody3d map", map_kind ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SlabComm& c = d->slab;
+  const int rc = rb3d_flow_device( ctx, d, map_kind, dt );
+  if( rc != SG_OK ) { return rc; }
+  const SlabCand sc = c.cand();
+  if( sc.band != nullptr ) { SG_CUDA( ctx, cudaMemsetAsync( sc.count, 0, 8, ctx->stream ) ); }
+  SG_LAUNCH( ctx, "slab_scan", double( c.n_owned ) * 16.0, k_rb3d_slab_scan<<<sg_div_up( c.n_owned > 0 ? c.n_owned : 1, 256 ), 256, 0, ctx->stream>>>( c.n_owned, d->q1.as<double>(), d->radius.as<double>(),
+             c.interval_enc.as<long long>(), c.xlim[0], c.xlim[1], c.ghost_counts.as<uint32_t>(), sc ) );
+  ++c.step;
+  SG_LAUNCH( ctx, "slab_interval", 16.0, k_slab_post_interval<<<1, 1, 0, ctx->stream>>>( c.interval_enc.as<long long>(), c.ghost_counts.as<uint32_t>(), nullptr, static_cast<SlabMailboxHdr*>( c.peer_mb[0] ),
+             static_cast<SlabMailboxHdr*>( c.peer_mb[1] ), c.step ) );
+  c.scan_done = true;
+  return SG_OK;
+}
+
+int sg_rb3d_slab_mailbox( sg_ctx* ctx, void** mailbox_dev, void* ipc_handle_64 )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( !d->slab.on ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_mailbox: call sg_rb3d_slab_init first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  return slab_comm_mailbox( ctx, d->slab, mailbox_dev, ipc_handle_64 );
+}
+
+int sg_rb3d_slab_connect( sg_ctx* ctx, int side, const void* ipc_handle_64, void* same_process_mailbox, int peer_device )
+{
+  if( ctx == nullptr || ( side != 0 && side != 1 ) || ( ipc_handle_64 == nullptr ) == ( same_process_mailbox == nullptr ) ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( !d->slab.on || d->slab.mailbox.ptr == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_connect: create this rank's mailbox first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  return slab_comm_connect( ctx, d->slab, side, ipc_handle_64, same_process_mailbox, peer_device );
+}
+
+int sg_rb3d_slab_disconnect( sg_ctx* ctx )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  return slab_comm_disconnect( ctx, d->slab );
+}
+
+// phase 1: wait for the neighbours' intervals, pack the spheres that reach them straight into their mailboxes; phase 2: wait for the
+// neighbours' halos and move them into the ghost slots; phase 0: both
+int sg_rb3d_slab_exchange( sg_ctx* ctx, int phase )
+{
+  if( ctx == nullptr || phase < 0 || phase > 2 ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  SlabComm& c = d->slab;
+  if( !c.on || c.mailbox.ptr == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_exchange: no mailbox" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  SlabMailboxHdr* mine = c.mailbox.as<SlabMailboxHdr>();
+  const bool any = c.peer_mb[0] != nullptr || c.peer_mb[1] != nullptr;
+  if( ( phase == 0 || phase == 1 ) && any )
+  {
+    if( !c.scan_done ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_exchange: call sg_rb3d_slab_flow first" ); }
+    Pack2Args<SphereGhostRec> pa;
+    for( int side = 0; side < 2; ++side )
+    {
+      pa.on[side] = c.peer_mb[side] != nullptr;
+      pa.iv[side] = &mine->iv[side][0]; pa.wait[side] = &mine->iv_flag[side]; pa.out[side] = nullptr; pa.post[side] = nullptr;
+      if( !pa.on[side] ) { continue; }
+      SlabMailboxHdr* peer = static_cast<SlabMailboxHdr*>( c.peer_mb[side] );
+      pa.out[side] = slab_mailbox_halo<SphereGhostRec>( peer, 1 - side, c.ghost_cap );
+      pa.post[side] = &peer->halo_flag[1 - side];
+    }
+    pa.err = &mine->err; pa.step = c.step;
+    Sphere3DSlabTraits::Src src;
+    src.q0 = d->q0.as<double>(); src.q1 = d->q1.as<double>(); src.r = d->radius.as<double>(); src.gid = c.gid.as<uint32_t>();
+    SG_LAUNCH( ctx, "slab_pack", double( c.ghost_cap ) * 2.0 * 64.0, k_slab_pack2<Sphere3DSlabTraits><<<unsigned( ctx->num_sms ), 256, 0, ctx->stream>>>( 0u, c.n_owned, src, c.ghost_cap, c.cand(), c.cand_state.as<SlabCandState>(),
+               d->bp.params.as<GridParams>(), pa ) );
+  }
+  if( ( phase == 0 || phase == 2 ) && any )
+  {
+    SphereUnpackArgs ua;
+    for( int side = 0; side < 2; ++side )
+    {
+      ua.on[side] = c.peer_mb[side] != nullptr;
+      ua.in[side] = slab_mailbox_halo<SphereGhostRec>( mine, side, c.ghost_cap );
+      ua.wait[side] = &mine->halo_flag[side];
+    }
+    ua.err = &mine->err; ua.step = c.step;
+    const unsigned bps = sg_div_up( c.ghost_cap > 0 ? c.ghost_cap : 1, 256 );
+    SG_LAUNCH( ctx, "slab_unpack", double( c.ghost_cap ) * 4.0, k_rb3d_slab_unpack<<<2 * bps, 256, 0, ctx->stream>>>( c.ghost_cap, bps, ua, c.n_owned, d->q0.as<double>(), d->q1.as<double>(), d->radius.as<double>(),
+               c.gid.as<uint32_t>(), c.ghost_counts.as<uint32_t>() ) );
+  }
+  return SG_OK;
+}
+
+int sg_rb3d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  SlabComm& c = d->slab;
+  if( !c.on ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_slab_detect: call sg_rb3d_slab_init first" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->bp.params.ptr == nullptr ) { SG_CUDA( ctx, d->bp.params.ensure( sizeof( GridParams ) ) ); SG_CUDA( ctx, cudaMemsetAsync( d->bp.params.ptr, 0, sizeof( GridParams ), ctx->stream ) ); }
+  const int rc = rb3d_active_set_device( ctx, d, true );
+  if( rc != SG_OK ) { return rc; }
+  c.scan_done = false;
+  uint32_t hg[4];
+  SG_CUDA( ctx, cudaMemcpy( hg, c.ghost_counts.ptr, 16, cudaMemcpyDeviceToHost ) );
+  if( hg[2] != 0u ) { return sg_fail( ctx, SG_ERR_INVALID, "slab halo exceeds the reserved ghost capacity %u: results are incomplete", c.ghost_cap ); }
+  if( hg[3] != 0u ) { return sg_fail( ctx, SG_ERR_REBALANCE, "a body of this slab left [%g, %g]: it may reach a non-neighbouring slab, re-partition the scene", c.xlim[0], c.xlim[1] ); }
+  if( c.mailbox.ptr != nullptr )
+  {
+    uint32_t err = 0u;
+    SG_CUDA( ctx, cudaMemcpy( &err, &c.mailbox.as<SlabMailboxHdr>()->err, 4, cudaMemcpyDeviceToHost ) );
+    if( err != 0u ) { return sg_fail( ctx, SG_ERR_INTERNAL, "slab exchange: a neighbour did not post its interval or halo within 10 s" ); }
+  }
+  if( ghosts_out != nullptr ) { ghosts_out[0] = hg[0]; ghosts_out[1] = hg[1]; }
+  if( out != nullptr )
+  {
+    memset( out, 0, sizeof( *out ) );
+    out->dim = 3;
+    out->n_candidates = d->n_cand;
+    out->n_body_body = d->n_bb;
+    out->n_plane = d->n_static;
+    out->n_active = d->n_bb + d->n_static;
+  }
   return SG_OK;
 }
 

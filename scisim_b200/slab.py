@@ -24,6 +24,8 @@ import ctypes as C
 import numpy as np
 
 REC_BYTES = 48
+# contact types whose j is a static geometry (drum, plane, cylinder), not a body: include/scisim_b200.h
+STATIC_TYPES = np.array([1, 2, 14, 15, 16, 17, 18, 23, 24], dtype=np.uint32)
 
 
 class RebalanceNeeded(RuntimeError):
@@ -93,7 +95,7 @@ def merge_active_sets(parts, n_static_geoms=None, n_bodies=None):
     if n_bodies is None:
         n_bodies = 1
         for p in parts:
-            for a in (p["candidates"], p["i"], p["j"][p["type"] == 0]):
+            for a in (p["candidates"], p["i"], p["j"][~np.isin(p["type"], STATIC_TYPES)]):
                 if a.size:
                     n_bodies = max(n_bodies, int(a.max()) + 1)
     cands = [np.ascontiguousarray(p["candidates"], dtype=np.uint32).reshape(-1, 2) for p in parts]
@@ -102,10 +104,11 @@ def merge_active_sets(parts, n_static_geoms=None, n_bodies=None):
     out["candidates"] = np.zeros((total, 2), dtype=np.uint32)
     for c, d in zip(cands, dests):
         out["candidates"][d] = c
-    keys = ("type", "i", "j", "n", "p", "depth")
-    nbb = [int(np.count_nonzero(p["type"] == 0)) for p in parts]
+    keys = tuple(k for k in ("type", "i", "j", "aux", "n", "p", "depth") if k in parts[0] and parts[0][k] is not None)
+    static = lambda t: np.isin(t, STATIC_TYPES)
+    nbb = [int(np.count_nonzero(~static(p["type"]))) for p in parts]
     for p, k in zip(parts, nbb):
-        assert np.all(p["type"][:k] == 0), "ball-ball contacts come first in a rank's list"
+        assert not np.any(static(p["type"][:k])), "body-body contacts come first in a rank's list"
     bb_dest = _merge_dest(n_bodies, [p["i"][:k] for p, k in zip(parts, nbb)], 1)
     n_bb = sum(nbb)
     # static contacts: (type, geometry, body)
@@ -432,4 +435,207 @@ class Ball2DSlabSim:
             q1g.reshape(-1, 2)[p["gids"]] = p["q1"].reshape(-1, 2)
             v1g.reshape(-1, 2)[p["gids"]] = p["v1"].reshape(-1, 2)
         merged["q1"], merged["v1"] = q1g, v1g
+        return merged
+
+
+# ---- rigidbody3d (all-sphere scenes: BASELINE configs[3]) ---------------------------------------------------------------------------
+class RB3DSlabBackend:
+    """One slab of an all-sphere rigidbody3d scene on one GPU through the sg_rb3d_slab_* calls (peer-memory exchange only)."""
+
+    def __init__(self, ctx, scene, gids, x_limits, ghost_cap):
+        """scene: the WHOLE scene's static description (geometry list, geo_of_body, m, I0, g, planes); gids: this rank's bodies, ascending."""
+        self.ctx, self.lib = ctx, ctx.lib
+        self.cap = int(ghost_cap)
+        s = scene
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        gt = np.ascontiguousarray(s["geo_type"], dtype=np.uint32)
+        gr, gh = np.ascontiguousarray(s["geo_r"], dtype=np.float64), np.ascontiguousarray(s["geo_half"], dtype=np.float64)
+        gm = np.ascontiguousarray(s["geo_mesh"], dtype=np.uint32)
+        ctx.check(self.lib.sg_rb3d_set_geometry(ctx.h, gt.shape[0], vp(gt), vp(gr), vp(gh), vp(gm)))
+        g = np.ascontiguousarray(s["g"], dtype=np.float64)
+        ctx.check(self.lib.sg_rb3d_set_gravity(ctx.h, vp(g)))
+        px, pn = np.ascontiguousarray(s["plane_x"], dtype=np.float64), np.ascontiguousarray(s["plane_n"], dtype=np.float64)
+        ctx.check(self.lib.sg_rb3d_set_planes(ctx.h, px.shape[0], vp(px), vp(pn)))
+        self.reinit(scene, gids, x_limits)
+
+    def reinit(self, scene, gids, x_limits):
+        ctx = self.ctx
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        self.n_owned = self.gids.shape[0]
+        geo = np.ascontiguousarray(np.asarray(scene["geo_of_body"])[self.gids], dtype=np.uint32)
+        m = np.ascontiguousarray(np.asarray(scene["m"])[self.gids], dtype=np.float64)
+        I0 = np.ascontiguousarray(np.asarray(scene["I0"]).reshape(-1, 3)[self.gids], dtype=np.float64)
+        lim = np.ascontiguousarray(x_limits, dtype=np.float64)
+        if np.any(np.asarray(scene["fixed"])[self.gids]):
+            raise RuntimeError("kinematically scripted bodies are not supported in slab mode")
+        ctx.check(self.lib.sg_rb3d_slab_init(ctx.h, self.n_owned, self.cap, vp(geo), vp(m), vp(I0), vp(self.gids), vp(lim)))
+
+    def upload(self, q_owned, v_owned):
+        q, v = np.ascontiguousarray(q_owned, dtype=np.float64), np.ascontiguousarray(v_owned, dtype=np.float64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.ctx.check(self.lib.sg_rb3d_upload(self.ctx.h, vp(q), vp(v)))
+
+    def mailbox(self):
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self.ctx.check(self.lib.sg_rb3d_slab_mailbox(self.ctx.h, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def connect(self, side, ipc_handle=None, same_process_ptr=None, peer_device=-1):
+        h = (C.c_ubyte * 64).from_buffer_copy(ipc_handle) if ipc_handle is not None else None
+        self.ctx.check(self.lib.sg_rb3d_slab_connect(self.ctx.h, int(side), h, C.c_void_p(same_process_ptr) if same_process_ptr is not None else None, int(peer_device)))
+
+    def disconnect(self):
+        self.ctx.check(self.lib.sg_rb3d_slab_disconnect(self.ctx.h))
+
+    def flow(self, kind, dt):
+        self.ctx.check(self.lib.sg_rb3d_slab_flow(self.ctx.h, int(kind), float(dt)))
+
+    def exchange(self, phase=0):
+        self.ctx.check(self.lib.sg_rb3d_slab_exchange(self.ctx.h, int(phase)))
+
+    def detect(self):
+        from ._lib import SG_ERR_REBALANCE, SgContacts
+        c = SgContacts()
+        g = (C.c_uint32 * 2)()
+        rc = self.lib.sg_rb3d_slab_detect(self.ctx.h, C.byref(c), g)
+        if rc == SG_ERR_REBALANCE:
+            raise RebalanceNeeded(self.lib.sg_last_error(self.ctx.h).decode())
+        self.ctx.check(rc)
+        self.ghosts = (int(g[0]), int(g[1]))
+        return int(c.n_candidates), int(c.n_active)
+
+    def fetch(self):
+        from ._lib import SG_OUT_ALL, SgContacts
+        from .host_api import ActiveSet
+        q1, v1 = np.empty(12 * self.n_owned), np.empty(6 * self.n_owned)
+        c = SgContacts()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.ctx.check(self.lib.sg_rb3d_fetch(self.ctx.h, SG_OUT_ALL, vp(q1), vp(v1), C.byref(c)))
+        a = ActiveSet(c)
+        return q1, v1, {"type": a.type, "i": a.i, "j": a.j, "aux": a.aux, "n": a.n, "p": a.p, "depth": a.depth, "candidates": a.candidates}
+
+
+def rb3d_owned_state(q, v, gids):
+    """The owned bodies' ( q, v ) in the layout of a smaller scene: q = [3 n | 9 n], v = [3 n | 3 n]."""
+    n = q.shape[0] // 12
+    x, R = q[:3 * n].reshape(n, 3), q[3 * n:].reshape(n, 9)
+    vl, w = v[:3 * n].reshape(n, 3), v[3 * n:].reshape(n, 3)
+    return np.concatenate([x[gids].ravel(), R[gids].ravel()]), np.concatenate([vl[gids].ravel(), w[gids].ravel()])
+
+
+def rb3d_scatter_state(n, parts):
+    """Inverse of rb3d_owned_state over all ranks: parts = [(gids, q_owned, v_owned)]."""
+    q, v = np.zeros(12 * n), np.zeros(6 * n)
+    for gids, qo, vo in parts:
+        k = gids.shape[0]
+        q[:3 * n].reshape(n, 3)[gids] = qo[:3 * k].reshape(k, 3)
+        q[3 * n:].reshape(n, 9)[gids] = qo[3 * k:].reshape(k, 9)
+        v[:3 * n].reshape(n, 3)[gids] = vo[:3 * k].reshape(k, 3)
+        v[3 * n:].reshape(n, 3)[gids] = vo[3 * k:].reshape(k, 3)
+    return q, v
+
+
+def partition_quantiles_3d(q, world):
+    """x-quantile slabs of a rigidbody3d scene ( q = [3N positions | 9N rotations] )."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    n = q.shape[0] // 12
+    rank_of = np.zeros(n, dtype=np.uint32)
+    cuts = np.zeros(world + 1, dtype=np.float64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _lib().sg_slab_partition(n, vp(q), 3, world, vp(rank_of), vp(cuts))
+    if rc != 0:
+        raise RuntimeError("sg_slab_partition failed (%d)" % rc)
+    return rank_of, cuts, [np.nonzero(rank_of == k)[0].astype(np.uint32) for k in range(world)]
+
+
+class RB3DSlabSim:
+    """One rank's handle on a WHOLE all-sphere rigidbody3d scene spread over `world` ranks, one process per GPU (CUDA IPC mailboxes):
+    the counterpart of Ball2DSlabSim.  upload() takes the global state and partitions it (deterministically, the same on every rank)."""
+
+    def __init__(self, ctx, scene, rank, world, dist, ghost_cap=None, agree=True):
+        self.ctx, self.scene, self.rank, self.world, self.dist = ctx, scene, rank, world, dist
+        self.ghost_cap, self.agree = ghost_cap, agree
+        self.backend = None
+        self.n = int(np.asarray(scene["m"]).shape[0])
+        self.n_partitions = 0
+        self.last_halo = (0, 0)
+
+    def _partition(self, q, v):
+        rank_of, cuts, gids = partition_quantiles_3d(q, self.world)
+        self.gids = gids[self.rank]
+        lim = slab_limits(cuts, self.rank)
+        if self.backend is None:
+            self.ghost_cap = self.ghost_cap or max(8192, max(g.shape[0] for g in gids) // 8)
+            self.backend = RB3DSlabBackend(self.ctx, self.scene, self.gids, lim, self.ghost_cap)
+            self._connect()
+        else:
+            self.backend.reinit(self.scene, self.gids, lim)
+        self.backend.upload(*rb3d_owned_state(q, v, self.gids))
+        self.n_partitions += 1
+
+    def _connect(self):
+        import torch
+        _, handle = self.backend.mailbox()
+        if self.world == 1:
+            return
+        dev = torch.device("cuda", self.ctx.device)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        self.dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().reshape(self.world, 64)
+        for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= peer < self.world:
+                self.backend.connect(side, ipc_handle=bytes(allh[peer]))
+        self.dist.barrier()
+
+    def upload(self, q, v, repartition=False):
+        q, v = np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)
+        self.q, self.v = q, v
+        if self.backend is None or repartition:
+            self._partition(q, v)
+        else:
+            self.backend.upload(*rb3d_owned_state(q, v, self.gids))
+
+    def _agree(self, flag):
+        if self.world == 1 or not self.agree:
+            return flag
+        import torch
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=torch.device("cuda", self.ctx.device))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return bool(int(t.item()))
+
+    def step(self, kind, dt):
+        for attempt in range(2):
+            need = False
+            self.backend.flow(kind, dt)
+            self.backend.exchange(0)
+            try:
+                res = self.backend.detect()
+                self.last_halo = self.backend.ghosts
+            except RebalanceNeeded:
+                need, res = True, (0, 0)
+            if not self._agree(need):
+                if need:
+                    raise RebalanceNeeded("rank %d needs a re-partition but the ranks do not agree on steps (agree=False)" % self.rank)
+                return res
+            if attempt == 1:
+                raise RuntimeError("the slabs of this scene are too thin for %d ranks" % self.world)
+            self._partition(self.q, self.v)
+        return res
+
+    def gather_merged(self, dst=0):
+        q1, v1, res = self.backend.fetch()
+        res = dict(res)
+        res["gids"], res["q1"], res["v1"] = self.gids, q1, v1
+        if self.world == 1:
+            parts = [res]
+        else:
+            parts = [None] * self.world if self.rank == dst else None
+            self.dist.gather_object(res, parts, dst=dst)
+            if self.rank != dst:
+                return None
+        merged = merge_active_sets(parts, n_bodies=self.n)
+        merged["q1"], merged["v1"] = rb3d_scatter_state(self.n, [(p["gids"], p["q1"], p["v1"]) for p in parts])
         return merged
