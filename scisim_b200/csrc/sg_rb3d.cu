@@ -1129,6 +1129,100 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_slab_unpack( const uint32_t cap,
   gid[slot] = u.g.gid;
 }
 
+// ---- body-plane / body-cylinder, all-sphere scenes: each sphere is loaded ONCE and tested against every plane and cylinder from registers
+// (the generic kernels above go through plane_contacts once per plane and body).  Same tests, same order: planes plane-major, then
+// cylinders, body ascending (RigidBody3DSim.cpp:1414-1557, StaticPlaneSphereConstraint.cpp:13-17, StaticCylinderSphereConstraint.cpp:10-19).
+__device__ __forceinline__ unsigned long long sphere_static_mask( const Planes3D& planes, const V3d x1, const double r )
+{
+  unsigned long long mask = 0ull;
+  for( uint32_t pl = 0; pl < planes.n; ++pl )
+  {
+    const V3d xp = v3( planes.x[pl][0], planes.x[pl][1], planes.x[pl][2] );
+    const V3d np = v3( planes.nrm[pl][0], planes.nrm[pl][1], planes.nrm[pl][2] );
+    if( dot3( np, x1 - xp ) <= r ) { mask |= 1ull << pl; }
+  }
+  for( uint32_t cy = 0; cy < planes.ncyl; ++cy )
+  {
+    const V3d xc = v3( planes.cx[cy][0], planes.cx[cy][1], planes.cx[cy][2] );
+    const V3d ax = v3( planes.cax[cy][0], planes.cax[cy][1], planes.cax[cy][2] );
+    const double rc = planes.cr[cy];
+    const V3d d = ( x1 - xc ) - dot3( ax, x1 - xc ) * ax;
+    if( dot3( d, d ) >= ( rc - r ) * ( rc - r ) ) { mask |= 1ull << ( planes.n + cy ); }
+  }
+  return mask;
+}
+
+template<bool EMIT>
+__global__ void __launch_bounds__( 256 ) k_rb3d_static_spheres( const uint32_t n_live, const __grid_constant__ Planes3D planes, const double* __restrict__ q0, const double* __restrict__ q1, const double* __restrict__ radius,
+                                                               const uint32_t* __restrict__ flags, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                               const unsigned long long* __restrict__ base_dev, const ContactOut3D out )
+{
+  __shared__ uint32_t s_w[SG_MAX_PLANES + SG_MAX_CYLINDERS][8];
+  const uint32_t ng = planes.n + planes.ncyl;
+  if( EMIT )
+  {
+    // most blocks touch nothing: the counts say so before any sphere is read
+    const int mine = ( threadIdx.x < ng ) ? int( counts[threadIdx.x * gridDim.x + blockIdx.x] != 0u ) : 0;
+    if( __syncthreads_or( mine ) == 0 ) { return; }
+  }
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long mask = 0ull;
+  V3d x1 = v3( 0.0, 0.0, 0.0 );
+  double r = 0.0;
+  if( b < n_live && ( __ldg( &flags[b] ) & SG_FIXED_BIT ) == 0u )
+  {
+    x1 = load_v3( q1, b );
+    r = __ldg( &radius[b] );
+    mask = sphere_static_mask( planes, x1, r );
+  }
+  for( uint32_t g = 0; g < ng; ++g )
+  {
+    const unsigned bal = __ballot_sync( 0xffffffffu, ( mask >> g ) & 1ull );
+    if( lane == 0 ) { s_w[g][warp] = __popc( bal ); }
+  }
+  __syncthreads();
+  if( !EMIT )
+  {
+    if( threadIdx.x < ng )
+    {
+      uint32_t c = 0u;
+      #pragma unroll
+      for( int w = 0; w < 8; ++w ) { c += s_w[threadIdx.x][w]; }
+      counts[threadIdx.x * gridDim.x + blockIdx.x] = c;
+    }
+    return;
+  }
+  const unsigned long long base = *base_dev;
+  const V3d x0 = ( mask != 0ull ) ? load_v3( q0, b ) : v3( 0.0, 0.0, 0.0 );
+  for( uint32_t g = 0; g < ng; ++g )
+  {
+    if( counts[g * gridDim.x + blockIdx.x] == 0u ) { continue; } // uniform across the block
+    const bool hit = ( ( mask >> g ) & 1ull ) != 0ull;
+    const unsigned bal = __ballot_sync( 0xffffffffu, hit ); // every lane of the warp is here
+    if( !hit ) { continue; }
+    uint32_t before = __popc( bal & ( ( 1u << lane ) - 1u ) );
+    for( int w = 0; w < warp; ++w ) { before += s_w[g][w]; }
+    const unsigned long long k = base + offsets[g * gridDim.x + blockIdx.x] + before;
+    if( g < planes.n )
+    {
+      const V3d xp = v3( planes.x[g][0], planes.x[g][1], planes.x[g][2] );
+      const V3d np = v3( planes.nrm[g][0], planes.nrm[g][1], planes.nrm[g][2] );
+      const double d = dot3( np, x1 - xp );
+      put_contact( out, k, SG_PLANE_SPHERE, b, g, 0u, np, x0 - r * np, fmin( 0.0, d - r ) );
+    }
+    else
+    {
+      const uint32_t cy = g - planes.n;
+      const V3d xc = v3( planes.cx[cy][0], planes.cx[cy][1], planes.cx[cy][2] );
+      const V3d ax = v3( planes.cax[cy][0], planes.cax[cy][1], planes.cax[cy][2] );
+      const V3d e0 = ( x0 - xc ) - dot3( ax, x0 - xc ) * ax;
+      const V3d n = normalized3( -e0 );
+      put_contact( out, k, SG_CYLINDER_SPHERE, b, cy, 0u, n, x0 - r * n, sg_nan() );
+    }
+  }
+}
+
 // small helper kernels
 __global__ void k_rb3d_sum_totals( const ScanPairCounts::Acc* __restrict__ bp_totals, const unsigned long long* __restrict__ narrow_total, const int fused, unsigned long long* __restrict__ out3 )
 {
@@ -1315,8 +1409,22 @@ static int rb3d_planes_device( sg_ctx* ctx, Rb3dData* d, const bool emit )
     SG_CUDA( ctx, d->st_counts.ensure( size_t( nst ) * 4 + 4 ) );
     SG_CUDA( ctx, d->st_offsets.ensure( size_t( nst ) * 4 + 4 ) );
     SG_CUDA( ctx, d->st_partials.ensure( ( size_t( nst ) / SG_SCAN_TILE + 2 ) * 4 ) );
-    SG_LAUNCH( ctx, "rb3d_plane_count", double( n ) * 32.0, k_rb3d_plane_count<<<nblk, 256, 0, ctx->stream>>>( dev, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->st_counts.as<uint32_t>() ) );
+    if( d->all_spheres )
+    {
+      SG_LAUNCH( ctx, "rb3d_plane_count", double( dev.n_live ) * 36.0, k_rb3d_static_spheres<false><<<nblk, 256, 0, ctx->stream>>>( dev.n_live, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->radius.as<double>(),
+                 d->flags.as<uint32_t>(), d->st_counts.as<uint32_t>(), nullptr, nullptr, rb3d_out( d ) ) );
+    }
+    else
+    {
+      SG_LAUNCH( ctx, "rb3d_plane_count", double( n ) * 32.0, k_rb3d_plane_count<<<nblk, 256, 0, ctx->stream>>>( dev, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->st_counts.as<uint32_t>() ) );
+    }
     return sg_exclusive_scan<ScanU32>( ctx, "rb3d_plane_scan", d->st_counts.as<uint32_t>(), nullptr, nst, nst, d->st_partials.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->st_total.as<uint32_t>(), false );
+  }
+  if( d->all_spheres )
+  {
+    SG_LAUNCH( ctx, "rb3d_plane_emit", double( n ) * 4.0, k_rb3d_static_spheres<true><<<nblk, 256, 0, ctx->stream>>>( dev.n_live, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->radius.as<double>(),
+               d->flags.as<uint32_t>(), d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(), d->totals3.as<unsigned long long>() + 1, rb3d_out( d ) ) );
+    return SG_OK;
   }
   SG_LAUNCH( ctx, "rb3d_plane_emit", double( n ) * 4.0, k_rb3d_plane_emit<<<nblk, 256, 0, ctx->stream>>>( dev, d->planes, d->q0.as<double>(), d->q1.as<double>(), d->st_counts.as<uint32_t>(), d->st_offsets.as<uint32_t>(),
              d->totals3.as<unsigned long long>() + 1, rb3d_out( d ) ) );
