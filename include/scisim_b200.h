@@ -234,6 +234,40 @@ int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg
 /* q1, v1 (either may be NULL) as the last flow / step / sg_ball2d_slab_flow on this context left them on the device (slab mode: the owned block) */
 int sg_ball2d_fetch_state( sg_ctx* ctx, double* q1, double* v1 );
 
+/* Device-side assembly for the solver's first step, from the contact arrays of the LAST active set on this context:
+ *   N      ImpactOperatorUtilities::computeN (scisim/ConstrainedMaps/ImpactMaps/ImpactOperatorUtilities.cpp:10-48) with the constraints'
+ *          evalgradg (ball2d/Constraints/BallBallConstraint.cpp:88-100, BallStaticPlaneConstraint.cpp:65-73, BallStaticDrumConstraint.cpp:59-66),
+ *          zeros pruned; n_dofs x n_constraints, compressed column-major (outer n_constraints + 1, inner / values n_nnz)
+ *   Q      N^T * Minv * N (ImpactMap.cpp:106-110): n_constraints^2, compressed column-major with sorted rows, Eigen's accumulation order
+ *   bases  computeContactBases (ball2d/Ball2DSim.cpp:188-201): 4 doubles per constraint, the column-major 2x2 [ n | t ]
+ * Pointers go into library-owned pinned host memory, valid until the next call on the context.  Contact types 0..2 only. */
+#define SG_ASM_N 1u
+#define SG_ASM_Q 2u
+#define SG_ASM_BASES 4u
+typedef struct sg_assembly
+{
+  uint64_t n_constraints;
+  uint64_t n_dofs;
+  uint64_t n_nnz;
+  const int32_t* n_outer;
+  const int32_t* n_inner;
+  const double* n_values;
+  uint64_t q_nnz;
+  const int32_t* q_outer;
+  const int32_t* q_inner;
+  const double* q_values;
+  const double* bases;
+} sg_assembly;
+int sg_ball2d_assemble( sg_ctx* ctx, uint32_t flags, sg_assembly* out );
+/* ConstraintCache (ball2d/ConstraintCache.cpp:20-122) on the device, as a sorted-key join:
+ *   store   cacheConstraint for every constraint of the current active set: r = ncomp values per constraint, active-set order (host)
+ *   lookup  getCachedConstraintImpulse for every constraint of the current active set: the stored values where the key
+ *           ( (i,j) | (plane,ball) | (drum,ball) ) was cached, zeros otherwise; *hits = constraints found
+ *   clear   clearConstraintCache */
+int sg_ball2d_cache_store( sg_ctx* ctx, uint32_t ncomp, const double* r );
+int sg_ball2d_cache_lookup( sg_ctx* ctx, uint32_t ncomp, double* r_out, uint64_t* hits );
+int sg_ball2d_cache_clear( sg_ctx* ctx );
+
 /* State I/O at the seam: Ball2DState's binary snapshot (ball2d/Ball2DState.cpp:259-312, scisim/Utilities.h:43-94,
    scisim/Math/MathUtilities.h:42-60, MathUtilities.cpp:142-177), byte for byte, written from / read into the device-resident state.
    serialize   which = 0: ( q0, v0 ) as uploaded, 1: ( q1, v1 ) of the last flow / step.  buf = NULL: *bytes <- size needed

@@ -6,6 +6,7 @@
 #include "ball2d.h"
 #include "ball2d_portals.h"
 #include "ball2d_parallel.h"
+#include "assembly2d.h"
 #include "broadphase.h"
 #include "ccd.h"
 
@@ -87,6 +88,9 @@ struct Ball2DHandle
   std::vector<Portal2D> portals;
   PortalActiveSetResult pres;
   std::vector<std::pair<unsigned,unsigned>> par_active;
+  Assembly2D assembly;
+  ConstraintCache2D cache;
+  unsigned cache_ncomp = 0;
 };
 
 // plane_n is normalised here exactly as StaticPlane's constructor does (ball2d/StaticGeometry/StaticPlane.cpp:10-14)
@@ -148,6 +152,40 @@ void orc_ball2d_copy_active( const void* hv, uint32_t* type, uint32_t* i, uint32
     p[2 * k] = c.p.x; p[2 * k + 1] = c.p.y;
     depth[k] = c.depth;
   }
+}
+
+// ---- N, Q, contact bases and the constraint cache for the last active set (oracle/assembly2d.h) ----
+// sizes: out[0] = constraints, out[1] = nnz( N ), out[2] = nnz( Q ); returns 0 when the active set holds an unsupported contact type
+int orc_ball2d_assemble( void* hv, uint64_t* out )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  assemble2d( h->scene, h->active, h->assembly );
+  out[0] = h->active.size(); out[1] = h->assembly.n_inner.size(); out[2] = h->assembly.q_inner.size();
+  return h->assembly.supported ? 1 : 0;
+}
+void orc_ball2d_copy_assembly( const void* hv, int32_t* n_outer, int32_t* n_inner, double* n_val, int32_t* q_outer, int32_t* q_inner, double* q_val, double* bases )
+{
+  const Assembly2D& a = static_cast<const Ball2DHandle*>( hv )->assembly;
+  std::copy( a.n_outer.begin(), a.n_outer.end(), n_outer ); std::copy( a.n_inner.begin(), a.n_inner.end(), n_inner ); std::copy( a.n_val.begin(), a.n_val.end(), n_val );
+  std::copy( a.q_outer.begin(), a.q_outer.end(), q_outer ); std::copy( a.q_inner.begin(), a.q_inner.end(), q_inner ); std::copy( a.q_val.begin(), a.q_val.end(), q_val );
+  std::copy( a.bases.begin(), a.bases.end(), bases );
+}
+void orc_ball2d_cache_clear( void* hv ) { static_cast<Ball2DHandle*>( hv )->cache.clear(); }
+// cacheConstraint for every constraint of the last active set
+void orc_ball2d_cache_store( void* hv, uint32_t ncomp, const double* r )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  h->cache.clear(); // the maps clear the cache before re-filling it (ImpactMap.cpp:98)
+  h->cache_ncomp = ncomp;
+  for( std::size_t c = 0; c < h->active.size(); ++c ) { h->cache.cache( h->active[c], r + c * ncomp, ncomp ); }
+}
+// getCachedConstraintImpulse for every constraint of the last active set; returns the number found
+uint64_t orc_ball2d_cache_lookup( void* hv, uint32_t ncomp, double* r_out )
+{
+  Ball2DHandle* h = static_cast<Ball2DHandle*>( hv );
+  uint64_t hits = 0;
+  for( std::size_t c = 0; c < h->active.size(); ++c ) { if( h->cache.get( h->active[c], r_out + c * ncomp, ncomp ) ) { ++hits; } }
+  return hits;
 }
 
 // ---- multi-core ball2d step (oracle/ball2d_parallel.h): NOT reference behaviour, the optional second CPU figure ----

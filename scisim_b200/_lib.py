@@ -37,6 +37,11 @@ class SgContacts(C.Structure):
                 ("n", c_dp), ("p", c_dp), ("depth", c_dp), ("cand_ij", c_up), ("aux", c_up)]
 
 
+class SgAssembly(C.Structure):
+    _fields_ = [("n_constraints", C.c_uint64), ("n_dofs", C.c_uint64), ("n_nnz", C.c_uint64), ("n_outer", C.POINTER(C.c_int32)), ("n_inner", C.POINTER(C.c_int32)), ("n_values", c_dp),
+                ("q_nnz", C.c_uint64), ("q_outer", C.POINTER(C.c_int32)), ("q_inner", C.POINTER(C.c_int32)), ("q_values", c_dp), ("bases", c_dp)]
+
+
 class SgTeleported(C.Structure):
     _fields_ = [("n_boxes", C.c_uint64), ("box_body", c_up), ("box_portal", c_up), ("n_regular", C.c_uint64), ("n_teleported", C.c_uint64),
                 ("portal0", c_up), ("portal1", c_up), ("x0", c_dp), ("x1", c_dp), ("kick", c_dp), ("delta0", c_dp), ("delta1", c_dp)]
@@ -92,6 +97,10 @@ def load():
         "sg_ball2d_slab_set_gids": (C.c_int, [vp, vp, vp]),
         "sg_ball2d_slab_upload_q1": (C.c_int, [vp, vp]),
         "sg_ball2d_slab_stats": (C.c_int, [vp, vp]),
+        "sg_ball2d_assemble": (C.c_int, [vp, C.c_uint32, C.POINTER(SgAssembly)]),
+        "sg_ball2d_cache_store": (C.c_int, [vp, C.c_uint32, vp]),
+        "sg_ball2d_cache_lookup": (C.c_int, [vp, C.c_uint32, vp, C.POINTER(C.c_uint64)]),
+        "sg_ball2d_cache_clear": (C.c_int, [vp]),
         "sg_ball2d_state_serialize": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64)]),
         "sg_ball2d_state_deserialize": (C.c_int, [vp, vp, C.c_uint64]),
         "sg_ball2d_fetch_state": (C.c_int, [vp, vp, vp]),

@@ -442,6 +442,7 @@ struct Ball2DData
   bool cand_valid = false;
   // planar / Lees-Edwards portals (sg_ball2d_portals.cuh): allocated by sg_ball2d_set_portals
   PortalData* px = nullptr;
+  struct AsmData* asmd = nullptr; // device-side assembly of N, Q, contact bases and the impulse cache (sg_ball2d_assembly.cuh)
   bool portal_result = false; // the last result came from the portal path (its candidate list lives in px->bp)
   // slab mode (one slab of a larger scene per GPU): the body arrays hold [left ghosts | owned | right ghosts] with
   // ghost_cap slots reserved on either side of the owned block (slot order == global index order); how many of
@@ -484,6 +485,7 @@ struct Ball2DData
 };
 
 static void ball2d_portal_release( Ball2DData* d );
+static void ball2d_asm_release( Ball2DData* d );
 static bool ball2d_has_portals( const Ball2DData* d );
 static int ball2d_portal_active_set_device( sg_ctx* ctx, Ball2DData* d, const int flow_kind, const double dt );
 static const DevBuf& ball2d_result_candidates( const Ball2DData* d );
@@ -501,6 +503,7 @@ void sg_ball2d_release( sg_ctx* ctx )
   for( int sde = 0; sde < 2; ++sde ) { if( d->peer_mb[sde] != nullptr && d->peer_ipc[sde] ) { cudaIpcCloseMemHandle( d->peer_mb[sde] ); } d->peer_mb[sde] = nullptr; }
   d->mailbox.release();
   ball2d_portal_release( d );
+  ball2d_asm_release( d );
   delete d;
   ctx->ball2d = nullptr;
 }
@@ -698,7 +701,12 @@ static int ball2d_copy_out( sg_ctx* ctx, Ball2DData* d, const uint32_t flags, sg
 }
 
 #include "sg_ball2d_portals.cuh"
+#include "sg_ball2d_assembly.cuh"
 
+static void ball2d_asm_release( Ball2DData* d )
+{
+  if( d->asmd != nullptr ) { d->asmd->release(); delete d->asmd; d->asmd = nullptr; }
+}
 static void ball2d_portal_release( Ball2DData* d )
 {
   if( d->px != nullptr ) { d->px->release(); delete d->px; d->px = nullptr; }
@@ -1824,6 +1832,170 @@ int sg_ball2d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes )
   std::vector<double> qq( 2 * n ), vv( 2 * n );
   memcpy( qq.data(), q, n * 16 ); memcpy( vv.data(), v, n * 16 );
   return sg_ball2d_upload( ctx, qq.data(), vv.data() );
+}
+
+
+// ---- device-side assembly for the solver's first step (sg_ball2d_assembly.cuh) ----------------------------------------
+static ContactOut2D ball2d_contacts_view( const Ball2DData* d )
+{
+  ContactOut2D out;
+  out.type = d->c_type.as<uint32_t>(); out.i = d->c_i.as<uint32_t>(); out.j = d->c_j.as<uint32_t>();
+  out.n = d->c_n.as<double2>(); out.p = d->c_p.as<double2>(); out.depth = d->c_depth.as<double>();
+  out.cap = d->act_cap;
+  return out;
+}
+
+int sg_ball2d_assemble( sg_ctx* ctx, uint32_t flags, sg_assembly* out )
+{
+  if( ctx == nullptr || out == nullptr ) { return SG_ERR_INVALID; }
+  memset( out, 0, sizeof( *out ) );
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_assemble: no active set has been computed" ); }
+  if( d->slab || d->portal_result ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_assemble: slab / portal active sets are not supported" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->asmd == nullptr ) { d->asmd = new AsmData; }
+  AsmData& A = *d->asmd;
+  const uint64_t nc = d->n_bb + d->n_static;
+  const uint32_t n = d->n;
+  out->n_constraints = nc; out->n_dofs = 2ull * n;
+  if( nc >= 0x7fffffffull / 4ull ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_assemble: more constraints than 32-bit sparse indices hold" ); }
+  const ContactOut2D a = ball2d_contacts_view( d );
+  SG_CUDA( ctx, A.ncnt.ensure( ( nc + 2 ) * 4 ) ); SG_CUDA( ctx, A.nouter.ensure( ( nc + 2 ) * 4 ) );
+  SG_CUDA( ctx, A.ninner.ensure( ( 4 * nc + 4 ) * 4 ) ); SG_CUDA( ctx, A.nval.ensure( ( 4 * nc + 4 ) * 8 ) );
+  SG_CUDA( ctx, A.deg.ensure( ( size_t( n ) + 2 ) * 4 ) ); SG_CUDA( ctx, A.inc_start.ensure( ( size_t( n ) + 2 ) * 4 ) ); SG_CUDA( ctx, A.inc_cursor.ensure( ( size_t( n ) + 2 ) * 4 ) );
+  SG_CUDA( ctx, A.inc.ensure( ( 2 * nc + 4 ) * 4 ) );
+  SG_CUDA( ctx, A.qcnt.ensure( ( nc + 2 ) * 4 ) ); SG_CUDA( ctx, A.qouter.ensure( ( nc + 2 ) * 4 ) );
+  SG_CUDA( ctx, A.bases.ensure( ( 4 * nc + 4 ) * 8 ) );
+  SG_CUDA( ctx, A.total.ensure( 16 ) ); SG_CUDA( ctx, A.bad.ensure( 4 ) );
+  SG_CUDA( ctx, cudaMemsetAsync( A.deg.ptr, 0, ( size_t( n ) + 2 ) * 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( A.inc_cursor.ptr, 0, ( size_t( n ) + 2 ) * 4, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemsetAsync( A.bad.ptr, 0, 4, ctx->stream ) );
+  uint32_t h_tot[2] = { 0u, 0u }, h_bad = 0u;
+  if( nc > 0 )
+  {
+    const unsigned nblk = sg_div_up( nc, 256 );
+    SG_LAUNCH( ctx, "asm_count", double( nc ) * 32.0, k_asm_count<<<nblk, 256, 0, ctx->stream>>>( nc, a, A.ncnt.as<uint32_t>(), A.deg.as<uint32_t>(), A.bad.as<uint32_t>() ) );
+    int rc = sg_exclusive_scan<ScanU32>( ctx, "asm_scan", A.ncnt.as<uint32_t>(), nullptr, uint32_t( nc ), uint32_t( nc ), nullptr, A.nouter.as<uint32_t>(), A.total.as<uint32_t>(), true );
+    if( rc != SG_OK ) { return rc; }
+    rc = sg_exclusive_scan<ScanU32>( ctx, "asm_scan", A.deg.as<uint32_t>(), nullptr, n, n, nullptr, A.inc_start.as<uint32_t>(), nullptr, true );
+    if( rc != SG_OK ) { return rc; }
+    SG_LAUNCH( ctx, "asm_n_emit", double( nc ) * 96.0, k_asm_n_emit<<<nblk, 256, 0, ctx->stream>>>( nc, a, A.nouter.as<uint32_t>(), A.ninner.as<int32_t>(), A.nval.as<double>(), A.inc_start.as<uint32_t>(),
+               A.inc_cursor.as<uint32_t>(), A.inc.as<uint32_t>(), A.bases.as<double>() ) );
+    SG_LAUNCH( ctx, "asm_sort_inc", double( nc ) * 16.0, k_asm_sort_incidence<<<sg_div_up( n, 256 ), 256, 0, ctx->stream>>>( n, A.inc_start.as<uint32_t>(), A.inc.as<uint32_t>() ) );
+    SG_LAUNCH( ctx, "asm_q_count", double( nc ) * 128.0, k_asm_q<false><<<nblk, 256, 0, ctx->stream>>>( nc, a, d->m.as<double>(), A.inc_start.as<uint32_t>(), A.inc.as<uint32_t>(), A.qcnt.as<uint32_t>(), nullptr, nullptr, nullptr ) );
+    rc = sg_exclusive_scan<ScanU32>( ctx, "asm_scan", A.qcnt.as<uint32_t>(), nullptr, uint32_t( nc ), uint32_t( nc ), nullptr, A.qouter.as<uint32_t>(), A.total.as<uint32_t>() + 1, true );
+    if( rc != SG_OK ) { return rc; }
+    SG_CUDA( ctx, cudaMemcpyAsync( h_tot, A.total.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( &h_bad, A.bad.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    if( h_bad != 0u ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_assemble: the active set holds contact types other than ball-ball, drum and plane" ); }
+    SG_CUDA( ctx, A.qinner.ensure( ( size_t( h_tot[1] ) + 4 ) * 4 ) ); SG_CUDA( ctx, A.qval.ensure( ( size_t( h_tot[1] ) + 4 ) * 8 ) );
+    SG_LAUNCH( ctx, "asm_q_emit", double( h_tot[1] ) * 12.0 + double( nc ) * 128.0, k_asm_q<true><<<nblk, 256, 0, ctx->stream>>>( nc, a, d->m.as<double>(), A.inc_start.as<uint32_t>(), A.inc.as<uint32_t>(), nullptr,
+               A.qouter.as<uint32_t>(), A.qinner.as<int32_t>(), A.qval.as<double>() ) );
+  }
+  out->n_nnz = h_tot[0]; out->q_nnz = h_tot[1];
+  // results to pinned host memory (the device copies stay valid until the next assemble on this context)
+  auto al = []( size_t b ) { return ( b + 63 ) & ~size_t( 63 ); };
+  size_t bytes = 64;
+  const size_t o_no = bytes; bytes += al( ( nc + 1 ) * 4 );
+  const size_t o_ni = bytes; bytes += al( size_t( h_tot[0] ) * 4 );
+  const size_t o_nv = bytes; bytes += al( size_t( h_tot[0] ) * 8 );
+  const size_t o_qo = bytes; bytes += al( ( nc + 1 ) * 4 );
+  const size_t o_qi = bytes; bytes += al( size_t( h_tot[1] ) * 4 );
+  const size_t o_qv = bytes; bytes += al( size_t( h_tot[1] ) * 8 );
+  const size_t o_b = bytes; bytes += al( 4 * nc * 8 );
+  SG_CUDA( ctx, A.host.ensure( bytes ) );
+  char* h = A.host.as<char>();
+  memset( h + o_no, 0, 4 ); memset( h + o_qo, 0, 4 );
+  if( nc > 0 )
+  {
+    if( flags & SG_ASM_N )
+    {
+      SG_CUDA( ctx, cudaMemcpyAsync( h + o_no, A.nouter.ptr, ( nc + 1 ) * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( h + o_ni, A.ninner.ptr, size_t( h_tot[0] ) * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( h + o_nv, A.nval.ptr, size_t( h_tot[0] ) * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+    }
+    if( flags & SG_ASM_Q )
+    {
+      SG_CUDA( ctx, cudaMemcpyAsync( h + o_qo, A.qouter.ptr, ( nc + 1 ) * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( h + o_qi, A.qinner.ptr, size_t( h_tot[1] ) * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+      SG_CUDA( ctx, cudaMemcpyAsync( h + o_qv, A.qval.ptr, size_t( h_tot[1] ) * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+    }
+    if( flags & SG_ASM_BASES ) { SG_CUDA( ctx, cudaMemcpyAsync( h + o_b, A.bases.ptr, 4 * nc * 8, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    sg_prof_collect( ctx );
+  }
+  if( flags & SG_ASM_N ) { out->n_outer = reinterpret_cast<const int32_t*>( h + o_no ); out->n_inner = reinterpret_cast<const int32_t*>( h + o_ni ); out->n_values = reinterpret_cast<const double*>( h + o_nv ); }
+  if( flags & SG_ASM_Q ) { out->q_outer = reinterpret_cast<const int32_t*>( h + o_qo ); out->q_inner = reinterpret_cast<const int32_t*>( h + o_qi ); out->q_values = reinterpret_cast<const double*>( h + o_qv ); }
+  if( flags & SG_ASM_BASES ) { out->bases = reinterpret_cast<const double*>( h + o_b ); }
+  return SG_OK;
+}
+
+// ConstrainedSystem::cacheConstraint for every constraint of the current active set (r: ncomp values per constraint, active-set order)
+int sg_ball2d_cache_store( sg_ctx* ctx, uint32_t ncomp, const double* r )
+{
+  if( ctx == nullptr || ncomp == 0u ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_cache_store: no active set has been computed" ); }
+  if( d->slab || d->portal_result ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_cache_store: slab / portal active sets are not supported" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->asmd == nullptr ) { d->asmd = new AsmData; }
+  AsmData& A = *d->asmd;
+  const uint64_t nc = d->n_bb + d->n_static;
+  if( nc > 0 && r == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_cache_store: null impulse array" ); }
+  // drums precede planes in the active set: how many drums, from the type column
+  std::vector<uint32_t> types( d->n_static );
+  if( d->n_static > 0 ) { SG_CUDA( ctx, cudaMemcpyAsync( types.data(), d->c_type.as<uint32_t>() + d->n_bb, d->n_static * 4, cudaMemcpyDeviceToHost, ctx->stream ) ); }
+  SG_CUDA( ctx, A.c_type.ensure( nc * 4 + 4 ) ); SG_CUDA( ctx, A.c_i.ensure( nc * 4 + 4 ) ); SG_CUDA( ctx, A.c_j.ensure( nc * 4 + 4 ) ); SG_CUDA( ctx, A.c_r.ensure( nc * ncomp * 8 + 8 ) );
+  if( nc > 0 )
+  {
+    SG_CUDA( ctx, cudaMemcpyAsync( A.c_type.ptr, d->c_type.ptr, nc * 4, cudaMemcpyDeviceToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( A.c_i.ptr, d->c_i.ptr, nc * 4, cudaMemcpyDeviceToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( A.c_j.ptr, d->c_j.ptr, nc * 4, cudaMemcpyDeviceToDevice, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( A.c_r.ptr, r, nc * ncomp * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+  }
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  uint64_t nd = 0;
+  for( uint32_t t : types ) { if( t > SG_BALL_PLANE ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_cache_store: contact type %u is not cacheable (ConstraintCache.cpp exits)", t ); } if( t == SG_BALL_DRUM ) { ++nd; } }
+  A.c_n = nc; A.c_nbb = d->n_bb; A.c_ndrum = nd; A.c_ncomp = ncomp;
+  return SG_OK;
+}
+
+int sg_ball2d_cache_clear( sg_ctx* ctx )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( d->asmd != nullptr ) { d->asmd->c_n = d->asmd->c_nbb = d->asmd->c_ndrum = 0; d->asmd->c_ncomp = 0; }
+  return SG_OK;
+}
+
+// ConstrainedSystem::getCachedConstraintImpulse for every constraint of the current active set; *hits = how many were found
+int sg_ball2d_cache_lookup( sg_ctx* ctx, uint32_t ncomp, double* r_out, uint64_t* hits )
+{
+  if( ctx == nullptr || ncomp == 0u ) { return SG_ERR_INVALID; }
+  Ball2DData* d = ball2d_data( ctx );
+  if( !d->have_result ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_cache_lookup: no active set has been computed" ); }
+  if( d->slab || d->portal_result ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_ball2d_cache_lookup: slab / portal active sets are not supported" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  if( d->asmd == nullptr ) { d->asmd = new AsmData; }
+  AsmData& A = *d->asmd;
+  const uint64_t nc = d->n_bb + d->n_static;
+  if( hits != nullptr ) { *hits = 0; }
+  if( nc == 0 ) { return SG_OK; }
+  if( r_out == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_cache_lookup: null output" ); }
+  if( A.c_n > 0 && A.c_ncomp != ncomp ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_cache_lookup: the cache holds %u values per constraint, %u asked for", A.c_ncomp, ncomp ); }
+  SG_CUDA( ctx, A.lookup.ensure( nc * ncomp * 8 + 16 ) );
+  SG_CUDA( ctx, A.total.ensure( 16 ) );
+  SG_CUDA( ctx, cudaMemsetAsync( A.total.ptr, 0, 16, ctx->stream ) );
+  SG_LAUNCH( ctx, "cache_lookup", double( nc ) * ( 12.0 + 8.0 * ncomp ), k_cache_lookup<<<sg_div_up( nc, 256 ), 256, 0, ctx->stream>>>( nc, ball2d_contacts_view( d ), ncomp, A.c_nbb, A.c_ndrum, A.c_n, A.c_type.as<uint32_t>(),
+             A.c_i.as<uint32_t>(), A.c_j.as<uint32_t>(), A.c_r.as<double>(), A.lookup.as<double>(), A.total.as<unsigned long long>() ) );
+  unsigned long long h = 0ull;
+  SG_CUDA( ctx, cudaMemcpyAsync( r_out, A.lookup.ptr, nc * ncomp * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaMemcpyAsync( &h, A.total.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+  SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  sg_prof_collect( ctx );
+  if( hits != nullptr ) { *hits = h; }
+  return SG_OK;
 }
 
 }

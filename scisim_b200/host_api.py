@@ -328,6 +328,34 @@ class Ball2DSim:
         self.ctx.check(self.ctx.lib.sg_ball2d_active_set(self.ctx.h, _ptr(q0), _ptr(qp), int(flags) | (SG_IN_RESIDENT if resident else 0), C.byref(c)))
         return ActiveSet(c, copy=copy)
 
+    # ---- device-side assembly for the solver's first step (ImpactMap.cpp:106-110, Ball2DSim.cpp:188-201) and the impulse cache ----
+    def assemble(self, flags=7):
+        """N (pruned, CSC), Q = N^T Minv N (CSC, sorted rows) and the contact bases of the LAST active set, computed on the device."""
+        from ._lib import SgAssembly
+        a = SgAssembly()
+        self.ctx.check(self.ctx.lib.sg_ball2d_assemble(self.ctx.h, int(flags), C.byref(a)))
+        nc, nn, nq = int(a.n_constraints), int(a.n_nnz), int(a.q_nnz)
+        arr = lambda p, n, dt: (np.ctypeslib.as_array(p, shape=(n,)).copy() if (p and n > 0) else np.zeros(n, dtype=dt))
+        return {"n_constraints": nc, "n_dofs": int(a.n_dofs),
+                "n_outer": arr(a.n_outer, nc + 1, np.int32), "n_inner": arr(a.n_inner, nn, np.int32), "n_values": arr(a.n_values, nn, np.float64),
+                "q_outer": arr(a.q_outer, nc + 1, np.int32), "q_inner": arr(a.q_inner, nq, np.int32), "q_values": arr(a.q_values, nq, np.float64),
+                "bases": arr(a.bases, 4 * nc, np.float64)}
+
+    def cacheConstraints(self, r, ncomp=1):
+        """cacheConstraint for every constraint of the current active set (ball2d/ConstraintCache.cpp:20-60)."""
+        r = _f64(r)
+        self.ctx.check(self.ctx.lib.sg_ball2d_cache_store(self.ctx.h, int(ncomp), _ptr(r)))
+
+    def getCachedConstraintImpulses(self, n_active, ncomp=1):
+        """getCachedConstraintImpulse for every constraint of the current active set: ( values, constraints found )."""
+        out = np.zeros(max(1, n_active * ncomp))
+        hits = C.c_uint64()
+        self.ctx.check(self.ctx.lib.sg_ball2d_cache_lookup(self.ctx.h, int(ncomp), _ptr(out), C.byref(hits)))
+        return out[: n_active * ncomp], int(hits.value)
+
+    def clearConstraintCache(self):
+        self.ctx.check(self.ctx.lib.sg_ball2d_cache_clear(self.ctx.h))
+
     # ---- state I/O: Ball2DState's binary snapshot (ball2d/Ball2DState.cpp:259-312) ----
     def serializeState(self, which=1):
         """bytes of Ball2DState::serialize for the device-resident state: which = 0 the uploaded ( q0, v0 ), 1 the last flow's ( q1, v1 )."""

@@ -136,6 +136,27 @@ class Ball2DOracle:
         out["seconds_flow"] = self.lib.orc_ball2d_seconds_flow(self.h)
         return out
 
+    # ---- N, Q, contact bases, constraint cache for the last active set (oracle/assembly2d.h) ----
+    def assemble(self):
+        sizes = np.zeros(3, dtype=np.uint64)
+        self.lib.orc_ball2d_assemble.restype = C.c_int
+        ok = self.lib.orc_ball2d_assemble(self.h, _p(sizes))
+        nc, nn, nq = [int(x) for x in sizes]
+        out = {"supported": bool(ok), "n_outer": np.zeros(nc + 1, np.int32), "n_inner": np.zeros(nn, np.int32), "n_values": np.zeros(nn), "q_outer": np.zeros(nc + 1, np.int32),
+               "q_inner": np.zeros(nq, np.int32), "q_values": np.zeros(nq), "bases": np.zeros(4 * nc)}
+        self.lib.orc_ball2d_copy_assembly(self.h, *[_p(out[k]) for k in ("n_outer", "n_inner", "n_values", "q_outer", "q_inner", "q_values", "bases")])
+        return out
+
+    def cache_store(self, r, ncomp):
+        r = _f64(r)
+        self.lib.orc_ball2d_cache_store(self.h, int(ncomp), _p(r))
+
+    def cache_lookup(self, n_active, ncomp):
+        out = np.zeros(max(1, n_active * ncomp))
+        self.lib.orc_ball2d_cache_lookup.restype = C.c_uint64
+        hits = int(self.lib.orc_ball2d_cache_lookup(self.h, int(ncomp), _p(out)))
+        return out[: n_active * ncomp], hits
+
     # ---- multi-core step (oracle/ball2d_parallel.h): NOT reference behaviour, the optional second CPU baseline ----
     def parallel_step(self, kind, q0, v0, dt, keep_lists=True):
         """flow + active set on all host threads. Returns dict(q1, v1, seconds, n_candidates, n_active, n_static, threads[, candidates, active])."""
