@@ -227,7 +227,10 @@ int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint3
 
 /* Resident variants: state stays in HBM between calls (what `value` in bench.py times).
  * upload: q,v -> device q0,v0.  step: flow(q0,v0)->(q1,v1) then active set on (q0,q1); nothing is copied
- * to the host except the counts in *out (array pointers are NULL).  fetch: copy the last step's lists. */
+ * to the host except the counts in *out (array pointers are NULL).  fetch: copy the last step's lists.
+ * The step reports n_candidates, n_body_body and n_active only: splitting the static contacts into n_drum / n_plane needs one
+ * more device read-back, which the step avoids -- sg_ball2d_step / sg_ball2d_slab_detect leave both at 0, sg_ball2d_fetch
+ * fills them (n_active = n_body_body + n_drum + n_plane holds for fetch and for sg_ball2d_active_set). */
 int sg_ball2d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_ball2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );

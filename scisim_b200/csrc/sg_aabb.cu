@@ -48,7 +48,7 @@ static int candidate_pairs_impl( sg_ctx* ctx, AabbData* d, const uint32_t n, con
   SG_CUDA( ctx, d->h_pairs.ensure( size_t( np ) * 8 + 64 ) );
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<P>( ctx, d->bp, n, true, NoOut{}, 0u );
+    rc = sg_bp_emit_lists<P>( ctx, d->bp, in, n, true, NoOut{}, 0u );
     if( rc != SG_OK ) { return rc; }
     SG_CUDA( ctx, cudaMemcpyAsync( d->h_pairs.ptr, d->bp.cand.ptr, size_t( np ) * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
     SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );

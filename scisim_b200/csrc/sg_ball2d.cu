@@ -60,30 +60,10 @@ struct ContactOut2D
   GidMap gid; // multi-GPU: local -> global body index (identity on one GPU)
 };
 
-// scisim/CollisionDetection/CollisionDetectionUtilities.cpp:3-121 (a = lower body index)
+// scisim/CollisionDetection/CollisionDetectionUtilities.cpp:3-121 (a = lower body index): sg_ccd.h
 __device__ __forceinline__ bool ccd_hit( const Ball2DRec& a, const Ball2DRec& b )
 {
-  const double d0x = a.q0x - b.q0x;
-  const double d0y = a.q0y - b.q0y;
-  const double d1x = ( a.q1x - b.q1x ) - d0x;
-  const double d1y = ( a.q1y - b.q1y ) - d0y;
-  const double rs = a.r + b.r;
-  const double c0 = ( d0x * d0x + d0y * d0y ) - rs * rs;
-  const double c1 = 2.0 * ( d0x * d1x + d0y * d1y );
-  const double c2 = d1x * d1x + d1y * d1y;
-  if( c2 != 0.0 )
-  {
-    const double c1c1 = c1 * c1;
-    const double fc2c0 = 4.0 * c2 * c0;
-    if( c1c1 < fc2c0 ) { return false; }
-    const double s = sqrt( c1c1 - fc2c0 );
-    const double root1 = ( c1 > 0.0 ) ? ( 2.0 * c0 ) / ( -c1 - s ) : ( -c1 + s ) / ( 2.0 * c2 );
-    if( root1 < 0.0 ) { return false; }
-    const double root0 = ( c1 >= 0.0 ) ? ( -c1 - s ) / ( 2.0 * c2 ) : ( 2.0 * c0 ) / ( -c1 + s );
-    if( root0 > 1.0 ) { return false; }
-    return true;
-  }
-  return c0 <= 0.0;
+  return sg_ccd_ball_ball( a.q0x, a.q0y, a.q1x, a.q1y, a.r, b.q0x, b.q0y, b.q1x, b.q1y, b.r );
 }
 
 struct Ball2DPolicy
@@ -615,7 +595,7 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
       SG_CUDA( ctx, cudaEventRecord( ctx->ev_fork, ctx->stream ) );
       SG_CUDA( ctx, cudaStreamWaitEvent( side, ctx->ev_fork, 0 ) );
     }
-    rc = sg_bp_emit_lists<Ball2DPolicy>( ctx, d->bp, n, want_cand, out, d->act_cap );
+    rc = sg_bp_emit_lists<Ball2DPolicy>( ctx, d->bp, in, n, want_cand, out, d->act_cap );
     if( rc != SG_OK ) { return rc; }
     if( ng > 0 )
     {
@@ -1020,6 +1000,7 @@ int sg_ball2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x, const double
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( n > SG_MAX_PLANES ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_planes: at most %d planes", SG_MAX_PLANES ); }
+  if( n > 0 && ( x == nullptr || nrm == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_planes: null array" ); }
   Ball2DData* d = ball2d_data( ctx );
   d->sg.nplanes = n;
   for( uint32_t p = 0; p < n; ++p )
@@ -1039,6 +1020,7 @@ int sg_ball2d_set_drums( sg_ctx* ctx, uint32_t n, const double* x, const double*
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( n > SG_MAX_DRUMS ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_drums: at most %d drums", SG_MAX_DRUMS ); }
+  if( n > 0 && ( x == nullptr || r == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_set_drums: null array" ); }
   Ball2DData* d = ball2d_data( ctx );
   d->sg.ndrums = n;
   for( uint32_t k = 0; k < n; ++k ) { d->sg.drum_x[k] = x[2 * k]; d->sg.drum_y[k] = x[2 * k + 1]; d->sg.drum_r[k] = r[k]; }
@@ -1214,6 +1196,7 @@ int sg_ball2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint3
     d->flow_resident = false;
   }
   const int rc = ball2d_active_set_device( ctx, d, ( out_flags & SG_OUT_CANDIDATES ) != 0u );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   return ball2d_copy_out( ctx, d, out_flags, out );
 }
@@ -1255,6 +1238,7 @@ int sg_ball2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
   if( d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_step: context is in slab mode, use the sg_ball2d_slab_* calls" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   const int rc = ball2d_active_set_device( ctx, d, true, map_kind, dt );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   if( out != nullptr )
   {
@@ -1612,6 +1596,7 @@ int sg_ball2d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
   if( !d->slab ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_ball2d_slab_detect: call sg_ball2d_slab_init first" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   const int rc = ball2d_active_set_device( ctx, d, true );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   uint32_t* hg = reinterpret_cast<uint32_t*>( d->h_totals.as<unsigned long long>() + 4 );
   SG_CUDA( ctx, cudaMemcpyAsync( hg, d->ghost_counts.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream ) );

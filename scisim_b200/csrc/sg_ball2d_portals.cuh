@@ -160,7 +160,7 @@ static int ball2d_portal_active_set_device( sg_ctx* ctx, Ball2DData* d, const in
   uint32_t nraw = 0;
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<PortalBoxPolicy>( ctx, x->bp, next, true, NoOut{}, 0u );
+    rc = sg_bp_emit_lists<PortalBoxPolicy>( ctx, x->bp, in, next, true, NoOut{}, 0u );
     if( rc != SG_OK ) { return rc; }
     SG_CUDA( ctx, x->reg_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->reg_off.ensure( size_t( np ) * 4 + 4 ) );
     SG_CUDA( ctx, x->tel_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->tel_off.ensure( size_t( np ) * 4 + 4 ) );

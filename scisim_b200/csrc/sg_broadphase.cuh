@@ -15,8 +15,8 @@
 //   scatter  write a 64-byte record per body at cell_start[key] + rank  => bodies sorted by cell
 //   pass 1   (count) per body: walk the 3^D neighbourhood as 3^(D-1) contiguous row segments, AABB test (+ narrow
 //            test) against partners with a larger index; leaves counts BY BODY INDEX and, by sorted position, 64-bit
-//            candidate / active masks over the visit sequence plus the walk plan.  2-D: TMA-fed, warp-specialised,
-//            double-buffered (sg_bp_count_tma); 3-D: records through L1/L2, cell ranges staged (sg_bp_count)
+//            candidate / active masks over the visit sequence plus the walk plan.  2-D: float-box prefilter, warp-balanced
+//            exact tests (sg_bp_count_l1); 3-D: records through L1/L2, cell ranges staged (sg_bp_count)
 //   scan     counts -> output offsets in body-index order, scattered to sorted-position order (cooperative launch)
 //   pass 2   (emit) no shared memory, no barriers: set mask bits -> partner positions via the plan -> partner indices
 //            -> register sorting network -> candidate pairs at the body's offset + a (p,q) work item per active pair
@@ -28,7 +28,9 @@
 #include "sg_common.cuh"
 #include "sg_scan.cuh"
 #include "sg_tma.cuh"
+#include "sg_ccd.h"
 
+#include <cstdlib>
 #include <cuda.h> // CUtensorMap (type only; the encoder is fetched at run time, see sg_bp_encode_recs_map)
 
 #define SG_BP_THREADS 256
@@ -54,14 +56,13 @@ struct BroadScratch
   DevBuf pair_partials; // ScanPairCounts::Acc[tiles]
   DevBuf totals;        // ScanPairCounts::Acc
   DevBuf cand;          // uint2[cand_cap]
-  DevBuf work;          // uint2[work_cap]  (own position, partner position) of every active pair, in output order
+  DevBuf work;          // uint2[work_cap]  (own body index, partner's sorted position) of every active pair, in output order
   uint64_t work_cap = 0;
   uint64_t cand_cap = 0;
   uint32_t max_cells = 0;
   SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
   DevBuf boxf;          // float4[n]  by sorted position (2-D pipelines): the body's box rounded outward to floats -- what pass 1's walk tests
   const uint32_t* ord_by_index = nullptr; // order word of body i (multi-GPU: the global-index table; nullptr: i itself), set per step by the caller
-  int attr_dev = -1;    // device on which pass 1's shared-memory opt-in was made for this context's kernels
   bool hist_clean = false; // cell_count is all zero (true after every scatter; false after (re)allocation or an aborted step)
   const void* hist_ptr = nullptr;
   uint32_t hist_slots = 0;
@@ -511,8 +512,9 @@ __device__ __forceinline__ void sg_bp_walk_pos( const GridParams& g, const uint3
 // The walk plan pass 1 leaves for pass 2: per body the window starts and lengths (clipped to 255; a body whose
 // walk is longer than 63 visits has incomplete masks anyway), NPLAN uint4 per body.  Masks and plan of sorted position p sit
 // side by side -- STRIDE = 1 + NPLAN uint4 words: [masks | plan words] -- so that pass 2, which visits the bodies in INDEX
-// order, finds everything it needs about a body in one 32-byte sector (2-D) / two (3-D).  `masks` and `plan` below are the
-// same buffer, offset by one word.
+// order, finds everything it needs about a body in one 32-byte sector (2-D) / two (3-D).  (Measured the other way round --
+// pass 1 scattering them by body index so that pass 2 reads them coalesced: on 16 M randomly numbered balls pass 2 gained 0.17 ms
+// and pass 1 lost 0.47 ms to the 32-byte random writes.)  `masks` and `plan` below are the same buffer, offset by one word.
 template<int D> struct BpPlan;
 template<> struct BpPlan<2> { static constexpr int NPLAN = 1; static constexpr int STRIDE = 2; };
 template<> struct BpPlan<3> { static constexpr int NPLAN = 3; static constexpr int STRIDE = 4; };
@@ -634,8 +636,7 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
   const GridParams g = *params;
   const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned (unused slots are not)
   const uint32_t p = blockIdx.x * Cfg::T + threadIdx.x;
-  if( p >= n && p < n_slots ) { masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slot: pass 2 skips it
-  if( blockIdx.x * Cfg::T >= n ) { return; }
+  if( blockIdx.x * Cfg::T >= n ) { return; } // (positions past the binned bodies belong to nobody: pass 2 finds a body's masks through pos_of)
   Rec me;
   if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the windows are staged
   sg_bp_stage<P, true>( g, n, cell_start, recs, nullptr, s_recs, s_cs, st );
@@ -652,36 +653,13 @@ __global__ void __launch_bounds__( BpCfg<P::D>::T, 4 ) sg_bp_count( const uint32
   sg_bp_count_body<P, Cfg::CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, my_ord, counts, masks, plan, sidx );
 }
 
-// ---- pass 1, box-prefiltered and bulk-copy fed (D = 2) ------------------------------------------------
+// ---- pass 1, box-prefiltered (D = 2): helpers ------------------------------------------------------------
 // What a body's walk over its 3 row windows needs per partner is a box test that almost always fails (config 3: 19 visits,
-// 2.7 boxes touched, 1.3 pairs owned).  So the walk does not touch the 64-byte records at all: the scatter also leaves, by
-// sorted position, the body's box rounded OUTWARD to four floats (16 bytes); a tile stages just those -- plus the 4-byte ORDER
-// words and the cell_start slices -- and the walk is one 128-bit shared-memory load and four float compares per partner,
-// branch-free, recording the survivors as one bit each.  Only the survivors (a conservative superset of the overlapping boxes:
-// outward rounding can add, never drop) get the exact FP64 test of the reference -- AABB::overlaps on the swept boxes, then
-// the narrow phase -- on the full records, read through L1/L2.
-// Structure: persistent CTAs, 8 consumer warps + 1 producer warp, double-buffered 26 KB stages (a third of the record stage:
-// three CTAs per SM instead of two, windows of 384 instead of 272).  The producer runs one tile ahead: the tile's first/last cell
-// keys -> the cell_start entries bounding its three row windows -> per window three 1-D bulk copies (cp.async.bulk: boxes, order
-// words, cell_start slice) completing on the stage's `full` mbarrier by byte count; consumers wait on it and hand the stage back
-// through the `empty` mbarrier.
-#define SG_BPX_WCAP 352
-#define SG_BPX_CSCAP 288
-#define SG_BPX_STAGES 2
-#define SG_BPX_CTAS_PER_SM 3
-#define SG_BPX_T 256
-
-struct BpxHdr
-{
-  BpStage<2> st;          // start, len (boxes staged), cs_klo, cs_len, full
-  uint32_t ord_shift[3];  // the order words were copied from a 16-byte aligned address: entry of slot 0
-};
-__host__ __device__ constexpr size_t sg_bpx_ord_off() { return size_t( 3 ) * SG_BPX_WCAP * 16; }
-__host__ __device__ constexpr size_t sg_bpx_cs_off() { return sg_bpx_ord_off() + size_t( 3 ) * ( SG_BPX_WCAP + 4 ) * 4; }
-__host__ __device__ constexpr size_t sg_bpx_hdr_off() { return sg_bpx_cs_off() + size_t( 3 ) * SG_BPX_CSCAP * 4; }
-__host__ __device__ constexpr size_t sg_bpx_stage_bytes() { return ( sg_bpx_hdr_off() + sizeof( BpxHdr ) + 127 ) & ~size_t( 127 ); }
-__host__ __device__ constexpr size_t sg_bpx_smem() { return SG_BPX_STAGES * sg_bpx_stage_bytes() + 64 + size_t( SG_BPX_T / 32 ) * 32 * 6 * sizeof( uint2 ); } // stages, barriers, per-warp survivor queues
-
+// 2.7 boxes touched, 1.3 pairs owned).  So the walk does not touch the 64-byte records at all: a coalesced pass after the scatter
+// leaves, by sorted position, the body's box rounded OUTWARD to four floats (16 bytes) and its ORDER word; the walk is one 128-bit
+// and one 32-bit load and five compares per partner, branch-free, recording the survivors as one bit each.  Only the survivors
+// (a conservative superset of the overlapping boxes: outward rounding can add, never drop) get the exact FP64 tests of the
+// reference -- AABB::overlaps on the swept boxes, then the narrow phase -- on the full records.
 // A body whose walk does not fit the survivor bitmaps (a window of more than 64 positions, or more than 63 visits in all):
 // the plain walk with exact tests, everything through L1/L2.  Leaves exact counts and the (incomplete) masks pass 2 expects.
 template<typename P>
@@ -715,33 +693,100 @@ __device__ __forceinline__ uint32_t sg_bpx_exact( const typename P::Rec& a, cons
 #define SG_BPX_QLANE 6u                       // survivors a lane hands to the warp's queue (the rest it tests itself)
 #define SG_BPX_QCAP ( 32u * SG_BPX_QLANE )    // queue entries per warp
 
-// One warp's share of a tile (32 consecutive sorted bodies; every lane calls, `part` = this lane has an owned body).
-//  1. walk: per lane, one 128-bit + one 32-bit shared-memory load and five compares per partner, branch-free; a set bit =
-//     "float boxes touch AND the partner's order word is larger than mine" (so the pair is mine to list)
-//  2. the few survivors of all 32 lanes are compacted into the warp's queue (shuffle prefix sum), so that
-//  3. the expensive part -- exact FP64 box test, ball-ball CCD with its divisions and square root -- runs with all lanes
-//     busy, one pair per lane, instead of inside 32 divergent per-lane loops
-//  4. every lane collects the verdicts of its own pairs into its masks and counts.
-template<typename P, bool STAGED>
-__device__ __forceinline__ void sg_bpx_warp( const GridParams& g, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, const float4* __restrict__ boxf,
-                                             const uint32_t* __restrict__ sidx, const unsigned char* stage, const uint32_t n_slots, const uint32_t p, const typename P::Rec& me, bool part,
-                                             uint2* wq, uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
+// ---- pass 1, box-prefiltered, every warp on its own (D = 2) -----------------------------------------------
+// One thread per sorted body, no staging: a body's three row windows are contiguous runs of the dense 16-byte float-box array, and
+// the 32 bodies of a warp walk overlapping runs, so the boxes come through L1 at the wavefront cost shared memory would have (a
+// 128-bit access of 32 lanes is four wavefronts either way).  Its predecessor staged the windows of a 256-body tile with bulk copies
+// (cp.async.bulk, producer warp + 8 consumer warps, two 26 KB stages); measured on the B200 this one is faster on every scene
+// (config 2: 80 vs 93 us, config 3 at 2 M: 181 vs 207 us, at 16 M: 1.37 vs 1.65 ms) -- the staged kernel lost a fifth of its time
+// to fast warps waiting for the slowest warp of the CTA to release a stage, and both end up bound by the L1 / shared-memory data
+// pipe (63 % of its peak) and by load-to-use latency at 32 warps per SM, not by how the boxes get on chip.
+// What makes the walk shorter than the staged one:
+//  * far-side pruning: a body whose box ends before the next cell column (row) begins cannot touch anything binned there -- bodies
+//    are binned by their LOWER corners -- so that column (the whole upper window) is dropped from its ranges.  With radii spread
+//    over 1:4 most boxes are much smaller than a cell: 9 cells become 6.5 on average (config 3);
+//  * the own box is read from the float-box array like the partners' (one 128-bit load instead of rebuilding it from the record);
+//  * the three windows advance together, CH partners of each per round, all loads of a round requested before the first compare;
+//  * the exact FP64 box test is skipped for a survivor whose float boxes overlap by more than their rounding (below): what is left
+//    per pair is the narrow phase (ball-ball: division-free, sg_ccd.h).
+// The survivors of all 32 lanes are compacted into the warp's queue (shared memory, the only use of it) and tested one pair per
+// lane, so the FP64 work runs with all lanes busy instead of inside 32 divergent per-lane loops; every lane then collects the
+// verdicts of its own pairs into its masks and counts.
+
+// Float boxes are the FP64 boxes rounded OUTWARD: lo_f <= lo < next( lo_f ), prev( hi_f ) < hi <= hi_f.  So hi_A >= lo_B is certain once
+// prev( hi_A_f ) >= next( lo_B_f ), which a gap of more than the two spacings guarantees: spacing <= 2^-23 |x| for normal floats, the
+// absolute term covers subnormals.  True for all four sides => AABB::overlaps holds for the FP64 boxes, no need to build them.
+__device__ __forceinline__ bool sg_box_gap_certain( const float hi, const float lo )
+{
+  return ( hi - lo ) > 4.0e-7f * ( fabsf( hi ) + fabsf( lo ) ) + 1.0e-37f;
+}
+__device__ __forceinline__ bool sg_boxes_certainly_overlap( const float4 a, const float4 b )
+{
+  return sg_box_gap_certain( a.z, b.x ) && sg_box_gap_certain( b.z, a.x ) && sg_box_gap_certain( a.w, b.y ) && sg_box_gap_certain( b.w, a.y );
+}
+
+template<typename P, int CH, int MINB>
+__global__ void __launch_bounds__( SG_BP_THREADS, MINB ) sg_bp_count_l1( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+                                                                         const typename P::Rec* __restrict__ recs, const float4* __restrict__ boxf, const uint32_t* __restrict__ sidx,
+                                                                         uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
 {
   using Rec = typename P::Rec;
-  const float4* s_box = reinterpret_cast<const float4*>( stage );
-  const uint32_t* s_ord = reinterpret_cast<const uint32_t*>( stage + sg_bpx_ord_off() );
-  const uint32_t* s_cs = reinterpret_cast<const uint32_t*>( stage + sg_bpx_cs_off() );
-  const BpxHdr* hdr = reinterpret_cast<const BpxHdr*>( stage + sg_bpx_hdr_off() );
-  const BpStage<2>* st = &hdr->st;
+  static_assert( P::D == 2, "the box-prefiltered pass 1 is laid out for the 2-D pipelines" );
+  __shared__ uint2 s_wq[SG_BP_THREADS / 32][SG_BPX_QCAP];
+  uint2* wq = s_wq[threadIdx.x >> 5];
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t qb[3] = { 0u, 0u, 0u }, qe[3] = { 0u, 0u, 0u };
-  unsigned long long pm[3] = { 0ull, 0ull, 0ull };
-  uint32_t my_idx = 0u;
+  const uint32_t p = blockIdx.x * SG_BP_THREADS + threadIdx.x;
+  const GridParams g = *params;
+  const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned
+  if( blockIdx.x * SG_BP_THREADS >= n ) { return; } // (positions past the binned bodies belong to nobody: pass 2 finds a body's masks through pos_of)
+  bool part = p < n;
+  uint32_t my_idx = 0u, my_ord = 0u, key = 0u, c1 = 0u;
   if( part )
   {
-    my_idx = P::rec_idx( me );
-    const uint32_t my_ord = P::rec_ord( me );
-    sg_bp_ranges<P, SG_BPX_CSCAP, STAGED>( g, cell_start, s_cs, st, P::rec_key( me ), P::rec_c1( me, g ), P::rec_c2( me, g ), qb, qe );
+    // coalesced; only its integer words are kept.  (The stream of whole records also leaves the tile's records in L2 for the exact
+    // tests below: reading the four words from a 16-byte side array instead made this kernel 8 % SLOWER on 16 M bodies.)
+    const Rec me = sg_load_rec_global<Rec>( &recs[p] );
+    my_idx = P::rec_idx( me ); my_ord = P::rec_ord( me ); key = P::rec_key( me ); c1 = P::rec_c1( me, g );
+    if( !P::owns( me ) )
+    {
+      // a ghost body (multi-GPU halo): present only as a partner, its pairs are kept by the rank that owns it
+      counts[my_idx] = make_uint2( 0u, 0u );
+      masks[size_t( p ) * BpPlan<2>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u );
+      part = false;
+    }
+  }
+  uint32_t qb[3] = { 0u, 0u, 0u }, qe[3] = { 0u, 0u, 0u };
+  unsigned long long pm[3] = { 0ull, 0ull, 0ull };
+  if( part )
+  {
+    const float4 mb = __ldg( &boxf[p] ); // { lo.x, lo.y, hi.x, hi.y } rounded outward
+    // ---- ranges, pruned on the far side
+    const uint32_t cx = key - g.dims[0] * c1;
+    const uint32_t x0 = ( cx > 0u ) ? cx - 1u : 0u;
+    uint32_t x1 = ( cx + 1u < g.dims[0] ) ? cx + 1u : cx;
+    // A body B binned in column >= cx + 1 has fl( fl( lo_B - origin ) / h ) >= cx + 1, hence lo_B >= origin + (cx + 1) h (1 - 2^-51).
+    // If this body's upper bound (rounded up to float) lies below that, with a margin far above the rounding of the bound computed
+    // here, no box of that column can reach it.
+    {
+      const double edge = double( cx + 1u ) * g.h;
+      if( double( mb.z ) < ( g.origin[0] + edge ) - 1.0e-9 * ( fabs( g.origin[0] ) + edge ) ) { x1 = cx; }
+    }
+    bool up = c1 + 1u < g.dims[1];
+    {
+      const double edge = double( c1 + 1u ) * g.h;
+      if( double( mb.w ) < ( g.origin[1] + edge ) - 1.0e-9 * ( fabs( g.origin[1] ) + edge ) ) { up = false; }
+    }
+    #pragma unroll
+    for( int w = 0; w < 3; ++w )
+    {
+      const bool ok = ( w == 0 ) ? ( c1 > 0u ) : ( ( w == 2 ) ? up : true );
+      if( ok )
+      {
+        const uint32_t row = g.dims[0] * ( c1 + uint32_t( w ) - 1u );
+        qb[w] = __ldg( &cell_start[row + x0] );
+        qe[w] = __ldg( &cell_start[row + x1 + 1u] );
+      }
+    }
     uint32_t total = 0u;
     bool fits = true;
     #pragma unroll
@@ -753,40 +798,57 @@ __device__ __forceinline__ void sg_bpx_warp( const GridParams& g, const GridPara
     }
     if( !fits || total > SG_BP_MASK_BITS )
     {
-      // does not fit the bitmaps: the plain walk, on its own
+      // does not fit the bitmaps: the plain walk with exact tests (its own, unpruned, ranges and plan)
       sg_bpx_body_slow<P>( params, cell_start, recs, sidx, n_slots, p, counts, masks, plan );
       part = false;
     }
     else
     {
       sg_bp_plan_store<2>( plan, n_slots, p, qb, qe );
-      double lo[2], hi[2];
-      P::rec_aabb( me, lo, hi );
-      const float4 mb = sg_box_outward( lo, hi );
-      #pragma unroll
-      for( int w = 0; w < 3; ++w )
+      // ---- walk: bit j of pm[w] = partner qb[w] + j survives.  The three windows advance together, CH partners of each per
+      // round, boxes AND order words of the whole round requested before the first compare: one memory latency per round
+      // instead of two per window and round.  (Both arrays have slack behind their last entry: a round reads up to the longest
+      // window's length past a shorter window's end; those lanes are masked out.)
+      const uint32_t L0 = qe[0] - qb[0], L1 = qe[1] - qb[1], L2 = qe[2] - qb[2];
+      const uint32_t Lmax = max( L0, max( L1, L2 ) );
+      unsigned long long m0 = 0ull, m1 = 0ull, m2 = 0ull;
+      for( uint32_t j = 0u; j < Lmax; j += uint32_t( CH ) )
       {
-        unsigned long long m = 0ull;
-        const uint32_t s0 = qb[w] - st->start[w];
-        const uint32_t L = qe[w] - qb[w];
-        const float4* wb = s_box + w * SG_BPX_WCAP;
-        const uint32_t* wo = s_ord + w * ( SG_BPX_WCAP + 4 ) + hdr->ord_shift[w];
-        #pragma unroll 2
-        for( uint32_t j = 0u; j < L; ++j )
+        float4 b[3][CH];
+        uint32_t o[3][CH];
+        #pragma unroll
+        for( int w = 0; w < 3; ++w )
         {
-          const uint32_t slot = s0 + j;
-          const bool in = STAGED || slot < st->len[w];
-          const float4 b = in ? wb[slot] : __ldg( &boxf[qb[w] + j] );
-          const uint32_t o_ord = ( in ? wo[slot] : __ldg( &sidx[qb[w] + j] ) ) & P::IDX_MASK;
-          const bool pass = !( mb.z < b.x ) && !( b.z < mb.x ) && !( mb.w < b.y ) && !( b.w < mb.y ) && o_ord > my_ord; // never the body itself: equal order words
-          m |= static_cast<unsigned long long>( pass ? 1u : 0u ) << j;
+          #pragma unroll
+          for( int u = 0; u < CH; ++u ) { b[w][u] = __ldg( boxf + qb[w] + j + u ); o[w][u] = __ldg( sidx + qb[w] + j + u ); }
         }
-        pm[w] = m;
+        uint32_t t[3] = { 0u, 0u, 0u };
+        #pragma unroll
+        for( int w = 0; w < 3; ++w )
+        {
+          const uint32_t L = ( w == 0 ) ? L0 : ( ( w == 1 ) ? L1 : L2 );
+          #pragma unroll
+          for( int u = 0; u < CH; ++u )
+          {
+            const bool pass = !( mb.z < b[w][u].x ) && !( b[w][u].z < mb.x ) && !( mb.w < b[w][u].y ) && !( b[w][u].w < mb.y ) && j + u < L
+                              && ( o[w][u] & P::IDX_MASK ) > my_ord; // never the body itself: equal order words
+            if( pass ) { t[w] |= 1u << u; }
+          }
+        }
+        m0 |= static_cast<unsigned long long>( t[0] ) << j;
+        m1 |= static_cast<unsigned long long>( t[1] ) << j;
+        m2 |= static_cast<unsigned long long>( t[2] ) << j;
       }
+      pm[0] = m0; pm[1] = m1; pm[2] = m2;
     }
   }
-  // ---- compact the survivors of the warp
+  // ---- compact the survivors of the warp into its queue: ( partner position, visit number | owner lane << 8 )
   const uint32_t cnt = uint32_t( __popcll( pm[0] ) + __popcll( pm[1] ) + __popcll( pm[2] ) ); // 0 for lanes that do not take part
+  if( __ballot_sync( 0xffffffffu, cnt != 0u ) == 0u )
+  {
+    if( part ) { counts[my_idx] = make_uint2( 0u, 0u ); masks[size_t( p ) * BpPlan<2>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u ); }
+    return;
+  }
   const uint32_t cq = ( cnt < SG_BPX_QLANE ) ? cnt : SG_BPX_QLANE;
   uint32_t off = cq;
   #pragma unroll
@@ -809,12 +871,12 @@ __device__ __forceinline__ void sg_bpx_warp( const GridParams& g, const GridPara
         const uint32_t j = uint32_t( __ffsll( static_cast<long long>( m ) ) ) - 1u;
         m &= m - 1ull;
         const uint32_t q = qb[w] + j;
-        const uint32_t k = base + j - ( ( mine && q > p ) ? 1u : 0u );
+        const uint32_t k = base + j - ( ( mine && q > p ) ? 1u : 0u ); // number of this visit in the body's visit sequence
         if( taken < SG_BPX_QLANE ) { wq[off + taken] = make_uint2( q, k | ( lane << 8 ) ); }
         else
         {
           // more survivors than this lane's share of the queue (dense scenes): tested here
-          const uint32_t res = sg_bpx_exact<P>( sg_load_rec_global<Rec>( &recs[p] ), sg_load_rec_global<Rec>( &recs[q] ) ); // (own record re-read: keeping it live through the warp phases would cost 16 registers)
+          const uint32_t res = sg_bpx_exact<P>( sg_load_rec_global<Rec>( &recs[p] ), sg_load_rec_global<Rec>( &recs[q] ) );
           if( res & 1u ) { ++nc; cmask |= 1ull << k; }
           if( res & 2u ) { ++na; amask |= 1ull << k; }
         }
@@ -824,14 +886,21 @@ __device__ __forceinline__ void sg_bpx_warp( const GridParams& g, const GridPara
     }
   }
   __syncwarp();
-  // ---- exact tests, one pair per lane
+  // ---- the tests, one pair per lane
   const uint32_t warp_first = p - lane; // sorted position of lane 0's body
   for( uint32_t e = lane; e < total_q; e += 32u )
   {
     const uint2 ent = wq[e];
-    const Rec a = sg_load_rec_global<Rec>( &recs[warp_first + ( ( ent.y >> 8 ) & 31u )] );
-    const Rec b = sg_load_rec_global<Rec>( &recs[ent.x] );
-    wq[e].y = ent.y | ( sg_bpx_exact<P>( a, b ) << 30 );
+    const uint32_t pa = warp_first + ( ( ent.y >> 8 ) & 31u );
+    uint32_t res;
+    if( sg_boxes_certainly_overlap( __ldg( &boxf[pa] ), __ldg( &boxf[ent.x] ) ) )
+    {
+      // the usual case: the pair is a candidate for certain, what is left is the narrow phase
+      res = 1u;
+      if( P::HAS_NARROW ) { if( P::narrow_test( sg_load_rec_global<Rec>( &recs[pa] ), sg_load_rec_global<Rec>( &recs[ent.x] ) ) ) { res |= 2u; } }
+    }
+    else { res = sg_bpx_exact<P>( sg_load_rec_global<Rec>( &recs[pa] ), sg_load_rec_global<Rec>( &recs[ent.x] ) ); } // boxes within rounding of touching: the FP64 boxes decide
+    wq[e].y = ent.y | ( res << 30 );
   }
   __syncwarp();
   // ---- verdicts back to the owners
@@ -842,140 +911,14 @@ __device__ __forceinline__ void sg_bpx_warp( const GridParams& g, const GridPara
     if( y & 0x40000000u ) { ++nc; cmask |= bit; }
     if( y & 0x80000000u ) { ++na; amask |= bit; }
   }
-  __syncwarp(); // the queue is reused by the next tile
   if( part )
   {
     counts[my_idx] = make_uint2( nc, na );
-    masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
+    masks[size_t( p ) * BpPlan<2>::STRIDE] = make_uint4( uint32_t( cmask ), uint32_t( cmask >> 32 ), uint32_t( amask ), uint32_t( amask >> 32 ) );
   }
 }
 
-template<typename P>
-__global__ void __launch_bounds__( SG_BPX_T + 32, SG_BPX_CTAS_PER_SM ) sg_bp_count_tma( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
-                                                                                const typename P::Rec* __restrict__ recs, const float4* __restrict__ boxf, const uint32_t* __restrict__ sidx,
-                                                                                uint2* __restrict__ counts, uint4* __restrict__ masks, uint4* __restrict__ plan )
-{
-  using Rec = typename P::Rec;
-  static_assert( P::D == 2, "the box-prefiltered pass 1 is laid out for the 2-D pipelines" );
-  extern __shared__ __align__( 1024 ) unsigned char s_raw[];
-  constexpr size_t STAGE = sg_bpx_stage_bytes();
-  uint64_t* bars = reinterpret_cast<uint64_t*>( s_raw + SG_BPX_STAGES * STAGE ); // full[0], full[1], empty[0], empty[1]
-  const GridParams g = *params;
-  const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned
-  const uint32_t ntiles = ( n_slots + SG_BPX_T - 1u ) / SG_BPX_T;
-  const bool producer = threadIdx.x >= uint32_t( SG_BPX_T );
-  if( threadIdx.x == 0 )
-  {
-    sg_mbar_init( &bars[0], 1u ); sg_mbar_init( &bars[1], 1u );
-    sg_mbar_init( &bars[2], SG_BPX_T / 32u ); sg_mbar_init( &bars[3], SG_BPX_T / 32u );
-  }
-  __syncthreads();
-
-  if( producer )
-  {
-    if( threadIdx.x != uint32_t( SG_BPX_T ) ) { return; } // one elected lane drives the copies
-    uint32_t it = 0u;
-    for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
-    {
-      const uint32_t b0 = t * SG_BPX_T;
-      if( b0 >= n ) { break; } // tiles past the binned bodies have nothing to stage (consumers only clear masks)
-      const uint32_t sgi = it % SG_BPX_STAGES, use = it / SG_BPX_STAGES;
-      unsigned char* stage = s_raw + sgi * STAGE;
-      BpxHdr* hdr = reinterpret_cast<BpxHdr*>( stage + sg_bpx_hdr_off() );
-      // the tile's plan (two dependent rounds of global loads) does not need the stage: fetch it first, wait after
-      const uint32_t b1 = ( n - b0 < uint32_t( SG_BPX_T ) ) ? n : b0 + SG_BPX_T;
-      const long long kf = __ldg( &recs[b0].key );
-      const long long kl = __ldg( &recs[b1 - 1u].key );
-      long long klo[3], khi[3];
-      uint32_t start[3], end[3];
-      #pragma unroll
-      for( int w = 0; w < 3; ++w )
-      {
-        const long long off = ( long long )( w - 1 ) * g.dims[0];
-        klo[w] = kf + off - 1; khi[w] = kl + off + 1;
-        const bool ok = khi[w] >= 0 && klo[w] <= ( long long )( g.ncells ) - 1;
-        klo[w] = ( klo[w] < 0 ) ? 0 : klo[w];
-        khi[w] = ( khi[w] > ( long long )( g.ncells ) - 1 ) ? ( long long )( g.ncells ) - 1 : khi[w];
-        if( !ok ) { klo[w] = 0; khi[w] = -1; }
-        start[w] = ok ? __ldg( &cell_start[klo[w]] ) : 0u;
-        end[w] = ok ? __ldg( &cell_start[khi[w] + 1] ) : 0u;
-      }
-      uint32_t bytes = 0u, all_staged = 1u;
-      uint32_t len[3], ord_first[3], ord_n[3], cs_first[3], cs_n[3];
-      if( use > 0u ) { sg_mbar_wait_backoff( &bars[2 + sgi], ( use - 1u ) & 1u ); } // consumers are done with this stage
-      #pragma unroll
-      for( int w = 0; w < 3; ++w )
-      {
-        len[w] = ( end[w] - start[w] < uint32_t( SG_BPX_WCAP ) ) ? end[w] - start[w] : uint32_t( SG_BPX_WCAP );
-        // order words: from a 16-byte aligned entry, whole 16-byte groups (the array has slack behind its end)
-        ord_first[w] = start[w] & ~3u;
-        ord_n[w] = ( len[w] == 0u ) ? 0u : ( ( start[w] - ord_first[w] + len[w] + 3u ) & ~3u );
-        // cell_start slice: entries klo .. khi+1, widened to whole 16-byte groups
-        const long long ncs = khi[w] - klo[w] + 2;
-        cs_first[w] = uint32_t( klo[w] ) & ~3u;
-        uint32_t want = ( khi[w] < klo[w] ) ? 0u : uint32_t( klo[w] - cs_first[w] + ncs );
-        want = ( want + 3u ) & ~3u;
-        cs_n[w] = ( want < uint32_t( SG_BPX_CSCAP ) ) ? want : uint32_t( SG_BPX_CSCAP );
-        hdr->st.start[w] = start[w]; hdr->st.len[w] = len[w]; hdr->st.cs_klo[w] = cs_first[w]; hdr->st.cs_len[w] = cs_n[w];
-        hdr->ord_shift[w] = start[w] - ord_first[w];
-        if( end[w] - start[w] > uint32_t( SG_BPX_WCAP ) || want > uint32_t( SG_BPX_CSCAP ) ) { all_staged = 0u; }
-        bytes += len[w] * 16u + ord_n[w] * 4u + cs_n[w] * 4u;
-      }
-      hdr->st.full = all_staged;
-      asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); // the stage's earlier generic reads vs the async writes to come
-      sg_mbar_arrive_expect_tx( &bars[sgi], bytes );
-      #pragma unroll
-      for( int w = 0; w < 3; ++w )
-      {
-        if( len[w] != 0u )
-        {
-          sg_bulk_g2s( stage + size_t( w ) * SG_BPX_WCAP * 16, boxf + start[w], len[w] * 16u, &bars[sgi] );
-          sg_bulk_g2s( stage + sg_bpx_ord_off() + size_t( w ) * ( SG_BPX_WCAP + 4 ) * 4, sidx + ord_first[w], ord_n[w] * 4u, &bars[sgi] );
-        }
-        if( cs_n[w] != 0u ) { sg_bulk_g2s( stage + sg_bpx_cs_off() + size_t( w ) * SG_BPX_CSCAP * 4, cell_start + cs_first[w], cs_n[w] * 4u, &bars[sgi] ); }
-      }
-    }
-    return;
-  }
-
-  // ---- consumers ----
-  uint2* wq = reinterpret_cast<uint2*>( s_raw + SG_BPX_STAGES * STAGE + 64 ) + ( threadIdx.x >> 5 ) * SG_BPX_QCAP; // this warp's survivor queue
-  uint32_t it = 0u;
-  for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
-  {
-    const uint32_t p = t * SG_BPX_T + threadIdx.x;
-    if( t * SG_BPX_T >= n )
-    {
-      if( p < n_slots ) { masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u ); } // unused slots: pass 2 skips them
-      continue;
-    }
-    const uint32_t sgi = it % SG_BPX_STAGES, use = it / SG_BPX_STAGES;
-    const unsigned char* stage = s_raw + sgi * STAGE;
-    Rec me;
-    if( p < n ) { me = sg_load_rec_global<Rec>( &recs[p] ); } // coalesced; in flight while the stage lands
-    sg_mbar_wait( &bars[sgi], use & 1u );
-    bool part = p < n;
-    if( part && !P::owns( me ) )
-    {
-      // a ghost body (multi-GPU halo): present only as a partner, its pairs are kept by the rank that owns it
-      counts[P::rec_idx( me )] = make_uint2( 0u, 0u );
-      masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u );
-      part = false;
-    }
-    else if( !part && p < n_slots ) { masks[size_t( p ) * BpPlan<P::D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u ); }
-    // tiles whose windows and cell_start slices were staged completely (the rule, not the exception) run a
-    // walk with no fallback code in it at all
-    const BpxHdr* hdr = reinterpret_cast<const BpxHdr*>( stage + sg_bpx_hdr_off() );
-    if( hdr->st.full != 0u ) { sg_bpx_warp<P, true>( g, params, cell_start, recs, boxf, sidx, stage, n_slots, p, me, part, wq, counts, masks, plan ); }
-    else { sg_bpx_warp<P, false>( g, params, cell_start, recs, boxf, sidx, stage, n_slots, p, me, part, wq, counts, masks, plan ); }
-    // this warp is done with the stage
-    __syncwarp();
-    if( ( threadIdx.x & 31u ) == 0u ) { sg_mbar_arrive( &bars[2 + sgi] ); }
-  }
-}
-
-// Dispatch: the 2-D pipelines take the TMA-fed kernel, the 3-D ones the block-staged kernel (their 9 windows do not
-// fit a double-buffered stage at a useful occupancy).
+// Dispatch: the 2-D pipelines take the box-prefiltered kernel, the 3-D ones the block-staged kernel.
 template<int D> struct SgBpCountLaunch;
 template<> struct SgBpCountLaunch<3>
 {
@@ -992,11 +935,7 @@ template<> struct SgBpCountLaunch<2>
 {
   template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const uint32_t n )
   {
-    constexpr size_t smem = sg_bpx_smem();
-    if( s.attr_dev != ctx->device ) { SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_tma<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) ); s.attr_dev = ctx->device; } // opt-in to > 48 KB, once per context
-    const unsigned ntiles = sg_div_up( n, SG_BPX_T );
-    const unsigned grid = ntiles < unsigned( ctx->num_sms ) * SG_BPX_CTAS_PER_SM ? ntiles : unsigned( ctx->num_sms ) * SG_BPX_CTAS_PER_SM;
-    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_tma<P><<<grid, SG_BPX_T + 32, smem, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_l1<P, 2, 4><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
                s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
     return SG_OK;
   }
@@ -1038,7 +977,7 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, con
   auto emit_one = [&]( const unsigned long long kc, const Rec& o, const uint32_t o_ord, const uint32_t q )
   {
     if( cand != nullptr && kc < cand_cap ) { cand[kc] = make_uint2( my_ord, o_ord ); }
-    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { if( ka < work_cap ) { work[ka] = make_uint2( p, q ); } ++ka; } }
+    if( P::HAS_NARROW ) { if( P::narrow_test( me, o ) ) { if( ka < work_cap ) { work[ka] = make_uint2( P::rec_idx( me ), q ); } ++ka; } }
   };
   if( nc <= SG_BP_LOCAL_CAP )
   {
@@ -1239,7 +1178,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t
       {
         if( uint32_t( j ) < nc && ( ( v[j] >> 31 ) & 1ull ) )
         {
-          if( ka < work_cap ) { work[ka] = make_uint2( p, uint32_t( v[j] & 0x7fffffffull ) ); }
+          if( ka < work_cap ) { work[ka] = make_uint2( i, uint32_t( v[j] & 0x7fffffffull ) ); }
           ++ka;
         }
       }
@@ -1250,11 +1189,13 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t
   sg_bp_emit_slow<P>( p, complete ? nc : 0xffffffffu, counts, off, my_ord, params, cell_start, recs, sidx, cand, cand_cap, work, work_cap );
 }
 
-// Pass 3 (policies with a fused narrow phase).  One thread per active pair, grid-stride over the work list pass 2
-// left in output order: both records come through L1/L2 (consecutive contacts share the first body), the contact
-// is written at its own index => every store of the SoA contact arrays is fully coalesced.
+// Pass 3 (policies with a fused narrow phase).  One thread per active pair, grid-stride over the work list pass 2 left in output
+// order: ( body index of the pair's first body, sorted position of its partner ).  The list is in index order, so the first body's
+// data is read from the caller's by-index arrays -- coalesced, consecutive contacts share it -- and only the partner's record is a
+// gather (one 64-byte line instead of two: on 16 M randomly numbered balls, where every gather is a DRAM access, that is most of
+// this kernel's traffic); the contact is written at its own index => every store of the SoA contact arrays is fully coalesced.
 template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS, 5 ) sg_bp_contacts( const ScanPairCounts::Acc* __restrict__ totals, const uint2* __restrict__ work, const uint64_t work_cap,
+__global__ void __launch_bounds__( SG_BP_THREADS, 5 ) sg_bp_contacts( const typename P::In in, const ScanPairCounts::Acc* __restrict__ totals, const uint2* __restrict__ work, const uint64_t work_cap,
                                                                   const typename P::Rec* __restrict__ recs, const typename P::Out out )
 {
   using Rec = typename P::Rec;
@@ -1263,7 +1204,7 @@ __global__ void __launch_bounds__( SG_BP_THREADS, 5 ) sg_bp_contacts( const Scan
   for( unsigned long long c = blockIdx.x * uint64_t( blockDim.x ) + threadIdx.x; c < na; c += uint64_t( gridDim.x ) * blockDim.x )
   {
     const uint2 w = __ldg( &work[c] );
-    const Rec a = sg_load_rec_global<Rec>( &recs[w.x] );
+    const Rec a = P::make_rec( in, w.x, 0u, 0u, 0u ); // what the scatter put into the body's record (cell words aside)
     const Rec b = sg_load_rec_global<Rec>( &recs[w.y] );
     unsigned long long k = c;
     P::contact_emit( out, k, a, b );
@@ -1292,8 +1233,8 @@ static int sg_bp_prepare_scratch( sg_ctx* ctx, BroadScratch& s, const uint32_t n
   SG_CUDA( ctx, s.key.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.rank.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.recs.ensure( size_t( n ) * 64 ) );
-  SG_CUDA( ctx, s.sidx.ensure( size_t( n ) * 4 + 64 ) ); // + slack: bulk copies read whole 16-byte groups
-  if( P::D == 2 ) { SG_CUDA( ctx, s.boxf.ensure( size_t( n ) * 16 ) ); }
+  SG_CUDA( ctx, s.sidx.ensure( size_t( n ) * 4 + 512 ) ); // + slack: bulk copies read whole 16-byte groups, pass 1 up to a window's length past the end
+  if( P::D == 2 ) { SG_CUDA( ctx, s.boxf.ensure( size_t( n ) * 16 + 2048 ) ); } // + slack: pass 1 reads up to a window's length (<= 64 entries) past the end
   SG_CUDA( ctx, s.pos_of.ensure( size_t( n ) * 4 ) );
   SG_CUDA( ctx, s.counts.ensure( size_t( n ) * sizeof( uint2 ) ) );
   SG_CUDA( ctx, s.masks.ensure( size_t( n ) * sizeof( uint4 ) * BpPlan<P::D>::STRIDE ) ); // masks and walk plan interleaved by position
@@ -1339,13 +1280,13 @@ static int sg_bp_bin_and_count( sg_ctx* ctx, BroadScratch& s, const typename P::
 template<bool> struct SgBpContactsLaunch;
 template<> struct SgBpContactsLaunch<false>
 {
-  template<typename P> static int run( sg_ctx*, BroadScratch&, const typename P::Out&, const uint64_t ) { return SG_OK; }
+  template<typename P> static int run( sg_ctx*, BroadScratch&, const typename P::In&, const typename P::Out&, const uint64_t ) { return SG_OK; }
 };
 template<> struct SgBpContactsLaunch<true>
 {
-  template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const typename P::Out& out, const uint64_t act_cap )
+  template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const typename P::In& in, const typename P::Out& out, const uint64_t act_cap )
   {
-    SG_LAUNCH( ctx, "bp_contacts", 0.0, sg_bp_contacts<P><<<unsigned( ctx->num_sms ) * 5u, SG_BP_THREADS, 0, ctx->stream>>>( s.totals.as<ScanPairCounts::Acc>(), s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap,
+    SG_LAUNCH( ctx, "bp_contacts", 0.0, sg_bp_contacts<P><<<unsigned( ctx->num_sms ) * 5u, SG_BP_THREADS, 0, ctx->stream>>>( in, s.totals.as<ScanPairCounts::Acc>(), s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap,
                s.recs.as<typename P::Rec>(), out ) );
     return SG_OK;
   }
@@ -1353,7 +1294,7 @@ template<> struct SgBpContactsLaunch<true>
 
 // act_cap = capacity of the caller's contact arrays (0 for policies without a narrow phase)
 template<typename P>
-static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, const bool want_cand, const typename P::Out& out, const uint64_t act_cap )
+static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const typename P::In& in, const uint32_t n, const bool want_cand, const typename P::Out& out, const uint64_t act_cap )
 {
   if( P::HAS_NARROW && act_cap > s.work_cap )
   {
@@ -1363,7 +1304,7 @@ static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const uint32_t n, con
   SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ), sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
              s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>(), s.ord_by_index, s.masks.as<uint4>(), s.masks.as<uint4>() + 1, s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap,
              s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap ) );
-  return SgBpContactsLaunch<P::HAS_NARROW>::template run<P>( ctx, s, out, act_cap );
+  return SgBpContactsLaunch<P::HAS_NARROW>::template run<P>( ctx, s, in, out, act_cap );
 }
 
 #endif

@@ -163,23 +163,7 @@ __global__ void __launch_bounds__( 256 ) k_rb2d_aabb( const Rb2dDev dev, const d
 // ---- narrow phase ----------------------------------------------------------------------------------
 __device__ __forceinline__ bool rb2d_ccd( const V2d q0a, const V2d q1a, const double ra, const V2d q0b, const V2d q1b, const double rb )
 {
-  const double d0x = q0a.x - q0b.x, d0y = q0a.y - q0b.y;
-  const double d1x = ( q1a.x - q1b.x ) - d0x, d1y = ( q1a.y - q1b.y ) - d0y;
-  const double rs = ra + rb;
-  const double c0 = ( d0x * d0x + d0y * d0y ) - rs * rs;
-  const double c1 = 2.0 * ( d0x * d1x + d0y * d1y );
-  const double c2 = d1x * d1x + d1y * d1y;
-  if( c2 != 0.0 )
-  {
-    const double c1c1 = c1 * c1, fc2c0 = 4.0 * c2 * c0;
-    if( c1c1 < fc2c0 ) { return false; }
-    const double s = sqrt( c1c1 - fc2c0 );
-    const double root1 = ( c1 > 0.0 ) ? ( 2.0 * c0 ) / ( -c1 - s ) : ( -c1 + s ) / ( 2.0 * c2 );
-    if( root1 < 0.0 ) { return false; }
-    const double root0 = ( c1 >= 0.0 ) ? ( -c1 - s ) / ( 2.0 * c2 ) : ( 2.0 * c0 ) / ( -c1 + s );
-    return !( root0 > 1.0 );
-  }
-  return c0 <= 0.0;
+  return sg_ccd_ball_ball( q0a.x, q0a.y, q1a.x, q1a.y, ra, q0b.x, q0b.y, q1b.x, q1b.y, rb ); // sg_ccd.h
 }
 
 __device__ __forceinline__ bool rb2d_axis( const double dist, const double widths, const int crnt, double& smallest, bool& invert, int& feature )
@@ -571,7 +555,7 @@ static int rb2d_active_set_device( sg_ctx* ctx, Rb2dData* d )
   if( np + 64 > d->bp.cand_cap ) { SG_CUDA( ctx, d->bp.cand.ensure( size_t( np + 64 ) * sizeof( uint2 ) ) ); d->bp.cand_cap = d->bp.cand.cap / sizeof( uint2 ); }
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<Box2DPolicy>( ctx, d->bp, n, true, NoOut2D{}, 0u );
+    rc = sg_bp_emit_lists<Box2DPolicy>( ctx, d->bp, in, n, true, NoOut2D{}, 0u );
     if( rc != SG_OK ) { return rc; }
   }
   SG_CUDA( ctx, d->pair_counts.ensure( size_t( np ) * 4 + 4 ) );
@@ -705,7 +689,7 @@ static int rb2d_portal_active_set_device( sg_ctx* ctx, Rb2dData* d )
   uint32_t nraw = 0;
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<Box2DPolicy>( ctx, d->bp, next, true, NoOut2D{}, 0u );
+    rc = sg_bp_emit_lists<Box2DPolicy>( ctx, d->bp, in, next, true, NoOut2D{}, 0u );
     if( rc != SG_OK ) { return rc; }
     SG_CUDA( ctx, x->reg_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->reg_off.ensure( size_t( np ) * 8 + 8 ) );
     SG_CUDA( ctx, x->tel_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->tel_off.ensure( size_t( np ) * 4 + 4 ) );
@@ -901,6 +885,7 @@ int sg_rb2d_set_planes( sg_ctx* ctx, uint32_t n, const double* x, const double* 
 {
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   if( n > SG_MAX_PLANES ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_set_planes: at most %d planes", SG_MAX_PLANES ); }
+  if( n > 0 && ( x == nullptr || nrm == nullptr ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_set_planes: null array" ); }
   Rb2dData* d = rb2d_data( ctx );
   d->planes.n = n;
   for( uint32_t p = 0; p < n; ++p ) { for( int k = 0; k < 2; ++k ) { d->planes.x[p][k] = x[2 * p + k]; d->planes.nrm[p][k] = nrm[2 * p + k]; } }
@@ -1046,6 +1031,7 @@ int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
     d->flow_resident = false;
   }
   const int rc = ( d->px != nullptr && d->px->portals.n > 0u ) ? rb2d_portal_active_set_device( ctx, d ) : rb2d_active_set_device( ctx, d );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   return rb2d_copy_out( ctx, d, out_flags, out );
 }
@@ -1077,6 +1063,7 @@ int sg_rb2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
                d->g[0], d->g[1], dt, d->q1.as<double>(), d->v1.as<double>() ) );
   }
   const int rc = ( d->px != nullptr && d->px->portals.n > 0u ) ? rb2d_portal_active_set_device( ctx, d ) : rb2d_active_set_device( ctx, d );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   if( out != nullptr )
   {

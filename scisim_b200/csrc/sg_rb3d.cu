@@ -1474,7 +1474,7 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
     SG_LAUNCH( ctx, "rb3d_totals", 0.0, k_rb3d_sum_totals<<<1, 1, 0, ctx->stream>>>( d->bp.totals.as<ScanPairCounts::Acc>(), d->narrow_total.as<unsigned long long>(), 1, d->totals3.as<unsigned long long>() ) );
     for( int attempt = 0; attempt < 2; ++attempt )
     {
-      rc = sg_bp_emit_lists<Sphere3DPolicy>( ctx, d->bp, n, want_cand, rb3d_out( d ), d->act_cap );
+      rc = sg_bp_emit_lists<Sphere3DPolicy>( ctx, d->bp, in, n, want_cand, rb3d_out( d ), d->act_cap );
       if( rc != SG_OK ) { return rc; }
       rc = rb3d_planes_device( ctx, d, true );
       if( rc != SG_OK ) { return rc; }
@@ -1513,7 +1513,7 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
   if( rc != SG_OK ) { return rc; }
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, n, true, NoOut3D{}, 0u );
+    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, in, n, true, NoOut3D{}, 0u );
     if( rc != SG_OK ) { return rc; }
   }
   if( np >= 0xffffffffull ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rb3d: more than 2^32 candidate pairs in the generic pipeline" ); }
@@ -1653,7 +1653,7 @@ static int rb3d_portal_active_set_device( sg_ctx* ctx, Rb3dData* d )
   uint32_t nraw = 0;
   if( np > 0 )
   {
-    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, next, true, NoOut3D{}, 0u );
+    rc = sg_bp_emit_lists<Box3DPolicy>( ctx, d->bp, in, next, true, NoOut3D{}, 0u );
     if( rc != SG_OK ) { return rc; }
     SG_CUDA( ctx, x->reg_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->reg_off.ensure( size_t( np ) * 8 + 8 ) );
     SG_CUDA( ctx, x->tel_cnt.ensure( size_t( np ) * 4 + 4 ) ); SG_CUDA( ctx, x->tel_off.ensure( size_t( np ) * 4 + 4 ) );
@@ -2132,6 +2132,7 @@ int sg_rb3d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
     d->q1_valid = false;
   }
   const int rc = rb3d_active_set_device( ctx, d, ( out_flags & SG_OUT_CANDIDATES ) != 0u );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   return rb3d_copy_out( ctx, d, out_flags, out );
 }
@@ -2175,6 +2176,7 @@ int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
   int rc = rb3d_flow_device( ctx, d, map_kind, dt );
   if( rc != SG_OK ) { return rc; }
   rc = rb3d_active_set_device( ctx, d, true );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   if( out != nullptr )
   {
@@ -2388,6 +2390,7 @@ int sg_rb3d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   if( d->bp.params.ptr == nullptr ) { SG_CUDA( ctx, d->bp.params.ensure( sizeof( GridParams ) ) ); SG_CUDA( ctx, cudaMemsetAsync( d->bp.params.ptr, 0, sizeof( GridParams ), ctx->stream ) ); }
   const int rc = rb3d_active_set_device( ctx, d, true );
+  if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
   c.scan_done = false;
   uint32_t hg[4];

@@ -240,6 +240,7 @@ void GpuRigidBody3DBackend::setBodies( const std::vector<uint32_t>& geo_of_body,
 {
   m_nbodies = static_cast<unsigned>( geo_of_body.size() );
   check( sg_rb3d_set_bodies( m_ctx, m_nbodies, geo_of_body.data(), fixed.data(), m.data(), I0.data() ), "sg_rb3d_set_bodies" );
+  m_m_updated = false; // a re-initialised state starts from the constructor's (transposed) inertia block again
 }
 
 void GpuRigidBody3DBackend::setGravity( const double gx, const double gy, const double gz )
