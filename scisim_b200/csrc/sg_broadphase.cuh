@@ -324,19 +324,44 @@ __global__ void __launch_bounds__( SG_BP_THREADS ) sg_bp_scatter( const typename
                                                                  const uint32_t* __restrict__ rank_in, typename P::Rec* __restrict__ recs, uint32_t* __restrict__ pos_of,
                                                                  uint32_t* __restrict__ cell_count, const uint32_t cell_slots )
 {
+  // A record goes to a random place, so what counts is how many memory requests it takes: a thread storing its own record issues four
+  // 16-byte writes to four different instructions' worth of scattered lines (each 32-byte sector is written in two halves).  Instead the
+  // warp passes its 32 records through shared memory and four lanes store one record together: every store instruction writes eight
+  // whole 64-byte records, a quarter of the requests and only full sectors.
+  __shared__ int4 s_rec[SG_BP_THREADS][4];
+  __shared__ uint32_t s_pos[SG_BP_THREADS];
   const uint32_t g_dims0 = params->dims[0], g_dims1 = params->dims[1];
   // the histogram has been consumed by the scan: leave it zeroed for the next step (grid-stride, coalesced)
   for( uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < cell_slots; c += gridDim.x * blockDim.x ) { cell_count[c] = 0u; }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if( i >= in.n ) { return; }
-  const uint32_t key = key_in[i];
-  if( key == 0xffffffffu ) { pos_of[i] = 0xffffffffu; return; }
-  const uint32_t pos = __ldg( &cell_start[key] ) + rank_in[i];
-  // cell coordinates travel with the record (no integer division in the pair kernels)
-  const uint32_t yz = key / g_dims0;
-  const typename P::Rec r = P::make_rec( in, i, key, ( P::D == 3 ) ? yz % g_dims1 : yz, ( P::D == 3 ) ? yz / g_dims1 : 0u );
-  sg_store_rec( &recs[pos], r );
-  pos_of[i] = pos;
+  uint32_t pos = 0xffffffffu;
+  if( i < in.n )
+  {
+    const uint32_t key = key_in[i];
+    if( key != 0xffffffffu )
+    {
+      pos = __ldg( &cell_start[key] ) + rank_in[i];
+      // cell coordinates travel with the record (no integer division in the pair kernels)
+      const uint32_t yz = key / g_dims0;
+      union { typename P::Rec r; int4 v[4]; } u;
+      u.r = P::make_rec( in, i, key, ( P::D == 3 ) ? yz % g_dims1 : yz, ( P::D == 3 ) ? yz / g_dims1 : 0u );
+      const uint32_t sw = ( threadIdx.x >> 1 ) & 3u; // chunk c of slot t at c ^ ((t >> 1) & 3): conflict-free 128-bit accesses both ways
+      #pragma unroll
+      for( uint32_t c = 0u; c < 4u; ++c ) { s_rec[threadIdx.x][c ^ sw] = u.v[c]; }
+    }
+    pos_of[i] = pos;
+  }
+  s_pos[threadIdx.x] = pos;
+  __syncwarp();
+  const uint32_t lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+  #pragma unroll
+  for( uint32_t round = 0u; round < 4u; ++round )
+  {
+    const uint32_t t = wbase + round * 8u + ( lane >> 2 ); // the record this lane helps to store
+    const uint32_t c = lane & 3u;                          // ... and which 16 bytes of it
+    const uint32_t tp = s_pos[t];
+    if( tp != 0xffffffffu ) { reinterpret_cast<int4*>( recs + tp )[c] = s_rec[t][c ^ ( ( t >> 1 ) & 3u )]; }
+  }
 }
 
 // The dense by-position side arrays of the sorted records, written in one coalesced pass (the scatter's writes are random:
