@@ -427,7 +427,22 @@ def main():
         t_e2e_local = time.perf_counter() - t0
         n_act, e2e_api = a.n_active, "sg_ball2d_flow (q0,v0 up; q1,v1 down) + sg_ball2d_active_set(SG_IN_RESIDENT: the flow's q0,q1 stay on the device; contacts down), pinned host buffers, wall clock"
         assert a.n_active == pa and a.n_candidates == pc
+        # the same call as SCISim's shim makes it: the reference's constraint constructors take (type, i, j) and the host
+        # state, so normals / points / depths need not cross the bus -- reported beside the headline e2e, which downloads everything
+        for it in range(1 + e2e_steps):
+            if it == 1:
+                ctx.synchronize()
+                t0 = time.perf_counter()
+            sim._flow(umap.kind, q0h, v0h, dt, q1h, v1h)
+            a2 = sim.computeActiveSet(q0h, q1h, flags=0, copy=False, resident=True)
+        ctx.synchronize()
+        t_shim = time.perf_counter() - t0
+        assert a2.n_active == pa
+        e2e_shim = {"value": pairs_local * e2e_steps / t_shim, "unit": UNIT, "ms_per_step": 1e3 * t_shim / e2e_steps, "h2d_bytes_per_step": 2 * 2 * n_local * 8,
+                    "d2h_bytes_per_step": 2 * 2 * n_local * 8 + int(a2.n_active) * 12,
+                    "api": "as e2e with out_flags = 0: (type, i, j) of every contact come back, no normals / points / depths -- what the SCISim-side shim needs to call the reference's constraint constructors"}
     else:
+        e2e_shim = None
         import ctypes as C
         from scisim_b200._lib import SgContacts
         vp = lambda x: x.ctypes.data_as(C.c_void_p)
@@ -510,6 +525,8 @@ def main():
                          "peak_source": peak_src, "share_of_step": ms / total_ms, "timed": "separate pass of the same %d steps with CUDA events around every kernel (rank 0)" % args.steps,
                          "kernels": kernels},
         }
+        if e2e_shim is not None:
+            line["e2e_indices_only"] = e2e_shim
         if extra is not None:
             line["config2"] = extra
         if not args.no_cpu_baseline:

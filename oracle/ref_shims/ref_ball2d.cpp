@@ -2,6 +2,8 @@
 //   ball2d/SpatialGridDetector.cpp                               (AABB, getPotentialOverlaps, getPotentialOverlapsAllPairs)
 //   scisim/CollisionDetection/CollisionDetectionUtilities.cpp    (computeCCDQuadraticCoeffs, ballBallCCDCollisionHappens)
 //   ball2d/StaticGeometry/StaticPlane.cpp, ball2d/Portals/PlanarPortal.cpp   (portal touch tests, teleports, kinematic velocities)
+//   ball2d/Constraints/{BallBall,BallStaticPlane,BallStaticDrum}Constraint.cpp, scisim/Constraints/Constraint.cpp   (isActive, constructors, normal,
+//                                                                 contact point, penetrationDepth, evalgradg, computeContactBasis)
 //   ball2d/SymplecticEulerMap.cpp, ball2d/VerletMap.cpp, ball2d/Forces/Ball2DGravityForce.cpp (+ Ball2DForce.cpp,
 //   scisim/UnconstrainedMaps/UnconstrainedMap.cpp, FlowableSystem.cpp)       (the two unconstrained maps with the gravity force)
 // compiled from /root/reference against oracle/eigen_standin (oracle/Makefile.ref).  The glue between them (swept boxes,
@@ -15,6 +17,9 @@
 #include "scisim/UnconstrainedMaps/FlowableSystem.h"
 #include "ball2d/StaticGeometry/StaticDrum.h"
 #include "scisim/Utilities.h"
+#include "ball2d/Constraints/BallBallConstraint.h"
+#include "ball2d/Constraints/BallStaticPlaneConstraint.h"
+#include "ball2d/Constraints/BallStaticDrumConstraint.h"
 
 #include <memory>
 #include <sstream>
@@ -203,6 +208,65 @@ void ref_ball2d_flow( const int kind, const uint32_t n, const double* m, const d
   if( kind == 0 ) { SymplecticEulerMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
   else { VerletMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
   for( uint32_t k = 0; k < 2 * n; ++k ) { q1[k] = vq1( int( k ) ); v1[k] = vv1( int( k ) ); }
+}
+
+}
+
+
+// ---- the constraint classes themselves: what Ball2DSim builds per contact (ball2d/Ball2DSim.cpp:596-607, 730-762) and what the impact maps
+// then ask of it (ImpactOperatorUtilities::computeN -> evalgradg, Ball2DSim::computeContactBases -> computeBasis) ---------------------------
+extern "C"
+{
+
+// kind 0: BallBallConstraint{ i, j, q0, r_i, r_j, false }      geo unused
+//      1: StaticPlaneConstraint{ i, r_i, StaticPlane{ x, n }, j }   geo = x[2], n[2]   (n is normalised by StaticPlane's constructor)
+//      2: StaticDrumConstraint{ i, q0, r_i, X, j }               geo = X[2], R
+// out[0]     the class's isActive at q1 (ball-ball: BallBallConstraint::isActive( i, j, q1, r ), what the portal path tests)
+// out[1..2]  getWorldSpaceContactNormal( q0 )      out[3..4] getWorldSpaceContactPoint( q0 )      out[5] penetrationDepth( q1 )
+// out[6..9]  computeBasis( q0, v ) column-major [ n | t ]
+// grad_rows / grad_vals: the ( row, value ) pairs evalgradg( q0, col = 0, G ) inserts, in insertion order; returns their number
+int ref_ball2d_constraint_probe( const int kind, const unsigned i, const unsigned j, const uint32_t nballs, const double* q0, const double* q1, const double* r, const double* geo,
+                                 double* out, int* grad_rows, double* grad_vals )
+{
+  const int nb = int( nballs );
+  VectorXs vq0{ 2 * nb }, vq1{ 2 * nb }, vr{ nb }, vv{ 2 * nb };
+  for( uint32_t k = 0; k < 2 * nballs; ++k ) { vq0( int( k ) ) = q0[k]; vq1( int( k ) ) = q1[k]; vv( int( k ) ) = 0.0; }
+  for( uint32_t k = 0; k < nballs; ++k ) { vr( int( k ) ) = r[k]; }
+  std::unique_ptr<Constraint> con;
+  bool active = false;
+  if( kind == 0 )
+  {
+    active = BallBallConstraint::isActive( i, j, vq1, vr );
+    con.reset( new BallBallConstraint{ i, j, vq0, r[i], r[j], false } );
+  }
+  else if( kind == 1 )
+  {
+    const StaticPlane plane{ Vector2s{ geo[0], geo[1] }, Vector2s{ geo[2], geo[3] } };
+    active = StaticPlaneConstraint::isActive( i, vq1, vr, plane.x(), plane.n() );
+    con.reset( new StaticPlaneConstraint{ i, r[i], plane, j } );
+  }
+  else
+  {
+    active = StaticDrumConstraint::isActive( i, vq1, vr, Vector2s{ geo[0], geo[1] }, geo[2] );
+    con.reset( new StaticDrumConstraint{ i, vq0, r[i], Vector2s{ geo[0], geo[1] }, j } );
+  }
+  out[0] = active ? 1.0 : 0.0;
+  VectorXs n, p;
+  con->getWorldSpaceContactNormal( vq0, n );
+  con->getWorldSpaceContactPoint( vq0, p );
+  out[1] = n( 0 ); out[2] = n( 1 ); out[3] = p( 0 ); out[4] = p( 1 );
+  out[5] = con->penetrationDepth( vq1 );
+  MatrixXXsc basis;
+  con->computeBasis( vq0, vv, basis );
+  out[6] = basis( 0, 0 ); out[7] = basis( 1, 0 ); out[8] = basis( 0, 1 ); out[9] = basis( 1, 1 );
+  std::vector<double> ones( nballs, 1.0 );
+  const double g0[2] = { 0.0, 0.0 };
+  ShimBall2DSystem sys{ nballs, ones.data(), r, g0 };
+  SparseMatrixsc G{ 2 * int( nballs ), 1 };
+  con->evalgradg( vq0, 0, G, sys );
+  const int nt = int( G.trip_row.size() );
+  for( int k = 0; k < nt; ++k ) { grad_rows[k] = G.trip_row[std::size_t( k )]; grad_vals[k] = G.trip_val[std::size_t( k )]; }
+  return nt;
 }
 
 }

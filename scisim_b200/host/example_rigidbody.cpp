@@ -16,6 +16,13 @@ struct TinySystem final : public FlowableSystem
   unsigned numVelDoFsPerBody() const override { return dim == 3 ? 6 : 3; }
   unsigned ambientSpaceDimensions() const override { return unsigned( dim ); }
   bool isKinematicallyScripted( const int ) const override { return false; }
+  // the sims' computeForce with their one NearEarthGravityForce: F = 0 + M g on the translational dofs (unit masses, g = -9.81 y)
+  void computeForce( const VectorXs&, const VectorXs&, const scalar&, VectorXs& F ) override
+  {
+    F.setZero();
+    const int n = dim == 3 ? nv / 6 : nv / 3;
+    for( int b = 0; b < n; ++b ) { F( 3 * b + 1 ) = 0.0 + 1.0 * -9.81; }
+  }
   std::string name() const override { return dim == 3 ? "rigid_body_3d" : "rigid_body_2d"; }
 };
 

@@ -8,6 +8,30 @@
 #include <limits>
 #include <numeric>
 
+void GravityOnlyGuard::verify( FlowableSystem& fsys, const VectorXs& q0, const VectorXs& v0, const scalar& t, const Layout layout, const char* who )
+{
+  if( m_checked ) { return; }
+  VectorXs F( v0.size() );
+  F.setZero();
+  fsys.computeForce( q0, v0, t, F );
+  const long n = static_cast<long>( m_mass.size() );
+  const int dim = ( layout == RIGIDBODY3D ) ? 3 : 2;
+  const long per_body = ( layout == BALL2D ) ? 2 : 3;
+  bool ok = F.size() == ( layout == RIGIDBODY3D ? 6 * n : per_body * n );
+  for( long i = 0; ok && i < n; ++i )
+  {
+    for( int k = 0; k < dim; ++k ) { ok = ok && F( per_body * i + k ) == 0.0 + m_mass[std::size_t( i )] * m_g[k]; } // 0 + m g: the accumulation into a zeroed F
+    if( layout == RIGIDBODY2D ) { ok = ok && F( 3 * i + 2 ) == 0.0; }
+    if( layout == RIGIDBODY3D ) { for( int k = 0; k < 3; ++k ) { ok = ok && F( 3 * n + 3 * i + k ) == 0.0; } }
+  }
+  if( !ok )
+  {
+    std::cerr << who << ": the system's forces are not the single near-earth gravity configured on the GPU back end; keep the CPU map for this scene. Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+  m_checked = true;
+}
+
 GpuBall2DBackend::GpuBall2DBackend( const int device )
 : m_ctx( nullptr )
 , m_nbodies( 0 )
@@ -35,12 +59,14 @@ void GpuBall2DBackend::setBodies( const VectorXs& r, const VectorXs& m )
 {
   m_nbodies = static_cast<unsigned>( r.size() );
   check( sg_ball2d_set_bodies( m_ctx, m_nbodies, r.data(), m.data() ), "sg_ball2d_set_bodies" );
+  m_guard.setMasses( m.data(), m_nbodies, 1 );
 }
 
 void GpuBall2DBackend::setGravity( const double gx, const double gy )
 {
   const double g[2] = { gx, gy };
   check( sg_ball2d_set_gravity( m_ctx, g ), "sg_ball2d_set_gravity" );
+  m_guard.setGravity( gx, gy, 0.0 );
 }
 
 void GpuBall2DBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n )
@@ -114,6 +140,28 @@ void GpuBall2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1,
   if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
 }
 
+void GpuBall2DBackend::assemble( const uint32_t flags, sg_assembly& out )
+{
+  check( sg_ball2d_assemble( m_ctx, flags, &out ), "sg_ball2d_assemble" );
+}
+
+void GpuBall2DBackend::cacheStore( const unsigned ncomp, const VectorXs& r )
+{
+  check( sg_ball2d_cache_store( m_ctx, ncomp, r.data() ), "sg_ball2d_cache_store" );
+}
+
+uint64_t GpuBall2DBackend::cacheLookup( const unsigned ncomp, VectorXs& r )
+{
+  uint64_t hits = 0;
+  check( sg_ball2d_cache_lookup( m_ctx, ncomp, r.data(), &hits ), "sg_ball2d_cache_lookup" );
+  return hits;
+}
+
+void GpuBall2DBackend::cacheClear()
+{
+  check( sg_ball2d_cache_clear( m_ctx ), "sg_ball2d_cache_clear" );
+}
+
 void GpuBall2DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps )
 {
   sg_pairs p;
@@ -123,13 +171,96 @@ void GpuBall2DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, s
   for( uint64_t k = 0; k < p.n; ++k ) { overlaps.emplace_back( p.ij[2 * k], p.ij[2 * k + 1] ); }
 }
 
-void GpuSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+void GpuSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::BALL2D, "GpuSymplecticEulerMap" );
   m_backend.flow( SG_MAP_SYMPLECTIC_EULER, q0, v0, dt, q1, v1 );
 }
 
-void GpuVerletMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+void GpuVerletMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::BALL2D, "GpuVerletMap" );
+  m_backend.flow( SG_MAP_VERLET, q0, v0, dt, q1, v1 );
+}
+
+// ---- several GPUs of this process -------------------------------------------------------------------
+GpuBall2DMultiBackend::GpuBall2DMultiBackend( const std::vector<int>& devices )
+: m_multi( nullptr )
+{
+  const int rc = sg_create_multi( &m_multi, static_cast<int>( devices.size() ), devices.data() );
+  if( rc != SG_OK )
+  {
+    std::cerr << "GpuBall2DMultiBackend: " << sg_multi_last_error( nullptr ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+GpuBall2DMultiBackend::~GpuBall2DMultiBackend() { sg_destroy_multi( m_multi ); }
+
+void GpuBall2DMultiBackend::check( const int rc, const char* what ) const
+{
+  if( rc != SG_OK )
+  {
+    std::cerr << what << ": " << sg_multi_last_error( m_multi ) << " Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+}
+
+void GpuBall2DMultiBackend::setBodies( const VectorXs& r, const VectorXs& m )
+{
+  check( sg_multi_ball2d_set_bodies( m_multi, static_cast<uint32_t>( r.size() ), r.data(), m.data() ), "sg_multi_ball2d_set_bodies" );
+  m_guard.setMasses( m.data(), static_cast<unsigned>( r.size() ), 1 );
+}
+void GpuBall2DMultiBackend::setGravity( const double gx, const double gy )
+{
+  const double g[2] = { gx, gy };
+  check( sg_multi_ball2d_set_gravity( m_multi, g ), "sg_multi_ball2d_set_gravity" );
+  m_guard.setGravity( gx, gy, 0.0 );
+}
+void GpuBall2DMultiBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n ) { check( sg_multi_ball2d_set_planes( m_multi, static_cast<uint32_t>( x.size() / 2 ), x.data(), n.data() ), "sg_multi_ball2d_set_planes" ); }
+void GpuBall2DMultiBackend::setDrums( const std::vector<double>& x, const std::vector<double>& r ) { check( sg_multi_ball2d_set_drums( m_multi, static_cast<uint32_t>( r.size() ), x.data(), r.data() ), "sg_multi_ball2d_set_drums" ); }
+
+void GpuBall2DMultiBackend::flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  if( q1.size() != q0.size() ) { q1.resize( q0.size() ); }
+  if( v1.size() != v0.size() ) { v1.resize( v0.size() ); }
+  check( sg_multi_ball2d_flow( m_multi, map_kind, q0.data(), v0.data(), dt, q1.data(), v1.data() ), "sg_multi_ball2d_flow" );
+}
+
+void GpuBall2DMultiBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates, const bool from_last_flow )
+{
+  sg_contacts c;
+  check( sg_multi_ball2d_active_set( m_multi, q0.data(), q1.data(), SG_OUT_NORMALS | SG_OUT_POINTS | SG_OUT_DEPTHS | ( from_last_flow ? SG_IN_RESIDENT : 0u ), &c ), "sg_multi_ball2d_active_set" );
+  contacts.resize( c.n_active );
+  for( uint64_t k = 0; k < c.n_active; ++k )
+  {
+    GpuContact2D& o = contacts[k];
+    o.type = c.type[k]; o.i = c.i[k]; o.j = c.j[k];
+    o.n[0] = c.n[2 * k]; o.n[1] = c.n[2 * k + 1];
+    o.p[0] = c.p[2 * k]; o.p[1] = c.p[2 * k + 1];
+    o.depth = c.depth[k];
+  }
+  if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
+}
+
+unsigned GpuBall2DMultiBackend::numGpus() const { return static_cast<unsigned>( sg_multi_n_gpus( m_multi ) ); }
+
+uint64_t GpuBall2DMultiBackend::numPartitions()
+{
+  uint64_t np = 0;
+  check( sg_multi_partition_info( m_multi, nullptr, nullptr, nullptr, &np ), "sg_multi_partition_info" );
+  return np;
+}
+
+void GpuMultiSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::BALL2D, "GpuMultiSymplecticEulerMap" );
+  m_backend.flow( SG_MAP_SYMPLECTIC_EULER, q0, v0, dt, q1, v1 );
+}
+
+void GpuMultiVerletMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+{
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::BALL2D, "GpuMultiVerletMap" );
   m_backend.flow( SG_MAP_VERLET, q0, v0, dt, q1, v1 );
 }
 
@@ -241,12 +372,14 @@ void GpuRigidBody3DBackend::setBodies( const std::vector<uint32_t>& geo_of_body,
   m_nbodies = static_cast<unsigned>( geo_of_body.size() );
   check( sg_rb3d_set_bodies( m_ctx, m_nbodies, geo_of_body.data(), fixed.data(), m.data(), I0.data() ), "sg_rb3d_set_bodies" );
   m_m_updated = false; // a re-initialised state starts from the constructor's (transposed) inertia block again
+  m_guard.setMasses( m.data(), m_nbodies, 1 );
 }
 
 void GpuRigidBody3DBackend::setGravity( const double gx, const double gy, const double gz )
 {
   const double g[3] = { gx, gy, gz };
   check( sg_rb3d_set_gravity( m_ctx, g ), "sg_rb3d_set_gravity" );
+  m_guard.setGravity( gx, gy, gz );
 }
 
 void GpuRigidBody3DBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n )
@@ -320,13 +453,15 @@ void GpuRigidBody3DBackend::getPotentialOverlaps( const std::vector<double>& aab
   for( uint64_t k = 0; k < p.n; ++k ) { overlaps.emplace_back( p.ij[2 * k], p.ij[2 * k + 1] ); }
 }
 
-void GpuSplitHamMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+void GpuSplitHamMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::RIGIDBODY3D, "GpuSplitHamMap" );
   m_backend.flow( SG_MAP_SPLIT_HAM, q0, v0, dt, q1, v1 );
 }
 
-void GpuDMVMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+void GpuDMVMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::RIGIDBODY3D, "GpuDMVMap" );
   m_backend.flow( SG_MAP_DMV, q0, v0, dt, q1, v1 );
 }
 
@@ -363,12 +498,14 @@ void GpuRigidBody2DBackend::setBodies( const std::vector<uint32_t>& geo_of_body,
 {
   m_nbodies = static_cast<unsigned>( geo_of_body.size() );
   check( sg_rb2d_set_bodies( m_ctx, m_nbodies, geo_of_body.data(), fixed.data(), M.data() ), "sg_rb2d_set_bodies" );
+  m_guard.setMasses( M.data(), m_nbodies, 3 ); // M = diag( m, m, I ) per body
 }
 
 void GpuRigidBody2DBackend::setGravity( const double gx, const double gy )
 {
   const double g[2] = { gx, gy };
   check( sg_rb2d_set_gravity( m_ctx, g ), "sg_rb2d_set_gravity" );
+  m_guard.setGravity( gx, gy, 0.0 );
 }
 
 void GpuRigidBody2DBackend::setPlanes( const std::vector<double>& x, const std::vector<double>& n )
@@ -434,12 +571,14 @@ void GpuRigidBody2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs
   if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
 }
 
-void GpuRB2DSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+void GpuRB2DSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::RIGIDBODY2D, "GpuRB2DSymplecticEulerMap" );
   m_backend.flow( SG_MAP_SYMPLECTIC_EULER, q0, v0, dt, q1, v1 );
 }
 
-void GpuRB2DVerletMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem&, const unsigned, const scalar& dt, VectorXs& q1, VectorXs& v1 )
+void GpuRB2DVerletMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )
 {
+  m_backend.forceGuard().verify( fsys, q0, v0, iteration * dt, GravityOnlyGuard::RIGIDBODY2D, "GpuRB2DVerletMap" );
   m_backend.flow( SG_MAP_VERLET, q0, v0, dt, q1, v1 );
 }

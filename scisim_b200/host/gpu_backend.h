@@ -3,6 +3,7 @@
 // (INTEGRATION.md).
 //
 //   GpuBall2DBackend        owns the sg_ctx; static scene data in, contact records out (reference order)
+//   GpuBall2DMultiBackend   the same calls over several GPUs of this process (sg_multi: x-slabs behind the interface)
 //   GpuSymplecticEulerMap,
 //   GpuVerletMap            UnconstrainedMap implementations registered beside ball2d's own maps
 //                           (ball2d/Ball2DUtilities.cpp:37, ball2dutils/Ball2DSceneParser.cpp:624-631)
@@ -44,6 +45,24 @@ struct GpuTeleportedContact2D
   double delta0[2], delta1[2]; // rigidbody2d only (TeleportedCircleCircleConstraint's displacements); NaN otherwise
 };
 
+// The GPU maps integrate with the single gravity vector pushed to the device and never call fsys.computeForce.  The guard checks once
+// per state -- on the first flow after the bodies or the gravity changed -- that the system's force IS that gravity:
+// F = fsys.computeForce( q0, v0, t ) must equal 0 + m g on every translational degree of freedom and 0 on the rotational ones.
+// Anything else (ball2d's PenaltyForce, a second force, another gravity) prints and exits, as the reference does for set-ups it does
+// not support -- the scene must then keep the CPU map.
+class GravityOnlyGuard final
+{
+public:
+  enum Layout { BALL2D, RIGIDBODY2D, RIGIDBODY3D }; // [x y]*, [x y theta]*, [x y z]* then [wx wy wz]*
+  void setMasses( const double* m, const unsigned n, const unsigned stride ) { m_mass.resize( n ); for( unsigned i = 0; i < n; ++i ) { m_mass[i] = m[std::size_t( i ) * stride]; } m_checked = false; }
+  void setGravity( const double gx, const double gy, const double gz ) { m_g[0] = gx; m_g[1] = gy; m_g[2] = gz; m_checked = false; }
+  void verify( FlowableSystem& fsys, const VectorXs& q0, const VectorXs& v0, const scalar& t, const Layout layout, const char* who );
+private:
+  std::vector<double> m_mass;
+  double m_g[3] = { 0.0, 0.0, 0.0 };
+  bool m_checked = false;
+};
+
 class GpuBall2DBackend final
 {
 public:
@@ -76,12 +95,49 @@ public:
   // SpatialGridDetector::getPotentialOverlaps (ball2d/SpatialGridDetector.h:39) on caller-built boxes [minx,miny,maxx,maxy]
   void getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps );
 
+  // What the impact maps build first from the active set just computed (ImpactMap.cpp:100-110, Ball2DSim.cpp:188-201), assembled on the
+  // device: N (zeros pruned), Q = N^T Minv N, contact bases -- compressed column-major, pointers valid until the next call (sg_ball2d_assemble)
+  void assemble( const uint32_t flags, sg_assembly& out );
+  // ConstraintCache (ball2d/ConstraintCache.cpp:20-122) for the whole active set at once: store the impulses (ncomp values per constraint,
+  // active-set order), look up the warm start of the current active set (zeros where a constraint was not cached; returns the hits)
+  void cacheStore( const unsigned ncomp, const VectorXs& r );
+  uint64_t cacheLookup( const unsigned ncomp, VectorXs& r );
+  void cacheClear();
+
   sg_ctx* context() { return m_ctx; }
+  GravityOnlyGuard& forceGuard() { return m_guard; }
 
 private:
   void check( const int rc, const char* what ) const;
   sg_ctx* m_ctx;
   unsigned m_nbodies;
+  GravityOnlyGuard m_guard;
+};
+
+// Ball2DSim's hot path on several GPUs of ONE process (include/scisim_b200.h, sg_multi): same calls, global vectors and indices.
+// The scene is cut into equal-count x-slabs behind the interface, re-cut when bodies migrate, and the per-slab lists come back merged
+// in the reference's order -- the caller cannot tell it from GpuBall2DBackend except by the clock.  Portals are not supported here.
+class GpuBall2DMultiBackend final
+{
+public:
+  explicit GpuBall2DMultiBackend( const std::vector<int>& devices );
+  ~GpuBall2DMultiBackend();
+  GpuBall2DMultiBackend( const GpuBall2DMultiBackend& ) = delete;
+  GpuBall2DMultiBackend& operator=( const GpuBall2DMultiBackend& ) = delete;
+  void setBodies( const VectorXs& r, const VectorXs& m );
+  void setGravity( const double gx, const double gy );
+  void setPlanes( const std::vector<double>& x, const std::vector<double>& n );
+  void setDrums( const std::vector<double>& x, const std::vector<double>& r );
+  void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
+  void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
+  unsigned numGpus() const;
+  uint64_t numPartitions(); // how often the scene has been (re-)partitioned so far
+  sg_multi* handle() { return m_multi; }
+  GravityOnlyGuard& forceGuard() { return m_guard; }
+private:
+  void check( const int rc, const char* what ) const;
+  sg_multi* m_multi;
+  GravityOnlyGuard m_guard;
 };
 
 class GpuSymplecticEulerMap final : public UnconstrainedMap
@@ -104,6 +160,29 @@ public:
   virtual void serialize( std::ostream& ) const override {}
 private:
   GpuBall2DBackend& m_backend;
+};
+
+// the same two maps over GpuBall2DMultiBackend
+class GpuMultiSymplecticEulerMap final : public UnconstrainedMap
+{
+public:
+  explicit GpuMultiSymplecticEulerMap( GpuBall2DMultiBackend& backend ) : m_backend( backend ) {}
+  virtual void flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 ) override;
+  virtual std::string name() const override { return "symplectic_euler"; }
+  virtual void serialize( std::ostream& ) const override {}
+private:
+  GpuBall2DMultiBackend& m_backend;
+};
+
+class GpuMultiVerletMap final : public UnconstrainedMap
+{
+public:
+  explicit GpuMultiVerletMap( GpuBall2DMultiBackend& backend ) : m_backend( backend ) {}
+  virtual void flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 ) override;
+  virtual std::string name() const override { return "verlet"; }
+  virtual void serialize( std::ostream& ) const override {}
+private:
+  GpuBall2DMultiBackend& m_backend;
 };
 
 // ball2d/ConstraintCache.{h,cpp}: three std::map<std::pair<unsigned,unsigned>,VectorXs> (ball-ball, plane-ball,
@@ -197,12 +276,14 @@ public:
   void getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps );
 
   sg_ctx* context() { return m_ctx; }
+  GravityOnlyGuard& forceGuard() { return m_guard; }
 
 private:
   void check( const int rc, const char* what ) const;
   sg_ctx* m_ctx;
   unsigned m_nbodies;
   bool m_m_updated = false;
+  GravityOnlyGuard m_guard;
 };
 
 class GpuSplitHamMap final : public UnconstrainedMap
@@ -259,11 +340,13 @@ public:
   void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
 
   sg_ctx* context() { return m_ctx; }
+  GravityOnlyGuard& forceGuard() { return m_guard; }
 
 private:
   void check( const int rc, const char* what ) const;
   sg_ctx* m_ctx;
   unsigned m_nbodies;
+  GravityOnlyGuard m_guard;
 };
 
 class GpuRB2DSymplecticEulerMap final : public UnconstrainedMap

@@ -39,8 +39,9 @@ private:
   std::vector<double> m_v;
 };
 
-// scisim/UnconstrainedMaps/FlowableSystem.h:6-58 (only what the GPU maps need: sizes and kinematic flags; masses and
-// forces are pushed to the device once through the back end)
+// scisim/UnconstrainedMaps/FlowableSystem.h:6-58 (only what the GPU maps need: sizes, kinematic flags and computeForce -- masses
+// and gravity are pushed to the device once through the back end; computeForce is called once per state by
+// GravityOnlyGuard to make sure the system's force IS that gravity)
 class FlowableSystem
 {
 public:
@@ -50,6 +51,7 @@ public:
   virtual unsigned numVelDoFsPerBody() const = 0;
   virtual unsigned ambientSpaceDimensions() const = 0;
   virtual bool isKinematicallyScripted( const int i ) const = 0;
+  virtual void computeForce( const VectorXs& q, const VectorXs& v, const scalar& t, VectorXs& F ) = 0; // FlowableSystem.h:24
   virtual std::string name() const = 0;
 };
 
