@@ -234,6 +234,7 @@ int ref_ball2d_constraint_probe( const int kind, const unsigned i, const unsigne
   for( uint32_t k = 0; k < nballs; ++k ) { vr( int( k ) ) = r[k]; }
   std::unique_ptr<Constraint> con;
   bool active = false;
+  const StaticPlane plane{ Vector2s{ geo[0], geo[1] }, ( kind == 1 ) ? Vector2s{ geo[2], geo[3] } : Vector2s{ 0.0, 1.0 } }; // outlives the constraint, which keeps a reference to it
   if( kind == 0 )
   {
     active = BallBallConstraint::isActive( i, j, vq1, vr );
@@ -241,7 +242,6 @@ int ref_ball2d_constraint_probe( const int kind, const unsigned i, const unsigne
   }
   else if( kind == 1 )
   {
-    const StaticPlane plane{ Vector2s{ geo[0], geo[1] }, Vector2s{ geo[2], geo[3] } };
     active = StaticPlaneConstraint::isActive( i, vq1, vr, plane.x(), plane.n() );
     con.reset( new StaticPlaneConstraint{ i, r[i], plane, j } );
   }

@@ -23,6 +23,10 @@
 #include "rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.h"
 #include "rigidbody3d/Forces/NearEarthGravityForce.h"
 #include "scisim/UnconstrainedMaps/FlowableSystem.h"
+#include "rigidbody3d/Constraints/SphereSphereConstraint.h"
+#include "rigidbody3d/Constraints/StaticPlaneSphereConstraint.h"
+#include "rigidbody3d/Constraints/StaticPlaneBoxConstraint.h"
+#include <memory>
 
 #include <sstream>
 
@@ -286,5 +290,84 @@ void ref_rb3d_mass_blocks( const uint32_t n, const double* q, const double* m, c
   const double g[3] = { 0.0, 0.0, 0.0 };
   ShimRB3DSystem sys{ n, q, m, I0, fixed.data(), g, m_updated != 0 };
   for( size_t k = 0; k < 9 * size_t( n ); ++k ) { I_blocks[k] = sys.mValues()[3 * size_t( n ) + k]; Iinv_blocks[k] = sys.minvValues()[3 * size_t( n ) + k]; }
+}
+}
+
+
+// ---- the constraint classes themselves (rigidbody3d/Constraints/{SphereSphere,StaticPlaneSphere,StaticPlaneBox}Constraint.cpp
+// + scisim/Constraints/Constraint.cpp, compiled unchanged): isActive at q1, the constraint built as the sim builds it, its normal, world-space
+// contact point at q0 and penetrationDepth at q1 ---------------------------------------------------------------------------------------------
+extern "C"
+{
+
+// q0, q1: 12 n doubles ( 3n positions | 9n row-major rotations ).
+// kind 0  sphere-sphere ( i, j ), geo = r_i, r_j.  n and p are formed as RigidBody3DSim::sphereSphereNarrowPhaseCollision forms them (RigidBody3DSim.cpp:803-808,
+//         two lines restated here, marked) and handed to the class's constructor
+// kind 1  plane-sphere: geo = x[3], n[3], r          kind 2  plane-box: geo = x[3], n[3], half[3], aux = corner number
+// (StaticCylinderSphereConstraint needs StaticCylinder.cpp, whose GUI-only R() multiplies an AngleAxis by a Quaternion: not in the stand-in; cylinders stay restated)
+// out[0] isActive at q1 (plane-box: the corner is among the active corners), out[1..3] normal, out[4..6] contact point at q0, out[7] penetrationDepth( q1 )
+void ref_rb3d_constraint_probe( const int kind, const unsigned i, const unsigned j, const unsigned aux, const uint32_t nbodies, const double* q0, const double* q1, const double* geo, double* out )
+{
+  const int nq = 12 * int( nbodies );
+  VectorXs wq0{ nq }, wq1{ nq };
+  for( int k = 0; k < nq; ++k ) { wq0( k ) = q0[k]; wq1( k ) = q1[k]; }
+  const VectorXs& vq0 = wq0; const VectorXs& vq1 = wq1; // const: segment<3>() reads
+  const Vector3s gx{ geo[0], geo[1], geo[2] }, gn{ geo[3], geo[4], geo[5] };
+  const StaticPlane plane{ gx, ( kind == 1 || kind == 2 ) ? gn : Vector3s{ 0.0, 1.0, 0.0 } };   // outlive the constraints, which keep references
+  std::unique_ptr<Constraint> con;
+  bool active = false;
+  if( kind == 0 )
+  {
+    const scalar r0 = geo[0], r1 = geo[1];
+    active = SphereSphereConstraint::isActive( vq1.segment<3>( 3 * i ), vq1.segment<3>( 3 * j ), r0, r1 );
+    // restated glue (RigidBody3DSim.cpp:803, 808):
+    const Vector3s n{ ( vq0.segment<3>( 3 * i ) - vq0.segment<3>( 3 * j ) ).normalized() };
+    const Vector3s p{ vq0.segment<3>( 3 * i ) + ( r0 / ( r0 + r1 ) ) * ( vq0.segment<3>( 3 * j ) - vq0.segment<3>( 3 * i ) ) };
+    con.reset( new SphereSphereConstraint{ i, j, n, p, r0, r1 } );
+  }
+  else if( kind == 1 )
+  {
+    active = StaticPlaneSphereConstraint::isActive( plane.x(), plane.n(), vq1.segment<3>( 3 * i ), geo[6] );
+    con.reset( new StaticPlaneSphereConstraint{ i, geo[6], plane, j } );
+  }
+  else
+  {
+    const Vector3s half{ geo[6], geo[7], geo[8] };
+    const Matrix33sr R{ Eigen::Map<const Matrix33sr>( vq1.segment<9>( 3 * int( nbodies ) + 9 * i ).data() ) };
+    std::vector<short> corners;
+    StaticPlaneBoxConstraint::isActive( plane.x(), plane.n(), vq1.segment<3>( 3 * i ), R, half, corners );
+    for( const short c : corners ) { if( unsigned( c ) == aux ) { active = true; } }
+    con.reset( new StaticPlaneBoxConstraint{ i, short( aux ), plane.n(), half, vq0, j } );
+  }
+  out[0] = active ? 1.0 : 0.0;
+  VectorXs n, p;
+  con->getWorldSpaceContactNormal( vq0, n );
+  con->getWorldSpaceContactPoint( vq0, p );
+  for( int k = 0; k < 3; ++k ) { out[1 + k] = n( k ); out[4 + k] = p( k ); }
+  out[7] = con->penetrationDepth( vq1 );
+}
+
+}
+
+
+// ---- RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462).  The file itself does not compile against the stand-in (sparse
+// matrix internals, serialisation), so this pins less than the entries above: the two assignments of its loop body, typed with the same Eigen
+// types and Maps, evaluated by the stand-in -- i.e. that the oracle's restatement is what the stand-in makes of the reference's EXPRESSIONS
+// ( R * I0.asDiagonal() * R.transpose() into a column-major Map ), not that the reference's file was compiled.
+extern "C"
+{
+void ref_rb3d_update_inertia_expr( const double* R_rowmajor9, const double* I0_3, const double* Iinv0_3, double* I_colmajor9, double* Iinv_colmajor9 )
+{
+  const Eigen::Map<const Matrix33sr> R{ R_rowmajor9 };
+  {
+    Eigen::Map<Matrix33sc> I{ I_colmajor9 };
+    const Eigen::Map<const Vector3s> I0{ I0_3 };
+    I = R * I0.asDiagonal() * R.transpose();      // RigidBody3DState.cpp:446
+  }
+  {
+    Eigen::Map<Matrix33sc> Iinv{ Iinv_colmajor9 };
+    const Eigen::Map<const Vector3s> Iinv0{ Iinv0_3 };
+    Iinv = R * Iinv0.asDiagonal() * R.transpose(); // RigidBody3DState.cpp:455
+  }
 }
 }

@@ -423,3 +423,110 @@ def test_rb3d_update_m_and_minv_equals_reference_expression(oracle):
     m, I0 = np.ascontiguousarray(s["m"], dtype=np.float64), np.ascontiguousarray(s["I0"], dtype=np.float64)
     ref.ref_rb3d_mass_blocks(C.c_uint32(n), vp(q), vp(m), vp(I0), C.c_int(1), vp(rI), vp(rIi))
     assert np.array_equal(I, rI) and np.array_equal(Ii, rIi)
+
+
+def test_ball2d_constraint_classes(oracle):
+    """The reference's own constraint classes (ball2d/Constraints/{BallBall,BallStaticPlane,BallStaticDrum}Constraint.cpp + scisim/Constraints/
+    Constraint.cpp, compiled unchanged): isActive, constructor -> normal, getWorldSpaceContactPoint( q0 ), penetrationDepth( q1 ), computeBasis and
+    evalgradg for EVERY contact of an oracle active set -- normals, points, depths, the contact bases and the pruned N of the oracle's
+    assembly must equal them bit for bit (rows a10-a12 and f2 of SURVEY.md section 8)."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_ball2d.so")
+    ref.ref_ball2d_constraint_probe.restype = C.c_int
+    ref.ref_ball2d_constraint_probe.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint32] + [C.c_void_p] * 7
+    seen = {0: 0, 1: 0, 2: 0}
+    for seed, nballs in ((5, 1500), (6, 900)):
+        s = scenes.ball2d_random(nballs, seed, nplanes=3, ndrums=2)
+        o = ob.Ball2DOracle(s)
+        q0 = np.ascontiguousarray(s["q"], dtype=np.float64)
+        q1, _ = o.flow(1, q0, s["v"], s["dt"])
+        a = o.active_set(q0, q1, "grid")
+        asm = o.assemble()
+        assert asm["supported"]
+        r = np.ascontiguousarray(s["r"], dtype=np.float64)
+        out, rows, vals = np.zeros(10), np.zeros(8, dtype=np.int32), np.zeros(8)
+        for k in range(a["type"].shape[0]):
+            t, i, j = int(a["type"][k]), int(a["i"][k]), int(a["j"][k])
+            if t == 1:
+                geo = np.concatenate([s["drum_x"][j], [s["drum_r"][j]]]).astype(np.float64)
+                kind = 2
+            elif t == 2:
+                geo = np.concatenate([s["plane_x"][j], s["plane_n"][j]]).astype(np.float64)
+                kind = 1
+            else:
+                geo, kind = np.zeros(4), 0
+            geo = np.ascontiguousarray(geo)
+            nt = ref.ref_ball2d_constraint_probe(kind, i, j, nballs, vp(q0), vp(q1), vp(r), vp(geo), vp(out), vp(rows), vp(vals))
+            if kind != 0:
+                assert out[0] == 1.0   # planes and drums enter the active set through the class's isActive at q1 (Ball2DSim.cpp:730-762)
+            assert np.array_equal(out[1:3], a["n"][k]) and np.array_equal(out[3:5], a["p"][k]), (t, i, j)
+            assert out[5] == a["depth"][k] or (np.isnan(out[5]) and np.isnan(a["depth"][k]))
+            assert np.array_equal(out[6:10], asm["bases"][4 * k: 4 * k + 4])
+            # column k of the pruned N: the class's insertions with the zeros dropped (computeN prunes), rows ascending
+            keep = [(int(rows[e]), float(vals[e])) for e in range(nt) if vals[e] != 0.0]
+            lo, hi = int(asm["n_outer"][k]), int(asm["n_outer"][k + 1])
+            assert [(int(asm["n_inner"][e]), float(asm["n_values"][e])) for e in range(lo, hi)] == sorted(keep), (t, i, j)
+            seen[kind] += 1
+    assert seen[0] > 200 and seen[1] > 20 and seen[2] > 5, seen
+
+
+def test_rb3d_constraint_classes(oracle):
+    """rigidbody3d/Constraints/{SphereSphere,StaticPlaneSphere,StaticPlaneBox}Constraint.cpp (+ scisim/Constraints/Constraint.cpp), compiled unchanged:
+    isActive at q1, the constraint built as RigidBody3DSim builds it, its normal, its world-space contact point at q0 and penetrationDepth( q1 ) for
+    every sphere-sphere, plane-sphere and plane-box contact of oracle active sets, bit for bit."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    ref.ref_rb3d_constraint_probe.restype = None
+    ref.ref_rb3d_constraint_probe.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    seen = {10: 0, 14: 0, 15: 0}
+    for s in (scenes.rb3d_random_spheres(900, 31, spin=True, nfixed_frac=0.0, nplanes=3), scenes.rb3d_random_boxes(500, 32, nfixed_frac=0.0, nplanes=3)):
+        o = ob.RB3DOracle(s)
+        nb = s["geo_of_body"].shape[0]
+        q0 = np.ascontiguousarray(s["q"], dtype=np.float64)
+        q1, _ = o.flow(1, q0, s["v"], s["dt"])
+        a = o.active_set(q0, q1, "grid")
+        assert a["supported"]
+        out = np.zeros(8)
+        for k in range(a["type"].shape[0]):
+            t, i, j, aux = int(a["type"][k]), int(a["i"][k]), int(a["j"][k]), int(a["aux"][k])
+            gi = int(s["geo_of_body"][i])
+            if t == 10:
+                geo, kind = np.array([s["geo_r"][gi], s["geo_r"][int(s["geo_of_body"][j])], 0, 0, 0, 0, 0, 0, 0], dtype=np.float64), 0
+            elif t == 14:
+                geo, kind = np.concatenate([s["plane_x"][j], s["plane_n"][j], [s["geo_r"][gi], 0, 0]]).astype(np.float64), 1
+            elif t == 15:
+                geo, kind = np.concatenate([s["plane_x"][j], s["plane_n"][j], s["geo_half"][gi]]).astype(np.float64), 2
+            else:
+                continue
+            geo = np.ascontiguousarray(geo)
+            ref.ref_rb3d_constraint_probe(kind, i, j, aux, nb, vp(q0), vp(q1), vp(geo), vp(out))
+            assert out[0] == 1.0, (t, i, j, aux)
+            assert np.array_equal(out[1:4], a["n"][k]) and np.array_equal(out[4:7], a["p"][k]), (t, i, j, aux, out, a["n"][k], a["p"][k])
+            assert out[7] == a["depth"][k] or (np.isnan(out[7]) and np.isnan(a["depth"][k])), (t, out[7], a["depth"][k])
+            seen[t] += 1
+    assert seen[10] > 100 and seen[14] > 10 and seen[15] > 10, seen
+
+
+def test_rb3d_update_m_and_minv_expressions(oracle):
+    """RigidBody3DState::updateMandMinv (RigidBody3DState.cpp:428-462): the file does not compile against the stand-in, so this is an EXPRESSION pin --
+    its two assignments ( R * I0.asDiagonal() * R.transpose() into column-major maps ), typed as in the reference and evaluated by the stand-in, against
+    the oracle's restatement, for spinning boxes at random orientations."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    ref.ref_rb3d_update_inertia_expr.restype = None
+    ref.ref_rb3d_update_inertia_expr.argtypes = [C.c_void_p] * 5
+    s = scenes.rb3d_random_boxes(400, 77, nfixed_frac=0.0, nplanes=0)
+    o = ob.RB3DOracle(s)
+    n = s["geo_of_body"].shape[0]
+    q1, _ = o.flow(1, s["q"], s["v"], s["dt"])   # rotations that are orthonormal only up to rounding, as in a running simulation
+    I, Ii = o.update_m_and_minv(q1)
+    I0 = np.ascontiguousarray(s["I0"], dtype=np.float64).reshape(n, 3)
+    a, b = np.zeros(9), np.zeros(9)
+    for k in range(n):
+        R = np.ascontiguousarray(q1[3 * n + 9 * k: 3 * n + 9 * k + 9])
+        i0 = np.ascontiguousarray(I0[k]); ii0 = np.ascontiguousarray(1.0 / I0[k])
+        ref.ref_rb3d_update_inertia_expr(vp(R), vp(i0), vp(ii0), vp(a), vp(b))
+        assert np.array_equal(a, I[9 * k: 9 * k + 9]) and np.array_equal(b, Ii[9 * k: 9 * k + 9]), k
