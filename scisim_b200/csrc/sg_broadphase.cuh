@@ -1086,9 +1086,12 @@ template<> __device__ __forceinline__ void sg_sort_keys<16>( unsigned long long*
 // Nothing is shared between threads: pass 1 left, per sorted position, the candidate/active masks over the visit
 // sequence and the walk plan (window starts and lengths), so a thread decodes its set bits straight to sorted
 // positions, gathers the partners' order words, orders its candidates (up to 8 in 2-D, 16 in 3-D) with a register sorting
-// network and stores them.  No staging, no barriers, no shared memory.
-template<typename P>
-__global__ void __launch_bounds__( SG_BP_THREADS, 4 ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
+// network and stores them.  No staging, no barriers, no shared memory.  The kernel is a chain of dependent gathers, i.e. latency-bound, and
+// the 2-D instance (8-key network) fits 48 or even 40 registers without spilling.  Measured (config 3): when the gathers go to DRAM (16 M
+// bodies) 48 warps per SM win -- 1007 / 875 / 816 us at 4 / 5 / 6 CTAs per SM; when they hit L2 (2 M) 40 warps do -- 125 / 122 / 135 us.
+// The launch picks by size; the 3-D instance (16 keys) keeps 64 registers.
+template<typename P, int MINB>
+__global__ void __launch_bounds__( SG_BP_THREADS, MINB ) sg_bp_emit( const uint32_t n_slots, const GridParams* __restrict__ params, const uint32_t* __restrict__ cell_start,
                                                               const typename P::Rec* __restrict__ recs, const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ pos_of, const uint32_t* __restrict__ ord_by_index,
                                                               const uint4* __restrict__ masks, const uint4* __restrict__ plan, const uint2* __restrict__ counts,
                                                               const ulonglong2* __restrict__ offsets, uint2* __restrict__ cand, const uint64_t cand_cap, uint2* __restrict__ work, const uint64_t work_cap )
@@ -1326,9 +1329,13 @@ static int sg_bp_emit_lists( sg_ctx* ctx, BroadScratch& s, const typename P::In&
     SG_CUDA( ctx, s.work.ensure( act_cap * sizeof( uint2 ) ) );
     s.work_cap = act_cap;
   }
-  SG_LAUNCH( ctx, "bp_emit", double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN ), sg_bp_emit<P><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-             s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>(), s.ord_by_index, s.masks.as<uint4>(), s.masks.as<uint4>() + 1, s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap,
-             s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap ) );
+  const double emit_bytes = double( n ) * ( 4.0 + 16.0 + 16.0 + 16.0 * BpPlan<P::D>::NPLAN );
+  #define SG_EMIT_ARGS n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(), s.recs.as<typename P::Rec>(), s.sidx.as<uint32_t>(), s.pos_of.as<uint32_t>(), s.ord_by_index, s.masks.as<uint4>(), s.masks.as<uint4>() + 1, \
+                       s.counts.as<uint2>(), s.offsets.as<ulonglong2>(), want_cand ? s.cand.as<uint2>() : nullptr, s.cand_cap, s.work.as<uint2>(), act_cap < s.work_cap ? act_cap : s.work_cap
+  if( P::D == 3 ) { SG_LAUNCH( ctx, "bp_emit", emit_bytes, sg_bp_emit<P, 4><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( SG_EMIT_ARGS ) ); }
+  else if( size_t( n ) * 64 > size_t( 192 ) << 20 ) { SG_LAUNCH( ctx, "bp_emit", emit_bytes, sg_bp_emit<P, ( P::D == 2 ) ? 6 : 4><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( SG_EMIT_ARGS ) ); } // records well beyond L2
+  else { SG_LAUNCH( ctx, "bp_emit", emit_bytes, sg_bp_emit<P, ( P::D == 2 ) ? 5 : 4><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( SG_EMIT_ARGS ) ); }
+  #undef SG_EMIT_ARGS
   return SgBpContactsLaunch<P::HAS_NARROW>::template run<P>( ctx, s, in, out, act_cap );
 }
 

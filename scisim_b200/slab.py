@@ -327,6 +327,70 @@ class Ball2DSlabs:
             return res
 
 
+class HostAgreement:
+    """"Does any rank want to re-partition?" after every step, without touching the GPUs.  The ranks of one node share a small
+    memory-mapped file under /dev/shm: rank r writes ( step number, flag ) into its slot of the step's parity buffer and spins until
+    every slot carries that step (two buffers, because a fast rank may already be writing step s + 1 while a slow one still reads
+    step s; it cannot reach step s + 2 before everybody has passed s + 1).  A device collective for these 4 bytes costs a kernel
+    launch, a device-to-host copy and a stream synchronisation per step -- a tenth of a 0.8 ms step at 8 GPUs.  Falls back to
+    dist.all_reduce when the file cannot be shared (several nodes, no /dev/shm)."""
+
+    def __init__(self, rank, world, dist, device=None):
+        import os
+        self.rank, self.world, self.dist, self.device = rank, world, dist, device
+        self.step_no = 0
+        self.arr = None
+        if world == 1:
+            return
+        name = [None]
+        if rank == 0:
+            name[0] = "/dev/shm/scisim_b200_agree_%d_%d" % (os.getpid(), id(self) & 0xffffff)
+            try:
+                with open(name[0], "wb") as f:
+                    f.write(b"\0" * (2 * world * 8))
+            except OSError:
+                name[0] = None
+        dist.broadcast_object_list(name, src=0)
+        ok = 1
+        try:
+            if name[0] is None:
+                raise OSError("no shared file")
+            self.arr = np.memmap(name[0], dtype=np.int64, mode="r+", shape=(2, world))
+        except Exception:
+            ok = 0
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
+        if not all(oks):
+            self.arr = None      # every rank must take the same road
+        dist.barrier()
+        if rank == 0 and name[0] is not None:
+            try:
+                os.unlink(name[0])   # the mappings stay valid; nothing is left behind
+            except OSError:
+                pass
+
+    def any(self, flag):
+        if self.world == 1:
+            return bool(flag)
+        if self.arr is None:
+            import torch
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self.device if self.device is not None else "cpu")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return bool(int(t.item()))
+        self.step_no += 1
+        buf = self.arr[self.step_no & 1]
+        want = 2 * self.step_no
+        buf[self.rank] = want + (1 if flag else 0)   # one aligned 8-byte store
+        spins = 0
+        while True:
+            vals = np.array(buf)                     # a snapshot
+            if bool((vals >= want).all()):
+                return bool(((vals - want) == 1).any())
+            spins += 1
+            if spins > 50_000_000:
+                raise RuntimeError("rank %d: the other ranks did not reach step %d" % (self.rank, self.step_no))
+
+
 class Ball2DSlabSim:
     """One rank's handle on a WHOLE ball2d scene (global arrays, arbitrary numbering) spread over `world` ranks.
     upload() partitions (the same partition on every rank: it is a deterministic function of q), step() runs one
@@ -341,7 +405,8 @@ class Ball2DSlabSim:
         self.factory = backend_factory
         self.want_transport = transport
         self.ghost_cap = ghost_cap
-        self.agree = agree           # all ranks agree on "re-partition" after every step (one 4-byte all_reduce)
+        self.agree = agree           # all ranks agree on "re-partition" after every step (HostAgreement: shared memory on one node, else a 4-byte all_reduce)
+        self._agreement = None
         self.backend = None
         self.driver = None
         self.n = int(np.asarray(scene["r"]).shape[0])
@@ -387,11 +452,9 @@ class Ball2DSlabSim:
     def _agree(self, flag):
         if self.world == 1 or not self.agree:
             return flag
-        import torch
-        dev = getattr(self.backend, "device", "cpu")
-        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return bool(int(t.item()))
+        if self._agreement is None:
+            self._agreement = HostAgreement(self.rank, self.world, self.dist, getattr(self.backend, "device", "cpu"))
+        return self._agreement.any(flag)
 
     def step(self, kind, dt):
         """One resident step of this rank's slab: (candidates, contacts) it owns.  If any rank reports a body outside its
@@ -557,6 +620,7 @@ class RB3DSlabSim:
     def __init__(self, ctx, scene, rank, world, dist, ghost_cap=None, agree=True):
         self.ctx, self.scene, self.rank, self.world, self.dist = ctx, scene, rank, world, dist
         self.ghost_cap, self.agree = ghost_cap, agree
+        self._agreement = None
         self.backend = None
         self.n = int(np.asarray(scene["m"]).shape[0])
         self.n_partitions = 0
@@ -601,10 +665,10 @@ class RB3DSlabSim:
     def _agree(self, flag):
         if self.world == 1 or not self.agree:
             return flag
-        import torch
-        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=torch.device("cuda", self.ctx.device))
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return bool(int(t.item()))
+        if self._agreement is None:
+            import torch
+            self._agreement = HostAgreement(self.rank, self.world, self.dist, torch.device("cuda", self.ctx.device))
+        return self._agreement.any(flag)
 
     def step(self, kind, dt):
         for attempt in range(2):
