@@ -422,6 +422,36 @@ __device__ inline void rb3d_flow_exponential_euler( const uint32_t b, const size
   vao[0] = w.x + dt * 0.0; vao[1] = w.y + dt * 0.0; vao[2] = w.z + dt * 0.0;
 }
 
+// One axis rotation of SplitHamMap (SplitHamMap.cpp:121-176): R1 <- R1 * AngleAxis( -angle, -e_K ), pB <- AngleAxis( angle, -e_K ) * pB.
+// The reference forms each rotation with AngleAxis::toRotationMatrix on the axis -e_K = ( -0, -0, -1 ) etc. and multiplies full 3x3
+// matrices.  Worked through with those axis components, toRotationMatrix( a, -e_z ) is exactly
+//     [  cs  sn  0 ]                                              [ cs   0  -sn ]                 [ e    0    0 ]
+//     [ -sn  cs  0 ]   with e = fl( fl( 1 - cs ) + cs ),   -e_y:  [  0   e   0  ]         -e_x:   [ 0   cs   sn ]
+//     [  0   0   e ]                                              [ sn   0   cs ]                 [ 0  -sn   cs ]
+// (every other entry a signed zero), and in a product ( a0 b0 + a1 b1 ) + a2 b2 a term with a zero factor adds nothing: what is left
+// per entry is the same one or two roundings the full product makes.  So the structured form below gives the reference's values bit
+// for bit (signs of exact zeros aside) with a third of the arithmetic -- and one sincos per rotation instead of two, sin( -a ) = -sin( a ).
+// This kernel is bound by FP64 issue (61 % issue-active at 24 % occupancy, DRAM 36 %; profiles/ncu_r2_c4.md), not by its loads.
+template<int K>
+__device__ __forceinline__ void splitham_axis_step( M3d& R, V3d& p, const double angle )
+{
+  double sn, cs;
+  sincos( angle, &sn, &cs );
+  const double e = ( 1.0 - cs ) + cs;
+  #pragma unroll
+  for( int r = 0; r < 3; ++r )
+  {
+    const double a0 = R.m[3 * r], a1 = R.m[3 * r + 1], a2 = R.m[3 * r + 2];
+    if( K == 2 ) { R.m[3 * r] = a0 * cs + a1 * sn; R.m[3 * r + 1] = a0 * ( -sn ) + a1 * cs; R.m[3 * r + 2] = a2 * e; }       // B = [ cs -sn 0 | sn cs 0 | 0 0 e ]
+    else if( K == 1 ) { R.m[3 * r] = a0 * cs + a2 * ( -sn ); R.m[3 * r + 1] = a1 * e; R.m[3 * r + 2] = a0 * sn + a2 * cs; }  // B = [ cs 0 sn | 0 e 0 | -sn 0 cs ]
+    else { R.m[3 * r] = a0 * e; R.m[3 * r + 1] = a1 * cs + a2 * sn; R.m[3 * r + 2] = a1 * ( -sn ) + a2 * cs; }               // B = [ e 0 0 | 0 cs -sn | 0 sn cs ]
+  }
+  const double px = p.x, py = p.y, pz = p.z;
+  if( K == 2 ) { p = v3( cs * px + sn * py, ( -sn ) * px + cs * py, e * pz ); }
+  else if( K == 1 ) { p = v3( cs * px + ( -sn ) * pz, e * py, sn * px + cs * pz ); }
+  else { p = v3( e * px, cs * py + sn * pz, ( -sn ) * py + cs * pz ); }
+}
+
 __global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind_flags, const uint32_t n, const uint32_t nrun, const double* __restrict__ q0, const double* __restrict__ v0, const double* __restrict__ mass,
                                                      const double* __restrict__ I0, const uint32_t* __restrict__ btype, const double gx, const double gy, const double gz, const double dt,
                                                      double* __restrict__ q1, double* __restrict__ v1 )
@@ -486,17 +516,12 @@ __global__ void __launch_bounds__( 128 ) k_rb3d_flow( const int kind_flags, cons
   {
     V3d pB = mulT3( R0, L );
     R1 = R0;
-    #pragma unroll 1
-    for( int st = 0; st < 5; ++st )
-    {
-      double angle;
-      V3d axis;
-      if( st == 0 || st == 4 ) { angle = 0.5 * dt * pB.z / I.z; axis = v3( -0.0, -0.0, -1.0 ); }
-      else if( st == 1 || st == 3 ) { angle = 0.5 * dt * pB.y / I.y; axis = v3( -0.0, -1.0, -0.0 ); }
-      else { angle = dt * pB.x / I.x; axis = v3( -1.0, -0.0, -0.0 ); }
-      R1 = mul33( R1, angle_axis_matrix( -angle, axis ) );
-      pB = mul3( angle_axis_matrix( angle, axis ), pB );
-    }
+    // the five axis rotations of the splitting (SplitHamMap.cpp:121-176): z, y, x, y, z
+    splitham_axis_step<2>( R1, pB, 0.5 * dt * pB.z / I.z );
+    splitham_axis_step<1>( R1, pB, 0.5 * dt * pB.y / I.y );
+    splitham_axis_step<0>( R1, pB, dt * pB.x / I.x );
+    splitham_axis_step<1>( R1, pB, 0.5 * dt * pB.y / I.y );
+    splitham_axis_step<2>( R1, pB, 0.5 * dt * pB.z / I.z );
   }
   else
   {
