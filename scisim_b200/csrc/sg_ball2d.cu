@@ -113,6 +113,7 @@ struct Ball2DPolicy
   __device__ static uint32_t rec_key( const Rec& s ) { return s.key; }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
+  __device__ static Rec load_pass1( const Rec* __restrict__ p ) { return sg_load_rec_global<Rec>( p ); }
   __device__ static bool narrow_test( const Rec& a, const Rec& b ) { return ccd_hit( a, b ); }
   // BallBallConstraint{ i, j, q0a, q0b, ra, rb }: n = (q0a - q0b).normalized(); point q0a - ra*n; depth at q1
   __device__ static void contact_emit( const Out& out, unsigned long long& k, const Rec& a, const Rec& b )

@@ -35,6 +35,7 @@
 
 #define SG_BP_THREADS 256
 #define SG_BP_LOCAL_CAP 12
+#define SG_BP_BATCH 24
 
 // Per-pipeline device scratch (owned by the caller's data block)
 struct BroadScratch
@@ -584,7 +585,7 @@ __device__ __forceinline__ typename P::Rec sg_bp_fetch( const typename P::Rec* _
   using Rec = typename P::Rec;
   const uint32_t slot = q - st->start[w];
   if( STAGED || slot < st->len[w] ) { return sg_load_rec_swizzled<Rec>( s_recs + size_t( w ) * BpCfg<P::D>::WCAP * 64, slot ); }
-  return sg_load_rec_global<Rec>( &recs[q] );
+  return P::load_pass1( &recs[q] ); // what pass 1 needs of a partner (a policy may keep that in the record's first half)
 }
 // ORDER word of the body at sorted position q (window w): what decides which body of a pair owns it and how a body's partners are
 // ranked.  Policies keep it inside the record (P::ORD_OFFSET) so that the staged walk never leaves shared memory.
@@ -1028,22 +1029,35 @@ __device__ __noinline__ void sg_bp_emit_slow( const uint32_t p, uint32_t nc, con
   }
   else
   {
-    // Crowded body: select partners in ascending order by repeated walks (O(count * neighbours))
+    // Crowded body: partners in ascending order, SG_BP_BATCH at a time -- each walk keeps the SG_BP_BATCH smallest order words above the
+    // last one emitted (bounded insertion into a sorted local list), so a body with nc candidates among m neighbours costs
+    // ceil( nc / SG_BP_BATCH ) walks of m visits instead of nc walks (a mesh among thousands of small bodies: 2.6 ms -> see DESIGN 4.3)
     uint32_t last = my_ord;
-    for( uint32_t j = 0u; j < nc; ++j )
+    uint32_t done = 0u;
+    while( done < nc )
     {
-      uint32_t best_ord = 0xffffffffu, best_q = 0u;
+      unsigned long long best[SG_BP_BATCH]; // ( order word << 32 | position ), ascending; nb entries
+      uint32_t nb = 0u;
       sg_bp_walk_pos<P>( g, cell_start, s_cs, st, p, key, c1, c2, [&]( const int w, const uint32_t q )
       {
         const uint32_t oi = ord_at( w, q );
-        if( oi <= last || oi >= best_ord ) { return; }
+        if( oi <= last ) { return; }
+        const unsigned long long v = ( static_cast<unsigned long long>( oi ) << 32 ) | q;
+        if( nb == uint32_t( SG_BP_BATCH ) && v >= best[SG_BP_BATCH - 1] ) { return; } // not among the smallest so far: skipped before touching the record
         const Rec o = sg_load_rec_global<Rec>( &recs[q] );
         if( !overlaps( o ) ) { return; }
-        best_ord = oi; best_q = q;
+        uint32_t j = ( nb < uint32_t( SG_BP_BATCH ) ) ? nb++ : uint32_t( SG_BP_BATCH - 1 );
+        while( j > 0u && best[j - 1u] > v ) { best[j] = best[j - 1u]; --j; }
+        best[j] = v;
       } );
-      const Rec o = sg_load_rec_global<Rec>( &recs[best_q] );
-      emit_one( off.x + j, o, best_ord, best_q );
-      last = best_ord;
+      if( nb == 0u ) { break; } // (cannot happen: pass 1 counted nc overlapping partners)
+      for( uint32_t j = 0u; j < nb && done < nc; ++j, ++done )
+      {
+        const uint32_t q = uint32_t( best[j] & 0xffffffffull );
+        const Rec o = sg_load_rec_global<Rec>( &recs[q] );
+        emit_one( off.x + done, o, uint32_t( best[j] >> 32 ), q );
+      }
+      last = uint32_t( best[nb - 1u] >> 32 );
     }
   }
 }

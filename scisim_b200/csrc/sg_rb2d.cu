@@ -87,6 +87,7 @@ struct Box2DPolicy
   __device__ static bool valid( const In&, const uint32_t ) { return true; }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
+  __device__ static Rec load_pass1( const Rec* __restrict__ p ) { return sg_load_rec_global<Rec>( p ); }
   __device__ static bool narrow_test( const Rec&, const Rec& ) { return false; }
   __device__ static void contact_emit( const Out&, unsigned long long&, const Rec&, const Rec& ) {}
 };

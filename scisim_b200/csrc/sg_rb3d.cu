@@ -112,14 +112,18 @@ struct Sphere3DIn
   const uint32_t* ghost_counts;
 };
 
+// Everything pass 1 needs of a PARTNER -- the box at q1 (x1 -/+ r), the sphere test at q1, "kinematically scripted" -- sits in the
+// first 32 bytes (one sector, two 128-bit loads instead of four; a lattice sphere owns 13 of its 26 neighbours, and those record
+// reads through L1 are what bounds the 3-D pass 1): the radius carries the scripted flag in its sign.
 struct alignas( 64 ) Sphere3DRec
 {
   double x1[3];
+  double r;      // < 0 (sign bit set): kinematically scripted; the radius is fabs( r )
   double x0[3];
-  double r;
   uint32_t idx;  // bit 31: kinematically scripted
   uint32_t key;
 };
+__device__ __forceinline__ bool sphere_rec_fixed( const double r ) { return __double_as_longlong( r ) < 0; }
 
 struct Sphere3DPolicy
 {
@@ -145,15 +149,19 @@ struct Sphere3DPolicy
     Rec rec;
     #pragma unroll
     for( int k = 0; k < 3; ++k ) { rec.x1[k] = __ldg( &in.q1[3 * size_t( i ) + k] ); rec.x0[k] = __ldg( &in.q0[3 * size_t( i ) + k] ); }
-    rec.r = __ldg( &in.r[i] );
-    rec.idx = i | __ldg( &in.flags[i] ) | ( ( in.ghost_counts != nullptr && i >= in.n_owned ) ? SG_GHOST_BIT3 : 0u );
+    const uint32_t fl = __ldg( &in.flags[i] );
+    const double rad = __ldg( &in.r[i] );
+    rec.r = ( fl & SG_FIXED_BIT ) ? -rad : rad;
+    rec.idx = i | fl | ( ( in.ghost_counts != nullptr && i >= in.n_owned ) ? SG_GHOST_BIT3 : 0u );
     rec.key = key;
     return rec;
   }
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
   {
     #pragma unroll
-    for( int k = 0; k < 3; ++k ) { lo[k] = s.x1[k] - s.r; hi[k] = s.x1[k] + s.r; }
+    const double rad = fabs( s.r );
+    #pragma unroll
+    for( int k = 0; k < 3; ++k ) { lo[k] = s.x1[k] - rad; hi[k] = s.x1[k] + rad; }
   }
   __device__ static uint32_t rec_idx( const Rec& s ) { return s.idx & IDX_MASK; }
   __device__ static uint32_t rec_idx_raw( const Rec& s ) { return s.idx; }
@@ -169,14 +177,22 @@ struct Sphere3DPolicy
   }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& g ) { return ( s.key / g.dims[0] ) % g.dims[1]; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& g ) { return s.key / ( g.dims[0] * g.dims[1] ); }
+  // a partner as pass 1 needs it: the first 32 bytes of its record (box at q1, sphere test, scripted flag)
+  __device__ static Rec load_pass1( const Rec* __restrict__ p )
+  {
+    union { Rec r; int4 v[4]; } u;
+    const int4* src = reinterpret_cast<const int4*>( p );
+    u.v[0] = __ldg( src ); u.v[1] = __ldg( src + 1 ); u.v[2] = make_int4( 0, 0, 0, 0 ); u.v[3] = make_int4( 0, 0, 0, 0 );
+    return u.r;
+  }
   __device__ static bool narrow_test( const Rec& a, const Rec& b )
   {
-    return sphere_pair_active( v3( a.x1[0], a.x1[1], a.x1[2] ), a.r, ( a.idx & SG_FIXED_BIT ) != 0u, v3( b.x1[0], b.x1[1], b.x1[2] ), b.r, ( b.idx & SG_FIXED_BIT ) != 0u );
+    return sphere_pair_active( v3( a.x1[0], a.x1[1], a.x1[2] ), fabs( a.r ), sphere_rec_fixed( a.r ), v3( b.x1[0], b.x1[1], b.x1[2] ), fabs( b.r ), sphere_rec_fixed( b.r ) ); // first 32 bytes only
   }
   __device__ static void contact_emit( const Out& out, unsigned long long& k, const Rec& a, const Rec& b )
   {
-    sphere_pair_emit( out, k, a.idx & IDX_MASK, v3( a.x0[0], a.x0[1], a.x0[2] ), v3( a.x1[0], a.x1[1], a.x1[2] ), a.r, ( a.idx & SG_FIXED_BIT ) != 0u,
-                      b.idx & IDX_MASK, v3( b.x0[0], b.x0[1], b.x0[2] ), v3( b.x1[0], b.x1[1], b.x1[2] ), b.r, ( b.idx & SG_FIXED_BIT ) != 0u );
+    sphere_pair_emit( out, k, a.idx & IDX_MASK, v3( a.x0[0], a.x0[1], a.x0[2] ), v3( a.x1[0], a.x1[1], a.x1[2] ), fabs( a.r ), ( a.idx & SG_FIXED_BIT ) != 0u,
+                      b.idx & IDX_MASK, v3( b.x0[0], b.x0[1], b.x0[2] ), v3( b.x1[0], b.x1[1], b.x1[2] ), fabs( b.r ), ( b.idx & SG_FIXED_BIT ) != 0u );
     ++k;
   }
 };
@@ -228,6 +244,7 @@ struct Box3DPolicy
   __device__ static bool valid( const In&, const uint32_t ) { return true; }
   __device__ static uint32_t rec_c1( const Rec& s, const GridParams& ) { return s.c1; }
   __device__ static uint32_t rec_c2( const Rec& s, const GridParams& ) { return s.c2; }
+  __device__ static Rec load_pass1( const Rec* __restrict__ p ) { return sg_load_rec_global<Rec>( p ); }
   __device__ static bool narrow_test( const Rec&, const Rec& ) { return false; }
   __device__ static void contact_emit( const Out&, unsigned long long&, const Rec&, const Rec& ) {}
 };
