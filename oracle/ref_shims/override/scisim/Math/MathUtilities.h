@@ -2,7 +2,8 @@
 // Found ahead of the reference's own scisim/Math/MathUtilities.h (oracle/Makefile.ref puts this directory first on the
 // include path) when ball2d/StaticGeometry/StaticPlane.cpp is compiled unchanged for oracle/_ref: the real header needs
 // Eigen/LU and Eigen::DenseBase, which the Eigen stand-in does not provide, and StaticPlane.cpp only uses its stream
-// (de)serialisers.  No arithmetic lives here.
+// (de)serialisers.  The one piece of arithmetic here is the reference's inline 2-D cross product (scisim/Math/MathUtilities.h:15-19, one expression),
+// which the rigidbody2d constraint classes call; it is restated, and marked, below.
 #ifndef SCISIM_B200_MATH_UTILITIES_OVERRIDE
 #define SCISIM_B200_MATH_UTILITIES_OVERRIDE
 
@@ -14,6 +15,9 @@
 
 namespace MathUtilities
 {
+  // RESTATED from scisim/Math/MathUtilities.h:16-19 (inline in the header this file shadows)
+  inline scalar cross( const Vector2s& a, const Vector2s& b ) { return a.x() * b.y() - a.y() * b.x(); }
+
   // fixed sizes: the raw coefficients; the dynamic shapes of the stand-in ( R x N, N x 1 ): rows, cols, then the coefficients.  Both ends
   // of every stream that goes through here are written by oracle/ref_shims (the reference's own file format is not involved).
   template<typename T> void readShape( T&, std::istream&, decltype( &T::s )* = nullptr ) {}

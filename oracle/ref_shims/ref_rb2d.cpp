@@ -16,6 +16,12 @@
 #include "rigidbody2d/VerletMap.h"
 #include "rigidbody2d/NearEarthGravityForce.h"
 #include "scisim/UnconstrainedMaps/FlowableSystem.h"
+#include "rigidbody2d/CircleCircleConstraint.h"
+#include "rigidbody2d/StaticPlaneCircleConstraint.h"
+#include "rigidbody2d/StaticPlaneBodyConstraint.h"
+#include "rigidbody2d/BodyBodyConstraint.h"
+#include "rigidbody2d/RigidBody2DStaticPlane.h"
+#include <memory>
 
 #include <cstdint>
 
@@ -154,6 +160,61 @@ void ref_rb2d_flow( const int kind, const uint32_t n, const double* M, const uin
   if( kind == 0 ) { SymplecticEulerMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
   else { VerletMap map; map.flow( vq0, vv0, sys, iteration, dt, vq1, vv1 ); }
   for( uint32_t k = 0; k < 3 * n; ++k ) { q1[k] = vq1( int( k ) ); v1[k] = vv1( int( k ) ); }
+}
+
+}
+
+
+// ---- the constraint classes themselves (rigidbody2d/{CircleCircle,StaticPlaneCircle,StaticPlaneBody,BodyBody}Constraint.cpp + scisim/Constraints/
+// Constraint.cpp, compiled unchanged): the constraint built as RigidBody2DSim builds it, its normal, world-space contact point at q0 and -- where the
+// class overrides it -- penetrationDepth at q1 -----------------------------------------------------------------------------------------------------
+extern "C"
+{
+
+// q0, q1: 3 n doubles ( x, y, theta per body ).
+// kind 0  circle-circle ( i, j ), geo = r_i, r_j: n, p formed as RigidBody2DSim.cpp:299-303 forms them (two lines restated, marked)
+// kind 1  plane-circle: geo = x[2], n[2], r;  out[0] = StaticPlaneCircleConstraint::isActive at q1
+// kind 2  plane-body (box corner): geo = x[2], n[2], arm[2] (body-space arm of the corner)
+// kind 3  body-body ( i, j ): geo = p[2], n[2] as the narrow phase produced them
+// out[0] isActive (kinds 0, 1; 1 otherwise), out[1..2] normal, out[3..4] contact point at q0, out[5] penetrationDepth( q1 ) (NaN where the class has no override)
+void ref_rb2d_constraint_probe( const int kind, const unsigned i, const unsigned j, const uint32_t nbodies, const double* q0, const double* q1, const double* geo, double* out )
+{
+  const int nq = 3 * int( nbodies );
+  VectorXs wq0{ nq }, wq1{ nq };
+  for( int k = 0; k < nq; ++k ) { wq0( k ) = q0[k]; wq1( k ) = q1[k]; }
+  const VectorXs& vq0 = wq0; const VectorXs& vq1 = wq1;
+  const RigidBody2DStaticPlane plane{ Vector2s{ geo[0], geo[1] }, ( kind == 1 || kind == 2 ) ? Vector2s{ geo[2], geo[3] } : Vector2s{ 0.0, 1.0 } }; // outlives the constraints
+  std::unique_ptr<Constraint> con;
+  bool active = true;
+  if( kind == 0 )
+  {
+    const scalar ra = geo[0], rb = geo[1];
+    const Vector2s q0a{ vq0.segment<2>( 3 * i ) }, q0b{ vq0.segment<2>( 3 * j ) };
+    active = CircleCircleConstraint::isActive( vq1.segment<2>( 3 * i ), vq1.segment<2>( 3 * j ), ra, rb );
+    // restated glue (RigidBody2DSim.cpp:299, 303):
+    const Vector2s n{ ( q0a - q0b ).normalized() };
+    const Vector2s p{ q0a + ( ra / ( ra + rb ) ) * ( q0b - q0a ) };
+    con.reset( new CircleCircleConstraint{ i, j, n, p, ra, rb } );
+  }
+  else if( kind == 1 )
+  {
+    active = StaticPlaneCircleConstraint::isActive( vq1.segment<2>( 3 * i ), geo[4], plane );
+    con.reset( new StaticPlaneCircleConstraint{ i, j, geo[4], plane } );
+  }
+  else if( kind == 2 )
+  {
+    con.reset( new StaticPlaneBodyConstraint{ i, Vector2s{ geo[4], geo[5] }, plane, j } );
+  }
+  else
+  {
+    con.reset( new BodyBodyConstraint{ i, j, Vector2s{ geo[0], geo[1] }, Vector2s{ geo[2], geo[3] }, vq0 } );
+  }
+  out[0] = active ? 1.0 : 0.0;
+  VectorXs n, p;
+  con->getWorldSpaceContactNormal( vq0, n );
+  con->getWorldSpaceContactPoint( vq0, p );
+  out[1] = n( 0 ); out[2] = n( 1 ); out[3] = p( 0 ); out[4] = p( 1 );
+  out[5] = con->penetrationDepth( vq1 );
 }
 
 }

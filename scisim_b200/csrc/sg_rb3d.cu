@@ -1526,7 +1526,12 @@ static int rb3d_active_set_device( sg_ctx* ctx, Rb3dData* d, const bool want_can
       SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
       sg_prof_collect( ctx );
       d->n_cand = ht[0]; d->n_bb = ht[1]; d->n_static = ht[2] & 0xffffffffull;
-      if( ctx->profile ) { ctx->prof[sg_prof_entry( ctx, "bp_emit" )].bytes += ( want_cand ? double( d->n_cand ) * 8.0 : 0.0 ) + double( d->n_bb ) * 72.0; }
+      if( ctx->profile )
+      {
+        // list sizes are only known now: add the emitted bytes to the kernels that wrote them
+        ctx->prof[sg_prof_entry( ctx, "bp_emit" )].bytes += ( want_cand ? double( d->n_cand ) * 8.0 : 0.0 ) + double( d->n_bb ) * 8.0;
+        ctx->prof[sg_prof_entry( ctx, "bp_contacts" )].bytes += double( d->n_bb ) * ( 8.0 + 76.0 ) + double( n ) * 64.0; // work item in, SoA contact out (type, i, j, aux, n, p, depth); every record needed once
+      }
       const uint64_t need = d->n_bb + d->n_static;
       if( ( !want_cand || d->n_cand <= d->bp.cand_cap ) && need <= d->act_cap ) { break; }
       if( attempt == 1 ) { return sg_fail( ctx, SG_ERR_INTERNAL, "rb3d: output lists still overflow after regrowth" ); }

@@ -530,3 +530,57 @@ def test_rb3d_update_m_and_minv_expressions(oracle):
         i0 = np.ascontiguousarray(I0[k]); ii0 = np.ascontiguousarray(1.0 / I0[k])
         ref.ref_rb3d_update_inertia_expr(vp(R), vp(i0), vp(ii0), vp(a), vp(b))
         assert np.array_equal(a, I[9 * k: 9 * k + 9]) and np.array_equal(b, Ii[9 * k: 9 * k + 9]), k
+
+
+def test_rb2d_constraint_classes(oracle):
+    """rigidbody2d/{CircleCircle,StaticPlaneCircle,StaticPlaneBody,BodyBody}Constraint.cpp (+ scisim/Constraints/Constraint.cpp), compiled unchanged:
+    the constraint built as RigidBody2DSim builds it -- normal, world-space contact point at q0, penetrationDepth( q1 ) (NaN where the class has no
+    override) -- for every contact of an oracle active set; StaticPlaneCircleConstraint::isActive at q1 for the plane-circle contacts."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb2d.so")
+    ref.ref_rb2d_constraint_probe.restype = None
+    ref.ref_rb2d_constraint_probe.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    seen = {20: 0, 22: 0, 23: 0, 24: 0}
+    for seed in (41, 42):
+        s = scenes.rb2d_random(1200, seed, nfixed_frac=0.0, nplanes=3)
+        o = ob.RB2DOracle(s)
+        nb = s["geo_of_body"].shape[0]
+        q0 = np.ascontiguousarray(s["q"], dtype=np.float64)
+        q1, _ = o.flow(0, q0, s["v"], s["dt"])
+        a = o.active_set(q0, q1, "grid")
+        assert a["supported"]
+        out = np.zeros(6)
+        for k in range(a["type"].shape[0]):
+            t, i, j = int(a["type"][k]), int(a["i"][k]), int(a["j"][k])
+            gi = int(s["geo_of_body"][i])
+            if t == 20:
+                geo, kind = np.array([s["geo_r"][gi], s["geo_r"][int(s["geo_of_body"][j])], 0, 0, 0, 0], dtype=np.float64), 0
+            elif t == 23:
+                geo, kind = np.concatenate([s["plane_x"][j], s["plane_n"][j], [s["geo_r"][gi], 0]]).astype(np.float64), 1
+            elif t == 24:
+                geo, kind = np.concatenate([s["plane_x"][j], s["plane_n"][j], a["p"][k]]).astype(np.float64), 2   # p carries the corner's body-space arm
+            elif t == 22:
+                geo, kind = np.concatenate([a["p"][k], a["n"][k], [0, 0]]).astype(np.float64), 3
+            else:
+                continue
+            geo = np.ascontiguousarray(geo)
+            ref.ref_rb2d_constraint_probe(kind, i, j, nb, vp(q0), vp(q1), vp(geo), vp(out))
+            assert np.array_equal(out[1:3], a["n"][k]), (t, i, j, out, a["n"][k])
+            if t == 23:
+                assert out[0] == 1.0
+            if t == 22:
+                # the class keeps body-space arms and re-derives the point from q0: equal to the constructor's p up to rounding
+                assert np.allclose(out[3:5], a["p"][k], rtol=0, atol=1e-12 * (1.0 + np.abs(a["p"][k]).max()))
+            elif t != 24:
+                assert np.array_equal(out[3:5], a["p"][k]), (t, i, j, out, a["p"][k])
+            else:
+                # the class's world-space point of the corner: x0 + R( theta0 ) * arm
+                th = q0[3 * i + 2]
+                c_, s_ = np.cos(th), np.sin(th)
+                arm = a["p"][k]
+                want = np.array([q0[3 * i] + (c_ * arm[0] - s_ * arm[1]), q0[3 * i + 1] + (s_ * arm[0] + c_ * arm[1])])
+                assert np.allclose(out[3:5], want, rtol=0, atol=1e-12 * (1.0 + np.abs(want).max()))
+            assert out[5] == a["depth"][k] or (np.isnan(out[5]) and np.isnan(a["depth"][k])), (t, out[5], a["depth"][k])
+            seen[t] += 1
+    assert seen[20] > 50 and seen[23] > 5 and seen[22] + seen[24] > 10, seen
