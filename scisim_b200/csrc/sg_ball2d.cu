@@ -616,6 +616,7 @@ static int ball2d_active_set_device( sg_ctx* ctx, Ball2DData* d, const bool want
     SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
     sg_prof_collect( ctx );
     d->n_cand = ht[0];
+    d->bp.dense = ht[0] * 2ull >= 5ull * uint64_t( n ); // >= 2.5 candidates per body: the next step's pass 1 stages the records (sg_bp_count_staged)
     d->n_bb = ht[1];
     d->n_static = ht[2] & 0xffffffffull;
     if( ctx->profile )

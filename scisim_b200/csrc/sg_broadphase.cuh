@@ -63,6 +63,12 @@ struct BroadScratch
   uint32_t max_cells = 0;
   SideScan side = { nullptr, 0u, nullptr, nullptr }; // optional small scan carried by the pair-count scan launch (set per step by the caller)
   DevBuf boxf;          // float4[n]  by sorted position (2-D pipelines): the body's box rounded outward to floats -- what pass 1's walk tests
+  CUtensorMap tm_recs;  // tensor map over the sorted records (dense-scene pass 1), valid for ( tm_ptr, tm_rows )
+  const void* tm_ptr = nullptr;
+  uint32_t tm_rows = 0;
+  void* tm_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime on first use
+  int staged_attr_dev = -1;   // device on which the staged kernel's shared-memory opt-in was made
+  bool dense = false;         // the previous step on this scratch found >= 2.5 candidates per body (set by the caller): pass 1 stages the records
   const uint32_t* ord_by_index = nullptr; // order word of body i (multi-GPU: the global-index table; nullptr: i itself), set per step by the caller
   bool hist_clean = false; // cell_count is all zero (true after every scatter; false after (re)allocation or an aborted step)
   const void* hist_ptr = nullptr;
@@ -944,7 +950,185 @@ __global__ void __launch_bounds__( SG_BP_THREADS, MINB ) sg_bp_count_l1( const u
   }
 }
 
-// Dispatch: the 2-D pipelines take the box-prefiltered kernel, the 3-D ones the block-staged kernel.
+// ---- pass 1 for DENSE scenes, TMA-fed (D = 2) ---------------------------------------------------------
+// When most box tests pass (a lattice pile: every ball owns four of its eight neighbours) the float-box prefilter of sg_bp_count_l1 prunes
+// nothing and its exact phase gathers two 64-byte records per pair through L1; here the records themselves are staged, so the walk and the
+// FP64 tests run out of shared memory (config 2: 49 us against 80 us; on the polydisperse gas it is the other way round, 500 against 181 us).
+// The launch picks by the previous step's candidates per body (BroadScratch::dense).
+// Same work as sg_bp_count, restructured so no thread ever waits for the staging: persistent CTAs (2 per SM),
+// each with 8 consumer warps and 1 producer warp.  The producer runs one tile ahead: it reads the tile's first/last
+// cell keys and the cell_start entries that bound its three row windows, then asks the TMA unit for the windows --
+// the 64-byte records as 2-D tensor copies with the hardware 64B swizzle (the same chunk ^ ((row >> 1) & 3)
+// pattern the software staging used), the cell_start slices as 1-D bulk copies -- into the other half of a
+// double-buffered shared-memory stage, completion counted in bytes on an mbarrier.  Consumers wait on that
+// barrier, walk entirely out of shared memory, and hand the stage back through a second mbarrier.
+#define SG_BP_TMA_ROWS 136   // rows per tensor copy (<= 256); two copies cover WCAP = 272
+#define SG_BP_TMA_CSCAP 288
+template<int D> __host__ __device__ constexpr size_t sg_bp_tma_stage_bytes()
+{
+  return ( size_t( BpCfg<D>::NW ) * BpCfg<D>::WCAP * 64 + size_t( BpCfg<D>::NW ) * SG_BP_TMA_CSCAP * 4 + sizeof( BpStage<D> ) + 1023 ) & ~size_t( 1023 );
+}
+#define SG_BP_TMA_STAGES 2      // shared-memory stages per CTA (measured: 1 stage x 4 CTAs/SM is 1.5x slower)
+#define SG_BP_TMA_CTAS_PER_SM 2 // resident CTAs per SM (stages x CTAs x 55 KB must fit the SM's 227 KB)
+template<int D> __host__ __device__ constexpr size_t sg_bp_tma_smem() { return SG_BP_TMA_STAGES * sg_bp_tma_stage_bytes<D>() + 64; }
+
+template<typename P>
+__global__ void __launch_bounds__( BpCfg<P::D>::T + 32, SG_BP_TMA_CTAS_PER_SM ) sg_bp_count_staged( const __grid_constant__ CUtensorMap tm_recs, const uint32_t n_slots, const GridParams* __restrict__ params,
+                                                                            const uint32_t* __restrict__ cell_start, const typename P::Rec* __restrict__ recs, uint2* __restrict__ counts,
+                                                                            uint4* __restrict__ masks, uint4* __restrict__ plan )
+{
+  constexpr int D = P::D;
+  using Cfg = BpCfg<D>;
+  using Rec = typename P::Rec;
+  static_assert( D == 2, "the TMA-fed pass 1 is laid out for the 2-D pipelines" );
+  static_assert( Cfg::WCAP == 2 * SG_BP_TMA_ROWS, "two tensor copies per window" );
+  extern __shared__ __align__( 1024 ) unsigned char s_raw[];
+  constexpr size_t STAGE = sg_bp_tma_stage_bytes<D>();
+  constexpr size_t CS_OFF = size_t( Cfg::NW ) * Cfg::WCAP * 64;
+  constexpr size_t ST_OFF = CS_OFF + size_t( Cfg::NW ) * SG_BP_TMA_CSCAP * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>( s_raw + SG_BP_TMA_STAGES * STAGE ); // full[0], full[1], empty[0], empty[1] (stage s uses full[s], empty[s])
+  const GridParams g = *params;
+  const uint32_t n = min( n_slots, __ldg( &cell_start[g.ncells] ) ); // bodies actually binned
+  const uint32_t ntiles = ( n_slots + Cfg::T - 1u ) / Cfg::T;
+  const bool producer = threadIdx.x >= uint32_t( Cfg::T );
+  if( threadIdx.x == 0 )
+  {
+    sg_mbar_init( &bars[0], 1u ); sg_mbar_init( &bars[1], 1u );
+    sg_mbar_init( &bars[2], Cfg::T / 32u ); sg_mbar_init( &bars[3], Cfg::T / 32u );
+  }
+  __syncthreads();
+
+  if( producer )
+  {
+    if( threadIdx.x != uint32_t( Cfg::T ) ) { return; } // one elected lane drives the copies
+    uint32_t it = 0u;
+    for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
+    {
+      const uint32_t b0 = t * Cfg::T;
+      if( b0 >= n ) { break; } // tiles past the binned bodies have nothing to stage (consumers only clear masks)
+      const uint32_t sgi = it % SG_BP_TMA_STAGES, use = it / SG_BP_TMA_STAGES;
+      unsigned char* stage = s_raw + sgi * STAGE;
+      BpStage<D>* st = reinterpret_cast<BpStage<D>*>( stage + ST_OFF );
+      // the tile's plan (two dependent rounds of global loads) does not need the stage: fetch it first, wait after
+      const uint32_t b1 = ( n - b0 < uint32_t( Cfg::T ) ) ? n : b0 + Cfg::T;
+      const long long kf = __ldg( &recs[b0].key );
+      const long long kl = __ldg( &recs[b1 - 1u].key );
+      long long klo[Cfg::NW], khi[Cfg::NW];
+      uint32_t start[Cfg::NW], end[Cfg::NW];
+      #pragma unroll
+      for( int w = 0; w < Cfg::NW; ++w )
+      {
+        const long long off = ( long long )( w % 3 - 1 ) * g.dims[0];
+        klo[w] = kf + off - 1; khi[w] = kl + off + 1;
+        const bool ok = khi[w] >= 0 && klo[w] <= ( long long )( g.ncells ) - 1;
+        klo[w] = ( klo[w] < 0 ) ? 0 : klo[w];
+        khi[w] = ( khi[w] > ( long long )( g.ncells ) - 1 ) ? ( long long )( g.ncells ) - 1 : khi[w];
+        if( !ok ) { klo[w] = 0; khi[w] = -1; }
+        start[w] = ok ? __ldg( &cell_start[klo[w]] ) : 0u;
+        end[w] = ok ? __ldg( &cell_start[khi[w] + 1] ) : 0u;
+      }
+      uint32_t bytes = 0u;
+      uint32_t ncopies[Cfg::NW], cs_first[Cfg::NW], cs_n[Cfg::NW];
+      uint32_t all_staged = 1u;
+      if( use > 0u ) { sg_mbar_wait_backoff( &bars[2 + sgi], ( use - 1u ) & 1u ); } // consumers are done with this stage
+      #pragma unroll
+      for( int w = 0; w < Cfg::NW; ++w )
+      {
+        const uint32_t len = ( end[w] - start[w] < uint32_t( Cfg::WCAP ) ) ? end[w] - start[w] : uint32_t( Cfg::WCAP );
+        ncopies[w] = ( len + SG_BP_TMA_ROWS - 1u ) / SG_BP_TMA_ROWS;
+        // cell_start slice: entries klo .. khi+1, widened to whole 16-byte groups for the bulk copy
+        const long long ncs = khi[w] - klo[w] + 2;
+        cs_first[w] = uint32_t( klo[w] ) & ~3u;
+        uint32_t want = ( khi[w] < klo[w] ) ? 0u : uint32_t( klo[w] - cs_first[w] + ncs );
+        want = ( want + 3u ) & ~3u;
+        cs_n[w] = ( want < uint32_t( SG_BP_TMA_CSCAP ) ) ? want : uint32_t( SG_BP_TMA_CSCAP );
+        st->start[w] = start[w]; st->len[w] = len; st->cs_klo[w] = cs_first[w]; st->cs_len[w] = cs_n[w];
+        if( end[w] - start[w] > uint32_t( Cfg::WCAP ) || want > uint32_t( SG_BP_TMA_CSCAP ) ) { all_staged = 0u; }
+        bytes += ncopies[w] * uint32_t( SG_BP_TMA_ROWS * 64 ) + cs_n[w] * 4u;
+      }
+      st->full = all_staged;
+      asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); // the stage's earlier generic reads vs the async writes to come
+      sg_mbar_arrive_expect_tx( &bars[sgi], bytes );
+      #pragma unroll
+      for( int w = 0; w < Cfg::NW; ++w )
+      {
+        for( uint32_t c = 0u; c < ncopies[w]; ++c )
+        {
+          sg_tma_load_2d( stage + ( size_t( w ) * Cfg::WCAP + size_t( c ) * SG_BP_TMA_ROWS ) * 64, &tm_recs, 0, int( start[w] + c * SG_BP_TMA_ROWS ), &bars[sgi] );
+        }
+        if( cs_n[w] != 0u ) { sg_bulk_g2s( stage + CS_OFF + size_t( w ) * SG_BP_TMA_CSCAP * 4, cell_start + cs_first[w], cs_n[w] * 4u, &bars[sgi] ); }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  uint32_t it = 0u;
+  for( uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it )
+  {
+    const uint32_t p = t * Cfg::T + threadIdx.x;
+    if( t * Cfg::T >= n )
+    {
+      continue; // positions past the binned bodies belong to nobody
+    }
+    const uint32_t sgi = it % SG_BP_TMA_STAGES, use = it / SG_BP_TMA_STAGES;
+    const unsigned char* stage = s_raw + sgi * STAGE;
+    const unsigned char* s_recs = stage;
+    const uint32_t* s_cs = reinterpret_cast<const uint32_t*>( stage + CS_OFF );
+    const BpStage<D>* st = reinterpret_cast<const BpStage<D>*>( stage + ST_OFF );
+    sg_mbar_wait( &bars[sgi], use & 1u );
+    if( p < n )
+    {
+      const Rec me = sg_bp_fetch<P>( recs, s_recs, st, 1, p ); // own row is window 1 (dy = 0)
+      const uint32_t my_idx = P::rec_idx( me );
+      if( !P::owns( me ) )
+      {
+        counts[my_idx] = make_uint2( 0u, 0u );
+        masks[size_t( p ) * BpPlan<D>::STRIDE] = make_uint4( 0u, 0u, 0u, 0u );
+      }
+      else
+      {
+        // tiles whose windows and cell_start slices were staged completely (the rule, not the exception) run a
+        // walk with no fallback code in it at all
+        if( st->full != 0u ) { sg_bp_count_body<P, SG_BP_TMA_CSCAP, true>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan ); }
+        else { sg_bp_count_body<P, SG_BP_TMA_CSCAP, false>( g, cell_start, recs, s_recs, s_cs, st, n_slots, p, me, my_idx, P::rec_ord( me ), counts, masks, plan ); }
+      }
+    }
+    // this warp is done with the stage
+    __syncwarp();
+    if( ( threadIdx.x & 31u ) == 0u ) { sg_mbar_arrive( &bars[2 + sgi] ); }
+  }
+}
+
+// Tensor map over the sorted records: n rows of 16 x u32, box = 16 x SG_BP_TMA_ROWS, 64-byte swizzle.
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
+static inline int sg_bp_encode_recs_map( sg_ctx* ctx, void** encode_fn, const void* recs, const uint32_t n, CUtensorMap* out )
+{
+  typedef CUresult ( *EncodeFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+  if( *encode_fn == nullptr )
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr )
+    {
+      cudaGetLastError();
+      return sg_fail( ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver" );
+    }
+    *encode_fn = fn;
+  }
+  const EncodeFn encode = reinterpret_cast<EncodeFn>( *encode_fn );
+  const cuuint64_t gdim[2] = { 16, n };
+  const cuuint64_t gstride[1] = { 64 };
+  const cuuint32_t box[2] = { 16, SG_BP_TMA_ROWS };
+  const cuuint32_t estr[2] = { 1, 1 };
+  const CUresult r = encode( out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>( recs ), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+  if( r != CUDA_SUCCESS ) { return sg_fail( ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled( sorted records ) -> %d", int( r ) ); }
+  return SG_OK;
+}
+
+// Dispatch: the 2-D pipelines take the box-prefiltered kernel (the record-staged one for dense scenes), the 3-D ones the block-staged kernel.
 template<int D> struct SgBpCountLaunch;
 template<> struct SgBpCountLaunch<3>
 {
@@ -961,6 +1145,22 @@ template<> struct SgBpCountLaunch<2>
 {
   template<typename P> static int run( sg_ctx* ctx, BroadScratch& s, const uint32_t n )
   {
+    if( s.dense )
+    {
+      if( s.recs.ptr != s.tm_ptr || n != s.tm_rows )
+      {
+        const int rc = sg_bp_encode_recs_map( ctx, &s.tm_encode, s.recs.ptr, n, &s.tm_recs );
+        if( rc != SG_OK ) { return rc; }
+        s.tm_ptr = s.recs.ptr; s.tm_rows = n;
+      }
+      constexpr size_t smem = sg_bp_tma_smem<2>();
+      if( s.staged_attr_dev != ctx->device ) { SG_CUDA( ctx, cudaFuncSetAttribute( sg_bp_count_staged<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smem ) ) ); s.staged_attr_dev = ctx->device; }
+      const unsigned ntiles = sg_div_up( n, BpCfg<2>::T );
+      const unsigned grid = ntiles < unsigned( ctx->num_sms ) * SG_BP_TMA_CTAS_PER_SM ? ntiles : unsigned( ctx->num_sms ) * SG_BP_TMA_CTAS_PER_SM;
+      SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_staged<P><<<grid, BpCfg<2>::T + 32, smem, ctx->stream>>>( s.tm_recs, n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+                 s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
+      return SG_OK;
+    }
     SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_l1<P, 2, 4><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
                s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
     return SG_OK;

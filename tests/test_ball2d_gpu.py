@@ -250,3 +250,33 @@ def test_active_set_on_resident_flow_result(gpu_ctx, oracle):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     with pytest.raises(sb.SciSimB200Error):
         sim.computeActiveSet(s["q"], q1, resident=True)   # the upload above replaced the resident pair
+
+
+@pytest.mark.parametrize("scene_kind", ["lattice", "shuffled_lattice", "dense3", "dense7", "dense12"])
+def test_dense_scenes_second_call_takes_the_record_staged_pass1(gpu_ctx, oracle, scene_kind):
+    """A context whose last active set had >= 2.5 candidates per body runs the next pass 1 with the records staged by tensor copies
+    (sg_bp_count_staged) instead of the float-box prefilter: same lists, first call and second, as the oracle -- on a lattice pile, on
+    the same pile randomly numbered, and at densities on both sides of what the 64-bit masks and the sorting network hold."""
+    from tests import oracle_binding as ob
+    if scene_kind in ("lattice", "shuffled_lattice"):
+        s = scenes.ball2d_lattice(180, 120)
+        n = 180 * 120
+        if scene_kind == "shuffled_lattice":
+            perm = np.random.default_rng(3).permutation(n)
+            s["q"] = np.ascontiguousarray(s["q"].reshape(n, 2)[perm].ravel()); s["v"] = np.ascontiguousarray(s["v"].reshape(n, 2)[perm].ravel())
+            s["r"] = np.ascontiguousarray(s["r"][perm]); s["m"] = np.ascontiguousarray(s["m"][perm])
+    else:
+        per_cell = float(scene_kind[5:])
+        n = 5000
+        s = scenes.ball2d_random(n, 31, nplanes=2, ndrums=1, rmin=0.2, rmax=0.4, vmax=2.0, dt=0.01)
+        rng = np.random.default_rng(int(per_cell))
+        half = 0.5 * np.sqrt(n * 0.85 * 0.85 / per_cell)
+        s["q"] = rng.uniform(-half, half, size=2 * n)
+    sim = make_sim(s, gpu_ctx)
+    o = ob.Ball2DOracle(s)
+    q1, _ = o.flow(0, s["q"], s["v"], s["dt"])
+    ref = o.active_set(s["q"], q1, "grid")
+    assert ref["candidates"].shape[0] >= 2.5 * n
+    assert_active_equal(sim.computeActiveSet(s["q"], q1), ref)   # float-box prefilter (nothing is known about the scene yet)
+    assert_active_equal(sim.computeActiveSet(s["q"], q1), ref)   # record-staged
+    assert_active_equal(sim.computeActiveSet(s["q"], q1), ref)
