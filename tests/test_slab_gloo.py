@@ -135,3 +135,43 @@ def test_quantile_slabs_of_a_randomly_numbered_scene(world, n, seed, mode):
     for k in ("type", "i", "j", "n", "p"):
         assert np.array_equal(m[k], ref[k]), k
     assert np.array_equal(m["depth"], ref["depth"], equal_nan=True)
+
+
+def _agree_worker(rank, world, port, outdir, force_fallback):
+    import torch.distributed as dist
+    from scisim_b200 import slab
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ag = slab.HostAgreement(rank, world, dist)
+    if force_fallback:
+        ag.arr = None            # what a multi-node job (or a box without /dev/shm) ends up with: the 4-byte all_reduce
+    used_shm = ag.arr is not None
+    got = []
+    # 200 steps with rank-dependent flags and rank-dependent delays: a fast rank runs ahead of the slow ones' reads
+    rng = np.random.default_rng(100 + rank)
+    for step in range(200):
+        flag = (step % 7 == rank % 7) or (step % 13 == 0 and rank == world - 1)
+        if rng.random() < 0.2:
+            import time
+            time.sleep(0.0005 * rng.random())
+        got.append(ag.any(flag))
+    pickle.dump({"got": got, "shm": used_shm}, open(os.path.join(outdir, "agree%d.pkl" % rank), "wb"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,force_fallback", [(2, False), (3, False), (3, True)])
+def test_host_agreement_is_a_logical_or_over_the_ranks(world, force_fallback):
+    """The per-step "does anyone need a re-partition?" exchange of the one-process-per-GPU driver: every rank must see the OR of all ranks'
+    flags of THAT step, through the shared-memory path and through the all_reduce fallback, also when ranks run ahead of each other."""
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_agree_worker, args=(world, _free_port(), d, force_fallback), nprocs=world, join=True)
+        parts = [pickle.load(open(os.path.join(d, "agree%d.pkl" % r), "rb")) for r in range(world)]
+    want = [any((step % 7 == r % 7) or (step % 13 == 0 and r == world - 1) for r in range(world)) for step in range(200)]
+    for p in parts:
+        assert p["got"] == want
+    if not force_fallback:
+        assert all(p["shm"] for p in parts) or not os.path.isdir("/dev/shm")
+    assert any(want) and not all(want)
