@@ -13,8 +13,12 @@
 //   ball2d/Constraints/BallStaticPlaneConstraint.cpp:10-15,171-174,220-223
 //   ball2d/Constraints/BallStaticDrumConstraint.cpp:8-26,168-171      (depth: base-class NaN)
 //   ball2d/StaticGeometry/StaticPlane.cpp:10-14    plane normal normalised at construction
-// Parity: unpinned by any stored reference output except through the CCD cases and the AABB fixtures
-// (SURVEY.md 8c); this file is kept line-traceable to the sources above.
+// Parity: the only STORED reference outputs for this path are the CCD cases and the AABB fixtures (tests/test_oracle_golden.py)
+// and config 1's two bundled scenes (tests/golden/ball2d_assets.npz).  Beyond them this file is pinned against the reference's own sources compiled
+// unchanged into oracle/_ref (oracle/Makefile.ref, tests/test_oracle_vs_reference.py): both maps + the gravity force (q1, v1), the spatial grid, the CCD,
+// and the three constraint classes -- isActive, normal, contact point, penetration depth, contact basis, evalgradg -- for every contact of its active
+// sets, bit for bit.  What stays restated only is the glue of Ball2DSim.cpp (loop order, which q each test reads); it is kept line-traceable to the
+// sources above.
 #ifndef ORACLE_BALL2D_H
 #define ORACLE_BALL2D_H
 

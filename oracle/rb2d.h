@@ -14,7 +14,9 @@
 //   rigidbody2d/RigidBody2DSim.cpp:638-694   computeBodyPlaneActiveSetAllPairs
 //   rigidbody2d/{CircleCircle,StaticPlaneCircle}Constraint.cpp  isActive / depth
 // Rotation2D(theta).matrix() = [[c,-s],[s,c]] with libm sin/cos (device: CUDA sincos => rotated boxes compare to 1e-12).
-// PARITY UNPINNED beyond the CCD cases.
+// Parity: stored reference outputs exist for the CCD cases only; beyond them the file is pinned against the reference's sources compiled
+// unchanged (oracle/_ref): both maps, the grid, BoxBoxTools, CircleBoxTools, the geometry classes' AABBs, the plane / portal classes and the constraint
+// classes CircleCircle / StaticPlaneCircle / StaticPlaneBody / BodyBody (normal, contact point, depth for every contact of its active sets).
 #ifndef ORACLE_RB2D_H
 #define ORACLE_RB2D_H
 
