@@ -120,20 +120,24 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel_name, config):
-    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture of this
-    workload (profiles/ncu_rNN_cK.json, written by profiles/summarize.py); None when no capture covers it."""
-    import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_c%d.json" % config))) or (sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*.json"))) if config == 2 else [])
-    if not files:
+def ncu_traffic(kernel_name, config, n_local):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_r2_c3_2m.json etc., written by profiles/summarize_r2.py): the capture's dram__bytes_read.sum + dram__bytes_write.sum of
+    that kernel, scaled by bodies per launch here / bodies in the capture (ncu cannot replay the 16M-ball scene: it saves and restores
+    the 11 GB of device memory around every pass).  None when no capture covers the workload."""
+    name = {3: "ncu_r2_c3_2m.json", 2: "ncu_r2_c2.json"}.get(config)
+    p = os.path.join(ROOT, "profiles", name) if name else None
+    if p is None or not os.path.exists(p):
         return None, None
-    data = json.load(open(files[-1]))
-    for k, v in data.items():
-        if ("sg_" + kernel_name) in k or kernel_name in k:
-            scale = v.get("bodies_scale", 1.0)   # capture taken on a smaller slice of the workload: traffic scales with the bodies
-            t = v.get("dram_traffic")
-            return (t * scale if t is not None else None), os.path.basename(files[-1])
-    return None, os.path.basename(files[-1])
+    data = json.load(open(p))
+    hit = None
+    for k, v in data.get("ncu_kernels", {}).items():
+        if ("sg_" + kernel_name) in k and "dram_read_MB" in v:
+            hit = v   # the last matching kernel of the warm step (config 2 holds both pass-1 kernels: the staged one comes later)
+    if hit is None:
+        return None, name
+    scale = float(n_local) / float(data["bodies"])
+    return (hit["dram_read_MB"] + hit.get("dram_write_MB", 0.0)) * 1e6 * scale, "%s (capture of %d bodies, scaled x%.3g)" % (name, data["bodies"], scale)
 
 
 def cpu_reference_step(scene, steps, warmup):
@@ -501,7 +505,7 @@ def main():
         top = max(prof.items(), key=lambda kv: kv[1][1])
         name, (nl, ms, by) = top
         achieved = (by / nl) / (ms / nl * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(name, args.config)
+        traffic, traffic_src = ncu_traffic(name, args.config, n_local)
         kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps, "share": v[1] / total_ms,
                        "alg_GBps": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         cfg = config_dict(args.config, n_total)
