@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL: the SG_BP_PASS1 knob (tma | 0..3) existed only in the development commits of sg_bp_count_l1 (git log: "Pass 1 (2-D) without staging");
+# the numbers it produced are quoted in DESIGN.md 4.2.1 / 4.4.  In the current tree the variable is ignored.
 # A/B of pass 1 (2-D): SG_BP_PASS1 = tma (staged, warp-specialised) | 0..3 (unstaged variants: chunk / min blocks per SM); parity first
 set -u
 mkdir -p gpurun_out

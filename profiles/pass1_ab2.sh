@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: SG_BP_NAR / SG_BP_PASS1 were development knobs (operand planes, kernel variants); the current tree ignores them.
 set -u
 python -m pytest tests/test_ball2d_gpu.py tests/test_slab_gpu.py tests/test_multi_gpu.py tests/test_rb2d_gpu.py tests/test_portals_gpu.py tests/test_config1_gpu.py -m gpu -x -q 2>&1 | tail -2
 for nar in 0 1; do
