@@ -158,7 +158,6 @@ struct Sphere3DPolicy
   }
   __device__ static void rec_aabb( const Rec& s, double* lo, double* hi )
   {
-    #pragma unroll
     const double rad = fabs( s.r );
     #pragma unroll
     for( int k = 0; k < 3; ++k ) { lo[k] = s.x1[k] - rad; hi[k] = s.x1[k] + rad; }
