@@ -1,0 +1,75 @@
+"""CPU check of the reasoning behind pass 1's far-side pruning (scisim_b200/csrc/sg_broadphase.cuh, sg_bp_count_l1): bodies are binned by the
+LOWER corner of their box, cell = uint32( ( lo - origin ) / h ) clamped, h >= every extent; a body drops the next cell column (row) from its walk when
+its upper bound, rounded UP to float, lies below  origin + ( c + 1 ) h  minus a margin.  Restated here in numpy with the kernel's expressions and run
+on adversarial inputs -- boxes that end exactly on, one ulp below and one ulp above cell edges, huge offsets, tiny cells: no overlapping pair may fall
+outside the pruned ranges of either of its bodies.  (What the kernel does with these formulas is checked on the GPU against the oracle; this test is
+about the formulas.)"""
+import numpy as np
+
+
+def _cells(lo, origin, h, dims):
+    v = np.floor((lo - origin) / h)          # lo >= origin, so the unsigned cast is a floor
+    v = np.minimum(v, dims - 1)
+    return v.astype(np.int64)
+
+
+def _pruned_hi_cell(c, hi, origin, h, dims):
+    """last cell column the walk of a body in column c visits: c + 1 unless the box ends below that column's lower edge"""
+    hi_f = np.nextafter(hi.astype(np.float32), np.float32(np.inf), where=hi.astype(np.float32).astype(np.float64) < hi, out=hi.astype(np.float32).copy()).astype(np.float64)  # __double2float_ru
+    edge = (c + 1).astype(np.float64) * h
+    skip = hi_f < (origin + edge) - 1.0e-9 * (np.abs(origin) + edge)
+    last = np.where(skip, c, np.minimum(c + 1, dims - 1))
+    return last
+
+
+def _check(lo, ext, h):
+    hi = lo + ext
+    origin = lo.min()
+    assert np.all(ext <= h)
+    dims = int(np.floor((lo.max() - origin) / h)) + 1
+    c = _cells(lo, origin, h, dims)
+    last = _pruned_hi_cell(c, hi, origin, h, dims)
+    first = np.maximum(c - 1, 0)
+    # every overlapping pair (closed intervals, as AABB::overlaps)
+    order = np.argsort(lo)
+    lo_s, hi_s, c_s, f_s, l_s = lo[order], hi[order], c[order], first[order], last[order]
+    n = lo.shape[0]
+    bad = 0
+    for i in range(n):
+        j = i + 1
+        while j < n and lo_s[j] <= hi_s[i]:
+            # i and j overlap ( lo_j <= hi_i and lo_i <= lo_j <= hi_j ): each must find the other's cell inside its own range
+            if not (f_s[i] <= c_s[j] <= l_s[i]) or not (f_s[j] <= c_s[i] <= l_s[j]):
+                bad += 1
+            j += 1
+    return bad, int((last == c).sum())
+
+
+def test_far_side_pruning_never_hides_an_overlapping_box():
+    rng = np.random.default_rng(12)
+    total_pruned = 0
+    for trial in range(60):
+        n = 400
+        scale = 10.0 ** rng.integers(-3, 7)           # coordinates from 1e-3 to 1e6
+        offset = rng.choice([0.0, 1.0e3, -7.7e5, 3.0e9]) * (1.0 if trial % 3 else 0.0)
+        h_true = scale * rng.uniform(0.5, 2.0)
+        ext = h_true * rng.uniform(0.05, 1.0, n)
+        ext[rng.integers(0, n)] = h_true              # the largest extent defines the cell size, as in sg_layout_grid
+        h = ext.max() * (1.0 + 9.5367431640625e-07)
+        lo = offset + rng.uniform(0.0, 40.0 * h, n)
+        # adversarial: upper bounds exactly on, just below and just above cell edges (origin = lo.min() is only known afterwards: anchor one body at it)
+        lo[0] = lo.min() - 0.25 * h
+        k = rng.integers(1, 38, n // 2)
+        edge = lo[0] + k * h
+        sel = np.arange(1, n // 2 + 1)
+        nudge = rng.integers(-2, 3, n // 2)
+        hi_target = edge.copy()
+        for s in range(n // 2):
+            for _ in range(abs(int(nudge[s]))):
+                hi_target[s] = np.nextafter(hi_target[s], np.inf if nudge[s] > 0 else -np.inf)
+        lo[sel] = hi_target - ext[sel]
+        lo[sel] = np.maximum(lo[sel], lo[0])
+        bad, pruned = _check(lo, ext, h)
+        assert bad == 0, (trial, bad)
+        total_pruned += pruned
+    assert total_pruned > 2000   # the pruning does happen on these inputs
