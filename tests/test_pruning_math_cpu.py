@@ -73,3 +73,35 @@ def test_far_side_pruning_never_hides_an_overlapping_box():
         assert bad == 0, (trial, bad)
         total_pruned += pruned
     assert total_pruned > 2000   # the pruning does happen on these inputs
+
+
+def _round_up_f32(x):
+    f = x.astype(np.float32)
+    return np.where(f.astype(np.float64) < x, np.nextafter(f, np.float32(np.inf)), f).astype(np.float32)
+
+
+def _round_down_f32(x):
+    f = x.astype(np.float32)
+    return np.where(f.astype(np.float64) > x, np.nextafter(f, np.float32(-np.inf)), f).astype(np.float32)
+
+
+def test_float_gap_certainty_implies_fp64_overlap():
+    """sg_box_gap_certain: with boxes rounded outward to floats ( lo_f <= lo, hi <= hi_f ), a float gap hi_f - lo_f above 4e-7 ( |hi_f| + |lo_f| ) + 1e-37
+    must imply hi >= lo for the FP64 values -- the condition under which pass 1 skips rebuilding the FP64 boxes.  Swept over magnitudes from
+    subnormal floats to 1e30 with hi placed within twenty float spacings of lo on either side."""
+    rng = np.random.default_rng(3)
+    n = 400_000
+    mag = 10.0 ** rng.uniform(-44, 30, n)
+    lo = mag * rng.choice([-1.0, 1.0], n) * rng.uniform(0.5, 1.0, n)
+    ulp32 = np.maximum(np.abs(lo) * 2.0 ** -23, 2.0 ** -149)
+    hi = lo + ulp32 * rng.uniform(-20.0, 20.0, n)
+    hi_f, lo_f = _round_up_f32(hi), _round_down_f32(lo)
+    with np.errstate(over="ignore", invalid="ignore"):
+        gap = (hi_f - lo_f).astype(np.float32)
+        rhs = (np.float32(4.0e-7) * (np.abs(hi_f) + np.abs(lo_f)).astype(np.float32)).astype(np.float32) + np.float32(1.0e-37)
+        certain = gap > rhs
+    assert certain.sum() > n // 20 and (~certain).sum() > n // 20
+    assert np.all(hi[certain] >= lo[certain])
+    # and it is not vacuous: among the undecided ones both outcomes occur
+    und = ~certain
+    assert (hi[und] >= lo[und]).any() and (hi[und] < lo[und]).any()
