@@ -1,4 +1,6 @@
-"""CPU check of the reasoning behind pass 1's far-side pruning (scisim_b200/csrc/sg_broadphase.cuh, sg_bp_count_l1): bodies are binned by the
+"""CPU checks of the reasoning behind three kernel shortcuts (formulas restated in numpy / plain Python and run on adversarial inputs; what the kernels do with them is checked on the GPU against the oracle).
+
+(1) pass 1 far-side pruning (scisim_b200/csrc/sg_broadphase.cuh, sg_bp_count_l1): bodies are binned by the
 LOWER corner of their box, cell = uint32( ( lo - origin ) / h ) clamped, h >= every extent; a body drops the next cell column (row) from its walk when
 its upper bound, rounded UP to float, lies below  origin + ( c + 1 ) h  minus a margin.  Restated here in numpy with the kernel's expressions and run
 on adversarial inputs -- boxes that end exactly on, one ulp below and one ulp above cell edges, huge offsets, tiny cells: no overlapping pair may fall
@@ -105,3 +107,58 @@ def test_float_gap_certainty_implies_fp64_overlap():
     # and it is not vacuous: among the undecided ones both outcomes occur
     und = ~certain
     assert (hi[und] >= lo[und]).any() and (hi[und] < lo[und]).any()
+
+
+def _angle_axis_matrix(sn, cs, axis):
+    """Eigen 3.3.4 AngleAxis::toRotationMatrix, expression for expression (Eigen/src/Geometry/AngleAxis.h), with sin / cos given"""
+    ax, ay, az = axis
+    sx, sy, sz = sn * ax, sn * ay, sn * az
+    c1x, c1y, c1z = (1.0 - cs) * ax, (1.0 - cs) * ay, (1.0 - cs) * az
+    m = [[0.0] * 3 for _ in range(3)]
+    tmp = c1x * ay
+    m[0][1] = tmp - sz; m[1][0] = tmp + sz
+    tmp = c1x * az
+    m[0][2] = tmp + sy; m[2][0] = tmp - sy
+    tmp = c1y * az
+    m[1][2] = tmp - sx; m[2][1] = tmp + sx
+    m[0][0] = c1x * ax + cs; m[1][1] = c1y * ay + cs; m[2][2] = c1z * az + cs
+    return m
+
+
+def test_structured_splitham_rotations_equal_the_full_products():
+    """splitham_axis_step (scisim_b200/csrc/sg_rb3d.cu): SplitHamMap's rotations are about -e_z, -e_y, -e_x; the kernel writes the products
+    R <- R * AngleAxis( -a, -e_K ).matrix() and p <- AngleAxis( a, -e_K ).matrix() * p in structured form.  With the same sin / cos, the structured
+    form must equal the full 3x3 products of Eigen's matrix -- every entry, bit for bit (signs of exact zeros aside)."""
+    import math
+    rng = np.random.default_rng(9)
+    for trial in range(3000):
+        R = rng.normal(size=(3, 3)).tolist()
+        p = rng.normal(size=3).tolist()
+        a = float(rng.uniform(-3.5, 3.5)) if trial % 10 else 0.0
+        sn, cs = math.sin(a), math.cos(a)
+        e = (1.0 - cs) + cs
+        for K in range(3):
+            axis = [-0.0, -0.0, -0.0]
+            axis[K] = -1.0
+            B = _angle_axis_matrix(-sn, cs, axis)     # AngleAxis( -a, axis ): sin( -a ) = -sin( a )
+            A = _angle_axis_matrix(sn, cs, axis)
+            full_R = [[(R[r][0] * B[0][c] + R[r][1] * B[1][c]) + R[r][2] * B[2][c] for c in range(3)] for r in range(3)]
+            full_p = [(A[r][0] * p[0] + A[r][1] * p[1]) + A[r][2] * p[2] for r in range(3)]
+            S = [[0.0] * 3 for _ in range(3)]
+            for r in range(3):
+                a0, a1, a2 = R[r]
+                if K == 2:
+                    S[r] = [a0 * cs + a1 * sn, a0 * (-sn) + a1 * cs, a2 * e]
+                elif K == 1:
+                    S[r] = [a0 * cs + a2 * (-sn), a1 * e, a0 * sn + a2 * cs]
+                else:
+                    S[r] = [a0 * e, a1 * cs + a2 * sn, a1 * (-sn) + a2 * cs]
+            px, py, pz = p
+            if K == 2:
+                sp = [cs * px + sn * py, (-sn) * px + cs * py, e * pz]
+            elif K == 1:
+                sp = [cs * px + (-sn) * pz, e * py, sn * px + cs * pz]
+            else:
+                sp = [e * px, cs * py + sn * pz, (-sn) * py + cs * pz]
+            assert np.array_equal(np.array(S), np.array(full_R)), (trial, K)
+            assert np.array_equal(np.array(sp), np.array(full_p)), (trial, K)
