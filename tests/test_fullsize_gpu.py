@@ -3,8 +3,8 @@
   config 4  3-D sphere box drop, 4 096 000 spheres, split_ham
   config 5  mixed sphere / box / mesh scene with 10 k bodies
 Properties: ascending unique (i<j) candidate order; every active pair is a candidate; unit normals; depths <= 0;
-detection idempotent; a random sample of bodies checked against brute force over ALL bodies (same predicate as the
-reference: closed AABB overlap, then the narrow-phase inequality)."""
+detection idempotent; a random sample of bodies checked against brute force over ALL bodies, and (config 3) every pair inside a window of a few
+thousand bodies against all-pairs in numpy (same predicate as the reference: closed AABB overlap, then the narrow-phase inequality)."""
 import numpy as np
 import pytest
 
@@ -43,11 +43,26 @@ def test_config3_gas_4m(gpu_ctx):
     lo = np.minimum(q0, q1r) - s["r"][:, None]
     hi = np.maximum(q0, q1r) + s["r"][:, None]
     rng = np.random.default_rng(0)
-    for i in rng.choice(n, size=64, replace=False):
+    for i in rng.choice(n, size=128, replace=False):
         ov = np.all(~(hi[i] < lo) & ~(hi < lo[i]), axis=1)
         ov[i] = False
         mine = set(a.candidates[a.candidates[:, 0] == i, 1].tolist()) | set(a.candidates[a.candidates[:, 1] == i, 0].tolist())
         assert mine == set(np.nonzero(ov)[0].tolist())
+    # every pair inside a window of the scene (a few thousand bodies): the exact candidate set among them, all-pairs in numpy, against the
+    # GPU list restricted to pairs with both bodies in the window
+    cx, cy = np.median(q0[:, 0]), np.median(q0[:, 1])
+    half = 0.5 * np.sqrt(4000.0 / n) * (q0[:, 0].max() - q0[:, 0].min())
+    inside = np.nonzero((np.abs(q0[:, 0] - cx) < half) & (np.abs(q0[:, 1] - cy) < half))[0]
+    assert 2000 < inside.shape[0] < 8000
+    L, H = lo[inside], hi[inside]
+    ovm = np.all(~(H[:, None, :] < L[None, :, :]) & ~(H[None, :, :] < L[:, None, :]), axis=2)
+    ii, jj = np.nonzero(np.triu(ovm, k=1))
+    gi, gj = inside[ii], inside[jj]
+    want = np.sort((np.minimum(gi, gj).astype(np.uint64) << np.uint64(32)) | np.maximum(gi, gj).astype(np.uint64))
+    member = np.zeros(n, dtype=bool)
+    member[inside] = True
+    sel = member[a.candidates[:, 0]] & member[a.candidates[:, 1]]
+    assert want.shape[0] > 1000 and np.array_equal(ck[sel], want)
     assert sim.step(sb.VerletMap(), s["dt"]) == (pc, pa)
 
 
