@@ -20,12 +20,14 @@
 // reductions (a0+a1)+a2; Quaternion(Matrix3) by Shoemake's method; Quaternion::normalize with the squared
 // norm reduced as (x^2+z^2)+(y^2+w^2) (packet reduction, see solveDMV); AngleAxis::toRotationMatrix and Quaternion::toRotationMatrix as in
 // Eigen/src/Geometry.  Parity: no reference test stores expected values for any of this; the file is pinned against
-// the reference's own sources compiled unchanged into oracle/_ref (oracle/Makefile.ref, tests/test_oracle_vs_reference.py): the three maps with the
-// gravity force, the spatial grid, BoxBoxUtilities, the geometry classes' AABBs, the triangle-mesh class with its SDF narrow phase, the plane and portal
-// classes, and the constraint classes SphereSphere / StaticPlaneSphere / StaticPlaneBox (isActive, normal, contact point, depth for every such contact
-// of its active sets), bit for bit.  Restated only: static cylinders, updateMandMinv (its two assignments are checked as expressions evaluated by the
-// Eigen stand-in), and the glue of RigidBody3DSim.cpp.  sin/cos come from libm here (as in the reference) and from CUDA on the device, so rotating
-// bodies are compared to 1e-12, everything else bit for bit.
+// the reference's own sources compiled unchanged into oracle/_ref (oracle/Makefile.ref, tests/test_oracle_vs_reference.py): SplitHamMap / DMVMap /
+// ExponentialEulerMap with the gravity force, the spatial grid, BoxBoxUtilities, the geometry classes' AABBs, the triangle-mesh class with its SDF narrow
+// phase, the plane, cylinder and portal classes, RigidBody3DState (the mass matrices of setState and of updateMandMinv), and the constraint classes
+// SphereSphere / KinematicSphereSphere / StaticPlaneSphere / StaticPlaneBox / StaticCylinderSphere / StaticCylinderBody (isActive, normal, contact point,
+// depth for every such contact of its active sets), bit for bit -- except ExponentialEulerMap's projected orientation, where the reference calls
+// Eigen::JacobiSVD and the stand-in supplies its own SVD: agreement to rounding (4e-15), not bit for bit.  Restated only: the glue of
+// RigidBody3DSim.cpp.  sin/cos come from libm here (as in the reference) and from CUDA on the device, so rotating bodies are compared to 1e-12,
+// everything else bit for bit.
 #ifndef ORACLE_RB3D_H
 #define ORACLE_RB3D_H
 

@@ -33,6 +33,27 @@ namespace MathUtilities
     const long long rc[2] = { v.rows(), v.cols() };
     stm.write( reinterpret_cast<const char*>( rc ), sizeof( rc ) );
   }
+  // sparse matrices (rigidbody3d/RigidBody3DState.cpp serialises its four mass matrices): rows, cols, nnz, then outer / inner indices and values of the
+  // stand-in's compressed storage -- again a private format of the shims, written and read only here
+  inline void serialize( const SparseMatrixsc& A, std::ostream& stm )
+  {
+    const long long hdr[3] = { A.rows(), A.cols(), A.nonZeros() };
+    stm.write( reinterpret_cast<const char*>( hdr ), sizeof( hdr ) );
+    stm.write( reinterpret_cast<const char*>( A.outerIndexPtr() ), ( A.cols() + 1 ) * sizeof( int ) );
+    stm.write( reinterpret_cast<const char*>( A.innerIndexPtr() ), A.nonZeros() * sizeof( int ) );
+    stm.write( reinterpret_cast<const char*>( A.valuePtr() ), A.nonZeros() * sizeof( scalar ) );
+  }
+  inline void deserialize( SparseMatrixsc& A, std::istream& stm )
+  {
+    long long hdr[3];
+    stm.read( reinterpret_cast<char*>( hdr ), sizeof( hdr ) );
+    std::vector<int> outer( static_cast<size_t>( hdr[1] ) + 1 ), inner( static_cast<size_t>( hdr[2] ) );
+    std::vector<scalar> values( static_cast<size_t>( hdr[2] ) );
+    stm.read( reinterpret_cast<char*>( outer.data() ), outer.size() * sizeof( int ) );
+    stm.read( reinterpret_cast<char*>( inner.data() ), inner.size() * sizeof( int ) );
+    stm.read( reinterpret_cast<char*>( values.data() ), values.size() * sizeof( scalar ) );
+    A.setCompressed( int( hdr[0] ), outer, inner, values );
+  }
   template<typename T> T deserialize( std::istream& stm ) { T v; readShape( v, stm ); stm.read( reinterpret_cast<char*>( v.data() ), v.size() * sizeof( *v.data() ) ); return v; }
   template<typename T> void serialize( const T& v, std::ostream& stm ) { writeShape( v, stm ); stm.write( reinterpret_cast<const char*>( v.data() ), v.size() * sizeof( *v.data() ) ); }
 }

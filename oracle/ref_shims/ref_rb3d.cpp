@@ -26,6 +26,11 @@
 #include "rigidbody3d/Constraints/SphereSphereConstraint.h"
 #include "rigidbody3d/Constraints/StaticPlaneSphereConstraint.h"
 #include "rigidbody3d/Constraints/StaticPlaneBoxConstraint.h"
+#include "rigidbody3d/Constraints/StaticCylinderSphereConstraint.h"
+#include "rigidbody3d/Constraints/StaticCylinderBodyConstraint.h"
+#include "rigidbody3d/Constraints/KinematicObjectSphereConstraint.h"
+#include "rigidbody3d/StaticGeometry/StaticCylinder.h"
+#include "rigidbody3d/RigidBody3DState.h"
 #include <memory>
 
 #include <sstream>
@@ -270,7 +275,8 @@ private:
 
 extern "C"
 {
-// kind 2: SplitHamMap::flow, 3: DMVMap::flow (the reference's own code); q: 12 n, v: 6 n
+// kind 2: SplitHamMap::flow, 3: DMVMap::flow, 4: ExponentialEulerMap::flow (the reference's own code; for kind 4 the stand-in's JacobiSVD is NOT
+// Eigen's algorithm, see eigen_standin/Eigen/Geometry: the projected rotation is pinned to rounding only, everything else bit for bit); q: 12 n, v: 6 n
 void ref_rb3d_flow( const int kind, const uint32_t n, const double* q0, const double* v0, const double* m, const double* I0, const uint8_t* fixed, const double* g, const double dt,
                     const int m_updated, double* q1, double* v1 )
 {
@@ -279,6 +285,7 @@ void ref_rb3d_flow( const int kind, const uint32_t n, const double* q0, const do
   for( uint32_t k = 0; k < 12 * n; ++k ) { q0v( int( k ) ) = q0[k]; }
   for( uint32_t k = 0; k < 6 * n; ++k ) { v0v( int( k ) ) = v0[k]; }
   if( kind == 2 ) { SplitHamMap map; map.flow( q0v, v0v, sys, 1, dt, q1v, v1v ); }
+  else if( kind == 4 ) { ExponentialEulerMap map; map.flow( q0v, v0v, sys, 1, dt, q1v, v1v ); }
   else { DMVMap map; map.flow( q0v, v0v, sys, 1, dt, q1v, v1v ); }
   for( uint32_t k = 0; k < 12 * n; ++k ) { q1[k] = q1v( int( k ) ); }
   for( uint32_t k = 0; k < 6 * n; ++k ) { v1[k] = v1v( int( k ) ); }
@@ -304,7 +311,10 @@ extern "C"
 // kind 0  sphere-sphere ( i, j ), geo = r_i, r_j.  n and p are formed as RigidBody3DSim::sphereSphereNarrowPhaseCollision forms them (RigidBody3DSim.cpp:803-808,
 //         two lines restated here, marked) and handed to the class's constructor
 // kind 1  plane-sphere: geo = x[3], n[3], r          kind 2  plane-box: geo = x[3], n[3], half[3], aux = corner number
-// (StaticCylinderSphereConstraint needs StaticCylinder.cpp, whose GUI-only R() multiplies an AngleAxis by a Quaternion: not in the stand-in; cylinders stay restated)
+// kind 3  cylinder-sphere: geo = x[3], axis[3] (as given to StaticCylinder's constructor, which normalises it), R, r_sphere; j = cylinder number
+// kind 4  cylinder-body (mesh hull vertex): geo = x[3], axis[3], R, collision point at q0 [3] (RigidBody3DSim.cpp:1541, formed by the caller); no isActive
+//         of its own (MeshMeshUtilities::computeMeshCylinderActiveSet decides): out[0] = 1
+// kind 5  free sphere i against kinematic sphere j: geo = r_i, r_j.  n as RigidBody3DSim.cpp:803 forms it (restated here, marked); KinematicSphereSphereConstraint
 // out[0] isActive at q1 (plane-box: the corner is among the active corners), out[1..3] normal, out[4..6] contact point at q0, out[7] penetrationDepth( q1 )
 void ref_rb3d_constraint_probe( const int kind, const unsigned i, const unsigned j, const unsigned aux, const uint32_t nbodies, const double* q0, const double* q1, const double* geo, double* out )
 {
@@ -314,6 +324,7 @@ void ref_rb3d_constraint_probe( const int kind, const unsigned i, const unsigned
   const VectorXs& vq0 = wq0; const VectorXs& vq1 = wq1; // const: segment<3>() reads
   const Vector3s gx{ geo[0], geo[1], geo[2] }, gn{ geo[3], geo[4], geo[5] };
   const StaticPlane plane{ gx, ( kind == 1 || kind == 2 ) ? gn : Vector3s{ 0.0, 1.0, 0.0 } };   // outlive the constraints, which keep references
+  const StaticCylinder cyl{ gx, ( kind == 3 || kind == 4 ) ? gn : Vector3s{ 0.0, 1.0, 0.0 }, ( kind == 3 || kind == 4 ) ? geo[6] : 1.0 };
   std::unique_ptr<Constraint> con;
   bool active = false;
   if( kind == 0 )
@@ -330,6 +341,24 @@ void ref_rb3d_constraint_probe( const int kind, const unsigned i, const unsigned
     active = StaticPlaneSphereConstraint::isActive( plane.x(), plane.n(), vq1.segment<3>( 3 * i ), geo[6] );
     con.reset( new StaticPlaneSphereConstraint{ i, geo[6], plane, j } );
   }
+  else if( kind == 3 )
+  {
+    active = StaticCylinderSphereConstraint::isActive( cyl.x(), cyl.axis(), cyl.r(), vq1.segment<3>( 3 * i ), geo[7] );
+    con.reset( new StaticCylinderSphereConstraint{ i, geo[7], cyl, j } );
+  }
+  else if( kind == 4 )
+  {
+    active = true;
+    con.reset( new StaticCylinderBodyConstraint{ i, Vector3s{ geo[7], geo[8], geo[9] }, cyl, j, vq0 } );
+  }
+  else if( kind == 5 )
+  {
+    const scalar r0 = geo[0], r1 = geo[1];
+    active = SphereSphereConstraint::isActive( vq1.segment<3>( 3 * i ), vq1.segment<3>( 3 * j ), r0, r1 );
+    // restated glue (RigidBody3DSim.cpp:803):
+    const Vector3s n{ ( vq0.segment<3>( 3 * i ) - vq0.segment<3>( 3 * j ) ).normalized() };
+    con.reset( new KinematicSphereSphereConstraint{ i, r0, n, j, vq0.segment<3>( 3 * j ), Vector3s::Zero(), Vector3s::Zero(), r1 } );
+  }
   else
   {
     const Vector3s half{ geo[6], geo[7], geo[8] };
@@ -340,6 +369,17 @@ void ref_rb3d_constraint_probe( const int kind, const unsigned i, const unsigned
     con.reset( new StaticPlaneBoxConstraint{ i, short( aux ), plane.n(), half, vq0, j } );
   }
   out[0] = active ? 1.0 : 0.0;
+  if( kind == 4 )
+  {
+    // the class implements neither getWorldSpaceContactNormal nor ...Point (the base class exits): its normal is column 0 of its contact basis
+    VectorXs vzero{ 6 * int( nbodies ) };
+    vzero.setZero();
+    MatrixXXsc basis;
+    con->computeBasis( vq0, vzero, basis ); // the public wrapper of computeContactBasis (scisim/Constraints/Constraint.cpp:10-16)
+    for( int k = 0; k < 3; ++k ) { out[1 + k] = basis( k, 0 ); out[4 + k] = geo[7 + k]; }
+    out[7] = con->penetrationDepth( vq1 );
+    return;
+  }
   VectorXs n, p;
   con->getWorldSpaceContactNormal( vq0, n );
   con->getWorldSpaceContactPoint( vq0, p );
@@ -369,5 +409,40 @@ void ref_rb3d_update_inertia_expr( const double* R_rowmajor9, const double* I0_3
     const Eigen::Map<const Vector3s> Iinv0{ Iinv0_3 };
     Iinv = R * Iinv0.asDiagonal() * R.transpose(); // RigidBody3DState.cpp:455
   }
+}
+}
+
+
+// ---- RigidBody3DState itself (rigidbody3d/RigidBody3DState.cpp, compiled unchanged): the mass matrices its setState builds
+// ( formWorldSpaceMassMatrix / ...InverseMassMatrix, :140-240 ) and what updateMandMinv ( :428-462 ) leaves in them after the orientations changed.
+// q_ctor, q_upd: 12 n doubles; all bodies are unit spheres as far as the geometry list goes (the matrices do not look at it).
+// Outputs: the 9 n values behind the 3 n linear entries of M and Minv, as stored (column-compressed), after construction and after the update.
+extern "C"
+{
+void ref_rb3d_state_mass_matrices( const uint32_t n, const double* q_ctor, const double* q_upd, const double* m, const double* I0,
+                                   double* M_ctor, double* Minv_ctor, double* M_upd, double* Minv_upd )
+{
+  std::vector<Vector3s> X( n ), V( n, Vector3s::Zero() ), omega( n, Vector3s::Zero() ), I0v( n );
+  std::vector<scalar> M( n );
+  std::vector<VectorXs> R( n );
+  std::vector<bool> fixed( n, false );
+  std::vector<unsigned> geo_idx( n, 0u );
+  std::vector<std::unique_ptr<RigidBodyGeometry>> geometry;
+  geometry.emplace_back( new RigidBodySphere{ 1.0 } );
+  for( uint32_t b = 0; b < n; ++b )
+  {
+    X[b] = Vector3s{ q_ctor[3 * b], q_ctor[3 * b + 1], q_ctor[3 * b + 2] };
+    M[b] = m[b];
+    I0v[b] = Vector3s{ I0[3 * b], I0[3 * b + 1], I0[3 * b + 2] };
+    R[b].resize( 9 );
+    for( int k = 0; k < 9; ++k ) { R[b]( k ) = q_ctor[3 * size_t( n ) + 9 * size_t( b ) + k]; }
+  }
+  RigidBody3DState state;
+  state.setState( X, V, M, R, omega, I0v, fixed, geo_idx, geometry );
+  const size_t off = 3 * size_t( n );
+  for( size_t k = 0; k < 9 * size_t( n ); ++k ) { M_ctor[k] = state.M().valuePtr()[off + k]; Minv_ctor[k] = state.Minv().valuePtr()[off + k]; }
+  for( size_t k = 0; k < 12 * size_t( n ); ++k ) { state.q()( int( k ) ) = q_upd[k]; }
+  state.updateMandMinv();
+  for( size_t k = 0; k < 9 * size_t( n ); ++k ) { M_upd[k] = state.M().valuePtr()[off + k]; Minv_upd[k] = state.Minv().valuePtr()[off + k]; }
 }
 }

@@ -410,6 +410,29 @@ def test_rb3d_maps_equal_reference_sources(oracle, kind, m_updated, scene_kind, 
         assert np.abs(q1[3 * n:] - q0[3 * n:]).max() > 1e-6   # the orientations did move
 
 
+def test_rb3d_exponential_euler_equals_reference_source(oracle):
+    """rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.cpp:13-91 compiled unchanged.  Positions and velocities (the explicit Euler parts, the
+    force evaluation, Minv * F) bit for bit.  The projected orientation U V^T: the reference calls Eigen::JacobiSVD, for which the stand-in supplies
+    ITS OWN algorithm (eigen-decomposition of A^T A), the oracle a one-sided Jacobi -- two independent routes to the same unique polar factor, so
+    they agree to rounding, not bit for bit; that is all that is claimed for it."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    for n, seed, m_updated in ((500, 5, False), (300, 6, True), (1, 7, False)):
+        s = scenes.rb3d_random_boxes(n, seed, spin=True, nfixed_frac=0.0)
+        o = ob.RB3DOracle(s)
+        q1, v1 = o.flow(4, s["q"], s["v"], s["dt"], m_updated=m_updated)
+        rq1, rv1 = np.zeros_like(q1), np.zeros_like(v1)
+        q0, v0 = np.ascontiguousarray(s["q"]), np.ascontiguousarray(s["v"])
+        m, I0 = np.ascontiguousarray(s["m"], dtype=np.float64), np.ascontiguousarray(s["I0"], dtype=np.float64)
+        fixed = np.ascontiguousarray(s["fixed"], dtype=np.uint8)
+        g = np.ascontiguousarray(s["g"], dtype=np.float64)
+        ref.ref_rb3d_flow(C.c_int(4), C.c_uint32(n), vp(q0), vp(v0), vp(m), vp(I0), vp(fixed), vp(g), C.c_double(s["dt"]), C.c_int(1 if m_updated else 0), vp(rq1), vp(rv1))
+        assert np.array_equal(q1[:3 * n], rq1[:3 * n]) and np.array_equal(v1, rv1)
+        assert np.abs(q1[3 * n:] - rq1[3 * n:]).max() < 4e-15, np.abs(q1[3 * n:] - rq1[3 * n:]).max()
+        assert np.abs(q1[3 * n:] - q0[3 * n:]).max() > 1e-4   # the orientations did move
+
+
 def test_rb3d_update_m_and_minv_equals_reference_expression(oracle):
     """The oracle's updateMandMinv blocks == R * I0.asDiagonal() * R^T evaluated by the stand-in in the layout of RigidBody3DState.cpp:428-462."""
     from scisim_b200 import scenes
@@ -507,6 +530,92 @@ def test_rb3d_constraint_classes(oracle):
             assert out[7] == a["depth"][k] or (np.isnan(out[7]) and np.isnan(a["depth"][k])), (t, out[7], a["depth"][k])
             seen[t] += 1
     assert seen[10] > 100 and seen[14] > 10 and seen[15] > 10, seen
+
+
+def test_rb3d_cylinder_and_kinematic_sphere_constraint_classes(oracle):
+    """rigidbody3d/StaticGeometry/StaticCylinder.cpp, Constraints/{StaticCylinderSphere,StaticCylinderBody,KinematicObjectSphere}Constraint.cpp compiled
+    unchanged: for every cylinder-sphere, cylinder-hull-vertex and free-sphere-vs-kinematic-sphere contact of oracle active sets -- isActive at q1
+    (the sphere classes), the constraint built as RigidBody3DSim builds it (RigidBody3DSim.cpp:803-816, 1504-1557), its normal and its world-space
+    contact point at q0, bit for bit."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    ref.ref_rb3d_constraint_probe.restype = None
+    ref.ref_rb3d_constraint_probe.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    seen = {11: 0, 17: 0, 18: 0}
+    sph = scenes.rb3d_random_spheres(1500, 51, spin=True, nfixed_frac=0.25, nplanes=0)
+    mesh = scenes.rb3d_random_meshes(60, 52, nfixed_frac=0.0, nplanes=0)
+    for s in (sph, mesh):
+        x = s["q"][:3 * s["geo_of_body"].shape[0]].reshape(-1, 3)
+        ext = float(np.abs(x).max())
+        s["cyl_x"] = np.array([[0.1, -0.2, 0.3], [0.0, 0.0, 0.0]])
+        s["cyl_axis"] = np.array([[0.2, 3.0, -0.1], [1.0, 0.1, 0.05]])
+        s["cyl_r"] = np.array([0.8 * ext, 0.95 * ext])
+        o = ob.RB3DOracle(s)
+        nb = s["geo_of_body"].shape[0]
+        q0 = np.ascontiguousarray(s["q"], dtype=np.float64)
+        q1, _ = o.flow(3, q0, s["v"], s["dt"])
+        a = o.active_set(q0, q1, "grid")
+        assert a["supported"]
+        out = np.zeros(8)
+        for k in range(a["type"].shape[0]):
+            t, i, j, aux = int(a["type"][k]), int(a["i"][k]), int(a["j"][k]), int(a["aux"][k])
+            gi = int(s["geo_of_body"][i])
+            if t == 17:
+                geo, kind = np.concatenate([s["cyl_x"][j], s["cyl_axis"][j], [s["cyl_r"][j], s["geo_r"][gi], 0, 0]]), 3
+            elif t == 18:
+                geo, kind = np.concatenate([s["cyl_x"][j], s["cyl_axis"][j], [s["cyl_r"][j]], a["p"][k]]), 4
+            elif t == 11:
+                geo, kind = np.array([s["geo_r"][gi], s["geo_r"][int(s["geo_of_body"][j])], 0, 0, 0, 0, 0, 0, 0, 0], dtype=np.float64), 5
+            else:
+                continue
+            geo = np.ascontiguousarray(geo, dtype=np.float64)
+            ref.ref_rb3d_constraint_probe(kind, i, j, aux, nb, vp(q0), vp(q1), vp(geo), vp(out))
+            assert out[0] == 1.0, (t, i, j, aux)
+            assert np.array_equal(out[1:4], a["n"][k]), (t, i, j, out[1:4], a["n"][k])
+            if t == 17:
+                assert np.array_equal(out[4:7], a["p"][k]), (t, i, j, out[4:7], a["p"][k])
+            elif t == 18:   # StaticCylinderBodyConstraint reports no contact point of its own (the base class exits); its normal is column 0 of computeContactBasis
+                pass
+            else:           # the list's p is the constructor argument X (the kinematic sphere's centre at q0); the class reports x_i - r_i n
+                assert np.array_equal(a["p"][k], q0[3 * j: 3 * j + 3]) and np.array_equal(out[4:7], q0[3 * i: 3 * i + 3] - s["geo_r"][gi] * a["n"][k])
+            seen[t] += 1
+    assert seen[11] > 50 and seen[17] > 20 and seen[18] > 20, seen
+
+
+def test_rb3d_state_mass_matrices_equal_reference_source(oracle):
+    """rigidbody3d/RigidBody3DState.cpp compiled unchanged: the world-space blocks of M and Minv as setState builds them (formWorldSpaceMassMatrix /
+    formWorldSpaceInverseMassMatrix, :140-240 -- stored TRANSPOSED, M( r, c ) = I( c, r )) and as updateMandMinv (:428-462) leaves them after the
+    orientations moved, against the oracle's two layouts ( m_updated = False / True of its maps; update_m_and_minv ), bit for bit.  This is the pin for
+    the 'two mass matrices' behaviour of DESIGN section 2 and for SG_MAP_M_UPDATED."""
+    from scisim_b200 import scenes
+    from tests import oracle_binding as ob
+    ref = _load("libref_rb3d.so")
+    ref.ref_rb3d_state_mass_matrices.restype = None
+    ref.ref_rb3d_state_mass_matrices.argtypes = [C.c_uint32] + [C.c_void_p] * 8
+    n = 600
+    s = scenes.rb3d_random_boxes(n, 91, spin=True, nfixed_frac=0.0, nplanes=0)
+    o = ob.RB3DOracle(s)
+    q0 = np.ascontiguousarray(s["q"], dtype=np.float64)
+    q1, _ = o.flow(2, q0, s["v"], s["dt"])      # orientations orthonormal only up to rounding, as in a running simulation
+    q1 = np.ascontiguousarray(q1)
+    m, I0 = np.ascontiguousarray(s["m"], dtype=np.float64), np.ascontiguousarray(s["I0"], dtype=np.float64)
+    Mc, Mic, Mu, Miu = (np.zeros(9 * n) for _ in range(4))
+    ref.ref_rb3d_state_mass_matrices(n, vp(q0), vp(q1), vp(m), vp(I0), vp(Mc), vp(Mic), vp(Mu), vp(Miu))
+    # after the update: the oracle's restatement of updateMandMinv at q1
+    I, Ii = o.update_m_and_minv(q1)
+    assert np.array_equal(Mu, I) and np.array_equal(Miu, Ii)
+    # as constructed: the same products at q0, each 3x3 block transposed
+    I, Ii = o.update_m_and_minv(q0)
+    T = lambda a: a.reshape(n, 3, 3).transpose(0, 2, 1).reshape(-1)
+    assert np.array_equal(Mc, T(I)) and np.array_equal(Mic, T(Ii))
+    assert not np.array_equal(Mc, I)            # I = R I0 R^T is symmetric only up to rounding: the two layouts do differ
+    # and the shim system the map tests drive (which restates the fill) holds exactly these values
+    rI, rIi = np.zeros(9 * n), np.zeros(9 * n)
+    ref.ref_rb3d_mass_blocks(C.c_uint32(n), vp(q0), vp(m), vp(I0), C.c_int(0), vp(rI), vp(rIi))
+    assert np.array_equal(rI, Mc) and np.array_equal(rIi, Mic)
+    ref.ref_rb3d_mass_blocks(C.c_uint32(n), vp(q1), vp(m), vp(I0), C.c_int(1), vp(rI), vp(rIi))
+    assert np.array_equal(rI, Mu) and np.array_equal(rIi, Miu)
 
 
 def test_rb3d_update_m_and_minv_expressions(oracle):
