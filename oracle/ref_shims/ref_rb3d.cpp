@@ -390,10 +390,9 @@ void ref_rb3d_constraint_probe( const int kind, const unsigned i, const unsigned
 }
 
 
-// ---- RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462).  The file itself does not compile against the stand-in (sparse
-// matrix internals, serialisation), so this pins less than the entries above: the two assignments of its loop body, typed with the same Eigen
-// types and Maps, evaluated by the stand-in -- i.e. that the oracle's restatement is what the stand-in makes of the reference's EXPRESSIONS
-// ( R * I0.asDiagonal() * R.transpose() into a column-major Map ), not that the reference's file was compiled.
+// ---- RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462) as EXPRESSIONS: the two assignments of its loop body, typed with the
+// same Eigen types and Maps, evaluated by the stand-in.  Kept from before the file itself compiled (ref_rb3d_state_mass_matrices below now drives the real
+// RigidBody3DState); a per-body probe that needs no state object.
 extern "C"
 {
 void ref_rb3d_update_inertia_expr( const double* R_rowmajor9, const double* I0_3, const double* Iinv0_3, double* I_colmajor9, double* Iinv_colmajor9 )

@@ -619,8 +619,8 @@ def test_rb3d_state_mass_matrices_equal_reference_source(oracle):
 
 
 def test_rb3d_update_m_and_minv_expressions(oracle):
-    """RigidBody3DState::updateMandMinv (RigidBody3DState.cpp:428-462): the file does not compile against the stand-in, so this is an EXPRESSION pin --
-    its two assignments ( R * I0.asDiagonal() * R.transpose() into column-major maps ), typed as in the reference and evaluated by the stand-in, against
+    """RigidBody3DState::updateMandMinv (RigidBody3DState.cpp:428-462) as an EXPRESSION pin (the file itself is driven by
+    test_rb3d_state_mass_matrices_equal_reference_source): its two assignments ( R * I0.asDiagonal() * R.transpose() into column-major maps ), typed as in the reference and evaluated by the stand-in, against
     the oracle's restatement, for spinning boxes at random orientations."""
     from scisim_b200 import scenes
     from tests import oracle_binding as ob
