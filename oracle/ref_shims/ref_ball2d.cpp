@@ -20,6 +20,7 @@
 #include "ball2d/Constraints/BallBallConstraint.h"
 #include "ball2d/Constraints/BallStaticPlaneConstraint.h"
 #include "ball2d/Constraints/BallStaticDrumConstraint.h"
+#include "ball2d/ConstraintCache.h"
 
 #include <memory>
 #include <sstream>
@@ -269,4 +270,43 @@ int ref_ball2d_constraint_probe( const int kind, const unsigned i, const unsigne
   return nt;
 }
 
+}
+
+// ---- ball2d/ConstraintCache.cpp compiled unchanged: cacheConstraint for a list of constraints, then getCachedConstraint for another list.
+// Constraints are built with the reference's own classes (only their indices and names matter to the cache).  type = the contact type codes of
+// include/scisim_b200.h; a = first body, b = second body / static object.  r: ncomp doubles per constraint.  Returns constraintCacheEmpty() after the stores.
+extern "C"
+{
+int ref_ball2d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
+                                const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout )
+{
+  uint32_t nb = 1;
+  for( uint32_t k = 0; k < nstore; ++k ) { nb = std::max( nb, std::max( sa[k], stype[k] == 0 ? sb[k] : 0u ) + 1u ); }
+  for( uint32_t k = 0; k < nquery; ++k ) { nb = std::max( nb, std::max( qa[k], qtype[k] == 0 ? qb[k] : 0u ) + 1u ); }
+  VectorXs wq{ int( 2 * nb ) };
+  for( uint32_t b = 0; b < nb; ++b ) { wq( int( 2 * b ) ) = double( b ); wq( int( 2 * b + 1 ) ) = 0.5 * double( b ); }
+  const VectorXs& q = wq;
+  const StaticPlane plane{ Vector2s{ 0.0, 0.0 }, Vector2s{ 0.0, 1.0 } };
+  const auto make = [&]( const uint32_t type, const uint32_t a, const uint32_t b ) -> std::unique_ptr<Constraint>
+  {
+    if( type == 0 ) { return std::unique_ptr<Constraint>{ new BallBallConstraint{ a, b, q, 0.5, 0.5, false } }; }
+    if( type == 2 ) { return std::unique_ptr<Constraint>{ new StaticPlaneConstraint{ a, 0.5, plane, b } }; }
+    return std::unique_ptr<Constraint>{ new StaticDrumConstraint{ a, q, 0.5, Vector2s{ -3.0, -4.0 }, b } };
+  };
+  ConstraintCache cache;
+  VectorXs r{ int( ncomp ) };
+  for( uint32_t k = 0; k < nstore; ++k )
+  {
+    for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = rstore[size_t( k ) * ncomp + c]; }
+    cache.cacheConstraint( *make( stype[k], sa[k], sb[k] ), r );
+  }
+  const int empty = cache.empty() ? 1 : 0;
+  for( uint32_t k = 0; k < nquery; ++k )
+  {
+    for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = -7.0; }
+    cache.getCachedConstraint( *make( qtype[k], qa[k], qb[k] ), r );
+    for( uint32_t c = 0; c < ncomp; ++c ) { rout[size_t( k ) * ncomp + c] = r( int( c ) ); }
+  }
+  return empty;
+}
 }

@@ -20,6 +20,8 @@
 #include "rigidbody2d/StaticPlaneCircleConstraint.h"
 #include "rigidbody2d/StaticPlaneBodyConstraint.h"
 #include "rigidbody2d/BodyBodyConstraint.h"
+#include "rigidbody2d/ConstraintCache.h"
+#include "rigidbody2d/KinematicObjectCircleConstraint.h"
 #include "rigidbody2d/RigidBody2DStaticPlane.h"
 #include <memory>
 
@@ -217,4 +219,46 @@ void ref_rb2d_constraint_probe( const int kind, const unsigned i, const unsigned
   out[5] = con->penetrationDepth( vq1 );
 }
 
+}
+
+// ---- rigidbody2d/ConstraintCache.cpp compiled unchanged: cacheConstraint for a list of constraints, then getCachedConstraint for another list.
+// Constraints are built with the reference's own classes (only their indices and names matter to the cache).  type = the contact type codes of
+// include/scisim_b200.h; a = first body, b = second body / static object.  r: ncomp doubles per constraint.  Returns constraintCacheEmpty() after the stores.
+// (20 circle-circle, 22 body-body, 21 kinematic circle, 23 plane-circle -- anything else exits, as in the reference)
+extern "C"
+{
+int ref_rb2d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
+                              const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout )
+{
+  uint32_t nb = 1;
+  for( uint32_t k = 0; k < nstore; ++k ) { nb = std::max( nb, std::max( sa[k], stype[k] != 23 ? sb[k] : 0u ) + 1u ); }
+  for( uint32_t k = 0; k < nquery; ++k ) { nb = std::max( nb, std::max( qa[k], qtype[k] != 23 ? qb[k] : 0u ) + 1u ); }
+  VectorXs wq{ int( 3 * nb ) };
+  for( uint32_t b = 0; b < nb; ++b ) { wq( int( 3 * b ) ) = double( b ); wq( int( 3 * b + 1 ) ) = 0.5 * double( b ); wq( int( 3 * b + 2 ) ) = 0.0; }
+  const VectorXs& q = wq;
+  const RigidBody2DStaticPlane plane{ Vector2s{ 0.0, 0.0 }, Vector2s{ 0.0, 1.0 } };
+  const Vector2s n{ 1.0, 0.0 }, p{ 0.0, 0.0 };
+  const auto make = [&]( const uint32_t type, const uint32_t a, const uint32_t b ) -> std::unique_ptr<Constraint>
+  {
+    if( type == 20 ) { return std::unique_ptr<Constraint>{ new CircleCircleConstraint{ a, b, n, p, 0.5, 0.5 } }; }
+    if( type == 22 ) { return std::unique_ptr<Constraint>{ new BodyBodyConstraint{ a, b, p, n, q } }; }
+    if( type == 23 ) { return std::unique_ptr<Constraint>{ new StaticPlaneCircleConstraint{ a, b, 0.5, plane } }; }
+    return std::unique_ptr<Constraint>{ new KinematicObjectCircleConstraint{ a, 0.5, n, b, p, Vector2s::Zero(), 0.0 } };
+  };
+  ConstraintCache cache;
+  VectorXs r{ int( ncomp ) };
+  for( uint32_t k = 0; k < nstore; ++k )
+  {
+    for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = rstore[size_t( k ) * ncomp + c]; }
+    cache.cacheConstraint( *make( stype[k], sa[k], sb[k] ), r );
+  }
+  const int empty = cache.empty() ? 1 : 0;
+  for( uint32_t k = 0; k < nquery; ++k )
+  {
+    for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = -7.0; }
+    cache.getCachedConstraint( *make( qtype[k], qa[k], qb[k] ), r );
+    for( uint32_t c = 0; c < ncomp; ++c ) { rout[size_t( k ) * ncomp + c] = r( int( c ) ); }
+  }
+  return empty;
+}
 }

@@ -31,6 +31,7 @@
 #include "rigidbody3d/Constraints/KinematicObjectSphereConstraint.h"
 #include "rigidbody3d/StaticGeometry/StaticCylinder.h"
 #include "rigidbody3d/RigidBody3DState.h"
+#include "rigidbody3d/ConstraintCache.h"
 #include <memory>
 
 #include <sstream>
@@ -443,5 +444,42 @@ void ref_rb3d_state_mass_matrices( const uint32_t n, const double* q_ctor, const
   for( size_t k = 0; k < 12 * size_t( n ); ++k ) { state.q()( int( k ) ) = q_upd[k]; }
   state.updateMandMinv();
   for( size_t k = 0; k < 9 * size_t( n ); ++k ) { M_upd[k] = state.M().valuePtr()[off + k]; Minv_upd[k] = state.Minv().valuePtr()[off + k]; }
+}
+}
+
+// ---- rigidbody3d/ConstraintCache.cpp compiled unchanged: cacheConstraint for a list of constraints, then getCachedConstraint for another list.
+// Constraints are built with the reference's own classes (only their indices and names matter to the cache).  type = the contact type codes of
+// include/scisim_b200.h; a = first body, b = second body / static object.  r: ncomp doubles per constraint.  Returns constraintCacheEmpty() after the stores.
+// (sphere constraints only: 10 sphere-sphere, 14 plane-sphere, 17 cylinder-sphere, 11 kinematic sphere-sphere -- anything else exits, as in the reference)
+extern "C"
+{
+int ref_rb3d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
+                              const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout )
+{
+  const StaticPlane plane{ Vector3s{ 0.0, 0.0, 0.0 }, Vector3s{ 0.0, 1.0, 0.0 } };
+  const StaticCylinder cyl{ Vector3s{ 0.0, 0.0, 0.0 }, Vector3s{ 0.0, 1.0, 0.0 }, 10.0 };
+  const Vector3s n{ 1.0, 0.0, 0.0 }, p{ 0.0, 0.0, 0.0 };
+  const auto make = [&]( const uint32_t type, const uint32_t a, const uint32_t b ) -> std::unique_ptr<Constraint>
+  {
+    if( type == 10 ) { return std::unique_ptr<Constraint>{ new SphereSphereConstraint{ a, b, n, p, 0.5, 0.5 } }; }
+    if( type == 14 ) { return std::unique_ptr<Constraint>{ new StaticPlaneSphereConstraint{ a, 0.5, plane, b } }; }
+    if( type == 17 ) { return std::unique_ptr<Constraint>{ new StaticCylinderSphereConstraint{ a, 0.5, cyl, b } }; }
+    return std::unique_ptr<Constraint>{ new KinematicSphereSphereConstraint{ a, 0.5, n, b, p, Vector3s::Zero(), Vector3s::Zero(), 0.5 } };
+  };
+  ConstraintCache cache;
+  VectorXs r{ int( ncomp ) };
+  for( uint32_t k = 0; k < nstore; ++k )
+  {
+    for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = rstore[size_t( k ) * ncomp + c]; }
+    cache.cacheConstraint( *make( stype[k], sa[k], sb[k] ), r );
+  }
+  const int empty = cache.empty() ? 1 : 0;
+  for( uint32_t k = 0; k < nquery; ++k )
+  {
+    for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = -7.0; }
+    cache.getCachedConstraint( *make( qtype[k], qa[k], qb[k] ), r );
+    for( uint32_t c = 0; c < ncomp; ++c ) { rout[size_t( k ) * ncomp + c] = r( int( c ) ); }
+  }
+  return empty;
 }
 }

@@ -269,7 +269,8 @@ void PairImpulseCache::Table::sortIfNeeded()
   if( sorted ) { return; }
   std::vector<std::size_t> order( keys.size() );
   std::iota( order.begin(), order.end(), std::size_t( 0 ) );
-  std::sort( order.begin(), order.end(), [this]( const std::size_t a, const std::size_t b ) { return keys[a] < keys[b]; } );
+  // stable: of several entries with one key the first stored stays first, and lookup returns the first (std::map::insert keeps the first)
+  std::stable_sort( order.begin(), order.end(), [this]( const std::size_t a, const std::size_t b ) { return keys[a] < keys[b]; } );
   std::vector<uint64_t> k2( keys.size() );
   std::vector<double> v2( values.size() );
   for( std::size_t n = 0; n < order.size(); ++n )
@@ -325,6 +326,26 @@ void PairImpulseCache::getCachedConstraint( const int kind, const unsigned a, co
   }
   // If the constraint was not found set to a default force of 0 (ball2d/ConstraintCache.cpp:122)
   r.setZero();
+}
+
+extern "C"
+{
+void* sgh_cache_create() { return new PairImpulseCache; }
+void sgh_cache_destroy( void* cache ) { delete static_cast<PairImpulseCache*>( cache ); }
+void sgh_cache_clear( void* cache ) { static_cast<PairImpulseCache*>( cache )->clear(); }
+int sgh_cache_empty( const void* cache ) { return static_cast<const PairImpulseCache*>( cache )->empty() ? 1 : 0; }
+void sgh_cache_store( void* cache, int kind, unsigned a, unsigned b, const double* r, unsigned ncomp )
+{
+  VectorXs v( static_cast<long>( ncomp ) );
+  for( unsigned c = 0; c < ncomp; ++c ) { v( c ) = r[c]; }
+  static_cast<PairImpulseCache*>( cache )->cacheConstraint( kind, a, b, v );
+}
+void sgh_cache_lookup( const void* cache, int kind, unsigned a, unsigned b, double* r, unsigned ncomp )
+{
+  VectorXs v( static_cast<long>( ncomp ) );
+  static_cast<const PairImpulseCache*>( cache )->getCachedConstraint( kind, a, b, v );
+  for( unsigned c = 0; c < ncomp; ++c ) { r[c] = v( c ); }
+}
 }
 
 // ---- rigidbody3d ---------------------------------------------------------------------------------------------------

@@ -197,7 +197,9 @@ public:
   //   ball2d       0 ball-ball (i,j)      1 plane-ball (plane, ball)    2 drum-ball (drum, ball)      (ball2d/ConstraintCache.cpp:20-122)
   //   rigidbody3d  0 sphere-sphere (i,j)  1 plane-sphere (plane, body)  2 cylinder-sphere (cyl, body)  3 kinematic sphere-sphere
   //                (rigidbody3d/ConstraintCache.cpp:14-72 -- like the reference, only sphere constraints can be cached)
-  //   rigidbody2d  0 circle-circle (i,j)  1 plane-circle (plane, body)  3 kinematic circle-circle
+  //   rigidbody2d  0 circle-circle (i,j)  1 plane-circle (plane, body)  2 body-body (i,j)  3 kinematic object - circle ( min, max of the two bodies )
+  //                (rigidbody2d/ConstraintCache.cpp:14-60)
+  // A key stored twice keeps its FIRST impulse, as std::map::insert does (box-box gives two body-body contacts per pair: both read the first one's).
   void cacheConstraint( const int kind, const unsigned a, const unsigned b, const VectorXs& r );
   void getCachedConstraint( const int kind, const unsigned a, const unsigned b, VectorXs& r ) const;
 private:
@@ -211,6 +213,17 @@ private:
   };
   mutable Table m_tables[4];
 };
+
+// PairImpulseCache behind plain C calls (what the parity tests bind with ctypes to compare it with the reference's three ConstraintCache.cpp)
+extern "C"
+{
+void* sgh_cache_create();
+void sgh_cache_destroy( void* cache );
+void sgh_cache_clear( void* cache );
+int sgh_cache_empty( const void* cache );
+void sgh_cache_store( void* cache, int kind, unsigned a, unsigned b, const double* r, unsigned ncomp );
+void sgh_cache_lookup( const void* cache, int kind, unsigned a, unsigned b, double* r, unsigned ncomp );
+}
 
 // ---- rigidbody3d ---------------------------------------------------------------------------------------------------
 // One entry per Constraint RigidBody3DSim::computeActiveSet would emplace_back (RigidBody3DSim.cpp:250-262), same order
