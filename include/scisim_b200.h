@@ -66,7 +66,7 @@ extern "C" {
 #define SG_PLANE_SPHERE 14            /* StaticPlaneSphereConstraint: j = plane */
 #define SG_PLANE_BOX 15               /* StaticPlaneBoxConstraint: j = plane, aux = corner number, p = x0 + R0*corner */
 #define SG_PLANE_BODY 16              /* StaticPlaneBodyConstraint: j = plane, aux = convex hull vertex, p = collision point at q0 */
-#define SG_CYLINDER_SPHERE 17         /* StaticCylinderSphereConstraint{ i, r_i, staticCylinder(j), j }: n = computeN( q0 ), p = x0 - r n */
+#define SG_CYLINDER_SPHERE 17         /* StaticCylinderSphereConstraint{ i, r_i, staticCylinder(j), j }: n = computeN( q0 ), p = x0 - r n, depth = min( 0, R - dist( q1 ) - r ) */
 #define SG_CYLINDER_BODY 18           /* StaticCylinderBodyConstraint{ i, p, staticCylinder(j), j, q0 }: aux = hull vertex, n from the centre of mass */
 /* with portals (rigidbody3d/RigidBody3DSim.cpp:1338-1397): after the contacts of the un-teleported pairs, ascending body pair */
 #define SG_SPHERE_SPHERE_TELEPORTED 19           /* TeleportedSphereSphereConstraint{ i, j, x0, x1, ri, rj }: p = q0_i + ri/(ri+rj) (x1 - x0) */

@@ -631,7 +631,7 @@ inline bool computeStaticActiveSet( const RB3DScene& s, const double* q0, const 
           c.type = CYLINDER_SPHERE; c.i = b; c.j = cy; c.aux = 0;
           c.n = normalized( m0 );
           c.p = x0 - g.r * c.n;         // getWorldSpaceContactPoint (:324-327)
-          c.depth = NaN;
+          c.depth = std::min( 0.0, rc - norm( d ) - g.r ); // computePenetrationDepth at q1 (:311-317) -- found by running the reference's own RigidBody3DSim
           active_set.emplace_back( c );
         }
       }

@@ -939,7 +939,8 @@ __device__ inline uint32_t plane_contacts( const Rb3dDev& dev, const Planes3D& p
           const V3d x0 = load_v3( q0, b );
           const V3d e0 = ( x0 - xc ) - dot3( ax, x0 - xc ) * ax;
           const V3d n = normalized3( -e0 );                          // computeN( q0 ) (:237-244)
-          put_contact( out, emit_base, SG_CYLINDER_SPHERE, b, cy, 0u, n, x0 - r * n, sg_nan() );
+          // computePenetrationDepth( q1 ) = min( 0, R - |d| - r ) (StaticCylinderSphereConstraint.cpp:311-317)
+          put_contact( out, emit_base, SG_CYLINDER_SPHERE, b, cy, 0u, n, x0 - r * n, fmin( 0.0, rc - sqrt( dot3( d, d ) ) - r ) );
         }
         cnt = 1u;
       }
@@ -1259,7 +1260,9 @@ __global__ void __launch_bounds__( 256 ) k_rb3d_static_spheres( const uint32_t n
       const V3d ax = v3( planes.cax[cy][0], planes.cax[cy][1], planes.cax[cy][2] );
       const V3d e0 = ( x0 - xc ) - dot3( ax, x0 - xc ) * ax;
       const V3d n = normalized3( -e0 );
-      put_contact( out, k, SG_CYLINDER_SPHERE, b, cy, 0u, n, x0 - r * n, sg_nan() );
+      const V3d d1 = ( x1 - xc ) - dot3( ax, x1 - xc ) * ax;
+      // computePenetrationDepth( q1 ) = min( 0, R - |d| - r ) (StaticCylinderSphereConstraint.cpp:311-317)
+      put_contact( out, k, SG_CYLINDER_SPHERE, b, cy, 0u, n, x0 - r * n, fmin( 0.0, planes.cr[cy] - sqrt( dot3( d1, d1 ) ) - r ) );
     }
   }
 }

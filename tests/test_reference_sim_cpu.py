@@ -146,3 +146,138 @@ def test_ball2d_sim_with_portals(oracle, axes, le, oblique, seed):
         seen |= set(int(t) for t in got["type"])
         q, v = q1w, v1w
     assert 0 in seen and (3 in seen or 4 in seen) and (le == 0.0 or 4 in seen) and (axes != "xy" or 3 in seen)
+
+
+# ---- rigidbody3d ------------------------------------------------------------------------------------------------------------------------------------
+class RefRB3DSim:
+    def __init__(self, s, portals=None):
+        self.lib = lib = _lib("libref_rb3d.so")
+        V = C.c_void_p
+        lib.ref_rb3d_mesh_create.restype = V
+        lib.ref_rb3d_mesh_create.argtypes = [C.c_uint32, V, C.c_uint32, V, C.c_uint32, V, V, V, V, V]
+        lib.ref_rb3d_mesh_destroy.argtypes = [V]
+        lib.ref_rb3d_sim_create.restype = V
+        lib.ref_rb3d_sim_create.argtypes = [C.c_uint32, V, V, V, V, V, V, C.c_uint32, V, V, V, V, V, C.c_uint32, V, V, C.c_uint32, V, V, V, C.c_uint32, V, V, V, V, V]
+        lib.ref_rb3d_sim_destroy.argtypes = [V]
+        lib.ref_rb3d_sim_active_set.restype = C.c_uint64
+        lib.ref_rb3d_sim_active_set.argtypes = [V, V, V, C.c_uint64, V, V, V, V, V, V, V]
+        self.n = n = s["geo_of_body"].shape[0]
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+        self.meshes = []
+        for m in s["meshes"]:
+            a = [f64(m[k]) for k in ("verts", "samples", "hull", "cell_delta", "origin", "sdf")]
+            self.meshes.append(lib.ref_rb3d_mesh_create(a[0].shape[0], vp(a[0]), a[1].shape[0], vp(a[1]), a[2].shape[0], vp(a[2]), vp(a[3]), vp(u32(m["dims"])), vp(a[4]), vp(a[5])))
+        ngeo = s["geo_type"].shape[0]
+        handles = (C.c_void_p * max(1, ngeo))()
+        for k in range(ngeo):
+            handles[k] = self.meshes[int(s["geo_mesh"][k])] if int(s["geo_type"][k]) == 3 else None
+        cyl = (f64(s["cyl_x"]), f64(s["cyl_axis"]), f64(s["cyl_r"])) if "cyl_r" in s and len(s["cyl_r"]) else (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+        p = portals or {"plane_a_x": np.zeros((0, 3)), "plane_a_n": np.zeros((0, 3)), "plane_b_x": np.zeros((0, 3)), "plane_b_n": np.zeros((0, 3)), "mult": np.zeros((0, 3), np.int32)}
+        mult = np.ascontiguousarray(p["mult"], dtype=np.int32)
+        k = [f64(s["q"]), f64(s["v"]), f64(s["m"]), f64(s["I0"]), np.ascontiguousarray(s["fixed"], dtype=np.uint8), u32(s["geo_of_body"]), u32(s["geo_type"]), f64(s["geo_r"]),
+             f64(s["geo_half"]), f64(s["g"]), f64(s["plane_x"]), f64(s["plane_n"]), f64(p["plane_a_x"]), f64(p["plane_a_n"]), f64(p["plane_b_x"]), f64(p["plane_b_n"])]
+        self.h = lib.ref_rb3d_sim_create(n, vp(k[0]), vp(k[1]), vp(k[2]), vp(k[3]), vp(k[4]), vp(k[5]), ngeo, vp(k[6]), vp(k[7]), vp(k[8]), C.cast(handles, V), vp(k[9]),
+                                         k[10].shape[0], vp(k[10]), vp(k[11]), cyl[2].shape[0], vp(cyl[0]), vp(cyl[1]), vp(cyl[2]),
+                                         mult.shape[0], vp(k[12]), vp(k[13]), vp(k[14]), vp(k[15]), vp(mult))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_rb3d_sim_destroy(self.h)
+            self.h = None
+            for m in self.meshes:
+                self.lib.ref_rb3d_mesh_destroy(m)
+
+    def active_set(self, q0, q1, cap=None):
+        q0, q1 = f64(q0), f64(q1)
+        cap = cap or 64 * self.n + 4096
+        out = {"type": np.zeros(cap, np.uint32), "i": np.zeros(cap, np.uint32), "j": np.zeros(cap, np.uint32), "static": np.zeros(cap, np.uint32),
+               "n": np.zeros((cap, 3)), "p": np.zeros((cap, 3)), "depth": np.zeros(cap)}
+        na = int(self.lib.ref_rb3d_sim_active_set(self.h, vp(q0), vp(q1), cap, vp(out["type"]), vp(out["i"]), vp(out["j"]), vp(out["static"]), vp(out["n"]), vp(out["p"]), vp(out["depth"])))
+        if na > cap:
+            return self.active_set(q0, q1, cap=na)
+        return {k: v[:na] for k, v in out.items()}
+
+
+BODY_PAIR = (10, 11, 12, 13, 19, 30)
+STATIC_WITH_INDEX = (14, 15, 16, 17)
+
+
+def _same_rb3d_active_set(got, want, s, q0):
+    """got: from the reference's classes; want: the oracle's list (the ABI's conventions: i = first / free body, j = second body or static object)."""
+    assert got["type"].shape[0] == want["type"].shape[0], (got["type"].shape[0], want["type"].shape[0])
+    assert np.array_equal(got["type"], want["type"])
+    t = want["type"]
+    assert np.array_equal(got["i"], want["i"])
+    pair = np.isin(t, BODY_PAIR)
+    assert np.array_equal(got["j"][pair], want["j"][pair])
+    st = np.isin(t, STATIC_WITH_INDEX)
+    assert np.array_equal(got["static"][st], want["j"][st])
+    assert np.array_equal(got["n"], want["n"])
+    exact = np.isin(t, (10, 14, 15, 17, 19))
+    assert np.array_equal(got["p"][exact], want["p"][exact])
+    # body-body and plane-body classes keep lever arms ( p - x0 ) and report x0 + arm: the point handed to their constructor up to rounding
+    arm = np.isin(t, (12, 13, 16))
+    if arm.any():
+        assert np.abs(got["p"][arm] - want["p"][arm]).max() < 1e-12
+    # a free sphere against a kinematic one: the list's p is the constructor argument X (the kinematic sphere's centre at q0); the class reports x_i - r_i n
+    kin = np.isin(t, (11, 30))
+    if kin.any():
+        n = s["geo_of_body"].shape[0]
+        x0 = q0[:3 * n].reshape(n, 3)
+        r = s["geo_r"][s["geo_of_body"][want["i"][kin]]]
+        assert np.array_equal(got["p"][kin], x0[want["i"][kin]] - r[:, None] * want["n"][kin])
+    assert np.array_equal(got["depth"], want["depth"], equal_nan=True)
+
+
+def _with_cylinders(s):
+    x = s["q"][:3 * s["geo_of_body"].shape[0]].reshape(-1, 3)
+    ext = float(np.abs(x).max())
+    s["cyl_x"] = np.array([[0.1, -0.2, 0.3], [0.0, 0.0, 0.0]])
+    s["cyl_axis"] = np.array([[0.2, 3.0, -0.1], [1.0, 0.1, 0.05]])
+    s["cyl_r"] = np.array([0.8 * ext, 0.95 * ext])
+    return s
+
+
+@pytest.mark.parametrize("scene", ["spheres_kinematic_cylinders", "boxes", "meshes_cylinders", "mixed"])
+def test_rb3d_sim_compute_active_set(oracle, scene):
+    """RigidBody3DSim::computeActiveSet (RigidBody3DSim.cpp:250-262, 665-962, 1057-1260, 1414-1557): every body-body narrow phase the reference supports, the
+    kinematic rules, planes and cylinders, in the reference's order."""
+    if scene == "spheres_kinematic_cylinders":
+        s = _with_cylinders(scenes.rb3d_random_spheres(1800, 81, spin=True, nfixed_frac=0.2, nplanes=3))
+        expect = {10, 11, 14, 17}
+    elif scene == "boxes":
+        s = scenes.rb3d_random_boxes(700, 82, nfixed_frac=0.0, nplanes=3)
+        expect = {12, 15}
+    elif scene == "meshes_cylinders":
+        s = _with_cylinders(scenes.rb3d_random_meshes(50, 83, nfixed_frac=0.15, nplanes=2))
+        expect = {12, 13, 16, 18}
+    else:
+        s = scenes.rb3d_mixed_segregated(120)
+        expect = {10, 11, 12, 13}
+    o = ob.RB3DOracle(s)
+    ref = RefRB3DSim(s)
+    q0 = f64(s["q"])
+    q1, _ = o.flow(3, q0, s["v"], s["dt"])
+    want = o.active_set(q0, q1, "grid")
+    assert want["supported"]
+    got = ref.active_set(q0, q1)
+    _same_rb3d_active_set(got, want, s, q0)
+    assert expect <= set(int(t) for t in got["type"]), set(int(t) for t in got["type"])
+
+
+@pytest.mark.parametrize("axes,nfixed,tilt,seed", [("x", 0.0, False, 91), ("xz", 0.15, False, 92), ("xyz", 0.0, True, 93)])
+def test_rb3d_sim_with_portals(oracle, axes, nfixed, tilt, seed):
+    """The portal branch (RigidBody3DSim.cpp:965-1397): teleported boxes, the TeleportedCollision set, TeleportedSphereSphereConstraint and
+    KinematicObjectSphereConstraint from teleported centres, behind the un-teleported contacts."""
+    s = scenes.rb3d_periodic_spheres(900, seed, axes=axes, nfixed_frac=nfixed, tilt=tilt)
+    o = ob.RB3DOracle(s)
+    o.set_portals(s["portals"])
+    ref = RefRB3DSim(s, s["portals"])
+    q0 = o.enforce_portals(f64(s["q"]))
+    q1, _ = o.flow(3, q0, s["v"], s["dt"])
+    want = o.active_set_portals(q0, q1, "grid")
+    assert want["supported"]
+    got = ref.active_set(q0, q1)
+    _same_rb3d_active_set(got, want, s, q0)
+    seen = set(int(t) for t in got["type"])
+    assert 10 in seen and 19 in seen and (nfixed == 0.0 or 30 in seen)
