@@ -15,6 +15,11 @@
 #include "rigidbody3d/Portals/PlanarPortal.h"
 #include "scisim/Constraints/Constraint.h"
 #include "scisim/ConstrainedMaps/ImpactMaps/ImpactMap.h"
+#include "scisim/Math/Rational.h"
+#include "rigidbody3d/PythonScripting.h"
+#include "rigidbody3d/UnconstrainedMaps/SplitHamMap.h"
+#include "rigidbody3d/UnconstrainedMaps/DMVMap.h"
+#include "rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.h"
 
 #include <cmath>
 #include <cstdint>
@@ -134,6 +139,21 @@ uint64_t ref_rb3d_sim_active_set( void* h, const double* q0, const double* q1, c
     ++k;
   }
   return k;
+}
+
+// RigidBody3DSim::flow( call_back, iteration, dt, umap ) (rigidbody3d/RigidBody3DSim.cpp:398-460): the unconstrained map on the simulation's own state,
+// then updateMandMinv and the periodic boundaries; the state is advanced and returned.  kind 2: SplitHamMap, 3: DMVMap, 4: ExponentialEulerMap.
+void ref_rb3d_sim_flow( void* h, const int kind, const unsigned iteration, const long long dt_num, const long long dt_den, double* q_out, double* v_out )
+{
+  RigidBody3DSim& sim = *static_cast<RigidBody3DSim*>( h );
+  PythonScripting call_back;
+  const Rational<std::intmax_t> dt{ std::intmax_t( dt_num ), std::intmax_t( dt_den ) };
+  if( kind == 2 ) { SplitHamMap umap; sim.flow( call_back, iteration, dt, umap ); }
+  else if( kind == 4 ) { ExponentialEulerMap umap; sim.flow( call_back, iteration, dt, umap ); }
+  else { DMVMap umap; sim.flow( call_back, iteration, dt, umap ); }
+  const int nb = int( sim.getState().nbodies() );
+  for( int k = 0; k < 12 * nb; ++k ) { q_out[k] = sim.getState().q()( k ); }
+  for( int k = 0; k < 6 * nb; ++k ) { v_out[k] = sim.getState().v()( k ); }
 }
 
 }
