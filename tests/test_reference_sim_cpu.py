@@ -307,3 +307,108 @@ def test_rb3d_sim_flow_over_steps(oracle, kind):
             differs = differs or not (np.array_equal(qa, q1) and np.array_equal(va, v1))
         q, v = q1, v1
     assert differs   # the two layouts are observable: a later step integrated with the constructor's matrix gives other bits
+
+
+# ---- rigidbody2d ------------------------------------------------------------------------------------------------------------------------------------
+class RefRB2DSim:
+    def __init__(self, s, portals=None):
+        self.lib = lib = _lib("libref_rb2d.so")
+        V = C.c_void_p
+        lib.ref_rb2d_sim_create.restype = V
+        lib.ref_rb2d_sim_create.argtypes = [C.c_uint32, V, V, V, V, V, C.c_uint32, V, V, V, V, C.c_uint32, V, V, C.c_uint32, V, V, V, V, V, V]
+        lib.ref_rb2d_sim_destroy.argtypes = [V]
+        lib.ref_rb2d_sim_active_set.restype = C.c_uint64
+        lib.ref_rb2d_sim_active_set.argtypes = [V, V, V, C.c_uint64, V, V, V, V, V, V, V]
+        lib.ref_rb2d_sim_flow.argtypes = [V, C.c_int, C.c_uint, C.c_longlong, C.c_longlong, V, V]
+        lib.ref_rb2d_sim_set_state.argtypes = [V, V, V]
+        self.n = n = s["geo_of_body"].shape[0]
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+        p = portals or {"plane_a_x": np.zeros((0, 2)), "plane_a_n": np.zeros((0, 2)), "plane_b_x": np.zeros((0, 2)), "plane_b_n": np.zeros((0, 2)), "v": np.zeros(0), "bounds": np.zeros(0)}
+        k = [f64(s["q"]), f64(s["v"]), f64(s["M"]), np.ascontiguousarray(s["fixed"], dtype=np.uint8), u32(s["geo_of_body"]), u32(s["geo_type"]), f64(s["geo_r"]), f64(s["geo_half"]), f64(s["g"]),
+             f64(s["plane_x"]), f64(s["plane_n"]), f64(p["plane_a_x"]), f64(p["plane_a_n"]), f64(p["plane_b_x"]), f64(p["plane_b_n"]), f64(p["v"]), f64(p["bounds"])]
+        self.h = lib.ref_rb2d_sim_create(n, vp(k[0]), vp(k[1]), vp(k[2]), vp(k[3]), vp(k[4]), k[5].shape[0], vp(k[5]), vp(k[6]), vp(k[7]), vp(k[8]), k[9].shape[0], vp(k[9]), vp(k[10]),
+                                         k[15].shape[0], vp(k[11]), vp(k[12]), vp(k[13]), vp(k[14]), vp(k[15]), vp(k[16]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_rb2d_sim_destroy(self.h)
+            self.h = None
+
+    def active_set(self, q0, q1, cap=None):
+        q0, q1 = f64(q0), f64(q1)
+        cap = cap or 32 * self.n + 1024
+        out = {"type": np.zeros(cap, np.uint32), "i": np.zeros(cap, np.uint32), "j": np.zeros(cap, np.uint32), "static": np.zeros(cap, np.uint32),
+               "n": np.zeros((cap, 2)), "p": np.zeros((cap, 2)), "depth": np.zeros(cap)}
+        na = int(self.lib.ref_rb2d_sim_active_set(self.h, vp(q0), vp(q1), cap, vp(out["type"]), vp(out["i"]), vp(out["j"]), vp(out["static"]), vp(out["n"]), vp(out["p"]), vp(out["depth"])))
+        if na > cap:
+            return self.active_set(q0, q1, cap=na)
+        return {k: v[:na] for k, v in out.items()}
+
+    def flow(self, kind, iteration, dt_num, dt_den):
+        q, v = np.zeros(3 * self.n), np.zeros(3 * self.n)
+        self.lib.ref_rb2d_sim_flow(self.h, kind, iteration, dt_num, dt_den, vp(q), vp(v))
+        return q, v
+
+    def set_state(self, q, v):
+        self.lib.ref_rb2d_sim_set_state(self.h, vp(f64(q)), vp(f64(v)))
+
+
+def _same_rb2d_active_set(got, want):
+    assert got["type"].shape[0] == want["type"].shape[0], (got["type"].shape[0], want["type"].shape[0])
+    assert np.array_equal(got["type"], want["type"])
+    t = want["type"]
+    assert np.array_equal(got["i"], want["i"])
+    pair = np.isin(t, (20, 21, 22, 25, 26))
+    assert np.array_equal(got["j"][pair], want["j"][pair])
+    st = np.isin(t, (23, 24))
+    assert np.array_equal(got["static"][st], want["j"][st])
+    assert np.array_equal(got["n"], want["n"])
+    exact = np.isin(t, (20, 23, 25, 26))
+    assert np.array_equal(got["p"][exact], want["p"][exact])
+    arm = t == 22   # BodyBodyConstraint keeps lever arms and reports x0 + arm: the point handed to its constructor up to rounding
+    if arm.any():
+        assert np.abs(got["p"][arm] - want["p"][arm]).max() < 1e-12
+    # ( 21: the list's p is the kinematic body's position handed to the constructor; 24: the corner's body-space arm -- the classes report world-space points )
+    assert np.array_equal(got["depth"], want["depth"], equal_nan=True)
+
+
+@pytest.mark.parametrize("kinds,nfixed,seed,kind", [(("circle", "box"), 0.0, 101, 0), (("circle",), 0.2, 102, 1), (("box",), 0.0, 103, 1), (("circle", "box"), 0.0, 104, 0)])
+def test_rb2d_sim_compute_active_set(oracle, kinds, nfixed, seed, kind):
+    """RigidBody2DSim::computeActiveSet (RigidBody2DSim.cpp:184-348, 638-714): circle-circle CCD, circle-box, box-box, kinematic circles, plane contacts."""
+    s = scenes.rb2d_random(1400, seed, kinds=kinds, nfixed_frac=nfixed, nplanes=3)
+    o = ob.RB2DOracle(s)
+    ref = RefRB2DSim(s)
+    q0 = f64(s["q"])
+    q1, _ = o.flow(kind, q0, s["v"], s["dt"])
+    want = o.active_set(q0, q1, "grid")
+    assert want["supported"]
+    got = ref.active_set(q0, q1)
+    _same_rb2d_active_set(got, want)
+    seen = set(int(t) for t in got["type"])
+    assert ("circle" not in kinds or 20 in seen or 22 in seen) and ("box" not in kinds or 22 in seen) and (nfixed == 0.0 or 21 in seen) and (23 in seen or 24 in seen)
+
+
+@pytest.mark.parametrize("case", [dict(n=500, seed=111, side=10.0), dict(n=500, seed=112, side=10.0, lees_edwards=0.7, oblique=True), dict(n=500, seed=113, side=7.0, axes="y", lees_edwards=-0.9)])
+def test_rb2d_sim_with_portals(oracle, case):
+    """The portal branch (RigidBody2DSim.cpp:350-636, 832-1040) and RigidBody2DSim::flow's portal bookkeeping over 8 steps without contact response."""
+    s = scenes.rb2d_periodic(**case)
+    o = ob.RB2DOracle(s)
+    o.set_portals(s["portals"])
+    ref = RefRB2DSim(s, s["portals"])
+    q, v = o.enforce_portals(f64(s["q"]), f64(s["v"]))
+    ref.set_state(q, v)
+    assert s["dt"] == 0.01
+    seen = set()
+    for it in range(1, 9):
+        o.update_portals(it * s["dt"])
+        q1, v1 = o.flow(0, q, v, s["dt"])
+        want = o.active_set_portals(q, q1, "grid")
+        assert want["supported"]
+        rq, rv = ref.flow(0, it, 1, 100)
+        q1w, v1w = o.enforce_portals(q1, v1)
+        assert np.array_equal(rq, q1w) and np.array_equal(rv, v1w)
+        got = ref.active_set(q, q1)
+        _same_rb2d_active_set(got, want)
+        seen |= set(int(t) for t in got["type"])
+        q, v = q1w, v1w
+    assert 20 in seen and (25 in seen or 26 in seen)
