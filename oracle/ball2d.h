@@ -17,8 +17,10 @@
 // and config 1's two bundled scenes (tests/golden/ball2d_assets.npz).  Beyond them this file is pinned against the reference's own sources compiled
 // unchanged into oracle/_ref (oracle/Makefile.ref, tests/test_oracle_vs_reference.py): both maps + the gravity force (q1, v1), the spatial grid, the CCD,
 // and the three constraint classes -- isActive, normal, contact point, penetration depth, contact basis, evalgradg -- for every contact of its active
-// sets, bit for bit.  What stays restated only is the glue of Ball2DSim.cpp (loop order, which q each test reads); it is kept line-traceable to the
-// sources above.
+// sets, bit for bit.  The GLUE (loop order, which q each test reads, the portal branch) is pinned by running the reference's own simulation class:
+// Ball2DSim.cpp + Ball2DState.cpp compiled unchanged (oracle/ref_shims/ref_ball2d_sim.cpp), Ball2DSim::computeActiveSet and Ball2DSim::flow on random
+// scenes, the bundled scenes and portal / Lees-Edwards scenes over many steps == this file and ball2d_portals.h, element by element, bit for bit
+// (tests/test_reference_sim_cpu.py).
 #ifndef ORACLE_BALL2D_H
 #define ORACLE_BALL2D_H
 

@@ -16,7 +16,9 @@
 // Rotation2D(theta).matrix() = [[c,-s],[s,c]] with libm sin/cos (device: CUDA sincos => rotated boxes compare to 1e-12).
 // Parity: stored reference outputs exist for the CCD cases only; beyond them the file is pinned against the reference's sources compiled
 // unchanged (oracle/_ref): both maps, the grid, BoxBoxTools, CircleBoxTools, the geometry classes' AABBs, the plane / portal classes and the constraint
-// classes CircleCircle / StaticPlaneCircle / StaticPlaneBody / BodyBody (normal, contact point, depth for every contact of its active sets).
+// classes CircleCircle / StaticPlaneCircle / StaticPlaneBody / BodyBody (normal, contact point, depth for every contact of its active sets); and, for the
+// glue, against the reference's own RigidBody2DSim (RigidBody2DSim.cpp + RigidBody2DState.cpp compiled unchanged, oracle/ref_shims/ref_rb2d_sim.cpp):
+// computeActiveSet and flow as a whole, portals included, equal this file and rb2d_portals.h bit for bit (tests/test_reference_sim_cpu.py).
 #ifndef ORACLE_RB2D_H
 #define ORACLE_RB2D_H
 

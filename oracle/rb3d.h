@@ -25,8 +25,10 @@
 // phase, the plane, cylinder and portal classes, RigidBody3DState (the mass matrices of setState and of updateMandMinv), and the constraint classes
 // SphereSphere / KinematicSphereSphere / StaticPlaneSphere / StaticPlaneBox / StaticCylinderSphere / StaticCylinderBody (isActive, normal, contact point,
 // depth for every such contact of its active sets), bit for bit -- except ExponentialEulerMap's projected orientation, where the reference calls
-// Eigen::JacobiSVD and the stand-in supplies its own SVD: agreement to rounding (4e-15), not bit for bit.  Restated only: the glue of
-// RigidBody3DSim.cpp.  sin/cos come from libm here (as in the reference) and from CUDA on the device, so rotating bodies are compared to 1e-12,
+// Eigen::JacobiSVD and the stand-in supplies its own SVD: agreement to rounding (4e-15), not bit for bit.  The glue of RigidBody3DSim.cpp is pinned by
+// running the reference's own RigidBody3DSim (compiled unchanged with 12 more of its sources, oracle/ref_shims/ref_rb3d_sim.cpp): computeActiveSet as a
+// whole (every narrow phase, kinematic rules, planes, cylinders, portals) and flow over steps equal this file and rb3d_portals.h
+// (tests/test_reference_sim_cpu.py).  sin/cos come from libm here (as in the reference) and from CUDA on the device, so rotating bodies are compared to 1e-12,
 // everything else bit for bit.
 #ifndef ORACLE_RB3D_H
 #define ORACLE_RB3D_H
