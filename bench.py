@@ -18,8 +18,8 @@ reference's own bundled scene (tests/golden/ball2d_assets.npz).
   e2e       the same step through the host-buffer C ABI: H2D of q0,v0 from pinned memory and D2H of q1,v1 and the
             whole active set inside the timed region
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
-  cpu_baseline  the reference's own CPU path (its SpatialGridDetector.cpp / CollisionDetectionUtilities.cpp compiled
-            unchanged, single thread like the reference) on a bounded sample of the same workload, timed on this box
+  cpu_baseline  the reference's own CPU path (its Ball2DSim::flow + Ball2DSim::computeActiveSet, compiled unchanged, single
+            thread like the reference) on a bounded sample of the same workload, timed on this box
   parity_check  a reduced-size scene of the same kind through the same code path at this N (partition, halo exchange,
             merge included), compared with the CPU oracle bit for bit
 """
@@ -143,37 +143,50 @@ def ncu_traffic(kernel_name, config, n_local):
 def cpu_reference_step(scene, steps, warmup):
     """The reference's CPU path, 1 thread (its hot path is single-threaded even with USE_OPENMP).  Returns
     (pairs per step, per-step seconds, kind, description).
-    kind "reference": broad phase + CCD are the reference's OWN ball2d/SpatialGridDetector.cpp and
-    scisim/CollisionDetection/CollisionDetectionUtilities.cpp, compiled unchanged from the reference tree against the Eigen
-    stand-in (oracle/_ref/libref_ball2d.so, oracle/Makefile.ref); the map and the swept boxes around them are the oracle's
-    restatement; the static-plane pass (a few thousand contacts) is neither timed nor counted.
+    kind "reference": the step IS the reference's own code -- Ball2DSim::flow( call_back, iteration, dt, umap ) followed by
+    Ball2DSim::computeActiveSet( q0, q1, v ) of ball2d/Ball2DSim.cpp, with Ball2DState.cpp, the maps, SpatialGridDetector.cpp,
+    CollisionDetectionUtilities.cpp and the constraint classes, all compiled unchanged from the reference tree against the Eigen
+    stand-in (oracle/_ref/libref_ball2d.so, oracle/Makefile.ref, oracle/ref_shims/ref_ball2d_sim.cpp): its std::map grid, its std::set
+    of pairs, one heap-allocated Constraint per contact, the drum and plane loops.  Timed inside the library around those two calls.
+    The candidate count (which the reference's API does not return) comes from one untimed call of its detector.
     kind "port": everything is the restatement (oracle/_ref not built)."""
     import ctypes as C
-    from tests import oracle_binding as ob
-    o = ob.Ball2DOracle(scene)
     kind = map_kind(scene)
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_ball2d.so")
     times, pairs = [], 0
     if os.path.exists(ref_path):
         import numpy as np
+        from fractions import Fraction
+        from tests.reference_sim_binding import RefBall2DSim
         ref = C.CDLL(ref_path)
+        sim = RefBall2DSim(scene)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
         q0 = np.ascontiguousarray(scene["q"], dtype=np.float64)
+        v0 = np.ascontiguousarray(scene["v"], dtype=np.float64)
         r = np.ascontiguousarray(scene["r"], dtype=np.float64)
         n = r.shape[0]
+        dt = Fraction(scene["dt"]).limit_denominator(1 << 40)
+        assert float(dt.numerator) / float(dt.denominator) == scene["dt"]   # scalar( Rational ) = numerator / denominator in double
+        ref.ref_ball2d_sim_step_timed.restype = C.c_double
+        ref.ref_ball2d_sim_step_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]
+        nc = None
         for it in range(warmup + steps):
-            q1, v1 = o.flow(kind, scene["q"], scene["v"], scene["dt"])
-            t_flow = float(o.lib.orc_ball2d_seconds_flow(o.h))
-            nc, na = C.c_uint64(0), C.c_uint64(0)
-            q1c = np.ascontiguousarray(q1)
-            t0 = time.perf_counter()
-            ref.ref_ball2d_detect(C.c_uint32(n), q0.ctypes.data_as(C.c_void_p), q1c.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), C.byref(nc), C.byref(na), None, C.c_uint64(0))
-            t = time.perf_counter() - t0 + t_flow
-            pairs = int(nc.value) + int(na.value)
+            na, tf = C.c_uint64(0), C.c_double(0.0)
+            t = float(ref.ref_ball2d_sim_step_timed(sim.h, vp(q0), vp(v0), kind, 1, dt.numerator, dt.denominator, C.byref(na), C.byref(tf)))
+            if nc is None:
+                sim.set_state(q0, v0)
+                q1, _ = sim.flow(kind, 1, dt.numerator, dt.denominator)
+                c, a = C.c_uint64(0), C.c_uint64(0)
+                ref.ref_ball2d_detect(C.c_uint32(n), vp(q0), vp(np.ascontiguousarray(q1)), vp(r), C.byref(c), C.byref(a), None, C.c_uint64(0))
+                nc = int(c.value)
+            pairs = nc + int(na.value)
             if it >= warmup:
                 times.append(t)
-        return pairs, times, "reference", ("broad phase + CCD = the reference's own SpatialGridDetector.cpp / CollisionDetectionUtilities.cpp (compiled unchanged against "
-                                           "oracle/eigen_standin), map + swept boxes = oracle restatement (the map checked bit for bit against the reference's compiled maps, tests/test_oracle_vs_reference.py); "
-                                           "static-plane contacts neither timed nor counted")
+        return pairs, times, "reference", ("the reference's own Ball2DSim::flow + Ball2DSim::computeActiveSet (ball2d/Ball2DSim.cpp, Ball2DState.cpp, the maps, SpatialGridDetector.cpp, "
+                                           "CollisionDetectionUtilities.cpp and the constraint classes compiled unchanged against oracle/eigen_standin; -O3 -DNDEBUG, timed around the two calls "
+                                           "inside the library; static-geometry contacts timed and counted, as in the GPU arm)")
+    from tests import oracle_binding as ob
+    o = ob.Ball2DOracle(scene)
     for it in range(warmup + steps):
         q1, v1 = o.flow(kind, scene["q"], scene["v"], scene["dt"])
         a = o.active_set(scene["q"], q1, "grid")
@@ -244,7 +257,7 @@ def run_reference(args):
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args.config, full_n),
         "note": how + "; the reference's hot path is single-threaded even with USE_OPENMP (SURVEY.md F2); warm-up steps actually run: %d" % warm,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "%s, %d bodies, %d timed steps (flow + spatial-grid broad phase + CCD); %s" % (sample, scene["r"].shape[0], len(times), how)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "%s, %d bodies, %d timed steps (flow + computeActiveSet); %s" % (sample, scene["r"].shape[0], len(times), how)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": len(times) / total,
         "cpu_baseline_parallel": cpu_parallel_guarded(args.config, 3, 1),

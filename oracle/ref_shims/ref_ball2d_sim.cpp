@@ -19,6 +19,7 @@
 #include "scisim/ConstrainedMaps/ImpactMaps/ImpactMap.h"
 #include "scisim/Math/Rational.h"
 
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
@@ -130,6 +131,36 @@ void ref_ball2d_sim_set_state( void* h, const double* q, const double* v )
   Ball2DSim& sim = *static_cast<Ball2DSim*>( h );
   const int nq = int( sim.state().q().size() );
   for( int k = 0; k < nq; ++k ) { sim.state().q()( k ) = q[k]; sim.state().v()( k ) = v[k]; }
+}
+
+// One benchmark step of the reference's own code, timed (bench.py --impl reference / cpu_baseline): the state is set to ( q0, v0 ) (untimed),
+// Ball2DSim::flow( call_back, iteration, dt, umap ) is timed, then Ball2DSim::computeActiveSet( q0, q1, v1 ) is timed -- constraint objects allocated
+// as the reference allocates them; freeing them afterwards is not timed.  Returns the seconds of the two calls; *n_active = active_set.size().
+double ref_ball2d_sim_step_timed( void* h, const double* q0, const double* v0, const int kind, const unsigned iteration, const long long dt_num, const long long dt_den,
+                                  uint64_t* n_active, double* seconds_flow )
+{
+  Ball2DSim& sim = *static_cast<Ball2DSim*>( h );
+  const int nq = int( sim.state().q().size() );
+  VectorXs wq0{ nq };
+  for( int k = 0; k < nq; ++k ) { wq0( k ) = q0[k]; sim.state().q()( k ) = q0[k]; sim.state().v()( k ) = v0[k]; }
+  PythonScripting call_back;
+  const Rational<std::intmax_t> dt{ std::intmax_t( dt_num ), std::intmax_t( dt_den ) };
+  SymplecticEulerMap se;
+  VerletMap verlet;
+  UnconstrainedMap& umap = ( kind == 0 ) ? static_cast<UnconstrainedMap&>( se ) : static_cast<UnconstrainedMap&>( verlet );
+  const auto t0 = std::chrono::steady_clock::now();
+  sim.flow( call_back, iteration, dt, umap );
+  const auto t1 = std::chrono::steady_clock::now();
+  const VectorXs q1{ sim.state().q() };
+  const VectorXs v1{ sim.state().v() };
+  std::vector<std::unique_ptr<Constraint>> active_set;
+  const auto t2 = std::chrono::steady_clock::now();
+  sim.computeActiveSet( wq0, q1, v1, active_set );
+  const auto t3 = std::chrono::steady_clock::now();
+  *n_active = active_set.size();
+  const double tf = std::chrono::duration<double>( t1 - t0 ).count();
+  if( seconds_flow != nullptr ) { *seconds_flow = tf; }
+  return tf + std::chrono::duration<double>( t3 - t2 ).count();
 }
 
 }
