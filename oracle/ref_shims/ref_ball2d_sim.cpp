@@ -24,6 +24,8 @@
 #include <cstdlib>
 #include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 
 // stub: see the header comment
 void ImpactMap::flow( ScriptingCallback&, FlowableSystem&, ConstrainedSystem&, UnconstrainedMap&, ImpactOperator&, const unsigned, const scalar&, const scalar&, const VectorXs&, const VectorXs&, VectorXs&, VectorXs& )
@@ -161,6 +163,28 @@ double ref_ball2d_sim_step_timed( void* h, const double* q0, const double* v0, c
   const double tf = std::chrono::duration<double>( t1 - t0 ).count();
   if( seconds_flow != nullptr ) { *seconds_flow = tf; }
   return tf + std::chrono::duration<double>( t3 - t2 ).count();
+}
+
+// Ball2DState::serialize (ball2d/Ball2DState.cpp:259-272) of the simulation's current state: the reference's binary snapshot.  Returns its length;
+// the bytes are written when they fit cap.
+uint64_t ref_ball2d_sim_serialize_state( void* h, void* buf, const uint64_t cap )
+{
+  const Ball2DSim& sim = *static_cast<const Ball2DSim*>( h );
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  sim.state().serialize( stm );
+  const std::string bytes = stm.str();
+  if( bytes.size() <= cap ) { std::memcpy( buf, bytes.data(), bytes.size() ); }
+  return bytes.size();
+}
+
+// Ball2DState::deserialize (ball2d/Ball2DState.cpp:274-312) of a snapshot (the product's sg_ball2d_state_serialize output, say) into a fresh Ball2DSim
+void* ref_ball2d_sim_from_snapshot( const void* buf, const uint64_t bytes )
+{
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  stm.write( static_cast<const char*>( buf ), std::streamsize( bytes ) );
+  Ball2DSim* sim = new Ball2DSim;
+  sim->state().deserialize( stm );
+  return sim;
 }
 
 }

@@ -60,6 +60,32 @@ class RefBall2DSim:
     def set_state(self, q, v):
         self.lib.ref_ball2d_sim_set_state(self.h, vp(f64(q)), vp(f64(v)))
 
+    def serialize_state(self):
+        """Ball2DState::serialize of the simulation's current state (the reference's binary snapshot)."""
+        self.lib.ref_ball2d_sim_serialize_state.restype = C.c_uint64
+        self.lib.ref_ball2d_sim_serialize_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        need = int(self.lib.ref_ball2d_sim_serialize_state(self.h, None, 0))
+        buf = np.zeros(need, dtype=np.uint8)
+        assert int(self.lib.ref_ball2d_sim_serialize_state(self.h, vp(buf), need)) == need
+        return buf.tobytes()
+
+    @classmethod
+    def from_snapshot(cls, blob, n):
+        """Ball2DState::deserialize of a snapshot into a fresh reference simulation."""
+        self = cls.__new__(cls)
+        self.lib = lib = _lib("libref_ball2d.so")
+        lib.ref_ball2d_sim_from_snapshot.restype = C.c_void_p
+        lib.ref_ball2d_sim_from_snapshot.argtypes = [C.c_void_p, C.c_uint64]
+        lib.ref_ball2d_sim_destroy.argtypes = [C.c_void_p]
+        lib.ref_ball2d_sim_active_set.restype = C.c_uint64
+        lib.ref_ball2d_sim_active_set.argtypes = [C.c_void_p] * 4 + [C.c_uint64] + [C.c_void_p] * 6
+        lib.ref_ball2d_sim_flow.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]
+        lib.ref_ball2d_sim_set_state.argtypes = [C.c_void_p] * 3
+        raw = np.frombuffer(blob, dtype=np.uint8).copy()
+        self.n = n
+        self.h = lib.ref_ball2d_sim_from_snapshot(vp(raw), raw.shape[0])
+        return self
+
 
 class RefRB2DSim:
     def __init__(self, s, portals=None):

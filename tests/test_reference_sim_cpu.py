@@ -271,3 +271,39 @@ def test_rb2d_sim_with_portals(oracle, case):
         seen |= set(int(t) for t in got["type"])
         q, v = q1w, v1w
     assert 20 in seen and (25 in seen or 26 in seen)
+
+
+def test_ball2d_state_snapshot_of_the_reference(oracle):
+    """Ball2DState::serialize / deserialize compiled unchanged (with the leaf (de)serialisers of MathUtilities restated in the reference's byte layout,
+    oracle/ref_shims/override): the snapshot decodes with the layout the product writes (tests/test_state_io_gpu.py compares the product's bytes with
+    these on the GPU), and a simulation restored from it continues exactly like the one that wrote it."""
+    s = scenes.ball2d_periodic(400, 121, axes="x", lees_edwards=0.0)
+    s["drum_x"], s["drum_r"] = np.array([[3.0, 4.0]]), np.array([90.0])
+    s["g"] = np.array([0.3, -9.81])
+    n = 400
+    ref = RefBall2DSim(s, s["portals"])
+    for it in range(1, 4):
+        ref.flow(0, it, 1, 100)
+    blob = ref.serialize_state()
+    off = 0
+    q = None
+    for cnt in (2 * n, 2 * n, n):
+        assert np.frombuffer(blob, np.int64, 1, off)[0] == cnt
+        q = q if q is not None else np.frombuffer(blob, np.float64, cnt, off + 8)
+        off += 8 + 8 * cnt
+    assert np.frombuffer(blob, np.uint64, 1, off)[0] == n
+    off += 8 + n
+    for name in ("M", "Minv"):
+        rows, cols, nnz = np.frombuffer(blob, np.int64, 3, off)
+        assert rows == cols == nnz == 2 * n
+        off += 24
+        assert np.array_equal(np.frombuffer(blob, np.int32, 2 * n, off), np.arange(2 * n)); off += 8 * n
+        assert np.array_equal(np.frombuffer(blob, np.int32, 2 * n + 1, off), np.arange(2 * n + 1)); off += 4 * (2 * n + 1)
+        vals = np.frombuffer(blob, np.float64, 2 * n, off); off += 16 * n
+        assert np.array_equal(vals, np.repeat(s["m"] if name == "M" else 1.0 / s["m"], 2))
+    again = RefBall2DSim.from_snapshot(blob, n)
+    assert again.serialize_state() == blob
+    qa, va = ref.flow(0, 4, 1, 100)
+    qb, vb = again.flow(0, 4, 1, 100)
+    assert np.array_equal(qa, qb) and np.array_equal(va, vb) and not np.array_equal(qa[:2 * n], q)
+    _same_active_set(again.active_set(q, qa), ref.active_set(q, qa), 2)

@@ -86,3 +86,31 @@ def test_snapshot_layout_and_resume(oracle, gpu_ctx):
         assert np.array_equal(getattr(aa, k), getattr(ab, k)), k
     assert np.array_equal(aa.depth, ab.depth, equal_nan=True)
     ctx2.close()
+
+
+def test_snapshot_is_the_references_own_byte_for_byte(oracle, gpu_ctx):
+    """The whole snapshot, not only its tail: the reference's own Ball2DState::serialize (ball2d/Ball2DState.cpp compiled unchanged, the leaf serialisers of
+    MathUtilities restated in its byte layout -- tests/test_reference_sim_cpu.py checks that side on the CPU) of a reference simulation holding the same
+    state writes exactly the bytes sg_ball2d_state_serialize writes from the device; and the reference's Ball2DState::deserialize accepts the product's
+    snapshot and writes it back unchanged."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built (the reference tree is not mounted here)")
+    import scisim_b200 as sb
+    from tests.reference_sim_binding import RefBall2DSim
+    s = scenes.ball2d_periodic(2000, 6, axes="x")
+    s["drum_x"], s["drum_r"] = np.array([[3.0, 4.0], [-1.0, 2.0]]), np.array([90.0, 120.0])
+    s["g"] = np.array([0.3, -9.81])
+    n = 2000
+    st = sb.Ball2DState(s["r"], s["m"], s["g"], s["plane_x"], s["plane_n"], s["drum_x"], s["drum_r"], planar_portals=sb.PlanarPortal.from_arrays(s["portals"]))
+    sim = sb.Ball2DSim(st, ctx=gpu_ctx)
+    sim.upload(s["q"], s["v"])
+    sim.step(sb.SymplecticEulerMap(), s["dt"])
+    q1, v1, _ = sim.fetch()
+    blob = sim.serializeState(which=1)
+    ref = RefBall2DSim(s, s["portals"])
+    ref.set_state(q1, v1)
+    theirs = ref.serialize_state()
+    assert len(theirs) == len(blob)
+    assert theirs == blob
+    again = RefBall2DSim.from_snapshot(blob, n)
+    assert again.serialize_state() == blob
