@@ -17,6 +17,7 @@
 #include "ball2d/Constraints/BallStaticPlaneConstraint.h"
 #include "ball2d/Constraints/BallStaticDrumConstraint.h"
 #include "scisim/ConstrainedMaps/ImpactMaps/ImpactMap.h"
+#include "scisim/ConstrainedMaps/ImpactMaps/ImpactOperatorUtilities.h"
 #include "scisim/Math/Rational.h"
 
 #include <chrono>
@@ -185,6 +186,36 @@ void* ref_ball2d_sim_from_snapshot( const void* buf, const uint64_t bytes )
   Ball2DSim* sim = new Ball2DSim;
   sim->state().deserialize( stm );
   return sim;
+}
+
+// ImpactOperatorUtilities::computeN (scisim/ConstrainedMaps/ImpactMaps/ImpactOperatorUtilities.cpp:10-48, compiled unchanged) on the active set
+// Ball2DSim::computeActiveSet( q0, q1, v ) returns, exactly as ImpactMap::flow calls it (ImpactMap.cpp:106-107: N sized Minv.cols() x ncollisions,
+// gradients evaluated at q0), and Ball2DSim::computeContactBases (Ball2DSim.cpp:188-201) at ( q0, v ).  Outputs: N column-compressed ( outer: ncols + 1,
+// inner / values: nnz ) and the 2 x 2 ncols contact bases, column-major.  Returns the number of constraints; *nnz = N.nonZeros().
+uint64_t ref_ball2d_sim_compute_N( void* h, const double* q0, const double* q1, const double* v, const uint64_t cap_cols, const uint64_t cap_nnz, uint64_t* nnz,
+                                   int* outer, int* inner, double* values, double* bases )
+{
+  Ball2DSim& sim = *static_cast<Ball2DSim*>( h );
+  const int nq = int( sim.state().q().size() );
+  VectorXs wq0{ nq }, wq1{ nq }, wv{ nq };
+  for( int k = 0; k < nq; ++k ) { wq0( k ) = q0[k]; wq1( k ) = q1[k]; wv( k ) = v[k]; }
+  const VectorXs& vq0 = wq0; const VectorXs& vq1 = wq1; const VectorXs& vv = wv;
+  std::vector<std::unique_ptr<Constraint>> active_set;
+  sim.computeActiveSet( vq0, vq1, vv, active_set );
+  const unsigned ncollisions = unsigned( active_set.size() );
+  const FlowableSystem& fsys = (const FlowableSystem&) sim; // Ball2DSim derives from FlowableSystem privately; ImpactMap receives it as a FlowableSystem&
+  SparseMatrixsc N{ fsys.Minv().cols(), SparseMatrixsc::Index( ncollisions ) };
+  ImpactOperatorUtilities::computeN( fsys, active_set, vq0, N );
+  MatrixXXsc contact_bases;
+  sim.computeContactBases( vq0, vv, active_set, contact_bases );
+  *nnz = uint64_t( N.nonZeros() );
+  if( ncollisions <= cap_cols && uint64_t( N.nonZeros() ) <= cap_nnz && ncollisions > 0 )
+  {
+    for( unsigned c = 0; c <= ncollisions; ++c ) { outer[c] = N.outerIndexPtr()[c]; }
+    for( int e = 0; e < N.nonZeros(); ++e ) { inner[e] = N.innerIndexPtr()[e]; values[e] = N.valuePtr()[e]; }
+    for( unsigned c = 0; c < ncollisions; ++c ) { for( int k = 0; k < 4; ++k ) { bases[4 * c + k] = contact_bases( k % 2, int( 2 * c ) + k / 2 ); } }
+  }
+  return ncollisions;
 }
 
 }

@@ -307,3 +307,30 @@ def test_ball2d_state_snapshot_of_the_reference(oracle):
     qb, vb = again.flow(0, 4, 1, 100)
     assert np.array_equal(qa, qb) and np.array_equal(va, vb) and not np.array_equal(qa[:2 * n], q)
     _same_active_set(again.active_set(q, qa), ref.active_set(q, qa), 2)
+
+
+def test_ball2d_compute_N_and_contact_bases_of_the_reference(oracle):
+    """8(f2): ImpactOperatorUtilities::computeN (ImpactOperatorUtilities.cpp:10-48, compiled unchanged) on the active set of the reference's own Ball2DSim, sized
+    and called as ImpactMap::flow does (ImpactMap.cpp:106-107), and Ball2DSim::computeContactBases (Ball2DSim.cpp:188-201): the pruned, column-compressed N --
+    pattern and values -- and the 2x2 bases equal the oracle's assembly (oracle/assembly2d.h), which the device-side assembly is compared with on the GPU."""
+    s = scenes.ball2d_random(600, 131, nplanes=3, ndrums=1)
+    o = ob.Ball2DOracle(s)
+    ref = RefBall2DSim(s)
+    lib = ref.lib
+    lib.ref_ball2d_sim_compute_N.restype = C.c_uint64
+    lib.ref_ball2d_sim_compute_N.argtypes = [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64] + [C.c_void_p] * 5
+    q0, v0 = f64(s["q"]), f64(s["v"])
+    q1, v1 = o.flow(0, q0, v0, s["dt"])
+    a = o.active_set(q0, q1, "grid")
+    asm = o.assemble()
+    assert asm["supported"]
+    na = a["type"].shape[0]
+    assert na > 100 and (a["type"] == 1).any() and (a["type"] == 2).any()
+    nnz = C.c_uint64(0)
+    outer, inner, values, bases = np.zeros(na + 1, np.int32), np.zeros(4 * na, np.int32), np.zeros(4 * na), np.zeros(4 * na)
+    # the bases depend on v only through the tangent's sign convention of the 2-D classes; the oracle builds them from the normals: pass v0 as the map does
+    nc = int(lib.ref_ball2d_sim_compute_N(ref.h, vp(q0), vp(q1), vp(v0), na, 4 * na, C.byref(nnz), vp(outer), vp(inner), vp(values), vp(bases)))
+    assert nc == na and int(nnz.value) == asm["n_values"].shape[0]
+    k = int(nnz.value)
+    assert np.array_equal(outer, asm["n_outer"]) and np.array_equal(inner[:k], asm["n_inner"]) and np.array_equal(values[:k], asm["n_values"])
+    assert np.array_equal(bases, asm["bases"])
