@@ -27,6 +27,9 @@
 #include <iostream>
 #include <limits>
 #include <memory>
+#include <sstream>
+#include <string>
+#include <cstring>
 
 // stubs: see the header comment (RigidBody3DSim holds an ImpactMap member)
 ImpactMap::ImpactMap( const bool warm_start ) : m_warm_start( warm_start ) {}
@@ -154,6 +157,35 @@ void ref_rb3d_sim_flow( void* h, const int kind, const unsigned iteration, const
   const int nb = int( sim.getState().nbodies() );
   for( int k = 0; k < 12 * nb; ++k ) { q_out[k] = sim.getState().q()( k ); }
   for( int k = 0; k < 6 * nb; ++k ) { v_out[k] = sim.getState().v()( k ); }
+}
+
+// RigidBody3DState::serialize (rigidbody3d/RigidBody3DState.cpp:586-612) of the simulation's current state: the reference's binary snapshot.  Returns its
+// length; the bytes are written when they fit cap.  ( q, v ) may be replaced first (set != 0), and updateMandMinv run (update != 0), as RigidBody3DSim::flow does.
+uint64_t ref_rb3d_sim_serialize_state( void* h, const int set, const double* q, const double* v, const int update, void* buf, const uint64_t cap )
+{
+  RigidBody3DSim& sim = *static_cast<RigidBody3DSim*>( h );
+  const int nb = int( sim.getState().nbodies() );
+  if( set != 0 )
+  {
+    for( int k = 0; k < 12 * nb; ++k ) { sim.getState().q()( k ) = q[k]; }
+    for( int k = 0; k < 6 * nb; ++k ) { sim.getState().v()( k ) = v[k]; }
+  }
+  if( update != 0 ) { sim.getState().updateMandMinv(); }
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  sim.getState().serialize( stm );
+  const std::string bytes = stm.str();
+  if( bytes.size() <= cap ) { std::memcpy( buf, bytes.data(), bytes.size() ); }
+  return bytes.size();
+}
+
+// RigidBody3DState::deserialize of a snapshot into a fresh RigidBody3DSim
+void* ref_rb3d_sim_from_snapshot( const void* buf, const uint64_t bytes )
+{
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  stm.write( static_cast<const char*>( buf ), std::streamsize( bytes ) );
+  RigidBody3DSim* sim = new RigidBody3DSim;
+  sim->getState().deserialize( stm );
+  return sim;
 }
 
 }

@@ -19,6 +19,7 @@
 #include "sg_boxbox.cuh"
 #include "sg_broadphase.cuh"
 #include "sg_slab.cuh"
+#include "sg_rb3d_snapshot.h"
 
 #include <cstdlib>
 #include <cuda.h> // CUtensorMap (types only; the encoder is fetched at run time through cudaGetDriverEntryPoint)
@@ -1336,6 +1337,8 @@ struct Rb3dData
   // geometry list (host copy) and per-body expansion
   std::vector<uint32_t> geo_type, geo_mesh;
   std::vector<double> geo_r, geo_half;
+  std::vector<uint32_t> h_geo_of_body; // host copies of sg_rb3d_set_bodies' tables (the state snapshot writes them back)
+  std::vector<uint8_t> h_fixed;
   std::vector<MeshHost*> meshes;
   DevBuf d_meshes; // MeshDev[]
   DevBuf mesh_stats;
@@ -1973,6 +1976,8 @@ int sg_rb3d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, co
   d->q1_valid = false;
   const int rc = rb3d_expand_bodies( ctx, d, n, geo_of_body, fixed );
   if( rc != SG_OK ) { d->n = 0; return rc; }
+  d->h_geo_of_body.assign( geo_of_body, geo_of_body + n );
+  d->h_fixed.assign( fixed, fixed + n );
   if( n == 0 ) { return SG_OK; }
   SG_CUDA( ctx, d->mass.ensure( size_t( n ) * 8 ) );
   SG_CUDA( ctx, d->I0.ensure( size_t( n ) * 24 ) );
@@ -2463,6 +2468,108 @@ int sg_rb3d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
     out->n_active = d->n_bb + d->n_static;
   }
   return SG_OK;
+}
+
+// ---- state I/O at the seam: RigidBody3DState's binary snapshot (rigidbody3d/RigidBody3DState.cpp:586-668), sg_rb3d_snapshot.h ----
+int sg_rb3d_state_serialize( sg_ctx* ctx, int which, int m_updated, void* buf, uint64_t cap, uint64_t* bytes )
+{
+  if( ctx == nullptr || bytes == nullptr || ( which != 0 && which != 1 ) ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( d->slab.on ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: a slab holds part of a scene; serialise through the owner of the whole state" ); }
+  if( which == 1 && !d->q1_valid && d->n > 0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_state_serialize: which = 1 without a preceding sg_rb3d_flow / sg_rb3d_step on this context" ); }
+  for( const uint32_t t : d->geo_type ) { if( t != SG_GEO_BOX && t != SG_GEO_SPHERE ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: a triangle mesh's snapshot holds its whole input file (RigidBodyTriangleMesh.cpp:215-232), which never crosses this ABI" ); } }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  const uint32_t n = d->n;
+  sg_snapshot::Rb3dState s;
+  s.n = n;
+  s.q.resize( size_t( 12 ) * n ); s.v.resize( size_t( 6 ) * n ); s.m.resize( n ); s.I0.resize( size_t( 3 ) * n ); s.I.resize( size_t( 9 ) * n ); s.Iinv.resize( size_t( 9 ) * n );
+  if( n > 0 )
+  {
+    const double* qd = ( which == 0 ) ? d->q0.as<double>() : d->q1.as<double>();
+    const double* vd = ( which == 0 ) ? d->v0.as<double>() : d->v1.as<double>();
+    const size_t bb = size_t( n ) * 72;
+    SG_CUDA( ctx, d->minertia.ensure( 2 * bb ) );
+    double* blocks = d->minertia.as<double>();
+    SG_LAUNCH( ctx, "rb3d_update_minertia", double( n ) * ( 96.0 + 144.0 ), k_rb3d_update_minertia<<<sg_div_up( n, 128 ), 128, 0, ctx->stream>>>( n, qd, d->I0.as<double>(), blocks, blocks + 9 * size_t( n ) ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.q.data(), qd, size_t( n ) * 96, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.v.data(), vd, size_t( n ) * 48, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.m.data(), d->mass.ptr, size_t( n ) * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.I0.data(), d->I0.ptr, size_t( n ) * 24, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.I.data(), blocks, bb, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.Iinv.data(), blocks + 9 * size_t( n ), bb, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+    sg_prof_collect( ctx );
+    if( !m_updated )
+    {
+      // as RigidBody3DState's constructor stores the blocks: transposed (formWorldSpaceMassMatrix, RigidBody3DState.cpp:165-182)
+      for( std::vector<double>* blk : { &s.I, &s.Iinv } )
+      {
+        for( uint32_t b = 0; b < n; ++b )
+        {
+          double* a = blk->data() + 9 * size_t( b );
+          double t;
+          t = a[1]; a[1] = a[3]; a[3] = t; t = a[2]; a[2] = a[6]; a[6] = t; t = a[5]; a[5] = a[7]; a[7] = t;
+        }
+      }
+    }
+  }
+  s.fixed = d->h_fixed; s.geo_of_body = d->h_geo_of_body;
+  s.geo_type.resize( d->geo_type.size() );
+  for( size_t k = 0; k < d->geo_type.size(); ++k ) { s.geo_type[k] = ( d->geo_type[k] == SG_GEO_BOX ) ? 0u : 1u; }
+  s.geo_r = d->geo_r; s.geo_half = d->geo_half;
+  for( int k = 0; k < 3; ++k ) { s.g[k] = d->g[k]; }
+  for( uint32_t p = 0; p < d->planes.n; ++p ) { for( int k = 0; k < 3; ++k ) { s.plane_x.push_back( d->planes.x[p][k] ); s.plane_n.push_back( d->planes.nrm[p][k] ); } }
+  for( uint32_t c = 0; c < d->planes.ncyl; ++c ) { for( int k = 0; k < 3; ++k ) { s.cyl_x.push_back( d->planes.cx[c][k] ); s.cyl_axis.push_back( d->planes.cax[c][k] ); } s.cyl_r.push_back( d->planes.cr[c] ); }
+  if( d->px != nullptr )
+  {
+    for( uint32_t p = 0; p < d->px->portals.n; ++p )
+    {
+      const SgPortal3D& pt = d->px->portals.p[p];
+      for( int k = 0; k < 3; ++k ) { s.portal_ax.push_back( pt.ax[k] ); s.portal_an.push_back( pt.an[k] ); s.portal_bx.push_back( pt.bx[k] ); s.portal_bn.push_back( pt.bn[k] ); s.portal_mult.push_back( pt.mult[k] ); }
+    }
+  }
+  sg_snapshot::Sink out{ static_cast<unsigned char*>( buf ), cap, 0 };
+  if( !sg_snapshot::serialize( s, out ) ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: a geometry that is neither box nor sphere" ); }
+  *bytes = out.n;
+  if( buf != nullptr && out.n > cap ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_state_serialize: buffer of %llu bytes, %llu needed", ( unsigned long long )( cap ), ( unsigned long long )( out.n ) ); }
+  return SG_OK;
+}
+
+// RigidBody3DState::deserialize (rigidbody3d/RigidBody3DState.cpp:650-668): configures the context from a snapshot and uploads ( q, v )
+int sg_rb3d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes )
+{
+  if( ctx == nullptr || buf == nullptr ) { return SG_ERR_INVALID; }
+  sg_snapshot::Source in{ static_cast<const unsigned char*>( buf ), bytes, 0, true };
+  sg_snapshot::Rb3dState s;
+  const char* why = "";
+  const int prc = sg_snapshot::parse( in, s, &why );
+  if( prc == 1 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_state_deserialize: %s", why ); }
+  if( prc == 2 ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_deserialize: %s", why ); }
+  if( s.plane_x.size() / 3 > SG_MAX_PLANES || s.cyl_r.size() > SG_MAX_CYLINDERS || s.portal_mult.size() / 3 > SG_MAX_PORTALS ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_deserialize: more planes, cylinders or portals than this library holds" ); }
+  const uint32_t ngeo = uint32_t( s.geo_type.size() );
+  std::vector<uint32_t> type( ngeo ), mesh( ngeo, 0u );
+  for( uint32_t k = 0; k < ngeo; ++k ) { type[k] = ( s.geo_type[k] == 0u ) ? uint32_t( SG_GEO_BOX ) : uint32_t( SG_GEO_SPHERE ); }
+  int rc = sg_rb3d_set_geometry( ctx, ngeo, type.data(), s.geo_r.data(), s.geo_half.data(), mesh.data() );
+  if( rc != SG_OK ) { return rc; }
+  rc = sg_rb3d_set_bodies( ctx, s.n, s.geo_of_body.data(), s.fixed.data(), s.m.data(), s.I0.data() );
+  if( rc != SG_OK ) { return rc; }
+  Rb3dData* d = rb3d_data( ctx );
+  for( int k = 0; k < 3; ++k ) { d->g[k] = s.g[k]; }
+  // StaticPlane( std::istream& ) / StaticCylinder( std::istream& ) read x and n back as stored: the normals are NOT normalised again
+  d->planes.n = uint32_t( s.plane_x.size() / 3 );
+  for( uint32_t p = 0; p < d->planes.n; ++p ) { for( int k = 0; k < 3; ++k ) { d->planes.x[p][k] = s.plane_x[3 * p + k]; d->planes.nrm[p][k] = s.plane_n[3 * p + k]; } }
+  d->planes.ncyl = uint32_t( s.cyl_r.size() );
+  for( uint32_t c = 0; c < d->planes.ncyl; ++c ) { for( int k = 0; k < 3; ++k ) { d->planes.cx[c][k] = s.cyl_x[3 * c + k]; d->planes.cax[c][k] = s.cyl_axis[3 * c + k]; } d->planes.cr[c] = s.cyl_r[c]; }
+  const uint32_t npo = uint32_t( s.portal_mult.size() / 3 );
+  if( npo > 0 || d->px != nullptr )
+  {
+    rc = sg_rb3d_set_portals( ctx, npo, s.portal_ax.data(), s.portal_an.data(), s.portal_bx.data(), s.portal_bn.data(), s.portal_mult.data() );
+    if( rc != SG_OK ) { return rc; }
+    // the tangents come from the stored normals as the reference computes them on demand; the normals themselves stay as stored
+    for( uint32_t p = 0; p < npo; ++p ) { for( int k = 0; k < 3; ++k ) { d->px->portals.p[p].an[k] = s.portal_an[3 * p + k]; d->px->portals.p[p].bn[k] = s.portal_bn[3 * p + k]; } }
+  }
+  if( s.n == 0 ) { return SG_OK; }
+  return sg_rb3d_upload( ctx, s.q.data(), s.v.data() );
 }
 
 }

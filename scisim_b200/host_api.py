@@ -610,6 +610,34 @@ class RigidBody3DSim:
         self.m_updated = True
         return I, Ii
 
+    # ---- state I/O (rigidbody3d/RigidBody3DState.cpp:586-668) ----
+    def serializeState(self, which=1, m_updated=None):
+        """bytes of RigidBody3DState::serialize for the device-resident state (spheres and boxes): which = 0 the uploaded ( q0, v0 ), 1 the last flow's
+        ( q1, v1 ).  m_updated: the layout of the world-space blocks of M / Minv -- as the constructor stores them (False) or as updateMandMinv leaves them
+        (True); None: True for which = 1 (RigidBody3DSim::flow runs updateMandMinv after every map), else what this sim has done so far."""
+        if m_updated is None:
+            m_updated = True if which == 1 else self.m_updated
+        need = C.c_uint64()
+        self.ctx.check(self.ctx.lib.sg_rb3d_state_serialize(self.ctx.h, int(which), 1 if m_updated else 0, None, 0, C.byref(need)))
+        buf = np.zeros(int(need.value), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.sg_rb3d_state_serialize(self.ctx.h, int(which), 1 if m_updated else 0, _ptr(buf), buf.shape[0], C.byref(need)))
+        return buf.tobytes()
+
+    @staticmethod
+    def deserializeState(blob, ctx, m_updated=True):
+        """RigidBody3DState::deserialize: a sim configured from a snapshot, its ( q, v ) uploaded.  m_updated: whether the snapshot was taken from a running
+        simulation (its M is updateMandMinv's; every flow of the restored sim then carries SG_MAP_M_UPDATED) or from a freshly constructed state."""
+        sim = RigidBody3DSim.__new__(RigidBody3DSim)
+        sim.ctx = ctx
+        buf = np.frombuffer(blob, dtype=np.uint8).copy()
+        ctx.check(ctx.lib.sg_rb3d_state_deserialize(ctx.h, _ptr(buf), buf.shape[0]))
+        n = int(np.frombuffer(blob[:4], dtype=np.uint32)[0])
+        # the context holds the real tables; the host-side state object only answers nbodies()
+        sim.state = RigidBody3DState([1], [1.0], [[0.0, 0.0, 0.0]], [0], [], np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.ones(n), np.ones((n, 3)), [0.0, 0.0, 0.0],
+                                     np.zeros((0, 3)), np.zeros((0, 3)))
+        sim.m_updated = bool(m_updated)
+        return sim
+
     # ---- portals (rigidbody3d/RigidBody3DSim.cpp:642-663) ----
     def enforcePeriodicBoundaryConditions(self, q):
         """Teleports the centres of mass that left through a portal; returns the new q."""

@@ -168,6 +168,33 @@ class RefRB3DSim:
             for m in self.meshes:
                 self.lib.ref_rb3d_mesh_destroy(m)
 
+    def serialize_state(self, q=None, v=None, update=False):
+        """RigidBody3DState::serialize of the simulation's state, after replacing ( q, v ) and / or running updateMandMinv."""
+        f = self.lib.ref_rb3d_sim_serialize_state
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        if q is not None:
+            q, v = f64(q), f64(v)
+        need = int(f(self.h, 1 if q is not None else 0, vp(q), vp(v), 1 if update else 0, None, 0))
+        buf = np.zeros(need, dtype=np.uint8)
+        assert int(f(self.h, 0, None, None, 0, vp(buf), need)) == need
+        return buf.tobytes()
+
+    @classmethod
+    def from_snapshot(cls, blob, n):
+        self = cls.__new__(cls)
+        self.lib = lib = _lib("libref_rb3d.so")
+        V = C.c_void_p
+        lib.ref_rb3d_sim_from_snapshot.restype = V
+        lib.ref_rb3d_sim_from_snapshot.argtypes = [V, C.c_uint64]
+        lib.ref_rb3d_sim_destroy.argtypes = [V]
+        lib.ref_rb3d_sim_active_set.restype = C.c_uint64
+        lib.ref_rb3d_sim_active_set.argtypes = [V, V, V, C.c_uint64, V, V, V, V, V, V, V]
+        raw = np.frombuffer(blob, dtype=np.uint8).copy()
+        self.n, self.meshes = n, []
+        self.h = lib.ref_rb3d_sim_from_snapshot(vp(raw), raw.shape[0])
+        return self
+
     def active_set(self, q0, q1, cap=None):
         q0, q1 = f64(q0), f64(q1)
         cap = cap or 64 * self.n + 4096
