@@ -69,6 +69,7 @@ struct BroadScratch
   void* tm_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime on first use
   int staged_attr_dev = -1;   // device on which the staged kernel's shared-memory opt-in was made
   bool dense = false;         // the previous step on this scratch found >= 2.5 candidates per body (set by the caller): pass 1 stages the records
+  int pass1_minb = 0;         // EXPERIMENT knob (SG_BP_MINB = 4 | 5 | 6): resident CTAs per SM the un-staged 2-D pass 1 is compiled for; 0 = not read yet
   const uint32_t* ord_by_index = nullptr; // order word of body i (multi-GPU: the global-index table; nullptr: i itself), set per step by the caller
   bool hist_clean = false; // cell_count is all zero (true after every scatter; false after (re)allocation or an aborted step)
   const void* hist_ptr = nullptr;
@@ -1161,8 +1162,24 @@ template<> struct SgBpCountLaunch<2>
                  s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
       return SG_OK;
     }
-    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_l1<P, 2, 4><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-               s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
+    if( s.pass1_minb == 0 ) { const char* e = getenv( "SG_BP_MINB" ); s.pass1_minb = ( e != nullptr && ( e[0] == '5' || e[0] == '6' ) ) ? ( e[0] - '0' ) : 4; }
+    const double bytes = double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN );
+    const unsigned grid = sg_div_up( n, SG_BP_THREADS );
+    if( s.pass1_minb == 5 )
+    {
+      SG_LAUNCH( ctx, "bp_count", bytes, sg_bp_count_l1<P, 2, 5><<<grid, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+                 s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
+    }
+    else if( s.pass1_minb == 6 )
+    {
+      SG_LAUNCH( ctx, "bp_count", bytes, sg_bp_count_l1<P, 2, 6><<<grid, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+                 s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
+    }
+    else
+    {
+      SG_LAUNCH( ctx, "bp_count", bytes, sg_bp_count_l1<P, 2, 4><<<grid, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+                 s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
+    }
     return SG_OK;
   }
 };
