@@ -1,4 +1,4 @@
-"""Experiment (round 2, last session): resident CTAs per SM of the un-staged 2-D pass 1 (sg_bp_count_l1<P, 2, MINB>): 4 (64 registers), 5 (48, a few spills),
+"""HISTORICAL (the knob SG_BP_MINB was removed after this run; result: profiles/minb_ab_r2.jsonl).  Experiment (round 2, last session): resident CTAs per SM of the un-staged 2-D pass 1 (sg_bp_count_l1<P, 2, MINB>): 4 (64 registers), 5 (48, a few spills),
 6 (40, more spills).  One process, the scene generated once per size, one context per variant (the knob SG_BP_MINB is read when a context first launches pass 1).
   python profiles/minb_ab.py [--sizes 2097152,16777216]
 Prints one JSON line per (size, variant): ms/step and the us of bp_count; the candidate / contact counts must agree between variants."""

@@ -69,7 +69,6 @@ struct BroadScratch
   void* tm_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime on first use
   int staged_attr_dev = -1;   // device on which the staged kernel's shared-memory opt-in was made
   bool dense = false;         // the previous step on this scratch found >= 2.5 candidates per body (set by the caller): pass 1 stages the records
-  int pass1_minb = 0;         // EXPERIMENT knob (SG_BP_MINB = 4 | 5 | 6): resident CTAs per SM the un-staged 2-D pass 1 is compiled for; 0 = not read yet
   const uint32_t* ord_by_index = nullptr; // order word of body i (multi-GPU: the global-index table; nullptr: i itself), set per step by the caller
   bool hist_clean = false; // cell_count is all zero (true after every scatter; false after (re)allocation or an aborted step)
   const void* hist_ptr = nullptr;
@@ -1162,24 +1161,11 @@ template<> struct SgBpCountLaunch<2>
                  s.recs.as<typename P::Rec>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
       return SG_OK;
     }
-    if( s.pass1_minb == 0 ) { const char* e = getenv( "SG_BP_MINB" ); s.pass1_minb = ( e != nullptr && ( e[0] == '5' || e[0] == '6' ) ) ? ( e[0] - '0' ) : 4; }
-    const double bytes = double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN );
-    const unsigned grid = sg_div_up( n, SG_BP_THREADS );
-    if( s.pass1_minb == 5 )
-    {
-      SG_LAUNCH( ctx, "bp_count", bytes, sg_bp_count_l1<P, 2, 5><<<grid, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-                 s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
-    }
-    else if( s.pass1_minb == 6 )
-    {
-      SG_LAUNCH( ctx, "bp_count", bytes, sg_bp_count_l1<P, 2, 6><<<grid, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-                 s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
-    }
-    else
-    {
-      SG_LAUNCH( ctx, "bp_count", bytes, sg_bp_count_l1<P, 2, 4><<<grid, SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
-                 s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
-    }
+    // 4 resident CTAs per SM (64 registers): measured against 5 (48 registers, 164 B of spills) and 6 (40, 284 B) on the B200 -- 185 / 231 / 285 us on 2 M
+    // balls, 1.41 / 1.73 / 2.15 ms on 16 M (profiles/minb_ab_r2.jsonl) -- and against 3 (85 registers: 203 us).  The kernel is bound by issue slots and
+    // load-to-use latency; spilled values cost more than the extra warps hide.
+    SG_LAUNCH( ctx, "bp_count", double( n ) * ( 64.0 + 16.0 + 4.0 + 8.0 + 16.0 + 16.0 * BpPlan<2>::NPLAN ), sg_bp_count_l1<P, 2, 4><<<sg_div_up( n, SG_BP_THREADS ), SG_BP_THREADS, 0, ctx->stream>>>( n, s.params.as<GridParams>(), s.cell_start.as<uint32_t>(),
+               s.recs.as<typename P::Rec>(), s.boxf.as<float4>(), s.sidx.as<uint32_t>(), s.counts.as<uint2>(), s.masks.as<uint4>(), s.masks.as<uint4>() + 1 ) );
     return SG_OK;
   }
 };
