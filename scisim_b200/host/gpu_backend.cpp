@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <iterator>
 #include <limits>
 #include <numeric>
 
@@ -160,6 +161,22 @@ uint64_t GpuBall2DBackend::cacheLookup( const unsigned ncomp, VectorXs& r )
 void GpuBall2DBackend::cacheClear()
 {
   check( sg_ball2d_cache_clear( m_ctx ), "sg_ball2d_cache_clear" );
+}
+
+void GpuBall2DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow )
+{
+  uint64_t bytes = 0;
+  check( sg_ball2d_state_serialize( m_ctx, from_last_flow ? 1 : 0, nullptr, 0, &bytes ), "sg_ball2d_state_serialize" );
+  std::vector<char> buf( bytes );
+  check( sg_ball2d_state_serialize( m_ctx, from_last_flow ? 1 : 0, buf.data(), bytes, &bytes ), "sg_ball2d_state_serialize" );
+  output_stream.write( buf.data(), static_cast<std::streamsize>( bytes ) );
+}
+
+void GpuBall2DBackend::deserializeState( std::istream& input_stream )
+{
+  // the snapshot is self-delimiting only to its parser: hand over the rest of the stream (Ball2DSim::deserialize reads the state last, Ball2DSim.cpp:800-807)
+  const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
+  check( sg_ball2d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_ball2d_state_deserialize" );
 }
 
 void GpuBall2DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps )
@@ -449,6 +466,25 @@ void GpuRigidBody3DBackend::updateMandMinv( const VectorXs& q, double* m_values,
 {
   check( sg_rb3d_update_m_and_minv( m_ctx, from_last_flow ? nullptr : q.data(), m_values, minv_values ), "sg_rb3d_update_m_and_minv" );
   m_m_updated = true;
+}
+
+void GpuRigidBody3DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow )
+{
+  uint64_t bytes = 0;
+  const int updated = ( from_last_flow || m_m_updated ) ? 1 : 0; // RigidBody3DSim::flow runs updateMandMinv after every map
+  check( sg_rb3d_state_serialize( m_ctx, from_last_flow ? 1 : 0, updated, nullptr, 0, &bytes ), "sg_rb3d_state_serialize" );
+  std::vector<char> buf( bytes );
+  check( sg_rb3d_state_serialize( m_ctx, from_last_flow ? 1 : 0, updated, buf.data(), bytes, &bytes ), "sg_rb3d_state_serialize" );
+  output_stream.write( buf.data(), static_cast<std::streamsize>( bytes ) );
+}
+
+void GpuRigidBody3DBackend::deserializeState( std::istream& input_stream, const bool from_running_simulation )
+{
+  const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
+  check( sg_rb3d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_rb3d_state_deserialize" );
+  m_nbodies = 0;
+  if( buf.size() >= sizeof( unsigned ) ) { std::memcpy( &m_nbodies, buf.data(), sizeof( unsigned ) ); }
+  m_m_updated = from_running_simulation;
 }
 
 void GpuRigidBody3DBackend::computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates, const bool from_last_flow )

@@ -22,6 +22,8 @@
 
 #include <cstdint>
 #include <utility>
+#include <istream>
+#include <ostream>
 #include <vector>
 
 // One entry per Constraint the reference would emplace_back, in the reference's order
@@ -103,6 +105,10 @@ public:
   void cacheStore( const unsigned ncomp, const VectorXs& r );
   uint64_t cacheLookup( const unsigned ncomp, VectorXs& r );
   void cacheClear();
+  // Ball2DState::serialize / deserialize (ball2d/Ball2DState.cpp:259-312) from / into the device-resident state: what Ball2DSim::serialize writes for its
+  // state.  from_last_flow: ( q1, v1 ) of the last flow / step, else ( q0, v0 ) as uploaded.
+  void serializeState( std::ostream& output_stream, const bool from_last_flow = true );
+  void deserializeState( std::istream& input_stream );
 
   sg_ctx* context() { return m_ctx; }
   GravityOnlyGuard& forceGuard() { return m_guard; }
@@ -283,6 +289,10 @@ public:
   // blocks of M and of Minv in place -- pass &M.data().value( 3 * nbodies ) and &Minv.data().value( 3 * nbodies ).  from_last_flow:
   // q is the q1 the last flow() wrote (still on the device).  Flows after this call read the updated M (SG_MAP_M_UPDATED).
   void updateMandMinv( const VectorXs& q, double* m_values, double* minv_values, const bool from_last_flow = false );
+  // RigidBody3DState::serialize / deserialize (rigidbody3d/RigidBody3DState.cpp:586-668) from / into the device-resident state (spheres and boxes; the mass
+  // matrices in the layout this backend's flows read: the constructor's until updateMandMinv has run, its own afterwards)
+  void serializeState( std::ostream& output_stream, const bool from_last_flow = true );
+  void deserializeState( std::istream& input_stream, const bool from_running_simulation = true );
   // false + message on std::cerr where the reference would print and exit (unsupported geometry pairing): the caller exits
   void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
   // rigidbody3d/SpatialGridDetector.h:37 on caller-built boxes [minx,miny,minz,maxx,maxy,maxz]
