@@ -21,6 +21,7 @@
 #include "rigidbody3d/UnconstrainedMaps/DMVMap.h"
 #include "rigidbody3d/UnconstrainedMaps/ExponentialEulerMap.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -186,6 +187,38 @@ void* ref_rb3d_sim_from_snapshot( const void* buf, const uint64_t bytes )
   RigidBody3DSim* sim = new RigidBody3DSim;
   sim->getState().deserialize( stm );
   return sim;
+}
+
+// One benchmark step of the reference's own code, timed (profiles/config4_reference.py): the state is set to ( q0, v0 ) (untimed),
+// RigidBody3DSim::flow( call_back, iteration, dt, umap ) is timed (the map, updateMandMinv, the boundary treatment), then
+// RigidBody3DSim::computeActiveSet( q0, q1, v1 ) is timed -- one heap-allocated Constraint per contact, as the reference allocates them; freeing
+// them is not timed.  Returns the seconds of the two calls; *n_active = active_set.size().  kind 2: SplitHamMap, 3: DMVMap.
+double ref_rb3d_sim_step_timed( void* h, const double* q0, const double* v0, const int kind, const unsigned iteration, const long long dt_num, const long long dt_den,
+                                uint64_t* n_active, double* seconds_flow )
+{
+  RigidBody3DSim& sim = *static_cast<RigidBody3DSim*>( h );
+  const int nb = int( sim.getState().nbodies() );
+  VectorXs wq0{ 12 * nb };
+  for( int k = 0; k < 12 * nb; ++k ) { wq0( k ) = q0[k]; sim.getState().q()( k ) = q0[k]; }
+  for( int k = 0; k < 6 * nb; ++k ) { sim.getState().v()( k ) = v0[k]; }
+  PythonScripting call_back;
+  const Rational<std::intmax_t> dt{ std::intmax_t( dt_num ), std::intmax_t( dt_den ) };
+  SplitHamMap sh;
+  DMVMap dmv;
+  UnconstrainedMap& umap = ( kind == 2 ) ? static_cast<UnconstrainedMap&>( sh ) : static_cast<UnconstrainedMap&>( dmv );
+  const auto t0 = std::chrono::steady_clock::now();
+  sim.flow( call_back, iteration, dt, umap );
+  const auto t1 = std::chrono::steady_clock::now();
+  const VectorXs q1{ sim.getState().q() };
+  const VectorXs v1{ sim.getState().v() };
+  std::vector<std::unique_ptr<Constraint>> active_set;
+  const auto t2 = std::chrono::steady_clock::now();
+  sim.computeActiveSet( wq0, q1, v1, active_set );
+  const auto t3 = std::chrono::steady_clock::now();
+  *n_active = active_set.size();
+  const double tf = std::chrono::duration<double>( t1 - t0 ).count();
+  if( seconds_flow != nullptr ) { *seconds_flow = tf; }
+  return tf + std::chrono::duration<double>( t3 - t2 ).count();
 }
 
 }

@@ -38,6 +38,21 @@ def build(cfg, ctx, args):
         sim = make_sim(s, ctx)
         sim.upload(s["q"], s["v"])
         return (lambda: sim.step(sb.DMVMap(), s["dt"])), "config 5: %d mixed sphere/box/mesh bodies, dmv" % s["geo_of_body"].shape[0], s["geo_of_body"].shape[0]
+    if cfg == 6:
+        # rigidbody2d: circles and rotated boxes (circle-circle CCD, circle-box, box-box, planes), symplectic Euler
+        s = scenes.rb2d_random(args.n, 61, nfixed_frac=0.0, nplanes=3)
+        from tests.test_rb2d_gpu import make_sim
+        sim = make_sim(s, ctx)
+        sim.upload(s["q"], s["v"])
+        return (lambda: sim.step(sb.SymplecticEulerMap(), s["dt"])), "rigidbody2d: %d circles and boxes, symplectic Euler" % args.n, args.n
+    if cfg == 7:
+        # ball2d with portals: planar portal in x, Lees-Edwards in y (the portal branch of Ball2DSim::computeActiveSet)
+        s = scenes.ball2d_periodic(args.n, 62, lees_edwards=0.7, t=0.3)
+        from tests.test_portals_gpu import make_sim
+        sim = make_sim(s, ctx)
+        sim.updatePeriodicBoundaryConditionsStartOfStep(3, 0.1)
+        sim.upload(s["q"], s["v"])
+        return (lambda: sim.step(sb.SymplecticEulerMap(), s["dt"])), "ball2d with portals: %d balls, planar portal in x, Lees-Edwards in y" % args.n, args.n
     raise SystemExit("unknown config")
 
 

@@ -55,7 +55,7 @@ for tag in sys.argv[1:] or ["c2", "c3_2m", "c3_16m", "c4", "c5"]:
     if os.path.exists(lp):
         rows = [r for r in csv.reader(open(lp)) if len(r) > 10 and r[0].isdigit()]
         names = [short(r[4]) for r in rows]
-        first = max([i for i, n in enumerate(names) if "k_ball2d_prep" in n or "k_rb3d_flow" in n] or [0])
+        first = max([i for i, n in enumerate(names) if "k_ball2d_prep" in n or "k_rb3d_flow" in n or "k_rb2d_flow" in n or "k_ball2d_flow" in n] or [0])
         step = rows[first:]
         tot = sum(float(r[-1]) for r in step)
         launches = [{"kernel": short(r[4]), "grid": r[8], "block": r[7], "ns": float(r[-1]), "share": float(r[-1]) / tot} for r in step]
