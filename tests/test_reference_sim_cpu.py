@@ -334,3 +334,103 @@ def test_ball2d_compute_N_and_contact_bases_of_the_reference(oracle):
     k = int(nnz.value)
     assert np.array_equal(outer, asm["n_outer"]) and np.array_equal(inner[:k], asm["n_inner"]) and np.array_equal(values[:k], asm["n_values"])
     assert np.array_equal(bases, asm["bases"])
+
+
+# ---- many small scenes ------------------------------------------------------------------------------------------------------------------------------
+def test_fuzz_ball2d_sim_against_oracle(oracle):
+    """160 small ball2d scenes (with and without portals, both maps, crowded and sparse, a few balls exactly on top of each other or exactly touching):
+    the reference's own Ball2DSim::computeActiveSet against the oracle after each of three steps."""
+    rng = np.random.default_rng(2024)
+    total = 0
+    for case in range(160):
+        n = int(rng.integers(2, 260))
+        kind = int(rng.integers(0, 2))
+        if case % 4 == 3:
+            s = scenes.ball2d_periodic(n, 1000 + case, axes=("x", "y", "xy")[case % 3], lees_edwards=float(rng.choice([0.0, 0.6, -1.1])), oblique=bool(case % 8 == 7))
+            portals = s["portals"]
+        else:
+            s = scenes.ball2d_random(n, 1000 + case, nplanes=int(rng.integers(0, 4)), ndrums=int(rng.integers(0, 3)), vmax=float(rng.choice([0.0, 5.0, 60.0])))
+            portals = None
+        q, v = s["q"].copy(), s["v"].copy()
+        if portals is None and n >= 6:
+            qq = q.reshape(-1, 2)
+            qq[1] = qq[0]                                        # coincident centres: the normal is the zero vector left as it is
+            qq[3] = qq[2] + np.array([s["r"][2] + s["r"][3], 0.0])   # exactly touching
+            v.reshape(-1, 2)[:4] = 0.0
+        o = ob.Ball2DOracle(s)
+        ref = RefBall2DSim(dict(s, q=q, v=v), portals)
+        if portals is not None:
+            o.set_portals(portals)
+            q, v = o.enforce_portals(q, v)
+            ref.set_state(q, v)
+        for it in range(1, 4):
+            if portals is not None:
+                o.update_portals(it * s["dt"])
+            q1, v1 = o.flow(kind, q, v, s["dt"])
+            want = o.active_set_portals(q, q1, "grid") if portals is not None else o.active_set(q, q1, "grid")
+            if want is None:
+                break                                            # a ball touching both planes of one portal: the reference exits there
+            rq, rv = ref.flow(kind, it, 1, 100)
+            if portals is not None:
+                q1w, v1w = o.enforce_portals(q1, v1)
+            else:
+                q1w, v1w = q1, v1
+            assert np.array_equal(rq, q1w) and np.array_equal(rv, v1w), (case, it)
+            got = ref.active_set(q, q1)
+            _same_active_set(got, want, 2)
+            total += got["type"].shape[0]
+            q, v = q1w, v1w
+    assert total > 8000
+
+
+def test_fuzz_rb3d_and_rb2d_sims_against_oracle(oracle):
+    """72 small rigidbody3d and 72 small rigidbody2d scenes of every body mix the reference supports: the reference's own computeActiveSet against the oracle."""
+    total = 0
+    for case in range(72):
+        pick = case % 4
+        if pick == 0:
+            s = scenes.rb3d_random_spheres(40 + 5 * case, 2000 + case, spin=True, nfixed_frac=0.25, nplanes=case % 3)
+        elif pick == 1:
+            s = scenes.rb3d_random_boxes(30 + 3 * case, 2000 + case, nfixed_frac=0.0, nplanes=case % 4)
+        elif pick == 2:
+            s = scenes.rb3d_random_meshes(5 + case // 8, 2000 + case, nfixed_frac=0.2, nplanes=1 + case % 2)
+        else:
+            ax = ("x", "xz", "xyz")[case % 3]
+            s = scenes.rb3d_periodic_spheres(60 + 4 * case, 2000 + case, axes=ax, nfixed_frac=0.0, tilt=(ax == "xyz"))   # (untilted, a y portal's normal is opposite to UnitY: Eigen's SVD branch of FromTwoVectors)
+        portals = s.get("portals") if pick == 3 else None
+        o = ob.RB3DOracle(s)
+        ref = RefRB3DSim(s, portals)
+        q0 = f64(s["q"])
+        if portals is not None:
+            o.set_portals(portals)
+            q0 = o.enforce_portals(q0)
+        q1, _ = o.flow(3, q0, s["v"], s["dt"])
+        want = o.active_set_portals(q0, q1, "grid") if portals is not None else o.active_set(q0, q1, "grid")
+        assert want["supported"], case
+        got = ref.active_set(q0, q1)
+        _same_rb3d_active_set(got, want, s, q0)
+        total += got["type"].shape[0]
+    for case in range(72):
+        kinds = (("circle", "box"), ("circle",), ("box",))[case % 3]
+        if case % 4 == 3:
+            s = scenes.rb2d_periodic(80 + 4 * case, 3000 + case, side=8.0 + case % 5, axes=("x", "y", "xy")[case % 3], lees_edwards=(0.0, 0.8)[case % 2])
+            portals = s["portals"]
+        else:
+            s = scenes.rb2d_random(60 + 7 * case, 3000 + case, kinds=kinds, nfixed_frac=0.2 if kinds == ("circle",) else 0.0, nplanes=case % 4)
+            portals = None
+        o = ob.RB2DOracle(s)
+        ref = RefRB2DSim(s, portals)
+        q0, v0 = f64(s["q"]), f64(s["v"])
+        if portals is not None:
+            o.set_portals(portals)
+            q0, v0 = o.enforce_portals(q0, v0)
+            o.update_portals(s["dt"])
+            ref.set_state(q0, v0)
+            ref.flow(0, 1, 1, 100)       # advances the reference's portals to the step's time (its own state is not used below)
+        q1, _ = o.flow(0, q0, v0, s["dt"])
+        want = o.active_set_portals(q0, q1, "grid") if portals is not None else o.active_set(q0, q1, "grid")
+        assert want["supported"], case
+        got = ref.active_set(q0, q1)
+        _same_rb2d_active_set(got, want)
+        total += got["type"].shape[0]
+    assert total > 9000
