@@ -434,3 +434,27 @@ def test_fuzz_rb3d_and_rb2d_sims_against_oracle(oracle):
         _same_rb2d_active_set(got, want)
         total += got["type"].shape[0]
     assert total > 9000
+
+
+@pytest.mark.parametrize("name", ["gas", "lattice"])
+def test_headline_scene_generators_through_the_reference_sim(oracle, name):
+    """The bench's own scene generators at reduced size -- configs[2]'s polydisperse gas (Verlet, 4 walls) and configs[1]'s lattice pile (symplectic Euler,
+    3 planes) -- through the reference's own Ball2DSim: the oracle that bench.py's parity_check compares the GPU path with equals it."""
+    if name == "gas":
+        s, kind, den = scenes.ball2d_gas(n=30000), 1, 1000
+    else:
+        s, kind, den = scenes.ball2d_lattice(150, 150), 0, 1000
+    assert s["dt"] == 1.0 / den
+    o = ob.Ball2DOracle(s)
+    ref = RefBall2DSim(s)
+    q, v = s["q"].copy(), s["v"].copy()
+    n = s["r"].shape[0]
+    for it in range(1, 3):
+        q1, v1 = o.flow(kind, q, v, s["dt"])
+        want = o.active_set(q, q1, "grid")
+        got = ref.active_set(q, q1)
+        _same_active_set(got, want, 2)
+        rq, rv = ref.flow(kind, it, 1, den)
+        assert np.array_equal(rq, q1) and np.array_equal(rv, v1)
+        assert got["type"].shape[0] > 0.8 * n
+        q, v = q1, v1
