@@ -546,7 +546,7 @@ def main():
             line["e2e_indices_only"] = e2e_shim
         if extra is not None:
             line["config2"] = extra
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU figure is reported at N = 1 only (the other N of a scaling run would just repeat it)
             sc, sample = cpu_sample_scene(args.config)
             pairs_cpu, times, ckind, how = cpu_reference_step(sc, 2, 1)
             v = pairs_cpu * len(times) / sum(times)
