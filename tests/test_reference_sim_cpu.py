@@ -458,3 +458,80 @@ def test_headline_scene_generators_through_the_reference_sim(oracle, name):
         assert np.array_equal(rq, q1) and np.array_equal(rv, v1)
         assert got["type"].shape[0] > 0.8 * n
         q, v = q1, v1
+
+
+# ---- where the reference prints and exits -----------------------------------------------------------------------------------------------------------
+def _reference_exits(fn):
+    """Runs fn in a forked child (the reference reports unsupported pairings with std::exit( EXIT_FAILURE )): True when the child did not return normally."""
+    import os
+    pid = os.fork()
+    if pid == 0:
+        try:
+            null = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(null, 1); os.dup2(null, 2)
+            fn()
+        finally:
+            os._exit(0)
+    _, status = os.waitpid(pid, 0)
+    return os.WIFSIGNALED(status) or os.WEXITSTATUS(status) != 0
+
+
+def test_unsupported_verdicts_are_exactly_where_the_reference_exits(oracle):
+    """The oracle's `supported = False` (which the product turns into SG_ERR_UNSUPPORTED, tests/test_rb3d_gpu.py, test_rb2d_gpu.py, test_zz_*_portals_gpu.py) against the
+    reference itself: for every construction the GPU tests use -- a box on a sphere, free boxes inside a static cylinder, kinematic boxes in 2-D, boxes reaching a
+    portal, kinematic circles / boxes in teleported collisions -- the reference's own computeActiveSet, run in a forked child, exits; for the supported controls it returns."""
+    cases = []
+    # rigidbody3d: a box moved onto a sphere (sphere-box: "bring box-sphere back up", RigidBody3DSim.cpp:711)
+    s = scenes.rb3d_mixed_segregated(40)
+    box0 = int(np.nonzero(s["geo_type"][s["geo_of_body"]] == 0)[0][0])
+    s["q"][3 * box0:3 * box0 + 3] = s["q"][0:3]
+    cases.append(("rb3d", s, None, f64(s["q"]), f64(s["q"])))
+    cases.append(("rb3d", scenes.rb3d_mixed_segregated(40), None, None, None))                                   # control
+    # rigidbody3d: free boxes inside a static cylinder (RigidBody3DSim.cpp:1549-1553)
+    s = scenes.rb3d_random_boxes(50, 25, nplanes=0)
+    s["cyl_x"] = np.zeros((1, 3)); s["cyl_axis"] = np.array([[0.0, 1.0, 0.0]]); s["cyl_r"] = np.array([100.0])
+    cases.append(("rb3d", s, None, None, None))
+    # rigidbody3d: boxes in a scene with portals
+    s = scenes.rb3d_random_boxes(50, 3, nplanes=0)
+    p = scenes.rb3d_periodic_spheres(4, 1, side=2.0)["portals"]
+    cases.append(("rb3d", s, p, f64(s["q"]), f64(s["q"])))
+    # rigidbody2d: kinematic boxes
+    s = scenes.rb2d_random(300, 5, kinds=("box",), box=2.0)
+    s["fixed"][:] = 0
+    s["fixed"][::7] = 1
+    cases.append(("rb2d", s, None, f64(s["q"]), f64(s["q"])))
+    cases.append(("rb2d", scenes.rb2d_random(300, 5, kinds=("box",), box=2.0, nfixed_frac=0.0), None, None, None))  # control
+    # rigidbody2d: boxes reaching the portals; kinematic circles in teleported collisions
+    s = scenes.rb2d_periodic(300, 8, side=9.0, boxes=True)
+    q = s["q"].reshape(-1, 3)
+    q[:, :2] = np.random.default_rng(2).uniform(0.0, s["side"], size=q[:, :2].shape)
+    s["q"] = q.ravel().copy()
+    cases.append(("rb2d", s, s["portals"], f64(s["q"]), f64(s["q"])))
+    s = scenes.rb2d_periodic(300, 9, side=9.0)
+    s["fixed"][::3] = 1
+    cases.append(("rb2d", s, s["portals"], f64(s["q"]), f64(s["q"])))
+    cases.append(("rb2d", scenes.rb2d_periodic(300, 9, side=9.0), scenes.rb2d_periodic(300, 9, side=9.0)["portals"], None, None))   # control
+    seen = {True: 0, False: 0}
+    for sim, s, portals, q0, q1 in cases:
+        if sim == "rb3d":
+            o = ob.RB3DOracle(s)
+            if portals is not None:
+                o.set_portals(portals)
+            if q0 is None:
+                q0 = f64(s["q"])
+                q1, _ = o.flow(3, q0, s["v"], s["dt"])
+            want = o.active_set_portals(q0, q1, "grid") if portals is not None else o.active_set(q0, q1, "grid")
+            exits = _reference_exits(lambda: RefRB3DSim(s, portals).active_set(q0, q1))
+        else:
+            o = ob.RB2DOracle(s)
+            if portals is not None:
+                o.set_portals(portals)
+                o.update_portals(0.0)
+            if q0 is None:
+                q0 = f64(s["q"])
+                q1, _ = o.flow(0, q0, s["v"], s["dt"])
+            want = o.active_set_portals(q0, q1, "grid") if portals is not None else o.active_set(q0, q1, "grid")
+            exits = _reference_exits(lambda: RefRB2DSim(s, portals).active_set(q0, q1))
+        assert exits == (not want["supported"]), (sim, exits, want["supported"])
+        seen[exits] += 1
+    assert seen[True] >= 5 and seen[False] >= 3, seen
