@@ -20,9 +20,11 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <limits>
 #include <memory>
+#include <sstream>
 
 // stub: see the header comment
 void ImpactMap::flow( ScriptingCallback&, FlowableSystem&, ConstrainedSystem&, UnconstrainedMap&, ImpactOperator&, const unsigned, const scalar&, const scalar&, const VectorXs&, const VectorXs&, VectorXs&, VectorXs& )
@@ -137,6 +139,44 @@ void ref_rb2d_sim_set_state( void* h, const double* q, const double* v )
   RigidBody2DSim& sim = *static_cast<RigidBody2DSim*>( h );
   const int nq = int( sim.state().q().size() );
   for( int k = 0; k < nq; ++k ) { sim.state().q()( k ) = q[k]; sim.state().v()( k ) = v[k]; }
+}
+
+// RigidBody2DState::serialize (rigidbody2d/RigidBody2DState.cpp:485-498) of the simulation's current state: the reference's binary snapshot.  Returns its
+// length; the bytes are written when they fit cap.
+uint64_t ref_rb2d_sim_serialize_state( void* h, void* buf, const uint64_t cap )
+{
+  RigidBody2DSim& sim = *static_cast<RigidBody2DSim*>( h );
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  sim.state().serialize( stm );
+  const std::string bytes = stm.str();
+  if( bytes.size() <= cap ) { std::memcpy( buf, bytes.data(), bytes.size() ); }
+  return bytes.size();
+}
+
+// RigidBody2DState::deserialize (rigidbody2d/RigidBody2DState.cpp:542-556) of a snapshot (the product's sg_rb2d_state_serialize output, say) into a fresh
+// RigidBody2DSim; *n_out = its body count
+void* ref_rb2d_sim_from_snapshot( const void* buf, const uint64_t bytes, uint32_t* n_out )
+{
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  stm.write( static_cast<const char*>( buf ), std::streamsize( bytes ) );
+  RigidBody2DSim* sim = new RigidBody2DSim;
+  sim->state().deserialize( stm );
+  *n_out = sim->state().nbodies();
+  return sim;
+}
+
+// PlanarPortal::updateMovingPortals( t ) on every portal of the state (what RigidBody2DSim::flow does before the map): a snapshot holds each portal's m_dx
+void ref_rb2d_sim_update_portals( void* h, const double t )
+{
+  RigidBody2DSim& sim = *static_cast<RigidBody2DSim*>( h );
+  for( PlanarPortal& p : sim.state().planarPortals() ) { p.updateMovingPortals( t ); }
+}
+
+void ref_rb2d_sim_get_state( void* h, double* q, double* v )
+{
+  RigidBody2DSim& sim = *static_cast<RigidBody2DSim*>( h );
+  const int nq = int( sim.state().q().size() );
+  for( int k = 0; k < nq; ++k ) { q[k] = sim.state().q()( k ); v[k] = sim.state().v()( k ); }
 }
 
 }

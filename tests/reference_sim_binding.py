@@ -129,6 +129,46 @@ class RefRB2DSim:
     def set_state(self, q, v):
         self.lib.ref_rb2d_sim_set_state(self.h, vp(f64(q)), vp(f64(v)))
 
+    def get_state(self):
+        q, v = np.zeros(3 * self.n), np.zeros(3 * self.n)
+        self.lib.ref_rb2d_sim_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.ref_rb2d_sim_get_state(self.h, vp(q), vp(v))
+        return q, v
+
+    def update_portals(self, t):
+        """PlanarPortal::updateMovingPortals( t ) on every portal, as RigidBody2DSim::flow does before the map."""
+        self.lib.ref_rb2d_sim_update_portals.argtypes = [C.c_void_p, C.c_double]
+        self.lib.ref_rb2d_sim_update_portals(self.h, float(t))
+
+    def serialize_state(self):
+        """RigidBody2DState::serialize of the simulation's current state (the reference's binary snapshot)."""
+        f = self.lib.ref_rb2d_sim_serialize_state
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        need = int(f(self.h, None, 0))
+        buf = np.zeros(need, dtype=np.uint8)
+        assert int(f(self.h, vp(buf), need)) == need
+        return buf.tobytes()
+
+    @classmethod
+    def from_snapshot(cls, blob):
+        """RigidBody2DState::deserialize of a snapshot into a fresh reference simulation."""
+        self = cls.__new__(cls)
+        self.lib = lib = _lib("libref_rb2d.so")
+        V = C.c_void_p
+        lib.ref_rb2d_sim_from_snapshot.restype = V
+        lib.ref_rb2d_sim_from_snapshot.argtypes = [V, C.c_uint64, V]
+        lib.ref_rb2d_sim_destroy.argtypes = [V]
+        lib.ref_rb2d_sim_active_set.restype = C.c_uint64
+        lib.ref_rb2d_sim_active_set.argtypes = [V, V, V, C.c_uint64, V, V, V, V, V, V, V]
+        lib.ref_rb2d_sim_flow.argtypes = [V, C.c_int, C.c_uint, C.c_longlong, C.c_longlong, V, V]
+        lib.ref_rb2d_sim_set_state.argtypes = [V, V, V]
+        raw = np.frombuffer(blob, dtype=np.uint8).copy()
+        n = C.c_uint32(0)
+        self.h = lib.ref_rb2d_sim_from_snapshot(vp(raw), raw.shape[0], C.byref(n))
+        self.n = int(n.value)
+        return self
+
 
 class RefRB3DSim:
     def __init__(self, s, portals=None):

@@ -247,6 +247,25 @@ def test_rb2d_sim_compute_active_set(oracle, kinds, nfixed, seed, kind):
     assert ("circle" not in kinds or 20 in seen or 22 in seen) and ("box" not in kinds or 22 in seen) and (nfixed == 0.0 or 21 in seen) and (23 in seen or 24 in seen)
 
 
+@pytest.mark.parametrize("kind", [0, 1])
+def test_rb2d_sim_flow_under_gravity(oracle, kind):
+    """RigidBody2DSim::flow( call_back, iteration, dt, umap ) with a NearEarthGravityForce that is not zero, kinematic circles included, over five steps:
+    the reference's own state (its M / Minv built by generateM / generateMinv, RigidBody2DState.cpp:15-43) against the oracle, bit for bit.  (The portal
+    scenes above run without gravity; with this test the stand-in's finalize() + makeCompressed() sequence is exercised with forces that matter.)"""
+    s = scenes.rb2d_random(700, 121 + kind, kinds=("circle",), nfixed_frac=0.15, nplanes=2)
+    assert s["g"][1] != 0.0 and s["fixed"].sum() > 10
+    o = ob.RB2DOracle(s)
+    ref = RefRB2DSim(s)
+    q, v = f64(s["q"]), f64(s["v"])
+    for it in range(1, 6):
+        q1, v1 = o.flow(kind, q, v, s["dt"])
+        rq, rv = ref.flow(kind, it, 1, 100)
+        assert np.array_equal(rq, q1) and np.array_equal(rv, v1)
+        q, v = q1, v1
+    free = np.repeat(s["fixed"] == 0, 3)
+    assert np.abs(v - f64(s["v"]))[free].max() > 0.4   # 5 steps of g dt
+
+
 @pytest.mark.parametrize("case", [dict(n=500, seed=111, side=10.0), dict(n=500, seed=112, side=10.0, lees_edwards=0.7, oblique=True), dict(n=500, seed=113, side=7.0, axes="y", lees_edwards=-0.9)])
 def test_rb2d_sim_with_portals(oracle, case):
     """The portal branch (RigidBody2DSim.cpp:350-636, 832-1040) and RigidBody2DSim::flow's portal bookkeeping over 8 steps without contact response."""
