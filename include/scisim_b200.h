@@ -393,6 +393,14 @@ int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
 int sg_rb2d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_rb2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_rb2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
+/* State I/O at the seam: RigidBody2DState's binary snapshot (rigidbody2d/RigidBody2DState.cpp:485-556, scisim/Utilities.h:43-94,
+   scisim/Math/MathUtilities.h:42-60, MathUtilities.cpp:142-177), byte for byte, written from / read into the device-resident state.
+   serialize   which = 0: ( q0, v0 ) as uploaded, 1: ( q1, v1 ) of the last flow / step.  Portals are written with the offset ( m_dx ) of the
+               last sg_rb2d_update_portals.  buf = NULL: *bytes <- size needed
+   deserialize configures geometry, bodies, gravity, planes and portals (frames and offsets as stored) from a snapshot and uploads ( q, v );
+               SG_ERR_UNSUPPORTED for a moving plane or a plane whose stored tangent is not ( -n.y, n.x ) */
+int sg_rb2d_state_serialize( sg_ctx* ctx, int which, void* buf, uint64_t cap, uint64_t* bytes );
+int sg_rb2d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes );
 
 /* Planar and Lees-Edwards portals of the 2-D rigid-body sim (rigidbody2d/PlanarPortal.h; at most 8), arguments as
  * sg_ball2d_set_portals except that plane normals are used as given (RigidBody2DStaticPlane does not normalise).  With portals

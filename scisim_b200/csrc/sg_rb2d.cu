@@ -445,6 +445,7 @@ struct ScanU32To64b
 // ---- portals (rigidbody2d/PlanarPortal.h): kernels, per-context data ------------------------------------
 #include "sg_rb2d_portal_kernels.cuh"
 #include "sg_pair_sort_host.cuh"
+#include "sg_rb2d_snapshot.h"
 
 struct Rb2dPortalData
 {
@@ -481,6 +482,9 @@ struct Rb2dData
   Planes2D planes;
   std::vector<uint32_t> geo_type;
   std::vector<double> geo_r, geo_half;
+  std::vector<uint8_t> h_fixed;          // as given to sg_rb2d_set_bodies (the snapshot writes them back)
+  std::vector<uint32_t> h_geo_of_body;
+  bool q1_valid = false;                 // ( q1, v1 ) on the device are the output of a flow / step on this context
   DevBuf btype, bparam, M, q0, v0, q1, v1, boxes;
   BroadScratch bp;
   DevBuf pair_counts, pair_offsets, pair_partials, narrow_total, bad_flag;
@@ -864,6 +868,8 @@ int sg_rb2d_set_bodies( sg_ctx* ctx, uint32_t n, const uint32_t* geo_of_body, co
   d->n = n;
   d->have_result = false;
   d->flow_resident = false;
+  d->q1_valid = false;
+  d->h_fixed.assign( fixed, fixed + n ); d->h_geo_of_body.assign( geo_of_body, geo_of_body + n );
   if( n == 0 ) { return SG_OK; }
   SG_CUDA( ctx, d->btype.ensure( size_t( n ) * 4 ) ); SG_CUDA( ctx, d->bparam.ensure( size_t( n ) * 16 ) ); SG_CUDA( ctx, d->M.ensure( size_t( n ) * 24 ) );
   SG_CUDA( ctx, d->q0.ensure( size_t( n ) * 24 ) ); SG_CUDA( ctx, d->q1.ensure( size_t( n ) * 24 ) ); SG_CUDA( ctx, d->v0.ensure( size_t( n ) * 24 ) ); SG_CUDA( ctx, d->v1.ensure( size_t( n ) * 24 ) );
@@ -1011,6 +1017,7 @@ int sg_rb2d_flow( sg_ctx* ctx, int map_kind, const double* q0, const double* v0,
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   sg_prof_collect( ctx );
   d->flow_resident = true;
+  d->q1_valid = true;
   return SG_OK;
 }
 
@@ -1030,6 +1037,7 @@ int sg_rb2d_active_set( sg_ctx* ctx, const double* q0, const double* q1, uint32_
     SG_CUDA( ctx, cudaMemcpyAsync( d->q0.ptr, q0, size_t( d->n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
     SG_CUDA( ctx, cudaMemcpyAsync( d->q1.ptr, q1, size_t( d->n ) * 24, cudaMemcpyHostToDevice, ctx->stream ) );
     d->flow_resident = false;
+    d->q1_valid = false; // q1 is the caller's, v1 whatever an earlier flow left
   }
   const int rc = ( d->px != nullptr && d->px->portals.n > 0u ) ? rb2d_portal_active_set_device( ctx, d ) : rb2d_active_set_device( ctx, d );
   if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
@@ -1042,6 +1050,7 @@ int sg_rb2d_upload( sg_ctx* ctx, const double* q, const double* v )
   if( ctx == nullptr ) { return SG_ERR_INVALID; }
   Rb2dData* d = rb2d_data( ctx );
   d->flow_resident = false;
+  d->q1_valid = false;
   if( d->n == 0 ) { return SG_OK; }
   if( q == nullptr || v == nullptr ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_upload: null vector" ); }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
@@ -1063,6 +1072,7 @@ int sg_rb2d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out )
     SG_LAUNCH( ctx, "rb2d_flow", double( d->n ) * 120.0, k_rb2d_flow<<<sg_div_up( d->n, 256 ), 256, 0, ctx->stream>>>( map_kind, d->n, d->q0.as<double>(), d->v0.as<double>(), d->M.as<double>(), d->btype.as<uint32_t>(),
                d->g[0], d->g[1], dt, d->q1.as<double>(), d->v1.as<double>() ) );
   }
+  d->q1_valid = true;
   const int rc = ( d->px != nullptr && d->px->portals.n > 0u ) ? rb2d_portal_active_set_device( ctx, d ) : rb2d_active_set_device( ctx, d );
   if( rc != SG_OK ) { d->have_result = false; } // a failed call leaves nothing to fetch (partial or stale lists)
   if( rc != SG_OK ) { return rc; }
@@ -1089,6 +1099,102 @@ int sg_rb2d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_c
   if( out != nullptr ) { return rb2d_copy_out( ctx, d, out_flags, out ); }
   SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
   return SG_OK;
+}
+
+// ---- state I/O at the seam: RigidBody2DState's binary snapshot (rigidbody2d/RigidBody2DState.cpp:485-556), sg_rb2d_snapshot.h ----
+int sg_rb2d_state_serialize( sg_ctx* ctx, int which, void* buf, uint64_t cap, uint64_t* bytes )
+{
+  if( ctx == nullptr || bytes == nullptr || ( which != 0 && which != 1 ) ) { return SG_ERR_INVALID; }
+  Rb2dData* d = rb2d_data( ctx );
+  if( which == 1 && !d->q1_valid && d->n > 0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_state_serialize: which = 1 without a preceding sg_rb2d_flow / sg_rb2d_step on this context" ); }
+  SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
+  const uint32_t n = d->n;
+  sg_snapshot::Rb2dState s;
+  s.n = n;
+  s.q.resize( size_t( 3 ) * n ); s.v.resize( size_t( 3 ) * n ); s.M.resize( size_t( 3 ) * n );
+  if( n > 0 )
+  {
+    const size_t nb = size_t( n ) * 24;
+    SG_CUDA( ctx, cudaMemcpyAsync( s.q.data(), ( which == 0 ) ? d->q0.ptr : d->q1.ptr, nb, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.v.data(), ( which == 0 ) ? d->v0.ptr : d->v1.ptr, nb, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaMemcpyAsync( s.M.data(), d->M.ptr, nb, cudaMemcpyDeviceToHost, ctx->stream ) );
+    SG_CUDA( ctx, cudaStreamSynchronize( ctx->stream ) );
+  }
+  s.fixed = d->h_fixed; s.geo_of_body = d->h_geo_of_body;
+  s.geo_type.resize( d->geo_type.size() );
+  for( size_t k = 0; k < d->geo_type.size(); ++k ) { s.geo_type[k] = ( d->geo_type[k] == SG_GEO2_CIRCLE ) ? 0u : ( d->geo_type[k] == SG_GEO2_BOX ) ? 1u : 2u; }
+  s.geo_r = d->geo_r; s.geo_half = d->geo_half;
+  s.g[0] = d->g[0]; s.g[1] = d->g[1];
+  for( uint32_t p = 0; p < d->planes.n; ++p )
+  {
+    // RigidBody2DStaticPlane( x, n ): m_t = ( -n.y, n.x ) (rigidbody2d/RigidBody2DStaticPlane.cpp:10-14)
+    s.plane_x.push_back( d->planes.x[p][0] ); s.plane_x.push_back( d->planes.x[p][1] );
+    s.plane_n.push_back( d->planes.nrm[p][0] ); s.plane_n.push_back( d->planes.nrm[p][1] );
+    s.plane_t.push_back( -d->planes.nrm[p][1] ); s.plane_t.push_back( d->planes.nrm[p][0] );
+  }
+  if( d->px != nullptr )
+  {
+    for( uint32_t p = 0; p < d->px->portals.n; ++p )
+    {
+      const SgPortal2D& pt = d->px->portals.p[p];
+      for( int k = 0; k < 2; ++k )
+      {
+        s.portal_ax.push_back( pt.ax[k] ); s.portal_an.push_back( pt.an[k] ); s.portal_at.push_back( pt.at[k] );
+        s.portal_bx.push_back( pt.bx[k] ); s.portal_bn.push_back( pt.bn[k] ); s.portal_bt.push_back( pt.bt[k] );
+      }
+      s.portal_v.push_back( pt.v ); s.portal_bounds.push_back( pt.bounds ); s.portal_dx.push_back( pt.dx );
+    }
+  }
+  sg_snapshot::Sink out{ static_cast<unsigned char*>( buf ), cap, 0 };
+  if( !sg_snapshot::serialize( s, out ) ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb2d_state_serialize: a geometry that is neither circle nor box" ); }
+  *bytes = out.n;
+  if( buf != nullptr && out.n > cap ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_state_serialize: buffer of %llu bytes, %llu needed", ( unsigned long long )( cap ), ( unsigned long long )( out.n ) ); }
+  return SG_OK;
+}
+
+// RigidBody2DState::deserialize (rigidbody2d/RigidBody2DState.cpp:542-556): configures the context from a snapshot and uploads ( q, v )
+int sg_rb2d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes )
+{
+  if( ctx == nullptr || buf == nullptr ) { return SG_ERR_INVALID; }
+  sg_snapshot::Source in{ static_cast<const unsigned char*>( buf ), bytes, 0, true };
+  sg_snapshot::Rb2dState s;
+  const char* why = "";
+  const int prc = sg_snapshot::parse( in, s, &why );
+  if( prc == 1 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_state_deserialize: %s", why ); }
+  if( prc == 2 ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb2d_state_deserialize: %s", why ); }
+  const uint32_t npl = uint32_t( s.plane_x.size() / 2 ), npo = uint32_t( s.portal_v.size() );
+  if( npl > SG_MAX_PLANES || npo > SG_MAX_PORTALS ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb2d_state_deserialize: more planes or portals than this library holds" ); }
+  // the kernels take a plane's tangent as ( -n.y, n.x ), which is what the reference's constructor stores: a snapshot with another frame is not this path's
+  for( uint32_t p = 0; p < npl; ++p )
+  {
+    if( s.plane_t[2 * p] != -s.plane_n[2 * p + 1] || s.plane_t[2 * p + 1] != s.plane_n[2 * p] ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb2d_state_deserialize: plane %u has a tangent other than ( -n.y, n.x )", p ); }
+  }
+  for( uint32_t p = 0; p < npo; ++p ) { if( !( s.portal_bounds[p] >= 0.0 ) ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb2d_state_deserialize: portal %u has negative bounds", p ); } }
+  const uint32_t ngeo = uint32_t( s.geo_type.size() );
+  std::vector<uint32_t> type( ngeo );
+  for( uint32_t k = 0; k < ngeo; ++k ) { type[k] = ( s.geo_type[k] == 0u ) ? uint32_t( SG_GEO2_CIRCLE ) : uint32_t( SG_GEO2_BOX ); }
+  int rc = sg_rb2d_set_geometry( ctx, ngeo, type.data(), s.geo_r.data(), s.geo_half.data() );
+  if( rc != SG_OK ) { return rc; }
+  rc = sg_rb2d_set_bodies( ctx, s.n, s.geo_of_body.data(), s.fixed.data(), s.M.data() );
+  if( rc != SG_OK ) { return rc; }
+  Rb2dData* d = rb2d_data( ctx );
+  d->g[0] = s.g[0]; d->g[1] = s.g[1];
+  rc = sg_rb2d_set_planes( ctx, npl, s.plane_x.data(), s.plane_n.data() ); // RigidBody2DStaticPlane( std::istream& ) reads x and n back as stored
+  if( rc != SG_OK ) { return rc; }
+  if( npo > 0 || d->px != nullptr )
+  {
+    rc = sg_rb2d_set_portals( ctx, npo, s.portal_ax.data(), s.portal_an.data(), s.portal_bx.data(), s.portal_bn.data(), s.portal_v.data(), s.portal_bounds.data() );
+    if( rc != SG_OK ) { return rc; }
+    // the frames and the Lees-Edwards offset stay as stored (PlanarPortal( std::istream& ), rigidbody2d/PlanarPortal.cpp:101-109)
+    for( uint32_t p = 0; p < npo; ++p )
+    {
+      SgPortal2D& pt = d->px->portals.p[p];
+      for( int k = 0; k < 2; ++k ) { pt.at[k] = s.portal_at[2 * p + k]; pt.bt[k] = s.portal_bt[2 * p + k]; }
+      pt.dx = s.portal_dx[p];
+    }
+  }
+  if( s.n == 0 ) { return SG_OK; }
+  return sg_rb2d_upload( ctx, s.q.data(), s.v.data() );
 }
 
 }

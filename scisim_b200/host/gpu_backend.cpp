@@ -1,5 +1,7 @@
 // gpu_backend.cpp -- see gpu_backend.h
 #include "gpu_backend.h"
+#include "../csrc/sg_rb2d_snapshot.h" // plain C++ writers / parsers of the reference's snapshots (also includes sg_rb3d_snapshot.h): after a
+                                       // deserializeState the force guard is told the masses and the gravity the device now holds
 
 #include <algorithm>
 #include <cstdlib>
@@ -177,6 +179,35 @@ void GpuBall2DBackend::deserializeState( std::istream& input_stream )
   // the snapshot is self-delimiting only to its parser: hand over the rest of the stream (Ball2DSim::deserialize reads the state last, Ball2DSim.cpp:800-807)
   const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
   check( sg_ball2d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_ball2d_state_deserialize" );
+  // the library accepted the stream, so the layout is Ball2DState's (ball2d/Ball2DState.cpp:259-272): q, v, r, fixed, M, Minv, drums, planes, portals, forces.
+  // Tell the guard what the device now integrates with: the masses ( M's values, two per ball ) and the summed gravity.
+  sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf.data() ), buf.size(), 0, true };
+  const uint64_t nq = uint64_t( in.val<long long>() ), n = nq / 2;
+  in.take( nq * 8 );                                   // q
+  in.take( 8 + nq * 8 );                               // v
+  in.take( 8 + n * 8 );                                // r
+  in.take( 8 + n );                                    // fixed
+  in.take( 24 + nq * 4 + ( nq + 1 ) * 4 );             // M: header, inner, outer
+  std::vector<double> mass( nq );
+  in.doubles( mass.data(), nq );
+  in.take( 24 + nq * 4 + ( nq + 1 ) * 4 + nq * 8 );    // Minv
+  const uint64_t ndrums = in.val<size_t>(); in.take( ndrums * 24 );
+  const uint64_t nplanes = in.val<size_t>(); in.take( nplanes * 64 );
+  const uint64_t nportals = in.val<size_t>(); in.take( nportals * ( 2 * 64 + 24 ) );
+  const uint64_t nforces = in.val<size_t>();
+  double g[2] = { 0.0, 0.0 };
+  for( uint64_t k = 0; k < nforces && in.ok; ++k )
+  {
+    const uint64_t len = in.val<size_t>();
+    in.take( len );
+    double gk[2] = { 0.0, 0.0 };
+    in.doubles( gk, 2 );
+    g[0] += gk[0]; g[1] += gk[1];
+  }
+  if( !in.ok ) { std::cerr << "GpuBall2DBackend::deserializeState: the snapshot ends early. Exiting." << std::endl; std::exit( EXIT_FAILURE ); }
+  m_nbodies = static_cast<unsigned>( n );
+  m_guard.setMasses( mass.data(), m_nbodies, 2 );
+  m_guard.setGravity( g[0], g[1], 0.0 );
 }
 
 void GpuBall2DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps )
@@ -482,8 +513,13 @@ void GpuRigidBody3DBackend::deserializeState( std::istream& input_stream, const 
 {
   const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
   check( sg_rb3d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_rb3d_state_deserialize" );
-  m_nbodies = 0;
-  if( buf.size() >= sizeof( unsigned ) ) { std::memcpy( &m_nbodies, buf.data(), sizeof( unsigned ) ); }
+  sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf.data() ), buf.size(), 0, true };
+  sg_snapshot::Rb3dState st;
+  const char* why = "";
+  if( sg_snapshot::parse( in, st, &why ) != 0 ) { std::cerr << "GpuRigidBody3DBackend::deserializeState: " << why << ". Exiting." << std::endl; std::exit( EXIT_FAILURE ); }
+  m_nbodies = st.n;
+  m_guard.setMasses( st.m.data(), m_nbodies, 1 );   // what the device now integrates with
+  m_guard.setGravity( st.g[0], st.g[1], st.g[2] );
   m_m_updated = from_running_simulation;
 }
 
@@ -626,6 +662,30 @@ void GpuRigidBody2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs
     o.depth = c.depth[k];
   }
   if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
+}
+
+void GpuRigidBody2DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow )
+{
+  uint64_t bytes = 0;
+  check( sg_rb2d_state_serialize( m_ctx, from_last_flow ? 1 : 0, nullptr, 0, &bytes ), "sg_rb2d_state_serialize" );
+  std::vector<char> buf( bytes );
+  check( sg_rb2d_state_serialize( m_ctx, from_last_flow ? 1 : 0, buf.data(), bytes, &bytes ), "sg_rb2d_state_serialize" );
+  output_stream.write( buf.data(), static_cast<std::streamsize>( bytes ) );
+}
+
+void GpuRigidBody2DBackend::deserializeState( std::istream& input_stream )
+{
+  // the snapshot is self-delimiting only to its parser: hand over the rest of the stream (RigidBody2DSim::deserialize reads the constraint cache after the
+  // state, RigidBody2DSim.cpp:1147-1152: split the stream before calling this where a cache follows)
+  const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
+  check( sg_rb2d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_rb2d_state_deserialize" );
+  sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf.data() ), buf.size(), 0, true };
+  sg_snapshot::Rb2dState st;
+  const char* why = "";
+  if( sg_snapshot::parse( in, st, &why ) != 0 ) { std::cerr << "GpuRigidBody2DBackend::deserializeState: " << why << ". Exiting." << std::endl; std::exit( EXIT_FAILURE ); }
+  m_nbodies = st.n;
+  m_guard.setMasses( st.M.data(), m_nbodies, 3 );   // what the device now integrates with
+  m_guard.setGravity( st.g[0], st.g[1], 0.0 );
 }
 
 void GpuRB2DSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )

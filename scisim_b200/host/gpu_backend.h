@@ -361,6 +361,9 @@ public:
   void flow( const int map_kind, const VectorXs& q0, const VectorXs& v0, const scalar& dt, VectorXs& q1, VectorXs& v1 );
   // contacts use GpuContact2D with the rigidbody2d type codes (SG_CIRCLE_CIRCLE ... SG_PLANE_BODY_2D)
   void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
+  // RigidBody2DState::serialize / deserialize (rigidbody2d/RigidBody2DState.cpp:485-556) from / into the device-resident state
+  void serializeState( std::ostream& output_stream, const bool from_last_flow = true );
+  void deserializeState( std::istream& input_stream );
 
   sg_ctx* context() { return m_ctx; }
   GravityOnlyGuard& forceGuard() { return m_guard; }

@@ -799,3 +799,42 @@ class RigidBody2DSim:
         c = SgContacts()
         self.ctx.check(self.ctx.lib.sg_rb2d_fetch(self.ctx.h, int(flags), _ptr(q1) if want_state else None, _ptr(v1) if want_state else None, C.byref(c)))
         return q1, v1, ActiveSet(c)
+
+    # ---- state I/O: RigidBody2DState's binary snapshot (rigidbody2d/RigidBody2DState.cpp:485-556) ----
+    def serializeState(self, which=1):
+        """bytes of RigidBody2DState::serialize for the device-resident state: which = 0 the uploaded ( q0, v0 ), 1 the last flow's ( q1, v1 )."""
+        need = C.c_uint64()
+        self.ctx.check(self.ctx.lib.sg_rb2d_state_serialize(self.ctx.h, int(which), None, 0, C.byref(need)))
+        buf = np.zeros(int(need.value), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.sg_rb2d_state_serialize(self.ctx.h, int(which), _ptr(buf), buf.shape[0], C.byref(need)))
+        return buf.tobytes()
+
+    @staticmethod
+    def deserializeState(blob, ctx):
+        """RigidBody2DState::deserialize: a sim configured from a snapshot, its ( q, v ) uploaded."""
+        sim = RigidBody2DSim.__new__(RigidBody2DSim)
+        sim.ctx = ctx
+        buf = np.frombuffer(blob, dtype=np.uint8).copy()
+        ctx.check(ctx.lib.sg_rb2d_state_deserialize(ctx.h, _ptr(buf), buf.shape[0]))
+        n, nportals = rb2d_snapshot_counts(blob)
+        # the context holds the real tables; the host-side state object only answers nbodies() and how many portals there are
+        sim.state = RigidBody2DState([0], [1.0], [[0.0, 0.0]], np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.ones(3 * n), planar_portals=[None] * nportals)
+        return sim
+
+
+def rb2d_snapshot_counts(blob):
+    """( bodies, portals ) of a RigidBody2DState snapshot the library has accepted: a walk over the layout of scisim_b200/csrc/sg_rb2d_snapshot.h."""
+    i64 = lambda at: int(np.frombuffer(blob[at:at + 8], dtype=np.int64)[0])
+    nq = i64(0)
+    n = nq // 3
+    at = 2 * (8 + 8 * nq)                          # q, v
+    at += 2 * (24 + 4 * nq + 4 * (nq + 1) + 8 * nq)  # M, Minv
+    at += 8 + n                                    # fixed
+    at += 8 + 4 * n                                # geometry indices
+    ngeo = i64(at); at += 8
+    for _ in range(ngeo):
+        t = int(np.frombuffer(blob[at:at + 4], dtype=np.int32)[0])
+        at += 4 + (8 if t == 0 else 16)
+    nforces = i64(at); at += 8 + nforces * (4 + 16)
+    nplanes = i64(at); at += 8 + nplanes * 72
+    return n, i64(at)

@@ -178,3 +178,77 @@ def test_replay_rb2d_resident_gpu_tests(monkeypatch, oracle):
     import tests.test_zx_rb2d_resident_gpu as m
     monkeypatch.setattr(m, "make_sim", lambda s, ctx: OracleBackedRB2D(s))
     m.test_rb2d_resident_step_matches_oracle(None, oracle)
+
+
+class OracleBackedRB2DWithSnapshots:
+    """RigidBody2DSim's resident stepping answered by the oracle; its snapshots written by the product's own writer (scisim_b200/csrc/sg_rb2d_snapshot.h compiled
+    for the host, as in tests/test_rb2d_snapshot_cpu.py) from the stand-in's arrays; a restore re-reads ( q, v ) from the bytes and keeps the scene."""
+
+    def __init__(self, s, portals, harness, t=None):
+        from tests import oracle_binding as ob
+        self.s, self.portals, self.harness, self.t, self.q1 = s, portals, harness, t, None
+        self.o = ob.RB2DOracle(s)
+        if portals is not None:
+            self.o.set_portals(portals)
+            if t is not None:
+                self.o.update_portals(t)
+
+    def nqdofs(self):
+        return 3 * self.s["geo_of_body"].shape[0]
+
+    def upload(self, q, v):
+        self.q, self.v, self.q1 = np.array(q, dtype=np.float64).ravel(), np.array(v, dtype=np.float64).ravel(), None
+
+    def updatePeriodicBoundaryConditionsStartOfStep(self, it, dt):
+        self.t = it * dt
+        return self.o.update_portals(self.t)
+
+    def step(self, umap, dt):
+        from scisim_b200 import SG_MAP_SYMPLECTIC_EULER
+        self.q1, self.v1 = self.o.flow(0 if umap.kind == SG_MAP_SYMPLECTIC_EULER else 1, self.q, self.v, dt)
+        ref = self.o.active_set_portals(self.q, self.q1) if self.portals is not None else self.o.active_set(self.q, self.q1, "grid")
+        assert ref["supported"]
+        na = ref["type"].shape[0]
+        self.res = SimpleNamespace(n_candidates=ref["candidates"].shape[0], n_active=na, type=ref["type"], i=ref["i"], j=ref["j"], aux=ref.get("aux", np.zeros(na, np.uint32)),
+                                   n=ref["n"], p=ref["p"], depth=ref["depth"])
+        return self.res.n_candidates, na
+
+    def fetch(self):
+        return self.q1, self.v1, self.res
+
+    def serializeState(self, which=1):
+        from tests.test_rb2d_snapshot_cpu import product_bytes
+        if which == 1 and self.q1 is None:
+            raise sb.SciSimB200Error("which = 1 without a flow (replay)")
+        q, v = (self.q, self.v) if which == 0 else (self.q1, self.v1)
+        return product_bytes(self.harness, self.s, q, v, self.portals, t=self.t if self.portals is not None else None)
+
+
+def test_replay_rb2d_state_io_gpu_tests(monkeypatch, oracle, tmp_path_factory):
+    import os
+    import tests.test_zzz_rb2d_state_io_gpu as m
+    from tests.test_rb2d_snapshot_cpu import harness as harness_fixture
+    if not os.path.exists(os.path.join(m.ROOT, "oracle", "_ref", "libref_rb2d.so")):
+        pytest.skip("oracle/_ref not built (the reference tree is not mounted here)")
+    lib = harness_fixture.__wrapped__(tmp_path_factory)
+    made = []
+
+    def make(s, ctx, portals=None):
+        made.append(OracleBackedRB2DWithSnapshots(s, portals, lib))
+        return made[-1]
+
+    def restore(blob, ctx):
+        nq = int(np.frombuffer(blob[:8], dtype=np.int64)[0])
+        if len(blob) != len(made[-1].serializeState(which=0)):
+            raise sb.SciSimB200Error("truncated (replay)")
+        src = made[-1]
+        sim = OracleBackedRB2DWithSnapshots(src.s, src.portals, lib, t=src.t)
+        sim.upload(np.frombuffer(blob[8:8 + 8 * nq], dtype=np.float64), np.frombuffer(blob[16 + 8 * nq:16 + 16 * nq], dtype=np.float64))
+        return sim
+
+    monkeypatch.setattr(m, "_sim", make)
+    monkeypatch.setattr(m, "_restore", restore)
+    monkeypatch.setattr(m, "_context", lambda: SimpleNamespace(close=lambda: None))
+    for scene in ("circles_boxes", "kinematic_circles", "lees_edwards"):
+        m.test_rb2d_snapshot_is_the_references_own_and_resumes(oracle, None, scene)
+    m.test_rb2d_snapshot_refusals(None)
