@@ -35,6 +35,59 @@ void GravityOnlyGuard::verify( FlowableSystem& fsys, const VectorXs& q0, const V
   m_checked = true;
 }
 
+// After a deserializeState the device integrates with the masses and the gravity of the snapshot: the guard is told both, so that the first GPU map flow
+// after a restore is checked against them.  The library has accepted the stream when this runs; a stream it would not accept ends the process here.
+unsigned GravityOnlyGuard::configureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, const char* who )
+{
+  sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf ), bytes, 0, true };
+  const char* why = "";
+  unsigned n = 0;
+  if( layout == BALL2D )
+  {
+    // Ball2DState::serialize (ball2d/Ball2DState.cpp:259-272): q, v, r, fixed, M, Minv, drums, planes, portals, forces; M's values hold each mass twice
+    const uint64_t nq = uint64_t( in.val<long long>() ), nb = nq / 2;
+    in.take( nq * 8 );                                   // q
+    in.take( 8 + nq * 8 );                               // v
+    in.take( 8 + nb * 8 );                               // r
+    in.take( 8 + nb );                                   // fixed
+    in.take( 24 + nq * 4 + ( nq + 1 ) * 4 );             // M: header, inner, outer
+    std::vector<double> mass( in.ok && nq * 8 <= bytes ? nq : 0 );
+    in.doubles( mass.data(), nq );
+    in.take( 24 + nq * 4 + ( nq + 1 ) * 4 + nq * 8 );    // Minv
+    const uint64_t ndrums = in.val<size_t>(); in.take( ndrums * 24 );
+    const uint64_t nplanes = in.val<size_t>(); in.take( nplanes * 64 );
+    const uint64_t nportals = in.val<size_t>(); in.take( nportals * ( 2 * 64 + 24 ) );
+    const uint64_t nforces = in.val<size_t>();
+    double g[2] = { 0.0, 0.0 };
+    for( uint64_t k = 0; k < nforces && in.ok; ++k )
+    {
+      const uint64_t len = in.val<size_t>();
+      in.take( len );
+      double gk[2] = { 0.0, 0.0 };
+      in.doubles( gk, 2 );
+      g[0] += gk[0]; g[1] += gk[1];                      // forces accumulate
+    }
+    if( !in.ok ) { why = "the snapshot ends early"; }
+    else { n = static_cast<unsigned>( nb ); setMasses( mass.data(), n, 2 ); setGravity( g[0], g[1], 0.0 ); }
+  }
+  else if( layout == RIGIDBODY2D )
+  {
+    sg_snapshot::Rb2dState st;
+    if( sg_snapshot::parse( in, st, &why ) == 0 ) { n = st.n; setMasses( st.M.data(), n, 3 ); setGravity( st.g[0], st.g[1], 0.0 ); } // M = diag( m, m, I ) per body
+  }
+  else
+  {
+    sg_snapshot::Rb3dState st;
+    if( sg_snapshot::parse( in, st, &why ) == 0 ) { n = st.n; setMasses( st.m.data(), n, 1 ); setGravity( st.g[0], st.g[1], st.g[2] ); }
+  }
+  if( why[0] != '\0' )
+  {
+    std::cerr << who << ": " << why << ". Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+  return n;
+}
+
 GpuBall2DBackend::GpuBall2DBackend( const int device )
 : m_ctx( nullptr )
 , m_nbodies( 0 )
@@ -179,35 +232,7 @@ void GpuBall2DBackend::deserializeState( std::istream& input_stream )
   // the snapshot is self-delimiting only to its parser: hand over the rest of the stream (Ball2DSim::deserialize reads the state last, Ball2DSim.cpp:800-807)
   const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
   check( sg_ball2d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_ball2d_state_deserialize" );
-  // the library accepted the stream, so the layout is Ball2DState's (ball2d/Ball2DState.cpp:259-272): q, v, r, fixed, M, Minv, drums, planes, portals, forces.
-  // Tell the guard what the device now integrates with: the masses ( M's values, two per ball ) and the summed gravity.
-  sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf.data() ), buf.size(), 0, true };
-  const uint64_t nq = uint64_t( in.val<long long>() ), n = nq / 2;
-  in.take( nq * 8 );                                   // q
-  in.take( 8 + nq * 8 );                               // v
-  in.take( 8 + n * 8 );                                // r
-  in.take( 8 + n );                                    // fixed
-  in.take( 24 + nq * 4 + ( nq + 1 ) * 4 );             // M: header, inner, outer
-  std::vector<double> mass( nq );
-  in.doubles( mass.data(), nq );
-  in.take( 24 + nq * 4 + ( nq + 1 ) * 4 + nq * 8 );    // Minv
-  const uint64_t ndrums = in.val<size_t>(); in.take( ndrums * 24 );
-  const uint64_t nplanes = in.val<size_t>(); in.take( nplanes * 64 );
-  const uint64_t nportals = in.val<size_t>(); in.take( nportals * ( 2 * 64 + 24 ) );
-  const uint64_t nforces = in.val<size_t>();
-  double g[2] = { 0.0, 0.0 };
-  for( uint64_t k = 0; k < nforces && in.ok; ++k )
-  {
-    const uint64_t len = in.val<size_t>();
-    in.take( len );
-    double gk[2] = { 0.0, 0.0 };
-    in.doubles( gk, 2 );
-    g[0] += gk[0]; g[1] += gk[1];
-  }
-  if( !in.ok ) { std::cerr << "GpuBall2DBackend::deserializeState: the snapshot ends early. Exiting." << std::endl; std::exit( EXIT_FAILURE ); }
-  m_nbodies = static_cast<unsigned>( n );
-  m_guard.setMasses( mass.data(), m_nbodies, 2 );
-  m_guard.setGravity( g[0], g[1], 0.0 );
+  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::BALL2D, buf.data(), buf.size(), "GpuBall2DBackend::deserializeState" );
 }
 
 void GpuBall2DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps )
@@ -513,13 +538,7 @@ void GpuRigidBody3DBackend::deserializeState( std::istream& input_stream, const 
 {
   const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
   check( sg_rb3d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_rb3d_state_deserialize" );
-  sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf.data() ), buf.size(), 0, true };
-  sg_snapshot::Rb3dState st;
-  const char* why = "";
-  if( sg_snapshot::parse( in, st, &why ) != 0 ) { std::cerr << "GpuRigidBody3DBackend::deserializeState: " << why << ". Exiting." << std::endl; std::exit( EXIT_FAILURE ); }
-  m_nbodies = st.n;
-  m_guard.setMasses( st.m.data(), m_nbodies, 1 );   // what the device now integrates with
-  m_guard.setGravity( st.g[0], st.g[1], st.g[2] );
+  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::RIGIDBODY3D, buf.data(), buf.size(), "GpuRigidBody3DBackend::deserializeState" );
   m_m_updated = from_running_simulation;
 }
 
@@ -679,13 +698,7 @@ void GpuRigidBody2DBackend::deserializeState( std::istream& input_stream )
   // state, RigidBody2DSim.cpp:1147-1152: split the stream before calling this where a cache follows)
   const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
   check( sg_rb2d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_rb2d_state_deserialize" );
-  sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf.data() ), buf.size(), 0, true };
-  sg_snapshot::Rb2dState st;
-  const char* why = "";
-  if( sg_snapshot::parse( in, st, &why ) != 0 ) { std::cerr << "GpuRigidBody2DBackend::deserializeState: " << why << ". Exiting." << std::endl; std::exit( EXIT_FAILURE ); }
-  m_nbodies = st.n;
-  m_guard.setMasses( st.M.data(), m_nbodies, 3 );   // what the device now integrates with
-  m_guard.setGravity( st.g[0], st.g[1], 0.0 );
+  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::RIGIDBODY2D, buf.data(), buf.size(), "GpuRigidBody2DBackend::deserializeState" );
 }
 
 void GpuRB2DSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )

@@ -59,6 +59,8 @@ public:
   void setMasses( const double* m, const unsigned n, const unsigned stride ) { m_mass.resize( n ); for( unsigned i = 0; i < n; ++i ) { m_mass[i] = m[std::size_t( i ) * stride]; } m_checked = false; }
   void setGravity( const double gx, const double gy, const double gz ) { m_g[0] = gx; m_g[1] = gy; m_g[2] = gz; m_checked = false; }
   void verify( FlowableSystem& fsys, const VectorXs& q0, const VectorXs& v0, const scalar& t, const Layout layout, const char* who );
+  // masses and gravity from a state snapshot the library has accepted (the three *State::serialize layouts); returns the body count
+  unsigned configureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, const char* who );
 private:
   std::vector<double> m_mass;
   double m_g[3] = { 0.0, 0.0, 0.0 };
