@@ -468,13 +468,18 @@ int sg_rb3d_upload( sg_ctx* ctx, const double* q, const double* v );
 int sg_rb3d_step( sg_ctx* ctx, int map_kind, double dt, sg_contacts* out );
 int sg_rb3d_fetch( sg_ctx* ctx, uint32_t out_flags, double* q1, double* v1, sg_contacts* out );
 /* State I/O at the seam: RigidBody3DState's binary snapshot (rigidbody3d/RigidBody3DState.cpp:586-668, scisim/Utilities.h:43-94,
-   scisim/Math/MathUtilities.h:42-60, MathUtilities.cpp:142-177), byte for byte, for scenes of spheres and boxes (a triangle mesh's snapshot holds its
-   whole input file, RigidBodyTriangleMesh.cpp:215-232, which never crosses this ABI: SG_ERR_UNSUPPORTED).
+   scisim/Math/MathUtilities.h:42-60, MathUtilities.cpp:142-177), byte for byte, for scenes of spheres, boxes and triangle meshes (a mesh's snapshot holds its
+   whole input file, RigidBodyTriangleMesh.cpp:215-232: attach it with sg_rb3d_set_mesh_snapshot; without it serialize returns SG_ERR_UNSUPPORTED).
    serialize   which = 0: ( q0, v0 ) as uploaded, 1: ( q1, v1 ) of the last flow / step.  m_updated = 0: the world-space blocks of M / Minv as
                RigidBody3DState's constructor stores them (a state that no flow has touched), 1: as updateMandMinv leaves them (see SG_MAP_M_UPDATED).
                buf = NULL: *bytes <- size needed
    deserialize configures geometry, bodies, gravity, planes, cylinders and portals from a snapshot and uploads ( q, v ) */
 int sg_rb3d_state_serialize( sg_ctx* ctx, int which, int m_updated, void* buf, uint64_t cap, uint64_t* bytes );
+/* A triangle mesh's own record for the snapshot: the bytes RigidBodyTriangleMesh::serialize writes (rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp:215-232, type byte
+   included) for mesh `mesh_index` of sg_rb3d_add_mesh.  The record holds what only the caller has (file name, faces, volume, moments); the library checks that
+   it is well formed and sized like the mesh, keeps it, and writes it back verbatim.  sg_rb3d_state_deserialize adds the meshes of a snapshot
+   (RigidBodyTriangleMesh( std::istream& ), RigidBodyTriangleMesh.cpp:105-129) and keeps their records itself. */
+int sg_rb3d_set_mesh_snapshot( sg_ctx* ctx, uint32_t mesh_index, const void* record, uint64_t bytes );
 int sg_rb3d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes );
 /* Diagnostics for the mesh narrow phase: how many sample sweeps (one per direction of a mesh-mesh pair,
    MeshMeshUtilities.cpp:10-65) read the distance field from a TMA-staged shared-memory brick and how many read

@@ -159,6 +159,16 @@ void* ref_rb3d_mesh_create( const uint32_t nverts, const double* verts, const ui
   return new RigidBodyTriangleMesh{ stm };
 }
 void ref_rb3d_mesh_destroy( void* m ) { delete static_cast<RigidBodyTriangleMesh*>( m ); }
+// RigidBodyTriangleMesh::serialize (rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp:215-232): the mesh's own record of a state snapshot -- what a caller hands to
+// sg_rb3d_set_mesh_snapshot.  Returns its length; the bytes are written when they fit cap.
+uint64_t ref_rb3d_mesh_serialize( const void* m, void* buf, const uint64_t cap )
+{
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  static_cast<const RigidBodyTriangleMesh*>( m )->serialize( stm );
+  const std::string bytes = stm.str();
+  if( bytes.size() <= cap ) { std::memcpy( buf, bytes.data(), bytes.size() ); }
+  return bytes.size();
+}
 static Matrix33sr toR( const double* R )
 {
   Matrix33sr Rm;

@@ -105,6 +105,7 @@ def load():
         "sg_ball2d_state_deserialize": (C.c_int, [vp, vp, C.c_uint64]),
         "sg_rb3d_state_serialize": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64)]),
         "sg_rb3d_state_deserialize": (C.c_int, [vp, vp, C.c_uint64]),
+        "sg_rb3d_set_mesh_snapshot": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64]),
         "sg_rb2d_state_serialize": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64)]),
         "sg_rb2d_state_deserialize": (C.c_int, [vp, vp, C.c_uint64]),
         "sg_ball2d_fetch_state": (C.c_int, [vp, vp, vp]),

@@ -1340,6 +1340,7 @@ struct Rb3dData
   std::vector<uint32_t> h_geo_of_body; // host copies of sg_rb3d_set_bodies' tables (the state snapshot writes them back)
   std::vector<uint8_t> h_fixed;
   std::vector<MeshHost*> meshes;
+  std::vector<std::vector<unsigned char>> mesh_record; // per mesh: its RigidBodyTriangleMesh::serialize record (sg_rb3d_set_mesh_snapshot), written back verbatim by the state snapshot
   DevBuf d_meshes; // MeshDev[]
   DevBuf mesh_stats;
   DevBuf btype, bparam, bmesh, radius, flags, mass, I0;
@@ -2470,6 +2471,28 @@ int sg_rb3d_slab_detect( sg_ctx* ctx, sg_contacts* out, uint32_t* ghosts_out )
   return SG_OK;
 }
 
+// A triangle mesh's own record for the state snapshot (RigidBodyTriangleMesh::serialize, rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp:215-232; type byte
+// included).  It holds what this library has no use for (file name, faces, volume, moments) next to what sg_rb3d_add_mesh was given; it is checked to be a
+// well-formed record whose arrays have the sizes of mesh `mesh_index`, kept on the host, and written back verbatim.
+int sg_rb3d_set_mesh_snapshot( sg_ctx* ctx, uint32_t mesh_index, const void* record, uint64_t bytes )
+{
+  if( ctx == nullptr ) { return SG_ERR_INVALID; }
+  Rb3dData* d = rb3d_data( ctx );
+  if( mesh_index >= d->meshes.size() ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_mesh_snapshot: mesh %u of %zu", mesh_index, d->meshes.size() ); }
+  if( record == nullptr || bytes == 0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_mesh_snapshot: empty record" ); }
+  sg_snapshot::Source in{ static_cast<const unsigned char*>( record ), bytes, 0, true };
+  sg_snapshot::Rb3dState::Mesh mm;
+  if( in.val<unsigned char>() != 3 || !sg_snapshot::take_mesh( in, mm ) || in.n != bytes ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_mesh_snapshot: not a RigidBodyTriangleMesh record of %llu bytes", ( unsigned long long )( bytes ) ); }
+  const MeshDev& dev = d->meshes[mesh_index]->dev;
+  if( mm.verts.size() / 3 != dev.nverts || mm.samples.size() / 3 != dev.nsamples || mm.hull.size() / 3 != dev.nhull || mm.dims[0] != dev.dims[0] || mm.dims[1] != dev.dims[1] || mm.dims[2] != dev.dims[2] )
+  {
+    return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_set_mesh_snapshot: the record's vertex, sample, hull or grid sizes are not those of mesh %u", mesh_index );
+  }
+  if( d->mesh_record.size() < d->meshes.size() ) { d->mesh_record.resize( d->meshes.size() ); }
+  d->mesh_record[mesh_index].assign( static_cast<const unsigned char*>( record ), static_cast<const unsigned char*>( record ) + bytes );
+  return SG_OK;
+}
+
 // ---- state I/O at the seam: RigidBody3DState's binary snapshot (rigidbody3d/RigidBody3DState.cpp:586-668), sg_rb3d_snapshot.h ----
 int sg_rb3d_state_serialize( sg_ctx* ctx, int which, int m_updated, void* buf, uint64_t cap, uint64_t* bytes )
 {
@@ -2477,7 +2500,14 @@ int sg_rb3d_state_serialize( sg_ctx* ctx, int which, int m_updated, void* buf, u
   Rb3dData* d = rb3d_data( ctx );
   if( d->slab.on ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: a slab holds part of a scene; serialise through the owner of the whole state" ); }
   if( which == 1 && !d->q1_valid && d->n > 0 ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_state_serialize: which = 1 without a preceding sg_rb3d_flow / sg_rb3d_step on this context" ); }
-  for( const uint32_t t : d->geo_type ) { if( t != SG_GEO_BOX && t != SG_GEO_SPHERE ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: a triangle mesh's snapshot holds its whole input file (RigidBodyTriangleMesh.cpp:215-232), which never crosses this ABI" ); } }
+  for( size_t k = 0; k < d->geo_type.size(); ++k )
+  {
+    const uint32_t t = d->geo_type[k];
+    if( t == SG_GEO_BOX || t == SG_GEO_SPHERE ) { continue; }
+    // a triangle mesh's snapshot holds its whole input file (names, faces, volume ...: RigidBodyTriangleMesh.cpp:215-232): written back from the record the caller attached
+    const bool have = t == SG_GEO_MESH && d->geo_mesh[k] < d->mesh_record.size() && !d->mesh_record[d->geo_mesh[k]].empty();
+    if( !have ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: geometry %zu is a triangle mesh without its record (sg_rb3d_set_mesh_snapshot), or a geometry this path does not hold", k ); }
+  }
   SG_CUDA( ctx, cudaSetDevice( ctx->device ) );
   const uint32_t n = d->n;
   sg_snapshot::Rb3dState s;
@@ -2515,7 +2545,12 @@ int sg_rb3d_state_serialize( sg_ctx* ctx, int which, int m_updated, void* buf, u
   }
   s.fixed = d->h_fixed; s.geo_of_body = d->h_geo_of_body;
   s.geo_type.resize( d->geo_type.size() );
-  for( size_t k = 0; k < d->geo_type.size(); ++k ) { s.geo_type[k] = ( d->geo_type[k] == SG_GEO_BOX ) ? 0u : 1u; }
+  s.geo_blob.assign( d->geo_type.size(), std::vector<unsigned char>() );
+  for( size_t k = 0; k < d->geo_type.size(); ++k )
+  {
+    s.geo_type[k] = ( d->geo_type[k] == SG_GEO_BOX ) ? 0u : ( d->geo_type[k] == SG_GEO_SPHERE ) ? 1u : 3u;
+    if( s.geo_type[k] == 3u ) { s.geo_blob[k] = d->mesh_record[d->geo_mesh[k]]; }
+  }
   s.geo_r = d->geo_r; s.geo_half = d->geo_half;
   for( int k = 0; k < 3; ++k ) { s.g[k] = d->g[k]; }
   for( uint32_t p = 0; p < d->planes.n; ++p ) { for( int k = 0; k < 3; ++k ) { s.plane_x.push_back( d->planes.x[p][k] ); s.plane_n.push_back( d->planes.nrm[p][k] ); } }
@@ -2529,7 +2564,7 @@ int sg_rb3d_state_serialize( sg_ctx* ctx, int which, int m_updated, void* buf, u
     }
   }
   sg_snapshot::Sink out{ static_cast<unsigned char*>( buf ), cap, 0 };
-  if( !sg_snapshot::serialize( s, out ) ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: a geometry that is neither box nor sphere" ); }
+  if( !sg_snapshot::serialize( s, out ) ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_serialize: a geometry that is neither box, sphere nor a mesh with its record" ); }
   *bytes = out.n;
   if( buf != nullptr && out.n > cap ) { return sg_fail( ctx, SG_ERR_INVALID, "sg_rb3d_state_serialize: buffer of %llu bytes, %llu needed", ( unsigned long long )( cap ), ( unsigned long long )( out.n ) ); }
   return SG_OK;
@@ -2548,8 +2583,20 @@ int sg_rb3d_state_deserialize( sg_ctx* ctx, const void* buf, uint64_t bytes )
   if( s.plane_x.size() / 3 > SG_MAX_PLANES || s.cyl_r.size() > SG_MAX_CYLINDERS || s.portal_mult.size() / 3 > SG_MAX_PORTALS ) { return sg_fail( ctx, SG_ERR_UNSUPPORTED, "sg_rb3d_state_deserialize: more planes, cylinders or portals than this library holds" ); }
   const uint32_t ngeo = uint32_t( s.geo_type.size() );
   std::vector<uint32_t> type( ngeo ), mesh( ngeo, 0u );
-  for( uint32_t k = 0; k < ngeo; ++k ) { type[k] = ( s.geo_type[k] == 0u ) ? uint32_t( SG_GEO_BOX ) : uint32_t( SG_GEO_SPHERE ); }
-  int rc = sg_rb3d_set_geometry( ctx, ngeo, type.data(), s.geo_r.data(), s.geo_half.data(), mesh.data() );
+  int rc = SG_OK;
+  for( uint32_t k = 0; k < ngeo; ++k )
+  {
+    type[k] = ( s.geo_type[k] == 0u ) ? uint32_t( SG_GEO_BOX ) : ( s.geo_type[k] == 1u ) ? uint32_t( SG_GEO_SPHERE ) : uint32_t( SG_GEO_MESH );
+    if( s.geo_type[k] != 3u ) { continue; }
+    // RigidBodyTriangleMesh( std::istream& ) (RigidBodyTriangleMesh.cpp:105-129): the mesh as stored; its record is kept for the next snapshot
+    const sg_snapshot::Rb3dState::Mesh& mm = s.mesh[k];
+    rc = sg_rb3d_add_mesh( ctx, uint32_t( mm.verts.size() / 3 ), mm.verts.data(), uint32_t( mm.samples.size() / 3 ), mm.samples.data(), uint32_t( mm.hull.size() / 3 ), mm.hull.data(),
+                           mm.delta, mm.dims, mm.origin, mm.sdf.data(), &mesh[k] );
+    if( rc != SG_OK ) { return rc; }
+    rc = sg_rb3d_set_mesh_snapshot( ctx, mesh[k], s.geo_blob[k].data(), s.geo_blob[k].size() );
+    if( rc != SG_OK ) { return rc; }
+  }
+  rc = sg_rb3d_set_geometry( ctx, ngeo, type.data(), s.geo_r.data(), s.geo_half.data(), mesh.data() );
   if( rc != SG_OK ) { return rc; }
   rc = sg_rb3d_set_bodies( ctx, s.n, s.geo_of_body.data(), s.fixed.data(), s.m.data(), s.I0.data() );
   if( rc != SG_OK ) { return rc; }

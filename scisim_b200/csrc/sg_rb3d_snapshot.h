@@ -9,8 +9,13 @@
 //   M, Minv                sparse 6N x 6N, 12N non-zeros: the 3N linear entries, then per body the 3 x 3 world-space block, column by column
 //                          ( sparse = rows, cols, nnz as Eigen::Index; nnz inner indices, cols + 1 outer indices as int; nnz doubles )
 //   fixed                  size_t count + one byte per body
-//   geometry               size_t count + per geometry: RigidBodyGeometryType ( uint8: BOX 0, SPHERE 1, TRIANGLE_MESH 3 ) then half widths (3) / radius
-//                          ( a mesh writes its whole input file -- names, faces, volume ... -- which never crosses the C ABI: SG_ERR_UNSUPPORTED )
+//   geometry               size_t count + per geometry: RigidBodyGeometryType ( uint8: BOX 0, SPHERE 1, TRIANGLE_MESH 3 ) then half widths (3) / radius /
+//                          the mesh's whole record (RigidBodyTriangleMesh::serialize, rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp:215-232): file name
+//                          ( size_t length + chars ), vertices and faces ( Eigen::Index columns + 3 per column; doubles / unsigned ), volume, I / rho (3),
+//                          centre of mass (3), R (9), surface samples and convex-hull vertices ( as the vertices ), cell delta (3), grid dimensions
+//                          ( 3 unsigned ), grid origin (3), signed distances ( Eigen::Index rows + doubles, x fastest ), grid end (3).  The library keeps a
+//                          mesh's record as the caller handed it over (sg_rb3d_set_mesh_snapshot) and writes it back verbatim; reading one yields the
+//                          arrays sg_rb3d_add_mesh takes
 //   geometry indices       size_t count + unsigned per body
 //   forces                 size_t count + { size_t length + "near_earth_gravity", g (3 doubles) }
 //   static planes          size_t count + { x, n, v, omega (3 doubles each) }
@@ -52,8 +57,13 @@ struct Rb3dState
   std::vector<double> I, Iinv;         // 9 n each: the world-space blocks as M / Minv store them (column-major values of each 3 x 3 block)
   std::vector<uint8_t> fixed;          // n
   std::vector<uint32_t> geo_of_body;   // n
-  std::vector<uint32_t> geo_type;      // 0 box, 1 sphere
+  std::vector<uint32_t> geo_type;      // 0 box, 1 sphere, 3 triangle mesh
   std::vector<double> geo_r, geo_half; // ngeo, 3 ngeo
+  // triangle meshes: geo_blob[k] = the record of geometry k as the reference writes it, type byte included (empty for boxes and spheres; may be left
+  // unsized when there is no mesh); parse() also fills mesh[k] with what sg_rb3d_add_mesh takes
+  struct Mesh { std::vector<double> verts, samples, hull, sdf; double delta[3] = { 0.0, 0.0, 0.0 }, origin[3] = { 0.0, 0.0, 0.0 }; uint32_t dims[3] = { 0u, 0u, 0u }; };
+  std::vector<std::vector<unsigned char>> geo_blob;
+  std::vector<Mesh> mesh;
   double g[3] = { 0.0, 0.0, 0.0 };
   std::vector<double> plane_x, plane_n;            // 3 each
   std::vector<double> cyl_x, cyl_axis, cyl_r;      // 3, 3, 1 each
@@ -89,7 +99,7 @@ inline void put_plane( Sink& out, const double* x, const double* nrm )
   for( int k = 0; k < 6; ++k ) { out.val<double>( 0.0 ); } // m_v, m_omega: planes of this path do not move
 }
 
-// returns false when the state cannot be written in the reference's format (a geometry that is neither box nor sphere)
+// returns false when the state cannot be written in the reference's format (a geometry that is neither box nor sphere nor a mesh with its record)
 inline bool serialize( const Rb3dState& s, Sink& out )
 {
   const uint32_t n = s.n;
@@ -107,6 +117,7 @@ inline bool serialize( const Rb3dState& s, Sink& out )
   {
     if( s.geo_type[k] == 0u ) { out.val<unsigned char>( 0 ); out.put( &s.geo_half[3 * k], 24 ); }
     else if( s.geo_type[k] == 1u ) { out.val<unsigned char>( 1 ); out.val<double>( s.geo_r[k] ); }
+    else if( s.geo_type[k] == 3u && k < s.geo_blob.size() && !s.geo_blob[k].empty() ) { out.put( s.geo_blob[k].data(), s.geo_blob[k].size() ); }
     else { return false; }
   }
   out.val<size_t>( size_t( n ) );
@@ -139,6 +150,39 @@ inline bool serialize( const Rb3dState& s, Sink& out )
   for( int k = 0; k < 3; ++k ) { out.val<double>( std::numeric_limits<double>::min() ); }   // RigidBody3DState.cpp:38-39
   for( int k = 0; k < 3; ++k ) { out.val<double>( std::numeric_limits<double>::max() ); }
   return true;
+}
+
+// 3 x ncols doubles behind an Eigen::Index column count (a Matrix3Xsc)
+inline bool take_matrix3x( Source& in, std::vector<double>& out )
+{
+  const long long ncols = in.val<long long>();
+  if( !in.ok || ncols < 0 || uint64_t( ncols ) > ( in.cap - in.n ) / 24 ) { in.ok = false; return false; }
+  out.resize( size_t( 3 ) * size_t( ncols ) );
+  in.doubles( out.data(), uint64_t( 3 ) * uint64_t( ncols ) );
+  return in.ok;
+}
+
+// a triangle mesh's record after its type byte (RigidBodyTriangleMesh( std::istream& ), RigidBodyTriangleMesh.cpp:105-129)
+inline bool take_mesh( Source& in, Rb3dState::Mesh& m )
+{
+  const size_t len = in.val<size_t>();
+  if( !in.ok || len > in.cap - in.n ) { in.ok = false; return false; }
+  in.take( len );                                                          // m_input_file_name
+  if( !take_matrix3x( in, m.verts ) ) { return false; }
+  const long long nfaces = in.val<long long>();
+  if( !in.ok || nfaces < 0 || uint64_t( nfaces ) > ( in.cap - in.n ) / 12 ) { in.ok = false; return false; }
+  in.take( uint64_t( nfaces ) * 12 );                                      // m_faces
+  in.take( 8 + 24 + 24 + 72 );                                             // m_volume, m_I_on_rho, m_center_of_mass, m_R
+  if( !take_matrix3x( in, m.samples ) || !take_matrix3x( in, m.hull ) ) { return false; }
+  in.doubles( m.delta, 3 );
+  for( int k = 0; k < 3; ++k ) { m.dims[k] = in.val<unsigned>(); }
+  in.doubles( m.origin, 3 );
+  const long long nsd = in.val<long long>();
+  if( !in.ok || nsd < 0 || uint64_t( nsd ) > ( in.cap - in.n ) / 8 || uint64_t( nsd ) != uint64_t( m.dims[0] ) * m.dims[1] * m.dims[2] ) { in.ok = false; return false; }
+  m.sdf.resize( size_t( nsd ) );
+  in.doubles( m.sdf.data(), uint64_t( nsd ) );
+  in.take( 24 );                                                           // m_grid_end: origin + ( dims - 1 ) * delta, recomputed by sg_rb3d_add_mesh
+  return in.ok;
 }
 
 inline bool take_plane( Source& in, double* x, double* nrm )
@@ -180,12 +224,21 @@ inline int parse( Source& in, Rb3dState& s, const char** why )
   const size_t ngeo = in.val<size_t>();
   if( !in.ok || ngeo > ( 1u << 24 ) ) { *why = "bad geometry count"; return 1; }
   s.geo_type.assign( ngeo, 0u ); s.geo_r.assign( ngeo, 0.0 ); s.geo_half.assign( 3 * ngeo, 0.0 );
+  s.geo_blob.assign( ngeo, std::vector<unsigned char>() ); s.mesh.assign( ngeo, Rb3dState::Mesh() );
   for( size_t k = 0; k < ngeo; ++k )
   {
+    const uint64_t at = in.n;
     const unsigned char t = in.val<unsigned char>();
+    if( !in.ok ) { *why = "truncated"; return 1; }
     if( t == 0 ) { s.geo_type[k] = 0u; in.doubles( &s.geo_half[3 * k], 3 ); }
     else if( t == 1 ) { s.geo_type[k] = 1u; s.geo_r[k] = in.val<double>(); }
-    else { *why = "a geometry other than box or sphere (a mesh's snapshot holds its whole input file)"; return 2; }
+    else if( t == 3 )
+    {
+      s.geo_type[k] = 3u;
+      if( !take_mesh( in, s.mesh[k] ) ) { *why = "a malformed or truncated triangle-mesh record"; return 1; }
+      s.geo_blob[k].assign( in.p + at, in.p + in.n );
+    }
+    else { *why = "a geometry other than box, sphere or triangle mesh (staples are not on this path)"; return 2; }
   }
   if( in.val<size_t>() != size_t( n ) ) { *why = "geometry indices of another length"; return 1; }
   s.geo_of_body.resize( n );

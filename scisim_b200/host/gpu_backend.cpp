@@ -461,6 +461,11 @@ uint32_t GpuRigidBody3DBackend::addMesh( const std::vector<double>& verts, const
   return index;
 }
 
+void GpuRigidBody3DBackend::setMeshSnapshot( const uint32_t mesh_index, const std::string& record )
+{
+  check( sg_rb3d_set_mesh_snapshot( m_ctx, mesh_index, record.data(), record.size() ), "sg_rb3d_set_mesh_snapshot" );
+}
+
 void GpuRigidBody3DBackend::setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& m, const VectorXs& I0 )
 {
   m_nbodies = static_cast<unsigned>( geo_of_body.size() );

@@ -269,6 +269,8 @@ public:
   // reference), signed-distance grid (cell_delta, dimensions, origin, values with x fastest)
   uint32_t addMesh( const std::vector<double>& verts, const std::vector<double>& samples, const std::vector<double>& hull, const double cell_delta[3], const uint32_t dims[3],
                     const double origin[3], const std::vector<double>& sdf );
+  // the mesh's own snapshot record: what RigidBodyTriangleMesh::serialize( stm ) writes for it (RigidBodyTriangleMesh.cpp:215-232); serializeState writes it back
+  void setMeshSnapshot( const uint32_t mesh_index, const std::string& record );
   // per body: geometry index, isKinematicallyScripted, total mass and body-frame inertia (the diagonals of M0)
   void setBodies( const std::vector<uint32_t>& geo_of_body, const std::vector<uint8_t>& fixed, const VectorXs& m, const VectorXs& I0 );
   void setGravity( const double gx, const double gy, const double gz );

@@ -574,11 +574,18 @@ class RigidBody3DSim:
         self.ctx = ctx or Context(device)
         self.state = st = state
         lib, h = self.ctx.lib, self.ctx.h
+        # a context numbers its meshes in the order they were added over its whole life: the state's own mesh numbers go through the indices add_mesh returns
+        self.mesh_index = []
         for mesh in st.meshes:
             idx = C.c_uint32()
             self.ctx.check(lib.sg_rb3d_add_mesh(h, mesh.verts.shape[0], _ptr(mesh.verts), mesh.samples.shape[0], _ptr(mesh.samples), mesh.hull.shape[0], _ptr(mesh.hull),
                                                 _ptr(mesh.cell_delta), _ptr(mesh.dims), _ptr(mesh.origin), _ptr(mesh.sdf), C.byref(idx)))
-        self.ctx.check(lib.sg_rb3d_set_geometry(h, st.geo_type.shape[0], _ptr(st.geo_type), _ptr(st.geo_r), _ptr(st.geo_half), _ptr(st.geo_mesh)))
+            self.mesh_index.append(int(idx.value))
+        geo_mesh = np.ascontiguousarray(st.geo_mesh, dtype=np.uint32).copy()
+        for k in range(geo_mesh.shape[0]):
+            if int(st.geo_type[k]) == 3 and int(geo_mesh[k]) < len(self.mesh_index):   # SG_GEO_MESH
+                geo_mesh[k] = self.mesh_index[int(geo_mesh[k])]
+        self.ctx.check(lib.sg_rb3d_set_geometry(h, st.geo_type.shape[0], _ptr(st.geo_type), _ptr(st.geo_r), _ptr(st.geo_half), _ptr(geo_mesh)))
         self.ctx.check(lib.sg_rb3d_set_bodies(h, st.nbodies(), _ptr(st.geo_of_body), _ptr(st.fixed), _ptr(st.m), _ptr(st.I0)))
         self.ctx.check(lib.sg_rb3d_set_gravity(h, _ptr(st.g)))
         self.ctx.check(lib.sg_rb3d_set_planes(h, st.plane_x.shape[0], _ptr(st.plane_x), _ptr(st.plane_n)))
@@ -596,6 +603,12 @@ class RigidBody3DSim:
 
     def name(self):
         return "rigid_body_3d"
+
+    def setMeshSnapshot(self, mesh, record):
+        """The bytes RigidBodyTriangleMesh::serialize writes for mesh number `mesh` of this sim's state (rigidbody3d/Geometry/RigidBodyTriangleMesh.cpp:215-232):
+        kept by the library and written back verbatim by serializeState."""
+        buf = np.frombuffer(record, dtype=np.uint8).copy()
+        self.ctx.check(self.ctx.lib.sg_rb3d_set_mesh_snapshot(self.ctx.h, self.mesh_index[int(mesh)], _ptr(buf), buf.shape[0]))
 
     def updateMandMinv(self, q=None):
         """RigidBody3DState::updateMandMinv (rigidbody3d/RigidBody3DState.cpp:428-462): returns ( I blocks, Iinv blocks ), 9 doubles per
@@ -636,6 +649,7 @@ class RigidBody3DSim:
         sim.state = RigidBody3DState([1], [1.0], [[0.0, 0.0, 0.0]], [0], [], np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.ones(n), np.ones((n, 3)), [0.0, 0.0, 0.0],
                                      np.zeros((0, 3)), np.zeros((0, 3)))
         sim.m_updated = bool(m_updated)
+        sim.mesh_index = []   # the library re-added the snapshot's meshes and keeps their records itself
         return sim
 
     # ---- portals (rigidbody3d/RigidBody3DSim.cpp:642-663) ----

@@ -208,6 +208,16 @@ class RefRB3DSim:
             for m in self.meshes:
                 self.lib.ref_rb3d_mesh_destroy(m)
 
+    def mesh_record(self, k):
+        """RigidBodyTriangleMesh::serialize of mesh k: the mesh's own record of a state snapshot (what sg_rb3d_set_mesh_snapshot takes)."""
+        f = self.lib.ref_rb3d_mesh_serialize
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        need = int(f(self.meshes[k], None, 0))
+        buf = np.zeros(need, dtype=np.uint8)
+        assert int(f(self.meshes[k], vp(buf), need)) == need
+        return buf.tobytes()
+
     def serialize_state(self, q=None, v=None, update=False):
         """RigidBody3DState::serialize of the simulation's state, after replacing ( q, v ) and / or running updateMandMinv."""
         f = self.lib.ref_rb3d_sim_serialize_state

@@ -252,3 +252,78 @@ def test_replay_rb2d_state_io_gpu_tests(monkeypatch, oracle, tmp_path_factory):
     for scene in ("circles_boxes", "kinematic_circles", "lees_edwards"):
         m.test_rb2d_snapshot_is_the_references_own_and_resumes(oracle, None, scene)
     m.test_rb2d_snapshot_refusals(None)
+
+
+class OracleBackedRB3DWithSnapshots:
+    """RigidBody3DSim's resident stepping answered by the oracle; its snapshots written by the product's own writer (scisim_b200/csrc/sg_rb3d_snapshot.h compiled
+    for the host, as in tests/test_rb3d_snapshot_cpu.py) with the mesh records the test attaches; a restore re-reads ( q, v ) from the bytes and keeps the scene."""
+
+    def __init__(self, s, harness, records=None, m_updated=False):
+        from tests import oracle_binding as ob
+        self.s, self.harness, self.o, self.m_updated, self.q1 = s, harness, ob.RB3DOracle(s), m_updated, None
+        self.records = dict(records or {})
+
+    def setMeshSnapshot(self, k, record):
+        m = self.s["meshes"][k]
+        want = 1 + 8 + 4 + 8 + 24 * m["verts"].shape[0] + 8 + 8 + 24 + 24 + 72 + 8 + 24 * m["samples"].shape[0] + 8 + 24 * m["hull"].shape[0] + 24 + 12 + 24 + 8 + 8 * int(np.prod(m["dims"])) + 24
+        if len(record) != want:   # the reference shim names its meshes "shim" ( 4 characters ) and gives them no faces
+            raise sb.SciSimB200Error("not a whole record (replay)")
+        self.records[k] = record
+
+    def upload(self, q, v):
+        self.q, self.v, self.q1 = np.array(q, dtype=np.float64).ravel(), np.array(v, dtype=np.float64).ravel(), None
+
+    def updateMandMinv(self, q=None):
+        self.m_updated = True
+
+    def step(self, umap, dt):
+        self.q1, self.v1 = self.o.flow(umap.kind, self.q, self.v, dt, m_updated=self.m_updated)
+        ref = self.o.active_set(self.q, self.q1, "grid")
+        assert ref["supported"]
+        na = ref["type"].shape[0]
+        self.res = SimpleNamespace(n_candidates=ref["candidates"].shape[0], n_active=na, **{k: ref[k] for k in ("type", "i", "j", "aux", "n", "p", "depth")})
+        return self.res.n_candidates, na
+
+    def fetch(self):
+        return self.q1, self.v1, self.res
+
+    def serializeState(self, which=1, m_updated=None):
+        from tests.test_rb3d_snapshot_cpu import _transposed, product_bytes
+        if m_updated is None:
+            m_updated = True if which == 1 else self.m_updated
+        q, v = (self.q, self.v) if which == 0 else (self.q1, self.v1)
+        n = self.s["geo_of_body"].shape[0]
+        I, Ii = self.o.update_m_and_minv(q)
+        blocks = (I, Ii) if m_updated else (_transposed(I, n), _transposed(Ii, n))
+        recs = [self.records.get(int(self.s["geo_mesh"][k]), b"") if int(self.s["geo_type"][k]) == 3 else b"" for k in range(len(self.s["geo_type"]))]
+        out = product_bytes(self.harness, self.s, q, v, blocks, mesh_records=recs)
+        if out is None:
+            raise sb.SciSimB200Error("a mesh without its record (replay)")
+        return out
+
+
+def test_replay_rb3d_mesh_state_io_gpu_tests(monkeypatch, oracle, tmp_path_factory):
+    import os
+    import tests.test_zzz_rb3d_mesh_state_io_gpu as m
+    from tests.test_rb3d_snapshot_cpu import harness as harness_fixture
+    if not os.path.exists(os.path.join(m.ROOT, "oracle", "_ref", "libref_rb3d.so")):
+        pytest.skip("oracle/_ref not built (the reference tree is not mounted here)")
+    lib = harness_fixture.__wrapped__(tmp_path_factory)
+    made = []
+
+    def make(s, ctx):
+        made.append(OracleBackedRB3DWithSnapshots(s, lib))
+        return made[-1]
+
+    def restore(blob, ctx):
+        src = made[-1]
+        n = int(np.frombuffer(blob[:4], dtype=np.uint32)[0])
+        sim = OracleBackedRB3DWithSnapshots(src.s, lib, records=src.records, m_updated=True)
+        sim.upload(np.frombuffer(blob[12:12 + 96 * n], dtype=np.float64), np.frombuffer(blob[20 + 96 * n:20 + 144 * n], dtype=np.float64))
+        return sim
+
+    monkeypatch.setattr(m, "_sim", make)
+    monkeypatch.setattr(m, "_restore", restore)
+    monkeypatch.setattr(m, "_context", lambda: SimpleNamespace(close=lambda: None))
+    for scene in ("meshes", "mixed"):
+        m.test_rb3d_mesh_snapshot_is_the_references_own_and_resumes(oracle, None, scene)

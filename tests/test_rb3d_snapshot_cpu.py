@@ -24,7 +24,9 @@ def harness(tmp_path_factory):
     lib = C.CDLL(out)
     V = C.c_void_p
     lib.snap_serialize.restype = C.c_uint64
-    lib.snap_serialize.argtypes = [C.c_uint32] + [V] * 8 + [C.c_uint32] + [V] * 4 + [C.c_uint32, V, V, C.c_uint32, V, V, V, C.c_uint32, V, V, V, V, V, V, C.c_uint64]
+    lib.snap_serialize.argtypes = [C.c_uint32] + [V] * 8 + [C.c_uint32] + [V] * 4 + [C.c_uint32, V, V, C.c_uint32, V, V, V, C.c_uint32, V, V, V, V, V, V, C.c_uint64, V, V]
+    lib.snap_mesh_records.restype = C.c_int
+    lib.snap_mesh_records.argtypes = [V, C.c_uint64, C.c_uint32, V, V, V, V]
     lib.snap_roundtrip.restype = C.c_int
     lib.snap_roundtrip.argtypes = [V, C.c_uint64, V, C.c_uint64, V, V, V]
     return lib
@@ -37,11 +39,12 @@ def _normalized(n):
     return n / np.sqrt(z)[:, None]
 
 
-def product_bytes(lib, s, q, v, blocks, portals=None):
+def product_bytes(lib, s, q, v, blocks, portals=None, mesh_records=None):
+    """mesh_records: per geometry, the bytes RigidBodyTriangleMesh::serialize writes for it (None / b"" for boxes and spheres)."""
     n = s["geo_of_body"].shape[0]
     u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
     I, Iinv = blocks
-    gt = u32([0 if int(t) == 0 else 1 for t in s["geo_type"]])
+    gt = u32([int(t) if int(t) in (0, 3) else 1 for t in s["geo_type"]])
     px, pn = f64(s["plane_x"]).reshape(-1, 3), _normalized(f64(s["plane_n"]).reshape(-1, 3)) if len(s["plane_x"]) else np.zeros((0, 3))
     cyl = (f64(s["cyl_x"]), _normalized(s["cyl_axis"]), f64(s["cyl_r"])) if "cyl_r" in s and len(s["cyl_r"]) else (np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
     p = portals or {"plane_a_x": np.zeros((0, 3)), "plane_a_n": np.zeros((0, 3)), "plane_b_x": np.zeros((0, 3)), "plane_b_n": np.zeros((0, 3)), "mult": np.zeros((0, 3), np.int32)}
@@ -52,10 +55,17 @@ def product_bytes(lib, s, q, v, blocks, portals=None):
          f64(px), f64(pn), f64(cyl[0]), f64(cyl[1]), f64(cyl[2]), f64(p["plane_a_x"]), f64(pan), f64(p["plane_b_x"]), f64(pbn)]
     args = [n] + [vp(a) for a in k[:8]] + [gt.shape[0]] + [vp(a) for a in k[8:12]] + [k[12].shape[0], vp(k[12]), vp(k[13]), k[16].shape[0], vp(k[14]), vp(k[15]), vp(k[16]),
                                                                                          mult.shape[0], vp(k[17]), vp(k[18]), vp(k[19]), vp(k[20]), vp(mult)]
-    need = int(lib.snap_serialize(*args, None, 0))
-    assert need > 0
+    rec = (None, None)
+    if mesh_records is not None:
+        raws = [np.frombuffer(r or b"", dtype=np.uint8).copy() for r in mesh_records]
+        ptrs = (C.c_void_p * len(raws))(*[r.ctypes.data if r.shape[0] else None for r in raws])
+        sizes = np.array([r.shape[0] for r in raws], dtype=np.uint64)
+        rec = (ptrs, vp(sizes))
+    need = int(lib.snap_serialize(*args, None, 0, *rec))
+    if need == 0:
+        return None
     buf = np.zeros(need, dtype=np.uint8)
-    assert int(lib.snap_serialize(*args, vp(buf), need)) == need
+    assert int(lib.snap_serialize(*args, vp(buf), need, *rec)) == need
     return buf.tobytes()
 
 
@@ -113,8 +123,55 @@ def test_truncated_and_foreign_snapshots_are_refused(oracle, harness):
     nb, nn, g = C.c_uint64(0), C.c_uint32(0), np.zeros(3)
     for cut in (3, 100, blob.shape[0] // 2, blob.shape[0] - 1):
         assert harness.snap_roundtrip(vp(blob), cut, vp(out), out.shape[0], C.byref(nb), C.byref(nn), vp(g)) == 1
-    # a mesh scene: the reference writes the mesh's whole input file; the parser says "unsupported", the writer refuses
+    # a mesh without its record: the writer refuses
     m = scenes.rb3d_random_meshes(4, 145, nplanes=0)
-    mref = RefRB3DSim(m)
-    mb = np.frombuffer(mref.serialize_state(), dtype=np.uint8).copy()
-    assert harness.snap_roundtrip(vp(mb), mb.shape[0], vp(out), 0, C.byref(nb), C.byref(nn), vp(g)) == 2
+    o = ob.RB3DOracle(m)
+    I, Ii = o.update_m_and_minv(f64(m["q"]))
+    assert product_bytes(harness, m, f64(m["q"]), f64(m["v"]), (I, Ii)) is None
+    assert product_bytes(harness, m, f64(m["q"]), f64(m["v"]), (I, Ii), mesh_records=[b"", b""]) is None
+
+
+@pytest.mark.parametrize("scene", ["meshes", "mixed"])
+def test_mesh_snapshots(oracle, harness, scene):
+    """Triangle meshes: the state snapshot holds each mesh's own record (RigidBodyTriangleMesh::serialize, RigidBodyTriangleMesh.cpp:215-232).  With the records a
+    caller attaches (here: the reference's own, mesh by mesh) the product's bytes are the reference's; the parser finds every record's extent and the arrays
+    sg_rb3d_add_mesh takes; the reference resumes from the product's bytes."""
+    s = scenes.rb3d_random_meshes(30, 146, nplanes=2) if scene == "meshes" else scenes.rb3d_mixed_segregated(40, 147)
+    n = s["geo_of_body"].shape[0]
+    o = ob.RB3DOracle(s)
+    ref = RefRB3DSim(s)
+    records = [ref.mesh_record(int(s["geo_mesh"][k])) if int(s["geo_type"][k]) == 3 else b"" for k in range(len(s["geo_type"]))]
+    assert sum(1 for r in records if r) >= 2 and all(r[0] == 3 for r in records if r)
+    q0, v0 = f64(s["q"]), f64(s["v"])
+    I, Ii = o.update_m_and_minv(q0)
+    theirs = ref.serialize_state()
+    mine = product_bytes(harness, s, q0, v0, (_transposed(I, n), _transposed(Ii, n)), mesh_records=records)
+    assert mine is not None and len(mine) == len(theirs) and mine == theirs
+    # what the parser extracts: record extents and array sizes, per geometry
+    raw = np.frombuffer(theirs, dtype=np.uint8).copy()
+    ngeo = len(records)
+    got_n, nbytes, sizes, sdf_sum = C.c_uint32(0), np.zeros(ngeo, np.uint64), np.zeros(4 * ngeo, np.uint32), np.zeros(ngeo)
+    assert harness.snap_mesh_records(vp(raw), raw.shape[0], ngeo, C.byref(got_n), vp(nbytes), vp(sizes), vp(sdf_sum)) == 0
+    assert int(got_n.value) == ngeo
+    for k in range(ngeo):
+        assert int(nbytes[k]) == len(records[k])
+        if records[k]:
+            m = s["meshes"][int(s["geo_mesh"][k])]
+            assert list(sizes[4 * k:4 * k + 4]) == [m["verts"].shape[0], m["samples"].shape[0], m["hull"].shape[0], int(np.prod(m["dims"]))]
+            assert np.isclose(sdf_sum[k], f64(m["sdf"]).sum(), rtol=1e-9)
+    # parse -> write is the identity (the records travel through), truncated mesh records are refused
+    out = np.zeros(raw.shape[0], dtype=np.uint8)
+    nb, nn, g = C.c_uint64(0), C.c_uint32(0), np.zeros(3)
+    assert harness.snap_roundtrip(vp(raw), raw.shape[0], vp(out), out.shape[0], C.byref(nb), C.byref(nn), vp(g)) == 0
+    assert int(nb.value) == raw.shape[0] and np.array_equal(out, raw)
+    rec0 = [r for r in records if r][0]
+    first = theirs.index(rec0)
+    for cut in (first + 5, first + 40, first + len(rec0) // 2, first + len(rec0) - 1):
+        assert harness.snap_roundtrip(vp(raw), cut, vp(out), out.shape[0], C.byref(nb), C.byref(nn), vp(g)) == 1
+    # the reference reads the product's bytes back and detects what the original detects
+    again = RefRB3DSim.from_snapshot(mine, n)
+    assert again.serialize_state() == mine
+    q1, _ = o.flow(3, q0, v0, s["dt"])
+    a, b = ref.active_set(q0, q1), again.active_set(q0, q1)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
