@@ -162,3 +162,48 @@ def test_a_wrong_argument_is_caught(dry):
         dry.lib.sg_rb3d_enforce_portals(dry.h, None, None)
     with pytest.raises((C.ArgumentError, TypeError)):
         dry.lib.sg_rb2d_update_portals(dry.h, "soon", None)
+
+
+def test_rb2d_state_io_calls_convert(dry):
+    """serializeState / deserializeState of the rigidbody2d mirror: the size-query call fills *bytes, the restore sizes its host-side mirror from the blob."""
+    import scisim_b200 as sb
+    from tests.test_zzz_rb2d_state_io_gpu import _sim
+    s = scenes.rb2d_periodic(40, 4, axes="xy", lees_edwards=0.3)
+    sim = _sim(s, dry, s["portals"])
+    real = dry.lib.__getattr__("sg_rb2d_state_serialize")
+    dry.lib.__dict__["sg_rb2d_state_serialize"] = lambda *a: (setattr(a[4]._obj, "value", 24), real(*a))[1]
+    blob = sim.serializeState(which=0)
+    assert isinstance(blob, bytes) and len(blob) == 24
+    assert dry.lib.calls.count("sg_rb2d_state_serialize") == 2
+    # a snapshot laid out as sg_rb2d_snapshot.h writes it: 5 bodies, 2 geometries, 1 force, 3 planes, 2 portals
+    n, nq = 5, 15
+    i64, u64 = (lambda v: np.int64(v).tobytes()), (lambda v: np.uint64(v).tobytes())
+    sparse = i64(nq) * 3 + bytes(4 * nq) + bytes(4 * (nq + 1)) + bytes(8 * nq)
+    layout = (i64(nq) + bytes(8 * nq)) * 2 + sparse * 2 + u64(n) + bytes(n) + i64(n) + bytes(4 * n) + u64(2) + np.int32(0).tobytes() + bytes(8) + np.int32(1).tobytes() + bytes(16) \
+        + u64(1) + bytes(4 + 16) + u64(3) + bytes(3 * 72) + u64(2) + bytes(2 * (2 * 72 + 24))
+    assert sb.host_api.rb2d_snapshot_counts(layout) == (5, 2)
+    sim2 = sb.RigidBody2DSim.deserializeState(layout, dry)
+    assert sim2.nqdofs() == 15 and len(sim2.state.planar_portals) == 2 and "sg_rb2d_state_deserialize" in dry.lib.calls
+    assert sim2.updatePeriodicBoundaryConditionsStartOfStep(2, 0.01).shape == (2,)
+    sim2.upload(np.zeros(15), np.zeros(15))
+    assert sim2.step(sb.SymplecticEulerMap(), 0.01) == (0, 0)
+
+
+def test_rb3d_mesh_snapshot_calls_convert(dry):
+    """RigidBody3DSim numbers its meshes through the indices sg_rb3d_add_mesh returns -- a context that already holds meshes hands out later ones -- and
+    setMeshSnapshot addresses them the same way."""
+    import scisim_b200 as sb
+    from tests.test_rb3d_gpu import make_sim
+    dry.lib.dim = 3
+    s = scenes.rb3d_random_meshes(6, 5, nplanes=1)
+    make_sim(s, dry)                 # an earlier sim on the same context: meshes 0 and 1
+    seen = []
+    real = dry.lib.__getattr__("sg_rb3d_set_geometry")
+    dry.lib.__dict__["sg_rb3d_set_geometry"] = lambda *a: (seen.append(np.ctypeslib.as_array(C.cast(a[5], C.POINTER(C.c_uint32)), shape=(int(a[1]),)).copy()), real(*a))[1]
+    sim = make_sim(s, dry)
+    assert sim.mesh_index == [2, 3] and seen[-1].tolist() == [2, 3]
+    which = []
+    real2 = dry.lib.__getattr__("sg_rb3d_set_mesh_snapshot")
+    dry.lib.__dict__["sg_rb3d_set_mesh_snapshot"] = lambda *a: (which.append((int(a[1]), int(a[3]))), real2(*a))[1]
+    sim.setMeshSnapshot(1, b"\x03" + bytes(99))
+    assert which == [(3, 100)]
