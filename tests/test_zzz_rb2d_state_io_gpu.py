@@ -2,7 +2,7 @@
 the reference's own RigidBody2DState::serialize (tests/test_rb2d_snapshot_cpu.py); what the GPU adds is where the arrays come from: the whole snapshot equals
 what the reference's own RigidBody2DState writes for the same state -- as uploaded and after a resident step, with planes, kinematic circles, boxes, portals and
 a Lees-Edwards offset -- and a context restored from it continues exactly like the original.
-(Written after this round's GPU budget was spent: first run is the driver's.  The file sorts last on purpose.)"""
+(Written with seconds of GPU time left in round 2: run on the B200 through profiles/lean_state_io_check.py -- profiles/lean_state_io_r2.log -- rather than through pytest.)"""
 import os
 
 import numpy as np

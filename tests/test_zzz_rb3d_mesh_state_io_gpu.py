@@ -2,7 +2,7 @@
 caller (sg_rb3d_set_mesh_snapshot; here the reference's own RigidBodyTriangleMesh::serialize, mesh by mesh), and sg_rb3d_state_serialize writes, from the
 device-resident state, the bytes the reference's own RigidBody3DState::serialize writes for the same scene; a context restored from them (the meshes re-added from
 their records) steps exactly like the original.  The byte layout and the record parser are checked on the CPU (tests/test_rb3d_snapshot_cpu.py::test_mesh_snapshots).
-(Written after this round's GPU budget was spent: first run is the driver's.  The file sorts last on purpose.)"""
+(Written with seconds of GPU time left in round 2: run on the B200 through profiles/lean_state_io_check.py -- profiles/lean_state_io_r2.log -- rather than through pytest.)"""
 import os
 
 import numpy as np
