@@ -266,10 +266,16 @@ def test_rb2d_sim_flow_under_gravity(oracle, kind):
     assert np.abs(v - f64(s["v"]))[free].max() > 0.4   # 5 steps of g dt
 
 
-@pytest.mark.parametrize("case", [dict(n=500, seed=111, side=10.0), dict(n=500, seed=112, side=10.0, lees_edwards=0.7, oblique=True), dict(n=500, seed=113, side=7.0, axes="y", lees_edwards=-0.9)])
+@pytest.mark.parametrize("case", [dict(n=500, seed=111, side=10.0), dict(n=500, seed=112, side=10.0, lees_edwards=0.7, oblique=True), dict(n=500, seed=113, side=7.0, axes="y", lees_edwards=-0.9),
+                                  dict(n=500, seed=114, side=10.0, lees_edwards=0.5, gravity=(0.4, -9.81))])
 def test_rb2d_sim_with_portals(oracle, case):
-    """The portal branch (RigidBody2DSim.cpp:350-636, 832-1040) and RigidBody2DSim::flow's portal bookkeeping over 8 steps without contact response."""
+    """The portal branch (RigidBody2DSim.cpp:350-636, 832-1040) and RigidBody2DSim::flow's portal bookkeeping over 8 steps without contact response
+    (the generator's scenes are weightless; the last case adds a gravity, so the reference's own M / Minv matter to its flow)."""
+    case = dict(case)
+    gravity = case.pop("gravity", None)
     s = scenes.rb2d_periodic(**case)
+    if gravity is not None:
+        s["g"] = np.array(gravity, dtype=np.float64)
     o = ob.RB2DOracle(s)
     o.set_portals(s["portals"])
     ref = RefRB2DSim(s, s["portals"])
