@@ -23,6 +23,7 @@
 #include "ball2d/ConstraintCache.h"
 
 #include <memory>
+#include <cstring>
 #include <sstream>
 
 #include <cstdint>
@@ -277,8 +278,9 @@ int ref_ball2d_constraint_probe( const int kind, const unsigned i, const unsigne
 // include/scisim_b200.h; a = first body, b = second body / static object.  r: ncomp doubles per constraint.  Returns constraintCacheEmpty() after the stores.
 extern "C"
 {
-int ref_ball2d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
-                                const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout )
+int ref_ball2d_cache_roundtrip_ex( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
+                                const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout,
+                                 void* ser_out, const uint64_t ser_cap, uint64_t* ser_bytes, const void* deser_in, const uint64_t deser_bytes )
 {
   uint32_t nb = 1;
   for( uint32_t k = 0; k < nstore; ++k ) { nb = std::max( nb, std::max( sa[k], stype[k] == 0 ? sb[k] : 0u ) + 1u ); }
@@ -301,12 +303,35 @@ int ref_ball2d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, co
     cache.cacheConstraint( *make( stype[k], sa[k], sb[k] ), r );
   }
   const int empty = cache.empty() ? 1 : 0;
+  // optionally: ConstraintCache::serialize of what was stored, handed to the caller, and / or the queries answered by a second cache that
+  // ConstraintCache::deserialize filled from the caller's bytes
+  if( ser_bytes != nullptr )
+  {
+    std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+    cache.serialize( stm );
+    const std::string bytes = stm.str();
+    *ser_bytes = bytes.size();
+    if( ser_out != nullptr && bytes.size() <= ser_cap ) { std::memcpy( ser_out, bytes.data(), bytes.size() ); }
+  }
+  ConstraintCache restored;
+  if( deser_in != nullptr )
+  {
+    std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+    stm.write( static_cast<const char*>( deser_in ), std::streamsize( deser_bytes ) );
+    restored.deserialize( stm );
+  }
+  ConstraintCache& qcache = ( deser_in != nullptr ) ? restored : cache;
   for( uint32_t k = 0; k < nquery; ++k )
   {
     for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = -7.0; }
-    cache.getCachedConstraint( *make( qtype[k], qa[k], qb[k] ), r );
+    qcache.getCachedConstraint( *make( qtype[k], qa[k], qb[k] ), r );
     for( uint32_t c = 0; c < ncomp; ++c ) { rout[size_t( k ) * ncomp + c] = r( int( c ) ); }
   }
   return empty;
+}
+int ref_ball2d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
+                                const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout )
+{
+  return ref_ball2d_cache_roundtrip_ex( nstore, stype, sa, sb, ncomp, rstore, nquery, qtype, qa, qb, rout, nullptr, 0, nullptr, nullptr, 0 );
 }
 }

@@ -33,6 +33,7 @@
 #include "rigidbody3d/RigidBody3DState.h"
 #include "rigidbody3d/ConstraintCache.h"
 #include <memory>
+#include <cstring>
 
 #include <sstream>
 
@@ -463,8 +464,9 @@ void ref_rb3d_state_mass_matrices( const uint32_t n, const double* q_ctor, const
 // (sphere constraints only: 10 sphere-sphere, 14 plane-sphere, 17 cylinder-sphere, 11 kinematic sphere-sphere -- anything else exits, as in the reference)
 extern "C"
 {
-int ref_rb3d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
-                              const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout )
+int ref_rb3d_cache_roundtrip_ex( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
+                              const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout,
+                                 void* ser_out, const uint64_t ser_cap, uint64_t* ser_bytes, const void* deser_in, const uint64_t deser_bytes )
 {
   const StaticPlane plane{ Vector3s{ 0.0, 0.0, 0.0 }, Vector3s{ 0.0, 1.0, 0.0 } };
   const StaticCylinder cyl{ Vector3s{ 0.0, 0.0, 0.0 }, Vector3s{ 0.0, 1.0, 0.0 }, 10.0 };
@@ -484,12 +486,35 @@ int ref_rb3d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, cons
     cache.cacheConstraint( *make( stype[k], sa[k], sb[k] ), r );
   }
   const int empty = cache.empty() ? 1 : 0;
+  // optionally: ConstraintCache::serialize of what was stored, handed to the caller, and / or the queries answered by a second cache that
+  // ConstraintCache::deserialize filled from the caller's bytes
+  if( ser_bytes != nullptr )
+  {
+    std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+    cache.serialize( stm );
+    const std::string bytes = stm.str();
+    *ser_bytes = bytes.size();
+    if( ser_out != nullptr && bytes.size() <= ser_cap ) { std::memcpy( ser_out, bytes.data(), bytes.size() ); }
+  }
+  ConstraintCache restored;
+  if( deser_in != nullptr )
+  {
+    std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+    stm.write( static_cast<const char*>( deser_in ), std::streamsize( deser_bytes ) );
+    restored.deserialize( stm );
+  }
+  ConstraintCache& qcache = ( deser_in != nullptr ) ? restored : cache;
   for( uint32_t k = 0; k < nquery; ++k )
   {
     for( uint32_t c = 0; c < ncomp; ++c ) { r( int( c ) ) = -7.0; }
-    cache.getCachedConstraint( *make( qtype[k], qa[k], qb[k] ), r );
+    qcache.getCachedConstraint( *make( qtype[k], qa[k], qb[k] ), r );
     for( uint32_t c = 0; c < ncomp; ++c ) { rout[size_t( k ) * ncomp + c] = r( int( c ) ); }
   }
   return empty;
+}
+int ref_rb3d_cache_roundtrip( const uint32_t nstore, const uint32_t* stype, const uint32_t* sa, const uint32_t* sb, const uint32_t ncomp, const double* rstore,
+                              const uint32_t nquery, const uint32_t* qtype, const uint32_t* qa, const uint32_t* qb, double* rout )
+{
+  return ref_rb3d_cache_roundtrip_ex( nstore, stype, sa, sb, ncomp, rstore, nquery, qtype, qa, qb, rout, nullptr, 0, nullptr, nullptr, 0 );
 }
 }

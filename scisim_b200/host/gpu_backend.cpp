@@ -10,6 +10,7 @@
 #include <iterator>
 #include <limits>
 #include <numeric>
+#include <sstream>
 
 void GravityOnlyGuard::verify( FlowableSystem& fsys, const VectorXs& q0, const VectorXs& v0, const scalar& t, const Layout layout, const char* who )
 {
@@ -401,6 +402,64 @@ void PairImpulseCache::getCachedConstraint( const int kind, const unsigned a, co
   r.setZero();
 }
 
+// the order in which each sim's ConstraintCache::serialize writes its maps, as kinds of this class (see the header); -1 ends the list
+static const int g_cache_order[3][5] = { { 0, 1, 2, -1, -1 },     // ball2d: ball-ball, plane-ball, drum-ball
+                                         { 0, 2, 3, 1, -1 },      // rigidbody2d: circle-circle, body-body, kinematic object - circle, plane-circle
+                                         { 0, 1, 2, 3, -1 } };    // rigidbody3d: sphere-sphere, plane-sphere, cylinder-sphere, kinematic sphere-sphere
+
+void PairImpulseCache::serialize( const Sim sim, std::ostream& output_stream ) const
+{
+  for( const int* kind = g_cache_order[sim]; *kind >= 0; ++kind )
+  {
+    Table& t = m_tables[*kind];
+    t.sortIfNeeded();
+    // a key stored twice occupies two slots here and one in the reference's std::map (its first impulse): count and write the first of each run
+    std::size_t unique = 0;
+    for( std::size_t n = 0; n < t.keys.size(); ++n ) { if( n == 0 || t.keys[n] != t.keys[n - 1] ) { ++unique; } }
+    output_stream.write( reinterpret_cast<const char*>( &unique ), sizeof( std::size_t ) );
+    for( std::size_t n = 0; n < t.keys.size(); ++n )
+    {
+      if( n > 0 && t.keys[n] == t.keys[n - 1] ) { continue; }
+      const unsigned first = static_cast<unsigned>( t.keys[n] >> 32 ), second = static_cast<unsigned>( t.keys[n] & 0xffffffffu );
+      const long long rows = static_cast<long long>( t.width );
+      output_stream.write( reinterpret_cast<const char*>( &first ), sizeof( unsigned ) );
+      output_stream.write( reinterpret_cast<const char*>( &second ), sizeof( unsigned ) );
+      output_stream.write( reinterpret_cast<const char*>( &rows ), sizeof( long long ) );
+      output_stream.write( reinterpret_cast<const char*>( &t.values[n * t.width] ), std::streamsize( t.width * sizeof( double ) ) );
+    }
+  }
+}
+
+bool PairImpulseCache::deserialize( const Sim sim, std::istream& input_stream )
+{
+  clear();
+  for( const int* kind = g_cache_order[sim]; *kind >= 0; ++kind )
+  {
+    Table& t = m_tables[*kind];
+    std::size_t count = 0;
+    input_stream.read( reinterpret_cast<char*>( &count ), sizeof( std::size_t ) );
+    if( !input_stream.good() ) { clear(); return false; }
+    for( std::size_t n = 0; n < count; ++n )
+    {
+      unsigned first = 0, second = 0;
+      long long rows = -1;
+      input_stream.read( reinterpret_cast<char*>( &first ), sizeof( unsigned ) );
+      input_stream.read( reinterpret_cast<char*>( &second ), sizeof( unsigned ) );
+      input_stream.read( reinterpret_cast<char*>( &rows ), sizeof( long long ) );
+      // one width per map: the impulses of one constraint class have one length
+      if( !input_stream.good() || rows < 0 || rows > 64 || ( n > 0 && static_cast<unsigned>( rows ) != t.width ) ) { clear(); return false; }
+      if( n == 0 ) { t.width = static_cast<unsigned>( rows ); }
+      const uint64_t key = ( uint64_t( first ) << 32 ) | second;
+      if( !t.keys.empty() && key <= t.keys.back() ) { t.sorted = false; }
+      t.keys.push_back( key );
+      t.values.resize( t.values.size() + t.width );
+      input_stream.read( reinterpret_cast<char*>( t.values.data() + ( t.values.size() - t.width ) ), std::streamsize( t.width * sizeof( double ) ) );
+      if( !input_stream.good() ) { clear(); return false; }
+    }
+  }
+  return true;
+}
+
 extern "C"
 {
 void* sgh_cache_create() { return new PairImpulseCache; }
@@ -418,6 +477,19 @@ void sgh_cache_lookup( const void* cache, int kind, unsigned a, unsigned b, doub
   VectorXs v( static_cast<long>( ncomp ) );
   static_cast<const PairImpulseCache*>( cache )->getCachedConstraint( kind, a, b, v );
   for( unsigned c = 0; c < ncomp; ++c ) { r[c] = v( c ); }
+}
+uint64_t sgh_cache_serialize( const void* cache, int sim, void* buf, uint64_t cap )
+{
+  std::ostringstream stm( std::ios::out | std::ios::binary );
+  static_cast<const PairImpulseCache*>( cache )->serialize( static_cast<PairImpulseCache::Sim>( sim ), stm );
+  const std::string bytes = stm.str();
+  if( buf != nullptr && bytes.size() <= cap ) { std::memcpy( buf, bytes.data(), bytes.size() ); }
+  return bytes.size();
+}
+int sgh_cache_deserialize( void* cache, int sim, const void* buf, uint64_t bytes )
+{
+  std::istringstream stm( std::string( static_cast<const char*>( buf ), static_cast<std::size_t>( bytes ) ), std::ios::in | std::ios::binary );
+  return static_cast<PairImpulseCache*>( cache )->deserialize( static_cast<PairImpulseCache::Sim>( sim ), stm ) ? 1 : 0;
 }
 }
 

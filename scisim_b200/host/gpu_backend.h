@@ -210,6 +210,12 @@ public:
   // A key stored twice keeps its FIRST impulse, as std::map::insert does (box-box gives two body-body contacts per pair: both read the first one's).
   void cacheConstraint( const int kind, const unsigned a, const unsigned b, const VectorXs& r );
   void getCachedConstraint( const int kind, const unsigned a, const unsigned b, VectorXs& r ) const;
+  // ConstraintCache::serialize / deserialize of the three sims, byte for byte (ball2d/ConstraintCache.cpp:125-174, rigidbody2d/ConstraintCache.cpp:140-191,
+  // rigidbody3d/ConstraintCache.cpp:168-220): per keyed map, in the order the sim's class writes them, a size_t count and then, in ascending key order,
+  // { unsigned first, unsigned second, Eigen::Index rows, rows doubles }.  <Sim>::serialize writes the state first and this after it.
+  enum Sim { BALL2D = 0, RIGIDBODY2D = 1, RIGIDBODY3D = 2 };
+  void serialize( const Sim sim, std::ostream& output_stream ) const;
+  bool deserialize( const Sim sim, std::istream& input_stream ); // false on a truncated or malformed stream (the cache is then empty)
 private:
   struct Table
   {
@@ -231,6 +237,8 @@ void sgh_cache_clear( void* cache );
 int sgh_cache_empty( const void* cache );
 void sgh_cache_store( void* cache, int kind, unsigned a, unsigned b, const double* r, unsigned ncomp );
 void sgh_cache_lookup( const void* cache, int kind, unsigned a, unsigned b, double* r, unsigned ncomp );
+uint64_t sgh_cache_serialize( const void* cache, int sim, void* buf, uint64_t cap );        /* returns the length; written when it fits cap */
+int sgh_cache_deserialize( void* cache, int sim, const void* buf, uint64_t bytes );          /* 1 ok, 0 malformed */
 }
 
 // ---- rigidbody3d ---------------------------------------------------------------------------------------------------

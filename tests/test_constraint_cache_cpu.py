@@ -145,3 +145,87 @@ def test_oracle_cache_equals_reference_cache(oracle):
     ref(na, vp(u32(a["type"])), vp(u32(a["i"])), vp(u32(a["j"])), 2, vp(np.ascontiguousarray(r)), nb, vp(u32(b["type"])), vp(u32(b["i"])), vp(u32(b["j"])), vp(want))
     assert np.array_equal(got.reshape(nb, 2), want)
     assert hits == int((want != 0.0).any(axis=1).sum()) and 0 < hits < nb
+
+
+SIM_CODE = {"ball2d": 0, "rb2d": 1, "rb3d": 2}
+
+
+@pytest.mark.parametrize("sim", ["ball2d", "rb3d", "rb2d"])
+@pytest.mark.parametrize("ncomp,unique", [(1, True), (2, False)])
+def test_host_cache_snapshot_equals_reference_cache_snapshot(sim, ncomp, unique):
+    """ConstraintCache::serialize / deserialize (ball2d/ConstraintCache.cpp:125-174 and the two rigid-body twins), the second half of <Sim>::serialize: the
+    host cache writes the reference's bytes for the same stores (a key stored twice is written once, with its first impulse), reads the reference's bytes back
+    and answers like it, and the reference's own cache, filled from the host cache's bytes, answers like the original."""
+    path = os.path.join(REF, "libref_%s.so" % sim)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs the reference tree)")
+    ref = getattr(C.CDLL(path), "ref_%s_cache_roundtrip_ex" % sim)
+    ref.restype = C.c_int
+    V = C.c_void_p
+    ref.argtypes = [C.c_uint32, V, V, V, C.c_uint32, V, C.c_uint32, V, V, V, V, V, C.c_uint64, V, V, C.c_uint64]
+    host = _host()
+    host.sgh_cache_serialize.restype = C.c_uint64
+    host.sgh_cache_serialize.argtypes = [V, C.c_int, V, C.c_uint64]
+    host.sgh_cache_deserialize.argtypes = [V, C.c_int, V, C.c_uint64]
+    rng = np.random.default_rng({"ball2d": 500, "rb3d": 600, "rb2d": 700}[sim] + ncomp)
+    st, si, sj = _random_contacts(sim, rng, 2000, 300, 4, False)
+    if unique:
+        key = (st.astype(np.uint64) << np.uint64(50)) | (si.astype(np.uint64) << np.uint64(25)) | sj.astype(np.uint64)
+        _, first = np.unique(key, return_index=True)
+        first.sort()
+        st, si, sj = (np.ascontiguousarray(a[first]) for a in (st, si, sj))
+    ns = st.shape[0]
+    r = rng.normal(size=(ns, ncomp))
+    qt, qi, qj = _random_contacts(sim, rng, ns, 300, 4, False)
+    perm = rng.permutation(ns)
+    qt, qi, qj = (np.ascontiguousarray(np.concatenate([a[perm], b])) for a, b in ((st, qt), (si, qi), (sj, qj)))
+    nq = qt.shape[0]
+    # the reference: answers and its own snapshot
+    want = np.zeros((nq, ncomp))
+    nbytes = C.c_uint64(0)
+    ref(ns, vp(st), vp(si), vp(sj), ncomp, vp(r), nq, vp(qt), vp(qi), vp(qj), vp(want), None, 0, C.byref(nbytes), None, 0)
+    theirs = np.zeros(int(nbytes.value), dtype=np.uint8)
+    ref(ns, vp(st), vp(si), vp(sj), ncomp, vp(r), nq, vp(qt), vp(qi), vp(qj), vp(want), vp(theirs), theirs.shape[0], C.byref(nbytes), None, 0)
+    assert (want != 0.0).any(axis=1)[:ns].all()
+
+    def fill(h):
+        for k in range(ns):
+            kind, keyf = KINDS[sim][int(st[k])]
+            a, b = keyf(int(si[k]), int(sj[k]))
+            host.sgh_cache_store(h, kind, a, b, vp(np.ascontiguousarray(r[k])), ncomp)
+
+    def answers(h):
+        got, row = np.full((nq, ncomp), -7.0), np.zeros(ncomp)
+        for k in range(nq):
+            kind, keyf = KINDS[sim][int(qt[k])]
+            a, b = keyf(int(qi[k]), int(qj[k]))
+            host.sgh_cache_lookup(h, kind, a, b, vp(row), ncomp)
+            got[k] = row
+        return got
+
+    h, h2 = host.sgh_cache_create(), host.sgh_cache_create()
+    try:
+        fill(h)
+        need = int(host.sgh_cache_serialize(h, SIM_CODE[sim], None, 0))
+        mine = np.zeros(need, dtype=np.uint8)
+        assert int(host.sgh_cache_serialize(h, SIM_CODE[sim], vp(mine), need)) == need
+        assert need == theirs.shape[0] and np.array_equal(mine, theirs)
+        # the host cache from the reference's bytes
+        assert host.sgh_cache_deserialize(h2, SIM_CODE[sim], vp(theirs), theirs.shape[0]) == 1
+        assert np.array_equal(answers(h2), want)
+        assert int(host.sgh_cache_serialize(h2, SIM_CODE[sim], vp(mine), need)) == need and np.array_equal(mine, theirs)
+        # truncated streams are refused and leave an empty cache
+        for cut in (3, need // 2, need - 1):
+            assert host.sgh_cache_deserialize(h2, SIM_CODE[sim], vp(theirs), cut) == 0
+            assert host.sgh_cache_empty(h2) == 1
+        # the reference's cache from the host cache's bytes
+        again = np.full((nq, ncomp), 3.0)
+        z, none = np.zeros(0, dtype=np.uint32), np.zeros((0, ncomp))
+        ref(0, vp(z), vp(z), vp(z), ncomp, vp(none), nq, vp(qt), vp(qi), vp(qj), vp(again), None, 0, None, vp(mine), need)
+        assert np.array_equal(again, want)
+        # an empty cache: one zero count per map
+        host.sgh_cache_clear(h)
+        assert int(host.sgh_cache_serialize(h, SIM_CODE[sim], None, 0)) == 8 * (3 if sim == "ball2d" else 4)
+    finally:
+        host.sgh_cache_destroy(h)
+        host.sgh_cache_destroy(h2)
