@@ -38,11 +38,24 @@ void GravityOnlyGuard::verify( FlowableSystem& fsys, const VectorXs& q0, const V
 
 // After a deserializeState the device integrates with the masses and the gravity of the snapshot: the guard is told both, so that the first GPU map flow
 // after a restore is checked against them.  The library has accepted the stream when this runs; a stream it would not accept ends the process here.
-unsigned GravityOnlyGuard::configureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, const char* who )
+unsigned GravityOnlyGuard::configureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, const char* who, std::size_t* consumed )
+{
+  unsigned n = 0;
+  const char* why = tryConfigureFromSnapshot( layout, buf, bytes, n, consumed );
+  if( why[0] != '\0' )
+  {
+    std::cerr << who << ": " << why << ". Exiting." << std::endl;
+    std::exit( EXIT_FAILURE );
+  }
+  return n;
+}
+
+// "" on success, else what is wrong with the stream (nothing is configured then)
+const char* GravityOnlyGuard::tryConfigureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, unsigned& n, std::size_t* consumed )
 {
   sg_snapshot::Source in{ reinterpret_cast<const unsigned char*>( buf ), bytes, 0, true };
   const char* why = "";
-  unsigned n = 0;
+  n = 0;
   if( layout == BALL2D )
   {
     // Ball2DState::serialize (ball2d/Ball2DState.cpp:259-272): q, v, r, fixed, M, Minv, drums, planes, portals, forces; M's values hold each mass twice
@@ -81,12 +94,24 @@ unsigned GravityOnlyGuard::configureFromSnapshot( const Layout layout, const cha
     sg_snapshot::Rb3dState st;
     if( sg_snapshot::parse( in, st, &why ) == 0 ) { n = st.n; setMasses( st.m.data(), n, 1 ); setGravity( st.g[0], st.g[1], st.g[2] ); }
   }
-  if( why[0] != '\0' )
-  {
-    std::cerr << who << ": " << why << ". Exiting." << std::endl;
-    std::exit( EXIT_FAILURE );
-  }
-  return n;
+  if( why[0] == '\0' && consumed != nullptr ) { *consumed = static_cast<std::size_t>( in.n ); }
+  return why;
+}
+
+// <Sim>::deserialize reads the state and then the constraint cache from one stream (Ball2DSim.cpp:817-822, RigidBody2DSim.cpp:1147-1152, RigidBody3DSim.cpp:1600-1606).
+// A state snapshot is self-delimiting only to its parser, so the wrappers below read the rest of the stream, hand it to the library (which ignores what follows
+// the state) and then put the stream back to the first byte after the state, ready for PairImpulseCache::deserialize.
+std::vector<char> sghReadRest( std::istream& input_stream, std::istream::pos_type& start )
+{
+  start = input_stream.tellg();
+  return std::vector<char>( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
+}
+
+void sghRewindBehindState( std::istream& input_stream, const std::istream::pos_type start, const std::size_t consumed )
+{
+  if( start == std::istream::pos_type( -1 ) ) { return; } // not seekable: the caller gave a stream that ends with the state
+  input_stream.clear();
+  input_stream.seekg( start + std::streamoff( consumed ) );
 }
 
 GpuBall2DBackend::GpuBall2DBackend( const int device )
@@ -230,10 +255,12 @@ void GpuBall2DBackend::serializeState( std::ostream& output_stream, const bool f
 
 void GpuBall2DBackend::deserializeState( std::istream& input_stream )
 {
-  // the snapshot is self-delimiting only to its parser: hand over the rest of the stream (Ball2DSim::deserialize reads the state last, Ball2DSim.cpp:800-807)
-  const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
+  std::istream::pos_type start;
+  const std::vector<char> buf = sghReadRest( input_stream, start );
   check( sg_ball2d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_ball2d_state_deserialize" );
-  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::BALL2D, buf.data(), buf.size(), "GpuBall2DBackend::deserializeState" );
+  std::size_t consumed = 0;
+  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::BALL2D, buf.data(), buf.size(), "GpuBall2DBackend::deserializeState", &consumed );
+  sghRewindBehindState( input_stream, start, consumed );
 }
 
 void GpuBall2DBackend::getPotentialOverlaps( const std::vector<double>& aabbs, std::vector<std::pair<unsigned,unsigned>>& overlaps )
@@ -486,6 +513,15 @@ uint64_t sgh_cache_serialize( const void* cache, int sim, void* buf, uint64_t ca
   if( buf != nullptr && bytes.size() <= cap ) { std::memcpy( buf, bytes.data(), bytes.size() ); }
   return bytes.size();
 }
+uint64_t sgh_state_snapshot_length( int sim, const void* buf, uint64_t bytes )
+{
+  GravityOnlyGuard guard;
+  unsigned n = 0;
+  std::size_t consumed = 0;
+  const GravityOnlyGuard::Layout layout = sim == 0 ? GravityOnlyGuard::BALL2D : sim == 1 ? GravityOnlyGuard::RIGIDBODY2D : GravityOnlyGuard::RIGIDBODY3D;
+  const char* why = guard.tryConfigureFromSnapshot( layout, static_cast<const char*>( buf ), static_cast<std::size_t>( bytes ), n, &consumed );
+  return why[0] == '\0' ? uint64_t( consumed ) : 0u;
+}
 int sgh_cache_deserialize( void* cache, int sim, const void* buf, uint64_t bytes )
 {
   std::istringstream stm( std::string( static_cast<const char*>( buf ), static_cast<std::size_t>( bytes ) ), std::ios::in | std::ios::binary );
@@ -613,9 +649,12 @@ void GpuRigidBody3DBackend::serializeState( std::ostream& output_stream, const b
 
 void GpuRigidBody3DBackend::deserializeState( std::istream& input_stream, const bool from_running_simulation )
 {
-  const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
+  std::istream::pos_type start;
+  const std::vector<char> buf = sghReadRest( input_stream, start );
   check( sg_rb3d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_rb3d_state_deserialize" );
-  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::RIGIDBODY3D, buf.data(), buf.size(), "GpuRigidBody3DBackend::deserializeState" );
+  std::size_t consumed = 0;
+  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::RIGIDBODY3D, buf.data(), buf.size(), "GpuRigidBody3DBackend::deserializeState", &consumed );
+  sghRewindBehindState( input_stream, start, consumed );
   m_m_updated = from_running_simulation;
 }
 
@@ -771,11 +810,12 @@ void GpuRigidBody2DBackend::serializeState( std::ostream& output_stream, const b
 
 void GpuRigidBody2DBackend::deserializeState( std::istream& input_stream )
 {
-  // the snapshot is self-delimiting only to its parser: hand over the rest of the stream (RigidBody2DSim::deserialize reads the constraint cache after the
-  // state, RigidBody2DSim.cpp:1147-1152: split the stream before calling this where a cache follows)
-  const std::vector<char> buf( ( std::istreambuf_iterator<char>( input_stream ) ), std::istreambuf_iterator<char>() );
+  std::istream::pos_type start;
+  const std::vector<char> buf = sghReadRest( input_stream, start );
   check( sg_rb2d_state_deserialize( m_ctx, buf.data(), buf.size() ), "sg_rb2d_state_deserialize" );
-  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::RIGIDBODY2D, buf.data(), buf.size(), "GpuRigidBody2DBackend::deserializeState" );
+  std::size_t consumed = 0;
+  m_nbodies = m_guard.configureFromSnapshot( GravityOnlyGuard::RIGIDBODY2D, buf.data(), buf.size(), "GpuRigidBody2DBackend::deserializeState", &consumed );
+  sghRewindBehindState( input_stream, start, consumed );
 }
 
 void GpuRB2DSymplecticEulerMap::flow( const VectorXs& q0, const VectorXs& v0, FlowableSystem& fsys, const unsigned iteration, const scalar& dt, VectorXs& q1, VectorXs& v1 )

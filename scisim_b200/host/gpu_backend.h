@@ -60,12 +60,19 @@ public:
   void setGravity( const double gx, const double gy, const double gz ) { m_g[0] = gx; m_g[1] = gy; m_g[2] = gz; m_checked = false; }
   void verify( FlowableSystem& fsys, const VectorXs& q0, const VectorXs& v0, const scalar& t, const Layout layout, const char* who );
   // masses and gravity from a state snapshot the library has accepted (the three *State::serialize layouts); returns the body count
-  unsigned configureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, const char* who );
+  // *consumed <- the length of the state's snapshot inside buf (what follows -- the constraint cache in <Sim>::serialize's stream -- is not the state's)
+  unsigned configureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, const char* who, std::size_t* consumed = nullptr );
+  const char* tryConfigureFromSnapshot( const Layout layout, const char* buf, const std::size_t bytes, unsigned& n, std::size_t* consumed );
 private:
   std::vector<double> m_mass;
   double m_g[3] = { 0.0, 0.0, 0.0 };
   bool m_checked = false;
 };
+
+// what the deserializeState wrappers do around the library call: read the rest of the stream (its position goes to start), and afterwards put a seekable
+// stream back to the first byte behind the state's `consumed` bytes
+std::vector<char> sghReadRest( std::istream& input_stream, std::istream::pos_type& start );
+void sghRewindBehindState( std::istream& input_stream, const std::istream::pos_type start, const std::size_t consumed );
 
 class GpuBall2DBackend final
 {
@@ -239,6 +246,9 @@ void sgh_cache_store( void* cache, int kind, unsigned a, unsigned b, const doubl
 void sgh_cache_lookup( const void* cache, int kind, unsigned a, unsigned b, double* r, unsigned ncomp );
 uint64_t sgh_cache_serialize( const void* cache, int sim, void* buf, uint64_t cap );        /* returns the length; written when it fits cap */
 int sgh_cache_deserialize( void* cache, int sim, const void* buf, uint64_t bytes );          /* 1 ok, 0 malformed */
+/* the length of the state snapshot ( sim 0 Ball2DState, 1 RigidBody2DState, 2 RigidBody3DState ) at the head of buf -- where the constraint cache starts in a
+   <Sim>::serialize stream; 0 = not a state snapshot */
+uint64_t sgh_state_snapshot_length( int sim, const void* buf, uint64_t bytes );
 }
 
 // ---- rigidbody3d ---------------------------------------------------------------------------------------------------

@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <fstream>
 #include <iterator>
+#include <sstream>
+#include <string>
 #include <vector>
 
 struct ForceOnly final : public FlowableSystem
@@ -36,8 +38,31 @@ static std::vector<char> slurp( const char* path )
   return std::vector<char>( ( std::istreambuf_iterator<char>( f ) ), std::istreambuf_iterator<char>() );
 }
 
+// guard_harness split <layout> <file: a <Sim>::serialize stream = state, then the constraint cache> <prefix bytes to skip first>: the stream handling of the
+// deserializeState wrappers (sghReadRest, the guard's parser, sghRewindBehindState); prints how many bytes are left behind the state and their sum
+static int split( const int layout, const char* path, const int prefix )
+{
+  const std::vector<char> all = slurp( path );
+  std::stringstream stm( std::ios::in | std::ios::out | std::ios::binary );
+  stm.write( all.data(), std::streamsize( all.size() ) );
+  stm.seekg( prefix );
+  std::istream::pos_type start;
+  const std::vector<char> rest = sghReadRest( stm, start );
+  GravityOnlyGuard guard;
+  const GravityOnlyGuard::Layout lay = layout == 0 ? GravityOnlyGuard::BALL2D : layout == 1 ? GravityOnlyGuard::RIGIDBODY2D : GravityOnlyGuard::RIGIDBODY3D;
+  std::size_t consumed = 0;
+  guard.configureFromSnapshot( lay, rest.data(), rest.size(), "guard_harness", &consumed );
+  sghRewindBehindState( stm, start, consumed );
+  const std::vector<char> behind( ( std::istreambuf_iterator<char>( stm ) ), std::istreambuf_iterator<char>() );
+  unsigned long sum = 0;
+  for( const char c : behind ) { sum += static_cast<unsigned char>( c ); }
+  std::printf( "behind=%zu sum=%lu consumed=%zu\n", behind.size(), sum, consumed );
+  return 0;
+}
+
 int main( int argc, char** argv )
 {
+  if( argc >= 5 && std::string( argv[1] ) == "split" ) { return split( std::atoi( argv[2] ), argv[3], std::atoi( argv[4] ) ); }
   if( argc < 4 ) { return 2; }
   const int layout = std::atoi( argv[1] );
   const std::vector<char> blob = slurp( argv[2] ), mg = slurp( argv[3] );

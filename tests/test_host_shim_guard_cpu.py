@@ -63,3 +63,37 @@ def test_guard_follows_the_snapshot(oracle, harness, tmp_path):
         assert cut.returncode == 1 and "Exiting" in cut.stdout, cut.stdout
         seen += 1
     assert seen == 3
+
+
+def test_state_snapshot_length_splits_a_sim_stream(oracle, harness, tmp_path):
+    """<Sim>::serialize writes the state and then the constraint cache into one stream (Ball2DSim.cpp:810-822 and the twins).  sgh_state_snapshot_length -- the
+    same parser the deserializeState wrappers use to put the stream back behind the state -- finds where the reference's own state snapshot ends, whatever
+    follows it: here the reference's own ConstraintCache::serialize bytes."""
+    import ctypes as C
+    from tests.test_constraint_cache_cpu import KINDS, REF, _random_contacts, vp
+    host = C.CDLL(os.path.join(HOST, "libscisim_b200_host.so"))
+    host.sgh_state_snapshot_length.restype = C.c_uint64
+    host.sgh_state_snapshot_length.argtypes = [C.c_int, C.c_void_p, C.c_uint64]
+    V = C.c_void_p
+    for (layout, blob, m, g), sim in zip(_cases(), ("ball2d", "rb2d", "rb3d")):
+        ref = getattr(C.CDLL(os.path.join(REF, "libref_%s.so" % sim)), "ref_%s_cache_roundtrip_ex" % sim)
+        ref.restype = C.c_int
+        ref.argtypes = [C.c_uint32, V, V, V, C.c_uint32, V, C.c_uint32, V, V, V, V, V, C.c_uint64, V, V, C.c_uint64]
+        rng = np.random.default_rng(layout)
+        st, si, sj = _random_contacts(sim, rng, 200, 50, 3, True)
+        r = rng.normal(size=(200, 2))
+        z, none, nb = np.zeros(0, dtype=np.uint32), np.zeros((0, 2)), C.c_uint64(0)
+        ref(200, vp(st), vp(si), vp(sj), 2, vp(r), 0, vp(z), vp(z), vp(z), vp(none), None, 0, C.byref(nb), None, 0)
+        cache = np.zeros(int(nb.value), dtype=np.uint8)
+        ref(200, vp(st), vp(si), vp(sj), 2, vp(r), 0, vp(z), vp(z), vp(z), vp(none), vp(cache), cache.shape[0], C.byref(nb), None, 0)
+        assert cache.shape[0] > 200 * 8
+        stream = np.frombuffer(blob + cache.tobytes(), dtype=np.uint8).copy()
+        assert int(host.sgh_state_snapshot_length(layout, vp(stream), stream.shape[0])) == len(blob)
+        assert int(host.sgh_state_snapshot_length(layout, vp(stream), len(blob))) == len(blob)
+        assert int(host.sgh_state_snapshot_length(layout, vp(stream), len(blob) - 1)) == 0
+        assert int(host.sgh_state_snapshot_length(layout, vp(stream), 5)) == 0
+        # the wrappers' stream handling: read the rest, parse, seek back -- what is left in the stream is the cache, whatever came before the state
+        for prefix in (0, 11):
+            (tmp_path / "stream").write_bytes(b"x" * prefix + stream.tobytes())
+            out = subprocess.run([harness, "split", str(layout), str(tmp_path / "stream"), str(prefix)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            assert out.returncode == 0 and out.stdout.strip() == "behind=%d sum=%d consumed=%d" % (cache.shape[0], int(cache.astype(np.uint64).sum()), len(blob)), out.stdout
