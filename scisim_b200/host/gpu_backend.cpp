@@ -244,7 +244,7 @@ void GpuBall2DBackend::cacheClear()
   check( sg_ball2d_cache_clear( m_ctx ), "sg_ball2d_cache_clear" );
 }
 
-void GpuBall2DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow )
+void GpuBall2DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow ) const
 {
   uint64_t bytes = 0;
   check( sg_ball2d_state_serialize( m_ctx, from_last_flow ? 1 : 0, nullptr, 0, &bytes ), "sg_ball2d_state_serialize" );
@@ -637,7 +637,7 @@ void GpuRigidBody3DBackend::updateMandMinv( const VectorXs& q, double* m_values,
   m_m_updated = true;
 }
 
-void GpuRigidBody3DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow )
+void GpuRigidBody3DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow ) const
 {
   uint64_t bytes = 0;
   const int updated = ( from_last_flow || m_m_updated ) ? 1 : 0; // RigidBody3DSim::flow runs updateMandMinv after every map
@@ -799,7 +799,7 @@ void GpuRigidBody2DBackend::computeActiveSet( const VectorXs& q0, const VectorXs
   if( num_candidates != nullptr ) { *num_candidates = c.n_candidates; }
 }
 
-void GpuRigidBody2DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow )
+void GpuRigidBody2DBackend::serializeState( std::ostream& output_stream, const bool from_last_flow ) const
 {
   uint64_t bytes = 0;
   check( sg_rb2d_state_serialize( m_ctx, from_last_flow ? 1 : 0, nullptr, 0, &bytes ), "sg_rb2d_state_serialize" );

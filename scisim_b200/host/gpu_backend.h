@@ -116,7 +116,7 @@ public:
   void cacheClear();
   // Ball2DState::serialize / deserialize (ball2d/Ball2DState.cpp:259-312) from / into the device-resident state: what Ball2DSim::serialize writes for its
   // state.  from_last_flow: ( q1, v1 ) of the last flow / step, else ( q0, v0 ) as uploaded.
-  void serializeState( std::ostream& output_stream, const bool from_last_flow = true );
+  void serializeState( std::ostream& output_stream, const bool from_last_flow = true ) const;
   void deserializeState( std::istream& input_stream );
 
   sg_ctx* context() { return m_ctx; }
@@ -313,7 +313,7 @@ public:
   void updateMandMinv( const VectorXs& q, double* m_values, double* minv_values, const bool from_last_flow = false );
   // RigidBody3DState::serialize / deserialize (rigidbody3d/RigidBody3DState.cpp:586-668) from / into the device-resident state (spheres and boxes; the mass
   // matrices in the layout this backend's flows read: the constructor's until updateMandMinv has run, its own afterwards)
-  void serializeState( std::ostream& output_stream, const bool from_last_flow = true );
+  void serializeState( std::ostream& output_stream, const bool from_last_flow = true ) const;
   void deserializeState( std::istream& input_stream, const bool from_running_simulation = true );
   // false + message on std::cerr where the reference would print and exit (unsupported geometry pairing): the caller exits
   void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact3D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
@@ -384,7 +384,7 @@ public:
   // contacts use GpuContact2D with the rigidbody2d type codes (SG_CIRCLE_CIRCLE ... SG_PLANE_BODY_2D)
   void computeActiveSet( const VectorXs& q0, const VectorXs& q1, std::vector<GpuContact2D>& contacts, uint64_t* num_candidates = nullptr, const bool from_last_flow = false );
   // RigidBody2DState::serialize / deserialize (rigidbody2d/RigidBody2DState.cpp:485-556) from / into the device-resident state
-  void serializeState( std::ostream& output_stream, const bool from_last_flow = true );
+  void serializeState( std::ostream& output_stream, const bool from_last_flow = true ) const;
   void deserializeState( std::istream& input_stream );
 
   sg_ctx* context() { return m_ctx; }
