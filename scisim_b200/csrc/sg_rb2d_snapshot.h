@@ -129,7 +129,7 @@ inline int parse( Source& in, Rb2dState& s, const char** why )
   s.geo_of_body.resize( n );
   for( uint32_t b = 0; b < n; ++b ) { s.geo_of_body[b] = in.val<unsigned>(); }
   const size_t ngeo = in.val<size_t>();
-  if( !in.ok || ngeo > ( 1u << 24 ) ) { *why = "bad geometry count"; return 1; }
+  if( !in.ok || ngeo > ( 1u << 24 ) || ngeo > ( in.cap - in.n ) / 12 ) { *why = "bad geometry count"; return 1; } // a geometry takes at least a type int and a double
   s.geo_type.assign( ngeo, 0u ); s.geo_r.assign( ngeo, 0.0 ); s.geo_half.assign( 2 * ngeo, 0.0 );
   for( size_t k = 0; k < ngeo; ++k )
   {

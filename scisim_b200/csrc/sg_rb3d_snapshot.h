@@ -222,7 +222,7 @@ inline int parse( Source& in, Rb3dState& s, const char** why )
   s.fixed.resize( n );
   for( unsigned b = 0; b < n; ++b ) { s.fixed[b] = in.val<unsigned char>(); }
   const size_t ngeo = in.val<size_t>();
-  if( !in.ok || ngeo > ( 1u << 24 ) ) { *why = "bad geometry count"; return 1; }
+  if( !in.ok || ngeo > ( 1u << 24 ) || ngeo > ( in.cap - in.n ) / 9 ) { *why = "bad geometry count"; return 1; } // a geometry takes at least a type byte and a double
   s.geo_type.assign( ngeo, 0u ); s.geo_r.assign( ngeo, 0.0 ); s.geo_half.assign( 3 * ngeo, 0.0 );
   s.geo_blob.assign( ngeo, std::vector<unsigned char>() ); s.mesh.assign( ngeo, Rb3dState::Mesh() );
   for( size_t k = 0; k < ngeo; ++k )
